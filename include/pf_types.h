@@ -1,0 +1,151 @@
+/*
+ * pf_types.h — flat, VPR-free data model of one PathFinder routing problem and its result.
+ *
+ * Everything the `--route` hot path of chinhau5/parallel_eda reads lives in global AoS
+ * structures (reference vpr/SRC/base/globals.c:48-97).  The drop-in boundary
+ * flattens those globals into the plain arrays below; nothing here includes a VPR header.
+ *
+ *   reference global                         (file:line)                      field here
+ *   ---------------------------------------------------------------------------------------
+ *   nx, ny                                   globals.c:53-54                  nx, ny
+ *   num_rr_nodes, rr_node[]                  globals.c:84-85, vpr_types.h:946 num_nodes, node SoA
+ *   rr_node[i].edges[]/switches[]            vpr_types.h:977-978              row_ptr/edge_to/edge_sw (CSR,
+ *                                                                             per-row order preserved:
+ *                                                                             prev_edge is an index into it)
+ *   switch_inf[]                             physical_types.h:744             switches[]
+ *   num_rr_indexed_data, rr_indexed_data[]   vpr_types.h:1047                 indexed[]
+ *   num_nets, clb_net[], net_rr_terminals    vpr_types.h:521, globals.c:78    net_ptr/net_terminals/net_is_global
+ *   route_bb[]                               route_common.c:1065              net_bb
+ *   clb_opins_used_locally + rr_blk_source   route_common.c:1435              opin_group_*
+ *   struct s_router_opts                     vpr_types.h:742                  pf_router_opts
+ *   trace_head[]/trace_tail[] (s_trace)      vpr_types.h:922, route_common.c:638  pf_result.trace_*
+ *   net_delay[inet][ipin]                    route_tree_timing.c:515          pf_result.net_delay
+ */
+#ifndef PF_TYPES_H
+#define PF_TYPES_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* rr node types: same numbering as t_rr_type (reference vpr/SRC/base/vpr_types.h:910). */
+enum { PF_SOURCE = 0, PF_SINK = 1, PF_IPIN = 2, PF_OPIN = 3, PF_CHANX = 4, PF_CHANY = 5 };
+
+/* cost-index rows: e_cost_indices (reference vpr_types.h:1087-1093). */
+enum { PF_SOURCE_COST_INDEX = 0, PF_SINK_COST_INDEX = 1, PF_OPIN_COST_INDEX = 2,
+       PF_IPIN_COST_INDEX = 3, PF_CHANX_COST_INDEX_START = 4 };
+
+#define PF_NO_PREVIOUS (-1)            /* vpr_types.h:944 */
+#define PF_OPEN (-1)                   /* iswitch of a SINK trace element */
+#define PF_HUGE_POSITIVE_FLOAT 1.e30f  /* vpr_types.h:84 */
+#define PF_HIGH_FANOUT_NET_LIM 64      /* vpr_types.h:91 */
+#define PF_FIRST_ITER_WIRELENGTH_LIMIT 0.85f /* vpr_types.h:93 (FIRST_ITER_WIRELENTH_LIMIT) */
+
+typedef struct pf_switch {      /* s_switch_inf, physical_types.h:744 */
+	int32_t buffered;
+	float R, Cin, Cout, Tdel;
+} pf_switch;
+
+typedef struct pf_indexed {     /* t_rr_indexed_data, vpr_types.h:1047 */
+	float base_cost;
+	float saved_base_cost;
+	int32_t ortho_cost_index;
+	int32_t seg_index;
+	float inv_length;
+	float T_linear;
+	float T_quadratic;
+	float C_load;
+} pf_indexed;
+
+typedef struct pf_router_opts { /* the s_router_opts fields the path reads, route_timing.c:140-170,283-292 */
+	float first_iter_pres_fac;
+	float initial_pres_fac;
+	float pres_fac_mult;
+	float acc_fac;
+	float bend_cost;
+	float astar_fac;
+	float max_criticality;
+	float criticality_exp;
+	int32_t max_router_iterations;
+	int32_t timing_analysis_enabled; /* boolean argument of try_timing_driven_route */
+	int32_t bb_factor;               /* informational: net_bb is already expanded */
+	int32_t reserved;
+} pf_router_opts;
+
+typedef struct pf_problem {
+	int32_t nx, ny;
+	int32_t num_nodes;
+	int32_t num_edges;
+	/* node SoA, [num_nodes] */
+	int16_t *xlow, *ylow, *xhigh, *yhigh;
+	int16_t *ptc_num;
+	int16_t *cost_index;
+	int16_t *capacity;
+	uint8_t *type;       /* PF_SOURCE .. PF_CHANY */
+	uint8_t *direction;  /* e_direction, vpr_types.h:855 (informational) */
+	float *R, *C;
+	/* CSR out-edges */
+	int32_t *row_ptr;    /* [num_nodes+1] */
+	int32_t *edge_to;    /* [num_edges] */
+	int16_t *edge_sw;    /* [num_edges] index into switches[] */
+	int32_t num_switches;
+	pf_switch *switches;
+	int32_t num_indexed;
+	pf_indexed *indexed;
+	/* nets: terminal 0 of a net is its SOURCE rr node, 1..num_sinks its SINK rr nodes */
+	int32_t num_nets;
+	int32_t num_terminals;   /* = net_ptr[num_nets] */
+	int32_t *net_ptr;        /* [num_nets+1] */
+	int32_t *net_terminals;  /* [num_terminals] */
+	uint8_t *net_is_global;  /* [num_nets] global nets are never routed */
+	int32_t *net_bb;         /* [num_nets][4] xmin,xmax,ymin,ymax (s_bb order, vpr_types.h:554) */
+	/* reserve_locally_used_opins (route_common.c:1435): for each (block,class) that keeps
+	 * `count` OPINs for intra-block use, the class SOURCE node whose out-edges are the OPINs */
+	int32_t num_opin_groups;
+	int32_t *opin_group_source;
+	int32_t *opin_group_count;
+	pf_router_opts opts;
+} pf_problem;
+
+/* One PathFinder iteration's counters (reference prints pushes route_timing.c:332; overuse is
+ * what feasible_routing route_common.c:509 counts). */
+typedef struct pf_iter_stats {
+	int32_t overused_nodes;
+	int32_t nets_routed;
+	int64_t heap_pushes;      /* labels offered to the queue   (reference num_heap_pushes) */
+	int64_t heap_pops;        /* labels taken from the queue                                */
+	int64_t edge_visits;      /* out-edges examined in the expansion loop                   */
+	float pres_fac;
+	float crit_path_delay;    /* filled by the STA callback if any, else 0                  */
+} pf_iter_stats;
+
+typedef struct pf_result {
+	int32_t success;          /* TRUE iff legal routing found within max_router_iterations */
+	int32_t iterations;
+	int32_t serial_num;       /* "magic cookie", route_common.c:224-254 */
+	int32_t total_wirelength; /* stats.c:186-243 over CHANX/CHANY trace elements */
+	/* traceback in the exact s_trace order of update_traceback (route_common.c:638):
+	 * per net a concatenation of segments, each ending at a SINK (iswitch PF_OPEN); every
+	 * segment after the first begins with the join node already in the routing. */
+	int32_t num_nets;
+	int32_t *trace_ptr;       /* [num_nets+1] */
+	int32_t *trace_node;      /* [trace_ptr[num_nets]] */
+	int16_t *trace_switch;    /* [trace_ptr[num_nets]] */
+	int32_t num_terminals;
+	float *net_delay;         /* [num_terminals], aligned with net_terminals (entry 0 of a net = 0) */
+	int32_t num_nodes;
+	int32_t *occ;             /* [num_nodes] final occupancy */
+	int32_t num_iter_stats;
+	pf_iter_stats *iter_stats;
+	/* optional: timing criticalities used in each iteration (golden files of timing-driven
+	 * reference runs): [iterations][num_terminals], iteration i (1-based) at (i-1)*num_terminals */
+	int32_t num_crit_iters;
+	float *iter_crit;
+} pf_result;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_TYPES_H */

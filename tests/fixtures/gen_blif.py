@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""Fixture generator (test infrastructure): random LUT/FF netlist in BLIF for the reference
+flow.  Deterministic for a given seed (Python's Mersenne Twister).
+
+usage: gen_blif.py OUT.blif --luts 300 --pis 16 --window 60 --seed 1
+"""
+import argparse
+import random
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("out")
+    ap.add_argument("--luts", type=int, default=300)
+    ap.add_argument("--pis", type=int, default=16)
+    ap.add_argument("--window", type=int, default=60)
+    ap.add_argument("--latch_frac", type=float, default=0.3)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--name", default="toy")
+    a = ap.parse_args()
+    rng = random.Random(a.seed)
+    signals = ["pi%d" % i for i in range(a.pis)]
+    used = set()
+    body = []
+    latches = 0
+    for i in range(a.luts):
+        k = rng.randint(3, 6)
+        pool = signals[-a.window:]
+        ins = rng.sample(pool, min(k, len(pool)))
+        used.update(ins)
+        out = "n%d" % i
+        body.append(".names %s %s" % (" ".join(ins), out))
+        # random single-cube cover with at least one care literal
+        cube = "".join(rng.choice("01-") for _ in ins)
+        if set(cube) == {"-"}:
+            cube = "1" + cube[1:]
+        body.append("%s 1" % cube)
+        if rng.random() < a.latch_frac:
+            q = "q%d" % i
+            body.append(".latch %s %s re clk 0" % (out, q))
+            used.add(out)
+            signals.append(q)
+            latches += 1
+        else:
+            signals.append(out)
+    outs = [s for s in signals if s not in used and not s.startswith("pi")]
+    # unused primary inputs would be dangling: feed each into an extra output buffer-less PO is illegal,
+    # so only declare the primary inputs that are actually used.
+    pis = [s for s in signals[:a.pis] if s in used]
+    with open(a.out, "w") as f:
+        f.write(".model %s\n" % a.name)
+        f.write(".inputs %s%s\n" % (" ".join(pis), " clk" if latches else ""))
+        f.write(".outputs %s\n" % " ".join(outs))
+        f.write("\n".join(body))
+        f.write("\n.end\n")
+    print("wrote %s: %d luts, %d latches, %d inputs, %d outputs" % (a.out, a.luts, latches, len(pis), len(outs)))
+
+
+if __name__ == "__main__":
+    main()
