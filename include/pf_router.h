@@ -1,0 +1,125 @@
+/*
+ * pf_router.h — C-ABI of the B200 PathFinder router (libpf_router.so).
+ *
+ * This is the drop-in boundary for the `--route` hot path of chinhau5/parallel_eda (VPR 7.0).
+ * The reference has no plugin API: the seam is the link-time symbol
+ *
+ *     boolean try_timing_driven_route(struct s_router_opts router_opts, float **net_delay,
+ *             t_slack *slacks, t_ivec **clb_opins_used_locally, boolean timing_analysis_enabled);
+ *             // decl vpr/SRC/route/route_timing.h:1, sole caller vpr/SRC/route/route_common.c:500
+ *
+ * whose inputs and outputs are global AoS structures.  A reference-side adapter (INTEGRATION.md,
+ * integration/vpr_adapter.cxx) flattens those globals into a pf_problem (pf_types.h) and calls
+ * the entry points below; every signature uses plain pointers and sizes only.
+ *
+ *   entry point                      replaces (reference file:line)
+ *   -------------------------------------------------------------------------------------------
+ *   pf_try_timing_driven_route       try_timing_driven_route           route/route_timing.c:85-343
+ *   pf_router_create                 alloc_and_load_rr_node_route_structs route/route_common.c:1012,
+ *                                    rr_node[] storage → device CSR     route/rr_graph.c:521,1532
+ *   pf_route_iteration               the net loop calling timing_driven_route_net
+ *                                                                       route/route_timing.c:161-183,399-563
+ *   pf_reserve_opins                 reserve_locally_used_opins         route/route_common.c:1435-1491
+ *   pf_update_costs                  feasible_routing + pathfinder_update_cost
+ *                                                                       route/route_common.c:509-531,581-610
+ *   pf_total_wirelength              first-iteration wirelength abort   route/route_timing.c:189-225
+ *   pf_get_net_delay                 update_net_delays_from_route_tree  route/route_tree_timing.c:515-528
+ *   pf_get_result                    trace_head[]/trace_tail[] lists    route/route_common.c:638-706
+ *   pf_comm_export_delta /           MPI_Allreduce(occupancy) of the reference's MPI router
+ *   pf_update_costs_synced           parallel_route/spatial.cxx:3371-3383 (sync_recalc_occ)
+ *
+ * All functions return PF_OK (0) or a negative PF_E* code (pf_file.h); none calls exit().
+ * pf_last_error() describes the last failure of the calling process.  There is no CPU fallback:
+ * without a visible sm_100 device pf_router_create fails with PF_ECUDA.
+ */
+#ifndef PF_ROUTER_H
+#define PF_ROUTER_H
+
+#include "pf_types.h"
+#include "pf_file.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pf_router pf_router;
+
+typedef struct pf_config {
+	int32_t device;           /* CUDA device ordinal */
+	int32_t rank, nranks;     /* net sharding: this process routes nets i with i % nranks == rank
+	                             of the fanout-sorted order (one process per GPU) */
+	int32_t num_slots;        /* concurrent warps (nets in flight); 0 = 16 per SM */
+	int32_t warps_per_block;  /* 0 = 4 */
+	int32_t label_log2;       /* per-warp label table capacity = 2^label_log2; 0 = 13 */
+	int32_t tree_cap;         /* per-warp route-tree entries; 0 = 2048 */
+	int32_t far_cap;          /* per-warp far-list entries; 0 = 8192 */
+	int32_t sink_cap;         /* nets with more sinks go to the big slots; 0 = 64 */
+	int32_t big_slots;        /* warps with large scratch for big / overflowed nets; 0 = 64 */
+	int32_t big_label_log2, big_tree_cap, big_far_cap;   /* 0 = sized from the problem */
+	int32_t max_batch;        /* labels settled per step, 1..8; 0 = 2 */
+	float pop_slack;          /* settle labels within this cost of the minimum together; <0 = auto */
+	float win_rel, win_abs;   /* near-set window; 0 = auto */
+	int32_t verbose;
+	int32_t reroute_all_iters;/* the first K iterations re-route every net (the serial reference re-routes
+	                             every net in every iteration, route_timing.c:161-183); later iterations
+	                             re-route only nets that touch an overused rr node, like "phase two" of the
+	                             reference's parallel router (partitioning_multi_sink…cxx:6241-6269).
+	                             0 = auto (1); < 0 = always every net */
+	int32_t inflight_div;     /* nets in flight <= ceil(nets this iteration / inflight_div): bounds how
+	                             stale the congestion seen by concurrent nets can be; 0 = auto (16) */
+	int32_t min_slots;        /* lower bound for the above; 0 = auto (1) */
+	int32_t reserved[1];
+} pf_config;
+
+typedef struct pf_timing {    /* accumulated since create / last reset */
+	double route_kernel_ms;   /* CUDA-event time of pf_route_kernel launches */
+	double update_kernel_ms;  /* pf_update_cost_kernel */
+	double aux_kernel_ms;     /* delta export, wirelength, OPIN reservation */
+	int64_t route_launches, update_launches, aux_launches;
+	int64_t h2d_bytes, d2h_bytes;
+} pf_timing;
+
+/* Host STA hook, called between iterations when opts.timing_analysis_enabled (the reference
+ * calls load_timing_graph_net_delays + do_timing_analysis, route_timing.c:295-309):
+ * in  net_delay[num_terminals]  out crit[num_terminals] (timing_criticality), *crit_path_delay */
+typedef void (*pf_sta_fn)(void *user, int iters_done, const float *net_delay, float *crit, float *crit_path_delay);
+
+void pf_config_default(pf_config *cfg);
+const char *pf_last_error(void);
+const char *pf_backend_name(void);
+int pf_device_count(void);
+
+int pf_router_create(const pf_problem *p, const pf_config *cfg, pf_router **out);
+void pf_router_destroy(pf_router *r);
+/* forget all routing and congestion history (occ = 0, acc_cost = 1): a fresh first iteration */
+int pf_router_reset(pf_router *r);
+
+/* One PathFinder iteration over this rank's nets: rip-up, route, commit (live occupancy).
+ * crit: host array [num_terminals] or NULL to keep the criticalities already on the device. */
+int pf_route_iteration(pf_router *r, float pres_fac, const float *crit, pf_iter_stats *stats);
+int pf_reserve_opins(pf_router *r, float pres_fac, int rip_up_local_opins);
+int pf_update_costs(pf_router *r, float acc_fac, int *overused_nodes);
+int pf_total_wirelength(pf_router *r, int64_t *wirelength, int64_t *available);
+int pf_get_net_delay(pf_router *r, float *net_delay);
+/* Fills trace_*, net_delay, occ, serial_num, total_wirelength (free with pf_result_free). */
+int pf_get_result(pf_router *r, pf_result *out);
+int pf_get_timing(pf_router *r, pf_timing *t, int reset);
+
+/* Multi-GPU iteration boundary (device pointers, int32[num_nodes] / float[num_terminals]):
+ *   1. pf_comm_export_delta(r, d)       d[i] = occ change made by this rank's nets
+ *   2. all-reduce(sum) d across ranks   (NCCL over NVLink; the caller owns the communicator)
+ *   3. pf_update_costs_synced(r, acc_fac, d, &overused)   fold + cost update in one pass
+ * pf_comm_net_delay_ptr returns the device float[num_terminals] delay vector; entries of nets
+ * routed by other ranks are zero, so an all-reduce(sum) assembles the full vector in place. */
+int pf_comm_export_delta(pf_router *r, void *dev_delta);
+int pf_update_costs_synced(pf_router *r, float acc_fac, const void *dev_delta, int *overused_nodes);
+void *pf_comm_net_delay_ptr(pf_router *r);
+
+/* The whole of try_timing_driven_route (single GPU): iterate until legal or out of iterations.
+ * sta may be NULL when opts.timing_analysis_enabled == 0. */
+int pf_try_timing_driven_route(const pf_problem *p, const pf_config *cfg, pf_sta_fn sta, void *user, pf_result *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_ROUTER_H */

@@ -1,0 +1,64 @@
+"""Builds libpf_router.so (CUDA, sm_100a) in-tree.  nvcc cross-compiles without a GPU.
+
+    python -m parallel_eda_b200.build          # or: from parallel_eda_b200.build import build; build()
+
+Flags: -gencode arch=compute_100a,code=sm_100a (B200 only, no fallback arch), -lineinfo so ncu's
+source page maps to pf_device.cuh, -fmad=false so the cost arithmetic rounds like the CPU
+reference (the kernels are memory-latency bound; FMA contraction buys nothing here).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libpf_router.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+]
+
+
+def _newer(target: str, sources) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    srcs = [os.path.join(CSRC, f) for f in ("pf_kernels.cu", "pf_router.cpp", "pf_file.c")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("pf_device.cuh", "pf_backend.h")] + [
+        os.path.join(ROOT, "include", f) for f in ("pf_router.h", "pf_types.h", "pf_file.h")]
+    if not force and _newer(LIB, deps):
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    bdir = os.path.join(HERE, "_build")
+    os.makedirs(bdir, exist_ok=True)
+    objs = []
+    for s in srcs:
+        o = os.path.join(bdir, os.path.basename(s) + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-x", "cu"] if s.endswith(".cu") else []) + ["-c", s, "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on %s" % s)
+        if s.endswith(".cu"):
+            with open(os.path.join(bdir, "ptxas_pf_kernels.txt"), "w") as f:
+                f.write(r.stderr)
+        objs.append(o)
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

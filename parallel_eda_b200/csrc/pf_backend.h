@@ -1,0 +1,56 @@
+/*
+ * pf_backend.h — the seam between the host-side PathFinder driver (pf_router.cpp) and the device.
+ * The product implementation is pf_kernels.cu (CUDA, sm_100a).  tests/emu/pf_backend_emu.cpp
+ * implements the same functions over the fiber warp emulator so that the identical driver and
+ * device source can be exercised on a CPU-only box; it is test infrastructure, built only by
+ * tests/ into its own library, never linked into libpf_router.so.
+ */
+#ifndef PF_BACKEND_H
+#define PF_BACKEND_H
+
+#include <stddef.h>
+#include "pf_layout.h"
+
+struct PfLaunchTimes {            /* accumulated device time (CUDA events on the router's stream) */
+	double route_ms, update_ms, aux_ms;
+	long long route_launches, update_launches, aux_launches;
+};
+
+int pfb_init(int device);                         /* select device, create the stream; <0 on failure */
+int pfb_device_count(void);
+const char *pfb_name(void);                       /* "cuda:sm_100a" | "emu" */
+const char *pfb_last_error(void);
+void *pfb_alloc(size_t bytes);                    /* device memory, zero-filled; NULL on failure */
+void pfb_free(void *p);
+int pfb_h2d(void *dst, const void *src, size_t bytes);
+int pfb_d2h(void *dst, const void *src, size_t bytes);
+int pfb_d2d(void *dst, const void *src, size_t bytes);
+int pfb_zero(void *dst, size_t bytes);
+int pfb_sync(void);
+void pfb_times(PfLaunchTimes *out, int reset);
+int pfb_num_sms(void);
+
+/* the warp-per-net router: num_slots warps, each looping over the work queue */
+int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block);
+/* pathfinder_update_cost + feasible_routing (route_common.c:581-610,509-531) in one pass; when
+ * base/delta are non-NULL the pass first folds the all-reduced occupancy delta into the node
+ * records: occ = base + delta, base = occ (multi-GPU iteration boundary) */
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
+		int *occ_base, const int *occ_delta);
+/* delta[i] = nodes[i].occ - base[i]: what this GPU's nets changed since the last sync */
+int pfb_launch_export_delta(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta);
+/* total wirelength of all trees in the route store (route_timing.c:189-225 sanity abort) */
+int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long long *d_out);
+/* reserve_locally_used_opins (route_common.c:1435-1491): one thread per (block, class) group */
+int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
+		int num_groups, const int *group_source, const int *group_count, const int *group_off,
+		int *chosen, int rip_up, float pres_fac);
+/* work list of the next iteration: the nets of `all_nets` that touch an overused node (or every
+ * net when force_all), split into the small/big slot classes by net_big[]; counts[0]/counts[1] */
+int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
+		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts);
+/* copy every live tree of `all_nets` from one log to another (garbage collection of the route store) */
+int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
+		unsigned long long *dst_head);
+
+#endif

@@ -1,0 +1,982 @@
+/*
+ * pf_device.cuh — the warp-per-net PathFinder net router (device code, sm_100a).
+ *
+ * One warp routes one net at a time: rip-up → criticality shaping + sink order → per-sink
+ * A*-directed label-correcting search with a shared-memory frontier (near set) that spills to a
+ * per-warp far list in HBM (two-level delta-stepping: the near set holds every label within a
+ * cost window of the current minimum; the far list is re-bucketed when the near set runs dry) →
+ * back-trace → Elmore route-tree update → occupancy commit.  It replaces, for this path,
+ *   timing_driven_route_net            reference vpr/SRC/route/route_timing.c:399-563
+ *   add_route_tree_to_heap             route_timing.c:565-601      (tree seeding)
+ *   timing_driven_expand_neighbours    route_timing.c:603-691      (edge relaxation)
+ *   get_timing_driven_expected_cost    route_timing.c:693-840      (A* lookahead)
+ *   mark_node_expansion_by_bin         route_timing.c:867-960      (high-fanout window)
+ *   node_to_heap/add_to_heap/get_heap_head  route_common.c:780-803,1142-1216 (→ frontier)
+ *   pathfinder_update_one_cost         route_common.c:533-579      (→ atomics on occ)
+ *   update_traceback                   route_common.c:638-706      (→ tree entries)
+ *   update_route_tree & friends        route_tree_timing.c:155-456 (Elmore)
+ *
+ * The arithmetic of every cost expression keeps the reference's float/double mix (SURVEY.md
+ * Appendix E); the file is compiled with -fmad=false so the device evaluates them with the same
+ * roundings as the CPU reference.  What differs from the serial reference is the ORDER in which
+ * equal-cost labels are settled (a heap pops one label at a time, a warp settles a batch), so
+ * route trees can differ where costs tie — never the cost model.
+ *
+ * The code is written against a dozen warp primitives (pf_shfl_*, pf_ballot, pf_match_any, ...).
+ * Under nvcc they are the hardware intrinsics below.  tests/emu/pf_emu.h provides the same names
+ * on top of cooperative fibers so the identical source can be exercised on a CPU-only box; that
+ * emulator is test infrastructure and is never part of libpf_router.so.
+ */
+#ifndef PF_DEVICE_CUH
+#define PF_DEVICE_CUH
+
+#include <stdint.h>
+
+#ifndef PF_EMU
+#include <cuda_runtime.h>
+#define PF_DEV static __device__ __forceinline__
+#define PF_WARP 32
+typedef uint4 pf_u4;
+PF_DEV int pf_lane(void) { return (int)(threadIdx.x & 31u); }
+PF_DEV void pf_syncwarp(void) { __syncwarp(); }
+PF_DEV unsigned pf_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
+PF_DEV int pf_any(int pred) { return __any_sync(0xffffffffu, pred); }
+PF_DEV int pf_shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PF_DEV float pf_shfl_f(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PF_DEV uint64_t pf_shfl_u64(uint64_t v, int src) { return __shfl_sync(0xffffffffu, (unsigned long long)v, src); }
+PF_DEV unsigned pf_match_any(int key) { return __match_any_sync(0xffffffffu, key); }
+PF_DEV uint64_t pf_warp_min_u64(uint64_t v) {
+	/* two 32-bit hardware reductions (REDUX): high word first, then the low word among the ties */
+	unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+	unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+	unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+	return ((uint64_t)mh << 32) | ml;
+}
+PF_DEV float pf_warp_min_f(float v) {
+	/* valid for non-negative floats and +inf: their bit patterns order like unsigned ints */
+	return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
+}
+PF_DEV int pf_warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
+PF_DEV int pf_warp_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }
+PF_DEV int pf_popc(unsigned m) { return __popc(m); }
+PF_DEV int pf_ffs(unsigned m) { return __ffs((int)m); }
+PF_DEV unsigned pf_lanemask_lt(void) { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+PF_DEV int pf_atomic_add_i(int *p, int v) { return atomicAdd(p, v); }
+PF_DEV unsigned long long pf_atomic_add_ull(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
+PF_DEV int pf_atomic_or_i(int *p, int v) { return atomicOr(p, v); }
+PF_DEV pf_u4 pf_ld_cg_u4(const void *p) { return __ldcg((const uint4 *)p); }   /* L2-coherent: sees other SMs' atomics */
+PF_DEV pf_u4 pf_ld_u4(const void *p) { return *(const uint4 *)p; }
+PF_DEV void pf_st_u4(void *p, pf_u4 v) { *(uint4 *)p = v; }
+PF_DEV float pf_int_as_float(int i) { return __int_as_float(i); }
+PF_DEV int pf_float_as_int(float f) { return __float_as_int(f); }
+PF_DEV double pf_ceil(double x) { return ceil(x); }
+PF_DEV float pf_sqrtf(float x) { return sqrtf(x); }
+PF_DEV float pf_ceilf(float x) { return ceilf(x); }
+PF_DEV float pf_powf(float x, float y) { return powf(x, y); }
+#else
+#include "pf_emu.h"   /* tests/emu: fiber warp emulator, test builds only */
+#endif
+
+#include "pf_layout.h"
+
+/* ------------------------------------------------------------------ per-warp context */
+struct PfWarp {
+	const PfParams *P;
+	/* shared memory */
+	uint64_t *fr;                 /* [PF_SH_FRONTIER] key = tot bits << 32 | node */
+	uint64_t *b_key;              /* [PF_MAX_BATCH] */
+	int *b_node; float *b_back; float *b_R; int *b_start; int *b_pre; int *b_type;
+	float *base_cost;             /* [PF_MAX_INDEXED] per-net rescaled base costs */
+	PfIndexedDev *idx;            /* [PF_MAX_INDEXED] */
+	PfSwitchDev *sw;              /* [PF_MAX_SWITCHES] */
+	/* slot memory */
+	PfLabel *labels; unsigned label_mask; int label_shift;
+	PfTreeNode *tree; uint64_t *far; int *iscratch;
+	/* search state: warp-uniform */
+	unsigned epoch; int n_labels; int sh_n; int far_n; float T_hi; float far_min; float best;
+	int overflow;
+	/* per-net constants */
+	int bb_xmin, bb_xmax, bb_ymin, bb_ymax; int num_sinks;
+	/* counters */
+	unsigned long long pops, pushes, visits, refills, stale;
+};
+
+/* fr 1536 + b_key 64 + idx 1024 + sw 768 + base_cost 128 + 5 batch arrays 160 + b_pre 36 = 3716 → 3840 */
+#define PF_SMEM_PER_WARP 3840
+
+PF_DEV float pf_key_tot(uint64_t k) { return pf_int_as_float((int)(k >> 32)); }
+PF_DEV int pf_key_node(uint64_t k) { return (int)(uint32_t)k; }
+PF_DEV uint64_t pf_make_key(float tot, int node) { return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | (uint32_t)node; }
+#define PF_INF_F 3.0e38f
+#define PF_KEY_MAX 0xffffffffffffffffull
+
+/* ------------------------------------------------------------------ A* lookahead
+ * get_expected_segs_to_target + get_timing_driven_expected_cost, route_timing.c:693-840 */
+#define PF_ROUND_UP(x) (pf_ceil((x) - 0.001))
+
+PF_DEV float pf_expected_cost(const PfWarp &w, int type, int ci, int ixlow, int ixhigh, int iylow, int iyhigh,
+		int target_x, int target_y, float criticality_fac, float R_upstream) {
+	if (type == 4 || type == 5) {
+		int num_segs_same_dir, num_segs_ortho_dir, no_need_to_pass_by_clb;
+		const PfIndexedDev &I = w.idx[ci];
+		int oci = I.ortho;
+		const PfIndexedDev &O = w.idx[oci];
+		float inv_length = I.inv_length, ortho_inv_length = O.inv_length;
+		float ylow = iylow, yhigh = iyhigh, xlow = ixlow, xhigh = ixhigh;
+		if (type == 4) { /* CHANX */
+			if (ylow > target_y) {
+				num_segs_ortho_dir = (int)(PF_ROUND_UP((ylow - target_y + 1.) * ortho_inv_length));
+				no_need_to_pass_by_clb = 1;
+			} else if (ylow < target_y - 1) {
+				num_segs_ortho_dir = (int)(PF_ROUND_UP((target_y - ylow) * ortho_inv_length));
+				no_need_to_pass_by_clb = 1;
+			} else {
+				num_segs_ortho_dir = 0;
+				no_need_to_pass_by_clb = 0;
+			}
+			if (xlow > target_x + no_need_to_pass_by_clb)
+				num_segs_same_dir = (int)(PF_ROUND_UP((xlow - no_need_to_pass_by_clb - target_x) * inv_length));
+			else if (xhigh < target_x - no_need_to_pass_by_clb)
+				num_segs_same_dir = (int)(PF_ROUND_UP((target_x - no_need_to_pass_by_clb - xhigh) * inv_length));
+			else
+				num_segs_same_dir = 0;
+		} else { /* CHANY */
+			if (xlow > target_x) {
+				num_segs_ortho_dir = (int)(PF_ROUND_UP((xlow - target_x + 1.) * ortho_inv_length));
+				no_need_to_pass_by_clb = 1;
+			} else if (xlow < target_x - 1) {
+				num_segs_ortho_dir = (int)(PF_ROUND_UP((target_x - xlow) * ortho_inv_length));
+				no_need_to_pass_by_clb = 1;
+			} else {
+				num_segs_ortho_dir = 0;
+				no_need_to_pass_by_clb = 0;
+			}
+			if (ylow > target_y + no_need_to_pass_by_clb)
+				num_segs_same_dir = (int)(PF_ROUND_UP((ylow - no_need_to_pass_by_clb - target_y) * inv_length));
+			else if (yhigh < target_y - no_need_to_pass_by_clb)
+				num_segs_same_dir = (int)(PF_ROUND_UP((target_y - no_need_to_pass_by_clb - yhigh) * inv_length));
+			else
+				num_segs_same_dir = 0;
+		}
+		float cong_cost = num_segs_same_dir * w.base_cost[ci] + num_segs_ortho_dir * w.base_cost[oci];
+		cong_cost += w.base_cost[3] + w.base_cost[1];   /* IPIN_COST_INDEX, SINK_COST_INDEX */
+		float Tdel = num_segs_same_dir * I.T_linear + num_segs_ortho_dir * O.T_linear
+				+ num_segs_same_dir * num_segs_same_dir * I.T_quadratic
+				+ num_segs_ortho_dir * num_segs_ortho_dir * O.T_quadratic
+				+ R_upstream * (num_segs_same_dir * I.C_load + num_segs_ortho_dir * O.C_load);
+		Tdel += w.idx[3].T_linear;
+		float expected_cost = criticality_fac * Tdel + (1. - criticality_fac) * cong_cost;
+		return expected_cost;
+	} else if (type == 2) { /* IPIN */
+		return w.base_cost[1];
+	}
+	return 0.f;
+}
+
+/* ------------------------------------------------------------------ label table */
+PF_DEV unsigned pf_hash(const PfWarp &w, int node) {
+	return ((uint32_t)node * 2654435761u) >> w.label_shift;
+}
+
+/* Look up an existing label (used at settle time and in the back-trace).  Per-lane, no collectives. */
+PF_DEV int pf_label_find(const PfWarp &w, int node) {
+	unsigned h = pf_hash(w, node);
+	for (;;) {
+		const PfLabel *L = &w.labels[h];
+		pf_u4 a = pf_ld_u4(L);
+		if (a.y != w.epoch) return -1;
+		if ((int)a.x == node) return (int)h;
+		h = (h + 1) & w.label_mask;
+	}
+}
+
+/* Warp-collective relax: every lane may offer one candidate label (valid != 0).  Candidates for
+ * the same node are reduced to the cheapest; a candidate replaces an existing label only if both
+ * its total and its backward cost are lower (the pop rule of route_timing.c:511, applied at
+ * relax time); slot claims by different nodes in the same probe round are arbitrated by lane
+ * order.  Returns 1 in lanes whose candidate was written. */
+PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back, float R_up, int prev, int prev_sw) {
+	const int lane = pf_lane();
+	/* same-node duplicates inside this chunk */
+	{
+		unsigned grp = pf_match_any(valid ? node : (int)(0x80000000u | (unsigned)lane));
+		if (pf_any(valid && (grp & (grp - 1)) != 0)) {
+			for (int b = 0; b < PF_WARP; b++) {
+				float t = pf_shfl_f(tot, b);
+				if (valid && ((grp >> b) & 1u) && b != lane && (t < tot || (t == tot && b < lane))) valid = 0;
+			}
+		}
+	}
+	unsigned h = pf_hash(w, node);
+	int pending = valid, written = 0;
+	while (pf_any(pending)) {
+		int claim = 0;
+		if (pending) {
+			PfLabel *L = &w.labels[h];
+			pf_u4 a = pf_ld_u4(L);
+			if (a.y == w.epoch) {
+				if ((int)a.x == node) {
+					float otot = pf_int_as_float((int)a.z), oback = pf_int_as_float((int)a.w);
+					if (tot < otot && back < oback) {
+						pf_u4 n0, n1;
+						n0.x = (unsigned)node; n0.y = w.epoch; n0.z = (unsigned)pf_float_as_int(tot); n0.w = (unsigned)pf_float_as_int(back);
+						n1.x = (unsigned)pf_float_as_int(R_up); n1.y = (unsigned)prev; n1.z = (unsigned)prev_sw; n1.w = 0;
+						pf_st_u4(L, n0); pf_st_u4((char *)L + 16, n1);
+						written = 1;
+					}
+					pending = 0;
+				} else {
+					h = (h + 1) & w.label_mask;
+				}
+			} else {
+				claim = 1;
+			}
+		}
+		unsigned cg = pf_match_any(claim ? (int)h : (int)(0x80000000u | (unsigned)lane));
+		if (claim && (pf_ffs(cg) - 1) == lane) {
+			PfLabel *L = &w.labels[h];
+			pf_u4 n0, n1;
+			n0.x = (unsigned)node; n0.y = w.epoch; n0.z = (unsigned)pf_float_as_int(tot); n0.w = (unsigned)pf_float_as_int(back);
+			n1.x = (unsigned)pf_float_as_int(R_up); n1.y = (unsigned)prev; n1.z = (unsigned)prev_sw; n1.w = 0;
+			pf_st_u4(L, n0); pf_st_u4((char *)L + 16, n1);
+			written = 1; pending = 0;
+		}
+		unsigned newm = pf_ballot(claim && !pending);   /* also orders the stores before the next probe round */
+		w.n_labels += pf_popc(newm);
+	}
+	if (w.n_labels > (int)(w.label_mask >> 1)) w.overflow = 1;
+	return written;
+}
+
+/* ------------------------------------------------------------------ frontier */
+/* Warp-collective push.  Labels inside the near window go to shared memory, the rest (and any
+ * near-set overflow) to the far list in HBM; far_min guards the best-first order. */
+PF_DEV void pf_push(PfWarp &w, int valid, float tot, int node) {
+	uint64_t key = pf_make_key(tot, node);
+	int to_sh = valid && tot <= w.T_hi;
+	unsigned m1 = pf_ballot(to_sh);
+	int pos = w.sh_n + pf_popc(m1 & pf_lanemask_lt());
+	if (to_sh && pos < PF_SH_FRONTIER) w.fr[pos] = key;
+	int spill = to_sh && pos >= PF_SH_FRONTIER;
+	int cnt = pf_popc(m1);
+	w.sh_n = (w.sh_n + cnt < PF_SH_FRONTIER) ? w.sh_n + cnt : PF_SH_FRONTIER;
+	int to_far = (valid && !to_sh) || spill;
+	unsigned m2 = pf_ballot(to_far);
+	if (m2) {
+		int fpos = w.far_n + pf_popc(m2 & pf_lanemask_lt());
+		if (to_far) {
+			if (fpos < w.P->far_cap) w.far[fpos] = key;
+		}
+		w.far_n += pf_popc(m2);
+		if (w.far_n > w.P->far_cap) { w.far_n = w.P->far_cap; w.overflow = 1; }
+		float fm = pf_warp_min_f(to_far ? tot : PF_INF_F);
+		if (fm < w.far_min) w.far_min = fm;
+	}
+	w.pushes += (unsigned long long)pf_popc(pf_ballot(valid));
+	pf_syncwarp();
+}
+
+/* Re-bucket: move the near set to the far list, find the new minimum, open a window above it and
+ * pull every far label inside the window back into shared memory (at most PF_SH_REFILL; the
+ * window is narrowed until they fit, down to exact ties of the minimum). */
+PF_DEV void pf_refill(PfWarp &w) {
+	const int lane = pf_lane();
+	w.refills++;
+	/* 1. near → far */
+	for (int base = 0; base < w.sh_n; base += PF_WARP) {
+		int i = base + lane;
+		if (i < w.sh_n) {
+			int fpos = w.far_n + i;
+			if (fpos < w.P->far_cap) w.far[fpos] = w.fr[i];
+		}
+	}
+	w.far_n += w.sh_n;
+	w.sh_n = 0;
+	if (w.far_n > w.P->far_cap) { w.far_n = w.P->far_cap; w.overflow = 1; }
+	pf_syncwarp();
+	/* 2. minimum */
+	uint64_t mk = PF_KEY_MAX;
+	for (int i = lane; i < w.far_n; i += PF_WARP) { uint64_t k = w.far[i]; if (k < mk) mk = k; }
+	mk = pf_warp_min_u64(mk);
+	float m = pf_key_tot(mk);
+	/* 3. window */
+	float win = m * w.P->win_rel;
+	if (win < w.P->win_abs) win = w.P->win_abs;
+	float T = m + win;
+	for (;;) {
+		int c = 0;
+		for (int i = lane; i < w.far_n; i += PF_WARP) if (pf_key_tot(w.far[i]) <= T) c++;
+		c = pf_warp_sum_i(c);
+		if (c <= PF_SH_REFILL || T <= m) break;
+		win *= 0.25f;
+		T = m + win;
+	}
+	/* 4. move (first PF_SH_REFILL qualifying), compact the far list, track the far minimum */
+	int kept = 0, taken = 0;
+	float fmin = PF_INF_F;
+	for (int base = 0; base < w.far_n; base += PF_WARP) {
+		int i = base + lane;
+		uint64_t k = (i < w.far_n) ? w.far[i] : PF_KEY_MAX;
+		int q = (i < w.far_n) && pf_key_tot(k) <= T;
+		unsigned mq = pf_ballot(q);
+		int rank = taken + pf_popc(mq & pf_lanemask_lt());
+		int take = q && rank < PF_SH_REFILL;
+		unsigned mt = pf_ballot(take);
+		int keep = (i < w.far_n) && !take;
+		unsigned mkp = pf_ballot(keep);
+		if (take) w.fr[taken + pf_popc(mt & pf_lanemask_lt())] = k;
+		if (keep) {
+			w.far[kept + pf_popc(mkp & pf_lanemask_lt())] = k;   /* kept + rank <= i: in-place is safe after the ballots */
+			float t = pf_key_tot(k);
+			if (t < fmin) fmin = t;
+		}
+		taken += pf_popc(mt);
+		kept += pf_popc(mkp);
+	}
+	w.sh_n = taken;
+	w.far_n = kept;
+	w.far_min = pf_warp_min_f(fmin);
+	w.T_hi = T;
+	pf_syncwarp();
+}
+
+/* ------------------------------------------------------------------ node record access */
+struct PfNodeView { int xlow, ylow, xhigh, yhigh; float R, C; int occ; float acc; int edge_start, num_edges, type, ci, cap; };
+
+PF_DEV PfNodeView pf_load_node(const PfParams *P, int v) {
+	const char *p = (const char *)&P->nodes[v];
+	pf_u4 lo = pf_ld_cg_u4(p), hi = pf_ld_cg_u4(p + 16);
+	PfNodeView n;
+	n.xlow = (short)(lo.x & 0xffffu); n.ylow = (short)(lo.x >> 16);
+	n.xhigh = (short)(lo.y & 0xffffu); n.yhigh = (short)(lo.y >> 16);
+	n.R = pf_int_as_float((int)lo.z); n.C = pf_int_as_float((int)lo.w);
+	n.occ = (int)hi.x; n.acc = pf_int_as_float((int)hi.y); n.edge_start = (int)hi.z;
+	n.num_edges = (int)(hi.w & 0xffffu);
+	int tc = (int)((hi.w >> 16) & 0xffu);
+	n.type = tc & 7; n.ci = tc >> 3; n.cap = (int)(hi.w >> 24);
+	return n;
+}
+
+/* ------------------------------------------------------------------ sink order: heapsort (util/heapsort.c:13-96)
+ * run by one lane so that equal criticalities come out in the reference's order. */
+PF_DEV void pf_heapsort_lane(int *heap /*[1..n]*/, const float *v /*[1..n]*/, int n) {
+	for (int i = 1; i <= n; i++) {
+		unsigned ifrom = i, ito = ifrom / 2;
+		heap[i] = i;
+		while (ito >= 1 && v[heap[ifrom]] < v[heap[ito]]) {
+			int t = heap[ito]; heap[ito] = heap[ifrom]; heap[ifrom] = t;
+			ifrom = ito; ito = ifrom / 2;
+		}
+	}
+	for (int tail = n; tail >= 1; tail--) {
+		int smallest = heap[1];
+		heap[1] = heap[tail];
+		unsigned heap_end = tail - 1, ifrom = 1, ito = 2;
+		while (ito <= heap_end) {
+			if (v[heap[ito + 1]] < v[heap[ito]]) ito++;   /* reads the vacated slot like the reference */
+			if (v[heap[ito]] > v[heap[ifrom]]) break;
+			int t = heap[ito]; heap[ito] = heap[ifrom]; heap[ifrom] = t;
+			ifrom = ito; ito = 2 * ifrom;
+		}
+		heap[tail] = smallest;
+	}
+}
+
+/* ------------------------------------------------------------------ one sink search */
+/* Returns 1 when the target was reached (label present), 0 if the frontier was exhausted, -1 on
+ * scratch overflow.  tree_n = current number of tree entries. */
+PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, int rlim) {
+	const PfParams *P = w.P;
+	const int lane = pf_lane();
+	const float astar = P->astar_fac;
+	PfNodeView tn = pf_load_node(P, target_node);
+	const int tgt_xl = tn.xlow, tgt_yl = tn.ylow;       /* lookahead uses xlow/ylow (route_timing.c:764) */
+	const int tgt_xh = tn.xhigh, tgt_yh = tn.yhigh;     /* pruning uses xhigh/yhigh (route_timing.c:622) */
+	const int highfan = w.num_sinks >= 64;
+
+	w.epoch++;
+	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.far_min = PF_INF_F; w.best = PF_INF_F;
+
+	/* ---- seed with the current route tree (add_route_tree_to_heap) */
+	float smin = PF_INF_F;
+	for (int i = lane; i < tree_n; i += PF_WARP) {
+		PfTreeNode t = w.tree[i];
+		if (t.flags & PF_TF_REEXPAND) {
+			float back = crit * t.Tdel;
+			float tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
+			if (tot < smin) smin = tot;
+		}
+	}
+	smin = pf_warp_min_f(smin);
+	if (!(smin < PF_INF_F)) return 0;
+	{
+		float win = smin * P->win_rel;
+		if (win < P->win_abs) win = P->win_abs;
+		w.T_hi = smin + win;
+	}
+	for (int base = 0; base < tree_n; base += PF_WARP) {
+		int i = base + lane;
+		int valid = 0, node = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
+		if (i < tree_n) {
+			PfTreeNode t = w.tree[i];
+			if (t.flags & PF_TF_REEXPAND) {
+				valid = 1; node = t.node; R_up = t.R_up;
+				back = crit * t.Tdel;
+				tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
+			}
+		}
+		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0);
+		pf_push(w, wr, tot, node);
+		if (w.overflow) return -1;
+	}
+
+	/* ---- settle loop */
+	for (;;) {
+		if (w.overflow) return -1;
+		uint64_t mk = PF_KEY_MAX;
+		for (int i = lane; i < w.sh_n; i += PF_WARP) { uint64_t k = w.fr[i]; if (k < mk) mk = k; }
+		mk = pf_warp_min_u64(mk);
+		float mtot = (w.sh_n > 0) ? pf_key_tot(mk) : PF_INF_F;
+		if (w.far_min < mtot) {                 /* a cheaper label sits in the far list (or near set empty) */
+			if (w.far_min >= w.best) break;
+			pf_refill(w);
+			continue;
+		}
+		if (w.sh_n == 0) break;                 /* both exhausted */
+		if (mtot >= w.best) break;              /* target settled: nothing cheaper remains */
+
+		/* -- select the batch: every near label within pop_slack of the minimum, at most max_batch */
+		float thr = mtot + P->pop_slack;
+		int taken = 0, kept = 0;
+		for (int base = 0; base < w.sh_n; base += PF_WARP) {
+			int i = base + lane;
+			uint64_t k = (i < w.sh_n) ? w.fr[i] : PF_KEY_MAX;
+			int q = (i < w.sh_n) && pf_key_tot(k) <= thr;
+			unsigned mq = pf_ballot(q);
+			int rank = taken + pf_popc(mq & pf_lanemask_lt());
+			int take = q && rank < P->max_batch;
+			unsigned mt = pf_ballot(take);
+			int keep = (i < w.sh_n) && !take;
+			unsigned mkp = pf_ballot(keep);
+			if (take) w.b_key[taken + pf_popc(mt & pf_lanemask_lt())] = k;
+			if (keep) w.fr[kept + pf_popc(mkp & pf_lanemask_lt())] = k;
+			taken += pf_popc(mt);
+			kept += pf_popc(mkp);
+		}
+		w.sh_n = kept;
+		pf_syncwarp();
+
+		/* -- validate each settled label and fetch its node row */
+		int deg = 0, ok = 0;
+		if (lane < taken) {
+			uint64_t k = w.b_key[lane];
+			int u = pf_key_node(k);
+			int h = pf_label_find(w, u);
+			if (h >= 0) {
+				const PfLabel *L = &w.labels[h];
+				pf_u4 a = pf_ld_u4(L), b = pf_ld_u4((const char *)L + 16);
+				if (pf_int_as_float((int)a.z) == pf_key_tot(k)) {   /* else stale: the node was re-labelled cheaper */
+					PfNodeView un = pf_load_node(P, u);
+					w.b_node[lane] = u; w.b_back[lane] = pf_int_as_float((int)a.w); w.b_R[lane] = pf_int_as_float((int)b.x);
+					w.b_start[lane] = un.edge_start; w.b_type[lane] = un.type;
+					deg = un.num_edges;
+					ok = 1;
+				}
+			}
+			if (!ok) { w.b_node[lane] = -1; w.b_start[lane] = 0; w.b_type[lane] = 0; w.b_back[lane] = 0.f; w.b_R[lane] = 0.f; }
+		}
+		{
+			int nok = pf_popc(pf_ballot(ok));
+			w.pops += (unsigned long long)nok;
+			w.stale += (unsigned long long)(taken - nok);
+		}
+		/* exclusive prefix of the degrees over the first `taken` lanes */
+		int incl = deg;
+		for (int d = 1; d < PF_MAX_BATCH; d <<= 1) {
+			int o = pf_shfl_i(incl, lane - d);
+			if (lane >= d) incl += o;
+		}
+		if (lane < taken) w.b_pre[lane] = incl - deg;
+		int M = pf_shfl_i(incl, taken - 1);
+		if (lane == 0) w.b_pre[taken] = M;
+		pf_syncwarp();
+		w.visits += (unsigned long long)M;
+
+		/* -- relax every out-edge of the batch, 32 edges per pass */
+		for (int base = 0; base < M; base += PF_WARP) {
+			int e = base + lane;
+			int valid = e < M;
+			int to = 0, u = 0, isw = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
+			if (valid) {
+				int j = 0;
+				while (w.b_pre[j + 1] <= e) j++;
+				u = w.b_node[j];
+				uint32_t ew = P->edges[w.b_start[j] + (e - w.b_pre[j])];
+				to = (int)(ew & PF_EDGE_NODE_MASK); isw = (int)(ew >> PF_EDGE_NODE_BITS);
+				PfNodeView n = pf_load_node(P, to);
+				if (n.xhigh < w.bb_xmin || n.xlow > w.bb_xmax || n.yhigh < w.bb_ymin || n.ylow > w.bb_ymax) valid = 0;
+				if (valid && highfan && (n.xhigh < tgt_xh - rlim || n.xlow > tgt_xh + rlim || n.yhigh < tgt_yh - rlim || n.ylow > tgt_yh + rlim)) valid = 0;
+				if (valid && n.type == 2 && (n.xhigh != tgt_xh || n.yhigh != tgt_yh)) valid = 0;
+				if (valid) {
+					/* get_rr_cong_cost with the present cost derived from the live occupancy:
+					 * pres = occ < cap ? 1 : 1 + (occ + 1 - cap) * pres_fac  (route_common.c:563-568) */
+					float pres;
+					if (n.occ < n.cap) pres = 1.;
+					else pres = 1. + (n.occ + 1 - n.cap) * P->pres_fac;
+					float cong = w.base_cost[n.ci] * n.acc * pres;
+					float old_back = w.b_back[j], Ru = w.b_R[j];
+					float new_back = old_back + (1. - crit) * cong;
+					float new_R;
+					const PfSwitchDev S = w.sw[isw];
+					if (S.buffered) new_R = S.R; else new_R = Ru + S.R;
+					float Tdel = n.C * (new_R + 0.5 * n.R);
+					Tdel += S.Tdel;
+					new_R += n.R;
+					new_back += crit * Tdel;
+					if (P->bend_cost != 0.) {
+						int ft = w.b_type[j];
+						if ((ft == 4 && n.type == 5) || (ft == 5 && n.type == 4)) new_back += P->bend_cost;
+					}
+					tot = new_back + astar * pf_expected_cost(w, n.type, n.ci, n.xlow, n.xhigh, n.ylow, n.yhigh, tgt_xl, tgt_yl, crit, new_R);
+					back = new_back; R_up = new_R;
+				}
+			}
+			int wr = pf_label_relax(w, valid, to, tot, back, R_up, u, isw);
+			/* the target SINK is never expanded; only its best total matters */
+			float tb = pf_warp_min_f((wr && to == target_node) ? tot : PF_INF_F);
+			if (tb < w.best) w.best = tb;
+			pf_push(w, wr && to != target_node, tot, to);
+			if (w.overflow) return -1;
+		}
+	}
+	return (w.best < PF_INF_F) ? 1 : 0;
+}
+
+/* ------------------------------------------------------------------ high-fanout window
+ * mark_node_expansion_by_bin, route_timing.c:867-960: only the root's direct children are
+ * examined and re-flagged (kept as in the reference). */
+PF_DEV int pf_highfanout_rlim(PfWarp &w, int tree_n, int target_node) {
+	const PfParams *P = w.P;
+	const int lane = pf_lane();
+	if (w.num_sinks < 64) return 1;
+	PfNodeView tn = pf_load_node(P, target_node);
+	int target_x = tn.xlow, target_y = tn.ylow;
+	float area = (float)((w.bb_xmax - w.bb_xmin) * (w.bb_ymax - w.bb_ymin));
+	if (area <= 0) area = 1;
+	int rlim = (int)(pf_ceilf(pf_sqrtf(area / (float)w.num_sinks)));
+	int maxdim = (P->nx + 2 > P->ny + 2) ? P->nx + 2 : P->ny + 2;
+	/* does the root have children? */
+	int has_child = 0;
+	for (int i = lane; i < tree_n; i += PF_WARP) if (i > 0 && w.tree[i].parent == 0) has_child = 1;
+	if (!pf_any(has_child)) return maxdim;
+	for (;;) {
+		int hit = 0;
+		for (int i = lane; i < tree_n; i += PF_WARP) {
+			if (i > 0) {
+				PfTreeNode t = w.tree[i];
+				int ty = t.type_ci & 7;
+				if (t.parent == 0 && !(ty == 2 || ty == 1)
+						&& t.xlow <= target_x + rlim && t.xhigh >= target_x - rlim
+						&& t.ylow <= target_y + rlim && t.yhigh >= target_y - rlim) hit = 1;
+			}
+		}
+		if (pf_any(hit)) { rlim += 4; break; }
+		if (rlim > maxdim) return -1;
+		rlim *= 2;
+	}
+	for (int i = lane; i < tree_n; i += PF_WARP) {
+		if (i > 0) {
+			PfTreeNode t = w.tree[i];
+			int ty = t.type_ci & 7;
+			if (t.parent == 0 && !(ty == 2 || ty == 1)) {
+				int in = t.xlow <= target_x + rlim && t.xhigh >= target_x - rlim && t.ylow <= target_y + rlim && t.yhigh >= target_y - rlim;
+				w.tree[i].flags = (unsigned char)((t.flags & ~PF_TF_REEXPAND) | (in ? PF_TF_REEXPAND : 0));
+			}
+		}
+	}
+	pf_syncwarp();
+	return rlim;
+}
+
+/* ------------------------------------------------------------------ back-trace + Elmore + commit
+ * update_traceback (route_common.c:638) and update_route_tree (route_tree_timing.c:181-456).
+ * Returns the tree index of the new SINK entry, or -1 on tree overflow. */
+PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
+	const PfParams *P = w.P;
+	const int lane = pf_lane();
+	int tree_n = *tree_n_io;
+	int *pathbuf = w.iscratch + 3 * (P->sink_cap + 2);     /* reversed path: node ids, then switches */
+	const int pcap = P->tree_cap;                          /* iscratch holds 2*tree_cap ints behind the sink arrays */
+	int L = 0, join = -1;
+	if (lane == 0) {
+		int v = target_node;
+		for (;;) {
+			int h = pf_label_find(w, v);
+			if (h < 0) { L = -1; break; }
+			const PfLabel *lab = &w.labels[h];
+			pf_u4 b = pf_ld_u4((const char *)lab + 16);
+			int prev = (int)b.y;
+			if (prev < 0 && v != target_node) { join = ~prev; break; }
+			if (prev < 0) { L = -1; break; }               /* target itself is a seed: cannot happen (SINKs are never seeds) */
+			if (L >= pcap) { L = -2; break; }
+			pathbuf[L] = v; pathbuf[pcap + L] = (int)b.z;  /* switch used to enter v */
+			L++;
+			v = prev;
+		}
+	}
+	L = pf_shfl_i(L, 0); join = pf_shfl_i(join, 0);
+	if (L < 0) { if (L == -1 && lane == 0) pf_atomic_or_i(P->status, PF_ST_INTERNAL); return -1; }
+	if (tree_n + L > P->tree_cap) return -1;
+	pf_syncwarp();
+	/* materialise the entries in path order (join's child first, SINK last) */
+	for (int i = lane; i < L; i += PF_WARP) {
+		int v = pathbuf[L - 1 - i];
+		PfNodeView n = pf_load_node(P, v);
+		PfTreeNode t;
+		t.node = v; t.parent = (i == 0) ? join : tree_n + i - 1;
+		t.R_up = n.R; t.C_down = n.C; t.Tdel = 0.f;     /* R_up/C_down temporarily hold the node's own R and C */
+		t.xlow = (short)n.xlow; t.ylow = (short)n.ylow; t.xhigh = (short)n.xhigh; t.yhigh = (short)n.yhigh;
+		t.sw = (unsigned char)pathbuf[pcap + L - 1 - i];
+		t.type_ci = (unsigned char)(n.type | (n.ci << 3));
+		t.flags = (n.type == 2 || n.type == 1) ? 0 : PF_TF_REEXPAND;   /* IPIN / SINK are not re-expanded */
+		t.pad = 0;
+		w.tree[tree_n + i] = t;
+		pf_atomic_add_i(&P->nodes[v].occ, 1);           /* commit: pathfinder_update_one_cost(+1) */
+	}
+	pf_syncwarp();
+	if (lane == 0) {
+		PfTreeNode *T = w.tree;
+		const int a = tree_n, z = tree_n + L - 1;
+		/* node R of each new entry is parked in R_up, node C in C_down */
+		/* C_downstream, sink → join (add_path_to_route_tree :286-297) */
+		float Cd = T[z].C_down;                          /* C of the SINK */
+		/* keep the per-node R and C while rewriting: walk backwards for C_down */
+		float Cnode;
+		for (int i = z - 1; i >= a; i--) {
+			Cnode = T[i].C_down;
+			int isw = T[i + 1].sw;
+			if (!w.sw[isw].buffered) Cd += Cnode; else Cd = Cnode;
+			T[i].C_down = Cd;
+		}
+		/* R_upstream, join → sink (load_new_path_R_upstream :340-390) */
+		{
+			int isw = T[a].sw;
+			float Rn = T[a].R_up;
+			float Ru = w.sw[isw].R + Rn;
+			if (!w.sw[isw].buffered) Ru += T[join].R_up;
+			T[a].R_up = Ru;
+			/* Tdel needs the node R afterwards: stash it in Tdel for now */
+			T[a].Tdel = Rn;
+			for (int i = a + 1; i <= z; i++) {
+				isw = T[i].sw;
+				Rn = T[i].R_up;
+				if (w.sw[isw].buffered) Ru = w.sw[isw].R + Rn; else Ru += w.sw[isw].R + Rn;
+				T[i].R_up = Ru;
+				T[i].Tdel = Rn;
+			}
+		}
+		/* ancestors (update_unbuffered_ancestors_C_downstream :393-417) */
+		int rt = a;
+		{
+			float C_add = T[a].C_down;
+			int parent = T[a].parent, isw = T[a].sw;
+			while (parent != -1 && !w.sw[isw].buffered) {
+				rt = parent;
+				T[rt].C_down += C_add;
+				parent = T[rt].parent;
+				isw = T[rt].sw;
+			}
+		}
+		/* Tdel of the affected subtree (load_rt_subtree_Tdel :419-456) */
+		if (rt == a) {
+			/* the usual case: a buffered switch isolates the new branch; only its own chain changes */
+			float Tarr;
+			{
+				int isw = T[a].sw;
+				Tarr = T[join].Tdel;
+				Tarr += w.sw[isw].R * T[a].C_down;
+				Tarr += w.sw[isw].Tdel;
+			}
+			for (int i = a; i <= z; i++) {
+				float Rn = T[i].Tdel;                    /* stashed node R */
+				float Td = Tarr + 0.5 * T[i].C_down * Rn;
+				T[i].Tdel = Td;
+				if (i < z) {
+					int isw = T[i + 1].sw;
+					Tarr = Td + w.sw[isw].R * T[i + 1].C_down;
+					Tarr += w.sw[isw].Tdel;
+				}
+			}
+		} else {
+			/* generic sweep: entries are in topological order, so one forward pass over the
+			 * descendants of rt (marked on the fly) recomputes every affected Tdel */
+			float Tstart;
+			if (T[rt].parent != -1) {
+				int isw = T[rt].sw;
+				Tstart = T[T[rt].parent].Tdel;
+				Tstart += w.sw[isw].R * T[rt].C_down;
+				Tstart += w.sw[isw].Tdel;
+			} else {
+				Tstart = 0.;
+			}
+			for (int i = rt; i <= z; i++) {
+				int affected = (i == rt) || (T[i].parent >= rt && (T[T[i].parent].flags & PF_TF_MARK));
+				if (!affected) continue;
+				float Rn = (i >= a) ? T[i].Tdel : pf_load_node(P, T[i].node).R;
+				float Tarr;
+				if (i == rt) Tarr = Tstart;
+				else {
+					int isw = T[i].sw;
+					Tarr = T[T[i].parent].Tdel + w.sw[isw].R * T[i].C_down;
+					Tarr += w.sw[isw].Tdel;
+				}
+				T[i].Tdel = Tarr + 0.5 * T[i].C_down * Rn;
+				T[i].flags |= PF_TF_MARK;
+			}
+			for (int i = rt; i <= z; i++) T[i].flags &= (unsigned char)~PF_TF_MARK;
+		}
+	}
+	pf_syncwarp();
+	*tree_n_io = tree_n + L;
+	return tree_n + L - 1;
+}
+
+/* ------------------------------------------------------------------ one net
+ * timing_driven_route_net, route_timing.c:399-563 */
+PF_DEV void pf_route_net(PfWarp &w, int inet) {
+	const PfParams *P = w.P;
+	const int lane = pf_lane();
+	const int t0 = P->net_ptr[inet];
+	const int ns = P->net_ptr[inet + 1] - t0 - 1;
+	w.num_sinks = ns;
+	w.bb_xmin = P->net_bb[4 * inet + 0]; w.bb_xmax = P->net_bb[4 * inet + 1];
+	w.bb_ymin = P->net_bb[4 * inet + 2]; w.bb_ymax = P->net_bb[4 * inet + 3];
+	w.overflow = 0;
+
+	/* rip-up: pathfinder_update_one_cost(trace_head[inet], -1) — one atomic per tree entry */
+	if (!P->skip_ripup) {
+		PfNetLoc loc = P->loc[inet];
+		for (int i = lane; i < loc.count; i += PF_WARP) pf_atomic_add_i(&P->nodes[P->pool[loc.off + i].node].occ, -1);
+	}
+	if (ns > P->sink_cap) { w.overflow = 1; }
+
+	float *pin_crit = (float *)w.iscratch;                   /* [1..ns] */
+	int *sink_order = w.iscratch + (P->sink_cap + 2);        /* [1..ns] */
+	int *rt_of_sink = w.iscratch + 2 * (P->sink_cap + 2);    /* [1..ns] */
+	int tree_n = 0;
+	int fail = 0;
+	if (!w.overflow) {
+		/* pin criticalities, route_timing.c:424-454 */
+		for (int ipin = 1 + lane; ipin <= ns; ipin += PF_WARP) {
+			float c = P->crit[t0 + ipin];
+			double d = c - (1.0 - P->max_crit);
+			c = (d > 0.0) ? d : 0.0;
+			if (P->crit_exp != 1.0f) c = pf_powf(c, P->crit_exp);
+			if (c > P->max_crit) c = P->max_crit;
+			pin_crit[ipin] = c;
+		}
+		pf_syncwarp();
+		if (lane == 0) pf_heapsort_lane(sink_order, pin_crit, ns);
+		/* update_rr_base_costs, route_timing.c:842-864 */
+		if (lane < P->num_indexed) {
+			float bc = w.idx[lane].base_cost;
+			if (lane >= 4) {
+				float factor = pf_sqrtf((float)ns);
+				bc = (w.idx[lane].T_quadratic > 0.) ? w.idx[lane].saved_base_cost * factor : w.idx[lane].saved_base_cost;
+			}
+			w.base_cost[lane] = bc;
+		}
+		/* init_route_tree_to_source, route_tree_timing.c:155-178 */
+		if (lane == 0) {
+			int src = P->net_term[t0];
+			PfNodeView n = pf_load_node(P, src);
+			PfTreeNode t;
+			t.node = src; t.parent = -1; t.R_up = n.R; t.C_down = n.C; t.Tdel = 0.5 * n.R * n.C;
+			t.xlow = (short)n.xlow; t.ylow = (short)n.ylow; t.xhigh = (short)n.xhigh; t.yhigh = (short)n.yhigh;
+			t.sw = 0; t.type_ci = (unsigned char)(n.type | (n.ci << 3)); t.flags = PF_TF_REEXPAND; t.pad = 0;
+			w.tree[0] = t;
+			pf_atomic_add_i(&P->nodes[src].occ, 1);          /* the SOURCE is the head of the first trace segment */
+		}
+		tree_n = 1;
+		pf_syncwarp();
+
+		for (int itarget = 1; itarget <= ns; itarget++) {
+			int target_pin = sink_order[itarget];
+			int target_node = P->net_term[t0 + target_pin];
+			float crit = pin_crit[target_pin];
+			int rlim = pf_highfanout_rlim(w, tree_n, target_node);
+			if (rlim < 0) { fail = PF_ST_INTERNAL; break; }
+			int r = pf_search_sink(w, tree_n, target_node, crit, rlim);
+			if (r < 0) break;                                 /* overflow: retry in a bigger slot */
+			if (r == 0) { fail = PF_ST_UNROUTABLE; break; }
+			int si = pf_add_path(w, &tree_n, target_node);
+			if (si < 0) { w.overflow = 1; break; }
+			if (lane == 0) rt_of_sink[target_pin] = si;
+			pf_syncwarp();
+		}
+	}
+
+	if (w.overflow || fail) {
+		/* undo this net's commits; it owns no routing until it is retried */
+		for (int i = lane; i < tree_n; i += PF_WARP) pf_atomic_add_i(&P->nodes[w.tree[i].node].occ, -1);
+		if (lane == 0) {
+			P->loc[inet].off = 0; P->loc[inet].count = 0;
+			if (fail) { pf_atomic_add_i(P->status + 1, 1); pf_atomic_or_i(P->status, fail); P->status[2] = inet; }
+			else { int k = pf_atomic_add_i(P->retry_count, 1); P->retry_list[k] = inet; }
+		}
+		pf_syncwarp();
+		return;
+	}
+	/* update_net_delays_from_route_tree, route_tree_timing.c:515-528 */
+	for (int ipin = 1 + lane; ipin <= ns; ipin += PF_WARP) P->net_delay[t0 + ipin] = w.tree[rt_of_sink[ipin]].Tdel;
+	/* publish the tree in the route store */
+	unsigned long long off = 0;
+	if (lane == 0) off = pf_atomic_add_ull(P->pool_head, (unsigned long long)tree_n);
+	off = pf_shfl_u64(off, 0);
+	if ((long long)(off + tree_n) > P->pool_cap) {
+		if (lane == 0) { pf_atomic_or_i(P->status, PF_ST_POOL_OVERFLOW); P->loc[inet].off = 0; P->loc[inet].count = 0; }
+		for (int i = lane; i < tree_n; i += PF_WARP) pf_atomic_add_i(&P->nodes[w.tree[i].node].occ, -1);
+		pf_syncwarp();
+		return;
+	}
+	for (int i = lane; i < tree_n; i += PF_WARP) P->pool[off + i] = w.tree[i];
+	if (lane == 0) { P->loc[inet].off = (int)off; P->loc[inet].count = tree_n; }
+	pf_syncwarp();
+}
+
+/* ------------------------------------------------------------------ warp main: persistent work loop */
+PF_DEV void pf_warp_main(const PfParams *P, int slot, unsigned char *smem_warp) {
+	const int lane = pf_lane();
+	PfWarp w;
+	w.P = P;
+	unsigned char *s = smem_warp;
+	w.fr = (uint64_t *)s; s += PF_SH_FRONTIER * 8;
+	w.b_key = (uint64_t *)s; s += PF_MAX_BATCH * 8;
+	w.idx = (PfIndexedDev *)s; s += PF_MAX_INDEXED * 32;
+	w.sw = (PfSwitchDev *)s; s += PF_MAX_SWITCHES * 12;
+	w.base_cost = (float *)s; s += PF_MAX_INDEXED * 4;
+	w.b_node = (int *)s; s += PF_MAX_BATCH * 4;
+	w.b_back = (float *)s; s += PF_MAX_BATCH * 4;
+	w.b_R = (float *)s; s += PF_MAX_BATCH * 4;
+	w.b_start = (int *)s; s += PF_MAX_BATCH * 4;
+	w.b_type = (int *)s; s += PF_MAX_BATCH * 4;
+	w.b_pre = (int *)s; s += (PF_MAX_BATCH + 1) * 4;
+	for (int i = lane; i < P->num_indexed; i += PF_WARP) w.idx[i] = P->indexed[i];
+	for (int i = lane; i < P->num_sw; i += PF_WARP) w.sw[i] = P->sw[i];
+	const long long cap = 1ll << P->label_log2;
+	w.labels = P->labels + (long long)slot * cap;
+	w.label_mask = (unsigned)(cap - 1);
+	w.label_shift = 32 - P->label_log2;
+	w.tree = P->tree + (long long)slot * P->tree_cap;
+	w.far = P->far + (long long)slot * P->far_cap;
+	w.iscratch = P->iscratch + (long long)slot * (3 * (P->sink_cap + 2) + 2 * P->tree_cap);
+	w.epoch = P->epochs[slot];
+	w.pops = w.pushes = w.visits = w.refills = w.stale = 0;
+	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.T_hi = 0.f; w.far_min = PF_INF_F; w.best = PF_INF_F; w.overflow = 0;
+	w.bb_xmin = w.bb_xmax = w.bb_ymin = w.bb_ymax = 0; w.num_sinks = 0;
+	pf_syncwarp();
+	unsigned long long nets = 0;
+	for (;;) {
+		int k = 0;
+		if (lane == 0) k = pf_atomic_add_i(P->work_head, 1);
+		k = pf_shfl_i(k, 0);
+		if (k >= P->num_work) break;
+		pf_route_net(w, P->work[k]);
+		nets++;
+	}
+	if (lane == 0) {
+		P->epochs[slot] = w.epoch;
+		pf_atomic_add_ull(&P->stats->pops, w.pops);
+		pf_atomic_add_ull(&P->stats->pushes, w.pushes);
+		pf_atomic_add_ull(&P->stats->visits, w.visits);
+		pf_atomic_add_ull(&P->stats->refills, w.refills);
+		pf_atomic_add_ull(&P->stats->stale, w.stale);
+		pf_atomic_add_ull(&P->stats->nets, nets);
+	}
+}
+
+/* ------------------------------------------------------------------ per-element bodies of the streaming kernels
+ * (shared by pf_kernels.cu and the test emulator) */
+
+/* pathfinder_update_cost (route_common.c:581-610) for one node; returns 1 if the node is overused
+ * (feasible_routing, route_common.c:509-531).  pres_cost is not stored: it is a function of occ. */
+PF_DEV int pf_update_cost_one(PfNode *nodes, int i, float acc_fac, int *occ_base, const int *occ_delta) {
+	PfNode *n = &nodes[i];
+	int occ = n->occ;
+	if (occ_base) {                       /* fold the all-reduced delta of every GPU's nets */
+		occ = occ_base[i] + occ_delta[i];
+		occ_base[i] = occ;
+		n->occ = occ;
+	}
+	int cap = n->capacity;
+	if (occ > cap) {
+		n->acc_cost += (occ - cap) * acc_fac;
+		return 1;
+	}
+	return 0;
+}
+
+PF_DEV unsigned pf_tree_wirelength_one(const PfTreeNode *t) {
+	int ty = t->type_ci & 7;
+	if (ty == 4 || ty == 5) return (unsigned)(1 + t->xhigh - t->xlow + t->yhigh - t->ylow);
+	return 0u;
+}
+
+/* reserve_locally_used_opins (route_common.c:1435-1491) for one (block, class) group, executed
+ * by one thread: rip up last iteration's picks, then take the `count` cheapest OPINs of the class
+ * SOURCE in the order the reference's binary heap (route_common.c:1142-1216) would deliver them. */
+#define PF_OPIN_HEAP_MAX 128
+PF_DEV void pf_reserve_opins_group(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
+		int source, int count, int *chosen, int rip_up, float pres_fac) {
+	if (rip_up) for (int k = 0; k < count; k++) pf_atomic_add_i(&nodes[chosen[k]].occ, -1);
+	if (count == 0) return;
+	float hc[PF_OPIN_HEAP_MAX + 2]; int hn[PF_OPIN_HEAP_MAX + 2];
+	int tail = 1;
+	int e0 = nodes[source].edge_start, ne = nodes[source].num_edges;
+	if (ne > PF_OPIN_HEAP_MAX) ne = PF_OPIN_HEAP_MAX;
+	for (int k = 0; k < ne; k++) {
+		int to = (int)(edges[e0 + k] & PF_EDGE_NODE_MASK);
+		const PfNode *n = &nodes[to];
+		float pres;
+		if (n->occ < n->capacity) pres = 1.; else pres = 1. + (n->occ + 1 - n->capacity) * pres_fac;
+		float cost = indexed[n->type_ci >> 3].base_cost * n->acc_cost * pres;
+		/* add_to_heap */
+		hc[tail] = cost; hn[tail] = to;
+		int ifrom = tail, ito = ifrom / 2;
+		tail++;
+		while (ito >= 1 && hc[ifrom] < hc[ito]) {
+			float tc = hc[ito]; hc[ito] = hc[ifrom]; hc[ifrom] = tc;
+			int tn = hn[ito]; hn[ito] = hn[ifrom]; hn[ifrom] = tn;
+			ifrom = ito; ito = ifrom / 2;
+		}
+	}
+	for (int k = 0; k < count; k++) {
+		if (tail == 1) { chosen[k] = chosen[k > 0 ? k - 1 : 0]; continue; }
+		int pick = hn[1];
+		/* get_heap_head */
+		tail--;
+		hc[1] = hc[tail]; hn[1] = hn[tail];
+		int ifrom = 1, ito = 2;
+		while (ito < tail) {
+			if (hc[ito + 1] < hc[ito]) ito++;
+			if (hc[ito] > hc[ifrom]) break;
+			float tc = hc[ito]; hc[ito] = hc[ifrom]; hc[ifrom] = tc;
+			int tn = hn[ito]; hn[ito] = hn[ifrom]; hn[ifrom] = tn;
+			ifrom = ito; ito = 2 * ifrom;
+		}
+		pf_atomic_add_i(&nodes[pick].occ, 1);
+		chosen[k] = pick;
+	}
+}
+
+/* Does this net touch an overused rr node?  (the test the reference's parallel router uses to pick
+ * the nets of its "phase two", parallel_route/partitioning_multi_sink_delta_stepping_route.cxx:6241-6269) */
+PF_DEV int pf_net_is_congested(const PfNode *nodes, const PfTreeNode *pool, PfNetLoc loc) {
+	for (int i = 0; i < loc.count; i++) {
+		const PfNode *n = &nodes[pool[loc.off + i].node];
+		if (n->occ > n->capacity) return 1;
+	}
+	return 0;
+}
+
+#endif /* PF_DEVICE_CUH */

@@ -1,0 +1,243 @@
+/*
+ * pf_kernels.cu — CUDA backend (sm_100a) of the PathFinder router: the __global__ entry points
+ * around the device code in pf_device.cuh, launch wrappers, device memory and event timing.
+ * Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false (see build.py).
+ *
+ * Kernels
+ *   pf_route_kernel        persistent warp-per-net router (the hot path; see pf_device.cuh)
+ *   pf_update_cost_kernel  pathfinder_update_cost + feasible_routing, optionally fused with the
+ *                          fold-in of the all-reduced occupancy delta (multi-GPU)
+ *   pf_export_delta_kernel occupancy delta of this GPU's nets since the last sync
+ *   pf_wirelength_kernel   first-iteration wirelength sanity sum
+ *   pf_reserve_opins_kernel locally-used OPIN reservation
+ */
+#include "pf_backend.h"
+#include "pf_device.cuh"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+static char g_err[512] = "";
+static cudaStream_t g_stream = 0;
+static int g_device = -1;
+static int g_sms = 0;
+static PfLaunchTimes g_times;
+
+struct PendingEvent { cudaEvent_t a, b; int kind; };
+static PendingEvent g_pending[64];
+static int g_npending = 0;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	snprintf(g_err, sizeof(g_err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return -1; } } while (0)
+
+const char *pfb_last_error(void) { return g_err; }
+const char *pfb_name(void) { return "cuda:sm_100a"; }
+
+int pfb_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "no CUDA device / driver"); return 0; }
+	return n;
+}
+
+int pfb_init(int device) {
+	int n = pfb_device_count();
+	if (n <= 0) { snprintf(g_err, sizeof(g_err), "pf_router needs a CUDA device (sm_100a); none is visible — there is no CPU fallback"); return -1; }
+	if (device < 0 || device >= n) { snprintf(g_err, sizeof(g_err), "device %d out of range (%d visible)", device, n); return -1; }
+	CK(cudaSetDevice(device));
+	if (g_device != device || !g_stream) {
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, device));
+		if (prop.major < 10) { snprintf(g_err, sizeof(g_err), "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return -1; }
+		g_sms = prop.multiProcessorCount;
+		if (g_stream) cudaStreamDestroy(g_stream);
+		CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+		g_device = device;
+		memset(&g_times, 0, sizeof(g_times));
+	}
+	return 0;
+}
+
+int pfb_num_sms(void) { return g_sms; }
+
+void *pfb_alloc(size_t bytes) {
+	void *p = NULL;
+	if (bytes == 0) bytes = 16;
+	if (cudaMalloc(&p, bytes) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMalloc(%zu) failed", bytes); cudaGetLastError(); return NULL; }
+	if (cudaMemsetAsync(p, 0, bytes, g_stream) != cudaSuccess) { cudaFree(p); return NULL; }
+	return p;
+}
+void pfb_free(void *p) { if (p) cudaFree(p); }
+int pfb_h2d(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); CK(cudaStreamSynchronize(g_stream)); return 0; }
+int pfb_d2h(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream)); return 0; }
+int pfb_d2d(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream)); return 0; }
+int pfb_zero(void *dst, size_t bytes) { if (!bytes) return 0; CK(cudaMemsetAsync(dst, 0, bytes, g_stream)); return 0; }
+
+static int drain_events(void) {
+	for (int i = 0; i < g_npending; i++) {
+		float ms = 0.f;
+		CK(cudaEventSynchronize(g_pending[i].b));
+		CK(cudaEventElapsedTime(&ms, g_pending[i].a, g_pending[i].b));
+		if (g_pending[i].kind == 0) { g_times.route_ms += ms; g_times.route_launches++; }
+		else if (g_pending[i].kind == 1) { g_times.update_ms += ms; g_times.update_launches++; }
+		else { g_times.aux_ms += ms; g_times.aux_launches++; }
+		cudaEventDestroy(g_pending[i].a);
+		cudaEventDestroy(g_pending[i].b);
+	}
+	g_npending = 0;
+	return 0;
+}
+
+int pfb_sync(void) { CK(cudaStreamSynchronize(g_stream)); return drain_events(); }
+
+void pfb_times(PfLaunchTimes *out, int reset) {
+	drain_events();
+	if (out) *out = g_times;
+	if (reset) memset(&g_times, 0, sizeof(g_times));
+}
+
+static int ev_begin(int kind) {
+	if (g_npending == 64 && drain_events() != 0) return -1;
+	PendingEvent *p = &g_pending[g_npending];
+	p->kind = kind;
+	CK(cudaEventCreate(&p->a));
+	CK(cudaEventCreate(&p->b));
+	CK(cudaEventRecord(p->a, g_stream));
+	return 0;
+}
+static int ev_end(void) {
+	CK(cudaEventRecord(g_pending[g_npending].b, g_stream));
+	g_npending++;
+	CK(cudaGetLastError());
+	return 0;
+}
+
+/* ------------------------------------------------------------------ kernels */
+extern __shared__ __align__(16) unsigned char pf_smem[];
+
+__global__ void __launch_bounds__(256) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
+	const int warp_in_block = (int)(threadIdx.x >> 5);
+	const int slot = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp_in_block;
+	if (slot >= num_slots) return;
+	pf_warp_main(&P, slot, pf_smem + (size_t)warp_in_block * PF_SMEM_PER_WARP);
+}
+
+__global__ void pf_update_cost_kernel(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
+		int *occ_base, const int *occ_delta) {
+	int over = 0;
+	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x))
+		over += pf_update_cost_one(nodes, i, acc_fac, occ_base, occ_delta);
+	over = __reduce_add_sync(0xffffffffu, over);
+	if ((threadIdx.x & 31u) == 0 && over) atomicAdd(d_overused, over);
+}
+
+__global__ void pf_export_delta_kernel(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta) {
+	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x))
+		occ_delta[i] = nodes[i].occ - occ_base[i];
+}
+
+__global__ void pf_wirelength_kernel(const PfTreeNode *pool, long long count, unsigned long long *d_out) {
+	unsigned acc = 0;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+		acc += pf_tree_wirelength_one(&pool[i]);
+	acc = __reduce_add_sync(0xffffffffu, acc);
+	if ((threadIdx.x & 31u) == 0 && acc) atomicAdd(d_out, (unsigned long long)acc);
+}
+
+__global__ void pf_reserve_opins_kernel(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
+		int num_groups, const int *group_source, const int *group_count, const int *group_off,
+		int *chosen, int rip_up, float pres_fac) {
+	int g = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (g < num_groups)
+		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac);
+}
+
+__global__ void pf_select_nets_kernel(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
+		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts) {
+	int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (k >= num_all) return;
+	int net = all_nets[k];
+	if (force_all || pf_net_is_congested(nodes, pool, loc[net])) {
+		if (net_big[net]) list_big[atomicAdd(&counts[1], 1)] = net;
+		else list_small[atomicAdd(&counts[0], 1)] = net;
+	}
+}
+
+/* one warp per net: reserve space in the destination log, copy the tree with coalesced 32-byte entries */
+__global__ void pf_compact_kernel(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
+		unsigned long long *dst_head) {
+	int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31u);
+	int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+	for (int k = warp; k < num_all; k += nwarps) {
+		int net = all_nets[k];
+		PfNetLoc l = loc[net];
+		if (l.count == 0) continue;
+		unsigned long long off = 0;
+		if (lane == 0) off = atomicAdd(dst_head, (unsigned long long)l.count);
+		off = __shfl_sync(0xffffffffu, off, 0);
+		for (int i = lane; i < l.count; i += 32) dst[off + i] = src[l.off + i];
+		if (lane == 0) loc[net].off = (int)off;
+	}
+}
+
+/* ------------------------------------------------------------------ launchers */
+int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
+	if (warps_per_block < 1) warps_per_block = 1;
+	if (warps_per_block > 8) warps_per_block = 8;
+	int blocks = (num_slots + warps_per_block - 1) / warps_per_block;
+	size_t smem = (size_t)warps_per_block * PF_SMEM_PER_WARP;
+	if (ev_begin(0) != 0) return -1;
+	pf_route_kernel<<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
+	return ev_end();
+}
+
+static int stream_grid(long long n) {
+	long long b = (n + 255) / 256;
+	long long cap = (long long)(g_sms > 0 ? g_sms : 148) * 8;   /* a multiple of the SM count */
+	if (b > cap) b = cap;
+	if (b < 1) b = 1;
+	return (int)b;
+}
+
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, int *occ_base, const int *occ_delta) {
+	if (ev_begin(1) != 0) return -1;
+	pf_update_cost_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, acc_fac, d_overused, occ_base, occ_delta);
+	return ev_end();
+}
+
+int pfb_launch_export_delta(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta) {
+	if (ev_begin(2) != 0) return -1;
+	pf_export_delta_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, occ_base, occ_delta);
+	return ev_end();
+}
+
+int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long long *d_out) {
+	if (ev_begin(2) != 0) return -1;
+	pf_wirelength_kernel<<<stream_grid(count), 256, 0, g_stream>>>(pool, count, d_out);
+	return ev_end();
+}
+
+int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
+		int num_groups, const int *group_source, const int *group_count, const int *group_off,
+		int *chosen, int rip_up, float pres_fac) {
+	if (num_groups <= 0) return 0;
+	if (ev_begin(2) != 0) return -1;
+	pf_reserve_opins_kernel<<<(num_groups + 127) / 128, 128, 0, g_stream>>>(nodes, edges, indexed, num_groups, group_source, group_count, group_off, chosen, rip_up, pres_fac);
+	return ev_end();
+}
+
+int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
+		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts) {
+	if (num_all <= 0) return 0;
+	if (ev_begin(2) != 0) return -1;
+	pf_select_nets_kernel<<<(num_all + 127) / 128, 128, 0, g_stream>>>(nodes, pool, loc, all_nets, num_all, net_big, force_all, list_small, list_big, counts);
+	return ev_end();
+}
+
+int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
+		unsigned long long *dst_head) {
+	if (num_all <= 0) return 0;
+	if (ev_begin(2) != 0) return -1;
+	pf_compact_kernel<<<stream_grid((long long)num_all * 32), 256, 0, g_stream>>>(src, dst, loc, all_nets, num_all, dst_head);
+	return ev_end();
+}

@@ -1,0 +1,101 @@
+/*
+ * pf_layout.h — device data layout of the B200 PathFinder router (plain structs shared by the
+ * host driver pf_router.cpp, the CUDA kernels and the test emulator).  See DESIGN.md §3.
+ */
+#ifndef PF_LAYOUT_H
+#define PF_LAYOUT_H
+
+#include <stdint.h>
+
+/* ------------------------------------------------------------------ device data layout */
+
+/* rr node, 32 B = one HBM sector: everything one edge relaxation needs about its target.
+ * Replaces the 104-byte AoS t_rr_node (vpr_types.h:946) + t_rr_node_route_inf (route_common_types.h:56). */
+struct PfNode {
+	short xlow, ylow, xhigh, yhigh;   /* 8  */
+	float R, C;                       /* 8  */
+	int occ;                          /* 4  mutable: atomics (rip-up / commit) */
+	float acc_cost;                   /* 4  mutable: once per iteration */
+	int edge_start;                   /* 4  row_ptr */
+	unsigned short num_edges;         /* 2  */
+	unsigned char type_ci;            /* 1  type | cost_index << 3 */
+	unsigned char capacity;           /* 1  */
+};
+
+/* out-edge word: target node in the low 26 bits, switch id in the high 6 */
+#define PF_EDGE_NODE_BITS 26
+#define PF_EDGE_NODE_MASK 0x03ffffffu
+#define PF_MAX_SWITCHES 64
+#define PF_MAX_INDEXED 32
+
+struct PfSwitchDev { float R, Tdel; int buffered; };
+struct PfIndexedDev { float base_cost, saved_base_cost, inv_length, T_linear, T_quadratic, C_load; int ortho; int pad; };
+
+/* search label, 32 B (one sector), open-addressed per-warp hash table keyed by node id.
+ * `epoch` makes clearing free: a slot belongs to the current sink search iff epoch matches. */
+struct PfLabel {
+	int key; unsigned epoch; float tot; float back;       /* probed / compared */
+	float R_up; int prev; int prev_sw; int pad;           /* prev >= 0: rr node; prev < 0: ~tree index (seed) */
+};
+
+/* route-tree entry, 32 B.  Entries are appended in path order, so parent index < child index. */
+struct PfTreeNode {
+	int node;
+	int parent;                    /* tree index, -1 at the root */
+	float R_up, C_down, Tdel;
+	short xlow, ylow, xhigh, yhigh;
+	unsigned char sw;              /* switch parent→this */
+	unsigned char type_ci;
+	unsigned char flags;           /* bit0 re_expand, bit1 scratch mark */
+	unsigned char pad;
+};
+#define PF_TF_REEXPAND 1
+#define PF_TF_MARK 2
+
+struct PfNetLoc { int off, count; };   /* a net's tree in the route store */
+
+#define PF_SH_FRONTIER 192      /* near-set entries per warp in shared memory */
+#define PF_SH_REFILL 96         /* refill the near set to at most this many */
+#define PF_MAX_BATCH 8          /* labels settled per step */
+
+/* error/status bits written to PfParams.status[0] */
+#define PF_ST_UNROUTABLE 1
+#define PF_ST_POOL_OVERFLOW 2
+#define PF_ST_INTERNAL 4
+
+struct PfStats { unsigned long long pops, pushes, visits, refills, nets, label_probes, stale; unsigned long long pad; };
+
+struct PfParams {
+	PfNode *nodes;
+	const uint32_t *edges;
+	int num_nodes, nx, ny;
+	const PfSwitchDev *sw; int num_sw;
+	const PfIndexedDev *indexed; int num_indexed;
+	/* nets */
+	const int *net_ptr; const int *net_term; const int *net_bb;   /* bb: xmin,xmax,ymin,ymax */
+	const int *work; int num_work; int *work_head;
+	const float *crit;     /* [num_terminals] timing criticality per terminal */
+	float *net_delay;      /* [num_terminals] */
+	/* options */
+	float pres_fac, astar_fac, bend_cost, max_crit, crit_exp;
+	float pop_slack;       /* settle every label within this of the minimum in one step */
+	float win_rel, win_abs;/* near-set window: max(min*win_rel, win_abs) */
+	int max_batch;
+	int skip_ripup;
+	/* per-warp slot memory */
+	PfLabel *labels; int label_log2;
+	unsigned *epochs;
+	PfTreeNode *tree; int tree_cap;
+	uint64_t *far; int far_cap;
+	int *iscratch; int sink_cap;   /* per slot: 3 * (sink_cap+2) ints */
+	/* route store: append-only log of route trees; loc[net] points at the net's current tree.
+	 * A re-routed net appends its new tree and repoints loc; the log is compacted between
+	 * iterations when it is more than half garbage. */
+	PfTreeNode *pool; PfNetLoc *loc; unsigned long long *pool_head; long long pool_cap;
+	/* status */
+	int *status;
+	int *retry_list; int *retry_count;
+	PfStats *stats;
+};
+
+#endif /* PF_LAYOUT_H */

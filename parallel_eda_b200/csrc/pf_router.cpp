@@ -1,0 +1,662 @@
+/*
+ * pf_router.cpp — host side of the B200 PathFinder router behind the C-ABI of pf_router.h.
+ * Owns device memory, flattens the pf_problem into the device layout (32-byte node records,
+ * packed edge words), runs the PathFinder outer loop (reference route_timing.c:85-343) and turns
+ * the device route store back into s_trace-ordered lists.  All device work goes through
+ * pf_backend.h; this file contains no routing arithmetic.
+ */
+#include "../../include/pf_router.h"
+#include "pf_backend.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+static char g_router_err[512] = "";
+#define FAILF(code, ...) do { snprintf(g_router_err, sizeof(g_router_err), __VA_ARGS__); return (code); } while (0)
+#define CUDA_FAIL() do { snprintf(g_router_err, sizeof(g_router_err), "%s", pfb_last_error()); return PF_ECUDA; } while (0)
+#define CKB(x) do { if ((x) != 0) CUDA_FAIL(); } while (0)
+
+extern "C" const char *pf_last_error(void) { return g_router_err; }
+extern "C" const char *pf_backend_name(void) { return pfb_name(); }
+extern "C" int pf_device_count(void) { return pfb_device_count(); }
+
+extern "C" void pf_config_default(pf_config *c) {
+	memset(c, 0, sizeof(*c));
+	c->nranks = 1;
+	c->pop_slack = -1.f;
+}
+
+struct SlotClass {
+	int num_slots, label_log2, tree_cap, far_cap, sink_cap;
+	PfLabel *labels; unsigned *epochs; PfTreeNode *tree; uint64_t *far; int *iscratch;
+	int *work; int num_work; int *work_head;
+};
+
+struct pf_router {
+	pf_config cfg;
+	const pf_problem *prob;       /* caller-owned; must outlive the router */
+	int N, E, T, n;
+	PfNode *nodes; uint32_t *edges;
+	PfSwitchDev *sw; PfIndexedDev *indexed;
+	int *net_ptr, *net_term, *net_bb;
+	float *crit, *net_delay;
+	SlotClass small, big;
+	PfTreeNode *pool[2]; PfNetLoc *loc; int cur;      /* pool[cur] is the live route-tree log */
+	long long pool_cap; unsigned long long *pool_head;
+	int *all_nets; int num_all; unsigned char *net_big; int *sel_counts;
+	std::vector<unsigned char> h_net_big;
+	int iter_count;
+	int *status, *retry_list, *retry_count;
+	PfStats *stats;
+	int *d_overused; unsigned long long *d_wl;
+	int *occ_base;                /* multi-GPU only */
+	int *occ_delta;
+	/* OPIN reservation */
+	int num_groups; int *g_source, *g_count, *g_off, *g_chosen;
+	long long avail_wl;
+	int64_t h2d_bytes, d2h_bytes;
+	std::vector<int> work_small, work_big;
+	float win_abs_auto;
+};
+
+static int ceil_log2(long long v) { int l = 0; while ((1ll << l) < v) l++; return l; }
+
+static void free_slot_class(SlotClass &s) {
+	pfb_free(s.labels); pfb_free(s.epochs); pfb_free(s.tree); pfb_free(s.far); pfb_free(s.iscratch);
+	pfb_free(s.work); pfb_free(s.work_head);
+	memset(&s, 0, sizeof(s));
+}
+
+static int alloc_slot_class(SlotClass &s, int max_work) {
+	size_t cap = (size_t)1 << s.label_log2;
+	s.labels = (PfLabel *)pfb_alloc(sizeof(PfLabel) * cap * s.num_slots);
+	s.epochs = (unsigned *)pfb_alloc(sizeof(unsigned) * s.num_slots);
+	s.tree = (PfTreeNode *)pfb_alloc(sizeof(PfTreeNode) * (size_t)s.tree_cap * s.num_slots);
+	s.far = (uint64_t *)pfb_alloc(sizeof(uint64_t) * (size_t)s.far_cap * s.num_slots);
+	s.iscratch = (int *)pfb_alloc(sizeof(int) * ((size_t)3 * (s.sink_cap + 2) + (size_t)2 * s.tree_cap) * s.num_slots);
+	s.work = (int *)pfb_alloc(sizeof(int) * (size_t)(max_work > 0 ? max_work : 1));
+	s.work_head = (int *)pfb_alloc(sizeof(int) * 4);
+	if (!s.labels || !s.epochs || !s.tree || !s.far || !s.iscratch || !s.work || !s.work_head) return -1;
+	return 0;
+}
+
+extern "C" void pf_router_destroy(pf_router *r) {
+	if (!r) return;
+	pfb_sync();
+	pfb_free(r->nodes); pfb_free(r->edges); pfb_free(r->sw); pfb_free(r->indexed);
+	pfb_free(r->net_ptr); pfb_free(r->net_term); pfb_free(r->net_bb);
+	pfb_free(r->crit); pfb_free(r->net_delay);
+	free_slot_class(r->small); free_slot_class(r->big);
+	pfb_free(r->pool[0]); pfb_free(r->pool[1]); pfb_free(r->loc);
+	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->sel_counts);
+	pfb_free(r->pool_head); pfb_free(r->status); pfb_free(r->retry_list); pfb_free(r->retry_count);
+	pfb_free(r->stats); pfb_free(r->d_overused); pfb_free(r->d_wl);
+	pfb_free(r->occ_base); pfb_free(r->occ_delta);
+	pfb_free(r->g_source); pfb_free(r->g_count); pfb_free(r->g_off); pfb_free(r->g_chosen);
+	delete r;
+}
+
+static int upload_nodes(pf_router *r, bool keep_nothing) {
+	const pf_problem *p = r->prob;
+	std::vector<PfNode> h((size_t)r->N);
+	for (int i = 0; i < r->N; i++) {
+		PfNode &d = h[i];
+		d.xlow = p->xlow[i]; d.ylow = p->ylow[i]; d.xhigh = p->xhigh[i]; d.yhigh = p->yhigh[i];
+		d.R = p->R[i]; d.C = p->C[i];
+		d.occ = 0; d.acc_cost = 1.f;                 /* alloc_and_load_rr_node_route_structs, route_common.c:1012-1034 */
+		d.edge_start = p->row_ptr[i];
+		d.num_edges = (unsigned short)(p->row_ptr[i + 1] - p->row_ptr[i]);
+		d.type_ci = (unsigned char)(p->type[i] | (p->cost_index[i] << 3));
+		d.capacity = (unsigned char)p->capacity[i];
+	}
+	(void)keep_nothing;
+	CKB(pfb_h2d(r->nodes, h.data(), sizeof(PfNode) * (size_t)r->N));
+	r->h2d_bytes += (int64_t)sizeof(PfNode) * r->N;
+	return PF_OK;
+}
+
+extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf_router **out) {
+	char msg[256];
+	*out = NULL;
+	if (!p || !cfg_in) FAILF(PF_EINVAL, "null argument");
+	if (pf_problem_check(p, msg, sizeof(msg)) != PF_OK) FAILF(PF_EINVAL, "invalid problem: %s", msg);
+	if (p->num_nodes > (1 << PF_EDGE_NODE_BITS)) FAILF(PF_EINVAL, "num_rr_nodes %d exceeds the %d-bit edge word", p->num_nodes, PF_EDGE_NODE_BITS);
+	if (p->num_switches > PF_MAX_SWITCHES) FAILF(PF_EINVAL, "%d switch types (max %d)", p->num_switches, PF_MAX_SWITCHES);
+	if (p->num_indexed > PF_MAX_INDEXED) FAILF(PF_EINVAL, "%d rr_indexed_data rows (max %d)", p->num_indexed, PF_MAX_INDEXED);
+	for (int i = 0; i < p->num_nodes; i++) {
+		if (p->capacity[i] > 255) FAILF(PF_EINVAL, "rr node %d capacity %d > 255", i, p->capacity[i]);
+		if (p->cost_index[i] > 31) FAILF(PF_EINVAL, "rr node %d cost_index %d > 31", i, p->cost_index[i]);
+	}
+	if (cfg_in->nranks < 1 || cfg_in->rank < 0 || cfg_in->rank >= cfg_in->nranks) FAILF(PF_EINVAL, "bad rank %d / nranks %d", cfg_in->rank, cfg_in->nranks);
+	if (pfb_init(cfg_in->device) != 0) CUDA_FAIL();
+
+	pf_router *r = new pf_router();
+	memset((void *)&r->cfg, 0, sizeof(pf_config));
+	r->cfg = *cfg_in;
+	pf_config &c = r->cfg;
+	r->prob = p; r->N = p->num_nodes; r->E = p->num_edges; r->T = p->num_terminals; r->n = p->num_nets;
+	r->nodes = NULL; r->edges = NULL; r->sw = NULL; r->indexed = NULL; r->net_ptr = r->net_term = r->net_bb = NULL;
+	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
+	r->pool[0] = r->pool[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
+	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->iter_count = 0;
+	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
+	r->occ_base = r->occ_delta = NULL; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
+	r->h2d_bytes = r->d2h_bytes = 0;
+
+	int sms = pfb_num_sms();
+	if (c.warps_per_block <= 0) c.warps_per_block = 4;
+	if (c.num_slots <= 0) c.num_slots = (sms > 0 ? sms : 148) * 16;
+	if (c.label_log2 <= 0) c.label_log2 = 13;
+	if (c.tree_cap <= 0) c.tree_cap = 2048;
+	if (c.far_cap <= 0) c.far_cap = 8192;
+	if (c.sink_cap <= 0) c.sink_cap = 64;
+	if (c.big_slots <= 0) c.big_slots = 64;
+	if (c.max_batch <= 0) c.max_batch = 2;
+	if (c.reroute_all_iters == 0) c.reroute_all_iters = 1;
+	if (c.inflight_div <= 0) c.inflight_div = 16;
+	if (c.min_slots <= 0) c.min_slots = 1;
+	if (c.max_batch > PF_MAX_BATCH) c.max_batch = PF_MAX_BATCH;
+
+	/* work lists: routed nets in decreasing-fanout order (route_timing.c:98-106), sharded by rank */
+	std::vector<int> order;
+	int max_sinks = 1;
+	for (int i = 0; i < r->n; i++) {
+		int ns = p->net_ptr[i + 1] - p->net_ptr[i] - 1;
+		if (p->net_is_global[i] || ns < 1) continue;     /* SURVEY §8b edge case (i) */
+		order.push_back(i);
+		max_sinks = std::max(max_sinks, ns);
+	}
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+		return (p->net_ptr[a + 1] - p->net_ptr[a]) > (p->net_ptr[b + 1] - p->net_ptr[b]); });
+	for (size_t k = 0; k < order.size(); k++) {
+		if ((int)(k % (size_t)c.nranks) != c.rank) continue;
+		int i = order[k], ns = p->net_ptr[i + 1] - p->net_ptr[i] - 1;
+		if (ns > c.sink_cap) r->work_big.push_back(i); else r->work_small.push_back(i);
+	}
+	if (c.big_label_log2 <= 0) c.big_label_log2 = std::min(21, std::max(c.label_log2 + 2, ceil_log2(2ll * r->N)));
+	if (c.big_tree_cap <= 0) c.big_tree_cap = std::max(1 << 16, 64 * max_sinks);
+	if (c.big_far_cap <= 0) c.big_far_cap = 1 << 19;
+	if (c.num_slots > (int)r->work_small.size() + 32) c.num_slots = std::max(32, (int)((r->work_small.size() + 31) / 32 * 32));
+
+	/* device graph */
+	r->nodes = (PfNode *)pfb_alloc(sizeof(PfNode) * (size_t)r->N);
+	r->edges = (uint32_t *)pfb_alloc(sizeof(uint32_t) * (size_t)std::max(r->E, 1));
+	r->sw = (PfSwitchDev *)pfb_alloc(sizeof(PfSwitchDev) * PF_MAX_SWITCHES);
+	r->indexed = (PfIndexedDev *)pfb_alloc(sizeof(PfIndexedDev) * PF_MAX_INDEXED);
+	r->net_ptr = (int *)pfb_alloc(sizeof(int) * ((size_t)r->n + 1));
+	r->net_term = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(r->T, 1));
+	r->net_bb = (int *)pfb_alloc(sizeof(int) * 4 * (size_t)std::max(r->n, 1));
+	r->crit = (float *)pfb_alloc(sizeof(float) * (size_t)std::max(r->T, 1));
+	r->net_delay = (float *)pfb_alloc(sizeof(float) * (size_t)std::max(r->T, 1));
+	if (!r->nodes || !r->edges || !r->sw || !r->indexed || !r->net_ptr || !r->net_term || !r->net_bb || !r->crit || !r->net_delay) {
+		pf_router_destroy(r); CUDA_FAIL();
+	}
+	{
+		std::vector<uint32_t> ew((size_t)std::max(r->E, 1));
+		for (int k = 0; k < r->E; k++) ew[k] = (uint32_t)p->edge_to[k] | ((uint32_t)p->edge_sw[k] << PF_EDGE_NODE_BITS);
+		std::vector<PfSwitchDev> sw(PF_MAX_SWITCHES);
+		for (int s = 0; s < p->num_switches; s++) { sw[s].R = p->switches[s].R; sw[s].Tdel = p->switches[s].Tdel; sw[s].buffered = p->switches[s].buffered; }
+		std::vector<PfIndexedDev> ix(PF_MAX_INDEXED);
+		float min_base = 0.f;
+		for (int i = 0; i < p->num_indexed; i++) {
+			ix[i].base_cost = p->indexed[i].base_cost; ix[i].saved_base_cost = p->indexed[i].saved_base_cost;
+			ix[i].inv_length = p->indexed[i].inv_length; ix[i].T_linear = p->indexed[i].T_linear;
+			ix[i].T_quadratic = p->indexed[i].T_quadratic; ix[i].C_load = p->indexed[i].C_load;
+			ix[i].ortho = p->indexed[i].ortho_cost_index; ix[i].pad = 0;
+			if (i >= PF_CHANX_COST_INDEX_START && (min_base == 0.f || p->indexed[i].base_cost < min_base)) min_base = p->indexed[i].base_cost;
+		}
+		r->win_abs_auto = 4.f * min_base;             /* a few wire hops of base cost */
+		if (upload_nodes(r, true) != PF_OK) { pf_router_destroy(r); return PF_ECUDA; }
+		if (pfb_h2d(r->edges, ew.data(), sizeof(uint32_t) * (size_t)r->E) || pfb_h2d(r->sw, sw.data(), sizeof(PfSwitchDev) * PF_MAX_SWITCHES)
+				|| pfb_h2d(r->indexed, ix.data(), sizeof(PfIndexedDev) * PF_MAX_INDEXED)
+				|| pfb_h2d(r->net_ptr, p->net_ptr, sizeof(int) * ((size_t)r->n + 1))
+				|| pfb_h2d(r->net_term, p->net_terminals, sizeof(int) * (size_t)r->T)
+				|| pfb_h2d(r->net_bb, p->net_bb, sizeof(int) * 4 * (size_t)r->n)) { pf_router_destroy(r); CUDA_FAIL(); }
+		r->h2d_bytes += (int64_t)sizeof(uint32_t) * r->E + (int64_t)sizeof(int) * (r->n + 1 + r->T + 4 * (int64_t)r->n);
+		r->avail_wl = 0;
+		for (int i = 0; i < r->N; i++)
+			if (p->type[i] == PF_CHANX || p->type[i] == PF_CHANY) r->avail_wl += 1 + p->xhigh[i] - p->xlow[i] + p->yhigh[i] - p->ylow[i];
+	}
+	/* initial criticalities (route_timing.c:116-128) */
+	{
+		std::vector<float> cr((size_t)std::max(r->T, 1), 0.f);
+		float v = p->opts.timing_analysis_enabled ? 1.f : 0.f;
+		for (int i = 0; i < r->n; i++)
+			if (!p->net_is_global[i]) for (int k = p->net_ptr[i] + 1; k < p->net_ptr[i + 1]; k++) cr[k] = v;
+		if (pfb_h2d(r->crit, cr.data(), sizeof(float) * (size_t)r->T)) { pf_router_destroy(r); CUDA_FAIL(); }
+	}
+	/* slots */
+	r->small.num_slots = c.num_slots; r->small.label_log2 = c.label_log2; r->small.tree_cap = c.tree_cap;
+	r->small.far_cap = c.far_cap; r->small.sink_cap = c.sink_cap;
+	r->big.num_slots = c.big_slots; r->big.label_log2 = c.big_label_log2; r->big.tree_cap = c.big_tree_cap;
+	r->big.far_cap = c.big_far_cap; r->big.sink_cap = std::max(max_sinks, c.sink_cap);
+	int nwork = (int)(r->work_small.size() + r->work_big.size());
+	if (alloc_slot_class(r->small, nwork) || alloc_slot_class(r->big, nwork)) { pf_router_destroy(r); CUDA_FAIL(); }
+	/* route store */
+	r->pool_cap = std::max<long long>(1 << 16, 4ll * r->N + 96ll * r->T);
+	for (int k = 0; k < 2; k++) {
+		r->pool[k] = (PfTreeNode *)pfb_alloc(sizeof(PfTreeNode) * (size_t)r->pool_cap);
+		if (!r->pool[k]) { pf_router_destroy(r); CUDA_FAIL(); }
+	}
+	r->loc = (PfNetLoc *)pfb_alloc(sizeof(PfNetLoc) * (size_t)std::max(r->n, 1));
+	{
+		std::vector<int> all(r->work_big);
+		all.insert(all.end(), r->work_small.begin(), r->work_small.end());
+		r->num_all = (int)all.size();
+		r->h_net_big.assign((size_t)std::max(r->n, 1), 0);
+		for (int i : r->work_big) r->h_net_big[i] = 1;
+		r->all_nets = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(r->num_all, 1));
+		r->net_big = (unsigned char *)pfb_alloc((size_t)std::max(r->n, 1));
+		r->sel_counts = (int *)pfb_alloc(sizeof(int) * 4);
+		if (!r->loc || !r->all_nets || !r->net_big || !r->sel_counts
+				|| pfb_h2d(r->all_nets, all.data(), sizeof(int) * (size_t)r->num_all)
+				|| pfb_h2d(r->net_big, r->h_net_big.data(), (size_t)r->n)) { pf_router_destroy(r); CUDA_FAIL(); }
+	}
+	r->pool_head = (unsigned long long *)pfb_alloc(sizeof(unsigned long long) * 2);
+	r->status = (int *)pfb_alloc(sizeof(int) * 8);
+	r->retry_list = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(nwork, 1));
+	r->retry_count = (int *)pfb_alloc(sizeof(int) * 4);
+	r->stats = (PfStats *)pfb_alloc(sizeof(PfStats));
+	r->d_overused = (int *)pfb_alloc(sizeof(int) * 4);
+	r->d_wl = (unsigned long long *)pfb_alloc(sizeof(unsigned long long) * 2);
+	if (!r->pool_head || !r->status || !r->retry_list || !r->retry_count || !r->stats || !r->d_overused || !r->d_wl) { pf_router_destroy(r); CUDA_FAIL(); }
+	if (c.nranks > 1) {
+		r->occ_base = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
+		r->occ_delta = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
+		if (!r->occ_base || !r->occ_delta) { pf_router_destroy(r); CUDA_FAIL(); }
+	}
+	/* OPIN groups */
+	r->num_groups = p->num_opin_groups;
+	if (r->num_groups > 0) {
+		std::vector<int> off((size_t)r->num_groups);
+		int tot = 0;
+		for (int g = 0; g < r->num_groups; g++) { off[g] = tot; tot += p->opin_group_count[g]; }
+		r->g_source = (int *)pfb_alloc(sizeof(int) * (size_t)r->num_groups);
+		r->g_count = (int *)pfb_alloc(sizeof(int) * (size_t)r->num_groups);
+		r->g_off = (int *)pfb_alloc(sizeof(int) * (size_t)r->num_groups);
+		r->g_chosen = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(tot, 1));
+		if (!r->g_source || !r->g_count || !r->g_off || !r->g_chosen
+				|| pfb_h2d(r->g_source, p->opin_group_source, sizeof(int) * (size_t)r->num_groups)
+				|| pfb_h2d(r->g_count, p->opin_group_count, sizeof(int) * (size_t)r->num_groups)
+				|| pfb_h2d(r->g_off, off.data(), sizeof(int) * (size_t)r->num_groups)) { pf_router_destroy(r); CUDA_FAIL(); }
+	}
+	if (pfb_sync() != 0) { pf_router_destroy(r); CUDA_FAIL(); }
+	if (c.verbose)
+		fprintf(stderr, "pf_router[%s] rank %d/%d: N=%d E=%d nets=%zu+%zu slots=%d(2^%d labels)+%d(2^%d) pool=%lld\n", pfb_name(), c.rank, c.nranks,
+				r->N, r->E, r->work_small.size(), r->work_big.size(), c.num_slots, c.label_log2, c.big_slots, c.big_label_log2, r->pool_cap);
+	*out = r;
+	return PF_OK;
+}
+
+extern "C" int pf_router_reset(pf_router *r) {
+	if (!r) FAILF(PF_EINVAL, "null router");
+	if (upload_nodes(r, true) != PF_OK) return PF_ECUDA;
+	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
+	CKB(pfb_zero(r->pool_head, sizeof(unsigned long long) * 2));
+	r->iter_count = 0;
+	CKB(pfb_zero(r->net_delay, sizeof(float) * (size_t)std::max(r->T, 1)));
+	if (r->occ_base) CKB(pfb_zero(r->occ_base, sizeof(int) * (size_t)r->N));
+	{
+		const pf_problem *p = r->prob;
+		std::vector<float> cr((size_t)std::max(r->T, 1), 0.f);
+		float v = p->opts.timing_analysis_enabled ? 1.f : 0.f;
+		for (int i = 0; i < r->n; i++)
+			if (!p->net_is_global[i]) for (int k = p->net_ptr[i] + 1; k < p->net_ptr[i + 1]; k++) cr[k] = v;
+		CKB(pfb_h2d(r->crit, cr.data(), sizeof(float) * (size_t)r->T));
+	}
+	CKB(pfb_sync());
+	return PF_OK;
+}
+
+static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pres_fac) {
+	const pf_problem *p = r->prob;
+	const pf_config &c = r->cfg;
+	memset(&P, 0, sizeof(P));
+	P.nodes = r->nodes; P.edges = r->edges; P.num_nodes = r->N; P.nx = p->nx; P.ny = p->ny;
+	P.sw = r->sw; P.num_sw = p->num_switches; P.indexed = r->indexed; P.num_indexed = p->num_indexed;
+	P.net_ptr = r->net_ptr; P.net_term = r->net_term; P.net_bb = r->net_bb;
+	P.work = s.work; P.num_work = s.num_work; P.work_head = s.work_head;
+	P.crit = r->crit; P.net_delay = r->net_delay;
+	P.pres_fac = pres_fac; P.astar_fac = p->opts.astar_fac; P.bend_cost = p->opts.bend_cost;
+	P.max_crit = p->opts.max_criticality; P.crit_exp = p->opts.criticality_exp;
+	P.pop_slack = c.pop_slack >= 0.f ? c.pop_slack : 0.f;
+	P.win_rel = c.win_rel > 0.f ? c.win_rel : 0.05f;
+	P.win_abs = c.win_abs > 0.f ? c.win_abs : r->win_abs_auto;
+	P.max_batch = c.max_batch;
+	P.skip_ripup = 0;
+	P.labels = s.labels; P.label_log2 = s.label_log2; P.epochs = s.epochs;
+	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap;
+	P.iscratch = s.iscratch; P.sink_cap = s.sink_cap;
+	P.pool = r->pool[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;
+	P.status = r->status; P.retry_list = r->retry_list; P.retry_count = r->retry_count; P.stats = r->stats;
+}
+
+static int set_work(pf_router *r, SlotClass &s, const int *list, int count) {
+	s.num_work = count;
+	if (count > 0) { CKB(pfb_h2d(s.work, list, sizeof(int) * (size_t)count)); r->h2d_bytes += (int64_t)sizeof(int) * count; }
+	CKB(pfb_zero(s.work_head, sizeof(int) * 4));
+	return PF_OK;
+}
+
+/* device-resident work list (from pf_select_nets) → slot class queue */
+static int set_work_dev(pf_router *r, SlotClass &s, int count) {
+	s.num_work = count;
+	CKB(pfb_zero(s.work_head, sizeof(int) * 4));
+	(void)r;
+	return PF_OK;
+}
+
+static int slots_for(const pf_router *r, int total_work, int class_slots) {
+	int s = (total_work + r->cfg.inflight_div - 1) / r->cfg.inflight_div;
+	s = std::max(s, r->cfg.min_slots);
+	return std::max(1, std::min(s, class_slots));
+}
+
+extern "C" int pf_route_iteration(pf_router *r, float pres_fac, const float *crit, pf_iter_stats *st) {
+	if (!r) FAILF(PF_EINVAL, "null router");
+	int rc;
+	if (crit) { CKB(pfb_h2d(r->crit, crit, sizeof(float) * (size_t)r->T)); r->h2d_bytes += (int64_t)sizeof(float) * r->T; }
+	CKB(pfb_zero(r->status, sizeof(int) * 8));
+	CKB(pfb_zero(r->retry_count, sizeof(int) * 4));
+	CKB(pfb_zero(r->stats, sizeof(PfStats)));
+	/* garbage-collect the route-tree log when it is more than half full */
+	{
+		unsigned long long head[2];
+		CKB(pfb_d2h(head, r->pool_head, sizeof(head)));
+		if ((long long)head[0] > r->pool_cap / 2) {
+			CKB(pfb_zero(r->pool_head, sizeof(unsigned long long) * 2));
+			CKB(pfb_launch_compact(r->pool[r->cur], r->pool[r->cur ^ 1], r->loc, r->all_nets, r->num_all, r->pool_head));
+			r->cur ^= 1;
+			CKB(pfb_d2h(head, r->pool_head, sizeof(head)));
+			if ((long long)head[0] > r->pool_cap / 2) FAILF(PF_EOVERFLOW, "route store too small: %llu live tree entries of %lld", head[0], r->pool_cap);
+		}
+	}
+	if (r->cfg.nranks > 1) CKB(pfb_zero(r->net_delay, sizeof(float) * (size_t)std::max(r->T, 1)));
+	/* which nets are routed in this iteration */
+	const bool all = r->cfg.reroute_all_iters < 0 || r->iter_count < r->cfg.reroute_all_iters;
+	int n_small, n_big;
+	if (all) {
+		std::vector<int> sm, bg;
+		for (int i : r->work_big) bg.push_back(i);
+		for (int i : r->work_small) (r->h_net_big[i] ? bg : sm).push_back(i);
+		if ((rc = set_work(r, r->small, sm.data(), (int)sm.size())) != PF_OK) return rc;
+		if ((rc = set_work(r, r->big, bg.data(), (int)bg.size())) != PF_OK) return rc;
+		n_small = (int)sm.size(); n_big = (int)bg.size();
+	} else {
+		int counts[4];
+		CKB(pfb_zero(r->sel_counts, sizeof(int) * 4));
+		CKB(pfb_launch_select_nets(r->nodes, r->pool[r->cur], r->loc, r->all_nets, r->num_all, r->net_big, 0,
+				r->small.work, r->big.work, r->sel_counts));
+		CKB(pfb_d2h(counts, r->sel_counts, sizeof(int) * 4));
+		r->d2h_bytes += 16;
+		n_small = counts[0]; n_big = counts[1];
+		if ((rc = set_work_dev(r, r->small, n_small)) != PF_OK) return rc;
+		if ((rc = set_work_dev(r, r->big, n_big)) != PF_OK) return rc;
+	}
+	r->iter_count++;
+	PfParams P;
+	int total = n_small + n_big;
+	if (n_big > 0) {                       /* long nets first */
+		fill_params(r, P, r->big, pres_fac);
+		CKB(pfb_launch_route(&P, slots_for(r, total, std::min(r->big.num_slots, n_big)), 1));
+	}
+	if (n_small > 0) {
+		fill_params(r, P, r->small, pres_fac);
+		CKB(pfb_launch_route(&P, slots_for(r, total, r->small.num_slots), r->cfg.warps_per_block));
+	}
+	CKB(pfb_sync());
+	/* nets whose scratch overflowed in a small slot are re-routed in the big slots, and stay there */
+	int h_retry[4] = { 0, 0, 0, 0 };
+	CKB(pfb_d2h(h_retry, r->retry_count, sizeof(int) * 4));
+	int rounds = 0;
+	while (h_retry[0] > 0) {
+		std::vector<int> lst((size_t)h_retry[0]);
+		CKB(pfb_d2h(lst.data(), r->retry_list, sizeof(int) * (size_t)h_retry[0]));
+		if (++rounds > 1) FAILF(PF_EOVERFLOW, "%d nets overflow the big slots (first net %d; label 2^%d, tree %d, far %d)", h_retry[0], lst[0],
+				r->big.label_log2, r->big.tree_cap, r->big.far_cap);
+		if (r->cfg.verbose) fprintf(stderr, "pf_router: %d nets moved to the big slots\n", h_retry[0]);
+		for (int i : lst) r->h_net_big[i] = 1;
+		CKB(pfb_h2d(r->net_big, r->h_net_big.data(), (size_t)r->n));
+		CKB(pfb_zero(r->retry_count, sizeof(int) * 4));
+		if ((rc = set_work(r, r->big, lst.data(), (int)lst.size())) != PF_OK) return rc;
+		fill_params(r, P, r->big, pres_fac);
+		P.skip_ripup = 1;
+		CKB(pfb_launch_route(&P, slots_for(r, (int)lst.size(), std::min(r->big.num_slots, (int)lst.size())), 1));
+		CKB(pfb_sync());
+		CKB(pfb_d2h(h_retry, r->retry_count, sizeof(int) * 4));
+	}
+	int h_status[8];
+	CKB(pfb_d2h(h_status, r->status, sizeof(int) * 8));
+	r->d2h_bytes += 48;
+	if (h_status[0] & PF_ST_POOL_OVERFLOW) FAILF(PF_EOVERFLOW, "route store overflow (capacity %lld tree entries)", r->pool_cap);
+	if (h_status[0] & PF_ST_INTERNAL) FAILF(PF_ECUDA, "internal error in the device router (net %d)", h_status[2]);
+	if (h_status[0] & PF_ST_UNROUTABLE) FAILF(PF_EUNROUTABLE, "net %d has no possible path (disconnected rr graph)", h_status[2]);
+	if (st) {
+		PfStats hs;
+		CKB(pfb_d2h(&hs, r->stats, sizeof(PfStats)));
+		memset(st, 0, sizeof(*st));
+		st->nets_routed = (int)hs.nets; st->heap_pushes = (int64_t)hs.pushes; st->heap_pops = (int64_t)hs.pops;
+		st->edge_visits = (int64_t)hs.visits; st->pres_fac = pres_fac;
+	}
+	return PF_OK;
+}
+
+extern "C" int pf_reserve_opins(pf_router *r, float pres_fac, int rip_up) {
+	if (!r) FAILF(PF_EINVAL, "null router");
+	if (r->num_groups == 0) return PF_OK;
+	CKB(pfb_launch_reserve_opins(r->nodes, r->edges, r->indexed, r->num_groups, r->g_source, r->g_count, r->g_off, r->g_chosen, rip_up, pres_fac));
+	return PF_OK;
+}
+
+static int update_costs_impl(pf_router *r, float acc_fac, const int *delta, int *overused) {
+	CKB(pfb_zero(r->d_overused, sizeof(int) * 4));
+	CKB(pfb_launch_update_cost(r->nodes, r->N, acc_fac, r->d_overused, delta ? r->occ_base : NULL, delta));
+	int h[4];
+	CKB(pfb_d2h(h, r->d_overused, sizeof(int) * 4));
+	r->d2h_bytes += 16;
+	if (overused) *overused = h[0];
+	return PF_OK;
+}
+
+extern "C" int pf_update_costs(pf_router *r, float acc_fac, int *overused) {
+	if (!r) FAILF(PF_EINVAL, "null router");
+	return update_costs_impl(r, acc_fac, NULL, overused);
+}
+
+extern "C" int pf_comm_export_delta(pf_router *r, void *dev_delta) {
+	if (!r || !dev_delta) FAILF(PF_EINVAL, "null argument");
+	if (!r->occ_base) FAILF(PF_EINVAL, "router was created with nranks == 1");
+	CKB(pfb_launch_export_delta(r->nodes, r->N, r->occ_base, (int *)dev_delta));
+	CKB(pfb_sync());
+	return PF_OK;
+}
+
+extern "C" int pf_update_costs_synced(pf_router *r, float acc_fac, const void *dev_delta, int *overused) {
+	if (!r || !dev_delta) FAILF(PF_EINVAL, "null argument");
+	if (!r->occ_base) FAILF(PF_EINVAL, "router was created with nranks == 1");
+	return update_costs_impl(r, acc_fac, (const int *)dev_delta, overused);
+}
+
+extern "C" void *pf_comm_net_delay_ptr(pf_router *r) { return r ? (void *)r->net_delay : NULL; }
+
+extern "C" int pf_total_wirelength(pf_router *r, int64_t *wl, int64_t *avail) {
+	if (!r) FAILF(PF_EINVAL, "null router");
+	unsigned long long head[2];
+	CKB(pfb_d2h(head, r->pool_head, sizeof(head)));
+	CKB(pfb_zero(r->d_wl, sizeof(unsigned long long) * 2));
+	CKB(pfb_launch_wirelength(r->pool[r->cur], (long long)head[0], r->d_wl));
+	unsigned long long h[2];
+	CKB(pfb_d2h(h, r->d_wl, sizeof(h)));
+	r->d2h_bytes += 32;
+	if (wl) *wl = (int64_t)h[0];
+	if (avail) *avail = r->avail_wl;
+	return PF_OK;
+}
+
+extern "C" int pf_get_net_delay(pf_router *r, float *net_delay) {
+	if (!r || !net_delay) FAILF(PF_EINVAL, "null argument");
+	CKB(pfb_d2h(net_delay, r->net_delay, sizeof(float) * (size_t)r->T));
+	r->d2h_bytes += (int64_t)sizeof(float) * r->T;
+	return PF_OK;
+}
+
+extern "C" int pf_get_timing(pf_router *r, pf_timing *t, int reset) {
+	if (!r || !t) FAILF(PF_EINVAL, "null argument");
+	PfLaunchTimes lt;
+	pfb_times(&lt, reset);
+	t->route_kernel_ms = lt.route_ms; t->update_kernel_ms = lt.update_ms; t->aux_kernel_ms = lt.aux_ms;
+	t->route_launches = lt.route_launches; t->update_launches = lt.update_launches; t->aux_launches = lt.aux_launches;
+	t->h2d_bytes = r->h2d_bytes; t->d2h_bytes = r->d2h_bytes;
+	if (reset) { r->h2d_bytes = 0; r->d2h_bytes = 0; }
+	return PF_OK;
+}
+
+/* Route store → s_trace-ordered lists (update_traceback, route_common.c:638-706): the first
+ * segment runs SOURCE … SINK; every later segment starts with its join node (whose iswitch is
+ * the switch into the first new node) and ends at a SINK (iswitch OPEN). */
+extern "C" int pf_get_result(pf_router *r, pf_result *out) {
+	if (!r || !out) FAILF(PF_EINVAL, "null argument");
+	const pf_problem *p = r->prob;
+	memset(out, 0, sizeof(*out));
+	unsigned long long head[2];
+	CKB(pfb_d2h(head, r->pool_head, sizeof(head)));
+	std::vector<PfNetLoc> loc((size_t)std::max(r->n, 1));
+	CKB(pfb_d2h(loc.data(), r->loc, sizeof(PfNetLoc) * (size_t)r->n));
+	long long used = 0;
+	for (int i = 0; i < r->n; i++) used = std::max<long long>(used, (long long)loc[i].off + loc[i].count);
+	std::vector<PfTreeNode> pool((size_t)std::max<long long>(used, 1));
+	CKB(pfb_d2h(pool.data(), r->pool[r->cur], sizeof(PfTreeNode) * (size_t)used));
+	std::vector<PfNode> nodes((size_t)r->N);
+	CKB(pfb_d2h(nodes.data(), r->nodes, sizeof(PfNode) * (size_t)r->N));
+	r->d2h_bytes += (int64_t)sizeof(PfTreeNode) * used + (int64_t)sizeof(PfNode) * r->N + (int64_t)sizeof(PfNetLoc) * r->n;
+
+	std::vector<int32_t> tptr((size_t)r->n + 1, 0), tnode;
+	std::vector<int16_t> tsw;
+	int wl = 0;
+	for (int i = 0; i < r->n; i++) {
+		const PfTreeNode *t = pool.data() + loc[i].off;
+		int cnt = loc[i].count;
+		int k = 0;
+		while (k < cnt) {
+			/* one segment: entries k..e where e is the next SINK */
+			int e = k;
+			while (e < cnt && (t[e].type_ci & 7) != PF_SINK) e++;
+			if (e >= cnt) { if (k == 0 && cnt == 1) break; FAILF(PF_ECUDA, "net %d: route tree does not end in a SINK", i); }
+			if (k > 0) {   /* join node first */
+				int j = t[k].parent;
+				tnode.push_back(t[j].node); tsw.push_back((int16_t)t[k].sw);
+			}
+			for (int q = k; q <= e; q++) {
+				tnode.push_back(t[q].node);
+				tsw.push_back(q < e ? (int16_t)t[q + 1].sw : (int16_t)PF_OPEN);
+				int ty = t[q].type_ci & 7;
+				if (ty == PF_CHANX || ty == PF_CHANY) wl += 1 + t[q].xhigh - t[q].xlow + t[q].yhigh - t[q].ylow;
+			}
+			k = e + 1;
+		}
+		tptr[i + 1] = (int32_t)tnode.size();
+	}
+	out->num_nets = r->n;
+	out->trace_ptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)r->n + 1));
+	out->trace_node = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(tnode.size(), 1));
+	out->trace_switch = (int16_t *)malloc(sizeof(int16_t) * std::max<size_t>(tsw.size(), 1));
+	out->net_delay = (float *)malloc(sizeof(float) * (size_t)std::max(r->T, 1));
+	out->occ = (int32_t *)malloc(sizeof(int32_t) * (size_t)r->N);
+	if (!out->trace_ptr || !out->trace_node || !out->trace_switch || !out->net_delay || !out->occ) { pf_result_free(out); FAILF(PF_ENOMEM, "out of host memory"); }
+	memcpy(out->trace_ptr, tptr.data(), sizeof(int32_t) * ((size_t)r->n + 1));
+	if (!tnode.empty()) { memcpy(out->trace_node, tnode.data(), sizeof(int32_t) * tnode.size()); memcpy(out->trace_switch, tsw.data(), sizeof(int16_t) * tsw.size()); }
+	out->num_terminals = r->T;
+	if (pfb_d2h(out->net_delay, r->net_delay, sizeof(float) * (size_t)r->T)) { pf_result_free(out); CUDA_FAIL(); }
+	out->num_nodes = r->N;
+	for (int i = 0; i < r->N; i++) out->occ[i] = nodes[i].occ;
+	out->total_wirelength = wl;
+	{   /* get_serial_num, route_common.c:224-254 */
+		int serial = 0;
+		for (int i = 0; i < r->n; i++)
+			for (int k = tptr[i]; k < tptr[i + 1]; k++) {
+				int v = tnode[k];
+				serial += (i + 1) * (p->xlow[v] * (p->nx + 1) - p->yhigh[v]);
+				serial -= p->ptc_num[v] * (i + 1) * 10;
+				serial -= p->type[v] * (i + 1) * 100;
+				serial %= 2000000000;
+			}
+		out->serial_num = serial;
+	}
+	return PF_OK;
+}
+
+/* try_timing_driven_route, reference route_timing.c:85-343, single GPU */
+extern "C" int pf_try_timing_driven_route(const pf_problem *p, const pf_config *cfg, pf_sta_fn sta, void *user, pf_result *out) {
+	pf_router *r = NULL;
+	int rc = pf_router_create(p, cfg, &r);
+	if (rc != PF_OK) return rc;
+	const pf_router_opts &o = p->opts;
+	int max_iters = o.max_router_iterations;
+	std::vector<pf_iter_stats> stats;
+	std::vector<float> crit((size_t)std::max(p->num_terminals, 1)), delay((size_t)std::max(p->num_terminals, 1));
+	std::vector<float> crit_hist;
+	{
+		float v = o.timing_analysis_enabled ? 1.f : 0.f;
+		std::fill(crit.begin(), crit.end(), 0.f);
+		for (int i = 0; i < p->num_nets; i++)
+			if (!p->net_is_global[i]) for (int k = p->net_ptr[i] + 1; k < p->net_ptr[i + 1]; k++) crit[k] = v;
+	}
+	float pres_fac = o.first_iter_pres_fac;
+	int success = 0, itry;
+	bool have_crit = false;
+	for (itry = 1; itry <= max_iters; itry++) {
+		pf_iter_stats st;
+		crit_hist.insert(crit_hist.end(), crit.begin(), crit.begin() + p->num_terminals);
+		rc = pf_route_iteration(r, pres_fac, have_crit ? crit.data() : NULL, &st);
+		if (rc != PF_OK) break;
+		if (itry == 1) {
+			int64_t wl = 0, avail = 1;
+			if ((rc = pf_total_wirelength(r, &wl, &avail)) != PF_OK) break;
+			if ((float)wl / (float)avail > PF_FIRST_ITER_WIRELENGTH_LIMIT) { stats.push_back(st); itry++; break; }
+		}
+		if ((rc = pf_reserve_opins(r, pres_fac, itry != 1)) != PF_OK) break;
+		float acc_fac;
+		if (itry == 1) { pres_fac = o.initial_pres_fac; acc_fac = 0.f; }
+		else {
+			pres_fac *= o.pres_fac_mult;
+			pres_fac = fminf(pres_fac, (float)(PF_HUGE_POSITIVE_FLOAT / 1e5));
+			acc_fac = o.acc_fac;
+		}
+		int overused = 0;
+		/* feasibility is decided on the occupancies before the cost update; when nothing is
+		 * overused the update is a no-op, so one fused pass serves both */
+		if ((rc = pf_update_costs(r, acc_fac, &overused)) != PF_OK) break;
+		st.overused_nodes = overused;
+		stats.push_back(st);
+		if (overused == 0) { success = 1; itry++; break; }
+		if (o.timing_analysis_enabled && sta) {
+			if ((rc = pf_get_net_delay(r, delay.data())) != PF_OK) break;
+			float cpd = 0.f;
+			sta(user, itry, delay.data(), crit.data(), &cpd);
+			stats.back().crit_path_delay = cpd;
+			have_crit = true;
+		} else if (!o.timing_analysis_enabled) {
+			have_crit = false;   /* criticalities stay 0 on the device */
+		}
+	}
+	itry--;
+	if (rc == PF_OK) {
+		rc = pf_get_result(r, out);
+		if (rc == PF_OK) {
+			out->success = success;
+			out->iterations = itry;
+			out->num_iter_stats = (int)stats.size();
+			out->iter_stats = (pf_iter_stats *)malloc(sizeof(pf_iter_stats) * std::max<size_t>(stats.size(), 1));
+			memcpy(out->iter_stats, stats.data(), sizeof(pf_iter_stats) * stats.size());
+			out->num_crit_iters = p->num_terminals ? (int)(crit_hist.size() / (size_t)p->num_terminals) : 0;
+			out->iter_crit = (float *)malloc(sizeof(float) * std::max<size_t>(crit_hist.size(), 1));
+			memcpy(out->iter_crit, crit_hist.data(), sizeof(float) * crit_hist.size());
+		}
+	}
+	pf_router_destroy(r);
+	return rc;
+}

@@ -1,0 +1,304 @@
+"""Host-side Python mirror of the router boundary: ctypes binding of include/pf_router.h.
+
+The names follow the reference's own interface for this path — ``try_timing_driven_route``
+(reference vpr/SRC/route/route_timing.c:85), ``pathfinder_update_cost`` / ``feasible_routing``
+(route_common.c:581,509), ``reserve_locally_used_opins`` (route_common.c:1435) — so the parity
+tests read like the reference's call sequence.  All compute happens in libpf_router.so (CUDA,
+sm_100a); this module only marshals numpy arrays across the C-ABI.  There is no CPU fallback: if
+the library is missing or no B200 is visible the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import pfio
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "libpf_router.so")
+
+PF_OK = 0
+ERRORS = {-1: "PF_EIO", -2: "PF_EFORMAT", -3: "PF_ENOMEM", -4: "PF_EINVAL", -5: "PF_ECUDA", -6: "PF_EOVERFLOW",
+          -7: "PF_EUNROUTABLE"}
+
+
+class RouterError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "PF_E?"), code, msg))
+        self.code = code
+
+
+class _Opts(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("first_iter_pres_fac", "initial_pres_fac", "pres_fac_mult", "acc_fac",
+                                         "bend_cost", "astar_fac", "max_criticality", "criticality_exp")] + \
+               [(n, C.c_int32) for n in ("max_router_iterations", "timing_analysis_enabled", "bb_factor", "reserved")]
+
+
+class _Problem(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("num_nodes", C.c_int32), ("num_edges", C.c_int32),
+                ("xlow", C.c_void_p), ("ylow", C.c_void_p), ("xhigh", C.c_void_p), ("yhigh", C.c_void_p),
+                ("ptc_num", C.c_void_p), ("cost_index", C.c_void_p), ("capacity", C.c_void_p),
+                ("type", C.c_void_p), ("direction", C.c_void_p), ("R", C.c_void_p), ("C", C.c_void_p),
+                ("row_ptr", C.c_void_p), ("edge_to", C.c_void_p), ("edge_sw", C.c_void_p),
+                ("num_switches", C.c_int32), ("switches", C.c_void_p),
+                ("num_indexed", C.c_int32), ("indexed", C.c_void_p),
+                ("num_nets", C.c_int32), ("num_terminals", C.c_int32),
+                ("net_ptr", C.c_void_p), ("net_terminals", C.c_void_p), ("net_is_global", C.c_void_p),
+                ("net_bb", C.c_void_p),
+                ("num_opin_groups", C.c_int32), ("opin_group_source", C.c_void_p), ("opin_group_count", C.c_void_p),
+                ("opts", _Opts)]
+
+
+class IterStats(C.Structure):
+    _fields_ = [("overused_nodes", C.c_int32), ("nets_routed", C.c_int32), ("heap_pushes", C.c_int64),
+                ("heap_pops", C.c_int64), ("edge_visits", C.c_int64), ("pres_fac", C.c_float),
+                ("crit_path_delay", C.c_float)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("success", C.c_int32), ("iterations", C.c_int32), ("serial_num", C.c_int32),
+                ("total_wirelength", C.c_int32), ("num_nets", C.c_int32),
+                ("trace_ptr", C.POINTER(C.c_int32)), ("trace_node", C.POINTER(C.c_int32)),
+                ("trace_switch", C.POINTER(C.c_int16)), ("num_terminals", C.c_int32),
+                ("net_delay", C.POINTER(C.c_float)), ("num_nodes", C.c_int32), ("occ", C.POINTER(C.c_int32)),
+                ("num_iter_stats", C.c_int32), ("iter_stats", C.POINTER(IterStats)),
+                ("num_crit_iters", C.c_int32), ("iter_crit", C.POINTER(C.c_float))]
+
+
+class Config(C.Structure):
+    """pf_config (include/pf_router.h).  Zero fields mean "auto"."""
+    _fields_ = [(n, C.c_int32) for n in ("device", "rank", "nranks", "num_slots", "warps_per_block", "label_log2",
+                                         "tree_cap", "far_cap", "sink_cap", "big_slots", "big_label_log2",
+                                         "big_tree_cap", "big_far_cap", "max_batch")] + \
+               [("pop_slack", C.c_float), ("win_rel", C.c_float), ("win_abs", C.c_float), ("verbose", C.c_int32),
+                ("reroute_all_iters", C.c_int32), ("inflight_div", C.c_int32), ("min_slots", C.c_int32),
+                ("reserved", C.c_int32 * 1)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("route_kernel_ms", C.c_double), ("update_kernel_ms", C.c_double), ("aux_kernel_ms", C.c_double),
+                ("route_launches", C.c_int64), ("update_launches", C.c_int64), ("aux_launches", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+STA_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float))
+
+_libs = {}
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    path = os.path.abspath(path or DEFAULT_LIB)
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise RuntimeError("%s not found: build it with `python -m parallel_eda_b200.build` "
+                           "(the router has no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    lib.pf_last_error.restype = C.c_char_p
+    lib.pf_backend_name.restype = C.c_char_p
+    lib.pf_config_default.argtypes = [C.POINTER(Config)]
+    lib.pf_router_create.argtypes = [C.POINTER(_Problem), C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.pf_router_destroy.argtypes = [C.c_void_p]
+    lib.pf_router_destroy.restype = None
+    lib.pf_router_reset.argtypes = [C.c_void_p]
+    lib.pf_route_iteration.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.POINTER(IterStats)]
+    lib.pf_reserve_opins.argtypes = [C.c_void_p, C.c_float, C.c_int]
+    lib.pf_update_costs.argtypes = [C.c_void_p, C.c_float, C.POINTER(C.c_int)]
+    lib.pf_total_wirelength.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.pf_get_net_delay.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pf_get_result.argtypes = [C.c_void_p, C.POINTER(_Result)]
+    lib.pf_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing), C.c_int]
+    lib.pf_comm_export_delta.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pf_update_costs_synced.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
+    lib.pf_comm_net_delay_ptr.argtypes = [C.c_void_p]
+    lib.pf_comm_net_delay_ptr.restype = C.c_void_p
+    lib.pf_try_timing_driven_route.argtypes = [C.POINTER(_Problem), C.POINTER(Config), STA_FN, C.c_void_p,
+                                               C.POINTER(_Result)]
+    lib.pf_result_free.argtypes = [C.POINTER(_Result)]
+    lib.pf_result_free.restype = None
+    _libs[path] = lib
+    return lib
+
+
+def _ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+class _ProblemHolder:
+    """Keeps contiguous numpy arrays alive while a C pf_problem points into them."""
+
+    def __init__(self, p: pfio.Problem):
+        self.arrays = {}
+        cp = _Problem()
+        cp.nx, cp.ny, cp.num_nodes, cp.num_edges = p.nx, p.ny, p.num_nodes, p.num_edges
+        for name, dt, _ in pfio._PROB_FIELDS:
+            a = np.ascontiguousarray(getattr(p, name), dtype=np.dtype(dt))
+            self.arrays[name] = a
+            setattr(cp, name, _ptr(a))
+        cp.num_switches, cp.num_indexed = len(p.switches), len(p.indexed)
+        cp.num_nets, cp.num_terminals = p.num_nets, p.num_terminals
+        cp.num_opin_groups = len(p.opin_group_source)
+        o = np.asarray(p.opts, dtype=pfio.OPTS_DT)
+        for f in _Opts._fields_:
+            setattr(cp.opts, f[0], o[f[0]].item())
+        self.c = cp
+
+
+def _take_result(lib, cr: _Result, T: int, with_stats: bool = True) -> pfio.Result:
+    n = cr.num_nets
+    tp = np.ctypeslib.as_array(cr.trace_ptr, shape=(n + 1,)).copy()
+    nt = int(tp[n])
+    tn = np.ctypeslib.as_array(cr.trace_node, shape=(max(nt, 1),))[:nt].copy()
+    ts = np.ctypeslib.as_array(cr.trace_switch, shape=(max(nt, 1),))[:nt].copy()
+    nd = np.ctypeslib.as_array(cr.net_delay, shape=(max(cr.num_terminals, 1),))[:cr.num_terminals].copy()
+    occ = np.ctypeslib.as_array(cr.occ, shape=(cr.num_nodes,)).copy()
+    stats = np.zeros(cr.num_iter_stats if with_stats else 0, dtype=pfio.ITER_STATS_DT)
+    for i in range(len(stats)):
+        s = cr.iter_stats[i]
+        stats[i] = (s.overused_nodes, s.nets_routed, s.heap_pushes, s.heap_pops, s.edge_visits, s.pres_fac,
+                    s.crit_path_delay)
+    crit = None
+    if cr.num_crit_iters and cr.iter_crit:
+        crit = np.ctypeslib.as_array(cr.iter_crit, shape=(cr.num_crit_iters * T,)).reshape(cr.num_crit_iters, T).copy()
+    res = pfio.Result(cr.success, cr.iterations, cr.serial_num, cr.total_wirelength, tp, tn, ts, nd, occ, stats, crit)
+    lib.pf_result_free(C.byref(cr))
+    return res
+
+
+class Router:
+    """A device-resident routing problem (pf_router handle)."""
+
+    def __init__(self, problem: pfio.Problem, config: Optional[Config] = None, lib_path: Optional[str] = None):
+        self.lib = load_library(lib_path)
+        self.problem = problem
+        self._holder = _ProblemHolder(problem)
+        if config is None:
+            config = default_config(self.lib)
+        self.config = config
+        h = C.c_void_p()
+        rc = self.lib.pf_router_create(C.byref(self._holder.c), C.byref(config), C.byref(h))
+        if rc != PF_OK:
+            raise RouterError(rc, self.lib.pf_last_error().decode())
+        self._h = h
+
+    def _ck(self, rc: int):
+        if rc != PF_OK:
+            raise RouterError(rc, self.lib.pf_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.pf_router_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._ck(self.lib.pf_router_reset(self._h))
+
+    def route_iteration(self, pres_fac: float, crit: Optional[np.ndarray] = None) -> IterStats:
+        st = IterStats()
+        cp = None
+        if crit is not None:
+            crit = np.ascontiguousarray(crit, dtype=np.float32)
+            assert crit.shape[0] == self.problem.num_terminals
+            cp = _ptr(crit)
+        self._ck(self.lib.pf_route_iteration(self._h, pres_fac, cp, C.byref(st)))
+        return st
+
+    def reserve_locally_used_opins(self, pres_fac: float, rip_up_local_opins: bool):
+        self._ck(self.lib.pf_reserve_opins(self._h, pres_fac, 1 if rip_up_local_opins else 0))
+
+    def pathfinder_update_cost(self, acc_fac: float) -> int:
+        """pathfinder_update_cost + feasible_routing in one pass; returns the overused-node count."""
+        over = C.c_int(0)
+        self._ck(self.lib.pf_update_costs(self._h, acc_fac, C.byref(over)))
+        return over.value
+
+    def total_wirelength(self):
+        wl, av = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.pf_total_wirelength(self._h, C.byref(wl), C.byref(av)))
+        return wl.value, av.value
+
+    def net_delay(self) -> np.ndarray:
+        out = np.zeros(max(self.problem.num_terminals, 1), dtype=np.float32)
+        self._ck(self.lib.pf_get_net_delay(self._h, _ptr(out)))
+        return out[:self.problem.num_terminals]
+
+    def result(self) -> pfio.Result:
+        cr = _Result()
+        self._ck(self.lib.pf_get_result(self._h, C.byref(cr)))
+        return _take_result(self.lib, cr, self.problem.num_terminals, with_stats=False)
+
+    def timing(self, reset: bool = False) -> Timing:
+        t = Timing()
+        self._ck(self.lib.pf_get_timing(self._h, C.byref(t), 1 if reset else 0))
+        return t
+
+    # multi-GPU iteration boundary (device pointers, e.g. torch tensors' data_ptr())
+    def comm_export_delta(self, dev_ptr: int):
+        self._ck(self.lib.pf_comm_export_delta(self._h, C.c_void_p(dev_ptr)))
+
+    def update_costs_synced(self, acc_fac: float, dev_ptr: int) -> int:
+        over = C.c_int(0)
+        self._ck(self.lib.pf_update_costs_synced(self._h, acc_fac, C.c_void_p(dev_ptr), C.byref(over)))
+        return over.value
+
+    def comm_net_delay_ptr(self) -> int:
+        return int(self.lib.pf_comm_net_delay_ptr(self._h))
+
+
+def default_config(lib=None, **kw) -> Config:
+    lib = lib or load_library()
+    c = Config()
+    lib.pf_config_default(C.byref(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+StaFn = Callable[[int, np.ndarray], "tuple[np.ndarray, float]"]
+
+
+def try_timing_driven_route(problem: pfio.Problem, config: Optional[Config] = None, sta: Optional[StaFn] = None,
+                            lib_path: Optional[str] = None) -> pfio.Result:
+    """The whole PathFinder loop on one GPU (reference route_timing.c:85-343).
+
+    ``sta(iters_done, net_delay) -> (timing_criticality[num_terminals], crit_path_delay)`` stands in for the
+    reference's load_timing_graph_net_delays + do_timing_analysis (route_timing.c:295-309)."""
+    lib = load_library(lib_path)
+    holder = _ProblemHolder(problem)
+    if config is None:
+        config = default_config(lib)
+    T = problem.num_terminals
+
+    def _cb(_user, iters_done, nd, crit, cpd):
+        delays = np.ctypeslib.as_array(nd, shape=(max(T, 1),))[:T]
+        c, d = sta(iters_done, delays)
+        np.ctypeslib.as_array(crit, shape=(max(T, 1),))[:T] = np.asarray(c, dtype=np.float32)
+        cpd[0] = float(d)
+
+    cb = STA_FN(_cb) if sta is not None else C.cast(None, STA_FN)
+    cr = _Result()
+    rc = lib.pf_try_timing_driven_route(C.byref(holder.c), C.byref(config), cb, None, C.byref(cr))
+    if rc != PF_OK:
+        raise RouterError(rc, lib.pf_last_error().decode())
+    return _take_result(lib, cr, T)
+
+
+def replay_sta(golden: pfio.Result) -> StaFn:
+    """STA stand-in that replays criticalities recorded from a reference run (iter_crit row k is what
+    the reference's STA produced after k iterations)."""
+
+    def fn(iters_done: int, _delay: np.ndarray):
+        k = min(iters_done, golden.iter_crit.shape[0] - 1)
+        cpd = float(golden.iter_stats["crit_path_delay"][iters_done - 1]) if 1 <= iters_done <= len(golden.iter_stats) else 0.0
+        return golden.iter_crit[k], cpd
+
+    return fn

@@ -1,0 +1,100 @@
+/*
+ * TEST INFRASTRUCTURE: pf_backend.h over the fiber warp emulator (pf_emu.h).  "Device memory" is
+ * host memory, a kernel launch runs the same device functions as the CUDA build on emulated
+ * warps.  Built only by tests/ into tests/emu/_build/libpf_router_emu.so.
+ */
+#include "pf_backend.h"
+#include "pf_device.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+static char g_err[256] = "";
+static PfLaunchTimes g_times;
+
+int pfb_init(int) { return 0; }
+int pfb_device_count(void) { return 1; }
+const char *pfb_name(void) { return "emu"; }
+const char *pfb_last_error(void) { return g_err; }
+void *pfb_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
+void pfb_free(void *p) { free(p); }
+int pfb_h2d(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
+int pfb_d2h(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
+int pfb_d2d(void *d, const void *s, size_t n) { if (n) memmove(d, s, n); return 0; }
+int pfb_zero(void *d, size_t n) { if (n) memset(d, 0, n); return 0; }
+int pfb_sync(void) { return 0; }
+void pfb_times(PfLaunchTimes *out, int reset) { if (out) *out = g_times; if (reset) memset(&g_times, 0, sizeof(g_times)); }
+int pfb_num_sms(void) { const char *e = getenv("PF_EMU_SMS"); return e ? atoi(e) : 1; }
+
+struct RouteArg { const PfParams *P; std::vector<unsigned char> *smem; };
+static void route_warp(void *arg, int warp_id) {
+	RouteArg *a = (RouteArg *)arg;
+	pf_warp_main(a->P, warp_id, a->smem->data() + (size_t)warp_id * PF_SMEM_PER_WARP);
+}
+
+int pfb_launch_route(const PfParams *P, int num_slots, int) {
+	std::vector<unsigned char> smem((size_t)num_slots * PF_SMEM_PER_WARP);
+	RouteArg a = { P, &smem };
+	pf_emu_launch(route_warp, &a, num_slots);
+	g_times.route_launches++;
+	return 0;
+}
+
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, int *occ_base, const int *occ_delta) {
+	int over = 0;
+	for (int i = 0; i < num_nodes; i++) over += pf_update_cost_one(nodes, i, acc_fac, occ_base, occ_delta);
+	*d_overused += over;
+	g_times.update_launches++;
+	return 0;
+}
+
+int pfb_launch_export_delta(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta) {
+	for (int i = 0; i < num_nodes; i++) occ_delta[i] = nodes[i].occ - occ_base[i];
+	g_times.aux_launches++;
+	return 0;
+}
+
+int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long long *d_out) {
+	unsigned long long acc = 0;
+	for (long long i = 0; i < count; i++) acc += pf_tree_wirelength_one(&pool[i]);
+	*d_out += acc;
+	g_times.aux_launches++;
+	return 0;
+}
+
+int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed, int num_groups,
+		const int *group_source, const int *group_count, const int *group_off, int *chosen, int rip_up, float pres_fac) {
+	for (int g = 0; g < num_groups; g++)
+		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac);
+	g_times.aux_launches++;
+	return 0;
+}
+
+int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
+		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts) {
+	for (int k = 0; k < num_all; k++) {
+		int net = all_nets[k];
+		if (force_all || pf_net_is_congested(nodes, pool, loc[net])) {
+			if (net_big[net]) list_big[counts[1]++] = net; else list_small[counts[0]++] = net;
+		}
+	}
+	g_times.aux_launches++;
+	return 0;
+}
+
+int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
+		unsigned long long *dst_head) {
+	for (int k = 0; k < num_all; k++) {
+		int net = all_nets[k];
+		PfNetLoc l = loc[net];
+		if (l.count == 0) continue;
+		unsigned long long off = *dst_head;
+		*dst_head += (unsigned long long)l.count;
+		memcpy(dst + off, src + l.off, sizeof(PfTreeNode) * (size_t)l.count);
+		loc[net].off = (int)off;
+	}
+	g_times.aux_launches++;
+	return 0;
+}
