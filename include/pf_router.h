@@ -56,8 +56,8 @@ typedef struct pf_config {
 	int32_t sink_cap;         /* nets with more sinks go to the big slots; 0 = 64 */
 	int32_t big_slots;        /* warps with large scratch for big / overflowed nets; 0 = 64 */
 	int32_t big_label_log2, big_tree_cap, big_far_cap;   /* 0 = sized from the problem */
-	int32_t max_batch;        /* labels settled per step, 1..8; 0 = 2 */
-	float pop_slack;          /* settle labels within this cost of the minimum together; <0 = auto */
+	int32_t max_batch;        /* labels settled per step (delta bucket), 1..32; 0 = 32 */
+	float pop_slack;          /* delta-stepping bucket width in units of the cheapest edge cost; <0 = auto (0.25) */
 	float win_rel, win_abs;   /* near-set window; 0 = auto */
 	int32_t verbose;
 	int32_t reroute_all_iters;/* the first K iterations re-route every net (the serial reference re-routes
@@ -66,7 +66,7 @@ typedef struct pf_config {
 	                             reference's parallel router (partitioning_multi_sink…cxx:6241-6269).
 	                             0 = auto (1); < 0 = always every net */
 	int32_t inflight_div;     /* nets in flight <= ceil(nets this iteration / inflight_div): bounds how
-	                             stale the congestion seen by concurrent nets can be; 0 = auto (16) */
+	                             stale the congestion seen by concurrent nets can be; 0 = auto (32) */
 	int32_t min_slots;        /* lower bound for the above; 0 = auto (1) */
 	int32_t reserved[1];
 } pf_config;

@@ -101,8 +101,8 @@ struct PfWarp {
 	unsigned long long pops, pushes, visits, refills, stale;
 };
 
-/* fr 1536 + b_key 64 + idx 1024 + sw 768 + base_cost 128 + 5 batch arrays 160 + b_pre 36 = 3716 → 3840 */
-#define PF_SMEM_PER_WARP 3840
+/* fr 1536 + b_key 256 + idx 1024 + sw 768 + base_cost 128 + 5 batch arrays 640 + b_pre 136 = 4488 → 4608 */
+#define PF_SMEM_PER_WARP 4608
 
 PF_DEV float pf_key_tot(uint64_t k) { return pf_int_as_float((int)(k >> 32)); }
 PF_DEV int pf_key_node(uint64_t k) { return (int)(uint32_t)k; }
@@ -195,7 +195,7 @@ PF_DEV int pf_label_find(const PfWarp &w, int node) {
  * its total and its backward cost are lower (the pop rule of route_timing.c:511, applied at
  * relax time); slot claims by different nodes in the same probe round are arbitrated by lane
  * order.  Returns 1 in lanes whose candidate was written. */
-PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back, float R_up, int prev, int prev_sw) {
+PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back, float R_up, int prev, int info, int edge_start) {
 	const int lane = pf_lane();
 	/* same-node duplicates inside this chunk */
 	{
@@ -220,7 +220,7 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 					if (tot < otot && back < oback) {
 						pf_u4 n0, n1;
 						n0.x = (unsigned)node; n0.y = w.epoch; n0.z = (unsigned)pf_float_as_int(tot); n0.w = (unsigned)pf_float_as_int(back);
-						n1.x = (unsigned)pf_float_as_int(R_up); n1.y = (unsigned)prev; n1.z = (unsigned)prev_sw; n1.w = 0;
+						n1.x = (unsigned)pf_float_as_int(R_up); n1.y = (unsigned)prev; n1.z = (unsigned)info; n1.w = (unsigned)edge_start;
 						pf_st_u4(L, n0); pf_st_u4((char *)L + 16, n1);
 						written = 1;
 					}
@@ -237,7 +237,7 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 			PfLabel *L = &w.labels[h];
 			pf_u4 n0, n1;
 			n0.x = (unsigned)node; n0.y = w.epoch; n0.z = (unsigned)pf_float_as_int(tot); n0.w = (unsigned)pf_float_as_int(back);
-			n1.x = (unsigned)pf_float_as_int(R_up); n1.y = (unsigned)prev; n1.z = (unsigned)prev_sw; n1.w = 0;
+			n1.x = (unsigned)pf_float_as_int(R_up); n1.y = (unsigned)prev; n1.z = (unsigned)info; n1.w = (unsigned)edge_start;
 			pf_st_u4(L, n0); pf_st_u4((char *)L + 16, n1);
 			written = 1; pending = 0;
 		}
@@ -396,6 +396,17 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 
 	w.epoch++;
 	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.far_min = PF_INF_F; w.best = PF_INF_F;
+	/* delta-stepping bucket width: a multiple of the cheapest possible edge for this criticality
+	 * (an uncongested wire: (1-crit)*base_cost + crit*T_linear) */
+	float slack;
+	{
+		float mb = PF_INF_F, mt = PF_INF_F;
+		for (int i = 4; i < P->num_indexed; i++) {
+			if (w.base_cost[i] < mb) mb = w.base_cost[i];
+			if (w.idx[i].T_linear < mt) mt = w.idx[i].T_linear;
+		}
+		slack = P->pop_slack * ((1.f - crit) * mb + crit * mt);
+	}
 
 	/* ---- seed with the current route tree (add_route_tree_to_heap) */
 	float smin = PF_INF_F;
@@ -425,7 +436,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 				tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
 			}
 		}
-		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0);
+		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
 		pf_push(w, wr, tot, node);
 		if (w.overflow) return -1;
 	}
@@ -446,7 +457,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 		if (mtot >= w.best) break;              /* target settled: nothing cheaper remains */
 
 		/* -- select the batch: every near label within pop_slack of the minimum, at most max_batch */
-		float thr = mtot + P->pop_slack;
+		float thr = mtot + slack;
 		int taken = 0, kept = 0;
 		for (int base = 0; base < w.sh_n; base += PF_WARP) {
 			int i = base + lane;
@@ -466,7 +477,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 		w.sh_n = kept;
 		pf_syncwarp();
 
-		/* -- validate each settled label and fetch its node row */
+		/* -- validate each settled label; its row (start, degree, type) travels in the label */
 		int deg = 0, ok = 0;
 		if (lane < taken) {
 			uint64_t k = w.b_key[lane];
@@ -476,14 +487,18 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 				const PfLabel *L = &w.labels[h];
 				pf_u4 a = pf_ld_u4(L), b = pf_ld_u4((const char *)L + 16);
 				if (pf_int_as_float((int)a.z) == pf_key_tot(k)) {   /* else stale: the node was re-labelled cheaper */
-					PfNodeView un = pf_load_node(P, u);
+					int es = (int)b.w, ty = (int)((b.z >> 8) & 0xffu);
+					deg = (int)(b.z >> 16);
+					if (es < 0) {                                  /* seed: row not cached in the label */
+						PfNodeView un = pf_load_node(P, u);
+						es = un.edge_start; ty = un.type; deg = un.num_edges;
+					}
 					w.b_node[lane] = u; w.b_back[lane] = pf_int_as_float((int)a.w); w.b_R[lane] = pf_int_as_float((int)b.x);
-					w.b_start[lane] = un.edge_start; w.b_type[lane] = un.type;
-					deg = un.num_edges;
+					w.b_start[lane] = es; w.b_type[lane] = ty;
 					ok = 1;
 				}
 			}
-			if (!ok) { w.b_node[lane] = -1; w.b_start[lane] = 0; w.b_type[lane] = 0; w.b_back[lane] = 0.f; w.b_R[lane] = 0.f; }
+			if (!ok) { w.b_node[lane] = -1; w.b_start[lane] = 0; w.b_type[lane] = 0; w.b_back[lane] = 0.f; w.b_R[lane] = 0.f; deg = 0; }
 		}
 		{
 			int nok = pf_popc(pf_ballot(ok));
@@ -492,7 +507,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 		}
 		/* exclusive prefix of the degrees over the first `taken` lanes */
 		int incl = deg;
-		for (int d = 1; d < PF_MAX_BATCH; d <<= 1) {
+		for (int d = 1; d < PF_WARP; d <<= 1) {
 			int o = pf_shfl_i(incl, lane - d);
 			if (lane >= d) incl += o;
 		}
@@ -506,10 +521,10 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 		for (int base = 0; base < M; base += PF_WARP) {
 			int e = base + lane;
 			int valid = e < M;
-			int to = 0, u = 0, isw = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
+			int to = 0, u = 0, isw = 0, info = 0, es = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
 			if (valid) {
-				int j = 0;
-				while (w.b_pre[j + 1] <= e) j++;
+				int j = 0, hi = taken - 1;                      /* owner: last j with b_pre[j] <= e */
+				while (j < hi) { int mid = (j + hi + 1) >> 1; if (w.b_pre[mid] <= e) j = mid; else hi = mid - 1; }
 				u = w.b_node[j];
 				uint32_t ew = P->edges[w.b_start[j] + (e - w.b_pre[j])];
 				to = (int)(ew & PF_EDGE_NODE_MASK); isw = (int)(ew >> PF_EDGE_NODE_BITS);
@@ -539,9 +554,10 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 					}
 					tot = new_back + astar * pf_expected_cost(w, n.type, n.ci, n.xlow, n.xhigh, n.ylow, n.yhigh, tgt_xl, tgt_yl, crit, new_R);
 					back = new_back; R_up = new_R;
+					info = isw | (n.type << 8) | (n.num_edges << 16); es = n.edge_start;
 				}
 			}
-			int wr = pf_label_relax(w, valid, to, tot, back, R_up, u, isw);
+			int wr = pf_label_relax(w, valid, to, tot, back, R_up, u, info, es);
 			/* the target SINK is never expanded; only its best total matters */
 			float tb = pf_warp_min_f((wr && to == target_node) ? tot : PF_INF_F);
 			if (tb < w.best) w.best = tb;
@@ -619,7 +635,7 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
 			if (prev < 0 && v != target_node) { join = ~prev; break; }
 			if (prev < 0) { L = -1; break; }               /* target itself is a seed: cannot happen (SINKs are never seeds) */
 			if (L >= pcap) { L = -2; break; }
-			pathbuf[L] = v; pathbuf[pcap + L] = (int)b.z;  /* switch used to enter v */
+			pathbuf[L] = v; pathbuf[pcap + L] = (int)(b.z & 0xffu);  /* switch used to enter v */
 			L++;
 			v = prev;
 		}

@@ -35,7 +35,9 @@ struct PfIndexedDev { float base_cost, saved_base_cost, inv_length, T_linear, T_
  * `epoch` makes clearing free: a slot belongs to the current sink search iff epoch matches. */
 struct PfLabel {
 	int key; unsigned epoch; float tot; float back;       /* probed / compared */
-	float R_up; int prev; int prev_sw; int pad;           /* prev >= 0: rr node; prev < 0: ~tree index (seed) */
+	float R_up; int prev; int info; int edge_start;       /* prev >= 0: rr node; prev < 0: ~tree index (seed)
+	                                                         info = entering switch | type << 8 | out-degree << 16;
+	                                                         edge_start < 0: row unknown (seed), read the node record */
 };
 
 /* route-tree entry, 32 B.  Entries are appended in path order, so parent index < child index. */
@@ -56,7 +58,7 @@ struct PfNetLoc { int off, count; };   /* a net's tree in the route store */
 
 #define PF_SH_FRONTIER 192      /* near-set entries per warp in shared memory */
 #define PF_SH_REFILL 96         /* refill the near set to at most this many */
-#define PF_MAX_BATCH 8          /* labels settled per step */
+#define PF_MAX_BATCH 32         /* labels settled per step (one delta bucket) */
 
 /* error/status bits written to PfParams.status[0] */
 #define PF_ST_UNROUTABLE 1
@@ -78,7 +80,8 @@ struct PfParams {
 	float *net_delay;      /* [num_terminals] */
 	/* options */
 	float pres_fac, astar_fac, bend_cost, max_crit, crit_exp;
-	float pop_slack;       /* settle every label within this of the minimum in one step */
+	float pop_slack;       /* delta-stepping bucket width in units of the cheapest edge cost for the
+	                          sink's criticality: every label within it of the minimum is settled in one step */
 	float win_rel, win_abs;/* near-set window: max(min*win_rel, win_abs) */
 	int max_batch;
 	int skip_ripup;

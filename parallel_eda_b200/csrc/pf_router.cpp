@@ -155,9 +155,9 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.far_cap <= 0) c.far_cap = 8192;
 	if (c.sink_cap <= 0) c.sink_cap = 64;
 	if (c.big_slots <= 0) c.big_slots = 64;
-	if (c.max_batch <= 0) c.max_batch = 2;
+	if (c.max_batch <= 0) c.max_batch = 32;
 	if (c.reroute_all_iters == 0) c.reroute_all_iters = 1;
-	if (c.inflight_div <= 0) c.inflight_div = 16;
+	if (c.inflight_div <= 0) c.inflight_div = 32;
 	if (c.min_slots <= 0) c.min_slots = 1;
 	if (c.max_batch > PF_MAX_BATCH) c.max_batch = PF_MAX_BATCH;
 
@@ -323,7 +323,7 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.crit = r->crit; P.net_delay = r->net_delay;
 	P.pres_fac = pres_fac; P.astar_fac = p->opts.astar_fac; P.bend_cost = p->opts.bend_cost;
 	P.max_crit = p->opts.max_criticality; P.crit_exp = p->opts.criticality_exp;
-	P.pop_slack = c.pop_slack >= 0.f ? c.pop_slack : 0.f;
+	P.pop_slack = c.pop_slack >= 0.f ? c.pop_slack : 0.25f;
 	P.win_rel = c.win_rel > 0.f ? c.win_rel : 0.05f;
 	P.win_abs = c.win_abs > 0.f ? c.win_abs : r->win_abs_auto;
 	P.max_batch = c.max_batch;

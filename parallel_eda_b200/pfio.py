@@ -8,6 +8,7 @@ turn cites the reference globals each array flattens (vpr/SRC/base/globals.c:48-
 from __future__ import annotations
 
 import dataclasses
+import lzma
 import struct
 from typing import Optional
 
@@ -107,8 +108,13 @@ _PROB_FIELDS = [
     ("opin_group_source", "<i4", "G"), ("opin_group_count", "<i4", "G")]
 
 
+def _open(path: str):
+    """Fixtures are committed xz-compressed; both forms read the same."""
+    return lzma.open(path, "rb") if path.endswith(".xz") else open(path, "rb")
+
+
 def read_problem(path: str) -> Problem:
-    with open(path, "rb") as f:
+    with _open(path) as f:
         if f.read(8) != PROB_MAGIC:
             raise ValueError("%s: not a PFPROB01 file" % path)
         hdr = struct.unpack("<16i", f.read(64))
@@ -161,7 +167,7 @@ class Result:
 
 
 def read_result(path: str) -> Result:
-    with open(path, "rb") as f:
+    with _open(path) as f:
         if f.read(8) != RSLT_MAGIC:
             raise ValueError("%s: not a PFRSLT01 file" % path)
         hdr = struct.unpack("<16i", f.read(64))
