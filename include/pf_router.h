@@ -68,7 +68,8 @@ typedef struct pf_config {
 	int32_t inflight_div;     /* nets in flight <= ceil(nets this iteration / inflight_div): bounds how
 	                             stale the congestion seen by concurrent nets can be; 0 = auto (32) */
 	int32_t min_slots;        /* lower bound for the above; 0 = auto (1) */
-	int32_t reserved[1];
+	int32_t stall_iters;      /* overuse not improved for this many iterations => one iteration re-routes every
+	                             net with 8x fewer nets in flight; 0 = auto (3); < 0 = never */
 } pf_config;
 
 typedef struct pf_timing {    /* accumulated since create / last reset */
@@ -97,6 +98,10 @@ int pf_router_reset(pf_router *r);
 /* One PathFinder iteration over this rank's nets: rip-up, route, commit (live occupancy).
  * crit: host array [num_terminals] or NULL to keep the criticalities already on the device. */
 int pf_route_iteration(pf_router *r, float pres_fac, const float *crit, pf_iter_stats *stats);
+/* The same in two steps, for multi-GPU sub-rounds: begin chooses this iteration's nets, route_part routes
+ * slice `part` of `nparts` of them; the caller syncs occupancy (export delta / all-reduce / fold) after each part. */
+int pf_iteration_begin(pf_router *r, const float *crit);
+int pf_iteration_route_part(pf_router *r, float pres_fac, int part, int nparts, pf_iter_stats *stats);
 int pf_reserve_opins(pf_router *r, float pres_fac, int rip_up_local_opins);
 int pf_update_costs(pf_router *r, float acc_fac, int *overused_nodes);
 int pf_total_wirelength(pf_router *r, int64_t *wirelength, int64_t *available);
@@ -113,6 +118,7 @@ int pf_get_timing(pf_router *r, pf_timing *t, int reset);
  * routed by other ranks are zero, so an all-reduce(sum) assembles the full vector in place. */
 int pf_comm_export_delta(pf_router *r, void *dev_delta);
 int pf_update_costs_synced(pf_router *r, float acc_fac, const void *dev_delta, int *overused_nodes);
+int pf_comm_fold_delta(pf_router *r, const void *dev_delta);   /* fold only (between sub-rounds) */
 void *pf_comm_net_delay_ptr(pf_router *r);
 
 /* The whole of try_timing_driven_route (single GPU): iterate until legal or out of iterations.

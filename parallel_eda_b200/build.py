@@ -31,9 +31,9 @@ def _newer(target: str, sources) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("pf_kernels.cu", "pf_router.cpp", "pf_file.c")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("pf_device.cuh", "pf_backend.h")] + [
-        os.path.join(ROOT, "include", f) for f in ("pf_router.h", "pf_types.h", "pf_file.h")]
+    srcs = [os.path.join(CSRC, f) for f in ("pf_kernels.cu", "pf_router.cpp", "pf_gen.cpp", "pf_file.c")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("pf_device.cuh", "pf_backend.h", "pf_layout.h")] + [
+        os.path.join(ROOT, "include", f) for f in ("pf_router.h", "pf_types.h", "pf_file.h", "pf_gen.h")]
     if not force and _newer(LIB, deps):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -52,7 +52,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             with open(os.path.join(bdir, "ptxas_pf_kernels.txt"), "w") as f:
                 f.write(r.stderr)
         objs.append(o)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    # link with the host compiler: `nvcc -shared` would add a default-arch (sm_52) device-link stub
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
+    cmd = ["g++", "-shared", "-o", LIB] + objs + ["-L" + cuda_lib, "-Wl,-rpath," + cuda_lib, "-lcudart", "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

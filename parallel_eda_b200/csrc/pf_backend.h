@@ -44,7 +44,7 @@ int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long
 /* reserve_locally_used_opins (route_common.c:1435-1491): one thread per (block, class) group */
 int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
 		int num_groups, const int *group_source, const int *group_count, const int *group_off,
-		int *chosen, int rip_up, float pres_fac);
+		int *chosen, int rip_up, float pres_fac, int *occ_base);
 /* work list of the next iteration: the nets of `all_nets` that touch an overused node (or every
  * net when force_all), split into the small/big slot classes by net_big[]; counts[0]/counts[1] */
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,

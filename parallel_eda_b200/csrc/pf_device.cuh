@@ -943,8 +943,10 @@ PF_DEV unsigned pf_tree_wirelength_one(const PfTreeNode *t) {
  * SOURCE in the order the reference's binary heap (route_common.c:1142-1216) would deliver them. */
 #define PF_OPIN_HEAP_MAX 128
 PF_DEV void pf_reserve_opins_group(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
-		int source, int count, int *chosen, int rip_up, float pres_fac) {
-	if (rip_up) for (int k = 0; k < count; k++) pf_atomic_add_i(&nodes[chosen[k]].occ, -1);
+		int source, int count, int *chosen, int rip_up, float pres_fac, int *occ_base) {
+	/* occ_base (multi-GPU): the reservation is made identically by every rank after the occupancy sync,
+	 * so it belongs to the synced base, not to this rank's exported delta */
+	if (rip_up) for (int k = 0; k < count; k++) { pf_atomic_add_i(&nodes[chosen[k]].occ, -1); if (occ_base) occ_base[chosen[k]] -= 1; }
 	if (count == 0) return;
 	float hc[PF_OPIN_HEAP_MAX + 2]; int hn[PF_OPIN_HEAP_MAX + 2];
 	int tail = 1;
@@ -981,6 +983,7 @@ PF_DEV void pf_reserve_opins_group(PfNode *nodes, const uint32_t *edges, const P
 			ifrom = ito; ito = 2 * ifrom;
 		}
 		pf_atomic_add_i(&nodes[pick].occ, 1);
+		if (occ_base) occ_base[pick] += 1;
 		chosen[k] = pick;
 	}
 }

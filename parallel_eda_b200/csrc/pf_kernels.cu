@@ -146,10 +146,10 @@ __global__ void pf_wirelength_kernel(const PfTreeNode *pool, long long count, un
 
 __global__ void pf_reserve_opins_kernel(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
 		int num_groups, const int *group_source, const int *group_count, const int *group_off,
-		int *chosen, int rip_up, float pres_fac) {
+		int *chosen, int rip_up, float pres_fac, int *occ_base) {
 	int g = (int)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (g < num_groups)
-		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac);
+		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac, occ_base);
 }
 
 __global__ void pf_select_nets_kernel(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
@@ -219,10 +219,10 @@ int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long
 
 int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
 		int num_groups, const int *group_source, const int *group_count, const int *group_off,
-		int *chosen, int rip_up, float pres_fac) {
+		int *chosen, int rip_up, float pres_fac, int *occ_base) {
 	if (num_groups <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
-	pf_reserve_opins_kernel<<<(num_groups + 127) / 128, 128, 0, g_stream>>>(nodes, edges, indexed, num_groups, group_source, group_count, group_off, chosen, rip_up, pres_fac);
+	pf_reserve_opins_kernel<<<(num_groups + 127) / 128, 128, 0, g_stream>>>(nodes, edges, indexed, num_groups, group_source, group_count, group_off, chosen, rip_up, pres_fac, occ_base);
 	return ev_end();
 }
 

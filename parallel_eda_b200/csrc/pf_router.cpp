@@ -50,6 +50,8 @@ struct pf_router {
 	int *all_nets; int num_all; unsigned char *net_big; int *sel_counts;
 	std::vector<unsigned char> h_net_big;
 	int iter_count;
+	int best_overused, stall_count;   /* convergence watchdog, see pf_iteration_begin */
+	int cur_div, n_small, n_big; int *retry_work;
 	int *status, *retry_list, *retry_count;
 	PfStats *stats;
 	int *d_overused; unsigned long long *d_wl;
@@ -92,7 +94,7 @@ extern "C" void pf_router_destroy(pf_router *r) {
 	pfb_free(r->crit); pfb_free(r->net_delay);
 	free_slot_class(r->small); free_slot_class(r->big);
 	pfb_free(r->pool[0]); pfb_free(r->pool[1]); pfb_free(r->loc);
-	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->sel_counts);
+	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->sel_counts); pfb_free(r->retry_work);
 	pfb_free(r->pool_head); pfb_free(r->status); pfb_free(r->retry_list); pfb_free(r->retry_count);
 	pfb_free(r->stats); pfb_free(r->d_overused); pfb_free(r->d_wl);
 	pfb_free(r->occ_base); pfb_free(r->occ_delta);
@@ -143,6 +145,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
 	r->pool[0] = r->pool[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
 	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->iter_count = 0;
+	r->best_overused = 0x7fffffff; r->stall_count = 0; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
 	r->occ_base = r->occ_delta = NULL; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
 	r->h2d_bytes = r->d2h_bytes = 0;
@@ -159,6 +162,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.reroute_all_iters == 0) c.reroute_all_iters = 1;
 	if (c.inflight_div <= 0) c.inflight_div = 32;
 	if (c.min_slots <= 0) c.min_slots = 1;
+	if (c.stall_iters == 0) c.stall_iters = 3;
 	if (c.max_batch > PF_MAX_BATCH) c.max_batch = PF_MAX_BATCH;
 
 	/* work lists: routed nets in decreasing-fanout order (route_timing.c:98-106), sharded by rank */
@@ -260,10 +264,11 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->status = (int *)pfb_alloc(sizeof(int) * 8);
 	r->retry_list = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(nwork, 1));
 	r->retry_count = (int *)pfb_alloc(sizeof(int) * 4);
+	r->retry_work = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(nwork, 1));
 	r->stats = (PfStats *)pfb_alloc(sizeof(PfStats));
 	r->d_overused = (int *)pfb_alloc(sizeof(int) * 4);
 	r->d_wl = (unsigned long long *)pfb_alloc(sizeof(unsigned long long) * 2);
-	if (!r->pool_head || !r->status || !r->retry_list || !r->retry_count || !r->stats || !r->d_overused || !r->d_wl) { pf_router_destroy(r); CUDA_FAIL(); }
+	if (!r->pool_head || !r->status || !r->retry_list || !r->retry_count || !r->retry_work || !r->stats || !r->d_overused || !r->d_wl) { pf_router_destroy(r); CUDA_FAIL(); }
 	if (c.nranks > 1) {
 		r->occ_base = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
 		r->occ_delta = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
@@ -297,7 +302,7 @@ extern "C" int pf_router_reset(pf_router *r) {
 	if (upload_nodes(r, true) != PF_OK) return PF_ECUDA;
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
 	CKB(pfb_zero(r->pool_head, sizeof(unsigned long long) * 2));
-	r->iter_count = 0;
+	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0;
 	CKB(pfb_zero(r->net_delay, sizeof(float) * (size_t)std::max(r->T, 1)));
 	if (r->occ_base) CKB(pfb_zero(r->occ_base, sizeof(int) * (size_t)r->N));
 	{
@@ -350,19 +355,17 @@ static int set_work_dev(pf_router *r, SlotClass &s, int count) {
 	return PF_OK;
 }
 
-static int slots_for(const pf_router *r, int total_work, int class_slots) {
-	int s = (total_work + r->cfg.inflight_div - 1) / r->cfg.inflight_div;
+static int slots_for(const pf_router *r, int total_work, int class_slots, int div) {
+	int s = (total_work + div - 1) / div;
 	s = std::max(s, r->cfg.min_slots);
 	return std::max(1, std::min(s, class_slots));
 }
 
-extern "C" int pf_route_iteration(pf_router *r, float pres_fac, const float *crit, pf_iter_stats *st) {
+/* Start of one PathFinder iteration: garbage-collect the route store and choose the nets to re-route. */
+extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	if (!r) FAILF(PF_EINVAL, "null router");
 	int rc;
 	if (crit) { CKB(pfb_h2d(r->crit, crit, sizeof(float) * (size_t)r->T)); r->h2d_bytes += (int64_t)sizeof(float) * r->T; }
-	CKB(pfb_zero(r->status, sizeof(int) * 8));
-	CKB(pfb_zero(r->retry_count, sizeof(int) * 4));
-	CKB(pfb_zero(r->stats, sizeof(PfStats)));
 	/* garbage-collect the route-tree log when it is more than half full */
 	{
 		unsigned long long head[2];
@@ -376,16 +379,21 @@ extern "C" int pf_route_iteration(pf_router *r, float pres_fac, const float *cri
 		}
 	}
 	if (r->cfg.nranks > 1) CKB(pfb_zero(r->net_delay, sizeof(float) * (size_t)std::max(r->T, 1)));
-	/* which nets are routed in this iteration */
-	const bool all = r->cfg.reroute_all_iters < 0 || r->iter_count < r->cfg.reroute_all_iters;
-	int n_small, n_big;
+	/* Congested-only re-routing negotiates locally; on a tight instance it can ping-pong between a few
+	 * nets while every free resource nearby is held by legal nets.  When the overuse has not improved
+	 * for stall_iters iterations, fall back to the serial reference's policy for one iteration — every
+	 * net ripped up and re-routed (route_timing.c:161-183) — with few nets in flight. */
+	const bool stalled = r->cfg.stall_iters > 0 && r->stall_count >= r->cfg.stall_iters;
+	if (stalled) { r->stall_count = 0; if (r->cfg.verbose) fprintf(stderr, "pf_router: overuse stalled at %d, re-routing every net\n", r->best_overused); }
+	const bool all = stalled || r->cfg.reroute_all_iters < 0 || r->iter_count < r->cfg.reroute_all_iters;
+	r->cur_div = stalled ? r->cfg.inflight_div * 8 : r->cfg.inflight_div;
 	if (all) {
 		std::vector<int> sm, bg;
 		for (int i : r->work_big) bg.push_back(i);
 		for (int i : r->work_small) (r->h_net_big[i] ? bg : sm).push_back(i);
 		if ((rc = set_work(r, r->small, sm.data(), (int)sm.size())) != PF_OK) return rc;
 		if ((rc = set_work(r, r->big, bg.data(), (int)bg.size())) != PF_OK) return rc;
-		n_small = (int)sm.size(); n_big = (int)bg.size();
+		r->n_small = (int)sm.size(); r->n_big = (int)bg.size();
 	} else {
 		int counts[4];
 		CKB(pfb_zero(r->sel_counts, sizeof(int) * 4));
@@ -393,20 +401,39 @@ extern "C" int pf_route_iteration(pf_router *r, float pres_fac, const float *cri
 				r->small.work, r->big.work, r->sel_counts));
 		CKB(pfb_d2h(counts, r->sel_counts, sizeof(int) * 4));
 		r->d2h_bytes += 16;
-		n_small = counts[0]; n_big = counts[1];
-		if ((rc = set_work_dev(r, r->small, n_small)) != PF_OK) return rc;
-		if ((rc = set_work_dev(r, r->big, n_big)) != PF_OK) return rc;
+		r->n_small = counts[0]; r->n_big = counts[1];
 	}
 	r->iter_count++;
+	return PF_OK;
+}
+
+/* Route slice `part` of `nparts` of this iteration's nets (nparts > 1: multi-GPU sub-rounds with an
+ * occupancy sync after each, so ranks see each other's routes several times per iteration). */
+extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, int nparts, pf_iter_stats *st) {
+	if (!r || nparts < 1 || part < 0 || part >= nparts) FAILF(PF_EINVAL, "bad argument");
+	int rc;
+	CKB(pfb_zero(r->status, sizeof(int) * 8));
+	CKB(pfb_zero(r->retry_count, sizeof(int) * 4));
+	CKB(pfb_zero(r->stats, sizeof(PfStats)));
+	const int div = r->cur_div;
+	auto slice = [&](int n, int &off, int &cnt) { off = (int)((long long)n * part / nparts); cnt = (int)((long long)n * (part + 1) / nparts) - off; };
+	int so, sc, bo, bc;
+	slice(r->n_small, so, sc); slice(r->n_big, bo, bc);
 	PfParams P;
-	int total = n_small + n_big;
-	if (n_big > 0) {                       /* long nets first */
+	int total = sc + bc;
+	if (bc > 0) {                          /* long nets first */
+		CKB(pfb_zero(r->big.work_head, sizeof(int) * 4));
+		r->big.num_work = bc;
 		fill_params(r, P, r->big, pres_fac);
-		CKB(pfb_launch_route(&P, slots_for(r, total, std::min(r->big.num_slots, n_big)), 1));
+		P.work = r->big.work + bo;
+		CKB(pfb_launch_route(&P, slots_for(r, total, std::min(r->big.num_slots, bc), div), 1));
 	}
-	if (n_small > 0) {
+	if (sc > 0) {
+		CKB(pfb_zero(r->small.work_head, sizeof(int) * 4));
+		r->small.num_work = sc;
 		fill_params(r, P, r->small, pres_fac);
-		CKB(pfb_launch_route(&P, slots_for(r, total, r->small.num_slots), r->cfg.warps_per_block));
+		P.work = r->small.work + so;
+		CKB(pfb_launch_route(&P, slots_for(r, total, r->small.num_slots, div), r->cfg.warps_per_block));
 	}
 	CKB(pfb_sync());
 	/* nets whose scratch overflowed in a small slot are re-routed in the big slots, and stay there */
@@ -422,10 +449,14 @@ extern "C" int pf_route_iteration(pf_router *r, float pres_fac, const float *cri
 		for (int i : lst) r->h_net_big[i] = 1;
 		CKB(pfb_h2d(r->net_big, r->h_net_big.data(), (size_t)r->n));
 		CKB(pfb_zero(r->retry_count, sizeof(int) * 4));
-		if ((rc = set_work(r, r->big, lst.data(), (int)lst.size())) != PF_OK) return rc;
+		/* the retry list is routed from the scratch queue so the iteration's own work lists stay intact */
+		CKB(pfb_h2d(r->retry_work, lst.data(), sizeof(int) * lst.size()));
+		CKB(pfb_zero(r->big.work_head, sizeof(int) * 4));
+		r->big.num_work = (int)lst.size();
 		fill_params(r, P, r->big, pres_fac);
+		P.work = r->retry_work;
 		P.skip_ripup = 1;
-		CKB(pfb_launch_route(&P, slots_for(r, (int)lst.size(), std::min(r->big.num_slots, (int)lst.size())), 1));
+		CKB(pfb_launch_route(&P, slots_for(r, (int)lst.size(), std::min(r->big.num_slots, (int)lst.size()), div), 1));
 		CKB(pfb_sync());
 		CKB(pfb_d2h(h_retry, r->retry_count, sizeof(int) * 4));
 	}
@@ -442,13 +473,20 @@ extern "C" int pf_route_iteration(pf_router *r, float pres_fac, const float *cri
 		st->nets_routed = (int)hs.nets; st->heap_pushes = (int64_t)hs.pushes; st->heap_pops = (int64_t)hs.pops;
 		st->edge_visits = (int64_t)hs.visits; st->pres_fac = pres_fac;
 	}
+	(void)rc;
 	return PF_OK;
+}
+
+extern "C" int pf_route_iteration(pf_router *r, float pres_fac, const float *crit, pf_iter_stats *st) {
+	int rc = pf_iteration_begin(r, crit);
+	if (rc != PF_OK) return rc;
+	return pf_iteration_route_part(r, pres_fac, 0, 1, st);
 }
 
 extern "C" int pf_reserve_opins(pf_router *r, float pres_fac, int rip_up) {
 	if (!r) FAILF(PF_EINVAL, "null router");
 	if (r->num_groups == 0) return PF_OK;
-	CKB(pfb_launch_reserve_opins(r->nodes, r->edges, r->indexed, r->num_groups, r->g_source, r->g_count, r->g_off, r->g_chosen, rip_up, pres_fac));
+	CKB(pfb_launch_reserve_opins(r->nodes, r->edges, r->indexed, r->num_groups, r->g_source, r->g_count, r->g_off, r->g_chosen, rip_up, pres_fac, r->occ_base));
 	return PF_OK;
 }
 
@@ -459,6 +497,7 @@ static int update_costs_impl(pf_router *r, float acc_fac, const int *delta, int 
 	CKB(pfb_d2h(h, r->d_overused, sizeof(int) * 4));
 	r->d2h_bytes += 16;
 	if (overused) *overused = h[0];
+	if (h[0] < r->best_overused) { r->best_overused = h[0]; r->stall_count = 0; } else r->stall_count++;
 	return PF_OK;
 }
 
@@ -479,6 +518,16 @@ extern "C" int pf_update_costs_synced(pf_router *r, float acc_fac, const void *d
 	if (!r || !dev_delta) FAILF(PF_EINVAL, "null argument");
 	if (!r->occ_base) FAILF(PF_EINVAL, "router was created with nranks == 1");
 	return update_costs_impl(r, acc_fac, (const int *)dev_delta, overused);
+}
+
+/* fold an all-reduced occupancy delta into the node records without touching costs (between sub-rounds) */
+extern "C" int pf_comm_fold_delta(pf_router *r, const void *dev_delta) {
+	if (!r || !dev_delta) FAILF(PF_EINVAL, "null argument");
+	if (!r->occ_base) FAILF(PF_EINVAL, "router was created with nranks == 1");
+	CKB(pfb_zero(r->d_overused, sizeof(int) * 4));
+	CKB(pfb_launch_update_cost(r->nodes, r->N, 0.f, r->d_overused, r->occ_base, (const int *)dev_delta));
+	CKB(pfb_sync());
+	return PF_OK;
 }
 
 extern "C" void *pf_comm_net_delay_ptr(pf_router *r) { return r ? (void *)r->net_delay : NULL; }

@@ -1,0 +1,68 @@
+"""torch.distributed plumbing for the multi-GPU router: one process per GPU, NCCL over NVLink.
+
+Only the collectives live here; the routing itself is in libpf_router.so.  On a CPU box the same
+code runs over gloo with host tensors (tests/test_multi_rank_gloo.py), which is how the N>1 host
+logic is covered without GPUs.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class Comm:
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+
+    def all_reduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
+        return t
+
+    def all_reduce_scalar(self, v, op=dist.ReduceOp.SUM):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, op=op)
+        return t.item()
+
+    def all_reduce_max(self, v: float) -> float:
+        return self.all_reduce_scalar(v, dist.ReduceOp.MAX)
+
+    def barrier(self):
+        dist.barrier()
+
+
+def init_from_env(backend: str | None = None) -> Comm | None:
+    """Join the process group torchrun described in RANK / WORLD_SIZE / MASTER_*; None if single process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return None
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    use_cuda = torch.cuda.is_available()
+    if backend is None:
+        backend = "nccl" if use_cuda else "gloo"
+    if use_cuda:
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group(backend=backend)
+    return Comm(torch.device("cuda", local) if use_cuda else torch.device("cpu"))
+
+
+def wrap_device_floats(ptr: int, n: int, device: torch.device) -> torch.Tensor:
+    """A float32 tensor view of n floats at a raw device pointer owned by the router (no copy)."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+    if device.type == "cuda":
+        return torch.as_tensor(h, device=device)
+    import ctypes
+    import numpy as np
+    arr = np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr))
+    return torch.from_numpy(arr)

@@ -1,0 +1,107 @@
+"""The PathFinder outer loop on top of the C-ABI step functions, one process per GPU.
+
+``route`` mirrors try_timing_driven_route (reference vpr/SRC/route/route_timing.c:85-343): route
+every net, reserve locally used OPINs, test feasibility, raise pres_fac, update costs, run the host
+STA.  With ``world_size > 1`` it is the data-parallel scheme of the reference's own MPI router
+(parallel_route/mpi_route_load_balanced_nonblocking_send_recv_encoded.cxx): nets are sharded over
+ranks, every rank keeps a full graph + congestion replica, and once per iteration the occupancy
+changes are summed across ranks — there `MPI_Allreduce` (spatial.cxx:3371-3383), here one NCCL
+all-reduce of an int32[num_rr_nodes] delta over NVLink, folded into the node records by the same
+pass that updates the costs (pf_update_costs_synced).
+
+``comm`` is anything with ``all_reduce_sum_(tensor)``; parallel_eda_b200.distributed wraps
+torch.distributed (NCCL on GPUs; gloo on CPU tensors for the host-logic tests).
+"""
+from __future__ import annotations
+
+import dataclasses
+import time
+from typing import Callable, List, Optional
+
+import numpy as np
+
+from . import pfio, router
+
+HUGE_POSITIVE_FLOAT = 1.0e30
+FIRST_ITER_WIRELENGTH_LIMIT = 0.85
+
+
+@dataclasses.dataclass
+class RouteReport:
+    success: bool
+    iterations: int
+    nets_routed: int                 # sum over iterations and ranks of nets (re-)routed
+    overused: List[int]
+    per_iter_nets: List[int]
+    heap_pops: int
+    heap_pushes: int
+    edge_visits: int
+    wall_s: float
+
+
+def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delta_buf=None, delay_buf=None,
+          max_iters: Optional[int] = None, sync_rounds: int = 4) -> RouteReport:
+    """Iterate until legal.  ``delta_buf``: device int32[num_nodes] tensor (required when comm is given);
+    ``delay_buf``: tensor aliasing the router's device net_delay vector (optional, for the host STA)."""
+    o = r.problem.opts
+    n_iter = int(max_iters or o["max_router_iterations"])
+    pres_fac = float(o["first_iter_pres_fac"])
+    crit = None
+    overused, per_iter = [], []
+    pops = pushes = visits = total_nets = 0
+    t0 = time.perf_counter()
+    success = False
+    it = 0
+    for it in range(1, n_iter + 1):
+        if comm is None:
+            st = r.route_iteration(pres_fac, crit)
+            nets = st.nets_routed
+            pops += st.heap_pops; pushes += st.heap_pushes; visits += st.edge_visits
+        else:
+            # sub-rounds: each rank routes 1/sync_rounds of its nets, then the occupancy changes of all
+            # ranks are summed and folded in, so a rank works on congestion at most one sub-round stale
+            r.iteration_begin(crit)
+            nets = 0
+            for part in range(sync_rounds):
+                st = r.iteration_route_part(pres_fac, part, sync_rounds)
+                nets += st.nets_routed
+                pops += st.heap_pops; pushes += st.heap_pushes; visits += st.edge_visits
+                r.comm_export_delta(delta_buf.data_ptr())
+                comm.all_reduce_sum_(delta_buf)          # NCCL over NVLink / NVSwitch
+                if part + 1 < sync_rounds:
+                    r.comm_fold_delta(delta_buf.data_ptr())
+            nets = int(comm.all_reduce_scalar(nets))
+        total_nets += nets
+        per_iter.append(nets)
+        if it == 1:
+            wl, avail = r.total_wirelength()
+            if comm is not None:
+                wl = int(comm.all_reduce_scalar(wl))
+            if wl / max(avail, 1) > FIRST_ITER_WIRELENGTH_LIMIT:     # route_timing.c:189-225
+                overused.append(-1)
+                break
+        # NB: with several ranks the OPIN reservation must see the synced occupancy: fold first
+        if it == 1:
+            new_pres, acc_fac = float(o["initial_pres_fac"]), 0.0
+        else:
+            new_pres = min(pres_fac * float(o["pres_fac_mult"]), HUGE_POSITIVE_FLOAT / 1e5)
+            acc_fac = float(o["acc_fac"])
+        if comm is not None:
+            # fold the last sub-round, reserve OPINs on the synced occupancy, then update costs / count overuse
+            r.comm_fold_delta(delta_buf.data_ptr())
+            r.reserve_locally_used_opins(pres_fac, it != 1)
+            over = r.pathfinder_update_cost(acc_fac)
+        else:
+            r.reserve_locally_used_opins(pres_fac, it != 1)
+            over = r.pathfinder_update_cost(acc_fac)
+        pres_fac = new_pres
+        overused.append(over)
+        if over == 0:
+            success = True
+            break
+        if sta is not None and int(o["timing_analysis_enabled"]):
+            if comm is not None and delay_buf is not None:
+                comm.all_reduce_sum_(delay_buf)          # assemble every rank's sink delays
+            crit, _cpd = sta(it, r.net_delay())
+            crit = np.ascontiguousarray(crit, dtype=np.float32)
+    return RouteReport(success, it, total_nets, overused, per_iter, pops, pushes, visits, time.perf_counter() - t0)

@@ -75,13 +75,20 @@ class Config(C.Structure):
                                          "big_tree_cap", "big_far_cap", "max_batch")] + \
                [("pop_slack", C.c_float), ("win_rel", C.c_float), ("win_abs", C.c_float), ("verbose", C.c_int32),
                 ("reroute_all_iters", C.c_int32), ("inflight_div", C.c_int32), ("min_slots", C.c_int32),
-                ("reserved", C.c_int32 * 1)]
+                ("stall_iters", C.c_int32)]
 
 
 class Timing(C.Structure):
     _fields_ = [("route_kernel_ms", C.c_double), ("update_kernel_ms", C.c_double), ("aux_kernel_ms", C.c_double),
                 ("route_launches", C.c_int64), ("update_launches", C.c_int64), ("aux_launches", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+class GenParams(C.Structure):
+    """pf_gen_params (include/pf_gen.h)."""
+    _fields_ = [(n, C.c_int32) for n in ("nx", "ny", "W", "L", "num_nets", "sinks_per_net", "window")] + \
+               [("seed", C.c_uint32), ("fc_in", C.c_float), ("fc_out", C.c_float), ("io_capacity", C.c_int32),
+                ("bb_factor", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 STA_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float))
@@ -105,6 +112,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_router_destroy.restype = None
     lib.pf_router_reset.argtypes = [C.c_void_p]
     lib.pf_route_iteration.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.POINTER(IterStats)]
+    lib.pf_iteration_begin.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pf_iteration_route_part.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.POINTER(IterStats)]
     lib.pf_reserve_opins.argtypes = [C.c_void_p, C.c_float, C.c_int]
     lib.pf_update_costs.argtypes = [C.c_void_p, C.c_float, C.POINTER(C.c_int)]
     lib.pf_total_wirelength.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -113,12 +122,19 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing), C.c_int]
     lib.pf_comm_export_delta.argtypes = [C.c_void_p, C.c_void_p]
     lib.pf_update_costs_synced.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
+    lib.pf_comm_fold_delta.argtypes = [C.c_void_p, C.c_void_p]
     lib.pf_comm_net_delay_ptr.argtypes = [C.c_void_p]
     lib.pf_comm_net_delay_ptr.restype = C.c_void_p
     lib.pf_try_timing_driven_route.argtypes = [C.POINTER(_Problem), C.POINTER(Config), STA_FN, C.c_void_p,
                                                C.POINTER(_Result)]
     lib.pf_result_free.argtypes = [C.POINTER(_Result)]
     lib.pf_result_free.restype = None
+    lib.pf_gen_params_default.argtypes = [C.POINTER(GenParams)]
+    lib.pf_gen_params_default.restype = None
+    lib.pf_gen_grid_problem.argtypes = [C.POINTER(GenParams), C.POINTER(_Problem)]
+    lib.pf_problem_free.argtypes = [C.POINTER(_Problem)]
+    lib.pf_problem_free.restype = None
+    lib.pf_problem_write.argtypes = [C.c_char_p, C.POINTER(_Problem)]
     _libs[path] = lib
     return lib
 
@@ -212,6 +228,18 @@ class Router:
         self._ck(self.lib.pf_route_iteration(self._h, pres_fac, cp, C.byref(st)))
         return st
 
+    def iteration_begin(self, crit: Optional[np.ndarray] = None):
+        cp = None
+        if crit is not None:
+            crit = np.ascontiguousarray(crit, dtype=np.float32)
+            cp = _ptr(crit)
+        self._ck(self.lib.pf_iteration_begin(self._h, cp))
+
+    def iteration_route_part(self, pres_fac: float, part: int, nparts: int) -> IterStats:
+        st = IterStats()
+        self._ck(self.lib.pf_iteration_route_part(self._h, pres_fac, part, nparts, C.byref(st)))
+        return st
+
     def reserve_locally_used_opins(self, pres_fac: float, rip_up_local_opins: bool):
         self._ck(self.lib.pf_reserve_opins(self._h, pres_fac, 1 if rip_up_local_opins else 0))
 
@@ -249,6 +277,9 @@ class Router:
         over = C.c_int(0)
         self._ck(self.lib.pf_update_costs_synced(self._h, acc_fac, C.c_void_p(dev_ptr), C.byref(over)))
         return over.value
+
+    def comm_fold_delta(self, dev_ptr: int):
+        self._ck(self.lib.pf_comm_fold_delta(self._h, C.c_void_p(dev_ptr)))
 
     def comm_net_delay_ptr(self) -> int:
         return int(self.lib.pf_comm_net_delay_ptr(self._h))
@@ -302,3 +333,33 @@ def replay_sta(golden: pfio.Result) -> StaFn:
         return golden.iter_crit[k], cpd
 
     return fn
+
+
+def generate_grid_problem(lib_path: Optional[str] = None, **kw) -> pfio.Problem:
+    """Synthetic k6_N10-style grid + random nets (pf_gen_grid_problem).  Keyword arguments override
+    pf_gen_params_default (nx, ny, W, L, num_nets, sinks_per_net, window, seed, ...)."""
+    lib = load_library(lib_path)
+    g = GenParams()
+    lib.pf_gen_params_default(C.byref(g))
+    for k, v in kw.items():
+        setattr(g, k, v)
+    cp = _Problem()
+    rc = lib.pf_gen_grid_problem(C.byref(g), C.byref(cp))
+    if rc != PF_OK:
+        raise RouterError(rc, "pf_gen_grid_problem failed")
+    counts = {"N": cp.num_nodes, "N1": cp.num_nodes + 1, "E": cp.num_edges, "S": cp.num_switches, "I": cp.num_indexed,
+              "n": cp.num_nets, "n1": cp.num_nets + 1, "n4": 4 * cp.num_nets, "T": cp.num_terminals,
+              "G": cp.num_opin_groups}
+    arrs = {}
+    for name, dt, c in pfio._PROB_FIELDS:
+        dt = np.dtype(dt)
+        nbytes = counts[c] * dt.itemsize
+        buf = (C.c_char * nbytes).from_address(getattr(cp, name)) if nbytes else b""
+        arrs[name] = np.frombuffer(bytes(buf) if nbytes else b"", dtype=dt).copy()
+    arrs["net_bb"] = arrs["net_bb"].reshape(cp.num_nets, 4)
+    opts = np.zeros((), dtype=pfio.OPTS_DT)
+    for f in _Opts._fields_:
+        opts[f[0]] = getattr(cp.opts, f[0])
+    p = pfio.Problem(nx=cp.nx, ny=cp.ny, opts=opts, **arrs)
+    lib.pf_problem_free(C.byref(cp))
+    return p

@@ -65,9 +65,9 @@ int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long
 }
 
 int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed, int num_groups,
-		const int *group_source, const int *group_count, const int *group_off, int *chosen, int rip_up, float pres_fac) {
+		const int *group_source, const int *group_count, const int *group_off, int *chosen, int rip_up, float pres_fac, int *occ_base) {
 	for (int g = 0; g < num_groups; g++)
-		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac);
+		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac, occ_base);
 	g_times.aux_launches++;
 	return 0;
 }

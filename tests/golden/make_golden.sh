@@ -1,0 +1,20 @@
+#!/bin/sh
+# Regenerates tests/golden/*.xz by running the UNMODIFIED reference (oracle/_ref/vpr_ref, built from
+# /root/reference by `make -C oracle ref`).  Only works where /root/reference exists.
+#   toy : tests/fixtures/gen_blif.py --luts 300  --pis 16 --window 60  --seed 1, W=64
+#   mid : tests/fixtures/gen_blif.py --luts 4000 --pis 64 --window 400 --seed 2, W=200
+set -e
+HERE=$(cd "$(dirname "$0")" && pwd); ROOT=$(cd "$HERE/../.." && pwd)
+REF=$ROOT/oracle/_ref/vpr_ref; W=$(mktemp -d); cd "$W"
+cp "$ROOT/tests/fixtures/k6_N10_like.xml" .
+python "$ROOT/tests/fixtures/gen_blif.py" toy.blif --luts 300 --pis 16 --window 60 --seed 1 --name toy
+python "$ROOT/tests/fixtures/gen_blif.py" mid.blif --luts 4000 --pis 64 --window 400 --seed 2 --name mid
+for c in toy:64 mid:200; do
+  n=${c%%:*}; w=${c##*:}
+  "$REF" flow k6_N10_like.xml $n --nodisp --pack --place > /dev/null
+  PF_DUMP_PROBLEM=${n}_w$w.pfp PF_DUMP_RESULT=${n}_w$w.pfr "$REF" flow k6_N10_like.xml $n --nodisp --route --route_chan_width $w > /dev/null
+  "$REF" inject ${n}_w$w.pfp --result ${n}_w${w}_nt.pfr > /dev/null
+  for f in ${n}_w$w.pfp ${n}_w$w.pfr ${n}_w${w}_nt.pfr; do xz -9 -c $f > "$HERE/$f.xz"; done
+done
+cp toy.blif toy.place "$HERE/"; xz -9 -c toy.net > "$HERE/toy.net.xz"
+echo "goldens written to $HERE"

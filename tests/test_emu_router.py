@@ -1,0 +1,87 @@
+"""The device router source (pf_device.cuh) + host driver (pf_router.cpp), executed on the fiber warp
+emulator (tests/emu) — CPU-side coverage of the exact code nvcc compiles for the GPU.  This is test
+infrastructure: the product library has no CPU path.  Parity is judged like on the GPU: an independent
+legality + from-scratch Elmore check, and aggregate quality against the reference's golden routing
+(route trees are integer node lists whose shape depends on float-cost ties, BASELINE.json north_star)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from parallel_eda_b200 import check_route, pfio, router
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _toy(timing):
+    p = pfio.read_problem(os.path.join(G, "toy_w64.pfp.xz"))
+    p.opts["timing_analysis_enabled"] = 1 if timing else 0
+    return p
+
+
+def test_single_warp_matches_reference_quality(emu_lib):
+    """One slot = nets routed one after the other, like the serial reference: the wirelength must land
+    within 2 % of the reference's and the routing must be legal with correct incremental delays."""
+    p = _toy(False)
+    g = pfio.read_result(os.path.join(G, "toy_w64_nt.pfr.xz"))
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=1, big_slots=1, pop_slack=0.0, max_batch=1)
+    r = router.try_timing_driven_route(p, cfg, lib_path=emu_lib)
+    assert r.success == 1
+    m = check_route.check_route(p, r)          # legality + Elmore from scratch (tol 1e-4)
+    assert m["overused"] == 0
+    assert abs(r.total_wirelength - g.total_wirelength) <= 0.02 * g.total_wirelength
+    assert r.iterations <= int(1.5 * g.iterations)
+
+
+def test_lane_order_independence(emu_lib, tmp_path):
+    """Resuming lanes in descending order must give the same routing: catches a missing warp sync between a
+    store and another lane's dependent load.  (Separate process: the order is read at launch.)"""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from parallel_eda_b200 import pfio, router\n"
+        "p = pfio.read_problem(%r); p.opts['timing_analysis_enabled'] = 0\n"
+        "cfg = router.default_config(router.load_library(%r), num_slots=4, big_slots=1)\n"
+        "r = router.try_timing_driven_route(p, cfg, lib_path=%r)\n"
+        "print(r.success, r.iterations, r.serial_num, r.total_wirelength)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(G, "toy_w64.pfp.xz"), emu_lib, emu_lib)
+    outs = []
+    for rev in ("0", "1"):
+        env = dict(os.environ, PF_EMU_REVERSE=rev)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout)
+    assert outs[0] == outs[1] and outs[0].startswith("1 ")
+
+
+def test_concurrent_warps_timing_driven(emu_lib):
+    """Several nets in flight against live occupancy, timing-driven with the reference's criticalities replayed."""
+    p = _toy(True)
+    g = pfio.read_result(os.path.join(G, "toy_w64.pfr.xz"))
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=8, big_slots=1)
+    r = router.try_timing_driven_route(p, cfg, sta=router.replay_sta(g), lib_path=emu_lib)
+    assert r.success == 1
+    check_route.check_route(p, r)
+    assert r.total_wirelength <= 1.10 * g.total_wirelength and r.iterations <= 50
+    # criticality-weighted delay (what the timing-driven cost minimises) within 10 % of the reference's
+    w = g.iter_crit[-1]
+    assert float((w * r.net_delay).sum()) <= 1.10 * float((w * g.net_delay).sum())
+
+
+def test_scratch_overflow_is_retried_in_big_slots(emu_lib):
+    """Tiny per-warp scratch: nets that overflow must be re-routed in the big slots, result still legal."""
+    p = _toy(False)
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=2, big_slots=1, label_log2=7, far_cap=64, tree_cap=64)
+    r = router.try_timing_driven_route(p, cfg, lib_path=emu_lib)
+    assert r.success == 1
+    check_route.check_route(p, r)
+
+
+def test_reroute_all_policy_single_warp(emu_lib):
+    """reroute_all_iters < 0 reproduces the serial reference's policy (every net every iteration)."""
+    p = _toy(False)
+    g = pfio.read_result(os.path.join(G, "toy_w64_nt.pfr.xz"))
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=1, big_slots=1, reroute_all_iters=-1, pop_slack=0.0, max_batch=1)
+    r = router.try_timing_driven_route(p, cfg, lib_path=emu_lib)
+    assert r.success == 1 and all(int(x) == 293 for x in r.iter_stats["nets_routed"])
+    check_route.check_route(p, r)
+    assert abs(r.total_wirelength - g.total_wirelength) <= 0.03 * g.total_wirelength

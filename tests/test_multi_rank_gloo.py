@@ -1,0 +1,56 @@
+"""N>1 host logic on CPU: two processes over gloo, each routing its shard of the nets with the emulated device
+code, exchanging the occupancy delta once per iteration exactly as the NCCL path does on GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch
+from parallel_eda_b200 import pfio, router, pathfinder, distributed, check_route
+comm = distributed.init_from_env("gloo")
+p = pfio.read_problem(os.path.join(%(root)r, "tests", "golden", "toy_w64.pfp.xz")); p.opts["timing_analysis_enabled"] = 0
+lib = %(emu)r
+cfg = router.default_config(router.load_library(lib), num_slots=2, big_slots=1, rank=comm.rank, nranks=comm.world)
+R = router.Router(p, cfg, lib_path=lib)
+delta = torch.zeros(p.num_nodes, dtype=torch.int32)
+rep = pathfinder.route(R, comm=comm, delta_buf=delta)
+res = R.result()
+# every rank holds the full occupancy; traces only of its own nets
+occ = torch.from_numpy(res.occ.astype(np.int64)); ref = occ.clone(); torch.distributed.broadcast(ref, 0)
+own = [i for i in p.routed_nets() if res.trace_ptr[i + 1] > res.trace_ptr[i]]
+parts = [None] * comm.world
+torch.distributed.all_gather_object(parts, (own, [res.net_trace(int(i)) for i in own]))
+if comm.rank == 0:
+    seen = {}
+    for o, tr in parts:
+        for i, t in zip(o, tr): assert i not in seen; seen[int(i)] = t
+    assert sorted(seen) == [int(i) for i in p.routed_nets()]
+    tp = [0]; tn = []; ts = []
+    for i in range(p.num_nets):
+        if i in seen: tn.append(seen[i][0]); ts.append(seen[i][1])
+        tp.append(tp[-1] + (len(seen[i][0]) if i in seen else 0))
+    full = pfio.Result(int(rep.success), rep.iterations, 0, 0, np.array(tp, np.int32), np.concatenate(tn), np.concatenate(ts), res.net_delay, res.occ, res.iter_stats)
+    m = check_route.check_route(p, full, check_delays=False)
+    print(json.dumps({"success": rep.success, "iters": rep.iterations, "occ_equal": bool(torch.equal(occ, ref)), "overused": m["overused"], "nets": rep.nets_routed}))
+else:
+    assert torch.equal(occ, ref)
+'''
+
+
+def test_two_ranks_gloo(emu_lib, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT, "emu": emu_lib})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    import json
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["success"] and out["occ_equal"] and out["overused"] == 0

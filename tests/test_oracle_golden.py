@@ -1,0 +1,55 @@
+"""Pins the CPU oracle (oracle/pf_oracle.c) to the UNMODIFIED reference router.
+
+The golden .pfr files were written by oracle/_ref/vpr_ref — the reference's own
+try_timing_driven_route (vpr/SRC/route/route_timing.c:85) compiled from /root/reference — see
+tests/golden/make_golden.sh.  The oracle must reproduce them bit for bit: identical s_trace lists
+of every net, iteration count, "magic cookie" (route_common.c:224-254), per-sink Elmore delays,
+final occupancy and per-iteration overuse, in timing-driven mode (criticalities replayed from the
+reference's own STA) and with timing analysis off.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from parallel_eda_b200 import pfio
+
+CASES = [
+    ("toy_w64", "toy_w64.pfr", True),        # 294 nets, 6x6, W=64, timing-driven: 21 iterations
+    ("toy_w64", "toy_w64_nt.pfr", False),    # timing analysis off: 14 iterations
+    ("mid_w200", "mid_w200_nt.pfr", False),  # 3852 nets, 21x21, W=200, timing off: 12 iterations
+    ("mid_w200", "mid_w200.pfr", True),      # timing-driven: 21 iterations, 80,871 net routes
+]
+
+
+@pytest.mark.parametrize("prob,gold,timing", CASES)
+def test_oracle_reproduces_reference_bit_for_bit(prob, gold, timing, oracle_cli, unxz, tmp_path):
+    out = str(tmp_path / "o.pfr")
+    cmd = [oracle_cli, unxz(prob + ".pfp"), "--result", out]
+    if timing:
+        cmd += ["--crit", unxz(gold)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    g = pfio.read_result(unxz(gold))
+    o = pfio.read_result(out)
+    assert (o.success, o.iterations) == (g.success, g.iterations)
+    assert o.serial_num == g.serial_num
+    assert o.total_wirelength == g.total_wirelength
+    assert np.array_equal(o.trace_ptr, g.trace_ptr)
+    assert np.array_equal(o.trace_node, g.trace_node)
+    assert np.array_equal(o.trace_switch, g.trace_switch)
+    assert np.array_equal(o.net_delay.view(np.uint32), g.net_delay.view(np.uint32))   # bit-exact floats
+    assert np.array_equal(o.occ, g.occ)
+    assert list(o.iter_stats["overused_nodes"]) == list(g.iter_stats["overused_nodes"])
+
+
+def test_reference_binary_agrees_when_present(ref_bin, oracle_cli, unxz, tmp_path):
+    """Where oracle/_ref was built, re-run the real reference on the flat problem (inject mode)."""
+    out_r, out_o = str(tmp_path / "r.pfr"), str(tmp_path / "o.pfr")
+    prob = unxz("toy_w64.pfp")
+    subprocess.run([ref_bin, "inject", prob, "--result", out_r], check=True, capture_output=True)
+    subprocess.run([oracle_cli, prob, "--result", out_o], check=True, capture_output=True)
+    r, o = pfio.read_result(out_r), pfio.read_result(out_o)
+    assert r.serial_num == o.serial_num and np.array_equal(r.trace_node, o.trace_node)
+    assert np.array_equal(r.net_delay.view(np.uint32), o.net_delay.view(np.uint32))
