@@ -109,6 +109,10 @@ int pf_get_net_delay(pf_router *r, float *net_delay);
 /* Fills trace_*, net_delay, occ, serial_num, total_wirelength (free with pf_result_free). */
 int pf_get_result(pf_router *r, pf_result *out);
 int pf_get_timing(pf_router *r, pf_timing *t, int reset);
+/* Device-side stopwatch: CUDA events recorded on the router's own stream (whole-step timing). */
+int pf_timer_start(pf_router *r);
+int pf_timer_stop(pf_router *r, double *elapsed_ms);
+void *pf_stream(pf_router *r);   /* the cudaStream_t every kernel of this router is launched on */
 
 /* Multi-GPU iteration boundary (device pointers, int32[num_nodes] / float[num_terminals]):
  *   1. pf_comm_export_delta(r, d)       d[i] = occ change made by this rank's nets

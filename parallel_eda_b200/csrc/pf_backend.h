@@ -29,6 +29,9 @@ int pfb_zero(void *dst, size_t bytes);
 int pfb_sync(void);
 void pfb_times(PfLaunchTimes *out, int reset);
 int pfb_num_sms(void);
+int pfb_timer_start(void);                        /* CUDA events on the router's stream */
+int pfb_timer_stop(double *ms);
+void *pfb_stream(void);
 
 /* the warp-per-net router: num_slots warps, each looping over the work queue */
 int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block);

@@ -96,6 +96,23 @@ void pfb_times(PfLaunchTimes *out, int reset) {
 	if (reset) memset(&g_times, 0, sizeof(g_times));
 }
 
+/* whole-step timer: device time between two points of the router's stream */
+static cudaEvent_t g_t0 = 0, g_t1 = 0;
+int pfb_timer_start(void) {
+	if (!g_t0) { CK(cudaEventCreate(&g_t0)); CK(cudaEventCreate(&g_t1)); }
+	CK(cudaEventRecord(g_t0, g_stream));
+	return 0;
+}
+int pfb_timer_stop(double *ms) {
+	float f = 0.f;
+	CK(cudaEventRecord(g_t1, g_stream));
+	CK(cudaEventSynchronize(g_t1));
+	CK(cudaEventElapsedTime(&f, g_t0, g_t1));
+	*ms = f;
+	return 0;
+}
+void *pfb_stream(void) { return (void *)g_stream; }
+
 static int ev_begin(int kind) {
 	if (g_npending == 64 && drain_events() != 0) return -1;
 	PendingEvent *p = &g_pending[g_npending];

@@ -553,6 +553,10 @@ extern "C" int pf_get_net_delay(pf_router *r, float *net_delay) {
 	return PF_OK;
 }
 
+extern "C" int pf_timer_start(pf_router *r) { if (!r) FAILF(PF_EINVAL, "null router"); CKB(pfb_timer_start()); return PF_OK; }
+extern "C" int pf_timer_stop(pf_router *r, double *ms) { if (!r || !ms) FAILF(PF_EINVAL, "null argument"); CKB(pfb_timer_stop(ms)); return PF_OK; }
+extern "C" void *pf_stream(pf_router *r) { (void)r; return pfb_stream(); }
+
 extern "C" int pf_get_timing(pf_router *r, pf_timing *t, int reset) {
 	if (!r || !t) FAILF(PF_EINVAL, "null argument");
 	PfLaunchTimes lt;

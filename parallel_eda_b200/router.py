@@ -120,6 +120,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_get_net_delay.argtypes = [C.c_void_p, C.c_void_p]
     lib.pf_get_result.argtypes = [C.c_void_p, C.POINTER(_Result)]
     lib.pf_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing), C.c_int]
+    lib.pf_timer_start.argtypes = [C.c_void_p]
+    lib.pf_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.pf_comm_export_delta.argtypes = [C.c_void_p, C.c_void_p]
     lib.pf_update_costs_synced.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
     lib.pf_comm_fold_delta.argtypes = [C.c_void_p, C.c_void_p]
@@ -268,6 +270,14 @@ class Router:
         t = Timing()
         self._ck(self.lib.pf_get_timing(self._h, C.byref(t), 1 if reset else 0))
         return t
+
+    def timer_start(self):
+        self._ck(self.lib.pf_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0.0)
+        self._ck(self.lib.pf_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     # multi-GPU iteration boundary (device pointers, e.g. torch tensors' data_ptr())
     def comm_export_delta(self, dev_ptr: int):

@@ -26,6 +26,12 @@ int pfb_d2d(void *d, const void *s, size_t n) { if (n) memmove(d, s, n); return 
 int pfb_zero(void *d, size_t n) { if (n) memset(d, 0, n); return 0; }
 int pfb_sync(void) { return 0; }
 void pfb_times(PfLaunchTimes *out, int reset) { if (out) *out = g_times; if (reset) memset(&g_times, 0, sizeof(g_times)); }
+#include <time.h>
+static double g_tt0;
+static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+int pfb_timer_start(void) { g_tt0 = now_ms(); return 0; }
+int pfb_timer_stop(double *ms) { *ms = now_ms() - g_tt0; return 0; }
+void *pfb_stream(void) { return NULL; }
 int pfb_num_sms(void) { const char *e = getenv("PF_EMU_SMS"); return e ? atoi(e) : 1; }
 
 struct RouteArg { const PfParams *P; std::vector<unsigned char> *smem; };

@@ -1,0 +1,124 @@
+"""GPU parity tests (-m gpu): the CUDA router through the C-ABI versus the CPU oracle / the reference's golden
+routings.  Route trees are integer rr-node lists whose shape depends on float-cost ties and on which nets are
+in flight together, so — as BASELINE.json's north_star states — parity is: a LEGAL routing (independent
+check_route), incremental Elmore delays equal to a from-scratch recomputation (rel. 1e-4, the reference's own
+ERROR_TOL), occupancy recomputed from the traces bit-equal to the device's, and total wirelength /
+criticality-weighted delay within the stated tolerance of the reference's routing of the same input:
+    one warp (serial order, like the reference):  wirelength within 2 %
+    full concurrency:                             wirelength within 8 %, iterations <= 2x
+"""
+import os
+
+import numpy as np
+import pytest
+
+from parallel_eda_b200 import check_route, pfio, router
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name, timing):
+    p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
+    p.opts["timing_analysis_enabled"] = 1 if timing else 0
+    g = pfio.read_result(os.path.join(G, name + (".pfr.xz" if timing else "_nt.pfr.xz")))
+    return p, g
+
+
+def test_native_library_is_the_one_running():
+    lib = router.load_library()
+    assert lib.pf_backend_name() == b"cuda:sm_100a" and lib.pf_device_count() >= 1
+
+
+@pytest.mark.parametrize("name", ["toy_w64", "mid_w200"])
+def test_single_warp_serial_order_matches_reference(name):
+    p, g = _load(name, False)
+    r = router.try_timing_driven_route(p, router.default_config(num_slots=1, big_slots=1, pop_slack=0.0, max_batch=1))
+    assert r.success == 1
+    check_route.check_route(p, r)
+    assert abs(r.total_wirelength - g.total_wirelength) <= 0.02 * g.total_wirelength
+    assert r.iterations <= int(1.5 * g.iterations) + 1
+
+
+@pytest.mark.parametrize("name", ["toy_w64", "mid_w200"])
+def test_concurrent_routing_timing_off(name):
+    p, g = _load(name, False)
+    r = router.try_timing_driven_route(p, router.default_config())
+    assert r.success == 1
+    m = check_route.check_route(p, r)
+    assert m["overused"] == 0
+    assert r.total_wirelength <= 1.08 * g.total_wirelength
+    assert r.iterations <= 2 * g.iterations + 2
+
+
+@pytest.mark.parametrize("name", ["toy_w64", "mid_w200"])
+def test_concurrent_routing_timing_driven(name):
+    """Timing-driven mode with the reference's own per-iteration criticalities replayed as the STA."""
+    p, g = _load(name, True)
+    r = router.try_timing_driven_route(p, router.default_config(), sta=router.replay_sta(g))
+    assert r.success == 1
+    check_route.check_route(p, r)
+    assert r.total_wirelength <= 1.08 * g.total_wirelength
+    w = g.iter_crit[-1]
+    assert float((w * r.net_delay).sum()) <= 1.08 * float((w * g.net_delay).sum())
+
+
+def test_step_api_matches_reference_call_sequence():
+    """The reference's loop written out with the step functions (route_timing.c:152-310)."""
+    p, g = _load("mid_w200", False)
+    R = router.Router(p)
+    o = p.opts
+    pres = float(o["first_iter_pres_fac"])
+    for it in range(1, int(o["max_router_iterations"]) + 1):
+        st = R.route_iteration(pres)
+        assert st.nets_routed > 0
+        if it == 1:
+            wl, avail = R.total_wirelength()
+            assert 0 < wl < 0.85 * avail
+        R.reserve_locally_used_opins(pres, it != 1)
+        pres, acc = (float(o["initial_pres_fac"]), 0.0) if it == 1 else (pres * float(o["pres_fac_mult"]), float(o["acc_fac"]))
+        if R.pathfinder_update_cost(acc) == 0:
+            break
+    res = R.result()
+    res.success = 1
+    check_route.check_route(p, res)
+    # reset really forgets: a second run from scratch behaves like a first
+    R.reset()
+    st = R.route_iteration(float(o["first_iter_pres_fac"]))
+    assert st.nets_routed == len(p.routed_nets())
+    R.close()
+
+
+def test_large_grid_properties():
+    """BASELINE configs[4] density on a 100x100 slice: size-independent properties — legality, occupancy
+    recomputed from the traces bit-equal to the device's, every sink reached, sampled edge adjacency."""
+    p = router.generate_grid_problem(nx=100, ny=100, W=100, num_nets=12500)
+    r = router.try_timing_driven_route(p, router.default_config())
+    assert r.success == 1
+    m = check_route.check_route_fast(p, r)
+    assert m["overused"] == 0 and m["sinks"] == 3 * p.num_nets
+
+
+def test_generated_grid_full_check_against_oracle(tmp_path):
+    """A generated 30x30 problem: full check_route incl. Elmore, and wirelength against the CPU oracle's routing."""
+    import subprocess
+    p = router.generate_grid_problem(nx=30, ny=30, W=60, num_nets=1500, window=8, seed=3)
+    r = router.try_timing_driven_route(p, router.default_config())
+    assert r.success == 1
+    check_route.check_route(p, r)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "oracle", "_build", "pf_oracle_cli")
+    if not os.path.exists(cli):
+        subprocess.run(["make", "-s", "-C", os.path.join(root, "oracle")], check=True)
+    prob, out = str(tmp_path / "g.pfp"), str(tmp_path / "g.pfr")
+    pfio.write_problem(prob, p)
+    subprocess.run([cli, prob, "--result", out], check=True, capture_output=True)
+    o = pfio.read_result(out)
+    assert o.success == 1 and r.total_wirelength <= 1.08 * o.total_wirelength
+
+
+def test_overflow_retry_and_small_scratch():
+    p, g = _load("toy_w64", False)
+    r = router.try_timing_driven_route(p, router.default_config(label_log2=7, far_cap=64, tree_cap=64, big_slots=4))
+    assert r.success == 1
+    check_route.check_route(p, r)
