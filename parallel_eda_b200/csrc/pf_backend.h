@@ -42,6 +42,8 @@ int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_o
 		int *occ_base, const int *occ_delta);
 /* delta[i] = nodes[i].occ - base[i]: what this GPU's nets changed since the last sync */
 int pfb_launch_export_delta(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta);
+/* occ_out[i] = nodes[i].occ (compact copy for the host) */
+int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out);
 /* total wirelength of all trees in the route store (route_timing.c:189-225 sanity abort) */
 int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long long *d_out);
 /* reserve_locally_used_opins (route_common.c:1435-1491): one thread per (block, class) group */

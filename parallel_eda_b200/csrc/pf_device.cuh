@@ -241,7 +241,8 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 			pf_st_u4(L, n0); pf_st_u4((char *)L + 16, n1);
 			written = 1; pending = 0;
 		}
-		unsigned newm = pf_ballot(claim && !pending);   /* also orders the stores before the next probe round */
+		pf_syncwarp();                                  /* order the label stores before the next probe round */
+		unsigned newm = pf_ballot(claim && !pending);
 		w.n_labels += pf_popc(newm);
 	}
 	if (w.n_labels > (int)(w.label_mask >> 1)) w.overflow = 1;

@@ -153,6 +153,10 @@ __global__ void pf_export_delta_kernel(const PfNode *nodes, int num_nodes, const
 		occ_delta[i] = nodes[i].occ - occ_base[i];
 }
 
+__global__ void pf_extract_occ_kernel(const PfNode *nodes, int num_nodes, int *occ_out) {
+	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x)) occ_out[i] = nodes[i].occ;
+}
+
 __global__ void pf_wirelength_kernel(const PfTreeNode *pool, long long count, unsigned long long *d_out) {
 	unsigned acc = 0;
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
@@ -256,5 +260,11 @@ int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, co
 	if (num_all <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
 	pf_compact_kernel<<<stream_grid((long long)num_all * 32), 256, 0, g_stream>>>(src, dst, loc, all_nets, num_all, dst_head);
+	return ev_end();
+}
+
+int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out) {
+	if (ev_begin(2) != 0) return -1;
+	pf_extract_occ_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, occ_out);
 	return ev_end();
 }

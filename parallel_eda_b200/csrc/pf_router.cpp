@@ -49,6 +49,7 @@ struct pf_router {
 	long long pool_cap; unsigned long long *pool_head;
 	int *all_nets; int num_all; unsigned char *net_big; int *sel_counts;
 	std::vector<unsigned char> h_net_big;
+	std::vector<int> net_rank;        /* position of a net in the fanout-sorted order */
 	int iter_count;
 	int best_overused, stall_count;   /* convergence watchdog, see pf_iteration_begin */
 	int cur_div, n_small, n_big; int *retry_work;
@@ -64,6 +65,20 @@ struct pf_router {
 	std::vector<int> work_small, work_big;
 	float win_abs_auto;
 };
+
+#include <chrono>
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#include <thread>
+/* simple static-partition parallel loop for the host-side flattening of 10^7..10^8-element arrays */
+template <class F> static void parallel_for(long long n, F f) {
+	unsigned hw = std::thread::hardware_concurrency();
+	int nt = (int)std::min<long long>(hw ? hw : 4, std::max<long long>(1, n / (1 << 16)));
+	if (nt > 32) nt = 32;
+	if (nt <= 1) { f(0, n); return; }
+	std::vector<std::thread> th;
+	for (int t = 0; t < nt; t++) th.emplace_back([=]() { f(n * t / nt, n * (t + 1) / nt); });
+	for (auto &t : th) t.join();
+}
 
 static int ceil_log2(long long v) { int l = 0; while ((1ll << l) < v) l++; return l; }
 
@@ -105,7 +120,8 @@ extern "C" void pf_router_destroy(pf_router *r) {
 static int upload_nodes(pf_router *r, bool keep_nothing) {
 	const pf_problem *p = r->prob;
 	std::vector<PfNode> h((size_t)r->N);
-	for (int i = 0; i < r->N; i++) {
+	parallel_for(r->N, [&](long long lo, long long hi) {
+	for (long long i = lo; i < hi; i++) {
 		PfNode &d = h[i];
 		d.xlow = p->xlow[i]; d.ylow = p->ylow[i]; d.xhigh = p->xhigh[i]; d.yhigh = p->yhigh[i];
 		d.R = p->R[i]; d.C = p->C[i];
@@ -115,6 +131,7 @@ static int upload_nodes(pf_router *r, bool keep_nothing) {
 		d.type_ci = (unsigned char)(p->type[i] | (p->cost_index[i] << 3));
 		d.capacity = (unsigned char)p->capacity[i];
 	}
+	});
 	(void)keep_nothing;
 	CKB(pfb_h2d(r->nodes, h.data(), sizeof(PfNode) * (size_t)r->N));
 	r->h2d_bytes += (int64_t)sizeof(PfNode) * r->N;
@@ -125,7 +142,9 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	char msg[256];
 	*out = NULL;
 	if (!p || !cfg_in) FAILF(PF_EINVAL, "null argument");
+	double t_a = now_s();
 	if (pf_problem_check(p, msg, sizeof(msg)) != PF_OK) FAILF(PF_EINVAL, "invalid problem: %s", msg);
+	double t_b = now_s();
 	if (p->num_nodes > (1 << PF_EDGE_NODE_BITS)) FAILF(PF_EINVAL, "num_rr_nodes %d exceeds the %d-bit edge word", p->num_nodes, PF_EDGE_NODE_BITS);
 	if (p->num_switches > PF_MAX_SWITCHES) FAILF(PF_EINVAL, "%d switch types (max %d)", p->num_switches, PF_MAX_SWITCHES);
 	if (p->num_indexed > PF_MAX_INDEXED) FAILF(PF_EINVAL, "%d rr_indexed_data rows (max %d)", p->num_indexed, PF_MAX_INDEXED);
@@ -176,6 +195,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	}
 	std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
 		return (p->net_ptr[a + 1] - p->net_ptr[a]) > (p->net_ptr[b + 1] - p->net_ptr[b]); });
+	r->net_rank.assign((size_t)std::max(r->n, 1), 0);
+	for (size_t k = 0; k < order.size(); k++) r->net_rank[order[k]] = (int)k;
 	for (size_t k = 0; k < order.size(); k++) {
 		if ((int)(k % (size_t)c.nranks) != c.rank) continue;
 		int i = order[k], ns = p->net_ptr[i + 1] - p->net_ptr[i] - 1;
@@ -201,7 +222,9 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	}
 	{
 		std::vector<uint32_t> ew((size_t)std::max(r->E, 1));
-		for (int k = 0; k < r->E; k++) ew[k] = (uint32_t)p->edge_to[k] | ((uint32_t)p->edge_sw[k] << PF_EDGE_NODE_BITS);
+		parallel_for(r->E, [&](long long lo, long long hi) {
+			for (long long k = lo; k < hi; k++) ew[k] = (uint32_t)p->edge_to[k] | ((uint32_t)p->edge_sw[k] << PF_EDGE_NODE_BITS);
+		});
 		std::vector<PfSwitchDev> sw(PF_MAX_SWITCHES);
 		for (int s = 0; s < p->num_switches; s++) { sw[s].R = p->switches[s].R; sw[s].Tdel = p->switches[s].Tdel; sw[s].buffered = p->switches[s].buffered; }
 		std::vector<PfIndexedDev> ix(PF_MAX_INDEXED);
@@ -290,6 +313,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 				|| pfb_h2d(r->g_off, off.data(), sizeof(int) * (size_t)r->num_groups)) { pf_router_destroy(r); CUDA_FAIL(); }
 	}
 	if (pfb_sync() != 0) { pf_router_destroy(r); CUDA_FAIL(); }
+	if (c.verbose) fprintf(stderr, "pf_router: create %.3f s (problem check %.3f s)\n", now_s() - t_a, t_b - t_a);
 	if (c.verbose)
 		fprintf(stderr, "pf_router[%s] rank %d/%d: N=%d E=%d nets=%zu+%zu slots=%d(2^%d labels)+%d(2^%d) pool=%lld\n", pfb_name(), c.rank, c.nranks,
 				r->N, r->E, r->work_small.size(), r->work_big.size(), c.num_slots, c.label_log2, c.big_slots, c.big_label_log2, r->pool_cap);
@@ -402,6 +426,18 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 		CKB(pfb_d2h(counts, r->sel_counts, sizeof(int) * 4));
 		r->d2h_bytes += 16;
 		r->n_small = counts[0]; r->n_big = counts[1];
+		/* the selection kernel appends in atomic order; restore the fanout order of the reference's net
+		 * loop (route_timing.c:98-106) so long nets start first and runs are reproducible */
+		for (int k = 0; k < 2; k++) {
+			SlotClass &sc = k ? r->big : r->small;
+			int cnt = k ? r->n_big : r->n_small;
+			if (cnt < 2) continue;
+			std::vector<int> lst((size_t)cnt);
+			CKB(pfb_d2h(lst.data(), sc.work, sizeof(int) * (size_t)cnt));
+			std::sort(lst.begin(), lst.end(), [&](int a, int b) { return r->net_rank[a] < r->net_rank[b]; });
+			CKB(pfb_h2d(sc.work, lst.data(), sizeof(int) * (size_t)cnt));
+			r->d2h_bytes += (int64_t)sizeof(int) * cnt; r->h2d_bytes += (int64_t)sizeof(int) * cnt;
+		}
 	}
 	r->iter_count++;
 	return PF_OK;
@@ -583,9 +619,7 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 	for (int i = 0; i < r->n; i++) used = std::max<long long>(used, (long long)loc[i].off + loc[i].count);
 	std::vector<PfTreeNode> pool((size_t)std::max<long long>(used, 1));
 	CKB(pfb_d2h(pool.data(), r->pool[r->cur], sizeof(PfTreeNode) * (size_t)used));
-	std::vector<PfNode> nodes((size_t)r->N);
-	CKB(pfb_d2h(nodes.data(), r->nodes, sizeof(PfNode) * (size_t)r->N));
-	r->d2h_bytes += (int64_t)sizeof(PfTreeNode) * used + (int64_t)sizeof(PfNode) * r->N + (int64_t)sizeof(PfNetLoc) * r->n;
+	r->d2h_bytes += (int64_t)sizeof(PfTreeNode) * used + (int64_t)sizeof(int) * r->N + (int64_t)sizeof(PfNetLoc) * r->n;
 
 	std::vector<int32_t> tptr((size_t)r->n + 1, 0), tnode;
 	std::vector<int16_t> tsw;
@@ -625,7 +659,13 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 	out->num_terminals = r->T;
 	if (pfb_d2h(out->net_delay, r->net_delay, sizeof(float) * (size_t)r->T)) { pf_result_free(out); CUDA_FAIL(); }
 	out->num_nodes = r->N;
-	for (int i = 0; i < r->N; i++) out->occ[i] = nodes[i].occ;
+	{   /* occupancy: compacted on the device, one 4-byte word per rr node crosses PCIe */
+		int *d_occ = r->occ_delta ? r->occ_delta : (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
+		if (!d_occ) { pf_result_free(out); CUDA_FAIL(); }
+		int bad = pfb_launch_extract_occ(r->nodes, r->N, d_occ) || pfb_d2h(out->occ, d_occ, sizeof(int) * (size_t)r->N);
+		if (!r->occ_delta) pfb_free(d_occ);
+		if (bad) { pf_result_free(out); CUDA_FAIL(); }
+	}
 	out->total_wirelength = wl;
 	{   /* get_serial_num, route_common.c:224-254 */
 		int serial = 0;

@@ -104,3 +104,9 @@ int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, co
 	g_times.aux_launches++;
 	return 0;
 }
+
+int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out) {
+	for (int i = 0; i < num_nodes; i++) occ_out[i] = nodes[i].occ;
+	g_times.aux_launches++;
+	return 0;
+}

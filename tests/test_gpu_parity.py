@@ -30,6 +30,16 @@ def test_native_library_is_the_one_running():
     assert lib.pf_backend_name() == b"cuda:sm_100a" and lib.pf_device_count() >= 1
 
 
+def test_single_warp_is_bit_identical_to_the_emulated_device_code():
+    """One warp is deterministic, and the sm_100a build must compute exactly what the same source computes on
+    the CPU warp emulator (tests/test_emu_router.py pins the same constants): identical routing, hence identical
+    magic cookie (route_common.c:224-254).  Catches any GPU-only arithmetic or memory-ordering difference."""
+    from test_emu_router import SINGLE_WARP_TOY
+    p, g = _load("toy_w64", False)
+    r = router.try_timing_driven_route(p, router.default_config(num_slots=1, big_slots=1, pop_slack=0.0, max_batch=1))
+    assert (r.serial_num, r.total_wirelength, r.iterations) == SINGLE_WARP_TOY
+
+
 @pytest.mark.parametrize("name", ["toy_w64", "mid_w200"])
 def test_single_warp_serial_order_matches_reference(name):
     p, g = _load(name, False)
