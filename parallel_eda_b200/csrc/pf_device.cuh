@@ -87,6 +87,7 @@ struct PfWarp {
 	uint64_t *b_key;              /* [PF_MAX_BATCH] */
 	int *b_node; float *b_back; float *b_R; int *b_start; int *b_pre; int *b_type;
 	float *base_cost;             /* [PF_MAX_INDEXED] per-net rescaled base costs */
+	int *ticket;                  /* [PF_TICKETS] slot-write arbitration */
 	PfIndexedDev *idx;            /* [PF_MAX_INDEXED] */
 	PfSwitchDev *sw;              /* [PF_MAX_SWITCHES] */
 	/* slot memory */
@@ -101,8 +102,9 @@ struct PfWarp {
 	unsigned long long pops, pushes, visits, refills, stale;
 };
 
-/* fr 1536 + b_key 256 + idx 1024 + sw 768 + base_cost 128 + 5 batch arrays 640 + b_pre 136 = 4488 → 4608 */
-#define PF_SMEM_PER_WARP 4608
+/* fr 1536 + b_key 256 + idx 1024 + sw 768 + base_cost 128 + 5 batch arrays 640 + b_pre 136 + tickets 256 = 4744 → 4864 */
+#define PF_TICKETS 64
+#define PF_SMEM_PER_WARP 4864
 
 PF_DEV float pf_key_tot(uint64_t k) { return pf_int_as_float((int)(k >> 32)); }
 PF_DEV int pf_key_node(uint64_t k) { return (int)(uint32_t)k; }
@@ -190,50 +192,38 @@ PF_DEV int pf_label_find(const PfWarp &w, int node) {
 	}
 }
 
-/* Warp-collective relax: every lane may offer one candidate label (valid != 0).  Candidates for
- * the same node are reduced to the cheapest; a candidate replaces an existing label only if both
- * its total and its backward cost are lower (the pop rule of route_timing.c:511, applied at
- * relax time); slot claims by different nodes in the same probe round are arbitrated by lane
- * order.  Returns 1 in lanes whose candidate was written. */
-PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back, float R_up, int prev, int info, int edge_start) {
+/* Warp-collective relax: every lane may offer one candidate label (valid != 0).  A candidate replaces an
+ * existing label only if both its total and its backward cost are lower (the pop rule of
+ * route_timing.c:511, applied at relax time).  Two lanes may target the same table slot in the same
+ * round — the same node reached over two edges, or two nodes probing the same empty slot; a per-warp
+ * shared-memory ticket array arbitrates: one writer per ticket and round, the others re-probe in the
+ * next round and see the winner's label.  `pre` is the caller's prefetch of the first probe (issued
+ * together with the node-record load so the two HBM round trips overlap).  Returns 1 in lanes whose
+ * candidate was written. */
+PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back, float R_up, int prev, int info,
+		int edge_start, unsigned h, pf_u4 pre) {
 	const int lane = pf_lane();
-	/* same-node duplicates inside this chunk */
-	{
-		unsigned grp = pf_match_any(valid ? node : (int)(0x80000000u | (unsigned)lane));
-		if (pf_any(valid && (grp & (grp - 1)) != 0)) {
-			for (int b = 0; b < PF_WARP; b++) {
-				float t = pf_shfl_f(tot, b);
-				if (valid && ((grp >> b) & 1u) && b != lane && (t < tot || (t == tot && b < lane))) valid = 0;
-			}
-		}
-	}
-	unsigned h = pf_hash(w, node);
-	int pending = valid, written = 0;
+	int pending = valid, written = 0, first = 1;
 	while (pf_any(pending)) {
-		int claim = 0;
+		int want = 0;                                   /* 1: claim an empty slot, 2: improve my node's label */
 		if (pending) {
-			PfLabel *L = &w.labels[h];
-			pf_u4 a = pf_ld_u4(L);
+			pf_u4 a = first ? pre : pf_ld_u4(&w.labels[h]);
 			if (a.y == w.epoch) {
 				if ((int)a.x == node) {
 					float otot = pf_int_as_float((int)a.z), oback = pf_int_as_float((int)a.w);
-					if (tot < otot && back < oback) {
-						pf_u4 n0, n1;
-						n0.x = (unsigned)node; n0.y = w.epoch; n0.z = (unsigned)pf_float_as_int(tot); n0.w = (unsigned)pf_float_as_int(back);
-						n1.x = (unsigned)pf_float_as_int(R_up); n1.y = (unsigned)prev; n1.z = (unsigned)info; n1.w = (unsigned)edge_start;
-						pf_st_u4(L, n0); pf_st_u4((char *)L + 16, n1);
-						written = 1;
-					}
-					pending = 0;
+					if (tot < otot && back < oback) want = 2; else pending = 0;
 				} else {
 					h = (h + 1) & w.label_mask;
 				}
 			} else {
-				claim = 1;
+				want = 1;
 			}
 		}
-		unsigned cg = pf_match_any(claim ? (int)h : (int)(0x80000000u | (unsigned)lane));
-		if (claim && (pf_ffs(cg) - 1) == lane) {
+		first = 0;
+		if (want) w.ticket[h & (PF_TICKETS - 1)] = lane;
+		pf_syncwarp();
+		int win = want && w.ticket[h & (PF_TICKETS - 1)] == lane;
+		if (win) {
 			PfLabel *L = &w.labels[h];
 			pf_u4 n0, n1;
 			n0.x = (unsigned)node; n0.y = w.epoch; n0.z = (unsigned)pf_float_as_int(tot); n0.w = (unsigned)pf_float_as_int(back);
@@ -241,9 +231,8 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 			pf_st_u4(L, n0); pf_st_u4((char *)L + 16, n1);
 			written = 1; pending = 0;
 		}
-		pf_syncwarp();                                  /* order the label stores before the next probe round */
-		unsigned newm = pf_ballot(claim && !pending);
-		w.n_labels += pf_popc(newm);
+		pf_syncwarp();                                  /* tickets reusable; label stores ordered before re-probes */
+		w.n_labels += pf_popc(pf_ballot(win && want == 1));
 	}
 	if (w.n_labels > (int)(w.label_mask >> 1)) w.overflow = 1;
 	return written;
@@ -437,7 +426,9 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 				tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
 			}
 		}
-		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
+		unsigned h0 = pf_hash(w, node);
+		pf_u4 pre0 = pf_ld_u4(&w.labels[h0]);
+		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1, h0, pre0);
 		pf_push(w, wr, tot, node);
 		if (w.overflow) return -1;
 	}
@@ -523,12 +514,15 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 			int e = base + lane;
 			int valid = e < M;
 			int to = 0, u = 0, isw = 0, info = 0, es = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
+			unsigned h0 = 0; pf_u4 pre0; pre0.x = pre0.y = pre0.z = pre0.w = 0;
 			if (valid) {
 				int j = 0, hi = taken - 1;                      /* owner: last j with b_pre[j] <= e */
 				while (j < hi) { int mid = (j + hi + 1) >> 1; if (w.b_pre[mid] <= e) j = mid; else hi = mid - 1; }
 				u = w.b_node[j];
 				uint32_t ew = P->edges[w.b_start[j] + (e - w.b_pre[j])];
 				to = (int)(ew & PF_EDGE_NODE_MASK); isw = (int)(ew >> PF_EDGE_NODE_BITS);
+				h0 = pf_hash(w, to);
+				pre0 = pf_ld_u4(&w.labels[h0]);              /* first label probe in flight with the node record */
 				PfNodeView n = pf_load_node(P, to);
 				if (n.xhigh < w.bb_xmin || n.xlow > w.bb_xmax || n.yhigh < w.bb_ymin || n.ylow > w.bb_ymax) valid = 0;
 				if (valid && highfan && (n.xhigh < tgt_xh - rlim || n.xlow > tgt_xh + rlim || n.yhigh < tgt_yh - rlim || n.ylow > tgt_yh + rlim)) valid = 0;
@@ -558,7 +552,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 					info = isw | (n.type << 8) | (n.num_edges << 16); es = n.edge_start;
 				}
 			}
-			int wr = pf_label_relax(w, valid, to, tot, back, R_up, u, info, es);
+			int wr = pf_label_relax(w, valid, to, tot, back, R_up, u, info, es, h0, pre0);
 			/* the target SINK is never expanded; only its best total matters */
 			float tb = pf_warp_min_f((wr && to == target_node) ? tot : PF_INF_F);
 			if (tb < w.best) w.best = tb;
@@ -877,7 +871,8 @@ PF_DEV void pf_warp_main(const PfParams *P, int slot, unsigned char *smem_warp) 
 	w.b_R = (float *)s; s += PF_MAX_BATCH * 4;
 	w.b_start = (int *)s; s += PF_MAX_BATCH * 4;
 	w.b_type = (int *)s; s += PF_MAX_BATCH * 4;
-	w.b_pre = (int *)s; s += (PF_MAX_BATCH + 1) * 4;
+	w.b_pre = (int *)s; s += (PF_MAX_BATCH + 1 + 1) * 4;
+	w.ticket = (int *)s; s += PF_TICKETS * 4;
 	for (int i = lane; i < P->num_indexed; i += PF_WARP) w.idx[i] = P->indexed[i];
 	for (int i = lane; i < P->num_sw; i += PF_WARP) w.sw[i] = P->sw[i];
 	const long long cap = 1ll << P->label_log2;

@@ -13,7 +13,9 @@ import pytest
 from parallel_eda_b200 import check_route, pfio, router
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-SINGLE_WARP_TOY = (-252784082, 3245, 11)   # (magic cookie, wirelength, iterations) of the emulated device code
+import json
+_sw = json.load(open(os.path.join(G, "single_warp_toy.json")))
+SINGLE_WARP_TOY = (_sw["serial_num"], _sw["total_wirelength"], _sw["iterations"])
 
 
 def _toy(timing):

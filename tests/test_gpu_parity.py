@@ -34,7 +34,9 @@ def test_single_warp_is_bit_identical_to_the_emulated_device_code():
     """One warp is deterministic, and the sm_100a build must compute exactly what the same source computes on
     the CPU warp emulator (tests/test_emu_router.py pins the same constants): identical routing, hence identical
     magic cookie (route_common.c:224-254).  Catches any GPU-only arithmetic or memory-ordering difference."""
-    from test_emu_router import SINGLE_WARP_TOY
+    import json
+    sw = json.load(open(os.path.join(G, "single_warp_toy.json")))
+    SINGLE_WARP_TOY = (sw["serial_num"], sw["total_wirelength"], sw["iterations"])
     p, g = _load("toy_w64", False)
     r = router.try_timing_driven_route(p, router.default_config(num_slots=1, big_slots=1, pop_slack=0.0, max_batch=1))
     assert (r.serial_num, r.total_wirelength, r.iterations) == SINGLE_WARP_TOY
