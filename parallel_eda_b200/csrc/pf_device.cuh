@@ -64,6 +64,7 @@ PF_DEV unsigned pf_lanemask_lt(void) { unsigned m; asm("mov.u32 %0, %%lanemask_l
 PF_DEV int pf_atomic_add_i(int *p, int v) { return atomicAdd(p, v); }
 PF_DEV unsigned long long pf_atomic_add_ull(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 PF_DEV int pf_atomic_or_i(int *p, int v) { return atomicOr(p, v); }
+PF_DEV int pf_atomic_min_i(int *p, int v) { return atomicMin(p, v); }   /* used on shared memory (ATOMS) */
 PF_DEV pf_u4 pf_ld_cg_u4(const void *p) { return __ldcg((const uint4 *)p); }   /* L2-coherent: sees other SMs' atomics */
 PF_DEV pf_u4 pf_ld_u4(const void *p) { return *(const uint4 *)p; }
 PF_DEV void pf_st_u4(void *p, pf_u4 v) { *(uint4 *)p = v; }
@@ -94,7 +95,7 @@ struct PfWarp {
 	PfLabel *labels; unsigned label_mask; int label_shift;
 	PfTreeNode *tree; uint64_t *far; int *iscratch;
 	/* search state: warp-uniform */
-	unsigned epoch; int n_labels; int sh_n; int far_n; float T_hi; float far_min; float best;
+	unsigned epoch; unsigned round; int n_labels; int sh_n; int far_n; float T_hi; float far_min; float best;
 	int overflow;
 	/* per-net constants */
 	int bb_xmin, bb_xmax, bb_ymin, bb_ymax; int num_sinks;
@@ -196,8 +197,8 @@ PF_DEV int pf_label_find(const PfWarp &w, int node) {
  * existing label only if both its total and its backward cost are lower (the pop rule of
  * route_timing.c:511, applied at relax time).  Two lanes may target the same table slot in the same
  * round — the same node reached over two edges, or two nodes probing the same empty slot; a per-warp
- * shared-memory ticket array arbitrates: one writer per ticket and round, the others re-probe in the
- * next round and see the winner's label.  `pre` is the caller's prefetch of the first probe (issued
+ * shared-memory ticket array arbitrates (atomicMin: lowest lane wins): one writer per ticket and round,
+ * the others re-probe in the next round and see the winner's label.  `pre` is the caller's prefetch of the first probe (issued
  * together with the node-record load so the two HBM round trips overlap).  Returns 1 in lanes whose
  * candidate was written. */
 PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back, float R_up, int prev, int info,
@@ -220,9 +221,13 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 			}
 		}
 		first = 0;
-		if (want) w.ticket[h & (PF_TICKETS - 1)] = lane;
+		/* lowest lane wins a contested ticket (deterministic); the round tag decreases every round so
+		 * tickets never need clearing */
+		const int tk = (int)(((0x3ffffffu - (w.round & 0x3ffffffu)) << 5) | (unsigned)lane);
+		w.round++;
+		if (want) pf_atomic_min_i(&w.ticket[h & (PF_TICKETS - 1)], tk);
 		pf_syncwarp();
-		int win = want && w.ticket[h & (PF_TICKETS - 1)] == lane;
+		int win = want && w.ticket[h & (PF_TICKETS - 1)] == tk;
 		if (win) {
 			PfLabel *L = &w.labels[h];
 			pf_u4 n0, n1;
@@ -883,6 +888,8 @@ PF_DEV void pf_warp_main(const PfParams *P, int slot, unsigned char *smem_warp) 
 	w.far = P->far + (long long)slot * P->far_cap;
 	w.iscratch = P->iscratch + (long long)slot * (3 * (P->sink_cap + 2) + 2 * P->tree_cap);
 	w.epoch = P->epochs[slot];
+	w.round = 0;
+	for (int i = lane; i < PF_TICKETS; i += PF_WARP) w.ticket[i] = 0x7fffffff;
 	w.pops = w.pushes = w.visits = w.refills = w.stale = 0;
 	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.T_hi = 0.f; w.far_min = PF_INF_F; w.best = PF_INF_F; w.overflow = 0;
 	w.bb_xmin = w.bb_xmax = w.bb_ymin = w.bb_ymax = 0; w.num_sinks = 0;
