@@ -67,6 +67,13 @@ PF_DEV int pf_atomic_or_i(int *p, int v) { return atomicOr(p, v); }
 PF_DEV int pf_atomic_min_i(int *p, int v) { return atomicMin(p, v); }   /* used on shared memory (ATOMS) */
 PF_DEV pf_u4 pf_ld_cg_u4(const void *p) { return __ldcg((const uint4 *)p); }   /* L2-coherent: sees other SMs' atomics */
 PF_DEV pf_u4 pf_ld_u4(const void *p) { return *(const uint4 *)p; }
+struct pf_u8 { unsigned a, b, c, d, e, f, g, h; };
+/* one 256-bit L2-coherent load (LDG.E.256, sm_100): a whole 32-byte node record in one request */
+PF_DEV pf_u8 pf_ld_cg_u8(const void *p) {
+	pf_u8 v;
+	asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(v.a), "=r"(v.b), "=r"(v.c), "=r"(v.d), "=r"(v.e), "=r"(v.f), "=r"(v.g), "=r"(v.h) : "l"(p));
+	return v;
+}
 PF_DEV void pf_st_u4(void *p, pf_u4 v) { *(uint4 *)p = v; }
 PF_DEV float pf_int_as_float(int i) { return __int_as_float(i); }
 PF_DEV int pf_float_as_int(float f) { return __float_as_int(f); }
@@ -92,7 +99,7 @@ struct PfWarp {
 	PfIndexedDev *idx;            /* [PF_MAX_INDEXED] */
 	PfSwitchDev *sw;              /* [PF_MAX_SWITCHES] */
 	/* slot memory */
-	PfLabel *labels; unsigned label_mask; int label_shift;
+	uint64_t *hot; PfCold *cold; unsigned label_mask; int label_shift; int label_limit;
 	PfTreeNode *tree; uint64_t *far; int *iscratch;
 	/* search state: warp-uniform */
 	unsigned epoch; unsigned round; int n_labels; int sh_n; int far_n; float T_hi; float far_min; float best;
@@ -105,7 +112,7 @@ struct PfWarp {
 
 /* fr 1536 + b_key 256 + idx 1024 + sw 768 + base_cost 128 + 5 batch arrays 640 + b_pre 136 + tickets 256 = 4744 → 4864 */
 #define PF_TICKETS 64
-#define PF_SMEM_PER_WARP 4864
+#define PF_SMEM_PER_WARP 4864                       /* + PF_SMEM_HOT_ENTRIES * 8 when the hot table is in shared memory */
 
 PF_DEV float pf_key_tot(uint64_t k) { return pf_int_as_float((int)(k >> 32)); }
 PF_DEV int pf_key_node(uint64_t k) { return (int)(uint32_t)k; }
@@ -180,15 +187,19 @@ PF_DEV float pf_expected_cost(const PfWarp &w, int type, int ci, int ixlow, int 
 PF_DEV unsigned pf_hash(const PfWarp &w, int node) {
 	return ((uint32_t)node * 2654435761u) >> w.label_shift;
 }
+PF_DEV uint64_t pf_hot_make(const PfWarp &w, float tot, int node) {
+	return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | ((w.epoch & 63u) << PF_HOT_TAG_SHIFT) | (uint32_t)node;
+}
+PF_DEV int pf_hot_live(const PfWarp &w, uint64_t k) { return (((uint32_t)k) >> PF_HOT_TAG_SHIFT) == (w.epoch & 63u); }
+PF_DEV int pf_hot_node(uint64_t k) { return (int)((uint32_t)k & PF_HOT_NODE_MASK); }
 
 /* Look up an existing label (used at settle time and in the back-trace).  Per-lane, no collectives. */
 PF_DEV int pf_label_find(const PfWarp &w, int node) {
 	unsigned h = pf_hash(w, node);
 	for (;;) {
-		const PfLabel *L = &w.labels[h];
-		pf_u4 a = pf_ld_u4(L);
-		if (a.y != w.epoch) return -1;
-		if ((int)a.x == node) return (int)h;
+		uint64_t k = w.hot[h];
+		if (!pf_hot_live(w, k)) return -1;
+		if (pf_hot_node(k) == node) return (int)h;
 		h = (h + 1) & w.label_mask;
 	}
 }
@@ -198,21 +209,21 @@ PF_DEV int pf_label_find(const PfWarp &w, int node) {
  * route_timing.c:511, applied at relax time).  Two lanes may target the same table slot in the same
  * round — the same node reached over two edges, or two nodes probing the same empty slot; a per-warp
  * shared-memory ticket array arbitrates (atomicMin: lowest lane wins): one writer per ticket and round,
- * the others re-probe in the next round and see the winner's label.  `pre` is the caller's prefetch of the first probe (issued
- * together with the node-record load so the two HBM round trips overlap).  Returns 1 in lanes whose
+ * the others re-probe in the next round and see the winner's label.  Returns 1 in lanes whose
  * candidate was written. */
 PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back, float R_up, int prev, int info,
-		int edge_start, unsigned h, pf_u4 pre) {
+		int edge_start) {
 	const int lane = pf_lane();
-	int pending = valid, written = 0, first = 1;
+	unsigned h = pf_hash(w, node);
+	int pending = valid, written = 0;
 	while (pf_any(pending)) {
 		int want = 0;                                   /* 1: claim an empty slot, 2: improve my node's label */
 		if (pending) {
-			pf_u4 a = first ? pre : pf_ld_u4(&w.labels[h]);
-			if (a.y == w.epoch) {
-				if ((int)a.x == node) {
-					float otot = pf_int_as_float((int)a.z), oback = pf_int_as_float((int)a.w);
-					if (tot < otot && back < oback) want = 2; else pending = 0;
+			uint64_t k = w.hot[h];
+			if (pf_hot_live(w, k)) {
+				if (pf_hot_node(k) == node) {
+					float otot = pf_int_as_float((int)(k >> 32));
+					if (tot < otot && back < w.cold[h].back) want = 2; else pending = 0;
 				} else {
 					h = (h + 1) & w.label_mask;
 				}
@@ -220,7 +231,6 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 				want = 1;
 			}
 		}
-		first = 0;
 		/* lowest lane wins a contested ticket (deterministic); the round tag decreases every round so
 		 * tickets never need clearing */
 		const int tk = (int)(((0x3ffffffu - (w.round & 0x3ffffffu)) << 5) | (unsigned)lane);
@@ -229,17 +239,17 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 		pf_syncwarp();
 		int win = want && w.ticket[h & (PF_TICKETS - 1)] == tk;
 		if (win) {
-			PfLabel *L = &w.labels[h];
-			pf_u4 n0, n1;
-			n0.x = (unsigned)node; n0.y = w.epoch; n0.z = (unsigned)pf_float_as_int(tot); n0.w = (unsigned)pf_float_as_int(back);
-			n1.x = (unsigned)pf_float_as_int(R_up); n1.y = (unsigned)prev; n1.z = (unsigned)info; n1.w = (unsigned)edge_start;
-			pf_st_u4(L, n0); pf_st_u4((char *)L + 16, n1);
+			pf_u4 c0, c1;
+			c0.x = (unsigned)pf_float_as_int(back); c0.y = (unsigned)pf_float_as_int(R_up); c0.z = (unsigned)prev; c0.w = (unsigned)info;
+			c1.x = (unsigned)edge_start; c1.y = c1.z = c1.w = 0;
+			w.hot[h] = pf_hot_make(w, tot, node);
+			pf_st_u4(&w.cold[h], c0); pf_st_u4((char *)&w.cold[h] + 16, c1);
 			written = 1; pending = 0;
 		}
 		pf_syncwarp();                                  /* tickets reusable; label stores ordered before re-probes */
 		w.n_labels += pf_popc(pf_ballot(win && want == 1));
 	}
-	if (w.n_labels > (int)(w.label_mask >> 1)) w.overflow = 1;
+	if (w.n_labels > w.label_limit) w.overflow = 1;
 	return written;
 }
 
@@ -339,16 +349,15 @@ PF_DEV void pf_refill(PfWarp &w) {
 struct PfNodeView { int xlow, ylow, xhigh, yhigh; float R, C; int occ; float acc; int edge_start, num_edges, type, ci, cap; };
 
 PF_DEV PfNodeView pf_load_node(const PfParams *P, int v) {
-	const char *p = (const char *)&P->nodes[v];
-	pf_u4 lo = pf_ld_cg_u4(p), hi = pf_ld_cg_u4(p + 16);
+	pf_u8 r = pf_ld_cg_u8(&P->nodes[v]);
 	PfNodeView n;
-	n.xlow = (short)(lo.x & 0xffffu); n.ylow = (short)(lo.x >> 16);
-	n.xhigh = (short)(lo.y & 0xffffu); n.yhigh = (short)(lo.y >> 16);
-	n.R = pf_int_as_float((int)lo.z); n.C = pf_int_as_float((int)lo.w);
-	n.occ = (int)hi.x; n.acc = pf_int_as_float((int)hi.y); n.edge_start = (int)hi.z;
-	n.num_edges = (int)(hi.w & 0xffffu);
-	int tc = (int)((hi.w >> 16) & 0xffu);
-	n.type = tc & 7; n.ci = tc >> 3; n.cap = (int)(hi.w >> 24);
+	n.xlow = (short)(r.a & 0xffffu); n.ylow = (short)(r.a >> 16);
+	n.xhigh = (short)(r.b & 0xffffu); n.yhigh = (short)(r.b >> 16);
+	n.R = pf_int_as_float((int)r.c); n.C = pf_int_as_float((int)r.d);
+	n.occ = (int)r.e; n.acc = pf_int_as_float((int)r.f); n.edge_start = (int)r.g;
+	n.num_edges = (int)(r.h & 0xffffu);
+	int tc = (int)((r.h >> 16) & 0xffu);
+	n.type = tc & 7; n.ci = tc >> 3; n.cap = (int)(r.h >> 24);
 	return n;
 }
 
@@ -390,6 +399,11 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 	const int highfan = w.num_sinks >= 64;
 
 	w.epoch++;
+	if ((w.epoch & 63u) == 0) {                  /* tag wrapped: wipe the hot table, skip tag 0 (= never written) */
+		for (unsigned i = (unsigned)lane; i <= w.label_mask; i += PF_WARP) w.hot[i] = 0;
+		w.epoch++;
+		pf_syncwarp();
+	}
 	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.far_min = PF_INF_F; w.best = PF_INF_F;
 	/* delta-stepping bucket width: a multiple of the cheapest possible edge for this criticality
 	 * (an uncongested wire: (1-crit)*base_cost + crit*T_linear) */
@@ -431,9 +445,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 				tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
 			}
 		}
-		unsigned h0 = pf_hash(w, node);
-		pf_u4 pre0 = pf_ld_u4(&w.labels[h0]);
-		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1, h0, pre0);
+		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
 		pf_push(w, wr, tot, node);
 		if (w.overflow) return -1;
 	}
@@ -481,16 +493,16 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 			int u = pf_key_node(k);
 			int h = pf_label_find(w, u);
 			if (h >= 0) {
-				const PfLabel *L = &w.labels[h];
-				pf_u4 a = pf_ld_u4(L), b = pf_ld_u4((const char *)L + 16);
-				if (pf_int_as_float((int)a.z) == pf_key_tot(k)) {   /* else stale: the node was re-labelled cheaper */
-					int es = (int)b.w, ty = (int)((b.z >> 8) & 0xffu);
-					deg = (int)(b.z >> 16);
+				uint64_t hk = w.hot[h];
+				if (pf_int_as_float((int)(hk >> 32)) == pf_key_tot(k)) {   /* else stale: the node was re-labelled cheaper */
+					pf_u4 a = pf_ld_u4(&w.cold[h]), b = pf_ld_u4((const char *)&w.cold[h] + 16);
+					int es = (int)b.x, ty = (int)((a.w >> 8) & 0xffu);
+					deg = (int)(a.w >> 16);
 					if (es < 0) {                                  /* seed: row not cached in the label */
 						PfNodeView un = pf_load_node(P, u);
 						es = un.edge_start; ty = un.type; deg = un.num_edges;
 					}
-					w.b_node[lane] = u; w.b_back[lane] = pf_int_as_float((int)a.w); w.b_R[lane] = pf_int_as_float((int)b.x);
+					w.b_node[lane] = u; w.b_back[lane] = pf_int_as_float((int)a.x); w.b_R[lane] = pf_int_as_float((int)a.y);
 					w.b_start[lane] = es; w.b_type[lane] = ty;
 					ok = 1;
 				}
@@ -519,15 +531,12 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 			int e = base + lane;
 			int valid = e < M;
 			int to = 0, u = 0, isw = 0, info = 0, es = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
-			unsigned h0 = 0; pf_u4 pre0; pre0.x = pre0.y = pre0.z = pre0.w = 0;
 			if (valid) {
 				int j = 0, hi = taken - 1;                      /* owner: last j with b_pre[j] <= e */
 				while (j < hi) { int mid = (j + hi + 1) >> 1; if (w.b_pre[mid] <= e) j = mid; else hi = mid - 1; }
 				u = w.b_node[j];
 				uint32_t ew = P->edges[w.b_start[j] + (e - w.b_pre[j])];
 				to = (int)(ew & PF_EDGE_NODE_MASK); isw = (int)(ew >> PF_EDGE_NODE_BITS);
-				h0 = pf_hash(w, to);
-				pre0 = pf_ld_u4(&w.labels[h0]);              /* first label probe in flight with the node record */
 				PfNodeView n = pf_load_node(P, to);
 				if (n.xhigh < w.bb_xmin || n.xlow > w.bb_xmax || n.yhigh < w.bb_ymin || n.ylow > w.bb_ymax) valid = 0;
 				if (valid && highfan && (n.xhigh < tgt_xh - rlim || n.xlow > tgt_xh + rlim || n.yhigh < tgt_yh - rlim || n.ylow > tgt_yh + rlim)) valid = 0;
@@ -557,7 +566,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 					info = isw | (n.type << 8) | (n.num_edges << 16); es = n.edge_start;
 				}
 			}
-			int wr = pf_label_relax(w, valid, to, tot, back, R_up, u, info, es, h0, pre0);
+			int wr = pf_label_relax(w, valid, to, tot, back, R_up, u, info, es);
 			/* the target SINK is never expanded; only its best total matters */
 			float tb = pf_warp_min_f((wr && to == target_node) ? tot : PF_INF_F);
 			if (tb < w.best) w.best = tb;
@@ -629,13 +638,12 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
 		for (;;) {
 			int h = pf_label_find(w, v);
 			if (h < 0) { L = -1; break; }
-			const PfLabel *lab = &w.labels[h];
-			pf_u4 b = pf_ld_u4((const char *)lab + 16);
-			int prev = (int)b.y;
+			pf_u4 b = pf_ld_u4(&w.cold[h]);
+			int prev = (int)b.z;
 			if (prev < 0 && v != target_node) { join = ~prev; break; }
 			if (prev < 0) { L = -1; break; }               /* target itself is a seed: cannot happen (SINKs are never seeds) */
 			if (L >= pcap) { L = -2; break; }
-			pathbuf[L] = v; pathbuf[pcap + L] = (int)(b.z & 0xffu);  /* switch used to enter v */
+			pathbuf[L] = v; pathbuf[pcap + L] = (int)(b.w & 0xffu);  /* switch used to enter v */
 			L++;
 			v = prev;
 		}
@@ -881,9 +889,17 @@ PF_DEV void pf_warp_main(const PfParams *P, int slot, unsigned char *smem_warp) 
 	for (int i = lane; i < P->num_indexed; i += PF_WARP) w.idx[i] = P->indexed[i];
 	for (int i = lane; i < P->num_sw; i += PF_WARP) w.sw[i] = P->sw[i];
 	const long long cap = 1ll << P->label_log2;
-	w.labels = P->labels + (long long)slot * cap;
+	w.cold = P->cold + (long long)slot * cap;
 	w.label_mask = (unsigned)(cap - 1);
 	w.label_shift = 32 - P->label_log2;
+	if (P->hot) {                                     /* big-net slots: hot table in global memory, half full at most */
+		w.hot = P->hot + (long long)slot * cap;
+		w.label_limit = (int)(cap >> 1);
+	} else {                                          /* regular slots: hot table in shared memory, 3/4 full at most */
+		w.hot = (uint64_t *)s; s += PF_SMEM_HOT_ENTRIES * 8;
+		w.label_limit = (int)(cap - (cap >> 2));
+		for (int i = lane; i < PF_SMEM_HOT_ENTRIES; i += PF_WARP) w.hot[i] = 0;
+	}
 	w.tree = P->tree + (long long)slot * P->tree_cap;
 	w.far = P->far + (long long)slot * P->far_cap;
 	w.iscratch = P->iscratch + (long long)slot * (3 * (P->sink_cap + 2) + 2 * P->tree_cap);

@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(256) pf_route_kernel(const __grid_constant__ P
 	const int warp_in_block = (int)(threadIdx.x >> 5);
 	const int slot = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp_in_block;
 	if (slot >= num_slots) return;
-	pf_warp_main(&P, slot, pf_smem + (size_t)warp_in_block * PF_SMEM_PER_WARP);
+	const size_t per_warp = PF_SMEM_PER_WARP + (P.hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8);
+	pf_warp_main(&P, slot, pf_smem + (size_t)warp_in_block * per_warp);
 }
 
 __global__ void pf_update_cost_kernel(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
@@ -206,7 +207,9 @@ int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	if (warps_per_block < 1) warps_per_block = 1;
 	if (warps_per_block > 8) warps_per_block = 8;
 	int blocks = (num_slots + warps_per_block - 1) / warps_per_block;
-	size_t smem = (size_t)warps_per_block * PF_SMEM_PER_WARP;
+	size_t smem = (size_t)warps_per_block * (PF_SMEM_PER_WARP + (P->hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8));
+	static size_t smem_set = 0;
+	if (smem > smem_set) { CK(cudaFuncSetAttribute(pf_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
 	if (ev_begin(0) != 0) return -1;
 	pf_route_kernel<<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
 	return ev_end();

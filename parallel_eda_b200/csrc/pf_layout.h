@@ -31,13 +31,23 @@ struct PfNode {
 struct PfSwitchDev { float R, Tdel; int buffered; };
 struct PfIndexedDev { float base_cost, saved_base_cost, inv_length, T_linear, T_quadratic, C_load; int ortho; int pad; };
 
-/* search label, 32 B (one sector), open-addressed per-warp hash table keyed by node id.
- * `epoch` makes clearing free: a slot belongs to the current sink search iff epoch matches. */
-struct PfLabel {
-	int key; unsigned epoch; float tot; float back;       /* probed / compared */
-	float R_up; int prev; int info; int edge_start;       /* prev >= 0: rr node; prev < 0: ~tree index (seed)
-	                                                         info = entering switch | type << 8 | out-degree << 16;
-	                                                         edge_start < 0: row unknown (seed), read the node record */
+/* Search labels: an open-addressed hash table per warp, keyed by rr node, split in two.
+ *   hot  (8 B/entry): total cost | search tag | node — everything a probe compares.  For the regular
+ *        slots the hot table lives in SHARED memory (1024 entries = 8 KB per warp), so the probe that
+ *        sits on the critical path of every edge relaxation costs a shared-memory access instead of an
+ *        HBM round trip; big-net slots keep it in global memory.
+ *   cold (32 B/entry, global, indexed by the same slot): what a settled label carries — backward cost,
+ *        R_upstream, predecessor, entering switch and the node's CSR row.  Written once per accepted
+ *        relaxation, read once per settled label; 32 KB per warp, so the whole set stays L2-resident.
+ * The 6-bit search tag makes clearing free for 63 consecutive sink searches. */
+#define PF_SMEM_HOT_LOG2 10
+#define PF_SMEM_HOT_ENTRIES (1 << PF_SMEM_HOT_LOG2)
+#define PF_HOT_NODE_MASK 0x03ffffffu
+#define PF_HOT_TAG_SHIFT 26
+struct PfCold {
+	float back; float R_up; int prev; int info;           /* prev >= 0: rr node; prev < 0: ~tree index (seed) */
+	int edge_start; int pad0, pad1, pad2;                  /* info = entering switch | type << 8 | out-degree << 16;
+	                                                          edge_start < 0: row unknown (seed), read the node record */
 };
 
 /* route-tree entry, 32 B.  Entries are appended in path order, so parent index < child index. */
@@ -86,7 +96,8 @@ struct PfParams {
 	int max_batch;
 	int skip_ripup;
 	/* per-warp slot memory */
-	PfLabel *labels; int label_log2;
+	uint64_t *hot;         /* global hot tables (NULL: the hot table lives in shared memory) */
+	PfCold *cold; int label_log2;
 	unsigned *epochs;
 	PfTreeNode *tree; int tree_cap;
 	uint64_t *far; int far_cap;

@@ -32,7 +32,7 @@ extern "C" void pf_config_default(pf_config *c) {
 
 struct SlotClass {
 	int num_slots, label_log2, tree_cap, far_cap, sink_cap;
-	PfLabel *labels; unsigned *epochs; PfTreeNode *tree; uint64_t *far; int *iscratch;
+	uint64_t *hot; PfCold *cold; unsigned *epochs; PfTreeNode *tree; uint64_t *far; int *iscratch;
 	int *work; int num_work; int *work_head;
 };
 
@@ -83,21 +83,22 @@ template <class F> static void parallel_for(long long n, F f) {
 static int ceil_log2(long long v) { int l = 0; while ((1ll << l) < v) l++; return l; }
 
 static void free_slot_class(SlotClass &s) {
-	pfb_free(s.labels); pfb_free(s.epochs); pfb_free(s.tree); pfb_free(s.far); pfb_free(s.iscratch);
+	pfb_free(s.hot); pfb_free(s.cold); pfb_free(s.epochs); pfb_free(s.tree); pfb_free(s.far); pfb_free(s.iscratch);
 	pfb_free(s.work); pfb_free(s.work_head);
 	memset(&s, 0, sizeof(s));
 }
 
-static int alloc_slot_class(SlotClass &s, int max_work) {
+static int alloc_slot_class(SlotClass &s, int max_work, bool hot_in_smem) {
 	size_t cap = (size_t)1 << s.label_log2;
-	s.labels = (PfLabel *)pfb_alloc(sizeof(PfLabel) * cap * s.num_slots);
+	s.hot = hot_in_smem ? NULL : (uint64_t *)pfb_alloc(sizeof(uint64_t) * cap * s.num_slots);
+	s.cold = (PfCold *)pfb_alloc(sizeof(PfCold) * cap * s.num_slots);
 	s.epochs = (unsigned *)pfb_alloc(sizeof(unsigned) * s.num_slots);
 	s.tree = (PfTreeNode *)pfb_alloc(sizeof(PfTreeNode) * (size_t)s.tree_cap * s.num_slots);
 	s.far = (uint64_t *)pfb_alloc(sizeof(uint64_t) * (size_t)s.far_cap * s.num_slots);
 	s.iscratch = (int *)pfb_alloc(sizeof(int) * ((size_t)3 * (s.sink_cap + 2) + (size_t)2 * s.tree_cap) * s.num_slots);
 	s.work = (int *)pfb_alloc(sizeof(int) * (size_t)(max_work > 0 ? max_work : 1));
 	s.work_head = (int *)pfb_alloc(sizeof(int) * 4);
-	if (!s.labels || !s.epochs || !s.tree || !s.far || !s.iscratch || !s.work || !s.work_head) return -1;
+	if ((!hot_in_smem && !s.hot) || !s.cold || !s.epochs || !s.tree || !s.far || !s.iscratch || !s.work || !s.work_head) return -1;
 	return 0;
 }
 
@@ -172,7 +173,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	int sms = pfb_num_sms();
 	if (c.warps_per_block <= 0) c.warps_per_block = 4;
 	if (c.num_slots <= 0) c.num_slots = (sms > 0 ? sms : 148) * 16;
-	if (c.label_log2 <= 0) c.label_log2 = 13;
+	c.label_log2 = PF_SMEM_HOT_LOG2;                 /* regular slots: hot label table in shared memory */
 	if (c.tree_cap <= 0) c.tree_cap = 2048;
 	if (c.far_cap <= 0) c.far_cap = 8192;
 	if (c.sink_cap <= 0) c.sink_cap = 64;
@@ -262,7 +263,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->big.num_slots = c.big_slots; r->big.label_log2 = c.big_label_log2; r->big.tree_cap = c.big_tree_cap;
 	r->big.far_cap = c.big_far_cap; r->big.sink_cap = std::max(max_sinks, c.sink_cap);
 	int nwork = (int)(r->work_small.size() + r->work_big.size());
-	if (alloc_slot_class(r->small, nwork) || alloc_slot_class(r->big, nwork)) { pf_router_destroy(r); CUDA_FAIL(); }
+	if (alloc_slot_class(r->small, nwork, true) || alloc_slot_class(r->big, nwork, false)) { pf_router_destroy(r); CUDA_FAIL(); }
 	/* route store */
 	r->pool_cap = std::max<long long>(1 << 16, 4ll * r->N + 96ll * r->T);
 	for (int k = 0; k < 2; k++) {
@@ -357,7 +358,7 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.win_abs = c.win_abs > 0.f ? c.win_abs : r->win_abs_auto;
 	P.max_batch = c.max_batch;
 	P.skip_ripup = 0;
-	P.labels = s.labels; P.label_log2 = s.label_log2; P.epochs = s.epochs;
+	P.hot = s.hot; P.cold = s.cold; P.label_log2 = s.label_log2; P.epochs = s.epochs;
 	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap;
 	P.iscratch = s.iscratch; P.sink_cap = s.sink_cap;
 	P.pool = r->pool[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;

@@ -37,11 +37,11 @@ int pfb_num_sms(void) { const char *e = getenv("PF_EMU_SMS"); return e ? atoi(e)
 struct RouteArg { const PfParams *P; std::vector<unsigned char> *smem; };
 static void route_warp(void *arg, int warp_id) {
 	RouteArg *a = (RouteArg *)arg;
-	pf_warp_main(a->P, warp_id, a->smem->data() + (size_t)warp_id * PF_SMEM_PER_WARP);
+	pf_warp_main(a->P, warp_id, a->smem->data() + (size_t)warp_id * (PF_SMEM_PER_WARP + PF_SMEM_HOT_ENTRIES * 8));
 }
 
 int pfb_launch_route(const PfParams *P, int num_slots, int) {
-	std::vector<unsigned char> smem((size_t)num_slots * PF_SMEM_PER_WARP);
+	std::vector<unsigned char> smem((size_t)num_slots * (PF_SMEM_PER_WARP + PF_SMEM_HOT_ENTRIES * 8));
 	RouteArg a = { P, &smem };
 	pf_emu_launch(route_warp, &a, num_slots);
 	g_times.route_launches++;

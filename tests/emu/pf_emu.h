@@ -121,6 +121,8 @@ PF_DEV int pf_atomic_or_i(int *p, int v) { int o = *p; *p = o | v; return o; }
 PF_DEV int pf_atomic_min_i(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
 PF_DEV pf_u4 pf_ld_cg_u4(const void *p) { pf_u4 v; memcpy(&v, p, 16); return v; }   /* L2-coherent load */
 PF_DEV pf_u4 pf_ld_u4(const void *p) { pf_u4 v; memcpy(&v, p, 16); return v; }
+struct pf_u8 { unsigned a, b, c, d, e, f, g, h; };
+PF_DEV pf_u8 pf_ld_cg_u8(const void *p) { pf_u8 v; memcpy(&v, p, 32); return v; }
 PF_DEV void pf_st_u4(void *p, pf_u4 v) { memcpy(p, &v, 16); }
 PF_DEV float pf_int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 PF_DEV int pf_float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
