@@ -50,7 +50,8 @@ typedef struct pf_config {
 	                             of the fanout-sorted order (one process per GPU) */
 	int32_t num_slots;        /* concurrent warps (nets in flight); 0 = 16 per SM */
 	int32_t warps_per_block;  /* 0 = 4 */
-	int32_t label_log2;       /* per-warp label table capacity = 2^label_log2; 0 = 13 */
+	int32_t label_log2;       /* (fixed) the regular slots keep 2^10 hot label entries in shared memory */
+	int32_t label2_log2;      /* per-slot fallback label table in global memory, 2^n entries; 0 = 13, < 0 none */
 	int32_t tree_cap;         /* per-warp route-tree entries; 0 = 2048 */
 	int32_t far_cap;          /* per-warp far-list entries; 0 = 8192 */
 	int32_t sink_cap;         /* nets with more sinks go to the big slots; 0 = 64 */

@@ -100,6 +100,7 @@ struct PfWarp {
 	PfSwitchDev *sw;              /* [PF_MAX_SWITCHES] */
 	/* slot memory */
 	uint64_t *hot; PfCold *cold; unsigned label_mask; int label_shift; int label_limit;
+	uint64_t *hot_alt; PfCold *cold_alt; unsigned mask_alt; int shift_alt; int limit_alt; unsigned epoch_alt;   /* the other table */
 	PfTreeNode *tree; uint64_t *far; int *iscratch;
 	/* search state: warp-uniform */
 	unsigned epoch; unsigned round; int n_labels; int sh_n; int far_n; float T_hi; float far_min; float best;
@@ -111,6 +112,8 @@ struct PfWarp {
 };
 
 /* fr 1536 + b_key 256 + idx 1024 + sw 768 + base_cost 128 + 5 batch arrays 640 + b_pre 136 + tickets 256 = 4744 → 4864 */
+#define PF_OVF_LABELS 1   /* w.overflow bits */
+#define PF_OVF_OTHER 2
 #define PF_TICKETS 64
 #define PF_SMEM_PER_WARP 4864                       /* + PF_SMEM_HOT_ENTRIES * 8 when the hot table is in shared memory */
 
@@ -249,7 +252,7 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 		pf_syncwarp();                                  /* tickets reusable; label stores ordered before re-probes */
 		w.n_labels += pf_popc(pf_ballot(win && want == 1));
 	}
-	if (w.n_labels > w.label_limit) w.overflow = 1;
+	if (w.n_labels > w.label_limit) w.overflow |= PF_OVF_LABELS;
 	return written;
 }
 
@@ -273,7 +276,7 @@ PF_DEV void pf_push(PfWarp &w, int valid, float tot, int node) {
 			if (fpos < w.P->far_cap) w.far[fpos] = key;
 		}
 		w.far_n += pf_popc(m2);
-		if (w.far_n > w.P->far_cap) { w.far_n = w.P->far_cap; w.overflow = 1; }
+		if (w.far_n > w.P->far_cap) { w.far_n = w.P->far_cap; w.overflow |= PF_OVF_OTHER; }
 		float fm = pf_warp_min_f(to_far ? tot : PF_INF_F);
 		if (fm < w.far_min) w.far_min = fm;
 	}
@@ -297,7 +300,7 @@ PF_DEV void pf_refill(PfWarp &w) {
 	}
 	w.far_n += w.sh_n;
 	w.sh_n = 0;
-	if (w.far_n > w.P->far_cap) { w.far_n = w.P->far_cap; w.overflow = 1; }
+	if (w.far_n > w.P->far_cap) { w.far_n = w.P->far_cap; w.overflow |= PF_OVF_OTHER; }
 	pf_syncwarp();
 	/* 2. minimum */
 	uint64_t mk = PF_KEY_MAX;
@@ -765,9 +768,18 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
 	return tree_n + L - 1;
 }
 
+PF_DEV void pf_swap_tables(PfWarp &w) {
+	uint64_t *h = w.hot; w.hot = w.hot_alt; w.hot_alt = h;
+	PfCold *c = w.cold; w.cold = w.cold_alt; w.cold_alt = c;
+	unsigned m = w.label_mask; w.label_mask = w.mask_alt; w.mask_alt = m;
+	int s = w.label_shift; w.label_shift = w.shift_alt; w.shift_alt = s;
+	int l = w.label_limit; w.label_limit = w.limit_alt; w.limit_alt = l;
+	unsigned e = w.epoch; w.epoch = w.epoch_alt; w.epoch_alt = e;
+}
+
 /* ------------------------------------------------------------------ one net
  * timing_driven_route_net, route_timing.c:399-563 */
-PF_DEV void pf_route_net(PfWarp &w, int inet) {
+PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: routed, 0: handed to a bigger slot / failed */
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	const int t0 = P->net_ptr[inet];
@@ -782,7 +794,7 @@ PF_DEV void pf_route_net(PfWarp &w, int inet) {
 		PfNetLoc loc = P->loc[inet];
 		for (int i = lane; i < loc.count; i += PF_WARP) pf_atomic_add_i(&P->nodes[P->pool[loc.off + i].node].occ, -1);
 	}
-	if (ns > P->sink_cap) { w.overflow = 1; }
+	if (ns > P->sink_cap) { w.overflow = PF_OVF_OTHER; }
 
 	float *pin_crit = (float *)w.iscratch;                   /* [1..ns] */
 	int *sink_order = w.iscratch + (P->sink_cap + 2);        /* [1..ns] */
@@ -831,10 +843,26 @@ PF_DEV void pf_route_net(PfWarp &w, int inet) {
 			int rlim = pf_highfanout_rlim(w, tree_n, target_node);
 			if (rlim < 0) { fail = PF_ST_INTERNAL; break; }
 			int r = pf_search_sink(w, tree_n, target_node, crit, rlim);
+			if (r < 0 && w.overflow == PF_OVF_LABELS && w.hot_alt) {
+				/* the search outgrew the shared-memory label table: run it again on this slot's
+				 * fallback table in global memory, then come back for the next sink */
+				pf_swap_tables(w);
+				w.overflow = 0;
+				r = pf_search_sink(w, tree_n, target_node, crit, rlim);
+				if (r > 0) {
+					int si2 = pf_add_path(w, &tree_n, target_node);
+					pf_swap_tables(w);
+					if (si2 < 0) { w.overflow = PF_OVF_OTHER; break; }
+					if (lane == 0) rt_of_sink[target_pin] = si2;
+					pf_syncwarp();
+					continue;
+				}
+				pf_swap_tables(w);
+			}
 			if (r < 0) break;                                 /* overflow: retry in a bigger slot */
 			if (r == 0) { fail = PF_ST_UNROUTABLE; break; }
 			int si = pf_add_path(w, &tree_n, target_node);
-			if (si < 0) { w.overflow = 1; break; }
+			if (si < 0) { w.overflow = PF_OVF_OTHER; break; }
 			if (lane == 0) rt_of_sink[target_pin] = si;
 			pf_syncwarp();
 		}
@@ -849,7 +877,7 @@ PF_DEV void pf_route_net(PfWarp &w, int inet) {
 			else { int k = pf_atomic_add_i(P->retry_count, 1); P->retry_list[k] = inet; }
 		}
 		pf_syncwarp();
-		return;
+		return 0;
 	}
 	/* update_net_delays_from_route_tree, route_tree_timing.c:515-528 */
 	for (int ipin = 1 + lane; ipin <= ns; ipin += PF_WARP) P->net_delay[t0 + ipin] = w.tree[rt_of_sink[ipin]].Tdel;
@@ -861,11 +889,12 @@ PF_DEV void pf_route_net(PfWarp &w, int inet) {
 		if (lane == 0) { pf_atomic_or_i(P->status, PF_ST_POOL_OVERFLOW); P->loc[inet].off = 0; P->loc[inet].count = 0; }
 		for (int i = lane; i < tree_n; i += PF_WARP) pf_atomic_add_i(&P->nodes[w.tree[i].node].occ, -1);
 		pf_syncwarp();
-		return;
+		return 0;
 	}
 	for (int i = lane; i < tree_n; i += PF_WARP) P->pool[off + i] = w.tree[i];
 	if (lane == 0) { P->loc[inet].off = (int)off; P->loc[inet].count = tree_n; }
 	pf_syncwarp();
+	return 1;
 }
 
 /* ------------------------------------------------------------------ warp main: persistent work loop */
@@ -900,10 +929,18 @@ PF_DEV void pf_warp_main(const PfParams *P, int slot, unsigned char *smem_warp) 
 		w.label_limit = (int)(cap - (cap >> 2));
 		for (int i = lane; i < PF_SMEM_HOT_ENTRIES; i += PF_WARP) w.hot[i] = 0;
 	}
+	w.hot_alt = NULL; w.cold_alt = NULL; w.mask_alt = 0; w.shift_alt = 0; w.limit_alt = 0; w.epoch_alt = 0;
+	if (!P->hot && P->hot2) {
+		const long long cap2 = 1ll << P->label2_log2;
+		w.hot_alt = P->hot2 + (long long)slot * cap2; w.cold_alt = P->cold2 + (long long)slot * cap2;
+		w.mask_alt = (unsigned)(cap2 - 1); w.shift_alt = 32 - P->label2_log2; w.limit_alt = (int)(cap2 >> 1);
+		w.epoch_alt = P->epochs[2 * slot + 1];
+	}
 	w.tree = P->tree + (long long)slot * P->tree_cap;
 	w.far = P->far + (long long)slot * P->far_cap;
 	w.iscratch = P->iscratch + (long long)slot * (3 * (P->sink_cap + 2) + 2 * P->tree_cap);
-	w.epoch = P->epochs[slot];
+	/* the shared-memory table starts empty at every launch; a global table keeps its tags across launches */
+	w.epoch = P->hot ? P->epochs[2 * slot] : 0;
 	w.round = 0;
 	for (int i = lane; i < PF_TICKETS; i += PF_WARP) w.ticket[i] = 0x7fffffff;
 	w.pops = w.pushes = w.visits = w.refills = w.stale = 0;
@@ -916,11 +953,11 @@ PF_DEV void pf_warp_main(const PfParams *P, int slot, unsigned char *smem_warp) 
 		if (lane == 0) k = pf_atomic_add_i(P->work_head, 1);
 		k = pf_shfl_i(k, 0);
 		if (k >= P->num_work) break;
-		pf_route_net(w, P->work[k]);
-		nets++;
+		nets += (unsigned long long)pf_route_net(w, P->work[k]);
 	}
 	if (lane == 0) {
-		P->epochs[slot] = w.epoch;
+		if (P->hot) P->epochs[2 * slot] = w.epoch;
+		if (w.hot_alt) P->epochs[2 * slot + 1] = w.epoch_alt;
 		pf_atomic_add_ull(&P->stats->pops, w.pops);
 		pf_atomic_add_ull(&P->stats->pushes, w.pushes);
 		pf_atomic_add_ull(&P->stats->visits, w.visits);

@@ -98,7 +98,9 @@ struct PfParams {
 	/* per-warp slot memory */
 	uint64_t *hot;         /* global hot tables (NULL: the hot table lives in shared memory) */
 	PfCold *cold; int label_log2;
-	unsigned *epochs;
+	uint64_t *hot2; PfCold *cold2; int label2_log2;   /* per-slot fallback table in global memory: a sink search
+	                                                      that outgrows the shared-memory table is restarted on it */
+	unsigned *epochs;      /* [2 * slots]: search tags of the primary / fallback table */
 	PfTreeNode *tree; int tree_cap;
 	uint64_t *far; int far_cap;
 	int *iscratch; int sink_cap;   /* per slot: 3 * (sink_cap+2) ints */

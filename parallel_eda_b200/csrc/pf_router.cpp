@@ -32,7 +32,7 @@ extern "C" void pf_config_default(pf_config *c) {
 
 struct SlotClass {
 	int num_slots, label_log2, tree_cap, far_cap, sink_cap;
-	uint64_t *hot; PfCold *cold; unsigned *epochs; PfTreeNode *tree; uint64_t *far; int *iscratch;
+	uint64_t *hot; PfCold *cold; uint64_t *hot2; PfCold *cold2; int label2_log2; unsigned *epochs; PfTreeNode *tree; uint64_t *far; int *iscratch;
 	int *work; int num_work; int *work_head;
 };
 
@@ -83,7 +83,7 @@ template <class F> static void parallel_for(long long n, F f) {
 static int ceil_log2(long long v) { int l = 0; while ((1ll << l) < v) l++; return l; }
 
 static void free_slot_class(SlotClass &s) {
-	pfb_free(s.hot); pfb_free(s.cold); pfb_free(s.epochs); pfb_free(s.tree); pfb_free(s.far); pfb_free(s.iscratch);
+	pfb_free(s.hot); pfb_free(s.cold); pfb_free(s.hot2); pfb_free(s.cold2); pfb_free(s.epochs); pfb_free(s.tree); pfb_free(s.far); pfb_free(s.iscratch);
 	pfb_free(s.work); pfb_free(s.work_head);
 	memset(&s, 0, sizeof(s));
 }
@@ -92,7 +92,14 @@ static int alloc_slot_class(SlotClass &s, int max_work, bool hot_in_smem) {
 	size_t cap = (size_t)1 << s.label_log2;
 	s.hot = hot_in_smem ? NULL : (uint64_t *)pfb_alloc(sizeof(uint64_t) * cap * s.num_slots);
 	s.cold = (PfCold *)pfb_alloc(sizeof(PfCold) * cap * s.num_slots);
-	s.epochs = (unsigned *)pfb_alloc(sizeof(unsigned) * s.num_slots);
+	s.hot2 = NULL; s.cold2 = NULL;
+	if (hot_in_smem && s.label2_log2 > 0) {
+		size_t cap2 = (size_t)1 << s.label2_log2;
+		s.hot2 = (uint64_t *)pfb_alloc(sizeof(uint64_t) * cap2 * s.num_slots);
+		s.cold2 = (PfCold *)pfb_alloc(sizeof(PfCold) * cap2 * s.num_slots);
+		if (!s.hot2 || !s.cold2) return -1;
+	}
+	s.epochs = (unsigned *)pfb_alloc(sizeof(unsigned) * 2 * s.num_slots);
 	s.tree = (PfTreeNode *)pfb_alloc(sizeof(PfTreeNode) * (size_t)s.tree_cap * s.num_slots);
 	s.far = (uint64_t *)pfb_alloc(sizeof(uint64_t) * (size_t)s.far_cap * s.num_slots);
 	s.iscratch = (int *)pfb_alloc(sizeof(int) * ((size_t)3 * (s.sink_cap + 2) + (size_t)2 * s.tree_cap) * s.num_slots);
@@ -174,6 +181,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.warps_per_block <= 0) c.warps_per_block = 4;
 	if (c.num_slots <= 0) c.num_slots = (sms > 0 ? sms : 148) * 16;
 	c.label_log2 = PF_SMEM_HOT_LOG2;                 /* regular slots: hot label table in shared memory */
+	if (c.label2_log2 == 0) c.label2_log2 = 13;      /* per-slot fallback table in global memory; < 0: none */
+	if (c.label2_log2 < 0) c.label2_log2 = 0;
 	if (c.tree_cap <= 0) c.tree_cap = 2048;
 	if (c.far_cap <= 0) c.far_cap = 8192;
 	if (c.sink_cap <= 0) c.sink_cap = 64;
@@ -259,7 +268,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	}
 	/* slots */
 	r->small.num_slots = c.num_slots; r->small.label_log2 = c.label_log2; r->small.tree_cap = c.tree_cap;
-	r->small.far_cap = c.far_cap; r->small.sink_cap = c.sink_cap;
+	r->small.far_cap = c.far_cap; r->small.sink_cap = c.sink_cap; r->small.label2_log2 = c.label2_log2; r->big.label2_log2 = 0;
 	r->big.num_slots = c.big_slots; r->big.label_log2 = c.big_label_log2; r->big.tree_cap = c.big_tree_cap;
 	r->big.far_cap = c.big_far_cap; r->big.sink_cap = std::max(max_sinks, c.sink_cap);
 	int nwork = (int)(r->work_small.size() + r->work_big.size());
@@ -359,6 +368,7 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.max_batch = c.max_batch;
 	P.skip_ripup = 0;
 	P.hot = s.hot; P.cold = s.cold; P.label_log2 = s.label_log2; P.epochs = s.epochs;
+	P.hot2 = s.hot2; P.cold2 = s.cold2; P.label2_log2 = s.label2_log2;
 	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap;
 	P.iscratch = s.iscratch; P.sink_cap = s.sink_cap;
 	P.pool = r->pool[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;

@@ -70,7 +70,7 @@ class _Result(C.Structure):
 
 class Config(C.Structure):
     """pf_config (include/pf_router.h).  Zero fields mean "auto"."""
-    _fields_ = [(n, C.c_int32) for n in ("device", "rank", "nranks", "num_slots", "warps_per_block", "label_log2",
+    _fields_ = [(n, C.c_int32) for n in ("device", "rank", "nranks", "num_slots", "warps_per_block", "label_log2", "label2_log2",
                                          "tree_cap", "far_cap", "sink_cap", "big_slots", "big_label_log2",
                                          "big_tree_cap", "big_far_cap", "max_batch")] + \
                [("pop_slack", C.c_float), ("win_rel", C.c_float), ("win_abs", C.c_float), ("verbose", C.c_int32),
