@@ -51,6 +51,10 @@ def parse():
     ap.add_argument("--cpu-sample-iters", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--max-batch", type=int, default=0, help="tuning: labels settled per step (0 = library default)")
+    ap.add_argument("--pop-slack", type=float, default=-1.0, help="tuning: delta bucket width (<0 = library default)")
+    ap.add_argument("--inflight-div", type=int, default=0)
+    ap.add_argument("--slots", type=int, default=0)
     return ap.parse_args()
 
 
@@ -154,7 +158,8 @@ def run_ours(a):
     torch.cuda.set_device(dev)
 
     p = router.generate_grid_problem(nx=a.grid, ny=a.grid, W=a.width, num_nets=a.nets)
-    cfg = router.default_config(device=local, rank=rank, nranks=world)
+    cfg = router.default_config(device=local, rank=rank, nranks=world, max_batch=a.max_batch, pop_slack=a.pop_slack,
+                                inflight_div=a.inflight_div, num_slots=a.slots)
     R = router.Router(p, cfg)
     R.timing(reset=True)
     delta = torch.zeros(p.num_nodes, dtype=torch.int32, device=dev) if comm else None

@@ -57,8 +57,9 @@ typedef struct pf_config {
 	int32_t sink_cap;         /* nets with more sinks go to the big slots; 0 = 64 */
 	int32_t big_slots;        /* warps with large scratch for big / overflowed nets; 0 = 64 */
 	int32_t big_label_log2, big_tree_cap, big_far_cap;   /* 0 = sized from the problem */
-	int32_t max_batch;        /* labels settled per step (delta bucket), 1..32; 0 = 32 */
-	float pop_slack;          /* delta-stepping bucket width in units of the cheapest edge cost; <0 = auto (0.25) */
+	int32_t max_batch;        /* labels settled per step (delta bucket), 1..32; 0 = auto: 1 when nets >> warps
+	                             (traffic-bound: strict best-first does the least work), 32 otherwise (latency-bound) */
+	float pop_slack;          /* delta-stepping bucket width in units of the cheapest edge cost; <0 = auto (0 / 0.25) */
 	float win_rel, win_abs;   /* near-set window; 0 = auto */
 	int32_t verbose;
 	int32_t reroute_all_iters;/* the first K iterations re-route every net (the serial reference re-routes

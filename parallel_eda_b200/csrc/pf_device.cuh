@@ -118,8 +118,15 @@ struct PfWarp {
 #define PF_SMEM_PER_WARP 4864                       /* + PF_SMEM_HOT_ENTRIES * 8 when the hot table is in shared memory */
 
 PF_DEV float pf_key_tot(uint64_t k) { return pf_int_as_float((int)(k >> 32)); }
-PF_DEV int pf_key_node(uint64_t k) { return (int)(uint32_t)k; }
-PF_DEV uint64_t pf_make_key(float tot, int node) { return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | (uint32_t)node; }
+PF_DEV int pf_key_node(uint64_t k) { return (int)((uint32_t)k & 0x03ffffffu); }
+/* frontier key: total cost, then — among equal totals — the label that is further along (larger share of
+ * known backward cost) first, the classic A* tie-break that keeps a symmetric routing fabric from being
+ * flooded breadth-first; then the node id */
+PF_DEV uint64_t pf_make_key(float tot, float back, int node) {
+	int q = 63 - (int)(63.f * (back / (tot > 0.f ? tot : 1.f)));
+	q = q < 0 ? 0 : (q > 63 ? 63 : q);
+	return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | ((uint32_t)q << 26) | (uint32_t)node;
+}
 #define PF_INF_F 3.0e38f
 #define PF_KEY_MAX 0xffffffffffffffffull
 
@@ -259,8 +266,8 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 /* ------------------------------------------------------------------ frontier */
 /* Warp-collective push.  Labels inside the near window go to shared memory, the rest (and any
  * near-set overflow) to the far list in HBM; far_min guards the best-first order. */
-PF_DEV void pf_push(PfWarp &w, int valid, float tot, int node) {
-	uint64_t key = pf_make_key(tot, node);
+PF_DEV void pf_push(PfWarp &w, int valid, float tot, float back, int node) {
+	uint64_t key = pf_make_key(tot, back, node);
 	int to_sh = valid && tot <= w.T_hi;
 	unsigned m1 = pf_ballot(to_sh);
 	int pos = w.sh_n + pf_popc(m1 & pf_lanemask_lt());
@@ -449,7 +456,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 			}
 		}
 		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
-		pf_push(w, wr, tot, node);
+		pf_push(w, wr, tot, back, node);
 		if (w.overflow) return -1;
 	}
 
@@ -573,7 +580,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 			/* the target SINK is never expanded; only its best total matters */
 			float tb = pf_warp_min_f((wr && to == target_node) ? tot : PF_INF_F);
 			if (tb < w.best) w.best = tb;
-			pf_push(w, wr && to != target_node, tot, to);
+			pf_push(w, wr && to != target_node, tot, back, to);
 			if (w.overflow) return -1;
 		}
 	}

@@ -187,12 +187,12 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.far_cap <= 0) c.far_cap = 8192;
 	if (c.sink_cap <= 0) c.sink_cap = 64;
 	if (c.big_slots <= 0) c.big_slots = 64;
-	if (c.max_batch <= 0) c.max_batch = 32;
 	if (c.reroute_all_iters == 0) c.reroute_all_iters = 1;
 	if (c.inflight_div <= 0) c.inflight_div = 32;
 	if (c.min_slots <= 0) c.min_slots = 1;
 	if (c.stall_iters == 0) c.stall_iters = 3;
 	if (c.max_batch > PF_MAX_BATCH) c.max_batch = PF_MAX_BATCH;
+	if (c.max_batch < 0) c.max_batch = 0;
 
 	/* work lists: routed nets in decreasing-fanout order (route_timing.c:98-106), sharded by rank */
 	std::vector<int> order;
@@ -351,6 +351,16 @@ extern "C" int pf_router_reset(pf_router *r) {
 	return PF_OK;
 }
 
+/* Search granularity.  With many more nets than warps the kernel is bound by memory traffic, and strict
+ * best-first order (one label per step, no bucket slack) does the least work; with few nets per warp the
+ * latency of one search is what matters, and settling a whole delta bucket per step shortens it. */
+static void tune_granularity(const pf_router *r, PfParams &P, int work, int slots) {
+	const pf_config &c = r->cfg;
+	const bool throughput = slots > 0 && work >= 4 * slots;
+	P.max_batch = c.max_batch > 0 ? c.max_batch : (throughput ? 1 : 32);
+	P.pop_slack = c.pop_slack >= 0.f ? c.pop_slack : (throughput ? 0.f : 0.25f);
+}
+
 static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pres_fac) {
 	const pf_problem *p = r->prob;
 	const pf_config &c = r->cfg;
@@ -362,10 +372,10 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.crit = r->crit; P.net_delay = r->net_delay;
 	P.pres_fac = pres_fac; P.astar_fac = p->opts.astar_fac; P.bend_cost = p->opts.bend_cost;
 	P.max_crit = p->opts.max_criticality; P.crit_exp = p->opts.criticality_exp;
-	P.pop_slack = c.pop_slack >= 0.f ? c.pop_slack : 0.25f;
+	P.pop_slack = 0.f;
 	P.win_rel = c.win_rel > 0.f ? c.win_rel : 0.05f;
 	P.win_abs = c.win_abs > 0.f ? c.win_abs : r->win_abs_auto;
-	P.max_batch = c.max_batch;
+	P.max_batch = 1;
 	P.skip_ripup = 0;
 	P.hot = s.hot; P.cold = s.cold; P.label_log2 = s.label_log2; P.epochs = s.epochs;
 	P.hot2 = s.hot2; P.cold2 = s.cold2; P.label2_log2 = s.label2_log2;
@@ -473,14 +483,14 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 		r->big.num_work = bc;
 		fill_params(r, P, r->big, pres_fac);
 		P.work = r->big.work + bo;
-		CKB(pfb_launch_route(&P, slots_for(r, total, std::min(r->big.num_slots, bc), div), 1));
+		{ int sl = slots_for(r, total, std::min(r->big.num_slots, bc), div); tune_granularity(r, P, bc, sl); CKB(pfb_launch_route(&P, sl, 1)); }
 	}
 	if (sc > 0) {
 		CKB(pfb_zero(r->small.work_head, sizeof(int) * 4));
 		r->small.num_work = sc;
 		fill_params(r, P, r->small, pres_fac);
 		P.work = r->small.work + so;
-		CKB(pfb_launch_route(&P, slots_for(r, total, r->small.num_slots, div), r->cfg.warps_per_block));
+		{ int sl = slots_for(r, total, r->small.num_slots, div); tune_granularity(r, P, sc, sl); CKB(pfb_launch_route(&P, sl, r->cfg.warps_per_block)); }
 	}
 	CKB(pfb_sync());
 	/* nets whose scratch overflowed in a small slot are re-routed in the big slots, and stay there */
@@ -503,7 +513,7 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 		fill_params(r, P, r->big, pres_fac);
 		P.work = r->retry_work;
 		P.skip_ripup = 1;
-		CKB(pfb_launch_route(&P, slots_for(r, (int)lst.size(), std::min(r->big.num_slots, (int)lst.size()), div), 1));
+		{ int sl = slots_for(r, (int)lst.size(), std::min(r->big.num_slots, (int)lst.size()), div); tune_granularity(r, P, (int)lst.size(), sl); CKB(pfb_launch_route(&P, sl, 1)); }
 		CKB(pfb_sync());
 		CKB(pfb_d2h(h_retry, r->retry_count, sizeof(int) * 4));
 	}
