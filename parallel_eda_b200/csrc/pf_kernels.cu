@@ -52,6 +52,12 @@ int pfb_init(int device) {
 		g_sms = prop.multiProcessorCount;
 		if (g_stream) cudaStreamDestroy(g_stream);
 		CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+		{
+			cudaMemPool_t pool;
+			unsigned long long keep = ~0ull;
+			CK(cudaDeviceGetDefaultMemPool(&pool, device));
+			CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+		}
 		g_device = device;
 		memset(&g_times, 0, sizeof(g_times));
 	}
@@ -60,14 +66,35 @@ int pfb_init(int device) {
 
 int pfb_num_sms(void) { return g_sms; }
 
-void *pfb_alloc(size_t bytes) {
+/* Stream-ordered allocation from the device's default memory pool with an unlimited release threshold:
+ * the first router pays for mapping its ~GBs of scratch, later create/destroy cycles (the binary search
+ * over channel widths calls the router repeatedly, place_and_route.c:557,664) reuse the cached blocks. */
+void *pfb_alloc_raw(size_t bytes) {
 	void *p = NULL;
 	if (bytes == 0) bytes = 16;
-	if (cudaMalloc(&p, bytes) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMalloc(%zu) failed", bytes); cudaGetLastError(); return NULL; }
-	if (cudaMemsetAsync(p, 0, bytes, g_stream) != cudaSuccess) { cudaFree(p); return NULL; }
+	if (cudaMallocAsync(&p, bytes, g_stream) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMallocAsync(%zu) failed", bytes); cudaGetLastError(); return NULL; }
 	return p;
 }
-void pfb_free(void *p) { if (p) cudaFree(p); }
+void *pfb_alloc(size_t bytes) {
+	void *p = pfb_alloc_raw(bytes);
+	if (bytes == 0) bytes = 16;
+	if (p && cudaMemsetAsync(p, 0, bytes, g_stream) != cudaSuccess) { cudaFreeAsync(p, g_stream); return NULL; }
+	return p;
+}
+void pfb_free(void *p) { if (p) cudaFreeAsync(p, g_stream); }
+
+/* process-wide pinned staging buffer for host<->device transfers of the big arrays */
+static void *g_pinned = NULL; static size_t g_pinned_bytes = 0;
+void *pfb_pinned(size_t bytes) {
+	if (bytes <= g_pinned_bytes) return g_pinned;
+	if (g_pinned) { cudaStreamSynchronize(g_stream); cudaFreeHost(g_pinned); g_pinned = NULL; g_pinned_bytes = 0; }
+	size_t want = bytes + (bytes >> 3);
+	if (cudaHostAlloc(&g_pinned, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); g_pinned = NULL; return NULL; }
+	g_pinned_bytes = want;
+	return g_pinned;
+}
+int pfb_h2d_async(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); return 0; }
+int pfb_d2h_async(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); return 0; }
 int pfb_h2d(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); CK(cudaStreamSynchronize(g_stream)); return 0; }
 int pfb_d2h(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream)); return 0; }
 int pfb_d2d(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream)); return 0; }

@@ -80,6 +80,57 @@ template <class F> static void parallel_for(long long n, F f) {
 	for (auto &t : th) t.join();
 }
 
+/* pf_problem_check (pf_file.c) is a single-threaded scan; on 10^8 edges that is a visible part of the call.
+ * This runs the range checks of the big arrays in parallel and defers to the serial checker only for the
+ * error message. */
+static bool problem_arrays_ok(const pf_problem *p) {
+	if (p->nx <= 0 || p->ny <= 0 || p->num_nodes <= 0 || p->num_indexed < PF_CHANX_COST_INDEX_START) return false;
+	if (!p->row_ptr || p->row_ptr[0] != 0 || p->row_ptr[p->num_nodes] != p->num_edges) return false;
+	std::vector<int> bad(64, 0);
+	std::vector<int> *pb = &bad;
+	parallel_for(p->num_nodes, [=](long long lo, long long hi) {
+		int b = 0;
+		for (long long i = lo; i < hi; i++) {
+			int d = p->row_ptr[i + 1] - p->row_ptr[i];
+			b |= (d < 0) | (d > 32767) | (p->type[i] > PF_CHANY) | (p->cost_index[i] < 0) | (p->cost_index[i] >= p->num_indexed)
+				| (p->xlow[i] > p->xhigh[i]) | (p->ylow[i] > p->yhigh[i]) | (p->xlow[i] < 0) | (p->ylow[i] < 0)
+				| (p->xhigh[i] > p->nx + 1) | (p->yhigh[i] > p->ny + 1) | (p->capacity[i] < 0) | (p->capacity[i] > 255) | (p->cost_index[i] > 31);
+		}
+		if (b) (*pb)[(size_t)(lo % 64)] = 1;
+	});
+	parallel_for(p->num_edges, [=](long long lo, long long hi) {
+		int b = 0;
+		for (long long k = lo; k < hi; k++)
+			b |= (p->edge_to[k] < 0) | (p->edge_to[k] >= p->num_nodes) | (p->edge_sw[k] < 0) | (p->edge_sw[k] >= p->num_switches);
+		if (b) (*pb)[(size_t)(lo % 64)] = 1;
+	});
+	for (int v : bad) if (v) return false;
+	return true;
+}
+
+/* nets / tables part of pf_problem_check (small arrays), serial */
+static bool problem_nets_ok(const pf_problem *p) {
+	if (p->net_ptr[0] != 0 || p->net_ptr[p->num_nets] != p->num_terminals) return false;
+	for (int i = 0; i < p->num_nets; i++) {
+		int b = p->net_ptr[i], e = p->net_ptr[i + 1];
+		if (e <= b) return false;
+		if (p->net_bb[4 * i] > p->net_bb[4 * i + 1] || p->net_bb[4 * i + 2] > p->net_bb[4 * i + 3]) return false;
+		if (p->net_is_global[i]) continue;
+		for (int k = b; k < e; k++) {
+			int n = p->net_terminals[k];
+			if (n < 0 || n >= p->num_nodes || p->type[n] != (k == b ? PF_SOURCE : PF_SINK)) return false;
+		}
+	}
+	for (int i = PF_CHANX_COST_INDEX_START; i < p->num_indexed; i++)
+		if (p->indexed[i].ortho_cost_index < 0 || p->indexed[i].ortho_cost_index >= p->num_indexed) return false;
+	for (int i = 0; i < p->num_opin_groups; i++) {
+		int s = p->opin_group_source[i];
+		if (s < 0 || s >= p->num_nodes || p->type[s] != PF_SOURCE || p->opin_group_count[i] < 0
+				|| p->opin_group_count[i] > p->row_ptr[s + 1] - p->row_ptr[s]) return false;
+	}
+	return true;
+}
+
 static int ceil_log2(long long v) { int l = 0; while ((1ll << l) < v) l++; return l; }
 
 static void free_slot_class(SlotClass &s) {
@@ -91,19 +142,19 @@ static void free_slot_class(SlotClass &s) {
 static int alloc_slot_class(SlotClass &s, int max_work, bool hot_in_smem) {
 	size_t cap = (size_t)1 << s.label_log2;
 	s.hot = hot_in_smem ? NULL : (uint64_t *)pfb_alloc(sizeof(uint64_t) * cap * s.num_slots);
-	s.cold = (PfCold *)pfb_alloc(sizeof(PfCold) * cap * s.num_slots);
+	s.cold = (PfCold *)pfb_alloc_raw(sizeof(PfCold) * cap * s.num_slots);
 	s.hot2 = NULL; s.cold2 = NULL;
 	if (hot_in_smem && s.label2_log2 > 0) {
 		size_t cap2 = (size_t)1 << s.label2_log2;
 		s.hot2 = (uint64_t *)pfb_alloc(sizeof(uint64_t) * cap2 * s.num_slots);
-		s.cold2 = (PfCold *)pfb_alloc(sizeof(PfCold) * cap2 * s.num_slots);
+		s.cold2 = (PfCold *)pfb_alloc_raw(sizeof(PfCold) * cap2 * s.num_slots);
 		if (!s.hot2 || !s.cold2) return -1;
 	}
 	s.epochs = (unsigned *)pfb_alloc(sizeof(unsigned) * 2 * s.num_slots);
-	s.tree = (PfTreeNode *)pfb_alloc(sizeof(PfTreeNode) * (size_t)s.tree_cap * s.num_slots);
-	s.far = (uint64_t *)pfb_alloc(sizeof(uint64_t) * (size_t)s.far_cap * s.num_slots);
-	s.iscratch = (int *)pfb_alloc(sizeof(int) * ((size_t)3 * (s.sink_cap + 2) + (size_t)2 * s.tree_cap) * s.num_slots);
-	s.work = (int *)pfb_alloc(sizeof(int) * (size_t)(max_work > 0 ? max_work : 1));
+	s.tree = (PfTreeNode *)pfb_alloc_raw(sizeof(PfTreeNode) * (size_t)s.tree_cap * s.num_slots);
+	s.far = (uint64_t *)pfb_alloc_raw(sizeof(uint64_t) * (size_t)s.far_cap * s.num_slots);
+	s.iscratch = (int *)pfb_alloc_raw(sizeof(int) * ((size_t)3 * (s.sink_cap + 2) + (size_t)2 * s.tree_cap) * s.num_slots);
+	s.work = (int *)pfb_alloc_raw(sizeof(int) * (size_t)(max_work > 0 ? max_work : 1));
 	s.work_head = (int *)pfb_alloc(sizeof(int) * 4);
 	if ((!hot_in_smem && !s.hot) || !s.cold || !s.epochs || !s.tree || !s.far || !s.iscratch || !s.work || !s.work_head) return -1;
 	return 0;
@@ -125,9 +176,13 @@ extern "C" void pf_router_destroy(pf_router *r) {
 	delete r;
 }
 
-static int upload_nodes(pf_router *r, bool keep_nothing) {
+static int upload_nodes(pf_router *r, void *staging) {
 	const pf_problem *p = r->prob;
-	std::vector<PfNode> h((size_t)r->N);
+	/* flatten straight into the pinned staging buffer when there is one (one async H2D, no pageable bounce) */
+	PfNode *stage = staging ? (PfNode *)staging : NULL;
+	std::vector<PfNode> hv;
+	if (!stage) { hv.resize((size_t)r->N); stage = hv.data(); }
+	PfNode *h = stage;
 	parallel_for(r->N, [&](long long lo, long long hi) {
 	for (long long i = lo; i < hi; i++) {
 		PfNode &d = h[i];
@@ -140,8 +195,8 @@ static int upload_nodes(pf_router *r, bool keep_nothing) {
 		d.capacity = (unsigned char)p->capacity[i];
 	}
 	});
-	(void)keep_nothing;
-	CKB(pfb_h2d(r->nodes, h.data(), sizeof(PfNode) * (size_t)r->N));
+	if (staging) CKB(pfb_h2d_async(r->nodes, h, sizeof(PfNode) * (size_t)r->N));
+	else CKB(pfb_h2d(r->nodes, h, sizeof(PfNode) * (size_t)r->N));
 	r->h2d_bytes += (int64_t)sizeof(PfNode) * r->N;
 	return PF_OK;
 }
@@ -151,15 +206,14 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	*out = NULL;
 	if (!p || !cfg_in) FAILF(PF_EINVAL, "null argument");
 	double t_a = now_s();
-	if (pf_problem_check(p, msg, sizeof(msg)) != PF_OK) FAILF(PF_EINVAL, "invalid problem: %s", msg);
+	if (!problem_arrays_ok(p) || !problem_nets_ok(p)) {
+		if (pf_problem_check(p, msg, sizeof(msg)) != PF_OK) FAILF(PF_EINVAL, "invalid problem: %s", msg);
+		FAILF(PF_EINVAL, "invalid problem (capacity > 255 or cost_index > 31 on some rr node)");
+	}
 	double t_b = now_s();
 	if (p->num_nodes > (1 << PF_EDGE_NODE_BITS)) FAILF(PF_EINVAL, "num_rr_nodes %d exceeds the %d-bit edge word", p->num_nodes, PF_EDGE_NODE_BITS);
 	if (p->num_switches > PF_MAX_SWITCHES) FAILF(PF_EINVAL, "%d switch types (max %d)", p->num_switches, PF_MAX_SWITCHES);
 	if (p->num_indexed > PF_MAX_INDEXED) FAILF(PF_EINVAL, "%d rr_indexed_data rows (max %d)", p->num_indexed, PF_MAX_INDEXED);
-	for (int i = 0; i < p->num_nodes; i++) {
-		if (p->capacity[i] > 255) FAILF(PF_EINVAL, "rr node %d capacity %d > 255", i, p->capacity[i]);
-		if (p->cost_index[i] > 31) FAILF(PF_EINVAL, "rr node %d cost_index %d > 31", i, p->cost_index[i]);
-	}
 	if (cfg_in->nranks < 1 || cfg_in->rank < 0 || cfg_in->rank >= cfg_in->nranks) FAILF(PF_EINVAL, "bad rank %d / nranks %d", cfg_in->rank, cfg_in->nranks);
 	if (pfb_init(cfg_in->device) != 0) CUDA_FAIL();
 
@@ -212,14 +266,25 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		int i = order[k], ns = p->net_ptr[i + 1] - p->net_ptr[i] - 1;
 		if (ns > c.sink_cap) r->work_big.push_back(i); else r->work_small.push_back(i);
 	}
-	if (c.big_label_log2 <= 0) c.big_label_log2 = std::min(21, std::max(c.label_log2 + 2, ceil_log2(2ll * r->N)));
+	if (c.big_label_log2 <= 0) {
+		/* a search cannot label more rr nodes than its bounding box holds: size the big tables for twice the
+		 * largest box (at the grid's average node density), capped by twice the whole graph */
+		long long max_area = 1;
+		for (int i : order) {
+			const int *bb = &p->net_bb[4 * i];
+			max_area = std::max<long long>(max_area, (long long)(bb[1] - bb[0] + 1) * (bb[3] - bb[2] + 1));
+		}
+		double density = (double)r->N / ((double)(p->nx + 2) * (p->ny + 2));
+		long long est = (long long)(1.25 * density * (double)max_area) + 1024;
+		c.big_label_log2 = std::min(22, std::max(c.label2_log2 + 1, ceil_log2(2 * std::min<long long>(est, r->N))));
+	}
 	if (c.big_tree_cap <= 0) c.big_tree_cap = std::max(1 << 16, 64 * max_sinks);
-	if (c.big_far_cap <= 0) c.big_far_cap = 1 << 19;
+	if (c.big_far_cap <= 0) c.big_far_cap = std::min(1 << 19, 1 << c.big_label_log2);
 	if (c.num_slots > (int)r->work_small.size() + 32) c.num_slots = std::max(32, (int)((r->work_small.size() + 31) / 32 * 32));
 
 	/* device graph */
-	r->nodes = (PfNode *)pfb_alloc(sizeof(PfNode) * (size_t)r->N);
-	r->edges = (uint32_t *)pfb_alloc(sizeof(uint32_t) * (size_t)std::max(r->E, 1));
+	r->nodes = (PfNode *)pfb_alloc_raw(sizeof(PfNode) * (size_t)r->N);
+	r->edges = (uint32_t *)pfb_alloc_raw(sizeof(uint32_t) * (size_t)std::max(r->E, 1));
 	r->sw = (PfSwitchDev *)pfb_alloc(sizeof(PfSwitchDev) * PF_MAX_SWITCHES);
 	r->indexed = (PfIndexedDev *)pfb_alloc(sizeof(PfIndexedDev) * PF_MAX_INDEXED);
 	r->net_ptr = (int *)pfb_alloc(sizeof(int) * ((size_t)r->n + 1));
@@ -231,7 +296,12 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		pf_router_destroy(r); CUDA_FAIL();
 	}
 	{
-		std::vector<uint32_t> ew((size_t)std::max(r->E, 1));
+		const size_t nbytes = sizeof(PfNode) * (size_t)r->N, ebytes = sizeof(uint32_t) * (size_t)std::max(r->E, 1);
+		char *pin = (char *)pfb_pinned(nbytes + ebytes + 256);
+		void *stage_nodes = pin;
+		uint32_t *ew = pin ? (uint32_t *)(pin + ((nbytes + 255) & ~(size_t)255)) : NULL;
+		std::vector<uint32_t> ewv;
+		if (!ew) { ewv.resize((size_t)std::max(r->E, 1)); ew = ewv.data(); }
 		parallel_for(r->E, [&](long long lo, long long hi) {
 			for (long long k = lo; k < hi; k++) ew[k] = (uint32_t)p->edge_to[k] | ((uint32_t)p->edge_sw[k] << PF_EDGE_NODE_BITS);
 		});
@@ -247,8 +317,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			if (i >= PF_CHANX_COST_INDEX_START && (min_base == 0.f || p->indexed[i].base_cost < min_base)) min_base = p->indexed[i].base_cost;
 		}
 		r->win_abs_auto = 4.f * min_base;             /* a few wire hops of base cost */
-		if (upload_nodes(r, true) != PF_OK) { pf_router_destroy(r); return PF_ECUDA; }
-		if (pfb_h2d(r->edges, ew.data(), sizeof(uint32_t) * (size_t)r->E) || pfb_h2d(r->sw, sw.data(), sizeof(PfSwitchDev) * PF_MAX_SWITCHES)
+		if (upload_nodes(r, stage_nodes) != PF_OK) { pf_router_destroy(r); return PF_ECUDA; }
+		if ((pin ? pfb_h2d_async(r->edges, ew, sizeof(uint32_t) * (size_t)r->E) : pfb_h2d(r->edges, ew, sizeof(uint32_t) * (size_t)r->E)) || pfb_h2d(r->sw, sw.data(), sizeof(PfSwitchDev) * PF_MAX_SWITCHES)
 				|| pfb_h2d(r->indexed, ix.data(), sizeof(PfIndexedDev) * PF_MAX_INDEXED)
 				|| pfb_h2d(r->net_ptr, p->net_ptr, sizeof(int) * ((size_t)r->n + 1))
 				|| pfb_h2d(r->net_term, p->net_terminals, sizeof(int) * (size_t)r->T)
@@ -274,9 +344,10 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	int nwork = (int)(r->work_small.size() + r->work_big.size());
 	if (alloc_slot_class(r->small, nwork, true) || alloc_slot_class(r->big, nwork, false)) { pf_router_destroy(r); CUDA_FAIL(); }
 	/* route store */
-	r->pool_cap = std::max<long long>(1 << 16, 4ll * r->N + 96ll * r->T);
+	/* live trees hold about one entry per used rr node; the log needs room for one iteration of re-routes on top */
+	r->pool_cap = std::max<long long>(1 << 18, std::min<long long>(4ll * r->N + 96ll * r->T, 32ll * r->T + (1 << 20)));
 	for (int k = 0; k < 2; k++) {
-		r->pool[k] = (PfTreeNode *)pfb_alloc(sizeof(PfTreeNode) * (size_t)r->pool_cap);
+		r->pool[k] = (PfTreeNode *)pfb_alloc_raw(sizeof(PfTreeNode) * (size_t)r->pool_cap);
 		if (!r->pool[k]) { pf_router_destroy(r); CUDA_FAIL(); }
 	}
 	r->loc = (PfNetLoc *)pfb_alloc(sizeof(PfNetLoc) * (size_t)std::max(r->n, 1));
@@ -295,9 +366,9 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	}
 	r->pool_head = (unsigned long long *)pfb_alloc(sizeof(unsigned long long) * 2);
 	r->status = (int *)pfb_alloc(sizeof(int) * 8);
-	r->retry_list = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(nwork, 1));
+	r->retry_list = (int *)pfb_alloc_raw(sizeof(int) * (size_t)std::max(nwork, 1));
 	r->retry_count = (int *)pfb_alloc(sizeof(int) * 4);
-	r->retry_work = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(nwork, 1));
+	r->retry_work = (int *)pfb_alloc_raw(sizeof(int) * (size_t)std::max(nwork, 1));
 	r->stats = (PfStats *)pfb_alloc(sizeof(PfStats));
 	r->d_overused = (int *)pfb_alloc(sizeof(int) * 4);
 	r->d_wl = (unsigned long long *)pfb_alloc(sizeof(unsigned long long) * 2);
@@ -333,7 +404,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 
 extern "C" int pf_router_reset(pf_router *r) {
 	if (!r) FAILF(PF_EINVAL, "null router");
-	if (upload_nodes(r, true) != PF_OK) return PF_ECUDA;
+	if (upload_nodes(r, pfb_pinned(sizeof(PfNode) * (size_t)r->N)) != PF_OK) return PF_ECUDA;
+	CKB(pfb_sync());
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
 	CKB(pfb_zero(r->pool_head, sizeof(unsigned long long) * 2));
 	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0;
@@ -632,67 +704,83 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 	if (!r || !out) FAILF(PF_EINVAL, "null argument");
 	const pf_problem *p = r->prob;
 	memset(out, 0, sizeof(*out));
-	unsigned long long head[2];
-	CKB(pfb_d2h(head, r->pool_head, sizeof(head)));
 	std::vector<PfNetLoc> loc((size_t)std::max(r->n, 1));
 	CKB(pfb_d2h(loc.data(), r->loc, sizeof(PfNetLoc) * (size_t)r->n));
 	long long used = 0;
 	for (int i = 0; i < r->n; i++) used = std::max<long long>(used, (long long)loc[i].off + loc[i].count);
-	std::vector<PfTreeNode> pool((size_t)std::max<long long>(used, 1));
-	CKB(pfb_d2h(pool.data(), r->pool[r->cur], sizeof(PfTreeNode) * (size_t)used));
-	r->d2h_bytes += (int64_t)sizeof(PfTreeNode) * used + (int64_t)sizeof(int) * r->N + (int64_t)sizeof(PfNetLoc) * r->n;
+	/* the live part of the log and the compacted occupancy come back through the pinned staging buffer */
+	const size_t pbytes = sizeof(PfTreeNode) * (size_t)std::max<long long>(used, 1), obytes = sizeof(int) * (size_t)r->N;
+	char *pin = (char *)pfb_pinned(pbytes + obytes + 256);
+	std::vector<char> fallback;
+	if (!pin) { fallback.resize(pbytes + obytes + 256); pin = fallback.data(); }
+	const PfTreeNode *pool = (const PfTreeNode *)pin;
+	int *h_occ = (int *)(pin + ((pbytes + 255) & ~(size_t)255));
+	int *d_occ = r->occ_delta ? r->occ_delta : (int *)pfb_alloc_raw(obytes);
+	if (!d_occ) CUDA_FAIL();
+	int bad = pfb_launch_extract_occ(r->nodes, r->N, d_occ) || pfb_d2h_async((void *)pool, r->pool[r->cur], sizeof(PfTreeNode) * (size_t)used)
+			|| pfb_d2h_async(h_occ, d_occ, obytes) || pfb_sync();
+	if (!r->occ_delta) pfb_free(d_occ);
+	if (bad) CUDA_FAIL();
+	r->d2h_bytes += (int64_t)sizeof(PfTreeNode) * used + (int64_t)obytes + (int64_t)sizeof(PfNetLoc) * r->n;
 
-	std::vector<int32_t> tptr((size_t)r->n + 1, 0), tnode;
-	std::vector<int16_t> tsw;
-	int wl = 0;
-	for (int i = 0; i < r->n; i++) {
-		const PfTreeNode *t = pool.data() + loc[i].off;
-		int cnt = loc[i].count;
-		int k = 0;
-		while (k < cnt) {
-			/* one segment: entries k..e where e is the next SINK */
-			int e = k;
-			while (e < cnt && (t[e].type_ci & 7) != PF_SINK) e++;
-			if (e >= cnt) { if (k == 0 && cnt == 1) break; FAILF(PF_ECUDA, "net %d: route tree does not end in a SINK", i); }
-			if (k > 0) {   /* join node first */
-				int j = t[k].parent;
-				tnode.push_back(t[j].node); tsw.push_back((int16_t)t[k].sw);
-			}
-			for (int q = k; q <= e; q++) {
-				tnode.push_back(t[q].node);
-				tsw.push_back(q < e ? (int16_t)t[q + 1].sw : (int16_t)PF_OPEN);
-				int ty = t[q].type_ci & 7;
-				if (ty == PF_CHANX || ty == PF_CHANY) wl += 1 + t[q].xhigh - t[q].xlow + t[q].yhigh - t[q].ylow;
-			}
-			k = e + 1;
+	/* pass 1: trace length of every net (entries + one join element per later segment) */
+	std::vector<int32_t> tptr((size_t)r->n + 1, 0);
+	std::vector<int> err(1, -1);
+	std::vector<int> *perr = &err;
+	parallel_for(r->n, [&, perr](long long lo, long long hi) {
+		for (long long i = lo; i < hi; i++) {
+			const PfTreeNode *t = pool + loc[i].off;
+			int cnt = loc[i].count, sinks = 0;
+			for (int k = 0; k < cnt; k++) if ((t[k].type_ci & 7) == PF_SINK) sinks++;
+			if (cnt > 1 && (t[cnt - 1].type_ci & 7) != PF_SINK) (*perr)[0] = (int)i;
+			tptr[i + 1] = cnt <= 1 ? 0 : cnt + (sinks > 0 ? sinks - 1 : 0);
 		}
-		tptr[i + 1] = (int32_t)tnode.size();
-	}
+	});
+	if (err[0] >= 0) FAILF(PF_ECUDA, "net %d: route tree does not end in a SINK", err[0]);
+	for (int i = 0; i < r->n; i++) tptr[i + 1] += tptr[i];
+	const size_t total = (size_t)tptr[r->n];
 	out->num_nets = r->n;
 	out->trace_ptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)r->n + 1));
-	out->trace_node = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(tnode.size(), 1));
-	out->trace_switch = (int16_t *)malloc(sizeof(int16_t) * std::max<size_t>(tsw.size(), 1));
+	out->trace_node = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(total, 1));
+	out->trace_switch = (int16_t *)malloc(sizeof(int16_t) * std::max<size_t>(total, 1));
 	out->net_delay = (float *)malloc(sizeof(float) * (size_t)std::max(r->T, 1));
 	out->occ = (int32_t *)malloc(sizeof(int32_t) * (size_t)r->N);
 	if (!out->trace_ptr || !out->trace_node || !out->trace_switch || !out->net_delay || !out->occ) { pf_result_free(out); FAILF(PF_ENOMEM, "out of host memory"); }
 	memcpy(out->trace_ptr, tptr.data(), sizeof(int32_t) * ((size_t)r->n + 1));
-	if (!tnode.empty()) { memcpy(out->trace_node, tnode.data(), sizeof(int32_t) * tnode.size()); memcpy(out->trace_switch, tsw.data(), sizeof(int16_t) * tsw.size()); }
+	/* pass 2: fill; wirelength and the magic cookie are accumulated per net and combined in net order */
+	std::vector<int> wl_net((size_t)std::max(r->n, 1), 0);
+	int32_t *tn = out->trace_node; int16_t *ts = out->trace_switch;
+	parallel_for(r->n, [&](long long lo, long long hi) {
+		for (long long i = lo; i < hi; i++) {
+			const PfTreeNode *t = pool + loc[i].off;
+			int cnt = loc[i].count, w = tptr[i], wl = 0, k = 0;
+			if (cnt <= 1) continue;
+			while (k < cnt) {
+				int e = k;
+				while ((t[e].type_ci & 7) != PF_SINK) e++;
+				if (k > 0) { tn[w] = t[t[k].parent].node; ts[w] = (int16_t)t[k].sw; w++; }
+				for (int q = k; q <= e; q++) {
+					tn[w] = t[q].node; ts[w] = q < e ? (int16_t)t[q + 1].sw : (int16_t)PF_OPEN; w++;
+					int ty = t[q].type_ci & 7;
+					if (ty == PF_CHANX || ty == PF_CHANY) wl += 1 + t[q].xhigh - t[q].xlow + t[q].yhigh - t[q].ylow;
+				}
+				k = e + 1;
+			}
+			wl_net[i] = wl;
+		}
+	});
 	out->num_terminals = r->T;
 	if (pfb_d2h(out->net_delay, r->net_delay, sizeof(float) * (size_t)r->T)) { pf_result_free(out); CUDA_FAIL(); }
 	out->num_nodes = r->N;
-	{   /* occupancy: compacted on the device, one 4-byte word per rr node crosses PCIe */
-		int *d_occ = r->occ_delta ? r->occ_delta : (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
-		if (!d_occ) { pf_result_free(out); CUDA_FAIL(); }
-		int bad = pfb_launch_extract_occ(r->nodes, r->N, d_occ) || pfb_d2h(out->occ, d_occ, sizeof(int) * (size_t)r->N);
-		if (!r->occ_delta) pfb_free(d_occ);
-		if (bad) { pf_result_free(out); CUDA_FAIL(); }
-	}
-	out->total_wirelength = wl;
-	{   /* get_serial_num, route_common.c:224-254 */
+	memcpy(out->occ, h_occ, obytes);
+	long long wl = 0;
+	for (int i = 0; i < r->n; i++) wl += wl_net[i];
+	out->total_wirelength = (int32_t)wl;
+	{   /* get_serial_num, route_common.c:224-254 (sequential by definition: a running remainder) */
 		int serial = 0;
 		for (int i = 0; i < r->n; i++)
 			for (int k = tptr[i]; k < tptr[i + 1]; k++) {
-				int v = tnode[k];
+				int v = tn[k];
 				serial += (i + 1) * (p->xlow[v] * (p->nx + 1) - p->yhigh[v]);
 				serial -= p->ptc_num[v] * (i + 1) * 10;
 				serial -= p->type[v] * (i + 1) * 100;

@@ -19,6 +19,10 @@ int pfb_device_count(void) { return 1; }
 const char *pfb_name(void) { return "emu"; }
 const char *pfb_last_error(void) { return g_err; }
 void *pfb_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
+void *pfb_alloc_raw(size_t bytes) { return malloc(bytes ? bytes : 16); }
+void *pfb_pinned(size_t) { return NULL; }
+int pfb_h2d_async(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
+int pfb_d2h_async(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
 void pfb_free(void *p) { free(p); }
 int pfb_h2d(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
 int pfb_d2h(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
