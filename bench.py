@@ -10,7 +10,7 @@ Workload (config.workload): BASELINE.json configs[4] — synthetic 400x400 CLB k
 that fits one GPU; configs[1..3] need VTR benchmark files that are neither in the reference nor on the box
 (SURVEY.md §8c).  A step is one complete routing of the problem: reset congestion, then PathFinder
 iterations until the routing is legal.  N > 1 shards the nets of the SAME problem over N GPUs (strong
-scaling) with an NCCL all-reduce of the occupancy delta four times per iteration.
+scaling) with an NCCL all-reduce of the occupancy delta twice per iteration.
 
 value   = nets routed (summed over iterations and ranks) / device time of the step, graph already in HBM
 e2e     = the same through the public API with HOST buffers: flatten + H2D of the whole problem, route,
@@ -242,7 +242,7 @@ def run_ours(a):
             "config": {"workload": WORKLOAD.format(nx=a.grid, ny=a.grid, W=a.width, nets=a.nets),
                        "rr_nodes": p.num_nodes, "rr_edges": p.num_edges, "sinks": int(p.num_terminals - p.num_nets),
                        "router_opts": "VPR defaults: astar 1.2, pres_fac 0.5 x1.3, acc_fac 1, bb_factor 3, max 50 iterations",
-                       "parallelism": "nets sharded over %d GPU(s); occupancy all-reduce 4x per iteration" % world if world > 1 else "1 GPU",
+                       "parallelism": "nets sharded over %d GPU(s); occupancy all-reduce 2x per iteration" % world if world > 1 else "1 GPU",
                        "l2": "working set (node records %d MB + edges %d MB) far exceeds the 126 MB L2; no flush needed"
                              % (p.num_nodes * 32 >> 20, p.num_edges * 4 >> 20)},
             "route": {"iterations": [r.iterations for r in reps], "nets_routed_per_step": nets_routed / a.steps,

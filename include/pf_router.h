@@ -46,8 +46,8 @@ typedef struct pf_router pf_router;
 
 typedef struct pf_config {
 	int32_t device;           /* CUDA device ordinal */
-	int32_t rank, nranks;     /* net sharding: this process routes nets i with i % nranks == rank
-	                             of the fanout-sorted order (one process per GPU) */
+	int32_t rank, nranks;     /* net sharding (one process per GPU): nets are cut into nranks spatial stripes of
+	                             equal total fanout along x; this process routes stripe `rank` */
 	int32_t num_slots;        /* concurrent warps (nets in flight); 0 = 16 per SM */
 	int32_t warps_per_block;  /* 0 = 4 */
 	int32_t label_log2;       /* (fixed) the regular slots keep 2^10 hot label entries in shared memory */

@@ -261,8 +261,26 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		return (p->net_ptr[a + 1] - p->net_ptr[a]) > (p->net_ptr[b + 1] - p->net_ptr[b]); });
 	r->net_rank.assign((size_t)std::max(r->n, 1), 0);
 	for (size_t k = 0; k < order.size(); k++) r->net_rank[order[k]] = (int)k;
+	/* Sharding over ranks.  The reference's MPI router deals nets round-robin / LPT over ranks
+	 * (mpi_route_load_balanced…encoded.cxx:74-170) and pays for it with per-sink messages.  Here a rank only
+	 * learns other ranks' routes at the occupancy sync, so nets are sharded SPATIALLY: sort by bounding-box
+	 * centre along x and cut into nranks stripes of equal total fanout.  Nets of different stripes compete
+	 * for the same wires only near the cuts, which keeps the congestion a rank cannot see small. */
+	std::vector<int> owner((size_t)std::max(r->n, 1), 0);
+	if (c.nranks > 1) {
+		std::vector<int> byx(order);
+		std::stable_sort(byx.begin(), byx.end(), [&](int a, int b) {
+			int ca = p->net_bb[4 * a] + p->net_bb[4 * a + 1], cb = p->net_bb[4 * b] + p->net_bb[4 * b + 1];
+			return ca < cb; });
+		long long total_f = 0, acc_f = 0;
+		for (int i : byx) total_f += p->net_ptr[i + 1] - p->net_ptr[i];
+		for (int i : byx) {
+			owner[i] = (int)std::min<long long>(c.nranks - 1, acc_f * c.nranks / std::max<long long>(total_f, 1));
+			acc_f += p->net_ptr[i + 1] - p->net_ptr[i];
+		}
+	}
 	for (size_t k = 0; k < order.size(); k++) {
-		if ((int)(k % (size_t)c.nranks) != c.rank) continue;
+		if (owner[order[k]] != c.rank) continue;
 		int i = order[k], ns = p->net_ptr[i + 1] - p->net_ptr[i] - 1;
 		if (ns > c.sink_cap) r->work_big.push_back(i); else r->work_small.push_back(i);
 	}
@@ -549,7 +567,7 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 	int so, sc, bo, bc;
 	slice(r->n_small, so, sc); slice(r->n_big, bo, bc);
 	PfParams P;
-	int total = sc + bc;
+	int total = r->n_small + r->n_big;      /* the staleness bound is about the whole iteration's nets */
 	if (bc > 0) {                          /* long nets first */
 		CKB(pfb_zero(r->big.work_head, sizeof(int) * 4));
 		r->big.num_work = bc;

@@ -40,7 +40,7 @@ class RouteReport:
 
 
 def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delta_buf=None, delay_buf=None,
-          max_iters: Optional[int] = None, sync_rounds: int = 4) -> RouteReport:
+          max_iters: Optional[int] = None, sync_rounds: int = 2) -> RouteReport:
     """Iterate until legal.  ``delta_buf``: device int32[num_nodes] tensor (required when comm is given);
     ``delay_buf``: tensor aliasing the router's device net_delay vector (optional, for the host STA)."""
     o = r.problem.opts
