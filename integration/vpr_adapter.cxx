@@ -1,0 +1,176 @@
+/*
+ * vpr_adapter.cxx — the reference-side binding: makes the B200 router a drop-in for VPR's
+ * try_timing_driven_route (reference vpr/SRC/route/route_timing.c:85, sole caller route_common.c:500).
+ *
+ * This is the file a maintainer of chinhau5/parallel_eda adds to the VPR build.  It is a C++
+ * translation unit because every reference source is compiled as C++ and its headers use C++ types
+ * (vpr_types.h:499,533); it includes VPR headers, reads VPR's globals (base/globals.c:48-97), flattens them
+ * into the plain-array pf_problem of include/pf_types.h and calls the extern "C" ABI of libpf_router.so.
+ * Nothing here routes: the adapter is glue.
+ *
+ *   route_common.c is compiled with  -Dtry_timing_driven_route=pf_adapter_try_timing_driven_route
+ *   so the call at route_common.c:500 lands here; route_timing.c stays in the build unchanged (the placer's
+ *   delay lookup and the packer use its helpers, place/timing_place_lookup.c:461, pack/cluster_legality.c:642).
+ *
+ * Between iterations the reference's own STA runs on the host, exactly as in route_timing.c:295-309:
+ * load_timing_graph_net_delays + do_timing_analysis + get_critical_path_delay.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "vpr_types.h"
+#include "globals.h"
+#include "route_export.h"
+#include "route_common.h"
+#include "route_tree_timing.h"
+#include "route_timing.h"
+#include "path_delay.h"
+#include "net_delay.h"
+
+#include "pf_router.h"
+
+extern struct s_bb *route_bb;                       /* route/route_common.c:59 */
+void timing_driven_check_net_delays(float **net_delay);   /* route/route_timing.c:964 (not in its header) */
+extern t_rr_node_route_inf *rr_node_route_inf;      /* route/route_common.c:57 */
+
+namespace {
+
+struct StaCtx {
+	float **net_delay;
+	t_slack *slacks;
+	std::vector<int> net_ptr;
+};
+
+/* pf_sta_fn: the host step between iterations (route_timing.c:295-309) */
+void sta_callback(void *user, int /*iters_done*/, const float *delay, float *crit, float *cpd) {
+	StaCtx *c = (StaCtx *)user;
+	for (int i = 0; i < num_nets; i++)
+		for (int k = 1; k <= clb_net[i].num_sinks; k++) c->net_delay[i][k] = clb_net[i].is_global ? 0.f : delay[c->net_ptr[i] + k];
+	load_timing_graph_net_delays(c->net_delay);
+	do_timing_analysis(c->slacks, FALSE, FALSE, FALSE);
+	*cpd = get_critical_path_delay();
+	vpr_printf(TIO_MESSAGE_INFO, "Critical path: %g ns\n", *cpd);
+	for (int i = 0; i < num_nets; i++)
+		for (int k = 1; k <= clb_net[i].num_sinks; k++) crit[c->net_ptr[i] + k] = c->slacks->timing_criticality[i][k];
+}
+
+}  // namespace
+
+boolean pf_adapter_try_timing_driven_route(struct s_router_opts router_opts, float **net_delay, t_slack *slacks,
+		t_ivec **clb_opins_used_locally, boolean timing_analysis_enabled) {
+	/* ---- flatten the globals (rr_node[], rr_indexed_data[], switch_inf[], clb_net[], net_rr_terminals, route_bb) */
+	const int N = num_rr_nodes;
+	long E = 0;
+	for (int i = 0; i < N; i++) E += rr_node[i].num_edges;
+	std::vector<int16_t> xl(N), yl(N), xh(N), yh(N), ptc(N), ci(N), cap(N);
+	std::vector<uint8_t> ty(N), dir(N);
+	std::vector<float> R(N), C(N);
+	std::vector<int32_t> row(N + 1), to(E > 0 ? E : 1);
+	std::vector<int16_t> sw(E > 0 ? E : 1);
+	long e = 0;
+	int nsw = 0;
+	for (int i = 0; i < N; i++) {
+		const t_rr_node &n = rr_node[i];
+		xl[i] = n.xlow; yl[i] = n.ylow; xh[i] = n.xhigh; yh[i] = n.yhigh; ptc[i] = n.ptc_num; ci[i] = n.cost_index;
+		cap[i] = n.capacity; ty[i] = (uint8_t)n.type; dir[i] = (uint8_t)n.direction; R[i] = n.R; C[i] = n.C;
+		row[i] = (int32_t)e;
+		for (int k = 0; k < n.num_edges; k++) { to[e] = n.edges[k]; sw[e] = n.switches[k]; if (sw[e] + 1 > nsw) nsw = sw[e] + 1; e++; }
+	}
+	row[N] = (int32_t)e;
+	std::vector<pf_switch> sws(nsw);
+	for (int s = 0; s < nsw; s++) {
+		sws[s].buffered = switch_inf[s].buffered; sws[s].R = switch_inf[s].R; sws[s].Cin = switch_inf[s].Cin;
+		sws[s].Cout = switch_inf[s].Cout; sws[s].Tdel = switch_inf[s].Tdel;
+	}
+	std::vector<pf_indexed> idx(num_rr_indexed_data);
+	for (int i = 0; i < num_rr_indexed_data; i++) {
+		idx[i].base_cost = rr_indexed_data[i].base_cost; idx[i].saved_base_cost = rr_indexed_data[i].saved_base_cost;
+		idx[i].ortho_cost_index = rr_indexed_data[i].ortho_cost_index; idx[i].seg_index = rr_indexed_data[i].seg_index;
+		idx[i].inv_length = rr_indexed_data[i].inv_length; idx[i].T_linear = rr_indexed_data[i].T_linear;
+		idx[i].T_quadratic = rr_indexed_data[i].T_quadratic; idx[i].C_load = rr_indexed_data[i].C_load;
+	}
+	StaCtx ctx;
+	ctx.net_delay = net_delay; ctx.slacks = slacks;
+	ctx.net_ptr.assign(num_nets + 1, 0);
+	for (int i = 0; i < num_nets; i++) ctx.net_ptr[i + 1] = ctx.net_ptr[i] + clb_net[i].num_sinks + 1;
+	const int T = ctx.net_ptr[num_nets];
+	std::vector<int32_t> term(T > 0 ? T : 1), bb(4 * (size_t)(num_nets > 0 ? num_nets : 1));
+	std::vector<uint8_t> glob(num_nets > 0 ? num_nets : 1);
+	for (int i = 0; i < num_nets; i++) {
+		glob[i] = clb_net[i].is_global ? 1 : 0;
+		for (int k = 0; k <= clb_net[i].num_sinks; k++) term[ctx.net_ptr[i] + k] = net_rr_terminals[i][k];
+		bb[4 * i + 0] = route_bb[i].xmin; bb[4 * i + 1] = route_bb[i].xmax; bb[4 * i + 2] = route_bb[i].ymin; bb[4 * i + 3] = route_bb[i].ymax;
+	}
+	std::vector<int32_t> gsrc, gcnt;
+	for (int b = 0; b < num_blocks; b++)
+		for (int c = 0; c < block[b].type->num_class; c++)
+			if (clb_opins_used_locally[b][c].nelem > 0) { gsrc.push_back(rr_blk_source[b][c]); gcnt.push_back(clb_opins_used_locally[b][c].nelem); }
+
+	pf_problem p;
+	memset(&p, 0, sizeof(p));
+	p.nx = nx; p.ny = ny; p.num_nodes = N; p.num_edges = (int32_t)E;
+	p.xlow = xl.data(); p.ylow = yl.data(); p.xhigh = xh.data(); p.yhigh = yh.data(); p.ptc_num = ptc.data();
+	p.cost_index = ci.data(); p.capacity = cap.data(); p.type = ty.data(); p.direction = dir.data(); p.R = R.data(); p.C = C.data();
+	p.row_ptr = row.data(); p.edge_to = to.data(); p.edge_sw = sw.data();
+	p.num_switches = nsw; p.switches = sws.data(); p.num_indexed = num_rr_indexed_data; p.indexed = idx.data();
+	p.num_nets = num_nets; p.num_terminals = T; p.net_ptr = ctx.net_ptr.data(); p.net_terminals = term.data();
+	p.net_is_global = glob.data(); p.net_bb = bb.data();
+	p.num_opin_groups = (int)gsrc.size(); p.opin_group_source = gsrc.data(); p.opin_group_count = gcnt.data();
+	p.opts.first_iter_pres_fac = router_opts.first_iter_pres_fac; p.opts.initial_pres_fac = router_opts.initial_pres_fac;
+	p.opts.pres_fac_mult = router_opts.pres_fac_mult; p.opts.acc_fac = router_opts.acc_fac; p.opts.bend_cost = router_opts.bend_cost;
+	p.opts.astar_fac = router_opts.astar_fac; p.opts.max_criticality = router_opts.max_criticality;
+	p.opts.criticality_exp = router_opts.criticality_exp; p.opts.max_router_iterations = router_opts.max_router_iterations;
+	p.opts.timing_analysis_enabled = timing_analysis_enabled ? 1 : 0; p.opts.bb_factor = router_opts.bb_factor;
+
+	/* ---- route on the GPU */
+	pf_config cfg;
+	pf_config_default(&cfg);
+	if (getenv("PF_DEVICE")) cfg.device = atoi(getenv("PF_DEVICE"));
+	cfg.verbose = getenv("PF_VERBOSE") ? 1 : 0;
+	pf_result res;
+	int rc = pf_try_timing_driven_route(&p, &cfg, timing_analysis_enabled ? sta_callback : NULL, &ctx, &res);
+	if (rc != PF_OK) {
+		/* reference style: message + exit (route_timing.c:482-489 prints "Routing failed" and returns FALSE only
+		 * for an unroutable net) */
+		vpr_printf(TIO_MESSAGE_ERROR, "pf_router: %s\n", pf_last_error());
+		if (rc == PF_EUNROUTABLE) return FALSE;
+		exit(1);
+	}
+	vpr_printf(TIO_MESSAGE_INFO, "%s after %d routing iterations (B200 router).\n",
+			res.success ? "Successfully routed" : "Routing failed", res.iterations);
+
+	/* ---- hand the routing back: s_trace lists in update_traceback's segment convention (route_common.c:638),
+	 * net delays, occupancy.  The trace elements are plain mallocs we own; free_traceback only threads them
+	 * onto the reference's free list, which is harmless. */
+	for (int i = 0; i < num_nets; i++) {
+		trace_head[i] = trace_tail[i] = NULL;
+		for (int k = res.trace_ptr[i]; k < res.trace_ptr[i + 1]; k++) {
+			struct s_trace *t = (struct s_trace *)malloc(sizeof(struct s_trace));
+			t->index = res.trace_node[k]; t->iswitch = res.trace_switch[k]; t->next = NULL;
+			if (trace_tail[i]) trace_tail[i]->next = t; else trace_head[i] = t;
+			trace_tail[i] = t;
+		}
+		for (int k = 1; k <= clb_net[i].num_sinks; k++) net_delay[i][k] = clb_net[i].is_global ? 0.f : res.net_delay[ctx.net_ptr[i] + k];
+	}
+	/* occupancy of the nets; the locally used OPINs are then re-reserved by the reference's own routine so
+	 * that clb_opins_used_locally carries the node ids check_route expects (check_route.c:599) */
+	std::vector<int> occ(N, 0);
+	for (int i = 0; i < num_nets; i++) {
+		bool after_sink = false;
+		for (int k = res.trace_ptr[i]; k < res.trace_ptr[i + 1]; k++) {
+			int v = res.trace_node[k];
+			if (!(after_sink && k > res.trace_ptr[i])) occ[v]++;      /* the join element is not counted again */
+			after_sink = rr_node[v].type == SINK;
+		}
+	}
+	for (int i = 0; i < N; i++) { rr_node[i].occ = (short)occ[i]; rr_node_route_inf[i].pres_cost = 1.; rr_node_route_inf[i].acc_cost = 1.; }
+	reserve_locally_used_opins(router_opts.initial_pres_fac, FALSE, clb_opins_used_locally);
+	boolean ok = res.success ? TRUE : FALSE;
+#ifdef DEBUG
+	if (ok) timing_driven_check_net_delays(net_delay);              /* route_timing.c:964: from-scratch Elmore cross-check */
+#endif
+	pf_result_free(&res);
+	return ok;
+}

