@@ -35,8 +35,6 @@
 #ifndef PF_EMU
 #include <cuda_runtime.h>
 #define PF_DEV static __device__ __forceinline__
-#define PF_DEV_COLD static __device__ __noinline__   /* once-per-sink / rare paths: kept out of line so the settle
-                                                        loop stays resident in the instruction cache */
 #define PF_WARP 32
 typedef uint4 pf_u4;
 PF_DEV int pf_lane(void) { return (int)(threadIdx.x & 31u); }
@@ -296,7 +294,7 @@ PF_DEV void pf_push(PfWarp &w, int valid, float tot, float back, int node) {
 /* Re-bucket: move the near set to the far list, find the new minimum, open a window above it and
  * pull every far label inside the window back into shared memory (at most PF_SH_REFILL; the
  * window is narrowed until they fit, down to exact ties of the minimum). */
-PF_DEV_COLD void pf_refill(PfWarp &w) {
+PF_DEV void pf_refill(PfWarp &w) {
 	const int lane = pf_lane();
 	w.refills++;
 	/* 1. near → far */
@@ -375,7 +373,7 @@ PF_DEV PfNodeView pf_load_node(const PfParams *P, int v) {
 
 /* ------------------------------------------------------------------ sink order: heapsort (util/heapsort.c:13-96)
  * run by one lane so that equal criticalities come out in the reference's order. */
-PF_DEV_COLD void pf_heapsort_lane(int *heap /*[1..n]*/, const float *v /*[1..n]*/, int n) {
+PF_DEV void pf_heapsort_lane(int *heap /*[1..n]*/, const float *v /*[1..n]*/, int n) {
 	for (int i = 1; i <= n; i++) {
 		unsigned ifrom = i, ito = ifrom / 2;
 		heap[i] = i;
@@ -397,48 +395,6 @@ PF_DEV_COLD void pf_heapsort_lane(int *heap /*[1..n]*/, const float *v /*[1..n]*
 		heap[tail] = smallest;
 	}
 }
-
-/* add_route_tree_to_heap (route_timing.c:565-601): every re-expandable tree entry becomes a label with cost
- * crit * Tdel + astar * lookahead.  Two passes: the minimum first (it opens the near-set window), then the
- * inserts.  Returns 1, 0 when there is no seed, -1 on scratch overflow. */
-PF_DEV_COLD int pf_seed_tree(PfWarp &w, int tree_n, int tgt_xl, int tgt_yl, float crit) {
-	const PfParams *P = w.P;
-	const int lane = pf_lane();
-	const float astar = P->astar_fac;
-	float smin = PF_INF_F;
-	for (int i = lane; i < tree_n; i += PF_WARP) {
-		PfTreeNode t = w.tree[i];
-		if (t.flags & PF_TF_REEXPAND) {
-			float back = crit * t.Tdel;
-			float tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
-			if (tot < smin) smin = tot;
-		}
-	}
-	smin = pf_warp_min_f(smin);
-	if (!(smin < PF_INF_F)) return 0;
-	{
-		float win = smin * P->win_rel;
-		if (win < P->win_abs) win = P->win_abs;
-		w.T_hi = smin + win;
-	}
-	for (int base = 0; base < tree_n; base += PF_WARP) {
-		int i = base + lane;
-		int valid = 0, node = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
-		if (i < tree_n) {
-			PfTreeNode t = w.tree[i];
-			if (t.flags & PF_TF_REEXPAND) {
-				valid = 1; node = t.node; R_up = t.R_up;
-				back = crit * t.Tdel;
-				tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
-			}
-		}
-		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
-		pf_push(w, wr, tot, back, node);
-		if (w.overflow) return -1;
-	}
-	return 1;
-}
-
 
 /* ------------------------------------------------------------------ one sink search */
 /* Returns 1 when the target was reached (label present), 0 if the frontier was exhausted, -1 on
@@ -472,9 +428,36 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 	}
 
 	/* ---- seed with the current route tree (add_route_tree_to_heap) */
+	float smin = PF_INF_F;
+	for (int i = lane; i < tree_n; i += PF_WARP) {
+		PfTreeNode t = w.tree[i];
+		if (t.flags & PF_TF_REEXPAND) {
+			float back = crit * t.Tdel;
+			float tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
+			if (tot < smin) smin = tot;
+		}
+	}
+	smin = pf_warp_min_f(smin);
+	if (!(smin < PF_INF_F)) return 0;
 	{
-		int sr = pf_seed_tree(w, tree_n, tgt_xl, tgt_yl, crit);
-		if (sr <= 0) return sr;
+		float win = smin * P->win_rel;
+		if (win < P->win_abs) win = P->win_abs;
+		w.T_hi = smin + win;
+	}
+	for (int base = 0; base < tree_n; base += PF_WARP) {
+		int i = base + lane;
+		int valid = 0, node = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
+		if (i < tree_n) {
+			PfTreeNode t = w.tree[i];
+			if (t.flags & PF_TF_REEXPAND) {
+				valid = 1; node = t.node; R_up = t.R_up;
+				back = crit * t.Tdel;
+				tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
+			}
+		}
+		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
+		pf_push(w, wr, tot, back, node);
+		if (w.overflow) return -1;
 	}
 
 	/* ---- settle loop */
@@ -607,7 +590,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 /* ------------------------------------------------------------------ high-fanout window
  * mark_node_expansion_by_bin, route_timing.c:867-960: only the root's direct children are
  * examined and re-flagged (kept as in the reference). */
-PF_DEV_COLD int pf_highfanout_rlim(PfWarp &w, int tree_n, int target_node) {
+PF_DEV int pf_highfanout_rlim(PfWarp &w, int tree_n, int target_node) {
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	if (w.num_sinks < 64) return 1;
@@ -653,7 +636,7 @@ PF_DEV_COLD int pf_highfanout_rlim(PfWarp &w, int tree_n, int target_node) {
 /* ------------------------------------------------------------------ back-trace + Elmore + commit
  * update_traceback (route_common.c:638) and update_route_tree (route_tree_timing.c:181-456).
  * Returns the tree index of the new SINK entry, or -1 on tree overflow. */
-PF_DEV_COLD int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
+PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	int tree_n = *tree_n_io;

@@ -25,7 +25,6 @@
 #include <math.h>
 
 #define PF_DEV static inline
-#define PF_DEV_COLD static inline
 #define PF_WARP 32
 
 struct pf_u4 { unsigned x, y, z, w; };
