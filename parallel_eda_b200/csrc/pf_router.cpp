@@ -53,6 +53,7 @@ struct pf_router {
 	int iter_count;
 	int best_overused, stall_count;   /* convergence watchdog, see pf_iteration_begin */
 	int cur_div, n_small, n_big; int *retry_work;
+	char *ctl; unsigned long long h_pool_head;   /* device control block; host copy of the log head */
 	int *status, *retry_list, *retry_count;
 	PfStats *stats;
 	int *d_overused; unsigned long long *d_wl;
@@ -166,11 +167,11 @@ extern "C" void pf_router_destroy(pf_router *r) {
 	pfb_free(r->nodes); pfb_free(r->edges); pfb_free(r->sw); pfb_free(r->indexed);
 	pfb_free(r->net_ptr); pfb_free(r->net_term); pfb_free(r->net_bb);
 	pfb_free(r->crit); pfb_free(r->net_delay);
+	if (r->ctl) { r->small.work_head = NULL; r->big.work_head = NULL; }
 	free_slot_class(r->small); free_slot_class(r->big);
 	pfb_free(r->pool[0]); pfb_free(r->pool[1]); pfb_free(r->loc);
-	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->sel_counts); pfb_free(r->retry_work);
-	pfb_free(r->pool_head); pfb_free(r->status); pfb_free(r->retry_list); pfb_free(r->retry_count);
-	pfb_free(r->stats); pfb_free(r->d_overused); pfb_free(r->d_wl);
+	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->retry_work);
+	pfb_free(r->ctl); pfb_free(r->retry_list);
 	pfb_free(r->occ_base); pfb_free(r->occ_delta);
 	pfb_free(r->g_source); pfb_free(r->g_count); pfb_free(r->g_off); pfb_free(r->g_chosen);
 	delete r;
@@ -226,7 +227,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
 	r->pool[0] = r->pool[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
 	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->iter_count = 0;
-	r->best_overused = 0x7fffffff; r->stall_count = 0; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL;
+	r->best_overused = 0x7fffffff; r->stall_count = 0; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
 	r->occ_base = r->occ_delta = NULL; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
 	r->h2d_bytes = r->d2h_bytes = 0;
@@ -242,7 +243,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.sink_cap <= 0) c.sink_cap = 64;
 	if (c.big_slots <= 0) c.big_slots = 64;
 	if (c.reroute_all_iters == 0) c.reroute_all_iters = 1;
-	if (c.inflight_div <= 0) c.inflight_div = 32;
+	if (c.inflight_div <= 0) c.inflight_div = 16;
 	if (c.min_slots <= 0) c.min_slots = 1;
 	if (c.stall_iters == 0) c.stall_iters = 3;
 	if (c.max_batch > PF_MAX_BATCH) c.max_batch = PF_MAX_BATCH;
@@ -377,20 +378,28 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		for (int i : r->work_big) r->h_net_big[i] = 1;
 		r->all_nets = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(r->num_all, 1));
 		r->net_big = (unsigned char *)pfb_alloc((size_t)std::max(r->n, 1));
-		r->sel_counts = (int *)pfb_alloc(sizeof(int) * 4);
-		if (!r->loc || !r->all_nets || !r->net_big || !r->sel_counts
+		if (!r->loc || !r->all_nets || !r->net_big
 				|| pfb_h2d(r->all_nets, all.data(), sizeof(int) * (size_t)r->num_all)
 				|| pfb_h2d(r->net_big, r->h_net_big.data(), (size_t)r->n)) { pf_router_destroy(r); CUDA_FAIL(); }
 	}
-	r->pool_head = (unsigned long long *)pfb_alloc(sizeof(unsigned long long) * 2);
-	r->status = (int *)pfb_alloc(sizeof(int) * 8);
+	/* one 256-byte control block holds every small counter the host polls, so an iteration needs one
+	 * memset before and one 256-byte read after the route kernel instead of a handful of tiny copies:
+	 *   [0] status[8] [32] retry_count[4] [48] sel_counts[4] [64] overused[4] [80] wl[2] [96] PfStats
+	 *   [160] small.work_head[4] [176] big.work_head[4] | [192] pool_head[2] (not cleared per iteration) */
+	r->ctl = (char *)pfb_alloc(256);
+	if (!r->ctl) { pf_router_destroy(r); CUDA_FAIL(); }
+	r->pool_head = (unsigned long long *)(r->ctl + 192);
+	r->status = (int *)(r->ctl + 0);
 	r->retry_list = (int *)pfb_alloc_raw(sizeof(int) * (size_t)std::max(nwork, 1));
-	r->retry_count = (int *)pfb_alloc(sizeof(int) * 4);
+	r->retry_count = (int *)(r->ctl + 32);
 	r->retry_work = (int *)pfb_alloc_raw(sizeof(int) * (size_t)std::max(nwork, 1));
-	r->stats = (PfStats *)pfb_alloc(sizeof(PfStats));
-	r->d_overused = (int *)pfb_alloc(sizeof(int) * 4);
-	r->d_wl = (unsigned long long *)pfb_alloc(sizeof(unsigned long long) * 2);
-	if (!r->pool_head || !r->status || !r->retry_list || !r->retry_count || !r->retry_work || !r->stats || !r->d_overused || !r->d_wl) { pf_router_destroy(r); CUDA_FAIL(); }
+	r->stats = (PfStats *)(r->ctl + 96);
+	r->d_overused = (int *)(r->ctl + 64);
+	r->d_wl = (unsigned long long *)(r->ctl + 80);
+	r->sel_counts = (int *)(r->ctl + 48);
+	pfb_free(r->small.work_head); pfb_free(r->big.work_head);
+	r->small.work_head = (int *)(r->ctl + 160); r->big.work_head = (int *)(r->ctl + 176);
+	if (!r->retry_list || !r->retry_work) { pf_router_destroy(r); CUDA_FAIL(); }
 	if (c.nranks > 1) {
 		r->occ_base = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
 		r->occ_delta = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
@@ -425,7 +434,8 @@ extern "C" int pf_router_reset(pf_router *r) {
 	if (upload_nodes(r, pfb_pinned(sizeof(PfNode) * (size_t)r->N)) != PF_OK) return PF_ECUDA;
 	CKB(pfb_sync());
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
-	CKB(pfb_zero(r->pool_head, sizeof(unsigned long long) * 2));
+	CKB(pfb_zero(r->ctl, 256));
+	r->h_pool_head = 0;
 	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0;
 	CKB(pfb_zero(r->net_delay, sizeof(float) * (size_t)std::max(r->T, 1)));
 	if (r->occ_base) CKB(pfb_zero(r->occ_base, sizeof(int) * (size_t)r->N));
@@ -503,13 +513,13 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	if (crit) { CKB(pfb_h2d(r->crit, crit, sizeof(float) * (size_t)r->T)); r->h2d_bytes += (int64_t)sizeof(float) * r->T; }
 	/* garbage-collect the route-tree log when it is more than half full */
 	{
-		unsigned long long head[2];
-		CKB(pfb_d2h(head, r->pool_head, sizeof(head)));
+		unsigned long long head[2] = { r->h_pool_head, 0 };
 		if ((long long)head[0] > r->pool_cap / 2) {
 			CKB(pfb_zero(r->pool_head, sizeof(unsigned long long) * 2));
 			CKB(pfb_launch_compact(r->pool[r->cur], r->pool[r->cur ^ 1], r->loc, r->all_nets, r->num_all, r->pool_head));
 			r->cur ^= 1;
 			CKB(pfb_d2h(head, r->pool_head, sizeof(head)));
+			r->h_pool_head = head[0];
 			if ((long long)head[0] > r->pool_cap / 2) FAILF(PF_EOVERFLOW, "route store too small: %llu live tree entries of %lld", head[0], r->pool_cap);
 		}
 	}
@@ -559,9 +569,7 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, int nparts, pf_iter_stats *st) {
 	if (!r || nparts < 1 || part < 0 || part >= nparts) FAILF(PF_EINVAL, "bad argument");
 	int rc;
-	CKB(pfb_zero(r->status, sizeof(int) * 8));
-	CKB(pfb_zero(r->retry_count, sizeof(int) * 4));
-	CKB(pfb_zero(r->stats, sizeof(PfStats)));
+	CKB(pfb_zero(r->ctl, 192));            /* status, retry count, stats, both work-queue heads */
 	const int div = r->cur_div;
 	auto slice = [&](int n, int &off, int &cnt) { off = (int)((long long)n * part / nparts); cnt = (int)((long long)n * (part + 1) / nparts) - off; };
 	int so, sc, bo, bc;
@@ -569,23 +577,25 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 	PfParams P;
 	int total = r->n_small + r->n_big;      /* the staleness bound is about the whole iteration's nets */
 	if (bc > 0) {                          /* long nets first */
-		CKB(pfb_zero(r->big.work_head, sizeof(int) * 4));
 		r->big.num_work = bc;
 		fill_params(r, P, r->big, pres_fac);
 		P.work = r->big.work + bo;
 		{ int sl = slots_for(r, total, std::min(r->big.num_slots, bc), div); tune_granularity(r, P, bc, sl); CKB(pfb_launch_route(&P, sl, 1)); }
 	}
 	if (sc > 0) {
-		CKB(pfb_zero(r->small.work_head, sizeof(int) * 4));
 		r->small.num_work = sc;
 		fill_params(r, P, r->small, pres_fac);
 		P.work = r->small.work + so;
 		{ int sl = slots_for(r, total, r->small.num_slots, div); tune_granularity(r, P, sc, sl); CKB(pfb_launch_route(&P, sl, r->cfg.warps_per_block)); }
 	}
-	CKB(pfb_sync());
+	/* one read brings back status, retry count, counters and the log head */
+	char h_ctl[256];
+	CKB(pfb_d2h(h_ctl, r->ctl, 256));
+	int h_retry[4];
+	memcpy(h_retry, h_ctl + 32, sizeof(h_retry));
+	PfStats hs_total;
+	memcpy(&hs_total, h_ctl + 96, sizeof(PfStats));
 	/* nets whose scratch overflowed in a small slot are re-routed in the big slots, and stay there */
-	int h_retry[4] = { 0, 0, 0, 0 };
-	CKB(pfb_d2h(h_retry, r->retry_count, sizeof(int) * 4));
 	int rounds = 0;
 	while (h_retry[0] > 0) {
 		std::vector<int> lst((size_t)h_retry[0]);
@@ -595,27 +605,30 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 		if (r->cfg.verbose) fprintf(stderr, "pf_router: %d nets moved to the big slots\n", h_retry[0]);
 		for (int i : lst) r->h_net_big[i] = 1;
 		CKB(pfb_h2d(r->net_big, r->h_net_big.data(), (size_t)r->n));
-		CKB(pfb_zero(r->retry_count, sizeof(int) * 4));
+		CKB(pfb_zero(r->ctl + 32, 16));         /* retry count */
+		CKB(pfb_zero(r->ctl + 96, 96));         /* counters and work-queue heads */
 		/* the retry list is routed from the scratch queue so the iteration's own work lists stay intact */
 		CKB(pfb_h2d(r->retry_work, lst.data(), sizeof(int) * lst.size()));
-		CKB(pfb_zero(r->big.work_head, sizeof(int) * 4));
 		r->big.num_work = (int)lst.size();
 		fill_params(r, P, r->big, pres_fac);
 		P.work = r->retry_work;
 		P.skip_ripup = 1;
 		{ int sl = slots_for(r, (int)lst.size(), std::min(r->big.num_slots, (int)lst.size()), div); tune_granularity(r, P, (int)lst.size(), sl); CKB(pfb_launch_route(&P, sl, 1)); }
-		CKB(pfb_sync());
-		CKB(pfb_d2h(h_retry, r->retry_count, sizeof(int) * 4));
+		CKB(pfb_d2h(h_ctl, r->ctl, 256));
+		memcpy(h_retry, h_ctl + 32, sizeof(h_retry));
+		PfStats more;
+		memcpy(&more, h_ctl + 96, sizeof(PfStats));
+		hs_total.pops += more.pops; hs_total.pushes += more.pushes; hs_total.visits += more.visits; hs_total.nets += more.nets;
 	}
 	int h_status[8];
-	CKB(pfb_d2h(h_status, r->status, sizeof(int) * 8));
-	r->d2h_bytes += 48;
+	memcpy(h_status, h_ctl, sizeof(h_status));
+	memcpy(&r->h_pool_head, h_ctl + 192, sizeof(unsigned long long));
+	r->d2h_bytes += 256;
 	if (h_status[0] & PF_ST_POOL_OVERFLOW) FAILF(PF_EOVERFLOW, "route store overflow (capacity %lld tree entries)", r->pool_cap);
 	if (h_status[0] & PF_ST_INTERNAL) FAILF(PF_ECUDA, "internal error in the device router (net %d)", h_status[2]);
 	if (h_status[0] & PF_ST_UNROUTABLE) FAILF(PF_EUNROUTABLE, "net %d has no possible path (disconnected rr graph)", h_status[2]);
 	if (st) {
-		PfStats hs;
-		CKB(pfb_d2h(&hs, r->stats, sizeof(PfStats)));
+		const PfStats &hs = hs_total;
 		memset(st, 0, sizeof(*st));
 		st->nets_routed = (int)hs.nets; st->heap_pushes = (int64_t)hs.pushes; st->heap_pops = (int64_t)hs.pops;
 		st->edge_visits = (int64_t)hs.visits; st->pres_fac = pres_fac;
@@ -681,8 +694,7 @@ extern "C" void *pf_comm_net_delay_ptr(pf_router *r) { return r ? (void *)r->net
 
 extern "C" int pf_total_wirelength(pf_router *r, int64_t *wl, int64_t *avail) {
 	if (!r) FAILF(PF_EINVAL, "null router");
-	unsigned long long head[2];
-	CKB(pfb_d2h(head, r->pool_head, sizeof(head)));
+	unsigned long long head[2] = { r->h_pool_head, 0 };
 	CKB(pfb_zero(r->d_wl, sizeof(unsigned long long) * 2));
 	CKB(pfb_launch_wirelength(r->pool[r->cur], (long long)head[0], r->d_wl));
 	unsigned long long h[2];
