@@ -70,8 +70,8 @@ typedef struct pf_config {
 	int32_t inflight_div;     /* nets in flight <= ceil(nets this iteration / inflight_div): bounds how
 	                             stale the congestion seen by concurrent nets can be; 0 = auto (16) */
 	int32_t min_slots;        /* lower bound for the above; 0 = auto (1) */
-	int32_t stall_iters;      /* overuse not improved for this many iterations => one iteration re-routes every
-	                             net with 8x fewer nets in flight; 0 = auto (3); < 0 = never */
+	int32_t stall_iters;      /* overuse not down by 30 % over stall_iters+1 congested-only iterations => one
+	                             iteration re-routes every net with 8x fewer nets in flight; 0 = auto (3); < 0 = never */
 } pf_config;
 
 typedef struct pf_timing {    /* accumulated since create / last reset */

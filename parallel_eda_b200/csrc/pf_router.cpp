@@ -52,6 +52,7 @@ struct pf_router {
 	std::vector<int> net_rank;        /* position of a net in the fanout-sorted order */
 	int iter_count;
 	int best_overused, stall_count;   /* convergence watchdog, see pf_iteration_begin */
+	std::vector<int> over_hist; int since_full;
 	int cur_div, n_small, n_big; int *retry_work;
 	char *ctl; unsigned long long h_pool_head;   /* device control block; host copy of the log head */
 	int *status, *retry_list, *retry_count;
@@ -227,7 +228,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
 	r->pool[0] = r->pool[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
 	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->iter_count = 0;
-	r->best_overused = 0x7fffffff; r->stall_count = 0; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
+	r->best_overused = 0x7fffffff; r->stall_count = 0; r->since_full = 0; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
 	r->occ_base = r->occ_delta = NULL; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
 	r->h2d_bytes = r->d2h_bytes = 0;
@@ -436,7 +437,7 @@ extern "C" int pf_router_reset(pf_router *r) {
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
 	CKB(pfb_zero(r->ctl, 256));
 	r->h_pool_head = 0;
-	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0;
+	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0; r->over_hist.clear(); r->since_full = 0;
 	CKB(pfb_zero(r->net_delay, sizeof(float) * (size_t)std::max(r->T, 1)));
 	if (r->occ_base) CKB(pfb_zero(r->occ_base, sizeof(int) * (size_t)r->N));
 	{
@@ -528,7 +529,12 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	 * nets while every free resource nearby is held by legal nets.  When the overuse has not improved
 	 * for stall_iters iterations, fall back to the serial reference's policy for one iteration — every
 	 * net ripped up and re-routed (route_timing.c:161-183) — with few nets in flight. */
-	const bool stalled = r->cfg.stall_iters > 0 && r->stall_count >= r->cfg.stall_iters;
+	/* stalled: the overuse has not dropped by 30 % over the last stall_iters+1 congested-only iterations
+	 * (a healthy negotiation roughly halves it every iteration) */
+	const int K = r->cfg.stall_iters + 1;
+	const int H = (int)r->over_hist.size();
+	const bool stalled = r->cfg.stall_iters > 0 && r->since_full >= K && H > K
+			&& (double)r->over_hist[H - 1] > 0.7 * (double)r->over_hist[H - 1 - K];
 	if (stalled) { r->stall_count = 0; if (r->cfg.verbose) fprintf(stderr, "pf_router: overuse stalled at %d, re-routing every net\n", r->best_overused); }
 	const bool all = stalled || r->cfg.reroute_all_iters < 0 || r->iter_count < r->cfg.reroute_all_iters;
 	r->cur_div = stalled ? r->cfg.inflight_div * 8 : r->cfg.inflight_div;
@@ -561,6 +567,7 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 		}
 	}
 	r->iter_count++;
+	r->since_full = all ? 0 : r->since_full + 1;
 	return PF_OK;
 }
 
@@ -658,6 +665,7 @@ static int update_costs_impl(pf_router *r, float acc_fac, const int *delta, int 
 	r->d2h_bytes += 16;
 	if (overused) *overused = h[0];
 	if (h[0] < r->best_overused) { r->best_overused = h[0]; r->stall_count = 0; } else r->stall_count++;
+	r->over_hist.push_back(h[0]);
 	return PF_OK;
 }
 
