@@ -554,14 +554,19 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 		r->d2h_bytes += 16;
 		r->n_small = counts[0]; r->n_big = counts[1];
 		/* the selection kernel appends in atomic order; restore the fanout order of the reference's net
-		 * loop (route_timing.c:98-106) so long nets start first and runs are reproducible */
+		 * loop (route_timing.c:98-106) so long nets start first and runs are reproducible — reversed on
+		 * every other iteration: with a fixed order the net that is routed first is always the one that
+		 * has to give way, and a net squeezed between legal neighbours then wanders from one victim to
+		 * the next without either side ever yielding (the reference authors experimented with shuffling
+		 * the order for the same reason, route_timing.c:158) */
+		const bool reversed = (r->iter_count & 1) != 0;
 		for (int k = 0; k < 2; k++) {
 			SlotClass &sc = k ? r->big : r->small;
 			int cnt = k ? r->n_big : r->n_small;
 			if (cnt < 2) continue;
 			std::vector<int> lst((size_t)cnt);
 			CKB(pfb_d2h(lst.data(), sc.work, sizeof(int) * (size_t)cnt));
-			std::sort(lst.begin(), lst.end(), [&](int a, int b) { return r->net_rank[a] < r->net_rank[b]; });
+			std::sort(lst.begin(), lst.end(), [&](int a, int b) { return reversed ? r->net_rank[a] > r->net_rank[b] : r->net_rank[a] < r->net_rank[b]; });
 			CKB(pfb_h2d(sc.work, lst.data(), sizeof(int) * (size_t)cnt));
 			r->d2h_bytes += (int64_t)sizeof(int) * cnt; r->h2d_bytes += (int64_t)sizeof(int) * cnt;
 		}
@@ -872,6 +877,7 @@ extern "C" int pf_try_timing_driven_route(const pf_problem *p, const pf_config *
 		if ((rc = pf_update_costs(r, acc_fac, &overused)) != PF_OK) break;
 		st.overused_nodes = overused;
 		stats.push_back(st);
+		if (cfg->verbose) fprintf(stderr, "pf_router: iteration %d: %d nets routed, %d rr nodes overused, pres_fac %g\n", itry, st.nets_routed, overused, (double)st.pres_fac);
 		if (overused == 0) { success = 1; itry++; break; }
 		if (o.timing_analysis_enabled && sta) {
 			if ((rc = pf_get_net_delay(r, delay.data())) != PF_OK) break;
