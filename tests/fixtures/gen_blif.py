@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--latch_frac", type=float, default=0.3)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--name", default="toy")
+    ap.add_argument("--hub", type=int, default=0, help="number of LUTs that additionally read one shared hub signal (a high-fanout net)")
     a = ap.parse_args()
     rng = random.Random(a.seed)
     signals = ["pi%d" % i for i in range(a.pis)]
@@ -27,6 +28,8 @@ def main():
         k = rng.randint(3, 6)
         pool = signals[-a.window:]
         ins = rng.sample(pool, min(k, len(pool)))
+        if i < a.hub and "pi0" not in ins:
+            ins = ins[:5] + ["pi0"]          # pi0 becomes a net with >= 64 sinks (HIGH_FANOUT_NET_LIM, vpr_types.h:91)
         used.update(ins)
         out = "n%d" % i
         body.append(".names %s %s" % (" ".join(ins), out))

@@ -3,13 +3,15 @@
 # /root/reference by `make -C oracle ref`).  Only works where /root/reference exists.
 #   toy : tests/fixtures/gen_blif.py --luts 300  --pis 16 --window 60  --seed 1, W=64
 #   mid : tests/fixtures/gen_blif.py --luts 4000 --pis 64 --window 400 --seed 2, W=200
+#   hub : tests/fixtures/gen_blif.py --luts 900 --pis 24 --window 120 --seed 5 --hub 700, W=90 (one 84-sink net)
 set -e
 HERE=$(cd "$(dirname "$0")" && pwd); ROOT=$(cd "$HERE/../.." && pwd)
 REF=$ROOT/oracle/_ref/vpr_ref; W=$(mktemp -d); cd "$W"
 cp "$ROOT/tests/fixtures/k6_N10_like.xml" .
 python "$ROOT/tests/fixtures/gen_blif.py" toy.blif --luts 300 --pis 16 --window 60 --seed 1 --name toy
 python "$ROOT/tests/fixtures/gen_blif.py" mid.blif --luts 4000 --pis 64 --window 400 --seed 2 --name mid
-for c in toy:64 mid:200; do
+python "$ROOT/tests/fixtures/gen_blif.py" hub.blif --luts 900 --pis 24 --window 120 --seed 5 --name hub --hub 700
+for c in toy:64 mid:200 hub:90; do
   n=${c%%:*}; w=${c##*:}
   "$REF" flow k6_N10_like.xml $n --nodisp --pack --place > /dev/null
   PF_DUMP_PROBLEM=${n}_w$w.pfp PF_DUMP_RESULT=${n}_w$w.pfr "$REF" flow k6_N10_like.xml $n --nodisp --route --route_chan_width $w > /dev/null

@@ -90,3 +90,17 @@ def test_reroute_all_policy_single_warp(emu_lib):
     assert r.success == 1 and all(int(x) == 293 for x in r.iter_stats["nets_routed"])
     check_route.check_route(p, r)
     assert abs(r.total_wirelength - g.total_wirelength) <= 0.03 * g.total_wirelength
+
+
+def test_high_fanout_net_window(emu_lib):
+    """hub_w90 has a routed net with 84 sinks (>= HIGH_FANOUT_NET_LIM 64): the per-sink search window of
+    mark_node_expansion_by_bin (route_timing.c:867-960) and the big-slot class are exercised."""
+    p = pfio.read_problem(os.path.join(G, "hub_w90.pfp.xz"))
+    p.opts["timing_analysis_enabled"] = 0
+    g = pfio.read_result(os.path.join(G, "hub_w90_nt.pfr.xz"))
+    assert int((np.diff(p.net_ptr) - 1)[p.net_is_global == 0].max()) == 84
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=4, big_slots=2)
+    r = router.try_timing_driven_route(p, cfg, lib_path=emu_lib)
+    assert r.success == 1
+    check_route.check_route(p, r)
+    assert r.total_wirelength <= 1.08 * g.total_wirelength

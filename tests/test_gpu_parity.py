@@ -52,7 +52,7 @@ def test_single_warp_serial_order_matches_reference(name):
     assert r.iterations <= int(1.5 * g.iterations) + 1
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "mid_w200"])
+@pytest.mark.parametrize("name", ["toy_w64", "mid_w200", "hub_w90"])
 def test_concurrent_routing_timing_off(name):
     p, g = _load(name, False)
     r = router.try_timing_driven_route(p, router.default_config())
@@ -63,7 +63,7 @@ def test_concurrent_routing_timing_off(name):
     assert r.iterations <= 2 * g.iterations + 2
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "mid_w200"])
+@pytest.mark.parametrize("name", ["toy_w64", "mid_w200", "hub_w90"])
 def test_concurrent_routing_timing_driven(name):
     """Timing-driven mode with the reference's own per-iteration criticalities replayed as the STA."""
     p, g = _load(name, True)

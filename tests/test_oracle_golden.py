@@ -20,6 +20,8 @@ CASES = [
     ("toy_w64", "toy_w64_nt.pfr", False),    # timing analysis off: 14 iterations
     ("mid_w200", "mid_w200_nt.pfr", False),  # 3852 nets, 21x21, W=200, timing off: 12 iterations
     ("mid_w200", "mid_w200.pfr", True),      # timing-driven: 21 iterations, 80,871 net routes
+    ("hub_w90", "hub_w90.pfr", True),        # 865 nets, 10x10, W=90, one routed net with 84 sinks: exercises the
+    ("hub_w90", "hub_w90_nt.pfr", False),    # high-fanout window of mark_node_expansion_by_bin (route_timing.c:867)
 ]
 
 
