@@ -202,18 +202,24 @@ def run_ours(a):
     # end to end through the public API with host buffers (N GPUs)
     e2e = None
     if not a.no_e2e:
+        e2e_phases = []
+
         def e2e_step():
             if comm:
                 comm.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             R2 = router.Router(p, cfg)                 # flatten + H2D of the whole problem
+            t1 = time.perf_counter()
             rep = pathfinder.route(R2, comm=comm, delta_buf=delta)
+            t2 = time.perf_counter()
             res = R2.result()                          # D2H of traces, delays, occupancy
+            t3 = time.perf_counter()
             t = R2.timing()
             R2.close()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            e2e_phases.append((t1 - t0, t2 - t1, t3 - t2, dt - (t3 - t0)))
             if comm:
                 dt = comm.all_reduce_max(dt)
             return rep, dt, t.h2d_bytes, t.d2h_bytes, res
@@ -224,7 +230,8 @@ def run_ours(a):
             rep, dt, hb, db, _res = e2e_step()
             acc_n += rep.nets_routed; acc_t += dt
         e2e = {"value": acc_n / acc_t, "unit": "nets/s", "h2d_bytes_per_step": int(hb), "d2h_bytes_per_step": int(db),
-               "s_per_step": acc_t / max(1, min(a.steps, 2))}
+               "s_per_step": acc_t / max(1, min(a.steps, 2)),
+               "phases_s": dict(zip(("create_upload", "route", "result_download", "destroy"), [round(x, 4) for x in e2e_phases[-1]]))}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -46,6 +46,10 @@ int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_o
 		int *occ_base, const int *occ_delta);
 /* delta[i] = nodes[i].occ - base[i]: what this GPU's nets changed since the last sync */
 int pfb_launch_export_delta(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta);
+/* route trees → s_trace-ordered arrays on the device: pass 1 (trace_node == NULL) writes len[net];
+ * pass 2 writes trace_node/trace_switch at tptr[net] and adds the wirelength into *d_wl */
+int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num_nets, int *len, const int *tptr,
+		int *trace_node, short *trace_switch, unsigned long long *d_wl);
 /* occ_out[i] = nodes[i].occ (compact copy for the host) */
 int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out);
 /* total wirelength of all trees in the route store (route_timing.c:189-225 sanity abort) */

@@ -1051,6 +1051,31 @@ PF_DEV void pf_reserve_opins_group(PfNode *nodes, const uint32_t *edges, const P
 	}
 }
 
+/* Route tree → s_trace order (update_traceback, route_common.c:638-706), one net per call.
+ * pass 1 (out == NULL): returns the trace length; pass 2: writes node / switch at out[...] and returns the
+ * net's wirelength (get_num_bends_and_length, base/stats.c:355-409). */
+PF_DEV int pf_trace_of_net(const PfTreeNode *t, int cnt, int *out_node, short *out_sw) {
+	if (cnt <= 1) return 0;
+	if (!out_node) {
+		int sinks = 0;
+		for (int k = 0; k < cnt; k++) if ((t[k].type_ci & 7) == 1) sinks++;
+		return cnt + (sinks > 0 ? sinks - 1 : 0);
+	}
+	int w = 0, wl = 0, k = 0;
+	while (k < cnt) {
+		int e = k;
+		while (e < cnt - 1 && (t[e].type_ci & 7) != 1) e++;
+		if (k > 0) { out_node[w] = t[t[k].parent].node; out_sw[w] = (short)t[k].sw; w++; }
+		for (int q = k; q <= e; q++) {
+			out_node[w] = t[q].node; out_sw[w] = q < e ? (short)t[q + 1].sw : (short)-1; w++;
+			int ty = t[q].type_ci & 7;
+			if (ty == 4 || ty == 5) wl += 1 + t[q].xhigh - t[q].xlow + t[q].yhigh - t[q].ylow;
+		}
+		k = e + 1;
+	}
+	return wl;
+}
+
 /* Does this net touch an overused rr node?  (the test the reference's parallel router uses to pick
  * the nets of its "phase two", parallel_route/partitioning_multi_sink_delta_stepping_route.cxx:6241-6269) */
 PF_DEV int pf_net_is_congested(const PfNode *nodes, const PfTreeNode *pool, PfNetLoc loc) {

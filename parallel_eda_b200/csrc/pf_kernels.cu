@@ -181,6 +181,16 @@ __global__ void pf_export_delta_kernel(const PfNode *nodes, int num_nodes, const
 		occ_delta[i] = nodes[i].occ - occ_base[i];
 }
 
+__global__ void pf_build_traces_kernel(const PfTreeNode *pool, const PfNetLoc *loc, int num_nets, int *len, const int *tptr,
+		int *trace_node, short *trace_switch, unsigned long long *d_wl) {
+	int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i >= num_nets) return;
+	PfNetLoc l = loc[i];
+	if (!trace_node) { len[i] = pf_trace_of_net(pool + l.off, l.count, NULL, NULL); return; }
+	int wl = pf_trace_of_net(pool + l.off, l.count, trace_node + tptr[i], trace_switch + tptr[i]);
+	if (wl) atomicAdd(d_wl, (unsigned long long)wl);
+}
+
 __global__ void pf_extract_occ_kernel(const PfNode *nodes, int num_nodes, int *occ_out) {
 	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x)) occ_out[i] = nodes[i].occ;
 }
@@ -296,5 +306,13 @@ int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, co
 int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out) {
 	if (ev_begin(2) != 0) return -1;
 	pf_extract_occ_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, occ_out);
+	return ev_end();
+}
+
+int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num_nets, int *len, const int *tptr,
+		int *trace_node, short *trace_switch, unsigned long long *d_wl) {
+	if (num_nets <= 0) return 0;
+	if (ev_begin(2) != 0) return -1;
+	pf_build_traces_kernel<<<(num_nets + 127) / 128, 128, 0, g_stream>>>(pool, loc, num_nets, len, tptr, trace_node, trace_switch, d_wl);
 	return ev_end();
 }

@@ -746,89 +746,79 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 	if (!r || !out) FAILF(PF_EINVAL, "null argument");
 	const pf_problem *p = r->prob;
 	memset(out, 0, sizeof(*out));
-	std::vector<PfNetLoc> loc((size_t)std::max(r->n, 1));
-	CKB(pfb_d2h(loc.data(), r->loc, sizeof(PfNetLoc) * (size_t)r->n));
-	long long used = 0;
-	for (int i = 0; i < r->n; i++) used = std::max<long long>(used, (long long)loc[i].off + loc[i].count);
-	/* the live part of the log and the compacted occupancy come back through the pinned staging buffer */
-	const size_t pbytes = sizeof(PfTreeNode) * (size_t)std::max<long long>(used, 1), obytes = sizeof(int) * (size_t)r->N;
-	char *pin = (char *)pfb_pinned(pbytes + obytes + 256);
-	std::vector<char> fallback;
-	if (!pin) { fallback.resize(pbytes + obytes + 256); pin = fallback.data(); }
-	const PfTreeNode *pool = (const PfTreeNode *)pin;
-	int *h_occ = (int *)(pin + ((pbytes + 255) & ~(size_t)255));
-	int *d_occ = r->occ_delta ? r->occ_delta : (int *)pfb_alloc_raw(obytes);
-	if (!d_occ) CUDA_FAIL();
-	int bad = pfb_launch_extract_occ(r->nodes, r->N, d_occ) || pfb_d2h_async((void *)pool, r->pool[r->cur], sizeof(PfTreeNode) * (size_t)used)
-			|| pfb_d2h_async(h_occ, d_occ, obytes) || pfb_sync();
-	if (!r->occ_delta) pfb_free(d_occ);
-	if (bad) CUDA_FAIL();
-	r->d2h_bytes += (int64_t)sizeof(PfTreeNode) * used + (int64_t)obytes + (int64_t)sizeof(PfNetLoc) * r->n;
-
-	/* pass 1: trace length of every net (entries + one join element per later segment) */
-	std::vector<int32_t> tptr((size_t)r->n + 1, 0);
-	std::vector<int> err(1, -1);
-	std::vector<int> *perr = &err;
-	parallel_for(r->n, [&, perr](long long lo, long long hi) {
-		for (long long i = lo; i < hi; i++) {
-			const PfTreeNode *t = pool + loc[i].off;
-			int cnt = loc[i].count, sinks = 0;
-			for (int k = 0; k < cnt; k++) if ((t[k].type_ci & 7) == PF_SINK) sinks++;
-			if (cnt > 1 && (t[cnt - 1].type_ci & 7) != PF_SINK) (*perr)[0] = (int)i;
-			tptr[i + 1] = cnt <= 1 ? 0 : cnt + (sinks > 0 ? sinks - 1 : 0);
-		}
-	});
-	if (err[0] >= 0) FAILF(PF_ECUDA, "net %d: route tree does not end in a SINK", err[0]);
-	for (int i = 0; i < r->n; i++) tptr[i + 1] += tptr[i];
-	const size_t total = (size_t)tptr[r->n];
-	out->num_nets = r->n;
-	out->trace_ptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)r->n + 1));
+	const int n = r->n;
+	/* the traces are assembled on the device (pf_build_traces_kernel), so what crosses PCIe is the final
+	 * 6 bytes per trace element plus 4 bytes per rr node of occupancy — not the 32-byte tree entries */
+	int *d_len = (int *)pfb_alloc_raw(sizeof(int) * ((size_t)n + 1));
+	int *d_occ = r->occ_delta ? r->occ_delta : (int *)pfb_alloc_raw(sizeof(int) * (size_t)r->N);
+	if (!d_len || !d_occ) { pfb_free(d_len); if (!r->occ_delta) pfb_free(d_occ); CUDA_FAIL(); }
+	std::vector<int32_t> tptr((size_t)n + 1, 0);
+	int bad = pfb_launch_build_traces(r->pool[r->cur], r->loc, n, d_len, NULL, NULL, NULL, NULL) || pfb_d2h(tptr.data() + 1, d_len, sizeof(int) * (size_t)n);
+	if (bad) { pfb_free(d_len); if (!r->occ_delta) pfb_free(d_occ); CUDA_FAIL(); }
+	for (int i = 0; i < n; i++) tptr[i + 1] += tptr[i];
+	const size_t total = (size_t)tptr[n];
+	int *d_tn = (int *)pfb_alloc_raw(sizeof(int) * std::max<size_t>(total, 1));
+	short *d_ts = (short *)pfb_alloc_raw(sizeof(short) * std::max<size_t>(total, 1));
+	out->num_nets = n;
+	out->trace_ptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 1));
 	out->trace_node = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(total, 1));
 	out->trace_switch = (int16_t *)malloc(sizeof(int16_t) * std::max<size_t>(total, 1));
 	out->net_delay = (float *)malloc(sizeof(float) * (size_t)std::max(r->T, 1));
 	out->occ = (int32_t *)malloc(sizeof(int32_t) * (size_t)r->N);
-	if (!out->trace_ptr || !out->trace_node || !out->trace_switch || !out->net_delay || !out->occ) { pf_result_free(out); FAILF(PF_ENOMEM, "out of host memory"); }
-	memcpy(out->trace_ptr, tptr.data(), sizeof(int32_t) * ((size_t)r->n + 1));
-	/* pass 2: fill; wirelength and the magic cookie are accumulated per net and combined in net order */
-	std::vector<int> wl_net((size_t)std::max(r->n, 1), 0);
-	int32_t *tn = out->trace_node; int16_t *ts = out->trace_switch;
-	parallel_for(r->n, [&](long long lo, long long hi) {
-		for (long long i = lo; i < hi; i++) {
-			const PfTreeNode *t = pool + loc[i].off;
-			int cnt = loc[i].count, w = tptr[i], wl = 0, k = 0;
-			if (cnt <= 1) continue;
-			while (k < cnt) {
-				int e = k;
-				while ((t[e].type_ci & 7) != PF_SINK) e++;
-				if (k > 0) { tn[w] = t[t[k].parent].node; ts[w] = (int16_t)t[k].sw; w++; }
-				for (int q = k; q <= e; q++) {
-					tn[w] = t[q].node; ts[w] = q < e ? (int16_t)t[q + 1].sw : (int16_t)PF_OPEN; w++;
-					int ty = t[q].type_ci & 7;
-					if (ty == PF_CHANX || ty == PF_CHANY) wl += 1 + t[q].xhigh - t[q].xlow + t[q].yhigh - t[q].ylow;
-				}
-				k = e + 1;
-			}
-			wl_net[i] = wl;
+	const bool host_ok = out->trace_ptr && out->trace_node && out->trace_switch && out->net_delay && out->occ;
+	unsigned long long h_wl[2] = { 0, 0 };
+	bad = !d_tn || !d_ts || !host_ok;
+	if (!bad) {
+		/* pinned staging for the three big arrays when available */
+		const size_t b_tn = sizeof(int) * total, b_ts = sizeof(short) * total, b_occ = sizeof(int) * (size_t)r->N;
+		char *pin = (char *)pfb_pinned(b_tn + b_ts + b_occ + 1024);
+		char *h_tn = pin ? pin : (char *)out->trace_node;
+		char *h_ts = pin ? pin + ((b_tn + 255) & ~(size_t)255) : (char *)out->trace_switch;
+		char *h_occ = pin ? h_ts + ((b_ts + 255) & ~(size_t)255) : (char *)out->occ;
+		bad = pfb_h2d(d_len, tptr.data(), sizeof(int) * ((size_t)n + 1)) || pfb_zero(r->d_wl, sizeof(unsigned long long) * 2)
+				|| pfb_launch_build_traces(r->pool[r->cur], r->loc, n, NULL, d_len, d_tn, d_ts, r->d_wl)
+				|| pfb_launch_extract_occ(r->nodes, r->N, d_occ)
+				|| pfb_d2h_async(h_tn, d_tn, b_tn) || pfb_d2h_async(h_ts, d_ts, b_ts) || pfb_d2h_async(h_occ, d_occ, b_occ)
+				|| pfb_d2h(h_wl, r->d_wl, sizeof(h_wl)) || pfb_d2h(out->net_delay, r->net_delay, sizeof(float) * (size_t)r->T);
+		if (!bad && pin) {
+			parallel_for((long long)total, [&](long long lo, long long hi) {
+				memcpy(out->trace_node + lo, h_tn + sizeof(int) * (size_t)lo, sizeof(int) * (size_t)(hi - lo));
+				memcpy(out->trace_switch + lo, h_ts + sizeof(short) * (size_t)lo, sizeof(short) * (size_t)(hi - lo));
+			});
+			parallel_for(r->N, [&](long long lo, long long hi) { memcpy(out->occ + lo, h_occ + sizeof(int) * (size_t)lo, sizeof(int) * (size_t)(hi - lo)); });
 		}
-	});
+		r->d2h_bytes += (int64_t)(b_tn + b_ts + b_occ) + (int64_t)sizeof(int) * n + (int64_t)sizeof(float) * r->T;
+	}
+	pfb_free(d_len); pfb_free(d_tn); pfb_free(d_ts);
+	if (!r->occ_delta) pfb_free(d_occ);
+	if (bad) { pf_result_free(out); if (!host_ok) FAILF(PF_ENOMEM, "out of host memory"); CUDA_FAIL(); }
+	memcpy(out->trace_ptr, tptr.data(), sizeof(int32_t) * ((size_t)n + 1));
 	out->num_terminals = r->T;
-	if (pfb_d2h(out->net_delay, r->net_delay, sizeof(float) * (size_t)r->T)) { pf_result_free(out); CUDA_FAIL(); }
 	out->num_nodes = r->N;
-	memcpy(out->occ, h_occ, obytes);
-	long long wl = 0;
-	for (int i = 0; i < r->n; i++) wl += wl_net[i];
-	out->total_wirelength = (int32_t)wl;
-	{   /* get_serial_num, route_common.c:224-254 (sequential by definition: a running remainder) */
-		int serial = 0;
-		for (int i = 0; i < r->n; i++)
-			for (int k = tptr[i]; k < tptr[i + 1]; k++) {
-				int v = tn[k];
-				serial += (i + 1) * (p->xlow[v] * (p->nx + 1) - p->yhigh[v]);
-				serial -= p->ptc_num[v] * (i + 1) * 10;
-				serial -= p->type[v] * (i + 1) * 100;
-				serial %= 2000000000;
-			}
-		out->serial_num = serial;
+	out->total_wirelength = (int32_t)h_wl[0];
+	{   /* get_serial_num, route_common.c:224-254: a running 32-bit remainder, sequential by definition.  The three
+		 * per-element terms (random reads of xlow/yhigh/ptc/type) are gathered in parallel, the running update
+		 * then streams over contiguous arrays with the reference's exact operation order. */
+		std::vector<int> ta(std::max<size_t>(total, 1)), tb(std::max<size_t>(total, 1)), tc(std::max<size_t>(total, 1));
+		const int32_t *tn = out->trace_node;
+		parallel_for(n, [&](long long lo, long long hi) {
+			for (long long i = lo; i < hi; i++)
+				for (int k = tptr[i]; k < tptr[i + 1]; k++) {
+					int v = tn[k];
+					ta[k] = (int)((unsigned)(i + 1) * (unsigned)(p->xlow[v] * (p->nx + 1) - p->yhigh[v]));
+					tb[k] = (int)((unsigned)p->ptc_num[v] * (unsigned)(i + 1) * 10u);
+					tc[k] = (int)((unsigned)p->type[v] * (unsigned)(i + 1) * 100u);
+				}
+		});
+		unsigned serial = 0;      /* two's-complement wrap like the reference's int arithmetic */
+		int sv = 0;
+		for (size_t k = 0; k < total; k++) {
+			serial = (unsigned)sv + (unsigned)ta[k];
+			serial -= (unsigned)tb[k];
+			serial -= (unsigned)tc[k];
+			sv = (int)serial % 2000000000;
+		}
+		out->serial_num = sv;
 	}
 	return PF_OK;
 }

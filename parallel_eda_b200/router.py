@@ -165,14 +165,38 @@ class _ProblemHolder:
         self.c = cp
 
 
+class _ResultOwner:
+    """Keeps the C pf_result alive while numpy arrays view its buffers; frees it with the last view."""
+
+    def __init__(self, lib, cr):
+        self.lib, self.cr = lib, cr
+
+    def __del__(self):
+        try:
+            self.lib.pf_result_free(C.byref(self.cr))
+        except Exception:
+            pass
+
+
+def _view(owner, ptr, n, dtype):
+    """numpy view of n elements at a ctypes pointer (no copy); the array keeps `owner` alive."""
+    if n <= 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    ct = {np.dtype(np.int32): C.c_int32, np.dtype(np.int16): C.c_int16, np.dtype(np.float32): C.c_float}[np.dtype(dtype)]
+    buf = (ct * n).from_address(C.addressof(ptr.contents))
+    buf._owner = owner
+    return np.frombuffer(buf, dtype=dtype)
+
+
 def _take_result(lib, cr: _Result, T: int, with_stats: bool = True) -> pfio.Result:
+    owner = _ResultOwner(lib, cr)
     n = cr.num_nets
-    tp = np.ctypeslib.as_array(cr.trace_ptr, shape=(n + 1,)).copy()
+    tp = _view(owner, cr.trace_ptr, n + 1, np.int32)
     nt = int(tp[n])
-    tn = np.ctypeslib.as_array(cr.trace_node, shape=(max(nt, 1),))[:nt].copy()
-    ts = np.ctypeslib.as_array(cr.trace_switch, shape=(max(nt, 1),))[:nt].copy()
-    nd = np.ctypeslib.as_array(cr.net_delay, shape=(max(cr.num_terminals, 1),))[:cr.num_terminals].copy()
-    occ = np.ctypeslib.as_array(cr.occ, shape=(cr.num_nodes,)).copy()
+    tn = _view(owner, cr.trace_node, nt, np.int32)
+    ts = _view(owner, cr.trace_switch, nt, np.int16)
+    nd = _view(owner, cr.net_delay, cr.num_terminals, np.float32)
+    occ = _view(owner, cr.occ, cr.num_nodes, np.int32)
     stats = np.zeros(cr.num_iter_stats if with_stats else 0, dtype=pfio.ITER_STATS_DT)
     for i in range(len(stats)):
         s = cr.iter_stats[i]
@@ -180,10 +204,8 @@ def _take_result(lib, cr: _Result, T: int, with_stats: bool = True) -> pfio.Resu
                     s.crit_path_delay)
     crit = None
     if cr.num_crit_iters and cr.iter_crit:
-        crit = np.ctypeslib.as_array(cr.iter_crit, shape=(cr.num_crit_iters * T,)).reshape(cr.num_crit_iters, T).copy()
-    res = pfio.Result(cr.success, cr.iterations, cr.serial_num, cr.total_wirelength, tp, tn, ts, nd, occ, stats, crit)
-    lib.pf_result_free(C.byref(cr))
-    return res
+        crit = _view(owner, cr.iter_crit, cr.num_crit_iters * T, np.float32).reshape(cr.num_crit_iters, T)
+    return pfio.Result(cr.success, cr.iterations, cr.serial_num, cr.total_wirelength, tp, tn, ts, nd, occ, stats, crit)
 
 
 class Router:

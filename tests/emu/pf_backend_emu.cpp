@@ -114,3 +114,14 @@ int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out) {
 	g_times.aux_launches++;
 	return 0;
 }
+
+int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num_nets, int *len, const int *tptr,
+		int *trace_node, short *trace_switch, unsigned long long *d_wl) {
+	for (int i = 0; i < num_nets; i++) {
+		PfNetLoc l = loc[i];
+		if (!trace_node) { len[i] = pf_trace_of_net(pool + l.off, l.count, NULL, NULL); continue; }
+		*d_wl += (unsigned long long)pf_trace_of_net(pool + l.off, l.count, trace_node + tptr[i], trace_switch + tptr[i]);
+	}
+	g_times.aux_launches++;
+	return 0;
+}
