@@ -72,6 +72,10 @@ typedef struct pf_config {
 	int32_t min_slots;        /* lower bound for the above; 0 = auto (1) */
 	int32_t stall_iters;      /* overuse not down by 30 % over stall_iters+1 congested-only iterations => one
 	                             iteration re-routes every net with 8x fewer nets in flight; 0 = auto (3); < 0 = never */
+	int32_t history_window;   /* also re-route nets holding a node that was overused within the last K cost updates;
+	                             0 = off (default) */
+	int32_t keep_newcomer;    /* experimental: on an overused node, re-route every user except the one that committed it
+	                             last; 0 = off (default) */
 } pf_config;
 
 typedef struct pf_timing {    /* accumulated since create / last reset */

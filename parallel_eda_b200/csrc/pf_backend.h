@@ -43,7 +43,7 @@ int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block);
  * base/delta are non-NULL the pass first folds the all-reduced occupancy delta into the node
  * records: occ = base + delta, base = occ (multi-GPU iteration boundary) */
 int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
-		int *occ_base, const int *occ_delta);
+		int *occ_base, const int *occ_delta, unsigned char *last_over, int iter_tag);
 /* delta[i] = nodes[i].occ - base[i]: what this GPU's nets changed since the last sync */
 int pfb_launch_export_delta(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta);
 /* route trees → s_trace-ordered arrays on the device: pass 1 (trace_node == NULL) writes len[net];
@@ -61,7 +61,8 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
 /* work list of the next iteration: the nets of `all_nets` that touch an overused node (or every
  * net when force_all), split into the small/big slot classes by net_big[]; counts[0]/counts[1] */
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
-		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts);
+		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
+		const unsigned char *last_over, int iter_tag, int window, const int *committer);
 /* copy every live tree of `all_nets` from one log to another (garbage collection of the route store) */
 int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
 		unsigned long long *dst_head);

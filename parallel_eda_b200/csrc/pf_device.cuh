@@ -106,7 +106,7 @@ struct PfWarp {
 	unsigned epoch; unsigned round; int n_labels; int sh_n; int far_n; float T_hi; float far_min; float best;
 	int overflow;
 	/* per-net constants */
-	int bb_xmin, bb_xmax, bb_ymin, bb_ymax; int num_sinks;
+	int bb_xmin, bb_xmax, bb_ymin, bb_ymax; int num_sinks; int cur_net;
 	/* counters */
 	unsigned long long pops, pushes, visits, refills, stale;
 };
@@ -676,6 +676,7 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
 		t.pad = 0;
 		w.tree[tree_n + i] = t;
 		pf_atomic_add_i(&P->nodes[v].occ, 1);           /* commit: pathfinder_update_one_cost(+1) */
+		if (P->committer) P->committer[v] = w.cur_net;
 	}
 	pf_syncwarp();
 	if (lane == 0) {
@@ -791,7 +792,7 @@ PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: routed, 0: handed to a bi
 	const int lane = pf_lane();
 	const int t0 = P->net_ptr[inet];
 	const int ns = P->net_ptr[inet + 1] - t0 - 1;
-	w.num_sinks = ns;
+	w.num_sinks = ns; w.cur_net = inet;
 	w.bb_xmin = P->net_bb[4 * inet + 0]; w.bb_xmax = P->net_bb[4 * inet + 1];
 	w.bb_ymin = P->net_bb[4 * inet + 2]; w.bb_ymax = P->net_bb[4 * inet + 3];
 	w.overflow = 0;
@@ -979,7 +980,8 @@ PF_DEV void pf_warp_main(const PfParams *P, int slot, unsigned char *smem_warp) 
 
 /* pathfinder_update_cost (route_common.c:581-610) for one node; returns 1 if the node is overused
  * (feasible_routing, route_common.c:509-531).  pres_cost is not stored: it is a function of occ. */
-PF_DEV int pf_update_cost_one(PfNode *nodes, int i, float acc_fac, int *occ_base, const int *occ_delta) {
+PF_DEV int pf_update_cost_one(PfNode *nodes, int i, float acc_fac, int *occ_base, const int *occ_delta,
+		unsigned char *last_over, int iter_tag) {
 	PfNode *n = &nodes[i];
 	int occ = n->occ;
 	if (occ_base) {                       /* fold the all-reduced delta of every GPU's nets */
@@ -990,6 +992,7 @@ PF_DEV int pf_update_cost_one(PfNode *nodes, int i, float acc_fac, int *occ_base
 	int cap = n->capacity;
 	if (occ > cap) {
 		n->acc_cost += (occ - cap) * acc_fac;
+		if (last_over) last_over[i] = (unsigned char)iter_tag;   /* remembered for the re-route selection */
 		return 1;
 	}
 	return 0;
@@ -1078,10 +1081,23 @@ PF_DEV int pf_trace_of_net(const PfTreeNode *t, int cnt, int *out_node, short *o
 
 /* Does this net touch an overused rr node?  (the test the reference's parallel router uses to pick
  * the nets of its "phase two", parallel_route/partitioning_multi_sink_delta_stepping_route.cxx:6241-6269) */
-PF_DEV int pf_net_is_congested(const PfNode *nodes, const PfTreeNode *pool, PfNetLoc loc) {
+PF_DEV int pf_net_is_congested(const PfNode *nodes, const PfTreeNode *pool, PfNetLoc loc, const unsigned char *last_over,
+		int iter_tag, int window, const int *committer, int net) {
 	for (int i = 0; i < loc.count; i++) {
-		const PfNode *n = &nodes[pool[loc.off + i].node];
-		if (n->occ > n->capacity) return 1;
+		int v = pool[loc.off + i].node;
+		const PfNode *n = &nodes[v];
+		/* On an overused node every user is re-routed EXCEPT the one that committed it last: the newcomer was
+		 * squeezed onto it for lack of anything better, the incumbents usually have alternatives.  If both
+		 * were ripped up, the newcomer (routed first, still seeing the incumbent) would move on to its next
+		 * victim while the incumbent returns to the freed node, and the conflict would wander for ever. */
+		if (n->occ > n->capacity && (!committer || committer[v] != net)) return 1;
+		/* PathFinder's history cost is meant to be felt by every user of a contested resource, also by the
+		 * net that currently holds it legally: nets on nodes that were overused within the last `window`
+		 * iterations are re-routed too, so they can give way (tags are iteration numbers mod 255, 0 = never) */
+		if (last_over) {
+			int t = last_over[v];
+			if (t != 0 && ((iter_tag - t + 255) % 255) <= window) return 1;
+		}
 	}
 	return 0;
 }

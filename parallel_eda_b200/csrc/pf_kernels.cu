@@ -168,10 +168,10 @@ __global__ void __launch_bounds__(256) pf_route_kernel(const __grid_constant__ P
 }
 
 __global__ void pf_update_cost_kernel(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
-		int *occ_base, const int *occ_delta) {
+		int *occ_base, const int *occ_delta, unsigned char *last_over, int iter_tag) {
 	int over = 0;
 	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x))
-		over += pf_update_cost_one(nodes, i, acc_fac, occ_base, occ_delta);
+		over += pf_update_cost_one(nodes, i, acc_fac, occ_base, occ_delta, last_over, iter_tag);
 	over = __reduce_add_sync(0xffffffffu, over);
 	if ((threadIdx.x & 31u) == 0 && over) atomicAdd(d_overused, over);
 }
@@ -212,11 +212,12 @@ __global__ void pf_reserve_opins_kernel(PfNode *nodes, const uint32_t *edges, co
 }
 
 __global__ void pf_select_nets_kernel(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
-		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts) {
+		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
+		const unsigned char *last_over, int iter_tag, int window, const int *committer) {
 	int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (k >= num_all) return;
 	int net = all_nets[k];
-	if (force_all || pf_net_is_congested(nodes, pool, loc[net])) {
+	if (force_all || pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net)) {
 		if (net_big[net]) list_big[atomicAdd(&counts[1], 1)] = net;
 		else list_small[atomicAdd(&counts[0], 1)] = net;
 	}
@@ -260,9 +261,10 @@ static int stream_grid(long long n) {
 	return (int)b;
 }
 
-int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, int *occ_base, const int *occ_delta) {
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, int *occ_base, const int *occ_delta,
+		unsigned char *last_over, int iter_tag) {
 	if (ev_begin(1) != 0) return -1;
-	pf_update_cost_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, acc_fac, d_overused, occ_base, occ_delta);
+	pf_update_cost_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, acc_fac, d_overused, occ_base, occ_delta, last_over, iter_tag);
 	return ev_end();
 }
 
@@ -288,10 +290,11 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
 }
 
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
-		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts) {
+		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
+		const unsigned char *last_over, int iter_tag, int window, const int *committer) {
 	if (num_all <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
-	pf_select_nets_kernel<<<(num_all + 127) / 128, 128, 0, g_stream>>>(nodes, pool, loc, all_nets, num_all, net_big, force_all, list_small, list_big, counts);
+	pf_select_nets_kernel<<<(num_all + 127) / 128, 128, 0, g_stream>>>(nodes, pool, loc, all_nets, num_all, net_big, force_all, list_small, list_big, counts, last_over, iter_tag, window, committer);
 	return ev_end();
 }
 

@@ -108,6 +108,7 @@ struct PfParams {
 	 * A re-routed net appends its new tree and repoints loc; the log is compacted between
 	 * iterations when it is more than half garbage. */
 	PfTreeNode *pool; PfNetLoc *loc; unsigned long long *pool_head; long long pool_cap;
+	int *committer;        /* [num_nodes] net that committed this rr node last (re-route selection), may be NULL */
 	/* status */
 	int *status;
 	int *retry_list; int *retry_count;

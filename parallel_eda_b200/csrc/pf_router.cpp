@@ -53,6 +53,7 @@ struct pf_router {
 	int iter_count;
 	int best_overused, stall_count;   /* convergence watchdog, see pf_iteration_begin */
 	std::vector<int> over_hist; int since_full;
+	unsigned char *last_over; int cost_updates; int *committer;   /* per node: tag of the last cost update that found it overused */
 	int cur_div, n_small, n_big; int *retry_work;
 	char *ctl; unsigned long long h_pool_head;   /* device control block; host copy of the log head */
 	int *status, *retry_list, *retry_count;
@@ -172,7 +173,7 @@ extern "C" void pf_router_destroy(pf_router *r) {
 	free_slot_class(r->small); free_slot_class(r->big);
 	pfb_free(r->pool[0]); pfb_free(r->pool[1]); pfb_free(r->loc);
 	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->retry_work);
-	pfb_free(r->ctl); pfb_free(r->retry_list);
+	pfb_free(r->ctl); pfb_free(r->retry_list); pfb_free(r->last_over); pfb_free(r->committer);
 	pfb_free(r->occ_base); pfb_free(r->occ_delta);
 	pfb_free(r->g_source); pfb_free(r->g_count); pfb_free(r->g_off); pfb_free(r->g_chosen);
 	delete r;
@@ -228,7 +229,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
 	r->pool[0] = r->pool[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
 	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->iter_count = 0;
-	r->best_overused = 0x7fffffff; r->stall_count = 0; r->since_full = 0; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
+	r->best_overused = 0x7fffffff; r->stall_count = 0; r->since_full = 0; r->last_over = NULL; r->cost_updates = 0; r->committer = NULL; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
 	r->occ_base = r->occ_delta = NULL; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
 	r->h2d_bytes = r->d2h_bytes = 0;
@@ -247,6 +248,9 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.inflight_div <= 0) c.inflight_div = 16;
 	if (c.min_slots <= 0) c.min_slots = 1;
 	if (c.stall_iters == 0) c.stall_iters = 3;
+	if (c.history_window < 0) c.history_window = 0;   /* 0 = off (default) */
+	if (c.keep_newcomer < 0) c.keep_newcomer = 0;     /* 0 = off (default): measured on B200 it costs ~8 % wirelength and does
+	                                                    not shorten the tight-W tail */
 	if (c.max_batch > PF_MAX_BATCH) c.max_batch = PF_MAX_BATCH;
 	if (c.max_batch < 0) c.max_batch = 0;
 
@@ -392,6 +396,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->pool_head = (unsigned long long *)(r->ctl + 192);
 	r->status = (int *)(r->ctl + 0);
 	r->retry_list = (int *)pfb_alloc_raw(sizeof(int) * (size_t)std::max(nwork, 1));
+	r->last_over = (unsigned char *)pfb_alloc((size_t)r->N);
+	r->committer = c.keep_newcomer ? (int *)pfb_alloc_raw(sizeof(int) * (size_t)r->N) : NULL;
 	r->retry_count = (int *)(r->ctl + 32);
 	r->retry_work = (int *)pfb_alloc_raw(sizeof(int) * (size_t)std::max(nwork, 1));
 	r->stats = (PfStats *)(r->ctl + 96);
@@ -400,7 +406,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->sel_counts = (int *)(r->ctl + 48);
 	pfb_free(r->small.work_head); pfb_free(r->big.work_head);
 	r->small.work_head = (int *)(r->ctl + 160); r->big.work_head = (int *)(r->ctl + 176);
-	if (!r->retry_list || !r->retry_work) { pf_router_destroy(r); CUDA_FAIL(); }
+	if (!r->retry_list || !r->retry_work || !r->last_over) { pf_router_destroy(r); CUDA_FAIL(); }
 	if (c.nranks > 1) {
 		r->occ_base = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
 		r->occ_delta = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
@@ -437,7 +443,8 @@ extern "C" int pf_router_reset(pf_router *r) {
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
 	CKB(pfb_zero(r->ctl, 256));
 	r->h_pool_head = 0;
-	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0; r->over_hist.clear(); r->since_full = 0;
+	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0; r->over_hist.clear(); r->since_full = 0; r->cost_updates = 0;
+	CKB(pfb_zero(r->last_over, (size_t)r->N));
 	CKB(pfb_zero(r->net_delay, sizeof(float) * (size_t)std::max(r->T, 1)));
 	if (r->occ_base) CKB(pfb_zero(r->occ_base, sizeof(int) * (size_t)r->N));
 	{
@@ -483,6 +490,7 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap;
 	P.iscratch = s.iscratch; P.sink_cap = s.sink_cap;
 	P.pool = r->pool[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;
+	P.committer = r->committer;
 	P.status = r->status; P.retry_list = r->retry_list; P.retry_count = r->retry_count; P.stats = r->stats;
 }
 
@@ -549,7 +557,8 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 		int counts[4];
 		CKB(pfb_zero(r->sel_counts, sizeof(int) * 4));
 		CKB(pfb_launch_select_nets(r->nodes, r->pool[r->cur], r->loc, r->all_nets, r->num_all, r->net_big, 0,
-				r->small.work, r->big.work, r->sel_counts));
+				r->small.work, r->big.work, r->sel_counts, r->cfg.history_window > 0 ? r->last_over : NULL,
+				1 + (r->cost_updates + 254) % 255, r->cfg.history_window, r->committer));
 		CKB(pfb_d2h(counts, r->sel_counts, sizeof(int) * 4));
 		r->d2h_bytes += 16;
 		r->n_small = counts[0]; r->n_big = counts[1];
@@ -663,7 +672,9 @@ extern "C" int pf_reserve_opins(pf_router *r, float pres_fac, int rip_up) {
 
 static int update_costs_impl(pf_router *r, float acc_fac, const int *delta, int *overused) {
 	CKB(pfb_zero(r->d_overused, sizeof(int) * 4));
-	CKB(pfb_launch_update_cost(r->nodes, r->N, acc_fac, r->d_overused, delta ? r->occ_base : NULL, delta));
+	r->cost_updates++;
+	CKB(pfb_launch_update_cost(r->nodes, r->N, acc_fac, r->d_overused, delta ? r->occ_base : NULL, delta, r->last_over,
+			1 + (r->cost_updates + 254) % 255));
 	int h[4];
 	CKB(pfb_d2h(h, r->d_overused, sizeof(int) * 4));
 	r->d2h_bytes += 16;
@@ -697,7 +708,7 @@ extern "C" int pf_comm_fold_delta(pf_router *r, const void *dev_delta) {
 	if (!r || !dev_delta) FAILF(PF_EINVAL, "null argument");
 	if (!r->occ_base) FAILF(PF_EINVAL, "router was created with nranks == 1");
 	CKB(pfb_zero(r->d_overused, sizeof(int) * 4));
-	CKB(pfb_launch_update_cost(r->nodes, r->N, 0.f, r->d_overused, r->occ_base, (const int *)dev_delta));
+	CKB(pfb_launch_update_cost(r->nodes, r->N, 0.f, r->d_overused, r->occ_base, (const int *)dev_delta, NULL, 0));
 	CKB(pfb_sync());
 	return PF_OK;
 }

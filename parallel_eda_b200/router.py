@@ -75,7 +75,7 @@ class Config(C.Structure):
                                          "big_tree_cap", "big_far_cap", "max_batch")] + \
                [("pop_slack", C.c_float), ("win_rel", C.c_float), ("win_abs", C.c_float), ("verbose", C.c_int32),
                 ("reroute_all_iters", C.c_int32), ("inflight_div", C.c_int32), ("min_slots", C.c_int32),
-                ("stall_iters", C.c_int32)]
+                ("stall_iters", C.c_int32), ("history_window", C.c_int32), ("keep_newcomer", C.c_int32)]
 
 
 class Timing(C.Structure):

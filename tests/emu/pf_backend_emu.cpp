@@ -52,9 +52,10 @@ int pfb_launch_route(const PfParams *P, int num_slots, int) {
 	return 0;
 }
 
-int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, int *occ_base, const int *occ_delta) {
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, int *occ_base, const int *occ_delta,
+		unsigned char *last_over, int iter_tag) {
 	int over = 0;
-	for (int i = 0; i < num_nodes; i++) over += pf_update_cost_one(nodes, i, acc_fac, occ_base, occ_delta);
+	for (int i = 0; i < num_nodes; i++) over += pf_update_cost_one(nodes, i, acc_fac, occ_base, occ_delta, last_over, iter_tag);
 	*d_overused += over;
 	g_times.update_launches++;
 	return 0;
@@ -83,10 +84,11 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
 }
 
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
-		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts) {
+		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
+		const unsigned char *last_over, int iter_tag, int window, const int *committer) {
 	for (int k = 0; k < num_all; k++) {
 		int net = all_nets[k];
-		if (force_all || pf_net_is_congested(nodes, pool, loc[net])) {
+		if (force_all || pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net)) {
 			if (net_big[net]) list_big[counts[1]++] = net; else list_small[counts[0]++] = net;
 		}
 	}
