@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--pop-slack", type=float, default=-1.0, help="tuning: delta bucket width (<0 = library default)")
     ap.add_argument("--inflight-div", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
+    ap.add_argument("--sync-rounds", type=int, default=2, help="multi-GPU: occupancy syncs per PathFinder iteration")
     return ap.parse_args()
 
 
@@ -170,7 +171,7 @@ def run_ours(a):
             comm.barrier()
         torch.cuda.synchronize()
         R.timer_start()
-        rep = pathfinder.route(R, comm=comm, delta_buf=delta)
+        rep = pathfinder.route(R, comm=comm, delta_buf=delta, sync_rounds=a.sync_rounds)
         ms = R.timer_stop()
         torch.cuda.synchronize()
         if comm:
@@ -211,7 +212,7 @@ def run_ours(a):
             t0 = time.perf_counter()
             R2 = router.Router(p, cfg)                 # flatten + H2D of the whole problem
             t1 = time.perf_counter()
-            rep = pathfinder.route(R2, comm=comm, delta_buf=delta)
+            rep = pathfinder.route(R2, comm=comm, delta_buf=delta, sync_rounds=a.sync_rounds)
             t2 = time.perf_counter()
             res = R2.result()                          # D2H of traces, delays, occupancy
             t3 = time.perf_counter()
@@ -249,7 +250,7 @@ def run_ours(a):
             "config": {"workload": WORKLOAD.format(nx=a.grid, ny=a.grid, W=a.width, nets=a.nets),
                        "rr_nodes": p.num_nodes, "rr_edges": p.num_edges, "sinks": int(p.num_terminals - p.num_nets),
                        "router_opts": "VPR defaults: astar 1.2, pres_fac 0.5 x1.3, acc_fac 1, bb_factor 3, max 50 iterations",
-                       "parallelism": "nets sharded over %d GPU(s); occupancy all-reduce 2x per iteration" % world if world > 1 else "1 GPU",
+                       "parallelism": "nets sharded over %d GPU(s) in spatial stripes; occupancy all-reduce %dx per iteration" % (world, a.sync_rounds) if world > 1 else "1 GPU",
                        "l2": "working set (node records %d MB + edges %d MB) far exceeds the 126 MB L2; no flush needed"
                              % (p.num_nodes * 32 >> 20, p.num_edges * 4 >> 20)},
             "route": {"iterations": [r.iterations for r in reps], "nets_routed_per_step": nets_routed / a.steps,
