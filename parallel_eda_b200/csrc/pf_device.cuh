@@ -180,6 +180,9 @@ PF_DEV float pf_expected_cost(const PfWarp &w, int type, int ci, int ixlow, int 
 		}
 		float cong_cost = num_segs_same_dir * w.base_cost[ci] + num_segs_ortho_dir * w.base_cost[oci];
 		cong_cost += w.base_cost[3] + w.base_cost[1];   /* IPIN_COST_INDEX, SINK_COST_INDEX */
+		/* criticality 0 (timing analysis off, or a sink below the 1 - max_criticality cut): the delay term is
+		 * multiplied by exactly 0 and (1. - 0) * cong_cost is exact, so the result IS cong_cost bit for bit */
+		if (criticality_fac == 0.f) return cong_cost;
 		float Tdel = num_segs_same_dir * I.T_linear + num_segs_ortho_dir * O.T_linear
 				+ num_segs_same_dir * num_segs_same_dir * I.T_quadratic
 				+ num_segs_ortho_dir * num_segs_ortho_dir * O.T_quadratic
@@ -563,10 +566,12 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 					float new_R;
 					const PfSwitchDev S = w.sw[isw];
 					if (S.buffered) new_R = S.R; else new_R = Ru + S.R;
-					float Tdel = n.C * (new_R + 0.5 * n.R);
-					Tdel += S.Tdel;
+					if (crit != 0.f) {                       /* crit == 0: adds exactly +0 */
+						float Tdel = n.C * (new_R + 0.5 * n.R);
+						Tdel += S.Tdel;
+						new_back += crit * Tdel;
+					}
 					new_R += n.R;
-					new_back += crit * Tdel;
 					if (P->bend_cost != 0.) {
 						int ft = w.b_type[j];
 						if ((ft == 4 && n.type == 5) || (ft == 5 && n.type == 4)) new_back += P->bend_cost;
