@@ -48,8 +48,8 @@ typedef struct pf_config {
 	int32_t device;           /* CUDA device ordinal */
 	int32_t rank, nranks;     /* net sharding (one process per GPU): nets are cut into nranks spatial stripes of
 	                             equal total fanout along x; this process routes stripe `rank` */
-	int32_t num_slots;        /* concurrent warps (nets in flight); 0 = 16 per SM */
-	int32_t warps_per_block;  /* 0 = 4 */
+	int32_t num_slots;        /* concurrent warps (nets in flight); 0 = 20 per SM (one full wave) */
+	int32_t warps_per_block;  /* 0 = 4 (maximum) */
 	int32_t label_log2;       /* (fixed) the regular slots keep 2^10 hot label entries in shared memory */
 	int32_t label2_log2;      /* per-slot fallback label table in global memory, 2^n entries; 0 = 13, < 0 none */
 	int32_t tree_cap;         /* per-warp route-tree entries; 0 = 2048 */

@@ -111,11 +111,13 @@ struct PfWarp {
 	unsigned long long pops, pushes, visits, refills, stale;
 };
 
-/* fr 1536 + b_key 256 + idx 1024 + sw 768 + base_cost 128 + 5 batch arrays 640 + b_pre 136 + tickets 256 = 4744 → 4864 */
+/* per warp: fr 1024 + b_key 256 + base_cost 128 + 5 batch arrays 640 + b_pre 136 + tickets 256 = 2440 → 2448;
+ * per CTA: cost-index table 1024 + switch table 768 */
 #define PF_OVF_LABELS 1   /* w.overflow bits */
 #define PF_OVF_OTHER 2
 #define PF_TICKETS 64
-#define PF_SMEM_PER_WARP 4864                       /* + PF_SMEM_HOT_ENTRIES * 8 when the hot table is in shared memory */
+#define PF_SMEM_PER_WARP 2448                       /* + PF_SMEM_HOT_ENTRIES * 8 when the hot table is in shared memory */
+#define PF_SMEM_BLOCK_TABLES (PF_MAX_INDEXED * 32 + PF_MAX_SWITCHES * 12)
 
 PF_DEV float pf_key_tot(uint64_t k) { return pf_int_as_float((int)(k >> 32)); }
 PF_DEV int pf_key_node(uint64_t k) { return (int)((uint32_t)k & 0x03ffffffu); }
@@ -911,15 +913,14 @@ PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: routed, 0: handed to a bi
 }
 
 /* ------------------------------------------------------------------ warp main: persistent work loop */
-PF_DEV void pf_warp_main(const PfParams *P, int slot, unsigned char *smem_warp) {
+PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIndexedDev *idx_tab, PfSwitchDev *sw_tab, unsigned char *smem_warp) {
 	const int lane = pf_lane();
 	PfWarp w;
 	w.P = P;
 	unsigned char *s = smem_warp;
 	w.fr = (uint64_t *)s; s += PF_SH_FRONTIER * 8;
 	w.b_key = (uint64_t *)s; s += PF_MAX_BATCH * 8;
-	w.idx = (PfIndexedDev *)s; s += PF_MAX_INDEXED * 32;
-	w.sw = (PfSwitchDev *)s; s += PF_MAX_SWITCHES * 12;
+	w.idx = idx_tab; w.sw = sw_tab;               /* filled by the caller (one copy per CTA) */
 	w.base_cost = (float *)s; s += PF_MAX_INDEXED * 4;
 	w.b_node = (int *)s; s += PF_MAX_BATCH * 4;
 	w.b_back = (float *)s; s += PF_MAX_BATCH * 4;
@@ -928,8 +929,6 @@ PF_DEV void pf_warp_main(const PfParams *P, int slot, unsigned char *smem_warp) 
 	w.b_type = (int *)s; s += PF_MAX_BATCH * 4;
 	w.b_pre = (int *)s; s += (PF_MAX_BATCH + 1 + 1) * 4;
 	w.ticket = (int *)s; s += PF_TICKETS * 4;
-	for (int i = lane; i < P->num_indexed; i += PF_WARP) w.idx[i] = P->indexed[i];
-	for (int i = lane; i < P->num_sw; i += PF_WARP) w.sw[i] = P->sw[i];
 	const long long cap = 1ll << P->label_log2;
 	w.cold = P->cold + (long long)slot * cap;
 	w.label_mask = (unsigned)(cap - 1);

@@ -159,12 +159,19 @@ static int ev_end(void) {
 /* ------------------------------------------------------------------ kernels */
 extern __shared__ __align__(16) unsigned char pf_smem[];
 
-__global__ void __launch_bounds__(256) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
+__global__ void __launch_bounds__(128, 5) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
+	/* 96 registers and 43.3 KB of shared memory per 4-warp CTA: 5 CTAs = 20 warps per SM.
+	 * shared memory: [switch + cost-index tables, one copy per CTA][per-warp regions] */
 	const int warp_in_block = (int)(threadIdx.x >> 5);
 	const int slot = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp_in_block;
+	PfIndexedDev *idx = (PfIndexedDev *)pf_smem;
+	PfSwitchDev *sw = (PfSwitchDev *)(pf_smem + PF_MAX_INDEXED * sizeof(PfIndexedDev));
+	for (int i = (int)threadIdx.x; i < P.num_indexed; i += (int)blockDim.x) idx[i] = P.indexed[i];
+	for (int i = (int)threadIdx.x; i < P.num_sw; i += (int)blockDim.x) sw[i] = P.sw[i];
+	__syncthreads();
 	if (slot >= num_slots) return;
 	const size_t per_warp = PF_SMEM_PER_WARP + (P.hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8);
-	pf_warp_main(&P, slot, pf_smem + (size_t)warp_in_block * per_warp);
+	pf_warp_main(&P, slot, idx, sw, pf_smem + PF_SMEM_BLOCK_TABLES + (size_t)warp_in_block * per_warp);
 }
 
 __global__ void pf_update_cost_kernel(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
@@ -243,9 +250,9 @@ __global__ void pf_compact_kernel(const PfTreeNode *src, PfTreeNode *dst, PfNetL
 /* ------------------------------------------------------------------ launchers */
 int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	if (warps_per_block < 1) warps_per_block = 1;
-	if (warps_per_block > 8) warps_per_block = 8;
+	if (warps_per_block > 4) warps_per_block = 4;   /* __launch_bounds__(128, 5) */
 	int blocks = (num_slots + warps_per_block - 1) / warps_per_block;
-	size_t smem = (size_t)warps_per_block * (PF_SMEM_PER_WARP + (P->hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8));
+	size_t smem = PF_SMEM_BLOCK_TABLES + (size_t)warps_per_block * (PF_SMEM_PER_WARP + (P->hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8));
 	static size_t smem_set = 0;
 	if (smem > smem_set) { CK(cudaFuncSetAttribute(pf_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
 	if (ev_begin(0) != 0) return -1;

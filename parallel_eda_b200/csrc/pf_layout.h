@@ -66,8 +66,8 @@ struct PfTreeNode {
 
 struct PfNetLoc { int off, count; };   /* a net's tree in the route store */
 
-#define PF_SH_FRONTIER 192      /* near-set entries per warp in shared memory */
-#define PF_SH_REFILL 96         /* refill the near set to at most this many */
+#define PF_SH_FRONTIER 128      /* near-set entries per warp in shared memory */
+#define PF_SH_REFILL 64         /* refill the near set to at most this many */
 #define PF_MAX_BATCH 32         /* labels settled per step (one delta bucket) */
 
 /* error/status bits written to PfParams.status[0] */

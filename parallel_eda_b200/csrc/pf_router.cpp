@@ -236,7 +236,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 
 	int sms = pfb_num_sms();
 	if (c.warps_per_block <= 0) c.warps_per_block = 4;
-	if (c.num_slots <= 0) c.num_slots = (sms > 0 ? sms : 148) * 16;
+	if (c.num_slots <= 0) c.num_slots = (sms > 0 ? sms : 148) * 20;   /* 5 CTAs x 4 warps resident per SM */
 	c.label_log2 = PF_SMEM_HOT_LOG2;                 /* regular slots: hot label table in shared memory */
 	if (c.label2_log2 == 0) c.label2_log2 = 13;      /* per-slot fallback table in global memory; < 0: none */
 	if (c.label2_log2 < 0) c.label2_log2 = 0;

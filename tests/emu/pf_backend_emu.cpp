@@ -41,11 +41,20 @@ int pfb_num_sms(void) { const char *e = getenv("PF_EMU_SMS"); return e ? atoi(e)
 struct RouteArg { const PfParams *P; std::vector<unsigned char> *smem; };
 static void route_warp(void *arg, int warp_id) {
 	RouteArg *a = (RouteArg *)arg;
-	pf_warp_main(a->P, warp_id, a->smem->data() + (size_t)warp_id * (PF_SMEM_PER_WARP + PF_SMEM_HOT_ENTRIES * 8));
+	/* the emulator gives every warp its own copy of the per-CTA tables */
+	unsigned char *base = a->smem->data() + (size_t)warp_id * (PF_SMEM_BLOCK_TABLES + PF_SMEM_PER_WARP + PF_SMEM_HOT_ENTRIES * 8);
+	PfIndexedDev *idx = (PfIndexedDev *)base;
+	PfSwitchDev *sw = (PfSwitchDev *)(base + PF_MAX_INDEXED * sizeof(PfIndexedDev));
+	if (pf_lane() == 0) {
+		for (int i = 0; i < a->P->num_indexed; i++) idx[i] = a->P->indexed[i];
+		for (int i = 0; i < a->P->num_sw; i++) sw[i] = a->P->sw[i];
+	}
+	pf_syncwarp();
+	pf_warp_main(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
 }
 
 int pfb_launch_route(const PfParams *P, int num_slots, int) {
-	std::vector<unsigned char> smem((size_t)num_slots * (PF_SMEM_PER_WARP + PF_SMEM_HOT_ENTRIES * 8));
+	std::vector<unsigned char> smem((size_t)num_slots * (PF_SMEM_BLOCK_TABLES + PF_SMEM_PER_WARP + PF_SMEM_HOT_ENTRIES * 8));
 	RouteArg a = { P, &smem };
 	pf_emu_launch(route_warp, &a, num_slots);
 	g_times.route_launches++;
