@@ -49,7 +49,7 @@ int pfb_launch_export_delta(const PfNode *nodes, int num_nodes, const int *occ_b
 /* route trees → s_trace-ordered arrays on the device: pass 1 (trace_node == NULL) writes len[net];
  * pass 2 writes trace_node/trace_switch at tptr[net] and adds the wirelength into *d_wl */
 int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num_nets, int *len, const int *tptr,
-		int *trace_node, short *trace_switch, unsigned long long *d_wl);
+		int *trace_node, short *trace_switch, unsigned long long *d_wl, unsigned *trace_term, const short *ptc, int nx);
 /* occ_out[i] = nodes[i].occ (compact copy for the host) */
 int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out);
 /* total wirelength of all trees in the route store (route_timing.c:189-225 sanity abort) */
@@ -62,7 +62,9 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
  * net when force_all), split into the small/big slot classes by net_big[]; counts[0]/counts[1] */
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer);
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch);
+void pfb_bind_thread(void);                     /* make the router's device current in a helper thread */
+size_t pfb_select_scratch_bytes(int num_all);   /* size of `scratch` (device memory) */
 /* copy every live tree of `all_nets` from one log to another (garbage collection of the route store) */
 int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
 		unsigned long long *dst_head);

@@ -1060,8 +1060,16 @@ PF_DEV void pf_reserve_opins_group(PfNode *nodes, const uint32_t *edges, const P
 
 /* Route tree → s_trace order (update_traceback, route_common.c:638-706), one net per call.
  * pass 1 (out == NULL): returns the trace length; pass 2: writes node / switch at out[...] and returns the
- * net's wirelength (get_num_bends_and_length, base/stats.c:355-409). */
-PF_DEV int pf_trace_of_net(const PfTreeNode *t, int cnt, int *out_node, short *out_sw) {
+ * net's wirelength (get_num_bends_and_length, base/stats.c:355-409); out_term (optional) receives each element's
+ * contribution to the routing's serial number. */
+PF_DEV unsigned pf_serial_term(const PfTreeNode &n, const short *ptc, int nx, unsigned net_mult) {
+	/* get_serial_num, route_common.c:224-254: per trace element the reference adds (inet+1)*(xlow*(nx+1) - yhigh) and
+	 * subtracts ptc_num*(inet+1)*10 and type*(inet+1)*100, all in wrapping 32-bit arithmetic */
+	return net_mult * (unsigned)(n.xlow * (nx + 1) - n.yhigh - 10 * (int)ptc[n.node] - 100 * (int)(n.type_ci & 7));
+}
+
+PF_DEV int pf_trace_of_net(const PfTreeNode *t, int cnt, int *out_node, short *out_sw, unsigned *out_term, const short *ptc, int nx,
+		unsigned net_mult) {
 	if (cnt <= 1) return 0;
 	if (!out_node) {
 		int sinks = 0;
@@ -1072,9 +1080,16 @@ PF_DEV int pf_trace_of_net(const PfTreeNode *t, int cnt, int *out_node, short *o
 	while (k < cnt) {
 		int e = k;
 		while (e < cnt - 1 && (t[e].type_ci & 7) != 1) e++;
-		if (k > 0) { out_node[w] = t[t[k].parent].node; out_sw[w] = (short)t[k].sw; w++; }
+		if (k > 0) {
+			const PfTreeNode &j = t[t[k].parent];
+			out_node[w] = j.node; out_sw[w] = (short)t[k].sw;
+			if (out_term) out_term[w] = pf_serial_term(j, ptc, nx, net_mult);
+			w++;
+		}
 		for (int q = k; q <= e; q++) {
-			out_node[w] = t[q].node; out_sw[w] = q < e ? (short)t[q + 1].sw : (short)-1; w++;
+			out_node[w] = t[q].node; out_sw[w] = q < e ? (short)t[q + 1].sw : (short)-1;
+			if (out_term) out_term[w] = pf_serial_term(t[q], ptc, nx, net_mult);
+			w++;
 			int ty = t[q].type_ci & 7;
 			if (ty == 4 || ty == 5) wl += 1 + t[q].xhigh - t[q].xlow + t[q].yhigh - t[q].ylow;
 		}

@@ -65,6 +65,7 @@ int pfb_init(int device) {
 }
 
 int pfb_num_sms(void) { return g_sms; }
+void pfb_bind_thread(void) { if (g_device >= 0) cudaSetDevice(g_device); }
 
 /* Stream-ordered allocation from the device's default memory pool with an unlimited release threshold:
  * the first router pays for mapping its ~GBs of scratch, later create/destroy cycles (the binary search
@@ -189,12 +190,13 @@ __global__ void pf_export_delta_kernel(const PfNode *nodes, int num_nodes, const
 }
 
 __global__ void pf_build_traces_kernel(const PfTreeNode *pool, const PfNetLoc *loc, int num_nets, int *len, const int *tptr,
-		int *trace_node, short *trace_switch, unsigned long long *d_wl) {
+		int *trace_node, short *trace_switch, unsigned long long *d_wl, unsigned *trace_term, const short *ptc, int nx) {
 	int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (i >= num_nets) return;
 	PfNetLoc l = loc[i];
-	if (!trace_node) { len[i] = pf_trace_of_net(pool + l.off, l.count, NULL, NULL); return; }
-	int wl = pf_trace_of_net(pool + l.off, l.count, trace_node + tptr[i], trace_switch + tptr[i]);
+	if (!trace_node) { len[i] = pf_trace_of_net(pool + l.off, l.count, NULL, NULL, NULL, NULL, 0, 0u); return; }
+	int wl = pf_trace_of_net(pool + l.off, l.count, trace_node + tptr[i], trace_switch + tptr[i], trace_term ? trace_term + tptr[i] : NULL,
+			ptc, nx, (unsigned)(i + 1));
 	if (wl) atomicAdd(d_wl, (unsigned long long)wl);
 }
 
@@ -218,15 +220,51 @@ __global__ void pf_reserve_opins_kernel(PfNode *nodes, const uint32_t *edges, co
 		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac, occ_base);
 }
 
-__global__ void pf_select_nets_kernel(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
-		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
+/* Congested-net selection, order-preserving: pass 1 flags the nets (all_nets is in the reference's
+ * decreasing-fanout order) and counts per CTA, pass 2 turns the counts into offsets and scatters, so the two
+ * work lists come out in that same order without a host-side sort. */
+#define PF_SEL_BLOCK 256
+__global__ void __launch_bounds__(PF_SEL_BLOCK) pf_select_flag_kernel(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc,
+		const int *all_nets, int num_all, const unsigned char *net_big, int force_all, unsigned char *flag, int *block_counts,
 		const unsigned char *last_over, int iter_tag, int window, const int *committer) {
-	int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-	if (k >= num_all) return;
-	int net = all_nets[k];
-	if (force_all || pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net)) {
-		if (net_big[net]) list_big[atomicAdd(&counts[1], 1)] = net;
-		else list_small[atomicAdd(&counts[0], 1)] = net;
+	int k = (int)(blockIdx.x * PF_SEL_BLOCK + threadIdx.x);
+	int f = 0;
+	if (k < num_all) {
+		int net = all_nets[k];
+		if (force_all || pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net)) f = net_big[net] ? 2 : 1;
+		flag[k] = (unsigned char)f;
+	}
+	int cs = __syncthreads_count(f == 1), cb = __syncthreads_count(f == 2);
+	if (threadIdx.x == 0) { block_counts[2 * blockIdx.x] = cs; block_counts[2 * blockIdx.x + 1] = cb; }
+}
+
+__global__ void __launch_bounds__(PF_SEL_BLOCK) pf_select_scatter_kernel(const int *all_nets, int num_all, const unsigned char *flag,
+		const int *block_counts, int *list_small, int *list_big, int *counts) {
+	__shared__ int s_red[2][PF_SEL_BLOCK / 32];
+	__shared__ int s_warp[2][PF_SEL_BLOCK / 32];
+	const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+	/* offset of this CTA = counts of all earlier CTAs */
+	int ps = 0, pb = 0;
+	for (int b = (int)threadIdx.x; b < (int)blockIdx.x; b += PF_SEL_BLOCK) { ps += block_counts[2 * b]; pb += block_counts[2 * b + 1]; }
+	for (int o = 16; o > 0; o >>= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pb += __shfl_xor_sync(0xffffffffu, pb, o); }
+	int k = (int)(blockIdx.x * PF_SEL_BLOCK + threadIdx.x);
+	int f = k < num_all ? flag[k] : 0;
+	unsigned ms = __ballot_sync(0xffffffffu, f == 1), mb = __ballot_sync(0xffffffffu, f == 2);
+	if (lane == 0) { s_red[0][warp] = ps; s_red[1][warp] = pb; s_warp[0][warp] = __popc(ms); s_warp[1][warp] = __popc(mb); }
+	__syncthreads();
+	int base_s = 0, base_b = 0, tot_s = 0, tot_b = 0;
+	for (int w = 0; w < PF_SEL_BLOCK / 32; w++) {
+		base_s += s_red[0][w]; base_b += s_red[1][w];
+		if (w < warp) { base_s += s_warp[0][w]; base_b += s_warp[1][w]; }
+		tot_s += s_warp[0][w]; tot_b += s_warp[1][w];
+	}
+	const unsigned below = (1u << lane) - 1u;
+	if (f == 1) list_small[base_s + __popc(ms & below)] = all_nets[k];
+	else if (f == 2) list_big[base_b + __popc(mb & below)] = all_nets[k];
+	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+		int all_s = tot_s, all_b = tot_b;
+		for (int w = 0; w < PF_SEL_BLOCK / 32; w++) { all_s += s_red[0][w]; all_b += s_red[1][w]; }
+		counts[0] = all_s; counts[1] = all_b;
 	}
 }
 
@@ -298,11 +336,21 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
 
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer) {
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch) {
 	if (num_all <= 0) return 0;
+	/* scratch: [2 ints per CTA][one flag byte per net] — pfb_select_scratch_bytes() */
+	const int blocks = (num_all + PF_SEL_BLOCK - 1) / PF_SEL_BLOCK;
+	unsigned char *flag = (unsigned char *)(scratch + 2 * (size_t)blocks);
 	if (ev_begin(2) != 0) return -1;
-	pf_select_nets_kernel<<<(num_all + 127) / 128, 128, 0, g_stream>>>(nodes, pool, loc, all_nets, num_all, net_big, force_all, list_small, list_big, counts, last_over, iter_tag, window, committer);
+	pf_select_flag_kernel<<<blocks, PF_SEL_BLOCK, 0, g_stream>>>(nodes, pool, loc, all_nets, num_all, net_big, force_all, flag, scratch,
+			last_over, iter_tag, window, committer);
+	pf_select_scatter_kernel<<<blocks, PF_SEL_BLOCK, 0, g_stream>>>(all_nets, num_all, flag, scratch, list_small, list_big, counts);
 	return ev_end();
+}
+
+size_t pfb_select_scratch_bytes(int num_all) {
+	const size_t blocks = ((size_t)std::max(num_all, 1) + PF_SEL_BLOCK - 1) / PF_SEL_BLOCK;
+	return 8 * blocks + (size_t)std::max(num_all, 1) + 16;
 }
 
 int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
@@ -320,9 +368,9 @@ int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out) {
 }
 
 int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num_nets, int *len, const int *tptr,
-		int *trace_node, short *trace_switch, unsigned long long *d_wl) {
+		int *trace_node, short *trace_switch, unsigned long long *d_wl, unsigned *trace_term, const short *ptc, int nx) {
 	if (num_nets <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
-	pf_build_traces_kernel<<<(num_nets + 127) / 128, 128, 0, g_stream>>>(pool, loc, num_nets, len, tptr, trace_node, trace_switch, d_wl);
+	pf_build_traces_kernel<<<(num_nets + 127) / 128, 128, 0, g_stream>>>(pool, loc, num_nets, len, tptr, trace_node, trace_switch, d_wl, trace_term, ptc, nx);
 	return ev_end();
 }

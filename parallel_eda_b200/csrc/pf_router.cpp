@@ -47,7 +47,8 @@ struct pf_router {
 	SlotClass small, big;
 	PfTreeNode *pool[2]; PfNetLoc *loc; int cur;      /* pool[cur] is the live route-tree log */
 	long long pool_cap; unsigned long long *pool_head;
-	int *all_nets; int num_all; unsigned char *net_big; int *sel_counts;
+	int *all_nets; int num_all; unsigned char *net_big; int *sel_counts; int *sel_scratch;
+	short *ptc;                    /* rr_node[].ptc_num, only read when the result's serial number is assembled */
 	std::vector<unsigned char> h_net_big;
 	std::vector<int> net_rank;        /* position of a net in the fanout-sorted order */
 	int iter_count;
@@ -64,6 +65,7 @@ struct pf_router {
 	/* OPIN reservation */
 	int num_groups; int *g_source, *g_count, *g_off, *g_chosen;
 	long long avail_wl;
+	double t_mark[4];
 	int64_t h2d_bytes, d2h_bytes;
 	std::vector<int> work_small, work_big;
 	float win_abs_auto;
@@ -72,6 +74,7 @@ struct pf_router {
 #include <chrono>
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #include <thread>
+#include <atomic>
 /* simple static-partition parallel loop for the host-side flattening of 10^7..10^8-element arrays */
 template <class F> static void parallel_for(long long n, F f) {
 	unsigned hw = std::thread::hardware_concurrency();
@@ -84,30 +87,11 @@ template <class F> static void parallel_for(long long n, F f) {
 }
 
 /* pf_problem_check (pf_file.c) is a single-threaded scan; on 10^8 edges that is a visible part of the call.
- * This runs the range checks of the big arrays in parallel and defers to the serial checker only for the
- * error message. */
-static bool problem_arrays_ok(const pf_problem *p) {
+ * The range checks of the big arrays run inside the parallel flattening passes instead, and the serial
+ * checker is only consulted for the error message. */
+static bool problem_header_ok(const pf_problem *p) {
 	if (p->nx <= 0 || p->ny <= 0 || p->num_nodes <= 0 || p->num_indexed < PF_CHANX_COST_INDEX_START) return false;
 	if (!p->row_ptr || p->row_ptr[0] != 0 || p->row_ptr[p->num_nodes] != p->num_edges) return false;
-	std::vector<int> bad(64, 0);
-	std::vector<int> *pb = &bad;
-	parallel_for(p->num_nodes, [=](long long lo, long long hi) {
-		int b = 0;
-		for (long long i = lo; i < hi; i++) {
-			int d = p->row_ptr[i + 1] - p->row_ptr[i];
-			b |= (d < 0) | (d > 32767) | (p->type[i] > PF_CHANY) | (p->cost_index[i] < 0) | (p->cost_index[i] >= p->num_indexed)
-				| (p->xlow[i] > p->xhigh[i]) | (p->ylow[i] > p->yhigh[i]) | (p->xlow[i] < 0) | (p->ylow[i] < 0)
-				| (p->xhigh[i] > p->nx + 1) | (p->yhigh[i] > p->ny + 1) | (p->capacity[i] < 0) | (p->capacity[i] > 255) | (p->cost_index[i] > 31);
-		}
-		if (b) (*pb)[(size_t)(lo % 64)] = 1;
-	});
-	parallel_for(p->num_edges, [=](long long lo, long long hi) {
-		int b = 0;
-		for (long long k = lo; k < hi; k++)
-			b |= (p->edge_to[k] < 0) | (p->edge_to[k] >= p->num_nodes) | (p->edge_sw[k] < 0) | (p->edge_sw[k] >= p->num_switches);
-		if (b) (*pb)[(size_t)(lo % 64)] = 1;
-	});
-	for (int v : bad) if (v) return false;
 	return true;
 }
 
@@ -172,35 +156,92 @@ extern "C" void pf_router_destroy(pf_router *r) {
 	if (r->ctl) { r->small.work_head = NULL; r->big.work_head = NULL; }
 	free_slot_class(r->small); free_slot_class(r->big);
 	pfb_free(r->pool[0]); pfb_free(r->pool[1]); pfb_free(r->loc);
-	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->retry_work);
+	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->retry_work); pfb_free(r->sel_scratch); pfb_free(r->ptc);
 	pfb_free(r->ctl); pfb_free(r->retry_list); pfb_free(r->last_over); pfb_free(r->committer);
 	pfb_free(r->occ_base); pfb_free(r->occ_delta);
 	pfb_free(r->g_source); pfb_free(r->g_count); pfb_free(r->g_off); pfb_free(r->g_chosen);
 	delete r;
 }
 
-static int upload_nodes(pf_router *r, void *staging) {
+/* rr node records → HBM.  With a pinned staging buffer the host threads flatten 4 MB pieces and each issues
+ * the async copy of its own piece as soon as it is written, so packing and PCIe overlap; `bad` collects the
+ * range checks of pf_problem_check for the node arrays (done here so the arrays are read once). */
+#define PF_UPLOAD_PIECE (4u << 20)
+static int upload_nodes(pf_router *r, void *staging, int *bad_out, long long *avail_wl, short *stage_ptc) {
 	const pf_problem *p = r->prob;
-	/* flatten straight into the pinned staging buffer when there is one (one async H2D, no pageable bounce) */
 	PfNode *stage = staging ? (PfNode *)staging : NULL;
 	std::vector<PfNode> hv;
 	if (!stage) { hv.resize((size_t)r->N); stage = hv.data(); }
 	PfNode *h = stage;
+	std::atomic<int> bad(0), fail(0);
+	std::atomic<long long> wl(0);
+	const long long piece = PF_UPLOAD_PIECE / sizeof(PfNode);
 	parallel_for(r->N, [&](long long lo, long long hi) {
-	for (long long i = lo; i < hi; i++) {
-		PfNode &d = h[i];
-		d.xlow = p->xlow[i]; d.ylow = p->ylow[i]; d.xhigh = p->xhigh[i]; d.yhigh = p->yhigh[i];
-		d.R = p->R[i]; d.C = p->C[i];
-		d.occ = 0; d.acc_cost = 1.f;                 /* alloc_and_load_rr_node_route_structs, route_common.c:1012-1034 */
-		d.edge_start = p->row_ptr[i];
-		d.num_edges = (unsigned short)(p->row_ptr[i + 1] - p->row_ptr[i]);
-		d.type_ci = (unsigned char)(p->type[i] | (p->cost_index[i] << 3));
-		d.capacity = (unsigned char)p->capacity[i];
-	}
+		if (staging) pfb_bind_thread();
+		int b = 0;
+		long long w = 0;
+		for (long long c0 = lo; c0 < hi; c0 += piece) {
+			const long long c1 = std::min(hi, c0 + piece);
+			for (long long i = c0; i < c1; i++) {
+				PfNode &d = h[i];
+				const int ne = p->row_ptr[i + 1] - p->row_ptr[i];
+				b |= (ne < 0) | (ne > 32767) | (p->type[i] > PF_CHANY) | (p->cost_index[i] < 0) | (p->cost_index[i] >= p->num_indexed)
+					| (p->xlow[i] > p->xhigh[i]) | (p->ylow[i] > p->yhigh[i]) | (p->xlow[i] < 0) | (p->ylow[i] < 0)
+					| (p->xhigh[i] > p->nx + 1) | (p->yhigh[i] > p->ny + 1) | (p->capacity[i] < 0) | (p->capacity[i] > 255) | (p->cost_index[i] > 31);
+				d.xlow = p->xlow[i]; d.ylow = p->ylow[i]; d.xhigh = p->xhigh[i]; d.yhigh = p->yhigh[i];
+				d.R = p->R[i]; d.C = p->C[i];
+				d.occ = 0; d.acc_cost = 1.f;                 /* alloc_and_load_rr_node_route_structs, route_common.c:1012-1034 */
+				d.edge_start = p->row_ptr[i];
+				d.num_edges = (unsigned short)ne;
+				d.type_ci = (unsigned char)(p->type[i] | (p->cost_index[i] << 3));
+				d.capacity = (unsigned char)p->capacity[i];
+				if (p->type[i] == PF_CHANX || p->type[i] == PF_CHANY) w += 1 + p->xhigh[i] - p->xlow[i] + p->yhigh[i] - p->ylow[i];
+			}
+			if (staging && pfb_h2d_async(r->nodes + c0, h + c0, sizeof(PfNode) * (size_t)(c1 - c0)) != 0) fail = 1;
+			if (stage_ptc) {
+				memcpy(stage_ptc + c0, p->ptc_num + c0, sizeof(short) * (size_t)(c1 - c0));
+				if (pfb_h2d_async(r->ptc + c0, stage_ptc + c0, sizeof(short) * (size_t)(c1 - c0)) != 0) fail = 1;
+			}
+		}
+		if (b) bad = 1;
+		wl += w;
 	});
-	if (staging) CKB(pfb_h2d_async(r->nodes, h, sizeof(PfNode) * (size_t)r->N));
-	else CKB(pfb_h2d(r->nodes, h, sizeof(PfNode) * (size_t)r->N));
-	r->h2d_bytes += (int64_t)sizeof(PfNode) * r->N;
+	if (fail) return PF_ECUDA;
+	if (!staging) CKB(pfb_h2d(r->nodes, h, sizeof(PfNode) * (size_t)r->N));
+	if (avail_wl && !stage_ptc) CKB(pfb_h2d(r->ptc, p->ptc_num, sizeof(short) * (size_t)r->N));   /* first upload, no pinned staging */
+	r->h2d_bytes += (int64_t)sizeof(PfNode) * r->N + (avail_wl ? (int64_t)sizeof(short) * r->N : 0);
+	if (bad_out) *bad_out = bad;
+	if (avail_wl) *avail_wl = wl;
+	return PF_OK;
+}
+
+/* packed edge words → HBM, same scheme */
+static int upload_edges(pf_router *r, uint32_t *staging, int *bad_out) {
+	const pf_problem *p = r->prob;
+	std::vector<uint32_t> ewv;
+	uint32_t *ew = staging;
+	if (!ew) { ewv.resize((size_t)std::max(r->E, 1)); ew = ewv.data(); }
+	std::atomic<int> bad(0), fail(0);
+	const long long piece = PF_UPLOAD_PIECE / sizeof(uint32_t);
+	const unsigned N = (unsigned)p->num_nodes, S = (unsigned)p->num_switches;
+	parallel_for(r->E, [&](long long lo, long long hi) {
+		if (staging) pfb_bind_thread();
+		int b = 0;
+		for (long long c0 = lo; c0 < hi; c0 += piece) {
+			const long long c1 = std::min(hi, c0 + piece);
+			for (long long k = c0; k < c1; k++) {
+				const unsigned to = (unsigned)p->edge_to[k], s = (unsigned)(int)p->edge_sw[k];
+				b |= (to >= N) | (s >= S);
+				ew[k] = to | (s << PF_EDGE_NODE_BITS);
+			}
+			if (staging && pfb_h2d_async(r->edges + c0, ew + c0, sizeof(uint32_t) * (size_t)(c1 - c0)) != 0) fail = 1;
+		}
+		if (b) bad = 1;
+	});
+	if (fail) return PF_ECUDA;
+	if (!staging) CKB(pfb_h2d(r->edges, ew, sizeof(uint32_t) * (size_t)r->E));
+	r->h2d_bytes += (int64_t)sizeof(uint32_t) * r->E;
+	if (bad_out) *bad_out = bad;
 	return PF_OK;
 }
 
@@ -209,9 +250,11 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	*out = NULL;
 	if (!p || !cfg_in) FAILF(PF_EINVAL, "null argument");
 	double t_a = now_s();
-	if (!problem_arrays_ok(p) || !problem_nets_ok(p)) {
+	/* small arrays now; the 10^7..10^8-element node and edge arrays are range-checked by the passes that
+	 * flatten them (upload_nodes / upload_edges), so they are read once */
+	if (!problem_header_ok(p) || !problem_nets_ok(p)) {
 		if (pf_problem_check(p, msg, sizeof(msg)) != PF_OK) FAILF(PF_EINVAL, "invalid problem: %s", msg);
-		FAILF(PF_EINVAL, "invalid problem (capacity > 255 or cost_index > 31 on some rr node)");
+		FAILF(PF_EINVAL, "invalid problem");
 	}
 	double t_b = now_s();
 	if (p->num_nodes > (1 << PF_EDGE_NODE_BITS)) FAILF(PF_EINVAL, "num_rr_nodes %d exceeds the %d-bit edge word", p->num_nodes, PF_EDGE_NODE_BITS);
@@ -228,7 +271,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->nodes = NULL; r->edges = NULL; r->sw = NULL; r->indexed = NULL; r->net_ptr = r->net_term = r->net_bb = NULL;
 	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
 	r->pool[0] = r->pool[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
-	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->iter_count = 0;
+	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->sel_scratch = NULL; r->ptc = NULL; r->iter_count = 0;
 	r->best_overused = 0x7fffffff; r->stall_count = 0; r->since_full = 0; r->last_over = NULL; r->cost_updates = 0; r->committer = NULL; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
 	r->occ_base = r->occ_delta = NULL; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
@@ -309,6 +352,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	/* device graph */
 	r->nodes = (PfNode *)pfb_alloc_raw(sizeof(PfNode) * (size_t)r->N);
 	r->edges = (uint32_t *)pfb_alloc_raw(sizeof(uint32_t) * (size_t)std::max(r->E, 1));
+	r->ptc = (short *)pfb_alloc_raw(sizeof(short) * (size_t)r->N);
 	r->sw = (PfSwitchDev *)pfb_alloc(sizeof(PfSwitchDev) * PF_MAX_SWITCHES);
 	r->indexed = (PfIndexedDev *)pfb_alloc(sizeof(PfIndexedDev) * PF_MAX_INDEXED);
 	r->net_ptr = (int *)pfb_alloc(sizeof(int) * ((size_t)r->n + 1));
@@ -316,19 +360,16 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->net_bb = (int *)pfb_alloc(sizeof(int) * 4 * (size_t)std::max(r->n, 1));
 	r->crit = (float *)pfb_alloc(sizeof(float) * (size_t)std::max(r->T, 1));
 	r->net_delay = (float *)pfb_alloc(sizeof(float) * (size_t)std::max(r->T, 1));
-	if (!r->nodes || !r->edges || !r->sw || !r->indexed || !r->net_ptr || !r->net_term || !r->net_bb || !r->crit || !r->net_delay) {
+	if (!r->nodes || !r->edges || !r->ptc || !r->sw || !r->indexed || !r->net_ptr || !r->net_term || !r->net_bb || !r->crit || !r->net_delay) {
 		pf_router_destroy(r); CUDA_FAIL();
 	}
 	{
 		const size_t nbytes = sizeof(PfNode) * (size_t)r->N, ebytes = sizeof(uint32_t) * (size_t)std::max(r->E, 1);
-		char *pin = (char *)pfb_pinned(nbytes + ebytes + 256);
+		const size_t pbytes = sizeof(short) * (size_t)r->N;
+		char *pin = (char *)pfb_pinned(nbytes + ebytes + pbytes + 768);
 		void *stage_nodes = pin;
-		uint32_t *ew = pin ? (uint32_t *)(pin + ((nbytes + 255) & ~(size_t)255)) : NULL;
-		std::vector<uint32_t> ewv;
-		if (!ew) { ewv.resize((size_t)std::max(r->E, 1)); ew = ewv.data(); }
-		parallel_for(r->E, [&](long long lo, long long hi) {
-			for (long long k = lo; k < hi; k++) ew[k] = (uint32_t)p->edge_to[k] | ((uint32_t)p->edge_sw[k] << PF_EDGE_NODE_BITS);
-		});
+		uint32_t *stage_edges = pin ? (uint32_t *)(pin + ((nbytes + 255) & ~(size_t)255)) : NULL;
+		short *stage_ptc = pin ? (short *)((char *)stage_edges + ((ebytes + 255) & ~(size_t)255)) : NULL;
 		std::vector<PfSwitchDev> sw(PF_MAX_SWITCHES);
 		for (int s = 0; s < p->num_switches; s++) { sw[s].R = p->switches[s].R; sw[s].Tdel = p->switches[s].Tdel; sw[s].buffered = p->switches[s].buffered; }
 		std::vector<PfIndexedDev> ix(PF_MAX_INDEXED);
@@ -341,16 +382,24 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			if (i >= PF_CHANX_COST_INDEX_START && (min_base == 0.f || p->indexed[i].base_cost < min_base)) min_base = p->indexed[i].base_cost;
 		}
 		r->win_abs_auto = 4.f * min_base;             /* a few wire hops of base cost */
-		if (upload_nodes(r, stage_nodes) != PF_OK) { pf_router_destroy(r); return PF_ECUDA; }
-		if ((pin ? pfb_h2d_async(r->edges, ew, sizeof(uint32_t) * (size_t)r->E) : pfb_h2d(r->edges, ew, sizeof(uint32_t) * (size_t)r->E)) || pfb_h2d(r->sw, sw.data(), sizeof(PfSwitchDev) * PF_MAX_SWITCHES)
+		int bad_nodes = 0, bad_edges = 0;
+		long long wl_avail = 0;
+		r->t_mark[0] = now_s();
+		if (upload_edges(r, stage_edges, &bad_edges) != PF_OK || upload_nodes(r, stage_nodes, &bad_nodes, &wl_avail, stage_ptc) != PF_OK) { pf_router_destroy(r); return PF_ECUDA; }
+		if (bad_nodes || bad_edges) {
+			pfb_sync();
+			pf_router_destroy(r);
+			if (pf_problem_check(p, msg, sizeof(msg)) != PF_OK) FAILF(PF_EINVAL, "invalid problem: %s", msg);
+			FAILF(PF_EINVAL, "invalid problem (capacity > 255 or cost_index > 31 on some rr node)");
+		}
+		r->avail_wl = wl_avail;
+		r->t_mark[1] = now_s();
+		if (pfb_h2d(r->sw, sw.data(), sizeof(PfSwitchDev) * PF_MAX_SWITCHES)
 				|| pfb_h2d(r->indexed, ix.data(), sizeof(PfIndexedDev) * PF_MAX_INDEXED)
 				|| pfb_h2d(r->net_ptr, p->net_ptr, sizeof(int) * ((size_t)r->n + 1))
 				|| pfb_h2d(r->net_term, p->net_terminals, sizeof(int) * (size_t)r->T)
 				|| pfb_h2d(r->net_bb, p->net_bb, sizeof(int) * 4 * (size_t)r->n)) { pf_router_destroy(r); CUDA_FAIL(); }
-		r->h2d_bytes += (int64_t)sizeof(uint32_t) * r->E + (int64_t)sizeof(int) * (r->n + 1 + r->T + 4 * (int64_t)r->n);
-		r->avail_wl = 0;
-		for (int i = 0; i < r->N; i++)
-			if (p->type[i] == PF_CHANX || p->type[i] == PF_CHANY) r->avail_wl += 1 + p->xhigh[i] - p->xlow[i] + p->yhigh[i] - p->ylow[i];
+		r->h2d_bytes += (int64_t)sizeof(int) * (r->n + 1 + r->T + 4 * (int64_t)r->n);
 	}
 	/* initial criticalities (route_timing.c:116-128) */
 	{
@@ -376,14 +425,17 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	}
 	r->loc = (PfNetLoc *)pfb_alloc(sizeof(PfNetLoc) * (size_t)std::max(r->n, 1));
 	{
-		std::vector<int> all(r->work_big);
-		all.insert(all.end(), r->work_small.begin(), r->work_small.end());
+		/* every net this rank owns, in the decreasing-fanout order of the reference's net loop
+		 * (route_timing.c:98-106); the selection kernels keep that order in the work lists */
+		std::vector<int> all;
+		for (size_t k = 0; k < order.size(); k++) if (owner[order[k]] == c.rank) all.push_back(order[k]);
 		r->num_all = (int)all.size();
 		r->h_net_big.assign((size_t)std::max(r->n, 1), 0);
 		for (int i : r->work_big) r->h_net_big[i] = 1;
 		r->all_nets = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(r->num_all, 1));
 		r->net_big = (unsigned char *)pfb_alloc((size_t)std::max(r->n, 1));
-		if (!r->loc || !r->all_nets || !r->net_big
+		r->sel_scratch = (int *)pfb_alloc_raw(pfb_select_scratch_bytes(r->num_all));
+		if (!r->loc || !r->all_nets || !r->net_big || !r->sel_scratch
 				|| pfb_h2d(r->all_nets, all.data(), sizeof(int) * (size_t)r->num_all)
 				|| pfb_h2d(r->net_big, r->h_net_big.data(), (size_t)r->n)) { pf_router_destroy(r); CUDA_FAIL(); }
 	}
@@ -428,7 +480,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 				|| pfb_h2d(r->g_off, off.data(), sizeof(int) * (size_t)r->num_groups)) { pf_router_destroy(r); CUDA_FAIL(); }
 	}
 	if (pfb_sync() != 0) { pf_router_destroy(r); CUDA_FAIL(); }
-	if (c.verbose) fprintf(stderr, "pf_router: create %.3f s (problem check %.3f s)\n", now_s() - t_a, t_b - t_a);
+	if (c.verbose) fprintf(stderr, "pf_router: create %.3f s (net check %.3f s, setup + device alloc %.3f s, flatten + upload issue %.3f s, scratch + drain %.3f s)\n",
+			now_s() - t_a, t_b - t_a, r->t_mark[0] - t_b, r->t_mark[1] - r->t_mark[0], now_s() - r->t_mark[1]);
 	if (c.verbose)
 		fprintf(stderr, "pf_router[%s] rank %d/%d: N=%d E=%d nets=%zu+%zu slots=%d(2^%d labels)+%d(2^%d) pool=%lld\n", pfb_name(), c.rank, c.nranks,
 				r->N, r->E, r->work_small.size(), r->work_big.size(), c.num_slots, c.label_log2, c.big_slots, c.big_label_log2, r->pool_cap);
@@ -438,7 +491,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 
 extern "C" int pf_router_reset(pf_router *r) {
 	if (!r) FAILF(PF_EINVAL, "null router");
-	if (upload_nodes(r, pfb_pinned(sizeof(PfNode) * (size_t)r->N)) != PF_OK) return PF_ECUDA;
+	if (upload_nodes(r, pfb_pinned(sizeof(PfNode) * (size_t)r->N), NULL, NULL, NULL) != PF_OK) return PF_ECUDA;
 	CKB(pfb_sync());
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
 	CKB(pfb_zero(r->ctl, 256));
@@ -555,29 +608,16 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 		r->n_small = (int)sm.size(); r->n_big = (int)bg.size();
 	} else {
 		int counts[4];
-		CKB(pfb_zero(r->sel_counts, sizeof(int) * 4));
+		/* the work lists come back in the fanout order of the reference's net loop (route_timing.c:98-106): long
+		 * nets start first and runs are reproducible.  (Reversing the order on alternate iterations — the
+		 * reference authors experimented with shuffling it, route_timing.c:158 — was tried against the tight-W
+		 * tail and made the one-warp wirelength 4 % worse without shortening the tail.) */
 		CKB(pfb_launch_select_nets(r->nodes, r->pool[r->cur], r->loc, r->all_nets, r->num_all, r->net_big, 0,
 				r->small.work, r->big.work, r->sel_counts, r->cfg.history_window > 0 ? r->last_over : NULL,
-				1 + (r->cost_updates + 254) % 255, r->cfg.history_window, r->committer));
+				1 + (r->cost_updates + 254) % 255, r->cfg.history_window, r->committer, r->sel_scratch));
 		CKB(pfb_d2h(counts, r->sel_counts, sizeof(int) * 4));
 		r->d2h_bytes += 16;
 		r->n_small = counts[0]; r->n_big = counts[1];
-		/* the selection kernel appends in atomic order; restore the fanout order of the reference's net
-		 * loop (route_timing.c:98-106) so long nets start first and runs are reproducible.  (Reversing the
-		 * order on alternate iterations — the reference authors experimented with shuffling it,
-		 * route_timing.c:158 — was tried against the tight-W tail and made the one-warp wirelength 4 % worse
-		 * without shortening the tail.) */
-		const bool reversed = false;
-		for (int k = 0; k < 2; k++) {
-			SlotClass &sc = k ? r->big : r->small;
-			int cnt = k ? r->n_big : r->n_small;
-			if (cnt < 2) continue;
-			std::vector<int> lst((size_t)cnt);
-			CKB(pfb_d2h(lst.data(), sc.work, sizeof(int) * (size_t)cnt));
-			std::sort(lst.begin(), lst.end(), [&](int a, int b) { return reversed ? r->net_rank[a] > r->net_rank[b] : r->net_rank[a] < r->net_rank[b]; });
-			CKB(pfb_h2d(sc.work, lst.data(), sizeof(int) * (size_t)cnt));
-			r->d2h_bytes += (int64_t)sizeof(int) * cnt; r->h2d_bytes += (int64_t)sizeof(int) * cnt;
-		}
 	}
 	r->iter_count++;
 	r->since_full = all ? 0 : r->since_full + 1;
@@ -758,18 +798,20 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 	const pf_problem *p = r->prob;
 	memset(out, 0, sizeof(*out));
 	const int n = r->n;
+	const double t_0 = now_s();
 	/* the traces are assembled on the device (pf_build_traces_kernel), so what crosses PCIe is the final
 	 * 6 bytes per trace element plus 4 bytes per rr node of occupancy — not the 32-byte tree entries */
 	int *d_len = (int *)pfb_alloc_raw(sizeof(int) * ((size_t)n + 1));
 	int *d_occ = r->occ_delta ? r->occ_delta : (int *)pfb_alloc_raw(sizeof(int) * (size_t)r->N);
 	if (!d_len || !d_occ) { pfb_free(d_len); if (!r->occ_delta) pfb_free(d_occ); CUDA_FAIL(); }
 	std::vector<int32_t> tptr((size_t)n + 1, 0);
-	int bad = pfb_launch_build_traces(r->pool[r->cur], r->loc, n, d_len, NULL, NULL, NULL, NULL) || pfb_d2h(tptr.data() + 1, d_len, sizeof(int) * (size_t)n);
+	int bad = pfb_launch_build_traces(r->pool[r->cur], r->loc, n, d_len, NULL, NULL, NULL, NULL, NULL, NULL, 0) || pfb_d2h(tptr.data() + 1, d_len, sizeof(int) * (size_t)n);
 	if (bad) { pfb_free(d_len); if (!r->occ_delta) pfb_free(d_occ); CUDA_FAIL(); }
 	for (int i = 0; i < n; i++) tptr[i + 1] += tptr[i];
 	const size_t total = (size_t)tptr[n];
 	int *d_tn = (int *)pfb_alloc_raw(sizeof(int) * std::max<size_t>(total, 1));
 	short *d_ts = (short *)pfb_alloc_raw(sizeof(short) * std::max<size_t>(total, 1));
+	unsigned *d_tt = (unsigned *)pfb_alloc_raw(sizeof(unsigned) * std::max<size_t>(total, 1));
 	out->num_nets = n;
 	out->trace_ptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 1));
 	out->trace_node = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(total, 1));
@@ -778,59 +820,65 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 	out->occ = (int32_t *)malloc(sizeof(int32_t) * (size_t)r->N);
 	const bool host_ok = out->trace_ptr && out->trace_node && out->trace_switch && out->net_delay && out->occ;
 	unsigned long long h_wl[2] = { 0, 0 };
-	bad = !d_tn || !d_ts || !host_ok;
+	int serial_num = 0;
+	bad = !d_tn || !d_ts || !d_tt || !host_ok;
+	double t_1 = t_0, t_2 = t_0;
 	if (!bad) {
-		/* pinned staging for the three big arrays when available */
-		const size_t b_tn = sizeof(int) * total, b_ts = sizeof(short) * total, b_occ = sizeof(int) * (size_t)r->N;
-		char *pin = (char *)pfb_pinned(b_tn + b_ts + b_occ + 1024);
-		char *h_tn = pin ? pin : (char *)out->trace_node;
-		char *h_ts = pin ? pin + ((b_tn + 255) & ~(size_t)255) : (char *)out->trace_switch;
+		/* pinned staging for the big arrays when available */
+		const size_t b_tn = sizeof(int) * total, b_ts = sizeof(short) * total, b_tt = sizeof(unsigned) * total, b_occ = sizeof(int) * (size_t)r->N;
+		char *pin = (char *)pfb_pinned(b_tn + b_ts + b_tt + b_occ + 1024);
+		std::vector<unsigned> ttv;
+		if (!pin) ttv.resize(std::max<size_t>(total, 1));
+		char *h_tt = pin ? pin : (char *)ttv.data();
+		char *h_tn = pin ? h_tt + ((b_tt + 255) & ~(size_t)255) : (char *)out->trace_node;
+		char *h_ts = pin ? h_tn + ((b_tn + 255) & ~(size_t)255) : (char *)out->trace_switch;
 		char *h_occ = pin ? h_ts + ((b_ts + 255) & ~(size_t)255) : (char *)out->occ;
+		/* the serial-number terms come first: the running remainder below is sequential by definition and runs on
+		 * a helper thread while the traces and the occupancy cross PCIe and are copied out */
 		bad = pfb_h2d(d_len, tptr.data(), sizeof(int) * ((size_t)n + 1)) || pfb_zero(r->d_wl, sizeof(unsigned long long) * 2)
-				|| pfb_launch_build_traces(r->pool[r->cur], r->loc, n, NULL, d_len, d_tn, d_ts, r->d_wl)
-				|| pfb_launch_extract_occ(r->nodes, r->N, d_occ)
-				|| pfb_d2h_async(h_tn, d_tn, b_tn) || pfb_d2h_async(h_ts, d_ts, b_ts) || pfb_d2h_async(h_occ, d_occ, b_occ)
-				|| pfb_d2h(h_wl, r->d_wl, sizeof(h_wl)) || pfb_d2h(out->net_delay, r->net_delay, sizeof(float) * (size_t)r->T);
-		if (!bad && pin) {
-			parallel_for((long long)total, [&](long long lo, long long hi) {
-				memcpy(out->trace_node + lo, h_tn + sizeof(int) * (size_t)lo, sizeof(int) * (size_t)(hi - lo));
-				memcpy(out->trace_switch + lo, h_ts + sizeof(short) * (size_t)lo, sizeof(short) * (size_t)(hi - lo));
+				|| pfb_launch_build_traces(r->pool[r->cur], r->loc, n, NULL, d_len, d_tn, d_ts, r->d_wl, d_tt, r->ptc, p->nx)
+				|| pfb_d2h(h_tt, d_tt, b_tt);
+		std::thread chain;
+		if (!bad) {
+			const unsigned *tt = (const unsigned *)h_tt;
+			chain = std::thread([tt, total, &serial_num]() {
+				/* get_serial_num, route_common.c:224-254: serial = (serial + a - b - c) % 2000000000 per trace element, in
+				 * the reference's wrapping int arithmetic.  |x| < 2^31 < 2 * 2000000000, so C's truncating remainder is
+				 * one conditional add or subtract. */
+				const int M = 2000000000;
+				int sv = 0;
+				for (size_t k = 0; k < total; k++) {
+					int x = (int)((unsigned)sv + tt[k]);
+					sv = x >= M ? x - M : (x <= -M ? x + M : x);
+				}
+				serial_num = sv;
 			});
-			parallel_for(r->N, [&](long long lo, long long hi) { memcpy(out->occ + lo, h_occ + sizeof(int) * (size_t)lo, sizeof(int) * (size_t)(hi - lo)); });
+			t_1 = now_s();
+			bad = pfb_launch_extract_occ(r->nodes, r->N, d_occ)
+					|| pfb_d2h_async(h_tn, d_tn, b_tn) || pfb_d2h_async(h_ts, d_ts, b_ts) || pfb_d2h_async(h_occ, d_occ, b_occ)
+					|| pfb_d2h(h_wl, r->d_wl, sizeof(h_wl)) || pfb_d2h(out->net_delay, r->net_delay, sizeof(float) * (size_t)r->T);
+			if (!bad && pin) {
+				parallel_for((long long)total, [&](long long lo, long long hi) {
+					memcpy(out->trace_node + lo, h_tn + sizeof(int) * (size_t)lo, sizeof(int) * (size_t)(hi - lo));
+					memcpy(out->trace_switch + lo, h_ts + sizeof(short) * (size_t)lo, sizeof(short) * (size_t)(hi - lo));
+				});
+				parallel_for(r->N, [&](long long lo, long long hi) { memcpy(out->occ + lo, h_occ + sizeof(int) * (size_t)lo, sizeof(int) * (size_t)(hi - lo)); });
+			}
+			t_2 = now_s();
+			chain.join();
 		}
-		r->d2h_bytes += (int64_t)(b_tn + b_ts + b_occ) + (int64_t)sizeof(int) * n + (int64_t)sizeof(float) * r->T;
+		r->d2h_bytes += (int64_t)(b_tn + b_ts + b_tt + b_occ) + (int64_t)sizeof(int) * n + (int64_t)sizeof(float) * r->T;
 	}
-	pfb_free(d_len); pfb_free(d_tn); pfb_free(d_ts);
+	pfb_free(d_len); pfb_free(d_tn); pfb_free(d_ts); pfb_free(d_tt);
 	if (!r->occ_delta) pfb_free(d_occ);
 	if (bad) { pf_result_free(out); if (!host_ok) FAILF(PF_ENOMEM, "out of host memory"); CUDA_FAIL(); }
 	memcpy(out->trace_ptr, tptr.data(), sizeof(int32_t) * ((size_t)n + 1));
 	out->num_terminals = r->T;
 	out->num_nodes = r->N;
 	out->total_wirelength = (int32_t)h_wl[0];
-	{   /* get_serial_num, route_common.c:224-254: a running 32-bit remainder, sequential by definition.  The three
-		 * per-element terms (random reads of xlow/yhigh/ptc/type) are gathered in parallel, the running update
-		 * then streams over contiguous arrays with the reference's exact operation order. */
-		std::vector<int> ta(std::max<size_t>(total, 1)), tb(std::max<size_t>(total, 1)), tc(std::max<size_t>(total, 1));
-		const int32_t *tn = out->trace_node;
-		parallel_for(n, [&](long long lo, long long hi) {
-			for (long long i = lo; i < hi; i++)
-				for (int k = tptr[i]; k < tptr[i + 1]; k++) {
-					int v = tn[k];
-					ta[k] = (int)((unsigned)(i + 1) * (unsigned)(p->xlow[v] * (p->nx + 1) - p->yhigh[v]));
-					tb[k] = (int)((unsigned)p->ptc_num[v] * (unsigned)(i + 1) * 10u);
-					tc[k] = (int)((unsigned)p->type[v] * (unsigned)(i + 1) * 100u);
-				}
-		});
-		unsigned serial = 0;      /* two's-complement wrap like the reference's int arithmetic */
-		int sv = 0;
-		for (size_t k = 0; k < total; k++) {
-			serial = (unsigned)sv + (unsigned)ta[k];
-			serial -= (unsigned)tb[k];
-			serial -= (unsigned)tc[k];
-			sv = (int)serial % 2000000000;
-		}
-		out->serial_num = sv;
-	}
+	out->serial_num = serial_num;
+	if (r->cfg.verbose) fprintf(stderr, "pf_router: result %.3f s (trace build + serial terms to host %.3f s, traces + occupancy to host %.3f s, wait for serial number %.3f s)\n",
+			now_s() - t_0, t_1 - t_0, t_2 - t_1, now_s() - t_2);
 	return PF_OK;
 }
 

@@ -94,8 +94,10 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
 
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer) {
-	for (int k = 0; k < num_all; k++) {
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch) {
+	(void)scratch;
+	counts[0] = counts[1] = 0;
+	for (int k = 0; k < num_all; k++) {          /* all_nets is in fanout order; so are the lists */
 		int net = all_nets[k];
 		if (force_all || pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net)) {
 			if (net_big[net]) list_big[counts[1]++] = net; else list_small[counts[0]++] = net;
@@ -104,6 +106,9 @@ int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const Pf
 	g_times.aux_launches++;
 	return 0;
 }
+
+void pfb_bind_thread(void) {}
+size_t pfb_select_scratch_bytes(int num_all) { (void)num_all; return 16; }
 
 int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
 		unsigned long long *dst_head) {
@@ -127,11 +132,12 @@ int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out) {
 }
 
 int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num_nets, int *len, const int *tptr,
-		int *trace_node, short *trace_switch, unsigned long long *d_wl) {
+		int *trace_node, short *trace_switch, unsigned long long *d_wl, unsigned *trace_term, const short *ptc, int nx) {
 	for (int i = 0; i < num_nets; i++) {
 		PfNetLoc l = loc[i];
-		if (!trace_node) { len[i] = pf_trace_of_net(pool + l.off, l.count, NULL, NULL); continue; }
-		*d_wl += (unsigned long long)pf_trace_of_net(pool + l.off, l.count, trace_node + tptr[i], trace_switch + tptr[i]);
+		if (!trace_node) { len[i] = pf_trace_of_net(pool + l.off, l.count, NULL, NULL, NULL, NULL, 0, 0u); continue; }
+		*d_wl += (unsigned long long)pf_trace_of_net(pool + l.off, l.count, trace_node + tptr[i], trace_switch + tptr[i],
+				trace_term ? trace_term + tptr[i] : NULL, ptc, nx, (unsigned)(i + 1));
 	}
 	g_times.aux_launches++;
 	return 0;

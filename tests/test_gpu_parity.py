@@ -143,3 +143,22 @@ def test_overflow_retry_and_small_scratch():
     r = router.try_timing_driven_route(p, router.default_config(label_log2=7, far_cap=64, tree_cap=64, big_slots=4))
     assert r.success == 1
     check_route.check_route(p, r)
+
+
+def test_malformed_graph_is_rejected_with_the_checker_message():
+    """The node / edge range checks run inside the parallel upload passes; a bad array must still come back as
+    PF_EINVAL with pf_problem_check's message, and the library must stay usable afterwards."""
+    p, _ = _load("toy_w64", False)
+    keep = int(p.edge_to[5])
+    p.edge_to[5] = p.num_nodes + 7
+    with pytest.raises(router.RouterError) as e:
+        router.try_timing_driven_route(p)
+    assert e.value.code == -4 and "invalid problem" in str(e.value)
+    p.edge_to[5] = keep
+    keep = int(p.capacity[3])
+    p.capacity[3] = -1
+    with pytest.raises(router.RouterError) as e:
+        router.try_timing_driven_route(p)
+    assert e.value.code == -4
+    p.capacity[3] = keep
+    assert router.try_timing_driven_route(p).success == 1
