@@ -23,6 +23,7 @@ const char *pfb_last_error(void);
 void *pfb_alloc(size_t bytes);                    /* device memory, zero-filled; NULL on failure */
 void *pfb_alloc_raw(size_t bytes);                /* device memory, uninitialised */
 void *pfb_pinned(size_t bytes);                   /* process-wide pinned staging buffer of at least `bytes`; NULL if unavailable */
+void *pfb_pinned_upload(size_t bytes);            /* same, write-combined: host code must only WRITE it, sequentially */
 int pfb_h2d_async(void *dst, const void *src, size_t bytes);   /* ordered on the router's stream; src must stay valid until pfb_sync */
 int pfb_d2h_async(void *dst, const void *src, size_t bytes);
 void pfb_free(void *p);

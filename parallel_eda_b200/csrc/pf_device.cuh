@@ -145,41 +145,29 @@ PF_DEV float pf_expected_cost(const PfWarp &w, int type, int ci, int ixlow, int 
 		const PfIndexedDev &O = w.idx[oci];
 		float inv_length = I.inv_length, ortho_inv_length = O.inv_length;
 		float ylow = iylow, yhigh = iyhigh, xlow = ixlow, xhigh = ixhigh;
-		if (type == 4) { /* CHANX */
-			if (ylow > target_y) {
-				num_segs_ortho_dir = (int)(PF_ROUND_UP((ylow - target_y + 1.) * ortho_inv_length));
-				no_need_to_pass_by_clb = 1;
-			} else if (ylow < target_y - 1) {
-				num_segs_ortho_dir = (int)(PF_ROUND_UP((target_y - ylow) * ortho_inv_length));
-				no_need_to_pass_by_clb = 1;
-			} else {
-				num_segs_ortho_dir = 0;
-				no_need_to_pass_by_clb = 0;
-			}
-			if (xlow > target_x + no_need_to_pass_by_clb)
-				num_segs_same_dir = (int)(PF_ROUND_UP((xlow - no_need_to_pass_by_clb - target_x) * inv_length));
-			else if (xhigh < target_x - no_need_to_pass_by_clb)
-				num_segs_same_dir = (int)(PF_ROUND_UP((target_x - no_need_to_pass_by_clb - xhigh) * inv_length));
-			else
-				num_segs_same_dir = 0;
-		} else { /* CHANY */
-			if (xlow > target_x) {
-				num_segs_ortho_dir = (int)(PF_ROUND_UP((xlow - target_x + 1.) * ortho_inv_length));
-				no_need_to_pass_by_clb = 1;
-			} else if (xlow < target_x - 1) {
-				num_segs_ortho_dir = (int)(PF_ROUND_UP((target_x - xlow) * ortho_inv_length));
-				no_need_to_pass_by_clb = 1;
-			} else {
-				num_segs_ortho_dir = 0;
-				no_need_to_pass_by_clb = 0;
-			}
-			if (ylow > target_y + no_need_to_pass_by_clb)
-				num_segs_same_dir = (int)(PF_ROUND_UP((ylow - no_need_to_pass_by_clb - target_y) * inv_length));
-			else if (yhigh < target_y - no_need_to_pass_by_clb)
-				num_segs_same_dir = (int)(PF_ROUND_UP((target_y - no_need_to_pass_by_clb - yhigh) * inv_length));
-			else
-				num_segs_same_dir = 0;
+		/* the reference spells the CHANX and the CHANY case out separately (route_timing.c:711-772); they are the
+		 * same arithmetic with x and y exchanged, so one copy runs on (along-the-wire, across-the-wire)
+		 * coordinates — a warp holds both kinds, and two branches would execute one after the other */
+		const bool cx = (type == 4);
+		const float a_low = cx ? xlow : ylow, a_high = cx ? xhigh : yhigh;   /* along the wire */
+		const float o_low = cx ? ylow : xlow;                                /* across */
+		const int t_a = cx ? target_x : target_y, t_o = cx ? target_y : target_x;
+		if (o_low > t_o) {
+			num_segs_ortho_dir = (int)(PF_ROUND_UP((o_low - t_o + 1.) * ortho_inv_length));
+			no_need_to_pass_by_clb = 1;
+		} else if (o_low < t_o - 1) {
+			num_segs_ortho_dir = (int)(PF_ROUND_UP((t_o - o_low) * ortho_inv_length));
+			no_need_to_pass_by_clb = 1;
+		} else {
+			num_segs_ortho_dir = 0;
+			no_need_to_pass_by_clb = 0;
 		}
+		if (a_low > t_a + no_need_to_pass_by_clb)
+			num_segs_same_dir = (int)(PF_ROUND_UP((a_low - no_need_to_pass_by_clb - t_a) * inv_length));
+		else if (a_high < t_a - no_need_to_pass_by_clb)
+			num_segs_same_dir = (int)(PF_ROUND_UP((t_a - no_need_to_pass_by_clb - a_high) * inv_length));
+		else
+			num_segs_same_dir = 0;
 		float cong_cost = num_segs_same_dir * w.base_cost[ci] + num_segs_ortho_dir * w.base_cost[oci];
 		cong_cost += w.base_cost[3] + w.base_cost[1];   /* IPIN_COST_INDEX, SINK_COST_INDEX */
 		/* criticality 0 (timing analysis off, or a sink below the 1 - max_criticality cut): the delay term is
@@ -404,7 +392,7 @@ PF_DEV void pf_heapsort_lane(int *heap /*[1..n]*/, const float *v /*[1..n]*/, in
 /* ------------------------------------------------------------------ one sink search */
 /* Returns 1 when the target was reached (label present), 0 if the frontier was exhausted, -1 on
  * scratch overflow.  tree_n = current number of tree entries. */
-PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, int rlim) {
+template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, int rlim) {
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	const float astar = P->astar_fac;
@@ -432,46 +420,45 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 		slack = P->pop_slack * ((1.f - crit) * mb + crit * mt);
 	}
 
-	/* ---- seed with the current route tree (add_route_tree_to_heap) */
+	/* ---- seed with the current route tree (add_route_tree_to_heap): pass 0 finds the cheapest seed (it sets
+	 * the near-set window), pass 1 labels and pushes.  One loop body for both keeps a single inlined copy of
+	 * the lookahead. */
 	float smin = PF_INF_F;
-	for (int i = lane; i < tree_n; i += PF_WARP) {
-		PfTreeNode t = w.tree[i];
-		if (t.flags & PF_TF_REEXPAND) {
-			float back = crit * t.Tdel;
-			float tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
-			if (tot < smin) smin = tot;
-		}
-	}
-	smin = pf_warp_min_f(smin);
-	if (!(smin < PF_INF_F)) return 0;
-	{
-		float win = smin * P->win_rel;
-		if (win < P->win_abs) win = P->win_abs;
-		w.T_hi = smin + win;
-	}
-	for (int base = 0; base < tree_n; base += PF_WARP) {
-		int i = base + lane;
-		int valid = 0, node = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
-		if (i < tree_n) {
-			PfTreeNode t = w.tree[i];
-			if (t.flags & PF_TF_REEXPAND) {
-				valid = 1; node = t.node; R_up = t.R_up;
-				back = crit * t.Tdel;
-				tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
+	for (int pass = 0; pass < 2; pass++) {
+		for (int base = 0; base < tree_n; base += PF_WARP) {
+			int i = base + lane;
+			int valid = 0, node = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
+			if (i < tree_n) {
+				PfTreeNode t = w.tree[i];
+				if (t.flags & PF_TF_REEXPAND) {
+					valid = 1; node = t.node; R_up = t.R_up;
+					back = crit * t.Tdel;
+					tot = back + astar * pf_expected_cost(w, t.type_ci & 7, t.type_ci >> 3, t.xlow, t.xhigh, t.ylow, t.yhigh, tgt_xl, tgt_yl, crit, t.R_up);
+				}
+			}
+			if (pass == 0) {
+				if (valid && tot < smin) smin = tot;
+			} else {
+				int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
+				pf_push(w, wr, tot, back, node);
+				if (w.overflow) return -1;
 			}
 		}
-		int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
-		pf_push(w, wr, tot, back, node);
-		if (w.overflow) return -1;
+		if (pass == 0) {
+			smin = pf_warp_min_f(smin);
+			if (!(smin < PF_INF_F)) return 0;
+			float win = smin * P->win_rel;
+			if (win < P->win_abs) win = P->win_abs;
+			w.T_hi = smin + win;
+		}
 	}
 
 	/* ---- settle loop */
 	for (;;) {
 		if (w.overflow) return -1;
-		uint64_t mk = PF_KEY_MAX;
-		for (int i = lane; i < w.sh_n; i += PF_WARP) { uint64_t k = w.fr[i]; if (k < mk) mk = k; }
-		mk = pf_warp_min_u64(mk);
-		float mtot = (w.sh_n > 0) ? pf_key_tot(mk) : PF_INF_F;
+		float mtot = PF_INF_F;
+		for (int i = lane; i < w.sh_n; i += PF_WARP) { float t = pf_key_tot(w.fr[i]); if (t < mtot) mtot = t; }
+		mtot = pf_warp_min_f(mtot);
 		if (w.far_min < mtot) {                 /* a cheaper label sits in the far list (or near set empty) */
 			if (w.far_min >= w.best) break;
 			pf_refill(w);
@@ -480,9 +467,49 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 		if (w.sh_n == 0) break;                 /* both exhausted */
 		if (mtot >= w.best) break;              /* target settled: nothing cheaper remains */
 
+		const float thr = mtot + slack;
+		int taken, M;
+		/* the label(s) being expanded: uniform registers in strict mode, per-lane views of the batch otherwise */
+		int x_node = -1, x_start = 0, x_type = 0; float x_back = 0.f, x_R = 0.f;
+		if (STRICT) {
+			/* -- strict best-first: settle one label, the OLDEST near label within pop_slack of the minimum (what the
+			 * batch selection below yields for max_batch == 1), and close the gap so the near set stays in push
+			 * order.  Every lane then does the same label lookup (broadcast reads): nothing is staged. */
+			int li = 0x7fffffff;
+			for (int i = lane; i < w.sh_n; i += PF_WARP) if (pf_key_tot(w.fr[i]) <= thr) { li = i; break; }
+			const int idx = -pf_warp_max_i(-li);
+			const uint64_t mk = w.fr[idx];
+			uint64_t keep[PF_SH_FRONTIER / PF_WARP];
+			for (int c = 0; c < PF_SH_FRONTIER / PF_WARP; c++) { int i = lane + c * PF_WARP; keep[c] = (i > idx && i < w.sh_n) ? w.fr[i] : 0; }
+			pf_syncwarp();
+			for (int c = 0; c < PF_SH_FRONTIER / PF_WARP; c++) { int i = lane + c * PF_WARP; if (i > idx && i < w.sh_n) w.fr[i - 1] = keep[c]; }
+			w.sh_n--;
+			pf_syncwarp();
+			taken = 1; M = 0;
+			const int u = pf_key_node(mk);
+			const int h = pf_label_find(w, u);
+			int ok = 0;
+			if (h >= 0) {
+				uint64_t hk = w.hot[h];
+				if (pf_int_as_float((int)(hk >> 32)) == pf_key_tot(mk)) {      /* else stale: the node was re-labelled cheaper */
+					pf_u4 a = pf_ld_u4(&w.cold[h]), b = pf_ld_u4((const char *)&w.cold[h] + 16);
+					x_start = (int)b.x; x_type = (int)((a.w >> 8) & 0xffu);
+					M = (int)(a.w >> 16);
+					if (x_start < 0) {                                      /* seed: row not cached in the label */
+						PfNodeView un = pf_load_node(P, u);
+						x_start = un.edge_start; x_type = un.type; M = un.num_edges;
+					}
+					x_node = u; x_back = pf_int_as_float((int)a.x); x_R = pf_int_as_float((int)a.y);
+					ok = 1;
+				}
+			}
+			w.pops += (unsigned long long)ok;
+			w.stale += (unsigned long long)(1 - ok);
+			if (!ok) continue;
+		} else {
 		/* -- select the batch: every near label within pop_slack of the minimum, at most max_batch */
-		float thr = mtot + slack;
-		int taken = 0, kept = 0;
+		int kept = 0;
+		taken = 0;
 		for (int base = 0; base < w.sh_n; base += PF_WARP) {
 			int i = base + lane;
 			uint64_t k = (i < w.sh_n) ? w.fr[i] : PF_KEY_MAX;
@@ -536,9 +563,10 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 			if (lane >= d) incl += o;
 		}
 		if (lane < taken) w.b_pre[lane] = incl - deg;
-		int M = pf_shfl_i(incl, taken - 1);
+		M = pf_shfl_i(incl, taken - 1);
 		if (lane == 0) w.b_pre[taken] = M;
 		pf_syncwarp();
+		}
 		w.visits += (unsigned long long)M;
 
 		/* -- relax every out-edge of the batch, 32 edges per pass */
@@ -547,10 +575,15 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 			int valid = e < M;
 			int to = 0, u = 0, isw = 0, info = 0, es = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
 			if (valid) {
-				int j = 0, hi = taken - 1;                      /* owner: last j with b_pre[j] <= e */
-				while (j < hi) { int mid = (j + hi + 1) >> 1; if (w.b_pre[mid] <= e) j = mid; else hi = mid - 1; }
-				u = w.b_node[j];
-				uint32_t ew = P->edges[w.b_start[j] + (e - w.b_pre[j])];
+				int eoff = e;
+				if (!STRICT) {
+					int j = 0, hi = taken - 1;                  /* owner: last j with b_pre[j] <= e */
+					while (j < hi) { int mid = (j + hi + 1) >> 1; if (w.b_pre[mid] <= e) j = mid; else hi = mid - 1; }
+					x_node = w.b_node[j]; x_start = w.b_start[j]; x_type = w.b_type[j]; x_back = w.b_back[j]; x_R = w.b_R[j];
+					eoff = e - w.b_pre[j];
+				}
+				u = x_node;
+				uint32_t ew = P->edges[x_start + eoff];
 				to = (int)(ew & PF_EDGE_NODE_MASK); isw = (int)(ew >> PF_EDGE_NODE_BITS);
 				PfNodeView n = pf_load_node(P, to);
 				if (n.xhigh < w.bb_xmin || n.xlow > w.bb_xmax || n.yhigh < w.bb_ymin || n.ylow > w.bb_ymax) valid = 0;
@@ -563,7 +596,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 					if (n.occ < n.cap) pres = 1.;
 					else pres = 1. + (n.occ + 1 - n.cap) * P->pres_fac;
 					float cong = w.base_cost[n.ci] * n.acc * pres;
-					float old_back = w.b_back[j], Ru = w.b_R[j];
+					float old_back = x_back, Ru = x_R;
 					float new_back = old_back + (1. - crit) * cong;
 					float new_R;
 					const PfSwitchDev S = w.sw[isw];
@@ -575,7 +608,7 @@ PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, in
 					}
 					new_R += n.R;
 					if (P->bend_cost != 0.) {
-						int ft = w.b_type[j];
+						int ft = x_type;
 						if ((ft == 4 && n.type == 5) || (ft == 5 && n.type == 4)) new_back += P->bend_cost;
 					}
 					tot = new_back + astar * pf_expected_cost(w, n.type, n.ci, n.xlow, n.xhigh, n.ylow, n.yhigh, tgt_xl, tgt_yl, crit, new_R);
@@ -794,7 +827,7 @@ PF_DEV void pf_swap_tables(PfWarp &w) {
 
 /* ------------------------------------------------------------------ one net
  * timing_driven_route_net, route_timing.c:399-563 */
-PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: routed, 0: handed to a bigger slot / failed */
+template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: routed, 0: handed to a bigger slot / failed */
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	const int t0 = P->net_ptr[inet];
@@ -857,26 +890,25 @@ PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: routed, 0: handed to a bi
 			float crit = pin_crit[target_pin];
 			int rlim = pf_highfanout_rlim(w, tree_n, target_node);
 			if (rlim < 0) { fail = PF_ST_INTERNAL; break; }
-			int r = pf_search_sink(w, tree_n, target_node, crit, rlim);
-			if (r < 0 && w.overflow == PF_OVF_LABELS && w.hot_alt) {
-				/* the search outgrew the shared-memory label table: run it again on this slot's
-				 * fallback table in global memory, then come back for the next sink */
-				pf_swap_tables(w);
-				w.overflow = 0;
-				r = pf_search_sink(w, tree_n, target_node, crit, rlim);
-				if (r > 0) {
-					int si2 = pf_add_path(w, &tree_n, target_node);
+			/* a search that outgrows the shared-memory label table runs again on this slot's fallback table in
+			 * global memory; the tables are swapped back before the next sink.  (One call site each for the search
+			 * and the back-trace: the kernel's instruction footprint matters, see DESIGN.md.) */
+			int r, swapped = 0;
+			for (;;) {
+				r = pf_search_sink<STRICT>(w, tree_n, target_node, crit, rlim);
+				if (r < 0 && !swapped && w.overflow == PF_OVF_LABELS && w.hot_alt) {
 					pf_swap_tables(w);
-					if (si2 < 0) { w.overflow = PF_OVF_OTHER; break; }
-					if (lane == 0) rt_of_sink[target_pin] = si2;
-					pf_syncwarp();
+					w.overflow = 0;
+					swapped = 1;
 					continue;
 				}
-				pf_swap_tables(w);
+				break;
 			}
+			int si = 0;
+			if (r > 0) si = pf_add_path(w, &tree_n, target_node);
+			if (swapped) pf_swap_tables(w);
 			if (r < 0) break;                                 /* overflow: retry in a bigger slot */
 			if (r == 0) { fail = PF_ST_UNROUTABLE; break; }
-			int si = pf_add_path(w, &tree_n, target_node);
 			if (si < 0) { w.overflow = PF_OVF_OTHER; break; }
 			if (lane == 0) rt_of_sink[target_pin] = si;
 			pf_syncwarp();
@@ -913,7 +945,7 @@ PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: routed, 0: handed to a bi
 }
 
 /* ------------------------------------------------------------------ warp main: persistent work loop */
-PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIndexedDev *idx_tab, PfSwitchDev *sw_tab, unsigned char *smem_warp) {
+template <int STRICT> PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIndexedDev *idx_tab, PfSwitchDev *sw_tab, unsigned char *smem_warp) {
 	const int lane = pf_lane();
 	PfWarp w;
 	w.P = P;
@@ -965,7 +997,7 @@ PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIndexedDev *idx_tab, PfS
 		if (lane == 0) k = pf_atomic_add_i(P->work_head, 1);
 		k = pf_shfl_i(k, 0);
 		if (k >= P->num_work) break;
-		nets += (unsigned long long)pf_route_net(w, P->work[k]);
+		nets += (unsigned long long)pf_route_net<STRICT>(w, P->work[k]);
 	}
 	if (lane == 0) {
 		if (P->hot) P->epochs[2 * slot] = w.epoch;

@@ -85,15 +85,22 @@ void *pfb_alloc(size_t bytes) {
 void pfb_free(void *p) { if (p) cudaFreeAsync(p, g_stream); }
 
 /* process-wide pinned staging buffer for host<->device transfers of the big arrays */
-static void *g_pinned = NULL; static size_t g_pinned_bytes = 0;
-void *pfb_pinned(size_t bytes) {
-	if (bytes <= g_pinned_bytes) return g_pinned;
-	if (g_pinned) { cudaStreamSynchronize(g_stream); cudaFreeHost(g_pinned); g_pinned = NULL; g_pinned_bytes = 0; }
+/* Two process-wide pinned staging buffers.  [0] download: ordinary cached memory, the host copies results out
+ * of it.  [1] upload: write-combined — the flattening threads only ever write it front to back, the stores
+ * bypass the cache hierarchy (no read-for-ownership traffic) and the DMA engine does not have to snoop. */
+static void *g_pinned[2] = { NULL, NULL }; static size_t g_pinned_bytes[2] = { 0, 0 };
+static void *pinned_get(int which, size_t bytes) {
+	if (bytes <= g_pinned_bytes[which]) return g_pinned[which];
+	if (g_pinned[which]) { cudaStreamSynchronize(g_stream); cudaFreeHost(g_pinned[which]); g_pinned[which] = NULL; g_pinned_bytes[which] = 0; }
 	size_t want = bytes + (bytes >> 3);
-	if (cudaHostAlloc(&g_pinned, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); g_pinned = NULL; return NULL; }
-	g_pinned_bytes = want;
-	return g_pinned;
+	if (cudaHostAlloc(&g_pinned[which], want, which ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) {
+		cudaGetLastError(); g_pinned[which] = NULL; return NULL;
+	}
+	g_pinned_bytes[which] = want;
+	return g_pinned[which];
 }
+void *pfb_pinned(size_t bytes) { return pinned_get(0, bytes); }
+void *pfb_pinned_upload(size_t bytes) { return pinned_get(1, bytes); }
 int pfb_h2d_async(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); return 0; }
 int pfb_d2h_async(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); return 0; }
 int pfb_h2d(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); CK(cudaStreamSynchronize(g_stream)); return 0; }
@@ -160,7 +167,9 @@ static int ev_end(void) {
 /* ------------------------------------------------------------------ kernels */
 extern __shared__ __align__(16) unsigned char pf_smem[];
 
-__global__ void __launch_bounds__(128, 5) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
+/* STRICT = 1: strict best-first search (one label settled per step; P.max_batch == 1), the throughput mode;
+ * STRICT = 0: a delta bucket of up to P.max_batch labels per step, the latency mode for few nets per warp */
+template <int STRICT> __global__ void __launch_bounds__(128, 5) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
 	/* 96 registers and 43.3 KB of shared memory per 4-warp CTA: 5 CTAs = 20 warps per SM.
 	 * shared memory: [switch + cost-index tables, one copy per CTA][per-warp regions] */
 	const int warp_in_block = (int)(threadIdx.x >> 5);
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(128, 5) pf_route_kernel(const __grid_constant_
 	__syncthreads();
 	if (slot >= num_slots) return;
 	const size_t per_warp = PF_SMEM_PER_WARP + (P.hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8);
-	pf_warp_main(&P, slot, idx, sw, pf_smem + PF_SMEM_BLOCK_TABLES + (size_t)warp_in_block * per_warp);
+	pf_warp_main<STRICT>(&P, slot, idx, sw, pf_smem + PF_SMEM_BLOCK_TABLES + (size_t)warp_in_block * per_warp);
 }
 
 __global__ void pf_update_cost_kernel(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
@@ -292,9 +301,14 @@ int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	int blocks = (num_slots + warps_per_block - 1) / warps_per_block;
 	size_t smem = PF_SMEM_BLOCK_TABLES + (size_t)warps_per_block * (PF_SMEM_PER_WARP + (P->hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8));
 	static size_t smem_set = 0;
-	if (smem > smem_set) { CK(cudaFuncSetAttribute(pf_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+	if (smem > smem_set) {
+		CK(cudaFuncSetAttribute(pf_route_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(pf_route_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		smem_set = smem;
+	}
 	if (ev_begin(0) != 0) return -1;
-	pf_route_kernel<<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
+	if (P->max_batch == 1) pf_route_kernel<1><<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
+	else pf_route_kernel<0><<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
 	return ev_end();
 }
 

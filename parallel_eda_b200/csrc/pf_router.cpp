@@ -167,6 +167,14 @@ extern "C" void pf_router_destroy(pf_router *r) {
  * the async copy of its own piece as soon as it is written, so packing and PCIe overlap; `bad` collects the
  * range checks of pf_problem_check for the node arrays (done here so the arrays are read once). */
 #define PF_UPLOAD_PIECE (4u << 20)
+/* stores to write-combined memory sit in the core's WC buffers until flushed: drain them before the DMA reads */
+static inline void wc_fence() {
+#if defined(__x86_64__) || defined(__i386__)
+	__builtin_ia32_sfence();
+#else
+	std::atomic_thread_fence(std::memory_order_seq_cst);
+#endif
+}
 static int upload_nodes(pf_router *r, void *staging, int *bad_out, long long *avail_wl, short *stage_ptc) {
 	const pf_problem *p = r->prob;
 	PfNode *stage = staging ? (PfNode *)staging : NULL;
@@ -183,7 +191,7 @@ static int upload_nodes(pf_router *r, void *staging, int *bad_out, long long *av
 		for (long long c0 = lo; c0 < hi; c0 += piece) {
 			const long long c1 = std::min(hi, c0 + piece);
 			for (long long i = c0; i < c1; i++) {
-				PfNode &d = h[i];
+				PfNode d;                                    /* built in registers, stored whole (the staging buffer is write-combined) */
 				const int ne = p->row_ptr[i + 1] - p->row_ptr[i];
 				b |= (ne < 0) | (ne > 32767) | (p->type[i] > PF_CHANY) | (p->cost_index[i] < 0) | (p->cost_index[i] >= p->num_indexed)
 					| (p->xlow[i] > p->xhigh[i]) | (p->ylow[i] > p->yhigh[i]) | (p->xlow[i] < 0) | (p->ylow[i] < 0)
@@ -195,11 +203,13 @@ static int upload_nodes(pf_router *r, void *staging, int *bad_out, long long *av
 				d.num_edges = (unsigned short)ne;
 				d.type_ci = (unsigned char)(p->type[i] | (p->cost_index[i] << 3));
 				d.capacity = (unsigned char)p->capacity[i];
+				h[i] = d;
 				if (p->type[i] == PF_CHANX || p->type[i] == PF_CHANY) w += 1 + p->xhigh[i] - p->xlow[i] + p->yhigh[i] - p->ylow[i];
 			}
+			if (stage_ptc) memcpy(stage_ptc + c0, p->ptc_num + c0, sizeof(short) * (size_t)(c1 - c0));
+			if (staging) wc_fence();
 			if (staging && pfb_h2d_async(r->nodes + c0, h + c0, sizeof(PfNode) * (size_t)(c1 - c0)) != 0) fail = 1;
 			if (stage_ptc) {
-				memcpy(stage_ptc + c0, p->ptc_num + c0, sizeof(short) * (size_t)(c1 - c0));
 				if (pfb_h2d_async(r->ptc + c0, stage_ptc + c0, sizeof(short) * (size_t)(c1 - c0)) != 0) fail = 1;
 			}
 		}
@@ -234,6 +244,7 @@ static int upload_edges(pf_router *r, uint32_t *staging, int *bad_out) {
 				b |= (to >= N) | (s >= S);
 				ew[k] = to | (s << PF_EDGE_NODE_BITS);
 			}
+			if (staging) wc_fence();
 			if (staging && pfb_h2d_async(r->edges + c0, ew + c0, sizeof(uint32_t) * (size_t)(c1 - c0)) != 0) fail = 1;
 		}
 		if (b) bad = 1;
@@ -366,7 +377,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	{
 		const size_t nbytes = sizeof(PfNode) * (size_t)r->N, ebytes = sizeof(uint32_t) * (size_t)std::max(r->E, 1);
 		const size_t pbytes = sizeof(short) * (size_t)r->N;
-		char *pin = (char *)pfb_pinned(nbytes + ebytes + pbytes + 768);
+		char *pin = (char *)pfb_pinned_upload(nbytes + ebytes + pbytes + 768);
 		void *stage_nodes = pin;
 		uint32_t *stage_edges = pin ? (uint32_t *)(pin + ((nbytes + 255) & ~(size_t)255)) : NULL;
 		short *stage_ptc = pin ? (short *)((char *)stage_edges + ((ebytes + 255) & ~(size_t)255)) : NULL;
@@ -491,7 +502,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 
 extern "C" int pf_router_reset(pf_router *r) {
 	if (!r) FAILF(PF_EINVAL, "null router");
-	if (upload_nodes(r, pfb_pinned(sizeof(PfNode) * (size_t)r->N), NULL, NULL, NULL) != PF_OK) return PF_ECUDA;
+	if (upload_nodes(r, pfb_pinned_upload(sizeof(PfNode) * (size_t)r->N), NULL, NULL, NULL) != PF_OK) return PF_ECUDA;
 	CKB(pfb_sync());
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
 	CKB(pfb_zero(r->ctl, 256));

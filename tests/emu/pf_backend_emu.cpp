@@ -21,6 +21,7 @@ const char *pfb_last_error(void) { return g_err; }
 void *pfb_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
 void *pfb_alloc_raw(size_t bytes) { return malloc(bytes ? bytes : 16); }
 void *pfb_pinned(size_t) { return NULL; }
+void *pfb_pinned_upload(size_t) { return NULL; }
 int pfb_h2d_async(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
 int pfb_d2h_async(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
 void pfb_free(void *p) { free(p); }
@@ -50,7 +51,8 @@ static void route_warp(void *arg, int warp_id) {
 		for (int i = 0; i < a->P->num_sw; i++) sw[i] = a->P->sw[i];
 	}
 	pf_syncwarp();
-	pf_warp_main(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
+	if (a->P->max_batch == 1) pf_warp_main<1>(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
+	else pf_warp_main<0>(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
 }
 
 int pfb_launch_route(const PfParams *P, int num_slots, int) {
