@@ -75,6 +75,7 @@ PF_DEV pf_u8 pf_ld_cg_u8(const void *p) {
 	return v;
 }
 PF_DEV void pf_st_u4(void *p, pf_u4 v) { *(uint4 *)p = v; }
+PF_DEV void pf_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 PF_DEV float pf_int_as_float(int i) { return __int_as_float(i); }
 PF_DEV int pf_float_as_int(float f) { return __float_as_int(f); }
 PF_DEV double pf_ceil(double x) { return ceil(x); }
@@ -247,6 +248,8 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 			c1.x = (unsigned)edge_start; c1.y = c1.z = c1.w = 0;
 			w.hot[h] = pf_hot_make(w, tot, node);
 			pf_st_u4(&w.cold[h], c0); pf_st_u4((char *)&w.cold[h] + 16, c1);
+			/* the row of out-edges is the first thing read when this label is settled: start pulling it into L2 */
+			if (edge_start >= 0) pf_prefetch_l2(w.P->edges + edge_start);
 			written = 1; pending = 0;
 		}
 		pf_syncwarp();                                  /* tickets reusable; label stores ordered before re-probes */
@@ -413,11 +416,11 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 	float slack;
 	{
 		float mb = PF_INF_F, mt = PF_INF_F;
-		for (int i = 4; i < P->num_indexed; i++) {
+		if (P->pop_slack != 0.f) for (int i = 4; i < P->num_indexed; i++) {
 			if (w.base_cost[i] < mb) mb = w.base_cost[i];
 			if (w.idx[i].T_linear < mt) mt = w.idx[i].T_linear;
 		}
-		slack = P->pop_slack * ((1.f - crit) * mb + crit * mt);
+		slack = (P->pop_slack != 0.f) ? P->pop_slack * ((1.f - crit) * mb + crit * mt) : 0.f;
 	}
 
 	/* ---- seed with the current route tree (add_route_tree_to_heap): pass 0 finds the cheapest seed (it sets

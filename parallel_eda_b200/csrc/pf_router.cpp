@@ -490,9 +490,10 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 				|| pfb_h2d(r->g_count, p->opin_group_count, sizeof(int) * (size_t)r->num_groups)
 				|| pfb_h2d(r->g_off, off.data(), sizeof(int) * (size_t)r->num_groups)) { pf_router_destroy(r); CUDA_FAIL(); }
 	}
+	r->t_mark[2] = now_s();
 	if (pfb_sync() != 0) { pf_router_destroy(r); CUDA_FAIL(); }
-	if (c.verbose) fprintf(stderr, "pf_router: create %.3f s (net check %.3f s, setup + device alloc %.3f s, flatten + upload issue %.3f s, scratch + drain %.3f s)\n",
-			now_s() - t_a, t_b - t_a, r->t_mark[0] - t_b, r->t_mark[1] - r->t_mark[0], now_s() - r->t_mark[1]);
+	if (c.verbose) fprintf(stderr, "pf_router: create %.3f s (net check %.3f s, setup + device alloc %.3f s, flatten + upload issue %.3f s, scratch alloc %.3f s, drain %.3f s)\n",
+			now_s() - t_a, t_b - t_a, r->t_mark[0] - t_b, r->t_mark[1] - r->t_mark[0], r->t_mark[2] - r->t_mark[1], now_s() - r->t_mark[2]);
 	if (c.verbose)
 		fprintf(stderr, "pf_router[%s] rank %d/%d: N=%d E=%d nets=%zu+%zu slots=%d(2^%d labels)+%d(2^%d) pool=%lld\n", pfb_name(), c.rank, c.nranks,
 				r->N, r->E, r->work_small.size(), r->work_big.size(), c.num_slots, c.label_log2, c.big_slots, c.big_label_log2, r->pool_cap);

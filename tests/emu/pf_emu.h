@@ -111,6 +111,7 @@ PF_DEV int pf_warp_max_i(int v) {
 	int s = (int)(uint32_t)o[0]; for (int i = 1; i < PF_WARP; i++) if ((int)(uint32_t)o[i] > s) s = (int)(uint32_t)o[i];
 	return s;
 }
+PF_DEV void pf_prefetch_l2(const void *) {}
 PF_DEV int pf_popc(unsigned m) { return __builtin_popcount(m); }
 PF_DEV int pf_ffs(unsigned m) { return __builtin_ffs((int)m); }   /* 1-based, 0 if none */
 PF_DEV unsigned pf_lanemask_lt(void) { return (1u << pf_lane()) - 1u; }

@@ -16,7 +16,7 @@ for it in range(1, iters + 1):
     tk = R.timing(reset=True)
     pres, acc = (float(o["initial_pres_fac"]), 0.0) if it == 1 else (pres * float(o["pres_fac_mult"]), float(o["acc_fac"]))
     over = R.pathfinder_update_cost(acc)
-    print("iter", it, "nets", st.nets_routed, "overused", over, "pops", st.heap_pops, "visits", st.edge_visits, "route_kernel_ms %.2f" % tk.route_kernel_ms, "launches", tk.route_launches, flush=True)
+    print("iter", it, "nets", st.nets_routed, "overused", over, "pops", st.heap_pops, "pushes", st.heap_pushes, "visits", st.edge_visits, "route_kernel_ms %.2f" % tk.route_kernel_ms, "launches", tk.route_launches, flush=True)
     if over == 0: break
 t = R.timing()
 print("route kernel ms", t.route_kernel_ms, "launches", t.route_launches)
