@@ -250,7 +250,7 @@ def run_ours(a):
             "config": {"workload": WORKLOAD.format(nx=a.grid, ny=a.grid, W=a.width, nets=a.nets),
                        "rr_nodes": p.num_nodes, "rr_edges": p.num_edges, "sinks": int(p.num_terminals - p.num_nets),
                        "router_opts": "VPR defaults: astar 1.2, pres_fac 0.5 x1.3, acc_fac 1, bb_factor 3, max 50 iterations",
-                       "parallelism": "nets sharded over %d GPU(s) in spatial stripes; occupancy all-reduce %dx per iteration" % (world, a.sync_rounds) if world > 1 else "1 GPU",
+                       "parallelism": "nets sharded over %d GPU(s) in spatial stripes (stripe-interior nets, then cut-crossing nets); occupancy all-reduce %dx per iteration" % (world, a.sync_rounds) if world > 1 else "1 GPU",
                        "l2": "working set (node records %d MB + edges %d MB) far exceeds the 126 MB L2; no flush needed"
                              % (p.num_nodes * 32 >> 20, p.num_edges * 4 >> 20)},
             "route": {"iterations": [r.iterations for r in reps], "nets_routed_per_step": nets_routed / a.steps,

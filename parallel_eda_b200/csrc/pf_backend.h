@@ -63,7 +63,9 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
  * net when force_all), split into the small/big slot classes by net_big[]; counts[0]/counts[1] */
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch);
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count);
+/* counts[0..1] = lengths of list_small / list_big; counts[2..3] = how many of each come from the first head_count
+ * entries of all_nets (they are at the head of the lists: order is preserved) */
 void pfb_bind_thread(void);                     /* make the router's device current in a helper thread */
 size_t pfb_select_scratch_bytes(int num_all);   /* size of `scratch` (device memory) */
 /* copy every live tree of `all_nets` from one log to another (garbage collection of the route store) */

@@ -235,7 +235,7 @@ __global__ void pf_reserve_opins_kernel(PfNode *nodes, const uint32_t *edges, co
 #define PF_SEL_BLOCK 256
 __global__ void __launch_bounds__(PF_SEL_BLOCK) pf_select_flag_kernel(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc,
 		const int *all_nets, int num_all, const unsigned char *net_big, int force_all, unsigned char *flag, int *block_counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer) {
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int head_count, int *counts) {
 	int k = (int)(blockIdx.x * PF_SEL_BLOCK + threadIdx.x);
 	int f = 0;
 	if (k < num_all) {
@@ -244,7 +244,12 @@ __global__ void __launch_bounds__(PF_SEL_BLOCK) pf_select_flag_kernel(const PfNo
 		flag[k] = (unsigned char)f;
 	}
 	int cs = __syncthreads_count(f == 1), cb = __syncthreads_count(f == 2);
-	if (threadIdx.x == 0) { block_counts[2 * blockIdx.x] = cs; block_counts[2 * blockIdx.x + 1] = cb; }
+	int hs = __syncthreads_count(f == 1 && k < head_count), hb = __syncthreads_count(f == 2 && k < head_count);
+	if (threadIdx.x == 0) {
+		block_counts[2 * blockIdx.x] = cs; block_counts[2 * blockIdx.x + 1] = cb;
+		if (hs) atomicAdd(&counts[2], hs);
+		if (hb) atomicAdd(&counts[3], hb);
+	}
 }
 
 __global__ void __launch_bounds__(PF_SEL_BLOCK) pf_select_scatter_kernel(const int *all_nets, int num_all, const unsigned char *flag,
@@ -350,14 +355,15 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
 
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch) {
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count) {
+	if (cudaMemsetAsync(counts, 0, sizeof(int) * 4, g_stream) != cudaSuccess) return -1;
 	if (num_all <= 0) return 0;
 	/* scratch: [2 ints per CTA][one flag byte per net] — pfb_select_scratch_bytes() */
 	const int blocks = (num_all + PF_SEL_BLOCK - 1) / PF_SEL_BLOCK;
 	unsigned char *flag = (unsigned char *)(scratch + 2 * (size_t)blocks);
 	if (ev_begin(2) != 0) return -1;
 	pf_select_flag_kernel<<<blocks, PF_SEL_BLOCK, 0, g_stream>>>(nodes, pool, loc, all_nets, num_all, net_big, force_all, flag, scratch,
-			last_over, iter_tag, window, committer);
+			last_over, iter_tag, window, committer, head_count, counts);
 	pf_select_scatter_kernel<<<blocks, PF_SEL_BLOCK, 0, g_stream>>>(all_nets, num_all, flag, scratch, list_small, list_big, counts);
 	return ev_end();
 }

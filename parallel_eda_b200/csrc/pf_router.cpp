@@ -68,6 +68,9 @@ struct pf_router {
 	double t_mark[4];
 	int64_t h2d_bytes, d2h_bytes;
 	std::vector<int> work_small, work_big;
+	std::vector<int> h_all;           /* host copy of all_nets: interior nets first, then cut nets, each in fanout order */
+	int K1;                           /* number of interior nets at the head of all_nets */
+	int n1_small, n1_big;             /* interior nets at the head of this iteration's two work lists */
 	float win_abs_auto;
 };
 
@@ -282,7 +285,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->nodes = NULL; r->edges = NULL; r->sw = NULL; r->indexed = NULL; r->net_ptr = r->net_term = r->net_bb = NULL;
 	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
 	r->pool[0] = r->pool[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
-	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->sel_scratch = NULL; r->ptc = NULL; r->iter_count = 0;
+	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->sel_scratch = NULL; r->ptc = NULL; r->K1 = 0; r->n1_small = r->n1_big = 0; r->iter_count = 0;
 	r->best_overused = 0x7fffffff; r->stall_count = 0; r->since_full = 0; r->last_over = NULL; r->cost_updates = 0; r->committer = NULL; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
 	r->occ_base = r->occ_delta = NULL; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
@@ -324,9 +327,16 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	/* Sharding over ranks.  The reference's MPI router deals nets round-robin / LPT over ranks
 	 * (mpi_route_load_balanced…encoded.cxx:74-170) and pays for it with per-sink messages.  Here a rank only
 	 * learns other ranks' routes at the occupancy sync, so nets are sharded SPATIALLY: sort by bounding-box
-	 * centre along x and cut into nranks stripes of equal total fanout.  Nets of different stripes compete
-	 * for the same wires only near the cuts, which keeps the congestion a rank cannot see small. */
+	 * centre along x and cut the grid into nranks stripes of equal total fanout.
+	 *   interior nets  — bounding box inside one stripe, at least one maximum wire length away from the next
+	 *                    stripe's interior nets: a search never leaves its bounding box (route_timing.c:622), so
+	 *                    interior nets of different stripes cannot touch the same rr node.  They are routed
+	 *                    first, all ranks at once, and nobody works on a stale view of anybody.
+	 *   cut nets       — everything else (boxes that reach across a cut).  After the first occupancy sync the
+	 *                    rank that owns the cut routes them with every interior route visible.
+	 * The iteration therefore behaves like a one-GPU iteration with a particular net order. */
 	std::vector<int> owner((size_t)std::max(r->n, 1), 0);
+	std::vector<unsigned char> cut_net((size_t)std::max(r->n, 1), 0);
 	if (c.nranks > 1) {
 		std::vector<int> byx(order);
 		std::stable_sort(byx.begin(), byx.end(), [&](int a, int b) {
@@ -334,9 +344,26 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			return ca < cb; });
 		long long total_f = 0, acc_f = 0;
 		for (int i : byx) total_f += p->net_ptr[i + 1] - p->net_ptr[i];
+		/* cut[k] (k = 1..nranks-1): stripe k-1 holds boxes with xmax <= cut[k], stripe k boxes with xmin >= cut[k] + lmax */
+		std::vector<int> cut((size_t)c.nranks + 1, 0);
+		int prev_stripe = 0;
 		for (int i : byx) {
-			owner[i] = (int)std::min<long long>(c.nranks - 1, acc_f * c.nranks / std::max<long long>(total_f, 1));
+			int s = (int)std::min<long long>(c.nranks - 1, acc_f * c.nranks / std::max<long long>(total_f, 1));
+			for (; prev_stripe < s; prev_stripe++) cut[prev_stripe + 1] = (p->net_bb[4 * i] + p->net_bb[4 * i + 1]) / 2;
+			owner[i] = s;
 			acc_f += p->net_ptr[i + 1] - p->net_ptr[i];
+		}
+		for (; prev_stripe < c.nranks - 1; prev_stripe++) cut[prev_stripe + 1] = p->nx + 2;
+		int lmax = 1;                                /* longest wire, in tiles: 1 / inv_length of the CHAN cost indices */
+		for (int i = PF_CHANX_COST_INDEX_START; i < p->num_indexed; i++)
+			if (p->indexed[i].inv_length > 0.f) lmax = std::max(lmax, (int)(1.f / p->indexed[i].inv_length + 0.5f));
+		for (int i : byx) {
+			const int s = owner[i], xmin = p->net_bb[4 * i], xmax = p->net_bb[4 * i + 1];
+			const bool left_ok = s == 0 || xmin >= cut[s] + lmax;
+			const bool right_ok = s == c.nranks - 1 || xmax <= cut[s + 1];
+			if (left_ok && right_ok) continue;
+			cut_net[i] = 1;
+			owner[i] = right_ok ? s : s + 1;        /* the rank that owns the violated cut (cut k belongs to rank k) */
 		}
 	}
 	for (size_t k = 0; k < order.size(); k++) {
@@ -436,10 +463,15 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	}
 	r->loc = (PfNetLoc *)pfb_alloc(sizeof(PfNetLoc) * (size_t)std::max(r->n, 1));
 	{
-		/* every net this rank owns, in the decreasing-fanout order of the reference's net loop
-		 * (route_timing.c:98-106); the selection kernels keep that order in the work lists */
+		/* every net this rank owns: interior nets, then cut nets, each in the decreasing-fanout order of the
+		 * reference's net loop (route_timing.c:98-106); the selection kernels keep that order in the work lists */
 		std::vector<int> all;
-		for (size_t k = 0; k < order.size(); k++) if (owner[order[k]] == c.rank) all.push_back(order[k]);
+		for (int pass = 0; pass < 2; pass++)
+			for (size_t k = 0; k < order.size(); k++)
+				if (owner[order[k]] == c.rank && cut_net[order[k]] == pass) all.push_back(order[k]);
+		r->K1 = 0;
+		for (int i : all) if (!cut_net[i]) r->K1++;
+		r->h_all = all;
 		r->num_all = (int)all.size();
 		r->h_net_big.assign((size_t)std::max(r->n, 1), 0);
 		for (int i : r->work_big) r->h_net_big[i] = 1;
@@ -613,8 +645,12 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	r->cur_div = stalled ? r->cfg.inflight_div * 8 : r->cfg.inflight_div;
 	if (all) {
 		std::vector<int> sm, bg;
-		for (int i : r->work_big) bg.push_back(i);
-		for (int i : r->work_small) (r->h_net_big[i] ? bg : sm).push_back(i);
+		r->n1_small = r->n1_big = 0;
+		for (int k = 0; k < r->num_all; k++) {
+			const int i = r->h_all[(size_t)k];
+			(r->h_net_big[i] ? bg : sm).push_back(i);
+			if (k < r->K1) (r->h_net_big[i] ? r->n1_big : r->n1_small)++;
+		}
 		if ((rc = set_work(r, r->small, sm.data(), (int)sm.size())) != PF_OK) return rc;
 		if ((rc = set_work(r, r->big, bg.data(), (int)bg.size())) != PF_OK) return rc;
 		r->n_small = (int)sm.size(); r->n_big = (int)bg.size();
@@ -626,10 +662,11 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 		 * tail and made the one-warp wirelength 4 % worse without shortening the tail.) */
 		CKB(pfb_launch_select_nets(r->nodes, r->pool[r->cur], r->loc, r->all_nets, r->num_all, r->net_big, 0,
 				r->small.work, r->big.work, r->sel_counts, r->cfg.history_window > 0 ? r->last_over : NULL,
-				1 + (r->cost_updates + 254) % 255, r->cfg.history_window, r->committer, r->sel_scratch));
+				1 + (r->cost_updates + 254) % 255, r->cfg.history_window, r->committer, r->sel_scratch, r->K1));
 		CKB(pfb_d2h(counts, r->sel_counts, sizeof(int) * 4));
 		r->d2h_bytes += 16;
 		r->n_small = counts[0]; r->n_big = counts[1];
+		r->n1_small = counts[2]; r->n1_big = counts[3];
 	}
 	r->iter_count++;
 	r->since_full = all ? 0 : r->since_full + 1;
@@ -643,9 +680,14 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 	int rc;
 	CKB(pfb_zero(r->ctl, 192));            /* status, retry count, stats, both work-queue heads */
 	const int div = r->cur_div;
-	auto slice = [&](int n, int &off, int &cnt) { off = (int)((long long)n * part / nparts); cnt = (int)((long long)n * (part + 1) / nparts) - off; };
+	/* several ranks, two parts: interior nets, then cut nets (see pf_router_create); otherwise equal slices */
+	const bool by_class = r->cfg.nranks > 1 && nparts == 2;
+	auto slice = [&](int n, int n1, int &off, int &cnt) {
+		if (by_class) { off = part ? n1 : 0; cnt = part ? n - n1 : n1; }
+		else { off = (int)((long long)n * part / nparts); cnt = (int)((long long)n * (part + 1) / nparts) - off; }
+	};
 	int so, sc, bo, bc;
-	slice(r->n_small, so, sc); slice(r->n_big, bo, bc);
+	slice(r->n_small, r->n1_small, so, sc); slice(r->n_big, r->n1_big, bo, bc);
 	PfParams P;
 	int total = r->n_small + r->n_big;      /* the staleness bound is about the whole iteration's nets */
 	if (bc > 0) {                          /* long nets first */

@@ -4,10 +4,11 @@
 every net, reserve locally used OPINs, test feasibility, raise pres_fac, update costs, run the host
 STA.  With ``world_size > 1`` it is the data-parallel scheme of the reference's own MPI router
 (parallel_route/mpi_route_load_balanced_nonblocking_send_recv_encoded.cxx): nets are sharded over
-ranks, every rank keeps a full graph + congestion replica, and once per iteration the occupancy
-changes are summed across ranks — there `MPI_Allreduce` (spatial.cxx:3371-3383), here one NCCL
-all-reduce of an int32[num_rr_nodes] delta over NVLink, folded into the node records by the same
-pass that updates the costs (pf_update_costs_synced).
+ranks, every rank keeps a full graph + congestion replica, and the occupancy changes are summed
+across ranks — there `MPI_Allreduce` (spatial.cxx:3371-3383), here an NCCL all-reduce of an
+int32[num_rr_nodes] delta over NVLink, twice per iteration (after the stripe-interior nets and after
+the nets that cross a stripe cut), folded into the node records by the pass that updates the costs
+(pf_update_costs_synced).
 
 ``comm`` is anything with ``all_reduce_sum_(tensor)``; parallel_eda_b200.distributed wraps
 torch.distributed (NCCL on GPUs; gloo on CPU tensors for the host-logic tests).
@@ -58,8 +59,10 @@ def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delta_buf
             nets = st.nets_routed
             pops += st.heap_pops; pushes += st.heap_pushes; visits += st.edge_visits
         else:
-            # sub-rounds: each rank routes 1/sync_rounds of its nets, then the occupancy changes of all
-            # ranks are summed and folded in, so a rank works on congestion at most one sub-round stale
+            # two sub-rounds with an occupancy sync after each (pf_router_create): first every rank routes the nets
+            # whose bounding boxes lie inside its own stripe of the grid — those cannot touch another stripe's
+            # nets, so nobody works on a stale view — then the ranks that own a cut route the nets reaching across
+            # it, with all interior routes visible.  (sync_rounds != 2: plain equal slices.)
             r.iteration_begin(crit)
             nets = 0
             for part in range(sync_rounds):

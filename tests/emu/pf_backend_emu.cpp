@@ -96,13 +96,14 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
 
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch) {
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count) {
 	(void)scratch;
-	counts[0] = counts[1] = 0;
+	counts[0] = counts[1] = counts[2] = counts[3] = 0;
 	for (int k = 0; k < num_all; k++) {          /* all_nets is in fanout order; so are the lists */
 		int net = all_nets[k];
 		if (force_all || pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net)) {
-			if (net_big[net]) list_big[counts[1]++] = net; else list_small[counts[0]++] = net;
+			if (net_big[net]) { list_big[counts[1]++] = net; if (k < head_count) counts[3]++; }
+			else { list_small[counts[0]++] = net; if (k < head_count) counts[2]++; }
 		}
 	}
 	g_times.aux_launches++;
