@@ -10,7 +10,7 @@ Workload (config.workload): BASELINE.json configs[4] — synthetic 400x400 CLB k
 that fits one GPU; configs[1..3] need VTR benchmark files that are neither in the reference nor on the box
 (SURVEY.md §8c).  A step is one complete routing of the problem: reset congestion, then PathFinder
 iterations until the routing is legal.  N > 1 shards the nets of the SAME problem over N GPUs (strong
-scaling) with an NCCL all-reduce of the occupancy delta twice per iteration.
+scaling) with an NCCL all-gather of the ranks' occupancy event logs twice per iteration.
 
 value   = nets routed (summed over iterations and ranks) / device time of the step, graph already in HBM
 e2e     = the same through the public API with HOST buffers: flatten + H2D of the whole problem, route,
@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--max-batch", type=int, default=0, help="tuning: labels settled per step (0 = library default)")
     ap.add_argument("--pop-slack", type=float, default=-1.0, help="tuning: delta bucket width (<0 = library default)")
     ap.add_argument("--inflight-div", type=int, default=0)
+    ap.add_argument("--min-slots", type=int, default=0, help="tuning: lower bound on nets in flight (0 = library default)")
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--sync-rounds", type=int, default=2, help="multi-GPU: occupancy syncs per PathFinder iteration")
     return ap.parse_args()
@@ -160,10 +161,9 @@ def run_ours(a):
 
     p = router.generate_grid_problem(nx=a.grid, ny=a.grid, W=a.width, num_nets=a.nets)
     cfg = router.default_config(device=local, rank=rank, nranks=world, max_batch=a.max_batch, pop_slack=a.pop_slack,
-                                inflight_div=a.inflight_div, num_slots=a.slots)
+                                inflight_div=a.inflight_div, num_slots=a.slots, min_slots=a.min_slots)
     R = router.Router(p, cfg)
     R.timing(reset=True)
-    delta = torch.zeros(p.num_nodes, dtype=torch.int32, device=dev) if comm else None
 
     def one_step():
         R.reset()
@@ -171,7 +171,7 @@ def run_ours(a):
             comm.barrier()
         torch.cuda.synchronize()
         R.timer_start()
-        rep = pathfinder.route(R, comm=comm, delta_buf=delta, sync_rounds=a.sync_rounds)
+        rep = pathfinder.route(R, comm=comm, sync_rounds=a.sync_rounds)
         ms = R.timer_stop()
         torch.cuda.synchronize()
         if comm:
@@ -212,7 +212,7 @@ def run_ours(a):
             t0 = time.perf_counter()
             R2 = router.Router(p, cfg)                 # flatten + H2D of the whole problem
             t1 = time.perf_counter()
-            rep = pathfinder.route(R2, comm=comm, delta_buf=delta, sync_rounds=a.sync_rounds)
+            rep = pathfinder.route(R2, comm=comm, sync_rounds=a.sync_rounds)
             t2 = time.perf_counter()
             res = R2.result()                          # D2H of traces, delays, occupancy
             t3 = time.perf_counter()
@@ -250,7 +250,7 @@ def run_ours(a):
             "config": {"workload": WORKLOAD.format(nx=a.grid, ny=a.grid, W=a.width, nets=a.nets),
                        "rr_nodes": p.num_nodes, "rr_edges": p.num_edges, "sinks": int(p.num_terminals - p.num_nets),
                        "router_opts": "VPR defaults: astar 1.2, pres_fac 0.5 x1.3, acc_fac 1, bb_factor 3, max 50 iterations",
-                       "parallelism": "nets sharded over %d GPU(s) in spatial stripes (stripe-interior nets, then cut-crossing nets); occupancy all-reduce %dx per iteration" % (world, a.sync_rounds) if world > 1 else "1 GPU",
+                       "parallelism": "nets sharded over %d GPU(s) in spatial stripes (stripe-interior nets, then cut-crossing nets); occupancy event-log all-gather %dx per iteration" % (world, a.sync_rounds) if world > 1 else "1 GPU",
                        "l2": "working set (node records %d MB + edges %d MB) far exceeds the 126 MB L2; no flush needed"
                              % (p.num_nodes * 32 >> 20, p.num_edges * 4 >> 20)},
             "route": {"iterations": [r.iterations for r in reps], "nets_routed_per_step": nets_routed / a.steps,

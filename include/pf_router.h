@@ -25,8 +25,8 @@
  *   pf_total_wirelength              first-iteration wirelength abort   route/route_timing.c:189-225
  *   pf_get_net_delay                 update_net_delays_from_route_tree  route/route_tree_timing.c:515-528
  *   pf_get_result                    trace_head[]/trace_tail[] lists    route/route_common.c:638-706
- *   pf_comm_export_delta /           MPI_Allreduce(occupancy) of the reference's MPI router
- *   pf_update_costs_synced           parallel_route/spatial.cxx:3371-3383 (sync_recalc_occ)
+ *   pf_comm_events /                 MPI_Allreduce(occupancy) of the reference's MPI router
+ *   pf_comm_apply_events             parallel_route/spatial.cxx:3371-3383 (sync_recalc_occ)
  *
  * All functions return PF_OK (0) or a negative PF_E* code (pf_file.h); none calls exit().
  * pf_last_error() describes the last failure of the calling process.  There is no CPU fallback:
@@ -69,7 +69,7 @@ typedef struct pf_config {
 	                             0 = auto (1); < 0 = always every net */
 	int32_t inflight_div;     /* nets in flight <= ceil(nets this iteration / inflight_div): bounds how
 	                             stale the congestion seen by concurrent nets can be; 0 = auto (16) */
-	int32_t min_slots;        /* lower bound for the above; 0 = auto (1) */
+	int32_t min_slots;        /* lower bound for the above; 0 = auto (one net per 20 x 20 tiles of the grid, at least 1) */
 	int32_t stall_iters;      /* overuse not down by 30 % over stall_iters+1 congested-only iterations => one
 	                             iteration re-routes every net with 8x fewer nets in flight; 0 = auto (3); < 0 = never */
 	int32_t history_window;   /* also re-route nets holding a node that was overused within the last K cost updates;
@@ -120,15 +120,17 @@ int pf_timer_start(pf_router *r);
 int pf_timer_stop(pf_router *r, double *elapsed_ms);
 void *pf_stream(pf_router *r);   /* the cudaStream_t every kernel of this router is launched on */
 
-/* Multi-GPU iteration boundary (device pointers, int32[num_nodes] / float[num_terminals]):
- *   1. pf_comm_export_delta(r, d)       d[i] = occ change made by this rank's nets
- *   2. all-reduce(sum) d across ranks   (NCCL over NVLink; the caller owns the communicator)
- *   3. pf_update_costs_synced(r, acc_fac, d, &overused)   fold + cost update in one pass
+/* Multi-GPU occupancy sync after a route part (routers created with nranks > 1).  While routing, every
+ * occupancy change of this rank's nets (rip-up, commit, undo) is also appended to an event log in device
+ * memory: uint32 per event, rr node id in bits 0..30, bit 31 set = decrement.
+ *   1. pf_comm_events(r, &ptr, &n)          this rank's log of the last route part (device pointer, n events)
+ *   2. all-gather the logs across ranks     (NCCL over NVLink; the caller owns the communicator)
+ *   3. pf_comm_apply_events(r, ptr_k, n_k)  replay every OTHER rank's log on this rank's node records
+ * afterwards all ranks hold the same occupancy, and pf_reserve_opins / pf_update_costs run as on one GPU.
  * pf_comm_net_delay_ptr returns the device float[num_terminals] delay vector; entries of nets
  * routed by other ranks are zero, so an all-reduce(sum) assembles the full vector in place. */
-int pf_comm_export_delta(pf_router *r, void *dev_delta);
-int pf_update_costs_synced(pf_router *r, float acc_fac, const void *dev_delta, int *overused_nodes);
-int pf_comm_fold_delta(pf_router *r, const void *dev_delta);   /* fold only (between sub-rounds) */
+int pf_comm_events(pf_router *r, void **dev_events, int64_t *count);
+int pf_comm_apply_events(pf_router *r, const void *dev_events, int64_t count);
 void *pf_comm_net_delay_ptr(pf_router *r);
 
 /* The whole of try_timing_driven_route (single GPU): iterate until legal or out of iterations.

@@ -43,10 +43,10 @@ int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block);
 /* pathfinder_update_cost + feasible_routing (route_common.c:581-610,509-531) in one pass; when
  * base/delta are non-NULL the pass first folds the all-reduced occupancy delta into the node
  * records: occ = base + delta, base = occ (multi-GPU iteration boundary) */
-int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
-		int *occ_base, const int *occ_delta, unsigned char *last_over, int iter_tag);
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, unsigned char *last_over, int iter_tag);
 /* delta[i] = nodes[i].occ - base[i]: what this GPU's nets changed since the last sync */
-int pfb_launch_export_delta(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta);
+/* replay another rank's occupancy events (multi-GPU sync) */
+int pfb_launch_apply_events(PfNode *nodes, const unsigned *events, long long count);
 /* route trees → s_trace-ordered arrays on the device: pass 1 (trace_node == NULL) writes len[net];
  * pass 2 writes trace_node/trace_switch at tptr[net] and adds the wirelength into *d_wl */
 int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num_nets, int *len, const int *tptr,
@@ -58,7 +58,7 @@ int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long
 /* reserve_locally_used_opins (route_common.c:1435-1491): one thread per (block, class) group */
 int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
 		int num_groups, const int *group_source, const int *group_count, const int *group_off,
-		int *chosen, int rip_up, float pres_fac, int *occ_base);
+		int *chosen, int rip_up, float pres_fac);
 /* work list of the next iteration: the nets of `all_nets` that touch an overused node (or every
  * net when force_all), split into the small/big slot classes by net_big[]; counts[0]/counts[1] */
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,

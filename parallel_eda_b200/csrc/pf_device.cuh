@@ -676,6 +676,26 @@ PF_DEV int pf_highfanout_rlim(PfWarp &w, int tree_n, int target_node) {
 	return rlim;
 }
 
+/* Warp-collective occupancy change: the atomic on the node record (pathfinder_update_one_cost's occ += / -=,
+ * route_common.c:542-578) and, on several GPUs, an entry in this rank's event log. */
+#define PF_EVENT_DEC 0x80000000u
+PF_DEV void pf_occ_change(const PfParams *P, int active, int v, int d) {
+	if (active) pf_atomic_add_i(&P->nodes[v].occ, d);
+	if (P->events) {
+		const unsigned m = pf_ballot(active);
+		if (m) {
+			const int leader = pf_ffs(m) - 1;
+			unsigned long long base = 0;
+			if (pf_lane() == leader) base = pf_atomic_add_ull(P->event_head, (unsigned long long)pf_popc(m));
+			base = pf_shfl_u64(base, leader);
+			if (active) {
+				const unsigned long long at = base + (unsigned long long)pf_popc(m & pf_lanemask_lt());
+				if ((long long)at < P->event_cap) P->events[at] = (unsigned)v | (d < 0 ? PF_EVENT_DEC : 0u);
+			}
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ back-trace + Elmore + commit
  * update_traceback (route_common.c:638) and update_route_tree (route_tree_timing.c:181-456).
  * Returns the tree index of the new SINK entry, or -1 on tree overflow. */
@@ -706,20 +726,24 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
 	if (tree_n + L > P->tree_cap) return -1;
 	pf_syncwarp();
 	/* materialise the entries in path order (join's child first, SINK last) */
-	for (int i = lane; i < L; i += PF_WARP) {
-		int v = pathbuf[L - 1 - i];
-		PfNodeView n = pf_load_node(P, v);
-		PfTreeNode t;
-		t.node = v; t.parent = (i == 0) ? join : tree_n + i - 1;
-		t.R_up = n.R; t.C_down = n.C; t.Tdel = 0.f;     /* R_up/C_down temporarily hold the node's own R and C */
-		t.xlow = (short)n.xlow; t.ylow = (short)n.ylow; t.xhigh = (short)n.xhigh; t.yhigh = (short)n.yhigh;
-		t.sw = (unsigned char)pathbuf[pcap + L - 1 - i];
-		t.type_ci = (unsigned char)(n.type | (n.ci << 3));
-		t.flags = (n.type == 2 || n.type == 1) ? 0 : PF_TF_REEXPAND;   /* IPIN / SINK are not re-expanded */
-		t.pad = 0;
-		w.tree[tree_n + i] = t;
-		pf_atomic_add_i(&P->nodes[v].occ, 1);           /* commit: pathfinder_update_one_cost(+1) */
-		if (P->committer) P->committer[v] = w.cur_net;
+	for (int base = 0; base < L; base += PF_WARP) {
+		const int i = base + lane;
+		int v = 0;
+		if (i < L) {
+			v = pathbuf[L - 1 - i];
+			PfNodeView n = pf_load_node(P, v);
+			PfTreeNode t;
+			t.node = v; t.parent = (i == 0) ? join : tree_n + i - 1;
+			t.R_up = n.R; t.C_down = n.C; t.Tdel = 0.f;     /* R_up/C_down temporarily hold the node's own R and C */
+			t.xlow = (short)n.xlow; t.ylow = (short)n.ylow; t.xhigh = (short)n.xhigh; t.yhigh = (short)n.yhigh;
+			t.sw = (unsigned char)pathbuf[pcap + L - 1 - i];
+			t.type_ci = (unsigned char)(n.type | (n.ci << 3));
+			t.flags = (n.type == 2 || n.type == 1) ? 0 : PF_TF_REEXPAND;   /* IPIN / SINK are not re-expanded */
+			t.pad = 0;
+			w.tree[tree_n + i] = t;
+			if (P->committer) P->committer[v] = w.cur_net;
+		}
+		pf_occ_change(P, i < L, v, 1);                  /* commit: pathfinder_update_one_cost(+1) */
 	}
 	pf_syncwarp();
 	if (lane == 0) {
@@ -843,7 +867,10 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 	/* rip-up: pathfinder_update_one_cost(trace_head[inet], -1) — one atomic per tree entry */
 	if (!P->skip_ripup) {
 		PfNetLoc loc = P->loc[inet];
-		for (int i = lane; i < loc.count; i += PF_WARP) pf_atomic_add_i(&P->nodes[P->pool[loc.off + i].node].occ, -1);
+		for (int base = 0; base < loc.count; base += PF_WARP) {
+			const int i = base + lane;
+			pf_occ_change(P, i < loc.count, i < loc.count ? P->pool[loc.off + i].node : 0, -1);
+		}
 	}
 	if (ns > P->sink_cap) { w.overflow = PF_OVF_OTHER; }
 
@@ -882,8 +909,8 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 			t.xlow = (short)n.xlow; t.ylow = (short)n.ylow; t.xhigh = (short)n.xhigh; t.yhigh = (short)n.yhigh;
 			t.sw = 0; t.type_ci = (unsigned char)(n.type | (n.ci << 3)); t.flags = PF_TF_REEXPAND; t.pad = 0;
 			w.tree[0] = t;
-			pf_atomic_add_i(&P->nodes[src].occ, 1);          /* the SOURCE is the head of the first trace segment */
 		}
+		pf_occ_change(P, lane == 0, P->net_term[t0], 1);     /* the SOURCE is the head of the first trace segment */
 		tree_n = 1;
 		pf_syncwarp();
 
@@ -920,7 +947,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 
 	if (w.overflow || fail) {
 		/* undo this net's commits; it owns no routing until it is retried */
-		for (int i = lane; i < tree_n; i += PF_WARP) pf_atomic_add_i(&P->nodes[w.tree[i].node].occ, -1);
+		for (int base = 0; base < tree_n; base += PF_WARP) { const int i = base + lane; pf_occ_change(P, i < tree_n, i < tree_n ? w.tree[i].node : 0, -1); }
 		if (lane == 0) {
 			P->loc[inet].off = 0; P->loc[inet].count = 0;
 			if (fail) { pf_atomic_add_i(P->status + 1, 1); pf_atomic_or_i(P->status, fail); P->status[2] = inet; }
@@ -937,7 +964,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 	off = pf_shfl_u64(off, 0);
 	if ((long long)(off + tree_n) > P->pool_cap) {
 		if (lane == 0) { pf_atomic_or_i(P->status, PF_ST_POOL_OVERFLOW); P->loc[inet].off = 0; P->loc[inet].count = 0; }
-		for (int i = lane; i < tree_n; i += PF_WARP) pf_atomic_add_i(&P->nodes[w.tree[i].node].occ, -1);
+		for (int base = 0; base < tree_n; base += PF_WARP) { const int i = base + lane; pf_occ_change(P, i < tree_n, i < tree_n ? w.tree[i].node : 0, -1); }
 		pf_syncwarp();
 		return 0;
 	}
@@ -1019,15 +1046,9 @@ template <int STRICT> PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIn
 
 /* pathfinder_update_cost (route_common.c:581-610) for one node; returns 1 if the node is overused
  * (feasible_routing, route_common.c:509-531).  pres_cost is not stored: it is a function of occ. */
-PF_DEV int pf_update_cost_one(PfNode *nodes, int i, float acc_fac, int *occ_base, const int *occ_delta,
-		unsigned char *last_over, int iter_tag) {
+PF_DEV int pf_update_cost_one(PfNode *nodes, int i, float acc_fac, unsigned char *last_over, int iter_tag) {
 	PfNode *n = &nodes[i];
 	int occ = n->occ;
-	if (occ_base) {                       /* fold the all-reduced delta of every GPU's nets */
-		occ = occ_base[i] + occ_delta[i];
-		occ_base[i] = occ;
-		n->occ = occ;
-	}
 	int cap = n->capacity;
 	if (occ > cap) {
 		n->acc_cost += (occ - cap) * acc_fac;
@@ -1048,10 +1069,9 @@ PF_DEV unsigned pf_tree_wirelength_one(const PfTreeNode *t) {
  * SOURCE in the order the reference's binary heap (route_common.c:1142-1216) would deliver them. */
 #define PF_OPIN_HEAP_MAX 128
 PF_DEV void pf_reserve_opins_group(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
-		int source, int count, int *chosen, int rip_up, float pres_fac, int *occ_base) {
-	/* occ_base (multi-GPU): the reservation is made identically by every rank after the occupancy sync,
-	 * so it belongs to the synced base, not to this rank's exported delta */
-	if (rip_up) for (int k = 0; k < count; k++) { pf_atomic_add_i(&nodes[chosen[k]].occ, -1); if (occ_base) occ_base[chosen[k]] -= 1; }
+		int source, int count, int *chosen, int rip_up, float pres_fac) {
+	/* several GPUs: every rank makes the same reservation on the same synced occupancy, so it is not logged */
+	if (rip_up) for (int k = 0; k < count; k++) pf_atomic_add_i(&nodes[chosen[k]].occ, -1);
 	if (count == 0) return;
 	float hc[PF_OPIN_HEAP_MAX + 2]; int hn[PF_OPIN_HEAP_MAX + 2];
 	int tail = 1;
@@ -1088,7 +1108,6 @@ PF_DEV void pf_reserve_opins_group(PfNode *nodes, const uint32_t *edges, const P
 			ifrom = ito; ito = 2 * ifrom;
 		}
 		pf_atomic_add_i(&nodes[pick].occ, 1);
-		if (occ_base) occ_base[pick] += 1;
 		chosen[k] = pick;
 	}
 }

@@ -7,7 +7,7 @@
  *   pf_route_kernel        persistent warp-per-net router (the hot path; see pf_device.cuh)
  *   pf_update_cost_kernel  pathfinder_update_cost + feasible_routing, optionally fused with the
  *                          fold-in of the all-reduced occupancy delta (multi-GPU)
- *   pf_export_delta_kernel occupancy delta of this GPU's nets since the last sync
+ *   pf_apply_events_kernel replay of another GPU's occupancy changes (multi-GPU sync)
  *   pf_wirelength_kernel   first-iteration wirelength sanity sum
  *   pf_reserve_opins_kernel locally-used OPIN reservation
  */
@@ -185,17 +185,20 @@ template <int STRICT> __global__ void __launch_bounds__(128, 5) pf_route_kernel(
 }
 
 __global__ void pf_update_cost_kernel(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
-		int *occ_base, const int *occ_delta, unsigned char *last_over, int iter_tag) {
+		unsigned char *last_over, int iter_tag) {
 	int over = 0;
 	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x))
-		over += pf_update_cost_one(nodes, i, acc_fac, occ_base, occ_delta, last_over, iter_tag);
+		over += pf_update_cost_one(nodes, i, acc_fac, last_over, iter_tag);
 	over = __reduce_add_sync(0xffffffffu, over);
 	if ((threadIdx.x & 31u) == 0 && over) atomicAdd(d_overused, over);
 }
 
-__global__ void pf_export_delta_kernel(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta) {
-	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x))
-		occ_delta[i] = nodes[i].occ - occ_base[i];
+/* another rank's event log: one atomic per event on the node records */
+__global__ void pf_apply_events_kernel(PfNode *nodes, const unsigned *events, long long count) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+		const unsigned e = events[i];
+		atomicAdd(&nodes[e & ~PF_EVENT_DEC].occ, (e & PF_EVENT_DEC) ? -1 : 1);
+	}
 }
 
 __global__ void pf_build_traces_kernel(const PfTreeNode *pool, const PfNetLoc *loc, int num_nets, int *len, const int *tptr,
@@ -223,10 +226,10 @@ __global__ void pf_wirelength_kernel(const PfTreeNode *pool, long long count, un
 
 __global__ void pf_reserve_opins_kernel(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
 		int num_groups, const int *group_source, const int *group_count, const int *group_off,
-		int *chosen, int rip_up, float pres_fac, int *occ_base) {
+		int *chosen, int rip_up, float pres_fac) {
 	int g = (int)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (g < num_groups)
-		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac, occ_base);
+		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac);
 }
 
 /* Congested-net selection, order-preserving: pass 1 flags the nets (all_nets is in the reference's
@@ -325,16 +328,16 @@ static int stream_grid(long long n) {
 	return (int)b;
 }
 
-int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, int *occ_base, const int *occ_delta,
-		unsigned char *last_over, int iter_tag) {
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, unsigned char *last_over, int iter_tag) {
 	if (ev_begin(1) != 0) return -1;
-	pf_update_cost_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, acc_fac, d_overused, occ_base, occ_delta, last_over, iter_tag);
+	pf_update_cost_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, acc_fac, d_overused, last_over, iter_tag);
 	return ev_end();
 }
 
-int pfb_launch_export_delta(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta) {
+int pfb_launch_apply_events(PfNode *nodes, const unsigned *events, long long count) {
+	if (count <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
-	pf_export_delta_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, occ_base, occ_delta);
+	pf_apply_events_kernel<<<stream_grid(count), 256, 0, g_stream>>>(nodes, events, count);
 	return ev_end();
 }
 
@@ -346,10 +349,10 @@ int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long
 
 int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
 		int num_groups, const int *group_source, const int *group_count, const int *group_off,
-		int *chosen, int rip_up, float pres_fac, int *occ_base) {
+		int *chosen, int rip_up, float pres_fac) {
 	if (num_groups <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
-	pf_reserve_opins_kernel<<<(num_groups + 127) / 128, 128, 0, g_stream>>>(nodes, edges, indexed, num_groups, group_source, group_count, group_off, chosen, rip_up, pres_fac, occ_base);
+	pf_reserve_opins_kernel<<<(num_groups + 127) / 128, 128, 0, g_stream>>>(nodes, edges, indexed, num_groups, group_source, group_count, group_off, chosen, rip_up, pres_fac);
 	return ev_end();
 }
 

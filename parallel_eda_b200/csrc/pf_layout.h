@@ -108,6 +108,9 @@ struct PfParams {
 	 * A re-routed net appends its new tree and repoints loc; the log is compacted between
 	 * iterations when it is more than half garbage. */
 	PfTreeNode *pool; PfNetLoc *loc; unsigned long long *pool_head; long long pool_cap;
+	/* multi-GPU: every occupancy change this rank makes is also logged (node id, bit 31 = decrement) so that the
+	 * other ranks can replay it; NULL on one GPU */
+	unsigned *events; unsigned long long *event_head; long long event_cap;
 	int *committer;        /* [num_nodes] net that committed this rr node last (re-route selection), may be NULL */
 	/* status */
 	int *status;

@@ -60,8 +60,7 @@ struct pf_router {
 	int *status, *retry_list, *retry_count;
 	PfStats *stats;
 	int *d_overused; unsigned long long *d_wl;
-	int *occ_base;                /* multi-GPU only */
-	int *occ_delta;
+	unsigned *events; long long event_cap; long long h_events;   /* multi-GPU only: this rank's occupancy event log */
 	/* OPIN reservation */
 	int num_groups; int *g_source, *g_count, *g_off, *g_chosen;
 	long long avail_wl;
@@ -161,7 +160,7 @@ extern "C" void pf_router_destroy(pf_router *r) {
 	pfb_free(r->pool[0]); pfb_free(r->pool[1]); pfb_free(r->loc);
 	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->retry_work); pfb_free(r->sel_scratch); pfb_free(r->ptc);
 	pfb_free(r->ctl); pfb_free(r->retry_list); pfb_free(r->last_over); pfb_free(r->committer);
-	pfb_free(r->occ_base); pfb_free(r->occ_delta);
+	pfb_free(r->events);
 	pfb_free(r->g_source); pfb_free(r->g_count); pfb_free(r->g_off); pfb_free(r->g_chosen);
 	delete r;
 }
@@ -288,7 +287,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->sel_scratch = NULL; r->ptc = NULL; r->K1 = 0; r->n1_small = r->n1_big = 0; r->iter_count = 0;
 	r->best_overused = 0x7fffffff; r->stall_count = 0; r->since_full = 0; r->last_over = NULL; r->cost_updates = 0; r->committer = NULL; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
-	r->occ_base = r->occ_delta = NULL; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
+	r->events = NULL; r->event_cap = 0; r->h_events = 0; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
 	r->h2d_bytes = r->d2h_bytes = 0;
 
 	int sms = pfb_num_sms();
@@ -303,7 +302,9 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.big_slots <= 0) c.big_slots = 64;
 	if (c.reroute_all_iters == 0) c.reroute_all_iters = 1;
 	if (c.inflight_div <= 0) c.inflight_div = 16;
-	if (c.min_slots <= 0) c.min_slots = 1;
+	/* nets in flight: at least one per 20 x 20 tiles of fabric (the few hundred nets of a late iteration then go
+	 * out together instead of sixteen rounds deep), and never fewer than one */
+	if (c.min_slots <= 0) c.min_slots = std::max(1, (int)((long long)p->nx * p->ny / 400));
 	if (c.stall_iters == 0) c.stall_iters = 3;
 	if (c.history_window < 0) c.history_window = 0;   /* 0 = off (default) */
 	if (c.keep_newcomer < 0) c.keep_newcomer = 0;     /* 0 = off (default): measured on B200 it costs ~8 % wirelength and does
@@ -485,7 +486,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	/* one 256-byte control block holds every small counter the host polls, so an iteration needs one
 	 * memset before and one 256-byte read after the route kernel instead of a handful of tiny copies:
 	 *   [0] status[8] [32] retry_count[4] [48] sel_counts[4] [64] overused[4] [80] wl[2] [96] PfStats
-	 *   [160] small.work_head[4] [176] big.work_head[4] | [192] pool_head[2] (not cleared per iteration) */
+	 *   [160] small.work_head[4] [176] big.work_head[4] | [192] pool_head[2] (not cleared per iteration)
+	 *   [208] event_head (multi-GPU; cleared at the start of every route part) */
 	r->ctl = (char *)pfb_alloc(256);
 	if (!r->ctl) { pf_router_destroy(r); CUDA_FAIL(); }
 	r->pool_head = (unsigned long long *)(r->ctl + 192);
@@ -503,9 +505,11 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->small.work_head = (int *)(r->ctl + 160); r->big.work_head = (int *)(r->ctl + 176);
 	if (!r->retry_list || !r->retry_work || !r->last_over) { pf_router_destroy(r); CUDA_FAIL(); }
 	if (c.nranks > 1) {
-		r->occ_base = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
-		r->occ_delta = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
-		if (!r->occ_base || !r->occ_delta) { pf_router_destroy(r); CUDA_FAIL(); }
+		/* one event per occupancy change: a route part rips up at most the live trees and commits at most what
+		 * the route store can still take, so twice the store's capacity cannot overflow before the store does */
+		r->event_cap = 2 * r->pool_cap;
+		r->events = (unsigned *)pfb_alloc_raw(sizeof(unsigned) * (size_t)r->event_cap);
+		if (!r->events) { pf_router_destroy(r); CUDA_FAIL(); }
 	}
 	/* OPIN groups */
 	r->num_groups = p->num_opin_groups;
@@ -543,7 +547,6 @@ extern "C" int pf_router_reset(pf_router *r) {
 	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0; r->over_hist.clear(); r->since_full = 0; r->cost_updates = 0;
 	CKB(pfb_zero(r->last_over, (size_t)r->N));
 	CKB(pfb_zero(r->net_delay, sizeof(float) * (size_t)std::max(r->T, 1)));
-	if (r->occ_base) CKB(pfb_zero(r->occ_base, sizeof(int) * (size_t)r->N));
 	{
 		const pf_problem *p = r->prob;
 		std::vector<float> cr((size_t)std::max(r->T, 1), 0.f);
@@ -561,7 +564,10 @@ extern "C" int pf_router_reset(pf_router *r) {
  * latency of one search is what matters, and settling a whole delta bucket per step shortens it. */
 static void tune_granularity(const pf_router *r, PfParams &P, int work, int slots) {
 	const pf_config &c = r->cfg;
-	const bool throughput = slots > 0 && work >= 4 * slots;
+	/* a graph that does not fit in L2 pays DRAM round trips for every settled label: fewest labels wins there
+	 * even with one net per warp */
+	const bool in_l2 = (long long)r->N * (long long)sizeof(PfNode) + (long long)r->E * 4 < (96ll << 20);
+	const bool throughput = (slots > 0 && work >= 4 * slots) || !in_l2;
 	P.max_batch = c.max_batch > 0 ? c.max_batch : (throughput ? 1 : 32);
 	P.pop_slack = c.pop_slack >= 0.f ? c.pop_slack : (throughput ? 0.f : 0.25f);
 }
@@ -588,6 +594,7 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.iscratch = s.iscratch; P.sink_cap = s.sink_cap;
 	P.pool = r->pool[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;
 	P.committer = r->committer;
+	P.events = r->events; P.event_head = (unsigned long long *)(r->ctl + 208); P.event_cap = r->event_cap;
 	P.status = r->status; P.retry_list = r->retry_list; P.retry_count = r->retry_count; P.stats = r->stats;
 }
 
@@ -679,6 +686,7 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 	if (!r || nparts < 1 || part < 0 || part >= nparts) FAILF(PF_EINVAL, "bad argument");
 	int rc;
 	CKB(pfb_zero(r->ctl, 192));            /* status, retry count, stats, both work-queue heads */
+	if (r->events) CKB(pfb_zero(r->ctl + 208, 8));
 	const int div = r->cur_div;
 	/* several ranks, two parts: interior nets, then cut nets (see pf_router_create); otherwise equal slices */
 	const bool by_class = r->cfg.nranks > 1 && nparts == 2;
@@ -737,6 +745,8 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 	int h_status[8];
 	memcpy(h_status, h_ctl, sizeof(h_status));
 	memcpy(&r->h_pool_head, h_ctl + 192, sizeof(unsigned long long));
+	{ unsigned long long ne = 0; memcpy(&ne, h_ctl + 208, sizeof(ne)); r->h_events = (long long)ne; }
+	if (r->events && r->h_events > r->event_cap) FAILF(PF_EOVERFLOW, "occupancy event log overflow (%lld events, capacity %lld)", r->h_events, r->event_cap);
 	r->d2h_bytes += 256;
 	if (h_status[0] & PF_ST_POOL_OVERFLOW) FAILF(PF_EOVERFLOW, "route store overflow (capacity %lld tree entries)", r->pool_cap);
 	if (h_status[0] & PF_ST_INTERNAL) FAILF(PF_ECUDA, "internal error in the device router (net %d)", h_status[2]);
@@ -760,15 +770,15 @@ extern "C" int pf_route_iteration(pf_router *r, float pres_fac, const float *cri
 extern "C" int pf_reserve_opins(pf_router *r, float pres_fac, int rip_up) {
 	if (!r) FAILF(PF_EINVAL, "null router");
 	if (r->num_groups == 0) return PF_OK;
-	CKB(pfb_launch_reserve_opins(r->nodes, r->edges, r->indexed, r->num_groups, r->g_source, r->g_count, r->g_off, r->g_chosen, rip_up, pres_fac, r->occ_base));
+	CKB(pfb_launch_reserve_opins(r->nodes, r->edges, r->indexed, r->num_groups, r->g_source, r->g_count, r->g_off, r->g_chosen, rip_up, pres_fac));
 	return PF_OK;
 }
 
-static int update_costs_impl(pf_router *r, float acc_fac, const int *delta, int *overused) {
+extern "C" int pf_update_costs(pf_router *r, float acc_fac, int *overused) {
+	if (!r) FAILF(PF_EINVAL, "null router");
 	CKB(pfb_zero(r->d_overused, sizeof(int) * 4));
 	r->cost_updates++;
-	CKB(pfb_launch_update_cost(r->nodes, r->N, acc_fac, r->d_overused, delta ? r->occ_base : NULL, delta, r->last_over,
-			1 + (r->cost_updates + 254) % 255));
+	CKB(pfb_launch_update_cost(r->nodes, r->N, acc_fac, r->d_overused, r->last_over, 1 + (r->cost_updates + 254) % 255));
 	int h[4];
 	CKB(pfb_d2h(h, r->d_overused, sizeof(int) * 4));
 	r->d2h_bytes += 16;
@@ -778,32 +788,23 @@ static int update_costs_impl(pf_router *r, float acc_fac, const int *delta, int 
 	return PF_OK;
 }
 
-extern "C" int pf_update_costs(pf_router *r, float acc_fac, int *overused) {
-	if (!r) FAILF(PF_EINVAL, "null router");
-	return update_costs_impl(r, acc_fac, NULL, overused);
-}
-
-extern "C" int pf_comm_export_delta(pf_router *r, void *dev_delta) {
-	if (!r || !dev_delta) FAILF(PF_EINVAL, "null argument");
-	if (!r->occ_base) FAILF(PF_EINVAL, "router was created with nranks == 1");
-	CKB(pfb_launch_export_delta(r->nodes, r->N, r->occ_base, (int *)dev_delta));
-	CKB(pfb_sync());
+/* Multi-GPU occupancy sync.  Every occupancy change a rank makes while routing (rip-up, commit, undo) is
+ * also appended to its event log; after a route part the ranks all-gather their logs and replay the others'.
+ * What crosses NVLink is 4 bytes per changed rr node instead of a dense int32[num_rr_nodes] all-reduce, and no
+ * pass over the node array is needed on either side. */
+extern "C" int pf_comm_events(pf_router *r, void **dev_events, int64_t *count) {
+	if (!r || !dev_events || !count) FAILF(PF_EINVAL, "null argument");
+	if (!r->events) FAILF(PF_EINVAL, "router was created with nranks == 1");
+	*dev_events = r->events;
+	*count = (int64_t)r->h_events;
 	return PF_OK;
 }
 
-extern "C" int pf_update_costs_synced(pf_router *r, float acc_fac, const void *dev_delta, int *overused) {
-	if (!r || !dev_delta) FAILF(PF_EINVAL, "null argument");
-	if (!r->occ_base) FAILF(PF_EINVAL, "router was created with nranks == 1");
-	return update_costs_impl(r, acc_fac, (const int *)dev_delta, overused);
-}
-
-/* fold an all-reduced occupancy delta into the node records without touching costs (between sub-rounds) */
-extern "C" int pf_comm_fold_delta(pf_router *r, const void *dev_delta) {
-	if (!r || !dev_delta) FAILF(PF_EINVAL, "null argument");
-	if (!r->occ_base) FAILF(PF_EINVAL, "router was created with nranks == 1");
-	CKB(pfb_zero(r->d_overused, sizeof(int) * 4));
-	CKB(pfb_launch_update_cost(r->nodes, r->N, 0.f, r->d_overused, r->occ_base, (const int *)dev_delta, NULL, 0));
-	CKB(pfb_sync());
+extern "C" int pf_comm_apply_events(pf_router *r, const void *dev_events, int64_t count) {
+	if (!r || (!dev_events && count > 0)) FAILF(PF_EINVAL, "null argument");
+	if (!r->events) FAILF(PF_EINVAL, "router was created with nranks == 1");
+	CKB(pfb_launch_apply_events(r->nodes, (const unsigned *)dev_events, (long long)count));   /* stream-ordered; the caller keeps
+	                                                                                          * the buffer alive until the next call */
 	return PF_OK;
 }
 
@@ -856,11 +857,11 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 	/* the traces are assembled on the device (pf_build_traces_kernel), so what crosses PCIe is the final
 	 * 6 bytes per trace element plus 4 bytes per rr node of occupancy — not the 32-byte tree entries */
 	int *d_len = (int *)pfb_alloc_raw(sizeof(int) * ((size_t)n + 1));
-	int *d_occ = r->occ_delta ? r->occ_delta : (int *)pfb_alloc_raw(sizeof(int) * (size_t)r->N);
-	if (!d_len || !d_occ) { pfb_free(d_len); if (!r->occ_delta) pfb_free(d_occ); CUDA_FAIL(); }
+	int *d_occ = (int *)pfb_alloc_raw(sizeof(int) * (size_t)r->N);
+	if (!d_len || !d_occ) { pfb_free(d_len); pfb_free(d_occ); CUDA_FAIL(); }
 	std::vector<int32_t> tptr((size_t)n + 1, 0);
 	int bad = pfb_launch_build_traces(r->pool[r->cur], r->loc, n, d_len, NULL, NULL, NULL, NULL, NULL, NULL, 0) || pfb_d2h(tptr.data() + 1, d_len, sizeof(int) * (size_t)n);
-	if (bad) { pfb_free(d_len); if (!r->occ_delta) pfb_free(d_occ); CUDA_FAIL(); }
+	if (bad) { pfb_free(d_len); pfb_free(d_occ); CUDA_FAIL(); }
 	for (int i = 0; i < n; i++) tptr[i + 1] += tptr[i];
 	const size_t total = (size_t)tptr[n];
 	int *d_tn = (int *)pfb_alloc_raw(sizeof(int) * std::max<size_t>(total, 1));
@@ -924,7 +925,7 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 		r->d2h_bytes += (int64_t)(b_tn + b_ts + b_tt + b_occ) + (int64_t)sizeof(int) * n + (int64_t)sizeof(float) * r->T;
 	}
 	pfb_free(d_len); pfb_free(d_tn); pfb_free(d_ts); pfb_free(d_tt);
-	if (!r->occ_delta) pfb_free(d_occ);
+	pfb_free(d_occ);
 	if (bad) { pf_result_free(out); if (!host_ok) FAILF(PF_ENOMEM, "out of host memory"); CUDA_FAIL(); }
 	memcpy(out->trace_ptr, tptr.data(), sizeof(int32_t) * ((size_t)n + 1));
 	out->num_terminals = r->T;

@@ -17,12 +17,41 @@ class Comm:
         self.device = device
         self.rank = dist.get_rank()
         self.world = dist.get_world_size()
+        self._counts = None
+        self._events = None
 
     def all_reduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         if t.is_cuda:
             torch.cuda.current_stream(t.device).synchronize()
         return t
+
+    def sync_occupancy(self, r) -> int:
+        """All ranks end up with the same rr-node occupancy: all-gather every rank's event log of the last
+        route part (router.comm_events: 4 bytes per changed rr node) and replay the others' on this rank.
+        Returns the number of events received."""
+        ptr, n = r.comm_events()
+        mine = torch.tensor([n], dtype=torch.int64, device=self.device)
+        if self._counts is None:
+            self._counts = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(self._counts, mine)
+        counts = self._counts.tolist()
+        m = max(counts)
+        if m == 0:
+            return 0
+        send = wrap_device_ints(ptr, m, self.device)          # entries past n are padding, never replayed
+        if self._events is None or self._events.numel() < self.world * m:
+            self._events = torch.empty(self.world * (m + (m >> 2) + 1024), dtype=torch.int32, device=self.device)
+        recv = self._events[: self.world * m]
+        dist.all_gather_into_tensor(recv, send)
+        if recv.is_cuda:
+            torch.cuda.current_stream(recv.device).synchronize()
+        got = 0
+        for k in range(self.world):
+            if k != self.rank and counts[k] > 0:
+                r.comm_apply_events(recv.data_ptr() + 4 * k * m, counts[k])
+                got += counts[k]
+        return got
 
     def all_reduce_scalar(self, v, op=dist.ReduceOp.SUM):
         t = torch.tensor([float(v)], dtype=torch.float64, device=self.device)
@@ -50,6 +79,21 @@ def init_from_env(backend: str | None = None) -> Comm | None:
     if not dist.is_initialized():
         dist.init_process_group(backend=backend)
     return Comm(torch.device("cuda", local) if use_cuda else torch.device("cpu"))
+
+
+def wrap_device_ints(ptr: int, n: int, device: torch.device) -> torch.Tensor:
+    """An int32 tensor view of n words at a raw device pointer owned by the router (no copy)."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+    if device.type == "cuda":
+        return torch.as_tensor(h, device=device)
+    import ctypes
+    import numpy as np
+    return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_int32 * n).from_address(ptr)))
 
 
 def wrap_device_floats(ptr: int, n: int, device: torch.device) -> torch.Tensor:

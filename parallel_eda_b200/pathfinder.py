@@ -4,13 +4,13 @@
 every net, reserve locally used OPINs, test feasibility, raise pres_fac, update costs, run the host
 STA.  With ``world_size > 1`` it is the data-parallel scheme of the reference's own MPI router
 (parallel_route/mpi_route_load_balanced_nonblocking_send_recv_encoded.cxx): nets are sharded over
-ranks, every rank keeps a full graph + congestion replica, and the occupancy changes are summed
-across ranks — there `MPI_Allreduce` (spatial.cxx:3371-3383), here an NCCL all-reduce of an
-int32[num_rr_nodes] delta over NVLink, twice per iteration (after the stripe-interior nets and after
-the nets that cross a stripe cut), folded into the node records by the pass that updates the costs
-(pf_update_costs_synced).
+ranks, every rank keeps a full graph + congestion replica, and the occupancy changes are exchanged
+across ranks — there a dense `MPI_Allreduce` (spatial.cxx:3371-3383), here an NCCL all-gather of each
+rank's event log (4 bytes per changed rr node) over NVLink, twice per iteration (after the
+stripe-interior nets and after the nets that cross a stripe cut), replayed with atomics on the node
+records (pf_comm_events / pf_comm_apply_events).
 
-``comm`` is anything with ``all_reduce_sum_(tensor)``; parallel_eda_b200.distributed wraps
+``comm`` is anything with ``sync_occupancy(router)`` and ``all_reduce_*``; parallel_eda_b200.distributed wraps
 torch.distributed (NCCL on GPUs; gloo on CPU tensors for the host-logic tests).
 """
 from __future__ import annotations
@@ -40,10 +40,10 @@ class RouteReport:
     wall_s: float
 
 
-def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delta_buf=None, delay_buf=None,
+def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delay_buf=None,
           max_iters: Optional[int] = None, sync_rounds: int = 2) -> RouteReport:
-    """Iterate until legal.  ``delta_buf``: device int32[num_nodes] tensor (required when comm is given);
-    ``delay_buf``: tensor aliasing the router's device net_delay vector (optional, for the host STA)."""
+    """Iterate until legal.  ``delay_buf``: tensor aliasing the router's device net_delay vector (optional, for
+    the host STA when several ranks route)."""
     o = r.problem.opts
     n_iter = int(max_iters or o["max_router_iterations"])
     pres_fac = float(o["first_iter_pres_fac"])
@@ -69,10 +69,7 @@ def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delta_buf
                 st = r.iteration_route_part(pres_fac, part, sync_rounds)
                 nets += st.nets_routed
                 pops += st.heap_pops; pushes += st.heap_pushes; visits += st.edge_visits
-                r.comm_export_delta(delta_buf.data_ptr())
-                comm.all_reduce_sum_(delta_buf)          # NCCL over NVLink / NVSwitch
-                if part + 1 < sync_rounds:
-                    r.comm_fold_delta(delta_buf.data_ptr())
+                comm.sync_occupancy(r)                   # all-gather of the event logs over NVLink / NVSwitch
             nets = int(comm.all_reduce_scalar(nets))
         total_nets += nets
         per_iter.append(nets)
@@ -83,20 +80,13 @@ def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delta_buf
             if wl / max(avail, 1) > FIRST_ITER_WIRELENGTH_LIMIT:     # route_timing.c:189-225
                 overused.append(-1)
                 break
-        # NB: with several ranks the OPIN reservation must see the synced occupancy: fold first
         if it == 1:
             new_pres, acc_fac = float(o["initial_pres_fac"]), 0.0
         else:
             new_pres = min(pres_fac * float(o["pres_fac_mult"]), HUGE_POSITIVE_FLOAT / 1e5)
             acc_fac = float(o["acc_fac"])
-        if comm is not None:
-            # fold the last sub-round, reserve OPINs on the synced occupancy, then update costs / count overuse
-            r.comm_fold_delta(delta_buf.data_ptr())
-            r.reserve_locally_used_opins(pres_fac, it != 1)
-            over = r.pathfinder_update_cost(acc_fac)
-        else:
-            r.reserve_locally_used_opins(pres_fac, it != 1)
-            over = r.pathfinder_update_cost(acc_fac)
+        r.reserve_locally_used_opins(pres_fac, it != 1)   # every rank, on the same synced occupancy
+        over = r.pathfinder_update_cost(acc_fac)
         pres_fac = new_pres
         overused.append(over)
         if over == 0:

@@ -122,9 +122,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing), C.c_int]
     lib.pf_timer_start.argtypes = [C.c_void_p]
     lib.pf_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
-    lib.pf_comm_export_delta.argtypes = [C.c_void_p, C.c_void_p]
-    lib.pf_update_costs_synced.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
-    lib.pf_comm_fold_delta.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pf_comm_events.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.pf_comm_apply_events.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.pf_comm_net_delay_ptr.argtypes = [C.c_void_p]
     lib.pf_comm_net_delay_ptr.restype = C.c_void_p
     lib.pf_try_timing_driven_route.argtypes = [C.POINTER(_Problem), C.POINTER(Config), STA_FN, C.c_void_p,
@@ -302,16 +301,14 @@ class Router:
         return ms.value
 
     # multi-GPU iteration boundary (device pointers, e.g. torch tensors' data_ptr())
-    def comm_export_delta(self, dev_ptr: int):
-        self._ck(self.lib.pf_comm_export_delta(self._h, C.c_void_p(dev_ptr)))
+    def comm_events(self):
+        """(device pointer, count) of this rank's occupancy event log of the last route part."""
+        ptr = C.c_void_p(); n = C.c_int64(0)
+        self._ck(self.lib.pf_comm_events(self._h, C.byref(ptr), C.byref(n)))
+        return int(ptr.value or 0), int(n.value)
 
-    def update_costs_synced(self, acc_fac: float, dev_ptr: int) -> int:
-        over = C.c_int(0)
-        self._ck(self.lib.pf_update_costs_synced(self._h, acc_fac, C.c_void_p(dev_ptr), C.byref(over)))
-        return over.value
-
-    def comm_fold_delta(self, dev_ptr: int):
-        self._ck(self.lib.pf_comm_fold_delta(self._h, C.c_void_p(dev_ptr)))
+    def comm_apply_events(self, dev_ptr: int, count: int):
+        self._ck(self.lib.pf_comm_apply_events(self._h, C.c_void_p(dev_ptr), count))
 
     def comm_net_delay_ptr(self) -> int:
         return int(self.lib.pf_comm_net_delay_ptr(self._h))

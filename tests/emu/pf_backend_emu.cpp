@@ -63,17 +63,16 @@ int pfb_launch_route(const PfParams *P, int num_slots, int) {
 	return 0;
 }
 
-int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, int *occ_base, const int *occ_delta,
-		unsigned char *last_over, int iter_tag) {
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, unsigned char *last_over, int iter_tag) {
 	int over = 0;
-	for (int i = 0; i < num_nodes; i++) over += pf_update_cost_one(nodes, i, acc_fac, occ_base, occ_delta, last_over, iter_tag);
+	for (int i = 0; i < num_nodes; i++) over += pf_update_cost_one(nodes, i, acc_fac, last_over, iter_tag);
 	*d_overused += over;
 	g_times.update_launches++;
 	return 0;
 }
 
-int pfb_launch_export_delta(const PfNode *nodes, int num_nodes, const int *occ_base, int *occ_delta) {
-	for (int i = 0; i < num_nodes; i++) occ_delta[i] = nodes[i].occ - occ_base[i];
+int pfb_launch_apply_events(PfNode *nodes, const unsigned *events, long long count) {
+	for (long long i = 0; i < count; i++) nodes[events[i] & ~PF_EVENT_DEC].occ += (events[i] & PF_EVENT_DEC) ? -1 : 1;
 	g_times.aux_launches++;
 	return 0;
 }
@@ -87,9 +86,9 @@ int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long
 }
 
 int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed, int num_groups,
-		const int *group_source, const int *group_count, const int *group_off, int *chosen, int rip_up, float pres_fac, int *occ_base) {
+		const int *group_source, const int *group_count, const int *group_off, int *chosen, int rip_up, float pres_fac) {
 	for (int g = 0; g < num_groups; g++)
-		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac, occ_base);
+		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac);
 	g_times.aux_launches++;
 	return 0;
 }

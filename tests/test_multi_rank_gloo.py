@@ -1,5 +1,5 @@
 """N>1 host logic on CPU: two processes over gloo, each routing its shard of the nets with the emulated device
-code, exchanging the occupancy delta once per iteration exactly as the NCCL path does on GPUs."""
+code, exchanging their occupancy event logs after each route part exactly as the NCCL path does on GPUs."""
 import os
 import subprocess
 import sys
@@ -18,8 +18,7 @@ p = pfio.read_problem(os.path.join(%(root)r, "tests", "golden", "toy_w64.pfp.xz"
 lib = %(emu)r
 cfg = router.default_config(router.load_library(lib), num_slots=2, big_slots=1, rank=comm.rank, nranks=comm.world)
 R = router.Router(p, cfg, lib_path=lib)
-delta = torch.zeros(p.num_nodes, dtype=torch.int32)
-rep = pathfinder.route(R, comm=comm, delta_buf=delta)
+rep = pathfinder.route(R, comm=comm)
 res = R.result()
 # every rank holds the full occupancy; traces only of its own nets
 occ = torch.from_numpy(res.occ.astype(np.int64)); ref = occ.clone(); torch.distributed.broadcast(ref, 0)
