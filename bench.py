@@ -199,6 +199,14 @@ def run_ours(a):
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (tm.route_kernel_ms * 1e-3) / 1e9 if tm.route_kernel_ms > 0 else 0.0
     launches = int(tm.route_launches + tm.update_launches + tm.aux_launches)
+    # DRAM traffic of the dominant launch from the committed `ncu --set full` capture (iteration-1 launch of this very
+    # workload on 1 GPU: profiles/r01_ncu_full_pf_route_kernel.json, dram__bytes_read.sum + dram__bytes_write.sum);
+    # that launch's algorithmic bytes are 3.75e9 (7.78e7 visits, 5.12e6 pops, 4.00e7 label writes)
+    traffic = None
+    if world == 1 and (a.grid, a.nets, a.width) == (400, 200000, 100):
+        traffic = {"bytes_per_launch": 8.813320e9 + 1.612722e9, "launch": "iteration 1 (200000 nets)",
+                   "algorithmic_bytes_same_launch": 36.0 * 77.83e6 + 28.0 * 5.12e6 + 20.0 * 40.03e6,
+                   "source": "profiles/r01_ncu_full_pf_route_kernel.json"}
 
     # end to end through the public API with host buffers (N GPUs)
     e2e = None
@@ -256,7 +264,7 @@ def run_ours(a):
             "route": {"iterations": [r.iterations for r in reps], "nets_routed_per_step": nets_routed / a.steps,
                       "route_time_s": total_ms * 1e-3 / a.steps, "legal": True},
             "roofline": {"bound": "hbm", "kernel": "pf_route_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes": "36 B/edge visit + 28 B/pop + 20 B/label write (SURVEY.md §8d)",
                          "kernel_ms_per_step": tm.route_kernel_ms / a.steps, "kernel_launches_per_step": tm.route_launches / a.steps},
             "gpu_launches": launches,
