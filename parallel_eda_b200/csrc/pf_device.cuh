@@ -122,13 +122,10 @@ struct PfWarp {
 
 PF_DEV float pf_key_tot(uint64_t k) { return pf_int_as_float((int)(k >> 32)); }
 PF_DEV int pf_key_node(uint64_t k) { return (int)((uint32_t)k & 0x03ffffffu); }
-/* frontier key: total cost, then — among equal totals — the label that is further along (larger share of
- * known backward cost) first, the classic A* tie-break that keeps a symmetric routing fabric from being
- * flooded breadth-first; then the node id */
-PF_DEV uint64_t pf_make_key(float tot, float back, int node) {
-	int q = 63 - (int)(63.f * (back / (tot > 0.f ? tot : 1.f)));
-	q = q < 0 ? 0 : (q > 63 ? 63 : q);
-	return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | ((uint32_t)q << 26) | (uint32_t)node;
+/* frontier key: total cost | rr node.  Equal totals are settled oldest first (the near set keeps push order), so
+ * the key carries no tie-break field. */
+PF_DEV uint64_t pf_make_key(float tot, int node) {
+	return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | (uint32_t)node;
 }
 #define PF_INF_F 3.0e38f
 #define PF_KEY_MAX 0xffffffffffffffffull
@@ -262,8 +259,8 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 /* ------------------------------------------------------------------ frontier */
 /* Warp-collective push.  Labels inside the near window go to shared memory, the rest (and any
  * near-set overflow) to the far list in HBM; far_min guards the best-first order. */
-PF_DEV void pf_push(PfWarp &w, int valid, float tot, float back, int node) {
-	uint64_t key = pf_make_key(tot, back, node);
+PF_DEV void pf_push(PfWarp &w, int valid, float tot, int node) {
+	uint64_t key = pf_make_key(tot, node);
 	int to_sh = valid && tot <= w.T_hi;
 	unsigned m1 = pf_ballot(to_sh);
 	int pos = w.sh_n + pf_popc(m1 & pf_lanemask_lt());
@@ -443,7 +440,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 				if (valid && tot < smin) smin = tot;
 			} else {
 				int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
-				pf_push(w, wr, tot, back, node);
+				pf_push(w, wr, tot, node);
 				if (w.overflow) return -1;
 			}
 		}
@@ -460,7 +457,9 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 	for (;;) {
 		if (w.overflow) return -1;
 		float mtot = PF_INF_F;
-		for (int i = lane; i < w.sh_n; i += PF_WARP) { float t = pf_key_tot(w.fr[i]); if (t < mtot) mtot = t; }
+		int first = 0x7fffffff;                 /* this lane's oldest label at its local minimum */
+		for (int i = lane; i < w.sh_n; i += PF_WARP) { float t = pf_key_tot(w.fr[i]); if (t < mtot) { mtot = t; first = i; } }
+		const float my_min = mtot;
 		mtot = pf_warp_min_f(mtot);
 		if (w.far_min < mtot) {                 /* a cheaper label sits in the far list (or near set empty) */
 			if (w.far_min >= w.best) break;
@@ -479,7 +478,8 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 			 * batch selection below yields for max_batch == 1), and close the gap so the near set stays in push
 			 * order.  Every lane then does the same label lookup (broadcast reads): nothing is staged. */
 			int li = 0x7fffffff;
-			for (int i = lane; i < w.sh_n; i += PF_WARP) if (pf_key_tot(w.fr[i]) <= thr) { li = i; break; }
+			if (slack == 0.f) { if (my_min == mtot) li = first; }      /* within 0 of the minimum = at the minimum */
+			else for (int i = lane; i < w.sh_n; i += PF_WARP) if (pf_key_tot(w.fr[i]) <= thr) { li = i; break; }
 			const int idx = -pf_warp_max_i(-li);
 			const uint64_t mk = w.fr[idx];
 			uint64_t keep[PF_SH_FRONTIER / PF_WARP];
@@ -623,7 +623,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 			/* the target SINK is never expanded; only its best total matters */
 			float tb = pf_warp_min_f((wr && to == target_node) ? tot : PF_INF_F);
 			if (tb < w.best) w.best = tb;
-			pf_push(w, wr && to != target_node, tot, back, to);
+			pf_push(w, wr && to != target_node, tot, to);
 			if (w.overflow) return -1;
 		}
 	}
