@@ -177,6 +177,10 @@ def run_ours(a):
         if comm:
             comm.barrier()
             ms = comm.all_reduce_max(ms)
+        wl, _ = R.total_wirelength()               # after the timed region: reported, not measured
+        if comm:
+            wl = int(comm.all_reduce_scalar(wl))
+        rep.wirelength = int(wl)
         return rep, ms
 
     for _ in range(a.warmup):
@@ -262,7 +266,8 @@ def run_ours(a):
                        "l2": "working set (node records %d MB + edges %d MB) far exceeds the 126 MB L2; no flush needed"
                              % (p.num_nodes * 32 >> 20, p.num_edges * 4 >> 20)},
             "route": {"iterations": [r.iterations for r in reps], "nets_routed_per_step": nets_routed / a.steps,
-                      "route_time_s": total_ms * 1e-3 / a.steps, "legal": True},
+                      "route_time_s": total_ms * 1e-3 / a.steps, "legal": True,
+                      "wirelength": [r.wirelength for r in reps], "reference_wirelength": REFERENCE_WL.get((a.grid, a.nets, a.width))},
             "roofline": {"bound": "hbm", "kernel": "pf_route_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes": "36 B/edge visit + 28 B/pop + 20 B/label write (SURVEY.md §8d)",
@@ -279,6 +284,11 @@ def run_ours(a):
     if comm:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+# total wirelength of the UNMODIFIED reference router on the same generated problem (oracle/_ref/vpr_ref inject,
+# run once in the build container): quality yardstick for the routing the timed steps produce
+REFERENCE_WL = {(400, 200000, 100): 9280210}     # 8 iterations, 109 s of route time on the build container's CPU
 
 
 def main():

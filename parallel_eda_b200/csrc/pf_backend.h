@@ -54,7 +54,7 @@ int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num
 /* occ_out[i] = nodes[i].occ (compact copy for the host) */
 int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out);
 /* total wirelength of all trees in the route store (route_timing.c:189-225 sanity abort) */
-int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long long *d_out);
+int pfb_launch_wirelength(const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets, int num_all, unsigned long long *d_out);
 /* reserve_locally_used_opins (route_common.c:1435-1491): one thread per (block, class) group */
 int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
 		int num_groups, const int *group_source, const int *group_count, const int *group_off,

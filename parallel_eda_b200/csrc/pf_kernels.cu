@@ -216,10 +216,15 @@ __global__ void pf_extract_occ_kernel(const PfNode *nodes, int num_nodes, int *o
 	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x)) occ_out[i] = nodes[i].occ;
 }
 
-__global__ void pf_wirelength_kernel(const PfTreeNode *pool, long long count, unsigned long long *d_out) {
+/* wirelength of the LIVE route trees of this rank's nets (the route store is an append-only log: entries of
+ * re-routed nets stay behind until the next compaction, so the log itself cannot be summed) */
+__global__ void pf_wirelength_kernel(const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets, int num_all,
+		unsigned long long *d_out) {
 	unsigned acc = 0;
-	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
-		acc += pf_tree_wirelength_one(&pool[i]);
+	for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < num_all; k += (int)(gridDim.x * blockDim.x)) {
+		const PfNetLoc l = loc[all_nets[k]];
+		for (int i = 0; i < l.count; i++) acc += pf_tree_wirelength_one(&pool[l.off + i]);
+	}
 	acc = __reduce_add_sync(0xffffffffu, acc);
 	if ((threadIdx.x & 31u) == 0 && acc) atomicAdd(d_out, (unsigned long long)acc);
 }
@@ -341,9 +346,10 @@ int pfb_launch_apply_events(PfNode *nodes, const unsigned *events, long long cou
 	return ev_end();
 }
 
-int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long long *d_out) {
+int pfb_launch_wirelength(const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets, int num_all, unsigned long long *d_out) {
+	if (num_all <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
-	pf_wirelength_kernel<<<stream_grid(count), 256, 0, g_stream>>>(pool, count, d_out);
+	pf_wirelength_kernel<<<stream_grid(num_all), 256, 0, g_stream>>>(pool, loc, all_nets, num_all, d_out);
 	return ev_end();
 }
 

@@ -816,9 +816,8 @@ extern "C" void *pf_comm_net_delay_ptr(pf_router *r) { return r ? (void *)r->net
 
 extern "C" int pf_total_wirelength(pf_router *r, int64_t *wl, int64_t *avail) {
 	if (!r) FAILF(PF_EINVAL, "null router");
-	unsigned long long head[2] = { r->h_pool_head, 0 };
 	CKB(pfb_zero(r->d_wl, sizeof(unsigned long long) * 2));
-	CKB(pfb_launch_wirelength(r->pool[r->cur], (long long)head[0], r->d_wl));
+	CKB(pfb_launch_wirelength(r->pool[r->cur], r->loc, r->all_nets, r->num_all, r->d_wl));
 	unsigned long long h[2];
 	CKB(pfb_d2h(h, r->d_wl, sizeof(h)));
 	r->d2h_bytes += 32;

@@ -77,9 +77,12 @@ int pfb_launch_apply_events(PfNode *nodes, const unsigned *events, long long cou
 	return 0;
 }
 
-int pfb_launch_wirelength(const PfTreeNode *pool, long long count, unsigned long long *d_out) {
+int pfb_launch_wirelength(const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets, int num_all, unsigned long long *d_out) {
 	unsigned long long acc = 0;
-	for (long long i = 0; i < count; i++) acc += pf_tree_wirelength_one(&pool[i]);
+	for (int k = 0; k < num_all; k++) {
+		const PfNetLoc l = loc[all_nets[k]];
+		for (int i = 0; i < l.count; i++) acc += pf_tree_wirelength_one(&pool[l.off + i]);
+	}
 	*d_out += acc;
 	g_times.aux_launches++;
 	return 0;

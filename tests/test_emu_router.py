@@ -104,3 +104,17 @@ def test_high_fanout_net_window(emu_lib):
     assert r.success == 1
     check_route.check_route(p, r)
     assert r.total_wirelength <= 1.08 * g.total_wirelength
+
+
+def test_step_api_wirelength_counts_live_trees_only(emu_lib):
+    """pf_total_wirelength after several iterations: the route store is an append-only log that still holds the
+    trees of re-routed nets, the reported wirelength must be that of the current routing (= the result's)."""
+    from parallel_eda_b200 import pathfinder
+    p = _toy(False)
+    R = router.Router(p, router.default_config(router.load_library(emu_lib), num_slots=8, big_slots=1), lib_path=emu_lib)
+    rep = pathfinder.route(R)
+    assert rep.success and rep.iterations > 1
+    wl, avail = R.total_wirelength()
+    res = R.result()
+    assert wl == res.total_wirelength == check_route.check_route(p, res)["wirelength"] and avail > wl
+    R.close()
