@@ -222,7 +222,8 @@ def run_ours(a):
                 comm.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            R2 = router.Router(p, cfg)                 # flatten + H2D of the whole problem
+            # flatten + H2D of the whole problem (N GPUs: rank 0 uploads, the others receive over NVLink)
+            R2 = comm.create_router(p, cfg) if comm else router.Router(p, cfg)
             t1 = time.perf_counter()
             rep = pathfinder.route(R2, comm=comm, sync_rounds=a.sync_rounds)
             t2 = time.perf_counter()

@@ -76,6 +76,9 @@ typedef struct pf_config {
 	                             0 = off (default) */
 	int32_t keep_newcomer;    /* experimental: on an overused node, re-route every user except the one that committed it
 	                             last; 0 = off (default) */
+	int32_t defer_graph;      /* multi-GPU: allocate the device graph but do not pack and upload it from this process's
+	                             host arrays — the caller fills it from another rank's copy over NVLink
+	                             (pf_comm_graph_buffers, then pf_comm_graph_ready); 0 = upload here (default) */
 } pf_config;
 
 typedef struct pf_timing {    /* accumulated since create / last reset */
@@ -129,6 +132,12 @@ void *pf_stream(pf_router *r);   /* the cudaStream_t every kernel of this router
  * afterwards all ranks hold the same occupancy, and pf_reserve_opins / pf_update_costs run as on one GPU.
  * pf_comm_net_delay_ptr returns the device float[num_terminals] delay vector; entries of nets
  * routed by other ranks are zero, so an all-reduce(sum) assembles the full vector in place. */
+/* Multi-GPU create: every rank needs the same packed graph (rr node records, edge words, ptc numbers).  Rank 0
+ * packs and uploads it over PCIe; the other ranks are created with cfg.defer_graph = 1 and receive it by an NCCL
+ * broadcast over NVLink into the three device buffers named here, then call pf_comm_graph_ready.  (All ranks still
+ * pass the same pf_problem: nets, options and the reset path use the host arrays.) */
+int pf_comm_graph_buffers(pf_router *r, void *dev_ptrs[3], int64_t bytes[3]);
+int pf_comm_graph_ready(pf_router *r);
 int pf_comm_events(pf_router *r, void **dev_events, int64_t *count);
 int pf_comm_apply_events(pf_router *r, const void *dev_events, int64_t count);
 void *pf_comm_net_delay_ptr(pf_router *r);

@@ -60,6 +60,7 @@ struct pf_router {
 	int *status, *retry_list, *retry_count;
 	PfStats *stats;
 	int *d_overused; unsigned long long *d_wl;
+	int graph_ready;              /* 0 while a deferred graph has not been filled in */
 	unsigned *events; long long event_cap; long long h_events;   /* multi-GPU only: this rank's occupancy event log */
 	/* OPIN reservation */
 	int num_groups; int *g_source, *g_count, *g_off, *g_chosen;
@@ -291,7 +292,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->sel_scratch = NULL; r->ptc = NULL; r->K1 = 0; r->n1_small = r->n1_big = 0; r->iter_count = 0;
 	r->best_overused = 0x7fffffff; r->stall_count = 0; r->since_full = 0; r->last_over = NULL; r->cost_updates = 0; r->committer = NULL; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
-	r->events = NULL; r->event_cap = 0; r->h_events = 0; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
+	r->events = NULL; r->event_cap = 0; r->h_events = 0; r->graph_ready = 1; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
 	r->h2d_bytes = r->d2h_bytes = 0;
 
 	int sms = pfb_num_sms();
@@ -409,7 +410,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	{
 		const size_t nbytes = sizeof(PfNode) * (size_t)r->N, ebytes = sizeof(uint32_t) * (size_t)std::max(r->E, 1);
 		const size_t pbytes = sizeof(short) * (size_t)r->N;
-		char *pin = (char *)pfb_pinned_upload(nbytes + ebytes + pbytes + 768);
+		char *pin = (c.defer_graph && c.nranks > 1) ? NULL : (char *)pfb_pinned_upload(nbytes + ebytes + pbytes + 768);
 		void *stage_nodes = pin;
 		uint32_t *stage_edges = pin ? (uint32_t *)(pin + ((nbytes + 255) & ~(size_t)255)) : NULL;
 		short *stage_ptc = pin ? (short *)((char *)stage_edges + ((ebytes + 255) & ~(size_t)255)) : NULL;
@@ -428,7 +429,19 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		int bad_nodes = 0, bad_edges = 0;
 		long long wl_avail = 0;
 		r->t_mark[0] = now_s();
-		if (upload_edges(r, stage_edges, &bad_edges) != PF_OK || upload_nodes(r, stage_nodes, &bad_nodes, &wl_avail, stage_ptc) != PF_OK) { pf_router_destroy(r); return PF_ECUDA; }
+		if (c.defer_graph && c.nranks > 1) {
+			/* the packed graph arrives from another rank (pf_comm_graph_buffers); only the available wirelength,
+			 * which the first-iteration abort check needs, is computed from the host arrays here */
+			r->graph_ready = 0;
+			std::atomic<long long> wl(0);
+			parallel_for(r->N, [&](long long lo, long long hi) {
+				long long w = 0;
+				for (long long i = lo; i < hi; i++)
+					if (p->type[i] == PF_CHANX || p->type[i] == PF_CHANY) w += 1 + p->xhigh[i] - p->xlow[i] + p->yhigh[i] - p->ylow[i];
+				wl += w;
+			});
+			wl_avail = wl;
+		} else if (upload_edges(r, stage_edges, &bad_edges) != PF_OK || upload_nodes(r, stage_nodes, &bad_nodes, &wl_avail, stage_ptc) != PF_OK) { pf_router_destroy(r); return PF_ECUDA; }
 		if (bad_nodes || bad_edges) {
 			pfb_sync();
 			pf_router_destroy(r);
@@ -626,6 +639,7 @@ static int slots_for(const pf_router *r, int total_work, int class_slots, int di
 /* Start of one PathFinder iteration: garbage-collect the route store and choose the nets to re-route. */
 extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	if (!r) FAILF(PF_EINVAL, "null router");
+	if (!r->graph_ready) FAILF(PF_EINVAL, "the router was created with defer_graph: fill the graph buffers and call pf_comm_graph_ready first");
 	int rc;
 	if (crit) { CKB(pfb_h2d(r->crit, crit, sizeof(float) * (size_t)r->T)); r->h2d_bytes += (int64_t)sizeof(float) * r->T; }
 	/* garbage-collect the route-tree log when it is more than half full */
@@ -796,6 +810,21 @@ extern "C" int pf_update_costs(pf_router *r, float acc_fac, int *overused) {
  * also appended to its event log; after a route part the ranks all-gather their logs and replay the others'.
  * What crosses NVLink is 4 bytes per changed rr node instead of a dense int32[num_rr_nodes] all-reduce, and no
  * pass over the node array is needed on either side. */
+extern "C" int pf_comm_graph_buffers(pf_router *r, void *dev_ptrs[3], int64_t bytes[3]) {
+	if (!r || !dev_ptrs || !bytes) FAILF(PF_EINVAL, "null argument");
+	dev_ptrs[0] = r->nodes; bytes[0] = (int64_t)sizeof(PfNode) * r->N;
+	dev_ptrs[1] = r->edges; bytes[1] = (int64_t)sizeof(uint32_t) * std::max(r->E, 1);
+	dev_ptrs[2] = r->ptc; bytes[2] = (int64_t)sizeof(short) * r->N;
+	CKB(pfb_sync());                    /* the sender's uploads have landed before anybody reads the buffers */
+	return PF_OK;
+}
+
+extern "C" int pf_comm_graph_ready(pf_router *r) {
+	if (!r) FAILF(PF_EINVAL, "null router");
+	r->graph_ready = 1;
+	return PF_OK;
+}
+
 extern "C" int pf_comm_events(pf_router *r, void **dev_events, int64_t *count) {
 	if (!r || !dev_events || !count) FAILF(PF_EINVAL, "null argument");
 	if (!r->events) FAILF(PF_EINVAL, "router was created with nranks == 1");

@@ -75,7 +75,8 @@ class Config(C.Structure):
                                          "big_tree_cap", "big_far_cap", "max_batch")] + \
                [("pop_slack", C.c_float), ("win_rel", C.c_float), ("win_abs", C.c_float), ("verbose", C.c_int32),
                 ("reroute_all_iters", C.c_int32), ("inflight_div", C.c_int32), ("min_slots", C.c_int32),
-                ("stall_iters", C.c_int32), ("history_window", C.c_int32), ("keep_newcomer", C.c_int32)]
+                ("stall_iters", C.c_int32), ("history_window", C.c_int32), ("keep_newcomer", C.c_int32),
+                ("defer_graph", C.c_int32)]
 
 
 class Timing(C.Structure):
@@ -122,6 +123,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing), C.c_int]
     lib.pf_timer_start.argtypes = [C.c_void_p]
     lib.pf_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.pf_comm_graph_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p * 3), C.POINTER(C.c_int64 * 3)]
+    lib.pf_comm_graph_ready.argtypes = [C.c_void_p]
     lib.pf_comm_events.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     lib.pf_comm_apply_events.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.pf_comm_net_delay_ptr.argtypes = [C.c_void_p]
@@ -301,6 +304,15 @@ class Router:
         return ms.value
 
     # multi-GPU iteration boundary (device pointers, e.g. torch tensors' data_ptr())
+    def comm_graph_buffers(self):
+        """[(device pointer, bytes)] of the packed graph: node records, edge words, ptc numbers."""
+        ptrs = (C.c_void_p * 3)(); nb = (C.c_int64 * 3)()
+        self._ck(self.lib.pf_comm_graph_buffers(self._h, C.byref(ptrs), C.byref(nb)))
+        return [(int(ptrs[k] or 0), int(nb[k])) for k in range(3)]
+
+    def comm_graph_ready(self):
+        self._ck(self.lib.pf_comm_graph_ready(self._h))
+
     def comm_events(self):
         """(device pointer, count) of this rank's occupancy event log of the last route part."""
         ptr = C.c_void_p(); n = C.c_int64(0)

@@ -17,7 +17,7 @@ comm = distributed.init_from_env("gloo")
 p = pfio.read_problem(os.path.join(%(root)r, "tests", "golden", "toy_w64.pfp.xz")); p.opts["timing_analysis_enabled"] = 0
 lib = %(emu)r
 cfg = router.default_config(router.load_library(lib), num_slots=2, big_slots=1, rank=comm.rank, nranks=comm.world)
-R = router.Router(p, cfg, lib_path=lib)
+R = comm.create_router(p, cfg, lib_path=lib)     # rank 0 packs the graph, rank 1 receives it by broadcast
 rep = pathfinder.route(R, comm=comm)
 res = R.result()
 # every rank holds the full occupancy; traces only of its own nets
