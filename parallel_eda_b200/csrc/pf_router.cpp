@@ -344,10 +344,16 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	std::vector<int> owner((size_t)std::max(r->n, 1), 0);
 	std::vector<unsigned char> cut_net((size_t)std::max(r->n, 1), 0);
 	if (c.nranks > 1) {
-		std::vector<int> byx(order);
-		std::stable_sort(byx.begin(), byx.end(), [&](int a, int b) {
-			int ca = p->net_bb[4 * a] + p->net_bb[4 * a + 1], cb = p->net_bb[4 * b] + p->net_bb[4 * b + 1];
-			return ca < cb; });
+		/* stable counting sort by xmin + xmax (0 .. 2 nx + 4) */
+		std::vector<int> byx(order.size());
+		{
+			const int nkeys = 2 * (p->nx + 2) + 2;
+			std::vector<int> start((size_t)nkeys + 1, 0);
+			auto key = [&](int i) { return std::min(nkeys - 1, std::max(0, p->net_bb[4 * i] + p->net_bb[4 * i + 1])); };
+			for (int i : order) start[(size_t)key(i) + 1]++;
+			for (int k = 0; k < nkeys; k++) start[(size_t)k + 1] += start[(size_t)k];
+			for (int i : order) byx[(size_t)start[(size_t)key(i)]++] = i;
+		}
 		long long total_f = 0, acc_f = 0;
 		for (int i : byx) total_f += p->net_ptr[i + 1] - p->net_ptr[i];
 		/* cut[k] (k = 1..nranks-1): stripe k-1 holds boxes with xmax <= cut[k], stripe k boxes with xmin >= cut[k] + lmax */

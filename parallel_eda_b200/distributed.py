@@ -36,11 +36,16 @@ class Comm:
         cfg = _router.Config.from_buffer_copy(config if config is not None else _router.default_config(lib))
         cfg.rank, cfg.nranks = self.rank, self.world
         cfg.defer_graph = 0 if self.rank == 0 else 1
+        if os.environ.get("PF_COMM_DEBUG"):
+            cfg.verbose = 1
+        import time
         R, err = None, None
+        t0 = time.perf_counter()
         try:
             R = _router.Router(problem, cfg, lib_path=lib_path)
         except _router.RouterError as e:
             err = e
+        t1 = time.perf_counter()
         if self.all_reduce_scalar(1 if err else 0) > 0:          # nobody waits in a broadcast for a rank that failed
             if R is not None:
                 R.close()
@@ -52,6 +57,8 @@ class Comm:
             torch.cuda.current_stream(self.device).synchronize()
         if self.rank != 0:
             R.comm_graph_ready()
+        if os.environ.get("PF_COMM_DEBUG"):
+            print("rank %d create_router: create %.1f ms, status + broadcast %.1f ms" % (self.rank, (t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3), flush=True)
         return R
 
     def sync_occupancy(self, r) -> int:
