@@ -39,6 +39,18 @@ int pf_result_write(const char *path, const pf_result *r);
 int pf_result_read(const char *path, pf_result *r);
 void pf_result_free(pf_result *r);
 
+/* Timing graph:  "PFTIMG01" | int32 header[16] | arrays in struct order
+ * STA vectors:   "PFSTAV01" | int32 header[16] | net_delay | crit | cpd */
+int pf_timing_graph_write(const char *path, const pf_timing_graph *g);
+int pf_timing_graph_read(const char *path, pf_timing_graph *g);
+void pf_timing_graph_free(pf_timing_graph *g);
+/* ranges of every index, level lists a permutation with edges going to later levels, driver fan-outs equal to
+ * the nets' sink counts (net_ptr = pf_problem.net_ptr, may be NULL to skip that part) */
+int pf_timing_graph_check(const pf_timing_graph *g, const int32_t *net_ptr, char *msg, int msg_len);
+int pf_sta_vectors_write(const char *path, const pf_sta_vectors *v);
+int pf_sta_vectors_read(const char *path, pf_sta_vectors *v);
+void pf_sta_vectors_free(pf_sta_vectors *v);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,6 +145,43 @@ typedef struct pf_result {
 	float *iter_crit;
 } pf_result;
 
+/* ------------------------------------------------------------------ timing graph
+ * Flat image of the reference's post-packing timing graph (tnode[] / tedge, vpr_types.h:300-380, built by
+ * alloc_and_load_timing_graph, timing/path_delay.c:328) — what do_timing_analysis (path_delay.c:2258) reads when
+ * the router calls it between iterations (route_timing.c:295-309).  Pin k (1-based) of net i is out-edge k-1 of
+ * tnode net_driver[i] (path_delay.c:479-500); its delay comes from net_delay[net_ptr[i] + k] of the routing. */
+#define PF_TN_FF_SINK 11      /* e_tnode_type values the analysis distinguishes (vpr_types.h:305-323) */
+#define PF_TN_INPAD_SOURCE 0
+#define PF_TN_OUTPAD_SINK 3
+#define PF_TN_FF_SOURCE 12
+#define PF_TN_FF_CLOCK 13
+#define PF_TN_CONSTANT_GEN_SOURCE 14
+
+typedef struct pf_timing_graph {
+	int32_t num_tnodes, num_tedges;
+	int32_t *edge_ptr;        /* [num_tnodes+1] CSR of tnode[].out_edges, the reference's order */
+	int32_t *edge_to;         /* [num_tedges] tedge.to_node */
+	float *edge_Tdel;         /* [num_tedges] tedge.Tdel; the edges of net drivers are overwritten from net_delay */
+	uint8_t *type;            /* [num_tnodes] e_tnode_type */
+	int32_t *clock_domain;    /* [num_tnodes] index into the constrained clocks, -1 = none */
+	float *clock_delay;       /* [num_tnodes] */
+	int32_t num_levels;
+	int32_t *level_ptr;       /* [num_levels+1] tnodes_at_level (path_delay2.c) */
+	int32_t *level_nodes;     /* [num_tnodes] */
+	int32_t num_domains;      /* g_sdc->num_constrained_clocks */
+	float *constraint;        /* [num_domains * num_domains] g_sdc->domain_constraint, < 0 = DO_NOT_ANALYSE */
+	int32_t num_nets;         /* == pf_problem.num_nets */
+	int32_t *net_driver;      /* [num_nets] f_net_to_driver_tnode */
+} pf_timing_graph;
+
+/* golden vectors of the reference's analysis: K calls, each net_delay in -> timing_criticality out */
+typedef struct pf_sta_vectors {
+	int32_t num_terminals, num_calls;
+	float *net_delay;         /* [num_calls * num_terminals] */
+	float *crit;              /* [num_calls * num_terminals] slacks->timing_criticality, 0 at terminal 0 of a net */
+	float *cpd;               /* [num_calls] get_critical_path_delay() in ns */
+} pf_sta_vectors;
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,13 @@ void pf_oracle_heapsort(int *sort_index, float *sort_values, int nelem, int star
 /* get_serial_num (route_common.c:224-254) over a flat trace. */
 int pf_serial_num(const pf_problem *p, const int32_t *trace_ptr, const int32_t *trace_node);
 
+/* do_timing_analysis(slacks, FALSE, FALSE, FALSE) as the router calls it between iterations (route_timing.c:295-309;
+ * timing/path_delay.c:2258-2522 with SLACK_DEFINITION 'R', no PATH_COUNTING, not prepacked, no LUT rebalancing, not the
+ * final analysis) preceded by load_timing_graph_net_delays (path_delay.c:479-500), over the flat timing graph.
+ * net_ptr = pf_problem.net_ptr.  Fills crit[num_terminals] (timing_criticality; 0 where the reference leaves 0) and
+ * *cpd_ns (get_critical_path_delay, path_delay.c:3791-3810).  scratch-free: allocates its own T_arr / T_req. */
+int pf_oracle_sta(const pf_timing_graph *g, const int32_t *net_ptr, const float *net_delay, float *crit, float *cpd_ns);
+
 #ifdef __cplusplus
 }
 #endif

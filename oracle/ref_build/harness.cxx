@@ -10,6 +10,8 @@
  *        place_and_route_new cannot reach the timing-driven router).
  *        env PF_DUMP_PROBLEM=<file>  write the flat problem seen by try_timing_driven_route
  *        env PF_DUMP_RESULT=<file>   write traces / delays / per-iteration criticalities
+ *        env PF_DUMP_TGRAPH=<file>   write the flat timing graph (pf_timing_graph) do_timing_analysis runs on
+ *        env PF_DUMP_STA=<file>      write every (net_delay in, timing_criticality out, cpd) of the run's STA calls
  *   vpr_ref inject <problem.pfp> [--result out.pfr] [--crit golden.pfr] [--max_iters K]
  *                  [--limit_nets M]
  *        load a flat problem into the reference's globals and call the reference's own
@@ -36,6 +38,8 @@
 #include "route_tree_timing.h"
 #include "route_timing.h"
 #include "path_delay.h"
+#include "path_delay2.h"
+#include "read_sdc.h"
 #include "net_delay.h"
 #include "place_and_route.h"
 #include "stats.h"
@@ -77,6 +81,7 @@ static std::vector<int> g_net_ptr;       /* terminals prefix */
 static double g_t0 = 0;
 static std::vector<double> g_iter_time;
 static float g_last_cpd = 0;
+static std::vector<float> g_sta_delay, g_sta_crit, g_sta_cpd;   /* golden vectors of the reference's STA calls */
 
 static void build_net_ptr() {
 	g_net_ptr.assign(num_nets + 1, 0);
@@ -109,13 +114,23 @@ boolean pf_hook_feasible_routing(void) {
 }
 
 void pf_hook_load_timing_graph_net_delays(float **net_delay) {
-	if (!g_inject) load_timing_graph_net_delays(net_delay);
+	if (!g_inject) {
+		load_timing_graph_net_delays(net_delay);
+		size_t base = g_sta_delay.size();
+		g_sta_delay.resize(base + g_net_ptr[num_nets], 0.f);
+		for (int i = 0; i < num_nets; i++)
+			for (int k = 1; k <= clb_net[i].num_sinks; k++) g_sta_delay[base + g_net_ptr[i] + k] = net_delay[i][k];
+	}
 }
 
 static t_slack *g_slacks = NULL;
 void pf_hook_do_timing_analysis(t_slack *slacks, boolean a, boolean b, boolean c) {
 	if (!g_inject) {
 		do_timing_analysis(slacks, a, b, c);
+		size_t base = g_sta_crit.size();          /* every net, global ones too: the analysis covers them */
+		g_sta_crit.resize(base + g_net_ptr[num_nets], 0.f);
+		for (int i = 0; i < num_nets; i++)
+			for (int k = 1; k <= clb_net[i].num_sinks; k++) g_sta_crit[base + g_net_ptr[i] + k] = slacks->timing_criticality[i][k];
 	} else if (g_have_replay) {
 		/* criticalities for iteration g_iter+1 (g_iter iterations are complete) */
 		int it = g_iter < g_replay.num_crit_iters ? g_iter : g_replay.num_crit_iters - 1;
@@ -129,6 +144,7 @@ void pf_hook_do_timing_analysis(t_slack *slacks, boolean a, boolean b, boolean c
 
 float pf_hook_get_critical_path_delay(void) {
 	g_last_cpd = g_inject ? 0.f : get_critical_path_delay();
+	if (!g_inject) g_sta_cpd.push_back(g_last_cpd);
 	if (!g_stats.empty()) g_stats.back().crit_path_delay = g_last_cpd;
 	return g_last_cpd;
 }
@@ -271,12 +287,68 @@ static void report_times(boolean ok, double total) {
 	}
 }
 
+/* the reference's timing graph, flattened (include/pf_types.h: pf_timing_graph) */
+static void export_timing_graph(const char *path) {
+	pf_timing_graph g;
+	memset(&g, 0, sizeof(g));
+	g.num_tnodes = num_tnodes;
+	std::vector<int32_t> eptr(num_tnodes + 1, 0), eto, cdom(num_tnodes), lptr, lnodes, drv(num_nets, -1);
+	std::vector<float> etd, cdel(num_tnodes), cons;
+	std::vector<uint8_t> ty(num_tnodes);
+	for (int i = 0; i < num_tnodes; i++) {
+		eptr[i + 1] = eptr[i] + tnode[i].num_edges;
+		for (int k = 0; k < tnode[i].num_edges; k++) { eto.push_back(tnode[i].out_edges[k].to_node); etd.push_back(tnode[i].out_edges[k].Tdel); }
+		ty[i] = (uint8_t)tnode[i].type; cdom[i] = tnode[i].clock_domain; cdel[i] = tnode[i].clock_delay;
+		if (tnode[i].type == TN_CB_OPIN) {
+			int iblk, inet;
+			get_tnode_block_and_output_net(i, &iblk, &inet);
+			if (inet >= 0 && inet < num_nets) drv[inet] = i;
+		}
+	}
+	lptr.push_back(0);
+	for (int lv = 0; lv < num_tnode_levels; lv++) {
+		for (int k = 0; k < tnodes_at_level[lv].nelem; k++) lnodes.push_back(tnodes_at_level[lv].list[k]);
+		lptr.push_back((int32_t)lnodes.size());
+	}
+	const int C = g_sdc ? g_sdc->num_constrained_clocks : 0;
+	for (int i = 0; i < C; i++) for (int j = 0; j < C; j++) cons.push_back(g_sdc->domain_constraint[i][j]);
+	if (g_sdc && g_sdc->num_cf_constraints > 0) fprintf(stderr, "PF_REF warning: clock-to-flipflop override constraints are not exported\n");
+	g.num_tedges = (int32_t)eto.size();
+	g.edge_ptr = eptr.data(); g.edge_to = eto.data(); g.edge_Tdel = etd.data(); g.type = ty.data();
+	g.clock_domain = cdom.data(); g.clock_delay = cdel.data();
+	g.num_levels = num_tnode_levels; g.level_ptr = lptr.data(); g.level_nodes = lnodes.data();
+	g.num_domains = C; g.constraint = cons.data();
+	g.num_nets = num_nets; g.net_driver = drv.data();
+	char msg[256];
+	int rc = pf_timing_graph_check(&g, g_net_ptr.data(), msg, sizeof(msg));
+	if (rc != 0) { fprintf(stderr, "PF_REF timing graph export is inconsistent: %s\n", msg); exit(2); }
+	rc = pf_timing_graph_write(path, &g);
+	fprintf(stderr, "PF_REF wrote timing graph %s: %d tnodes, %d tedges, %d levels, %d clock domains (rc %d)\n", path, g.num_tnodes, g.num_tedges,
+			g.num_levels, g.num_domains, rc);
+}
+
+static void export_sta_vectors(const char *path) {
+	pf_sta_vectors v;
+	memset(&v, 0, sizeof(v));
+	v.num_terminals = g_net_ptr[num_nets];
+	v.num_calls = (int32_t)g_sta_cpd.size();
+	if ((size_t)v.num_calls * v.num_terminals != g_sta_crit.size() || g_sta_crit.size() != g_sta_delay.size()) {
+		fprintf(stderr, "PF_REF STA capture is inconsistent (%zu delays, %zu crits, %d calls)\n", g_sta_delay.size(), g_sta_crit.size(), v.num_calls);
+		exit(2);
+	}
+	v.net_delay = g_sta_delay.data(); v.crit = g_sta_crit.data(); v.cpd = g_sta_cpd.data();
+	int rc = pf_sta_vectors_write(path, &v);
+	fprintf(stderr, "PF_REF wrote STA vectors %s: %d calls x %d terminals (rc %d)\n", path, v.num_calls, v.num_terminals, rc);
+}
+
 boolean pf_hook_try_timing_driven_route(struct s_router_opts router_opts, float **net_delay, t_slack *slacks,
 		t_ivec **clb_opins_used_locally, boolean timing_analysis_enabled) {
 	const char *dp = getenv("PF_DUMP_PROBLEM"), *dr = getenv("PF_DUMP_RESULT");
 	if (dp) export_problem(dp, router_opts, timing_analysis_enabled, clb_opins_used_locally);
 	build_net_ptr();
 	g_iter = 0; g_stats.clear(); g_crit.clear(); g_iter_time.clear();
+	g_sta_delay.clear(); g_sta_crit.clear(); g_sta_cpd.clear();
+	if (getenv("PF_DUMP_TGRAPH") && timing_analysis_enabled && !g_inject) export_timing_graph(getenv("PF_DUMP_TGRAPH"));
 	/* criticalities of iteration 1 (route_timing.c:116-128) */
 	{
 		float v = timing_analysis_enabled ? 1.f : 0.f;
@@ -296,6 +368,7 @@ boolean pf_hook_try_timing_driven_route(struct s_router_opts router_opts, float 
 	}
 	report_times(ok, total);
 	if (dr) export_result(dr, ok, net_delay);
+	if (getenv("PF_DUMP_STA") && timing_analysis_enabled && !g_inject) export_sta_vectors(getenv("PF_DUMP_STA"));
 	return ok;
 }
 

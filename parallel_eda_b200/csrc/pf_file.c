@@ -213,3 +213,133 @@ void pf_result_free(pf_result *r) {
 	free(r->net_delay); free(r->occ); free(r->iter_stats); free(r->iter_crit);
 	memset(r, 0, sizeof(*r));
 }
+
+/* ------------------------------------------------------------------ timing graph / STA vectors */
+static const char TIMG_MAGIC[8] = { 'P', 'F', 'T', 'I', 'M', 'G', '0', '1' };
+static const char STAV_MAGIC[8] = { 'P', 'F', 'S', 'T', 'A', 'V', '0', '1' };
+
+int pf_timing_graph_write(const char *path, const pf_timing_graph *g) {
+	int rc = 0;
+	int32_t hdr[16];
+	FILE *f = fopen(path, "wb");
+	if (!f) return PF_EIO;
+	memset(hdr, 0, sizeof(hdr));
+	hdr[0] = g->num_tnodes; hdr[1] = g->num_tedges; hdr[2] = g->num_levels; hdr[3] = g->num_domains; hdr[4] = g->num_nets;
+	if ((rc = wr(f, TIMG_MAGIC, 8)) != 0) goto done;
+	if ((rc = wr(f, hdr, sizeof(hdr))) != 0) goto done;
+	W(g->edge_ptr, (size_t)g->num_tnodes + 1);
+	W(g->edge_to, g->num_tedges); W(g->edge_Tdel, g->num_tedges);
+	W(g->type, g->num_tnodes); W(g->clock_domain, g->num_tnodes); W(g->clock_delay, g->num_tnodes);
+	W(g->level_ptr, (size_t)g->num_levels + 1); W(g->level_nodes, g->num_tnodes);
+	W(g->constraint, (size_t)g->num_domains * (size_t)g->num_domains);
+	W(g->net_driver, g->num_nets);
+done:
+	if (fclose(f) != 0 && rc == 0) rc = PF_EIO;
+	return rc;
+}
+
+int pf_timing_graph_read(const char *path, pf_timing_graph *g) {
+	int rc = 0;
+	int32_t hdr[16];
+	char magic[8];
+	FILE *f = fopen(path, "rb");
+	memset(g, 0, sizeof(*g));
+	if (!f) return PF_EIO;
+	if (fread(magic, 1, 8, f) != 8 || memcmp(magic, TIMG_MAGIC, 8) != 0) { rc = PF_EFORMAT; goto done; }
+	if (fread(hdr, 1, sizeof(hdr), f) != sizeof(hdr)) { rc = PF_EIO; goto done; }
+	g->num_tnodes = hdr[0]; g->num_tedges = hdr[1]; g->num_levels = hdr[2]; g->num_domains = hdr[3]; g->num_nets = hdr[4];
+	if (g->num_tnodes < 0 || g->num_tedges < 0 || g->num_levels < 0 || g->num_domains < 0 || g->num_nets < 0) { rc = PF_EFORMAT; goto done; }
+	R(g->edge_ptr, (size_t)g->num_tnodes + 1);
+	R(g->edge_to, g->num_tedges); R(g->edge_Tdel, g->num_tedges);
+	R(g->type, g->num_tnodes); R(g->clock_domain, g->num_tnodes); R(g->clock_delay, g->num_tnodes);
+	R(g->level_ptr, (size_t)g->num_levels + 1); R(g->level_nodes, g->num_tnodes);
+	R(g->constraint, (size_t)g->num_domains * (size_t)g->num_domains);
+	R(g->net_driver, g->num_nets);
+done:
+	fclose(f);
+	if (rc != 0) pf_timing_graph_free(g);
+	return rc;
+}
+
+void pf_timing_graph_free(pf_timing_graph *g) {
+	free(g->edge_ptr); free(g->edge_to); free(g->edge_Tdel); free(g->type); free(g->clock_domain); free(g->clock_delay);
+	free(g->level_ptr); free(g->level_nodes); free(g->constraint); free(g->net_driver);
+	memset(g, 0, sizeof(*g));
+}
+
+#define TFAIL(...) do { if (msg) snprintf(msg, (size_t)msg_len, __VA_ARGS__); return PF_EINVAL; } while (0)
+int pf_timing_graph_check(const pf_timing_graph *g, const int32_t *net_ptr, char *msg, int msg_len) {
+	int i, k, lv;
+	int32_t *level_of;
+	if (g->num_tnodes <= 0 || !g->edge_ptr || g->edge_ptr[0] != 0 || g->edge_ptr[g->num_tnodes] != g->num_tedges) TFAIL("edge_ptr does not span the edges");
+	if (g->num_levels <= 0 || g->level_ptr[0] != 0 || g->level_ptr[g->num_levels] != g->num_tnodes) TFAIL("level_ptr does not span the tnodes");
+	level_of = (int32_t *)malloc(sizeof(int32_t) * (size_t)g->num_tnodes);
+	if (!level_of) return PF_ENOMEM;
+	for (i = 0; i < g->num_tnodes; i++) level_of[i] = -1;
+	for (lv = 0; lv < g->num_levels; lv++) {
+		if (g->level_ptr[lv + 1] < g->level_ptr[lv]) { free(level_of); TFAIL("level_ptr not monotonic at level %d", lv); }
+		for (k = g->level_ptr[lv]; k < g->level_ptr[lv + 1]; k++) {
+			int n = g->level_nodes[k];
+			if (n < 0 || n >= g->num_tnodes || level_of[n] >= 0) { free(level_of); TFAIL("level list entry %d is not a fresh tnode", k); }
+			level_of[n] = lv;
+		}
+	}
+	for (i = 0; i < g->num_tnodes; i++) {
+		if (g->edge_ptr[i + 1] < g->edge_ptr[i]) { free(level_of); TFAIL("edge_ptr not monotonic at tnode %d", i); }
+		if (g->clock_domain[i] < -1 || g->clock_domain[i] >= g->num_domains) { free(level_of); TFAIL("tnode %d: clock domain %d", i, g->clock_domain[i]); }
+		for (k = g->edge_ptr[i]; k < g->edge_ptr[i + 1]; k++) {
+			int to = g->edge_to[k];
+			if (to < 0 || to >= g->num_tnodes || level_of[to] <= level_of[i]) { free(level_of); TFAIL("tedge %d of tnode %d does not lead to a later level", k, i); }
+		}
+	}
+	free(level_of);
+	for (i = 0; i < g->num_nets; i++) {
+		int d = g->net_driver[i];
+		if (d < -1 || d >= g->num_tnodes) TFAIL("net %d: driver tnode %d", i, d);
+		if (d >= 0 && net_ptr && g->edge_ptr[d + 1] - g->edge_ptr[d] != net_ptr[i + 1] - net_ptr[i] - 1)
+			TFAIL("net %d: driver tnode %d has %d out-edges, the net %d sinks", i, d, g->edge_ptr[d + 1] - g->edge_ptr[d], net_ptr[i + 1] - net_ptr[i] - 1);
+	}
+	return PF_OK;
+}
+
+int pf_sta_vectors_write(const char *path, const pf_sta_vectors *v) {
+	int rc = 0;
+	int32_t hdr[16];
+	FILE *f = fopen(path, "wb");
+	if (!f) return PF_EIO;
+	memset(hdr, 0, sizeof(hdr));
+	hdr[0] = v->num_terminals; hdr[1] = v->num_calls;
+	if ((rc = wr(f, STAV_MAGIC, 8)) != 0) goto done;
+	if ((rc = wr(f, hdr, sizeof(hdr))) != 0) goto done;
+	W(v->net_delay, (size_t)v->num_calls * (size_t)v->num_terminals);
+	W(v->crit, (size_t)v->num_calls * (size_t)v->num_terminals);
+	W(v->cpd, v->num_calls);
+done:
+	if (fclose(f) != 0 && rc == 0) rc = PF_EIO;
+	return rc;
+}
+
+int pf_sta_vectors_read(const char *path, pf_sta_vectors *v) {
+	int rc = 0;
+	int32_t hdr[16];
+	char magic[8];
+	FILE *f = fopen(path, "rb");
+	memset(v, 0, sizeof(*v));
+	if (!f) return PF_EIO;
+	if (fread(magic, 1, 8, f) != 8 || memcmp(magic, STAV_MAGIC, 8) != 0) { rc = PF_EFORMAT; goto done; }
+	if (fread(hdr, 1, sizeof(hdr), f) != sizeof(hdr)) { rc = PF_EIO; goto done; }
+	v->num_terminals = hdr[0]; v->num_calls = hdr[1];
+	if (v->num_terminals < 0 || v->num_calls < 0) { rc = PF_EFORMAT; goto done; }
+	R(v->net_delay, (size_t)v->num_calls * (size_t)v->num_terminals);
+	R(v->crit, (size_t)v->num_calls * (size_t)v->num_terminals);
+	R(v->cpd, v->num_calls);
+done:
+	fclose(f);
+	if (rc != 0) pf_sta_vectors_free(v);
+	return rc;
+}
+
+void pf_sta_vectors_free(pf_sta_vectors *v) {
+	free(v->net_delay); free(v->crit); free(v->cpd);
+	memset(v, 0, sizeof(*v));
+}

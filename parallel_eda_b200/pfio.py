@@ -208,3 +208,76 @@ def write_result(path: str, r: Result) -> None:
         f.write(np.ascontiguousarray(r.iter_stats, dtype=ITER_STATS_DT).tobytes())
         if ncrit:
             f.write(np.ascontiguousarray(r.iter_crit, dtype="<f4").tobytes())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# timing graph / STA golden vectors (include/pf_types.h: pf_timing_graph, pf_sta_vectors)
+TIMG_MAGIC = b"PFTIMG01"
+STAV_MAGIC = b"PFSTAV01"
+
+
+@dataclasses.dataclass
+class TimingGraph:
+    """Flat image of the reference's timing graph (tnode[] / tedge, timing/path_delay.c:328)."""
+    edge_ptr: np.ndarray       # [num_tnodes+1] int32
+    edge_to: np.ndarray        # [num_tedges] int32
+    edge_Tdel: np.ndarray      # [num_tedges] float32
+    type: np.ndarray           # [num_tnodes] uint8 (e_tnode_type)
+    clock_domain: np.ndarray   # [num_tnodes] int32
+    clock_delay: np.ndarray    # [num_tnodes] float32
+    level_ptr: np.ndarray      # [num_levels+1] int32
+    level_nodes: np.ndarray    # [num_tnodes] int32
+    constraint: np.ndarray     # [num_domains, num_domains] float32
+    net_driver: np.ndarray     # [num_nets] int32
+
+    @property
+    def num_tnodes(self) -> int:
+        return len(self.type)
+
+    @property
+    def num_levels(self) -> int:
+        return len(self.level_ptr) - 1
+
+
+@dataclasses.dataclass
+class StaVectors:
+    net_delay: np.ndarray      # [calls, num_terminals]
+    crit: np.ndarray           # [calls, num_terminals]
+    cpd: np.ndarray            # [calls] ns
+
+
+def _rd(f, path, dt, count):
+    dt = np.dtype(dt)
+    buf = f.read(count * dt.itemsize)
+    if len(buf) != count * dt.itemsize:
+        raise ValueError("%s: truncated" % path)
+    return np.frombuffer(buf, dtype=dt).copy()
+
+
+def read_timing_graph(path: str) -> TimingGraph:
+    with _open(path) as f:
+        if f.read(8) != TIMG_MAGIC:
+            raise ValueError("%s: not a PFTIMG01 file" % path)
+        n, e, lv, c, nets = struct.unpack("<16i", f.read(64))[:5]
+        return TimingGraph(_rd(f, path, "<i4", n + 1), _rd(f, path, "<i4", e), _rd(f, path, "<f4", e), _rd(f, path, "u1", n),
+                           _rd(f, path, "<i4", n), _rd(f, path, "<f4", n), _rd(f, path, "<i4", lv + 1), _rd(f, path, "<i4", n),
+                           _rd(f, path, "<f4", c * c).reshape(c, c), _rd(f, path, "<i4", nets))
+
+
+def write_timing_graph(path: str, g: TimingGraph) -> None:
+    c = int(g.constraint.shape[0])
+    hdr = [g.num_tnodes, len(g.edge_to), g.num_levels, c, len(g.net_driver)] + [0] * 11
+    with open(path, "wb") as f:
+        f.write(TIMG_MAGIC)
+        f.write(struct.pack("<16i", *hdr))
+        for a, dt in ((g.edge_ptr, "<i4"), (g.edge_to, "<i4"), (g.edge_Tdel, "<f4"), (g.type, "u1"), (g.clock_domain, "<i4"),
+                      (g.clock_delay, "<f4"), (g.level_ptr, "<i4"), (g.level_nodes, "<i4"), (g.constraint, "<f4"), (g.net_driver, "<i4")):
+            f.write(np.ascontiguousarray(a, dtype=dt).tobytes())
+
+
+def read_sta_vectors(path: str) -> StaVectors:
+    with _open(path) as f:
+        if f.read(8) != STAV_MAGIC:
+            raise ValueError("%s: not a PFSTAV01 file" % path)
+        T, K = struct.unpack("<16i", f.read(64))[:2]
+        return StaVectors(_rd(f, path, "<f4", K * T).reshape(K, T), _rd(f, path, "<f4", K * T).reshape(K, T), _rd(f, path, "<f4", K))

@@ -14,9 +14,9 @@ python "$ROOT/tests/fixtures/gen_blif.py" hub.blif --luts 900 --pis 24 --window 
 for c in toy:64 mid:200 hub:90; do
   n=${c%%:*}; w=${c##*:}
   "$REF" flow k6_N10_like.xml $n --nodisp --pack --place > /dev/null
-  PF_DUMP_PROBLEM=${n}_w$w.pfp PF_DUMP_RESULT=${n}_w$w.pfr "$REF" flow k6_N10_like.xml $n --nodisp --route --route_chan_width $w > /dev/null
+  PF_DUMP_PROBLEM=${n}_w$w.pfp PF_DUMP_RESULT=${n}_w$w.pfr PF_DUMP_TGRAPH=${n}_w$w.pftg PF_DUMP_STA=${n}_w$w.pfsta "$REF" flow k6_N10_like.xml $n --nodisp --route --route_chan_width $w > /dev/null
   "$REF" inject ${n}_w$w.pfp --result ${n}_w${w}_nt.pfr > /dev/null
-  for f in ${n}_w$w.pfp ${n}_w$w.pfr ${n}_w${w}_nt.pfr; do xz -9 -c $f > "$HERE/$f.xz"; done
+  for f in ${n}_w$w.pfp ${n}_w$w.pfr ${n}_w${w}_nt.pfr ${n}_w$w.pftg ${n}_w$w.pfsta; do xz -9 -c $f > "$HERE/$f.xz"; done
 done
 cp toy.blif toy.place "$HERE/"; xz -9 -c toy.net > "$HERE/toy.net.xz"
 echo "goldens written to $HERE"

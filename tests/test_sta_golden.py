@@ -1,0 +1,59 @@
+"""Pins the oracle's static timing analysis (oracle/pf_oracle.c: pf_oracle_sta) to the UNMODIFIED reference.
+
+tests/golden/*.pftg.xz is the reference's own timing graph (tnode[] / tedge / levels / constraints, exported by
+oracle/ref_build/harness.cxx) and *.pfsta.xz every (net_delay in, timing_criticality out, critical path delay) of the
+do_timing_analysis calls the reference made while routing that fixture timing-driven (tests/golden/make_golden.sh).
+The restatement must reproduce every criticality and critical path delay BIT FOR BIT."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from parallel_eda_b200 import pfio
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class _TG(C.Structure):
+    _fields_ = [("num_tnodes", C.c_int32), ("num_tedges", C.c_int32), ("edge_ptr", C.c_void_p), ("edge_to", C.c_void_p),
+                ("edge_Tdel", C.c_void_p), ("type", C.c_void_p), ("clock_domain", C.c_void_p), ("clock_delay", C.c_void_p),
+                ("num_levels", C.c_int32), ("level_ptr", C.c_void_p), ("level_nodes", C.c_void_p), ("num_domains", C.c_int32),
+                ("constraint", C.c_void_p), ("num_nets", C.c_int32), ("net_driver", C.c_void_p)]
+
+
+def c_timing_graph(g: pfio.TimingGraph):
+    keep = [np.ascontiguousarray(a) for a in (g.edge_ptr, g.edge_to, g.edge_Tdel, g.type, g.clock_domain, g.clock_delay,
+                                               g.level_ptr, g.level_nodes, g.constraint, g.net_driver)]
+    p = [a.ctypes.data for a in keep]
+    t = _TG(g.num_tnodes, len(g.edge_to), p[0], p[1], p[2], p[3], p[4], p[5], g.num_levels, p[6], p[7], int(g.constraint.shape[0]),
+            p[8], len(g.net_driver), p[9])
+    return t, keep
+
+
+@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200"])
+def test_oracle_sta_reproduces_reference_bit_for_bit(name, oracle_lib):
+    lib = C.CDLL(oracle_lib)
+    lib.pf_oracle_sta.argtypes = [C.POINTER(_TG), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    lib.pf_timing_graph_check.argtypes = [C.POINTER(_TG), C.c_void_p, C.c_char_p, C.c_int]
+    p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
+    g = pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz"))
+    v = pfio.read_sta_vectors(os.path.join(G, name + ".pfsta.xz"))
+    tg, keep = c_timing_graph(g)
+    net_ptr = np.ascontiguousarray(p.net_ptr, dtype=np.int32)
+    msg = C.create_string_buffer(256)
+    assert lib.pf_timing_graph_check(C.byref(tg), net_ptr.ctypes.data, msg, 256) == 0, msg.value
+    assert v.net_delay.shape[1] == p.num_terminals and len(g.net_driver) == p.num_nets
+    calls = range(v.net_delay.shape[0]) if name != "mid_w200" else (0, 7, v.net_delay.shape[0] - 1)
+    for k in calls:
+        crit = np.zeros(p.num_terminals, np.float32)
+        cpd = C.c_float(0)
+        d = np.ascontiguousarray(v.net_delay[k])
+        assert lib.pf_oracle_sta(C.byref(tg), net_ptr.ctypes.data, d.ctypes.data, crit.ctypes.data, C.byref(cpd)) == 0
+        assert np.array_equal(crit.view(np.uint32), v.crit[k].view(np.uint32)), "call %d: %d criticalities differ" % (
+            k, int((crit.view(np.uint32) != v.crit[k].view(np.uint32)).sum()))
+        assert np.float32(cpd.value).view(np.uint32) == v.cpd[k].view(np.uint32)
+    # and the analysis is what the golden routing's per-iteration criticalities came from
+    gold = pfio.read_result(os.path.join(G, name + ".pfr.xz"))
+    routed = np.repeat(p.net_is_global == 0, np.diff(p.net_ptr))
+    assert np.array_equal(gold.iter_crit[1][routed], v.crit[0][routed])
