@@ -142,6 +142,20 @@ int pf_comm_events(pf_router *r, void **dev_events, int64_t *count);
 int pf_comm_apply_events(pf_router *r, const void *dev_events, int64_t count);
 void *pf_comm_net_delay_ptr(pf_router *r);
 
+/* ---- Device static timing analysis: what the reference runs on the host between iterations,
+ * load_timing_graph_net_delays + do_timing_analysis + get_critical_path_delay (route_timing.c:295-309;
+ * timing/path_delay.c:479, 2258, 3791), on the flat timing graph of pf_types.h.  The criticalities are
+ * bit-identical to the reference's (tests/test_sta_golden.py, tests/test_gpu_sta.py). */
+typedef struct pf_sta pf_sta;
+int pf_sta_create(const pf_timing_graph *g, const pf_problem *p, const pf_config *cfg, pf_sta **out);
+void pf_sta_destroy(pf_sta *s);
+/* host buffers: net_delay[num_terminals] in, crit[num_terminals] out, *cpd_ns = critical path delay in ns */
+int pf_sta_analyze(pf_sta *s, const float *net_delay, float *crit, float *cpd_ns);
+/* device buffers (e.g. a router's own delay and criticality vectors: nothing crosses PCIe) */
+int pf_sta_analyze_device(pf_sta *s, const void *dev_net_delay, void *dev_crit, float *cpd_ns);
+/* try_timing_driven_route with the analysis on the device: no host callback, no per-iteration copies */
+int pf_try_timing_driven_route_sta(const pf_problem *p, const pf_timing_graph *g, const pf_config *cfg, pf_result *out);
+
 /* The whole of try_timing_driven_route (single GPU): iterate until legal or out of iterations.
  * sta may be NULL when opts.timing_analysis_enabled == 0. */
 int pf_try_timing_driven_route(const pf_problem *p, const pf_config *cfg, pf_sta_fn sta, void *user, pf_result *out);

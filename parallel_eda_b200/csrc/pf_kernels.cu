@@ -13,6 +13,7 @@
  */
 #include "pf_backend.h"
 #include "pf_device.cuh"
+#include "pf_sta_device.cuh"
 
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -307,6 +308,44 @@ __global__ void pf_compact_kernel(const PfTreeNode *src, PfTreeNode *dst, PfNetL
 	}
 }
 
+/* ------------------------------------------------------------------ static timing analysis (pf_sta_device.cuh) */
+__global__ void pf_sta_load_kernel(PfStaDev S, const float *net_delay) {
+	for (int t = (int)(blockIdx.x * blockDim.x + threadIdx.x); t < S.num_terminals; t += (int)(gridDim.x * blockDim.x)) pf_sta_load_delay(S, t, net_delay);
+}
+
+__global__ void pf_sta_begin_pair_kernel(PfStaDev S, float *stat) {
+	const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i == 0) { stat[0] = (float)PF_STA_HUGE_NEG; stat[1] = (float)PF_STA_HUGE_NEG; stat[2] = (float)PF_STA_HUGE_POS; }
+	for (int n = i; n < S.num_tnodes; n += (int)(gridDim.x * blockDim.x)) pf_sta_reset_node(S, n);
+}
+
+/* A run of consecutive levels in ONE CTA: timing graphs are hundreds of levels deep and most levels hold a few
+ * hundred tnodes, so a launch per level would be all launch latency; __syncthreads() is the level barrier. */
+#define PF_STA_CTA 1024
+__global__ void __launch_bounds__(PF_STA_CTA) pf_sta_levels_kernel(PfStaDev S, int forward, int lv_begin, int lv_end, int domain,
+		float constraint, float *stat) {
+	for (int s = 0; s < lv_end - lv_begin; s++) {
+		const int lv = forward ? lv_begin + s : lv_end - 1 - s;
+		for (int k = S.level_ptr[lv] + (int)threadIdx.x; k < S.level_ptr[lv + 1]; k += PF_STA_CTA) {
+			const int n = S.level_nodes[k];
+			if (forward) pf_sta_forward_node(S, n, lv, domain, stat); else pf_sta_backward_node(S, n, domain, constraint, stat);
+		}
+		__syncthreads();
+	}
+}
+
+/* one wide level over the whole GPU */
+__global__ void pf_sta_level_kernel(PfStaDev S, int forward, int lv, int domain, float constraint, float *stat) {
+	for (int k = S.level_ptr[lv] + (int)(blockIdx.x * blockDim.x + threadIdx.x); k < S.level_ptr[lv + 1]; k += (int)(gridDim.x * blockDim.x)) {
+		const int n = S.level_nodes[k];
+		if (forward) pf_sta_forward_node(S, n, lv, domain, stat); else pf_sta_backward_node(S, n, domain, constraint, stat);
+	}
+}
+
+__global__ void pf_sta_update_kernel(PfStaDev S, float constraint, const float *stat, float *crit) {
+	for (int t = (int)(blockIdx.x * blockDim.x + threadIdx.x); t < S.num_terminals; t += (int)(gridDim.x * blockDim.x)) pf_sta_update_terminal(S, t, constraint, stat, crit);
+}
+
 /* ------------------------------------------------------------------ launchers */
 int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	if (warps_per_block < 1) warps_per_block = 1;
@@ -401,5 +440,34 @@ int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num
 	if (num_nets <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
 	pf_build_traces_kernel<<<(num_nets + 127) / 128, 128, 0, g_stream>>>(pool, loc, num_nets, len, tptr, trace_node, trace_switch, d_wl, trace_term, ptc, nx);
+	return ev_end();
+}
+
+/* ------------------------------------------------------------------ static timing analysis launchers */
+int pfb_sta_load(const PfStaDev *S, const float *dev_net_delay) {
+	if (S->num_terminals <= 0) return 0;
+	if (ev_begin(2) != 0) return -1;
+	pf_sta_load_kernel<<<stream_grid(S->num_terminals), 256, 0, g_stream>>>(*S, dev_net_delay);
+	return ev_end();
+}
+
+int pfb_sta_begin_pair(const PfStaDev *S, float *stat) {
+	if (ev_begin(2) != 0) return -1;
+	pf_sta_begin_pair_kernel<<<stream_grid(S->num_tnodes), 256, 0, g_stream>>>(*S, stat);
+	return ev_end();
+}
+
+int pfb_sta_sweep(const PfStaDev *S, int forward, int lv_begin, int lv_end, int spread, int domain, float constraint, float *stat) {
+	if (lv_end <= lv_begin) return 0;
+	if (ev_begin(2) != 0) return -1;
+	if (spread) pf_sta_level_kernel<<<stream_grid(S->num_tnodes), 256, 0, g_stream>>>(*S, forward, lv_begin, domain, constraint, stat);
+	else pf_sta_levels_kernel<<<1, PF_STA_CTA, 0, g_stream>>>(*S, forward, lv_begin, lv_end, domain, constraint, stat);
+	return ev_end();
+}
+
+int pfb_sta_update(const PfStaDev *S, float constraint, const float *stat, float *dev_crit) {
+	if (S->num_terminals <= 0) return 0;
+	if (ev_begin(2) != 0) return -1;
+	pf_sta_update_kernel<<<stream_grid(S->num_terminals), 256, 0, g_stream>>>(*S, constraint, stat, dev_crit);
 	return ev_end();
 }

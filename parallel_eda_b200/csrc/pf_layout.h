@@ -118,4 +118,20 @@ struct PfParams {
 	PfStats *stats;
 };
 
+/* device image of the timing graph for the static timing analysis (pf_sta_device.cuh, pf_sta.cpp) */
+struct PfStaDev {
+	int num_tnodes, num_terminals, num_levels;
+	const int *edge_ptr, *edge_to;           /* out-edges (reference order) */
+	float *Tdel;                             /* [num_tedges] working copy: static delays + this call's net delays */
+	const int *in_ptr, *in_from, *in_edge;   /* in-edges: source tnode and index of the edge in the out-edge arrays */
+	const unsigned char *type;
+	const int *clock_domain;
+	const float *clock_delay;
+	const int *level_ptr, *level_nodes;
+	const int *term_edge;                    /* [num_terminals] out-edge index the terminal's delay belongs to, -1 none */
+	const int *term_driver;                  /* [num_terminals] driver tnode of the terminal's net, -1 none */
+	float *T_arr, *T_req;
+	float *stat;                             /* per domain pair [3]: max_Tarr, cpd, least_slack */
+};
+
 #endif /* PF_LAYOUT_H */

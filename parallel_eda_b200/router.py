@@ -79,6 +79,25 @@ class Config(C.Structure):
                 ("defer_graph", C.c_int32)]
 
 
+class _TimingGraph(C.Structure):
+    """pf_timing_graph (include/pf_types.h)."""
+    _fields_ = [("num_tnodes", C.c_int32), ("num_tedges", C.c_int32), ("edge_ptr", C.c_void_p), ("edge_to", C.c_void_p),
+                ("edge_Tdel", C.c_void_p), ("type", C.c_void_p), ("clock_domain", C.c_void_p), ("clock_delay", C.c_void_p),
+                ("num_levels", C.c_int32), ("level_ptr", C.c_void_p), ("level_nodes", C.c_void_p), ("num_domains", C.c_int32),
+                ("constraint", C.c_void_p), ("num_nets", C.c_int32), ("net_driver", C.c_void_p)]
+
+
+class _TimingGraphHolder:
+    def __init__(self, g: "pfio.TimingGraph"):
+        self.keep = [np.ascontiguousarray(a, dtype=dt) for a, dt in (
+            (g.edge_ptr, np.int32), (g.edge_to, np.int32), (g.edge_Tdel, np.float32), (g.type, np.uint8), (g.clock_domain, np.int32),
+            (g.clock_delay, np.float32), (g.level_ptr, np.int32), (g.level_nodes, np.int32), (g.constraint, np.float32),
+            (g.net_driver, np.int32))]
+        q = [a.ctypes.data for a in self.keep]
+        self.c = _TimingGraph(g.num_tnodes, len(g.edge_to), q[0], q[1], q[2], q[3], q[4], q[5], g.num_levels, q[6], q[7],
+                              int(g.constraint.shape[0]), q[8], len(g.net_driver), q[9])
+
+
 class Timing(C.Structure):
     _fields_ = [("route_kernel_ms", C.c_double), ("update_kernel_ms", C.c_double), ("aux_kernel_ms", C.c_double),
                 ("route_launches", C.c_int64), ("update_launches", C.c_int64), ("aux_launches", C.c_int64),
@@ -123,6 +142,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing), C.c_int]
     lib.pf_timer_start.argtypes = [C.c_void_p]
     lib.pf_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.pf_sta_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.pf_sta_destroy.argtypes = [C.c_void_p]
+    lib.pf_sta_destroy.restype = None
+    lib.pf_sta_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    lib.pf_sta_analyze_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    lib.pf_try_timing_driven_route_sta.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Config), C.c_void_p]
     lib.pf_comm_graph_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p * 3), C.POINTER(C.c_int64 * 3)]
     lib.pf_comm_graph_ready.argtypes = [C.c_void_p]
     lib.pf_comm_events.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
@@ -326,6 +351,44 @@ class Router:
         return int(self.lib.pf_comm_net_delay_ptr(self._h))
 
 
+class Sta:
+    """Device-resident timing graph: the static timing analysis the reference runs on the host between router
+    iterations (load_timing_graph_net_delays + do_timing_analysis, route_timing.c:295-309), on the GPU."""
+
+    def __init__(self, graph: "pfio.TimingGraph", problem: pfio.Problem, config: Optional[Config] = None, lib_path: Optional[str] = None):
+        self.lib = load_library(lib_path)
+        self._g = _TimingGraphHolder(graph)
+        self._p = _ProblemHolder(problem)
+        self.num_terminals = problem.num_terminals
+        cfg = config if config is not None else default_config(self.lib)
+        h = C.c_void_p()
+        rc = self.lib.pf_sta_create(C.byref(self._g.c), C.byref(self._p.c), C.byref(cfg), C.byref(h))
+        if rc != PF_OK:
+            raise RouterError(rc, self.lib.pf_last_error().decode())
+        self._h = h
+
+    def analyze(self, net_delay: np.ndarray):
+        """net_delay[num_terminals] -> (timing_criticality[num_terminals], critical path delay in ns)."""
+        d = np.ascontiguousarray(net_delay, dtype=np.float32)
+        crit = np.zeros(self.num_terminals, np.float32)
+        cpd = C.c_float(0)
+        rc = self.lib.pf_sta_analyze(self._h, d.ctypes.data, crit.ctypes.data, C.byref(cpd))
+        if rc != PF_OK:
+            raise RouterError(rc, self.lib.pf_last_error().decode())
+        return crit, float(cpd.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.pf_sta_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def default_config(lib=None, **kw) -> Config:
     lib = lib or load_library()
     c = Config()
@@ -339,16 +402,24 @@ StaFn = Callable[[int, np.ndarray], "tuple[np.ndarray, float]"]
 
 
 def try_timing_driven_route(problem: pfio.Problem, config: Optional[Config] = None, sta: Optional[StaFn] = None,
-                            lib_path: Optional[str] = None) -> pfio.Result:
+                            lib_path: Optional[str] = None, timing_graph: "Optional[pfio.TimingGraph]" = None) -> pfio.Result:
     """The whole PathFinder loop on one GPU (reference route_timing.c:85-343).
 
     ``sta(iters_done, net_delay) -> (timing_criticality[num_terminals], crit_path_delay)`` stands in for the
-    reference's load_timing_graph_net_delays + do_timing_analysis (route_timing.c:295-309)."""
+    reference's load_timing_graph_net_delays + do_timing_analysis (route_timing.c:295-309); with ``timing_graph``
+    the analysis runs on the device instead (pf_try_timing_driven_route_sta) and nothing is copied per iteration."""
     lib = load_library(lib_path)
     holder = _ProblemHolder(problem)
     if config is None:
         config = default_config(lib)
     T = problem.num_terminals
+    if timing_graph is not None:
+        tg = _TimingGraphHolder(timing_graph)
+        cr = _Result()
+        rc = lib.pf_try_timing_driven_route_sta(C.byref(holder.c), C.byref(tg.c), C.byref(config), C.byref(cr))
+        if rc != PF_OK:
+            raise RouterError(rc, lib.pf_last_error().decode())
+        return _take_result(lib, cr, T)
 
     def _cb(_user, iters_done, nd, crit, cpd):
         delays = np.ctypeslib.as_array(nd, shape=(max(T, 1),))[:T]

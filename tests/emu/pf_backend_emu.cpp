@@ -5,6 +5,7 @@
  */
 #include "pf_backend.h"
 #include "pf_device.cuh"
+#include "pf_sta_device.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -144,6 +145,36 @@ int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num
 		*d_wl += (unsigned long long)pf_trace_of_net(pool + l.off, l.count, trace_node + tptr[i], trace_switch + tptr[i],
 				trace_term ? trace_term + tptr[i] : NULL, ptc, nx, (unsigned)(i + 1));
 	}
+	g_times.aux_launches++;
+	return 0;
+}
+
+/* ---- static timing analysis: the same per-element bodies, run serially */
+int pfb_sta_load(const PfStaDev *S, const float *net_delay) {
+	for (int t = 0; t < S->num_terminals; t++) pf_sta_load_delay(*S, t, net_delay);
+	g_times.aux_launches++;
+	return 0;
+}
+int pfb_sta_begin_pair(const PfStaDev *S, float *stat) {
+	stat[0] = (float)PF_STA_HUGE_NEG; stat[1] = (float)PF_STA_HUGE_NEG; stat[2] = (float)PF_STA_HUGE_POS;
+	for (int n = 0; n < S->num_tnodes; n++) pf_sta_reset_node(*S, n);
+	g_times.aux_launches++;
+	return 0;
+}
+int pfb_sta_sweep(const PfStaDev *S, int forward, int lv_begin, int lv_end, int spread, int domain, float constraint, float *stat) {
+	(void)spread;
+	for (int s = 0; s < lv_end - lv_begin; s++) {
+		const int lv = forward ? lv_begin + s : lv_end - 1 - s;
+		for (int k = S->level_ptr[lv]; k < S->level_ptr[lv + 1]; k++) {
+			const int n = S->level_nodes[k];
+			if (forward) pf_sta_forward_node(*S, n, lv, domain, stat); else pf_sta_backward_node(*S, n, domain, constraint, stat);
+		}
+	}
+	g_times.aux_launches++;
+	return 0;
+}
+int pfb_sta_update(const PfStaDev *S, float constraint, const float *stat, float *crit) {
+	for (int t = 0; t < S->num_terminals; t++) pf_sta_update_terminal(*S, t, constraint, stat, crit);
 	g_times.aux_launches++;
 	return 0;
 }

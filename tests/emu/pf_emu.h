@@ -120,6 +120,8 @@ PF_DEV int pf_atomic_add_i(int *p, int v) { int o = *p; *p = o + v; return o; }
 PF_DEV unsigned long long pf_atomic_add_ull(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 PF_DEV int pf_atomic_or_i(int *p, int v) { int o = *p; *p = o | v; return o; }
 PF_DEV int pf_atomic_min_i(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
+PF_DEV void pf_atomic_max_f(float *p, float v) { if (v > *p) *p = v; }
+PF_DEV void pf_atomic_min_f(float *p, float v) { if (v < *p) *p = v; }
 PF_DEV pf_u4 pf_ld_cg_u4(const void *p) { pf_u4 v; memcpy(&v, p, 16); return v; }   /* L2-coherent load */
 PF_DEV pf_u4 pf_ld_u4(const void *p) { pf_u4 v; memcpy(&v, p, 16); return v; }
 struct pf_u8 { unsigned a, b, c, d, e, f, g, h; };

@@ -1,0 +1,46 @@
+"""GPU tests (-m gpu) of the device static timing analysis: bit-exact criticalities against the
+golden vectors of the UNMODIFIED reference's do_timing_analysis, and the router with the analysis in the loop."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from parallel_eda_b200 import check_route, pfio, router
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200"])
+def test_device_sta_bit_identical_to_reference(name):
+    p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
+    g = pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz"))
+    v = pfio.read_sta_vectors(os.path.join(G, name + ".pfsta.xz"))
+    s = router.Sta(g, p)
+    for k in range(v.net_delay.shape[0]):
+        crit, cpd = s.analyze(v.net_delay[k])
+        assert np.array_equal(crit.view(np.uint32), v.crit[k].view(np.uint32)), "call %d" % k
+        assert np.float32(cpd).view(np.uint32) == v.cpd[k].view(np.uint32)
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["mid_w200", "hub_w90"])
+def test_route_with_device_sta(name):
+    p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
+    p.opts["timing_analysis_enabled"] = 1
+    p.opts["max_router_iterations"] = 150
+    g = pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz"))
+    gold = pfio.read_result(os.path.join(G, name + ".pfr.xz"))
+    t = time.perf_counter()
+    r = router.try_timing_driven_route(p, timing_graph=g)
+    dt = time.perf_counter() - t
+    assert r.success == 1
+    m = check_route.check_route(p, r)
+    assert m["overused"] == 0
+    # critical path delay of the last analysis against the reference's own (same circuit, same placement)
+    cpd = float(r.iter_stats["crit_path_delay"][-2]); ref = float(gold.iter_stats["crit_path_delay"][-2])
+    print("%s: %d iterations (reference %d), cpd %.3f ns (reference %.3f), wirelength x%.3f, %.3f s" % (
+        name, r.iterations, gold.iterations, cpd, ref, r.total_wirelength / gold.total_wirelength, dt))
+    tol = 0.12 if name == "hub_w90" else 0.08
+    assert abs(cpd - ref) <= tol * ref and r.total_wirelength <= (1 + tol) * gold.total_wirelength

@@ -57,3 +57,36 @@ def test_oracle_sta_reproduces_reference_bit_for_bit(name, oracle_lib):
     gold = pfio.read_result(os.path.join(G, name + ".pfr.xz"))
     routed = np.repeat(p.net_is_global == 0, np.diff(p.net_ptr))
     assert np.array_equal(gold.iter_crit[1][routed], v.crit[0][routed])
+
+
+@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200"])
+def test_device_sta_code_on_the_emulator_is_bit_identical(name, emu_lib):
+    """The device analysis (pf_sta_device.cuh behind pf_sta_analyze), compiled for the CPU emulator backend:
+    level-synchronous pull over in-edges instead of the reference's push along out-edges — same floats."""
+    from parallel_eda_b200 import router
+    p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
+    g = pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz"))
+    v = pfio.read_sta_vectors(os.path.join(G, name + ".pfsta.xz"))
+    s = router.Sta(g, p, router.default_config(router.load_library(emu_lib)), lib_path=emu_lib)
+    for k in ((0, v.net_delay.shape[0] - 1) if name == "mid_w200" else range(v.net_delay.shape[0])):
+        crit, cpd = s.analyze(v.net_delay[k])
+        assert np.array_equal(crit.view(np.uint32), v.crit[k].view(np.uint32))
+        assert np.float32(cpd).view(np.uint32) == v.cpd[k].view(np.uint32)
+    s.close()
+
+
+def test_route_with_device_sta_on_the_emulator(emu_lib):
+    """pf_try_timing_driven_route_sta: the router with the analysis in the loop (no host callback)."""
+    from parallel_eda_b200 import router, check_route
+    p = pfio.read_problem(os.path.join(G, "toy_w64.pfp.xz"))
+    p.opts["timing_analysis_enabled"] = 1
+    p.opts["max_router_iterations"] = 150
+    g = pfio.read_timing_graph(os.path.join(G, "toy_w64.pftg.xz"))
+    gold = pfio.read_result(os.path.join(G, "toy_w64.pfr.xz"))
+    r = router.try_timing_driven_route(p, router.default_config(router.load_library(emu_lib), num_slots=8, big_slots=1), lib_path=emu_lib,
+                                       timing_graph=g)
+    assert r.success == 1
+    check_route.check_route(p, r)
+    cpd = float(r.iter_stats["crit_path_delay"][-2])            # the last analysis ran before the final iteration
+    ref = float(gold.iter_stats["crit_path_delay"][-2])
+    assert abs(cpd - ref) <= 0.10 * ref and r.total_wirelength <= 1.12 * gold.total_wirelength
