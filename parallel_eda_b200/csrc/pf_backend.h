@@ -77,7 +77,8 @@ struct PfStaDev;
 int pfb_sta_load(const PfStaDev *S, const float *dev_net_delay);
 /* T_arr / T_req of every tnode and the three statistics of a domain pair back to "unset" */
 int pfb_sta_begin_pair(const PfStaDev *S, float *stat);
-/* levels [lv_begin, lv_end) in ascending (forward) or descending order; spread != 0: one level, many CTAs */
+/* levels [lv_begin, lv_end) in ascending (forward) or descending order; spread != 0: ONE level of that many
+ * tnodes, spread over many CTAs */
 int pfb_sta_sweep(const PfStaDev *S, int forward, int lv_begin, int lv_end, int spread, int domain, float constraint, float *stat);
 int pfb_sta_update(const PfStaDev *S, float constraint, const float *stat, float *dev_crit);
 

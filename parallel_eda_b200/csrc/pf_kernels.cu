@@ -443,31 +443,33 @@ int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num
 	return ev_end();
 }
 
-/* ------------------------------------------------------------------ static timing analysis launchers */
+/* ------------------------------------------------------------------ static timing analysis launchers
+ * (not individually timed: a wide graph issues ~1000 level launches per analysis, two event records each would
+ * double their cost) */
 int pfb_sta_load(const PfStaDev *S, const float *dev_net_delay) {
 	if (S->num_terminals <= 0) return 0;
-	if (ev_begin(2) != 0) return -1;
 	pf_sta_load_kernel<<<stream_grid(S->num_terminals), 256, 0, g_stream>>>(*S, dev_net_delay);
-	return ev_end();
+	CK(cudaGetLastError());
+	return 0;
 }
 
 int pfb_sta_begin_pair(const PfStaDev *S, float *stat) {
-	if (ev_begin(2) != 0) return -1;
 	pf_sta_begin_pair_kernel<<<stream_grid(S->num_tnodes), 256, 0, g_stream>>>(*S, stat);
-	return ev_end();
+	CK(cudaGetLastError());
+	return 0;
 }
 
 int pfb_sta_sweep(const PfStaDev *S, int forward, int lv_begin, int lv_end, int spread, int domain, float constraint, float *stat) {
 	if (lv_end <= lv_begin) return 0;
-	if (ev_begin(2) != 0) return -1;
-	if (spread) pf_sta_level_kernel<<<stream_grid(S->num_tnodes), 256, 0, g_stream>>>(*S, forward, lv_begin, domain, constraint, stat);
+	if (spread) pf_sta_level_kernel<<<stream_grid(spread), 256, 0, g_stream>>>(*S, forward, lv_begin, domain, constraint, stat);   /* spread = level width */
 	else pf_sta_levels_kernel<<<1, PF_STA_CTA, 0, g_stream>>>(*S, forward, lv_begin, lv_end, domain, constraint, stat);
-	return ev_end();
+	CK(cudaGetLastError());
+	return 0;
 }
 
 int pfb_sta_update(const PfStaDev *S, float constraint, const float *stat, float *dev_crit) {
 	if (S->num_terminals <= 0) return 0;
-	if (ev_begin(2) != 0) return -1;
 	pf_sta_update_kernel<<<stream_grid(S->num_terminals), 256, 0, g_stream>>>(*S, constraint, stat, dev_crit);
-	return ev_end();
+	CK(cudaGetLastError());
+	return 0;
 }

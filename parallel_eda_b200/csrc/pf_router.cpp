@@ -1114,12 +1114,12 @@ extern "C" int pf_sta_create(const pf_timing_graph *g, const pf_problem *p, cons
 	memset(&s->d, 0, sizeof(s->d));
 	s->num_owned = 0; s->num_domains = g->num_domains; s->num_tedges = E;
 	s->constraint.assign(g->constraint, g->constraint + (size_t)g->num_domains * g->num_domains);
-	/* sweep plan: a level wider than 16 K tnodes gets the whole GPU, runs of narrower ones share one CTA */
+	/* sweep plan: a level wider than 4 K tnodes gets the whole GPU, runs of narrower ones share one CTA */
 	for (int lv = 0; lv < g->num_levels;) {
 		const int width = g->level_ptr[lv + 1] - g->level_ptr[lv];
-		if (width > 16384) { s->seg_begin.push_back(lv); s->seg_end.push_back(lv + 1); s->seg_spread.push_back(1); lv++; continue; }
+		if (width > 4096) { s->seg_begin.push_back(lv); s->seg_end.push_back(lv + 1); s->seg_spread.push_back(width); lv++; continue; }
 		int e = lv;
-		while (e < g->num_levels && g->level_ptr[e + 1] - g->level_ptr[e] <= 16384) e++;
+		while (e < g->num_levels && g->level_ptr[e + 1] - g->level_ptr[e] <= 4096) e++;
 		s->seg_begin.push_back(lv); s->seg_end.push_back(e); s->seg_spread.push_back(0);
 		lv = e;
 	}
