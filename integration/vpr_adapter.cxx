@@ -12,8 +12,12 @@
  *   so the call at route_common.c:500 lands here; route_timing.c stays in the build unchanged (the placer's
  *   delay lookup and the packer use its helpers, place/timing_place_lookup.c:461, pack/cluster_legality.c:642).
  *
- * Between iterations the reference's own STA runs on the host, exactly as in route_timing.c:295-309:
- * load_timing_graph_net_delays + do_timing_analysis + get_critical_path_delay.
+ * Between iterations the reference runs load_timing_graph_net_delays + do_timing_analysis +
+ * get_critical_path_delay on the host (route_timing.c:295-309).  Here the timing graph (tnode[], tedge, levels,
+ * constraints) is flattened once and the same analysis runs on the device (pf_try_timing_driven_route_sta; the
+ * criticalities are bit-identical, tests/test_gpu_sta.py), so nothing crosses PCIe between iterations.  With
+ * PF_HOST_STA=1 in the environment, or when the design has clock-to-flipflop override constraints (not exported),
+ * the reference's own STA is called back on the host instead.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,6 +31,8 @@
 #include "route_tree_timing.h"
 #include "route_timing.h"
 #include "path_delay.h"
+#include "path_delay2.h"
+#include "read_sdc.h"
 #include "net_delay.h"
 
 #include "pf_router.h"
@@ -54,6 +60,42 @@ void sta_callback(void *user, int /*iters_done*/, const float *delay, float *cri
 	vpr_printf(TIO_MESSAGE_INFO, "Critical path: %g ns\n", *cpd);
 	for (int i = 0; i < num_nets; i++)
 		for (int k = 1; k <= clb_net[i].num_sinks; k++) crit[c->net_ptr[i] + k] = c->slacks->timing_criticality[i][k];
+}
+
+/* tnode[] / tnodes_at_level / g_sdc -> pf_timing_graph (include/pf_types.h); storage stays alive in `st` */
+struct TimingGraphStore {
+	std::vector<int32_t> eptr, eto, cdom, lptr, lnodes, drv;
+	std::vector<float> etd, cdel, cons;
+	std::vector<uint8_t> ty;
+};
+
+void flatten_timing_graph(TimingGraphStore &st, pf_timing_graph &g) {
+	memset(&g, 0, sizeof(g));
+	st.eptr.assign(num_tnodes + 1, 0); st.cdom.resize(num_tnodes); st.cdel.resize(num_tnodes); st.ty.resize(num_tnodes);
+	st.drv.assign(num_nets, -1);
+	for (int i = 0; i < num_tnodes; i++) {
+		st.eptr[i + 1] = st.eptr[i] + tnode[i].num_edges;
+		for (int k = 0; k < tnode[i].num_edges; k++) { st.eto.push_back(tnode[i].out_edges[k].to_node); st.etd.push_back(tnode[i].out_edges[k].Tdel); }
+		st.ty[i] = (uint8_t)tnode[i].type; st.cdom[i] = tnode[i].clock_domain; st.cdel[i] = tnode[i].clock_delay;
+		if (tnode[i].type == TN_CB_OPIN) {           /* the tnodes that drive inter-block nets (path_delay.c:3342) */
+			int iblk, inet;
+			get_tnode_block_and_output_net(i, &iblk, &inet);
+			if (inet >= 0 && inet < num_nets) st.drv[inet] = i;
+		}
+	}
+	st.lptr.push_back(0);
+	for (int lv = 0; lv < num_tnode_levels; lv++) {
+		for (int k = 0; k < tnodes_at_level[lv].nelem; k++) st.lnodes.push_back(tnodes_at_level[lv].list[k]);
+		st.lptr.push_back((int32_t)st.lnodes.size());
+	}
+	const int C = g_sdc->num_constrained_clocks;
+	for (int i = 0; i < C; i++) for (int j = 0; j < C; j++) st.cons.push_back(g_sdc->domain_constraint[i][j]);
+	g.num_tnodes = num_tnodes; g.num_tedges = (int32_t)st.eto.size();
+	g.edge_ptr = st.eptr.data(); g.edge_to = st.eto.data(); g.edge_Tdel = st.etd.data(); g.type = st.ty.data();
+	g.clock_domain = st.cdom.data(); g.clock_delay = st.cdel.data();
+	g.num_levels = num_tnode_levels; g.level_ptr = st.lptr.data(); g.level_nodes = st.lnodes.data();
+	g.num_domains = C; g.constraint = st.cons.data();
+	g.num_nets = num_nets; g.net_driver = st.drv.data();
 }
 
 }  // namespace
@@ -130,7 +172,18 @@ boolean pf_adapter_try_timing_driven_route(struct s_router_opts router_opts, flo
 	if (getenv("PF_DEVICE")) cfg.device = atoi(getenv("PF_DEVICE"));
 	cfg.verbose = getenv("PF_VERBOSE") ? 1 : 0;
 	pf_result res;
-	int rc = pf_try_timing_driven_route(&p, &cfg, timing_analysis_enabled ? sta_callback : NULL, &ctx, &res);
+	int rc;
+	const bool device_sta = timing_analysis_enabled && g_sdc && g_sdc->num_cf_constraints == 0 && !getenv("PF_HOST_STA");
+	if (device_sta) {
+		TimingGraphStore st;
+		pf_timing_graph tg;
+		flatten_timing_graph(st, tg);
+		rc = pf_try_timing_driven_route_sta(&p, &tg, &cfg, &res);
+		if (rc == PF_OK)
+			for (int i = 0; i < res.num_iter_stats - 1; i++) vpr_printf(TIO_MESSAGE_INFO, "Critical path: %g ns\n", res.iter_stats[i].crit_path_delay);
+	} else {
+		rc = pf_try_timing_driven_route(&p, &cfg, timing_analysis_enabled ? sta_callback : NULL, &ctx, &res);
+	}
 	if (rc != PF_OK) {
 		/* reference style: message + exit (route_timing.c:482-489 prints "Routing failed" and returns FALSE only
 		 * for an unroutable net) */
