@@ -141,6 +141,9 @@ int pf_comm_graph_ready(pf_router *r);
 int pf_comm_events(pf_router *r, void **dev_events, int64_t *count);
 int pf_comm_apply_events(pf_router *r, const void *dev_events, int64_t count);
 void *pf_comm_net_delay_ptr(pf_router *r);
+/* the device float[num_terminals] criticality vector the next iteration reads (pf_iteration_begin with crit == NULL
+ * keeps it): a device STA writes it in place (pf_sta_analyze_device) */
+void *pf_comm_crit_ptr(pf_router *r);
 
 /* ---- Device static timing analysis: what the reference runs on the host between iterations,
  * load_timing_graph_net_delays + do_timing_analysis + get_critical_path_delay (route_timing.c:295-309;

@@ -848,6 +848,7 @@ extern "C" int pf_comm_apply_events(pf_router *r, const void *dev_events, int64_
 }
 
 extern "C" void *pf_comm_net_delay_ptr(pf_router *r) { return r ? (void *)r->net_delay : NULL; }
+extern "C" void *pf_comm_crit_ptr(pf_router *r) { return r ? (void *)r->crit : NULL; }
 
 extern "C" int pf_total_wirelength(pf_router *r, int64_t *wl, int64_t *avail) {
 	if (!r) FAILF(PF_EINVAL, "null router");

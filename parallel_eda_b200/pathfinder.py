@@ -40,10 +40,11 @@ class RouteReport:
     wall_s: float
 
 
-def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delay_buf=None,
+def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delay_buf=None, dsta=None,
           max_iters: Optional[int] = None, sync_rounds: int = 2) -> RouteReport:
-    """Iterate until legal.  ``delay_buf``: tensor aliasing the router's device net_delay vector (optional, for
-    the host STA when several ranks route)."""
+    """Iterate until legal.  ``delay_buf``: tensor aliasing the router's device net_delay vector (needed when
+    several ranks route timing-driven: the ranks' sink delays are summed into it before the analysis);
+    ``sta``: host analysis callback; ``dsta``: a router.Sta — the analysis runs on the device in place."""
     o = r.problem.opts
     n_iter = int(max_iters or o["max_router_iterations"])
     pres_fac = float(o["first_iter_pres_fac"])
@@ -92,7 +93,13 @@ def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delay_buf
         if over == 0:
             success = True
             break
-        if sta is not None and int(o["timing_analysis_enabled"]):
+        if dsta is not None and int(o["timing_analysis_enabled"]):
+            # device STA (router.Sta): reads the router's delay vector, writes its criticality vector in place
+            if comm is not None and delay_buf is not None:
+                comm.all_reduce_sum_(delay_buf)
+            dsta.analyze_device(r.comm_net_delay_ptr(), r.comm_crit_ptr())
+            crit = None
+        elif sta is not None and int(o["timing_analysis_enabled"]):
             if comm is not None and delay_buf is not None:
                 comm.all_reduce_sum_(delay_buf)          # assemble every rank's sink delays
             crit, _cpd = sta(it, r.net_delay())

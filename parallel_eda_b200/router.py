@@ -154,6 +154,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_comm_apply_events.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.pf_comm_net_delay_ptr.argtypes = [C.c_void_p]
     lib.pf_comm_net_delay_ptr.restype = C.c_void_p
+    lib.pf_comm_crit_ptr.argtypes = [C.c_void_p]
+    lib.pf_comm_crit_ptr.restype = C.c_void_p
     lib.pf_try_timing_driven_route.argtypes = [C.POINTER(_Problem), C.POINTER(Config), STA_FN, C.c_void_p,
                                                C.POINTER(_Result)]
     lib.pf_result_free.argtypes = [C.POINTER(_Result)]
@@ -350,6 +352,9 @@ class Router:
     def comm_net_delay_ptr(self) -> int:
         return int(self.lib.pf_comm_net_delay_ptr(self._h))
 
+    def comm_crit_ptr(self) -> int:
+        return int(self.lib.pf_comm_crit_ptr(self._h))
+
 
 class Sta:
     """Device-resident timing graph: the static timing analysis the reference runs on the host between router
@@ -376,6 +381,14 @@ class Sta:
         if rc != PF_OK:
             raise RouterError(rc, self.lib.pf_last_error().decode())
         return crit, float(cpd.value)
+
+    def analyze_device(self, dev_net_delay: int, dev_crit: int) -> float:
+        """Device pointers in and out (e.g. Router.comm_net_delay_ptr() / comm_crit_ptr()); returns the cpd in ns."""
+        cpd = C.c_float(0)
+        rc = self.lib.pf_sta_analyze_device(self._h, C.c_void_p(dev_net_delay), C.c_void_p(dev_crit), C.byref(cpd))
+        if rc != PF_OK:
+            raise RouterError(rc, self.lib.pf_last_error().decode())
+        return float(cpd.value)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -90,3 +90,24 @@ def test_route_with_device_sta_on_the_emulator(emu_lib):
     cpd = float(r.iter_stats["crit_path_delay"][-2])            # the last analysis ran before the final iteration
     ref = float(gold.iter_stats["crit_path_delay"][-2])
     assert abs(cpd - ref) <= 0.10 * ref and r.total_wirelength <= 1.12 * gold.total_wirelength
+
+
+def test_step_loop_with_device_sta_on_the_emulator(emu_lib):
+    """pathfinder.route(dsta=...): the analysis writes the router's criticality vector in place between iterations."""
+    from parallel_eda_b200 import router, pathfinder, check_route
+    p = pfio.read_problem(os.path.join(G, "toy_w64.pfp.xz"))
+    p.opts["timing_analysis_enabled"] = 1
+    p.opts["max_router_iterations"] = 150
+    g = pfio.read_timing_graph(os.path.join(G, "toy_w64.pftg.xz"))
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=8, big_slots=1)
+    R = router.Router(p, cfg, lib_path=emu_lib)
+    S = router.Sta(g, p, cfg, lib_path=emu_lib)
+    rep = pathfinder.route(R, dsta=S)
+    assert rep.success
+    res = R.result()
+    res.success = 1
+    check_route.check_route(p, res)
+    # same routing as the C loop with the device analysis (both deterministic on the emulator)
+    r2 = router.try_timing_driven_route(p, cfg, lib_path=emu_lib, timing_graph=g)
+    assert (res.serial_num, res.total_wirelength) == (r2.serial_num, r2.total_wirelength) and rep.iterations == r2.iterations
+    S.close(); R.close()
