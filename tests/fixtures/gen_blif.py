@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--name", default="toy")
     ap.add_argument("--hub", type=int, default=0, help="number of LUTs that additionally read one shared hub signal (a high-fanout net)")
+    ap.add_argument("--clocks", type=int, default=1, help="number of clock domains the latches are spread over")
     a = ap.parse_args()
     rng = random.Random(a.seed)
     signals = ["pi%d" % i for i in range(a.pis)]
@@ -40,7 +41,7 @@ def main():
         body.append("%s 1" % cube)
         if rng.random() < a.latch_frac:
             q = "q%d" % i
-            body.append(".latch %s %s re clk 0" % (out, q))
+            body.append(".latch %s %s re %s 0" % (out, q, "clk" if a.clocks <= 1 else "clk%d" % (latches % a.clocks)))
             used.add(out)
             signals.append(q)
             latches += 1
@@ -52,7 +53,8 @@ def main():
     pis = [s for s in signals[:a.pis] if s in used]
     with open(a.out, "w") as f:
         f.write(".model %s\n" % a.name)
-        f.write(".inputs %s%s\n" % (" ".join(pis), " clk" if latches else ""))
+        clk_names = (["clk"] if a.clocks <= 1 else ["clk%d" % c for c in range(min(a.clocks, latches))]) if latches else []
+        f.write(".inputs %s\n" % " ".join(pis + clk_names))
         f.write(".outputs %s\n" % " ".join(outs))
         f.write("\n".join(body))
         f.write("\n.end\n")

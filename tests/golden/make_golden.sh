@@ -4,6 +4,7 @@
 #   toy : tests/fixtures/gen_blif.py --luts 300  --pis 16 --window 60  --seed 1, W=64
 #   mid : tests/fixtures/gen_blif.py --luts 4000 --pis 64 --window 400 --seed 2, W=200
 #   hub : tests/fixtures/gen_blif.py --luts 900 --pis 24 --window 120 --seed 5 --hub 700, W=90 (one 84-sink net)
+#   duo : tests/fixtures/gen_blif.py --luts 500 --pis 20 --window 80 --seed 7 --clocks 2, W=80 (two clock domains)
 set -e
 HERE=$(cd "$(dirname "$0")" && pwd); ROOT=$(cd "$HERE/../.." && pwd)
 REF=$ROOT/oracle/_ref/vpr_ref; W=$(mktemp -d); cd "$W"
@@ -11,7 +12,8 @@ cp "$ROOT/tests/fixtures/k6_N10_like.xml" .
 python "$ROOT/tests/fixtures/gen_blif.py" toy.blif --luts 300 --pis 16 --window 60 --seed 1 --name toy
 python "$ROOT/tests/fixtures/gen_blif.py" mid.blif --luts 4000 --pis 64 --window 400 --seed 2 --name mid
 python "$ROOT/tests/fixtures/gen_blif.py" hub.blif --luts 900 --pis 24 --window 120 --seed 5 --name hub --hub 700
-for c in toy:64 mid:200 hub:90; do
+python "$ROOT/tests/fixtures/gen_blif.py" duo.blif --luts 500 --pis 20 --window 80 --seed 7 --name duo --clocks 2
+for c in toy:64 mid:200 hub:90 duo:80; do
   n=${c%%:*}; w=${c##*:}
   "$REF" flow k6_N10_like.xml $n --nodisp --pack --place > /dev/null
   PF_DUMP_PROBLEM=${n}_w$w.pfp PF_DUMP_RESULT=${n}_w$w.pfr PF_DUMP_TGRAPH=${n}_w$w.pftg PF_DUMP_STA=${n}_w$w.pfsta "$REF" flow k6_N10_like.xml $n --nodisp --route --route_chan_width $w > /dev/null

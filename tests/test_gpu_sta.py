@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200"])
+@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200", "duo_w80"])
 def test_device_sta_bit_identical_to_reference(name):
     p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
     g = pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz"))
@@ -25,7 +25,7 @@ def test_device_sta_bit_identical_to_reference(name):
     s.close()
 
 
-@pytest.mark.parametrize("name", ["mid_w200", "hub_w90"])
+@pytest.mark.parametrize("name", ["mid_w200", "hub_w90", "duo_w80"])
 def test_route_with_device_sta(name):
     p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
     p.opts["timing_analysis_enabled"] = 1

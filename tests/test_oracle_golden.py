@@ -22,6 +22,8 @@ CASES = [
     ("mid_w200", "mid_w200.pfr", True),      # timing-driven: 21 iterations, 80,871 net routes
     ("hub_w90", "hub_w90.pfr", True),        # 865 nets, 10x10, W=90, one routed net with 84 sinks: exercises the
     ("hub_w90", "hub_w90_nt.pfr", False),    # high-fanout window of mark_node_expansion_by_bin (route_timing.c:867)
+    ("duo_w80", "duo_w80.pfr", True),        # 494 nets, W=80, TWO netlist clocks (+ the virtual I/O clock): 21 iterations
+    ("duo_w80", "duo_w80_nt.pfr", False),    # timing off: 11 iterations
 ]
 
 

@@ -1,5 +1,6 @@
 """Pins the oracle's static timing analysis (oracle/pf_oracle.c: pf_oracle_sta) to the UNMODIFIED reference.
 
+duo_w80 has two netlist clocks plus the virtual I/O clock: 3 domains, 7 analysed domain pairs, 2 DO_NOT_ANALYSE.
 tests/golden/*.pftg.xz is the reference's own timing graph (tnode[] / tedge / levels / constraints, exported by
 oracle/ref_build/harness.cxx) and *.pfsta.xz every (net_delay in, timing_criticality out, critical path delay) of the
 do_timing_analysis calls the reference made while routing that fixture timing-driven (tests/golden/make_golden.sh).
@@ -31,7 +32,7 @@ def c_timing_graph(g: pfio.TimingGraph):
     return t, keep
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200"])
+@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200", "duo_w80"])
 def test_oracle_sta_reproduces_reference_bit_for_bit(name, oracle_lib):
     lib = C.CDLL(oracle_lib)
     lib.pf_oracle_sta.argtypes = [C.POINTER(_TG), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
@@ -59,7 +60,7 @@ def test_oracle_sta_reproduces_reference_bit_for_bit(name, oracle_lib):
     assert np.array_equal(gold.iter_crit[1][routed], v.crit[0][routed])
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200"])
+@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200", "duo_w80"])
 def test_device_sta_code_on_the_emulator_is_bit_identical(name, emu_lib):
     """The device analysis (pf_sta_device.cuh behind pf_sta_analyze), compiled for the CPU emulator backend:
     level-synchronous pull over in-edges instead of the reference's push along out-edges — same floats."""
