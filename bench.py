@@ -243,9 +243,17 @@ def run_ours(a):
         for _ in range(max(1, min(a.steps, 2))):
             rep, dt, hb, db, _res = e2e_step()
             acc_n += rep.nets_routed; acc_t += dt
+        # independent look at the routing the public API handed back (outside the timed region): occupancy recomputed
+        # from the traces equals the reported one, every sink is reached, sampled trace pairs are real rr edges
+        check = None
+        if world == 1:
+            from parallel_eda_b200 import check_route
+            check = check_route.check_route_fast(p, _res)
+            check["wirelength"] = int(_res.total_wirelength)
         e2e = {"value": acc_n / acc_t, "unit": "nets/s", "h2d_bytes_per_step": int(hb), "d2h_bytes_per_step": int(db),
                "s_per_step": acc_t / max(1, min(a.steps, 2)),
-               "phases_s": dict(zip(("create_upload", "route", "result_download", "destroy"), [round(x, 4) for x in e2e_phases[-1]]))}
+               "phases_s": dict(zip(("create_upload", "route", "result_download", "destroy"), [round(x, 4) for x in e2e_phases[-1]])),
+               "result_check": check}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
