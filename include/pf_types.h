@@ -71,7 +71,7 @@ typedef struct pf_router_opts { /* the s_router_opts fields the path reads, rout
 	int32_t max_router_iterations;
 	int32_t timing_analysis_enabled; /* boolean argument of try_timing_driven_route */
 	int32_t bb_factor;               /* informational: net_bb is already expanded */
-	int32_t reserved;
+	int32_t router_algorithm; /* 0 = timing-driven / no-timing (route_timing.c), 1 = breadth-first (route_breadth_first.c) */
 } pf_router_opts;
 
 typedef struct pf_problem {

@@ -60,6 +60,8 @@ void do_timing_analysis(t_slack *slacks, boolean is_prepacked, boolean do_lut_in
 void load_timing_graph_net_delays(float **net_delay);
 float get_critical_path_delay(void);
 boolean feasible_routing(void);
+boolean try_breadth_first_route(struct s_router_opts router_opts, t_ivec **clb_opins_used_locally, int width_fac);
+boolean pf_hook_try_breadth_first_route(struct s_router_opts router_opts, t_ivec **clb_opins_used_locally, int width_fac);
 extern struct s_bb *route_bb;
 extern t_rr_node_route_inf *rr_node_route_inf;
 void alloc_route_static_structs(void);
@@ -224,6 +226,7 @@ static void export_problem(const char *path, struct s_router_opts ro, boolean ti
 	p.opts.astar_fac = ro.astar_fac; p.opts.max_criticality = ro.max_criticality;
 	p.opts.criticality_exp = ro.criticality_exp; p.opts.max_router_iterations = ro.max_router_iterations;
 	p.opts.timing_analysis_enabled = timing_enabled ? 1 : 0; p.opts.bb_factor = ro.bb_factor;
+	p.opts.router_algorithm = ro.router_algorithm == BREADTH_FIRST ? 1 : 0;
 
 	char msg[256];
 	if (pf_problem_check(&p, msg, sizeof(msg)) != 0) { fprintf(stderr, "PF_REF problem check failed: %s\n", msg); exit(2); }
@@ -263,7 +266,7 @@ static void export_result(const char *path, boolean ok, float **net_delay) {
 	}
 	std::vector<float> nd(g_net_ptr[num_nets], 0.f);
 	for (int i = 0; i < num_nets; i++)
-		for (int k = 1; k <= clb_net[i].num_sinks; k++) nd[g_net_ptr[i] + k] = net_delay[i][k];
+		for (int k = 1; k <= clb_net[i].num_sinks; k++) nd[g_net_ptr[i] + k] = net_delay ? net_delay[i][k] : 0.f;
 	std::vector<int32_t> occ(num_rr_nodes);
 	for (int i = 0; i < num_rr_nodes; i++) occ[i] = rr_node[i].occ;
 	r.success = ok ? 1 : 0; r.iterations = g_iter; r.serial_num = serial_num_of_routing(); r.total_wirelength = wl;
@@ -510,8 +513,28 @@ static int run_inject(int argc, char **argv) {
 		/* iteration-1 criticalities are set inside the router (1.0); the replay supplies the rest,
 		 * and the hook's index 0 row is skipped */
 	}
-	boolean ok = pf_hook_try_timing_driven_route(ro, net_delay, &slacks, opins, timing);
+	boolean ok;
+	if (p.opts.router_algorithm == 1) { ro.router_algorithm = BREADTH_FIRST; ok = pf_hook_try_breadth_first_route(ro, opins, 0); }
+	else ok = pf_hook_try_timing_driven_route(ro, net_delay, &slacks, opins, timing);
 	return ok ? 0 : 1;
+}
+
+/* route_common.c:495 dispatches `--router_algorithm breadth_first` here (try_route), bound by
+ * -Dtry_breadth_first_route=pf_hook_try_breadth_first_route; route_breadth_first.c itself is compiled with
+ * -Dfeasible_routing=pf_hook_feasible_routing so the per-iteration overuse is recorded */
+boolean pf_hook_try_breadth_first_route(struct s_router_opts router_opts, t_ivec **clb_opins_used_locally, int width_fac) {
+	const char *dp = getenv("PF_DUMP_PROBLEM"), *dr = getenv("PF_DUMP_RESULT");
+	router_opts.router_algorithm = BREADTH_FIRST;
+	if (dp) export_problem(dp, router_opts, FALSE, clb_opins_used_locally);
+	build_net_ptr();
+	g_iter = 0; g_stats.clear(); g_crit.clear(); g_iter_time.clear();
+	g_t0 = now_s();
+	boolean ok = try_breadth_first_route(router_opts, clb_opins_used_locally, width_fac);
+	double total = now_s() - g_t0;
+	g_crit.assign((size_t)g_net_ptr[num_nets] * (size_t)(g_iter > 0 ? g_iter : 1), 0.f);
+	report_times(ok, total);
+	if (dr) export_result(dr, ok, NULL);
+	return ok;
 }
 
 int main(int argc, char **argv) {

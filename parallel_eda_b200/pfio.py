@@ -24,7 +24,7 @@ INDEXED_DT = np.dtype([
 OPTS_DT = np.dtype([
     ("first_iter_pres_fac", "<f4"), ("initial_pres_fac", "<f4"), ("pres_fac_mult", "<f4"), ("acc_fac", "<f4"),
     ("bend_cost", "<f4"), ("astar_fac", "<f4"), ("max_criticality", "<f4"), ("criticality_exp", "<f4"),
-    ("max_router_iterations", "<i4"), ("timing_analysis_enabled", "<i4"), ("bb_factor", "<i4"), ("reserved", "<i4")])
+    ("max_router_iterations", "<i4"), ("timing_analysis_enabled", "<i4"), ("bb_factor", "<i4"), ("router_algorithm", "<i4")])
 ITER_STATS_DT = np.dtype([
     ("overused_nodes", "<i4"), ("nets_routed", "<i4"), ("heap_pushes", "<i8"), ("heap_pops", "<i8"),
     ("edge_visits", "<i8"), ("pres_fac", "<f4"), ("crit_path_delay", "<f4")])
@@ -32,6 +32,15 @@ assert SWITCH_DT.itemsize == 20 and INDEXED_DT.itemsize == 32 and OPTS_DT.itemsi
 
 SOURCE, SINK, IPIN, OPIN, CHANX, CHANY = range(6)
 OPEN = -1
+
+
+def breadth_first_opts(problem: "Problem") -> None:
+    """In place: the router options VPR uses for --router_algorithm breadth_first (SetupVPR defaults:
+    first_iter_pres_fac 0, acc_fac 0.2, no timing analysis) on an otherwise unchanged problem."""
+    problem.opts["router_algorithm"] = 1
+    problem.opts["timing_analysis_enabled"] = 0
+    problem.opts["first_iter_pres_fac"] = 0.0
+    problem.opts["acc_fac"] = 0.2
 
 
 def default_opts(timing: bool = False) -> np.ndarray:

@@ -34,7 +34,7 @@ class RouterError(RuntimeError):
 class _Opts(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("first_iter_pres_fac", "initial_pres_fac", "pres_fac_mult", "acc_fac",
                                          "bend_cost", "astar_fac", "max_criticality", "criticality_exp")] + \
-               [(n, C.c_int32) for n in ("max_router_iterations", "timing_analysis_enabled", "bb_factor", "reserved")]
+               [(n, C.c_int32) for n in ("max_router_iterations", "timing_analysis_enabled", "bb_factor", "router_algorithm")]
 
 
 class _Problem(C.Structure):

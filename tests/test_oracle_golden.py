@@ -48,6 +48,24 @@ def test_oracle_reproduces_reference_bit_for_bit(prob, gold, timing, oracle_cli,
     assert list(o.iter_stats["overused_nodes"]) == list(g.iter_stats["overused_nodes"])
 
 
+@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90"])
+def test_oracle_breadth_first_reproduces_reference_bit_for_bit(name, oracle_cli, unxz, tmp_path):
+    """--router_algorithm breadth_first (reference route_breadth_first.c): the golden *_bf.pfr was written by the
+    unmodified reference on the same rr graph with VPR's breadth-first option defaults."""
+    p = pfio.read_problem(unxz(name + ".pfp"))
+    pfio.breadth_first_opts(p)
+    prob, out = str(tmp_path / "bf.pfp"), str(tmp_path / "o.pfr")
+    pfio.write_problem(prob, p)
+    r = subprocess.run([oracle_cli, prob, "--result", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    g = pfio.read_result(unxz(name + "_bf.pfr"))
+    o = pfio.read_result(out)
+    assert (o.success, o.iterations, o.serial_num, o.total_wirelength) == (g.success, g.iterations, g.serial_num, g.total_wirelength)
+    assert np.array_equal(o.trace_ptr, g.trace_ptr) and np.array_equal(o.trace_node, g.trace_node)
+    assert np.array_equal(o.trace_switch, g.trace_switch) and np.array_equal(o.occ, g.occ)
+    assert list(o.iter_stats["overused_nodes"]) == list(g.iter_stats["overused_nodes"])
+
+
 def test_reference_binary_agrees_when_present(ref_bin, oracle_cli, unxz, tmp_path):
     """Where oracle/_ref was built, re-run the real reference on the flat problem (inject mode)."""
     out_r, out_o = str(tmp_path / "r.pfr"), str(tmp_path / "o.pfr")
