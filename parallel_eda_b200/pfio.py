@@ -34,15 +34,6 @@ SOURCE, SINK, IPIN, OPIN, CHANX, CHANY = range(6)
 OPEN = -1
 
 
-def breadth_first_opts(problem: "Problem") -> None:
-    """In place: the router options VPR uses for --router_algorithm breadth_first (SetupVPR defaults:
-    first_iter_pres_fac 0, acc_fac 0.2, no timing analysis) on an otherwise unchanged problem."""
-    problem.opts["router_algorithm"] = 1
-    problem.opts["timing_analysis_enabled"] = 0
-    problem.opts["first_iter_pres_fac"] = 0.0
-    problem.opts["acc_fac"] = 0.2
-
-
 def default_opts(timing: bool = False) -> np.ndarray:
     """VPR defaults for the timing-driven router (reference base/SetupVPR.c:330-605)."""
     o = np.zeros((), dtype=OPTS_DT)

@@ -18,6 +18,10 @@ for c in toy:64 mid:200 hub:90 duo:80; do
   "$REF" flow k6_N10_like.xml $n --nodisp --pack --place > /dev/null
   PF_DUMP_PROBLEM=${n}_w$w.pfp PF_DUMP_RESULT=${n}_w$w.pfr PF_DUMP_TGRAPH=${n}_w$w.pftg PF_DUMP_STA=${n}_w$w.pfsta "$REF" flow k6_N10_like.xml $n --nodisp --route --route_chan_width $w > /dev/null
   "$REF" inject ${n}_w$w.pfp --result ${n}_w${w}_nt.pfr > /dev/null
+  if [ $n != mid ]; then   # breadth-first (Dijkstra) takes the reference 70 s on mid
+    PF_DUMP_PROBLEM=${n}_w${w}_bf.pfp PF_DUMP_RESULT=${n}_w${w}_bf.pfr "$REF" flow k6_N10_like.xml $n --nodisp --route --route_chan_width $w --router_algorithm breadth_first > /dev/null
+    for f in ${n}_w${w}_bf.pfp ${n}_w${w}_bf.pfr; do xz -9 -c $f > "$HERE/$f.xz"; done
+  fi
   for f in ${n}_w$w.pfp ${n}_w$w.pfr ${n}_w${w}_nt.pfr ${n}_w$w.pftg ${n}_w$w.pfsta; do xz -9 -c $f > "$HERE/$f.xz"; done
 done
 cp toy.blif toy.place "$HERE/"; xz -9 -c toy.net > "$HERE/toy.net.xz"

@@ -51,12 +51,13 @@ def test_oracle_reproduces_reference_bit_for_bit(prob, gold, timing, oracle_cli,
 @pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90"])
 def test_oracle_breadth_first_reproduces_reference_bit_for_bit(name, oracle_cli, unxz, tmp_path):
     """--router_algorithm breadth_first (reference route_breadth_first.c): the golden *_bf.pfr was written by the
-    unmodified reference on the same rr graph with VPR's breadth-first option defaults."""
-    p = pfio.read_problem(unxz(name + ".pfp"))
-    pfio.breadth_first_opts(p)
-    prob, out = str(tmp_path / "bf.pfp"), str(tmp_path / "o.pfr")
-    pfio.write_problem(prob, p)
-    r = subprocess.run([oracle_cli, prob, "--result", out], capture_output=True, text=True)
+    unmodified reference; *_bf.pfp is the problem it saw (same rr graph as the timing-driven fixture, but
+    demand-only base costs — rr_graph_indexed_data.c — and VPR's breadth-first option defaults: first_iter_pres_fac
+    0, acc_fac 0.2)."""
+    p = pfio.read_problem(unxz(name + "_bf.pfp"))
+    assert int(p.opts["router_algorithm"]) == 1 and int(p.opts["timing_analysis_enabled"]) == 0
+    out = str(tmp_path / "o.pfr")
+    r = subprocess.run([oracle_cli, unxz(name + "_bf.pfp"), "--result", out], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     g = pfio.read_result(unxz(name + "_bf.pfr"))
     o = pfio.read_result(out)
