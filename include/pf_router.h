@@ -159,6 +159,12 @@ int pf_sta_analyze_device(pf_sta *s, const void *dev_net_delay, void *dev_crit, 
 /* try_timing_driven_route with the analysis on the device: no host callback, no per-iteration copies */
 int pf_try_timing_driven_route_sta(const pf_problem *p, const pf_timing_graph *g, const pf_config *cfg, pf_result *out);
 
+/* try_breadth_first_route (route/route_breadth_first.c:23-91; `--router_algorithm breadth_first`): problems with
+ * opts.router_algorithm == 1 are routed by one persistent maze wavefront per net (no lookahead, no delay term, the
+ * new segment re-enters the wave at cost 0), acc_fac applies from the first iteration and there is no
+ * first-iteration wirelength abort.  pf_try_timing_driven_route and the step functions dispatch on the same option. */
+int pf_try_breadth_first_route(const pf_problem *p, const pf_config *cfg, pf_result *out);
+
 /* The whole of try_timing_driven_route (single GPU): iterate until legal or out of iterations.
  * sta may be NULL when opts.timing_analysis_enabled == 0. */
 int pf_try_timing_driven_route(const pf_problem *p, const pf_config *cfg, pf_sta_fn sta, void *user, pf_result *out);

@@ -100,8 +100,23 @@ void flatten_timing_graph(TimingGraphStore &st, pf_timing_graph &g) {
 
 }  // namespace
 
+static boolean route_on_b200(struct s_router_opts router_opts, float **net_delay, t_slack *slacks,
+		t_ivec **clb_opins_used_locally, boolean timing_analysis_enabled, int router_algorithm);
+
+/* route_common.c:500 (try_route, TIMING_DRIVEN / NO_TIMING) lands here */
 boolean pf_adapter_try_timing_driven_route(struct s_router_opts router_opts, float **net_delay, t_slack *slacks,
 		t_ivec **clb_opins_used_locally, boolean timing_analysis_enabled) {
+	return route_on_b200(router_opts, net_delay, slacks, clb_opins_used_locally, timing_analysis_enabled, 0);
+}
+
+/* route_common.c:495 (try_route, BREADTH_FIRST; reference route_breadth_first.c:23) lands here when route_common.c
+ * is also compiled with -Dtry_breadth_first_route=pf_adapter_try_breadth_first_route */
+boolean pf_adapter_try_breadth_first_route(struct s_router_opts router_opts, t_ivec **clb_opins_used_locally, int /*width_fac*/) {
+	return route_on_b200(router_opts, NULL, NULL, clb_opins_used_locally, FALSE, 1);
+}
+
+static boolean route_on_b200(struct s_router_opts router_opts, float **net_delay, t_slack *slacks,
+		t_ivec **clb_opins_used_locally, boolean timing_analysis_enabled, int router_algorithm) {
 	/* ---- flatten the globals (rr_node[], rr_indexed_data[], switch_inf[], clb_net[], net_rr_terminals, route_bb) */
 	const int N = num_rr_nodes;
 	long E = 0;
@@ -165,6 +180,7 @@ boolean pf_adapter_try_timing_driven_route(struct s_router_opts router_opts, flo
 	p.opts.astar_fac = router_opts.astar_fac; p.opts.max_criticality = router_opts.max_criticality;
 	p.opts.criticality_exp = router_opts.criticality_exp; p.opts.max_router_iterations = router_opts.max_router_iterations;
 	p.opts.timing_analysis_enabled = timing_analysis_enabled ? 1 : 0; p.opts.bb_factor = router_opts.bb_factor;
+	p.opts.router_algorithm = router_algorithm;
 
 	/* ---- route on the GPU */
 	pf_config cfg;
@@ -205,7 +221,7 @@ boolean pf_adapter_try_timing_driven_route(struct s_router_opts router_opts, flo
 			if (trace_tail[i]) trace_tail[i]->next = t; else trace_head[i] = t;
 			trace_tail[i] = t;
 		}
-		for (int k = 1; k <= clb_net[i].num_sinks; k++) net_delay[i][k] = clb_net[i].is_global ? 0.f : res.net_delay[ctx.net_ptr[i] + k];
+		if (net_delay) for (int k = 1; k <= clb_net[i].num_sinks; k++) net_delay[i][k] = clb_net[i].is_global ? 0.f : res.net_delay[ctx.net_ptr[i] + k];
 	}
 	/* occupancy of the nets; the locally used OPINs are then re-reserved by the reference's own routine so
 	 * that clb_opins_used_locally carries the node ids check_route expects (check_route.c:599) */
@@ -222,7 +238,7 @@ boolean pf_adapter_try_timing_driven_route(struct s_router_opts router_opts, flo
 	reserve_locally_used_opins(router_opts.initial_pres_fac, FALSE, clb_opins_used_locally);
 	boolean ok = res.success ? TRUE : FALSE;
 #ifdef DEBUG
-	if (ok) timing_driven_check_net_delays(net_delay);              /* route_timing.c:964: from-scratch Elmore cross-check */
+	if (ok && net_delay) timing_driven_check_net_delays(net_delay);              /* route_timing.c:964: from-scratch Elmore cross-check */
 #endif
 	pf_result_free(&res);
 	return ok;

@@ -843,6 +843,117 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
 	return tree_n + L - 1;
 }
 
+/* ------------------------------------------------------------------ breadth-first router (route_breadth_first.c)
+ * breadth_first_route_net :93-171: ONE maze wavefront per net (no lookahead, no delay term).  The SOURCE enters the
+ * frontier at its congestion cost; whenever an unreached SINK of the net is settled its path joins the tree and its
+ * rr nodes re-enter the frontier at cost 0 (breadth_first_expand_trace_segment :173-257), and the same wave carries
+ * on.  Labels persist for the whole net.  Returns 1 (all sinks connected), 0 (frontier exhausted: no path),
+ * -1 (scratch overflow: retry in a bigger slot), -2 (two pins of the net on one SINK: not supported). */
+PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0, int ns, int *sink_done, int *rt_of_sink) {
+	const PfParams *P = w.P;
+	const int lane = pf_lane();
+	w.epoch++;
+	if ((w.epoch & 63u) == 0) {
+		for (unsigned i = (unsigned)lane; i <= w.label_mask; i += PF_WARP) w.hot[i] = 0;
+		w.epoch++;
+		pf_syncwarp();
+	}
+	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.far_min = PF_INF_F; w.best = PF_INF_F;
+	for (int k = 1 + lane; k <= ns; k += PF_WARP) sink_done[k] = 0;
+	{	/* breadth_first_add_source_to_heap :294-305 */
+		const int src = w.tree[0].node;
+		PfNodeView n = pf_load_node(P, src);
+		float pres;
+		if (n.occ < n.cap) pres = 1.; else pres = 1. + (n.occ + 1 - n.cap) * P->pres_fac;
+		const float c = w.base_cost[n.ci] * n.acc * pres;
+		float win = c * P->win_rel;
+		if (win < P->win_abs) win = P->win_abs;
+		w.T_hi = c + win;
+		int wr = pf_label_relax(w, lane == 0, src, c, c, 0.f, ~0, 0, -1);
+		pf_push(w, wr, c, src);
+	}
+	int remaining = ns;
+	while (remaining > 0) {
+		if (w.overflow) return -1;
+		float mtot = PF_INF_F;
+		int first = 0x7fffffff;
+		for (int i = lane; i < w.sh_n; i += PF_WARP) { float t = pf_key_tot(w.fr[i]); if (t < mtot) { mtot = t; first = i; } }
+		const float my_min = mtot;
+		mtot = pf_warp_min_f(mtot);
+		if (w.far_min < mtot) { pf_refill(w); continue; }
+		if (w.sh_n == 0) return 0;                          /* heap empty: "no possible path" :124 */
+		const int idx = -pf_warp_max_i(my_min == mtot ? -first : -0x7fffffff);
+		const uint64_t mk = w.fr[idx];
+		uint64_t keep[PF_SH_FRONTIER / PF_WARP];
+		for (int c = 0; c < PF_SH_FRONTIER / PF_WARP; c++) { int i = lane + c * PF_WARP; keep[c] = (i > idx && i < w.sh_n) ? w.fr[i] : 0; }
+		pf_syncwarp();
+		for (int c = 0; c < PF_SH_FRONTIER / PF_WARP; c++) { int i = lane + c * PF_WARP; if (i > idx && i < w.sh_n) w.fr[i - 1] = keep[c]; }
+		w.sh_n--;
+		pf_syncwarp();
+		/* the settled label (every lane does the same lookup) */
+		const int u = pf_key_node(mk);
+		const int h = pf_label_find(w, u);
+		if (h < 0) { w.stale++; continue; }
+		if (pf_int_as_float((int)(w.hot[h] >> 32)) != pf_key_tot(mk)) { w.stale++; continue; }   /* re-labelled cheaper */
+		pf_u4 a = pf_ld_u4(&w.cold[h]), b = pf_ld_u4((const char *)&w.cold[h] + 16);
+		int x_start = (int)b.x, x_type = (int)((a.w >> 8) & 0xffu), M = (int)(a.w >> 16);
+		const float x_back = pf_int_as_float((int)a.x);
+		if (x_start < 0) { PfNodeView un = pf_load_node(P, u); x_start = un.edge_start; x_type = un.type; M = un.num_edges; }
+		w.pops++;
+
+		if (x_type == 1) {                                  /* a SINK: one of ours, still unconnected? (target_flag, :132) */
+			int pin = 0x7fffffff, dup = 0;
+			for (int k = 1 + lane; k <= ns; k += PF_WARP) if (!sink_done[k] && P->net_term[t0 + k] == u) { dup++; if (k < pin) pin = k; }
+			pin = -pf_warp_max_i(-pin);
+			dup = pf_warp_sum_i(dup);
+			if (dup > 1) return -2;
+			if (dup == 1) {
+				const int a0 = *tree_n_io;
+				const int si = pf_add_path(w, tree_n_io, u);
+				if (si < 0) { w.overflow |= PF_OVF_OTHER; return -1; }
+				if (lane == 0) { rt_of_sink[pin] = si; sink_done[pin] = 1; }
+				pf_syncwarp();
+				remaining--;
+				/* the new segment re-enters the frontier at cost 0 */
+				for (int base = a0; base <= si; base += PF_WARP) {
+					const int i = base + lane;
+					const int valid = i <= si;
+					const int node = valid ? w.tree[i].node : 0;
+					int wr = pf_label_relax(w, valid, node, 0.f, 0.f, 0.f, ~i, 0, -1);
+					pf_push(w, wr, 0.f, node);
+					if (w.overflow) return -1;
+				}
+				continue;
+			}
+		}
+		/* breadth_first_expand_neighbours :259-292 */
+		w.visits += (unsigned long long)M;
+		for (int base = 0; base < M; base += PF_WARP) {
+			const int e = base + lane;
+			int valid = e < M, to = 0, info = 0, es = 0;
+			float tot = 0.f;
+			if (valid) {
+				const uint32_t ew = P->edges[x_start + e];
+				to = (int)(ew & PF_EDGE_NODE_MASK);
+				const int isw = (int)(ew >> PF_EDGE_NODE_BITS);
+				PfNodeView n = pf_load_node(P, to);
+				if (n.xhigh < w.bb_xmin || n.xlow > w.bb_xmax || n.yhigh < w.bb_ymin || n.ylow > w.bb_ymax) valid = 0;
+				if (valid) {
+					float pres;
+					if (n.occ < n.cap) pres = 1.; else pres = 1. + (n.occ + 1 - n.cap) * P->pres_fac;
+					tot = x_back + w.base_cost[n.ci] * n.acc * pres;
+					if (P->bend_cost != 0.) { if ((x_type == 4 && n.type == 5) || (x_type == 5 && n.type == 4)) tot += P->bend_cost; }
+					info = isw | (n.type << 8) | (n.num_edges << 16); es = n.edge_start;
+				}
+			}
+			int wr = pf_label_relax(w, valid, to, tot, tot, 0.f, u, info, es);
+			pf_push(w, wr, tot, to);
+			if (w.overflow) return -1;
+		}
+	}
+	return 1;
+}
+
 PF_DEV void pf_swap_tables(PfWarp &w) {
 	uint64_t *h = w.hot; w.hot = w.hot_alt; w.hot_alt = h;
 	PfCold *c = w.cold; w.cold = w.cold_alt; w.cold_alt = c;
@@ -854,6 +965,7 @@ PF_DEV void pf_swap_tables(PfWarp &w) {
 
 /* ------------------------------------------------------------------ one net
  * timing_driven_route_net, route_timing.c:399-563 */
+/* STRICT: 0 = delta buckets, 1 = strict best-first, 2 = breadth-first router (always strict order) */
 template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: routed, 0: handed to a bigger slot / failed */
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
@@ -914,6 +1026,19 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 		tree_n = 1;
 		pf_syncwarp();
 
+		if (STRICT == 2) {
+			/* breadth-first: no per-net base-cost rescaling (route_breadth_first.c never calls update_rr_base_costs),
+			 * and the wave floods the bounding box, so it runs on the slot's table in global memory */
+			if (lane < P->num_indexed) w.base_cost[lane] = w.idx[lane].base_cost;
+			pf_syncwarp();
+			const int swapped = w.hot_alt != NULL;
+			if (swapped) pf_swap_tables(w);
+			const int r = pf_route_wave_bf(w, &tree_n, t0, ns, sink_order /* reused: per-pin done flags */, rt_of_sink);
+			if (swapped) pf_swap_tables(w);
+			if (r == 0) fail = PF_ST_UNROUTABLE;
+			else if (r == -2) fail = PF_ST_INTERNAL;
+			else if (r < 0 && !w.overflow) w.overflow = PF_OVF_OTHER;
+		} else
 		for (int itarget = 1; itarget <= ns; itarget++) {
 			int target_pin = sink_order[itarget];
 			int target_node = P->net_term[t0 + target_pin];
@@ -925,7 +1050,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 			 * and the back-trace: the kernel's instruction footprint matters, see DESIGN.md.) */
 			int r, swapped = 0;
 			for (;;) {
-				r = pf_search_sink<STRICT>(w, tree_n, target_node, crit, rlim);
+				r = pf_search_sink<STRICT == 2 ? 1 : STRICT>(w, tree_n, target_node, crit, rlim);
 				if (r < 0 && !swapped && w.overflow == PF_OVF_LABELS && w.hot_alt) {
 					pf_swap_tables(w);
 					w.overflow = 0;

@@ -169,7 +169,8 @@ static int ev_end(void) {
 extern __shared__ __align__(16) unsigned char pf_smem[];
 
 /* STRICT = 1: strict best-first search (one label settled per step; P.max_batch == 1), the throughput mode;
- * STRICT = 0: a delta bucket of up to P.max_batch labels per step, the latency mode for few nets per warp */
+ * STRICT = 0: a delta bucket of up to P.max_batch labels per step, the latency mode for few nets per warp;
+ * STRICT = 2: the breadth-first router (one persistent wavefront per net, route_breadth_first.c) */
 template <int STRICT> __global__ void __launch_bounds__(128, 5) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
 	/* 96 registers and 43.3 KB of shared memory per 4-warp CTA: 5 CTAs = 20 warps per SM.
 	 * shared memory: [switch + cost-index tables, one copy per CTA][per-warp regions] */
@@ -356,10 +357,12 @@ int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	if (smem > smem_set) {
 		CK(cudaFuncSetAttribute(pf_route_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		CK(cudaFuncSetAttribute(pf_route_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(pf_route_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		smem_set = smem;
 	}
 	if (ev_begin(0) != 0) return -1;
-	if (P->max_batch == 1) pf_route_kernel<1><<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
+	if (P->algorithm == 1) pf_route_kernel<2><<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
+	else if (P->max_batch == 1) pf_route_kernel<1><<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
 	else pf_route_kernel<0><<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
 	return ev_end();
 }

@@ -93,6 +93,7 @@ struct PfParams {
 	float pop_slack;       /* delta-stepping bucket width in units of the cheapest edge cost for the
 	                          sink's criticality: every label within it of the minimum is settled in one step */
 	float win_rel, win_abs;/* near-set window: max(min*win_rel, win_abs) */
+	int algorithm;         /* 0 = timing-driven (route_timing.c), 1 = breadth-first (route_breadth_first.c) */
 	int max_batch;
 	int skip_ripup;
 	/* per-warp slot memory */

@@ -610,6 +610,7 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.win_rel = c.win_rel > 0.f ? c.win_rel : 0.05f;
 	P.win_abs = c.win_abs > 0.f ? c.win_abs : r->win_abs_auto;
 	P.max_batch = 1;
+	P.algorithm = p->opts.router_algorithm == 1 ? 1 : 0;
 	P.skip_ripup = 0;
 	P.hot = s.hot; P.cold = s.cold; P.label_log2 = s.label_log2; P.epochs = s.epochs;
 	P.hot2 = s.hot2; P.cold2 = s.cold2; P.label2_log2 = s.label2_log2;
@@ -1002,14 +1003,15 @@ static int route_loop(const pf_problem *p, const pf_config *cfg, pf_sta_fn sta, 
 		crit_hist.insert(crit_hist.end(), crit.begin(), crit.begin() + p->num_terminals);
 		rc = pf_route_iteration(r, pres_fac, have_crit ? crit.data() : NULL, &st);
 		if (rc != PF_OK) break;
-		if (itry == 1) {
+		const bool breadth_first = o.router_algorithm == 1;      /* try_breadth_first_route, route_breadth_first.c:23-91 */
+		if (itry == 1 && !breadth_first) {                      /* the timing-driven router's wirelength abort, route_timing.c:189-225 */
 			int64_t wl = 0, avail = 1;
 			if ((rc = pf_total_wirelength(r, &wl, &avail)) != PF_OK) break;
 			if ((float)wl / (float)avail > PF_FIRST_ITER_WIRELENGTH_LIMIT) { stats.push_back(st); itry++; break; }
 		}
 		if ((rc = pf_reserve_opins(r, pres_fac, itry != 1)) != PF_OK) break;
 		float acc_fac;
-		if (itry == 1) { pres_fac = o.initial_pres_fac; acc_fac = 0.f; }
+		if (itry == 1) { pres_fac = o.initial_pres_fac; acc_fac = breadth_first ? o.acc_fac : 0.f; }   /* route_breadth_first.c:84 */
 		else {
 			pres_fac *= o.pres_fac_mult;
 			pres_fac = fminf(pres_fac, (float)(PF_HUGE_POSITIVE_FLOAT / 1e5));
@@ -1058,6 +1060,13 @@ static int route_loop(const pf_problem *p, const pf_config *cfg, pf_sta_fn sta, 
 
 extern "C" int pf_try_timing_driven_route(const pf_problem *p, const pf_config *cfg, pf_sta_fn sta, void *user, pf_result *out) {
 	return route_loop(p, cfg, sta, user, NULL, out);
+}
+
+/* try_breadth_first_route (route_breadth_first.c:23): the same loop with opts.router_algorithm == 1 */
+extern "C" int pf_try_breadth_first_route(const pf_problem *p, const pf_config *cfg, pf_result *out) {
+	if (!p || !cfg || !out) FAILF(PF_EINVAL, "null argument");
+	if (p->opts.router_algorithm != 1) FAILF(PF_EINVAL, "opts.router_algorithm must be 1 (breadth-first)");
+	return route_loop(p, cfg, NULL, NULL, NULL, out);
 }
 
 /* ====================================================================== device static timing analysis

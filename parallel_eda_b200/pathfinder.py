@@ -74,7 +74,8 @@ def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delay_buf
             nets = int(comm.all_reduce_scalar(nets))
         total_nets += nets
         per_iter.append(nets)
-        if it == 1:
+        breadth_first = int(o["router_algorithm"]) == 1       # try_breadth_first_route, route_breadth_first.c:23-91
+        if it == 1 and not breadth_first:
             wl, avail = r.total_wirelength()
             if comm is not None:
                 wl = int(comm.all_reduce_scalar(wl))
@@ -82,7 +83,7 @@ def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delay_buf
                 overused.append(-1)
                 break
         if it == 1:
-            new_pres, acc_fac = float(o["initial_pres_fac"]), 0.0
+            new_pres, acc_fac = float(o["initial_pres_fac"]), (float(o["acc_fac"]) if breadth_first else 0.0)
         else:
             new_pres = min(pres_fac * float(o["pres_fac_mult"]), HUGE_POSITIVE_FLOAT / 1e5)
             acc_fac = float(o["acc_fac"])

@@ -52,7 +52,8 @@ static void route_warp(void *arg, int warp_id) {
 		for (int i = 0; i < a->P->num_sw; i++) sw[i] = a->P->sw[i];
 	}
 	pf_syncwarp();
-	if (a->P->max_batch == 1) pf_warp_main<1>(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
+	if (a->P->algorithm == 1) pf_warp_main<2>(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
+	else if (a->P->max_batch == 1) pf_warp_main<1>(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
 	else pf_warp_main<0>(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
 }
 

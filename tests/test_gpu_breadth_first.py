@@ -1,0 +1,35 @@
+"""GPU tests (-m gpu) of the breadth-first router mode (reference route_breadth_first.c) against the goldens the
+unmodified reference wrote with `--router_algorithm breadth_first` (tests/golden/*_bf.*)."""
+import os
+import time
+
+import pytest
+
+from parallel_eda_b200 import check_route, pfio, router
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90"])
+def test_breadth_first_routing(name):
+    p = pfio.read_problem(os.path.join(G, name + "_bf.pfp.xz"))
+    p.opts["max_router_iterations"] = 150
+    g = pfio.read_result(os.path.join(G, name + "_bf.pfr.xz"))
+    t = time.perf_counter()
+    r = router.try_timing_driven_route(p)
+    dt = time.perf_counter() - t
+    assert r.success == 1
+    m = check_route.check_route(p, r, check_delays=False)
+    assert m["overused"] == 0 and m["wirelength"] == r.total_wirelength
+    print("%s breadth-first: %d iterations (reference %d), wirelength x%.3f, %.3f s" % (name, r.iterations, g.iterations, r.total_wirelength / g.total_wirelength, dt))
+    assert r.total_wirelength <= 1.12 * g.total_wirelength
+
+
+def test_single_warp_breadth_first_is_bit_identical_to_the_emulated_device_code():
+    """One warp is deterministic: the sm_100a build must produce the emulator's routing (tests/golden/single_warp_toy_bf.json)."""
+    import json
+    sw = json.load(open(os.path.join(G, "single_warp_toy_bf.json")))
+    p = pfio.read_problem(os.path.join(G, "toy_w64_bf.pfp.xz"))
+    r = router.try_timing_driven_route(p, router.default_config(num_slots=1, big_slots=1))
+    assert (r.serial_num, r.total_wirelength, r.iterations) == (sw["serial_num"], sw["total_wirelength"], sw["iterations"])

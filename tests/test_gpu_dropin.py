@@ -34,8 +34,8 @@ def _stage(tmp, name):
                 o.write(f.read())
 
 
-def _run(binary, tmp, name, width, flow_prefix):
-    cmd = [binary] + flow_prefix + ["k6_N10_like.xml", name, "--nodisp", "--route", "--route_chan_width", str(width)]
+def _run(binary, tmp, name, width, flow_prefix, extra=()):
+    cmd = [binary] + flow_prefix + ["k6_N10_like.xml", name, "--nodisp", "--route", "--route_chan_width", str(width)] + list(extra)
     r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, timeout=1200)
     out = r.stdout
     assert r.returncode == 0, out[-3000:] + r.stderr[-2000:]
@@ -44,7 +44,8 @@ def _run(binary, tmp, name, width, flow_prefix):
     m_wl = re.search(r"Total wirelength: (\d+)", out)
     m_cp = re.search(r"Final critical path: ([0-9.eE+-]+) ns", out)
     assert m_it and m_wl and m_cp, out[-3000:]
-    assert "Completed net delay value cross check successfully" in out      # timing_driven_check_net_delays
+    if not extra:
+        assert "Completed net delay value cross check successfully" in out      # timing_driven_check_net_delays
     return int(m_it.group(1)), int(m_wl.group(1)), float(m_cp.group(1))
 
 
@@ -62,3 +63,19 @@ def test_vpr_flow_with_b200_router(name, width, tmp_path):
     assert wl_g <= (1.12 if name == "toy" else 1.08) * wl_r
     # the 6x6 toy has ~300 nets on 36 tiles: single nets move the critical path by several percent
     assert cp_g <= (1.08 if name == "toy" else 1.05) * cp_r
+
+
+def test_vpr_flow_breadth_first_with_b200_router(tmp_path):
+    """`--router_algorithm breadth_first`: route_common.c:495 lands in pf_adapter_try_breadth_first_route; the
+    reference's check_route runs inside the flow on the device router's traces."""
+    if not (os.path.exists(REF) and os.path.exists(B200)):
+        pytest.skip("oracle/_ref binaries not built (need /root/reference at build time)")
+    name, width = "toy", 70
+    d_ref, d_gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    os.makedirs(d_ref); os.makedirs(d_gpu)
+    _stage(d_ref, name); _stage(d_gpu, name)
+    bf = ["--router_algorithm", "breadth_first"]
+    it_r, wl_r, cp_r = _run(REF, d_ref, name, width, ["flow"], bf)
+    it_g, wl_g, cp_g = _run(B200, d_gpu, name, width, [], bf)
+    print("%s W=%d breadth-first: reference %d it, WL %d, CPD %.4f ns | B200 %d it, WL %d, CPD %.4f ns" % (name, width, it_r, wl_r, cp_r, it_g, wl_g, cp_g))
+    assert wl_g <= 1.10 * wl_r
