@@ -299,10 +299,11 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.warps_per_block <= 0) c.warps_per_block = 4;
 	if (c.num_slots <= 0) c.num_slots = (sms > 0 ? sms : 148) * 20;   /* 5 CTAs x 4 warps resident per SM */
 	c.label_log2 = PF_SMEM_HOT_LOG2;                 /* regular slots: hot label table in shared memory */
-	if (c.label2_log2 == 0) c.label2_log2 = 13;      /* per-slot fallback table in global memory; < 0: none */
+	const bool bf = p->opts.router_algorithm == 1;   /* the breadth-first wave floods the net's bounding box: larger per-slot scratch */
+	if (c.label2_log2 == 0) c.label2_log2 = bf ? 15 : 13;   /* per-slot fallback table in global memory; < 0: none */
 	if (c.label2_log2 < 0) c.label2_log2 = 0;
 	if (c.tree_cap <= 0) c.tree_cap = 2048;
-	if (c.far_cap <= 0) c.far_cap = 8192;
+	if (c.far_cap <= 0) c.far_cap = bf ? 32768 : 8192;
 	if (c.sink_cap <= 0) c.sink_cap = 64;
 	if (c.big_slots <= 0) c.big_slots = 64;
 	if (c.reroute_all_iters == 0) c.reroute_all_iters = 1;
