@@ -159,6 +159,24 @@ int pf_sta_analyze_device(pf_sta *s, const void *dev_net_delay, void *dev_crit, 
 /* try_timing_driven_route with the analysis on the device: no host callback, no per-iteration copies */
 int pf_try_timing_driven_route_sta(const pf_problem *p, const pf_timing_graph *g, const pf_config *cfg, pf_result *out);
 
+/* check_route (route/check_route.c:27-155) on the device, for ANY routing of the router's problem handed over as a
+ * pf_result (the router's own, the oracle's, the reference's): traces start at the SOURCE, segments end at the
+ * net's SINKs, consecutive elements are rr edges with the recorded switch, later segments branch off the net, every
+ * pin is reached once; the occupancy recomputed from the traces explains result.occ up to the locally used OPINs
+ * and respects capacity.  Never looks at the router's state — only at its copy of the rr graph. */
+typedef struct pf_check_report {
+	int32_t ok;                  /* 1 iff everything below is clean (overused_nodes may be > 0 for an unfinished routing) */
+	int32_t bad_nets;            /* nets with a structural violation */
+	int32_t first_bad_net;       /* lowest such net, -1 if none */
+	int32_t first_bad_code;      /* 1 no trace, 2 not at SOURCE, 3 open segment, 4 join not in net, 5 no such rr edge,
+	                                6 SINK carries a switch, 7 wrong sinks, 8 node id out of range */
+	int32_t occupancy_mismatch;  /* rr nodes whose reported occupancy the traces (+ OPIN reservations) do not explain */
+	int32_t overused_nodes;      /* reported occupancy above capacity */
+	int64_t wirelength;          /* of the structurally valid nets */
+	int64_t reserved_opins;      /* occupancy not due to traces (must equal the sum of opin_group_count) */
+} pf_check_report;
+int pf_check_route(pf_router *r, const pf_result *res, pf_check_report *rep);
+
 /* try_breadth_first_route (route/route_breadth_first.c:23-91; `--router_algorithm breadth_first`): problems with
  * opts.router_algorithm == 1 are routed by one persistent maze wavefront per net (no lookahead, no delay term, the
  * new segment re-enters the wave at cost 0), acc_fac applies from the first iteration and there is no

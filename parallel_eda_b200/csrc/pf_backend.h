@@ -82,4 +82,11 @@ int pfb_sta_begin_pair(const PfStaDev *S, float *stat);
 int pfb_sta_sweep(const PfStaDev *S, int forward, int lv_begin, int lv_end, int spread, int domain, float constraint, float *stat);
 int pfb_sta_update(const PfStaDev *S, float constraint, const float *stat, float *dev_crit);
 
+/* check_route over a finished routing (pf_check_net): report[0] bad nets, [1] lowest bad net (init INT_MAX), [2] its
+ * code, [3] rr nodes whose occupancy is not explained by the traces, [4] overused rr nodes; wl_extra[0] wirelength,
+ * [1] occupancy not accounted for by the traces (must equal the locally used OPINs) */
+int pfb_launch_check_route(const PfNode *nodes, const uint32_t *edges, int num_nodes, int num_nets, const int *net_ptr, const int *net_term,
+		const unsigned char *net_is_global, const int *trace_ptr, const int *trace_node, const short *trace_switch, unsigned char *matched,
+		int *occ2, const int *occ_reported, int *report, unsigned long long *wl_extra);
+
 #endif

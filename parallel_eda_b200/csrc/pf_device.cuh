@@ -1300,4 +1300,65 @@ PF_DEV int pf_net_is_congested(const PfNode *nodes, const PfTreeNode *pool, PfNe
 	return 0;
 }
 
+/* ------------------------------------------------------------------ check_route (route/check_route.c:27-155)
+ * One net of a finished routing, judged from its traceback alone: starts at the net's SOURCE; every segment ends
+ * at a SINK (iswitch OPEN) that is a still-unmatched pin of the net; consecutive elements are joined by a real rr
+ * edge carrying the recorded switch (check_adjacent, check_route.c:262 reduced to edge existence: the rr graph is
+ * the authority); every later segment starts at a node already in the net; all pins are reached.  Adds the net's
+ * occupancy to occ2 (recompute_occupancy_from_scratch, check_route.c:535-597: the join element of a segment is not
+ * counted again) and returns 0 or the first violation. */
+#define PF_CHK_NO_TRACE 1
+#define PF_CHK_NOT_AT_SOURCE 2
+#define PF_CHK_OPEN_SEGMENT 3
+#define PF_CHK_JOIN_NOT_IN_NET 4
+#define PF_CHK_NO_SUCH_EDGE 5
+#define PF_CHK_SINK_HAS_SWITCH 6
+#define PF_CHK_WRONG_SINKS 7
+#define PF_CHK_BAD_NODE 8
+PF_DEV int pf_check_net(const PfNode *nodes, const uint32_t *edges, int num_nodes, const int *term, int ns,
+		const int *tn, const short *ts, int len, unsigned char *matched /*[ns+1], zeroed*/, int *occ2, unsigned *wl_out) {
+	if (ns == 0) return 0;
+	if (len == 0) return PF_CHK_NO_TRACE;
+	for (int k = 0; k < len; k++) if (tn[k] < 0 || tn[k] >= num_nodes) return PF_CHK_BAD_NODE;
+	if (tn[0] != term[0]) return PF_CHK_NOT_AT_SOURCE;
+	int seg_start = 0, reached = 0;
+	unsigned wl = 0;
+	for (int k = 0; k < len; k++) {
+		const int v = tn[k];
+		const PfNode n = nodes[v];
+		const int ty = n.type_ci & 7;
+		const bool first_of_segment = (k == seg_start);
+		if (first_of_segment && k > 0) {                    /* the join node: must already belong to the net */
+			int found = 0;
+			for (int q = 0; q < k && !found; q++) found = (tn[q] == v);
+			if (!found) return PF_CHK_JOIN_NOT_IN_NET;
+		} else {
+			pf_atomic_add_i(&occ2[v], 1);
+			if (ty == 4 || ty == 5) wl += (unsigned)(1 + n.xhigh - n.xlow + n.yhigh - n.ylow);
+		}
+		if (ty == 1 && !(first_of_segment && k > 0)) {      /* a SINK closes the segment */
+			if (ts[k] != -1) return PF_CHK_SINK_HAS_SWITCH;
+			int hit = 0;
+			for (int q = 1; q <= ns && !hit; q++) if (!matched[q] && term[q] == v) { matched[q] = 1; hit = 1; }
+			if (!hit) return PF_CHK_WRONG_SINKS;
+			reached++;
+			seg_start = k + 1;
+			continue;
+		}
+		if (k + 1 >= len) return PF_CHK_OPEN_SEGMENT;       /* the traceback must end in a SINK */
+		{	/* an rr edge v -> tn[k+1] with the recorded switch */
+			const int to = tn[k + 1];
+			int ok = 0;
+			for (int e = 0; e < (int)n.num_edges && !ok; e++) {
+				const uint32_t ew = edges[n.edge_start + e];
+				ok = ((int)(ew & PF_EDGE_NODE_MASK) == to) && ((int)(ew >> PF_EDGE_NODE_BITS) == (int)ts[k]);
+			}
+			if (!ok) return PF_CHK_NO_SUCH_EDGE;
+		}
+	}
+	if (reached != ns) return PF_CHK_WRONG_SINKS;
+	*wl_out = wl;
+	return 0;
+}
+
 #endif /* PF_DEVICE_CUH */

@@ -347,6 +347,43 @@ __global__ void pf_sta_update_kernel(PfStaDev S, float constraint, const float *
 	for (int t = (int)(blockIdx.x * blockDim.x + threadIdx.x); t < S.num_terminals; t += (int)(gridDim.x * blockDim.x)) pf_sta_update_terminal(S, t, constraint, stat, crit);
 }
 
+/* ------------------------------------------------------------------ check_route (pf_check_net) */
+__global__ void pf_check_nets_kernel(const PfNode *nodes, const uint32_t *edges, int num_nodes, int num_nets, const int *net_ptr,
+		const int *net_term, const unsigned char *net_is_global, const int *trace_ptr, const int *trace_node, const short *trace_switch,
+		unsigned char *matched, int *occ2, int *report /* [0] bad nets [1] first bad net [2] its code */, unsigned long long *wl) {
+	const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i >= num_nets || net_is_global[i]) return;
+	const int t0 = net_ptr[i], ns = net_ptr[i + 1] - t0 - 1;
+	unsigned w = 0;
+	const int code = pf_check_net(nodes, edges, num_nodes, net_term + t0, ns, trace_node + trace_ptr[i], trace_switch + trace_ptr[i],
+			trace_ptr[i + 1] - trace_ptr[i], matched + t0, occ2, &w);
+	if (code) {
+		atomicAdd(&report[0], 1);
+		if (atomicMin(&report[1], i) > i) report[2] = code;          /* code of the lowest-numbered bad net (last writer wins among equals) */
+	} else if (w) atomicAdd(wl, (unsigned long long)w);
+}
+
+/* occupancy recomputed from the traces against the reported one: the difference may only be the locally used
+ * OPINs (reserve_locally_used_opins), i.e. non-negative and on OPIN nodes */
+__global__ void pf_check_occ_kernel(const PfNode *nodes, int num_nodes, const int *occ2, const int *occ_reported, int *report /* [3] mismatches [4] overused */,
+		unsigned long long *extra) {
+	int mism = 0, over = 0;
+	unsigned ex = 0;
+	for (int v = (int)(blockIdx.x * blockDim.x + threadIdx.x); v < num_nodes; v += (int)(gridDim.x * blockDim.x)) {
+		const int d = occ_reported[v] - occ2[v];
+		const int ty = nodes[v].type_ci & 7;
+		if (d < 0 || (d > 0 && ty != 3)) mism++;
+		else ex += (unsigned)d;
+		if (occ_reported[v] > (int)nodes[v].capacity) over++;
+	}
+	mism = __reduce_add_sync(0xffffffffu, mism); over = __reduce_add_sync(0xffffffffu, over); ex = __reduce_add_sync(0xffffffffu, ex);
+	if ((threadIdx.x & 31u) == 0) {
+		if (mism) atomicAdd(&report[3], mism);
+		if (over) atomicAdd(&report[4], over);
+		if (ex) atomicAdd(extra, (unsigned long long)ex);
+	}
+}
+
 /* ------------------------------------------------------------------ launchers */
 int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	if (warps_per_block < 1) warps_per_block = 1;
@@ -475,4 +512,15 @@ int pfb_sta_update(const PfStaDev *S, float constraint, const float *stat, float
 	pf_sta_update_kernel<<<stream_grid(S->num_terminals), 256, 0, g_stream>>>(*S, constraint, stat, dev_crit);
 	CK(cudaGetLastError());
 	return 0;
+}
+
+int pfb_launch_check_route(const PfNode *nodes, const uint32_t *edges, int num_nodes, int num_nets, const int *net_ptr, const int *net_term,
+		const unsigned char *net_is_global, const int *trace_ptr, const int *trace_node, const short *trace_switch, unsigned char *matched,
+		int *occ2, const int *occ_reported, int *report, unsigned long long *wl_extra) {
+	if (ev_begin(2) != 0) return -1;
+	if (num_nets > 0)
+		pf_check_nets_kernel<<<(num_nets + 127) / 128, 128, 0, g_stream>>>(nodes, edges, num_nodes, num_nets, net_ptr, net_term, net_is_global,
+				trace_ptr, trace_node, trace_switch, matched, occ2, report, wl_extra);
+	pf_check_occ_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, occ2, occ_reported, report, wl_extra + 1);
+	return ev_end();
 }

@@ -98,6 +98,12 @@ class _TimingGraphHolder:
                               int(g.constraint.shape[0]), q[8], len(g.net_driver), q[9])
 
 
+class CheckReport(C.Structure):
+    """pf_check_report (include/pf_router.h)."""
+    _fields_ = [("ok", C.c_int32), ("bad_nets", C.c_int32), ("first_bad_net", C.c_int32), ("first_bad_code", C.c_int32),
+                ("occupancy_mismatch", C.c_int32), ("overused_nodes", C.c_int32), ("wirelength", C.c_int64), ("reserved_opins", C.c_int64)]
+
+
 class Timing(C.Structure):
     _fields_ = [("route_kernel_ms", C.c_double), ("update_kernel_ms", C.c_double), ("aux_kernel_ms", C.c_double),
                 ("route_launches", C.c_int64), ("update_launches", C.c_int64), ("aux_launches", C.c_int64),
@@ -142,6 +148,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing), C.c_int]
     lib.pf_timer_start.argtypes = [C.c_void_p]
     lib.pf_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.pf_check_route.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CheckReport)]
     lib.pf_sta_create.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Config), C.POINTER(C.c_void_p)]
     lib.pf_sta_destroy.argtypes = [C.c_void_p]
     lib.pf_sta_destroy.restype = None
@@ -331,6 +338,20 @@ class Router:
         return ms.value
 
     # multi-GPU iteration boundary (device pointers, e.g. torch tensors' data_ptr())
+    def check_route(self, result: pfio.Result) -> dict:
+        """check_route (route/check_route.c:27) on the device for any routing of this problem: the router's own, the
+        oracle's or a golden of the reference.  Returns the pf_check_report as a dict."""
+        keep = [np.ascontiguousarray(result.trace_ptr, dtype=np.int32), np.ascontiguousarray(result.trace_node, dtype=np.int32),
+                np.ascontiguousarray(result.trace_switch, dtype=np.int16), np.ascontiguousarray(result.occ, dtype=np.int32)]
+        cr = _Result()
+        cr.num_nets = len(keep[0]) - 1
+        cr.trace_ptr = keep[0].ctypes.data_as(C.POINTER(C.c_int32)); cr.trace_node = keep[1].ctypes.data_as(C.POINTER(C.c_int32))
+        cr.trace_switch = keep[2].ctypes.data_as(C.POINTER(C.c_int16))
+        cr.num_nodes = len(keep[3]); cr.occ = keep[3].ctypes.data_as(C.POINTER(C.c_int32))
+        rep = CheckReport()
+        self._ck(self.lib.pf_check_route(self._h, C.byref(cr), C.byref(rep)))
+        return {f: int(getattr(rep, f)) for f, _ in CheckReport._fields_}
+
     def comm_graph_buffers(self):
         """[(device pointer, bytes)] of the packed graph: node records, edge words, ptc numbers."""
         ptrs = (C.c_void_p * 3)(); nb = (C.c_int64 * 3)()

@@ -179,3 +179,24 @@ int pfb_sta_update(const PfStaDev *S, float constraint, const float *stat, float
 	g_times.aux_launches++;
 	return 0;
 }
+
+int pfb_launch_check_route(const PfNode *nodes, const uint32_t *edges, int num_nodes, int num_nets, const int *net_ptr, const int *net_term,
+		const unsigned char *net_is_global, const int *trace_ptr, const int *trace_node, const short *trace_switch, unsigned char *matched,
+		int *occ2, const int *occ_reported, int *report, unsigned long long *wl_extra) {
+	for (int i = 0; i < num_nets; i++) {
+		if (net_is_global[i]) continue;
+		const int t0 = net_ptr[i], ns = net_ptr[i + 1] - t0 - 1;
+		unsigned w = 0;
+		const int code = pf_check_net(nodes, edges, num_nodes, net_term + t0, ns, trace_node + trace_ptr[i], trace_switch + trace_ptr[i],
+				trace_ptr[i + 1] - trace_ptr[i], matched + t0, occ2, &w);
+		if (code) { report[0]++; if (i < report[1]) { report[1] = i; report[2] = code; } }
+		else wl_extra[0] += w;
+	}
+	for (int v = 0; v < num_nodes; v++) {
+		const int d = occ_reported[v] - occ2[v];
+		if (d < 0 || (d > 0 && (nodes[v].type_ci & 7) != 3)) report[3]++; else wl_extra[1] += (unsigned long long)d;
+		if (occ_reported[v] > (int)nodes[v].capacity) report[4]++;
+	}
+	g_times.aux_launches++;
+	return 0;
+}

@@ -1,0 +1,80 @@
+"""check_route on the device (pf_check_route; reference route/check_route.c:27-155), here through the CPU emulator
+backend: the reference's own golden routings must pass, every seeded violation must be caught — and the verdicts
+must agree with the independent Python checker (parallel_eda_b200/check_route.py)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from parallel_eda_b200 import check_route, pfio, router
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def toy(emu_lib):
+    p = pfio.read_problem(os.path.join(G, "toy_w64.pfp.xz"))
+    g = pfio.read_result(os.path.join(G, "toy_w64.pfr.xz"))
+    R = router.Router(p, router.default_config(router.load_library(emu_lib), num_slots=1, big_slots=1), lib_path=emu_lib)
+    yield p, g, R
+    R.close()
+
+
+def test_reference_golden_routings_pass(toy, emu_lib):
+    p, g, R = toy
+    rep = R.check_route(g)
+    assert rep["ok"] == 1 and rep["bad_nets"] == 0 and rep["overused_nodes"] == 0 and rep["occupancy_mismatch"] == 0
+    assert rep["wirelength"] == g.total_wirelength == check_route.check_route(p, g)["wirelength"]
+    assert rep["reserved_opins"] == int(np.asarray(p.opin_group_count).sum())
+    for name in ("toy_w64_nt", "toy_w64_bf"):
+        assert R.check_route(pfio.read_result(os.path.join(G, name + ".pfr.xz")))["ok"] == 1
+
+
+def _net_with(p, g, min_len=6):
+    for i in p.routed_nets():
+        if g.trace_ptr[i + 1] - g.trace_ptr[i] >= min_len:
+            return int(i), int(g.trace_ptr[i]), int(g.trace_ptr[i + 1])
+    raise AssertionError
+
+
+@pytest.mark.parametrize("fault,code", [("source", 2), ("edge", 5), ("switch", 5), ("sink_switch", 6), ("drop_sink", 3), ("wrong_sink", 7), ("range", 8)])
+def test_seeded_violations_are_caught(toy, fault, code):
+    p, g, R = toy
+    bad = copy.deepcopy(g)
+    i, a, b = _net_with(p, g)
+    if fault == "source":
+        bad.trace_node[a] = bad.trace_node[a + 1]
+    elif fault == "edge":
+        bad.trace_node[a + 2] = bad.trace_node[a]                  # not a neighbour of element a+1
+    elif fault == "switch":
+        bad.trace_switch[a + 1] = (int(bad.trace_switch[a + 1]) + 1) % len(p.switches)
+    elif fault == "sink_switch":
+        k = a + int(np.nonzero(p.type[g.trace_node[a:b]] == pfio.SINK)[0][0])
+        bad.trace_switch[k] = 0
+    elif fault == "drop_sink":
+        keep = np.ones(len(bad.trace_node), bool); keep[b - 1] = False
+        bad.trace_node, bad.trace_switch = bad.trace_node[keep], bad.trace_switch[keep]
+        bad.trace_ptr = bad.trace_ptr.copy(); bad.trace_ptr[i + 1:] -= 1
+    elif fault == "wrong_sink":
+        other = [int(s) for s in p.net_terminals[p.net_ptr[i - 1] + 1:p.net_ptr[i]]] if i > 0 else []
+        sinks = np.nonzero(p.type == pfio.SINK)[0]
+        mine = set(int(s) for s in p.net_terminals[p.net_ptr[i] + 1:p.net_ptr[i + 1]])
+        bad.trace_node[b - 1] = next(int(s) for s in sinks if int(s) not in mine)
+    elif fault == "range":
+        bad.trace_node[a + 1] = p.num_nodes + 5
+    rep = R.check_route(bad)
+    assert rep["ok"] == 0 and rep["bad_nets"] >= 1 and rep["first_bad_net"] == i
+    assert rep["first_bad_code"] in ((code, 5) if fault in ("wrong_sink",) else (code,))
+    if fault != "range":
+        with pytest.raises(check_route.RouteCheckError):
+            check_route.check_route(p, bad, check_delays=False)
+
+
+def test_occupancy_tampering_is_caught(toy):
+    p, g, R = toy
+    bad = copy.deepcopy(g)
+    v = int(np.nonzero(p.type == pfio.CHANX)[0][0])
+    bad.occ = bad.occ.copy(); bad.occ[v] += 1
+    rep = R.check_route(bad)
+    assert rep["ok"] == 0 and rep["bad_nets"] == 0 and rep["occupancy_mismatch"] >= 1
