@@ -250,6 +250,9 @@ def run_ours(a):
             from parallel_eda_b200 import check_route
             check = check_route.check_route_fast(p, _res)
             check["wirelength"] = int(_res.total_wirelength)
+            # and the full check_route (every net, every edge, every sink) on the device, from the traces alone
+            check["device_check_route"] = R.check_route(_res)
+            assert check["device_check_route"]["ok"] == 1 and check["device_check_route"]["overused_nodes"] == 0
         e2e = {"value": acc_n / acc_t, "unit": "nets/s", "h2d_bytes_per_step": int(hb), "d2h_bytes_per_step": int(db),
                "s_per_step": acc_t / max(1, min(a.steps, 2)),
                "phases_s": dict(zip(("create_upload", "route", "result_download", "destroy"), [round(x, 4) for x in e2e_phases[-1]])),

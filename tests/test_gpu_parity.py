@@ -162,3 +162,22 @@ def test_malformed_graph_is_rejected_with_the_checker_message():
     assert e.value.code == -4
     p.capacity[3] = keep
     assert router.try_timing_driven_route(p).success == 1
+
+
+def test_device_check_route_agrees_with_the_python_checker():
+    """pf_check_route on the sm_100a build: golden routings of the reference pass, the router's own result passes,
+    a corrupted one is rejected with the offending net."""
+    p, g = _load("mid_w200", False)
+    R = router.Router(p)
+    rep = R.check_route(g)
+    assert rep["ok"] == 1 and rep["wirelength"] == g.total_wirelength and rep["overused_nodes"] == 0
+    r = router.try_timing_driven_route(p)
+    rep = R.check_route(r)
+    assert rep["ok"] == 1 and rep["wirelength"] == r.total_wirelength == check_route.check_route(p, r)["wirelength"]
+    import copy
+    bad = copy.deepcopy(r)
+    i = int(p.routed_nets()[7]); a = int(r.trace_ptr[i])
+    bad.trace_node[a + 1] = bad.trace_node[a]
+    rep = R.check_route(bad)
+    assert rep["ok"] == 0 and rep["first_bad_net"] == i and rep["first_bad_code"] == 5
+    R.close()
