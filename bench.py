@@ -205,10 +205,11 @@ def run_ours(a):
     launches = int(tm.route_launches + tm.update_launches + tm.aux_launches)
     # DRAM traffic of the dominant launch from the committed `ncu --set full` capture (iteration-1 launch of this very
     # workload on 1 GPU: profiles/r01_ncu_full_pf_route_kernel.json, dram__bytes_read.sum + dram__bytes_write.sum);
-    # that launch's algorithmic bytes are 3.75e9 (7.78e7 visits, 5.12e6 pops, 4.00e7 label writes)
+    # that launch's algorithmic bytes are 3.75e9 (7.78e7 visits, 5.12e6 pops, 4.00e7 label writes); 3.2e9 of the traffic
+    # are deliberate L2 prefetches of edge rows (10.4e9 without them, 2.5 % slower)
     traffic = None
     if world == 1 and (a.grid, a.nets, a.width) == (400, 200000, 100):
-        traffic = {"bytes_per_launch": 8.813320e9 + 1.612722e9, "launch": "iteration 1 (200000 nets)",
+        traffic = {"bytes_per_launch": 11.938608e9 + 1.684029e9, "launch": "iteration 1 (200000 nets)",
                    "algorithmic_bytes_same_launch": 36.0 * 77.83e6 + 28.0 * 5.12e6 + 20.0 * 40.03e6,
                    "source": "profiles/r01_ncu_full_pf_route_kernel.json"}
 
