@@ -53,3 +53,43 @@ def test_two_ranks_gloo(emu_lib, tmp_path):
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["success"] and out["occ_equal"] and out["overused"] == 0
+
+
+WORKER_TD = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch
+from parallel_eda_b200 import pfio, router, pathfinder, distributed
+comm = distributed.init_from_env("gloo")
+G = os.path.join(%(root)r, "tests", "golden")
+p = pfio.read_problem(os.path.join(G, "duo_w80.pfp.xz")); p.opts["timing_analysis_enabled"] = 1; p.opts["max_router_iterations"] = 150
+g = pfio.read_timing_graph(os.path.join(G, "duo_w80.pftg.xz"))
+lib = %(emu)r
+cfg = router.default_config(router.load_library(lib), num_slots=4, big_slots=1)
+R = comm.create_router(p, cfg, lib_path=lib)
+S = router.Sta(g, p, cfg, lib_path=lib)
+delay = distributed.wrap_device_floats(R.comm_net_delay_ptr(), p.num_terminals, comm.device)
+rep = pathfinder.route(R, comm=comm, dsta=S, delay_buf=delay)
+res = R.result()
+occ = torch.from_numpy(res.occ.astype(np.int64)); ref = occ.clone(); torch.distributed.broadcast(ref, 0)
+crit = distributed.wrap_device_floats(R.comm_crit_ptr(), p.num_terminals, comm.device).clone(); cref = crit.clone(); torch.distributed.broadcast(cref, 0)
+if comm.rank == 0:
+    print(json.dumps({"success": bool(rep.success), "iters": rep.iterations, "occ_equal": bool(torch.equal(occ, ref)), "crit_equal": bool(torch.equal(crit, cref)),
+                      "overused": int((res.occ > p.capacity).sum())}))
+else:
+    assert torch.equal(occ, ref) and torch.equal(crit, cref)
+'''
+
+
+def test_two_ranks_timing_driven_with_device_sta(emu_lib, tmp_path):
+    """Timing-driven on two ranks: the ranks' sink delays are summed (all-reduce) into the router's delay vector,
+    the device analysis then runs identically on every rank and writes the criticality vector in place."""
+    script = tmp_path / "worker_td.py"
+    script.write_text(WORKER_TD % {"root": ROOT, "emu": emu_lib})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    import json
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["success"] and out["occ_equal"] and out["crit_equal"] and out["overused"] == 0
