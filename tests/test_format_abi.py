@@ -70,3 +70,34 @@ def test_no_cpu_fallback_without_gpu(cuda_lib):
 def test_product_library_does_not_link_the_oracle_or_emulator(cuda_lib):
     syms = subprocess.run(["nm", "-D", cuda_lib], capture_output=True, text=True).stdout
     assert "pf_oracle" not in syms and "pf_emu" not in syms
+
+
+def test_timing_graph_container_python_and_c(unxz, cuda_lib, tmp_path):
+    """PFTIMG01 / PFSTAV01: the C reader/writer (pf_file.c, linked into the product library) and pfio agree, and
+    pf_timing_graph_check rejects a corrupted graph with a message."""
+    import ctypes as C
+    from test_sta_golden import _TG
+    lib = C.CDLL(cuda_lib)
+    lib.pf_timing_graph_read.argtypes = [C.c_char_p, C.POINTER(_TG)]
+    lib.pf_timing_graph_write.argtypes = [C.c_char_p, C.POINTER(_TG)]
+    lib.pf_timing_graph_free.argtypes = [C.POINTER(_TG)]
+    lib.pf_timing_graph_check.argtypes = [C.POINTER(_TG), C.c_void_p, C.c_char_p, C.c_int]
+    src = unxz("toy_w64.pftg")
+    g = _TG()
+    assert lib.pf_timing_graph_read(src.encode(), C.byref(g)) == 0
+    out = str(tmp_path / "copy.pftg")
+    assert lib.pf_timing_graph_write(out.encode(), C.byref(g)) == 0
+    assert open(out, "rb").read() == open(src, "rb").read()
+    a = pfio.read_timing_graph(out)
+    out2 = str(tmp_path / "copy2.pftg")
+    pfio.write_timing_graph(out2, a)
+    assert open(out2, "rb").read() == open(src, "rb").read()
+    p = pfio.read_problem(unxz("toy_w64.pfp"))
+    net_ptr = np.ascontiguousarray(p.net_ptr, dtype=np.int32)
+    msg = C.create_string_buffer(256)
+    assert lib.pf_timing_graph_check(C.byref(g), net_ptr.ctypes.data, msg, 256) == 0
+    C.cast(g.edge_to, C.POINTER(C.c_int32))[3] = -5
+    assert lib.pf_timing_graph_check(C.byref(g), net_ptr.ctypes.data, msg, 256) != 0 and b"tedge" in msg.value
+    lib.pf_timing_graph_free(C.byref(g))
+    v = pfio.read_sta_vectors(unxz("toy_w64.pfsta"))
+    assert v.net_delay.shape == v.crit.shape == (20, p.num_terminals) and v.cpd.shape == (20,)
