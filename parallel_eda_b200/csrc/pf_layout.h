@@ -121,10 +121,10 @@ struct PfParams {
 
 /* device image of the timing graph for the static timing analysis (pf_sta_device.cuh, pf_sta.cpp) */
 struct PfStaDev {
-	int num_tnodes, num_terminals, num_levels;
-	const int *edge_ptr, *edge_to;           /* out-edges (reference order) */
+	int num_tnodes, num_terminals, num_levels;   /* tnodes are renumbered in level order: level l = [level_ptr[l], level_ptr[l+1]) */
+	const int *edge_ptr, *edge_to;           /* out-edges (reference order within a tnode) */
 	float *Tdel;                             /* [num_tedges] working copy: static delays + this call's net delays */
-	const int *in_ptr, *in_from, *in_edge;   /* in-edges: source tnode and index of the edge in the out-edge arrays */
+	const int *in_ptr, *in_rec;              /* in-edges: pairs (source tnode, index of the edge in the out-edge arrays) */
 	const unsigned char *type;
 	const int *clock_domain;
 	const float *clock_delay;

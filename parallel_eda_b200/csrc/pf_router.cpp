@@ -1105,22 +1105,38 @@ extern "C" int pf_sta_create(const pf_timing_graph *g, const pf_problem *p, cons
 	if (pf_timing_graph_check(g, p->net_ptr, msg, sizeof(msg)) != PF_OK) FAILF(PF_EINVAL, "invalid timing graph: %s", msg);
 	if (pfb_init(cfg->device) != 0) CUDA_FAIL();
 	const int N = g->num_tnodes, E = g->num_tedges, T = p->num_terminals;
-	/* in-edges */
-	std::vector<int> in_ptr((size_t)N + 1, 0), in_from((size_t)std::max(E, 1)), in_edge((size_t)std::max(E, 1));
-	for (int e = 0; e < E; e++) in_ptr[(size_t)g->edge_to[e] + 1]++;
+	/* Renumber the tnodes in level order (new id = position in the level lists): a level is then a contiguous
+	 * range, its structural reads are coalesced, and the kernels need no level list.  Out-edges keep the
+	 * reference's order within a tnode, so "pin k of a net = out-edge k-1 of its driver" still holds. */
+	std::vector<int> pos((size_t)N), r_eptr((size_t)N + 1, 0), r_eto((size_t)std::max(E, 1)), r_dom((size_t)N), new_edge((size_t)std::max(E, 1));
+	std::vector<float> r_tdel((size_t)std::max(E, 1)), r_cdel((size_t)N);
+	std::vector<unsigned char> r_type((size_t)N);
+	for (int k = 0; k < N; k++) pos[(size_t)g->level_nodes[k]] = k;
+	for (int k = 0; k < N; k++) {
+		const int o = g->level_nodes[k];
+		r_eptr[(size_t)k + 1] = r_eptr[(size_t)k] + (g->edge_ptr[o + 1] - g->edge_ptr[o]);
+		r_dom[(size_t)k] = g->clock_domain[o]; r_cdel[(size_t)k] = g->clock_delay[o]; r_type[(size_t)k] = g->type[o];
+		for (int e = g->edge_ptr[o], q = r_eptr[(size_t)k]; e < g->edge_ptr[o + 1]; e++, q++) {
+			r_eto[(size_t)q] = pos[(size_t)g->edge_to[e]]; r_tdel[(size_t)q] = g->edge_Tdel[e]; new_edge[(size_t)e] = q;
+		}
+	}
+	/* in-edges as (source, edge) pairs */
+	std::vector<int> in_ptr((size_t)N + 1, 0), in_rec(2 * (size_t)std::max(E, 1));
+	for (int e = 0; e < E; e++) in_ptr[(size_t)r_eto[(size_t)e] + 1]++;
 	for (int n = 0; n < N; n++) in_ptr[(size_t)n + 1] += in_ptr[(size_t)n];
 	{
 		std::vector<int> fill(in_ptr.begin(), in_ptr.end() - 1);
 		for (int n = 0; n < N; n++)
-			for (int e = g->edge_ptr[n]; e < g->edge_ptr[n + 1]; e++) { int k = fill[(size_t)g->edge_to[e]]++; in_from[(size_t)k] = n; in_edge[(size_t)k] = e; }
+			for (int e = r_eptr[(size_t)n]; e < r_eptr[(size_t)n + 1]; e++) { int k = fill[(size_t)r_eto[(size_t)e]]++; in_rec[2 * (size_t)k] = n; in_rec[2 * (size_t)k + 1] = e; }
 	}
 	/* net pin -> (driver tnode, out-edge): pin k of net i is out-edge k-1 of its driver (path_delay.c:479-500) */
 	std::vector<int> term_edge((size_t)std::max(T, 1), -1), term_driver((size_t)std::max(T, 1), -1);
 	for (int i = 0; i < p->num_nets; i++) {
-		const int d = g->net_driver[i];
-		if (d < 0) continue;
-		for (int k = 1; k < p->net_ptr[i + 1] - p->net_ptr[i]; k++) { term_edge[(size_t)p->net_ptr[i] + k] = g->edge_ptr[d] + k - 1; term_driver[(size_t)p->net_ptr[i] + k] = d; }
+		if (g->net_driver[i] < 0) continue;
+		const int d = pos[(size_t)g->net_driver[i]];
+		for (int k = 1; k < p->net_ptr[i + 1] - p->net_ptr[i]; k++) { term_edge[(size_t)p->net_ptr[i] + k] = r_eptr[(size_t)d] + k - 1; term_driver[(size_t)p->net_ptr[i] + k] = d; }
 	}
+	(void)new_edge;
 	pf_sta *s = new pf_sta();
 	memset(&s->d, 0, sizeof(s->d));
 	s->num_owned = 0; s->num_domains = g->num_domains; s->num_tedges = E;
@@ -1137,21 +1153,18 @@ extern "C" int pf_sta_create(const pf_timing_graph *g, const pf_problem *p, cons
 	PfStaDev &d = s->d;
 	d.num_tnodes = N; d.num_terminals = T; d.num_levels = g->num_levels;
 	bool ok = true;
-	auto up_i = [&](const int32_t *src, size_t n) { std::vector<int> v(src, src + n); int *q = sta_upload(s, v); ok = ok && q; return (const int *)q; };
-	d.edge_ptr = up_i(g->edge_ptr, (size_t)N + 1);
-	d.edge_to = up_i(g->edge_to, (size_t)E);
-	d.in_ptr = sta_upload(s, in_ptr); d.in_from = sta_upload(s, in_from); d.in_edge = sta_upload(s, in_edge);
-	d.clock_domain = up_i(g->clock_domain, (size_t)N);
-	d.level_ptr = up_i(g->level_ptr, (size_t)g->num_levels + 1);
-	d.level_nodes = up_i(g->level_nodes, (size_t)N);
+	std::vector<int> ident((size_t)N), lptr(g->level_ptr, g->level_ptr + g->num_levels + 1);
+	for (int k = 0; k < N; k++) ident[(size_t)k] = k;
+	d.edge_ptr = sta_upload(s, r_eptr); d.edge_to = sta_upload(s, r_eto);
+	d.in_ptr = sta_upload(s, in_ptr); d.in_rec = sta_upload(s, in_rec);
+	d.clock_domain = sta_upload(s, r_dom);
+	d.level_ptr = sta_upload(s, lptr); d.level_nodes = sta_upload(s, ident);
 	d.term_edge = sta_upload(s, term_edge); d.term_driver = sta_upload(s, term_driver);
-	{ std::vector<float> v(g->edge_Tdel, g->edge_Tdel + E); d.Tdel = sta_upload(s, v); }
-	{ std::vector<float> v(g->clock_delay, g->clock_delay + N); d.clock_delay = sta_upload(s, v); }
-	{ std::vector<unsigned char> v(g->type, g->type + N); d.type = sta_upload(s, v); }
+	d.Tdel = sta_upload(s, r_tdel); d.clock_delay = sta_upload(s, r_cdel); d.type = sta_upload(s, r_type);
 	{ std::vector<float> v((size_t)N, 0.f); d.T_arr = sta_upload(s, v); d.T_req = sta_upload(s, v); }
 	{ std::vector<float> v((size_t)std::max(g->num_domains * g->num_domains, 1) * 4, 0.f); s->stat = sta_upload(s, v); }
 	{ std::vector<float> v((size_t)std::max(T, 1), 0.f); s->scratch_delay = sta_upload(s, v); s->scratch_crit = sta_upload(s, v); }
-	ok = ok && d.in_ptr && d.in_from && d.in_edge && d.term_edge && d.term_driver && d.Tdel && d.clock_delay && d.type && d.T_arr && d.T_req
+	ok = ok && d.edge_ptr && d.edge_to && d.clock_domain && d.level_ptr && d.level_nodes && d.in_ptr && d.in_rec && d.term_edge && d.term_driver && d.Tdel && d.clock_delay && d.type && d.T_arr && d.T_req
 		&& s->stat && s->scratch_delay && s->scratch_crit;
 	if (!ok || pfb_sync() != 0) { pf_sta_destroy(s); CUDA_FAIL(); }
 	*out = s;

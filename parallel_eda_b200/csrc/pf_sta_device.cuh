@@ -56,9 +56,9 @@ PF_DEV void pf_sta_forward_node(const PfStaDev &S, int n, int lv, int src_domain
 	float best = (float)PF_STA_HUGE_NEG;
 	int any = 0;
 	for (int k = S.in_ptr[n]; k < S.in_ptr[n + 1]; k++) {
-		const float ta = S.T_arr[S.in_from[k]];
+		const float ta = S.T_arr[S.in_rec[2 * k]];
 		if (ta < PF_STA_NEG_EPS) continue;               /* the predecessor is not in this traversal */
-		const float cand = ta + S.Tdel[S.in_edge[k]];
+		const float cand = ta + S.Tdel[S.in_rec[2 * k + 1]];
 		if (cand > best) best = cand;                    /* set_and_balance_arrival_time, :3449 */
 		any = 1;
 	}
