@@ -5,20 +5,9 @@
  * the device route store back into s_trace-ordered lists.  All device work goes through
  * pf_backend.h; this file contains no routing arithmetic.
  */
-#include "../../include/pf_router.h"
-#include "pf_backend.h"
+#include "pf_host.h"
 
-#include <math.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <algorithm>
-#include <vector>
-
-static char g_router_err[512] = "";
-#define FAILF(code, ...) do { snprintf(g_router_err, sizeof(g_router_err), __VA_ARGS__); return (code); } while (0)
-#define CUDA_FAIL() do { snprintf(g_router_err, sizeof(g_router_err), "%s", pfb_last_error()); return PF_ECUDA; } while (0)
-#define CKB(x) do { if ((x) != 0) CUDA_FAIL(); } while (0)
+char g_router_err[512] = "";
 
 extern "C" const char *pf_last_error(void) { return g_router_err; }
 extern "C" const char *pf_backend_name(void) { return pfb_name(); }
@@ -28,69 +17,6 @@ extern "C" void pf_config_default(pf_config *c) {
 	memset(c, 0, sizeof(*c));
 	c->nranks = 1;
 	c->pop_slack = -1.f;
-}
-
-struct SlotClass {
-	int num_slots, label_log2, tree_cap, far_cap, sink_cap;
-	uint64_t *hot; PfCold *cold; uint64_t *hot2; PfCold *cold2; int label2_log2; unsigned *epochs; PfTreeNode *tree; uint64_t *far; int *iscratch;
-	int *work; int num_work; int *work_head;
-};
-
-struct pf_router {
-	pf_config cfg;
-	const pf_problem *prob;       /* caller-owned; must outlive the router */
-	int N, E, T, n;
-	PfNode *nodes; uint32_t *edges;
-	PfSwitchDev *sw; PfIndexedDev *indexed;
-	int *net_ptr, *net_term, *net_bb;
-	float *crit, *net_delay;
-	SlotClass small, big;
-	PfTreeNode *pool[2]; PfNetLoc *loc; int cur;      /* pool[cur] is the live route-tree log */
-	long long pool_cap; unsigned long long *pool_head;
-	int *all_nets; int num_all; unsigned char *net_big; int *sel_counts; int *sel_scratch;
-	short *ptc;                    /* rr_node[].ptc_num, only read when the result's serial number is assembled */
-	std::vector<unsigned char> h_net_big;
-	std::vector<int> net_rank;        /* position of a net in the fanout-sorted order */
-	int iter_count;
-	int best_overused, stall_count;   /* convergence watchdog, see pf_iteration_begin */
-	std::vector<int> over_hist; int since_full;
-	unsigned char *last_over; int cost_updates; int *committer;   /* per node: tag of the last cost update that found it overused */
-	int cur_div, n_small, n_big; int *retry_work;
-	char *ctl; unsigned long long h_pool_head;   /* device control block; host copy of the log head */
-	int *status, *retry_list, *retry_count;
-	PfStats *stats;
-	int *d_overused; unsigned long long *d_wl;
-	int graph_ready;              /* 0 while a deferred graph has not been filled in */
-	unsigned *events; long long event_cap; long long h_events;   /* multi-GPU only: this rank's occupancy event log */
-	/* OPIN reservation */
-	int num_groups; int *g_source, *g_count, *g_off, *g_chosen;
-	long long avail_wl;
-	double t_mark[4];
-	int64_t h2d_bytes, d2h_bytes;
-	std::vector<int> work_small, work_big;
-	std::vector<int> h_all;           /* host copy of all_nets: interior nets first, then cut nets, each in fanout order */
-	int K1;                           /* number of interior nets at the head of all_nets */
-	int n1_small, n1_big;             /* interior nets at the head of this iteration's two work lists */
-	float win_abs_auto;
-};
-
-#include <chrono>
-static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-#include <thread>
-#include <atomic>
-/* simple static-partition parallel loop for the host-side flattening of 10^7..10^8-element arrays */
-template <class F> static void parallel_for(long long n, F f) {
-	unsigned hw = std::thread::hardware_concurrency();
-	int cap = 16;                                   /* memory-bound loops: more threads starve the DMA engine that drains the
-	                                                 * staging buffer behind them (measured 8: 51, 16: 45, 32-64: 52 ms per
-	                                                 * upload); PF_HOST_THREADS overrides */
-	if (const char *e = getenv("PF_HOST_THREADS")) { int v = atoi(e); if (v > 0) cap = v; }
-	int nt = (int)std::min<long long>(hw ? hw : 4, std::max<long long>(1, n / (1 << 16)));
-	if (nt > cap) nt = cap;
-	if (nt <= 1) { f(0, n); return; }
-	std::vector<std::thread> th;
-	for (int t = 0; t < nt; t++) th.emplace_back([=]() { f(n * t / nt, n * (t + 1) / nt); });
-	for (auto &t : th) t.join();
 }
 
 /* pf_problem_check (pf_file.c) is a single-threaded scan; on 10^8 edges that is a visible part of the call.
@@ -1070,146 +996,6 @@ extern "C" int pf_try_breadth_first_route(const pf_problem *p, const pf_config *
 	return route_loop(p, cfg, NULL, NULL, NULL, out);
 }
 
-/* ====================================================================== device static timing analysis
- * Host side: reverse CSR + per-terminal maps built once, the sweep plan (runs of narrow levels in one CTA, wide
- * levels spread over the GPU), and the per-call sequence.  The arithmetic is in pf_sta_device.cuh. */
-struct pf_sta {
-	PfStaDev d;
-	int num_domains, num_tedges;
-	std::vector<float> constraint;
-	std::vector<int> seg_begin, seg_end, seg_spread;     /* sweep plan over levels, ascending */
-	float *stat;                                         /* [num_domains^2][4] on the device */
-	float *scratch_delay, *scratch_crit;                 /* device staging for the host-buffer entry point */
-	void *owned[32]; int num_owned;
-};
-
-extern "C" void pf_sta_destroy(pf_sta *s) {
-	if (!s) return;
-	for (int i = 0; i < s->num_owned; i++) pfb_free(s->owned[i]);
-	delete s;
-}
-
-template <class T> static T *sta_upload(pf_sta *s, const std::vector<T> &v) {
-	T *d = (T *)pfb_alloc(sizeof(T) * std::max<size_t>(v.size(), 1));
-	if (!d) return NULL;
-	s->owned[s->num_owned++] = d;
-	if (!v.empty() && pfb_h2d(d, v.data(), sizeof(T) * v.size()) != 0) return NULL;
-	return d;
-}
-
-extern "C" int pf_sta_create(const pf_timing_graph *g, const pf_problem *p, const pf_config *cfg, pf_sta **out) {
-	char msg[256];
-	if (!g || !p || !cfg || !out) FAILF(PF_EINVAL, "null argument");
-	*out = NULL;
-	if (g->num_nets != p->num_nets) FAILF(PF_EINVAL, "timing graph has %d nets, the problem %d", g->num_nets, p->num_nets);
-	if (pf_timing_graph_check(g, p->net_ptr, msg, sizeof(msg)) != PF_OK) FAILF(PF_EINVAL, "invalid timing graph: %s", msg);
-	if (pfb_init(cfg->device) != 0) CUDA_FAIL();
-	const int N = g->num_tnodes, E = g->num_tedges, T = p->num_terminals;
-	/* Renumber the tnodes in level order (new id = position in the level lists): a level is then a contiguous
-	 * range, its structural reads are coalesced, and the kernels need no level list.  Out-edges keep the
-	 * reference's order within a tnode, so "pin k of a net = out-edge k-1 of its driver" still holds. */
-	std::vector<int> pos((size_t)N), r_eptr((size_t)N + 1, 0), r_eto((size_t)std::max(E, 1)), r_dom((size_t)N), new_edge((size_t)std::max(E, 1));
-	std::vector<float> r_tdel((size_t)std::max(E, 1)), r_cdel((size_t)N);
-	std::vector<unsigned char> r_type((size_t)N);
-	for (int k = 0; k < N; k++) pos[(size_t)g->level_nodes[k]] = k;
-	for (int k = 0; k < N; k++) {
-		const int o = g->level_nodes[k];
-		r_eptr[(size_t)k + 1] = r_eptr[(size_t)k] + (g->edge_ptr[o + 1] - g->edge_ptr[o]);
-		r_dom[(size_t)k] = g->clock_domain[o]; r_cdel[(size_t)k] = g->clock_delay[o]; r_type[(size_t)k] = g->type[o];
-		for (int e = g->edge_ptr[o], q = r_eptr[(size_t)k]; e < g->edge_ptr[o + 1]; e++, q++) {
-			r_eto[(size_t)q] = pos[(size_t)g->edge_to[e]]; r_tdel[(size_t)q] = g->edge_Tdel[e]; new_edge[(size_t)e] = q;
-		}
-	}
-	/* in-edges as (source, edge) pairs */
-	std::vector<int> in_ptr((size_t)N + 1, 0), in_rec(2 * (size_t)std::max(E, 1));
-	for (int e = 0; e < E; e++) in_ptr[(size_t)r_eto[(size_t)e] + 1]++;
-	for (int n = 0; n < N; n++) in_ptr[(size_t)n + 1] += in_ptr[(size_t)n];
-	{
-		std::vector<int> fill(in_ptr.begin(), in_ptr.end() - 1);
-		for (int n = 0; n < N; n++)
-			for (int e = r_eptr[(size_t)n]; e < r_eptr[(size_t)n + 1]; e++) { int k = fill[(size_t)r_eto[(size_t)e]]++; in_rec[2 * (size_t)k] = n; in_rec[2 * (size_t)k + 1] = e; }
-	}
-	/* net pin -> (driver tnode, out-edge): pin k of net i is out-edge k-1 of its driver (path_delay.c:479-500) */
-	std::vector<int> term_edge((size_t)std::max(T, 1), -1), term_driver((size_t)std::max(T, 1), -1);
-	for (int i = 0; i < p->num_nets; i++) {
-		if (g->net_driver[i] < 0) continue;
-		const int d = pos[(size_t)g->net_driver[i]];
-		for (int k = 1; k < p->net_ptr[i + 1] - p->net_ptr[i]; k++) { term_edge[(size_t)p->net_ptr[i] + k] = r_eptr[(size_t)d] + k - 1; term_driver[(size_t)p->net_ptr[i] + k] = d; }
-	}
-	(void)new_edge;
-	pf_sta *s = new pf_sta();
-	memset(&s->d, 0, sizeof(s->d));
-	s->num_owned = 0; s->num_domains = g->num_domains; s->num_tedges = E;
-	s->constraint.assign(g->constraint, g->constraint + (size_t)g->num_domains * g->num_domains);
-	/* sweep plan: a level wider than 4 K tnodes gets the whole GPU, runs of narrower ones share one CTA */
-	for (int lv = 0; lv < g->num_levels;) {
-		const int width = g->level_ptr[lv + 1] - g->level_ptr[lv];
-		if (width > 4096) { s->seg_begin.push_back(lv); s->seg_end.push_back(lv + 1); s->seg_spread.push_back(width); lv++; continue; }
-		int e = lv;
-		while (e < g->num_levels && g->level_ptr[e + 1] - g->level_ptr[e] <= 4096) e++;
-		s->seg_begin.push_back(lv); s->seg_end.push_back(e); s->seg_spread.push_back(0);
-		lv = e;
-	}
-	PfStaDev &d = s->d;
-	d.num_tnodes = N; d.num_terminals = T; d.num_levels = g->num_levels;
-	bool ok = true;
-	std::vector<int> ident((size_t)N), lptr(g->level_ptr, g->level_ptr + g->num_levels + 1);
-	for (int k = 0; k < N; k++) ident[(size_t)k] = k;
-	d.edge_ptr = sta_upload(s, r_eptr); d.edge_to = sta_upload(s, r_eto);
-	d.in_ptr = sta_upload(s, in_ptr); d.in_rec = sta_upload(s, in_rec);
-	d.clock_domain = sta_upload(s, r_dom);
-	d.level_ptr = sta_upload(s, lptr); d.level_nodes = sta_upload(s, ident);
-	d.term_edge = sta_upload(s, term_edge); d.term_driver = sta_upload(s, term_driver);
-	d.Tdel = sta_upload(s, r_tdel); d.clock_delay = sta_upload(s, r_cdel); d.type = sta_upload(s, r_type);
-	{ std::vector<float> v((size_t)N, 0.f); d.T_arr = sta_upload(s, v); d.T_req = sta_upload(s, v); }
-	{ std::vector<float> v((size_t)std::max(g->num_domains * g->num_domains, 1) * 4, 0.f); s->stat = sta_upload(s, v); }
-	{ std::vector<float> v((size_t)std::max(T, 1), 0.f); s->scratch_delay = sta_upload(s, v); s->scratch_crit = sta_upload(s, v); }
-	ok = ok && d.edge_ptr && d.edge_to && d.clock_domain && d.level_ptr && d.level_nodes && d.in_ptr && d.in_rec && d.term_edge && d.term_driver && d.Tdel && d.clock_delay && d.type && d.T_arr && d.T_req
-		&& s->stat && s->scratch_delay && s->scratch_crit;
-	if (!ok || pfb_sync() != 0) { pf_sta_destroy(s); CUDA_FAIL(); }
-	*out = s;
-	return PF_OK;
-}
-
-extern "C" int pf_sta_analyze_device(pf_sta *s, const void *dev_net_delay, void *dev_crit, float *cpd_ns) {
-	if (!s || !dev_net_delay || !dev_crit) FAILF(PF_EINVAL, "null argument");
-	const int C = s->num_domains, nseg = (int)s->seg_begin.size();
-	CKB(pfb_sta_load(&s->d, (const float *)dev_net_delay));
-	CKB(pfb_zero(dev_crit, sizeof(float) * (size_t)std::max(s->d.num_terminals, 1)));     /* path_delay.c:2403-2410 */
-	for (int i = 0; i < C; i++) for (int j = 0; j < C; j++) {
-		const float constraint = s->constraint[(size_t)i * C + j];
-		float *stat = s->stat + 4 * ((size_t)i * C + j);
-		if (!(constraint > -1.e-15)) continue;                                                /* DO_NOT_ANALYSE */
-		CKB(pfb_sta_begin_pair(&s->d, stat));
-		for (int k = 0; k < nseg; k++) CKB(pfb_sta_sweep(&s->d, 1, s->seg_begin[k], s->seg_end[k], s->seg_spread[k], i, constraint, stat));
-		for (int k = nseg - 1; k >= 0; k--) CKB(pfb_sta_sweep(&s->d, 0, s->seg_begin[k], s->seg_end[k], s->seg_spread[k], j, constraint, stat));
-		CKB(pfb_sta_update(&s->d, constraint, stat, (float *)dev_crit));
-	}
-	if (cpd_ns) {
-		/* get_critical_path_delay, path_delay.c:3791-3810: the cpd of the pair with the least slack */
-		std::vector<float> h((size_t)std::max(C * C, 1) * 4, 0.f);
-		CKB(pfb_d2h(h.data(), s->stat, sizeof(float) * h.size()));
-		float least = (float)1.e30, cpd = -1.f;
-		for (int i = 0; i < C; i++) for (int j = 0; j < C; j++) {
-			if (!(s->constraint[(size_t)i * C + j] > -1.e-15)) continue;
-			const float *st = &h[4 * ((size_t)i * C + j)];
-			if (least > st[2]) { least = st[2]; cpd = st[1]; }
-		}
-		*cpd_ns = (float)(cpd * 1e9);
-	}
-	return PF_OK;
-}
-
-extern "C" int pf_sta_analyze(pf_sta *s, const float *net_delay, float *crit, float *cpd_ns) {
-	if (!s || !net_delay || !crit) FAILF(PF_EINVAL, "null argument");
-	const size_t bytes = sizeof(float) * (size_t)s->d.num_terminals;
-	CKB(pfb_h2d(s->scratch_delay, net_delay, bytes));
-	int rc = pf_sta_analyze_device(s, s->scratch_delay, s->scratch_crit, cpd_ns);
-	if (rc != PF_OK) return rc;
-	CKB(pfb_d2h(crit, s->scratch_crit, bytes));
-	return PF_OK;
-}
-
 extern "C" int pf_try_timing_driven_route_sta(const pf_problem *p, const pf_timing_graph *g, const pf_config *cfg, pf_result *out) {
 	if (!p || !g || !cfg || !out) FAILF(PF_EINVAL, "null argument");
 	pf_sta *s = NULL;
@@ -1218,40 +1004,4 @@ extern "C" int pf_try_timing_driven_route_sta(const pf_problem *p, const pf_timi
 	rc = route_loop(p, cfg, NULL, NULL, s, out);
 	pf_sta_destroy(s);
 	return rc;
-}
-
-/* ====================================================================== check_route on the device */
-extern "C" int pf_check_route(pf_router *r, const pf_result *res, pf_check_report *rep) {
-	if (!r || !res || !rep) FAILF(PF_EINVAL, "null argument");
-	const pf_problem *p = r->prob;
-	if (res->num_nets != r->n || res->num_nodes != r->N || !res->trace_ptr || !res->occ) FAILF(PF_EINVAL, "result does not belong to this problem");
-	const size_t total = (size_t)res->trace_ptr[r->n];
-	int *d_tp = (int *)pfb_alloc_raw(sizeof(int) * ((size_t)r->n + 1));
-	int *d_tn = (int *)pfb_alloc_raw(sizeof(int) * std::max<size_t>(total, 1));
-	short *d_ts = (short *)pfb_alloc_raw(sizeof(short) * std::max<size_t>(total, 1));
-	int *d_occ = (int *)pfb_alloc_raw(sizeof(int) * (size_t)r->N);
-	int *d_occ2 = (int *)pfb_alloc(sizeof(int) * (size_t)r->N);
-	unsigned char *d_matched = (unsigned char *)pfb_alloc((size_t)std::max(r->T, 1));
-	unsigned char *d_glob = (unsigned char *)pfb_alloc_raw((size_t)std::max(r->n, 1));
-	int *d_rep = (int *)pfb_alloc(sizeof(int) * 8);
-	unsigned long long *d_wl = (unsigned long long *)pfb_alloc(sizeof(unsigned long long) * 2);
-	int h_rep[8] = { 0, 0x7fffffff, 0, 0, 0, 0, 0, 0 };
-	unsigned long long h_wl[2] = { 0, 0 };
-	int bad = !d_tp || !d_tn || !d_ts || !d_occ || !d_occ2 || !d_matched || !d_glob || !d_rep || !d_wl;
-	bad = bad || pfb_h2d(d_tp, res->trace_ptr, sizeof(int) * ((size_t)r->n + 1)) || pfb_h2d(d_tn, res->trace_node, sizeof(int) * total)
-		|| pfb_h2d(d_ts, res->trace_switch, sizeof(short) * total) || pfb_h2d(d_occ, res->occ, sizeof(int) * (size_t)r->N)
-		|| pfb_h2d(d_glob, p->net_is_global, (size_t)r->n) || pfb_h2d(d_rep, h_rep, sizeof(h_rep))
-		|| pfb_launch_check_route(r->nodes, r->edges, r->N, r->n, r->net_ptr, r->net_term, d_glob, d_tp, d_tn, d_ts, d_matched, d_occ2, d_occ, d_rep, d_wl)
-		|| pfb_d2h(h_rep, d_rep, sizeof(h_rep)) || pfb_d2h(h_wl, d_wl, sizeof(h_wl));
-	pfb_free(d_tp); pfb_free(d_tn); pfb_free(d_ts); pfb_free(d_occ); pfb_free(d_occ2); pfb_free(d_matched); pfb_free(d_glob); pfb_free(d_rep); pfb_free(d_wl);
-	if (bad) CUDA_FAIL();
-	long long reserved = 0;
-	for (int g = 0; g < p->num_opin_groups; g++) reserved += p->opin_group_count[g];
-	memset(rep, 0, sizeof(*rep));
-	rep->bad_nets = h_rep[0]; rep->first_bad_net = h_rep[0] ? h_rep[1] : -1; rep->first_bad_code = h_rep[0] ? h_rep[2] : 0;
-	rep->occupancy_mismatch = h_rep[3] + ((long long)h_wl[1] != reserved ? 1 : 0);
-	rep->overused_nodes = h_rep[4];
-	rep->wirelength = (int64_t)h_wl[0]; rep->reserved_opins = (int64_t)h_wl[1];
-	rep->ok = rep->bad_nets == 0 && rep->occupancy_mismatch == 0;
-	return PF_OK;
 }
