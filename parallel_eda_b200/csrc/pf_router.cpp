@@ -512,12 +512,14 @@ extern "C" int pf_router_reset(pf_router *r) {
 /* Search granularity.  With many more nets than warps the kernel is bound by memory traffic, and strict
  * best-first order (one label per step, no bucket slack) does the least work; with few nets per warp the
  * latency of one search is what matters, and settling a whole delta bucket per step shortens it. */
-static void tune_granularity(const pf_router *r, PfParams &P, int work, int slots) {
+static void tune_granularity(const pf_router *r, PfParams &P, int work, int slots, bool big_class = false) {
 	const pf_config &c = r->cfg;
 	/* a graph that does not fit in L2 pays DRAM round trips for every settled label: fewest labels wins there
 	 * even with one net per warp */
 	const bool in_l2 = (long long)r->N * (long long)sizeof(PfNode) + (long long)r->E * 4 < (96ll << 20);
-	const bool throughput = (slots > 0 && work >= 4 * slots) || !in_l2;
+	/* the big-slot class holds a few dozen warps: the GPU is mostly idle while they run, so what counts there is the
+	 * latency of one net, never throughput (timing-driven 3.8 k-net fixture: slowest iteration 75 -> 59 ms) */
+	const bool throughput = (slots > 0 && work >= 4 * slots && !big_class) || !in_l2;
 	P.max_batch = c.max_batch > 0 ? c.max_batch : (throughput ? 1 : 32);
 	P.pop_slack = c.pop_slack >= 0.f ? c.pop_slack : (throughput ? 0.f : 0.25f);
 }
@@ -654,7 +656,7 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 		r->big.num_work = bc;
 		fill_params(r, P, r->big, pres_fac);
 		P.work = r->big.work + bo;
-		{ int sl = slots_for(r, total, std::min(r->big.num_slots, bc), div); tune_granularity(r, P, bc, sl); CKB(pfb_launch_route(&P, sl, 1)); }
+		{ int sl = slots_for(r, total, std::min(r->big.num_slots, bc), div); tune_granularity(r, P, bc, sl, true); CKB(pfb_launch_route(&P, sl, 1)); }
 	}
 	if (sc > 0) {
 		r->small.num_work = sc;
@@ -687,7 +689,7 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 		fill_params(r, P, r->big, pres_fac);
 		P.work = r->retry_work;
 		P.skip_ripup = 1;
-		{ int sl = slots_for(r, (int)lst.size(), std::min(r->big.num_slots, (int)lst.size()), div); tune_granularity(r, P, (int)lst.size(), sl); CKB(pfb_launch_route(&P, sl, 1)); }
+		{ int sl = slots_for(r, (int)lst.size(), std::min(r->big.num_slots, (int)lst.size()), div); tune_granularity(r, P, (int)lst.size(), sl, true); CKB(pfb_launch_route(&P, sl, 1)); }
 		CKB(pfb_d2h(h_ctl, r->ctl, 256));
 		memcpy(h_retry, h_ctl + 32, sizeof(h_retry));
 		PfStats more;
