@@ -28,18 +28,27 @@ static bool problem_header_ok(const pf_problem *p) {
 	return true;
 }
 
-/* nets / tables part of pf_problem_check (small arrays), serial */
+/* nets / tables part of pf_problem_check (small arrays).  The shape (monotonic net_ptr, boxes, small tables) is
+ * checked before anything indexes with it; the terminal lookups — one random read of type[] per pin, 4 ms at
+ * 800 k pins — run on a helper thread next to the graph upload (problem_terminals_ok). */
+static bool problem_terminals_ok(const pf_problem *p) {
+	for (int i = 0; i < p->num_nets; i++) {
+		if (p->net_is_global[i]) continue;
+		const int b = p->net_ptr[i], e = p->net_ptr[i + 1];
+		for (int k = b; k < e; k++) {
+			int n = p->net_terminals[k];
+			if (n < 0 || n >= p->num_nodes || p->type[n] != (k == b ? PF_SOURCE : PF_SINK)) return false;
+		}
+	}
+	return true;
+}
+
 static bool problem_nets_ok(const pf_problem *p) {
 	if (p->net_ptr[0] != 0 || p->net_ptr[p->num_nets] != p->num_terminals) return false;
 	for (int i = 0; i < p->num_nets; i++) {
 		int b = p->net_ptr[i], e = p->net_ptr[i + 1];
 		if (e <= b) return false;
 		if (p->net_bb[4 * i] > p->net_bb[4 * i + 1] || p->net_bb[4 * i + 2] > p->net_bb[4 * i + 3]) return false;
-		if (p->net_is_global[i]) continue;
-		for (int k = b; k < e; k++) {
-			int n = p->net_terminals[k];
-			if (n < 0 || n >= p->num_nodes || p->type[n] != (k == b ? PF_SOURCE : PF_SINK)) return false;
-		}
 	}
 	for (int i = PF_CHANX_COST_INDEX_START; i < p->num_indexed; i++)
 		if (p->indexed[i].ortho_cost_index < 0 || p->indexed[i].ortho_cost_index >= p->num_indexed) return false;
@@ -201,6 +210,9 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		FAILF(PF_EINVAL, "invalid problem");
 	}
 	double t_b = now_s();
+	std::atomic<int> terminals_bad(0);
+	std::thread terminal_check([p, &terminals_bad]() { if (!problem_terminals_ok(p)) terminals_bad = 1; });
+	struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{terminal_check};   /* every return path */
 	if (p->num_nodes > (1 << PF_EDGE_NODE_BITS)) FAILF(PF_EINVAL, "num_rr_nodes %d exceeds the %d-bit edge word", p->num_nodes, PF_EDGE_NODE_BITS);
 	if (p->num_switches > PF_MAX_SWITCHES) FAILF(PF_EINVAL, "%d switch types (max %d)", p->num_switches, PF_MAX_SWITCHES);
 	if (p->num_indexed > PF_MAX_INDEXED) FAILF(PF_EINVAL, "%d rr_indexed_data rows (max %d)", p->num_indexed, PF_MAX_INDEXED);
@@ -478,6 +490,12 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	}
 	r->t_mark[2] = now_s();
 	if (pfb_sync() != 0) { pf_router_destroy(r); CUDA_FAIL(); }
+	terminal_check.join();
+	if (terminals_bad) {
+		pf_router_destroy(r);
+		if (pf_problem_check(p, msg, sizeof(msg)) != PF_OK) FAILF(PF_EINVAL, "invalid problem: %s", msg);
+		FAILF(PF_EINVAL, "invalid problem (net terminals)");
+	}
 	if (c.verbose) fprintf(stderr, "pf_router: create %.3f s (net check %.3f s, setup + device alloc %.3f s, flatten + upload issue %.3f s, scratch alloc %.3f s, drain %.3f s)\n",
 			now_s() - t_a, t_b - t_a, r->t_mark[0] - t_b, r->t_mark[1] - r->t_mark[0], r->t_mark[2] - r->t_mark[1], now_s() - r->t_mark[2]);
 	if (c.verbose)

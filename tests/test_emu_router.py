@@ -118,3 +118,18 @@ def test_step_api_wirelength_counts_live_trees_only(emu_lib):
     res = R.result()
     assert wl == res.total_wirelength == check_route.check_route(p, res)["wirelength"] and avail > wl
     R.close()
+
+
+def test_invalid_net_terminals_are_rejected(emu_lib):
+    """The terminal lookups of the problem check run on a helper thread next to the graph upload; a net whose pin is
+    not a SINK must still fail pf_router_create with PF_EINVAL, and the library must stay usable."""
+    p = _toy(False)
+    i = int(p.routed_nets()[3])
+    keep = int(p.net_terminals[p.net_ptr[i] + 1])
+    p.net_terminals[p.net_ptr[i] + 1] = int(p.net_terminals[p.net_ptr[i]])       # a SOURCE where a SINK belongs
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=2, big_slots=1)
+    with pytest.raises(router.RouterError) as e:
+        router.Router(p, cfg, lib_path=emu_lib)
+    assert e.value.code == -4
+    p.net_terminals[p.net_ptr[i] + 1] = keep
+    router.Router(p, cfg, lib_path=emu_lib).close()
