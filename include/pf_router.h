@@ -27,6 +27,10 @@
  *   pf_get_result                    trace_head[]/trace_tail[] lists    route/route_common.c:638-706
  *   pf_comm_events /                 MPI_Allreduce(occupancy) of the reference's MPI router
  *   pf_comm_apply_events             parallel_route/spatial.cxx:3371-3383 (sync_recalc_occ)
+ *   pf_try_breadth_first_route       try_breadth_first_route            route/route_breadth_first.c:23-305
+ *   pf_sta_create / pf_sta_analyze   load_timing_graph_net_delays + do_timing_analysis + get_critical_path_delay
+ *   pf_try_timing_driven_route_sta                                       timing/path_delay.c:479,2258-2522,3791 (route_timing.c:295-309)
+ *   pf_check_route                   check_route                        route/check_route.c:27-155
  *
  * All functions return PF_OK (0) or a negative PF_E* code (pf_file.h); none calls exit().
  * pf_last_error() describes the last failure of the calling process.  There is no CPU fallback:
