@@ -58,6 +58,8 @@ struct pf_router {
 	/* OPIN reservation */
 	int num_groups; int *g_source, *g_count, *g_off, *g_chosen;
 	long long avail_wl;
+	double util;                  /* routed wirelength / available wirelength after the first iteration; < 0 = unknown */
+	int div_explicit;             /* cfg.inflight_div was given by the caller */
 	double t_mark[4];
 	int64_t h2d_bytes, d2h_bytes;
 	std::vector<int> work_small, work_big;

@@ -245,6 +245,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.sink_cap <= 0) c.sink_cap = 64;
 	if (c.big_slots <= 0) c.big_slots = 64;
 	if (c.reroute_all_iters == 0) c.reroute_all_iters = 1;
+	r->div_explicit = c.inflight_div > 0; r->util = -1.;
 	if (c.inflight_div <= 0) c.inflight_div = 16;
 	/* nets in flight: at least one per 20 x 20 tiles of fabric (the few hundred nets of a late iteration then go
 	 * out together instead of sixteen rounds deep), and never fewer than one */
@@ -512,7 +513,7 @@ extern "C" int pf_router_reset(pf_router *r) {
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
 	CKB(pfb_zero(r->ctl, 256));
 	r->h_pool_head = 0;
-	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0; r->over_hist.clear(); r->since_full = 0; r->cost_updates = 0;
+	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0; r->over_hist.clear(); r->since_full = 0; r->cost_updates = 0; r->util = -1.;
 	CKB(pfb_zero(r->last_over, (size_t)r->N));
 	CKB(pfb_zero(r->net_delay, sizeof(float) * (size_t)std::max(r->T, 1)));
 	{
@@ -621,7 +622,11 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 			&& (double)r->over_hist[H - 1] > 0.7 * (double)r->over_hist[H - 1 - K];
 	if (stalled) { r->stall_count = 0; if (r->cfg.verbose) fprintf(stderr, "pf_router: overuse stalled at %d, re-routing every net\n", r->best_overused); }
 	const bool all = stalled || r->cfg.reroute_all_iters < 0 || r->iter_count < r->cfg.reroute_all_iters;
-	r->cur_div = stalled ? r->cfg.inflight_div * 8 : r->cfg.inflight_div;
+	/* how many nets may be in flight depends on how contested the fabric is: with the channels under 40 % full after
+	 * the first iteration (BASELINE configs[4]: 29 %; the near-minimum-width fixtures: 52-63 %) twice as many nets
+	 * in flight converge just as fast (cfg 4: 22.9 vs 24.9 ms measured), on a tight fabric they do not */
+	const int base_div = (!r->div_explicit && r->util >= 0. && r->util < 0.40) ? r->cfg.inflight_div / 2 : r->cfg.inflight_div;
+	r->cur_div = stalled ? r->cfg.inflight_div * 8 : base_div;
 	if (all) {
 		std::vector<int> sm, bg;
 		r->n1_small = r->n1_big = 0;
@@ -807,6 +812,7 @@ extern "C" int pf_total_wirelength(pf_router *r, int64_t *wl, int64_t *avail) {
 	r->d2h_bytes += 32;
 	if (wl) *wl = (int64_t)h[0];
 	if (avail) *avail = r->avail_wl;
+	if (r->iter_count <= 1 && r->avail_wl > 0) r->util = (double)h[0] * r->cfg.nranks / (double)r->avail_wl;   /* ranks hold equal shares */
 	return PF_OK;
 }
 
