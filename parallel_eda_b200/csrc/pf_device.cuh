@@ -334,6 +334,7 @@ PF_DEV void pf_refill(PfWarp &w) {
 		unsigned mt = pf_ballot(take);
 		int keep = (i < w.far_n) && !take;
 		unsigned mkp = pf_ballot(keep);
+		pf_syncwarp();                                      /* reads of this chunk are complete before the in-place writes */
 		if (take) w.fr[taken + pf_popc(mt & pf_lanemask_lt())] = k;
 		if (keep) {
 			w.far[kept + pf_popc(mkp & pf_lanemask_lt())] = k;   /* kept + rank <= i: in-place is safe after the ballots */
@@ -525,6 +526,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 			unsigned mt = pf_ballot(take);
 			int keep = (i < w.sh_n) && !take;
 			unsigned mkp = pf_ballot(keep);
+			pf_syncwarp();                                  /* every lane has its entry before slots of this chunk are overwritten */
 			if (take) w.b_key[taken + pf_popc(mt & pf_lanemask_lt())] = k;
 			if (keep) w.fr[kept + pf_popc(mkp & pf_lanemask_lt())] = k;
 			taken += pf_popc(mt);
