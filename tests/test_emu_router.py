@@ -133,3 +133,41 @@ def test_invalid_net_terminals_are_rejected(emu_lib):
     assert e.value.code == -4
     p.net_terminals[p.net_ptr[i] + 1] = keep
     router.Router(p, cfg, lib_path=emu_lib).close()
+
+
+def test_edge_cases_match_the_oracle(emu_lib, oracle_cli, tmp_path):
+    """SURVEY.md §8b edge cases: a problem whose nets are all global routes nothing and succeeds in one iteration;
+    one routed net among globals; a net whose sink lies outside its bounding box has no possible path
+    (route_timing.c:482-489 -> FALSE) — the device code and the oracle agree on each."""
+    import copy
+    p = _toy(False)
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=4, big_slots=1)
+
+    def oracle(q):
+        prob, out = str(tmp_path / "e.pfp"), str(tmp_path / "e.pfr")
+        pfio.write_problem(prob, q)
+        r = subprocess.run([oracle_cli, prob, "--result", out], capture_output=True, text=True)
+        return r.returncode, (pfio.read_result(out) if r.returncode == 0 else None)
+
+    a = copy.deepcopy(p); a.net_is_global[:] = 1
+    r = router.try_timing_driven_route(a, cfg, lib_path=emu_lib)
+    rc, o = oracle(a)
+    assert rc == 0 and (r.success, r.iterations, len(r.trace_node)) == (o.success, o.iterations, len(o.trace_node)) == (1, 1, 0)
+
+    i = int(p.routed_nets()[5])
+    b = copy.deepcopy(p); b.net_is_global[:] = 1; b.net_is_global[i] = 0
+    r = router.try_timing_driven_route(b, cfg, lib_path=emu_lib)
+    rc, o = oracle(b)
+    assert rc == 0 and r.success == o.success == 1 and r.iterations == o.iterations == 1
+    assert r.total_wirelength == o.total_wirelength and np.array_equal(r.trace_ptr, o.trace_ptr)   # an uncontested net: same tree size
+    check_route.check_route(b, r)
+
+    c = copy.deepcopy(p)
+    src = int(c.net_terminals[c.net_ptr[i]])
+    c.net_bb = c.net_bb.copy()
+    c.net_bb[i] = [int(c.xlow[src]), int(c.xhigh[src]), int(c.ylow[src]), int(c.yhigh[src])]      # net_bb is [n, 4]
+    with pytest.raises(router.RouterError) as e:
+        router.try_timing_driven_route(c, cfg, lib_path=emu_lib)
+    assert e.value.code == -7 and "net %d" % i in str(e.value)
+    rc, _ = oracle(c)
+    assert rc != 0
