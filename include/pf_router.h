@@ -143,6 +143,9 @@ void *pf_stream(pf_router *r);   /* the cudaStream_t every kernel of this router
  * pass the same pf_problem: nets, options and the reset path use the host arrays.) */
 int pf_comm_graph_buffers(pf_router *r, void *dev_ptrs[3], int64_t bytes[3]);
 int pf_comm_graph_ready(pf_router *r);
+/* the sharding decided at create: owner[num_nets] = rank routing the net, is_cut[num_nets] = 1 for nets whose bounding
+ * box reaches across a stripe cut (routed in the second part of an iteration), 0 for stripe-interior nets */
+int pf_comm_net_classes(pf_router *r, int32_t *owner, uint8_t *is_cut);
 int pf_comm_events(pf_router *r, void **dev_events, int64_t *count);
 int pf_comm_apply_events(pf_router *r, const void *dev_events, int64_t count);
 void *pf_comm_net_delay_ptr(pf_router *r);

@@ -63,6 +63,8 @@ struct pf_router {
 	double t_mark[4];
 	int64_t h2d_bytes, d2h_bytes;
 	std::vector<int> work_small, work_big;
+	std::vector<int> net_owner;       /* rank that routes each net (stripe sharding) */
+	std::vector<unsigned char> net_cut;   /* 1 = the net's box reaches across a stripe cut (second route part) */
 	std::vector<int> h_all;           /* host copy of all_nets: interior nets first, then cut nets, each in fanout order */
 	int K1;                           /* number of interior nets at the head of all_nets */
 	int n1_small, n1_big;             /* interior nets at the head of this iteration's two work lists */

@@ -318,6 +318,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			owner[i] = right_ok ? s : s + 1;        /* the rank that owns the violated cut (cut k belongs to rank k) */
 		}
 	}
+	r->net_owner = owner; r->net_cut = cut_net;
 	for (size_t k = 0; k < order.size(); k++) {
 		if (owner[order[k]] != c.rank) continue;
 		int i = order[k], ns = p->net_ptr[i + 1] - p->net_ptr[i] - 1;
@@ -781,6 +782,13 @@ extern "C" int pf_comm_graph_buffers(pf_router *r, void *dev_ptrs[3], int64_t by
 extern "C" int pf_comm_graph_ready(pf_router *r) {
 	if (!r) FAILF(PF_EINVAL, "null router");
 	r->graph_ready = 1;
+	return PF_OK;
+}
+
+/* introspection of the stripe sharding: for every net the rank that routes it and whether it is a cut net */
+extern "C" int pf_comm_net_classes(pf_router *r, int32_t *owner, uint8_t *is_cut) {
+	if (!r || !owner || !is_cut) FAILF(PF_EINVAL, "null argument");
+	for (int i = 0; i < r->n; i++) { owner[i] = r->net_owner[(size_t)i]; is_cut[i] = r->net_cut[(size_t)i]; }
 	return PF_OK;
 }
 

@@ -155,6 +155,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_sta_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     lib.pf_sta_analyze_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     lib.pf_try_timing_driven_route_sta.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Config), C.c_void_p]
+    lib.pf_comm_net_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pf_comm_graph_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p * 3), C.POINTER(C.c_int64 * 3)]
     lib.pf_comm_graph_ready.argtypes = [C.c_void_p]
     lib.pf_comm_events.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
@@ -351,6 +352,13 @@ class Router:
         rep = CheckReport()
         self._ck(self.lib.pf_check_route(self._h, C.byref(cr), C.byref(rep)))
         return {f: int(getattr(rep, f)) for f, _ in CheckReport._fields_}
+
+    def comm_net_classes(self):
+        """(owner[num_nets] int32, is_cut[num_nets] uint8): the stripe sharding decided at create."""
+        n = self.problem.num_nets
+        owner = np.zeros(n, np.int32); cut = np.zeros(n, np.uint8)
+        self._ck(self.lib.pf_comm_net_classes(self._h, owner.ctypes.data, cut.ctypes.data))
+        return owner, cut
 
     def comm_graph_buffers(self):
         """[(device pointer, bytes)] of the packed graph: node records, edge words, ptc numbers."""

@@ -93,3 +93,34 @@ def test_two_ranks_timing_driven_with_device_sta(emu_lib, tmp_path):
     import json
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert out["success"] and out["occ_equal"] and out["crit_equal"] and out["overused"] == 0
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_stripe_sharding_properties(nranks, emu_lib):
+    """The sharding every rank computes at create (no communication): all ranks agree, every routed net has one
+    owner, and stripe-interior nets of different ranks are at least one maximum wire length apart in x — they can
+    never touch the same rr node, which is what lets all ranks route them at once."""
+    import numpy as np
+    from parallel_eda_b200 import pfio, router
+    lib = router.load_library(emu_lib)
+    p = router.generate_grid_problem(lib_path=emu_lib, nx=48, ny=12, W=20, num_nets=600, window=6, seed=5)
+    owners = []
+    for rank in range(nranks):
+        R = router.Router(p, router.default_config(lib, num_slots=2, big_slots=1, rank=rank, nranks=nranks), lib_path=emu_lib)
+        owners.append(R.comm_net_classes())
+        R.close()
+    owner, cut = owners[0]
+    for o, c in owners[1:]:
+        assert np.array_equal(o, owner) and np.array_equal(c, cut)
+    routed = p.net_is_global == 0
+    assert owner[routed].min() >= 0 and owner[routed].max() == nranks - 1 and (cut[routed] == 0).sum() > 0
+    lmax = int(round(1.0 / float(p.indexed["inv_length"][4:].min())))
+    bb = p.net_bb.reshape(-1, 4)
+    interior = routed & (cut == 0)
+    for a in range(nranks):
+        for b in range(a + 1, nranks):
+            xa_max = bb[interior & (owner == a), 1].max(initial=-10**9)
+            xb_min = bb[interior & (owner == b), 0].min(initial=10**9)
+            assert xb_min - xa_max >= lmax, (a, b, xa_max, xb_min, lmax)
+    # cut nets belong to the rank that owns the cut they cross: never to rank 0
+    assert not ((cut == 1) & routed & (owner == 0)).any()
