@@ -181,3 +181,19 @@ def test_device_check_route_agrees_with_the_python_checker():
     rep = R.check_route(bad)
     assert rep["ok"] == 0 and rep["first_bad_net"] == i and rep["first_bad_code"] == 5
     R.close()
+
+
+def test_stand_alone_cli(tmp_path):
+    """python -m parallel_eda_b200 route / check over the flat containers (timing-driven with the device STA)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "duo.pfr")
+    r = subprocess.run([sys.executable, "-m", "parallel_eda_b200", "route", os.path.join(G, "duo_w80.pfp.xz"), "--timing-graph",
+                        os.path.join(G, "duo_w80.pftg.xz"), "--result", out, "--check", "--max-iters", "150"], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rep["success"] == 1 and rep["check_route"]["ok"] == 1 and rep["check_route"]["overused_nodes"] == 0
+    r = subprocess.run([sys.executable, "-m", "parallel_eda_b200", "check", os.path.join(G, "duo_w80.pfp.xz"), out], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0 and json.loads(r.stdout.strip().splitlines()[-1])["wirelength"] == rep["wirelength"]
