@@ -171,3 +171,23 @@ def test_edge_cases_match_the_oracle(emu_lib, oracle_cli, tmp_path):
     assert e.value.code == -7 and "net %d" % i in str(e.value)
     rc, _ = oracle(c)
     assert rc != 0
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_generated_problems_against_the_oracle(seed, emu_lib, oracle_cli, tmp_path):
+    """Seeded random problems from the native generator: the device code (emulated, 16 nets in flight) must produce
+    a routing that the independent checker accepts — legality, sinks, from-scratch Elmore delays — with a
+    wirelength within 10 % of the oracle's (which is bit-exact with the reference on the same flat input)."""
+    p = router.generate_grid_problem(lib_path=emu_lib, nx=10, ny=10, W=24, num_nets=150, window=5, seed=seed)
+    p.opts["timing_analysis_enabled"] = 0
+    prob, out = str(tmp_path / "g.pfp"), str(tmp_path / "g.pfr")
+    pfio.write_problem(prob, p)
+    r = subprocess.run([oracle_cli, prob, "--result", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    o = pfio.read_result(out)
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=16, big_slots=2)
+    e = router.try_timing_driven_route(p, cfg, lib_path=emu_lib)
+    assert e.success == o.success == 1
+    m = check_route.check_route(p, e)
+    assert m["overused"] == 0 and m["wirelength"] == e.total_wirelength
+    assert e.total_wirelength <= 1.10 * o.total_wirelength and e.iterations <= 2 * o.iterations + 3
