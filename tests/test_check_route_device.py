@@ -78,3 +78,36 @@ def test_occupancy_tampering_is_caught(toy):
     bad.occ = bad.occ.copy(); bad.occ[v] += 1
     rep = R.check_route(bad)
     assert rep["ok"] == 0 and rep["bad_nets"] == 0 and rep["occupancy_mismatch"] >= 1
+
+
+def test_random_mutations_agree_with_the_python_checker(toy):
+    """Differential test: 40 seeded single-element mutations of the reference's golden routing (node replaced by a
+    neighbour-ish id, switch changed, element removed); pf_check_route and the independent Python checker must
+    give the same accept / reject verdict on every one."""
+    p, g, R = toy
+    rng = np.random.default_rng(7)
+    routed = p.routed_nets()
+    rejected = 0
+    for _ in range(40):
+        bad = copy.deepcopy(g)
+        i = int(rng.choice(routed))
+        a, b = int(g.trace_ptr[i]), int(g.trace_ptr[i + 1])
+        k = int(rng.integers(a, b))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            bad.trace_node[k] = int(np.clip(int(bad.trace_node[k]) + int(rng.integers(-3, 4)), 0, p.num_nodes - 1))
+        elif kind == 1:
+            bad.trace_switch[k] = int(rng.integers(-1, len(p.switches)))
+        else:
+            keep = np.ones(len(bad.trace_node), bool); keep[k] = False
+            bad.trace_node, bad.trace_switch = bad.trace_node[keep], bad.trace_switch[keep]
+            bad.trace_ptr = bad.trace_ptr.copy(); bad.trace_ptr[i + 1:] -= 1
+        rep = R.check_route(bad)
+        try:
+            check_route.check_route(p, bad, check_delays=False)
+            py_ok = True
+        except check_route.RouteCheckError:
+            py_ok = False
+        assert bool(rep["ok"]) == py_ok, (i, k, kind, rep)
+        rejected += not py_ok
+    assert rejected >= 20          # most mutations break the routing; the rest are no-ops (same value drawn)
