@@ -112,3 +112,27 @@ def test_step_loop_with_device_sta_on_the_emulator(emu_lib):
     r2 = router.try_timing_driven_route(p, cfg, lib_path=emu_lib, timing_graph=g)
     assert (res.serial_num, res.total_wirelength) == (r2.serial_num, r2.total_wirelength) and rep.iterations == r2.iterations
     S.close(); R.close()
+
+
+def test_device_sta_equals_oracle_on_random_delays(oracle_lib, emu_lib):
+    """Beyond the reference's own vectors: random net delays (0 … 3x the golden ones, some exactly 0) on the
+    three-domain fixture — the device code must equal the oracle (itself pinned to the reference) bit for bit."""
+    from parallel_eda_b200 import router
+    lib = C.CDLL(oracle_lib)
+    lib.pf_oracle_sta.argtypes = [C.POINTER(_TG), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    p = pfio.read_problem(os.path.join(G, "duo_w80.pfp.xz"))
+    g = pfio.read_timing_graph(os.path.join(G, "duo_w80.pftg.xz"))
+    v = pfio.read_sta_vectors(os.path.join(G, "duo_w80.pfsta.xz"))
+    tg, keep = c_timing_graph(g)
+    net_ptr = np.ascontiguousarray(p.net_ptr, dtype=np.int32)
+    s = router.Sta(g, p, router.default_config(router.load_library(emu_lib)), lib_path=emu_lib)
+    rng = np.random.default_rng(3)
+    for k in range(6):
+        d = (v.net_delay[k % v.net_delay.shape[0]] * rng.uniform(0.0, 3.0, p.num_terminals)).astype(np.float32)
+        d[rng.random(p.num_terminals) < 0.05] = 0.0
+        want = np.zeros(p.num_terminals, np.float32); cpd = C.c_float(0)
+        assert lib.pf_oracle_sta(C.byref(tg), net_ptr.ctypes.data, d.ctypes.data, want.ctypes.data, C.byref(cpd)) == 0
+        got, got_cpd = s.analyze(d)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert np.float32(got_cpd).view(np.uint32) == np.float32(cpd.value).view(np.uint32)
+    s.close()
