@@ -124,3 +124,35 @@ def test_stripe_sharding_properties(nranks, emu_lib):
             assert xb_min - xa_max >= lmax, (a, b, xa_max, xb_min, lmax)
     # cut nets belong to the rank that owns the cut they cross: never to rank 0
     assert not ((cut == 1) & routed & (owner == 0)).any()
+
+
+WORKER_BF = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch
+from parallel_eda_b200 import pfio, router, pathfinder, distributed
+comm = distributed.init_from_env("gloo")
+p = pfio.read_problem(os.path.join(%(root)r, "tests", "golden", "toy_w64_bf.pfp.xz"))
+lib = %(emu)r
+R = comm.create_router(p, router.default_config(router.load_library(lib), num_slots=4, big_slots=1), lib_path=lib)
+rep = pathfinder.route(R, comm=comm)
+res = R.result()
+occ = torch.from_numpy(res.occ.astype(np.int64)); ref = occ.clone(); torch.distributed.broadcast(ref, 0)
+if comm.rank == 0:
+    print(json.dumps({"success": bool(rep.success), "occ_equal": bool(torch.equal(occ, ref)), "overused": int((res.occ > p.capacity).sum())}))
+else:
+    assert torch.equal(occ, ref)
+'''
+
+
+def test_two_ranks_breadth_first(emu_lib, tmp_path):
+    """The breadth-first router mode through the same two-part iteration and event-log sync."""
+    script = tmp_path / "worker_bf.py"
+    script.write_text(WORKER_BF % {"root": ROOT, "emu": emu_lib})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    import json
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["success"] and out["occ_equal"] and out["overused"] == 0
