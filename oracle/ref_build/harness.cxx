@@ -83,6 +83,7 @@ static std::vector<int> g_net_ptr;       /* terminals prefix */
 static double g_t0 = 0;
 static std::vector<double> g_iter_time;
 static float g_last_cpd = 0;
+static double g_sta_seconds = 0;
 static std::vector<float> g_sta_delay, g_sta_crit, g_sta_cpd;   /* golden vectors of the reference's STA calls */
 
 static void build_net_ptr() {
@@ -128,7 +129,9 @@ void pf_hook_load_timing_graph_net_delays(float **net_delay) {
 static t_slack *g_slacks = NULL;
 void pf_hook_do_timing_analysis(t_slack *slacks, boolean a, boolean b, boolean c) {
 	if (!g_inject) {
+		double t_sta = now_s();
 		do_timing_analysis(slacks, a, b, c);
+		g_sta_seconds += now_s() - t_sta;
 		size_t base = g_sta_crit.size();          /* every net, global ones too: the analysis covers them */
 		g_sta_crit.resize(base + g_net_ptr[num_nets], 0.f);
 		for (int i = 0; i < num_nets; i++)
@@ -341,7 +344,8 @@ static void export_sta_vectors(const char *path) {
 	}
 	v.net_delay = g_sta_delay.data(); v.crit = g_sta_crit.data(); v.cpd = g_sta_cpd.data();
 	int rc = pf_sta_vectors_write(path, &v);
-	fprintf(stderr, "PF_REF wrote STA vectors %s: %d calls x %d terminals (rc %d)\n", path, v.num_calls, v.num_terminals, rc);
+	fprintf(stderr, "PF_REF wrote STA vectors %s: %d calls x %d terminals (rc %d); do_timing_analysis took %.3f ms per call\n", path, v.num_calls,
+			v.num_terminals, rc, v.num_calls ? 1e3 * g_sta_seconds / v.num_calls : 0.);
 }
 
 boolean pf_hook_try_timing_driven_route(struct s_router_opts router_opts, float **net_delay, t_slack *slacks,
@@ -350,7 +354,7 @@ boolean pf_hook_try_timing_driven_route(struct s_router_opts router_opts, float 
 	if (dp) export_problem(dp, router_opts, timing_analysis_enabled, clb_opins_used_locally);
 	build_net_ptr();
 	g_iter = 0; g_stats.clear(); g_crit.clear(); g_iter_time.clear();
-	g_sta_delay.clear(); g_sta_crit.clear(); g_sta_cpd.clear();
+	g_sta_delay.clear(); g_sta_crit.clear(); g_sta_cpd.clear(); g_sta_seconds = 0;
 	if (getenv("PF_DUMP_TGRAPH") && timing_analysis_enabled && !g_inject) export_timing_graph(getenv("PF_DUMP_TGRAPH"));
 	/* criticalities of iteration 1 (route_timing.c:116-128) */
 	{
