@@ -1,10 +1,23 @@
 /* TEST INFRASTRUCTURE: command-line driver for the CPU restatement (pf_oracle.c).
- * usage: pf_oracle_cli problem.pfp [--crit golden.pfr] [--result out.pfr] [--max_iters K] [--limit_nets M] */
+ * usage: pf_oracle_cli problem.pfp [--crit golden.pfr | --timing-graph g.pftg] [--result out.pfr] [--max_iters K] [--limit_nets M]
+ *   --crit          timing-driven, replaying the criticalities the reference's STA produced (golden result)
+ *   --timing-graph  timing-driven with the oracle's own restatement of the STA in the loop: router + analysis together
+ *                   must then reproduce the reference's whole run */
 #include "pf_oracle.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+
+/* crit_fn running pf_oracle_sta on the flat timing graph (user = this struct) */
+struct sta_ctx { const pf_timing_graph *g; const pf_problem *p; };
+static void sta_crit(void *user, int iters_done, const float *net_delay, float *crit, float *cpd) {
+	struct sta_ctx *c = (struct sta_ctx *)user;
+	float ns = 0.f;
+	(void)iters_done;
+	if (pf_oracle_sta(c->g, c->p->net_ptr, net_delay, crit, &ns) != 0) { fprintf(stderr, "PF_ORACLE sta failed\n"); exit(3); }
+	*cpd = ns;
+}
 
 static double now_s(void) {
 	struct timespec ts;
@@ -13,7 +26,9 @@ static double now_s(void) {
 }
 
 int main(int argc, char **argv) {
-	const char *result_path = NULL, *crit_path = NULL;
+	const char *result_path = NULL, *crit_path = NULL, *tg_path = NULL;
+	pf_timing_graph tg;
+	struct sta_ctx sctx;
 	int max_iters = -1, limit_nets = -1, i, rc;
 	pf_problem p;
 	pf_result golden, out;
@@ -23,6 +38,7 @@ int main(int argc, char **argv) {
 	for (i = 2; i < argc; i++) {
 		if (!strcmp(argv[i], "--result") && i + 1 < argc) result_path = argv[++i];
 		else if (!strcmp(argv[i], "--crit") && i + 1 < argc) crit_path = argv[++i];
+		else if (!strcmp(argv[i], "--timing-graph") && i + 1 < argc) tg_path = argv[++i];
 		else if (!strcmp(argv[i], "--max_iters") && i + 1 < argc) max_iters = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--limit_nets") && i + 1 < argc) limit_nets = atoi(argv[++i]);
 		else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
@@ -33,11 +49,19 @@ int main(int argc, char **argv) {
 	if (crit_path) {
 		if (pf_result_read(crit_path, &golden) != 0 || golden.num_terminals != p.num_terminals) { fprintf(stderr, "bad --crit %s\n", crit_path); return 2; }
 		p.opts.timing_analysis_enabled = 1;
+	} else if (tg_path) {
+		char msg[256];
+		if (pf_timing_graph_read(tg_path, &tg) != 0 || pf_timing_graph_check(&tg, p.net_ptr, msg, sizeof(msg)) != 0 || tg.num_nets != p.num_nets) {
+			fprintf(stderr, "bad --timing-graph %s\n", tg_path); return 2;
+		}
+		sctx.g = &tg; sctx.p = &p;
+		p.opts.timing_analysis_enabled = 1;
 	} else {
 		p.opts.timing_analysis_enabled = 0;
 	}
 	t0 = now_s();
-	rc = pf_oracle_route(&p, crit_path ? pf_oracle_replay_crit : NULL, &golden, max_iters, &out);
+	if (tg_path && !crit_path) rc = pf_oracle_route(&p, sta_crit, &sctx, max_iters, &out);
+	else rc = pf_oracle_route(&p, crit_path ? pf_oracle_replay_crit : NULL, &golden, max_iters, &out);
 	t1 = now_s();
 	if (rc != 0) { fprintf(stderr, "PF_ORACLE route failed rc=%d\n", rc); return 3; }
 	for (i = 0; i < out.num_iter_stats; i++) {

@@ -76,3 +76,21 @@ def test_reference_binary_agrees_when_present(ref_bin, oracle_cli, unxz, tmp_pat
     r, o = pfio.read_result(out_r), pfio.read_result(out_o)
     assert r.serial_num == o.serial_num and np.array_equal(r.trace_node, o.trace_node)
     assert np.array_equal(r.net_delay.view(np.uint32), o.net_delay.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90", "mid_w200"])
+def test_oracle_router_and_sta_in_closed_loop_reproduce_the_reference_run(name, oracle_cli, unxz, tmp_path):
+    """No replay: the oracle router with the oracle's own static timing analysis between iterations (--timing-graph)
+    must reproduce the reference's WHOLE timing-driven run — iteration count, every trace, the cookie, bit-exact sink
+    delays and the criticalities of every iteration."""
+    out = str(tmp_path / "o.pfr")
+    r = subprocess.run([oracle_cli, unxz(name + ".pfp"), "--timing-graph", unxz(name + ".pftg"), "--result", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    p = pfio.read_problem(unxz(name + ".pfp"))
+    g = pfio.read_result(unxz(name + ".pfr"))
+    o = pfio.read_result(out)
+    assert (o.success, o.iterations, o.serial_num, o.total_wirelength) == (g.success, g.iterations, g.serial_num, g.total_wirelength)
+    assert np.array_equal(o.trace_ptr, g.trace_ptr) and np.array_equal(o.trace_node, g.trace_node) and np.array_equal(o.trace_switch, g.trace_switch)
+    assert np.array_equal(o.net_delay.view(np.uint32), g.net_delay.view(np.uint32)) and np.array_equal(o.occ, g.occ)
+    routed = np.repeat(p.net_is_global == 0, np.diff(p.net_ptr))
+    assert np.array_equal(o.iter_crit.view(np.uint32)[:, routed], g.iter_crit.view(np.uint32)[:, routed])
