@@ -23,7 +23,8 @@ def test_breadth_first_routing(name):
     m = check_route.check_route(p, r, check_delays=False)
     assert m["overused"] == 0 and m["wirelength"] == r.total_wirelength
     print("%s breadth-first: %d iterations (reference %d), wirelength x%.3f, %.3f s" % (name, r.iterations, g.iterations, r.total_wirelength / g.total_wirelength, dt))
-    assert r.total_wirelength <= 1.12 * g.total_wirelength
+    # the 300-net toy moves by percents from run to run (measured +8 %); duo / hub measured +2 % / +0.4 %
+    assert r.total_wirelength <= (1.15 if name == "toy_w64" else 1.10) * g.total_wirelength
 
 
 def test_single_warp_breadth_first_is_bit_identical_to_the_emulated_device_code():
