@@ -1,9 +1,15 @@
 """Stand-alone router CLI over the flat containers (include/pf_file.h):
 
     python -m parallel_eda_b200 route PROBLEM.pfp[.xz] [--timing-graph G.pftg[.xz]] [--result OUT.pfr]
+                                      [--route-file OUT.route [--names N.pfn[.xz]]]
                                       [--max-iters K] [--device D] [--check] [--verbose]
-    python -m parallel_eda_b200 check PROBLEM.pfp[.xz] RESULT.pfr[.xz]      (device check_route of any result)
+    python -m parallel_eda_b200 check PROBLEM.pfp[.xz] RESULT.pfr[.xz] | ROUTING.route   (device check_route)
     python -m parallel_eda_b200 info  PROBLEM.pfp[.xz]
+    python -m parallel_eda_b200 print-route PROBLEM.pfp[.xz] RESULT.pfr[.xz] OUT.route [--names N.pfn[.xz]]   (no GPU)
+    python -m parallel_eda_b200 read-route  PROBLEM.pfp[.xz] IN.route OUT.pfr                                  (no GPU)
+
+--route-file / print-route write VPR's .route text (print_route, reference route_common.c:1322; include/pf_text.h);
+without --names (the reference-side export of net / block names) nets are called n<i> and the IO ring is assumed.
 
 `route` runs try_timing_driven_route / try_breadth_first_route (opts.router_algorithm in the problem) on one GPU; with
 --timing-graph the static timing analysis between iterations runs on the device, otherwise a problem with
@@ -16,7 +22,7 @@ import json
 import sys
 import time
 
-from . import pfio, router
+from . import pfio, router, textio
 
 
 def main(argv=None) -> int:
@@ -24,11 +30,14 @@ def main(argv=None) -> int:
     sub = ap.add_subparsers(dest="cmd", required=True)
     r = sub.add_parser("route")
     r.add_argument("problem"); r.add_argument("--timing-graph"); r.add_argument("--result")
+    r.add_argument("--route-file"); r.add_argument("--names")
     r.add_argument("--max-iters", type=int, default=0); r.add_argument("--device", type=int, default=0)
     r.add_argument("--check", action="store_true", help="run the device check_route on the result")
     r.add_argument("--verbose", action="store_true")
     c = sub.add_parser("check"); c.add_argument("problem"); c.add_argument("result"); c.add_argument("--device", type=int, default=0)
     i = sub.add_parser("info"); i.add_argument("problem")
+    w = sub.add_parser("print-route"); w.add_argument("problem"); w.add_argument("result"); w.add_argument("route_file"); w.add_argument("--names")
+    g = sub.add_parser("read-route"); g.add_argument("problem"); g.add_argument("route_file"); g.add_argument("result")
     a = ap.parse_args(argv)
 
     p = pfio.read_problem(a.problem)
@@ -37,11 +46,29 @@ def main(argv=None) -> int:
                           "routed_nets": int(len(p.routed_nets())), "terminals": p.num_terminals,
                           "opts": {k: float(p.opts[k]) for k in p.opts.dtype.names}}))
         return 0
+    if a.cmd == "print-route":
+        names = textio.read_names(a.names) if a.names else textio.synthetic_names(p)
+        textio.check_names(names, p)
+        textio.write_route(a.route_file, p, names, pfio.read_result(a.result))
+        return 0
+    if a.cmd == "read-route":
+        res = textio.read_route(a.route_file, p)
+        pfio.write_result(a.result, res)
+        print(json.dumps({"nets": p.num_nets, "trace_elements": int(len(res.trace_node)), "wirelength": int(res.total_wirelength),
+                          "serial_num": int(res.serial_num)}))
+        return 0
     if a.cmd == "check":
-        res = pfio.read_result(a.result)
+        from_text = a.result.endswith(".route")
+        res = textio.read_route(a.result, p) if from_text else pfio.read_result(a.result)
+        if from_text:       # a .route file lists no occupancy: the traces' own; locally reserved OPINs are not in the file
+            from . import check_route as _cr
+            res.occ = _cr.recompute_occupancy(p, res)
         R = router.Router(p, router.default_config(device=a.device))
         rep = R.check_route(res)
         R.close()
+        if from_text and rep["bad_nets"] == 0 and rep["reserved_opins"] == 0 and rep["occupancy_mismatch"] == 1:
+            rep["ok"], rep["occupancy_mismatch"] = 1, 0
+            rep["note"] = "locally reserved OPINs (reserve_locally_used_opins) are not part of a .route file"
         print(json.dumps(rep))
         return 0 if rep["ok"] and rep["overused_nodes"] == 0 else 1
     if a.max_iters > 0:
@@ -58,6 +85,10 @@ def main(argv=None) -> int:
         R.close()
     if a.result:
         pfio.write_result(a.result, res)
+    if a.route_file:
+        names = textio.read_names(a.names) if a.names else textio.synthetic_names(p)
+        textio.check_names(names, p)
+        textio.write_route(a.route_file, p, names, res)
     print(json.dumps(out))
     return 0 if res.success else 1
 

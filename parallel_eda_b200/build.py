@@ -31,9 +31,9 @@ def _newer(target: str, sources) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("pf_kernels.cu", "pf_router.cpp", "pf_sta.cpp", "pf_check.cpp", "pf_gen.cpp", "pf_file.c")]
+    srcs = [os.path.join(CSRC, f) for f in ("pf_kernels.cu", "pf_router.cpp", "pf_sta.cpp", "pf_check.cpp", "pf_gen.cpp", "pf_file.c", "pf_text.c")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("pf_device.cuh", "pf_sta_device.cuh", "pf_backend.h", "pf_layout.h", "pf_host.h")] + [
-        os.path.join(ROOT, "include", f) for f in ("pf_router.h", "pf_types.h", "pf_file.h", "pf_gen.h")]
+        os.path.join(ROOT, "include", f) for f in ("pf_router.h", "pf_types.h", "pf_file.h", "pf_gen.h", "pf_text.h")]
     if not force and _newer(LIB, deps):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

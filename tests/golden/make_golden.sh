@@ -16,7 +16,10 @@ python "$ROOT/tests/fixtures/gen_blif.py" duo.blif --luts 500 --pis 20 --window 
 for c in toy:64 mid:200 hub:90 duo:80; do
   n=${c%%:*}; w=${c##*:}
   "$REF" flow k6_N10_like.xml $n --nodisp --pack --place > /dev/null
-  PF_DUMP_PROBLEM=${n}_w$w.pfp PF_DUMP_RESULT=${n}_w$w.pfr PF_DUMP_TGRAPH=${n}_w$w.pftg PF_DUMP_STA=${n}_w$w.pfsta "$REF" flow k6_N10_like.xml $n --nodisp --route --route_chan_width $w > /dev/null
+  PF_DUMP_PROBLEM=${n}_w$w.pfp PF_DUMP_RESULT=${n}_w$w.pfr PF_DUMP_NAMES=${n}_w$w.pfn PF_DUMP_TGRAPH=${n}_w$w.pftg PF_DUMP_STA=${n}_w$w.pfsta "$REF" flow k6_N10_like.xml $n --nodisp --route --route_chan_width $w > /dev/null
+  if [ $n = toy ] || [ $n = hub ]; then   # text-format goldens (include/pf_text.h): the reference's own print_route / print_place output
+    xz -9 -c $n.route > "$HERE/${n}_w$w.route.xz"; xz -9 -c ${n}_w$w.pfn > "$HERE/${n}_w$w.pfn.xz"; cp $n.place "$HERE/"
+  fi
   "$REF" inject ${n}_w$w.pfp --result ${n}_w${w}_nt.pfr > /dev/null
   if [ $n != mid ]; then   # breadth-first (Dijkstra) takes the reference 70 s on mid
     PF_DUMP_PROBLEM=${n}_w${w}_bf.pfp PF_DUMP_RESULT=${n}_w${w}_bf.pfr "$REF" flow k6_N10_like.xml $n --nodisp --route --route_chan_width $w --router_algorithm breadth_first > /dev/null

@@ -33,7 +33,7 @@ def test_result_roundtrip(unxz, tmp_path):
 
 def _declared_functions():
     names = []
-    for h in ("pf_router.h", "pf_file.h", "pf_gen.h"):
+    for h in ("pf_router.h", "pf_file.h", "pf_gen.h", "pf_text.h"):
         text = open(os.path.join(ROOT, "include", h)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names += re.findall(r"\b(pf_[a-z_0-9]+)\s*\(", text)

@@ -1,0 +1,193 @@
+"""VPR's text files either side of the route path (include/pf_text.h) — CPU only.
+
+Golden vectors are the UNMODIFIED reference's own output: `<circuit>.route` written by print_route
+(reference route/route_common.c:1322) and `<circuit>.place` written by print_place (base/read_place.c:266) in the
+same run that produced tests/golden/<circuit>_w<W>.pfp/.pfr; the names container (.pfn) was dumped by the
+reference-side hook in that run (tests/golden/make_golden.sh).  The bar is byte identity.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from parallel_eda_b200 import check_route, pfio, router, textio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+FIXTURES = [("toy", "toy_w64"), ("hub", "hub_w90")]
+
+
+def _load(unxz, stem):
+    p = pfio.read_problem(unxz(stem + ".pfp"))
+    r = pfio.read_result(unxz(stem + ".pfr"))
+    n = textio.read_names(unxz(stem + ".pfn"))
+    return p, r, n
+
+
+@pytest.mark.parametrize("circuit,stem", FIXTURES)
+def test_route_file_is_byte_identical_to_print_route(cuda_lib, unxz, tmp_path, circuit, stem):
+    p, r, n = _load(unxz, stem)
+    textio.check_names(n, p)
+    out = str(tmp_path / (circuit + ".route"))
+    textio.write_route(out, p, n, r)
+    assert open(out, "rb").read() == open(unxz(stem + ".route"), "rb").read()
+
+
+@pytest.mark.parametrize("circuit,stem", FIXTURES)
+def test_route_reader_recovers_the_reference_traceback(cuda_lib, unxz, circuit, stem):
+    """The reference's .route file parsed back: same s_trace order (nodes and switches), wirelength
+    (stats.c:355-409) and serial number (route_common.c:224-254) as the result the reference hook dumped."""
+    p, r, _ = _load(unxz, stem)
+    q = textio.read_route(unxz(stem + ".route"), p)
+    assert np.array_equal(q.trace_ptr, r.trace_ptr)
+    assert np.array_equal(q.trace_node, r.trace_node)
+    assert np.array_equal(q.trace_switch, r.trace_switch)
+    assert q.total_wirelength == r.total_wirelength and q.serial_num == r.serial_num
+    # with what a .route file cannot carry (delays, the occupancy incl. locally reserved OPINs) taken from the reference's
+    # dump, the independent checker accepts the parsed routing: traces explain the occupancy, Elmore delays match
+    full = pfio.Result(1, 0, q.serial_num, q.total_wirelength, q.trace_ptr, q.trace_node, q.trace_switch, r.net_delay,
+                       r.occ, r.iter_stats[:0], None)
+    rep = check_route.check_route(p, full, check_delays=True, require_legal=True)
+    assert rep["overused"] == 0
+
+
+@pytest.mark.parametrize("circuit,stem", FIXTURES)
+def test_place_file_write_and_read(cuda_lib, unxz, tmp_path, circuit, stem):
+    _, _, n = _load(unxz, stem)
+    ref = os.path.join(GOLDEN, circuit + ".place")
+    out = str(tmp_path / (circuit + ".place"))
+    textio.write_place(out, circuit + ".net", "k6_N10_like.xml", n)
+    assert open(out, "rb").read() == open(ref, "rb").read()          # print_place, byte for byte
+    want = (n.block_x.copy(), n.block_y.copy(), n.block_z.copy())
+    n.block_x[:] = -1
+    n.block_y[:] = -1
+    n.block_z[:] = -1
+    placed = textio.read_place(ref, n, net_file=circuit + ".net", arch_file="k6_N10_like.xml")
+    assert placed == n.num_blocks
+    assert all(np.array_equal(a, b) for a, b in zip(want, (n.block_x, n.block_y, n.block_z)))
+    # the reference's two file-name checks (read_place.c:55-64)
+    with pytest.raises(router.RouterError, match="Architecture file"):
+        textio.read_place(ref, n, net_file=circuit + ".net", arch_file="other.xml")
+    with pytest.raises(router.RouterError, match="Netlist file"):
+        textio.read_place(ref, n, net_file="other.net", arch_file="k6_N10_like.xml")
+
+
+def test_place_reader_tokenisation_follows_read_line_tokens(cuda_lib, unxz, tmp_path):
+    """libarchfpga/ReadLine.c:38-196: comments, blank lines, CR LF, backslash continuation, tabs or blanks."""
+    _, _, n = _load(unxz, "toy_w64")
+    names = [n.block_name(i) for i in range(3)]
+    f = tmp_path / "odd.place"
+    f.write_bytes(("Netlist file: a.net \\\n   Architecture file: b.xml\r\n"
+                   "Array size: %d x %d logic blocks\n\n# a comment line\n   \t \n"
+                   "%s 1 2 3 # trailing comment\n"
+                   "%s\t4\t5\t0\t#7\r\n"
+                   "%s   6 \\\n 1   2\n" % (n.nx, n.ny, names[0], names[1], names[2])).encode())
+    n.block_x[:] = -1
+    assert textio.read_place(str(f), n, net_file="a.net", arch_file="b.xml") == 3
+    assert (n.block_x[:3].tolist(), n.block_y[:3].tolist(), n.block_z[:3].tolist()) == ([1, 4, 6], [2, 5, 1], [3, 0, 2])
+    assert (n.block_x[3:] == -1).all()
+
+
+@pytest.mark.parametrize("text,err", [
+    ("Netlist: a.net Architecture file: b.xml\nArray size: 6 x 6 logic blocks\n", "Bad filename specification"),
+    ("Netlist file: a.net   Architecture file: b.xml\nArray size: 7 x 6 logic blocks\n", "different from size"),
+    ("Netlist file: a.net   Architecture file: b.xml\nArray size: six x 6 logic blocks\n", "Bad FPGA size"),
+    ("Netlist file: a.net   Architecture file: b.xml\nArray size: 6 x 6 logic blocks\nno_such_block 1 1 0\n", "does not exist in netlist"),
+    ("Netlist file: a.net   Architecture file: b.xml\nArray size: 6 x 6 logic blocks\nBLOCK0 1 1\n", "expected <block>"),
+    ("Netlist file: a.net   Architecture file: b.xml\nArray size: 6 x 6 logic blocks\nBLOCK0 1 x 0\n", "expected <block>"),
+])
+def test_place_reader_error_behaviour(cuda_lib, unxz, tmp_path, text, err):
+    """Where read_place.c exits (or dereferences a missing token) the reader returns PF_EFORMAT with the same message."""
+    _, _, n = _load(unxz, "toy_w64")
+    f = tmp_path / "bad.place"
+    f.write_text(text.replace("BLOCK0", n.block_name(0)))
+    with pytest.raises(router.RouterError, match=err) as e:
+        textio.read_place(str(f), n)
+    assert e.value.code == -2
+
+
+def test_route_reader_rejects_files_of_another_problem(cuda_lib, unxz, tmp_path):
+    p, r, n = _load(unxz, "toy_w64")
+    hub = pfio.read_problem(unxz("hub_w90.pfp"))
+    with pytest.raises(router.RouterError, match="array"):
+        textio.read_route(unxz("toy_w64.route"), hub)                # grid size differs
+    good = open(unxz("toy_w64.route")).read()
+    cases = {
+        "another rr graph": good.replace("Track: 16  ", "Track: 17  ", 1),
+        "unrecognised line": good.replace("Routing:", "Routed:", 1),
+        "follows net": good.replace("Net 1 (", "Net 2 (", 1),
+        "nets in the file": good[:good.index("\n\nNet 200 ")] + "\n",
+        "no rr edge|SINK": "\n".join(l for i, l in enumerate(good.split("\n")) if i != 7) + "\n",   # drop one CHAN node of net 0
+        "global in one of": good.replace("): global net connecting:", ")", 1),
+    }
+    for err, text in cases.items():
+        f = tmp_path / "bad.route"
+        f.write_text(text)
+        with pytest.raises(router.RouterError, match=err) as e:
+            textio.read_route(str(f), p)
+        assert e.value.code == -2, err
+    # the writer refuses inconsistent inputs instead of writing a wrong file
+    with pytest.raises(router.RouterError):
+        textio.write_route(str(tmp_path / "x.route"), hub, n, r)
+    bad = pfio.Result(1, 0, 0, 0, r.trace_ptr, np.where(r.trace_node == r.trace_node[3], p.num_nodes, r.trace_node),
+                      r.trace_switch, r.net_delay, r.occ, r.iter_stats, None)
+    with pytest.raises(router.RouterError, match="out of range"):
+        textio.write_route(str(tmp_path / "x.route"), p, n, bad)
+
+
+def test_names_container_roundtrip_python_and_c(cuda_lib, unxz, tmp_path):
+    import ctypes as C
+    src = unxz("hub_w90.pfn")
+    n = textio.read_names(src)
+    out = str(tmp_path / "rt.pfn")
+    textio.write_names(out, n)
+    assert open(out, "rb").read() == open(src, "rb").read()
+    lib = textio._lib()
+    c = textio._Names()
+    assert lib.pf_names_read(src.encode(), C.byref(c)) == 0          # the C reader / writer agree with numpy's
+    out2 = str(tmp_path / "rt2.pfn")
+    assert lib.pf_names_write(out2.encode(), C.byref(c)) == 0
+    lib.pf_names_free(C.byref(c))
+    assert open(out2, "rb").read() == open(src, "rb").read()
+    assert n.net_name(92 if n.num_nets == 294 else 0) and n.num_blocks == 153
+    # validation
+    m = textio.read_names(src)
+    m.net_name_chars[3] = ord(" ")
+    with pytest.raises(router.RouterError, match="white space"):
+        textio.check_names(m)
+    m = textio.read_names(src)
+    m.block_x[0] = m.nx + 2
+    with pytest.raises(router.RouterError, match="outside the grid"):
+        textio.check_names(m)
+    with pytest.raises(router.RouterError, match="problem has 6 x 6"):
+        textio.check_names(n, pfio.read_problem(unxz("toy_w64.pfp")))
+
+
+def test_generated_fabric_route_file_roundtrip(cuda_lib, oracle_cli, tmp_path):
+    """A generated grid (no netlist behind it): synthetic names, the oracle's routing, write -> read -> same traces,
+    and the IO ring prints 'Pad:' exactly where the reference's grid has IO tiles."""
+    import subprocess
+    p = router.generate_grid_problem(nx=8, ny=8, W=24, num_nets=60, sinks_per_net=3, seed=11)
+    pp, rr = str(tmp_path / "g.pfp"), str(tmp_path / "g.pfr")
+    pfio.write_problem(pp, p)
+    subprocess.run([oracle_cli, pp, "--result", rr], check=True, capture_output=True)
+    r = pfio.read_result(rr)
+    assert r.success == 1
+    n = textio.synthetic_names(p)
+    textio.check_names(n, p)
+    assert n.net_name(17) == "n17" and n.num_blocks == 0
+    io = n.tile_is_io.reshape(p.nx + 2, p.ny + 2)
+    assert io[0].all() and io[-1].all() and io[:, 0].all() and io[:, -1].all() and not io[1:-1, 1:-1].any()
+    out = str(tmp_path / "g.route")
+    textio.write_route(out, p, n, r)
+    q = textio.read_route(out, p)
+    assert np.array_equal(q.trace_ptr, r.trace_ptr) and np.array_equal(q.trace_node, r.trace_node)
+    assert np.array_equal(q.trace_switch, r.trace_switch)
+    assert q.total_wirelength == r.total_wirelength and q.serial_num == r.serial_num
+    text = open(out).read()
+    assert text.startswith("Array size: 8 x 8 logic blocks.\n\nRouting:\n\nNet 0 (n0)\n\nNode:\t")
+    for line in text.split("\n"):
+        if line.startswith("Node:") and ("SOURCE" in line or "SINK" in line or "PIN" in line):
+            x, y = (int(v) for v in line.split("(")[1].split(")")[0].split(","))
+            ring = x in (0, p.nx + 1) or y in (0, p.ny + 1)
+            assert ("Pad:" in line) == ring, line
