@@ -442,10 +442,11 @@ static int run_flow(int argc, char **argv) {
 /* ------------------------------------------------------------------ inject mode */
 static int run_inject(int argc, char **argv) {
 	const char *prob_path = argv[0];
-	const char *result_path = NULL, *crit_path = NULL;
+	const char *result_path = NULL, *crit_path = NULL, *route_file = NULL;
 	int max_iters = -1, limit_nets = -1;
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "--result") && i + 1 < argc) result_path = argv[++i];
+		else if (!strcmp(argv[i], "--route-file") && i + 1 < argc) route_file = argv[++i];
 		else if (!strcmp(argv[i], "--crit") && i + 1 < argc) crit_path = argv[++i];
 		else if (!strcmp(argv[i], "--max_iters") && i + 1 < argc) max_iters = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--limit_nets") && i + 1 < argc) limit_nets = atoi(argv[++i]);
@@ -490,9 +491,19 @@ static int run_inject(int argc, char **argv) {
 	num_nets = p.num_nets;
 	clb_net = new struct s_net[p.num_nets];
 	net_rr_terminals = (int **)malloc(sizeof(int *) * p.num_nets);
-	static char noname[] = "n";
+	/* nets are called n<i> and the fabric gets VPR's IO ring (what pf_names_synthetic of include/pf_text.h assumes),
+	 * so that the reference's own print_route can write the routing of a generated problem (--route-file) */
+	std::vector<char> name_chars((size_t)p.num_nets * 12 + 16);
+	static struct s_type_descriptor fake_io_type, fake_clb_type;
+	IO_TYPE = &fake_io_type;
+	grid = (struct s_grid_tile **)malloc(sizeof(struct s_grid_tile *) * (nx + 2));
+	for (int x = 0; x <= nx + 1; x++) {
+		grid[x] = (struct s_grid_tile *)calloc(ny + 2, sizeof(struct s_grid_tile));
+		for (int y = 0; y <= ny + 1; y++) grid[x][y].type = (x == 0 || y == 0 || x == nx + 1 || y == ny + 1) ? &fake_io_type : &fake_clb_type;
+	}
 	for (int i = 0; i < p.num_nets; i++) {
-		clb_net[i].name = noname;
+		clb_net[i].name = &name_chars[(size_t)i * 12];
+		sprintf(clb_net[i].name, "n%d", i);
 		clb_net[i].num_sinks = p.net_ptr[i + 1] - p.net_ptr[i] - 1;
 		clb_net[i].node_block = NULL; clb_net[i].node_block_port = NULL; clb_net[i].node_block_pin = NULL;
 		clb_net[i].is_global = p.net_is_global[i] ? TRUE : FALSE;
@@ -560,6 +571,11 @@ static int run_inject(int argc, char **argv) {
 	boolean ok;
 	if (p.opts.router_algorithm == 1) { ro.router_algorithm = BREADTH_FIRST; ok = pf_hook_try_breadth_first_route(ro, opins, 0); }
 	else ok = pf_hook_try_timing_driven_route(ro, net_delay, &slacks, opins, timing);
+	if (route_file) {
+		double t0 = now_s();
+		print_route((char *)route_file);                 /* the reference's own writer, route_common.c:1322 */
+		fprintf(stderr, "PF_REF print_route %s: %.3f s\n", route_file, now_s() - t0);
+	}
 	return ok ? 0 : 1;
 }
 
@@ -588,6 +604,6 @@ int main(int argc, char **argv) {
 	}
 	if (argc >= 3 && !strcmp(argv[1], "inject")) return run_inject(argc - 2, argv + 2);
 	fprintf(stderr, "usage: vpr_ref flow <arch.xml> <circuit> [vpr options]\n"
-			"       vpr_ref inject <problem.pfp> [--result out.pfr] [--crit golden.pfr] [--max_iters K] [--limit_nets M]\n");
+			"       vpr_ref inject <problem.pfp> [--result out.pfr] [--route-file out.route] [--crit golden.pfr] [--max_iters K] [--limit_nets M]\n");
 	return 2;
 }

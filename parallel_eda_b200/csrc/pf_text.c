@@ -11,10 +11,12 @@
 #include "pf_text.h"
 
 #include <ctype.h>
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 static const char NAME_MAGIC[8] = { 'P', 'F', 'N', 'A', 'M', 'E', '0', '1' };
 
@@ -172,7 +174,46 @@ int pf_names_synthetic(const pf_problem *p, pf_names *n) {
 	return PF_OK;
 }
 
-/* ------------------------------------------------------------------ buffered text output */
+/* ------------------------------------------------------------------ host threads
+ * The text of a 200 k-net routing is ~4 x 10^6 "Node:" lines, each needing six random reads of the 18 M-entry node
+ * arrays: one thread is bound by cache misses (1.6 s for the 224 MB file), so nets are formatted / parsed in chunks by
+ * all host threads (PF_TEXT_THREADS overrides the count). */
+typedef void (*par_fn)(void *ctx, int chunk);
+typedef struct { par_fn fn; void *ctx; int nchunks; int next; } par_job;
+static void *par_worker(void *arg) {
+	par_job *j = (par_job *)arg;
+	for (;;) {
+		int k = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+		if (k >= j->nchunks) return NULL;
+		j->fn(j->ctx, k);
+	}
+}
+static int par_threads(void) {
+	const char *e = getenv("PF_TEXT_THREADS");
+	long t = e ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+	if (t < 1) t = 1;
+	if (t > 64) t = 64;
+	return (int)t;
+}
+static void par_for(int nchunks, par_fn fn, void *ctx) {
+	pthread_t th[64];
+	par_job j;
+	int T = par_threads(), i, started = 0;
+	j.fn = fn; j.ctx = ctx; j.nchunks = nchunks; j.next = 0;
+	if (T > nchunks) T = nchunks;
+	for (i = 0; i < T - 1; i++) { if (pthread_create(&th[started], NULL, par_worker, &j) != 0) break; started++; }
+	par_worker(&j);                                  /* the caller works too (and alone, if no thread could start) */
+	for (i = 0; i < started; i++) pthread_join(th[i], NULL);
+}
+/* first error of a parallel phase: workers have their own thread-local g_err */
+typedef struct { int rc; char msg[256]; } par_err;
+static void par_fail(par_err *e, int rc) {
+	int expect = 0;
+	if (__atomic_compare_exchange_n(&e->rc, &expect, rc, 0, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) memcpy(e->msg, g_err, sizeof(e->msg));
+}
+
+/* ------------------------------------------------------------------ buffered text output
+ * f != NULL: a 4 MB window flushed to the file; f == NULL: a growing memory buffer (one per chunk of nets) */
 typedef struct {
 	FILE *f;
 	char *buf;
@@ -188,14 +229,29 @@ static int ob_open(outbuf *o, const char *path) {
 	if (!o->buf) { fclose(o->f); return PF_ENOMEM; }
 	return PF_OK;
 }
-static void ob_flush(outbuf *o) {
-	if (o->len && fwrite(o->buf, 1, o->len, o->f) != o->len) o->err = 1;
-	o->len = 0;
+static int ob_mem_open(outbuf *o, size_t cap) {
+	o->f = NULL; o->len = 0; o->err = 0; o->cap = cap < 4096 ? 4096 : cap;
+	o->buf = (char *)malloc(o->cap);
+	return o->buf ? PF_OK : PF_ENOMEM;
 }
-static inline void ob_room(outbuf *o, size_t need) { if (o->len + need > o->cap) ob_flush(o); }
+static void ob_flush(outbuf *o) {
+	if (o->f && o->len && fwrite(o->buf, 1, o->len, o->f) != o->len) o->err = 1;
+	if (o->f) o->len = 0;
+}
+static void ob_room_slow(outbuf *o, size_t need) {
+	if (o->f) { ob_flush(o); return; }
+	{
+		size_t nc = o->cap * 2 > o->len + need ? o->cap * 2 : o->len + need + o->cap;
+		char *nb = (char *)realloc(o->buf, nc);
+		if (!nb) { o->err = 2; o->len = 0; return; }      /* keeps the buffer valid; the chunk is reported as PF_ENOMEM */
+		o->buf = nb; o->cap = nc;
+	}
+}
+static inline void ob_room(outbuf *o, size_t need) { if (o->len + need > o->cap) ob_room_slow(o, need); }
 static inline void ob_mem(outbuf *o, const char *s, size_t n) {
-	if (n > o->cap) { ob_flush(o); if (fwrite(s, 1, n, o->f) != n) o->err = 1; return; }
+	if (o->f && n > o->cap) { ob_flush(o); if (fwrite(s, 1, n, o->f) != n) o->err = 1; return; }
 	ob_room(o, n);
+	if (o->len + n > o->cap) return;                     /* failed growth */
 	memcpy(o->buf + o->len, s, n); o->len += n;
 }
 #define ob_lit(o, s) ob_mem((o), (s), sizeof(s) - 1)
@@ -204,6 +260,7 @@ static inline void ob_int(outbuf *o, long v) {   /* "%d" */
 	int k = 0;
 	unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
 	ob_room(o, 24);
+	if (o->len + 24 > o->cap) return;
 	do { t[k++] = (char)('0' + u % 10); u /= 10; } while (u);
 	if (v < 0) o->buf[o->len++] = '-';
 	while (k) o->buf[o->len++] = t[--k];
@@ -227,53 +284,116 @@ static inline int tile_io(const pf_names *n, int x, int y) {
 	return n->tile_is_io[(size_t)x * (size_t)(n->ny + 2) + (size_t)y];
 }
 
-int pf_route_write(const char *path, const pf_problem *p, const pf_names *n, const pf_result *r) {
-	outbuf o;
-	int inet, k, rc;
-	if (!path || !p || !n || !r) return fail(PF_EINVAL, "pf_route_write: NULL argument");
-	if (n->num_nets != p->num_nets || r->num_nets != p->num_nets || n->nx != p->nx || n->ny != p->ny)
-		return fail(PF_EINVAL, "pf_route_write: problem, names and result disagree on nets or grid");
-	if ((rc = ob_open(&o, path)) != 0) return rc;
-	ob_lit(&o, "Array size: "); ob_int(&o, p->nx); ob_lit(&o, " x "); ob_int(&o, p->ny); ob_lit(&o, " logic blocks.\n");
-	ob_lit(&o, "\nRouting:");
-	for (inet = 0; inet < p->num_nets; inet++) {
+/* nets [lo, hi) in print_route's format (route_common.c:1333-1414) */
+static int format_nets(outbuf *o, const pf_problem *p, const pf_names *n, const pf_result *r, int lo, int hi) {
+	int inet, k;
+	for (inet = lo; inet < hi; inet++) {
 		const char *name = n->net_name_chars + n->net_name_ptr[inet];
 		size_t name_len = (size_t)(n->net_name_ptr[inet + 1] - n->net_name_ptr[inet]);
-		ob_lit(&o, "\n\nNet "); ob_int(&o, inet); ob_lit(&o, " ("); ob_mem(&o, name, name_len);
+		ob_lit(o, "\n\nNet "); ob_int(o, inet); ob_lit(o, " ("); ob_mem(o, name, name_len);
 		if (p->net_is_global[inet]) {                                        /* :1394-1412 */
-			ob_lit(&o, "): global net connecting:\n\n");
+			ob_lit(o, "): global net connecting:\n\n");
 			for (k = n->gpin_ptr[inet]; k < n->gpin_ptr[inet + 1]; k++) {
 				int b = n->gpin_block[k];
-				ob_lit(&o, "Block ");
-				ob_mem(&o, n->block_name_chars + n->block_name_ptr[b], (size_t)(n->block_name_ptr[b + 1] - n->block_name_ptr[b]));
-				ob_lit(&o, " (#"); ob_int(&o, b); ob_lit(&o, ") at ("); ob_int(&o, n->block_x[b]); ob_lit(&o, ", ");
-				ob_int(&o, n->block_y[b]); ob_lit(&o, "), Pin class "); ob_int(&o, n->gpin_class[k]); ob_lit(&o, ".\n");
+				ob_lit(o, "Block ");
+				ob_mem(o, n->block_name_chars + n->block_name_ptr[b], (size_t)(n->block_name_ptr[b + 1] - n->block_name_ptr[b]));
+				ob_lit(o, " (#"); ob_int(o, b); ob_lit(o, ") at ("); ob_int(o, n->block_x[b]); ob_lit(o, ", ");
+				ob_int(o, n->block_y[b]); ob_lit(o, "), Pin class "); ob_int(o, n->gpin_class[k]); ob_lit(o, ".\n");
 			}
 			continue;
 		}
-		ob_lit(&o, ")\n\n");
+		ob_lit(o, ")\n\n");
 		if (p->net_ptr[inet + 1] - p->net_ptr[inet] - 1 == 0) {               /* :1337-1339 */
-			ob_lit(&o, "\n\nUsed in local cluster only, reserved one CLB pin\n\n");
+			ob_lit(o, "\n\nUsed in local cluster only, reserved one CLB pin\n\n");
 			continue;
 		}
 		for (k = r->trace_ptr[inet]; k < r->trace_ptr[inet + 1]; k++) {      /* :1344-1389 */
 			int inode = r->trace_node[k], t, ilow, jlow;
-			if (inode < 0 || inode >= p->num_nodes) { rc = fail(PF_EINVAL, "net %d: trace node %d out of range", inet, inode); goto out; }
+			if (inode < 0 || inode >= p->num_nodes) return fail(PF_EINVAL, "net %d: trace node %d out of range", inet, inode);
 			t = p->type[inode]; ilow = p->xlow[inode]; jlow = p->ylow[inode];
-			if (t > PF_CHANY) { rc = fail(PF_EINVAL, "net %d: unexpected traceback element type %d", inet, t); goto out; }
-			ob_lit(&o, "Node:\t"); ob_int(&o, inode); ob_lit(&o, "\t"); ob_mem(&o, TYPE_PADDED[t], 6);
-			ob_lit(&o, " ("); ob_int(&o, ilow); ob_lit(&o, ","); ob_int(&o, jlow); ob_lit(&o, ") ");
+			if (t > PF_CHANY) return fail(PF_EINVAL, "net %d: unexpected traceback element type %d", inet, t);
+			ob_lit(o, "Node:\t"); ob_int(o, inode); ob_lit(o, "\t"); ob_mem(o, TYPE_PADDED[t], 6);
+			ob_lit(o, " ("); ob_int(o, ilow); ob_lit(o, ","); ob_int(o, jlow); ob_lit(o, ") ");
 			if (ilow != p->xhigh[inode] || jlow != p->yhigh[inode]) {
-				ob_lit(&o, "to ("); ob_int(&o, p->xhigh[inode]); ob_lit(&o, ","); ob_int(&o, p->yhigh[inode]); ob_lit(&o, ") ");
+				ob_lit(o, "to ("); ob_int(o, p->xhigh[inode]); ob_lit(o, ","); ob_int(o, p->yhigh[inode]); ob_lit(o, ") ");
 			}
-			if (t == PF_CHANX || t == PF_CHANY) ob_lit(&o, " Track: ");
-			else if (tile_io(n, ilow, jlow)) ob_lit(&o, " Pad: ");
-			else if (t == PF_IPIN || t == PF_OPIN) ob_lit(&o, " Pin: ");
-			else ob_lit(&o, " Class: ");
-			ob_int(&o, p->ptc_num[inode]); ob_lit(&o, "  \n");
+			if (t == PF_CHANX || t == PF_CHANY) ob_lit(o, " Track: ");
+			else if (tile_io(n, ilow, jlow)) ob_lit(o, " Pad: ");
+			else if (t == PF_IPIN || t == PF_OPIN) ob_lit(o, " Pin: ");
+			else ob_lit(o, " Class: ");
+			ob_int(o, p->ptc_num[inode]); ob_lit(o, "  \n");
 		}
 	}
+	if (o->err == 2) return fail(PF_ENOMEM, "out of memory formatting nets %d..%d", lo, hi);
+	return PF_OK;
+}
+
+/* net ranges of roughly equal trace length: bounds[0..nchunks], returns nchunks */
+static int chunk_nets(const int32_t *trace_ptr, int num_nets, long per_chunk, int **bounds_out) {
+	int cap = 16, nc = 0, inet, *b = (int *)malloc(sizeof(int) * (size_t)cap);
+	long start_elems = 0;
+	if (!b) return -1;
+	b[0] = 0;
+	for (inet = 0; inet < num_nets; inet++) {
+		if ((long)trace_ptr[inet + 1] - start_elems + 8L * (inet + 1 - b[nc]) >= per_chunk || inet == num_nets - 1) {
+			if (nc + 2 > cap) { int *nb = (int *)realloc(b, sizeof(int) * (size_t)(cap *= 2)); if (!nb) { free(b); return -1; } b = nb; }
+			b[++nc] = inet + 1;
+			start_elems = trace_ptr[inet + 1];
+		}
+	}
+	*bounds_out = b;
+	return nc;
+}
+
+typedef struct {
+	const pf_problem *p; const pf_names *n; const pf_result *r;
+	const int *bounds;
+	outbuf *bufs;
+	par_err err;
+} write_ctx;
+
+static void write_chunk(void *vctx, int k) {
+	write_ctx *c = (write_ctx *)vctx;
+	int lo = c->bounds[k], hi = c->bounds[k + 1], rc;
+	size_t est = (size_t)(c->r->trace_ptr[hi] - c->r->trace_ptr[lo]) * 56 + (size_t)(hi - lo) * 48 + 4096;
+	if (c->err.rc) { c->bufs[k].buf = NULL; c->bufs[k].len = 0; return; }
+	if (ob_mem_open(&c->bufs[k], est) != 0) { c->bufs[k].len = 0; fail(PF_ENOMEM, "out of memory"); par_fail(&c->err, PF_ENOMEM); return; }
+	rc = format_nets(&c->bufs[k], c->p, c->n, c->r, lo, hi);
+	if (rc) par_fail(&c->err, rc);
+}
+
+int pf_route_write(const char *path, const pf_problem *p, const pf_names *n, const pf_result *r) {
+	outbuf o;
+	int rc, k, nchunks, *bounds = NULL;
+	write_ctx c;
+	if (!path || !p || !n || !r) return fail(PF_EINVAL, "pf_route_write: NULL argument");
+	if (n->num_nets != p->num_nets || r->num_nets != p->num_nets || n->nx != p->nx || n->ny != p->ny)
+		return fail(PF_EINVAL, "pf_route_write: problem, names and result disagree on nets or grid");
+	for (k = 0; k < p->num_nets; k++)
+		if (r->trace_ptr[k + 1] < r->trace_ptr[k]) return fail(PF_EINVAL, "pf_route_write: trace_ptr not monotone at net %d", k);
+	if ((rc = ob_open(&o, path)) != 0) return fail(rc, "cannot open %s for writing", path);
+	ob_lit(&o, "Array size: "); ob_int(&o, p->nx); ob_lit(&o, " x "); ob_int(&o, p->ny); ob_lit(&o, " logic blocks.\n");
+	ob_lit(&o, "\nRouting:");
+	nchunks = p->num_nets > 0 ? chunk_nets(r->trace_ptr, p->num_nets, 1L << 16, &bounds) : 0;
+	if (nchunks < 0) { rc = PF_ENOMEM; goto out; }
+	if (nchunks <= 1 || par_threads() == 1) {                   /* small routing: straight into the file window */
+		rc = format_nets(&o, p, n, r, 0, p->num_nets);
+		goto out;
+	}
+	memset(&c, 0, sizeof(c));
+	c.p = p; c.n = n; c.r = r; c.bounds = bounds;
+	c.bufs = (outbuf *)calloc((size_t)nchunks, sizeof(outbuf));
+	if (!c.bufs) { rc = PF_ENOMEM; goto out; }
+	par_for(nchunks, write_chunk, &c);
+	if (c.err.rc) { rc = c.err.rc; memcpy(g_err, c.err.msg, sizeof(g_err)); }
+	ob_flush(&o);                                                /* the header precedes the chunks */
+	for (k = 0; k < nchunks; k++) {
+		if (!rc && c.bufs[k].len && fwrite(c.bufs[k].buf, 1, c.bufs[k].len, o.f) != c.bufs[k].len) o.err = 1;
+		free(c.bufs[k].buf);
+	}
+	free(c.bufs);
 out:
+	free(bounds);
 	k = ob_close(&o);
 	return rc ? rc : k;
 }
@@ -316,7 +436,7 @@ static inline int expect(const char **s, const char *lit) {
 typedef struct { int32_t *v; size_t n, cap; } ivec;
 static int iv_push(ivec *a, int32_t x) {
 	if (a->n == a->cap) {
-		size_t nc = a->cap ? a->cap * 2 : 1 << 16;
+		size_t nc = a->cap ? a->cap * 2 : 1 << 14;
 		int32_t *nv = (int32_t *)realloc(a->v, nc * sizeof(int32_t));
 		if (!nv) return PF_ENOMEM;
 		a->v = nv; a->cap = nc;
@@ -325,119 +445,223 @@ static int iv_push(ivec *a, int32_t x) {
 	return 0;
 }
 
-int pf_route_read(const char *path, const pf_problem *p, pf_result *r) {
-	char *data = NULL;
-	size_t len = 0, i;
-	const char *s, *end;
+/* one piece of a .route file: begins at the start of the file or at a "Net <i> (" line */
+typedef struct {
+	const char *begin, *end;
+	int first;               /* piece 0 carries the "Array size:" header */
+	ivec nodes;              /* rr nodes of the piece's Node lines */
+	ivec net_start;          /* for each net of the piece, in order: offset into nodes */
+	int first_net;           /* index of the piece's first net, -1 if it has none */
+	int rc, err_line;        /* err_line is local to the piece */
+	char msg[200];
+} route_piece;
+
+typedef struct { const char *path; const pf_problem *p; route_piece *pieces; } read_ctx;
+
+#define PIECE_FAIL(...) do { pc->rc = PF_EFORMAT; pc->err_line = line; snprintf(pc->msg, sizeof(pc->msg), __VA_ARGS__); return; } while (0)
+
+static void parse_piece(void *vctx, int k) {
+	read_ctx *ctx = (read_ctx *)vctx;
+	route_piece *pc = &ctx->pieces[k];
+	const pf_problem *p = ctx->p;
+	const char *s = pc->begin, *end = pc->end;
 	long a, b;
-	int line = 0, cur = -1, rc, inet;
-	ivec nodes = { 0, 0, 0 };
-	int32_t *tptr = NULL;
-	int16_t *tsw = NULL;
-	memset(r, 0, sizeof(*r));
-	g_err[0] = 0;
-	if ((rc = slurp(path, &data, &len)) != 0) return rc;
-	tptr = (int32_t *)calloc((size_t)p->num_nets + 1, sizeof(int32_t));
-	if (!tptr) { rc = PF_ENOMEM; goto done; }
-	for (inet = 0; inet <= p->num_nets; inet++) tptr[inet] = -1;
-	s = data; end = data + len;
+	int line = 0, cur = -1;
+	pc->first_net = -1;
 	while (s < end) {
 		const char *eol = (const char *)memchr(s, '\n', (size_t)(end - s));
 		const char *c = s;
 		if (!eol) eol = end;
 		line++;
 		if (eol == s) { s = eol + 1; continue; }
-		if (line == 1) {
-			if (!expect(&c, "Array size: ") || !scan_int(&c, &a) || !expect(&c, " x ") || !scan_int(&c, &b)) {
-				rc = fail(PF_EFORMAT, "%s:1: not a .route file (no 'Array size:' line)", path); goto done;
-			}
-			if (a != p->nx || b != p->ny) { rc = fail(PF_EFORMAT, "%s:1: routing of a %ld x %ld array, problem is %d x %d", path, a, b, p->nx, p->ny); goto done; }
+		if (pc->first && line == 1) {
+			if (!expect(&c, "Array size: ") || !scan_int(&c, &a) || !expect(&c, " x ") || !scan_int(&c, &b)) PIECE_FAIL("not a .route file (no 'Array size:' line)");
+			if (a != p->nx || b != p->ny) PIECE_FAIL("routing of a %ld x %ld array, problem is %d x %d", a, b, p->nx, p->ny);
 		} else if (c[0] == 'N' && c[1] == 'o') {                  /* "Node:\t<id>\t<type> (x,y) [to (x,y) ] <what>: <ptc>  " */
 			long id, x, y, xh, yh, ptc;
 			int t;
-			if (cur < 0 || p->net_is_global[cur]) { rc = fail(PF_EFORMAT, "%s:%d: Node line outside a routed net", path, line); goto done; }
-			if (!expect(&c, "Node:\t") || !scan_int(&c, &id) || *c != '\t') { rc = fail(PF_EFORMAT, "%s:%d: malformed Node line", path, line); goto done; }
+			if (cur < 0 || p->net_is_global[cur]) PIECE_FAIL("Node line outside a routed net");
+			if (!expect(&c, "Node:\t") || !scan_int(&c, &id) || *c != '\t') PIECE_FAIL("malformed Node line");
 			c++;
 			while (*c == ' ') c++;
 			for (t = 0; t < 6; t++) { size_t tl = strlen(TYPE_NAME[t]); if (strncmp(c, TYPE_NAME[t], tl) == 0 && c[tl] == ' ') { c += tl; break; } }
-			if (t == 6 || !expect(&c, " (") || !scan_int(&c, &x) || !expect(&c, ",") || !scan_int(&c, &y) || !expect(&c, ") ")) {
-				rc = fail(PF_EFORMAT, "%s:%d: malformed Node line", path, line); goto done;
-			}
+			if (t == 6 || !expect(&c, " (") || !scan_int(&c, &x) || !expect(&c, ",") || !scan_int(&c, &y) || !expect(&c, ") ")) PIECE_FAIL("malformed Node line");
 			xh = x; yh = y;
-			if (c[0] == 't') {
-				if (!expect(&c, "to (") || !scan_int(&c, &xh) || !expect(&c, ",") || !scan_int(&c, &yh) || !expect(&c, ") ")) {
-					rc = fail(PF_EFORMAT, "%s:%d: malformed 'to (x,y)'", path, line); goto done;
-				}
-			}
+			if (c[0] == 't' && (!expect(&c, "to (") || !scan_int(&c, &xh) || !expect(&c, ",") || !scan_int(&c, &yh) || !expect(&c, ") "))) PIECE_FAIL("malformed 'to (x,y)'");
 			while (c < eol && *c != ':') c++;                        /* " Pad" / " Pin" / " Track" / " Class" */
-			if (c >= eol || c[1] != ' ') { rc = fail(PF_EFORMAT, "%s:%d: malformed Node line", path, line); goto done; }
+			if (c >= eol || c[1] != ' ') PIECE_FAIL("malformed Node line");
 			c += 2;
-			if (!scan_int(&c, &ptc)) { rc = fail(PF_EFORMAT, "%s:%d: no track / pin / class number", path, line); goto done; }
-			if (id < 0 || id >= p->num_nodes) { rc = fail(PF_EFORMAT, "%s:%d: rr node %ld out of range", path, line, id); goto done; }
-			if (p->type[id] != t || p->xlow[id] != x || p->ylow[id] != y || p->xhigh[id] != xh || p->yhigh[id] != yh || p->ptc_num[id] != ptc) {
-				rc = fail(PF_EFORMAT, "%s:%d: rr node %ld is %s (%d,%d)-(%d,%d) ptc %d in the problem: the file belongs to another rr graph",
-						path, line, id, TYPE_NAME[p->type[id] <= PF_CHANY ? p->type[id] : 0], p->xlow[id], p->ylow[id], p->xhigh[id], p->yhigh[id], p->ptc_num[id]);
-				goto done;
-			}
-			if ((rc = iv_push(&nodes, (int32_t)id)) != 0) goto done;
+			if (!scan_int(&c, &ptc)) PIECE_FAIL("no track / pin / class number");
+			if (id < 0 || id >= p->num_nodes) PIECE_FAIL("rr node %ld out of range", id);
+			if (p->type[id] != t || p->xlow[id] != x || p->ylow[id] != y || p->xhigh[id] != xh || p->yhigh[id] != yh || p->ptc_num[id] != ptc)
+				PIECE_FAIL("rr node %ld is %s (%d,%d)-(%d,%d) ptc %d in the problem: the file belongs to another rr graph",
+						id, TYPE_NAME[p->type[id] <= PF_CHANY ? p->type[id] : 0], p->xlow[id], p->ylow[id], p->xhigh[id], p->yhigh[id], p->ptc_num[id]);
+			if (iv_push(&pc->nodes, (int32_t)id) != 0) { pc->rc = PF_ENOMEM; return; }
 		} else if (c[0] == 'N' && c[1] == 'e') {                  /* "Net <i> (<name>)" or "...): global net connecting:" */
-			if (!expect(&c, "Net ") || !scan_int(&c, &a) || !expect(&c, " (")) { rc = fail(PF_EFORMAT, "%s:%d: malformed Net line", path, line); goto done; }
-			if (a != cur + 1 || a >= p->num_nets) { rc = fail(PF_EFORMAT, "%s:%d: net %ld follows net %d (problem has %d nets)", path, line, a, cur, p->num_nets); goto done; }
+			static const char GLOB[] = "): global net connecting:";      /* matched at the tail: names may contain ')' */
+			const size_t gl = sizeof(GLOB) - 1;
+			int glob;
+			if (!expect(&c, "Net ") || !scan_int(&c, &a) || !expect(&c, " (")) PIECE_FAIL("malformed Net line");
+			if (a < 0 || a >= p->num_nets || (cur >= 0 && a != cur + 1) || (pc->first && cur < 0 && a != 0))
+				PIECE_FAIL("net %ld follows net %d (problem has %d nets)", a, cur, p->num_nets);
 			cur = (int)a;
-			tptr[cur] = (int32_t)nodes.n;
-			{
-				static const char GLOB[] = "): global net connecting:";      /* matched at the tail: names may contain ')' */
-				const size_t gl = sizeof(GLOB) - 1;
-				int glob = (size_t)(eol - c) >= gl && memcmp(eol - gl, GLOB, gl) == 0;
-				if (!glob && eol[-1] != ')') { rc = fail(PF_EFORMAT, "%s:%d: malformed Net line", path, line); goto done; }
-				if (glob != (p->net_is_global[cur] != 0)) { rc = fail(PF_EFORMAT, "%s:%d: net %d global in one of file / problem only", path, line, cur); goto done; }
-			}
+			if (pc->first_net < 0) pc->first_net = cur;
+			if (iv_push(&pc->net_start, (int32_t)pc->nodes.n) != 0) { pc->rc = PF_ENOMEM; return; }
+			glob = (size_t)(eol - c) >= gl && memcmp(eol - gl, GLOB, gl) == 0;
+			if (!glob && eol[-1] != ')') PIECE_FAIL("malformed Net line");
+			if (glob != (p->net_is_global[cur] != 0)) PIECE_FAIL("net %d global in one of file / problem only", cur);
 		} else if (strncmp(c, "Routing:", 8) == 0 || strncmp(c, "Block ", 6) == 0 || strncmp(c, "Used in local", 13) == 0) {
 			/* nothing to take from these */
 		} else {
-			rc = fail(PF_EFORMAT, "%s:%d: unrecognised line", path, line); goto done;
+			PIECE_FAIL("unrecognised line");
 		}
 		s = eol + 1;
 	}
-	if (cur != p->num_nets - 1) { rc = fail(PF_EFORMAT, "%s: %d nets in the file, %d in the problem", path, cur + 1, p->num_nets); goto done; }
-	tptr[p->num_nets] = (int32_t)nodes.n;
-	tsw = (int16_t *)malloc(sizeof(int16_t) * (nodes.n ? nodes.n : 1));
-	if (!tsw) { rc = PF_ENOMEM; goto done; }
-	{
-		long wl = 0;
-		int serial = 0;
-		for (inet = 0; inet < p->num_nets; inet++) {
-			size_t lo = (size_t)tptr[inet], hi = (size_t)tptr[inet + 1];
-			for (i = lo; i < hi; i++) {
-				int u = nodes.v[i], e, found = -1;
-				serial += (inet + 1) * (p->xlow[u] * (p->nx + 1) - p->yhigh[u]);     /* get_serial_num, route_common.c:224-254 */
-				serial -= p->ptc_num[u] * (inet + 1) * 10;
-				serial -= p->type[u] * (inet + 1) * 100;
-				serial %= 2000000000;
-				if (p->type[u] == PF_SINK) { tsw[i] = PF_OPEN; continue; }
-				if (i + 1 >= hi) { rc = fail(PF_EFORMAT, "%s: net %d does not end at a SINK", path, inet); goto done; }
-				for (e = p->row_ptr[u]; e < p->row_ptr[u + 1]; e++)
-					if (p->edge_to[e] == nodes.v[i + 1]) { found = e; break; }
-				if (found < 0) { rc = fail(PF_EFORMAT, "%s: net %d: no rr edge %d -> %d", path, inet, u, nodes.v[i + 1]); goto done; }
-				tsw[i] = p->edge_sw[found];
-			}
-			/* get_num_bends_and_length, base/stats.c:355-409: the first element and every element after a SINK are skipped */
-			for (i = lo + 1; i < hi; i++) {
-				int u = nodes.v[i], t = p->type[u];
-				if (t == PF_SINK) { i++; continue; }
-				if (t == PF_CHANX || t == PF_CHANY) wl += 1 + p->xhigh[u] - p->xlow[u] + p->yhigh[u] - p->ylow[u];
-			}
+}
+
+/* per net: the switch of every trace element, the element's serial-number term, the net's wirelength */
+typedef struct {
+	const char *path; const pf_problem *p;
+	const int *bounds;
+	const int32_t *tptr, *nodes;
+	int16_t *tsw;
+	uint32_t *term;
+	long *chunk_wl;
+	par_err err;
+} finish_ctx;
+
+static void finish_chunk(void *vctx, int k) {
+	finish_ctx *c = (finish_ctx *)vctx;
+	const pf_problem *p = c->p;
+	int inet;
+	long wl = 0;
+	for (inet = c->bounds[k]; inet < c->bounds[k + 1]; inet++) {
+		size_t lo = (size_t)c->tptr[inet], hi = (size_t)c->tptr[inet + 1], i;
+		const uint32_t mult = (uint32_t)(inet + 1);
+		for (i = lo; i < hi; i++) {
+			int u = c->nodes[i], e, found = -1;
+			/* get_serial_num, route_common.c:224-254, in the reference's wrapping int arithmetic */
+			c->term[i] = mult * (uint32_t)(p->xlow[u] * (p->nx + 1) - p->yhigh[u] - 10 * (int)p->ptc_num[u] - 100 * (int)p->type[u]);
+			if (p->type[u] == PF_SINK) { c->tsw[i] = PF_OPEN; continue; }
+			if (i + 1 >= hi) { fail(PF_EFORMAT, "%s: net %d does not end at a SINK", c->path, inet); par_fail(&c->err, PF_EFORMAT); return; }
+			for (e = p->row_ptr[u]; e < p->row_ptr[u + 1]; e++)
+				if (p->edge_to[e] == c->nodes[i + 1]) { found = e; break; }
+			if (found < 0) { fail(PF_EFORMAT, "%s: net %d: no rr edge %d -> %d", c->path, inet, u, c->nodes[i + 1]); par_fail(&c->err, PF_EFORMAT); return; }
+			c->tsw[i] = p->edge_sw[found];
 		}
+		/* get_num_bends_and_length, base/stats.c:355-409: the first element and every element after a SINK are skipped */
+		for (i = lo + 1; i < hi; i++) {
+			int u = c->nodes[i], t = p->type[u];
+			if (t == PF_SINK) { i++; continue; }
+			if (t == PF_CHANX || t == PF_CHANY) wl += 1 + p->xhigh[u] - p->xlow[u] + p->yhigh[u] - p->ylow[u];
+		}
+	}
+	c->chunk_wl[k] = wl;
+}
+
+int pf_route_read(const char *path, const pf_problem *p, pf_result *r) {
+	char *data = NULL;
+	size_t len = 0, total = 0, i;
+	int rc, k, npieces, nets_seen = 0, nchunks = 0, *bounds = NULL;
+	route_piece *pieces = NULL;
+	int32_t *tptr = NULL, *nodes = NULL;
+	int16_t *tsw = NULL;
+	uint32_t *term = NULL;
+	long *chunk_wl = NULL;
+	read_ctx rctx;
+	finish_ctx fctx;
+	memset(r, 0, sizeof(*r));
+	g_err[0] = 0;
+	if ((rc = slurp(path, &data, &len)) != 0) return rc;
+
+	/* pieces of >= 4 MB, cut where a "Net " header follows a blank line */
+	npieces = par_threads() * 4;
+	if ((size_t)npieces > len / ((size_t)4 << 20) + 1) npieces = (int)(len / ((size_t)4 << 20)) + 1;
+	pieces = (route_piece *)calloc((size_t)npieces, sizeof(route_piece));
+	if (!pieces) { rc = PF_ENOMEM; goto done; }
+	{
+		const char *at = data;
+		int made = 0;
+		for (k = 0; k < npieces; k++) {
+			const char *cut = data + len;
+			if (k + 1 < npieces) {
+				const char *from = data + len / (size_t)npieces * (size_t)(k + 1);
+				const char *hit = from > at ? strstr(from, "\n\nNet ") : NULL;
+				if (hit) cut = hit + 2;
+			}
+			if (cut <= at) continue;
+			pieces[made].begin = at; pieces[made].end = cut; pieces[made].first = made == 0;
+			made++;
+			at = cut;
+			if (cut == data + len) break;
+		}
+		npieces = made;
+	}
+	rctx.path = path; rctx.p = p; rctx.pieces = pieces;
+	if (npieces > 0) par_for(npieces, parse_piece, &rctx);
+	for (k = 0; k < npieces; k++) {
+		route_piece *pc = &pieces[k];
+		if (pc->rc == PF_EFORMAT) {
+			long line = pc->err_line;
+			const char *c;
+			for (c = data; c < pc->begin; c++) if (*c == '\n') line++;
+			rc = fail(PF_EFORMAT, "%s:%ld: %s", path, line, pc->msg); goto done;
+		}
+		if (pc->rc) { rc = pc->rc; goto done; }
+		if (pc->net_start.n && pc->first_net != nets_seen) { rc = fail(PF_EFORMAT, "%s: net %d follows net %d (problem has %d nets)", path, pc->first_net, nets_seen - 1, p->num_nets); goto done; }
+		nets_seen += (int)pc->net_start.n;
+		total += pc->nodes.n;
+	}
+	if (nets_seen != p->num_nets) { rc = fail(PF_EFORMAT, "%s: %d nets in the file, %d in the problem", path, nets_seen, p->num_nets); goto done; }
+	if (total > 0x7fffffffu) { rc = fail(PF_EFORMAT, "%s: more than 2^31 trace elements", path); goto done; }
+	tptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)p->num_nets + 1));
+	nodes = (int32_t *)malloc(sizeof(int32_t) * (total ? total : 1));
+	tsw = (int16_t *)malloc(sizeof(int16_t) * (total ? total : 1));
+	term = (uint32_t *)malloc(sizeof(uint32_t) * (total ? total : 1));
+	if (!tptr || !nodes || !tsw || !term) { rc = PF_ENOMEM; goto done; }
+	{
+		size_t base = 0;
+		int inet = 0;
+		for (k = 0; k < npieces; k++) {
+			route_piece *pc = &pieces[k];
+			for (i = 0; i < pc->net_start.n; i++) tptr[inet++] = (int32_t)(base + (size_t)pc->net_start.v[i]);
+			if (pc->nodes.n) memcpy(nodes + base, pc->nodes.v, sizeof(int32_t) * pc->nodes.n);
+			base += pc->nodes.n;
+			free(pc->nodes.v); pc->nodes.v = NULL;
+			free(pc->net_start.v); pc->net_start.v = NULL;
+		}
+		tptr[p->num_nets] = (int32_t)total;
+	}
+	nchunks = p->num_nets > 0 ? chunk_nets(tptr, p->num_nets, 1L << 16, &bounds) : 0;
+	if (nchunks < 0) { rc = PF_ENOMEM; goto done; }
+	chunk_wl = (long *)calloc((size_t)(nchunks ? nchunks : 1), sizeof(long));
+	if (!chunk_wl) { rc = PF_ENOMEM; goto done; }
+	memset(&fctx, 0, sizeof(fctx));
+	fctx.path = path; fctx.p = p; fctx.bounds = bounds; fctx.tptr = tptr; fctx.nodes = nodes; fctx.tsw = tsw; fctx.term = term; fctx.chunk_wl = chunk_wl;
+	if (nchunks > 0) par_for(nchunks, finish_chunk, &fctx);
+	if (fctx.err.rc) { rc = fctx.err.rc; memcpy(g_err, fctx.err.msg, sizeof(g_err)); goto done; }
+	{
+		/* the running remainder is sequential by definition: serial = (serial + term) % 2000000000 with C's truncating
+		 * remainder; |x| < 2^31 < 2 * 2000000000, so it is one conditional add or subtract */
+		const int M = 2000000000;
+		int sv = 0;
+		long wl = 0;
+		for (i = 0; i < total; i++) {
+			int x = (int)((uint32_t)sv + term[i]);
+			sv = x >= M ? x - M : (x <= -M ? x + M : x);
+		}
+		for (k = 0; k < nchunks; k++) wl += chunk_wl[k];
+		r->serial_num = sv;
 		r->total_wirelength = (int32_t)wl;
-		r->serial_num = serial;
 	}
 	r->num_nets = p->num_nets;
 	r->trace_ptr = tptr; tptr = NULL;
-	r->trace_node = nodes.v ? nodes.v : (int32_t *)calloc(1, sizeof(int32_t)); nodes.v = NULL;
+	r->trace_node = nodes; nodes = NULL;
 	r->trace_switch = tsw; tsw = NULL;
 	rc = PF_OK;
 done:
-	free(data); free(tptr); free(tsw); free(nodes.v);
+	if (pieces) for (k = 0; k < npieces; k++) { free(pieces[k].nodes.v); free(pieces[k].net_start.v); }
+	free(pieces); free(data); free(tptr); free(nodes); free(tsw); free(term); free(chunk_wl); free(bounds);
 	return rc;
 }
 

@@ -191,3 +191,53 @@ def test_generated_fabric_route_file_roundtrip(cuda_lib, oracle_cli, tmp_path):
             x, y = (int(v) for v in line.split("(")[1].split(")")[0].split(","))
             ring = x in (0, p.nx + 1) or y in (0, p.ny + 1)
             assert ("Pad:" in line) == ring, line
+
+
+def test_generated_fabric_matches_the_reference_print_route(cuda_lib, ref_bin, tmp_path):
+    """The UNMODIFIED reference routes a generated problem (inject mode) and writes it with its own print_route; the
+    native writer, given the result the reference dumped and pf_names_synthetic, produces the same bytes."""
+    import subprocess
+    p = router.generate_grid_problem(nx=10, ny=10, W=30, num_nets=120, sinks_per_net=3, seed=5)
+    pp, rr, rf = str(tmp_path / "g.pfp"), str(tmp_path / "g.pfr"), str(tmp_path / "g.ref.route")
+    pfio.write_problem(pp, p)
+    subprocess.run([ref_bin, "inject", pp, "--result", rr, "--route-file", rf], check=True, capture_output=True)
+    out = str(tmp_path / "g.route")
+    textio.write_route(out, p, textio.synthetic_names(p), pfio.read_result(rr))
+    assert open(out, "rb").read() == open(rf, "rb").read()
+
+
+def test_threaded_writer_and_reader_equal_the_single_thread_path(cuda_lib, oracle_cli, tmp_path, monkeypatch):
+    """Above 64 K trace elements the writer formats chunks of nets on all host threads and the reader parses 4 MB pieces
+    of the file in parallel (pf_text.c); both must give what one thread gives.  100x100 fabric, 12.5 k nets, one
+    PathFinder iteration of the oracle (legality does not matter for the text)."""
+    import subprocess
+    p = router.generate_grid_problem(nx=100, ny=100, W=100, num_nets=12500, sinks_per_net=3, seed=1)
+    pp, rr = str(tmp_path / "g.pfp"), str(tmp_path / "g.pfr")
+    pfio.write_problem(pp, p)
+    subprocess.run([oracle_cli, pp, "--result", rr, "--max_iters", "1"], capture_output=True)
+    r = pfio.read_result(rr)
+    assert len(r.trace_node) > 200000
+    n = textio.synthetic_names(p)
+    monkeypatch.setenv("PF_TEXT_THREADS", "1")
+    one = str(tmp_path / "one.route")
+    textio.write_route(one, p, n, r)
+    q1 = textio.read_route(one, p)
+    monkeypatch.setenv("PF_TEXT_THREADS", "6")
+    many = str(tmp_path / "many.route")
+    textio.write_route(many, p, n, r)
+    assert os.path.getsize(many) > 2 * (4 << 20)                    # several reader pieces
+    assert open(one, "rb").read() == open(many, "rb").read()
+    q = textio.read_route(many, p)
+    for a, b in ((q, q1), (q, r)):
+        assert np.array_equal(a.trace_ptr, b.trace_ptr) and np.array_equal(a.trace_node, b.trace_node)
+        assert np.array_equal(a.trace_switch, b.trace_switch)
+        assert a.total_wirelength == b.total_wirelength and a.serial_num == b.serial_num
+    # an error deep inside a later piece still reports the line of the whole file
+    text = open(many).read()
+    lines = text.split("\n")
+    k = max(i for i, l in enumerate(lines) if l.startswith("Node:") and "CHANX" in l)
+    lines[k] = lines[k].replace("CHANX", "CHANY")
+    bad = tmp_path / "bad.route"
+    bad.write_text("\n".join(lines))
+    with pytest.raises(router.RouterError, match=r"bad.route:%d: .*another rr graph" % (k + 1)):
+        textio.read_route(str(bad), p)
