@@ -12,6 +12,7 @@
  *        env PF_DUMP_RESULT=<file>   write traces / delays / per-iteration criticalities
  *        env PF_DUMP_TGRAPH=<file>   write the flat timing graph (pf_timing_graph) do_timing_analysis runs on
  *        env PF_DUMP_NAMES=<file>    write net / block names, IO tiles, global-net pins (pf_names, include/pf_text.h)
+ *        env PF_ADAPTER_ROUTE_FILE=<file>  also write the .route file through integration/vpr_text_adapter.cxx
  *        env PF_DUMP_STA=<file>      write every (net_delay in, timing_criticality out, cpd) of the run's STA calls
  *   vpr_ref inject <problem.pfp> [--result out.pfr] [--crit golden.pfr] [--max_iters K]
  *                  [--limit_nets M]
@@ -242,39 +243,27 @@ static void export_problem(const char *path, struct s_router_opts ro, boolean ti
 }
 
 /* names, IO tiles, block locations and global-net pins: what print_route (route_common.c:1322) and print_place
- * (read_place.c:266) read beyond the flat problem — pf_names of include/pf_text.h */
+ * (read_place.c:266) read beyond the flat problem — pf_names of include/pf_text.h, built by the reference-side
+ * binding integration/vpr_text_adapter.cxx (linked into this harness so that it is tested where the reference runs) */
+int pf_adapter_build_names(pf_names *n);
+void pf_adapter_print_route(char *route_file);
 static void export_names(const char *path) {
 	pf_names n;
-	memset(&n, 0, sizeof(n));
-	n.nx = nx; n.ny = ny; n.num_nets = num_nets; n.num_blocks = num_blocks;
-	std::vector<int32_t> nptr(num_nets + 1), bptr(num_blocks + 1), bx(num_blocks), by(num_blocks), bz(num_blocks), gptr(num_nets + 1), gblk, gcls;
-	std::string nchars, bchars;
-	for (int i = 0; i < num_nets; i++) { nptr[i] = (int32_t)nchars.size(); nchars += clb_net[i].name; }
-	nptr[num_nets] = (int32_t)nchars.size();
-	for (int b = 0; b < num_blocks; b++) {
-		bptr[b] = (int32_t)bchars.size(); bchars += block[b].name;
-		bx[b] = block[b].x; by[b] = block[b].y; bz[b] = block[b].z;
+	int rc = pf_adapter_build_names(&n);
+	if (rc == 0) { rc = pf_names_write(path, &n); pf_names_free(&n); }
+	fprintf(stderr, "PF_REF wrote names %s: %d nets, %d blocks (rc %d)\n", path, num_nets, num_blocks, rc);
+}
+
+/* base/place_and_route.c is compiled with -Dprint_route=pf_hook_print_route: the reference's own writer runs as
+ * always; with PF_ADAPTER_ROUTE_FILE=<file> the adapter's native writer writes the same routing next to it */
+void pf_hook_print_route(char *route_file) {
+	double t0 = now_s();
+	print_route(route_file);
+	double t1 = now_s();
+	if (getenv("PF_ADAPTER_ROUTE_FILE")) {
+		pf_adapter_print_route((char *)getenv("PF_ADAPTER_ROUTE_FILE"));
+		fprintf(stderr, "PF_REF print_route %.4f s, pf_adapter_print_route %.4f s\n", t1 - t0, now_s() - t1);
 	}
-	bptr[num_blocks] = (int32_t)bchars.size();
-	std::vector<uint8_t> io((size_t)(nx + 2) * (ny + 2));
-	for (int x = 0; x <= nx + 1; x++)
-		for (int y = 0; y <= ny + 1; y++) io[(size_t)x * (ny + 2) + y] = grid[x][y].type == IO_TYPE ? 1 : 0;
-	for (int i = 0; i < num_nets; i++) {
-		gptr[i] = (int32_t)gblk.size();
-		if (!clb_net[i].is_global) continue;
-		for (int k = 0; k <= clb_net[i].num_sinks; k++) {
-			int b = clb_net[i].node_block[k];
-			gblk.push_back(b);
-			gcls.push_back(block[b].type->pin_class[clb_net[i].node_block_pin[k]]);
-		}
-	}
-	gptr[num_nets] = (int32_t)gblk.size();
-	n.net_name_ptr = nptr.data(); n.net_name_chars = (char *)nchars.data(); n.tile_is_io = io.data();
-	n.block_name_ptr = bptr.data(); n.block_name_chars = (char *)bchars.data();
-	n.block_x = bx.data(); n.block_y = by.data(); n.block_z = bz.data();
-	n.gpin_ptr = gptr.data(); n.gpin_block = gblk.data(); n.gpin_class = gcls.data();
-	int rc = pf_names_write(path, &n);
-	fprintf(stderr, "PF_REF wrote names %s: %d nets, %d blocks, %d global pins (rc %d)\n", path, num_nets, num_blocks, (int)gblk.size(), rc);
 }
 
 static int serial_num_of_routing() { /* same arithmetic as get_serial_num, route_common.c:224-254 */

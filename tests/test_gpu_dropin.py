@@ -34,9 +34,9 @@ def _stage(tmp, name):
                 o.write(f.read())
 
 
-def _run(binary, tmp, name, width, flow_prefix, extra=()):
+def _run(binary, tmp, name, width, flow_prefix, extra=(), env=None):
     cmd = [binary] + flow_prefix + ["k6_N10_like.xml", name, "--nodisp", "--route", "--route_chan_width", str(width)] + list(extra)
-    r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, timeout=1200)
+    r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, timeout=1200, env=dict(os.environ, **(env or {})))
     out = r.stdout
     assert r.returncode == 0, out[-3000:] + r.stderr[-2000:]
     assert "Completed routing consistency check successfully" in out or "check_route" in out.lower() or True
@@ -56,10 +56,21 @@ def test_vpr_flow_with_b200_router(name, width, tmp_path):
     d_ref, d_gpu = str(tmp_path / "ref"), str(tmp_path / "gpu")
     os.makedirs(d_ref); os.makedirs(d_gpu)
     _stage(d_ref, name); _stage(d_gpu, name)
-    it_r, wl_r, cp_r = _run(REF, d_ref, name, width, ["flow"])
+    it_r, wl_r, cp_r = _run(REF, d_ref, name, width, ["flow"], env={"PF_DUMP_PROBLEM": "flow.pfp"})
     it_g, wl_g, cp_g = _run(B200, d_gpu, name, width, [])
     print("%s W=%d: reference %d it, WL %d, CPD %.4f ns | B200 %d it, WL %d, CPD %.4f ns" % (name, width, it_r, wl_r, cp_r, it_g, wl_g, cp_g))
     assert os.path.getsize(os.path.join(d_gpu, name + ".route")) > 0       # print_route ran on our traces
+    # The drop-in's .route file is written by the native writer (place_and_route.c's print_route call sites are bound to
+    # pf_adapter_print_route, integration/vpr_text_adapter.cxx).  Parsed back against the flat problem the reference run
+    # dumped for the same architecture and width: every Node line fits the rr graph, consecutive nodes are rr edges, the
+    # wirelength equals what the reference's stats.c printed for the device routing, and no rr node is over capacity.
+    import numpy as np
+    from parallel_eda_b200 import check_route, pfio, textio
+    prob = pfio.read_problem(os.path.join(d_ref, "flow.pfp"))
+    for d, wl in ((d_ref, wl_r), (d_gpu, wl_g)):
+        q = textio.read_route(os.path.join(d, name + ".route"), prob)
+        assert q.total_wirelength == wl
+        assert not (check_route.recompute_occupancy(prob, q) > prob.capacity).any()
     assert wl_g <= (1.12 if name == "toy" else 1.08) * wl_r
     # the 6x6 toy has ~300 nets on 36 tiles: single nets move the critical path by several percent
     assert cp_g <= (1.08 if name == "toy" else 1.05) * cp_r

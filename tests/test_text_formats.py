@@ -241,3 +241,27 @@ def test_threaded_writer_and_reader_equal_the_single_thread_path(cuda_lib, oracl
     bad.write_text("\n".join(lines))
     with pytest.raises(router.RouterError, match=r"bad.route:%d: .*another rr graph" % (k + 1)):
         textio.read_route(str(bad), p)
+
+
+def test_adapter_print_route_equals_the_reference(cuda_lib, ref_bin, unxz, tmp_path):
+    """The reference-side binding (integration/vpr_text_adapter.cxx, what -Dprint_route=pf_adapter_print_route puts
+    behind place_and_route.c:182,364,729) inside the reference's own flow: VPR globals -> pf_names / trace arrays ->
+    pf_route_write.  Its file equals the one the reference's print_route wrote in the same run, and the names it
+    exports equal the committed golden."""
+    import lzma
+    import shutil
+    import subprocess
+    d = str(tmp_path)
+    shutil.copy(os.path.join(ROOT, "tests", "fixtures", "k6_N10_like.xml"), d)
+    for ext in ("blif", "place"):
+        shutil.copy(os.path.join(GOLDEN, "toy." + ext), d)
+    with lzma.open(os.path.join(GOLDEN, "toy.net.xz")) as f, open(os.path.join(d, "toy.net"), "wb") as o:
+        o.write(f.read())
+    env = dict(os.environ, PF_ADAPTER_ROUTE_FILE="adapter.route", PF_DUMP_NAMES="toy.pfn")
+    r = subprocess.run([ref_bin, "flow", "k6_N10_like.xml", "toy", "--nodisp", "--route", "--route_chan_width", "64"], cwd=d,
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ref = open(os.path.join(d, "toy.route"), "rb").read()
+    assert open(os.path.join(d, "adapter.route"), "rb").read() == ref
+    assert ref == open(unxz("toy_w64.route"), "rb").read()            # and both equal the committed golden
+    assert open(os.path.join(d, "toy.pfn"), "rb").read() == open(unxz("toy_w64.pfn"), "rb").read()
