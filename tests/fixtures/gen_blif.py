@@ -19,13 +19,24 @@ def main():
     ap.add_argument("--name", default="toy")
     ap.add_argument("--hub", type=int, default=0, help="number of LUTs that additionally read one shared hub signal (a high-fanout net)")
     ap.add_argument("--clocks", type=int, default=1, help="number of clock domains the latches are spread over")
+    ap.add_argument("--mults", type=int, default=0, help="number of `.subckt mult4` instances (4x4 -> 8 bit hard blocks of the heterogeneous "
+                    "fixture architecture k6_N10_het.xml), spread evenly through the LUT sequence; 0 keeps the output of older versions")
     a = ap.parse_args()
     rng = random.Random(a.seed)
     signals = ["pi%d" % i for i in range(a.pis)]
     used = set()
     body = []
     latches = 0
+    mult_at = {(j + 1) * a.luts // (a.mults + 1): j for j in range(a.mults)}
     for i in range(a.luts):
+        if i in mult_at and len(signals) >= 8:
+            j = mult_at[i]
+            ins = rng.sample(signals[-a.window:], 8)
+            used.update(ins)
+            pins = ["a[%d]=%s" % (b, ins[b]) for b in range(4)] + ["b[%d]=%s" % (b, ins[4 + b]) for b in range(4)]
+            pins += ["out[%d]=m%d_%d" % (b, j, b) for b in range(8)]
+            body.append(".subckt mult4 " + " ".join(pins))
+            signals.extend("m%d_%d" % (j, b) for b in range(8))
         k = rng.randint(3, 6)
         pool = signals[-a.window:]
         ins = rng.sample(pool, min(k, len(pool)))
@@ -58,6 +69,9 @@ def main():
         f.write(".outputs %s\n" % " ".join(outs))
         f.write("\n".join(body))
         f.write("\n.end\n")
+        if a.mults:
+            f.write("\n.model mult4\n.inputs %s\n.outputs %s\n.blackbox\n.end\n" % (
+                " ".join(["a[%d]" % b for b in range(4)] + ["b[%d]" % b for b in range(4)]), " ".join("out[%d]" % b for b in range(8))))
     print("wrote %s: %d luts, %d latches, %d inputs, %d outputs" % (a.out, a.luts, latches, len(pis), len(outs)))
 
 

@@ -5,6 +5,8 @@
 #   mid : tests/fixtures/gen_blif.py --luts 4000 --pis 64 --window 400 --seed 2, W=200
 #   hub : tests/fixtures/gen_blif.py --luts 900 --pis 24 --window 120 --seed 5 --hub 700, W=90 (one 84-sink net)
 #   duo : tests/fixtures/gen_blif.py --luts 500 --pis 20 --window 80 --seed 7 --clocks 2, W=80 (two clock domains)
+#   het : tests/fixtures/gen_blif.py --luts 400 --pis 20 --window 80 --seed 9 --mults 6 on k6_N10_het.xml (height-2 hard blocks), W=70;
+#         W=60 is one track short: the reference fails after 50 iterations (golden of the failure)
 set -e
 HERE=$(cd "$(dirname "$0")" && pwd); ROOT=$(cd "$HERE/../.." && pwd)
 REF=$ROOT/oracle/_ref/vpr_ref; W=$(mktemp -d); cd "$W"
@@ -28,4 +30,14 @@ for c in toy:64 mid:200 hub:90 duo:80; do
   for f in ${n}_w$w.pfp ${n}_w$w.pfr ${n}_w${w}_nt.pfr ${n}_w$w.pftg ${n}_w$w.pfsta; do xz -9 -c $f > "$HERE/$f.xz"; done
 done
 cp toy.blif toy.place "$HERE/"; xz -9 -c toy.net > "$HERE/toy.net.xz"
+# heterogeneous fabric
+cp "$ROOT/tests/fixtures/k6_N10_het.xml" .
+python "$ROOT/tests/fixtures/gen_blif.py" het.blif --luts 400 --pis 20 --window 80 --seed 9 --name het --mults 6
+"$REF" flow k6_N10_het.xml het --nodisp --pack --place > /dev/null
+PF_DUMP_PROBLEM=het_w60.pfp PF_DUMP_RESULT=het_w60.pfr "$REF" flow k6_N10_het.xml het --nodisp --route --route_chan_width 60 > /dev/null || true
+PF_DUMP_PROBLEM=het_w70_bf.pfp PF_DUMP_RESULT=het_w70_bf.pfr "$REF" flow k6_N10_het.xml het --nodisp --route --route_chan_width 70 --router_algorithm breadth_first > /dev/null
+PF_DUMP_PROBLEM=het_w70.pfp PF_DUMP_RESULT=het_w70.pfr PF_DUMP_NAMES=het_w70.pfn PF_DUMP_TGRAPH=het_w70.pftg PF_DUMP_STA=het_w70.pfsta "$REF" flow k6_N10_het.xml het --nodisp --route --route_chan_width 70 > /dev/null
+"$REF" inject het_w70.pfp --result het_w70_nt.pfr > /dev/null
+for f in het_w70.pfp het_w70.pfr het_w70_nt.pfr het_w70.pftg het_w70.pfsta het_w70.pfn het_w70_bf.pfp het_w70_bf.pfr het_w60.pfp het_w60.pfr; do xz -9 -c $f > "$HERE/$f.xz"; done
+xz -9 -c het.route > "$HERE/het_w70.route.xz"; xz -9 -c het.net > "$HERE/het.net.xz"; cp het.place het.blif "$HERE/"
 echo "goldens written to $HERE"

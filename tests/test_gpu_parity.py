@@ -197,3 +197,18 @@ def test_stand_alone_cli(tmp_path):
     assert rep["success"] == 1 and rep["check_route"]["ok"] == 1 and rep["check_route"]["overused_nodes"] == 0
     r = subprocess.run([sys.executable, "-m", "parallel_eda_b200", "check", os.path.join(G, "duo_w80.pfp.xz"), out], cwd=root, capture_output=True, text=True)
     assert r.returncode == 0 and json.loads(r.stdout.strip().splitlines()[-1])["wirelength"] == rep["wirelength"]
+
+
+def test_heterogeneous_fabric_single_warp_equals_the_emulated_device_code():
+    """het_w70 (tests/fixtures/k6_N10_het.xml): height-2 hard blocks, i.e. SOURCE / SINK / pin rr nodes spanning two
+    tiles.  One warp with the serial reference's policy is deterministic; the sm_100a build must reproduce the routing the
+    same source produced on the CPU warp emulator (tests/test_emu_router.py pins the same constants), which is legal, has
+    correct Elmore delays and lies within 3 % of the reference's wirelength for this problem."""
+    import json
+    pin = json.load(open(os.path.join(G, "single_warp_het.json")))["serial_policy"]
+    p, g = _load("het_w70", False)
+    r = router.try_timing_driven_route(p, router.default_config(num_slots=1, big_slots=1, pop_slack=0.0, max_batch=1, reroute_all_iters=-1))
+    assert r.success == 1
+    assert check_route.check_route(p, r)["overused"] == 0
+    assert r.total_wirelength <= 1.03 * g.total_wirelength
+    assert (r.serial_num, r.total_wirelength, r.iterations) == (pin["serial_num"], pin["total_wirelength"], pin["iterations"])

@@ -24,7 +24,12 @@ CASES = [
     ("hub_w90", "hub_w90_nt.pfr", False),    # high-fanout window of mark_node_expansion_by_bin (route_timing.c:867)
     ("duo_w80", "duo_w80.pfr", True),        # 494 nets, W=80, TWO netlist clocks (+ the virtual I/O clock): 21 iterations
     ("duo_w80", "duo_w80_nt.pfr", False),    # timing off: 11 iterations
-]
+    # heterogeneous fabric (tests/fixtures/k6_N10_het.xml): a column of height-2 hard multiplier blocks every 5 columns,
+    # i.e. SOURCE / SINK / pin rr nodes that span two tiles, CLB columns interrupted, 441 nets, 8x8
+    ("het_w70", "het_w70.pfr", True),        # timing-driven: 18 iterations
+    ("het_w70", "het_w70_nt.pfr", False),    # timing off: 11 iterations
+    ("het_w60", "het_w60.pfr", True),        # one track too few: the reference gives up after max_router_iterations = 50
+]                                            # with 1 overused node (success = 0); the oracle must fail the same way
 
 
 @pytest.mark.parametrize("prob,gold,timing", CASES)
@@ -48,7 +53,7 @@ def test_oracle_reproduces_reference_bit_for_bit(prob, gold, timing, oracle_cli,
     assert list(o.iter_stats["overused_nodes"]) == list(g.iter_stats["overused_nodes"])
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90"])
+@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90", "het_w70"])
 def test_oracle_breadth_first_reproduces_reference_bit_for_bit(name, oracle_cli, unxz, tmp_path):
     """--router_algorithm breadth_first (reference route_breadth_first.c): the golden *_bf.pfr was written by the
     unmodified reference; *_bf.pfp is the problem it saw (same rr graph as the timing-driven fixture, but
@@ -78,7 +83,7 @@ def test_reference_binary_agrees_when_present(ref_bin, oracle_cli, unxz, tmp_pat
     assert np.array_equal(r.net_delay.view(np.uint32), o.net_delay.view(np.uint32))
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90", "mid_w200"])
+@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90", "mid_w200", "het_w70"])
 def test_oracle_router_and_sta_in_closed_loop_reproduce_the_reference_run(name, oracle_cli, unxz, tmp_path):
     """No replay: the oracle router with the oracle's own static timing analysis between iterations (--timing-graph)
     must reproduce the reference's WHOLE timing-driven run — iteration count, every trace, the cookie, bit-exact sink

@@ -32,7 +32,7 @@ def c_timing_graph(g: pfio.TimingGraph):
     return t, keep
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200", "duo_w80"])
+@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200", "duo_w80", "het_w70"])
 def test_oracle_sta_reproduces_reference_bit_for_bit(name, oracle_lib):
     lib = C.CDLL(oracle_lib)
     lib.pf_oracle_sta.argtypes = [C.POINTER(_TG), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
@@ -60,7 +60,7 @@ def test_oracle_sta_reproduces_reference_bit_for_bit(name, oracle_lib):
     assert np.array_equal(gold.iter_crit[1][routed], v.crit[0][routed])
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200", "duo_w80"])
+@pytest.mark.parametrize("name", ["toy_w64", "hub_w90", "mid_w200", "duo_w80", "het_w70"])
 def test_device_sta_code_on_the_emulator_is_bit_identical(name, emu_lib):
     """The device analysis (pf_sta_device.cuh behind pf_sta_analyze), compiled for the CPU emulator backend:
     level-synchronous pull over in-edges instead of the reference's push along out-edges — same floats."""

@@ -14,7 +14,8 @@ from parallel_eda_b200 import check_route, pfio, router, textio
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-FIXTURES = [("toy", "toy_w64"), ("hub", "hub_w90")]
+ARCH = {"toy": "k6_N10_like.xml", "hub": "k6_N10_like.xml", "het": "k6_N10_het.xml"}
+FIXTURES = [("toy", "toy_w64"), ("hub", "hub_w90"), ("het", "het_w70")]   # het: height-2 blocks, "to (x,y)" on pin lines
 
 
 def _load(unxz, stem):
@@ -56,20 +57,20 @@ def test_place_file_write_and_read(cuda_lib, unxz, tmp_path, circuit, stem):
     _, _, n = _load(unxz, stem)
     ref = os.path.join(GOLDEN, circuit + ".place")
     out = str(tmp_path / (circuit + ".place"))
-    textio.write_place(out, circuit + ".net", "k6_N10_like.xml", n)
+    textio.write_place(out, circuit + ".net", ARCH[circuit], n)
     assert open(out, "rb").read() == open(ref, "rb").read()          # print_place, byte for byte
     want = (n.block_x.copy(), n.block_y.copy(), n.block_z.copy())
     n.block_x[:] = -1
     n.block_y[:] = -1
     n.block_z[:] = -1
-    placed = textio.read_place(ref, n, net_file=circuit + ".net", arch_file="k6_N10_like.xml")
+    placed = textio.read_place(ref, n, net_file=circuit + ".net", arch_file=ARCH[circuit])
     assert placed == n.num_blocks
     assert all(np.array_equal(a, b) for a, b in zip(want, (n.block_x, n.block_y, n.block_z)))
     # the reference's two file-name checks (read_place.c:55-64)
     with pytest.raises(router.RouterError, match="Architecture file"):
         textio.read_place(ref, n, net_file=circuit + ".net", arch_file="other.xml")
     with pytest.raises(router.RouterError, match="Netlist file"):
-        textio.read_place(ref, n, net_file="other.net", arch_file="k6_N10_like.xml")
+        textio.read_place(ref, n, net_file="other.net", arch_file=ARCH[circuit])
 
 
 def test_place_reader_tokenisation_follows_read_line_tokens(cuda_lib, unxz, tmp_path):
