@@ -8,6 +8,10 @@ extern "C" int pf_check_route(pf_router *r, const pf_result *res, pf_check_repor
 	if (!r || !res || !rep) FAILF(PF_EINVAL, "null argument");
 	const pf_problem *p = r->prob;
 	if (res->num_nets != r->n || res->num_nodes != r->N || !res->trace_ptr || !res->occ) FAILF(PF_EINVAL, "result does not belong to this problem");
+	/* the kernel indexes trace_node / trace_switch through trace_ptr: offsets must be monotone from 0 (any result may be handed in) */
+	if (res->trace_ptr[0] != 0) FAILF(PF_EINVAL, "trace_ptr does not start at 0");
+	for (int i = 0; i < r->n; i++) if (res->trace_ptr[i + 1] < res->trace_ptr[i]) FAILF(PF_EINVAL, "trace_ptr not monotone at net %d", i);
+	if (res->trace_ptr[r->n] > 0 && (!res->trace_node || !res->trace_switch)) FAILF(PF_EINVAL, "result has no trace arrays");
 	const size_t total = (size_t)res->trace_ptr[r->n];
 	int *d_tp = (int *)pfb_alloc_raw(sizeof(int) * ((size_t)r->n + 1));
 	int *d_tn = (int *)pfb_alloc_raw(sizeof(int) * std::max<size_t>(total, 1));

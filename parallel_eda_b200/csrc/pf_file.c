@@ -136,6 +136,8 @@ int pf_problem_check(const pf_problem *p, char *msg, int msg_len) {
 		if (i >= PF_CHANX_COST_INDEX_START && (o < 0 || o >= p->num_indexed)) FAIL("indexed row %d ortho %d", i, o);
 	}
 	if (p->net_ptr[0] != 0 || p->net_ptr[p->num_nets] != p->num_terminals) FAIL("net_ptr ends do not match num_terminals");
+	for (i = 0; i < p->num_nets; i++)                        /* completely, before net_terminals is indexed through it */
+		if (p->net_ptr[i + 1] < p->net_ptr[i]) FAIL("net_ptr not monotone at net %d", i);
 	for (i = 0; i < p->num_nets; i++) {
 		int b = p->net_ptr[i], e = p->net_ptr[i + 1];
 		if (e < b) FAIL("net_ptr not monotone at net %d", i);
@@ -273,6 +275,9 @@ int pf_timing_graph_check(const pf_timing_graph *g, const int32_t *net_ptr, char
 	int32_t *level_of;
 	if (g->num_tnodes <= 0 || !g->edge_ptr || g->edge_ptr[0] != 0 || g->edge_ptr[g->num_tnodes] != g->num_tedges) TFAIL("edge_ptr does not span the edges");
 	if (g->num_levels <= 0 || g->level_ptr[0] != 0 || g->level_ptr[g->num_levels] != g->num_tnodes) TFAIL("level_ptr does not span the tnodes");
+	/* both offset arrays completely before anything is indexed through them */
+	for (lv = 0; lv < g->num_levels; lv++) if (g->level_ptr[lv + 1] < g->level_ptr[lv]) TFAIL("level_ptr not monotonic at level %d", lv);
+	for (i = 0; i < g->num_tnodes; i++) if (g->edge_ptr[i + 1] < g->edge_ptr[i]) TFAIL("edge_ptr not monotonic at tnode %d", i);
 	level_of = (int32_t *)malloc(sizeof(int32_t) * (size_t)g->num_tnodes);
 	if (!level_of) return PF_ENOMEM;
 	for (i = 0; i < g->num_tnodes; i++) level_of[i] = -1;

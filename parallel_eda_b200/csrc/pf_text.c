@@ -114,8 +114,9 @@ void pf_names_free(pf_names *n) {
 static int names_ok(const int32_t *ptr, const char *chars, int count, const char *what, char *msg, int msg_len) {
 	int i, k;
 	if (ptr[0] != 0) FAIL("%s name offsets do not start at 0", what);
-	for (i = 0; i < count; i++) {
+	for (i = 0; i < count; i++)                      /* all offsets first: the character array is ptr[count] long */
 		if (ptr[i + 1] <= ptr[i]) FAIL("%s %d has an empty name", what, i);
+	for (i = 0; i < count; i++) {
 		for (k = ptr[i]; k < ptr[i + 1]; k++)
 			if (chars[k] == 0 || chars[k] == '\n' || chars[k] == '\r' || chars[k] == ' ' || chars[k] == '\t')
 				FAIL("%s %d: white space or NUL in the name", what, i);
@@ -135,8 +136,9 @@ int pf_names_check(const pf_names *n, const pf_problem *p, char *msg, int msg_le
 		if (n->block_x[i] < 0 || n->block_x[i] > n->nx + 1 || n->block_y[i] < 0 || n->block_y[i] > n->ny + 1)
 			FAIL("block %d at (%d,%d) outside the grid", i, n->block_x[i], n->block_y[i]);
 	if (n->gpin_ptr[0] != 0) FAIL("gpin_ptr does not start at 0");
-	for (i = 0; i < n->num_nets; i++) {
+	for (i = 0; i < n->num_nets; i++)
 		if (n->gpin_ptr[i + 1] < n->gpin_ptr[i]) FAIL("gpin_ptr not monotone at net %d", i);
+	for (i = 0; i < n->num_nets; i++) {
 		if (p && !p->net_is_global[i] && n->gpin_ptr[i + 1] != n->gpin_ptr[i]) FAIL("routed net %d lists global pins", i);
 		for (k = n->gpin_ptr[i]; k < n->gpin_ptr[i + 1]; k++)
 			if (n->gpin_block[k] < 0 || n->gpin_block[k] >= n->num_blocks) FAIL("net %d: pin block %d out of range", i, n->gpin_block[k]);

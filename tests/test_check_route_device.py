@@ -111,3 +111,21 @@ def test_random_mutations_agree_with_the_python_checker(toy):
         assert bool(rep["ok"]) == py_ok, (i, k, kind, rep)
         rejected += not py_ok
     assert rejected >= 20          # most mutations break the routing; the rest are no-ops (same value drawn)
+
+
+def test_inconsistent_trace_offsets_are_refused_before_the_kernel_runs(toy):
+    """pf_check_route takes ANY result (a parsed .route file, another router's dump): offsets that are not monotone from 0
+    would send the kernel outside trace_node — PF_EINVAL instead."""
+    p, g, R = toy
+    for edit in ("swap", "start"):
+        bad = copy.deepcopy(g)
+        bad.trace_ptr = bad.trace_ptr.copy()
+        if edit == "swap":
+            i = int(p.routed_nets()[5])
+            bad.trace_ptr[i + 1] = bad.trace_ptr[-1] + 1000         # beyond the arrays, later offsets come back down
+        else:
+            bad.trace_ptr[0] = 3
+        with pytest.raises(router.RouterError, match="trace_ptr") as e:
+            R.check_route(bad)
+        assert e.value.code == -4
+    assert R.check_route(g)["ok"] == 1                               # the router handle is still usable
