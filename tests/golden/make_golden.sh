@@ -40,4 +40,24 @@ PF_DUMP_PROBLEM=het_w70.pfp PF_DUMP_RESULT=het_w70.pfr PF_DUMP_NAMES=het_w70.pfn
 "$REF" inject het_w70.pfp --result het_w70_nt.pfr > /dev/null
 for f in het_w70.pfp het_w70.pfr het_w70_nt.pfr het_w70.pftg het_w70.pfsta het_w70.pfn het_w70_bf.pfp het_w70_bf.pfr het_w60.pfp het_w60.pfr; do xz -9 -c $f > "$HERE/$f.xz"; done
 xz -9 -c het.route > "$HERE/het_w70.route.xz"; xz -9 -c het.net > "$HERE/het.net.xz"; cp het.place het.blif "$HERE/"
+# two wire types
+cp "$ROOT/tests/fixtures/k6_N10_mix.xml" .
+python "$ROOT/tests/fixtures/gen_blif.py" mix.blif --luts 350 --pis 18 --window 70 --seed 21 --name mix
+"$REF" flow k6_N10_mix.xml mix --nodisp --pack --place > /dev/null
+for w in 60 70; do PF_DUMP_PROBLEM=mix_w$w.pfp PF_DUMP_RESULT=mix_w$w.pfr PF_DUMP_TGRAPH=mix_w$w.pftg "$REF" flow k6_N10_mix.xml mix --nodisp --route --route_chan_width $w > /dev/null; done
+for f in mix_w70.pfp mix_w70.pfr mix_w70.pftg mix_w60.pfp mix_w60.pfr; do xz -9 -c $f > "$HERE/$f.xz"; done
+# pass-transistor wire switches: the switch table of toy_w64 edited (tests/test_oracle_golden.py::unbuffered_toy), routed by the
+# reference router in inject mode, timing off and timing-driven with the criticalities of toy_w64.pfr replayed
+(cd "$ROOT" && python - "$W" <<'PY'
+import sys
+sys.path.insert(0, "tests")
+from parallel_eda_b200 import pfio
+from test_oracle_golden import unbuffered_toy
+for timing, tag in ((False, "nt"), (True, "td")):
+    pfio.write_problem("%s/toy_w64_unbuf_%s.pfp" % (sys.argv[1], tag), unbuffered_toy("tests/golden/toy_w64.pfp.xz", timing))
+PY
+)
+"$REF" inject toy_w64_unbuf_nt.pfp --result toy_w64_unbuf_nt.pfr > /dev/null
+"$REF" inject toy_w64_unbuf_td.pfp --crit toy_w64.pfr --result toy_w64_unbuf_td.pfr > /dev/null
+for f in toy_w64_unbuf_nt.pfr toy_w64_unbuf_td.pfr; do xz -9 -c $f > "$HERE/$f.xz"; done
 echo "goldens written to $HERE"

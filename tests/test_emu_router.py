@@ -226,3 +226,41 @@ def test_heterogeneous_fabric_with_tall_blocks(timing, emu_lib):
     if timing:
         w = g.iter_crit[-1]
         assert float((w * r.net_delay).sum()) <= 1.10 * float((w * g.net_delay).sum())
+
+
+def test_two_wire_types(emu_lib):
+    """mix_w70 (tests/fixtures/k6_N10_mix.xml: length-1 and length-4 wires, 8 rr_indexed_data rows): the device lookahead
+    combines a row with its orthogonal row (route_timing.c:693-746).  One warp with the serial policy, timing-driven with
+    the reference's criticalities replayed: legal, Elmore-exact, 21 iterations against the reference's 22, wirelength -2 %."""
+    p = pfio.read_problem(os.path.join(G, "mix_w70.pfp.xz"))
+    g = pfio.read_result(os.path.join(G, "mix_w70.pfr.xz"))
+    assert len(p.indexed) == 8
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=1, big_slots=1, pop_slack=0.0, max_batch=1, reroute_all_iters=-1)
+    r = router.try_timing_driven_route(p, cfg, sta=router.replay_sta(g), lib_path=emu_lib)
+    assert r.success == 1
+    assert check_route.check_route(p, r)["overused"] == 0
+    assert r.total_wirelength <= 1.03 * g.total_wirelength and r.iterations <= int(1.5 * g.iterations)
+    w = g.iter_crit[-1]
+    assert float((w * r.net_delay).sum()) <= 1.05 * float((w * g.net_delay).sum())
+
+
+def test_unbuffered_switches(emu_lib):
+    """Pass-transistor wire switches (tests/test_oracle_golden.py::unbuffered_toy): a new branch loads every unbuffered
+    ancestor (route_tree_timing.c:393-417), so the incremental Elmore update of the device code walks up the tree.
+    check_route recomputes every sink delay from scratch (tolerance 1e-4, the reference's ERROR_TOL)."""
+    from test_oracle_golden import unbuffered_toy
+    p = unbuffered_toy(os.path.join(G, "toy_w64.pfp.xz"), True)
+    g = pfio.read_result(os.path.join(G, "toy_w64_unbuf_td.pfr.xz"))
+    assert int(p.switches["buffered"][0]) == 0
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=1, big_slots=1, pop_slack=0.0, max_batch=1, reroute_all_iters=-1)
+    r = router.try_timing_driven_route(p, cfg, sta=router.replay_sta(g), lib_path=emu_lib)
+    assert r.success == 1
+    assert check_route.check_route(p, r, check_delays=True)["overused"] == 0
+    assert abs(r.total_wirelength - g.total_wirelength) <= 0.03 * g.total_wirelength
+    w = g.iter_crit[-1]
+    assert float((w * r.net_delay).sum()) <= 1.05 * float((w * g.net_delay).sum())
+    # and with several nets in flight the routing stays legal and Elmore-exact
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=8, big_slots=1)
+    p.opts["max_router_iterations"] = 150
+    r = router.try_timing_driven_route(p, cfg, sta=router.replay_sta(g), lib_path=emu_lib)
+    assert r.success == 1 and check_route.check_route(p, r, check_delays=True)["overused"] == 0

@@ -28,6 +28,10 @@ CASES = [
     # i.e. SOURCE / SINK / pin rr nodes that span two tiles, CLB columns interrupted, 441 nets, 8x8
     ("het_w70", "het_w70.pfr", True),        # timing-driven: 18 iterations
     ("het_w70", "het_w70_nt.pfr", False),    # timing off: 11 iterations
+    # two wire types (tests/fixtures/k6_N10_mix.xml: 30 % length-1 + 70 % length-4): eight rr_indexed_data rows, the
+    # lookahead mixes the inv_length / T_linear / C_load of a row and of its orthogonal row (route_timing.c:693-746)
+    ("mix_w70", "mix_w70.pfr", True),        # 345 nets, 22 iterations
+    ("mix_w60", "mix_w60.pfr", True),        # near the minimum width: 34 iterations
     ("het_w60", "het_w60.pfr", True),        # one track too few: the reference gives up after max_router_iterations = 50
 ]                                            # with 1 overused node (success = 0); the oracle must fail the same way
 
@@ -83,7 +87,7 @@ def test_reference_binary_agrees_when_present(ref_bin, oracle_cli, unxz, tmp_pat
     assert np.array_equal(r.net_delay.view(np.uint32), o.net_delay.view(np.uint32))
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90", "mid_w200", "het_w70"])
+@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90", "mid_w200", "het_w70", "mix_w70"])
 def test_oracle_router_and_sta_in_closed_loop_reproduce_the_reference_run(name, oracle_cli, unxz, tmp_path):
     """No replay: the oracle router with the oracle's own static timing analysis between iterations (--timing-graph)
     must reproduce the reference's WHOLE timing-driven run — iteration count, every trace, the cookie, bit-exact sink
@@ -99,3 +103,48 @@ def test_oracle_router_and_sta_in_closed_loop_reproduce_the_reference_run(name, 
     assert np.array_equal(o.net_delay.view(np.uint32), g.net_delay.view(np.uint32)) and np.array_equal(o.occ, g.occ)
     routed = np.repeat(p.net_is_global == 0, np.diff(p.net_ptr))
     assert np.array_equal(o.iter_crit.view(np.uint32)[:, routed], g.iter_crit.view(np.uint32)[:, routed])
+
+
+def unbuffered_toy(unxz_or_path, timing):
+    """toy_w64 with switch 0 (every wire-to-wire and OPIN-to-wire edge) turned into a PASS TRANSISTOR: buffered = 0,
+    R = 400, Tdel = 10 ps.  All fixture architectures are unidirectional, whose mux switches are buffered, and the
+    reference's bidirectional rr-graph builder overflows a 2-entry stack array as soon as a wire switch is unbuffered
+    (rr_graph2.c:1436-1445: `switch_types[used]` with used == 2; ASan trace in DESIGN.md §5) — so the unbuffered branch
+    of the Elmore code (update_unbuffered_ancestors_C_downstream, route_tree_timing.c:393-417, and the R_upstream /
+    C_downstream bookkeeping of :216-390) is reached by editing the switch table of a flat problem and handing it to the
+    unmodified reference ROUTER (inject mode), which is how the *_unbuf goldens were made."""
+    p = pfio.read_problem(unxz_or_path)
+    p.switches = p.switches.copy()
+    p.switches["buffered"][0] = 0
+    p.switches["R"][0] = 400.0
+    p.switches["Tdel"][0] = 1e-11
+    p.opts = p.opts.copy()
+    p.opts["timing_analysis_enabled"] = 1 if timing else 0
+    return p
+
+
+@pytest.mark.parametrize("timing", [False, True])
+def test_oracle_unbuffered_switches_bit_for_bit(timing, oracle_cli, unxz, tmp_path):
+    prob, out = str(tmp_path / "u.pfp"), str(tmp_path / "o.pfr")
+    pfio.write_problem(prob, unbuffered_toy(unxz("toy_w64.pfp"), timing))
+    gold = unxz("toy_w64_unbuf_td.pfr" if timing else "toy_w64_unbuf_nt.pfr")
+    cmd = [oracle_cli, prob, "--result", out] + (["--crit", unxz("toy_w64.pfr")] if timing else [])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    g, o = pfio.read_result(gold), pfio.read_result(out)
+    assert (o.success, o.iterations, o.serial_num, o.total_wirelength) == (g.success, g.iterations, g.serial_num, g.total_wirelength)
+    assert np.array_equal(o.trace_node, g.trace_node) and np.array_equal(o.trace_switch, g.trace_switch)
+    assert np.array_equal(o.net_delay.view(np.uint32), g.net_delay.view(np.uint32)) and np.array_equal(o.occ, g.occ)
+    # the edit changed the delays (so the branch really ran): same problem with buffered switches gives other numbers
+    b = pfio.read_result(unxz("toy_w64.pfr" if timing else "toy_w64_nt.pfr"))
+    assert not np.array_equal(b.net_delay, g.net_delay)
+
+
+def test_reference_binary_agrees_on_unbuffered_switches_when_present(ref_bin, unxz, tmp_path):
+    """Regenerates the timing-driven *_unbuf golden with the real reference (criticalities of toy_w64.pfr replayed)."""
+    prob, out = str(tmp_path / "u.pfp"), str(tmp_path / "r.pfr")
+    pfio.write_problem(prob, unbuffered_toy(unxz("toy_w64.pfp"), True))
+    subprocess.run([ref_bin, "inject", prob, "--crit", unxz("toy_w64.pfr"), "--result", out], check=True, capture_output=True)
+    g, r = pfio.read_result(unxz("toy_w64_unbuf_td.pfr")), pfio.read_result(out)
+    assert r.serial_num == g.serial_num and np.array_equal(r.trace_node, g.trace_node)
+    assert np.array_equal(r.net_delay.view(np.uint32), g.net_delay.view(np.uint32))
