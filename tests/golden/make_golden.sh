@@ -40,6 +40,28 @@ PF_DUMP_PROBLEM=het_w70.pfp PF_DUMP_RESULT=het_w70.pfr PF_DUMP_NAMES=het_w70.pfn
 "$REF" inject het_w70.pfp --result het_w70_nt.pfr > /dev/null
 for f in het_w70.pfp het_w70.pfr het_w70_nt.pfr het_w70.pftg het_w70.pfsta het_w70.pfn het_w70_bf.pfp het_w70_bf.pfr het_w60.pfp het_w60.pfr; do xz -9 -c $f > "$HERE/$f.xz"; done
 xz -9 -c het.route > "$HERE/het_w70.route.xz"; xz -9 -c het.net > "$HERE/het.net.xz"; cp het.place het.blif "$HERE/"
+# heq: the het circuit with the multiplier's input ports declared logically equivalent and one signal wired to two pins of each
+# port, i.e. nets that connect TWICE to one SINK rr node (capacity 4).  The reference routes them, then its own DEBUG cross-check
+# timing_driven_check_net_delays (route_timing.c:246) aborts the run on exactly these nets, so the result is dumped the moment
+# the routing is legal (PF_DUMP_AT_SUCCESS=1).
+python - <<'PY'
+import re
+s = open("k6_N10_het.xml").read()
+top = s.index('<pb_type name="mult" height="2"')          # the cluster-level ports only
+s = s[:top] + s[top:].replace('<input name="a" num_pins="4"/>', '<input name="a" num_pins="4" equivalent="true"/>', 1) \
+                      .replace('<input name="b" num_pins="4"/>', '<input name="b" num_pins="4" equivalent="true"/>', 1)
+open("heq.xml", "w").write(s)
+out = []
+for line in open("het.blif").read().replace(".model het", ".model heq").split("\n"):
+    if line.startswith(".subckt mult4"):
+        line = re.sub(r"a\[1\]=\S+", "a[1]=" + re.search(r"a\[0\]=(\S+)", line).group(1), line)
+        line = re.sub(r"b\[3\]=\S+", "b[3]=" + re.search(r"b\[2\]=(\S+)", line).group(1), line)
+    out.append(line)
+open("heq.blif", "w").write("\n".join(out))
+PY
+"$REF" flow heq.xml heq --nodisp --pack --place > /dev/null
+PF_DUMP_AT_SUCCESS=1 PF_DUMP_PROBLEM=heq_w70.pfp PF_DUMP_RESULT=heq_w70.pfr PF_DUMP_TGRAPH=heq_w70.pftg "$REF" flow heq.xml heq --nodisp --route --route_chan_width 70 > /dev/null || true
+for f in heq_w70.pfp heq_w70.pfr heq_w70.pftg; do xz -9 -c $f > "$HERE/$f.xz"; done
 # two wire types
 cp "$ROOT/tests/fixtures/k6_N10_mix.xml" .
 python "$ROOT/tests/fixtures/gen_blif.py" mix.blif --luts 350 --pis 18 --window 70 --seed 21 --name mix

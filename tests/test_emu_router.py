@@ -264,3 +264,30 @@ def test_unbuffered_switches(emu_lib):
     p.opts["max_router_iterations"] = 150
     r = router.try_timing_driven_route(p, cfg, sta=router.replay_sta(g), lib_path=emu_lib)
     assert r.success == 1 and check_route.check_route(p, r, check_delays=True)["overused"] == 0
+
+
+def test_nets_that_connect_twice_to_one_sink(emu_lib):
+    """heq_w70: 12 nets reach the same SINK rr node with two pins (equivalent inputs of a hard block).  The device code must
+    end both connections at that SINK (two segments of the traceback close there), keep its occupancy at 2 and report sink
+    delays that the from-scratch Elmore recomputation confirms — the reference's own delays fail ITS cross-check on these nets
+    (route_timing.c:246), the device router's do not."""
+    p = pfio.read_problem(os.path.join(G, "heq_w70.pfp.xz"))
+    g = pfio.read_result(os.path.join(G, "heq_w70.pfr.xz"))
+    twice = []
+    for i in p.routed_nets():
+        t = p.net_terminals[p.net_ptr[i] + 1:p.net_ptr[i + 1]]
+        u, c = np.unique(t, return_counts=True)
+        if (c > 1).any():
+            twice.append((int(i), int(u[c > 1][0])))
+    assert len(twice) == 12
+    for slots in (1, 8):
+        kw = dict(num_slots=1, big_slots=1, pop_slack=0.0, max_batch=1, reroute_all_iters=-1) if slots == 1 else dict(num_slots=8, big_slots=1)
+        p.opts["max_router_iterations"] = 150
+        r = router.try_timing_driven_route(p, router.default_config(router.load_library(emu_lib), **kw), sta=router.replay_sta(g), lib_path=emu_lib)
+        assert r.success == 1
+        assert check_route.check_route(p, r, check_delays=True)["overused"] == 0
+        for inet, sink in twice:
+            nodes, _ = r.net_trace(inet)
+            assert int((nodes == sink).sum()) == 2 and int(r.occ[sink]) >= 2
+        if slots == 1:
+            assert r.total_wirelength <= 1.03 * g.total_wirelength and r.iterations <= int(1.5 * g.iterations)

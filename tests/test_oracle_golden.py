@@ -32,6 +32,11 @@ CASES = [
     # lookahead mixes the inv_length / T_linear / C_load of a row and of its orthogonal row (route_timing.c:693-746)
     ("mix_w70", "mix_w70.pfr", True),        # 345 nets, 22 iterations
     ("mix_w60", "mix_w60.pfr", True),        # near the minimum width: 34 iterations
+    # heq: 12 nets that connect TWICE to one SINK rr node (equivalent input pins of a hard block fed by one signal): mark_ends
+    # counts the target twice (route_common.c:764-778) and the second search must not stop at the first arrival.  The reference
+    # routes it and then fails its own DEBUG delay cross-check on exactly these nets (route_timing.c:246) — the golden was
+    # dumped at the moment of success; the oracle reproduces the reference's delays here too, bit for bit
+    ("heq_w70", "heq_w70.pfr", True),        # 442 nets, 25 iterations
     ("het_w60", "het_w60.pfr", True),        # one track too few: the reference gives up after max_router_iterations = 50
 ]                                            # with 1 overused node (success = 0); the oracle must fail the same way
 
@@ -87,7 +92,7 @@ def test_reference_binary_agrees_when_present(ref_bin, oracle_cli, unxz, tmp_pat
     assert np.array_equal(r.net_delay.view(np.uint32), o.net_delay.view(np.uint32))
 
 
-@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90", "mid_w200", "het_w70", "mix_w70"])
+@pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90", "mid_w200", "het_w70", "mix_w70", "heq_w70"])
 def test_oracle_router_and_sta_in_closed_loop_reproduce_the_reference_run(name, oracle_cli, unxz, tmp_path):
     """No replay: the oracle router with the oracle's own static timing analysis between iterations (--timing-graph)
     must reproduce the reference's WHOLE timing-driven run — iteration count, every trace, the cookie, bit-exact sink
