@@ -1040,7 +1040,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 			const int r = pf_route_wave_bf(w, &tree_n, t0, ns, sink_order /* reused: per-pin done flags */, rt_of_sink);
 			if (swapped) pf_swap_tables(w);
 			if (r == 0) fail = PF_ST_UNROUTABLE;
-			else if (r == -2) fail = PF_ST_INTERNAL;
+			else if (r == -2) fail = PF_ST_TWICE_TO_SINK_BF;
 			else if (r < 0 && !w.overflow) w.overflow = PF_OVF_OTHER;
 		} else
 		for (int itarget = 1; itarget <= ns; itarget++) {

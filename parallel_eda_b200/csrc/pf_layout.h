@@ -74,6 +74,7 @@ struct PfNetLoc { int off, count; };   /* a net's tree in the route store */
 #define PF_ST_UNROUTABLE 1
 #define PF_ST_POOL_OVERFLOW 2
 #define PF_ST_INTERNAL 4
+#define PF_ST_TWICE_TO_SINK_BF 8   /* breadth-first mode met a net with two pins on one SINK (route_breadth_first.c:208-256) */
 
 struct PfStats { unsigned long long pops, pushes, visits, refills, nets, label_probes, stale; unsigned long long pad; };
 

@@ -727,6 +727,10 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 	if (r->events && r->h_events > r->event_cap) FAILF(PF_EOVERFLOW, "occupancy event log overflow (%lld events, capacity %lld)", r->h_events, r->event_cap);
 	r->d2h_bytes += 256;
 	if (h_status[0] & PF_ST_POOL_OVERFLOW) FAILF(PF_EOVERFLOW, "route store overflow (capacity %lld tree entries)", r->pool_cap);
+	if (h_status[0] & PF_ST_TWICE_TO_SINK_BF)
+		FAILF(PF_EINVAL, "breadth-first router: net %d connects twice to one SINK; the reference's heap surgery for this case "
+				"(route_breadth_first.c:208-256) is not supported — its own check_route rejects the routing it produces. "
+				"Use the timing-driven / no-timing router (router_algorithm 0), which routes such nets", h_status[2]);
 	if (h_status[0] & PF_ST_INTERNAL) FAILF(PF_ECUDA, "internal error in the device router (net %d)", h_status[2]);
 	if (h_status[0] & PF_ST_UNROUTABLE) FAILF(PF_EUNROUTABLE, "net %d has no possible path (disconnected rr graph)", h_status[2]);
 	if (st) {

@@ -12,7 +12,7 @@ from parallel_eda_b200 import check_route, pfio, router
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name,slots", [("toy_w64", 1), ("toy_w64", 16)])
+@pytest.mark.parametrize("name,slots", [("toy_w64", 1), ("toy_w64", 16), ("het_w70", 8)])   # het: height-2 hard blocks
 def test_breadth_first_on_the_emulator(name, slots, emu_lib):
     p = pfio.read_problem(os.path.join(G, name + "_bf.pfp.xz"))
     g = pfio.read_result(os.path.join(G, name + "_bf.pfr.xz"))
@@ -24,3 +24,23 @@ def test_breadth_first_on_the_emulator(name, slots, emu_lib):
     assert m["overused"] == 0 and m["wirelength"] == r.total_wirelength
     print("%s slots %d: %d iterations (reference %d), wirelength x%.3f" % (name, slots, r.iterations, g.iterations, r.total_wirelength / g.total_wirelength))
     assert r.total_wirelength <= 1.08 * g.total_wirelength and r.iterations <= 2 * g.iterations + 2
+
+
+def test_breadth_first_refuses_nets_that_connect_twice_to_one_sink(emu_lib, oracle_cli, tmp_path):
+    """The reference handles a second connection to the same SINK with heap surgery (route_breadth_first.c:208-256,
+    invalidate_heap_entries) and its own check_route then rejects the routing ("check_sink: node ... does not connect to any
+    terminal", observed on this very circuit), so the mode is not restated: device router and oracle refuse such a problem
+    with PF_EINVAL and say why — they must not return a routing, crash, or call it an internal error.  The timing-driven
+    router routes the same problem (tests/test_emu_router.py::test_nets_that_connect_twice_to_one_sink)."""
+    import subprocess
+    p = pfio.read_problem(os.path.join(G, "heq_w70.pfp.xz"))
+    p.opts["router_algorithm"] = 1
+    p.opts["timing_analysis_enabled"] = 0
+    cfg = router.default_config(router.load_library(emu_lib), num_slots=4, big_slots=1)
+    with pytest.raises(router.RouterError, match="connects twice to one SINK") as e:
+        router.try_timing_driven_route(p, cfg, lib_path=emu_lib)
+    assert e.value.code == -4
+    pp = str(tmp_path / "p.pfp")
+    pfio.write_problem(pp, p)
+    r = subprocess.run([oracle_cli, pp], capture_output=True, text=True)
+    assert r.returncode != 0 and "rc=-4" in (r.stdout + r.stderr)
