@@ -306,3 +306,18 @@ def test_readers_survive_mutated_files(cuda_lib, unxz, tmp_path):
                 assert e.code == -2 and str(e).count(":") >= 1, str(e)
                 rejected += 1
         assert rejected > accepted // 4 and accepted + rejected == 120
+
+
+@pytest.mark.parametrize("circuit,stem", FIXTURES)
+def test_oracle_routing_prints_the_reference_route_file(cuda_lib, oracle_cli, unxz, tmp_path, circuit, stem):
+    """the `.route` file of the CPU restatement's routing equals the reference's byte for byte — router
+    oracle (closed loop with its own STA, no replay) -> traces -> pf_route_write vs the file the reference's print_route
+    wrote for its own run."""
+    import subprocess
+    out = str(tmp_path / "o.pfr")
+    r = subprocess.run([oracle_cli, unxz(stem + ".pfp"), "--timing-graph", unxz(stem + ".pftg"), "--result", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    p = pfio.read_problem(unxz(stem + ".pfp"))
+    rf = str(tmp_path / "o.route")
+    textio.write_route(rf, p, textio.read_names(unxz(stem + ".pfn")), pfio.read_result(out))
+    assert open(rf, "rb").read() == open(unxz(stem + ".route"), "rb").read()
