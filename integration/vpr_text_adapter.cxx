@@ -6,11 +6,14 @@
  * pf_names / pf_problem / pf_result views and calls pf_route_write.  Glue only; needs pf_text.c (part of
  * libpf_router.so, no CUDA call on this path).
  *
- *   base/place_and_route.c is compiled with  -Dprint_route=pf_adapter_print_route
- *   so its three call sites (place_and_route.c:182,364,729) land here; the reference's print_route
+ *   base/place_and_route.c is compiled with  -Dprint_route=pf_adapter_print_route -Dread_place=pf_adapter_read_place
+ *   so its three print_route call sites (place_and_route.c:182,364,729) land here; the reference's print_route
  *   (route/route_common.c:1322-1417) stays in the build unchanged.  The file written is byte-identical
- *   (tests/test_text_formats.py::test_adapter_print_route_equals_the_reference), ten times sooner on a 200 k-net
- *   routing (0.33 s instead of 3.2 s for the 224 MB file).
+ *   (tests/test_text_formats.py::test_adapter_print_route_and_read_place_equal_the_reference), ten times sooner on a 200 k-net
+ *   routing (0.33 s instead of 3.2 s for the 224 MB file).  The read_place call sites
+ *   (place_and_route.c:85,284) land in pf_adapter_read_place: same checks and messages, but one hash lookup per line where
+ *   read_place.c:108-114 runs strcmp down the whole block list ("O(B^2); 200 k-net fixtures ... expect
+ *   minutes in the reader").
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -107,4 +110,34 @@ void pf_adapter_print_route(char *route_file) {
 		vpr_printf(TIO_MESSAGE_ERROR, "in print_route: %s (%d)\n", pf_text_error(), rc);
 		exit(1);
 	}
+}
+
+/* place_and_route.c:85,284 land here (-Dread_place=pf_adapter_read_place).  Parameter order as in the reference's
+ * definition (read_place.c:15): the second argument is compared with the netlist name in the file, the third with the
+ * architecture name — the reference's parameter NAMES say the opposite, its callers pass (place, net, arch). */
+void pf_adapter_read_place(const char *place_file, const char *net_file, const char *arch_file, int L_nx, int L_ny,
+		int L_num_blocks, struct s_block block_list[]) {
+	pf_names n;
+	memset(&n, 0, sizeof(n));
+	n.nx = L_nx; n.ny = L_ny; n.num_blocks = L_num_blocks;
+	size_t chars = 0;
+	for (int b = 0; b < L_num_blocks; b++) chars += strlen(block_list[b].name);
+	std::vector<int32_t> ptr(L_num_blocks + 1), bx(L_num_blocks + 1), by(L_num_blocks + 1), bz(L_num_blocks + 1);
+	std::vector<char> names(chars + 1);
+	size_t at = 0;
+	for (int b = 0; b < L_num_blocks; b++) {
+		size_t l = strlen(block_list[b].name);
+		ptr[b] = (int32_t)at; memcpy(&names[at], block_list[b].name, l); at += l;
+		bx[b] = block_list[b].x; by[b] = block_list[b].y; bz[b] = block_list[b].z;
+	}
+	ptr[L_num_blocks] = (int32_t)at;
+	n.block_name_ptr = ptr.data(); n.block_name_chars = names.data();
+	n.block_x = bx.data(); n.block_y = by.data(); n.block_z = bz.data();
+	int placed = 0;
+	int rc = pf_place_read(place_file, net_file, arch_file, &n, &placed);
+	if (rc != PF_OK) {                                   /* reference style: message + exit (read_place.c:49-120) */
+		vpr_printf(TIO_MESSAGE_ERROR, "%s\n", rc == PF_EFORMAT ? pf_text_error() : "read_place: cannot read the placement file");
+		exit(1);
+	}
+	for (int b = 0; b < L_num_blocks; b++) { block_list[b].x = bx[b]; block_list[b].y = by[b]; block_list[b].z = bz[b]; }
 }

@@ -47,6 +47,7 @@
 #include "place_and_route.h"
 #include "stats.h"
 #include "rr_graph.h"
+#include "read_place.h"
 
 #include <string>
 #include "../../include/pf_file.h"
@@ -415,6 +416,28 @@ boolean pf_hook_try_timing_driven_route(struct s_router_opts router_opts, float 
 	if (dr) export_result(dr, ok, net_delay);
 	if (getenv("PF_DUMP_STA") && timing_analysis_enabled && !g_inject) export_sta_vectors(getenv("PF_DUMP_STA"));
 	return ok;
+}
+
+/* base/place_and_route.c is also compiled with -Dread_place=pf_hook_read_place: with PF_ADAPTER_READ_PLACE=1 the adapter's
+ * hashed reader (integration/vpr_text_adapter.cxx) reads the file first, then the reference's read_place; the two
+ * placements must agree */
+void pf_adapter_read_place(const char *place_file, const char *net_file, const char *arch_file, int L_nx, int L_ny, int L_num_blocks, struct s_block block_list[]);
+void pf_hook_read_place(const char *place_file, const char *a2, const char *a3, int L_nx, int L_ny, int L_num_blocks, struct s_block block_list[]) {
+	std::vector<int> ax, ay, az;
+	double t0 = now_s(), t1 = t0;
+	const bool both = getenv("PF_ADAPTER_READ_PLACE") != NULL;
+	if (both) {
+		pf_adapter_read_place(place_file, a2, a3, L_nx, L_ny, L_num_blocks, block_list);
+		t1 = now_s();
+		for (int b = 0; b < L_num_blocks; b++) { ax.push_back(block_list[b].x); ay.push_back(block_list[b].y); az.push_back(block_list[b].z); block_list[b].x = block_list[b].y = block_list[b].z = -7; }
+	}
+	read_place(place_file, a2, a3, L_nx, L_ny, L_num_blocks, block_list);
+	if (both) {
+		int diff = 0;
+		for (int b = 0; b < L_num_blocks; b++) diff += ax[b] != block_list[b].x || ay[b] != block_list[b].y || az[b] != block_list[b].z;
+		fprintf(stderr, "PF_REF read_place: adapter %.4f s, reference %.4f s, %d blocks, %d differ\n", t1 - t0, now_s() - t1, L_num_blocks, diff);
+		if (diff) exit(3);
+	}
 }
 
 /* ------------------------------------------------------------------ flow mode */

@@ -244,7 +244,7 @@ def test_threaded_writer_and_reader_equal_the_single_thread_path(cuda_lib, oracl
         textio.read_route(str(bad), p)
 
 
-def test_adapter_print_route_equals_the_reference(cuda_lib, ref_bin, unxz, tmp_path):
+def test_adapter_print_route_and_read_place_equal_the_reference(cuda_lib, ref_bin, unxz, tmp_path):
     """The reference-side binding (integration/vpr_text_adapter.cxx, what -Dprint_route=pf_adapter_print_route puts
     behind place_and_route.c:182,364,729) inside the reference's own flow: VPR globals -> pf_names / trace arrays ->
     pf_route_write.  Its file equals the one the reference's print_route wrote in the same run, and the names it
@@ -258,10 +258,12 @@ def test_adapter_print_route_equals_the_reference(cuda_lib, ref_bin, unxz, tmp_p
         shutil.copy(os.path.join(GOLDEN, "toy." + ext), d)
     with lzma.open(os.path.join(GOLDEN, "toy.net.xz")) as f, open(os.path.join(d, "toy.net"), "wb") as o:
         o.write(f.read())
-    env = dict(os.environ, PF_ADAPTER_ROUTE_FILE="adapter.route", PF_DUMP_NAMES="toy.pfn")
+    env = dict(os.environ, PF_ADAPTER_ROUTE_FILE="adapter.route", PF_DUMP_NAMES="toy.pfn", PF_ADAPTER_READ_PLACE="1")
     r = subprocess.run([ref_bin, "flow", "k6_N10_like.xml", "toy", "--nodisp", "--route", "--route_chan_width", "64"], cwd=d,
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    # place_and_route.c:284 went through pf_adapter_read_place first, then the reference's read_place: same placement
+    assert "read_place: adapter" in r.stderr and "64 blocks, 0 differ" in r.stderr, r.stderr[-1500:]
     ref = open(os.path.join(d, "toy.route"), "rb").read()
     assert open(os.path.join(d, "adapter.route"), "rb").read() == ref
     assert ref == open(unxz("toy_w64.route"), "rb").read()            # and both equal the committed golden
