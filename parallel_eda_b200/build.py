@@ -37,12 +37,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and _newer(LIB, deps):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = os.environ.get("PF_EXTRA_NVCC_FLAGS", "").split()     # experiments, e.g. -DPF_DEUNROLL_COLD=1 (pf_device.cuh)
     bdir = os.path.join(HERE, "_build")
     os.makedirs(bdir, exist_ok=True)
     objs = []
     for s in srcs:
         o = os.path.join(bdir, os.path.basename(s) + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-x", "cu"] if s.endswith(".cu") else []) + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-x", "cu"] if s.endswith(".cu") else []) + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

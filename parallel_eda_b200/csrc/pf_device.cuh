@@ -128,6 +128,15 @@ PF_DEV uint64_t pf_make_key(float tot, int node) {
 	return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | (uint32_t)node;
 }
 #define PF_INF_F 3.0e38f
+/* Cold per-net loops (rip-up, commit, undo, table wipes): nvcc unrolls them 4x and they are inlined at several sites, which
+ * is a fifth of the kernel's code (tools/sass_by_line.py).  -DPF_DEUNROLL_COLD=1 keeps one rolled copy per site — an
+ * experiment for the next GPU session (instruction fetch is 23 % of the stall samples); off by default, the shipped
+ * binary is unchanged. */
+#if defined(PF_DEUNROLL_COLD) && defined(__CUDACC__)
+#define PF_COLD_LOOP _Pragma("unroll 1")
+#else
+#define PF_COLD_LOOP
+#endif
 #define PF_KEY_MAX 0xffffffffffffffffull
 
 /* ------------------------------------------------------------------ A* lookahead
@@ -406,7 +415,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 
 	w.epoch++;
 	if ((w.epoch & 63u) == 0) {                  /* tag wrapped: wipe the hot table, skip tag 0 (= never written) */
-		for (unsigned i = (unsigned)lane; i <= w.label_mask; i += PF_WARP) w.hot[i] = 0;
+		PF_COLD_LOOP for (unsigned i = (unsigned)lane; i <= w.label_mask; i += PF_WARP) w.hot[i] = 0;
 		w.epoch++;
 		pf_syncwarp();
 	}
@@ -649,7 +658,7 @@ PF_DEV int pf_highfanout_rlim(PfWarp &w, int tree_n, int target_node) {
 	int maxdim = (P->nx + 2 > P->ny + 2) ? P->nx + 2 : P->ny + 2;
 	/* does the root have children? */
 	int has_child = 0;
-	for (int i = lane; i < tree_n; i += PF_WARP) if (i > 0 && w.tree[i].parent == 0) has_child = 1;
+	PF_COLD_LOOP for (int i = lane; i < tree_n; i += PF_WARP) if (i > 0 && w.tree[i].parent == 0) has_child = 1;
 	if (!pf_any(has_child)) return maxdim;
 	for (;;) {
 		int hit = 0;
@@ -858,7 +867,7 @@ PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0, int ns, int *sink
 	const int lane = pf_lane();
 	w.epoch++;
 	if ((w.epoch & 63u) == 0) {
-		for (unsigned i = (unsigned)lane; i <= w.label_mask; i += PF_WARP) w.hot[i] = 0;
+		PF_COLD_LOOP for (unsigned i = (unsigned)lane; i <= w.label_mask; i += PF_WARP) w.hot[i] = 0;
 		w.epoch++;
 		pf_syncwarp();
 	}
@@ -983,7 +992,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 	/* rip-up: pathfinder_update_one_cost(trace_head[inet], -1) — one atomic per tree entry */
 	if (!P->skip_ripup) {
 		PfNetLoc loc = P->loc[inet];
-		for (int base = 0; base < loc.count; base += PF_WARP) {
+		PF_COLD_LOOP for (int base = 0; base < loc.count; base += PF_WARP) {
 			const int i = base + lane;
 			pf_occ_change(P, i < loc.count, i < loc.count ? P->pool[loc.off + i].node : 0, -1);
 		}
@@ -1076,7 +1085,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 
 	if (w.overflow || fail) {
 		/* undo this net's commits; it owns no routing until it is retried */
-		for (int base = 0; base < tree_n; base += PF_WARP) { const int i = base + lane; pf_occ_change(P, i < tree_n, i < tree_n ? w.tree[i].node : 0, -1); }
+		PF_COLD_LOOP for (int base = 0; base < tree_n; base += PF_WARP) { const int i = base + lane; pf_occ_change(P, i < tree_n, i < tree_n ? w.tree[i].node : 0, -1); }
 		if (lane == 0) {
 			P->loc[inet].off = 0; P->loc[inet].count = 0;
 			if (fail) { pf_atomic_add_i(P->status + 1, 1); pf_atomic_or_i(P->status, fail); P->status[2] = inet; }
@@ -1093,7 +1102,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 	off = pf_shfl_u64(off, 0);
 	if ((long long)(off + tree_n) > P->pool_cap) {
 		if (lane == 0) { pf_atomic_or_i(P->status, PF_ST_POOL_OVERFLOW); P->loc[inet].off = 0; P->loc[inet].count = 0; }
-		for (int base = 0; base < tree_n; base += PF_WARP) { const int i = base + lane; pf_occ_change(P, i < tree_n, i < tree_n ? w.tree[i].node : 0, -1); }
+		PF_COLD_LOOP for (int base = 0; base < tree_n; base += PF_WARP) { const int i = base + lane; pf_occ_change(P, i < tree_n, i < tree_n ? w.tree[i].node : 0, -1); }
 		pf_syncwarp();
 		return 0;
 	}

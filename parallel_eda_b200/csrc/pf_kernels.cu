@@ -178,8 +178,8 @@ template <int STRICT> __global__ void __launch_bounds__(128, 5) pf_route_kernel(
 	const int slot = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp_in_block;
 	PfIndexedDev *idx = (PfIndexedDev *)pf_smem;
 	PfSwitchDev *sw = (PfSwitchDev *)(pf_smem + PF_MAX_INDEXED * sizeof(PfIndexedDev));
-	for (int i = (int)threadIdx.x; i < P.num_indexed; i += (int)blockDim.x) idx[i] = P.indexed[i];
-	for (int i = (int)threadIdx.x; i < P.num_sw; i += (int)blockDim.x) sw[i] = P.sw[i];
+	PF_COLD_LOOP for (int i = (int)threadIdx.x; i < P.num_indexed; i += (int)blockDim.x) idx[i] = P.indexed[i];
+	PF_COLD_LOOP for (int i = (int)threadIdx.x; i < P.num_sw; i += (int)blockDim.x) sw[i] = P.sw[i];
 	__syncthreads();
 	if (slot >= num_slots) return;
 	const size_t per_warp = PF_SMEM_PER_WARP + (P.hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8);
