@@ -30,15 +30,20 @@ def _newer(target: str, sources) -> bool:
     return all(os.path.getmtime(s) <= t for s in sources)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    """variant "" is the product library libpf_router.so.  A non-empty variant (or PF_LIB_VARIANT in the environment) builds
+    libpf_router_<variant>.so in its own object directory with PF_EXTRA_NVCC_FLAGS added — side-by-side experiment builds
+    that tools/ab_bench.sh compares on the GPU (the Python mirror loads $PF_ROUTER_LIB instead of the product library)."""
+    variant = variant or os.environ.get("PF_LIB_VARIANT", "")
+    lib_path = LIB if not variant else os.path.join(HERE, "libpf_router_%s.so" % variant)
     srcs = [os.path.join(CSRC, f) for f in ("pf_kernels.cu", "pf_router.cpp", "pf_sta.cpp", "pf_check.cpp", "pf_gen.cpp", "pf_file.c", "pf_text.c")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("pf_device.cuh", "pf_sta_device.cuh", "pf_backend.h", "pf_layout.h", "pf_host.h")] + [
         os.path.join(ROOT, "include", f) for f in ("pf_router.h", "pf_types.h", "pf_file.h", "pf_gen.h", "pf_text.h")]
-    if not force and _newer(LIB, deps):
-        return LIB
+    if not force and not variant and _newer(lib_path, deps):
+        return lib_path
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("PF_EXTRA_NVCC_FLAGS", "").split()     # experiments, e.g. -DPF_DEUNROLL_COLD=1 (pf_device.cuh)
-    bdir = os.path.join(HERE, "_build")
+    bdir = os.path.join(HERE, "_build" + ("_" + variant if variant else ""))
     os.makedirs(bdir, exist_ok=True)
     objs = []
     for s in srcs:
@@ -55,12 +60,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
     # link with the host compiler: `nvcc -shared` would add a default-arch (sm_52) device-link stub
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
-    cmd = ["g++", "-shared", "-o", LIB] + objs + ["-L" + cuda_lib, "-Wl,-rpath," + cuda_lib, "-lcudart", "-lm"]
+    cmd = ["g++", "-shared", "-o", lib_path] + objs + ["-L" + cuda_lib, "-Wl,-rpath," + cuda_lib, "-lcudart", "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

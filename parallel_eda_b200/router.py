@@ -18,7 +18,8 @@ import numpy as np
 from . import pfio
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(_HERE, "libpf_router.so")
+# PF_ROUTER_LIB: an experiment build (parallel_eda_b200/build.py variants, tools/ab_bench.sh) instead of the product library
+DEFAULT_LIB = os.environ.get("PF_ROUTER_LIB") or os.path.join(_HERE, "libpf_router.so")
 
 PF_OK = 0
 ERRORS = {-1: "PF_EIO", -2: "PF_EFORMAT", -3: "PF_ENOMEM", -4: "PF_EINVAL", -5: "PF_ECUDA", -6: "PF_EOVERFLOW",
