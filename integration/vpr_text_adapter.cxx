@@ -1,7 +1,7 @@
 /*
  * vpr_text_adapter.cxx — reference-side binding of the native text writers (include/pf_text.h).
  *
- * Second file a maintainer of chinhau5/parallel_eda adds to the VPR build (INTEGRATION.md §6): it reads VPR's
+ * Second file a maintainer of chinhau5/parallel_eda adds to the VPR build (INTEGRATION.md §5): it reads VPR's
  * globals (clb_net[], block[], grid[][], rr_node[], trace_head[]; base/globals.c:48-97), fills the plain-array
  * pf_names / pf_problem / pf_result views and calls pf_route_write.  Glue only; needs pf_text.c (part of
  * libpf_router.so, no CUDA call on this path).
