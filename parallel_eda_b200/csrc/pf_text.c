@@ -371,6 +371,9 @@ int pf_route_write(const char *path, const pf_problem *p, const pf_names *n, con
 	if (!path || !p || !n || !r) return fail(PF_EINVAL, "pf_route_write: NULL argument");
 	if (n->num_nets != p->num_nets || r->num_nets != p->num_nets || n->nx != p->nx || n->ny != p->ny)
 		return fail(PF_EINVAL, "pf_route_write: problem, names and result disagree on nets or grid");
+	if (!r->trace_ptr || (r->trace_ptr[p->num_nets] > 0 && !r->trace_node) || !n->net_name_ptr || !n->tile_is_io || !n->gpin_ptr
+			|| !p->net_ptr || !p->net_is_global || !p->type || !p->xlow || !p->ylow || !p->xhigh || !p->yhigh || !p->ptc_num)
+		return fail(PF_EINVAL, "pf_route_write: a required array is NULL");
 	for (k = 0; k < p->num_nets; k++)
 		if (r->trace_ptr[k + 1] < r->trace_ptr[k]) return fail(PF_EINVAL, "pf_route_write: trace_ptr not monotone at net %d", k);
 	if ((rc = ob_open(&o, path)) != 0) return fail(rc, "cannot open %s for writing", path);
@@ -422,8 +425,9 @@ static inline int scan_int(const char **s, long *v) {
 	int neg = 0;
 	long x = 0;
 	if (*c == '-') { neg = 1; c++; }
+	int digits = 0;
 	if (*c < '0' || *c > '9') return 0;
-	while (*c >= '0' && *c <= '9') { x = x * 10 + (*c - '0'); c++; }
+	while (*c >= '0' && *c <= '9') { if (++digits > 18) return 0; x = x * 10 + (*c - '0'); c++; }   /* no signed overflow */
 	*v = neg ? -x : x;
 	*s = c;
 	return 1;
