@@ -358,7 +358,8 @@ extern "C" int pf_gen_grid_problem(const pf_gen_params *gp, pf_problem *out) {
 			cx[k & 63] = tx; cy[k & 63] = ty;
 			sinks_used[G.tile(tx, ty)]++;
 			p.net_terminals[t0 + 1 + k] = G.tile_class0[G.tile(tx, ty)];
-			if (tx < xmin) xmin = tx; if (tx > xmax) xmax = tx; if (ty < ymin) ymin = ty; if (ty > ymax) ymax = ty;
+			xmin = tx < xmin ? tx : xmin; xmax = tx > xmax ? tx : xmax;
+			ymin = ty < ymin ? ty : ymin; ymax = ty > ymax ? ty : ymax;
 		}
 		/* load_route_bb, route_common.c:1065-1123 */
 		xmin -= 1; ymin -= 1;

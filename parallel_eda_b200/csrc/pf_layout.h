@@ -66,8 +66,14 @@ struct PfTreeNode {
 
 struct PfNetLoc { int off, count; };   /* a net's tree in the route store */
 
-#define PF_SH_FRONTIER 128      /* near-set entries per warp in shared memory */
+/* overridable for experiment builds (PF_EXTRA_NVCC_FLAGS, tools/ab_bench.sh): every pop scans the near set, every refill
+ * fills it to PF_SH_REFILL — e.g. -DPF_SH_FRONTIER=64 -DPF_SH_REFILL=32 halves the scan and doubles the refills */
+#ifndef PF_SH_FRONTIER
+#define PF_SH_FRONTIER 128      /* near-set entries per warp in shared memory (a multiple of 32) */
+#endif
+#ifndef PF_SH_REFILL
 #define PF_SH_REFILL 64         /* refill the near set to at most this many */
+#endif
 #define PF_MAX_BATCH 32         /* labels settled per step (one delta bucket) */
 
 /* error/status bits written to PfParams.status[0] */
