@@ -234,7 +234,13 @@ static boolean route_on_b200(struct s_router_opts router_opts, float **net_delay
 			after_sink = rr_node[v].type == SINK;
 		}
 	}
-	for (int i = 0; i < N; i++) { rr_node[i].occ = (short)occ[i]; rr_node_route_inf[i].pres_cost = 1.; rr_node_route_inf[i].acc_cost = 1.; }
+	for (int i = 0; i < N; i++) {
+		if (occ[i] > 32767) {                                /* rr_node[].occ is a short (vpr_types.h:965) */
+			vpr_printf(TIO_MESSAGE_ERROR, "pf_router: occupancy %d of rr node %d does not fit rr_node[].occ\n", occ[i], i);
+			exit(1);
+		}
+		rr_node[i].occ = (short)occ[i]; rr_node_route_inf[i].pres_cost = 1.; rr_node_route_inf[i].acc_cost = 1.;
+	}
 	reserve_locally_used_opins(router_opts.initial_pres_fac, FALSE, clb_opins_used_locally);
 	boolean ok = res.success ? TRUE : FALSE;
 #ifdef DEBUG
