@@ -207,11 +207,12 @@ def run_ours(a):
     # workload on 1 GPU: profiles/r01_ncu_full_pf_route_kernel.json, dram__bytes_read.sum + dram__bytes_write.sum);
     # that launch's algorithmic bytes are 3.75e9 (7.78e7 visits, 5.12e6 pops, 4.00e7 label writes); 3.2e9 of the traffic
     # are deliberate L2 prefetches of edge rows (10.4e9 without them, 2.5 % slower)
-    traffic = None
+    traffic, traffic_detail = None, None          # "traffic" is a number (bytes per launch) or null; the detail names the launch
     if world == 1 and (a.grid, a.nets, a.width) == (400, 200000, 100):
-        traffic = {"bytes_per_launch": 11.938608e9 + 1.684029e9, "launch": "iteration 1 (200000 nets)",
-                   "algorithmic_bytes_same_launch": 36.0 * 77.83e6 + 28.0 * 5.12e6 + 20.0 * 40.03e6,
-                   "source": "profiles/r01_ncu_full_pf_route_kernel.json"}
+        traffic_detail = {"bytes_per_launch": 11.938608e9 + 1.684029e9, "launch": "iteration 1 (200000 nets)",
+                          "algorithmic_bytes_same_launch": 36.0 * 77.83e6 + 28.0 * 5.12e6 + 20.0 * 40.03e6,
+                          "source": "profiles/r01_ncu_full_pf_route_kernel.json"}
+        traffic = traffic_detail["bytes_per_launch"]
 
     # end to end through the public API with host buffers (N GPUs)
     e2e = None
@@ -282,7 +283,7 @@ def run_ours(a):
                       "route_time_s": total_ms * 1e-3 / a.steps, "legal": True,
                       "wirelength": [r.wirelength for r in reps], "reference_wirelength": REFERENCE_WL.get((a.grid, a.nets, a.width))},
             "roofline": {"bound": "hbm", "kernel": "pf_route_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": peak_src,
                          "algorithmic_bytes": "36 B/edge visit + 28 B/pop + 20 B/label write (SURVEY.md §8d)",
                          "kernel_ms_per_step": tm.route_kernel_ms / a.steps, "kernel_launches_per_step": tm.route_launches / a.steps},
             "gpu_launches": launches,
