@@ -129,3 +129,19 @@ def test_inconsistent_trace_offsets_are_refused_before_the_kernel_runs(toy):
             R.check_route(bad)
         assert e.value.code == -4
     assert R.check_route(g)["ok"] == 1                               # the router handle is still usable
+
+
+@pytest.mark.parametrize("name", ["het_w70", "heq_w70", "mix_w70", "hub_w90", "duo_w80"])
+def test_reference_routings_of_every_fixture_pass(name, emu_lib):
+    """The reference's own check_route accepted these routings inside the flow that produced the goldens; the device checker
+    and the Python checker must accept them too — tall blocks (het), two pins of a net on one SINK (heq: the SINK is matched
+    once per pin), two wire types (mix), an 84-sink net (hub), two clock domains (duo) — and agree on the wirelength."""
+    p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
+    g = pfio.read_result(os.path.join(G, name + ".pfr.xz"))
+    R = router.Router(p, router.default_config(router.load_library(emu_lib), num_slots=1, big_slots=1), lib_path=emu_lib)
+    try:
+        rep = R.check_route(g)
+    finally:
+        R.close()
+    assert rep["ok"] == 1 and rep["bad_nets"] == 0 and rep["overused_nodes"] == 0 and rep["occupancy_mismatch"] == 0
+    assert rep["wirelength"] == g.total_wirelength == check_route.check_route(p, g, check_delays=True)["wirelength"]

@@ -264,8 +264,8 @@ def test_unbuffered_switches(emu_lib):
 def test_nets_that_connect_twice_to_one_sink(emu_lib):
     """heq_w70: 12 nets reach the same SINK rr node with two pins (equivalent inputs of a hard block).  The device code must
     end both connections at that SINK (two segments of the traceback close there), keep its occupancy at 2 and report sink
-    delays that the from-scratch Elmore recomputation confirms — the reference's own delays fail ITS cross-check on these nets
-    (route_timing.c:246), the device router's do not."""
+    delays that the from-scratch Elmore recomputation confirms, one per connection (the reference's own run aborts in its DEBUG
+    cross-check on these nets, route_timing.c:246, because net_delay.c:564-600 assigns both pins the larger of the two)."""
     p = pfio.read_problem(os.path.join(G, "heq_w70.pfp.xz"))
     g = pfio.read_result(os.path.join(G, "heq_w70.pfr.xz"))
     twice = []
