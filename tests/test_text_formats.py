@@ -323,3 +323,35 @@ def test_oracle_routing_prints_the_reference_route_file(cuda_lib, oracle_cli, un
     rf = str(tmp_path / "o.route")
     textio.write_route(rf, p, textio.read_names(unxz(stem + ".pfn")), pfio.read_result(out))
     assert open(rf, "rb").read() == open(unxz(stem + ".route"), "rb").read()
+
+
+def test_net_without_sinks_prints_the_local_cluster_text(cuda_lib, ref_bin, tmp_path):
+    """A routed (non-global) net with num_sinks == 0: the serial code leaves trace_head NULL (route_timing.c:163) and
+    print_route writes "Used in local cluster only, reserved one CLB pin" (route_common.c:1337-1339).  None of the circuit
+    fixtures has such a net, so one is made from a generated problem (net 5 loses its sinks) and the reference router + its own
+    print_route are run on it in inject mode."""
+    import subprocess
+    p = router.generate_grid_problem(nx=10, ny=10, W=30, num_nets=40, sinks_per_net=3, seed=3)
+    keep = np.ones(p.num_terminals, bool)
+    keep[p.net_ptr[5] + 1:p.net_ptr[6]] = False
+    counts = np.diff(p.net_ptr).copy()
+    counts[5] = 1
+    p.net_terminals = p.net_terminals[keep]
+    p.net_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    # (global nets are covered by the circuit goldens: inject mode has no blocks to print for them)
+    # breadth-first router: after a timing-driven success the reference's DEBUG delay cross-check builds an RC tree for every
+    # non-global net and aborts on the one without a traceback (net_delay.c: "Traceback for net 5 does not exist")
+    p.opts = p.opts.copy()
+    p.opts["router_algorithm"] = 1
+    pp, rr, rf = str(tmp_path / "g.pfp"), str(tmp_path / "g.pfr"), str(tmp_path / "g.ref.route")
+    pfio.write_problem(pp, p)
+    subprocess.run([ref_bin, "inject", pp, "--result", rr, "--route-file", rf], check=True, capture_output=True)
+    ref = open(rf, "rb").read()
+    assert b"\n\nNet 5 (n5)\n\n\n\nUsed in local cluster only, reserved one CLB pin\n\n" in ref
+    out = str(tmp_path / "g.route")
+    res = pfio.read_result(rr)
+    textio.write_route(out, p, textio.synthetic_names(p), res)
+    assert open(out, "rb").read() == ref
+    q = textio.read_route(out, p)
+    assert np.array_equal(q.trace_ptr, res.trace_ptr) and np.array_equal(q.trace_node, res.trace_node)
+    assert q.trace_ptr[6] == q.trace_ptr[5]
