@@ -162,6 +162,21 @@ def test_edge_cases_match_the_oracle(emu_lib, oracle_cli, tmp_path):
     assert r.total_wirelength == o.total_wirelength and np.array_equal(r.trace_ptr, o.trace_ptr)   # an uncontested net: same tree size
     check_route.check_route(b, r)
 
+    # a routed net without sinks (SURVEY.md §8b edge case i): the serial code calls the net router on it and leaves
+    # trace_head NULL (route_timing.c:163); here its trace stays empty and nothing is charged to its SOURCE
+    d = copy.deepcopy(p)
+    keep = np.ones(d.num_terminals, bool)
+    keep[d.net_ptr[i] + 1:d.net_ptr[i + 1]] = False
+    counts = np.diff(d.net_ptr).copy(); counts[i] = 1
+    d.net_terminals = d.net_terminals[keep]
+    d.net_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    r = router.try_timing_driven_route(d, cfg, lib_path=emu_lib)
+    rc, o = oracle(d)
+    assert rc == 0 and r.success == o.success == 1
+    assert r.trace_ptr[i + 1] == r.trace_ptr[i] and o.trace_ptr[i + 1] == o.trace_ptr[i]
+    assert abs(r.total_wirelength - o.total_wirelength) <= 0.08 * o.total_wirelength      # 4 warps on the tight toy: measured +5 %
+    check_route.check_route(d, r)
+
     c = copy.deepcopy(p)
     src = int(c.net_terminals[c.net_ptr[i]])
     c.net_bb = c.net_bb.copy()
