@@ -5,6 +5,7 @@
                                       [--max-iters K] [--device D] [--check] [--verbose]
     python -m parallel_eda_b200 check PROBLEM.pfp[.xz] RESULT.pfr[.xz] | ROUTING.route   (device check_route)
     python -m parallel_eda_b200 info  PROBLEM.pfp[.xz]
+    python -m parallel_eda_b200 gen   OUT.pfp --nx 400 [--ny 400] --width 100 --nets 200000 [--sinks 3] [--seed 1]   (no GPU)
     python -m parallel_eda_b200 print-route PROBLEM.pfp[.xz] RESULT.pfr[.xz] OUT.route [--names N.pfn[.xz]]   (no GPU)
     python -m parallel_eda_b200 read-route  PROBLEM.pfp[.xz] IN.route OUT.pfr                                  (no GPU)
 
@@ -38,8 +39,19 @@ def main(argv=None) -> int:
     i = sub.add_parser("info"); i.add_argument("problem")
     w = sub.add_parser("print-route"); w.add_argument("problem"); w.add_argument("result"); w.add_argument("route_file"); w.add_argument("--names")
     g = sub.add_parser("read-route"); g.add_argument("problem"); g.add_argument("route_file"); g.add_argument("result")
+    n = sub.add_parser("gen", help="uniform k6_N10-style grid + random nets (pf_gen_grid_problem, include/pf_gen.h)")
+    n.add_argument("problem"); n.add_argument("--nx", type=int, required=True); n.add_argument("--ny", type=int, default=0)
+    n.add_argument("--width", type=int, default=100); n.add_argument("--nets", type=int, required=True)
+    n.add_argument("--sinks", type=int, default=3); n.add_argument("--seed", type=int, default=1)
     a = ap.parse_args(argv)
 
+    if a.cmd == "gen":
+        t = time.perf_counter()
+        p = router.generate_grid_problem(nx=a.nx, ny=a.ny or a.nx, W=a.width, num_nets=a.nets, sinks_per_net=a.sinks, seed=a.seed)
+        pfio.write_problem(a.problem, p)
+        print(json.dumps({"rr_nodes": p.num_nodes, "rr_edges": p.num_edges, "nets": p.num_nets, "terminals": p.num_terminals,
+                          "seconds": round(time.perf_counter() - t, 2)}))
+        return 0
     p = pfio.read_problem(a.problem)
     if a.cmd == "info":
         print(json.dumps({"nx": p.nx, "ny": p.ny, "rr_nodes": p.num_nodes, "rr_edges": p.num_edges, "nets": p.num_nets,

@@ -355,3 +355,26 @@ def test_net_without_sinks_prints_the_local_cluster_text(cuda_lib, ref_bin, tmp_
     q = textio.read_route(out, p)
     assert np.array_equal(q.trace_ptr, res.trace_ptr) and np.array_equal(q.trace_node, res.trace_node)
     assert q.trace_ptr[6] == q.trace_ptr[5]
+
+
+def test_cli_chain_without_a_gpu(cuda_lib, oracle_cli, tmp_path):
+    """python -m parallel_eda_b200 gen | print-route | read-route | info: the GPU-free subcommands over the flat containers.
+    The routing in between comes from the CPU oracle (test infrastructure) — `route` itself needs a B200."""
+    import json
+    import subprocess
+    import sys
+    d = str(tmp_path)
+
+    def cli(*args):
+        r = subprocess.run([sys.executable, "-m", "parallel_eda_b200"] + list(args), cwd=ROOT, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1500:]
+        return r.stdout
+    gen = json.loads(cli("gen", d + "/g.pfp", "--nx", "12", "--width", "30", "--nets", "150", "--seed", "4"))
+    assert gen["nets"] == 150 and json.loads(cli("info", d + "/g.pfp"))["rr_nodes"] == gen["rr_nodes"]
+    out = subprocess.run([oracle_cli, d + "/g.pfp", "--result", d + "/g.pfr"], capture_output=True, text=True)
+    assert out.returncode == 0
+    cli("print-route", d + "/g.pfp", d + "/g.pfr", d + "/g.route")
+    back = json.loads(cli("read-route", d + "/g.pfp", d + "/g.route", d + "/g2.pfr"))
+    o = pfio.read_result(d + "/g.pfr")
+    assert (back["wirelength"], back["serial_num"], back["trace_elements"]) == (o.total_wirelength, o.serial_num, len(o.trace_node))
+    assert np.array_equal(pfio.read_result(d + "/g2.pfr").trace_node, o.trace_node)
