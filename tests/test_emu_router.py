@@ -301,3 +301,28 @@ def test_nets_that_connect_twice_to_one_sink(emu_lib):
             assert int((nodes == sink).sum()) == 2 and int(r.occ[sink]) >= 2
         if slots == 1:
             assert r.total_wirelength <= 1.03 * g.total_wirelength and r.iterations <= int(1.5 * g.iterations)
+
+
+def test_cli_route_and_check_through_the_emulated_device_code(emu_lib, tmp_path):
+    """`python -m parallel_eda_b200 route ... --timing-graph --route-file --names --check` and `check` on the result container
+    and on the `.route` text, with PF_ROUTER_LIB pointing at the emulator build of the same sources (the CLI's default
+    library is the CUDA product, which has no CPU path)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PF_ROUTER_LIB=emu_lib)
+    d = str(tmp_path)
+
+    def cli(*args):
+        r = subprocess.run([sys.executable, "-m", "parallel_eda_b200"] + list(args), cwd=root, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-800:] + r.stderr[-1500:]
+        return json.loads(r.stdout.strip().split("\n")[-1])
+    prob = os.path.join(G, "toy_w64.pfp.xz")
+    out = cli("route", prob, "--timing-graph", os.path.join(G, "toy_w64.pftg.xz"), "--result", d + "/r.pfr", "--route-file", d + "/r.route",
+              "--names", os.path.join(G, "toy_w64.pfn.xz"), "--check", "--max-iters", "150")
+    assert out["success"] == 1 and out["check_route"]["ok"] == 1 and out["check_route"]["overused_nodes"] == 0
+    a = cli("check", prob, d + "/r.pfr")
+    b = cli("check", prob, d + "/r.route")
+    assert a["ok"] == b["ok"] == 1 and a["wirelength"] == b["wirelength"] == out["wirelength"]
+    assert a["reserved_opins"] == 23 and b["reserved_opins"] == 0 and "note" in b
+    text = open(d + "/r.route").read()
+    assert text.startswith("Array size: 6 x 6 logic blocks.\n\nRouting:\n\nNet 0 (n299)\n\nNode:\t") and "Net 92 (clk): global net connecting:" in text
