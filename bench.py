@@ -152,6 +152,9 @@ def run_ours(a):
     from parallel_eda_b200 import distributed, pathfinder, pfio, router
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the router has no CPU path")
+    backend = router.load_library().pf_backend_name()
+    if not backend.startswith(b"cuda:"):
+        raise SystemExit("bench.py measures the CUDA library only (loaded: %s)" % backend.decode())
     comm = distributed.init_from_env("nccl")
     rank = comm.rank if comm else 0
     world = comm.world if comm else 1

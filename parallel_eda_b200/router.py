@@ -124,6 +124,7 @@ _libs = {}
 
 
 def load_library(path: Optional[str] = None) -> C.CDLL:
+    from_env = path is None and bool(os.environ.get("PF_ROUTER_LIB"))
     path = os.path.abspath(path or DEFAULT_LIB)
     if path in _libs:
         return _libs[path]
@@ -133,6 +134,11 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib = C.CDLL(path)
     lib.pf_last_error.restype = C.c_char_p
     lib.pf_backend_name.restype = C.c_char_p
+    if from_env and not lib.pf_backend_name().startswith(b"cuda:") and os.environ.get("PF_ALLOW_EMULATOR") != "1":
+        # PF_ROUTER_LIB is for experiment builds of the CUDA library; the warp emulator (tests/emu) is test infrastructure and
+        # must never become a silent CPU path of the product
+        raise RuntimeError("PF_ROUTER_LIB=%s is not a CUDA build (%s); set PF_ALLOW_EMULATOR=1 to load test infrastructure on purpose"
+                           % (path, lib.pf_backend_name().decode()))
     lib.pf_config_default.argtypes = [C.POINTER(Config)]
     lib.pf_router_create.argtypes = [C.POINTER(_Problem), C.POINTER(Config), C.POINTER(C.c_void_p)]
     lib.pf_router_destroy.argtypes = [C.c_void_p]

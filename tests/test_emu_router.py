@@ -309,8 +309,12 @@ def test_cli_route_and_check_through_the_emulated_device_code(emu_lib, tmp_path)
     library is the CUDA product, which has no CPU path)."""
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PF_ROUTER_LIB=emu_lib)
+    env = dict(os.environ, PF_ROUTER_LIB=emu_lib, PF_ALLOW_EMULATOR="1")
     d = str(tmp_path)
+    # without the explicit opt-in the Python mirror refuses a non-CUDA library named by the environment
+    r = subprocess.run([sys.executable, "-m", "parallel_eda_b200", "check", os.path.join(G, "toy_w64.pfp.xz"), os.path.join(G, "toy_w64.pfr.xz")],
+                       cwd=root, env=dict(os.environ, PF_ROUTER_LIB=emu_lib), capture_output=True, text=True)
+    assert r.returncode != 0 and "not a CUDA build" in r.stderr
 
     def cli(*args):
         r = subprocess.run([sys.executable, "-m", "parallel_eda_b200"] + list(args), cwd=root, env=env, capture_output=True, text=True)
