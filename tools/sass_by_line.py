@@ -51,11 +51,28 @@ def main():
         if fn and want in fn and re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
             by_line[line] += 1
             by_func[ctx] += 1
+    # mnemonics: what the kernel does to memory (load widths, atomics, prefetches), warp collectives, fp64
+    mnem = collections.Counter()
+    fn = None
+    for l in sass.split("\n"):
+        m = re.match(r"\s*\.text\.(\S+):", l)
+        if m:
+            fn = m.group(1)
+            continue
+        if fn and want in fn:
+            m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", l)
+            if m:
+                mnem[m.group(1)] += 1
     tot = sum(by_line.values())
     print("%s: %d SASS instructions = %.0f KB" % (want, tot, tot * 16 / 1024))
     print("\nby enclosing device function (intrinsics charged to the function they were inlined into):")
     for f, c in by_func.most_common(25):
         print("  %5d %5.1f%%  %s" % (c, 100.0 * c / tot, f))
+    keep = re.compile(r"^(LDG|STG|LDS|STS|ATOM|RED|REDUX|CCTL|SHFL|VOTE|MATCH|WARPSYNC|BAR|D[A-Z]+$|DSETP|F2F|MUFU|IMAD\.MOV|LDL|STL)")
+    print("\nmemory / collective / fp64 mnemonics (count in the kernel's SASS):")
+    for k, c in sorted(mnem.items(), key=lambda kv: -kv[1]):
+        if keep.match(k):
+            print("  %5d  %s" % (c, k))
     print("\nby source line:")
     for (f, n), c in by_line.most_common(40):
         text = src[n - 1].strip()[:110] if f == "pf_device.cuh" and n - 1 < len(src) else ""
