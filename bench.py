@@ -19,6 +19,8 @@ roofline: the dominant kernel (pf_route_kernel) against the measured HBM copy ba
 cpu_baseline / --impl reference: the reference's own serial router (oracle/_ref/vpr_ref, compiled from the
           unmodified reference) — or, where that binary is absent, the bit-exact C restatement — on a
           bounded sample of the same problem, on this box's host cores.
+cpu_parallel_baseline (extra): the same CPU algorithm on all host threads (oracle/pf_oracle_par.c, kind "port"), first
+          iterations of the whole problem — the stand-in for the reference's parallel routers (TBB / MPI: not buildable).
 """
 from __future__ import annotations
 
@@ -120,6 +122,27 @@ def cpu_reference_sample(problem_path: str, nets: int, iters: int):
         raise RuntimeError("CPU baseline run failed: " + r.stderr[-500:])
     its, secs = int(m.group(1)), float(m.group(2))
     return nets * its / secs, kind, 1, sample, secs
+
+
+def cpu_parallel_sample(problem_path: str, iters: int):
+    """The multi-threaded CPU router (oracle/pf_oracle_par.c: the bit-exact serial restatement run by all host threads on
+    shared occupancy — a stand-in for the reference's parallel routers, which need TBB / MPI / Boost and cannot be built):
+    the first `iters` PathFinder iterations of the WHOLE problem.  Returns a cpu_baseline-shaped dict; never raises."""
+    try:
+        exe = os.path.join(ROOT, "oracle", "_build", "pf_oracle_par_cli")
+        if not os.path.exists(exe):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        threads = max(1, min(os.cpu_count() or 1, 32))          # 0.44 GB of search state per thread on the 18 M-node graph
+        r = subprocess.run([exe, problem_path, "--threads", str(threads), "--max_iters", str(iters)], stdout=subprocess.DEVNULL,
+                           stderr=subprocess.PIPE, text=True, timeout=900)
+        m = re.search(r"PF_ORACLE_PAR threads=(\d+) .*?route_time_s=([0-9.]+) nets_routed=(\d+) nets_per_s=([0-9.]+)", r.stderr)
+        if not m:
+            return None
+        return {"value": float(m.group(4)), "unit": "nets/s", "cores": int(m.group(1)), "kind": "port",
+                "sample": "all nets x first %d PathFinder iterations of the same problem, %s host threads sharing the occupancy arrays "
+                          "(oracle/pf_oracle_par.c)" % (iters, m.group(1)), "sample_seconds": float(m.group(2))}
+    except Exception:
+        return None
 
 
 def run_reference(a):
@@ -263,13 +286,14 @@ def run_ours(a):
                "phases_s": dict(zip(("create_upload", "route", "result_download", "destroy"), [round(x, 4) for x in e2e_phases[-1]])),
                "result_check": check}
 
-    cpu = None
+    cpu, cpu_par = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         with tempfile.TemporaryDirectory() as d:
             path = os.path.join(d, "bench.pfp")
             pfio.write_problem(path, p)
             v, kind, cores, sample, secs = cpu_reference_sample(path, a.cpu_sample_nets, a.cpu_sample_iters)
             cpu = {"value": v, "unit": "nets/s", "cores": cores, "kind": kind, "sample": sample, "sample_seconds": secs}
+            cpu_par = cpu_parallel_sample(path, a.cpu_sample_iters)
 
     if rank == 0:
         out = {
@@ -296,6 +320,8 @@ def run_ours(a):
             out["e2e"] = e2e
         if cpu:
             out["cpu_baseline"] = cpu
+        if cpu_par:
+            out["cpu_parallel_baseline"] = cpu_par     # extra to the contract: the same CPU algorithm on all host threads
         print(json.dumps(out))
     R.close()
     if comm:
