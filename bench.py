@@ -159,14 +159,18 @@ def run_reference(a):
             v, kind, cores, sample, secs = cpu_reference_sample(path, a.cpu_sample_nets, a.cpu_sample_iters)
             if s >= a.warmup:
                 vals.append(v); total += secs
+        par = cpu_parallel_sample(path, a.cpu_sample_iters)      # extra: the same CPU algorithm on all host threads
     v = sum(vals) / len(vals)
-    print(json.dumps({
+    line = {
         "impl": "reference", "metric": "nets_routed_per_sec", "value": v, "unit": "nets/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * total / max(a.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD.format(nx=a.grid, ny=a.grid, W=a.width, nets=a.nets), "sample": sample},
         "cpu_baseline": {"value": v, "unit": "nets/s", "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": v, "unit": "nets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": v, "unit": "nets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if par:
+        line["cpu_parallel_baseline"] = par
+    print(json.dumps(line))
 
 
 def run_ours(a):
