@@ -73,13 +73,16 @@ static void *par_route(void *arg) {
 	}
 }
 
-int pf_oracle_route_parallel(const pf_problem *p, int nthreads, int max_iters_override, pf_result *out, double *iter_seconds /* [max_iters] or NULL */) {
+/* congested_only = 0: every net is re-routed in every iteration (the serial reference's policy, route_timing.c:152-187);
+ * congested_only = 1: from the second iteration on only nets whose current route touches an overused rr node (the device
+ * router's policy; reference precedent partitioning_multi_sink_delta_stepping_route.cxx:6241-6269) */
+int pf_oracle_route_parallel(const pf_problem *p, int nthreads, int congested_only, int max_iters_override, pf_result *out, double *iter_seconds /* [max_iters] or NULL */) {
 	oracle S;                                            /* shared state + the single-threaded steps */
 	par_worker *W;
 	pthread_t *th;
 	int N = p->num_nodes, n = p->num_nets, T = p->num_terminals;
 	int i, inet, itry, t, rc = PF_OK, max_pins = 0, success = 0, max_iters, next;
-	int *net_index;
+	int *net_index, *work, nwork;
 	float *sinks, *crit, *net_delay, pres_fac;
 	pf_iter_stats *stats;
 	memset(out, 0, sizeof(*out));
@@ -110,6 +113,7 @@ int pf_oracle_route_parallel(const pf_problem *p, int nthreads, int max_iters_ov
 	net_index = (int *)malloc(sizeof(int) * (size_t)(n + 1));
 	for (i = 0; i < n; i++) { sinks[i] = p->net_ptr[i + 1] - p->net_ptr[i] - 1; net_index[i] = i; }
 	pf_oracle_heapsort(net_index, sinks, n, 1);
+	work = (int *)malloc(sizeof(int) * (size_t)(n + 1));
 	crit = (float *)calloc((size_t)T + 1, sizeof(float));            /* timing analysis off: criticality 0 throughout */
 	net_delay = (float *)calloc((size_t)T + 1, sizeof(float));
 	pres_fac = p->opts.first_iter_pres_fac;
@@ -121,9 +125,18 @@ int pf_oracle_route_parallel(const pf_problem *p, int nthreads, int max_iters_ov
 		memset(&cur, 0, sizeof(cur));
 		cur.pres_fac = pres_fac;
 		next = 0;
+		/* this iteration's nets, in decreasing-fanout order */
+		nwork = 0;
+		for (i = 0; i < n; i++) {
+			int k, hit = !(congested_only && itry > 1);
+			inet = net_index[i];
+			if (p->net_is_global[inet]) continue;
+			for (k = 0; !hit && k < S.tr_n[inet]; k++) { int v = S.tr_node[inet][k]; hit = S.occ[v] > p->capacity[v]; }
+			if (hit) work[nwork++] = inet;
+		}
 		for (t = 0; t < nthreads; t++) {
 			memset(&W[t].o.cur, 0, sizeof(W[t].o.cur));
-			W[t].net_index = net_index; W[t].n = n; W[t].next = &next; W[t].pres_fac = pres_fac; W[t].crit = crit; W[t].net_delay = net_delay; W[t].rc = PF_OK;
+			W[t].net_index = work; W[t].n = nwork; W[t].next = &next; W[t].pres_fac = pres_fac; W[t].crit = crit; W[t].net_delay = net_delay; W[t].rc = PF_OK;
 		}
 		for (t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, par_route, &W[t]);
 		par_route(&W[0]);
@@ -183,16 +196,16 @@ int pf_oracle_route_parallel(const pf_problem *p, int nthreads, int max_iters_ov
 	free(S.occ); free(S.pres_cost); free(S.acc_cost);
 	for (inet = 0; inet < n; inet++) { free(S.tr_node[inet]); free(S.tr_sw[inet]); }
 	free(S.tr_node); free(S.tr_sw); free(S.tr_n); free(S.tr_cap);
-	free(W); free(th); free(sinks); free(net_index); free(crit); free(net_delay); free(stats);
+	free(W); free(th); free(sinks); free(net_index); free(work); free(crit); free(net_delay); free(stats);
 	return rc;
 }
 
 #ifdef PF_ORACLE_PAR_MAIN
 #include <unistd.h>
-/* usage: pf_oracle_par_cli problem.pfp [--threads T] [--result out.pfr] [--max_iters K] */
+/* usage: pf_oracle_par_cli problem.pfp [--threads T] [--congested-only] [--result out.pfr] [--max_iters K] */
 int main(int argc, char **argv) {
 	const char *result_path = NULL;
-	int threads = (int)sysconf(_SC_NPROCESSORS_ONLN), max_iters = -1, i, rc;
+	int threads = (int)sysconf(_SC_NPROCESSORS_ONLN), max_iters = -1, congested_only = 0, i, rc;
 	pf_problem p;
 	pf_result out;
 	double *secs, total = 0;
@@ -201,18 +214,20 @@ int main(int argc, char **argv) {
 	for (i = 2; i < argc; i++) {
 		if (!strcmp(argv[i], "--threads") && i + 1 < argc) threads = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--result") && i + 1 < argc) result_path = argv[++i];
+		else if (!strcmp(argv[i], "--congested-only")) congested_only = 1;
 		else if (!strcmp(argv[i], "--max_iters") && i + 1 < argc) max_iters = atoi(argv[++i]);
 		else { fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
 	}
 	if (pf_problem_read(argv[1], &p) != 0) { fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
 	p.opts.timing_analysis_enabled = 0;
 	secs = (double *)calloc((size_t)(max_iters > 0 ? max_iters : p.opts.max_router_iterations) + 1, sizeof(double));
-	rc = pf_oracle_route_parallel(&p, threads, max_iters, &out, secs);
+	rc = pf_oracle_route_parallel(&p, threads, congested_only, max_iters, &out, secs);
 	if (rc != 0) { fprintf(stderr, "PF_ORACLE_PAR route failed rc=%d\n", rc); return 1; }
 	for (i = 0; i < out.iterations; i++) {
 		total += secs[i]; routed += out.iter_stats[i].nets_routed;
 		fprintf(stderr, "PF_ORACLE_PAR iter %d dt_s=%.6f overused=%d nets=%d\n", i + 1, secs[i], out.iter_stats[i].overused_nodes, out.iter_stats[i].nets_routed);
 	}
+	fprintf(stderr, "PF_ORACLE_PAR policy=%s\n", congested_only ? "congested-only" : "all-nets");
 	fprintf(stderr, "PF_ORACLE_PAR threads=%d success=%d iterations=%d wirelength=%d route_time_s=%.6f nets_routed=%ld nets_per_s=%.1f\n",
 			threads, out.success, out.iterations, out.total_wirelength, total, routed, total > 0 ? routed / total : 0.);
 	if (result_path && pf_result_write(result_path, &out) != 0) { fprintf(stderr, "cannot write %s\n", result_path); return 2; }

@@ -189,3 +189,15 @@ def test_parallel_cpu_router_one_thread_is_the_serial_oracle_and_many_threads_st
             break
     else:
         raise AssertionError("no 4-thread run converged close to the serial routing: %s" % seen)
+    # --congested-only: the device router's re-route policy on the CPU threads; with it even the tight circuit fixtures
+    # converge under 8 threads (all-nets: 50 iterations are not enough on hub_w90)
+    hp = pfio.read_problem(unxz("hub_w90.pfp"))
+    hp.opts["timing_analysis_enabled"] = 0
+    for attempt in range(3):
+        r = subprocess.run([par, unxz("hub_w90.pfp"), "--threads", "8", "--congested-only", "--result", p_out], capture_output=True, text=True)
+        if r.returncode == 0:
+            break
+    assert r.returncode == 0 and "policy=congested-only" in r.stderr, r.stderr[-800:]
+    q = pfio.read_result(p_out)
+    assert check_route.check_route(hp, q, check_delays=True)["overused"] == 0
+    assert q.total_wirelength <= 1.08 * pfio.read_result(unxz("hub_w90_nt.pfr")).total_wirelength
