@@ -132,7 +132,11 @@ def cpu_parallel_sample(problem_path: str, iters: int):
         exe = os.path.join(ROOT, "oracle", "_build", "pf_oracle_par_cli")
         if not os.path.exists(exe):
             subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
-        threads = max(1, min(os.cpu_count() or 1, 32))          # 0.44 GB of search state per thread on the 18 M-node graph
+        try:
+            avail = len(os.sched_getaffinity(0))                   # the cores this process may run on (cpuset-aware)
+        except Exception:
+            avail = os.cpu_count() or 1
+        threads = max(1, min(avail, 32))                           # 0.44 GB of search state per thread on the 18 M-node graph
         r = subprocess.run([exe, problem_path, "--threads", str(threads), "--max_iters", str(iters)], stdout=subprocess.DEVNULL,
                            stderr=subprocess.PIPE, text=True, timeout=900)
         m = re.search(r"PF_ORACLE_PAR threads=(\d+) .*?route_time_s=([0-9.]+) nets_routed=(\d+) nets_per_s=([0-9.]+)", r.stderr)
