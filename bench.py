@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--cpu-sample-iters", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-reference", action="store_true", help="--impl reference: skip the one complete routing by vpr_ref (≈ 2 min)")
+    ap.add_argument("--step-api", action="store_true", help="drive the iterations from Python through the step API and torch collectives "
+                    "(the round-1 path) instead of pf_route_run with the in-library transport")
     ap.add_argument("--max-batch", type=int, default=0, help="tuning: labels settled per step (0 = library default)")
     ap.add_argument("--pop-slack", type=float, default=-1.0, help="tuning: delta bucket width (<0 = library default)")
     ap.add_argument("--inflight-div", type=int, default=0)
@@ -149,6 +152,54 @@ def cpu_parallel_sample(problem_path: str, iters: int):
         return None
 
 
+def cpu_reference_full(problem_path: str, timeout_s: float = 900.0):
+    """ONE complete routing of the same problem by the reference's own serial router (oracle/_ref/vpr_ref inject): the
+    like-for-like time-to-legal and the wirelength yardstick.  Returns a dict or None (binary absent / run failed / too slow)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "vpr_ref")
+    if not os.path.exists(ref):
+        return None
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            out = os.path.join(d, "ref.pfr")
+            t0 = time.perf_counter()
+            r = subprocess.run([ref, "inject", problem_path, "--result", out], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=timeout_s)
+            wall = time.perf_counter() - t0
+        m = re.search(r"PF_REF route success=(\d+) iterations=(\d+) route_time_s=([0-9.]+)", r.stderr)
+        w = re.search(r"wirelength=(-?\d+)", r.stderr)
+        if not m:
+            return None
+        return {"success": int(m.group(1)), "iterations": int(m.group(2)), "route_time_s": float(m.group(3)), "wall_s": wall,
+                "wirelength": int(w.group(1)) if w else None, "cores": 1, "kind": "reference",
+                "what": "one complete routing of the same problem by the unmodified reference router (every net re-routed in every iteration)"}
+    except Exception:
+        return None
+
+
+def cpu_parallel_full(problem_path: str):
+    """The multi-threaded CPU restatement with the DEVICE router's re-route policy (--congested-only) on all host threads,
+    run to a legal routing: the like-for-like CPU time-to-legal for the same algorithmic policy."""
+    try:
+        exe = os.path.join(ROOT, "oracle", "_build", "pf_oracle_par_cli")
+        if not os.path.exists(exe):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        try:
+            avail = len(os.sched_getaffinity(0))
+        except Exception:
+            avail = os.cpu_count() or 1
+        threads = max(1, min(avail, 32))
+        r = subprocess.run([exe, problem_path, "--threads", str(threads), "--congested-only"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE,
+                           text=True, timeout=900)
+        m = re.search(r"PF_ORACLE_PAR threads=(\d+) success=(\d+) iterations=(\d+) wirelength=(-?\d+) route_time_s=([0-9.]+) nets_routed=(\d+) nets_per_s=([0-9.]+)", r.stderr)
+        if not m:
+            return None
+        return {"value": float(m.group(7)), "unit": "nets/s", "cores": int(m.group(1)), "kind": "port", "success": int(m.group(2)),
+                "iterations": int(m.group(3)), "wirelength": int(m.group(4)), "route_time_s": float(m.group(5)), "nets_routed": int(m.group(6)),
+                "sample": "the WHOLE routing to legality, %s host threads sharing the occupancy arrays, congested-only re-route policy "
+                          "(oracle/pf_oracle_par.c --congested-only)" % m.group(1)}
+    except Exception:
+        return None
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -164,6 +215,8 @@ def run_reference(a):
             if s >= a.warmup:
                 vals.append(v); total += secs
         par = cpu_parallel_sample(path, a.cpu_sample_iters)      # extra: the same CPU algorithm on all host threads
+        par_full = cpu_parallel_full(path)                        # extra: the device router's policy on all host threads, to legality
+        full = None if a.no_full_reference else cpu_reference_full(path)   # extra: ONE complete routing by the unmodified reference
     v = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": "nets_routed_per_sec", "value": v, "unit": "nets/s", "n_gpus": a.gpus, "steps": a.steps,
@@ -174,6 +227,11 @@ def run_reference(a):
         "e2e": {"value": v, "unit": "nets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if par:
         line["cpu_parallel_baseline"] = par
+    if par_full:
+        line["cpu_parallel_congested_only_full"] = par_full
+    if full:
+        line["reference_full_run"] = full
+        line["reference_full_run"]["nets_per_s"] = a.nets * full["iterations"] / max(full["route_time_s"], 1e-9)
     print(json.dumps(line))
 
 
@@ -196,8 +254,13 @@ def run_ours(a):
     p = router.generate_grid_problem(nx=a.grid, ny=a.grid, W=a.width, num_nets=a.nets)
     cfg = router.default_config(device=local, rank=rank, nranks=world, max_batch=a.max_batch, pop_slack=a.pop_slack,
                                 inflight_div=a.inflight_div, num_slots=a.slots, min_slots=a.min_slots)
-    R = router.Router(p, cfg)
+    R = comm.create_router(p, cfg) if comm else router.Router(p, cfg)     # N > 1: includes the one-off pf_comm_export / pf_comm_init bootstrap
     R.timing(reset=True)
+
+    def route(Rx):
+        if a.step_api:
+            return pathfinder.route(Rx, comm=comm, sync_rounds=a.sync_rounds)
+        return pathfinder.run(Rx, comm=comm)       # pf_route_run: the loop, and for N > 1 the occupancy exchange, inside the library
 
     def one_step():
         R.reset()
@@ -205,7 +268,7 @@ def run_ours(a):
             comm.barrier()
         torch.cuda.synchronize()
         R.timer_start()
-        rep = pathfinder.route(R, comm=comm, sync_rounds=a.sync_rounds)
+        rep = route(R)
         ms = R.timer_stop()
         torch.cuda.synchronize()
         if comm:
@@ -214,6 +277,9 @@ def run_ours(a):
         wl, _ = R.total_wirelength()               # after the timed region: reported, not measured
         if comm:
             wl = int(comm.all_reduce_scalar(wl))
+            if not a.step_api:                     # per-rank counters of pf_route_run -> job totals (outside the timed region)
+                rep.per_rank_nets = rep.nets_routed
+                rep.nets_routed = int(comm.all_reduce_scalar(rep.nets_routed))
         rep.wirelength = int(wl)
         return rep, ms
 
@@ -241,12 +307,21 @@ def run_ours(a):
     # workload on 1 GPU: profiles/r01_ncu_full_pf_route_kernel.json, dram__bytes_read.sum + dram__bytes_write.sum);
     # that launch's algorithmic bytes are 3.75e9 (7.78e7 visits, 5.12e6 pops, 4.00e7 label writes); 3.2e9 of the traffic
     # are deliberate L2 prefetches of edge rows (10.4e9 without them, 2.5 % slower)
-    traffic, traffic_detail = None, None          # "traffic" is a number (bytes per launch) or null; the detail names the launch
-    if world == 1 and (a.grid, a.nets, a.width) == (400, 200000, 100):
-        traffic_detail = {"bytes_per_launch": 11.938608e9 + 1.684029e9, "launch": "iteration 1 (200000 nets)",
-                          "algorithmic_bytes_same_launch": 36.0 * 77.83e6 + 28.0 * 5.12e6 + 20.0 * 40.03e6,
-                          "source": "profiles/r01_ncu_full_pf_route_kernel.json"}
-        traffic = traffic_detail["bytes_per_launch"]
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch: read from the summary of the newest committed
+    # `ncu --set full` capture of THIS workload (tools/ncu_traffic.py writes profiles/*_traffic.json next to the raw csv);
+    # null when no capture of this configuration exists
+    traffic, traffic_detail = None, None
+    if world == 1:
+        import glob
+        for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+            try:
+                t = json.load(open(f))
+                if (t.get("grid"), t.get("nets"), t.get("width")) == (a.grid, a.nets, a.width):
+                    traffic_detail = dict(t, source=os.path.relpath(f, ROOT))
+                    traffic = float(t["dram_bytes_per_launch"])
+                    break
+            except Exception:
+                pass
 
     # end to end through the public API with host buffers (N GPUs)
     e2e = None
@@ -261,7 +336,9 @@ def run_ours(a):
             # flatten + H2D of the whole problem (N GPUs: rank 0 uploads, the others receive over NVLink)
             R2 = comm.create_router(p, cfg) if comm else router.Router(p, cfg)
             t1 = time.perf_counter()
-            rep = pathfinder.route(R2, comm=comm, sync_rounds=a.sync_rounds)
+            rep = route(R2)
+            if comm and not a.step_api:
+                rep.nets_routed = int(comm.all_reduce_scalar(rep.nets_routed))
             t2 = time.perf_counter()
             res = R2.result()                          # D2H of traces, delays, occupancy
             t3 = time.perf_counter()
@@ -294,7 +371,7 @@ def run_ours(a):
                "phases_s": dict(zip(("create_upload", "route", "result_download", "destroy"), [round(x, 4) for x in e2e_phases[-1]])),
                "result_check": check}
 
-    cpu, cpu_par = None, None
+    cpu, cpu_par, cpu_par_full = None, None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         with tempfile.TemporaryDirectory() as d:
             path = os.path.join(d, "bench.pfp")
@@ -302,6 +379,7 @@ def run_ours(a):
             v, kind, cores, sample, secs = cpu_reference_sample(path, a.cpu_sample_nets, a.cpu_sample_iters)
             cpu = {"value": v, "unit": "nets/s", "cores": cores, "kind": kind, "sample": sample, "sample_seconds": secs}
             cpu_par = cpu_parallel_sample(path, a.cpu_sample_iters)
+            cpu_par_full = cpu_parallel_full(path)
 
     if rank == 0:
         out = {
@@ -311,12 +389,13 @@ def run_ours(a):
             "config": {"workload": WORKLOAD.format(nx=a.grid, ny=a.grid, W=a.width, nets=a.nets),
                        "rr_nodes": p.num_nodes, "rr_edges": p.num_edges, "sinks": int(p.num_terminals - p.num_nets),
                        "router_opts": "VPR defaults: astar 1.2, pres_fac 0.5 x1.3, acc_fac 1, bb_factor 3, max 50 iterations",
-                       "parallelism": "nets sharded over %d GPU(s) in spatial stripes (stripe-interior nets, then cut-crossing nets); occupancy event-log all-gather %dx per iteration" % (world, a.sync_rounds) if world > 1 else "1 GPU",
+                       "parallelism": ("nets sharded over %d GPU(s) in spatial stripes (stripe-interior nets, then cut-crossing nets); occupancy event logs exchanged 2x per iteration "
+                                       "%s" % (world, "by torch.distributed all-gather (step API)" if a.step_api else "device-side over NVLink peer memory (pf_comm_exchange), one host sync per iteration")) if world > 1 else "1 GPU, one host sync per PathFinder iteration (pf_route_run)",
                        "l2": "working set (node records %d MB + edges %d MB) far exceeds the 126 MB L2; no flush needed"
                              % (p.num_nodes * 32 >> 20, p.num_edges * 4 >> 20)},
             "route": {"iterations": [r.iterations for r in reps], "nets_routed_per_step": nets_routed / a.steps,
                       "route_time_s": total_ms * 1e-3 / a.steps, "legal": True,
-                      "wirelength": [r.wirelength for r in reps], "reference_wirelength": REFERENCE_WL.get((a.grid, a.nets, a.width))},
+                      "wirelength": [r.wirelength for r in reps], "overused_per_iteration": reps[-1].overused},
             "roofline": {"bound": "hbm", "kernel": "pf_route_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": peak_src,
                          "algorithmic_bytes": "36 B/edge visit + 28 B/pop + 20 B/label write (SURVEY.md §8d)",
@@ -330,16 +409,14 @@ def run_ours(a):
             out["cpu_baseline"] = cpu
         if cpu_par:
             out["cpu_parallel_baseline"] = cpu_par     # extra to the contract: the same CPU algorithm on all host threads
+        if cpu_par_full:
+            out["cpu_parallel_congested_only_full"] = cpu_par_full   # the device router's policy on all host threads, to legality
         print(json.dumps(out))
     R.close()
     if comm:
         import torch.distributed as dist
         dist.destroy_process_group()
 
-
-# total wirelength of the UNMODIFIED reference router on the same generated problem (oracle/_ref/vpr_ref inject,
-# run once in the build container): quality yardstick for the routing the timed steps produce
-REFERENCE_WL = {(400, 200000, 100): 9280210}     # 8 iterations, 109 s of route time on the build container's CPU
 
 
 def main():

@@ -84,6 +84,16 @@ typedef struct pf_config {
 	int32_t defer_graph;      /* multi-GPU: allocate the device graph but do not pack and upload it from this process's
 	                             host arrays — the caller fills it from another rank's copy over NVLink
 	                             (pf_comm_graph_buffers, then pf_comm_graph_ready); 0 = upload here (default) */
+	int32_t validate_commits; /* optimistic concurrency control for nets in flight together: a new path whose commit finds an
+	                             rr node already full although its search saw it free lost a race against another net in
+	                             flight; it is taken back and the sink searched again on the current occupancy (what the
+	                             serial order would have seen), at most this many times per sink.  0 = auto (2), < 0 = off */
+	int32_t ripple;           /* ripple re-routing inside an iteration: a net that knowingly shares a full rr node pushes the net
+	                             holding it onto this iteration's work queue, so a chain of displacements is followed within one
+	                             PathFinder iteration, as in the serial reference where every net is re-routed every iteration;
+	                             0 = auto (on), < 0 = off */
+	int32_t polish;           /* > 0: when the routing first becomes legal, one more iteration re-routes EVERY net against the
+	                             final congestion picture and the loop continues until legal again (pf_try_* loops only) */
 } pf_config;
 
 typedef struct pf_timing {    /* accumulated since create / last reset */
@@ -149,6 +159,32 @@ int pf_comm_net_classes(pf_router *r, int32_t *owner, uint8_t *is_cut);
 int pf_comm_events(pf_router *r, void **dev_events, int64_t *count);
 int pf_comm_apply_events(pf_router *r, const void *dev_events, int64_t count);
 void *pf_comm_net_delay_ptr(pf_router *r);
+
+/* ---- The transport inside the library (SURVEY.md §8b `pf_comm_init`; the reference syncs in C as well,
+ * parallel_route/spatial.cxx:3371-3383): one process per GPU on one node, every rank's exchange region (occupancy event
+ * logs, published sink delays) mapped into the others through CUDA IPC and read over NVLink / NVSwitch by the kernels
+ * themselves.  Bootstrap once per router:
+ *   1. pf_comm_export(r, blob)            PF_COMM_HANDLE_BYTES describing this rank's region
+ *   2. all-gather the blobs in rank order (the caller's communicator: MPI_Allgather, torch.distributed, ...)
+ *   3. pf_comm_init(r, all_blobs)
+ * afterwards pf_comm_exchange (after every route part) and pf_comm_gather_delays (before a timing analysis) are
+ * stream-ordered device work — publish with a system-scope release, poll the peers with acquire loads, read their
+ * payload out of their memory — and pf_route_run runs whole multi-GPU routings with one host synchronisation per
+ * PathFinder iteration.  pf_comm_abort makes peers stop waiting for a rank that failed. */
+#define PF_COMM_HANDLE_BYTES 128
+int pf_comm_export(pf_router *r, void *handle);
+int pf_comm_init(pf_router *r, const void *all_handles);
+int pf_comm_exchange(pf_router *r);
+int pf_comm_gather_delays(pf_router *r);
+int pf_comm_abort(pf_router *r);
+
+/* try_timing_driven_route (route_timing.c:85-343) on an existing router, one GPU or — after pf_comm_init — one rank of
+ * several: iterate until legal or out of iterations, with ONE host-device synchronisation per iteration.  dsta: device
+ * timing analysis (or NULL), sta/user: host analysis callback (or NULL).  stats[stats_cap] receives one entry per
+ * iteration (may be NULL); every rank returns the same *iterations and *success.  The routing stays in the router
+ * (pf_get_result). */
+int pf_route_run(pf_router *r, struct pf_sta *dsta, pf_sta_fn sta, void *user, pf_iter_stats *stats, int stats_cap,
+		int *iterations, int *success);
 /* the device float[num_terminals] criticality vector the next iteration reads (pf_iteration_begin with crit == NULL
  * keeps it): a device STA writes it in place (pf_sta_analyze_device) */
 void *pf_comm_crit_ptr(pf_router *r);
@@ -164,6 +200,8 @@ void pf_sta_destroy(pf_sta *s);
 int pf_sta_analyze(pf_sta *s, const float *net_delay, float *crit, float *cpd_ns);
 /* device buffers (e.g. a router's own delay and criticality vectors: nothing crosses PCIe) */
 int pf_sta_analyze_device(pf_sta *s, const void *dev_net_delay, void *dev_crit, float *cpd_ns);
+/* the critical path delay (ns) of the last analysis — pf_sta_analyze_device with cpd_ns == NULL does not wait for it */
+int pf_sta_read_cpd(pf_sta *s, float *cpd_ns);
 /* try_timing_driven_route with the analysis on the device: no host callback, no per-iteration copies */
 int pf_try_timing_driven_route_sta(const pf_problem *p, const pf_timing_graph *g, const pf_config *cfg, pf_result *out);
 

@@ -239,7 +239,12 @@ static boolean route_on_b200(struct s_router_opts router_opts, float **net_delay
 			vpr_printf(TIO_MESSAGE_ERROR, "pf_router: occupancy %d of rr node %d does not fit rr_node[].occ\n", occ[i], i);
 			exit(1);
 		}
-		rr_node[i].occ = (short)occ[i]; rr_node_route_inf[i].pres_cost = 1.; rr_node_route_inf[i].acc_cost = 1.;
+		rr_node[i].occ = (short)occ[i]; rr_node_route_inf[i].acc_cost = 1.;
+		/* the present cost the reference keeps next to occ (route_common.c:563-568): reserve_locally_used_opins orders the
+		 * OPINs of a class by base * acc * pres, so an OPIN a routed net already occupies must look more expensive than a
+		 * free one — with a uniform 1 a class with equivalent outputs could re-reserve an occupied pin and overfill it */
+		const float pf = router_opts.initial_pres_fac;
+		rr_node_route_inf[i].pres_cost = occ[i] < rr_node[i].capacity ? 1.f : 1.f + (occ[i] + 1 - rr_node[i].capacity) * pf;
 	}
 	reserve_locally_used_opins(router_opts.initial_pres_fac, FALSE, clb_opins_used_locally);
 	boolean ok = res.success ? TRUE : FALSE;

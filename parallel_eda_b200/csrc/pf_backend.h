@@ -22,6 +22,8 @@ const char *pfb_name(void);                       /* "cuda:sm_100a" | "emu" */
 const char *pfb_last_error(void);
 void *pfb_alloc(size_t bytes);                    /* device memory, zero-filled; NULL on failure */
 void *pfb_alloc_raw(size_t bytes);                /* device memory, uninitialised */
+void *pfb_host_alloc(size_t bytes);               /* small pinned host buffer (control-block reads); NULL on failure */
+void pfb_host_free(void *p);
 void *pfb_pinned(size_t bytes);                   /* process-wide pinned staging buffer of at least `bytes`; NULL if unavailable */
 void *pfb_pinned_upload(size_t bytes);            /* same, write-combined: host code must only WRITE it, sequentially */
 int pfb_h2d_async(void *dst, const void *src, size_t bytes);   /* ordered on the router's stream; src must stay valid until pfb_sync */
@@ -31,6 +33,7 @@ int pfb_h2d(void *dst, const void *src, size_t bytes);
 int pfb_d2h(void *dst, const void *src, size_t bytes);
 int pfb_d2d(void *dst, const void *src, size_t bytes);
 int pfb_zero(void *dst, size_t bytes);
+int pfb_fill(void *dst, int byte, size_t bytes);
 int pfb_sync(void);
 void pfb_times(PfLaunchTimes *out, int reset);
 int pfb_num_sms(void);
@@ -43,7 +46,8 @@ int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block);
 /* pathfinder_update_cost + feasible_routing (route_common.c:581-610,509-531) in one pass; when
  * base/delta are non-NULL the pass first folds the all-reduced occupancy delta into the node
  * records: occ = base + delta, base = occ (multi-GPU iteration boundary) */
-int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, unsigned char *last_over, int iter_tag);
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, unsigned char *last_over, int iter_tag,
+		unsigned long long *d_wl_used);   /* d_wl_used (may be NULL) += occupancy x length over the CHANX / CHANY nodes */
 /* delta[i] = nodes[i].occ - base[i]: what this GPU's nets changed since the last sync */
 /* replay another rank's occupancy events (multi-GPU sync) */
 int pfb_launch_apply_events(PfNode *nodes, const unsigned *events, long long count);
@@ -63,7 +67,8 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
  * net when force_all), split into the small/big slot classes by net_big[]; counts[0]/counts[1] */
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count);
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count,
+		int *queued, int queued_tag);   /* queued != NULL: queued[net] = queued_tag for every selected net (ripple re-routing) */
 /* counts[0..1] = lengths of list_small / list_big; counts[2..3] = how many of each come from the first head_count
  * entries of all_nets (they are at the head of the lists: order is preserved) */
 void pfb_bind_thread(void);                     /* make the router's device current in a helper thread */
@@ -71,6 +76,22 @@ size_t pfb_select_scratch_bytes(int num_all);   /* size of `scratch` (device mem
 /* copy every live tree of `all_nets` from one log to another (garbage collection of the route store) */
 int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
 		unsigned long long *dst_head);
+
+/* ---- multi-GPU exchange over peer memory (PfXchgHeader, pf_layout.h) */
+/* device memory other processes of the node can map: returns the pointer and fills a 64-byte handle; NULL on failure */
+void *pfb_ipc_alloc(size_t bytes, void *handle64);
+void *pfb_ipc_open(const void *handle64);          /* map another process's region; NULL on failure */
+void pfb_ipc_close(void *p);
+void pfb_ipc_free(void *p);
+/* publish this rank's event log of exchange `seq` (count read from *event_head on the device), wait for every peer's,
+ * replay the peers' events on `nodes` — one launch, no host involvement */
+int pfb_launch_xchg_events(PfNode *nodes, const PfPeers *peers, int me, int nranks, unsigned seq, const unsigned long long *event_head,
+		long long event_cap, int *status, double timeout_s);
+/* sink delays: copy the delays of this rank's nets into its published buffer, release it, wait for the peers' and copy the
+ * delays of their nets into net_delay (term_owner[t] = rank that routes terminal t's net) */
+int pfb_launch_xchg_delays(float *net_delay, const unsigned char *term_owner, int num_terminals, const PfPeers *peers, int me, int nranks,
+		unsigned dseq, long long event_cap, int *status, double timeout_s);
+int pfb_launch_xchg_abort(const PfPeers *peers, int me);
 
 /* ---- device static timing analysis (pf_sta_device.cuh, pf_sta.cpp) */
 struct PfStaDev;

@@ -65,6 +65,11 @@ PF_DEV int pf_atomic_add_i(int *p, int v) { return atomicAdd(p, v); }
 PF_DEV unsigned long long pf_atomic_add_ull(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 PF_DEV int pf_atomic_or_i(int *p, int v) { return atomicOr(p, v); }
 PF_DEV int pf_atomic_min_i(int *p, int v) { return atomicMin(p, v); }   /* used on shared memory (ATOMS) */
+PF_DEV int pf_atomic_exch_i(int *p, int v) { return atomicExch(p, v); }
+PF_DEV int pf_atomic_cas_i(int *p, int cmp, int v) { return atomicCAS(p, cmp, v); }
+PF_DEV int pf_ld_volatile_i(const int *p) { return *(const volatile int *)p; }
+PF_DEV void pf_threadfence(void) { __threadfence(); }
+PF_DEV void pf_spin_pause(void) { __nanosleep(200); }
 PF_DEV pf_u4 pf_ld_cg_u4(const void *p) { return __ldcg((const uint4 *)p); }   /* L2-coherent: sees other SMs' atomics */
 PF_DEV pf_u4 pf_ld_u4(const void *p) { return *(const uint4 *)p; }
 struct pf_u8 { unsigned a, b, c, d, e, f, g, h; };
@@ -109,11 +114,12 @@ struct PfWarp {
 	/* per-net constants */
 	int bb_xmin, bb_xmax, bb_ymin, bb_ymax; int num_sinks; int cur_net;
 	/* counters */
-	unsigned long long pops, pushes, visits, refills, stale;
+	unsigned long long pops, pushes, visits, refills, stale, races;
 };
 
 /* per warp: fr 1024 + b_key 256 + base_cost 128 + 5 batch arrays 640 + b_pre 136 + tickets 256 = 2440 → 2448;
  * per CTA: cost-index table 1024 + switch table 768 */
+#define PF_INFO_SEEN_FULL_BIT 11   /* label info word: switch (8) | type (3) | node was full when priced (1) | out-degree << 16 */
 #define PF_OVF_LABELS 1   /* w.overflow bits */
 #define PF_OVF_OTHER 2
 #define PF_TICKETS 64
@@ -129,10 +135,10 @@ PF_DEV uint64_t pf_make_key(float tot, int node) {
 }
 #define PF_INF_F 3.0e38f
 /* Cold per-net loops (rip-up, commit, undo, table wipes): nvcc unrolls them 4x and they are inlined at several sites, which
- * is a fifth of the kernel's code (tools/sass_by_line.py).  -DPF_DEUNROLL_COLD=1 keeps one rolled copy per site — an
- * experiment for the next GPU session (instruction fetch is 23 % of the stall samples); off by default, the shipped
- * binary is unchanged. */
-#if defined(PF_DEUNROLL_COLD) && defined(__CUDACC__)
+ * was a fifth of the kernel's code (tools/sass_by_line.py).  They are kept rolled: 7,432 -> 5,432 SASS instructions for the
+ * strict kernel and 3 % less kernel time on BASELINE configs[4] (17.65 -> 17.05 ms, profiles/r02_ab_variants.txt);
+ * -DPF_UNROLL_COLD=1 restores nvcc's default for A/B builds. */
+#if !defined(PF_UNROLL_COLD) && defined(__CUDACC__)
 #define PF_COLD_LOOP _Pragma("unroll 1")
 #else
 #define PF_COLD_LOOP
@@ -243,6 +249,11 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 		}
 		/* lowest lane wins a contested ticket (deterministic); the round tag decreases every round so
 		 * tickets never need clearing */
+		if ((w.round & 0x3ffffffu) == 0x3ffffffu) {            /* the tag is about to wrap: start the tickets afresh */
+			for (int i = lane; i < PF_TICKETS; i += PF_WARP) w.ticket[i] = 0x7fffffff;
+			w.round++;
+			pf_syncwarp();
+		}
 		const int tk = (int)(((0x3ffffffu - (w.round & 0x3ffffffu)) << 5) | (unsigned)lane);
 		w.round++;
 		if (want) pf_atomic_min_i(&w.ticket[h & (PF_TICKETS - 1)], tk);
@@ -508,7 +519,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 				uint64_t hk = w.hot[h];
 				if (pf_int_as_float((int)(hk >> 32)) == pf_key_tot(mk)) {      /* else stale: the node was re-labelled cheaper */
 					pf_u4 a = pf_ld_u4(&w.cold[h]), b = pf_ld_u4((const char *)&w.cold[h] + 16);
-					x_start = (int)b.x; x_type = (int)((a.w >> 8) & 0xffu);
+					x_start = (int)b.x; x_type = (int)((a.w >> 8) & 7u);
 					M = (int)(a.w >> 16);
 					if (x_start < 0) {                                      /* seed: row not cached in the label */
 						PfNodeView un = pf_load_node(P, u);
@@ -554,7 +565,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 				uint64_t hk = w.hot[h];
 				if (pf_int_as_float((int)(hk >> 32)) == pf_key_tot(k)) {   /* else stale: the node was re-labelled cheaper */
 					pf_u4 a = pf_ld_u4(&w.cold[h]), b = pf_ld_u4((const char *)&w.cold[h] + 16);
-					int es = (int)b.x, ty = (int)((a.w >> 8) & 0xffu);
+					int es = (int)b.x, ty = (int)((a.w >> 8) & 7u);
 					deg = (int)(a.w >> 16);
 					if (es < 0) {                                  /* seed: row not cached in the label */
 						PfNodeView un = pf_load_node(P, u);
@@ -629,7 +640,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 					}
 					tot = new_back + astar * pf_expected_cost(w, n.type, n.ci, n.xlow, n.xhigh, n.ylow, n.yhigh, tgt_xl, tgt_yl, crit, new_R);
 					back = new_back; R_up = new_R;
-					info = isw | (n.type << 8) | (n.num_edges << 16); es = n.edge_start;
+					info = isw | (n.type << 8) | ((n.occ >= n.cap) << PF_INFO_SEEN_FULL_BIT) | (n.num_edges << 16); es = n.edge_start;
 				}
 			}
 			int wr = pf_label_relax(w, valid, to, tot, back, R_up, u, info, es);
@@ -692,8 +703,9 @@ PF_DEV int pf_highfanout_rlim(PfWarp &w, int tree_n, int target_node) {
 /* Warp-collective occupancy change: the atomic on the node record (pathfinder_update_one_cost's occ += / -=,
  * route_common.c:542-578) and, on several GPUs, an entry in this rank's event log. */
 #define PF_EVENT_DEC 0x80000000u
-PF_DEV void pf_occ_change(const PfParams *P, int active, int v, int d) {
-	if (active) pf_atomic_add_i(&P->nodes[v].occ, d);
+PF_DEV int pf_occ_change(const PfParams *P, int active, int v, int d) {
+	int old = 0;
+	if (active) old = pf_atomic_add_i(&P->nodes[v].occ, d);
 	if (P->events) {
 		const unsigned m = pf_ballot(active);
 		if (m) {
@@ -707,12 +719,29 @@ PF_DEV void pf_occ_change(const PfParams *P, int active, int v, int d) {
 			}
 		}
 	}
+	return old;
+}
+
+/* Ripple re-routing: `victim` holds an rr node that the running net has just knowingly overfilled; queue it for a
+ * re-route in this same iteration (once per iteration).  Per-lane, no collectives. */
+PF_DEV void pf_queue_victim(const PfParams *P, int victim) {
+	if (pf_atomic_exch_i(&P->queued[victim], P->iter_tag) == P->iter_tag) return;    /* already (to be) routed in this iteration */
+	const int cls = P->net_big[victim] ? 1 : 0;
+	const int pos = pf_atomic_add_i(&P->vq_ctl[2 * cls + 1], 1);
+	if (pos < P->vq_cap) P->vq[cls][pos] = victim;
 }
 
 /* ------------------------------------------------------------------ back-trace + Elmore + commit
  * update_traceback (route_common.c:638) and update_route_tree (route_tree_timing.c:181-456).
- * Returns the tree index of the new SINK entry, or -1 on tree overflow. */
-PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
+ * Returns the tree index of the new SINK entry, or -1 on tree overflow.
+ *
+ * validate != 0: optimistic concurrency control.  The search priced every node with the occupancy it saw at that
+ * moment; a net in flight at the same time may have committed the same node since.  The commit's atomic returns the
+ * occupancy it found: if that is already at capacity although the search saw the node free (PF_INFO_SEEN_FULL in the
+ * label), the serial router would have seen the other net's commit and priced the node as congested.  The path is
+ * then taken back (-3) and the caller searches this sink again on the current occupancy — what the serial order
+ * "other net first, then this one" would have produced.  Knowingly shared nodes (seen full) never trigger it. */
+PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node, int validate) {
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	int tree_n = *tree_n_io;
@@ -729,7 +758,7 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
 			if (prev < 0 && v != target_node) { join = ~prev; break; }
 			if (prev < 0) { L = -1; break; }               /* target itself is a seed: cannot happen (SINKs are never seeds) */
 			if (L >= pcap) { L = -2; break; }
-			pathbuf[L] = v; pathbuf[pcap + L] = (int)(b.w & 0xffu);  /* switch used to enter v */
+			pathbuf[L] = v; pathbuf[pcap + L] = (int)(b.w & 0xfffu);  /* switch used to enter v | seen-full flag (bit 11) */
 			L++;
 			v = prev;
 		}
@@ -739,9 +768,10 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
 	if (tree_n + L > P->tree_cap) return -1;
 	pf_syncwarp();
 	/* materialise the entries in path order (join's child first, SINK last) */
+	int raced = 0;
 	for (int base = 0; base < L; base += PF_WARP) {
 		const int i = base + lane;
-		int v = 0;
+		int v = 0, cap = 0x7fffffff, fcap = 0x7fffffff;
 		if (i < L) {
 			v = pathbuf[L - 1 - i];
 			PfNodeView n = pf_load_node(P, v);
@@ -749,14 +779,35 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node) {
 			t.node = v; t.parent = (i == 0) ? join : tree_n + i - 1;
 			t.R_up = n.R; t.C_down = n.C; t.Tdel = 0.f;     /* R_up/C_down temporarily hold the node's own R and C */
 			t.xlow = (short)n.xlow; t.ylow = (short)n.ylow; t.xhigh = (short)n.xhigh; t.yhigh = (short)n.yhigh;
-			t.sw = (unsigned char)pathbuf[pcap + L - 1 - i];
+			t.sw = (unsigned char)(pathbuf[pcap + L - 1 - i] & 0xff);
+			if (!((pathbuf[pcap + L - 1 - i] >> PF_INFO_SEEN_FULL_BIT) & 1)) cap = n.cap;   /* seen free: a full node now is a race */
 			t.type_ci = (unsigned char)(n.type | (n.ci << 3));
 			t.flags = (n.type == 2 || n.type == 1) ? 0 : PF_TF_REEXPAND;   /* IPIN / SINK are not re-expanded */
 			t.pad = 0;
 			w.tree[tree_n + i] = t;
-			if (P->committer) P->committer[v] = w.cur_net;
+			if (P->committer) fcap = n.cap;
 		}
-		pf_occ_change(P, i < L, v, 1);                  /* commit: pathfinder_update_one_cost(+1) */
+		const int old = pf_occ_change(P, i < L, v, 1);  /* commit: pathfinder_update_one_cost(+1) */
+		if (validate) raced |= (i < L && old >= cap);
+		if (i < L && old >= fcap) pathbuf[pcap + L - 1 - i] |= 1 << 12;   /* now overfull: its holder becomes a victim below */
+	}
+	if (validate && pf_any(raced)) {
+		PF_COLD_LOOP for (int base = 0; base < L; base += PF_WARP) {
+			const int i = base + lane;
+			pf_occ_change(P, i < L, i < L ? pathbuf[L - 1 - i] : 0, -1);
+		}
+		pf_syncwarp();
+		return -3;
+	}
+	if (P->committer) {
+		/* this net now holds the path; whoever held a node that is overfull now is re-routed in this iteration */
+		PF_COLD_LOOP for (int base = 0; base < L; base += PF_WARP) {
+			const int i = base + lane;
+			if (i < L) {
+				const int prev = pf_atomic_exch_i(&P->committer[pathbuf[L - 1 - i]], w.cur_net);
+				if (P->vq_ctl && ((pathbuf[pcap + L - 1 - i] >> 12) & 1) && prev >= 0 && prev != w.cur_net) pf_queue_victim(P, prev);
+			}
+		}
 	}
 	pf_syncwarp();
 	if (lane == 0) {
@@ -909,7 +960,7 @@ PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0, int ns, int *sink
 		if (h < 0) { w.stale++; continue; }
 		if (pf_int_as_float((int)(w.hot[h] >> 32)) != pf_key_tot(mk)) { w.stale++; continue; }   /* re-labelled cheaper */
 		pf_u4 a = pf_ld_u4(&w.cold[h]), b = pf_ld_u4((const char *)&w.cold[h] + 16);
-		int x_start = (int)b.x, x_type = (int)((a.w >> 8) & 0xffu), M = (int)(a.w >> 16);
+		int x_start = (int)b.x, x_type = (int)((a.w >> 8) & 7u), M = (int)(a.w >> 16);
 		const float x_back = pf_int_as_float((int)a.x);
 		if (x_start < 0) { PfNodeView un = pf_load_node(P, u); x_start = un.edge_start; x_type = un.type; M = un.num_edges; }
 		w.pops++;
@@ -922,7 +973,7 @@ PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0, int ns, int *sink
 			if (dup > 1) return -2;
 			if (dup == 1) {
 				const int a0 = *tree_n_io;
-				const int si = pf_add_path(w, tree_n_io, u);
+				const int si = pf_add_path(w, tree_n_io, u, 0);
 				if (si < 0) { w.overflow |= PF_OVF_OTHER; return -1; }
 				if (lane == 0) { rt_of_sink[pin] = si; sink_done[pin] = 1; }
 				pf_syncwarp();
@@ -979,7 +1030,7 @@ PF_DEV void pf_swap_tables(PfWarp &w) {
 /* ------------------------------------------------------------------ one net
  * timing_driven_route_net, route_timing.c:399-563 */
 /* STRICT: 0 = delta buckets, 1 = strict best-first, 2 = breadth-first router (always strict order) */
-template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: routed, 0: handed to a bigger slot / failed */
+template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) {   /* 1: routed, 0: handed to a bigger slot / failed */
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	const int t0 = P->net_ptr[inet];
@@ -990,11 +1041,13 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 	w.overflow = 0;
 
 	/* rip-up: pathfinder_update_one_cost(trace_head[inet], -1) — one atomic per tree entry */
-	if (!P->skip_ripup) {
+	if (ripup) {
 		PfNetLoc loc = P->loc[inet];
 		PF_COLD_LOOP for (int base = 0; base < loc.count; base += PF_WARP) {
 			const int i = base + lane;
-			pf_occ_change(P, i < loc.count, i < loc.count ? P->pool[loc.off + i].node : 0, -1);
+			const int v = i < loc.count ? P->pool[loc.off + i].node : 0;
+			pf_occ_change(P, i < loc.count, v, -1);
+			if (P->committer && i < loc.count) pf_atomic_cas_i(&P->committer[v], inet, -1);   /* no longer the holder */
 		}
 	}
 	if (ns > P->sink_cap) { w.overflow = PF_OVF_OTHER; }
@@ -1061,7 +1114,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 			/* a search that outgrows the shared-memory label table runs again on this slot's fallback table in
 			 * global memory; the tables are swapped back before the next sink.  (One call site each for the search
 			 * and the back-trace: the kernel's instruction footprint matters, see DESIGN.md.) */
-			int r, swapped = 0;
+			int r, swapped = 0, si = 0, tries = P->validate;
 			for (;;) {
 				r = pf_search_sink<STRICT == 2 ? 1 : STRICT>(w, tree_n, target_node, crit, rlim);
 				if (r < 0 && !swapped && w.overflow == PF_OVF_LABELS && w.hot_alt) {
@@ -1070,10 +1123,12 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 					swapped = 1;
 					continue;
 				}
+				if (r > 0) {
+					si = pf_add_path(w, &tree_n, target_node, tries > 0);
+					if (si == -3) { tries--; w.races++; continue; }      /* lost a race for a node: search again on the current occupancy */
+				}
 				break;
 			}
-			int si = 0;
-			if (r > 0) si = pf_add_path(w, &tree_n, target_node);
 			if (swapped) pf_swap_tables(w);
 			if (r < 0) break;                                 /* overflow: retry in a bigger slot */
 			if (r == 0) { fail = PF_ST_UNROUTABLE; break; }
@@ -1085,11 +1140,17 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet) {   /* 1: rou
 
 	if (w.overflow || fail) {
 		/* undo this net's commits; it owns no routing until it is retried */
-		PF_COLD_LOOP for (int base = 0; base < tree_n; base += PF_WARP) { const int i = base + lane; pf_occ_change(P, i < tree_n, i < tree_n ? w.tree[i].node : 0, -1); }
+		PF_COLD_LOOP for (int base = 0; base < tree_n; base += PF_WARP) {
+			const int i = base + lane;
+			const int v = i < tree_n ? w.tree[i].node : 0;
+			pf_occ_change(P, i < tree_n, v, -1);
+			if (P->committer && i < tree_n) pf_atomic_cas_i(&P->committer[v], inet, -1);
+		}
 		if (lane == 0) {
 			P->loc[inet].off = 0; P->loc[inet].count = 0;
 			if (fail) { pf_atomic_add_i(P->status + 1, 1); pf_atomic_or_i(P->status, fail); P->status[2] = inet; }
-			else { int k = pf_atomic_add_i(P->retry_count, 1); P->retry_list[k] = inet; }
+			else if (P->hot) { pf_atomic_or_i(P->status, PF_ST_BIG_OVERFLOW); P->status[2] = inet; }   /* already in a big slot */
+			else { int k = pf_atomic_add_i(P->retry_count, 1); P->retry_list[k] = inet; if (P->net_big) P->net_big[inet] = 1; }
 		}
 		pf_syncwarp();
 		return 0;
@@ -1155,17 +1216,50 @@ template <int STRICT> PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIn
 	w.epoch = P->hot ? P->epochs[2 * slot] : 0;
 	w.round = 0;
 	for (int i = lane; i < PF_TICKETS; i += PF_WARP) w.ticket[i] = 0x7fffffff;
-	w.pops = w.pushes = w.visits = w.refills = w.stale = 0;
+	w.pops = w.pushes = w.visits = w.refills = w.stale = w.races = 0;
 	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.T_hi = 0.f; w.far_min = PF_INF_F; w.best = PF_INF_F; w.overflow = 0;
 	w.bb_xmin = w.bb_xmax = w.bb_ymin = w.bb_ymax = 0; w.num_sinks = 0;
 	pf_syncwarp();
 	unsigned long long nets = 0;
+	/* work: this launch's list first, then — with ripple re-routing — the victim queue of the slot class, until no warp is
+	 * routing any more (only a routing warp can produce victims) */
+	int *const vctl = P->vq_ctl;
+	int *const vq = vctl ? P->vq[P->vq_class] : NULL;
 	for (;;) {
-		int k = 0;
-		if (lane == 0) k = pf_atomic_add_i(P->work_head, 1);
-		k = pf_shfl_i(k, 0);
-		if (k >= P->num_work) break;
-		nets += (unsigned long long)pf_route_net<STRICT>(w, P->work[k]);
+		int net = -1, ripup = !P->skip_ripup;
+		if (lane == 0) {
+			if (vctl) { pf_atomic_add_i(&vctl[4], 1); pf_threadfence(); }      /* counted as routing before the claim is visible */
+			const int k = pf_atomic_add_i(P->work_head, 1);
+			const int nw = P->num_work_ptr ? pf_ld_volatile_i(P->num_work_ptr) : P->num_work;
+			if (k < nw) net = P->work[k];
+			else if (vctl) { pf_atomic_add_i(&vctl[4], -1); net = -2; }
+		}
+		net = pf_shfl_i(net, 0);
+		while (net == -2) {                                    /* collective spin: one shuffle per turn */
+			int got = -2;
+			if (lane == 0) {
+				const int routing = pf_ld_volatile_i(&vctl[4]);
+				pf_threadfence();
+				const int h = pf_ld_volatile_i(&vctl[2 * P->vq_class]);
+				int t = pf_ld_volatile_i(&vctl[2 * P->vq_class + 1]);
+				if (t > P->vq_cap) t = P->vq_cap;
+				if (h < t) {
+					pf_atomic_add_i(&vctl[4], 1);
+					if (pf_atomic_cas_i(&vctl[2 * P->vq_class], h, h + 1) == h) {
+						int v;
+						while ((v = pf_ld_volatile_i(&vq[h])) < 0) pf_spin_pause();   /* the producer's store is a few cycles behind its ticket */
+						vq[h] = -1;
+						got = v;
+					} else pf_atomic_add_i(&vctl[4], -1);
+				} else if (routing == 0) got = -1;
+			}
+			net = pf_shfl_i(got, 0);
+			if (net == -2) pf_spin_pause();
+			else if (net >= 0) ripup = 1;                       /* a victim still owns its old route */
+		}
+		if (net < 0) break;
+		nets += (unsigned long long)pf_route_net<STRICT>(w, net, ripup);
+		if (vctl && lane == 0) { pf_threadfence(); pf_atomic_add_i(&vctl[4], -1); }
 	}
 	if (lane == 0) {
 		if (P->hot) P->epochs[2 * slot] = w.epoch;
@@ -1175,6 +1269,7 @@ template <int STRICT> PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIn
 		pf_atomic_add_ull(&P->stats->visits, w.visits);
 		pf_atomic_add_ull(&P->stats->refills, w.refills);
 		pf_atomic_add_ull(&P->stats->stale, w.stale);
+		if (w.races) pf_atomic_add_ull(&P->stats->races, w.races);
 		pf_atomic_add_ull(&P->stats->nets, nets);
 	}
 }
@@ -1194,6 +1289,14 @@ PF_DEV int pf_update_cost_one(PfNode *nodes, int i, float acc_fac, unsigned char
 		return 1;
 	}
 	return 0;
+}
+
+/* wirelength this rr node contributes to the routing in place: occupancy x length for CHANX / CHANY (stats.c:355-409
+ * counts a wire once per net using it) */
+PF_DEV unsigned pf_node_wirelength_in_use(const PfNode *n) {
+	const int ty = n->type_ci & 7;
+	if ((ty == 4 || ty == 5) && n->occ > 0) return (unsigned)n->occ * (unsigned)(1 + n->xhigh - n->xlow + n->yhigh - n->ylow);
+	return 0u;
 }
 
 PF_DEV unsigned pf_tree_wirelength_one(const PfTreeNode *t) {

@@ -69,6 +69,17 @@ struct pf_router {
 	int K1;                           /* number of interior nets at the head of all_nets */
 	int n1_small, n1_big;             /* interior nets at the head of this iteration's two work lists */
 	float win_abs_auto;
+	int *vq[2]; int *queued; int vq_cap;   /* ripple re-routing: victim queues per slot class, per-net iteration tags */
+	char *h_ctl;                          /* pinned host copy of the control block (fetch_ctl) */
+	PfStats h_stats, h_stats_seen;        /* counters of the running iteration / what the step API has reported of them */
+	bool sel_valid, sel_pending;          /* the next iteration's work lists and counts are already on the device / in h_ctl */
+	std::vector<int> h_list_small, h_list_big;
+	long long h_wl_used; unsigned xchg_seq;
+	std::vector<float> crit_hist;        /* criticalities per iteration of the last pf_route_run with a host analysis */
+	int comm_ready;                      /* pf_comm_init done */
+	unsigned char *xreg; size_t xreg_bytes; unsigned char xhandle[64]; PfPeers peers; unsigned char *term_owner; unsigned dseq;   /* exchange region (pf_layout.h) */
+	bool force_all_once;                  /* the next iteration re-routes every net (polish pass) */
+	bool iter_all;                        /* the running iteration re-routes every net */
 };
 
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }

@@ -100,6 +100,8 @@ static void *pinned_get(int which, size_t bytes) {
 	g_pinned_bytes[which] = want;
 	return g_pinned[which];
 }
+void *pfb_host_alloc(size_t bytes) { void *p = NULL; if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return NULL; } return p; }
+void pfb_host_free(void *p) { if (p) cudaFreeHost(p); }
 void *pfb_pinned(size_t bytes) { return pinned_get(0, bytes); }
 void *pfb_pinned_upload(size_t bytes) { return pinned_get(1, bytes); }
 int pfb_h2d_async(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); return 0; }
@@ -107,6 +109,7 @@ int pfb_d2h_async(void *dst, const void *src, size_t bytes) { if (!bytes) return
 int pfb_h2d(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); CK(cudaStreamSynchronize(g_stream)); return 0; }
 int pfb_d2h(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); CK(cudaStreamSynchronize(g_stream)); return 0; }
 int pfb_d2d(void *dst, const void *src, size_t bytes) { if (!bytes) return 0; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream)); return 0; }
+int pfb_fill(void *dst, int byte, size_t bytes) { if (!bytes) return 0; CK(cudaMemsetAsync(dst, byte, bytes, g_stream)); return 0; }
 int pfb_zero(void *dst, size_t bytes) { if (!bytes) return 0; CK(cudaMemsetAsync(dst, 0, bytes, g_stream)); return 0; }
 
 static int drain_events(void) {
@@ -187,12 +190,19 @@ template <int STRICT> __global__ void __launch_bounds__(128, 5) pf_route_kernel(
 }
 
 __global__ void pf_update_cost_kernel(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
-		unsigned char *last_over, int iter_tag) {
+		unsigned char *last_over, int iter_tag, unsigned long long *d_wl_used) {
 	int over = 0;
-	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x))
+	unsigned wl = 0;
+	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x)) {
 		over += pf_update_cost_one(nodes, i, acc_fac, last_over, iter_tag);
+		wl += pf_node_wirelength_in_use(&nodes[i]);
+	}
 	over = __reduce_add_sync(0xffffffffu, over);
-	if ((threadIdx.x & 31u) == 0 && over) atomicAdd(d_overused, over);
+	wl = __reduce_add_sync(0xffffffffu, wl);
+	if ((threadIdx.x & 31u) == 0) {
+		if (over) atomicAdd(d_overused, over);
+		if (wl && d_wl_used) atomicAdd(d_wl_used, (unsigned long long)wl);
+	}
 }
 
 /* another rank's event log: one atomic per event on the node records */
@@ -245,13 +255,15 @@ __global__ void pf_reserve_opins_kernel(PfNode *nodes, const uint32_t *edges, co
 #define PF_SEL_BLOCK 256
 __global__ void __launch_bounds__(PF_SEL_BLOCK) pf_select_flag_kernel(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc,
 		const int *all_nets, int num_all, const unsigned char *net_big, int force_all, unsigned char *flag, int *block_counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer, int head_count, int *counts) {
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int head_count, int *counts,
+		int *queued, int queued_tag) {
 	int k = (int)(blockIdx.x * PF_SEL_BLOCK + threadIdx.x);
 	int f = 0;
 	if (k < num_all) {
 		int net = all_nets[k];
 		if (force_all || pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net)) f = net_big[net] ? 2 : 1;
 		flag[k] = (unsigned char)f;
+		if (f && queued) queued[net] = queued_tag;
 	}
 	int cs = __syncthreads_count(f == 1), cb = __syncthreads_count(f == 2);
 	int hs = __syncthreads_count(f == 1 && k < head_count), hb = __syncthreads_count(f == 2 && k < head_count);
@@ -421,6 +433,112 @@ __global__ void pf_check_occ_kernel(const PfNode *nodes, int num_nodes, const in
 	}
 }
 
+
+/* ------------------------------------------------------------------ multi-GPU exchange over peer memory (NVLink / NVSwitch)
+ * One process per GPU; every rank's exchange region (PfXchgHeader + event logs + published delays) is mapped into the
+ * others through CUDA IPC.  A rank publishes by writing the payload, a system-scope fence and a release store of the
+ * sequence number; consumers poll the sequence number with acquire loads over NVLink and then read the payload straight
+ * out of the producer's memory (volatile loads: nothing of a previous round can be served from this SM's L1).  The host
+ * never waits: the kernels are stream-ordered behind the route kernels that produce the logs. */
+static __device__ __forceinline__ unsigned pf_ld_acquire_sys(const unsigned *p) {
+	unsigned v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+static __device__ __forceinline__ void pf_st_release_sys(unsigned *p, unsigned v) {
+	asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+static __device__ __forceinline__ unsigned long long pf_globaltimer(void) {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+static __device__ __forceinline__ uint4 pf_ld_volatile_u4(const void *p) {
+	uint4 v;
+	asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+	return v;
+}
+/* thread 0 of a CTA waits until *flag has reached `want` (wrap-safe), the peer aborted, or the timeout ran out */
+static __device__ int pf_wait_flag(const unsigned *flag, unsigned want, const PfXchgHeader *peer, int *status, unsigned long long timeout_ns) {
+	const unsigned long long t0 = pf_globaltimer();
+	while ((int)(pf_ld_acquire_sys(flag) - want) < 0) {
+		if (*(const volatile unsigned *)&peer->abort_flag) { atomicOr(status, PF_ST_COMM_ABORT); return 0; }
+		if (pf_globaltimer() - t0 > timeout_ns) { atomicOr(status, PF_ST_COMM_TIMEOUT); return 0; }
+		__nanosleep(64);
+	}
+	return 1;
+}
+
+__global__ void __launch_bounds__(256) pf_xchg_events_kernel(PfNode *nodes, const __grid_constant__ PfPeers peers, int me, int nranks, unsigned seq,
+		const unsigned long long *event_head, long long event_cap, int *status, unsigned long long timeout_ns) {
+	const int buf = (int)((seq - 1u) & 1u);
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		PfXchgHeader *mine = (PfXchgHeader *)peers.base[me];
+		unsigned long long c = *event_head;
+		if ((long long)c > event_cap) c = (unsigned long long)event_cap;      /* the overflow itself is reported by the host */
+		mine->count[buf] = c;
+		__threadfence_system();
+		pf_st_release_sys(&mine->seq[buf], seq);
+	}
+	__shared__ unsigned long long s_count;
+	__shared__ int s_ok;
+	for (int d = 1; d < nranks; d++) {
+		const int k = (me + d) % nranks;
+		const PfXchgHeader *ph = (const PfXchgHeader *)peers.base[k];
+		if (threadIdx.x == 0) {
+			const int ok = pf_wait_flag(&ph->seq[buf], seq, ph, status, timeout_ns);
+			s_ok = ok;
+			s_count = ok ? *(const volatile unsigned long long *)&ph->count[buf] : 0ull;
+		}
+		__syncthreads();
+		if (!s_ok) return;
+		const long long cnt = (long long)s_count;
+		const unsigned *log = (const unsigned *)(peers.base[k] + PF_XCHG_HEADER_BYTES) + (size_t)buf * (size_t)event_cap;
+		for (long long i = 4ll * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i < cnt; i += 4ll * (long long)gridDim.x * blockDim.x) {
+			const uint4 e = pf_ld_volatile_u4(log + i);
+			const unsigned ev[4] = { e.x, e.y, e.z, e.w };
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+				if (i + q < cnt) atomicAdd(&nodes[ev[q] & ~PF_EVENT_DEC].occ, (ev[q] & PF_EVENT_DEC) ? -1 : 1);
+		}
+		__syncthreads();
+	}
+}
+
+/* step 1 of the delay exchange: this rank's sink delays into its published buffer */
+__global__ void pf_xchg_delays_publish_kernel(const float *net_delay, const unsigned char *term_owner, int num_terminals, float *pub, int me) {
+	for (int t = (int)(blockIdx.x * blockDim.x + threadIdx.x); t < num_terminals; t += (int)(gridDim.x * blockDim.x))
+		if (term_owner[t] == me) pub[t] = net_delay[t];
+}
+/* step 2: release the buffer, wait for the peers', take the delays of the nets they route */
+__global__ void __launch_bounds__(256) pf_xchg_delays_gather_kernel(float *net_delay, const unsigned char *term_owner, int num_terminals,
+		const __grid_constant__ PfPeers peers, int me, int nranks, unsigned dseq, long long event_cap, int *status, unsigned long long timeout_ns) {
+	const int buf = (int)((dseq - 1u) & 1u);
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		PfXchgHeader *mine = (PfXchgHeader *)peers.base[me];
+		__threadfence_system();
+		pf_st_release_sys(&mine->dseq[buf], dseq);
+	}
+	__shared__ int s_ok;
+	if (threadIdx.x == 0) {
+		int ok = 1;
+		for (int d = 1; d < nranks && ok; d++) {
+			const PfXchgHeader *ph = (const PfXchgHeader *)peers.base[(me + d) % nranks];
+			ok = pf_wait_flag(&ph->dseq[buf], dseq, ph, status, timeout_ns);
+		}
+		s_ok = ok;
+	}
+	__syncthreads();
+	if (!s_ok) return;
+	const size_t off = PF_XCHG_HEADER_BYTES + 8 * (size_t)event_cap + sizeof(float) * (size_t)buf * (size_t)num_terminals;
+	for (int t = (int)(blockIdx.x * blockDim.x + threadIdx.x); t < num_terminals; t += (int)(gridDim.x * blockDim.x)) {
+		const int k = term_owner[t];
+		if (k != me && k < nranks) net_delay[t] = *(const volatile float *)((const float *)(peers.base[k] + off) + t);
+	}
+}
+
+__global__ void pf_xchg_abort_kernel(PfXchgHeader *mine) { mine->abort_flag = 1u; __threadfence_system(); }
+
 /* ------------------------------------------------------------------ launchers */
 int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	if (warps_per_block < 1) warps_per_block = 1;
@@ -449,9 +567,10 @@ static int stream_grid(long long n) {
 	return (int)b;
 }
 
-int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, unsigned char *last_over, int iter_tag) {
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, unsigned char *last_over, int iter_tag,
+		unsigned long long *d_wl_used) {
 	if (ev_begin(1) != 0) return -1;
-	pf_update_cost_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, acc_fac, d_overused, last_over, iter_tag);
+	pf_update_cost_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, acc_fac, d_overused, last_over, iter_tag, d_wl_used);
 	return ev_end();
 }
 
@@ -480,7 +599,8 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
 
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count) {
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count,
+		int *queued, int queued_tag) {
 	if (cudaMemsetAsync(counts, 0, sizeof(int) * 4, g_stream) != cudaSuccess) return -1;
 	if (num_all <= 0) return 0;
 	/* scratch: [2 ints per CTA][one flag byte per net] — pfb_select_scratch_bytes() */
@@ -488,7 +608,7 @@ int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const Pf
 	unsigned char *flag = (unsigned char *)(scratch + 2 * (size_t)blocks);
 	if (ev_begin(2) != 0) return -1;
 	pf_select_flag_kernel<<<blocks, PF_SEL_BLOCK, 0, g_stream>>>(nodes, pool, loc, all_nets, num_all, net_big, force_all, flag, scratch,
-			last_over, iter_tag, window, committer, head_count, counts);
+			last_over, iter_tag, window, committer, head_count, counts, queued, queued_tag);
 	pf_select_scatter_kernel<<<blocks, PF_SEL_BLOCK, 0, g_stream>>>(all_nets, num_all, flag, scratch, list_small, list_big, counts);
 	return ev_end();
 }
@@ -518,6 +638,55 @@ int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num
 	if (ev_begin(2) != 0) return -1;
 	pf_build_traces_kernel<<<(num_nets + 127) / 128, 128, 0, g_stream>>>(pool, loc, num_nets, len, tptr, trace_node, trace_switch, d_wl, trace_term, ptc, nx);
 	return ev_end();
+}
+
+
+/* ------------------------------------------------------------------ exchange launchers / IPC memory */
+void *pfb_ipc_alloc(size_t bytes, void *handle64) {
+	void *p = NULL;
+	if (cudaMalloc(&p, bytes) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMalloc(%zu) for the exchange region failed", bytes); cudaGetLastError(); return NULL; }
+	if (cudaMemsetAsync(p, 0, PF_XCHG_HEADER_BYTES, g_stream) != cudaSuccess || cudaStreamSynchronize(g_stream) != cudaSuccess
+			|| cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, p) != cudaSuccess) {
+		snprintf(g_err, sizeof(g_err), "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+		cudaFree(p);
+		return NULL;
+	}
+	return p;
+}
+void *pfb_ipc_open(const void *handle64) {
+	void *p = NULL;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof(h));
+	cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+	if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return NULL; }
+	return p;
+}
+void pfb_ipc_close(void *p) { if (p) cudaIpcCloseMemHandle(p); }
+void pfb_ipc_free(void *p) { if (p) { cudaStreamSynchronize(g_stream); cudaFree(p); } }
+
+int pfb_launch_xchg_events(PfNode *nodes, const PfPeers *peers, int me, int nranks, unsigned seq, const unsigned long long *event_head,
+		long long event_cap, int *status, double timeout_s) {
+	if (ev_begin(2) != 0) return -1;
+	const int grid = (g_sms > 0 ? g_sms : 148) * 2;
+	pf_xchg_events_kernel<<<grid, 256, 0, g_stream>>>(nodes, *peers, me, nranks, seq, event_head, event_cap, status, (unsigned long long)(timeout_s * 1e9));
+	return ev_end();
+}
+
+int pfb_launch_xchg_delays(float *net_delay, const unsigned char *term_owner, int num_terminals, const PfPeers *peers, int me, int nranks,
+		unsigned dseq, long long event_cap, int *status, double timeout_s) {
+	if (ev_begin(2) != 0) return -1;
+	const int buf = (int)((dseq - 1u) & 1u);
+	float *pub = (float *)(peers->base[me] + PF_XCHG_HEADER_BYTES + 8 * (size_t)event_cap) + (size_t)buf * (size_t)num_terminals;
+	pf_xchg_delays_publish_kernel<<<stream_grid(num_terminals), 256, 0, g_stream>>>(net_delay, term_owner, num_terminals, pub, me);
+	pf_xchg_delays_gather_kernel<<<(g_sms > 0 ? g_sms : 148) * 2, 256, 0, g_stream>>>(net_delay, term_owner, num_terminals, *peers, me, nranks, dseq,
+			event_cap, status, (unsigned long long)(timeout_s * 1e9));
+	return ev_end();
+}
+
+int pfb_launch_xchg_abort(const PfPeers *peers, int me) {
+	pf_xchg_abort_kernel<<<1, 1, 0, g_stream>>>((PfXchgHeader *)peers->base[me]);
+	CK(cudaGetLastError());
+	return 0;
 }
 
 /* ------------------------------------------------------------------ static timing analysis launchers

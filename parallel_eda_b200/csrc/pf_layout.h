@@ -81,8 +81,11 @@ struct PfNetLoc { int off, count; };   /* a net's tree in the route store */
 #define PF_ST_POOL_OVERFLOW 2
 #define PF_ST_INTERNAL 4
 #define PF_ST_TWICE_TO_SINK_BF 8   /* breadth-first mode met a net with two pins on one SINK (route_breadth_first.c:208-256) */
+#define PF_ST_BIG_OVERFLOW 16      /* a net outgrew the scratch of a big slot */
+#define PF_ST_COMM_TIMEOUT 32      /* multi-GPU exchange: a peer never published its event log */
+#define PF_ST_COMM_ABORT 64        /* multi-GPU exchange: a peer reported a failure */
 
-struct PfStats { unsigned long long pops, pushes, visits, refills, nets, label_probes, stale; unsigned long long pad; };
+struct PfStats { unsigned long long pops, pushes, visits, refills, nets, label_probes, stale; unsigned long long races; };
 
 struct PfParams {
 	PfNode *nodes;
@@ -93,6 +96,8 @@ struct PfParams {
 	/* nets */
 	const int *net_ptr; const int *net_term; const int *net_bb;   /* bb: xmin,xmax,ymin,ymax */
 	const int *work; int num_work; int *work_head;
+	const int *num_work_ptr;   /* non-NULL: the length of `work` is read from device memory (the retry launch: nets that
+	                              overflowed a regular slot, counted by the launch before it) */
 	const float *crit;     /* [num_terminals] timing criticality per terminal */
 	float *net_delay;      /* [num_terminals] */
 	/* options */
@@ -103,6 +108,8 @@ struct PfParams {
 	int algorithm;         /* 0 = timing-driven (route_timing.c), 1 = breadth-first (route_breadth_first.c) */
 	int max_batch;
 	int skip_ripup;
+	int validate;          /* > 0: a path whose commit finds a node full that its search saw free is taken back and the sink
+	                          searched again, at most this many times per sink (optimistic concurrency control) */
 	/* per-warp slot memory */
 	uint64_t *hot;         /* global hot tables (NULL: the hot table lives in shared memory) */
 	PfCold *cold; int label_log2;
@@ -119,12 +126,40 @@ struct PfParams {
 	/* multi-GPU: every occupancy change this rank makes is also logged (node id, bit 31 = decrement) so that the
 	 * other ranks can replay it; NULL on one GPU */
 	unsigned *events; unsigned long long *event_head; long long event_cap;
-	int *committer;        /* [num_nodes] net that committed this rr node last (re-route selection), may be NULL */
+	int *committer;        /* [num_nodes] net that committed this rr node last and still holds it, -1 none; may be NULL */
+	/* ripple re-routing (NULL = off): a commit that knowingly shares a full rr node pushes the net holding it (committer[])
+	 * onto the victim queue of that net's slot class, and the warps of this iteration's launches drain the queues after
+	 * their own work list: the chain "A displaces B, B displaces C" is followed inside ONE PathFinder iteration, as in the
+	 * serial reference, where every net is re-routed in every iteration (route_timing.c:161-183).  A net is queued at most
+	 * once per iteration (queued[net] == iter_tag). */
+	int *vq[2];            /* [vq_cap] victim queues of the regular / big slot class; -1 = empty entry */
+	int *vq_ctl;           /* [0] head, [1] tail of vq[0]; [2] head, [3] tail of vq[1]; [4] warps routing a net right now */
+	int vq_cap; int vq_class;   /* which queue this launch drains */
+	int *queued; int iter_tag;
+	unsigned char *net_big;    /* [num_nets] slot class of a net (written when a net moves to the big slots) */
 	/* status */
 	int *status;
 	int *retry_list; int *retry_count;
 	PfStats *stats;
 };
+
+/* ------------------------------------------------------------------ multi-GPU exchange region (one per rank)
+ * A single allocation that the other ranks of the node map through CUDA IPC and read over NVLink / NVSwitch:
+ *   PfXchgHeader | occupancy event log [2][event_cap] u32 | published sink delays [2][num_terminals] f32
+ * Both payloads are double-buffered by the parity of their sequence number: a rank can only publish number s+2 after it
+ * has consumed every peer's s+1, which the peers published after consuming its s — so buffer s & 1 is never rewritten
+ * while somebody still reads it, without any acknowledgement traffic. */
+#define PF_XCHG_MAX_RANKS 8
+#define PF_XCHG_HEADER_BYTES 128
+struct PfXchgHeader {
+	unsigned seq[2];               /* seq[b] = number of the last exchange published in log buffer b (release-stored last) */
+	unsigned dseq[2];              /* same for the delay buffers */
+	unsigned abort_flag;           /* non-zero: this rank failed; peers stop waiting */
+	unsigned pad0[3];
+	unsigned long long count[2];   /* events in log buffer b */
+	unsigned long long pad1[10];
+};
+struct PfPeers { unsigned char *base[PF_XCHG_MAX_RANKS]; };
 
 /* device image of the timing graph for the static timing analysis (pf_sta_device.cuh, pf_sta.cpp) */
 struct PfStaDev {

@@ -60,6 +60,37 @@ static bool problem_nets_ok(const pf_problem *p) {
 	return true;
 }
 
+/* ------------------------------------------------------------------ the device control block
+ * One 512-byte block holds every small counter the host reads, so that a PathFinder iteration costs ONE read
+ * (fetch_ctl) however many kernels it launched:
+ *   iteration scope (zeroed by pf_iteration_begin)
+ *     [0]   status[8]        error bits, failed-net count, offending net
+ *     [32]  PfStats          pops / pushes / visits / nets ... accumulated over the iteration's launches
+ *   written once per iteration by their kernels
+ *     [96]  sel_counts[4]    lengths of the two work lists of the NEXT iteration (pf_select_*), interior heads
+ *     [112] overused[4]      feasible_routing's count
+ *     [128] wl[2]            [0] wirelength of this rank's trees, [1] wirelength in use on the fabric (from occupancy)
+ *   part scope (zeroed before every route part)
+ *     [160] retry_count[4]   nets that outgrew a regular slot in this part
+ *     [176] heads of the regular / big / retry work queues (4 ints each)
+ *     [224] victim-queue heads, tails, routing-warp count (8 ints)
+ *     [256] event_head       multi-GPU: length of this part's occupancy event log
+ *   persistent
+ *     [272] pool_head[2]     route-store log head */
+enum { CTL_STATUS = 0, CTL_STATS = 32, CTL_SEL = 96, CTL_OVER = 112, CTL_WL = 128, CTL_PART = 160, CTL_RETRY = 160, CTL_HEAD_SMALL = 176,
+	CTL_HEAD_BIG = 192, CTL_HEAD_RETRY = 208, CTL_VQ = 224, CTL_EVENTS = 256, CTL_PART_END = 272, CTL_POOL = 272, CTL_BYTES = 512 };
+
+static void bind_ctl(pf_router *r) {
+	r->status = (int *)(r->ctl + CTL_STATUS);
+	r->stats = (PfStats *)(r->ctl + CTL_STATS);
+	r->sel_counts = (int *)(r->ctl + CTL_SEL);
+	r->d_overused = (int *)(r->ctl + CTL_OVER);
+	r->d_wl = (unsigned long long *)(r->ctl + CTL_WL);
+	r->retry_count = (int *)(r->ctl + CTL_RETRY);
+	r->small.work_head = (int *)(r->ctl + CTL_HEAD_SMALL); r->big.work_head = (int *)(r->ctl + CTL_HEAD_BIG);
+	r->pool_head = (unsigned long long *)(r->ctl + CTL_POOL);
+}
+
 static int ceil_log2(long long v) { int l = 0; while ((1ll << l) < v) l++; return l; }
 
 static void free_slot_class(SlotClass &s) {
@@ -99,8 +130,9 @@ extern "C" void pf_router_destroy(pf_router *r) {
 	free_slot_class(r->small); free_slot_class(r->big);
 	pfb_free(r->pool[0]); pfb_free(r->pool[1]); pfb_free(r->loc);
 	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->retry_work); pfb_free(r->sel_scratch); pfb_free(r->ptc);
-	pfb_free(r->ctl); pfb_free(r->retry_list); pfb_free(r->last_over); pfb_free(r->committer);
-	pfb_free(r->events);
+	pfb_free(r->ctl); pfb_host_free(r->h_ctl); pfb_free(r->retry_list); pfb_free(r->last_over); pfb_free(r->committer);
+	for (int k = 0; k < PF_XCHG_MAX_RANKS; k++) if (r->peers.base[k] && r->peers.base[k] != r->xreg) pfb_ipc_close(r->peers.base[k]);
+	pfb_ipc_free(r->xreg); pfb_free(r->term_owner); pfb_free(r->vq[0]); pfb_free(r->vq[1]); pfb_free(r->queued);
 	pfb_free(r->g_source); pfb_free(r->g_count); pfb_free(r->g_off); pfb_free(r->g_chosen);
 	delete r;
 }
@@ -231,7 +263,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->best_overused = 0x7fffffff; r->stall_count = 0; r->since_full = 0; r->last_over = NULL; r->cost_updates = 0; r->committer = NULL; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
 	r->events = NULL; r->event_cap = 0; r->h_events = 0; r->graph_ready = 1; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
-	r->h2d_bytes = r->d2h_bytes = 0;
+	r->h2d_bytes = r->d2h_bytes = 0; r->vq[0] = r->vq[1] = NULL; r->queued = NULL; r->vq_cap = 0; r->iter_all = true; r->force_all_once = false; r->h_ctl = NULL; r->xreg = NULL; r->xreg_bytes = 0; r->term_owner = NULL; r->comm_ready = 0; r->dseq = 0; memset(&r->peers, 0, sizeof(r->peers)); memset(r->xhandle, 0, sizeof(r->xhandle)); r->sel_valid = r->sel_pending = false; r->xchg_seq = 0; r->h_wl_used = 0;
+	memset(&r->h_stats, 0, sizeof(PfStats)); memset(&r->h_stats_seen, 0, sizeof(PfStats));
 
 	int sms = pfb_num_sms();
 	if (c.warps_per_block <= 0) c.warps_per_block = 4;
@@ -254,6 +287,10 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.history_window < 0) c.history_window = 0;   /* 0 = off (default) */
 	if (c.keep_newcomer < 0) c.keep_newcomer = 0;     /* 0 = off (default): measured on B200 it costs ~8 % wirelength and does
 	                                                    not shorten the tight-W tail */
+	if (c.ripple == 0) c.ripple = 1;
+	if (c.ripple < 0) c.ripple = 0;
+	if (c.validate_commits == 0) c.validate_commits = 2;
+	if (c.validate_commits < 0) c.validate_commits = 0;
 	if (c.max_batch > PF_MAX_BATCH) c.max_batch = PF_MAX_BATCH;
 	if (c.max_batch < 0) c.max_batch = 0;
 
@@ -315,7 +352,9 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			const bool right_ok = s == c.nranks - 1 || xmax <= cut[s + 1];
 			if (left_ok && right_ok) continue;
 			cut_net[i] = 1;
-			owner[i] = right_ok ? s : s + 1;        /* the rank that owns the violated cut (cut k belongs to rank k) */
+			owner[i] = right_ok ? s : s + 1;        /* the rank that owns the violated cut (cut k belongs to rank k).  Sharing a cut's
+			                                          * nets between its two neighbours was tried: two ranks then route overlapping nets on
+			                                          * stale views of each other, and on a small fabric the negotiation oscillates for ever */
 		}
 	}
 	r->net_owner = owner; r->net_cut = cut_net;
@@ -452,28 +491,43 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	 *   [0] status[8] [32] retry_count[4] [48] sel_counts[4] [64] overused[4] [80] wl[2] [96] PfStats
 	 *   [160] small.work_head[4] [176] big.work_head[4] | [192] pool_head[2] (not cleared per iteration)
 	 *   [208] event_head (multi-GPU; cleared at the start of every route part) */
-	r->ctl = (char *)pfb_alloc(256);
-	if (!r->ctl) { pf_router_destroy(r); CUDA_FAIL(); }
-	r->pool_head = (unsigned long long *)(r->ctl + 192);
-	r->status = (int *)(r->ctl + 0);
+	r->ctl = (char *)pfb_alloc(CTL_BYTES);
+	r->h_ctl = (char *)pfb_host_alloc(CTL_BYTES);
+	if (!r->ctl || !r->h_ctl) { pf_router_destroy(r); CUDA_FAIL(); }
+	memset(r->h_ctl, 0, CTL_BYTES);
+	pfb_free(r->small.work_head); pfb_free(r->big.work_head);
+	bind_ctl(r);
 	r->retry_list = (int *)pfb_alloc_raw(sizeof(int) * (size_t)std::max(nwork, 1));
 	r->last_over = (unsigned char *)pfb_alloc((size_t)r->N);
-	r->committer = c.keep_newcomer ? (int *)pfb_alloc_raw(sizeof(int) * (size_t)r->N) : NULL;
-	r->retry_count = (int *)(r->ctl + 32);
+	r->committer = (c.keep_newcomer || c.ripple > 0) ? (int *)pfb_alloc_raw(sizeof(int) * (size_t)r->N) : NULL;
+	if (r->committer && pfb_fill(r->committer, 0xff, sizeof(int) * (size_t)r->N)) { pf_router_destroy(r); CUDA_FAIL(); }
+	if (c.ripple > 0) {
+		r->vq_cap = std::max(nwork, 1);
+		for (int k = 0; k < 2; k++) {
+			r->vq[k] = (int *)pfb_alloc_raw(sizeof(int) * (size_t)r->vq_cap);
+			if (!r->vq[k] || pfb_fill(r->vq[k], 0xff, sizeof(int) * (size_t)r->vq_cap)) { pf_router_destroy(r); CUDA_FAIL(); }
+		}
+		r->queued = (int *)pfb_alloc(sizeof(int) * (size_t)std::max(r->n, 1));
+		if (!r->queued) { pf_router_destroy(r); CUDA_FAIL(); }
+	}
 	r->retry_work = (int *)pfb_alloc_raw(sizeof(int) * (size_t)std::max(nwork, 1));
-	r->stats = (PfStats *)(r->ctl + 96);
-	r->d_overused = (int *)(r->ctl + 64);
-	r->d_wl = (unsigned long long *)(r->ctl + 80);
-	r->sel_counts = (int *)(r->ctl + 48);
-	pfb_free(r->small.work_head); pfb_free(r->big.work_head);
-	r->small.work_head = (int *)(r->ctl + 160); r->big.work_head = (int *)(r->ctl + 176);
 	if (!r->retry_list || !r->retry_work || !r->last_over) { pf_router_destroy(r); CUDA_FAIL(); }
 	if (c.nranks > 1) {
 		/* one event per occupancy change: a route part rips up at most the live trees and commits at most what
-		 * the route store can still take, so twice the store's capacity cannot overflow before the store does */
-		r->event_cap = 2 * r->pool_cap;
-		r->events = (unsigned *)pfb_alloc_raw(sizeof(unsigned) * (size_t)r->event_cap);
-		if (!r->events) { pf_router_destroy(r); CUDA_FAIL(); }
+		 * the route store can still take, so twice the store's capacity cannot overflow before the store does.
+		 * The log lives in this rank's exchange region (PfXchgHeader, pf_layout.h), which the other ranks map through
+		 * CUDA IPC (pf_comm_export / pf_comm_init) and read over NVLink. */
+		if (c.nranks > PF_XCHG_MAX_RANKS) { pf_router_destroy(r); FAILF(PF_EINVAL, "at most %d ranks (one node)", PF_XCHG_MAX_RANKS); }
+		r->event_cap = (2 * r->pool_cap + 3) & ~3ll;
+		r->xreg_bytes = PF_XCHG_HEADER_BYTES + 8 * (size_t)r->event_cap + 2 * sizeof(float) * (size_t)std::max(r->T, 1);
+		r->xreg = (unsigned char *)pfb_ipc_alloc(r->xreg_bytes, r->xhandle);
+		if (!r->xreg) { pf_router_destroy(r); CUDA_FAIL(); }
+		r->events = (unsigned *)(r->xreg + PF_XCHG_HEADER_BYTES);
+		r->peers.base[c.rank] = r->xreg;
+		std::vector<unsigned char> to((size_t)std::max(r->T, 1), 255);
+		for (int i = 0; i < r->n; i++) for (int k = p->net_ptr[i]; k < p->net_ptr[i + 1]; k++) to[(size_t)k] = (unsigned char)owner[(size_t)i];
+		r->term_owner = (unsigned char *)pfb_alloc((size_t)std::max(r->T, 1));
+		if (!r->term_owner || pfb_h2d(r->term_owner, to.data(), (size_t)r->T)) { pf_router_destroy(r); CUDA_FAIL(); }
 	}
 	/* OPIN groups */
 	r->num_groups = p->num_opin_groups;
@@ -512,7 +566,10 @@ extern "C" int pf_router_reset(pf_router *r) {
 	if (upload_nodes(r, pfb_pinned_upload(sizeof(PfNode) * (size_t)r->N), NULL, NULL, NULL) != PF_OK) return PF_ECUDA;
 	CKB(pfb_sync());
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
-	CKB(pfb_zero(r->ctl, 256));
+	CKB(pfb_zero(r->ctl, CTL_BYTES));
+	r->sel_valid = r->sel_pending = false; r->iter_all = true; r->force_all_once = false;
+	if (r->committer) CKB(pfb_fill(r->committer, 0xff, sizeof(int) * (size_t)r->N));
+	if (r->queued) CKB(pfb_zero(r->queued, sizeof(int) * (size_t)std::max(r->n, 1)));
 	r->h_pool_head = 0;
 	r->iter_count = 0; r->best_overused = 0x7fffffff; r->stall_count = 0; r->over_hist.clear(); r->since_full = 0; r->cost_updates = 0; r->util = -1.;
 	CKB(pfb_zero(r->last_over, (size_t)r->N));
@@ -544,6 +601,18 @@ static void tune_granularity(const pf_router *r, PfParams &P, int work, int slot
 	P.pop_slack = c.pop_slack >= 0.f ? c.pop_slack : (throughput ? 0.f : 0.25f);
 }
 
+static int set_work(pf_router *r, SlotClass &s, const int *list, int count) {
+	s.num_work = count;
+	if (count > 0) { CKB(pfb_h2d_async(s.work, list, sizeof(int) * (size_t)count)); r->h2d_bytes += (int64_t)sizeof(int) * count; }
+	return PF_OK;
+}
+
+static int slots_for(const pf_router *r, int total_work, int class_slots, int div) {
+	int s = (total_work + div - 1) / div;
+	s = std::max(s, r->cfg.min_slots);
+	return std::max(1, std::min(s, class_slots));
+}
+
 static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pres_fac) {
 	const pf_problem *p = r->prob;
 	const pf_config &c = r->cfg;
@@ -561,56 +630,84 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.max_batch = 1;
 	P.algorithm = p->opts.router_algorithm == 1 ? 1 : 0;
 	P.skip_ripup = 0;
+	P.validate = (c.num_slots > 1 || c.big_slots > 1) ? c.validate_commits : 0;   /* one warp cannot race */
 	P.hot = s.hot; P.cold = s.cold; P.label_log2 = s.label_log2; P.epochs = s.epochs;
 	P.hot2 = s.hot2; P.cold2 = s.cold2; P.label2_log2 = s.label2_log2;
 	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap;
 	P.iscratch = s.iscratch; P.sink_cap = s.sink_cap;
 	P.pool = r->pool[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;
 	P.committer = r->committer;
-	P.events = r->events; P.event_head = (unsigned long long *)(r->ctl + 208); P.event_cap = r->event_cap;
+	P.net_big = r->net_big;
+	if (r->vq[0] && !r->iter_all) {          /* in an iteration that re-routes every net nobody can be displaced unrouted */
+		P.vq[0] = r->vq[0]; P.vq[1] = r->vq[1]; P.vq_ctl = (int *)(r->ctl + CTL_VQ); P.vq_cap = r->vq_cap;
+		P.vq_class = (&s == &r->big) ? 1 : 0; P.queued = r->queued; P.iter_tag = r->iter_count;
+	}
+	P.events = r->events ? r->events + (size_t)(r->xchg_seq & 1) * (size_t)r->event_cap : NULL;   /* double-buffered by exchange parity */
+	P.event_head = (unsigned long long *)(r->ctl + CTL_EVENTS); P.event_cap = r->event_cap;
 	P.status = r->status; P.retry_list = r->retry_list; P.retry_count = r->retry_count; P.stats = r->stats;
 }
 
-static int set_work(pf_router *r, SlotClass &s, const int *list, int count) {
-	s.num_work = count;
-	if (count > 0) { CKB(pfb_h2d(s.work, list, sizeof(int) * (size_t)count)); r->h2d_bytes += (int64_t)sizeof(int) * count; }
-	CKB(pfb_zero(s.work_head, sizeof(int) * 4));
+/* the select kernels: work lists of the iteration about to start (tag = its number) */
+static int launch_select(pf_router *r, int force_all) {
+	CKB(pfb_launch_select_nets(r->nodes, r->pool[r->cur], r->loc, r->all_nets, r->num_all, r->net_big, force_all,
+			r->small.work, r->big.work, r->sel_counts, r->cfg.history_window > 0 ? r->last_over : NULL,
+			1 + (r->cost_updates + 254) % 255, r->cfg.history_window, r->cfg.keep_newcomer ? r->committer : NULL, r->sel_scratch, r->K1,
+			r->queued, r->iter_count + 1));
 	return PF_OK;
 }
 
-/* device-resident work list (from pf_select_nets) → slot class queue */
-static int set_work_dev(pf_router *r, SlotClass &s, int count) {
-	s.num_work = count;
-	CKB(pfb_zero(s.work_head, sizeof(int) * 4));
-	(void)r;
+/* ONE read of the control block: everything the host needs to know about the launches since the last read.
+ * Raises the device-side error bits as PF_E* codes. */
+static int fetch_ctl(pf_router *r) {
+	CKB(pfb_d2h(r->h_ctl, r->ctl, CTL_BYTES));
+	r->d2h_bytes += CTL_BYTES;
+	const char *h = r->h_ctl;
+	int h_status[8], h_retry[4];
+	memcpy(h_status, h + CTL_STATUS, sizeof(h_status));
+	memcpy(h_retry, h + CTL_RETRY, sizeof(h_retry));
+	memcpy(&r->h_pool_head, h + CTL_POOL, sizeof(unsigned long long));
+	{ unsigned long long ne = 0; memcpy(&ne, h + CTL_EVENTS, sizeof(ne)); r->h_events = (long long)ne; }
+	memcpy(&r->h_stats, h + CTL_STATS, sizeof(PfStats));
+	if (r->events && r->h_events > r->event_cap) FAILF(PF_EOVERFLOW, "occupancy event log overflow (%lld events, capacity %lld)", r->h_events, r->event_cap);
+	if (h_status[0] & PF_ST_POOL_OVERFLOW) FAILF(PF_EOVERFLOW, "route store overflow (capacity %lld tree entries)", r->pool_cap);
+	if (h_status[0] & PF_ST_BIG_OVERFLOW) FAILF(PF_EOVERFLOW, "net %d overflows the big slots (label 2^%d, tree %d, far %d)", h_status[2],
+			r->big.label_log2, r->big.tree_cap, r->big.far_cap);
+	if (h_status[0] & PF_ST_TWICE_TO_SINK_BF)
+		FAILF(PF_EINVAL, "breadth-first router: net %d connects twice to one SINK; the reference's heap surgery for this case "
+				"(route_breadth_first.c:208-256) is not supported — its own check_route rejects the routing it produces. "
+				"Use the timing-driven / no-timing router (router_algorithm 0), which routes such nets", h_status[2]);
+	if (h_status[0] & PF_ST_COMM_TIMEOUT) FAILF(PF_ECUDA, "multi-GPU exchange timed out waiting for a peer rank's event log");
+	if (h_status[0] & PF_ST_COMM_ABORT) FAILF(PF_ECUDA, "a peer rank reported a failure during the occupancy exchange");
+	if (h_status[0] & PF_ST_INTERNAL) FAILF(PF_ECUDA, "internal error in the device router (net %d)", h_status[2]);
+	if (h_status[0] & PF_ST_UNROUTABLE) FAILF(PF_EUNROUTABLE, "net %d has no possible path (disconnected rr graph)", h_status[2]);
+	if (h_retry[0] > 0) {
+		/* nets that outgrew a regular slot were re-routed in the big slots by the retry launch and stay in that class:
+		 * mirror the device's net_big[] for the host-built work lists of "every net" iterations */
+		std::vector<int> lst((size_t)h_retry[0]);
+		CKB(pfb_d2h(lst.data(), r->retry_list, sizeof(int) * lst.size()));
+		for (int i : lst) r->h_net_big[(size_t)i] = 1;
+		if (r->cfg.verbose) fprintf(stderr, "pf_router: %d nets moved to the big slots\n", h_retry[0]);
+	}
 	return PF_OK;
 }
 
-static int slots_for(const pf_router *r, int total_work, int class_slots, int div) {
-	int s = (total_work + div - 1) / div;
-	s = std::max(s, r->cfg.min_slots);
-	return std::max(1, std::min(s, class_slots));
-}
-
-/* Start of one PathFinder iteration: garbage-collect the route store and choose the nets to re-route. */
+/* Start of one PathFinder iteration: garbage-collect the route store and choose the nets to re-route.
+ * No host-device synchronisation on the common path: the counts of the work lists were computed by the select
+ * kernels launched behind the previous iteration's cost update and arrived with that iteration's control block. */
 extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	if (!r) FAILF(PF_EINVAL, "null router");
 	if (!r->graph_ready) FAILF(PF_EINVAL, "the router was created with defer_graph: fill the graph buffers and call pf_comm_graph_ready first");
 	int rc;
 	if (crit) { CKB(pfb_h2d(r->crit, crit, sizeof(float) * (size_t)r->T)); r->h2d_bytes += (int64_t)sizeof(float) * r->T; }
 	/* garbage-collect the route-tree log when it is more than half full */
-	{
-		unsigned long long head[2] = { r->h_pool_head, 0 };
-		if ((long long)head[0] > r->pool_cap / 2) {
-			CKB(pfb_zero(r->pool_head, sizeof(unsigned long long) * 2));
-			CKB(pfb_launch_compact(r->pool[r->cur], r->pool[r->cur ^ 1], r->loc, r->all_nets, r->num_all, r->pool_head));
-			r->cur ^= 1;
-			CKB(pfb_d2h(head, r->pool_head, sizeof(head)));
-			r->h_pool_head = head[0];
-			if ((long long)head[0] > r->pool_cap / 2) FAILF(PF_EOVERFLOW, "route store too small: %llu live tree entries of %lld", head[0], r->pool_cap);
-		}
+	if ((long long)r->h_pool_head > r->pool_cap / 2) {
+		CKB(pfb_zero(r->pool_head, sizeof(unsigned long long) * 2));
+		CKB(pfb_launch_compact(r->pool[r->cur], r->pool[r->cur ^ 1], r->loc, r->all_nets, r->num_all, r->pool_head));
+		r->cur ^= 1;
+		r->h_pool_head = 0;       /* the live size arrives with the next control block; a log that is still too small then
+		                           * overflows in the route kernel and is reported as such */
+		r->sel_valid = false;     /* the lists are fine, but keep the rare path simple */
 	}
-	if (r->cfg.nranks > 1) CKB(pfb_zero(r->net_delay, sizeof(float) * (size_t)std::max(r->T, 1)));
 	/* Congested-only re-routing negotiates locally; on a tight instance it can ping-pong between a few
 	 * nets while every free resource nearby is held by legal nets.  When the overuse has not improved
 	 * for stall_iters iterations, fall back to the serial reference's policy for one iteration — every
@@ -622,14 +719,18 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	const bool stalled = r->cfg.stall_iters > 0 && r->since_full >= K && H > K
 			&& (double)r->over_hist[H - 1] > 0.7 * (double)r->over_hist[H - 1 - K];
 	if (stalled) { r->stall_count = 0; if (r->cfg.verbose) fprintf(stderr, "pf_router: overuse stalled at %d, re-routing every net\n", r->best_overused); }
-	const bool all = stalled || r->cfg.reroute_all_iters < 0 || r->iter_count < r->cfg.reroute_all_iters;
+	const bool all = stalled || r->force_all_once || r->cfg.reroute_all_iters < 0 || r->iter_count < r->cfg.reroute_all_iters;
+	r->force_all_once = false;
 	/* how many nets may be in flight depends on how contested the fabric is: with the channels under 40 % full after
 	 * the first iteration (BASELINE configs[4]: 29 %; the near-minimum-width fixtures: 52-63 %) twice as many nets
 	 * in flight converge just as fast (cfg 4: 22.9 vs 24.9 ms measured), on a tight fabric they do not */
 	const int base_div = (!r->div_explicit && r->util >= 0. && r->util < 0.40) ? r->cfg.inflight_div / 2 : r->cfg.inflight_div;
 	r->cur_div = stalled ? r->cfg.inflight_div * 8 : base_div;
+	r->iter_all = all;
 	if (all) {
-		std::vector<int> sm, bg;
+		/* host-built lists in the reference's net order (route_timing.c:98-106): interior nets, then cut nets */
+		std::vector<int> &sm = r->h_list_small, &bg = r->h_list_big;
+		sm.clear(); bg.clear();
 		r->n1_small = r->n1_big = 0;
 		for (int k = 0; k < r->num_all; k++) {
 			const int i = r->h_all[(size_t)k];
@@ -640,31 +741,30 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 		if ((rc = set_work(r, r->big, bg.data(), (int)bg.size())) != PF_OK) return rc;
 		r->n_small = (int)sm.size(); r->n_big = (int)bg.size();
 	} else {
-		int counts[4];
 		/* the work lists come back in the fanout order of the reference's net loop (route_timing.c:98-106): long
-		 * nets start first and runs are reproducible.  (Reversing the order on alternate iterations — the
-		 * reference authors experimented with shuffling it, route_timing.c:158 — was tried against the tight-W
-		 * tail and made the one-warp wirelength 4 % worse without shortening the tail.) */
-		CKB(pfb_launch_select_nets(r->nodes, r->pool[r->cur], r->loc, r->all_nets, r->num_all, r->net_big, 0,
-				r->small.work, r->big.work, r->sel_counts, r->cfg.history_window > 0 ? r->last_over : NULL,
-				1 + (r->cost_updates + 254) % 255, r->cfg.history_window, r->committer, r->sel_scratch, r->K1));
-		CKB(pfb_d2h(counts, r->sel_counts, sizeof(int) * 4));
-		r->d2h_bytes += 16;
+		 * nets start first and runs are reproducible */
+		if (!r->sel_valid) {
+			if ((rc = launch_select(r, 0)) != PF_OK) return rc;
+			if ((rc = fetch_ctl(r)) != PF_OK) return rc;
+		}
+		int counts[4];
+		memcpy(counts, r->h_ctl + CTL_SEL, sizeof(counts));
 		r->n_small = counts[0]; r->n_big = counts[1];
 		r->n1_small = counts[2]; r->n1_big = counts[3];
 	}
+	r->sel_valid = false;
+	CKB(pfb_zero(r->ctl, CTL_SEL));           /* status and counters of the iteration */
+	memset(&r->h_stats_seen, 0, sizeof(PfStats));
 	r->iter_count++;
 	r->since_full = all ? 0 : r->since_full + 1;
 	return PF_OK;
 }
 
-/* Route slice `part` of `nparts` of this iteration's nets (nparts > 1: multi-GPU sub-rounds with an
- * occupancy sync after each, so ranks see each other's routes several times per iteration). */
-extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, int nparts, pf_iter_stats *st) {
-	if (!r || nparts < 1 || part < 0 || part >= nparts) FAILF(PF_EINVAL, "bad argument");
-	int rc;
-	CKB(pfb_zero(r->ctl, 192));            /* status, retry count, stats, both work-queue heads */
-	if (r->events) CKB(pfb_zero(r->ctl + 208, 8));
+/* Launches of one route part (no synchronisation): the big class (long nets first), the regular class, then the
+ * retry launch in the big slots — nets that outgrew a regular slot (counted on the device) and, with ripple
+ * re-routing, big-class victims displaced by regular nets. */
+static int launch_routes(pf_router *r, float pres_fac, int part, int nparts) {
+	CKB(pfb_zero(r->ctl + CTL_PART, CTL_PART_END - CTL_PART));
 	const int div = r->cur_div;
 	/* several ranks, two parts: interior nets, then cut nets (see pf_router_create); otherwise equal slices */
 	const bool by_class = r->cfg.nranks > 1 && nparts == 2;
@@ -675,71 +775,53 @@ extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, i
 	int so, sc, bo, bc;
 	slice(r->n_small, r->n1_small, so, sc); slice(r->n_big, r->n1_big, bo, bc);
 	PfParams P;
-	int total = r->n_small + r->n_big;      /* the staleness bound is about the whole iteration's nets */
-	if (bc > 0) {                          /* long nets first */
+	const int total = r->n_small + r->n_big;      /* the staleness bound is about the whole iteration's nets */
+	const bool ripple = r->vq[0] && !r->iter_all;
+	if (bc > 0) {
 		r->big.num_work = bc;
 		fill_params(r, P, r->big, pres_fac);
 		P.work = r->big.work + bo;
-		{ int sl = slots_for(r, total, std::min(r->big.num_slots, bc), div); tune_granularity(r, P, bc, sl, true); CKB(pfb_launch_route(&P, sl, 1)); }
+		const int sl = slots_for(r, total, std::min(r->big.num_slots, bc), div);
+		tune_granularity(r, P, bc, sl, true);
+		CKB(pfb_launch_route(&P, sl, 1));
 	}
 	if (sc > 0) {
 		r->small.num_work = sc;
 		fill_params(r, P, r->small, pres_fac);
 		P.work = r->small.work + so;
-		{ int sl = slots_for(r, total, r->small.num_slots, div); tune_granularity(r, P, sc, sl); CKB(pfb_launch_route(&P, sl, r->cfg.warps_per_block)); }
+		const int sl = slots_for(r, total, r->small.num_slots, div);
+		tune_granularity(r, P, sc, sl);
+		CKB(pfb_launch_route(&P, sl, r->cfg.warps_per_block));
 	}
-	/* one read brings back status, retry count, counters and the log head */
-	char h_ctl[256];
-	CKB(pfb_d2h(h_ctl, r->ctl, 256));
-	int h_retry[4];
-	memcpy(h_retry, h_ctl + 32, sizeof(h_retry));
-	PfStats hs_total;
-	memcpy(&hs_total, h_ctl + 96, sizeof(PfStats));
-	/* nets whose scratch overflowed in a small slot are re-routed in the big slots, and stay there */
-	int rounds = 0;
-	while (h_retry[0] > 0) {
-		std::vector<int> lst((size_t)h_retry[0]);
-		CKB(pfb_d2h(lst.data(), r->retry_list, sizeof(int) * (size_t)h_retry[0]));
-		if (++rounds > 1) FAILF(PF_EOVERFLOW, "%d nets overflow the big slots (first net %d; label 2^%d, tree %d, far %d)", h_retry[0], lst[0],
-				r->big.label_log2, r->big.tree_cap, r->big.far_cap);
-		if (r->cfg.verbose) fprintf(stderr, "pf_router: %d nets moved to the big slots\n", h_retry[0]);
-		for (int i : lst) r->h_net_big[i] = 1;
-		CKB(pfb_h2d(r->net_big, r->h_net_big.data(), (size_t)r->n));
-		CKB(pfb_zero(r->ctl + 32, 16));         /* retry count */
-		CKB(pfb_zero(r->ctl + 96, 96));         /* counters and work-queue heads */
-		/* the retry list is routed from the scratch queue so the iteration's own work lists stay intact */
-		CKB(pfb_h2d(r->retry_work, lst.data(), sizeof(int) * lst.size()));
-		r->big.num_work = (int)lst.size();
+	if (sc > 0 || (ripple && bc > 0)) {
+		/* nets whose scratch overflowed in a regular slot are re-routed in the big slots, and stay there (the kernel marks
+		 * net_big[]); the length of the list is read on the device, so nobody waits for the host */
+		r->big.num_work = 0;
 		fill_params(r, P, r->big, pres_fac);
-		P.work = r->retry_work;
+		P.work = r->retry_list; P.num_work_ptr = r->retry_count; P.work_head = (int *)(r->ctl + CTL_HEAD_RETRY);
 		P.skip_ripup = 1;
-		{ int sl = slots_for(r, (int)lst.size(), std::min(r->big.num_slots, (int)lst.size()), div); tune_granularity(r, P, (int)lst.size(), sl, true); CKB(pfb_launch_route(&P, sl, 1)); }
-		CKB(pfb_d2h(h_ctl, r->ctl, 256));
-		memcpy(h_retry, h_ctl + 32, sizeof(h_retry));
-		PfStats more;
-		memcpy(&more, h_ctl + 96, sizeof(PfStats));
-		hs_total.pops += more.pops; hs_total.pushes += more.pushes; hs_total.visits += more.visits; hs_total.nets += more.nets;
+		const int sl = std::min(r->big.num_slots, std::max(8, r->cfg.min_slots));
+		tune_granularity(r, P, sl, sl, true);
+		CKB(pfb_launch_route(&P, sl, 1));
 	}
-	int h_status[8];
-	memcpy(h_status, h_ctl, sizeof(h_status));
-	memcpy(&r->h_pool_head, h_ctl + 192, sizeof(unsigned long long));
-	{ unsigned long long ne = 0; memcpy(&ne, h_ctl + 208, sizeof(ne)); r->h_events = (long long)ne; }
-	if (r->events && r->h_events > r->event_cap) FAILF(PF_EOVERFLOW, "occupancy event log overflow (%lld events, capacity %lld)", r->h_events, r->event_cap);
-	r->d2h_bytes += 256;
-	if (h_status[0] & PF_ST_POOL_OVERFLOW) FAILF(PF_EOVERFLOW, "route store overflow (capacity %lld tree entries)", r->pool_cap);
-	if (h_status[0] & PF_ST_TWICE_TO_SINK_BF)
-		FAILF(PF_EINVAL, "breadth-first router: net %d connects twice to one SINK; the reference's heap surgery for this case "
-				"(route_breadth_first.c:208-256) is not supported — its own check_route rejects the routing it produces. "
-				"Use the timing-driven / no-timing router (router_algorithm 0), which routes such nets", h_status[2]);
-	if (h_status[0] & PF_ST_INTERNAL) FAILF(PF_ECUDA, "internal error in the device router (net %d)", h_status[2]);
-	if (h_status[0] & PF_ST_UNROUTABLE) FAILF(PF_EUNROUTABLE, "net %d has no possible path (disconnected rr graph)", h_status[2]);
+	return PF_OK;
+}
+
+/* Route slice `part` of `nparts` of this iteration's nets (nparts > 1: multi-GPU sub-rounds with an
+ * occupancy sync after each, so ranks see each other's routes several times per iteration). */
+extern "C" int pf_iteration_route_part(pf_router *r, float pres_fac, int part, int nparts, pf_iter_stats *st) {
+	if (!r || nparts < 1 || part < 0 || part >= nparts) FAILF(PF_EINVAL, "bad argument");
+	int rc;
+	if ((rc = launch_routes(r, pres_fac, part, nparts)) != PF_OK) return rc;
+	if ((rc = fetch_ctl(r)) != PF_OK) return rc;
 	if (st) {
-		const PfStats &hs = hs_total;
+		/* the device counters accumulate over the iteration: report this part's share */
+		const PfStats &hs = r->h_stats, &seen = r->h_stats_seen;
 		memset(st, 0, sizeof(*st));
-		st->nets_routed = (int)hs.nets; st->heap_pushes = (int64_t)hs.pushes; st->heap_pops = (int64_t)hs.pops;
-		st->edge_visits = (int64_t)hs.visits; st->pres_fac = pres_fac;
+		st->nets_routed = (int)(hs.nets - seen.nets); st->heap_pushes = (int64_t)(hs.pushes - seen.pushes); st->heap_pops = (int64_t)(hs.pops - seen.pops);
+		st->edge_visits = (int64_t)(hs.visits - seen.visits); st->pres_fac = pres_fac;
 	}
-	(void)rc;
+	r->h_stats_seen = r->h_stats;
 	return PF_OK;
 }
 
@@ -752,22 +834,48 @@ extern "C" int pf_route_iteration(pf_router *r, float pres_fac, const float *cri
 extern "C" int pf_reserve_opins(pf_router *r, float pres_fac, int rip_up) {
 	if (!r) FAILF(PF_EINVAL, "null router");
 	if (r->num_groups == 0) return PF_OK;
+	r->sel_valid = false;
 	CKB(pfb_launch_reserve_opins(r->nodes, r->edges, r->indexed, r->num_groups, r->g_source, r->g_count, r->g_off, r->g_chosen, rip_up, pres_fac));
+	return PF_OK;
+}
+
+/* feasible_routing + pathfinder_update_cost in one pass over the node records; the same pass sums the wirelength in
+ * use on the fabric (occupancy x length of every CHANX / CHANY node: with several ranks that is the whole routing,
+ * not only this rank's trees), and the select kernels for the NEXT iteration run right behind it, so that one read
+ * of the control block ends the iteration. */
+static int update_costs_async(pf_router *r, float acc_fac) {
+	CKB(pfb_zero(r->ctl + CTL_OVER, CTL_PART - CTL_OVER));
+	r->cost_updates++;
+	CKB(pfb_launch_update_cost(r->nodes, r->N, acc_fac, r->d_overused, r->last_over, 1 + (r->cost_updates + 254) % 255, r->d_wl + 1));
+	if (r->cfg.reroute_all_iters >= 0 && r->iter_count >= r->cfg.reroute_all_iters) {
+		int rc = launch_select(r, 0);
+		if (rc != PF_OK) return rc;
+		r->sel_pending = true;
+	}
+	return PF_OK;
+}
+
+static int update_costs_finish(pf_router *r, int *overused) {
+	int rc = fetch_ctl(r);
+	if (rc != PF_OK) return rc;
+	int h[4];
+	memcpy(h, r->h_ctl + CTL_OVER, sizeof(h));
+	unsigned long long wl[2];
+	memcpy(wl, r->h_ctl + CTL_WL, sizeof(wl));
+	r->h_wl_used = (long long)wl[1];
+	if (r->iter_count <= 1 && r->avail_wl > 0) r->util = (double)wl[1] / (double)r->avail_wl;
+	r->sel_valid = r->sel_pending; r->sel_pending = false;
+	if (overused) *overused = h[0];
+	if (h[0] < r->best_overused) { r->best_overused = h[0]; r->stall_count = 0; } else r->stall_count++;
+	r->over_hist.push_back(h[0]);
 	return PF_OK;
 }
 
 extern "C" int pf_update_costs(pf_router *r, float acc_fac, int *overused) {
 	if (!r) FAILF(PF_EINVAL, "null router");
-	CKB(pfb_zero(r->d_overused, sizeof(int) * 4));
-	r->cost_updates++;
-	CKB(pfb_launch_update_cost(r->nodes, r->N, acc_fac, r->d_overused, r->last_over, 1 + (r->cost_updates + 254) % 255));
-	int h[4];
-	CKB(pfb_d2h(h, r->d_overused, sizeof(int) * 4));
-	r->d2h_bytes += 16;
-	if (overused) *overused = h[0];
-	if (h[0] < r->best_overused) { r->best_overused = h[0]; r->stall_count = 0; } else r->stall_count++;
-	r->over_hist.push_back(h[0]);
-	return PF_OK;
+	int rc = update_costs_async(r, acc_fac);
+	if (rc != PF_OK) return rc;
+	return update_costs_finish(r, overused);
 }
 
 /* Multi-GPU occupancy sync.  Every occupancy change a rank makes while routing (rip-up, commit, undo) is
@@ -796,10 +904,76 @@ extern "C" int pf_comm_net_classes(pf_router *r, int32_t *owner, uint8_t *is_cut
 	return PF_OK;
 }
 
+/* ---- the transport inside the library: peer memory over NVLink / NVSwitch (one process per GPU, one node).
+ * Bootstrap (once): every rank calls pf_comm_export, the caller all-gathers the PF_COMM_HANDLE_BYTES blobs with whatever
+ * it has (MPI_Allgather in the reference's MPI router, torch.distributed here) and hands all of them to pf_comm_init.
+ * From then on nothing crosses the host: pf_comm_exchange is one kernel behind the route kernels. */
+struct CommHandle { unsigned char ipc[64]; uint64_t bytes; int64_t event_cap; int32_t rank, nranks, T, magic; };
+static_assert(sizeof(CommHandle) <= PF_COMM_HANDLE_BYTES, "handle blob too small");
+#define PF_COMM_MAGIC 0x50465832   /* "PFX2" */
+
+static double comm_timeout_s() { const char *e = getenv("PF_COMM_TIMEOUT_S"); double v = e ? atof(e) : 0.; return v > 0. ? v : 30.; }
+
+extern "C" int pf_comm_export(pf_router *r, void *handle) {
+	if (!r || !handle) FAILF(PF_EINVAL, "null argument");
+	if (!r->xreg) FAILF(PF_EINVAL, "router was created with nranks == 1");
+	CommHandle h;
+	memset(&h, 0, sizeof(h));
+	memcpy(h.ipc, r->xhandle, 64);
+	h.bytes = r->xreg_bytes; h.event_cap = r->event_cap; h.rank = r->cfg.rank; h.nranks = r->cfg.nranks; h.T = r->T; h.magic = PF_COMM_MAGIC;
+	memset(handle, 0, PF_COMM_HANDLE_BYTES);
+	memcpy(handle, &h, sizeof(h));
+	return PF_OK;
+}
+
+extern "C" int pf_comm_init(pf_router *r, const void *all_handles) {
+	if (!r || !all_handles) FAILF(PF_EINVAL, "null argument");
+	if (!r->xreg) FAILF(PF_EINVAL, "router was created with nranks == 1");
+	if (r->comm_ready) return PF_OK;
+	for (int k = 0; k < r->cfg.nranks; k++) {
+		CommHandle h;
+		memcpy(&h, (const unsigned char *)all_handles + (size_t)k * PF_COMM_HANDLE_BYTES, sizeof(h));
+		if (h.magic != PF_COMM_MAGIC || h.rank != k || h.nranks != r->cfg.nranks) FAILF(PF_EINVAL, "handle %d is not rank %d's of %d", k, k, r->cfg.nranks);
+		if (h.event_cap != r->event_cap || h.T != r->T || h.bytes != r->xreg_bytes) FAILF(PF_EINVAL, "rank %d routes a different problem", k);
+		if (k == r->cfg.rank) continue;
+		r->peers.base[k] = (unsigned char *)pfb_ipc_open(h.ipc);
+		if (!r->peers.base[k]) CUDA_FAIL();
+	}
+	r->comm_ready = 1;
+	return PF_OK;
+}
+
+/* After a route part: publish this rank's occupancy event log, replay every peer's.  Stream-ordered, no host wait. */
+extern "C" int pf_comm_exchange(pf_router *r) {
+	if (!r) FAILF(PF_EINVAL, "null router");
+	if (!r->comm_ready) FAILF(PF_EINVAL, "pf_comm_init has not been called");
+	r->xchg_seq++;                          /* the route kernels since the last exchange wrote log buffer (xchg_seq - 1) & 1 */
+	r->sel_valid = false;
+	CKB(pfb_launch_xchg_events(r->nodes, &r->peers, r->cfg.rank, r->cfg.nranks, r->xchg_seq, (const unsigned long long *)(r->ctl + CTL_EVENTS),
+			r->event_cap, r->status, comm_timeout_s()));
+	return PF_OK;
+}
+
+/* Sink delays of the nets other ranks route, into this rank's delay vector (before a timing analysis / the result). */
+extern "C" int pf_comm_gather_delays(pf_router *r) {
+	if (!r) FAILF(PF_EINVAL, "null router");
+	if (!r->comm_ready) FAILF(PF_EINVAL, "pf_comm_init has not been called");
+	r->dseq++;
+	CKB(pfb_launch_xchg_delays(r->net_delay, r->term_owner, r->T, &r->peers, r->cfg.rank, r->cfg.nranks, r->dseq, r->event_cap, r->status, comm_timeout_s()));
+	return PF_OK;
+}
+
+extern "C" int pf_comm_abort(pf_router *r) {
+	if (!r || !r->xreg) return PF_OK;
+	pfb_launch_xchg_abort(&r->peers, r->cfg.rank);
+	pfb_sync();
+	return PF_OK;
+}
+
 extern "C" int pf_comm_events(pf_router *r, void **dev_events, int64_t *count) {
 	if (!r || !dev_events || !count) FAILF(PF_EINVAL, "null argument");
 	if (!r->events) FAILF(PF_EINVAL, "router was created with nranks == 1");
-	*dev_events = r->events;
+	*dev_events = r->events + (size_t)(r->xchg_seq & 1) * (size_t)r->event_cap;
 	*count = (int64_t)r->h_events;
 	return PF_OK;
 }
@@ -807,6 +981,7 @@ extern "C" int pf_comm_events(pf_router *r, void **dev_events, int64_t *count) {
 extern "C" int pf_comm_apply_events(pf_router *r, const void *dev_events, int64_t count) {
 	if (!r || (!dev_events && count > 0)) FAILF(PF_EINVAL, "null argument");
 	if (!r->events) FAILF(PF_EINVAL, "router was created with nranks == 1");
+	r->sel_valid = false;
 	CKB(pfb_launch_apply_events(r->nodes, (const unsigned *)dev_events, (long long)count));   /* stream-ordered; the caller keeps
 	                                                                                          * the buffer alive until the next call */
 	return PF_OK;
@@ -942,81 +1117,130 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 	return PF_OK;
 }
 
-/* try_timing_driven_route, reference route_timing.c:85-343, single GPU.  The analysis between iterations is
- * either the host callback `sta` (the reference's own STA in the drop-in flow) or the device analysis `dsta`,
- * which reads the router's delay vector and writes its criticality vector in place. */
-static int route_loop(const pf_problem *p, const pf_config *cfg, pf_sta_fn sta, void *user, pf_sta *dsta, pf_result *out) {
-	pf_router *r = NULL;
-	int rc = pf_router_create(p, cfg, &r);
-	if (rc != PF_OK) return rc;
+/* try_timing_driven_route, reference route_timing.c:85-343, on an existing router: iterate until the routing is
+ * legal or the iteration budget is spent.  ONE host-device synchronisation per PathFinder iteration (the read of the
+ * control block behind the cost update); with several ranks (pf_comm_init) the occupancy exchange after each route
+ * part is device-side as well.  The analysis between iterations is either the host callback `sta` (the reference's own
+ * STA in the drop-in flow) or the device analysis `dsta`, which reads the router's delay vector and writes its
+ * criticality vector in place. */
+extern "C" int pf_route_run(pf_router *r, pf_sta *dsta, pf_sta_fn sta, void *user, pf_iter_stats *stats_out, int stats_cap,
+		int *iterations_out, int *success_out) {
+	if (!r) FAILF(PF_EINVAL, "null router");
+	const pf_problem *p = r->prob;
+	const pf_config *cfg = &r->cfg;
 	const pf_router_opts &o = p->opts;
-	int max_iters = o.max_router_iterations;
-	std::vector<pf_iter_stats> stats;
-	std::vector<float> crit((size_t)std::max(p->num_terminals, 1)), delay((size_t)std::max(p->num_terminals, 1));
-	std::vector<float> crit_hist;
-	{
-		float v = o.timing_analysis_enabled ? 1.f : 0.f;
-		std::fill(crit.begin(), crit.end(), 0.f);
+	if (cfg->nranks > 1 && !r->comm_ready) FAILF(PF_EINVAL, "pf_route_run on %d ranks needs pf_comm_init first", cfg->nranks);
+	const int max_iters = o.max_router_iterations;
+	const int nparts = cfg->nranks > 1 ? 2 : 1;
+	std::vector<float> crit, delay;
+	r->crit_hist.clear();
+	if (sta && o.timing_analysis_enabled) {
+		crit.assign((size_t)std::max(p->num_terminals, 1), 0.f); delay.assign((size_t)std::max(p->num_terminals, 1), 0.f);
 		for (int i = 0; i < p->num_nets; i++)
-			if (!p->net_is_global[i]) for (int k = p->net_ptr[i] + 1; k < p->net_ptr[i + 1]; k++) crit[k] = v;
+			if (!p->net_is_global[i]) for (int k = p->net_ptr[i] + 1; k < p->net_ptr[i + 1]; k++) crit[k] = 1.f;
 	}
 	float pres_fac = o.first_iter_pres_fac;
-	int success = 0, itry;
-	bool have_crit = false;
+	int success = 0, itry, rc = PF_OK, nstats = 0;
+	bool have_crit = false, polished = false;
+	const bool breadth_first = o.router_algorithm == 1;      /* try_breadth_first_route, route_breadth_first.c:23-91 */
 	for (itry = 1; itry <= max_iters; itry++) {
 		pf_iter_stats st;
-		crit_hist.insert(crit_hist.end(), crit.begin(), crit.begin() + p->num_terminals);
-		rc = pf_route_iteration(r, pres_fac, have_crit ? crit.data() : NULL, &st);
-		if (rc != PF_OK) break;
-		const bool breadth_first = o.router_algorithm == 1;      /* try_breadth_first_route, route_breadth_first.c:23-91 */
-		if (itry == 1 && !breadth_first) {                      /* the timing-driven router's wirelength abort, route_timing.c:189-225 */
-			int64_t wl = 0, avail = 1;
-			if ((rc = pf_total_wirelength(r, &wl, &avail)) != PF_OK) break;
-			if ((float)wl / (float)avail > PF_FIRST_ITER_WIRELENGTH_LIMIT) { stats.push_back(st); itry++; break; }
+		memset(&st, 0, sizeof(st));
+		if (!crit.empty()) r->crit_hist.insert(r->crit_hist.end(), crit.begin(), crit.begin() + p->num_terminals);
+		if ((rc = pf_iteration_begin(r, have_crit ? crit.data() : NULL)) != PF_OK) break;
+		for (int part = 0; part < nparts && rc == PF_OK; part++) {
+			rc = launch_routes(r, pres_fac, part, nparts);
+			if (rc == PF_OK && cfg->nranks > 1) rc = pf_comm_exchange(r);
 		}
+		if (rc != PF_OK) break;
 		if ((rc = pf_reserve_opins(r, pres_fac, itry != 1)) != PF_OK) break;
 		float acc_fac;
+		st.pres_fac = pres_fac;
 		if (itry == 1) { pres_fac = o.initial_pres_fac; acc_fac = breadth_first ? o.acc_fac : 0.f; }   /* route_breadth_first.c:84 */
 		else {
 			pres_fac *= o.pres_fac_mult;
 			pres_fac = fminf(pres_fac, (float)(PF_HUGE_POSITIVE_FLOAT / 1e5));
 			acc_fac = o.acc_fac;
 		}
+		/* feasibility is decided on the occupancies before the cost update; when nothing is overused the update is a
+		 * no-op, so one fused pass serves both — and carries the wirelength of the first-iteration abort test */
+		if ((rc = update_costs_async(r, acc_fac)) != PF_OK) break;
+		const bool analyse = o.timing_analysis_enabled && dsta;
+		if (analyse) {
+			/* enqueued before the control block is read: the analysis of the final routing comes for free */
+			if (cfg->nranks > 1 && (rc = pf_comm_gather_delays(r)) != PF_OK) break;
+			if ((rc = pf_sta_analyze_device(dsta, r->net_delay, r->crit, NULL)) != PF_OK) break;
+		}
 		int overused = 0;
-		/* feasibility is decided on the occupancies before the cost update; when nothing is
-		 * overused the update is a no-op, so one fused pass serves both */
-		if ((rc = pf_update_costs(r, acc_fac, &overused)) != PF_OK) break;
+		if ((rc = update_costs_finish(r, &overused)) != PF_OK) break;
 		st.overused_nodes = overused;
-		stats.push_back(st);
-		if (cfg->verbose) fprintf(stderr, "pf_router: iteration %d: %d nets routed, %d rr nodes overused, pres_fac %g\n", itry, st.nets_routed, overused, (double)st.pres_fac);
-		if (overused == 0) { success = 1; itry++; break; }
+		st.nets_routed = (int)r->h_stats.nets; st.heap_pushes = (int64_t)r->h_stats.pushes; st.heap_pops = (int64_t)r->h_stats.pops;
+		st.edge_visits = (int64_t)r->h_stats.visits;
+		if (analyse) { float cpd = 0.f; if ((rc = pf_sta_read_cpd(dsta, &cpd)) != PF_OK) break; st.crit_path_delay = cpd; }
+		if (cfg->verbose) fprintf(stderr, "pf_router: iteration %d: %d nets routed (%llu lost races), %d rr nodes overused, pres_fac %g\n", itry, st.nets_routed,
+				(unsigned long long)r->h_stats.races, overused, (double)st.pres_fac);
+		if (itry == 1 && !breadth_first && r->avail_wl > 0
+				&& (float)r->h_wl_used / (float)r->avail_wl > PF_FIRST_ITER_WIRELENGTH_LIMIT) {   /* route_timing.c:189-225 */
+			if (stats_out && nstats < stats_cap) stats_out[nstats] = st;
+			nstats++; itry++;
+			break;
+		}
+		if (stats_out && nstats < stats_cap) stats_out[nstats] = st;
+		nstats++;
+		if (overused == 0) {
+			/* polish (off by default): the routing is legal, but under the congested-only policy a net routed around
+			 * congestion that has since dissolved keeps its detour.  One more iteration re-routes every net against the
+			 * final picture, then the negotiation carries on until the routing is legal again. */
+			if (!polished && cfg->polish > 0 && itry < max_iters && itry > 1) { polished = true; r->force_all_once = true; }
+			else { success = 1; itry++; break; }
+		}
 		if (o.timing_analysis_enabled && dsta) {
-			float cpd = 0.f;
-			if ((rc = pf_sta_analyze_device(dsta, r->net_delay, r->crit, &cpd)) != PF_OK) break;
-			stats.back().crit_path_delay = cpd;
 			have_crit = false;   /* already on the device */
 		} else if (o.timing_analysis_enabled && sta) {
+			if (cfg->nranks > 1 && (rc = pf_comm_gather_delays(r)) != PF_OK) break;
 			if ((rc = pf_get_net_delay(r, delay.data())) != PF_OK) break;
 			float cpd = 0.f;
 			sta(user, itry, delay.data(), crit.data(), &cpd);
-			stats.back().crit_path_delay = cpd;
+			if (stats_out && nstats - 1 < stats_cap) stats_out[nstats - 1].crit_path_delay = cpd;
 			have_crit = true;
 		} else if (!o.timing_analysis_enabled) {
 			have_crit = false;   /* criticalities stay 0 on the device */
 		}
 	}
 	itry--;
+	if (rc != PF_OK && cfg->nranks > 1) pf_comm_abort(r);      /* peers waiting in an exchange see it instead of timing out */
+	if (rc != PF_OK) return rc;
+	if (cfg->nranks > 1 && (rc = pf_comm_gather_delays(r)) != PF_OK) return rc;   /* the result carries every net's delays on every rank */
+	if (iterations_out) *iterations_out = itry;
+	if (success_out) *success_out = success;
+	return PF_OK;
+}
+
+static int route_loop(const pf_problem *p, const pf_config *cfg, pf_sta_fn sta, void *user, pf_sta *dsta, pf_result *out) {
+	if (!p || !cfg || !out) FAILF(PF_EINVAL, "null argument");
+	if (cfg->nranks > 1) FAILF(PF_EINVAL, "pf_try_* route on one GPU; for several ranks create the router, call pf_comm_init and pf_route_run");
+	pf_router *r = NULL;
+	int rc = pf_router_create(p, cfg, &r);
+	if (rc != PF_OK) return rc;
+	const int cap = std::max(p->opts.max_router_iterations, 1);
+	std::vector<pf_iter_stats> stats((size_t)cap);
+	int iterations = 0, success = 0;
+	rc = pf_route_run(r, dsta, sta, user, stats.data(), cap, &iterations, &success);
 	if (rc == PF_OK) {
 		rc = pf_get_result(r, out);
 		if (rc == PF_OK) {
+			const int ns = std::min(iterations, cap);
 			out->success = success;
-			out->iterations = itry;
-			out->num_iter_stats = (int)stats.size();
-			out->iter_stats = (pf_iter_stats *)malloc(sizeof(pf_iter_stats) * std::max<size_t>(stats.size(), 1));
-			memcpy(out->iter_stats, stats.data(), sizeof(pf_iter_stats) * stats.size());
-			out->num_crit_iters = p->num_terminals ? (int)(crit_hist.size() / (size_t)p->num_terminals) : 0;
-			out->iter_crit = (float *)malloc(sizeof(float) * std::max<size_t>(crit_hist.size(), 1));
-			memcpy(out->iter_crit, crit_hist.data(), sizeof(float) * crit_hist.size());
+			out->iterations = iterations;
+			out->num_iter_stats = ns;
+			out->iter_stats = (pf_iter_stats *)malloc(sizeof(pf_iter_stats) * (size_t)std::max(ns, 1));
+			memcpy(out->iter_stats, stats.data(), sizeof(pf_iter_stats) * (size_t)ns);
+			/* the criticalities each iteration used: known on the host only when the host analysis ran (with the device
+			 * analysis they never leave the GPU) */
+			const std::vector<float> &ch = r->crit_hist;
+			out->num_crit_iters = (p->num_terminals && !ch.empty()) ? (int)(ch.size() / (size_t)p->num_terminals) : 0;
+			out->iter_crit = (float *)malloc(sizeof(float) * std::max<size_t>(ch.size(), 1));
+			memcpy(out->iter_crit, ch.data(), sizeof(float) * ch.size());
 		}
 	}
 	pf_router_destroy(r);

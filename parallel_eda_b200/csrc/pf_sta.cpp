@@ -117,7 +117,14 @@ extern "C" int pf_sta_analyze_device(pf_sta *s, const void *dev_net_delay, void 
 		for (int k = nseg - 1; k >= 0; k--) CKB(pfb_sta_sweep(&s->d, 0, s->seg_begin[k], s->seg_end[k], s->seg_spread[k], j, constraint, stat));
 		CKB(pfb_sta_update(&s->d, constraint, stat, (float *)dev_crit));
 	}
-	if (cpd_ns) {
+	if (cpd_ns) return pf_sta_read_cpd(s, cpd_ns);
+	return PF_OK;
+}
+
+extern "C" int pf_sta_read_cpd(pf_sta *s, float *cpd_ns) {
+	if (!s || !cpd_ns) FAILF(PF_EINVAL, "null argument");
+	const int C = s->num_domains;
+	{
 		/* get_critical_path_delay, path_delay.c:3791-3810: the cpd of the pair with the least slack */
 		std::vector<float> h((size_t)std::max(C * C, 1) * 4, 0.f);
 		CKB(pfb_d2h(h.data(), s->stat, sizeof(float) * h.size()));

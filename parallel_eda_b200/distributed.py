@@ -57,9 +57,20 @@ class Comm:
             torch.cuda.current_stream(self.device).synchronize()
         if self.rank != 0:
             R.comm_graph_ready()
+        self.connect(R)
         if os.environ.get("PF_COMM_DEBUG"):
             print("rank %d create_router: create %.1f ms, status + broadcast %.1f ms" % (self.rank, (t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3), flush=True)
         return R
+
+    def connect(self, r) -> None:
+        """Bootstrap of the transport inside the library (pf_comm_export / pf_comm_init): all-gather the ranks' 128-byte
+        handles once; afterwards the occupancy exchange is device-side (peer memory over NVLink) and this class is no
+        longer on the path."""
+        mine = torch.frombuffer(bytearray(r.comm_export()), dtype=torch.uint8).to(self.device)
+        every = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(every, mine)
+        r.comm_init(bytes(every.cpu().numpy().tobytes()))
+        dist.barrier()                                    # every rank has mapped every region before anybody publishes
 
     def sync_occupancy(self, r) -> int:
         """All ranks end up with the same rr-node occupancy: all-gather every rank's event log of the last

@@ -40,6 +40,19 @@ class RouteReport:
     wall_s: float
 
 
+def run(r: router.Router, comm=None, sta: Optional[Callable] = None, dsta=None) -> RouteReport:
+    """The product path: the whole loop inside the library (pf_route_run) — one host-device synchronisation per
+    iteration, and with several ranks (``comm.connect(r)`` done) a device-side occupancy exchange over NVLink peer memory
+    after every route part.  ``comm`` is only used to add up the ranks' counters afterwards."""
+    t0 = time.perf_counter()
+    ok, it, st = r.run(sta=sta, dsta=dsta)
+    nets = [int(x) for x in st["nets_routed"]]
+    rep = RouteReport(ok, it, sum(nets), [int(x) for x in st["overused_nodes"]], nets, int(st["heap_pops"].sum()),
+                      int(st["heap_pushes"].sum()), int(st["edge_visits"].sum()), time.perf_counter() - t0)
+    rep.crit_path_delay = [float(x) for x in st["crit_path_delay"]]
+    return rep
+
+
 def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delay_buf=None, dsta=None,
           max_iters: Optional[int] = None, sync_rounds: int = 2) -> RouteReport:
     """Iterate until legal.  ``delay_buf``: tensor aliasing the router's device net_delay vector (needed when
@@ -85,7 +98,9 @@ def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delay_buf
         if it == 1:
             new_pres, acc_fac = float(o["initial_pres_fac"]), (float(o["acc_fac"]) if breadth_first else 0.0)
         else:
-            new_pres = min(pres_fac * float(o["pres_fac_mult"]), HUGE_POSITIVE_FLOAT / 1e5)
+            # single precision like the reference's `pres_fac *= router_opts.pres_fac_mult` (route_timing.c:288): a double
+            # product rounded once differs from it by an ulp after a few iterations, and with it the routing
+            new_pres = float(min(np.float32(pres_fac) * np.float32(o["pres_fac_mult"]), np.float32(HUGE_POSITIVE_FLOAT / 1e5)))
             acc_fac = float(o["acc_fac"])
         r.reserve_locally_used_opins(pres_fac, it != 1)   # every rank, on the same synced occupancy
         over = r.pathfinder_update_cost(acc_fac)
@@ -97,12 +112,31 @@ def route(r: router.Router, comm=None, sta: Optional[Callable] = None, delay_buf
         if dsta is not None and int(o["timing_analysis_enabled"]):
             # device STA (router.Sta): reads the router's delay vector, writes its criticality vector in place
             if comm is not None and delay_buf is not None:
-                comm.all_reduce_sum_(delay_buf)
+                _assemble_delays(r, comm, delay_buf)
             dsta.analyze_device(r.comm_net_delay_ptr(), r.comm_crit_ptr())
             crit = None
         elif sta is not None and int(o["timing_analysis_enabled"]):
             if comm is not None and delay_buf is not None:
-                comm.all_reduce_sum_(delay_buf)          # assemble every rank's sink delays
+                _assemble_delays(r, comm, delay_buf)     # assemble every rank's sink delays
             crit, _cpd = sta(it, r.net_delay())
             crit = np.ascontiguousarray(crit, dtype=np.float32)
+    if success and comm is not None and delay_buf is not None and int(o["timing_analysis_enabled"]):
+        _assemble_delays(r, comm, delay_buf)             # the result carries every net's delays on every rank
     return RouteReport(success, it, total_nets, overused, per_iter, pops, pushes, visits, time.perf_counter() - t0)
+
+
+def _assemble_delays(r, comm, delay_buf):
+    """Step-API transport (torch collectives): every rank keeps the delays of the nets IT routes up to date — also of
+    nets it did not re-route this iteration; the entries of other ranks' nets are whatever the last assembly left there.
+    Sum only the owned entries."""
+    import torch
+    mask = getattr(r, "_own_mask", None)
+    if mask is None:
+        owner, _cut = r.comm_net_classes()
+        p = r.problem
+        per_term = np.repeat(owner, np.diff(p.net_ptr))
+        mask = torch.from_numpy((per_term == r.config.rank).astype(np.float32)).to(delay_buf.device)
+        r._own_mask = mask
+    tmp = delay_buf * mask
+    comm.all_reduce_sum_(tmp)
+    delay_buf.copy_(tmp)

@@ -77,7 +77,7 @@ class Config(C.Structure):
                [("pop_slack", C.c_float), ("win_rel", C.c_float), ("win_abs", C.c_float), ("verbose", C.c_int32),
                 ("reroute_all_iters", C.c_int32), ("inflight_div", C.c_int32), ("min_slots", C.c_int32),
                 ("stall_iters", C.c_int32), ("history_window", C.c_int32), ("keep_newcomer", C.c_int32),
-                ("defer_graph", C.c_int32)]
+                ("defer_graph", C.c_int32), ("validate_commits", C.c_int32), ("ripple", C.c_int32), ("polish", C.c_int32)]
 
 
 class _TimingGraph(C.Structure):
@@ -171,6 +171,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_comm_net_delay_ptr.restype = C.c_void_p
     lib.pf_comm_crit_ptr.argtypes = [C.c_void_p]
     lib.pf_comm_crit_ptr.restype = C.c_void_p
+    lib.pf_comm_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pf_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pf_comm_exchange.argtypes = [C.c_void_p]
+    lib.pf_comm_gather_delays.argtypes = [C.c_void_p]
+    lib.pf_comm_abort.argtypes = [C.c_void_p]
+    lib.pf_route_run.argtypes = [C.c_void_p, C.c_void_p, STA_FN, C.c_void_p, C.POINTER(IterStats), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.pf_try_timing_driven_route.argtypes = [C.POINTER(_Problem), C.POINTER(Config), STA_FN, C.c_void_p,
                                                C.POINTER(_Result)]
     lib.pf_result_free.argtypes = [C.POINTER(_Result)]
@@ -387,6 +393,51 @@ class Router:
 
     def comm_net_delay_ptr(self) -> int:
         return int(self.lib.pf_comm_net_delay_ptr(self._h))
+
+    # the transport inside the library (peer memory over NVLink; include/pf_router.h)
+    COMM_HANDLE_BYTES = 128
+
+    def comm_export(self) -> bytes:
+        buf = (C.c_ubyte * self.COMM_HANDLE_BYTES)()
+        self._ck(self.lib.pf_comm_export(self._h, buf))
+        return bytes(buf)
+
+    def comm_init(self, all_handles: bytes):
+        assert len(all_handles) == self.COMM_HANDLE_BYTES * self.config.nranks
+        buf = (C.c_ubyte * len(all_handles)).from_buffer_copy(all_handles)
+        self._ck(self.lib.pf_comm_init(self._h, buf))
+
+    def comm_exchange(self):
+        self._ck(self.lib.pf_comm_exchange(self._h))
+
+    def comm_gather_delays(self):
+        self._ck(self.lib.pf_comm_gather_delays(self._h))
+
+    def comm_abort(self):
+        self.lib.pf_comm_abort(self._h)
+
+    def run(self, sta: "Optional[StaFn]" = None, dsta: "Optional[Sta]" = None):
+        """pf_route_run: the whole PathFinder loop on this router (one GPU, or one rank of several after comm_init)
+        with one host-device synchronisation per iteration.  Returns (success, iterations, stats[iterations])."""
+        T = self.problem.num_terminals
+        cap = max(int(self.problem.opts["max_router_iterations"]), 1)
+        stats = (IterStats * cap)()
+        it, ok = C.c_int(0), C.c_int(0)
+
+        def _cb(_user, iters_done, nd, crit, cpd):
+            delays = np.ctypeslib.as_array(nd, shape=(max(T, 1),))[:T]
+            c, d = sta(iters_done, delays)
+            np.ctypeslib.as_array(crit, shape=(max(T, 1),))[:T] = np.asarray(c, dtype=np.float32)
+            cpd[0] = float(d)
+
+        cb = STA_FN(_cb) if sta is not None else C.cast(None, STA_FN)
+        self._ck(self.lib.pf_route_run(self._h, dsta._h if dsta is not None else None, cb, None, stats, cap, C.byref(it), C.byref(ok)))
+        n = min(it.value, cap)
+        out = np.zeros(n, dtype=pfio.ITER_STATS_DT)
+        for i in range(n):
+            for f, _ in IterStats._fields_:
+                out[f][i] = getattr(stats[i], f)
+        return bool(ok.value), int(it.value), out
 
     def comm_crit_ptr(self) -> int:
         return int(self.lib.pf_comm_crit_ptr(self._h))

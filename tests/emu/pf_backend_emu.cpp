@@ -21,6 +21,8 @@ const char *pfb_name(void) { return "emu"; }
 const char *pfb_last_error(void) { return g_err; }
 void *pfb_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
 void *pfb_alloc_raw(size_t bytes) { return malloc(bytes ? bytes : 16); }
+void *pfb_host_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
+void pfb_host_free(void *p) { free(p); }
 void *pfb_pinned(size_t) { return NULL; }
 void *pfb_pinned_upload(size_t) { return NULL; }
 int pfb_h2d_async(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
@@ -29,6 +31,7 @@ void pfb_free(void *p) { free(p); }
 int pfb_h2d(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
 int pfb_d2h(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
 int pfb_d2d(void *d, const void *s, size_t n) { if (n) memmove(d, s, n); return 0; }
+int pfb_fill(void *d, int b, size_t n) { if (n) memset(d, b, n); return 0; }
 int pfb_zero(void *d, size_t n) { if (n) memset(d, 0, n); return 0; }
 int pfb_sync(void) { return 0; }
 void pfb_times(PfLaunchTimes *out, int reset) { if (out) *out = g_times; if (reset) memset(&g_times, 0, sizeof(g_times)); }
@@ -65,10 +68,13 @@ int pfb_launch_route(const PfParams *P, int num_slots, int) {
 	return 0;
 }
 
-int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, unsigned char *last_over, int iter_tag) {
+int pfb_launch_update_cost(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused, unsigned char *last_over, int iter_tag,
+		unsigned long long *d_wl_used) {
 	int over = 0;
-	for (int i = 0; i < num_nodes; i++) over += pf_update_cost_one(nodes, i, acc_fac, last_over, iter_tag);
+	unsigned long long wl = 0;
+	for (int i = 0; i < num_nodes; i++) { over += pf_update_cost_one(nodes, i, acc_fac, last_over, iter_tag); wl += pf_node_wirelength_in_use(&nodes[i]); }
 	*d_overused += over;
+	if (d_wl_used) *d_wl_used += wl;
 	g_times.update_launches++;
 	return 0;
 }
@@ -100,12 +106,14 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndex
 
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
-		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count) {
+		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count,
+		int *queued, int queued_tag) {
 	(void)scratch;
 	counts[0] = counts[1] = counts[2] = counts[3] = 0;
 	for (int k = 0; k < num_all; k++) {          /* all_nets is in fanout order; so are the lists */
 		int net = all_nets[k];
 		if (force_all || pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net)) {
+			if (queued) queued[net] = queued_tag;
 			if (net_big[net]) { list_big[counts[1]++] = net; if (k < head_count) counts[3]++; }
 			else { list_small[counts[0]++] = net; if (k < head_count) counts[2]++; }
 		}
@@ -147,6 +155,103 @@ int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num
 				trace_term ? trace_term + tptr[i] : NULL, ptc, nx, (unsigned)(i + 1));
 	}
 	g_times.aux_launches++;
+	return 0;
+}
+
+
+/* ---- multi-rank exchange: the "peer memory" of the emulator is POSIX shared memory, the ranks are processes; the protocol
+ * (payload, fence, release of the sequence number; acquire-polling consumers) is the one of pf_kernels.cu */
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <map>
+#include <string>
+struct ShmRegion { std::string name; size_t bytes; bool owner; };
+static std::map<void *, ShmRegion> g_shm;
+
+void *pfb_ipc_alloc(size_t bytes, void *handle64) {
+	static int counter = 0;
+	char name[64];
+	snprintf(name, sizeof(name), "/pf_emu_%d_%d", (int)getpid(), counter++);
+	int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+	if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) { snprintf(g_err, sizeof(g_err), "shm_open(%s) failed", name); if (fd >= 0) close(fd); return NULL; }
+	void *p = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	close(fd);
+	if (p == MAP_FAILED) { shm_unlink(name); snprintf(g_err, sizeof(g_err), "mmap of %s failed", name); return NULL; }
+	memset(handle64, 0, 64);
+	snprintf((char *)handle64, 64, "%s", name);
+	g_shm[p] = ShmRegion{ name, bytes, true };
+	return p;
+}
+void *pfb_ipc_open(const void *handle64) {
+	char name[65];
+	memcpy(name, handle64, 64); name[64] = 0;
+	int fd = shm_open(name, O_RDWR, 0600);
+	if (fd < 0) { snprintf(g_err, sizeof(g_err), "shm_open(%s) failed", name); return NULL; }
+	struct stat st;
+	if (fstat(fd, &st) != 0) { close(fd); return NULL; }
+	void *p = mmap(NULL, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	close(fd);
+	if (p == MAP_FAILED) return NULL;
+	g_shm[p] = ShmRegion{ name, (size_t)st.st_size, false };
+	return p;
+}
+void pfb_ipc_close(void *p) { auto it = g_shm.find(p); if (it != g_shm.end()) { munmap(p, it->second.bytes); g_shm.erase(it); } }
+void pfb_ipc_free(void *p) { auto it = g_shm.find(p); if (it != g_shm.end()) { munmap(p, it->second.bytes); shm_unlink(it->second.name.c_str()); g_shm.erase(it); } }
+
+static int emu_wait_flag(const unsigned *flag, unsigned want, const PfXchgHeader *peer, int *status, double timeout_s) {
+	const double t0 = now_ms();
+	while ((int)(__atomic_load_n(flag, __ATOMIC_ACQUIRE) - want) < 0) {
+		if (__atomic_load_n(&peer->abort_flag, __ATOMIC_RELAXED)) { *status |= PF_ST_COMM_ABORT; return 0; }
+		if (now_ms() - t0 > timeout_s * 1e3) { *status |= PF_ST_COMM_TIMEOUT; return 0; }
+		usleep(50);
+	}
+	return 1;
+}
+
+int pfb_launch_xchg_events(PfNode *nodes, const PfPeers *peers, int me, int nranks, unsigned seq, const unsigned long long *event_head,
+		long long event_cap, int *status, double timeout_s) {
+	const int buf = (int)((seq - 1u) & 1u);
+	PfXchgHeader *mine = (PfXchgHeader *)peers->base[me];
+	unsigned long long c = *event_head;
+	if ((long long)c > event_cap) c = (unsigned long long)event_cap;
+	mine->count[buf] = c;
+	__atomic_store_n(&mine->seq[buf], seq, __ATOMIC_RELEASE);
+	for (int d = 1; d < nranks; d++) {
+		const int k = (me + d) % nranks;
+		const PfXchgHeader *ph = (const PfXchgHeader *)peers->base[k];
+		if (!emu_wait_flag(&ph->seq[buf], seq, ph, status, timeout_s)) return 0;
+		const long long cnt = (long long)ph->count[buf];
+		const volatile unsigned *log = (const volatile unsigned *)(peers->base[k] + PF_XCHG_HEADER_BYTES) + (size_t)buf * (size_t)event_cap;
+		for (long long i = 0; i < cnt; i++) { const unsigned e = log[i]; nodes[e & ~PF_EVENT_DEC].occ += (e & PF_EVENT_DEC) ? -1 : 1; }
+	}
+	g_times.aux_launches++;
+	return 0;
+}
+
+int pfb_launch_xchg_delays(float *net_delay, const unsigned char *term_owner, int num_terminals, const PfPeers *peers, int me, int nranks,
+		unsigned dseq, long long event_cap, int *status, double timeout_s) {
+	const int buf = (int)((dseq - 1u) & 1u);
+	const size_t off = PF_XCHG_HEADER_BYTES + 8 * (size_t)event_cap + sizeof(float) * (size_t)buf * (size_t)num_terminals;
+	float *pub = (float *)(peers->base[me] + off);
+	for (int t = 0; t < num_terminals; t++) if (term_owner[t] == me) pub[t] = net_delay[t];
+	PfXchgHeader *mine = (PfXchgHeader *)peers->base[me];
+	__atomic_store_n(&mine->dseq[buf], dseq, __ATOMIC_RELEASE);
+	for (int d = 1; d < nranks; d++) {
+		const PfXchgHeader *ph = (const PfXchgHeader *)peers->base[(me + d) % nranks];
+		if (!emu_wait_flag(&ph->dseq[buf], dseq, ph, status, timeout_s)) return 0;
+	}
+	for (int t = 0; t < num_terminals; t++) {
+		const int k = term_owner[t];
+		if (k != me && k < nranks) net_delay[t] = *(const volatile float *)((const float *)(peers->base[k] + off) + t);
+	}
+	g_times.aux_launches++;
+	return 0;
+}
+
+int pfb_launch_xchg_abort(const PfPeers *peers, int me) {
+	__atomic_store_n(&((PfXchgHeader *)peers->base[me])->abort_flag, 1u, __ATOMIC_RELEASE);
 	return 0;
 }
 

@@ -120,6 +120,11 @@ PF_DEV int pf_atomic_add_i(int *p, int v) { int o = *p; *p = o + v; return o; }
 PF_DEV unsigned long long pf_atomic_add_ull(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 PF_DEV int pf_atomic_or_i(int *p, int v) { int o = *p; *p = o | v; return o; }
 PF_DEV int pf_atomic_min_i(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
+PF_DEV int pf_atomic_exch_i(int *p, int v) { int o = *p; *p = v; return o; }
+PF_DEV int pf_atomic_cas_i(int *p, int cmp, int v) { int o = *p; if (o == cmp) *p = v; return o; }
+PF_DEV int pf_ld_volatile_i(const int *p) { return *(const volatile int *)p; }
+PF_DEV void pf_threadfence(void) {}
+PF_DEV void pf_spin_pause(void) {}     /* spin loops in the device code contain a warp collective per turn: that is the yield */
 PF_DEV void pf_atomic_max_f(float *p, float v) { if (v > *p) *p = v; }
 PF_DEV void pf_atomic_min_f(float *p, float v) { if (v < *p) *p = v; }
 PF_DEV pf_u4 pf_ld_cg_u4(const void *p) { pf_u4 v; memcpy(&v, p, 16); return v; }   /* L2-coherent load */

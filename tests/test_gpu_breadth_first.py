@@ -6,6 +6,7 @@ import time
 import pytest
 
 from parallel_eda_b200 import check_route, pfio, router
+import parity_bar
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -14,17 +15,14 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 @pytest.mark.parametrize("name", ["toy_w64", "duo_w80", "hub_w90"])
 def test_breadth_first_routing(name):
     p = pfio.read_problem(os.path.join(G, name + "_bf.pfp.xz"))
-    p.opts["max_router_iterations"] = 150
     g = pfio.read_result(os.path.join(G, name + "_bf.pfr.xz"))
     t = time.perf_counter()
     r = router.try_timing_driven_route(p)
     dt = time.perf_counter() - t
-    assert r.success == 1
+    print("%s breadth-first: %d iterations (reference %d), wirelength x%.3f, %.3f s" % (name, r.iterations, g.iterations, r.total_wirelength / g.total_wirelength, dt))
+    parity_bar.check("breadth_first", name, r, g)
     m = check_route.check_route(p, r, check_delays=False)
     assert m["overused"] == 0 and m["wirelength"] == r.total_wirelength
-    print("%s breadth-first: %d iterations (reference %d), wirelength x%.3f, %.3f s" % (name, r.iterations, g.iterations, r.total_wirelength / g.total_wirelength, dt))
-    # the 300-net toy moves by percents from run to run (measured +8 %); duo / hub measured +2 % / +0.4 %
-    assert r.total_wirelength <= (1.15 if name == "toy_w64" else 1.10) * g.total_wirelength
 
 
 def test_single_warp_breadth_first_is_bit_identical_to_the_emulated_device_code():

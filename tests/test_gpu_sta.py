@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from parallel_eda_b200 import check_route, pfio, router
+import parity_bar
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -29,18 +30,16 @@ def test_device_sta_bit_identical_to_reference(name):
 def test_route_with_device_sta(name):
     p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
     p.opts["timing_analysis_enabled"] = 1
-    p.opts["max_router_iterations"] = 150
     g = pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz"))
     gold = pfio.read_result(os.path.join(G, name + ".pfr.xz"))
     t = time.perf_counter()
     r = router.try_timing_driven_route(p, timing_graph=g)
     dt = time.perf_counter() - t
-    assert r.success == 1
-    m = check_route.check_route(p, r)
-    assert m["overused"] == 0
-    # critical path delay of the last analysis against the reference's own (same circuit, same placement)
-    cpd = float(r.iter_stats["crit_path_delay"][-2]); ref = float(gold.iter_stats["crit_path_delay"][-2])
+    # critical path delay of the analysis of the FINAL routing against the reference's last analysis (same circuit, same
+    # placement; the reference analyses before its last iteration, pf_route_run also after it)
+    cpd = float(r.iter_stats["crit_path_delay"][-1]); ref = float(gold.iter_stats["crit_path_delay"][-2])
     print("%s: %d iterations (reference %d), cpd %.3f ns (reference %.3f), wirelength x%.3f, %.3f s" % (
         name, r.iterations, gold.iterations, cpd, ref, r.total_wirelength / gold.total_wirelength, dt))
-    tol = 0.12 if name == "hub_w90" else 0.08
-    assert abs(cpd - ref) <= tol * ref and r.total_wirelength <= (1 + tol) * gold.total_wirelength
+    parity_bar.check("closed_loop_device_sta", name, r, gold, weighted=(cpd, ref))
+    m = check_route.check_route(p, r)
+    assert m["overused"] == 0

@@ -156,3 +156,63 @@ def test_two_ranks_breadth_first(emu_lib, tmp_path):
     import json
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert out["success"] and out["occ_equal"] and out["overused"] == 0
+
+
+WORKER_NATIVE = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch
+from parallel_eda_b200 import pfio, router, pathfinder, distributed, check_route
+comm = distributed.init_from_env("gloo")
+G = os.path.join(%(root)r, "tests", "golden")
+td = %(td)d
+name = "duo_w80" if td else "hub_w90"
+p = pfio.read_problem(os.path.join(G, name + ".pfp.xz")); p.opts["timing_analysis_enabled"] = td
+if td: p.opts["max_router_iterations"] = 100
+lib = %(emu)r
+cfg = router.default_config(router.load_library(lib), num_slots=4, big_slots=2, rank=comm.rank, nranks=comm.world)
+R = comm.create_router(p, cfg, lib_path=lib)      # includes comm.connect(R): pf_comm_export / all-gather / pf_comm_init
+S = router.Sta(pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz")), p, cfg, lib_path=lib) if td else None
+rep = pathfinder.run(R, comm=comm, dsta=S)         # pf_route_run: exchange over (emulated) peer memory, no torch collective
+res = R.result()
+occ = torch.from_numpy(res.occ.astype(np.int64)); ref = occ.clone(); torch.distributed.broadcast(ref, 0)
+nd = torch.from_numpy(res.net_delay.copy()); ndref = nd.clone(); torch.distributed.broadcast(ndref, 0)
+own = [i for i in p.routed_nets() if res.trace_ptr[i + 1] > res.trace_ptr[i]]
+parts = [None] * comm.world
+torch.distributed.all_gather_object(parts, (own, [res.net_trace(int(i)) for i in own]))
+if comm.rank == 0:
+    seen = {}
+    for o, tr in parts:
+        for i, t in zip(o, tr): assert i not in seen; seen[int(i)] = t
+    assert sorted(seen) == [int(i) for i in p.routed_nets()]
+    tp = [0]; tn = []; ts = []
+    for i in range(p.num_nets):
+        if i in seen: tn.append(seen[i][0]); ts.append(seen[i][1])
+        tp.append(tp[-1] + (len(seen[i][0]) if i in seen else 0))
+    full = pfio.Result(int(rep.success), rep.iterations, 0, 0, np.array(tp, np.int32), np.concatenate(tn), np.concatenate(ts), res.net_delay, res.occ, res.iter_stats)
+    # legality of the union of the ranks' traces AND every sink delay (also of nets the OTHER rank routed, and of nets that were
+    # not re-routed in the last iterations) against a from-scratch Elmore recomputation
+    m = check_route.check_route(p, full, check_delays=bool(td))
+    print(json.dumps({"success": bool(rep.success), "iters": rep.iterations, "occ_equal": bool(torch.equal(occ, ref)), "delay_equal": bool(torch.equal(nd, ndref)),
+                      "overused": m["overused"], "routed_by": [len(o) for o, _ in parts]}))
+else:
+    assert torch.equal(occ, ref) and torch.equal(nd, ndref)
+'''
+
+
+@pytest.mark.parametrize("td", [0, 1])
+def test_two_ranks_native_transport(td, emu_lib, tmp_path):
+    """pf_comm_export / pf_comm_init / pf_route_run: the transport inside the library.  On the emulator the ranks'
+    exchange regions are POSIX shared memory and the device-side protocol (payload, release of the sequence number,
+    acquire-polling consumers, double buffering by parity) is the one the CUDA kernels run over NVLink.  Timing-driven:
+    the ranks publish the sink delays of their nets and gather the others' before the device analysis."""
+    script = tmp_path / "worker_native.py"
+    script.write_text(WORKER_NATIVE % {"root": ROOT, "emu": emu_lib, "td": td})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29537 + td), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    import json
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["success"] and out["occ_equal"] and out["delay_equal"] and out["overused"] == 0
+    assert min(out["routed_by"]) > 0, out          # both ranks actually routed nets
