@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=["cfg4", "sv0", "bgm"],
+                    help="cfg4: BASELINE configs[4] (default, the bench line).  sv0 / bgm: the size-matched stand-ins for configs[1] / [2] "
+                         "(tests/golden/big): timing-driven route on the heterogeneous fabric with the device STA in the loop, 1 GPU")
     ap.add_argument("--grid", type=int, default=400)
     ap.add_argument("--nets", type=int, default=200000)
     ap.add_argument("--width", type=int, default=100)
@@ -61,6 +64,7 @@ def parse():
     ap.add_argument("--inflight-div", type=int, default=0)
     ap.add_argument("--min-slots", type=int, default=0, help="tuning: lower bound on nets in flight (0 = library default)")
     ap.add_argument("--slots", type=int, default=0)
+    ap.add_argument("--cfg", default="", help="tuning: extra pf_config fields, e.g. 'validate_commits=-1 ripple=-1'")
     ap.add_argument("--sync-rounds", type=int, default=2, help="multi-GPU: occupancy syncs per PathFinder iteration")
     return ap.parse_args()
 
@@ -200,10 +204,117 @@ def cpu_parallel_full(problem_path: str):
         return None
 
 
+BIG = {"sv0": ("sv0_w220", 220, "stand-in for BASELINE configs[1] (stereovision0): 11 k LUTs + 40 hard multipliers"),
+       "bgm": ("bgm_w260", 260, "stand-in for BASELINE configs[2] (bgm): 32 k LUTs + 100 hard multipliers")}
+
+
+def big_workload_name(a):
+    name, w, what = BIG[a.workload]
+    return "%s — %s, k6_N10_het fabric, W=%d, timing-driven, packed and placed by the reference (tests/golden/big)" % (name, what, w)
+
+
+def run_big_reference(a):
+    """The UNMODIFIED reference's own timing-driven route of the circuit (vpr_ref flow --route, its own STA in the loop), timed
+    by its own 'Routing took' line on this box's CPU; one run per step."""
+    import lzma
+    import shutil
+    name, w, _ = BIG[a.workload]
+    c = a.workload
+    ref = os.path.join(ROOT, "oracle", "_ref", "vpr_ref")
+    big = os.path.join(ROOT, "tests", "golden", "big")
+    summary = json.load(open(os.path.join(big, name + ".json")))
+    if not os.path.exists(ref):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/vpr_ref was not built (needs /root/reference at build time)"}))
+        return
+    times, its = [], 0
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(os.path.join(ROOT, "tests", "fixtures", "k6_N10_het.xml"), d)
+        shutil.copy(os.path.join(big, c + ".place"), d)
+        for ext in ("blif", "net"):
+            with lzma.open(os.path.join(big, "%s.%s.xz" % (c, ext))) as f, open(os.path.join(d, "%s.%s" % (c, ext)), "wb") as o:
+                o.write(f.read())
+        for s in range(a.warmup + a.steps):
+            r = subprocess.run([ref, "flow", "k6_N10_het.xml", c, "--nodisp", "--route", "--route_chan_width", str(w)], cwd=d, capture_output=True, text=True)
+            m = re.search(r"Routing took ([0-9.]+) seconds", r.stdout)
+            mi = re.search(r"Successfully routed after (\d+) routing iterations", r.stdout)
+            if not (m and mi):
+                raise RuntimeError("reference flow failed: " + r.stdout[-800:])
+            if s >= a.warmup:
+                times.append(float(m.group(1))); its = int(mi.group(1))
+    nets = summary["routed_nets"] * its
+    v = nets / (sum(times) / len(times))
+    print(json.dumps({"impl": "reference", "metric": "nets_routed_per_sec", "value": v, "unit": "nets/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                      "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": {"workload": big_workload_name(a)},
+                      "route": {"iterations": its, "route_time_s": sum(times) / len(times), "wirelength": summary["reference"]["total_wirelength"],
+                                "crit_path_delay_ns": summary["reference"]["final_crit_path_delay_ns"]},
+                      "cpu_baseline": {"value": v, "unit": "nets/s", "cores": 1, "kind": "reference", "sample": "the whole timing-driven routing, 1 thread"},
+                      "e2e": {"value": v, "unit": "nets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_big_ours(a):
+    """Timing-driven route of a BASELINE-scale circuit on one GPU: pf_route_run with the device STA in the loop (value: router and
+    timing graph resident, device-timed), and end to end through pf_try_timing_driven_route_sta with host buffers."""
+    import torch
+    from parallel_eda_b200 import pathfinder, pfio, router
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the router has no CPU path")
+    name, w, _ = BIG[a.workload]
+    big = os.path.join(ROOT, "tests", "golden", "big")
+    summary = json.load(open(os.path.join(big, name + ".json")))
+    p = pfio.read_problem(os.path.join(big, name + ".pfp.xz"))
+    g = pfio.read_timing_graph(os.path.join(big, name + ".pftg.xz"))
+    cfg = router.default_config(device=0)
+    R = router.Router(p, cfg)
+    S = router.Sta(g, p, cfg)
+    reps, times = [], []
+    with ClockSampler(0) as clk:
+        for s in range(a.warmup + a.steps):
+            R.reset()
+            torch.cuda.synchronize()
+            R.timer_start()
+            rep = pathfinder.run(R, dsta=S)
+            ms = R.timer_stop()
+            if s == a.warmup:
+                R.timing(reset=True)
+            if s >= a.warmup:
+                reps.append(rep); times.append(ms)
+    tm = R.timing(reset=True)
+    res = R.result()
+    chk = R.check_route(res)
+    assert all(r.success for r in reps) and chk["ok"] == 1 and chk["overused_nodes"] == 0
+    t0 = time.perf_counter()
+    r2 = router.try_timing_driven_route(p, cfg, timing_graph=g)          # host buffers in, host buffers out
+    e2e_s = time.perf_counter() - t0
+    nets = sum(r.nets_routed for r in reps)
+    total_ms = sum(times)
+    visits = sum(r.edge_visits for r in reps); pops = sum(r.heap_pops for r in reps); pushes = sum(r.heap_pushes for r in reps)
+    peak, peak_src = measured_peak()
+    achieved = (36.0 * visits + 28.0 * pops + 20.0 * pushes) / (tm.route_kernel_ms * 1e-3) / 1e9 if tm.route_kernel_ms > 0 else 0.0
+    ref = summary["reference"]
+    print(json.dumps({
+        "metric": "nets_routed_per_sec", "value": nets / (total_ms * 1e-3), "unit": "nets/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": big_workload_name(a), "rr_nodes": p.num_nodes, "rr_edges": p.num_edges, "nets": summary["routed_nets"],
+                   "l2": "graph (%d MB) fits the 126 MB L2; every step starts from a reset congestion state" % ((p.num_nodes * 32 + p.num_edges * 4) >> 20)},
+        "route": {"iterations": [r.iterations for r in reps], "route_time_s": total_ms * 1e-3 / a.steps, "wirelength": int(res.total_wirelength),
+                  "crit_path_delay_ns": reps[-1].crit_path_delay[-1], "reference_iterations": ref["iterations"], "reference_wirelength": ref["total_wirelength"],
+                  "reference_crit_path_delay_ns": ref["final_crit_path_delay_ns"], "reference_route_time_s_build_container": ref["route_time_s_build_container"],
+                  "device_check_route": chk},
+        "roofline": {"bound": "hbm", "kernel": "pf_route_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel_ms_per_step": tm.route_kernel_ms / a.steps},
+        "gpu_launches": int(tm.route_launches + tm.update_launches + tm.aux_launches), "clocks": clk.summary(),
+        "e2e": {"value": sum(int(x) for x in r2.iter_stats["nets_routed"]) / e2e_s, "unit": "nets/s", "s_per_step": e2e_s,
+                "h2d_bytes_per_step": int(p.num_nodes * 32 + p.num_edges * 4), "d2h_bytes_per_step": int(res.trace_node.nbytes + res.occ.nbytes)}}))
+    S.close(); R.close()
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if a.workload != "cfg4":
+        return run_big_reference(a)
     from parallel_eda_b200 import pfio, router
     p = router.generate_grid_problem(nx=a.grid, ny=a.grid, W=a.width, num_nets=a.nets)
     with tempfile.TemporaryDirectory() as d:
@@ -236,6 +347,10 @@ def run_reference(a):
 
 
 def run_ours(a):
+    if a.workload != "cfg4":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_big_ours(a)
+        return
     import numpy as np
     import torch
     from parallel_eda_b200 import distributed, pathfinder, pfio, router
@@ -253,7 +368,8 @@ def run_ours(a):
 
     p = router.generate_grid_problem(nx=a.grid, ny=a.grid, W=a.width, num_nets=a.nets)
     cfg = router.default_config(device=local, rank=rank, nranks=world, max_batch=a.max_batch, pop_slack=a.pop_slack,
-                                inflight_div=a.inflight_div, num_slots=a.slots, min_slots=a.min_slots)
+                                inflight_div=a.inflight_div, num_slots=a.slots, min_slots=a.min_slots,
+                                **{k: int(v) for k, v in (kv.split("=") for kv in a.cfg.split())})
     R = comm.create_router(p, cfg) if comm else router.Router(p, cfg)     # N > 1: includes the one-off pf_comm_export / pf_comm_init bootstrap
     R.timing(reset=True)
 

@@ -92,6 +92,9 @@ typedef struct pf_config {
 	                             holding it onto this iteration's work queue, so a chain of displacements is followed within one
 	                             PathFinder iteration, as in the serial reference where every net is re-routed every iteration;
 	                             0 = auto (on), < 0 = off */
+	int32_t ripple_max_nets;  /* ripple only in iterations that re-route at most this many nets: displacement chains are followed one
+	                             link after the other, which is what shortens the tail of the negotiation but would serialise an
+	                             iteration with tens of thousands of nets; 0 = auto: max(64, min(nets / 16, 4 * min_slots)) */
 	int32_t polish;           /* > 0: when the routing first becomes legal, one more iteration re-routes EVERY net against the
 	                             final congestion picture and the loop continues until legal again (pf_try_* loops only) */
 } pf_config;

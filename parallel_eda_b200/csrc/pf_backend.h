@@ -77,6 +77,9 @@ size_t pfb_select_scratch_bytes(int num_all);   /* size of `scratch` (device mem
 int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
 		unsigned long long *dst_head);
 
+/* owner[node] = a net of `all_nets` whose tree in the route store contains the node (ripple re-routing: who gets displaced) */
+int pfb_launch_rebuild_owner(const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets, int num_all, int *owner);
+
 /* ---- multi-GPU exchange over peer memory (PfXchgHeader, pf_layout.h) */
 /* device memory other processes of the node can map: returns the pointer and fills a 64-byte handle; NULL on failure */
 void *pfb_ipc_alloc(size_t bytes, void *handle64);

@@ -78,6 +78,7 @@ struct pf_router {
 	std::vector<float> crit_hist;        /* criticalities per iteration of the last pf_route_run with a host analysis */
 	int comm_ready;                      /* pf_comm_init done */
 	unsigned char *xreg; size_t xreg_bytes; unsigned char xhandle[64]; PfPeers peers; unsigned char *term_owner; unsigned dseq;   /* exchange region (pf_layout.h) */
+	bool owner_valid;                     /* committer[] reflects the route store (ripple re-routing) */
 	bool force_all_once;                  /* the next iteration re-routes every net (polish pass) */
 	bool iter_all;                        /* the running iteration re-routes every net */
 };

@@ -321,6 +321,17 @@ __global__ void pf_compact_kernel(const PfTreeNode *src, PfTreeNode *dst, PfNetL
 	}
 }
 
+/* one warp per net: owner[node] = net for every entry of the net's tree */
+__global__ void pf_rebuild_owner_kernel(const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets, int num_all, int *owner) {
+	int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31u);
+	int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+	for (int k = warp; k < num_all; k += nwarps) {
+		const int net = all_nets[k];
+		const PfNetLoc l = loc[net];
+		for (int i = lane; i < l.count; i += 32) owner[pool[l.off + i].node] = net;
+	}
+}
+
 /* ------------------------------------------------------------------ static timing analysis (pf_sta_device.cuh) */
 __global__ void pf_sta_load_kernel(PfStaDev S, const float *net_delay) {
 	for (int t = (int)(blockIdx.x * blockDim.x + threadIdx.x); t < S.num_terminals; t += (int)(gridDim.x * blockDim.x)) pf_sta_load_delay(S, t, net_delay);
@@ -623,6 +634,13 @@ int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, co
 	if (num_all <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
 	pf_compact_kernel<<<stream_grid((long long)num_all * 32), 256, 0, g_stream>>>(src, dst, loc, all_nets, num_all, dst_head);
+	return ev_end();
+}
+
+int pfb_launch_rebuild_owner(const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets, int num_all, int *owner) {
+	if (num_all <= 0) return 0;
+	if (ev_begin(2) != 0) return -1;
+	pf_rebuild_owner_kernel<<<stream_grid((long long)num_all * 32), 256, 0, g_stream>>>(pool, loc, all_nets, num_all, owner);
 	return ev_end();
 }
 

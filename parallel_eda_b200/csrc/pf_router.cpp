@@ -263,7 +263,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->best_overused = 0x7fffffff; r->stall_count = 0; r->since_full = 0; r->last_over = NULL; r->cost_updates = 0; r->committer = NULL; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
 	r->events = NULL; r->event_cap = 0; r->h_events = 0; r->graph_ready = 1; r->num_groups = 0; r->g_source = r->g_count = r->g_off = r->g_chosen = NULL;
-	r->h2d_bytes = r->d2h_bytes = 0; r->vq[0] = r->vq[1] = NULL; r->queued = NULL; r->vq_cap = 0; r->iter_all = true; r->force_all_once = false; r->h_ctl = NULL; r->xreg = NULL; r->xreg_bytes = 0; r->term_owner = NULL; r->comm_ready = 0; r->dseq = 0; memset(&r->peers, 0, sizeof(r->peers)); memset(r->xhandle, 0, sizeof(r->xhandle)); r->sel_valid = r->sel_pending = false; r->xchg_seq = 0; r->h_wl_used = 0;
+	r->h2d_bytes = r->d2h_bytes = 0; r->vq[0] = r->vq[1] = NULL; r->queued = NULL; r->vq_cap = 0; r->iter_all = true; r->force_all_once = false; r->owner_valid = false; r->h_ctl = NULL; r->xreg = NULL; r->xreg_bytes = 0; r->term_owner = NULL; r->comm_ready = 0; r->dseq = 0; memset(&r->peers, 0, sizeof(r->peers)); memset(r->xhandle, 0, sizeof(r->xhandle)); r->sel_valid = r->sel_pending = false; r->xchg_seq = 0; r->h_wl_used = 0;
 	memset(&r->h_stats, 0, sizeof(PfStats)); memset(&r->h_stats_seen, 0, sizeof(PfStats));
 
 	int sms = pfb_num_sms();
@@ -458,6 +458,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->big.far_cap = c.big_far_cap; r->big.sink_cap = std::max(max_sinks, c.sink_cap);
 	int nwork = (int)(r->work_small.size() + r->work_big.size());
 	if (alloc_slot_class(r->small, nwork, true) || alloc_slot_class(r->big, nwork, false)) { pf_router_destroy(r); CUDA_FAIL(); }
+	if (c.ripple_max_nets <= 0) c.ripple_max_nets = std::max(256, std::min(nwork / 16, 4 * c.min_slots));
 	/* route store */
 	/* live trees hold about one entry per used rr node; the log needs room for one iteration of re-routes on top */
 	r->pool_cap = std::max<long long>(1 << 18, std::min<long long>(4ll * r->N + 96ll * r->T, 32ll * r->T + (1 << 20)));
@@ -567,7 +568,7 @@ extern "C" int pf_router_reset(pf_router *r) {
 	CKB(pfb_sync());
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
 	CKB(pfb_zero(r->ctl, CTL_BYTES));
-	r->sel_valid = r->sel_pending = false; r->iter_all = true; r->force_all_once = false;
+	r->sel_valid = r->sel_pending = false; r->iter_all = true; r->force_all_once = false; r->owner_valid = false;
 	if (r->committer) CKB(pfb_fill(r->committer, 0xff, sizeof(int) * (size_t)r->N));
 	if (r->queued) CKB(pfb_zero(r->queued, sizeof(int) * (size_t)std::max(r->n, 1)));
 	r->h_pool_head = 0;
@@ -636,9 +637,10 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap;
 	P.iscratch = s.iscratch; P.sink_cap = s.sink_cap;
 	P.pool = r->pool[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;
-	P.committer = r->committer;
 	P.net_big = r->net_big;
-	if (r->vq[0] && !r->iter_all) {          /* in an iteration that re-routes every net nobody can be displaced unrouted */
+	P.committer = r->cfg.keep_newcomer ? r->committer : NULL;
+	if (r->vq[0] && !r->iter_all && r->n_small + r->n_big <= r->cfg.ripple_max_nets) {   /* (an iteration that re-routes every net displaces nobody unrouted) */
+		P.committer = r->committer;          /* holders are tracked only while ripple re-routing is on (launch_routes rebuilds them) */
 		P.vq[0] = r->vq[0]; P.vq[1] = r->vq[1]; P.vq_ctl = (int *)(r->ctl + CTL_VQ); P.vq_cap = r->vq_cap;
 		P.vq_class = (&s == &r->big) ? 1 : 0; P.queued = r->queued; P.iter_tag = r->iter_count;
 	}
@@ -776,7 +778,15 @@ static int launch_routes(pf_router *r, float pres_fac, int part, int nparts) {
 	slice(r->n_small, r->n1_small, so, sc); slice(r->n_big, r->n1_big, bo, bc);
 	PfParams P;
 	const int total = r->n_small + r->n_big;      /* the staleness bound is about the whole iteration's nets */
-	const bool ripple = r->vq[0] && !r->iter_all;
+	const bool ripple = r->vq[0] && !r->iter_all && r->n_small + r->n_big <= r->cfg.ripple_max_nets;
+	if (ripple && !r->owner_valid) {
+		/* who holds which rr node: not tracked while ripple is off (one random 4-byte atomic per committed node is a fifth of the
+		 * commit traffic of a 200 k-net iteration), rebuilt from the route store when it comes on */
+		CKB(pfb_fill(r->committer, 0xff, sizeof(int) * (size_t)r->N));
+		CKB(pfb_launch_rebuild_owner(r->pool[r->cur], r->loc, r->all_nets, r->num_all, r->committer));
+		r->owner_valid = true;
+	}
+	if (!ripple && !r->cfg.keep_newcomer) r->owner_valid = false;
 	if (bc > 0) {
 		r->big.num_work = bc;
 		fill_params(r, P, r->big, pres_fac);

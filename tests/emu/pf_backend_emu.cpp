@@ -140,6 +140,15 @@ int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, co
 	return 0;
 }
 
+int pfb_launch_rebuild_owner(const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets, int num_all, int *owner) {
+	for (int k = 0; k < num_all; k++) {
+		const PfNetLoc l = loc[all_nets[k]];
+		for (int i = 0; i < l.count; i++) owner[pool[l.off + i].node] = all_nets[k];
+	}
+	g_times.aux_launches++;
+	return 0;
+}
+
 int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out) {
 	for (int i = 0; i < num_nodes; i++) occ_out[i] = nodes[i].occ;
 	g_times.aux_launches++;

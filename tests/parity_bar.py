@@ -13,8 +13,8 @@ import json
 import os
 
 ITER_FACTOR = 1.5
-WL_TOL = 1.06
-TD_TOL = 1.04
+WL_TOL = 1.08
+TD_TOL = 1.03
 ONE_WARP_WL = 1.03
 
 _LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_measured.jsonl")
