@@ -40,6 +40,10 @@ int pfb_num_sms(void);
 int pfb_timer_start(void);                        /* CUDA events on the router's stream */
 int pfb_timer_stop(double *ms);
 void *pfb_stream(void);
+/* phase marks: an event on the router's stream now; pfb_marks_read returns, after a sync, the device time in ms between
+ * consecutive marks since the last read and forgets them (profiling aid of pf_route_run, PF_PHASES=1) */
+int pfb_mark(void);
+int pfb_marks_read(double *ms, int cap);
 
 /* the warp-per-net router: num_slots warps, each looping over the work queue */
 int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block);
@@ -60,7 +64,7 @@ int pfb_launch_extract_occ(const PfNode *nodes, int num_nodes, int *occ_out);
 /* total wirelength of all trees in the route store (route_timing.c:189-225 sanity abort) */
 int pfb_launch_wirelength(const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets, int num_all, unsigned long long *d_out);
 /* reserve_locally_used_opins (route_common.c:1435-1491): one thread per (block, class) group */
-int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
+int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, int node_bits, const PfIndexedDev *indexed,
 		int num_groups, const int *group_source, const int *group_count, const int *group_off,
 		int *chosen, int rip_up, float pres_fac);
 /* work list of the next iteration: the nets of `all_nets` that touch an overused node (or every
@@ -109,7 +113,7 @@ int pfb_sta_update(const PfStaDev *S, float constraint, const float *stat, float
 /* check_route over a finished routing (pf_check_net): report[0] bad nets, [1] lowest bad net (init INT_MAX), [2] its
  * code, [3] rr nodes whose occupancy is not explained by the traces, [4] overused rr nodes; wl_extra[0] wirelength,
  * [1] occupancy not accounted for by the traces (must equal the locally used OPINs) */
-int pfb_launch_check_route(const PfNode *nodes, const uint32_t *edges, int num_nodes, int num_nets, const int *net_ptr, const int *net_term,
+int pfb_launch_check_route(const PfNode *nodes, const uint32_t *edges, int node_bits, int num_nodes, int num_nets, const int *net_ptr, const int *net_term,
 		const unsigned char *net_is_global, const int *trace_ptr, const int *trace_node, const short *trace_switch, unsigned char *matched,
 		int *occ2, const int *occ_reported, int *report, unsigned long long *wl_extra);
 

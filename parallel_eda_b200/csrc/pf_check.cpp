@@ -28,7 +28,7 @@ extern "C" int pf_check_route(pf_router *r, const pf_result *res, pf_check_repor
 	bad = bad || pfb_h2d(d_tp, res->trace_ptr, sizeof(int) * ((size_t)r->n + 1)) || pfb_h2d(d_tn, res->trace_node, sizeof(int) * total)
 		|| pfb_h2d(d_ts, res->trace_switch, sizeof(short) * total) || pfb_h2d(d_occ, res->occ, sizeof(int) * (size_t)r->N)
 		|| pfb_h2d(d_glob, p->net_is_global, (size_t)r->n) || pfb_h2d(d_rep, h_rep, sizeof(h_rep))
-		|| pfb_launch_check_route(r->nodes, r->edges, r->N, r->n, r->net_ptr, r->net_term, d_glob, d_tp, d_tn, d_ts, d_matched, d_occ2, d_occ, d_rep, d_wl)
+		|| pfb_launch_check_route(r->nodes, r->edges, r->node_bits, r->N, r->n, r->net_ptr, r->net_term, d_glob, d_tp, d_tn, d_ts, d_matched, d_occ2, d_occ, d_rep, d_wl)
 		|| pfb_d2h(h_rep, d_rep, sizeof(h_rep)) || pfb_d2h(h_wl, d_wl, sizeof(h_wl));
 	pfb_free(d_tp); pfb_free(d_tn); pfb_free(d_ts); pfb_free(d_occ); pfb_free(d_occ2); pfb_free(d_matched); pfb_free(d_glob); pfb_free(d_rep); pfb_free(d_wl);
 	if (bad) CUDA_FAIL();

@@ -127,7 +127,7 @@ struct PfWarp {
 #define PF_SMEM_BLOCK_TABLES (PF_MAX_INDEXED * 32 + PF_MAX_SWITCHES * 12)
 
 PF_DEV float pf_key_tot(uint64_t k) { return pf_int_as_float((int)(k >> 32)); }
-PF_DEV int pf_key_node(uint64_t k) { return (int)((uint32_t)k & 0x03ffffffu); }
+PF_DEV int pf_key_node(uint64_t k) { return (int)(uint32_t)k; }
 /* frontier key: total cost | rr node.  Equal totals are settled oldest first (the near set keeps push order), so
  * the key carries no tie-break field. */
 PF_DEV uint64_t pf_make_key(float tot, int node) {
@@ -200,14 +200,16 @@ PF_DEV float pf_expected_cost(const PfWarp &w, int type, int ci, int ixlow, int 
 }
 
 /* ------------------------------------------------------------------ label table */
+PF_DEV unsigned pf_node_mask(int node_bits) { return (1u << node_bits) - 1u; }
+PF_DEV unsigned pf_tag_mask(const PfParams *P) { return (1u << (32 - P->node_bits)) - 1u; }      /* search tag: the bits above the node id */
 PF_DEV unsigned pf_hash(const PfWarp &w, int node) {
 	return ((uint32_t)node * 2654435761u) >> w.label_shift;
 }
 PF_DEV uint64_t pf_hot_make(const PfWarp &w, float tot, int node) {
-	return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | ((w.epoch & 63u) << PF_HOT_TAG_SHIFT) | (uint32_t)node;
+	return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | ((w.epoch & pf_tag_mask(w.P)) << w.P->node_bits) | (uint32_t)node;
 }
-PF_DEV int pf_hot_live(const PfWarp &w, uint64_t k) { return (((uint32_t)k) >> PF_HOT_TAG_SHIFT) == (w.epoch & 63u); }
-PF_DEV int pf_hot_node(uint64_t k) { return (int)((uint32_t)k & PF_HOT_NODE_MASK); }
+PF_DEV int pf_hot_live(const PfWarp &w, uint64_t k) { return (((uint32_t)k) >> w.P->node_bits) == (w.epoch & pf_tag_mask(w.P)); }
+PF_DEV int pf_hot_node(const PfWarp &w, uint64_t k) { return (int)((uint32_t)k & pf_node_mask(w.P->node_bits)); }
 
 /* Look up an existing label (used at settle time and in the back-trace).  Per-lane, no collectives. */
 PF_DEV int pf_label_find(const PfWarp &w, int node) {
@@ -215,7 +217,7 @@ PF_DEV int pf_label_find(const PfWarp &w, int node) {
 	for (;;) {
 		uint64_t k = w.hot[h];
 		if (!pf_hot_live(w, k)) return -1;
-		if (pf_hot_node(k) == node) return (int)h;
+		if (pf_hot_node(w, k) == node) return (int)h;
 		h = (h + 1) & w.label_mask;
 	}
 }
@@ -237,7 +239,7 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 		if (pending) {
 			uint64_t k = w.hot[h];
 			if (pf_hot_live(w, k)) {
-				if (pf_hot_node(k) == node) {
+				if (pf_hot_node(w, k) == node) {
 					float otot = pf_int_as_float((int)(k >> 32));
 					if (tot < otot && back < w.cold[h].back) want = 2; else pending = 0;
 				} else {
@@ -425,7 +427,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 	const int highfan = w.num_sinks >= 64;
 
 	w.epoch++;
-	if ((w.epoch & 63u) == 0) {                  /* tag wrapped: wipe the hot table, skip tag 0 (= never written) */
+	if ((w.epoch & pf_tag_mask(w.P)) == 0) {                  /* tag wrapped: wipe the hot table, skip tag 0 (= never written) */
 		PF_COLD_LOOP for (unsigned i = (unsigned)lane; i <= w.label_mask; i += PF_WARP) w.hot[i] = 0;
 		w.epoch++;
 		pf_syncwarp();
@@ -611,7 +613,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 				}
 				u = x_node;
 				uint32_t ew = P->edges[x_start + eoff];
-				to = (int)(ew & PF_EDGE_NODE_MASK); isw = (int)(ew >> PF_EDGE_NODE_BITS);
+				to = (int)(ew & pf_node_mask(P->node_bits)); isw = (int)(ew >> P->node_bits);
 				PfNodeView n = pf_load_node(P, to);
 				if (n.xhigh < w.bb_xmin || n.xlow > w.bb_xmax || n.yhigh < w.bb_ymin || n.ylow > w.bb_ymax) valid = 0;
 				if (valid && highfan && (n.xhigh < tgt_xh - rlim || n.xlow > tgt_xh + rlim || n.yhigh < tgt_yh - rlim || n.ylow > tgt_yh + rlim)) valid = 0;
@@ -741,7 +743,7 @@ PF_DEV void pf_queue_victim(const PfParams *P, int victim) {
  * label), the serial router would have seen the other net's commit and priced the node as congested.  The path is
  * then taken back (-3) and the caller searches this sink again on the current occupancy — what the serial order
  * "other net first, then this one" would have produced.  Knowingly shared nodes (seen full) never trigger it. */
-PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node, int validate) {
+template <int RIP> PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node, int validate) {
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	int tree_n = *tree_n_io;
@@ -785,11 +787,11 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node, int validate)
 			t.flags = (n.type == 2 || n.type == 1) ? 0 : PF_TF_REEXPAND;   /* IPIN / SINK are not re-expanded */
 			t.pad = 0;
 			w.tree[tree_n + i] = t;
-			if (P->committer) fcap = n.cap;
+			if (RIP && P->committer) fcap = n.cap;
 		}
 		const int old = pf_occ_change(P, i < L, v, 1);  /* commit: pathfinder_update_one_cost(+1) */
 		if (validate) raced |= (i < L && old >= cap);
-		if (i < L && old >= fcap) pathbuf[pcap + L - 1 - i] |= 1 << 12;   /* now overfull: its holder becomes a victim below */
+		if (RIP && i < L && old >= fcap) pathbuf[pcap + L - 1 - i] |= 1 << 12;   /* now overfull: its holder becomes a victim below */
 	}
 	if (validate && pf_any(raced)) {
 		PF_COLD_LOOP for (int base = 0; base < L; base += PF_WARP) {
@@ -799,7 +801,7 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node, int validate)
 		pf_syncwarp();
 		return -3;
 	}
-	if (P->committer) {
+	if (RIP && P->committer) {
 		/* this net now holds the path; whoever held a node that is overfull now is re-routed in this iteration */
 		PF_COLD_LOOP for (int base = 0; base < L; base += PF_WARP) {
 			const int i = base + lane;
@@ -913,11 +915,11 @@ PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_node, int validate)
  * rr nodes re-enter the frontier at cost 0 (breadth_first_expand_trace_segment :173-257), and the same wave carries
  * on.  Labels persist for the whole net.  Returns 1 (all sinks connected), 0 (frontier exhausted: no path),
  * -1 (scratch overflow: retry in a bigger slot), -2 (two pins of the net on one SINK: not supported). */
-PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0, int ns, int *sink_done, int *rt_of_sink) {
+template <int RIP> PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0, int ns, int *sink_done, int *rt_of_sink) {
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	w.epoch++;
-	if ((w.epoch & 63u) == 0) {
+	if ((w.epoch & pf_tag_mask(w.P)) == 0) {
 		PF_COLD_LOOP for (unsigned i = (unsigned)lane; i <= w.label_mask; i += PF_WARP) w.hot[i] = 0;
 		w.epoch++;
 		pf_syncwarp();
@@ -973,7 +975,7 @@ PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0, int ns, int *sink
 			if (dup > 1) return -2;
 			if (dup == 1) {
 				const int a0 = *tree_n_io;
-				const int si = pf_add_path(w, tree_n_io, u, 0);
+				const int si = pf_add_path<RIP>(w, tree_n_io, u, 0);
 				if (si < 0) { w.overflow |= PF_OVF_OTHER; return -1; }
 				if (lane == 0) { rt_of_sink[pin] = si; sink_done[pin] = 1; }
 				pf_syncwarp();
@@ -998,8 +1000,8 @@ PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0, int ns, int *sink
 			float tot = 0.f;
 			if (valid) {
 				const uint32_t ew = P->edges[x_start + e];
-				to = (int)(ew & PF_EDGE_NODE_MASK);
-				const int isw = (int)(ew >> PF_EDGE_NODE_BITS);
+				to = (int)(ew & pf_node_mask(P->node_bits));
+				const int isw = (int)(ew >> P->node_bits);
 				PfNodeView n = pf_load_node(P, to);
 				if (n.xhigh < w.bb_xmin || n.xlow > w.bb_xmax || n.yhigh < w.bb_ymin || n.ylow > w.bb_ymax) valid = 0;
 				if (valid) {
@@ -1030,7 +1032,7 @@ PF_DEV void pf_swap_tables(PfWarp &w) {
 /* ------------------------------------------------------------------ one net
  * timing_driven_route_net, route_timing.c:399-563 */
 /* STRICT: 0 = delta buckets, 1 = strict best-first, 2 = breadth-first router (always strict order) */
-template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) {   /* 1: routed, 0: handed to a bigger slot / failed */
+template <int STRICT, int RIP> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) {   /* 1: routed, 0: handed to a bigger slot / failed */
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	const int t0 = P->net_ptr[inet];
@@ -1047,7 +1049,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) { 
 			const int i = base + lane;
 			const int v = i < loc.count ? P->pool[loc.off + i].node : 0;
 			pf_occ_change(P, i < loc.count, v, -1);
-			if (P->committer && i < loc.count) pf_atomic_cas_i(&P->committer[v], inet, -1);   /* no longer the holder */
+			if (RIP && P->committer && i < loc.count) pf_atomic_cas_i(&P->committer[v], inet, -1);   /* no longer the holder */
 		}
 	}
 	if (ns > P->sink_cap) { w.overflow = PF_OVF_OTHER; }
@@ -1099,7 +1101,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) { 
 			pf_syncwarp();
 			const int swapped = w.hot_alt != NULL;
 			if (swapped) pf_swap_tables(w);
-			const int r = pf_route_wave_bf(w, &tree_n, t0, ns, sink_order /* reused: per-pin done flags */, rt_of_sink);
+			const int r = pf_route_wave_bf<RIP>(w, &tree_n, t0, ns, sink_order /* reused: per-pin done flags */, rt_of_sink);
 			if (swapped) pf_swap_tables(w);
 			if (r == 0) fail = PF_ST_UNROUTABLE;
 			else if (r == -2) fail = PF_ST_TWICE_TO_SINK_BF;
@@ -1114,7 +1116,11 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) { 
 			/* a search that outgrows the shared-memory label table runs again on this slot's fallback table in
 			 * global memory; the tables are swapped back before the next sink.  (One call site each for the search
 			 * and the back-trace: the kernel's instruction footprint matters, see DESIGN.md.) */
+#ifdef PF_NO_VALIDATE
+			int r, swapped = 0, si = 0, tries = 0;           /* A/B build: commit validation compiled out */
+#else
 			int r, swapped = 0, si = 0, tries = P->validate;
+#endif
 			for (;;) {
 				r = pf_search_sink<STRICT == 2 ? 1 : STRICT>(w, tree_n, target_node, crit, rlim);
 				if (r < 0 && !swapped && w.overflow == PF_OVF_LABELS && w.hot_alt) {
@@ -1124,7 +1130,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) { 
 					continue;
 				}
 				if (r > 0) {
-					si = pf_add_path(w, &tree_n, target_node, tries > 0);
+					si = pf_add_path<RIP>(w, &tree_n, target_node, tries > 0);
 					if (si == -3) { tries--; w.races++; continue; }      /* lost a race for a node: search again on the current occupancy */
 				}
 				break;
@@ -1144,7 +1150,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) { 
 			const int i = base + lane;
 			const int v = i < tree_n ? w.tree[i].node : 0;
 			pf_occ_change(P, i < tree_n, v, -1);
-			if (P->committer && i < tree_n) pf_atomic_cas_i(&P->committer[v], inet, -1);
+			if (RIP && P->committer && i < tree_n) pf_atomic_cas_i(&P->committer[v], inet, -1);
 		}
 		if (lane == 0) {
 			P->loc[inet].off = 0; P->loc[inet].count = 0;
@@ -1174,7 +1180,7 @@ template <int STRICT> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) { 
 }
 
 /* ------------------------------------------------------------------ warp main: persistent work loop */
-template <int STRICT> PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIndexedDev *idx_tab, PfSwitchDev *sw_tab, unsigned char *smem_warp) {
+template <int STRICT, int RIP> PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIndexedDev *idx_tab, PfSwitchDev *sw_tab, unsigned char *smem_warp) {
 	const int lane = pf_lane();
 	PfWarp w;
 	w.P = P;
@@ -1223,7 +1229,7 @@ template <int STRICT> PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIn
 	unsigned long long nets = 0;
 	/* work: this launch's list first, then — with ripple re-routing — the victim queue of the slot class, until no warp is
 	 * routing any more (only a routing warp can produce victims) */
-	int *const vctl = P->vq_ctl;
+	int *const vctl = RIP ? P->vq_ctl : NULL;      /* RIP == 0: the kernel variant without any ripple code (big iterations) */
 	int *const vq = vctl ? P->vq[P->vq_class] : NULL;
 	for (;;) {
 		int net = -1, ripup = !P->skip_ripup;
@@ -1258,7 +1264,7 @@ template <int STRICT> PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIn
 			else if (net >= 0) ripup = 1;                       /* a victim still owns its old route */
 		}
 		if (net < 0) break;
-		nets += (unsigned long long)pf_route_net<STRICT>(w, net, ripup);
+		nets += (unsigned long long)pf_route_net<STRICT, RIP>(w, net, ripup);
 		if (vctl && lane == 0) { pf_threadfence(); pf_atomic_add_i(&vctl[4], -1); }
 	}
 	if (lane == 0) {
@@ -1309,7 +1315,7 @@ PF_DEV unsigned pf_tree_wirelength_one(const PfTreeNode *t) {
  * by one thread: rip up last iteration's picks, then take the `count` cheapest OPINs of the class
  * SOURCE in the order the reference's binary heap (route_common.c:1142-1216) would deliver them. */
 #define PF_OPIN_HEAP_MAX 128
-PF_DEV void pf_reserve_opins_group(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
+PF_DEV void pf_reserve_opins_group(PfNode *nodes, const uint32_t *edges, int node_bits, const PfIndexedDev *indexed,
 		int source, int count, int *chosen, int rip_up, float pres_fac) {
 	/* several GPUs: every rank makes the same reservation on the same synced occupancy, so it is not logged */
 	if (rip_up) for (int k = 0; k < count; k++) pf_atomic_add_i(&nodes[chosen[k]].occ, -1);
@@ -1319,7 +1325,7 @@ PF_DEV void pf_reserve_opins_group(PfNode *nodes, const uint32_t *edges, const P
 	int e0 = nodes[source].edge_start, ne = nodes[source].num_edges;
 	if (ne > PF_OPIN_HEAP_MAX) ne = PF_OPIN_HEAP_MAX;
 	for (int k = 0; k < ne; k++) {
-		int to = (int)(edges[e0 + k] & PF_EDGE_NODE_MASK);
+		int to = (int)(edges[e0 + k] & pf_node_mask(node_bits));
 		const PfNode *n = &nodes[to];
 		float pres;
 		if (n->occ < n->capacity) pres = 1.; else pres = 1. + (n->occ + 1 - n->capacity) * pres_fac;
@@ -1431,7 +1437,7 @@ PF_DEV int pf_net_is_congested(const PfNode *nodes, const PfTreeNode *pool, PfNe
 #define PF_CHK_SINK_HAS_SWITCH 6
 #define PF_CHK_WRONG_SINKS 7
 #define PF_CHK_BAD_NODE 8
-PF_DEV int pf_check_net(const PfNode *nodes, const uint32_t *edges, int num_nodes, const int *term, int ns,
+PF_DEV int pf_check_net(const PfNode *nodes, const uint32_t *edges, int node_bits, int num_nodes, const int *term, int ns,
 		const int *tn, const short *ts, int len, unsigned char *matched /*[ns+1], zeroed*/, int *occ2, unsigned *wl_out) {
 	if (ns == 0) return 0;
 	if (len == 0) return PF_CHK_NO_TRACE;
@@ -1467,7 +1473,7 @@ PF_DEV int pf_check_net(const PfNode *nodes, const uint32_t *edges, int num_node
 			int ok = 0;
 			for (int e = 0; e < (int)n.num_edges && !ok; e++) {
 				const uint32_t ew = edges[n.edge_start + e];
-				ok = ((int)(ew & PF_EDGE_NODE_MASK) == to) && ((int)(ew >> PF_EDGE_NODE_BITS) == (int)ts[k]);
+				ok = ((int)(ew & pf_node_mask(node_bits)) == to) && ((int)(ew >> node_bits) == (int)ts[k]);
 			}
 			if (!ok) return PF_CHK_NO_SUCH_EDGE;
 		}

@@ -153,7 +153,7 @@ extern "C" int pf_gen_grid_problem(const pf_gen_params *gp, pf_problem *out) {
 			}
 	}
 	const int N = (int)G.type.size();
-	if (N >= (1 << 26)) return PF_EINVAL;
+	if (N >= (1 << 30)) return PF_EINVAL;
 
 	/* ---- edges, collected per source node in two passes (count, fill) through a callback */
 	std::vector<int32_t> deg((size_t)N + 1, 0);

@@ -33,6 +33,7 @@ struct pf_router {
 	pf_config cfg;
 	const pf_problem *prob;       /* caller-owned; must outlive the router */
 	int N, E, T, n;
+	int node_bits;                /* edge word / hot label layout (pf_layout.h) */
 	PfNode *nodes; uint32_t *edges;
 	PfSwitchDev *sw; PfIndexedDev *indexed;
 	int *net_ptr, *net_term, *net_bb;

@@ -152,6 +152,28 @@ int pfb_timer_stop(double *ms) {
 }
 void *pfb_stream(void) { return (void *)g_stream; }
 
+static cudaEvent_t g_marks[4096];
+static int g_nmarks = 0;
+int pfb_mark(void) {
+	if (g_nmarks >= 4096) return 0;
+	CK(cudaEventCreate(&g_marks[g_nmarks]));
+	CK(cudaEventRecord(g_marks[g_nmarks], g_stream));
+	g_nmarks++;
+	return 0;
+}
+int pfb_marks_read(double *ms, int cap) {
+	int n = 0;
+	if (g_nmarks > 0) cudaEventSynchronize(g_marks[g_nmarks - 1]);
+	for (int i = 1; i < g_nmarks; i++) {
+		float f = 0.f;
+		cudaEventElapsedTime(&f, g_marks[i - 1], g_marks[i]);
+		if (n < cap) ms[n++] = f;
+	}
+	for (int i = 0; i < g_nmarks; i++) cudaEventDestroy(g_marks[i]);
+	g_nmarks = 0;
+	return n;
+}
+
 static int ev_begin(int kind) {
 	if (g_npending == 64 && drain_events() != 0) return -1;
 	PendingEvent *p = &g_pending[g_npending];
@@ -174,7 +196,7 @@ extern __shared__ __align__(16) unsigned char pf_smem[];
 /* STRICT = 1: strict best-first search (one label settled per step; P.max_batch == 1), the throughput mode;
  * STRICT = 0: a delta bucket of up to P.max_batch labels per step, the latency mode for few nets per warp;
  * STRICT = 2: the breadth-first router (one persistent wavefront per net, route_breadth_first.c) */
-template <int STRICT> __global__ void __launch_bounds__(128, 5) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
+template <int STRICT, int RIP> __global__ void __launch_bounds__(128, 5) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
 	/* 96 registers and 43.3 KB of shared memory per 4-warp CTA: 5 CTAs = 20 warps per SM.
 	 * shared memory: [switch + cost-index tables, one copy per CTA][per-warp regions] */
 	const int warp_in_block = (int)(threadIdx.x >> 5);
@@ -186,7 +208,7 @@ template <int STRICT> __global__ void __launch_bounds__(128, 5) pf_route_kernel(
 	__syncthreads();
 	if (slot >= num_slots) return;
 	const size_t per_warp = PF_SMEM_PER_WARP + (P.hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8);
-	pf_warp_main<STRICT>(&P, slot, idx, sw, pf_smem + PF_SMEM_BLOCK_TABLES + (size_t)warp_in_block * per_warp);
+	pf_warp_main<STRICT, RIP>(&P, slot, idx, sw, pf_smem + PF_SMEM_BLOCK_TABLES + (size_t)warp_in_block * per_warp);
 }
 
 __global__ void pf_update_cost_kernel(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
@@ -241,12 +263,12 @@ __global__ void pf_wirelength_kernel(const PfTreeNode *pool, const PfNetLoc *loc
 	if ((threadIdx.x & 31u) == 0 && acc) atomicAdd(d_out, (unsigned long long)acc);
 }
 
-__global__ void pf_reserve_opins_kernel(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
+__global__ void pf_reserve_opins_kernel(PfNode *nodes, const uint32_t *edges, int node_bits, const PfIndexedDev *indexed,
 		int num_groups, const int *group_source, const int *group_count, const int *group_off,
 		int *chosen, int rip_up, float pres_fac) {
 	int g = (int)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (g < num_groups)
-		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac);
+		pf_reserve_opins_group(nodes, edges, node_bits, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac);
 }
 
 /* Congested-net selection, order-preserving: pass 1 flags the nets (all_nets is in the reference's
@@ -408,14 +430,14 @@ __global__ void pf_sta_update_kernel(PfStaDev S, float constraint, const float *
 }
 
 /* ------------------------------------------------------------------ check_route (pf_check_net) */
-__global__ void pf_check_nets_kernel(const PfNode *nodes, const uint32_t *edges, int num_nodes, int num_nets, const int *net_ptr,
+__global__ void pf_check_nets_kernel(const PfNode *nodes, const uint32_t *edges, int node_bits, int num_nodes, int num_nets, const int *net_ptr,
 		const int *net_term, const unsigned char *net_is_global, const int *trace_ptr, const int *trace_node, const short *trace_switch,
 		unsigned char *matched, int *occ2, int *report /* [0] bad nets [1] first bad net [2] its code */, unsigned long long *wl) {
 	const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (i >= num_nets || net_is_global[i]) return;
 	const int t0 = net_ptr[i], ns = net_ptr[i + 1] - t0 - 1;
 	unsigned w = 0;
-	const int code = pf_check_net(nodes, edges, num_nodes, net_term + t0, ns, trace_node + trace_ptr[i], trace_switch + trace_ptr[i],
+	const int code = pf_check_net(nodes, edges, node_bits, num_nodes, net_term + t0, ns, trace_node + trace_ptr[i], trace_switch + trace_ptr[i],
 			trace_ptr[i + 1] - trace_ptr[i], matched + t0, occ2, &w);
 	if (code) {
 		atomicAdd(&report[0], 1);
@@ -558,15 +580,22 @@ int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	size_t smem = PF_SMEM_BLOCK_TABLES + (size_t)warps_per_block * (PF_SMEM_PER_WARP + (P->hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8));
 	static size_t smem_set = 0;
 	if (smem > smem_set) {
-		CK(cudaFuncSetAttribute(pf_route_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(pf_route_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(pf_route_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(pf_route_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(pf_route_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(pf_route_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(pf_route_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(pf_route_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaFuncSetAttribute(pf_route_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		smem_set = smem;
 	}
 	if (ev_begin(0) != 0) return -1;
-	if (P->algorithm == 1) pf_route_kernel<2><<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
-	else if (P->max_batch == 1) pf_route_kernel<1><<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
-	else pf_route_kernel<0><<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
+	/* the ripple variant (victim queues, node ownership) only where the launch uses them: the throughput-bound launches of
+	 * the first iterations run the variant that does not carry that code at all */
+	const bool rip = P->vq_ctl != NULL || P->committer != NULL;
+	const int th = warps_per_block * 32;
+	if (P->algorithm == 1) { if (rip) pf_route_kernel<2, 1><<<blocks, th, smem, g_stream>>>(*P, num_slots); else pf_route_kernel<2, 0><<<blocks, th, smem, g_stream>>>(*P, num_slots); }
+	else if (P->max_batch == 1) { if (rip) pf_route_kernel<1, 1><<<blocks, th, smem, g_stream>>>(*P, num_slots); else pf_route_kernel<1, 0><<<blocks, th, smem, g_stream>>>(*P, num_slots); }
+	else { if (rip) pf_route_kernel<0, 1><<<blocks, th, smem, g_stream>>>(*P, num_slots); else pf_route_kernel<0, 0><<<blocks, th, smem, g_stream>>>(*P, num_slots); }
 	return ev_end();
 }
 
@@ -599,12 +628,12 @@ int pfb_launch_wirelength(const PfTreeNode *pool, const PfNetLoc *loc, const int
 	return ev_end();
 }
 
-int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed,
+int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, int node_bits, const PfIndexedDev *indexed,
 		int num_groups, const int *group_source, const int *group_count, const int *group_off,
 		int *chosen, int rip_up, float pres_fac) {
 	if (num_groups <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
-	pf_reserve_opins_kernel<<<(num_groups + 127) / 128, 128, 0, g_stream>>>(nodes, edges, indexed, num_groups, group_source, group_count, group_off, chosen, rip_up, pres_fac);
+	pf_reserve_opins_kernel<<<(num_groups + 127) / 128, 128, 0, g_stream>>>(nodes, edges, node_bits, indexed, num_groups, group_source, group_count, group_off, chosen, rip_up, pres_fac);
 	return ev_end();
 }
 
@@ -738,12 +767,12 @@ int pfb_sta_update(const PfStaDev *S, float constraint, const float *stat, float
 	return 0;
 }
 
-int pfb_launch_check_route(const PfNode *nodes, const uint32_t *edges, int num_nodes, int num_nets, const int *net_ptr, const int *net_term,
+int pfb_launch_check_route(const PfNode *nodes, const uint32_t *edges, int node_bits, int num_nodes, int num_nets, const int *net_ptr, const int *net_term,
 		const unsigned char *net_is_global, const int *trace_ptr, const int *trace_node, const short *trace_switch, unsigned char *matched,
 		int *occ2, const int *occ_reported, int *report, unsigned long long *wl_extra) {
 	if (ev_begin(2) != 0) return -1;
 	if (num_nets > 0)
-		pf_check_nets_kernel<<<(num_nets + 127) / 128, 128, 0, g_stream>>>(nodes, edges, num_nodes, num_nets, net_ptr, net_term, net_is_global,
+		pf_check_nets_kernel<<<(num_nets + 127) / 128, 128, 0, g_stream>>>(nodes, edges, node_bits, num_nodes, num_nets, net_ptr, net_term, net_is_global,
 				trace_ptr, trace_node, trace_switch, matched, occ2, report, wl_extra);
 	pf_check_occ_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, occ2, occ_reported, report, wl_extra + 1);
 	return ev_end();

@@ -22,9 +22,11 @@ struct PfNode {
 	unsigned char capacity;           /* 1  */
 };
 
-/* out-edge word: target node in the low 26 bits, switch id in the high 6 */
-#define PF_EDGE_NODE_BITS 26
-#define PF_EDGE_NODE_MASK 0x03ffffffu
+/* out-edge word: target node in the low `node_bits` bits, switch id above them.  node_bits is chosen per router
+ * (PfParams.node_bits, 26 .. 30): 26 leaves 6 bits = 64 switch types and a 6-bit search tag in the hot label word;
+ * graphs beyond 2^26 rr nodes (an 800 x 800 fabric has 7.3e7) take bits from both */
+#define PF_MIN_NODE_BITS 26
+#define PF_MAX_NODE_BITS 30
 #define PF_MAX_SWITCHES 64
 #define PF_MAX_INDEXED 32
 
@@ -42,8 +44,6 @@ struct PfIndexedDev { float base_cost, saved_base_cost, inv_length, T_linear, T_
  * The 6-bit search tag makes clearing free for 63 consecutive sink searches. */
 #define PF_SMEM_HOT_LOG2 10
 #define PF_SMEM_HOT_ENTRIES (1 << PF_SMEM_HOT_LOG2)
-#define PF_HOT_NODE_MASK 0x03ffffffu
-#define PF_HOT_TAG_SHIFT 26
 struct PfCold {
 	float back; float R_up; int prev; int info;           /* prev >= 0: rr node; prev < 0: ~tree index (seed) */
 	int edge_start; int pad0, pad1, pad2;                  /* info = entering switch | type << 8 | out-degree << 16;
@@ -91,6 +91,7 @@ struct PfParams {
 	PfNode *nodes;
 	const uint32_t *edges;
 	int num_nodes, nx, ny;
+	int node_bits;         /* see PF_MIN_NODE_BITS */
 	const PfSwitchDev *sw; int num_sw;
 	const PfIndexedDev *indexed; int num_indexed;
 	/* nets */

@@ -208,6 +208,7 @@ static int upload_edges(pf_router *r, uint32_t *staging, int *bad_out) {
 	std::atomic<int> bad(0), fail(0);
 	const long long piece = PF_UPLOAD_PIECE / sizeof(uint32_t);
 	const unsigned N = (unsigned)p->num_nodes, S = (unsigned)p->num_switches;
+	const int nb = r->node_bits;
 	parallel_for(r->E, [&](long long lo, long long hi) {
 		if (staging) pfb_bind_thread();
 		int b = 0;
@@ -216,7 +217,7 @@ static int upload_edges(pf_router *r, uint32_t *staging, int *bad_out) {
 			for (long long k = c0; k < c1; k++) {
 				const unsigned to = (unsigned)p->edge_to[k], s = (unsigned)(int)p->edge_sw[k];
 				b |= (to >= N) | (s >= S);
-				ew[k] = to | (s << PF_EDGE_NODE_BITS);
+				ew[k] = to | (s << nb);
 			}
 			if (staging) wc_fence();
 			if (staging && pfb_h2d_async(r->edges + c0, ew + c0, sizeof(uint32_t) * (size_t)(c1 - c0)) != 0) fail = 1;
@@ -245,8 +246,11 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	std::atomic<int> terminals_bad(0);
 	std::thread terminal_check([p, &terminals_bad]() { if (!problem_terminals_ok(p)) terminals_bad = 1; });
 	struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{terminal_check};   /* every return path */
-	if (p->num_nodes > (1 << PF_EDGE_NODE_BITS)) FAILF(PF_EINVAL, "num_rr_nodes %d exceeds the %d-bit edge word", p->num_nodes, PF_EDGE_NODE_BITS);
-	if (p->num_switches > PF_MAX_SWITCHES) FAILF(PF_EINVAL, "%d switch types (max %d)", p->num_switches, PF_MAX_SWITCHES);
+	/* edge word = target node | switch << node_bits; the bits above the node id are also the search tag of the hot labels */
+	const int node_bits = std::max(PF_MIN_NODE_BITS, ceil_log2((long long)p->num_nodes));
+	if (node_bits > PF_MAX_NODE_BITS) FAILF(PF_EINVAL, "num_rr_nodes %d exceeds the %d-bit node field", p->num_nodes, PF_MAX_NODE_BITS);
+	if (p->num_switches > PF_MAX_SWITCHES || p->num_switches > (1 << (32 - node_bits)))
+		FAILF(PF_EINVAL, "%d switch types (max %d with %d rr nodes)", p->num_switches, std::min(PF_MAX_SWITCHES, 1 << (32 - node_bits)), p->num_nodes);
 	if (p->num_indexed > PF_MAX_INDEXED) FAILF(PF_EINVAL, "%d rr_indexed_data rows (max %d)", p->num_indexed, PF_MAX_INDEXED);
 	if (cfg_in->nranks < 1 || cfg_in->rank < 0 || cfg_in->rank >= cfg_in->nranks) FAILF(PF_EINVAL, "bad rank %d / nranks %d", cfg_in->rank, cfg_in->nranks);
 	if (pfb_init(cfg_in->device) != 0) CUDA_FAIL();
@@ -255,6 +259,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	memset((void *)&r->cfg, 0, sizeof(pf_config));
 	r->cfg = *cfg_in;
 	pf_config &c = r->cfg;
+	r->node_bits = node_bits;
 	r->prob = p; r->N = p->num_nodes; r->E = p->num_edges; r->T = p->num_terminals; r->n = p->num_nets;
 	r->nodes = NULL; r->edges = NULL; r->sw = NULL; r->indexed = NULL; r->net_ptr = r->net_term = r->net_bb = NULL;
 	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
@@ -618,7 +623,7 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	const pf_problem *p = r->prob;
 	const pf_config &c = r->cfg;
 	memset(&P, 0, sizeof(P));
-	P.nodes = r->nodes; P.edges = r->edges; P.num_nodes = r->N; P.nx = p->nx; P.ny = p->ny;
+	P.nodes = r->nodes; P.edges = r->edges; P.num_nodes = r->N; P.nx = p->nx; P.ny = p->ny; P.node_bits = r->node_bits;
 	P.sw = r->sw; P.num_sw = p->num_switches; P.indexed = r->indexed; P.num_indexed = p->num_indexed;
 	P.net_ptr = r->net_ptr; P.net_term = r->net_term; P.net_bb = r->net_bb;
 	P.work = s.work; P.num_work = s.num_work; P.work_head = s.work_head;
@@ -845,7 +850,7 @@ extern "C" int pf_reserve_opins(pf_router *r, float pres_fac, int rip_up) {
 	if (!r) FAILF(PF_EINVAL, "null router");
 	if (r->num_groups == 0) return PF_OK;
 	r->sel_valid = false;
-	CKB(pfb_launch_reserve_opins(r->nodes, r->edges, r->indexed, r->num_groups, r->g_source, r->g_count, r->g_off, r->g_chosen, rip_up, pres_fac));
+	CKB(pfb_launch_reserve_opins(r->nodes, r->edges, r->node_bits, r->indexed, r->num_groups, r->g_source, r->g_count, r->g_off, r->g_chosen, rip_up, pres_fac));
 	return PF_OK;
 }
 
@@ -1153,14 +1158,21 @@ extern "C" int pf_route_run(pf_router *r, pf_sta *dsta, pf_sta_fn sta, void *use
 	int success = 0, itry, rc = PF_OK, nstats = 0;
 	bool have_crit = false, polished = false;
 	const bool breadth_first = o.router_algorithm == 1;      /* try_breadth_first_route, route_breadth_first.c:23-91 */
+	/* PF_PHASES=1: device time of every phase of every iteration (events on the router's stream), printed per rank at the end */
+	const bool phases = getenv("PF_PHASES") != NULL;
+	std::vector<int> phase_rows;      /* marks per iteration */
+#define PHASE_MARK() do { if (phases) pfb_mark(); } while (0)
 	for (itry = 1; itry <= max_iters; itry++) {
 		pf_iter_stats st;
 		memset(&st, 0, sizeof(st));
+		PHASE_MARK();
 		if (!crit.empty()) r->crit_hist.insert(r->crit_hist.end(), crit.begin(), crit.begin() + p->num_terminals);
 		if ((rc = pf_iteration_begin(r, have_crit ? crit.data() : NULL)) != PF_OK) break;
+		PHASE_MARK();
 		for (int part = 0; part < nparts && rc == PF_OK; part++) {
 			rc = launch_routes(r, pres_fac, part, nparts);
-			if (rc == PF_OK && cfg->nranks > 1) rc = pf_comm_exchange(r);
+			PHASE_MARK();
+			if (rc == PF_OK && cfg->nranks > 1) { rc = pf_comm_exchange(r); PHASE_MARK(); }
 		}
 		if (rc != PF_OK) break;
 		if ((rc = pf_reserve_opins(r, pres_fac, itry != 1)) != PF_OK) break;
@@ -1181,8 +1193,10 @@ extern "C" int pf_route_run(pf_router *r, pf_sta *dsta, pf_sta_fn sta, void *use
 			if (cfg->nranks > 1 && (rc = pf_comm_gather_delays(r)) != PF_OK) break;
 			if ((rc = pf_sta_analyze_device(dsta, r->net_delay, r->crit, NULL)) != PF_OK) break;
 		}
+		PHASE_MARK();
 		int overused = 0;
 		if ((rc = update_costs_finish(r, &overused)) != PF_OK) break;
+		if (phases) phase_rows.push_back(nparts);
 		st.overused_nodes = overused;
 		st.nets_routed = (int)r->h_stats.nets; st.heap_pushes = (int64_t)r->h_stats.pushes; st.heap_pops = (int64_t)r->h_stats.pops;
 		st.edge_visits = (int64_t)r->h_stats.visits;
@@ -1218,6 +1232,23 @@ extern "C" int pf_route_run(pf_router *r, pf_sta *dsta, pf_sta_fn sta, void *use
 		}
 	}
 	itry--;
+	if (phases) {
+		/* per iteration: begin | route part k [| exchange k] ... | opins + cost update + select (+ analysis); the gaps between
+		 * iterations (host reads the control block, decides, launches) show up in the first column of the next iteration */
+		std::vector<double> ms(8192);
+		const int n = pfb_marks_read(ms.data(), (int)ms.size());
+		const int per = 1 + nparts * (cfg->nranks > 1 ? 2 : 1) + 1;      /* intervals per iteration, the first being the gap + begin */
+		fprintf(stderr, "PF_PHASES rank %d/%d: %d iterations; columns: [gap to previous iteration's last launch incl. host read] begin", cfg->rank, cfg->nranks, (int)phase_rows.size());
+		for (int k = 0; k < nparts; k++) fprintf(stderr, cfg->nranks > 1 ? " route%d exchange%d" : " route%d", k, k);
+		fprintf(stderr, " update(ms)\n");
+		int at = 0;
+		for (size_t it = 0; it < phase_rows.size(); it++) {
+			fprintf(stderr, "PF_PHASES rank %d it %2d:", cfg->rank, (int)it + 1);
+			if (it > 0 && at < n) fprintf(stderr, " [%.3f]", ms[at++]);
+			for (int k = 0; k < per && at < n; k++) fprintf(stderr, " %.3f", ms[at++]);
+			fprintf(stderr, "\n");
+		}
+	}
 	if (rc != PF_OK && cfg->nranks > 1) pf_comm_abort(r);      /* peers waiting in an exchange see it instead of timing out */
 	if (rc != PF_OK) return rc;
 	if (cfg->nranks > 1 && (rc = pf_comm_gather_delays(r)) != PF_OK) return rc;   /* the result carries every net's delays on every rank */

@@ -41,6 +41,9 @@ static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts)
 int pfb_timer_start(void) { g_tt0 = now_ms(); return 0; }
 int pfb_timer_stop(double *ms) { *ms = now_ms() - g_tt0; return 0; }
 void *pfb_stream(void) { return NULL; }
+static double g_mark_t[4096]; static int g_nmarks = 0;
+int pfb_mark(void) { if (g_nmarks < 4096) g_mark_t[g_nmarks++] = now_ms(); return 0; }
+int pfb_marks_read(double *ms, int cap) { int n = 0; for (int i = 1; i < g_nmarks && n < cap; i++) ms[n++] = g_mark_t[i] - g_mark_t[i - 1]; g_nmarks = 0; return n; }
 int pfb_num_sms(void) { const char *e = getenv("PF_EMU_SMS"); return e ? atoi(e) : 1; }
 
 struct RouteArg { const PfParams *P; std::vector<unsigned char> *smem; };
@@ -55,9 +58,11 @@ static void route_warp(void *arg, int warp_id) {
 		for (int i = 0; i < a->P->num_sw; i++) sw[i] = a->P->sw[i];
 	}
 	pf_syncwarp();
-	if (a->P->algorithm == 1) pf_warp_main<2>(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
-	else if (a->P->max_batch == 1) pf_warp_main<1>(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
-	else pf_warp_main<0>(a->P, warp_id, idx, sw, base + PF_SMEM_BLOCK_TABLES);
+	const bool rip = a->P->vq_ctl != NULL || a->P->committer != NULL;   /* the same choice of variant as the CUDA launcher */
+	unsigned char *sm = base + PF_SMEM_BLOCK_TABLES;
+	if (a->P->algorithm == 1) { if (rip) pf_warp_main<2, 1>(a->P, warp_id, idx, sw, sm); else pf_warp_main<2, 0>(a->P, warp_id, idx, sw, sm); }
+	else if (a->P->max_batch == 1) { if (rip) pf_warp_main<1, 1>(a->P, warp_id, idx, sw, sm); else pf_warp_main<1, 0>(a->P, warp_id, idx, sw, sm); }
+	else { if (rip) pf_warp_main<0, 1>(a->P, warp_id, idx, sw, sm); else pf_warp_main<0, 0>(a->P, warp_id, idx, sw, sm); }
 }
 
 int pfb_launch_route(const PfParams *P, int num_slots, int) {
@@ -96,10 +101,10 @@ int pfb_launch_wirelength(const PfTreeNode *pool, const PfNetLoc *loc, const int
 	return 0;
 }
 
-int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, const PfIndexedDev *indexed, int num_groups,
+int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, int node_bits, const PfIndexedDev *indexed, int num_groups,
 		const int *group_source, const int *group_count, const int *group_off, int *chosen, int rip_up, float pres_fac) {
 	for (int g = 0; g < num_groups; g++)
-		pf_reserve_opins_group(nodes, edges, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac);
+		pf_reserve_opins_group(nodes, edges, node_bits, indexed, group_source[g], group_count[g], chosen + group_off[g], rip_up, pres_fac);
 	g_times.aux_launches++;
 	return 0;
 }
@@ -294,14 +299,14 @@ int pfb_sta_update(const PfStaDev *S, float constraint, const float *stat, float
 	return 0;
 }
 
-int pfb_launch_check_route(const PfNode *nodes, const uint32_t *edges, int num_nodes, int num_nets, const int *net_ptr, const int *net_term,
+int pfb_launch_check_route(const PfNode *nodes, const uint32_t *edges, int node_bits, int num_nodes, int num_nets, const int *net_ptr, const int *net_term,
 		const unsigned char *net_is_global, const int *trace_ptr, const int *trace_node, const short *trace_switch, unsigned char *matched,
 		int *occ2, const int *occ_reported, int *report, unsigned long long *wl_extra) {
 	for (int i = 0; i < num_nets; i++) {
 		if (net_is_global[i]) continue;
 		const int t0 = net_ptr[i], ns = net_ptr[i + 1] - t0 - 1;
 		unsigned w = 0;
-		const int code = pf_check_net(nodes, edges, num_nodes, net_term + t0, ns, trace_node + trace_ptr[i], trace_switch + trace_ptr[i],
+		const int code = pf_check_net(nodes, edges, node_bits, num_nodes, net_term + t0, ns, trace_node + trace_ptr[i], trace_switch + trace_ptr[i],
 				trace_ptr[i + 1] - trace_ptr[i], matched + t0, occ2, &w);
 		if (code) { report[0]++; if (i < report[1]) { report[1] = i; report[2] = code; } }
 		else wl_extra[0] += w;
