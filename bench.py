@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-reference", action="store_true", help="--impl reference: skip the one complete routing by vpr_ref (≈ 2 min)")
+    ap.add_argument("--upload-graph", action="store_true", help="build the rr graph on the host and upload it (round-1 path) instead of generating it on the device")
     ap.add_argument("--step-api", action="store_true", help="drive the iterations from Python through the step API and torch collectives "
                     "(the round-1 path) instead of pf_route_run with the in-library transport")
     ap.add_argument("--max-batch", type=int, default=0, help="tuning: labels settled per step (0 = library default)")
@@ -366,11 +367,14 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
 
-    p = router.generate_grid_problem(nx=a.grid, ny=a.grid, W=a.width, num_nets=a.nets)
+    p = router.generate_grid_problem(nx=a.grid, ny=a.grid, W=a.width, num_nets=a.nets)     # full host copy: CPU legs and the independent checks
+    # what the router itself gets: the nets (host buffers) and the generator's parameters — the rr graph is built ON the device
+    # (pf_router_create_generated; --upload-graph restores the 1.4 GB host -> device path of round 1)
+    nets, gen = (p, None) if a.upload_graph else router.generate_grid_nets(nx=a.grid, ny=a.grid, W=a.width, num_nets=a.nets)
     cfg = router.default_config(device=local, rank=rank, nranks=world, max_batch=a.max_batch, pop_slack=a.pop_slack,
                                 inflight_div=a.inflight_div, num_slots=a.slots, min_slots=a.min_slots,
                                 **{k: int(v) for k, v in (kv.split("=") for kv in a.cfg.split())})
-    R = comm.create_router(p, cfg) if comm else router.Router(p, cfg)     # N > 1: includes the one-off pf_comm_export / pf_comm_init bootstrap
+    R = comm.create_router(nets, cfg, generated=gen) if comm else router.Router(nets, cfg, generated=gen)   # N > 1: incl. the one-off pf_comm_export / pf_comm_init
     R.timing(reset=True)
 
     def route(Rx):
@@ -449,8 +453,9 @@ def run_ours(a):
                 comm.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            # flatten + H2D of the whole problem (N GPUs: rank 0 uploads, the others receive over NVLink)
-            R2 = comm.create_router(p, cfg) if comm else router.Router(p, cfg)
+            # H2D of the problem: the nets; the rr graph is generated on every rank's device (--upload-graph: flatten + 1.4 GB H2D,
+            # N GPUs: rank 0 uploads, the others receive over NVLink)
+            R2 = comm.create_router(nets, cfg, generated=gen) if comm else router.Router(nets, cfg, generated=gen)
             t1 = time.perf_counter()
             rep = route(R2)
             if comm and not a.step_api:
@@ -485,6 +490,7 @@ def run_ours(a):
         e2e = {"value": acc_n / acc_t, "unit": "nets/s", "h2d_bytes_per_step": int(hb), "d2h_bytes_per_step": int(db),
                "s_per_step": acc_t / max(1, min(a.steps, 2)),
                "phases_s": dict(zip(("create_upload", "route", "result_download", "destroy"), [round(x, 4) for x in e2e_phases[-1]])),
+               "graph": "uploaded from host arrays" if a.upload_graph else "generated on the device from the fabric parameters (pf_router_create_generated); H2D = nets, boxes, tables",
                "result_check": check}
 
     cpu, cpu_par, cpu_par_full = None, None, None

@@ -31,6 +31,10 @@ typedef struct pf_gen_params {
 void pf_gen_params_default(pf_gen_params *g);
 /* Allocates every array of *out with malloc (release with pf_problem_free). */
 int pf_gen_grid_problem(const pf_gen_params *g, pf_problem *out);
+/* The same problem WITHOUT the rr graph arrays (node SoA, CSR stay NULL; num_nodes is set, num_edges is 0): nets, bounding
+ * boxes, switch / cost-index tables and router options — what pf_router_create_generated (pf_router.h) needs from the host
+ * when the graph itself is built on the device. */
+int pf_gen_grid_nets(const pf_gen_params *g, pf_problem *out);
 
 #ifdef __cplusplus
 }

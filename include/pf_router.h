@@ -119,6 +119,13 @@ int pf_device_count(void);
 
 int pf_router_create(const pf_problem *p, const pf_config *cfg, pf_router **out);
 void pf_router_destroy(pf_router *r);
+/* The same for a fabric described by generator parameters (pf_gen.h): `nets` comes from pf_gen_grid_nets (no node / edge
+ * arrays) and the rr graph is built ON the device (rr_graph.c:385 build_rr_graph's role) — nothing but the
+ * nets crosses PCIe.  Bit-identical to creating from pf_gen_grid_problem's arrays (pf_debug_graph_hash). */
+struct pf_gen_params;
+int pf_router_create_generated(const struct pf_gen_params *g, const pf_problem *nets, const pf_config *cfg, pf_router **out);
+/* order-independent hashes of the device graph: node records, edge words, ptc numbers (tests) */
+int pf_debug_graph_hash(pf_router *r, uint64_t out[3], int64_t *num_edges);
 /* forget all routing and congestion history (occ = 0, acc_cost = 1): a fresh first iteration */
 int pf_router_reset(pf_router *r);
 

@@ -84,6 +84,18 @@ int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, co
 /* owner[node] = a net of `all_nets` whose tree in the route store contains the node (ripple re-routing: who gets displaced) */
 int pfb_launch_rebuild_owner(const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets, int num_all, int *owner);
 
+/* ---- rr graph built on the device (pf_gen_device.cuh) */
+struct PfGenDev;
+/* pass 1: out-degree of every node into row[0..N), exclusive prefix sum in place (row[v] = start of v's edge row), total in
+ * *num_edges (host).  G->cb_inv is a HOST pointer here; the backend stages it. */
+int pfb_gen_count(const PfGenDev *G, int *row, long long *num_edges);
+/* pass 2: node records, packed edge words, ptc numbers; *avail_wl (host) = total wirelength of the CHANX / CHANY nodes */
+int pfb_gen_fill(const PfGenDev *G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc, long long *avail_wl);
+/* occ = 0, acc_cost = 1 on every node record: a fresh first iteration (pf_router_reset) */
+int pfb_reset_nodes(PfNode *nodes, int num_nodes);
+/* order-independent 64-bit hashes of the node records / edge words / ptc numbers (tests: generated == uploaded graph) */
+int pfb_graph_hash(const PfNode *nodes, int num_nodes, const uint32_t *edges, long long num_edges, const short *ptc, unsigned long long out[3]);
+
 /* ---- multi-GPU exchange over peer memory (PfXchgHeader, pf_layout.h) */
 /* device memory other processes of the node can map: returns the pointer and fills a 64-byte handle; NULL on failure */
 void *pfb_ipc_alloc(size_t bytes, void *handle64);

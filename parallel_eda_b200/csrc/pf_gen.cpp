@@ -22,6 +22,10 @@
  * per CLB, no net has two sinks in one CLB, MT19937 seed 20260921, timing analysis off.
  */
 #include "../../include/pf_gen.h"
+#ifndef PF_DEV
+#define PF_DEV static inline
+#endif
+#include "pf_gen_device.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -81,6 +85,135 @@ extern "C" void pf_gen_params_default(pf_gen_params *g) {
 	g->nx = 400; g->ny = 400; g->W = 100; g->L = 4;
 	g->num_nets = 200000; g->sinks_per_net = 3; g->window = 16; g->seed = 20260921u;
 	g->fc_in = 0.15f; g->fc_out = 0.10f; g->io_capacity = 8; g->bb_factor = 3;
+}
+
+
+/* closed-form layout of the generated graph (shared with the device generator, pf_gen_device.cuh) */
+extern "C" int pf_gen_dev_params(const pf_gen_params *gp, PfGenDev *G, short *cb_inv /* [PF_GEN_MAX_W] */) {
+	if (!gp || gp->nx < 2 || gp->ny < 2 || gp->W < 8 || (gp->W & 1) || gp->W > PF_GEN_MAX_W || gp->L < 1 || gp->nx > 30000 || gp->ny > 30000) return PF_EINVAL;
+	memset(G, 0, sizeof(*G));
+	G->nx = gp->nx; G->ny = gp->ny; G->W = gp->W; G->L = gp->L; G->io_cap = gp->io_capacity > 0 ? gp->io_capacity : 8;
+	G->fc_in = (int)(gp->fc_in * G->W + 0.5f); if (G->fc_in < 2) G->fc_in = 2;
+	G->fc_out = (int)(gp->fc_out * G->W + 0.5f); if (G->fc_out < 2) G->fc_out = 2;
+	G->io_nodes = 6 * G->io_cap;
+	G->col0 = G->ny * G->io_nodes;
+	G->col_inner = 2 * G->io_nodes + G->ny * PF_GEN_CLB_NODES;
+	G->R_metal = R_METAL; G->C_per_tile = C_PER_TILE;
+	G->wpc_x = pf_gen_pref(*G, G->nx + 1); G->wpc_y = pf_gen_pref(*G, G->ny + 1);
+	const long long chanx0 = 2ll * G->col0 + (long long)G->nx * G->col_inner;
+	const long long chany0 = chanx0 + (long long)(G->ny + 1) * G->wpc_x;
+	const long long N = chany0 + (long long)(G->nx + 1) * G->wpc_y;
+	if (N >= (1ll << 30)) return PF_EINVAL;
+	G->chanx0 = (int)chanx0; G->chany0 = (int)chany0; G->num_nodes = (int)N;
+	int nb = PF_MIN_NODE_BITS; while ((1ll << nb) < N) nb++;
+	G->node_bits = nb;
+	for (int d = 0; d < G->W; d++) cb_inv[d] = -1;
+	for (int k = 0; k < G->fc_in; k++) cb_inv[(k * G->W) / G->fc_in] = (short)k;
+	G->cb_inv = cb_inv;
+	return PF_OK;
+}
+
+/* switch / cost-index tables, nets and router options of the generated problem (p.nx, p.ny are set by the caller) */
+static int gen_tables_and_nets(const pf_gen_params *gp, const PfGenDev &G, pf_problem &p) {
+	const int nx = G.nx, ny = G.ny, L = G.L;
+	p.num_switches = 3;
+	p.switches = (pf_switch *)calloc(3, sizeof(pf_switch));
+	p.switches[0].buffered = 1; p.switches[0].R = 551.f; p.switches[0].Cin = .77e-15f; p.switches[0].Cout = 4e-15f; p.switches[0].Tdel = 58e-12f;
+	p.switches[1].buffered = 1; p.switches[1].R = 0.f; p.switches[1].Cin = 596e-18f; p.switches[1].Cout = 0.f; p.switches[1].Tdel = 101.2e-12f;
+	p.switches[2].buffered = 1;
+	/* rr_indexed_data (rr_graph_indexed_data.c): buffered segment ⇒ T_linear = Tsw + Rsw*C + 0.5*R*C,
+	 * T_quadratic = C_load = 0; DELAY_NORMALIZED: base = T_linear * inv_length for SOURCE/OPIN/CHAN,
+	 * 0.95x for IPIN, 0 for SINK */
+	p.num_indexed = 6;
+	p.indexed = (pf_indexed *)calloc(6, sizeof(pf_indexed));
+	{
+		float Cw = C_PER_TILE * L, Rw = R_METAL * L;
+		float T_lin = p.switches[0].Tdel + p.switches[0].R * Cw + 0.5f * Rw * Cw;
+		float inv_len = 1.f / (float)(L < nx ? L : nx);
+		float norm = T_lin * inv_len;
+		for (int i = 0; i < 6; i++) {
+			p.indexed[i].ortho_cost_index = -1; p.indexed[i].seg_index = -1; p.indexed[i].inv_length = -1.f;
+			p.indexed[i].T_linear = -1.f; p.indexed[i].T_quadratic = -1.f; p.indexed[i].C_load = -1.f;
+			p.indexed[i].base_cost = p.indexed[i].saved_base_cost = norm;
+		}
+		p.indexed[PF_SINK_COST_INDEX].base_cost = p.indexed[PF_SINK_COST_INDEX].saved_base_cost = 0.f;
+		p.indexed[PF_IPIN_COST_INDEX].base_cost = p.indexed[PF_IPIN_COST_INDEX].saved_base_cost = 0.95f * norm;
+		p.indexed[PF_IPIN_COST_INDEX].T_linear = p.switches[1].Tdel;
+		for (int i = 4; i < 6; i++) {
+			p.indexed[i].ortho_cost_index = (i == 4) ? 5 : 4; p.indexed[i].seg_index = 0; p.indexed[i].inv_length = inv_len;
+			p.indexed[i].T_linear = T_lin; p.indexed[i].T_quadratic = 0.f; p.indexed[i].C_load = 0.f;
+		}
+	}
+
+	/* ---- nets */
+	const int n = gp->num_nets, spn = gp->sinks_per_net > 0 ? gp->sinks_per_net : 3;
+	const int win = gp->window > 0 ? gp->window : 16, bbf = gp->bb_factor >= 0 ? gp->bb_factor : 3;
+	p.num_nets = n; p.num_terminals = n * (spn + 1);
+	p.net_ptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 1));
+	p.net_terminals = (int32_t *)malloc(sizeof(int32_t) * (size_t)(p.num_terminals ? p.num_terminals : 1));
+	p.net_is_global = (uint8_t *)calloc((size_t)(n ? n : 1), 1);
+	p.net_bb = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(n ? n : 1));
+	p.opin_group_source = (int32_t *)malloc(4); p.opin_group_count = (int32_t *)malloc(4); p.num_opin_groups = 0;
+	if (!p.net_ptr || !p.net_terminals || !p.net_is_global || !p.net_bb) { pf_problem_free(&p); return PF_ENOMEM; }
+	if ((long long)n > (long long)nx * ny * CLB_OUT) { pf_problem_free(&p); return PF_EINVAL; }
+	std::mt19937 rng(gp->seed);
+	std::vector<uint16_t> out_used((size_t)(nx + 2) * (ny + 2), 0);
+	std::vector<uint8_t> sinks_used((size_t)(nx + 2) * (ny + 2), 0);
+	for (int i = 0; i < n; i++) {
+		int sx, sy, o;
+		for (;;) {
+			sx = 1 + (int)(rng() % (unsigned)nx); sy = 1 + (int)(rng() % (unsigned)ny);
+			uint16_t m = out_used[(size_t)sx * (ny + 2) + sy];
+			if (m == (1u << CLB_OUT) - 1) continue;
+			o = (int)(rng() % CLB_OUT);
+			while (m & (1u << o)) o = (o + 1) % CLB_OUT;
+			out_used[(size_t)sx * (ny + 2) + sy] = (uint16_t)(m | (1u << o));
+			break;
+		}
+		int t0 = i * (spn + 1);
+		p.net_ptr[i] = t0;
+		p.net_terminals[t0] = pf_gen_tile_base(G, sx, sy) + 1 + o;
+		int xmin = sx, xmax = sx, ymin = sy, ymax = sy;
+		int cx[64], cy[64];
+		for (int k = 0; k < spn; k++) {
+			int tx, ty, tries = 0;
+			for (;;) {
+				int x0 = sx - win < 1 ? 1 : sx - win, x1 = sx + win > nx ? nx : sx + win;
+				int y0 = sy - win < 1 ? 1 : sy - win, y1 = sy + win > ny ? ny : sy + win;
+				tx = x0 + (int)(rng() % (unsigned)(x1 - x0 + 1)); ty = y0 + (int)(rng() % (unsigned)(y1 - y0 + 1));
+				bool bad = (tx == sx && ty == sy) || sinks_used[(size_t)tx * (ny + 2) + ty] >= CLB_IN;
+				for (int q = 0; q < k && !bad; q++) if (cx[q] == tx && cy[q] == ty) bad = true;
+				if (!bad || ++tries > 1000) break;
+			}
+			cx[k & 63] = tx; cy[k & 63] = ty;
+			sinks_used[(size_t)tx * (ny + 2) + ty]++;
+			p.net_terminals[t0 + 1 + k] = pf_gen_tile_base(G, tx, ty);
+			xmin = tx < xmin ? tx : xmin; xmax = tx > xmax ? tx : xmax;
+			ymin = ty < ymin ? ty : ymin; ymax = ty > ymax ? ty : ymax;
+		}
+		/* load_route_bb, route_common.c:1065-1123 */
+		xmin -= 1; ymin -= 1;
+		p.net_bb[4 * i + 0] = xmin - bbf < 0 ? 0 : xmin - bbf;
+		p.net_bb[4 * i + 1] = xmax + bbf > nx + 1 ? nx + 1 : xmax + bbf;
+		p.net_bb[4 * i + 2] = ymin - bbf < 0 ? 0 : ymin - bbf;
+		p.net_bb[4 * i + 3] = ymax + bbf > ny + 1 ? ny + 1 : ymax + bbf;
+	}
+	p.net_ptr[n] = n * (spn + 1);
+	/* VPR defaults (SetupVPR.c:330-605), timing analysis off */
+	p.opts.first_iter_pres_fac = 0.5f; p.opts.initial_pres_fac = 0.5f; p.opts.pres_fac_mult = 1.3f; p.opts.acc_fac = 1.f;
+	p.opts.bend_cost = 0.f; p.opts.astar_fac = 1.2f; p.opts.max_criticality = 0.99f; p.opts.criticality_exp = 1.f;
+	p.opts.max_router_iterations = 50; p.opts.timing_analysis_enabled = 0; p.opts.bb_factor = bbf;
+	return PF_OK;
+}
+
+extern "C" int pf_gen_grid_nets(const pf_gen_params *gp, pf_problem *out) {
+	memset(out, 0, sizeof(*out));
+	PfGenDev G;
+	std::vector<short> inv(PF_GEN_MAX_W);
+	int rc = pf_gen_dev_params(gp, &G, inv.data());
+	if (rc != PF_OK) return rc;
+	out->nx = G.nx; out->ny = G.ny; out->num_nodes = G.num_nodes; out->num_edges = 0;
+	return gen_tables_and_nets(gp, G, *out);
 }
 
 extern "C" int pf_gen_grid_problem(const pf_gen_params *gp, pf_problem *out) {
@@ -286,92 +419,13 @@ extern "C" int pf_gen_grid_problem(const pf_gen_params *gp, pf_problem *out) {
 	COPYV(p.ptc_num, G.ptc, int16_t); COPYV(p.cost_index, G.ci, int16_t); COPYV(p.capacity, G.cap, int16_t);
 	COPYV(p.type, G.type, uint8_t); COPYV(p.direction, G.dir, uint8_t); COPYV(p.R, G.R, float); COPYV(p.C, G.C, float);
 	COPYV(p.row_ptr, deg, int32_t);
-	p.num_switches = 3;
-	p.switches = (pf_switch *)calloc(3, sizeof(pf_switch));
-	p.switches[0].buffered = 1; p.switches[0].R = 551.f; p.switches[0].Cin = .77e-15f; p.switches[0].Cout = 4e-15f; p.switches[0].Tdel = 58e-12f;
-	p.switches[1].buffered = 1; p.switches[1].R = 0.f; p.switches[1].Cin = 596e-18f; p.switches[1].Cout = 0.f; p.switches[1].Tdel = 101.2e-12f;
-	p.switches[2].buffered = 1;
-	/* rr_indexed_data (rr_graph_indexed_data.c): buffered segment ⇒ T_linear = Tsw + Rsw*C + 0.5*R*C,
-	 * T_quadratic = C_load = 0; DELAY_NORMALIZED: base = T_linear * inv_length for SOURCE/OPIN/CHAN,
-	 * 0.95x for IPIN, 0 for SINK */
-	p.num_indexed = 6;
-	p.indexed = (pf_indexed *)calloc(6, sizeof(pf_indexed));
 	{
-		float Cw = C_PER_TILE * L, Rw = R_METAL * L;
-		float T_lin = p.switches[0].Tdel + p.switches[0].R * Cw + 0.5f * Rw * Cw;
-		float inv_len = 1.f / (float)(L < nx ? L : nx);
-		float norm = T_lin * inv_len;
-		for (int i = 0; i < 6; i++) {
-			p.indexed[i].ortho_cost_index = -1; p.indexed[i].seg_index = -1; p.indexed[i].inv_length = -1.f;
-			p.indexed[i].T_linear = -1.f; p.indexed[i].T_quadratic = -1.f; p.indexed[i].C_load = -1.f;
-			p.indexed[i].base_cost = p.indexed[i].saved_base_cost = norm;
-		}
-		p.indexed[PF_SINK_COST_INDEX].base_cost = p.indexed[PF_SINK_COST_INDEX].saved_base_cost = 0.f;
-		p.indexed[PF_IPIN_COST_INDEX].base_cost = p.indexed[PF_IPIN_COST_INDEX].saved_base_cost = 0.95f * norm;
-		p.indexed[PF_IPIN_COST_INDEX].T_linear = p.switches[1].Tdel;
-		for (int i = 4; i < 6; i++) {
-			p.indexed[i].ortho_cost_index = (i == 4) ? 5 : 4; p.indexed[i].seg_index = 0; p.indexed[i].inv_length = inv_len;
-			p.indexed[i].T_linear = T_lin; p.indexed[i].T_quadratic = 0.f; p.indexed[i].C_load = 0.f;
-		}
+		PfGenDev Gd;
+		std::vector<short> inv(PF_GEN_MAX_W);
+		int rc = pf_gen_dev_params(gp, &Gd, inv.data());
+		if (rc != PF_OK || Gd.num_nodes != N) { pf_problem_free(&p); return rc != PF_OK ? rc : PF_EINVAL; }   /* the closed forms and the tables agree */
+		rc = gen_tables_and_nets(gp, Gd, p);
+		if (rc != PF_OK) return rc;
 	}
-
-	/* ---- nets */
-	const int n = gp->num_nets, spn = gp->sinks_per_net > 0 ? gp->sinks_per_net : 3;
-	const int win = gp->window > 0 ? gp->window : 16, bbf = gp->bb_factor >= 0 ? gp->bb_factor : 3;
-	p.num_nets = n; p.num_terminals = n * (spn + 1);
-	p.net_ptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 1));
-	p.net_terminals = (int32_t *)malloc(sizeof(int32_t) * (size_t)(p.num_terminals ? p.num_terminals : 1));
-	p.net_is_global = (uint8_t *)calloc((size_t)(n ? n : 1), 1);
-	p.net_bb = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(n ? n : 1));
-	p.opin_group_source = (int32_t *)malloc(4); p.opin_group_count = (int32_t *)malloc(4); p.num_opin_groups = 0;
-	if (!p.net_ptr || !p.net_terminals || !p.net_is_global || !p.net_bb) { pf_problem_free(&p); return PF_ENOMEM; }
-	if ((long long)n > (long long)nx * ny * CLB_OUT) { pf_problem_free(&p); return PF_EINVAL; }
-	std::mt19937 rng(gp->seed);
-	std::vector<uint16_t> out_used((size_t)(nx + 2) * (ny + 2), 0);
-	std::vector<uint8_t> sinks_used((size_t)(nx + 2) * (ny + 2), 0);
-	for (int i = 0; i < n; i++) {
-		int sx, sy, o;
-		for (;;) {
-			sx = 1 + (int)(rng() % (unsigned)nx); sy = 1 + (int)(rng() % (unsigned)ny);
-			uint16_t m = out_used[G.tile(sx, sy)];
-			if (m == (1u << CLB_OUT) - 1) continue;
-			o = (int)(rng() % CLB_OUT);
-			while (m & (1u << o)) o = (o + 1) % CLB_OUT;
-			out_used[G.tile(sx, sy)] = (uint16_t)(m | (1u << o));
-			break;
-		}
-		int t0 = i * (spn + 1);
-		p.net_ptr[i] = t0;
-		p.net_terminals[t0] = G.tile_class0[G.tile(sx, sy)] + 1 + o;
-		int xmin = sx, xmax = sx, ymin = sy, ymax = sy;
-		int cx[64], cy[64];
-		for (int k = 0; k < spn; k++) {
-			int tx, ty, tries = 0;
-			for (;;) {
-				int x0 = sx - win < 1 ? 1 : sx - win, x1 = sx + win > nx ? nx : sx + win;
-				int y0 = sy - win < 1 ? 1 : sy - win, y1 = sy + win > ny ? ny : sy + win;
-				tx = x0 + (int)(rng() % (unsigned)(x1 - x0 + 1)); ty = y0 + (int)(rng() % (unsigned)(y1 - y0 + 1));
-				bool bad = (tx == sx && ty == sy) || sinks_used[G.tile(tx, ty)] >= CLB_IN;
-				for (int q = 0; q < k && !bad; q++) if (cx[q] == tx && cy[q] == ty) bad = true;
-				if (!bad || ++tries > 1000) break;
-			}
-			cx[k & 63] = tx; cy[k & 63] = ty;
-			sinks_used[G.tile(tx, ty)]++;
-			p.net_terminals[t0 + 1 + k] = G.tile_class0[G.tile(tx, ty)];
-			xmin = tx < xmin ? tx : xmin; xmax = tx > xmax ? tx : xmax;
-			ymin = ty < ymin ? ty : ymin; ymax = ty > ymax ? ty : ymax;
-		}
-		/* load_route_bb, route_common.c:1065-1123 */
-		xmin -= 1; ymin -= 1;
-		p.net_bb[4 * i + 0] = xmin - bbf < 0 ? 0 : xmin - bbf;
-		p.net_bb[4 * i + 1] = xmax + bbf > nx + 1 ? nx + 1 : xmax + bbf;
-		p.net_bb[4 * i + 2] = ymin - bbf < 0 ? 0 : ymin - bbf;
-		p.net_bb[4 * i + 3] = ymax + bbf > ny + 1 ? ny + 1 : ymax + bbf;
-	}
-	p.net_ptr[n] = n * (spn + 1);
-	/* VPR defaults (SetupVPR.c:330-605), timing analysis off */
-	p.opts.first_iter_pres_fac = 0.5f; p.opts.initial_pres_fac = 0.5f; p.opts.pres_fac_mult = 1.3f; p.opts.acc_fac = 1.f;
-	p.opts.bend_cost = 0.f; p.opts.astar_fac = 1.2f; p.opts.max_criticality = 0.99f; p.opts.criticality_exp = 1.f;
-	p.opts.max_router_iterations = 50; p.opts.timing_analysis_enabled = 0; p.opts.bb_factor = bbf;
 	return PF_OK;
 }

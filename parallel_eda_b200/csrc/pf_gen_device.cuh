@@ -18,6 +18,7 @@
 #ifndef PF_GEN_DEVICE_CUH
 #define PF_GEN_DEVICE_CUH
 
+#include <stddef.h>
 #include "pf_layout.h"
 
 #define PF_GEN_CLB_PINS 51

@@ -54,6 +54,7 @@ struct pf_router {
 	int *status, *retry_list, *retry_count;
 	PfStats *stats;
 	int *d_overused; unsigned long long *d_wl;
+	bool generated;               /* the rr graph was built on the device (pf_router_create_generated): no host node / edge arrays */
 	int graph_ready;              /* 0 while a deferred graph has not been filled in */
 	unsigned *events; long long event_cap; long long h_events;   /* multi-GPU only: this rank's occupancy event log */
 	/* OPIN reservation */

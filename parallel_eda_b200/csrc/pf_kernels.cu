@@ -14,6 +14,7 @@
 #include "pf_backend.h"
 #include "pf_device.cuh"
 #include "pf_sta_device.cuh"
+#include "pf_gen_device.cuh"
 
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -572,6 +573,93 @@ __global__ void __launch_bounds__(256) pf_xchg_delays_gather_kernel(float *net_d
 
 __global__ void pf_xchg_abort_kernel(PfXchgHeader *mine) { mine->abort_flag = 1u; __threadfence_system(); }
 
+/* ------------------------------------------------------------------ rr graph built on the device (pf_gen_device.cuh) */
+__global__ void pf_gen_degree_kernel(const __grid_constant__ PfGenDev G, int *row) {
+	for (int v = (int)(blockIdx.x * blockDim.x + threadIdx.x); v < G.num_nodes; v += (int)(gridDim.x * blockDim.x)) {
+		const PfGenNode nd = pf_gen_decode(G, v);
+		row[v] = pf_gen_node_edges(G, v, nd, NULL);
+	}
+}
+/* exclusive prefix sum of an int array in three passes: per-CTA totals, one CTA scans the totals, per-CTA local scan */
+#define PF_SCAN_CTA 1024
+__global__ void __launch_bounds__(PF_SCAN_CTA) pf_scan_totals_kernel(const int *a, int n, long long *totals) {
+	__shared__ long long s[PF_SCAN_CTA / 32];
+	const int i = (int)blockIdx.x * PF_SCAN_CTA + (int)threadIdx.x;
+	long long v = i < n ? a[i] : 0;
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31u) == 0) s[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) { long long t = 0; for (int w = 0; w < PF_SCAN_CTA / 32; w++) t += s[w]; totals[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(PF_SCAN_CTA) pf_scan_offsets_kernel(long long *totals, int nblocks, long long *grand) {
+	/* one CTA: exclusive scan of the CTA totals, chunk by chunk */
+	__shared__ long long s[PF_SCAN_CTA];
+	__shared__ long long carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < nblocks; base += PF_SCAN_CTA) {
+		const int i = base + (int)threadIdx.x;
+		const long long v = i < nblocks ? totals[i] : 0;
+		s[threadIdx.x] = v;
+		__syncthreads();
+		for (int o = 1; o < PF_SCAN_CTA; o <<= 1) {
+			const long long t = threadIdx.x >= (unsigned)o ? s[threadIdx.x - o] : 0;
+			__syncthreads();
+			s[threadIdx.x] += t;
+			__syncthreads();
+		}
+		if (i < nblocks) totals[i] = carry + s[threadIdx.x] - v;
+		__syncthreads();
+		if (threadIdx.x == PF_SCAN_CTA - 1) carry += s[PF_SCAN_CTA - 1];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *grand = carry;
+}
+__global__ void __launch_bounds__(PF_SCAN_CTA) pf_scan_apply_kernel(int *a, int n, const long long *totals) {
+	__shared__ int s[PF_SCAN_CTA];
+	const int i = (int)blockIdx.x * PF_SCAN_CTA + (int)threadIdx.x;
+	const int v = i < n ? a[i] : 0;
+	s[threadIdx.x] = v;
+	__syncthreads();
+	for (int o = 1; o < PF_SCAN_CTA; o <<= 1) {
+		const int t = threadIdx.x >= (unsigned)o ? s[threadIdx.x - o] : 0;
+		__syncthreads();
+		s[threadIdx.x] += t;
+		__syncthreads();
+	}
+	if (i < n) a[i] = (int)(totals[blockIdx.x] + s[threadIdx.x] - v);
+}
+__global__ void pf_gen_fill_kernel(const __grid_constant__ PfGenDev G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc, unsigned long long *avail_wl) {
+	unsigned wl = 0;
+	for (int v = (int)(blockIdx.x * blockDim.x + threadIdx.x); v < G.num_nodes; v += (int)(gridDim.x * blockDim.x)) {
+		const PfGenNode nd = pf_gen_decode(G, v);
+		const int start = row[v];
+		const int deg = pf_gen_node_edges(G, v, nd, edges + start);
+		pf_gen_write_node(nd, start, deg, &nodes[v], &ptc[v]);
+		if (nd.type == 4 || nd.type == 5) wl += (unsigned)(1 + nd.x1 - nd.x0 + nd.y1 - nd.y0);
+	}
+	wl = __reduce_add_sync(0xffffffffu, wl);
+	if ((threadIdx.x & 31u) == 0 && wl) atomicAdd(avail_wl, (unsigned long long)wl);
+}
+__global__ void pf_reset_nodes_kernel(PfNode *nodes, int num_nodes) {
+	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x)) { nodes[i].occ = 0; nodes[i].acc_cost = 1.f; }
+}
+static __device__ __forceinline__ unsigned long long pf_mix64(unsigned long long x) {
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+	return x;
+}
+__global__ void pf_graph_hash_kernel(const PfNode *nodes, int num_nodes, const uint32_t *edges, long long num_edges, const short *ptc, unsigned long long *out) {
+	unsigned long long h0 = 0, h1 = 0, h2 = 0;
+	const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+	for (long long i = tid; i < num_nodes; i += step) {
+		const unsigned long long *w = (const unsigned long long *)&nodes[i];
+		h0 += pf_mix64(w[0] ^ pf_mix64((unsigned long long)i)) + pf_mix64(w[1] + 0x9e3779b97f4a7c15ull * (unsigned long long)i) + pf_mix64(w[2] ^ (unsigned long long)(3 * i + 1)) + pf_mix64(w[3] ^ (unsigned long long)(5 * i + 2));
+		h2 += pf_mix64(((unsigned long long)(unsigned short)ptc[i] << 32) ^ (unsigned long long)i);
+	}
+	for (long long i = tid; i < num_edges; i += step) h1 += pf_mix64(((unsigned long long)edges[i] << 32) ^ (unsigned long long)i);
+	atomicAdd(&out[0], h0); atomicAdd(&out[1], h1); atomicAdd(&out[2], h2);
+}
+
 /* ------------------------------------------------------------------ launchers */
 int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	if (warps_per_block < 1) warps_per_block = 1;
@@ -687,6 +775,63 @@ int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num
 	return ev_end();
 }
 
+
+/* ------------------------------------------------------------------ device graph generation launchers */
+static int gen_stage(const PfGenDev *G, PfGenDev *Gd, short **d_inv) {
+	*Gd = *G;
+	*d_inv = (short *)pfb_alloc_raw(sizeof(short) * (size_t)G->W);
+	if (!*d_inv) return -1;
+	CK(cudaMemcpyAsync(*d_inv, G->cb_inv, sizeof(short) * (size_t)G->W, cudaMemcpyHostToDevice, g_stream));
+	Gd->cb_inv = *d_inv;
+	return 0;
+}
+int pfb_gen_count(const PfGenDev *G, int *row, long long *num_edges) {
+	PfGenDev Gd; short *d_inv = NULL;
+	if (gen_stage(G, &Gd, &d_inv) != 0) return -1;
+	const int n = G->num_nodes, nb = (n + PF_SCAN_CTA - 1) / PF_SCAN_CTA;
+	long long *totals = (long long *)pfb_alloc_raw(sizeof(long long) * ((size_t)nb + 1));
+	if (!totals) { pfb_free(d_inv); return -1; }
+	if (ev_begin(2) != 0) return -1;
+	pf_gen_degree_kernel<<<stream_grid(n), 256, 0, g_stream>>>(Gd, row);
+	pf_scan_totals_kernel<<<nb, PF_SCAN_CTA, 0, g_stream>>>(row, n, totals);
+	pf_scan_offsets_kernel<<<1, PF_SCAN_CTA, 0, g_stream>>>(totals, nb, totals + nb);
+	pf_scan_apply_kernel<<<nb, PF_SCAN_CTA, 0, g_stream>>>(row, n, totals);
+	if (ev_end() != 0) return -1;
+	CK(cudaMemcpyAsync(num_edges, totals + nb, sizeof(long long), cudaMemcpyDeviceToHost, g_stream));
+	CK(cudaStreamSynchronize(g_stream));
+	pfb_free(totals); pfb_free(d_inv);
+	return 0;
+}
+int pfb_gen_fill(const PfGenDev *G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc, long long *avail_wl) {
+	PfGenDev Gd; short *d_inv = NULL;
+	if (gen_stage(G, &Gd, &d_inv) != 0) return -1;
+	unsigned long long *d_wl = (unsigned long long *)pfb_alloc(sizeof(unsigned long long));
+	if (!d_wl) { pfb_free(d_inv); return -1; }
+	if (ev_begin(2) != 0) return -1;
+	pf_gen_fill_kernel<<<stream_grid(G->num_nodes), 256, 0, g_stream>>>(Gd, row, nodes, edges, ptc, d_wl);
+	if (ev_end() != 0) return -1;
+	unsigned long long h = 0;
+	CK(cudaMemcpyAsync(&h, d_wl, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+	CK(cudaStreamSynchronize(g_stream));
+	*avail_wl = (long long)h;
+	pfb_free(d_wl); pfb_free(d_inv);
+	return 0;
+}
+int pfb_reset_nodes(PfNode *nodes, int num_nodes) {
+	if (ev_begin(2) != 0) return -1;
+	pf_reset_nodes_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes);
+	return ev_end();
+}
+int pfb_graph_hash(const PfNode *nodes, int num_nodes, const uint32_t *edges, long long num_edges, const short *ptc, unsigned long long out[3]) {
+	unsigned long long *d = (unsigned long long *)pfb_alloc(sizeof(unsigned long long) * 3);
+	if (!d) return -1;
+	pf_graph_hash_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes, edges, num_edges, ptc, d);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(out, d, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost, g_stream));
+	CK(cudaStreamSynchronize(g_stream));
+	pfb_free(d);
+	return 0;
+}
 
 /* ------------------------------------------------------------------ exchange launchers / IPC memory */
 void *pfb_ipc_alloc(size_t bytes, void *handle64) {

@@ -6,6 +6,15 @@
  * pf_backend.h; this file contains no routing arithmetic.
  */
 #include "pf_host.h"
+#include "../../include/pf_gen.h"
+#ifndef PF_DEV
+#define PF_DEV static inline
+#endif
+#include "pf_gen_device.cuh"
+extern "C" int pf_gen_dev_params(const pf_gen_params *gp, PfGenDev *G, short *cb_inv);
+
+/* set by pf_router_create_generated for the pf_router_create call it makes: build the rr graph on the device */
+static thread_local const pf_gen_params *g_generate = NULL;
 
 char g_router_err[512] = "";
 
@@ -238,16 +247,36 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	double t_a = now_s();
 	/* small arrays now; the 10^7..10^8-element node and edge arrays are range-checked by the passes that
 	 * flatten them (upload_nodes / upload_edges), so they are read once */
-	if (!problem_header_ok(p) || !problem_nets_ok(p)) {
+	const pf_gen_params *gen = g_generate;
+	g_generate = NULL;
+	PfGenDev Gd;
+	std::vector<short> gen_inv(PF_GEN_MAX_W);
+	if (gen) {
+		/* the rr graph is a closed-form function of the generator parameters (pf_gen_device.cuh): no host arrays */
+		if (pf_gen_dev_params(gen, &Gd, gen_inv.data()) != PF_OK) FAILF(PF_EINVAL, "invalid generator parameters");
+		if (p->nx != Gd.nx || p->ny != Gd.ny || p->num_nodes != Gd.num_nodes || p->num_opin_groups != 0 || p->num_switches != 3 || p->num_indexed != 6)
+			FAILF(PF_EINVAL, "the nets-only problem does not belong to these generator parameters (use pf_gen_grid_nets)");
+		if (p->num_nets < 0 || !p->net_ptr || !problem_nets_ok(p)) FAILF(PF_EINVAL, "invalid problem (nets)");
+	} else if (!problem_header_ok(p) || !problem_nets_ok(p)) {
 		if (pf_problem_check(p, msg, sizeof(msg)) != PF_OK) FAILF(PF_EINVAL, "invalid problem: %s", msg);
 		FAILF(PF_EINVAL, "invalid problem");
 	}
 	double t_b = now_s();
 	std::atomic<int> terminals_bad(0);
-	std::thread terminal_check([p, &terminals_bad]() { if (!problem_terminals_ok(p)) terminals_bad = 1; });
+	const PfGenDev *Gp = gen ? &Gd : NULL;
+	std::thread terminal_check([p, Gp, &terminals_bad]() {
+		if (!Gp) { if (!problem_terminals_ok(p)) terminals_bad = 1; return; }
+		for (int i = 0; i < p->num_nets; i++) {               /* terminal types from the closed form */
+			if (p->net_is_global[i]) continue;
+			for (int k = p->net_ptr[i]; k < p->net_ptr[i + 1]; k++) {
+				const int n = p->net_terminals[k];
+				if (n < 0 || n >= Gp->num_nodes || pf_gen_decode(*Gp, n).type != (k == p->net_ptr[i] ? PF_SOURCE : PF_SINK)) { terminals_bad = 1; return; }
+			}
+		}
+	});
 	struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{terminal_check};   /* every return path */
 	/* edge word = target node | switch << node_bits; the bits above the node id are also the search tag of the hot labels */
-	const int node_bits = std::max(PF_MIN_NODE_BITS, ceil_log2((long long)p->num_nodes));
+	const int node_bits = gen ? Gd.node_bits : std::max(PF_MIN_NODE_BITS, ceil_log2((long long)p->num_nodes));
 	if (node_bits > PF_MAX_NODE_BITS) FAILF(PF_EINVAL, "num_rr_nodes %d exceeds the %d-bit node field", p->num_nodes, PF_MAX_NODE_BITS);
 	if (p->num_switches > PF_MAX_SWITCHES || p->num_switches > (1 << (32 - node_bits)))
 		FAILF(PF_EINVAL, "%d switch types (max %d with %d rr nodes)", p->num_switches, std::min(PF_MAX_SWITCHES, 1 << (32 - node_bits)), p->num_nodes);
@@ -260,7 +289,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->cfg = *cfg_in;
 	pf_config &c = r->cfg;
 	r->node_bits = node_bits;
-	r->prob = p; r->N = p->num_nodes; r->E = p->num_edges; r->T = p->num_terminals; r->n = p->num_nets;
+	r->prob = p; r->N = p->num_nodes; r->E = p->num_edges; r->generated = gen != NULL; r->T = p->num_terminals; r->n = p->num_nets;
 	r->nodes = NULL; r->edges = NULL; r->sw = NULL; r->indexed = NULL; r->net_ptr = r->net_term = r->net_bb = NULL;
 	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
 	r->pool[0] = r->pool[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
@@ -386,6 +415,15 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 
 	/* device graph */
 	r->nodes = (PfNode *)pfb_alloc_raw(sizeof(PfNode) * (size_t)r->N);
+	int *gen_row = NULL;
+	if (gen) {
+		/* pass 1 of the device generator: out-degrees and their prefix sum give the number of edges */
+		long long ne = 0;
+		gen_row = (int *)pfb_alloc_raw(sizeof(int) * ((size_t)r->N + 1));
+		if (!r->nodes || !gen_row || pfb_gen_count(&Gd, gen_row, &ne) != 0) { pfb_free(gen_row); pf_router_destroy(r); CUDA_FAIL(); }
+		if (ne >= 2147483647ll) { pfb_free(gen_row); pf_router_destroy(r); FAILF(PF_EINVAL, "%lld rr edges exceed the 31-bit edge index", ne); }
+		r->E = (int)ne;
+	}
 	r->edges = (uint32_t *)pfb_alloc_raw(sizeof(uint32_t) * (size_t)std::max(r->E, 1));
 	r->ptc = (short *)pfb_alloc_raw(sizeof(short) * (size_t)r->N);
 	r->sw = (PfSwitchDev *)pfb_alloc(sizeof(PfSwitchDev) * PF_MAX_SWITCHES);
@@ -401,7 +439,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	{
 		const size_t nbytes = sizeof(PfNode) * (size_t)r->N, ebytes = sizeof(uint32_t) * (size_t)std::max(r->E, 1);
 		const size_t pbytes = sizeof(short) * (size_t)r->N;
-		char *pin = (c.defer_graph && c.nranks > 1) ? NULL : (char *)pfb_pinned_upload(nbytes + ebytes + pbytes + 768);
+		char *pin = (gen || (c.defer_graph && c.nranks > 1)) ? NULL : (char *)pfb_pinned_upload(nbytes + ebytes + pbytes + 768);
 		void *stage_nodes = pin;
 		uint32_t *stage_edges = pin ? (uint32_t *)(pin + ((nbytes + 255) & ~(size_t)255)) : NULL;
 		short *stage_ptc = pin ? (short *)((char *)stage_edges + ((ebytes + 255) & ~(size_t)255)) : NULL;
@@ -420,7 +458,11 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		int bad_nodes = 0, bad_edges = 0;
 		long long wl_avail = 0;
 		r->t_mark[0] = now_s();
-		if (c.defer_graph && c.nranks > 1) {
+		if (gen) {
+			/* pass 2: node records, edge words and ptc numbers written straight into HBM */
+			if (pfb_gen_fill(&Gd, gen_row, r->nodes, r->edges, r->ptc, &wl_avail) != 0) { pfb_free(gen_row); pf_router_destroy(r); CUDA_FAIL(); }
+			pfb_free(gen_row);
+		} else if (c.defer_graph && c.nranks > 1) {
 			/* the packed graph arrives from another rank (pf_comm_graph_buffers); only the available wirelength,
 			 * which the first-iteration abort check needs, is computed from the host arrays here */
 			r->graph_ready = 0;
@@ -567,10 +609,28 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	return PF_OK;
 }
 
+/* pf_router_create for a fabric described by generator parameters: the rr graph (node records, CSR edge words, ptc numbers)
+ * is built ON the device from the closed forms of pf_gen_device.cuh — what crosses PCIe is the nets. */
+extern "C" int pf_router_create_generated(const pf_gen_params *g, const pf_problem *nets, const pf_config *cfg, pf_router **out) {
+	if (!g || !nets || !cfg || !out) FAILF(PF_EINVAL, "null argument");
+	g_generate = g;
+	const int rc = pf_router_create(nets, cfg, out);
+	g_generate = NULL;
+	return rc;
+}
+
+extern "C" int pf_debug_graph_hash(pf_router *r, uint64_t out[3], int64_t *num_edges) {
+	if (!r || !out) FAILF(PF_EINVAL, "null argument");
+	unsigned long long h[3] = { 0, 0, 0 };
+	CKB(pfb_graph_hash(r->nodes, r->N, r->edges, r->E, r->ptc, h));
+	out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+	if (num_edges) *num_edges = r->E;
+	return PF_OK;
+}
+
 extern "C" int pf_router_reset(pf_router *r) {
 	if (!r) FAILF(PF_EINVAL, "null router");
-	if (upload_nodes(r, pfb_pinned_upload(sizeof(PfNode) * (size_t)r->N), NULL, NULL, NULL) != PF_OK) return PF_ECUDA;
-	CKB(pfb_sync());
+	CKB(pfb_reset_nodes(r->nodes, r->N));       /* occ = 0, acc_cost = 1: alloc_and_load_rr_node_route_structs' initial state */
 	CKB(pfb_zero(r->loc, sizeof(PfNetLoc) * (size_t)std::max(r->n, 1)));
 	CKB(pfb_zero(r->ctl, CTL_BYTES));
 	r->sel_valid = r->sel_pending = false; r->iter_all = true; r->force_all_once = false; r->owner_valid = false;

@@ -26,7 +26,7 @@ class Comm:
             torch.cuda.current_stream(t.device).synchronize()
         return t
 
-    def create_router(self, problem, config=None, lib_path=None):
+    def create_router(self, problem, config=None, lib_path=None, generated=None):
         """A Router on every rank with ONE upload over PCIe: rank 0 packs the graph and uploads it, the other
         ranks are created with defer_graph and receive the packed node records / edge words / ptc numbers by an
         NCCL broadcast over NVLink (with N processes packing and uploading at once the host memory system is the
@@ -35,14 +35,15 @@ class Comm:
         lib = _router.load_library(lib_path)
         cfg = _router.Config.from_buffer_copy(config if config is not None else _router.default_config(lib))
         cfg.rank, cfg.nranks = self.rank, self.world
-        cfg.defer_graph = 0 if self.rank == 0 else 1
+        # a generated fabric is built on every rank's own device (pf_router_create_generated): nothing to broadcast
+        cfg.defer_graph = 0 if (self.rank == 0 or generated is not None) else 1
         if os.environ.get("PF_COMM_DEBUG"):
             cfg.verbose = 1
         import time
         R, err = None, None
         t0 = time.perf_counter()
         try:
-            R = _router.Router(problem, cfg, lib_path=lib_path)
+            R = _router.Router(problem, cfg, lib_path=lib_path, generated=generated)
         except _router.RouterError as e:
             err = e
         t1 = time.perf_counter()
@@ -50,12 +51,12 @@ class Comm:
             if R is not None:
                 R.close()
             raise err or _router.RouterError(-5, "another rank could not create its router")
-        for ptr, nbytes in R.comm_graph_buffers():
+        for ptr, nbytes in (R.comm_graph_buffers() if generated is None else []):
             t = wrap_device_bytes(ptr, nbytes, self.device)
             dist.broadcast(t, src=0)
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
-        if self.rank != 0:
+        if self.rank != 0 and generated is None:
             R.comm_graph_ready()
         self.connect(R)
         if os.environ.get("PF_COMM_DEBUG"):

@@ -141,6 +141,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
                            % (path, lib.pf_backend_name().decode()))
     lib.pf_config_default.argtypes = [C.POINTER(Config)]
     lib.pf_router_create.argtypes = [C.POINTER(_Problem), C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.pf_router_create_generated.argtypes = [C.POINTER(GenParams), C.POINTER(_Problem), C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.pf_gen_grid_nets.argtypes = [C.POINTER(GenParams), C.POINTER(_Problem)]
+    lib.pf_debug_graph_hash.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 3), C.POINTER(C.c_int64)]
     lib.pf_router_destroy.argtypes = [C.c_void_p]
     lib.pf_router_destroy.restype = None
     lib.pf_router_reset.argtypes = [C.c_void_p]
@@ -201,7 +204,8 @@ class _ProblemHolder:
     def __init__(self, p: pfio.Problem):
         self.arrays = {}
         cp = _Problem()
-        cp.nx, cp.ny, cp.num_nodes, cp.num_edges = p.nx, p.ny, p.num_nodes, p.num_edges
+        # a nets-only problem (generate_grid_nets) has no node arrays: its node count is the generator's closed form
+        cp.nx, cp.ny, cp.num_nodes, cp.num_edges = p.nx, p.ny, getattr(p, "gen_num_nodes", None) or p.num_nodes, p.num_edges
         for name, dt, _ in pfio._PROB_FIELDS:
             a = np.ascontiguousarray(getattr(p, name), dtype=np.dtype(dt))
             self.arrays[name] = a
@@ -261,7 +265,10 @@ def _take_result(lib, cr: _Result, T: int, with_stats: bool = True) -> pfio.Resu
 class Router:
     """A device-resident routing problem (pf_router handle)."""
 
-    def __init__(self, problem: pfio.Problem, config: Optional[Config] = None, lib_path: Optional[str] = None):
+    def __init__(self, problem: pfio.Problem, config: Optional[Config] = None, lib_path: Optional[str] = None,
+                 generated: "Optional[GenParams]" = None):
+        """``generated``: the rr graph is built on the device from these generator parameters (``problem`` then comes from
+        generate_grid_nets and carries no node / edge arrays) — pf_router_create_generated."""
         self.lib = load_library(lib_path)
         self.problem = problem
         self._holder = _ProblemHolder(problem)
@@ -269,7 +276,11 @@ class Router:
             config = default_config(self.lib)
         self.config = config
         h = C.c_void_p()
-        rc = self.lib.pf_router_create(C.byref(self._holder.c), C.byref(config), C.byref(h))
+        if generated is not None:
+            self._gen = generated
+            rc = self.lib.pf_router_create_generated(C.byref(generated), C.byref(self._holder.c), C.byref(config), C.byref(h))
+        else:
+            rc = self.lib.pf_router_create(C.byref(self._holder.c), C.byref(config), C.byref(h))
         if rc != PF_OK:
             raise RouterError(rc, self.lib.pf_last_error().decode())
         self._h = h
@@ -291,6 +302,12 @@ class Router:
 
     def reset(self):
         self._ck(self.lib.pf_router_reset(self._h))
+
+    def graph_hash(self):
+        """(hash of node records, hash of edge words, hash of ptc numbers, number of edges) of the device graph."""
+        h = (C.c_uint64 * 3)(); ne = C.c_int64(0)
+        self._ck(self.lib.pf_debug_graph_hash(self._h, C.byref(h), C.byref(ne)))
+        return int(h[0]), int(h[1]), int(h[2]), int(ne.value)
 
     def route_iteration(self, pres_fac: float, crit: Optional[np.ndarray] = None) -> IterStats:
         st = IterStats()
@@ -547,7 +564,13 @@ def replay_sta(golden: pfio.Result) -> StaFn:
     return fn
 
 
-def generate_grid_problem(lib_path: Optional[str] = None, **kw) -> pfio.Problem:
+def generate_grid_nets(lib_path: Optional[str] = None, **kw):
+    """(nets-only Problem, GenParams) of the same synthetic problem: nets, boxes, tables and options on the host, NO rr graph
+    arrays — ``Router(nets, cfg, generated=params)`` builds the graph on the device (pf_router_create_generated)."""
+    return generate_grid_problem(lib_path, nets_only=True, **kw)
+
+
+def generate_grid_problem(lib_path: Optional[str] = None, nets_only: bool = False, **kw):
     """Synthetic k6_N10-style grid + random nets (pf_gen_grid_problem).  Keyword arguments override
     pf_gen_params_default (nx, ny, W, L, num_nets, sinks_per_net, window, seed, ...)."""
     lib = load_library(lib_path)
@@ -556,7 +579,7 @@ def generate_grid_problem(lib_path: Optional[str] = None, **kw) -> pfio.Problem:
     for k, v in kw.items():
         setattr(g, k, v)
     cp = _Problem()
-    rc = lib.pf_gen_grid_problem(C.byref(g), C.byref(cp))
+    rc = (lib.pf_gen_grid_nets if nets_only else lib.pf_gen_grid_problem)(C.byref(g), C.byref(cp))
     if rc != PF_OK:
         raise RouterError(rc, "pf_gen_grid_problem failed")
     counts = {"N": cp.num_nodes, "N1": cp.num_nodes + 1, "E": cp.num_edges, "S": cp.num_switches, "I": cp.num_indexed,
@@ -566,12 +589,19 @@ def generate_grid_problem(lib_path: Optional[str] = None, **kw) -> pfio.Problem:
     for name, dt, c in pfio._PROB_FIELDS:
         dt = np.dtype(dt)
         nbytes = counts[c] * dt.itemsize
-        buf = (C.c_char * nbytes).from_address(getattr(cp, name)) if nbytes else b""
+        ptr = getattr(cp, name)
+        if not ptr:
+            nbytes = 0                        # nets-only problem: the rr graph arrays are NULL
+        buf = (C.c_char * nbytes).from_address(ptr) if nbytes else b""
         arrs[name] = np.frombuffer(bytes(buf) if nbytes else b"", dtype=dt).copy()
     arrs["net_bb"] = arrs["net_bb"].reshape(cp.num_nets, 4)
     opts = np.zeros((), dtype=pfio.OPTS_DT)
     for f in _Opts._fields_:
         opts[f[0]] = getattr(cp.opts, f[0])
     p = pfio.Problem(nx=cp.nx, ny=cp.ny, opts=opts, **arrs)
+    closed_form_nodes = int(cp.num_nodes)
     lib.pf_problem_free(C.byref(cp))
+    if nets_only:
+        p.gen_num_nodes = closed_form_nodes   # node count of the graph the device generator will build
+        return p, g
     return p

@@ -6,6 +6,7 @@
 #include "pf_backend.h"
 #include "pf_device.cuh"
 #include "pf_sta_device.cuh"
+#include "pf_gen_device.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -172,6 +173,40 @@ int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num
 	return 0;
 }
 
+
+/* ---- rr graph built "on the device": the same closed-form functions, plain loops */
+int pfb_gen_count(const PfGenDev *G, int *row, long long *num_edges) {
+	long long acc = 0;
+	for (int v = 0; v < G->num_nodes; v++) { const PfGenNode nd = pf_gen_decode(*G, v); const int d = pf_gen_node_edges(*G, v, nd, NULL); row[v] = (int)acc; acc += d; }
+	*num_edges = acc;
+	g_times.aux_launches++;
+	return 0;
+}
+int pfb_gen_fill(const PfGenDev *G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc, long long *avail_wl) {
+	long long wl = 0;
+	for (int v = 0; v < G->num_nodes; v++) {
+		const PfGenNode nd = pf_gen_decode(*G, v);
+		const int deg = pf_gen_node_edges(*G, v, nd, edges + row[v]);
+		pf_gen_write_node(nd, row[v], deg, &nodes[v], &ptc[v]);
+		if (nd.type == 4 || nd.type == 5) wl += 1 + nd.x1 - nd.x0 + nd.y1 - nd.y0;
+	}
+	*avail_wl = wl;
+	g_times.aux_launches++;
+	return 0;
+}
+int pfb_reset_nodes(PfNode *nodes, int num_nodes) { for (int i = 0; i < num_nodes; i++) { nodes[i].occ = 0; nodes[i].acc_cost = 1.f; } return 0; }
+static unsigned long long emu_mix64(unsigned long long x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; }
+int pfb_graph_hash(const PfNode *nodes, int num_nodes, const uint32_t *edges, long long num_edges, const short *ptc, unsigned long long out[3]) {
+	unsigned long long h0 = 0, h1 = 0, h2 = 0;
+	for (long long i = 0; i < num_nodes; i++) {
+		unsigned long long w[4]; memcpy(w, &nodes[i], 32);
+		h0 += emu_mix64(w[0] ^ emu_mix64((unsigned long long)i)) + emu_mix64(w[1] + 0x9e3779b97f4a7c15ull * (unsigned long long)i) + emu_mix64(w[2] ^ (unsigned long long)(3 * i + 1)) + emu_mix64(w[3] ^ (unsigned long long)(5 * i + 2));
+		h2 += emu_mix64(((unsigned long long)(unsigned short)ptc[i] << 32) ^ (unsigned long long)i);
+	}
+	for (long long i = 0; i < num_edges; i++) h1 += emu_mix64(((unsigned long long)edges[i] << 32) ^ (unsigned long long)i);
+	out[0] = h0; out[1] = h1; out[2] = h2;
+	return 0;
+}
 
 /* ---- multi-rank exchange: the "peer memory" of the emulator is POSIX shared memory, the ranks are processes; the protocol
  * (payload, fence, release of the sequence number; acquire-polling consumers) is the one of pf_kernels.cu */

@@ -68,3 +68,32 @@ def test_oracle_routes_it_and_reference_agrees(small, oracle_cli, tmp_path):
         out2 = str(tmp_path / "r.pfr")
         subprocess.run([ref, "inject", prob, "--result", out2], check=True, capture_output=True)
         assert pfio.read_result(out2).serial_num == r.serial_num
+
+
+@pytest.mark.parametrize("kw", [dict(nx=6, ny=5, W=20, num_nets=40, window=3), dict(nx=13, ny=9, W=36, num_nets=200, window=5, seed=7),
+                                dict(nx=24, ny=24, W=100, num_nets=600, window=8), dict(nx=7, ny=12, W=8, L=3, num_nets=60, window=4),
+                                dict(nx=9, ny=9, W=14, L=5, num_nets=60, window=4, io_capacity=3)])
+def test_device_built_graph_is_bit_identical_to_the_host_generator(kw, emu_lib):
+    """pf_router_create_generated builds the rr graph ON the device from the closed forms of
+    pf_gen_device.cuh (node numbering, wire spans, per-row edge order).  It must be the very graph pf_gen.cpp builds with its
+    lookup tables and uploads: equal hashes of the 32-byte node records, of the packed edge words and of the ptc numbers, the
+    same nets — and therefore the same routing.  (Emulator backend: the same device functions, run in plain loops.)"""
+    lib = router.load_library(emu_lib)
+    p = router.generate_grid_problem(lib_path=emu_lib, **kw)
+    nets, g = router.generate_grid_nets(lib_path=emu_lib, **kw)
+    assert nets.gen_num_nodes == p.num_nodes and len(nets.xlow) == 0 and len(nets.edge_to) == 0
+    assert np.array_equal(nets.net_terminals, p.net_terminals) and np.array_equal(nets.net_bb, p.net_bb) and np.array_equal(nets.net_ptr, p.net_ptr)
+    cfg = router.default_config(lib, num_slots=1, big_slots=1, pop_slack=0.0, max_batch=1)
+    A = router.Router(p, cfg, lib_path=emu_lib)
+    B = router.Router(nets, cfg, lib_path=emu_lib, generated=g)
+    assert A.graph_hash() == B.graph_hash() and A.graph_hash()[3] == p.num_edges
+    if kw["nx"] <= 13:                       # one warp is deterministic: identical graphs give identical routings
+        from parallel_eda_b200 import pathfinder
+        ra, rb = pathfinder.run(A), pathfinder.run(B)
+        assert ra.success == rb.success and ra.iterations == rb.iterations and ra.overused == rb.overused   # (W = 8 is unroutable: equally so)
+        xa, xb = A.result(), B.result()
+        assert xa.serial_num == xb.serial_num and xa.total_wirelength == xb.total_wirelength
+        B.reset()                            # reset of a generated router: a kernel, no host arrays to re-upload
+        rc = pathfinder.run(B)
+        assert rc.success == ra.success and B.result().serial_num == xa.serial_num
+    A.close(); B.close()

@@ -205,3 +205,27 @@ def test_heterogeneous_fabric_single_warp_equals_the_emulated_device_code():
     assert r.total_wirelength <= 1.03 * g.total_wirelength
     assert (r.serial_num, r.total_wirelength, r.iterations) == (pin["serial_num"], pin["total_wirelength"], pin["iterations"])
 
+
+
+def test_device_built_graph_equals_the_uploaded_one():
+    """pf_router_create_generated on the B200: the closed-form generator kernels (pf_gen_device.cuh) produce the very node
+    records, edge words and ptc numbers pf_gen.cpp builds on the host and uploads (hashes computed on the device), at a size
+    with a million rr nodes; a routing on the generated graph is legal by the independent checker (which reads the host copy)."""
+    kw = dict(nx=100, ny=100, W=100, num_nets=12500)
+    p = router.generate_grid_problem(**kw)
+    nets, g = router.generate_grid_nets(**kw)
+    A = router.Router(p)
+    B = router.Router(nets, generated=g)
+    ha, hb = A.graph_hash(), B.graph_hash()
+    assert ha == hb and ha[3] == p.num_edges
+    A.close()
+    from parallel_eda_b200 import pathfinder
+    rep = pathfinder.run(B)
+    res = B.result()
+    res.success = int(rep.success)
+    assert rep.success
+    m = check_route.check_route_fast(p, res)
+    assert m["overused"] == 0 and m["sinks"] == 3 * p.num_nets
+    B.reset()
+    assert pathfinder.run(B).success
+    B.close()
