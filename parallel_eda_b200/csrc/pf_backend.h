@@ -72,13 +72,15 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, int node_bits
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
 		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count,
-		int *queued, int queued_tag);   /* queued != NULL: queued[net] = queued_tag for every selected net (ripple re-routing) */
+		int *queued, int queued_tag,
+		const int *pool_node, const unsigned char *over_now, int over_tag);   /* over_now != NULL: fast test (pf_net_is_congested_fast) */
+		/* queued != NULL: queued[net] = queued_tag for every selected net (ripple re-routing) */
 /* counts[0..1] = lengths of list_small / list_big; counts[2..3] = how many of each come from the first head_count
  * entries of all_nets (they are at the head of the lists: order is preserved) */
 void pfb_bind_thread(void);                     /* make the router's device current in a helper thread */
 size_t pfb_select_scratch_bytes(int num_all);   /* size of `scratch` (device memory) */
 /* copy every live tree of `all_nets` from one log to another (garbage collection of the route store) */
-int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
+int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, const int *src_node, int *dst_node, PfNetLoc *loc, const int *all_nets, int num_all,
 		unsigned long long *dst_head);
 
 /* owner[node] = a net of `all_nets` whose tree in the route store contains the node (ripple re-routing: who gets displaced) */

@@ -109,12 +109,13 @@ struct PfWarp {
 	uint64_t *hot_alt; PfCold *cold_alt; unsigned mask_alt; int shift_alt; int limit_alt; unsigned epoch_alt;   /* the other table */
 	PfTreeNode *tree; uint64_t *far; int *iscratch;
 	/* search state: warp-uniform */
+	unsigned tag_mask; int nb;    /* search-tag mask and node-id width of this router (PfParams.node_bits), kept in registers */
 	unsigned epoch; unsigned round; int n_labels; int sh_n; int far_n; float T_hi; float far_min; float best;
 	int overflow;
 	/* per-net constants */
 	int bb_xmin, bb_xmax, bb_ymin, bb_ymax; int num_sinks; int cur_net;
 	/* counters */
-	unsigned long long pops, pushes, visits, refills, stale, races;
+	unsigned pops, pushes, visits, refills, stale, races;   /* per launch and warp: 32 bits are plenty, and six registers fewer */
 };
 
 /* per warp: fr 1024 + b_key 256 + base_cost 128 + 5 batch arrays 640 + b_pre 136 + tickets 256 = 2440 → 2448;
@@ -142,6 +143,13 @@ PF_DEV uint64_t pf_make_key(float tot, int node) {
 #define PF_COLD_LOOP _Pragma("unroll 1")
 #else
 #define PF_COLD_LOOP
+#endif
+/* pf_refill's passes over the far list: unrolled 4x they are 1,170 SASS instructions in the middle of the search loop — a fifth
+ * of the kernel's code for a function that runs once per few dozen settled labels */
+#if !defined(PF_UNROLL_REFILL) && defined(__CUDACC__)
+#define PF_REFILL_LOOP _Pragma("unroll 1")
+#else
+#define PF_REFILL_LOOP
 #endif
 #define PF_KEY_MAX 0xffffffffffffffffull
 
@@ -200,16 +208,21 @@ PF_DEV float pf_expected_cost(const PfWarp &w, int type, int ci, int ixlow, int 
 }
 
 /* ------------------------------------------------------------------ label table */
+#ifdef PF_FIXED_NODE_BITS            /* A/B builds: the node-id width as a compile-time constant */
+#define PF_NB(P) PF_FIXED_NODE_BITS
+#else
+#define PF_NB(P) ((P)->node_bits)
+#endif
 PF_DEV unsigned pf_node_mask(int node_bits) { return (1u << node_bits) - 1u; }
-PF_DEV unsigned pf_tag_mask(const PfParams *P) { return (1u << (32 - P->node_bits)) - 1u; }      /* search tag: the bits above the node id */
+PF_DEV unsigned pf_tag_mask(const PfParams *P) { return (1u << (32 - PF_NB(P))) - 1u; }      /* search tag: the bits above the node id */
 PF_DEV unsigned pf_hash(const PfWarp &w, int node) {
 	return ((uint32_t)node * 2654435761u) >> w.label_shift;
 }
 PF_DEV uint64_t pf_hot_make(const PfWarp &w, float tot, int node) {
-	return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | ((w.epoch & pf_tag_mask(w.P)) << w.P->node_bits) | (uint32_t)node;
+	return ((uint64_t)(uint32_t)pf_float_as_int(tot) << 32) | ((w.epoch & w.tag_mask) << w.nb) | (uint32_t)node;
 }
-PF_DEV int pf_hot_live(const PfWarp &w, uint64_t k) { return (((uint32_t)k) >> w.P->node_bits) == (w.epoch & pf_tag_mask(w.P)); }
-PF_DEV int pf_hot_node(const PfWarp &w, uint64_t k) { return (int)((uint32_t)k & pf_node_mask(w.P->node_bits)); }
+PF_DEV int pf_hot_live(const PfWarp &w, uint64_t k) { return (((uint32_t)k) >> w.nb) == (w.epoch & w.tag_mask); }
+PF_DEV int pf_hot_node(const PfWarp &w, uint64_t k) { return (int)((uint32_t)k & ~(w.tag_mask << w.nb)); }
 
 /* Look up an existing label (used at settle time and in the back-trace).  Per-lane, no collectives. */
 PF_DEV int pf_label_find(const PfWarp &w, int node) {
@@ -304,7 +317,7 @@ PF_DEV void pf_push(PfWarp &w, int valid, float tot, int node, int edge_start) {
 		float fm = pf_warp_min_f(to_far ? tot : PF_INF_F);
 		if (fm < w.far_min) w.far_min = fm;
 	}
-	w.pushes += (unsigned long long)pf_popc(pf_ballot(valid));
+	w.pushes += (unsigned)pf_popc(pf_ballot(valid));
 	pf_syncwarp();
 }
 
@@ -315,7 +328,7 @@ PF_DEV void pf_refill(PfWarp &w) {
 	const int lane = pf_lane();
 	w.refills++;
 	/* 1. near → far */
-	for (int base = 0; base < w.sh_n; base += PF_WARP) {
+	PF_REFILL_LOOP for (int base = 0; base < w.sh_n; base += PF_WARP) {
 		int i = base + lane;
 		if (i < w.sh_n) {
 			int fpos = w.far_n + i;
@@ -328,7 +341,7 @@ PF_DEV void pf_refill(PfWarp &w) {
 	pf_syncwarp();
 	/* 2. minimum */
 	uint64_t mk = PF_KEY_MAX;
-	for (int i = lane; i < w.far_n; i += PF_WARP) { uint64_t k = w.far[i]; if (k < mk) mk = k; }
+	PF_REFILL_LOOP for (int i = lane; i < w.far_n; i += PF_WARP) { uint64_t k = w.far[i]; if (k < mk) mk = k; }
 	mk = pf_warp_min_u64(mk);
 	float m = pf_key_tot(mk);
 	/* 3. window */
@@ -337,7 +350,7 @@ PF_DEV void pf_refill(PfWarp &w) {
 	float T = m + win;
 	for (;;) {
 		int c = 0;
-		for (int i = lane; i < w.far_n; i += PF_WARP) if (pf_key_tot(w.far[i]) <= T) c++;
+		PF_REFILL_LOOP for (int i = lane; i < w.far_n; i += PF_WARP) if (pf_key_tot(w.far[i]) <= T) c++;
 		c = pf_warp_sum_i(c);
 		if (c <= PF_SH_REFILL || T <= m) break;
 		win *= 0.25f;
@@ -346,7 +359,7 @@ PF_DEV void pf_refill(PfWarp &w) {
 	/* 4. move (first PF_SH_REFILL qualifying), compact the far list, track the far minimum */
 	int kept = 0, taken = 0;
 	float fmin = PF_INF_F;
-	for (int base = 0; base < w.far_n; base += PF_WARP) {
+	PF_REFILL_LOOP for (int base = 0; base < w.far_n; base += PF_WARP) {
 		int i = base + lane;
 		uint64_t k = (i < w.far_n) ? w.far[i] : PF_KEY_MAX;
 		int q = (i < w.far_n) && pf_key_tot(k) <= T;
@@ -427,7 +440,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 	const int highfan = w.num_sinks >= 64;
 
 	w.epoch++;
-	if ((w.epoch & pf_tag_mask(w.P)) == 0) {                  /* tag wrapped: wipe the hot table, skip tag 0 (= never written) */
+	if ((w.epoch & w.tag_mask) == 0) {                  /* tag wrapped: wipe the hot table, skip tag 0 (= never written) */
 		PF_COLD_LOOP for (unsigned i = (unsigned)lane; i <= w.label_mask; i += PF_WARP) w.hot[i] = 0;
 		w.epoch++;
 		pf_syncwarp();
@@ -438,7 +451,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 	float slack;
 	{
 		float mb = PF_INF_F, mt = PF_INF_F;
-		if (P->pop_slack != 0.f) for (int i = 4; i < P->num_indexed; i++) {
+		if (P->pop_slack != 0.f) PF_COLD_LOOP for (int i = 4; i < P->num_indexed; i++) {
 			if (w.base_cost[i] < mb) mb = w.base_cost[i];
 			if (w.idx[i].T_linear < mt) mt = w.idx[i].T_linear;
 		}
@@ -483,9 +496,36 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 		if (w.overflow) return -1;
 		float mtot = PF_INF_F;
 		int first = 0x7fffffff;                 /* this lane's oldest label at its local minimum */
-		for (int i = lane; i < w.sh_n; i += PF_WARP) { float t = pf_key_tot(w.fr[i]); if (t < mtot) { mtot = t; first = i; } }
+#if defined(PF_TIE_NODE)
+		/* A/B build: ties between equal totals are broken by the rr node id instead of by age — the minimum is then ONE 64-bit
+		 * warp reduction over the keys and the popped entry is replaced by the last one (no order to preserve) */
+		uint64_t my_key = PF_KEY_MAX;
+		if (STRICT) {
+#pragma unroll
+			for (int c = 0; c < PF_SH_FRONTIER / PF_WARP; c++) {
+				const int i = lane + c * PF_WARP;
+				const uint64_t k = i < w.sh_n ? w.fr[i] : PF_KEY_MAX;
+				if (k < my_key) { my_key = k; first = i; }
+			}
+			mtot = pf_key_tot(my_key);
+		} else
+#endif
+		{	/* branch-free: the near set holds at most PF_SH_FRONTIER / 32 entries per lane; only the total (high word) is read */
+			const uint32_t *hi = (const uint32_t *)w.fr + 1;
+#pragma unroll
+			for (int c = 0; c < PF_SH_FRONTIER / PF_WARP; c++) {
+				const int i = lane + c * PF_WARP;
+				const float t = i < w.sh_n ? pf_int_as_float((int)hi[2 * i]) : PF_INF_F;
+				if (t < mtot) { mtot = t; first = i; }
+			}
+		}
 		const float my_min = mtot;
+#if defined(PF_TIE_NODE)
+		const uint64_t min_key = STRICT ? pf_warp_min_u64(my_key) : 0;
+		mtot = STRICT ? (w.sh_n > 0 ? pf_key_tot(min_key) : PF_INF_F) : pf_warp_min_f(mtot);
+#else
 		mtot = pf_warp_min_f(mtot);
+#endif
 		if (w.far_min < mtot) {                 /* a cheaper label sits in the far list (or near set empty) */
 			if (w.far_min >= w.best) break;
 			pf_refill(w);
@@ -502,6 +542,18 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 			/* -- strict best-first: settle one label, the OLDEST near label within pop_slack of the minimum (what the
 			 * batch selection below yields for max_batch == 1), and close the gap so the near set stays in push
 			 * order.  Every lane then does the same label lookup (broadcast reads): nothing is staged. */
+#if defined(PF_TIE_NODE)
+			const uint64_t mk = min_key;
+			(void)my_min; (void)thr;
+			{	/* the lane that holds the minimum (keys are unique: a node re-enters only with a lower total) moves the last
+				 * entry into its place */
+				const unsigned own = pf_ballot(my_key == mk);
+				const int idx = pf_shfl_i(first, pf_ffs(own) - 1);
+				if (lane == 0) w.fr[idx] = w.fr[w.sh_n - 1];
+				w.sh_n--;
+				pf_syncwarp();
+			}
+#else
 			int li = 0x7fffffff;
 			if (slack == 0.f) { if (my_min == mtot) li = first; }      /* within 0 of the minimum = at the minimum */
 			else for (int i = lane; i < w.sh_n; i += PF_WARP) if (pf_key_tot(w.fr[i]) <= thr) { li = i; break; }
@@ -513,6 +565,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 			for (int c = 0; c < PF_SH_FRONTIER / PF_WARP; c++) { int i = lane + c * PF_WARP; if (i > idx && i < w.sh_n) w.fr[i - 1] = keep[c]; }
 			w.sh_n--;
 			pf_syncwarp();
+#endif
 			taken = 1; M = 0;
 			const int u = pf_key_node(mk);
 			const int h = pf_label_find(w, u);
@@ -531,8 +584,8 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 					ok = 1;
 				}
 			}
-			w.pops += (unsigned long long)ok;
-			w.stale += (unsigned long long)(1 - ok);
+			w.pops += (unsigned)ok;
+			w.stale += (unsigned)(1 - ok);
 			if (!ok) continue;
 		} else {
 		/* -- select the batch: every near label within pop_slack of the minimum, at most max_batch */
@@ -582,8 +635,8 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 		}
 		{
 			int nok = pf_popc(pf_ballot(ok));
-			w.pops += (unsigned long long)nok;
-			w.stale += (unsigned long long)(taken - nok);
+			w.pops += (unsigned)nok;
+			w.stale += (unsigned)(taken - nok);
 		}
 		/* exclusive prefix of the degrees over the first `taken` lanes */
 		int incl = deg;
@@ -596,7 +649,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 		if (lane == 0) w.b_pre[taken] = M;
 		pf_syncwarp();
 		}
-		w.visits += (unsigned long long)M;
+		w.visits += (unsigned)M;
 
 		/* -- relax every out-edge of the batch, 32 edges per pass */
 		for (int base = 0; base < M; base += PF_WARP) {
@@ -613,7 +666,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 				}
 				u = x_node;
 				uint32_t ew = P->edges[x_start + eoff];
-				to = (int)(ew & pf_node_mask(P->node_bits)); isw = (int)(ew >> P->node_bits);
+				to = (int)(ew & pf_node_mask(PF_NB(P))); isw = (int)(ew >> PF_NB(P));
 				PfNodeView n = pf_load_node(P, to);
 				if (n.xhigh < w.bb_xmin || n.xlow > w.bb_xmax || n.yhigh < w.bb_ymin || n.ylow > w.bb_ymax) valid = 0;
 				if (valid && highfan && (n.xhigh < tgt_xh - rlim || n.xlow > tgt_xh + rlim || n.yhigh < tgt_yh - rlim || n.ylow > tgt_yh + rlim)) valid = 0;
@@ -919,7 +972,7 @@ template <int RIP> PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	w.epoch++;
-	if ((w.epoch & pf_tag_mask(w.P)) == 0) {
+	if ((w.epoch & w.tag_mask) == 0) {
 		PF_COLD_LOOP for (unsigned i = (unsigned)lane; i <= w.label_mask; i += PF_WARP) w.hot[i] = 0;
 		w.epoch++;
 		pf_syncwarp();
@@ -993,15 +1046,15 @@ template <int RIP> PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0
 			}
 		}
 		/* breadth_first_expand_neighbours :259-292 */
-		w.visits += (unsigned long long)M;
+		w.visits += (unsigned)M;
 		for (int base = 0; base < M; base += PF_WARP) {
 			const int e = base + lane;
 			int valid = e < M, to = 0, info = 0, es = 0;
 			float tot = 0.f;
 			if (valid) {
 				const uint32_t ew = P->edges[x_start + e];
-				to = (int)(ew & pf_node_mask(P->node_bits));
-				const int isw = (int)(ew >> P->node_bits);
+				to = (int)(ew & pf_node_mask(PF_NB(P)));
+				const int isw = (int)(ew >> PF_NB(P));
 				PfNodeView n = pf_load_node(P, to);
 				if (n.xhigh < w.bb_xmin || n.xlow > w.bb_xmax || n.yhigh < w.bb_ymin || n.ylow > w.bb_ymax) valid = 0;
 				if (valid) {
@@ -1047,7 +1100,7 @@ template <int STRICT, int RIP> PF_DEV int pf_route_net(PfWarp &w, int inet, int 
 		PfNetLoc loc = P->loc[inet];
 		PF_COLD_LOOP for (int base = 0; base < loc.count; base += PF_WARP) {
 			const int i = base + lane;
-			const int v = i < loc.count ? P->pool[loc.off + i].node : 0;
+			const int v = i < loc.count ? P->pool_node[loc.off + i] : 0;
 			pf_occ_change(P, i < loc.count, v, -1);
 			if (RIP && P->committer && i < loc.count) pf_atomic_cas_i(&P->committer[v], inet, -1);   /* no longer the holder */
 		}
@@ -1173,7 +1226,7 @@ template <int STRICT, int RIP> PF_DEV int pf_route_net(PfWarp &w, int inet, int 
 		pf_syncwarp();
 		return 0;
 	}
-	for (int i = lane; i < tree_n; i += PF_WARP) P->pool[off + i] = w.tree[i];
+	for (int i = lane; i < tree_n; i += PF_WARP) { P->pool[off + i] = w.tree[i]; P->pool_node[off + i] = w.tree[i].node; }
 	if (lane == 0) { P->loc[inet].off = (int)off; P->loc[inet].count = tree_n; }
 	pf_syncwarp();
 	return 1;
@@ -1221,6 +1274,7 @@ template <int STRICT, int RIP> PF_DEV void pf_warp_main(const PfParams *P, int s
 	/* the shared-memory table starts empty at every launch; a global table keeps its tags across launches */
 	w.epoch = P->hot ? P->epochs[2 * slot] : 0;
 	w.round = 0;
+	w.nb = PF_NB(P); w.tag_mask = pf_tag_mask(P);
 	for (int i = lane; i < PF_TICKETS; i += PF_WARP) w.ticket[i] = 0x7fffffff;
 	w.pops = w.pushes = w.visits = w.refills = w.stale = w.races = 0;
 	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.T_hi = 0.f; w.far_min = PF_INF_F; w.best = PF_INF_F; w.overflow = 0;
@@ -1270,12 +1324,12 @@ template <int STRICT, int RIP> PF_DEV void pf_warp_main(const PfParams *P, int s
 	if (lane == 0) {
 		if (P->hot) P->epochs[2 * slot] = w.epoch;
 		if (w.hot_alt) P->epochs[2 * slot + 1] = w.epoch_alt;
-		pf_atomic_add_ull(&P->stats->pops, w.pops);
-		pf_atomic_add_ull(&P->stats->pushes, w.pushes);
-		pf_atomic_add_ull(&P->stats->visits, w.visits);
-		pf_atomic_add_ull(&P->stats->refills, w.refills);
-		pf_atomic_add_ull(&P->stats->stale, w.stale);
-		if (w.races) pf_atomic_add_ull(&P->stats->races, w.races);
+		pf_atomic_add_ull(&P->stats->pops, (unsigned long long)w.pops);
+		pf_atomic_add_ull(&P->stats->pushes, (unsigned long long)w.pushes);
+		pf_atomic_add_ull(&P->stats->visits, (unsigned long long)w.visits);
+		pf_atomic_add_ull(&P->stats->refills, (unsigned long long)w.refills);
+		pf_atomic_add_ull(&P->stats->stale, (unsigned long long)w.stale);
+		if (w.races) pf_atomic_add_ull(&P->stats->races, (unsigned long long)w.races);
 		pf_atomic_add_ull(&P->stats->nets, nets);
 	}
 }
@@ -1419,6 +1473,13 @@ PF_DEV int pf_net_is_congested(const PfNode *nodes, const PfTreeNode *pool, PfNe
 			if (t != 0 && ((iter_tag - t + 255) % 255) <= window) return 1;
 		}
 	}
+	return 0;
+}
+
+/* The same test right behind the cost update, from the 4-byte node list and the byte map the update pass just wrote
+ * (over[v] == tag  <=>  v is overused now): 5 bytes per tree entry instead of 64. */
+PF_DEV int pf_net_is_congested_fast(const int *pool_node, PfNetLoc loc, const unsigned char *over, int tag) {
+	for (int i = 0; i < loc.count; i++) if (over[pool_node[loc.off + i]] == (unsigned char)tag) return 1;
 	return 0;
 }
 

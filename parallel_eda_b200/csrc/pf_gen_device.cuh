@@ -80,6 +80,14 @@ PF_DEV int pf_gen_wire_at(const PfGenDev &G, int horiz, int chan, int p, int t, 
 	return (horiz ? G.chanx0 + chan * G.wpc_x : G.chany0 + chan * G.wpc_y) + pf_gen_pref(G, a) + rank;
 }
 
+/* does the INC (even) / DEC (odd) wire of track t that covers position pos START there?  (an INC wire is entered at its low end
+ * a, a DEC wire at its high end b; segments are clipped at 1 and P) */
+PF_DEV int pf_gen_starts_here(const PfGenDev &G, int pos, int t, int P) {
+	const int s = (t / 2) % G.L;
+	if (t & 1) return pos == P || ((pos - s) % G.L + G.L) % G.L == 0;
+	return pos == 1 || ((pos - 1 - s) % G.L + G.L) % G.L == 0;
+}
+
 struct PfGenNode { int type, x0, y0, x1, y1, ptc, ci, cap; float R, C; int horiz, chan, t; /* wires */ int tx, ty, local, clb; /* tile nodes */ };
 
 /* everything about node v but its edges */
@@ -152,18 +160,20 @@ PF_DEV int pf_gen_turns(const PfGenDev &G, int horiz, int chan, int q, int t, ui
 		const int pos = base + 1;
 		for (int k = 0; k < half; k++) {
 			const int t2 = 2 * ((g + qx + qy + k) % half);
-			int a2;
-			const int w2 = pf_gen_wire_at(G, !horiz, pchan, pos, t2, &a2, NULL);
-			if (a2 == pos) { if (out) out[n] = (uint32_t)w2 | ((uint32_t)PF_GEN_SW_WIRE << G.node_bits); n++; break; }
+			if (!pf_gen_starts_here(G, pos, t2, P2)) continue;
+			if (out) out[n] = (uint32_t)pf_gen_wire_at(G, !horiz, pchan, pos, t2, NULL, NULL) | ((uint32_t)PF_GEN_SW_WIRE << G.node_bits);
+			n++;
+			break;
 		}
 	}
 	if (base >= 1) {                              /* a DEC wire starting at base (its high end) */
 		const int pos = base;
 		for (int k = 0; k < half; k++) {
 			const int t2 = 2 * ((g + 2 * qx + qy + k) % half) + 1;
-			int b2;
-			const int w2 = pf_gen_wire_at(G, !horiz, pchan, pos, t2, NULL, &b2);
-			if (b2 == pos) { if (out) out[n] = (uint32_t)w2 | ((uint32_t)PF_GEN_SW_WIRE << G.node_bits); n++; break; }
+			if (!pf_gen_starts_here(G, pos, t2, P2)) continue;
+			if (out) out[n] = (uint32_t)pf_gen_wire_at(G, !horiz, pchan, pos, t2, NULL, NULL) | ((uint32_t)PF_GEN_SW_WIRE << G.node_bits);
+			n++;
+			break;
 		}
 	}
 	return n;
@@ -179,11 +189,26 @@ PF_DEV int pf_gen_cb_tile(const PfGenDev &G, int x, int y, int side, int pos, in
 		const int io_side = (x == 0) ? 1 : (x == G.nx + 1) ? 3 : (y == 0) ? 0 : 2;
 		if (io_side != side) return n;
 	}
-	for (int p = 0; p < npins; p++) {
-		const int is_out = clb ? (p >= PF_GEN_CLB_IN && p < PF_GEN_CLB_IN + PF_GEN_CLB_OUT) : (p % 3 == 1);
-		if (is_out || (clb && (p & 3) != side)) continue;
-		const int d = ((t - p * 7 - pos) % G.W + G.W) % G.W;
-		if (G.cb_inv[d] >= 0) { if (out) out[n] = (uint32_t)(pin0 + p) | ((uint32_t)PF_GEN_SW_IPIN << G.node_bits); n++; }
+	/* the pattern t == (p * 7 + pos + (k * W) / fc_in) % W inverted: d = (t - pos - 7 p) mod W must be one of the fc_in offsets.
+	 * Only the pins that face this side are visited, and d is stepped instead of recomputed. */
+	int d = (t - pos) % G.W;
+	if (d < 0) d += G.W;
+	const int m7 = 7 % G.W;
+	if (clb) {
+		for (int q = 0; q < side; q++) { d -= m7; if (d < 0) d += G.W; }
+		const int m28 = 28 % G.W;
+		for (int p = side; p < PF_GEN_CLB_PINS; p += 4) {
+			if (!(p >= PF_GEN_CLB_IN && p < PF_GEN_CLB_IN + PF_GEN_CLB_OUT) && G.cb_inv[d] >= 0) {
+				if (out) out[n] = (uint32_t)(pin0 + p) | ((uint32_t)PF_GEN_SW_IPIN << G.node_bits);
+				n++;
+			}
+			d -= m28; if (d < 0) d += G.W;
+		}
+	} else {
+		for (int p = 0; p < npins; p++) {
+			if (p % 3 != 1 && G.cb_inv[d] >= 0) { if (out) out[n] = (uint32_t)(pin0 + p) | ((uint32_t)PF_GEN_SW_IPIN << G.node_bits); n++; }
+			d -= m7; if (d < 0) d += G.W;
+		}
 	}
 	return n;
 }
@@ -213,11 +238,13 @@ PF_DEV int pf_gen_node_edges(const PfGenDev &G, int v, const PfGenNode &nd, uint
 		const int chan = horiz ? (side == 0 ? y : y - 1) : (side == 1 ? x : x - 1);
 		const int pos = horiz ? x : y, P = horiz ? G.nx : G.ny;
 		if (pos < 1 || pos > P) return 0;
+		int t = (p * 11 + pos * 3) % G.W;
 		for (int k = 0; k < G.W && n < G.fc_out; k++) {
-			const int t = (p * 11 + pos * 3 + k) % G.W;
-			int a, b;
-			const int w = pf_gen_wire_at(G, horiz, chan, pos, t, &a, &b);
-			if ((t & 1) ? b == pos : a == pos) { if (out) out[n] = (uint32_t)w | ((uint32_t)PF_GEN_SW_WIRE << G.node_bits); n++; }
+			if (pf_gen_starts_here(G, pos, t, P)) {
+				if (out) out[n] = (uint32_t)pf_gen_wire_at(G, horiz, chan, pos, t, NULL, NULL) | ((uint32_t)PF_GEN_SW_WIRE << G.node_bits);
+				n++;
+			}
+			if (++t == G.W) t = 0;
 		}
 		return n;
 	}

@@ -39,7 +39,7 @@ struct pf_router {
 	int *net_ptr, *net_term, *net_bb;
 	float *crit, *net_delay;
 	SlotClass small, big;
-	PfTreeNode *pool[2]; PfNetLoc *loc; int cur;      /* pool[cur] is the live route-tree log */
+	PfTreeNode *pool[2]; int *pool_node[2]; PfNetLoc *loc; int cur;      /* pool[cur] is the live route-tree log */
 	long long pool_cap; unsigned long long *pool_head;
 	int *all_nets; int num_all; unsigned char *net_big; int *sel_counts; int *sel_scratch;
 	short *ptc;                    /* rr_node[].ptc_num, only read when the result's serial number is assembled */

@@ -279,12 +279,14 @@ __global__ void pf_reserve_opins_kernel(PfNode *nodes, const uint32_t *edges, in
 __global__ void __launch_bounds__(PF_SEL_BLOCK) pf_select_flag_kernel(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc,
 		const int *all_nets, int num_all, const unsigned char *net_big, int force_all, unsigned char *flag, int *block_counts,
 		const unsigned char *last_over, int iter_tag, int window, const int *committer, int head_count, int *counts,
-		int *queued, int queued_tag) {
+		int *queued, int queued_tag, const int *pool_node, const unsigned char *over_now, int over_tag) {
 	int k = (int)(blockIdx.x * PF_SEL_BLOCK + threadIdx.x);
 	int f = 0;
 	if (k < num_all) {
 		int net = all_nets[k];
-		if (force_all || pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net)) f = net_big[net] ? 2 : 1;
+		const int hit = force_all ? 1 : over_now ? pf_net_is_congested_fast(pool_node, loc[net], over_now, over_tag)
+				: pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net);
+		if (hit) f = net_big[net] ? 2 : 1;
 		flag[k] = (unsigned char)f;
 		if (f && queued) queued[net] = queued_tag;
 	}
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(PF_SEL_BLOCK) pf_select_scatter_kernel(const i
 }
 
 /* one warp per net: reserve space in the destination log, copy the tree with coalesced 32-byte entries */
-__global__ void pf_compact_kernel(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
+__global__ void pf_compact_kernel(const PfTreeNode *src, PfTreeNode *dst, const int *src_node, int *dst_node, PfNetLoc *loc, const int *all_nets, int num_all,
 		unsigned long long *dst_head) {
 	int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31u);
 	int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
@@ -339,7 +341,7 @@ __global__ void pf_compact_kernel(const PfTreeNode *src, PfTreeNode *dst, PfNetL
 		unsigned long long off = 0;
 		if (lane == 0) off = atomicAdd(dst_head, (unsigned long long)l.count);
 		off = __shfl_sync(0xffffffffu, off, 0);
-		for (int i = lane; i < l.count; i += 32) dst[off + i] = src[l.off + i];
+		for (int i = lane; i < l.count; i += 32) { dst[off + i] = src[l.off + i]; dst_node[off + i] = src_node[l.off + i]; }
 		if (lane == 0) loc[net].off = (int)off;
 	}
 }
@@ -728,7 +730,7 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, int node_bits
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
 		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count,
-		int *queued, int queued_tag) {
+		int *queued, int queued_tag, const int *pool_node, const unsigned char *over_now, int over_tag) {
 	if (cudaMemsetAsync(counts, 0, sizeof(int) * 4, g_stream) != cudaSuccess) return -1;
 	if (num_all <= 0) return 0;
 	/* scratch: [2 ints per CTA][one flag byte per net] — pfb_select_scratch_bytes() */
@@ -736,7 +738,7 @@ int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const Pf
 	unsigned char *flag = (unsigned char *)(scratch + 2 * (size_t)blocks);
 	if (ev_begin(2) != 0) return -1;
 	pf_select_flag_kernel<<<blocks, PF_SEL_BLOCK, 0, g_stream>>>(nodes, pool, loc, all_nets, num_all, net_big, force_all, flag, scratch,
-			last_over, iter_tag, window, committer, head_count, counts, queued, queued_tag);
+			last_over, iter_tag, window, committer, head_count, counts, queued, queued_tag, pool_node, over_now, over_tag);
 	pf_select_scatter_kernel<<<blocks, PF_SEL_BLOCK, 0, g_stream>>>(all_nets, num_all, flag, scratch, list_small, list_big, counts);
 	return ev_end();
 }
@@ -746,11 +748,11 @@ size_t pfb_select_scratch_bytes(int num_all) {
 	return 8 * blocks + (size_t)std::max(num_all, 1) + 16;
 }
 
-int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
+int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, const int *src_node, int *dst_node, PfNetLoc *loc, const int *all_nets, int num_all,
 		unsigned long long *dst_head) {
 	if (num_all <= 0) return 0;
 	if (ev_begin(2) != 0) return -1;
-	pf_compact_kernel<<<stream_grid((long long)num_all * 32), 256, 0, g_stream>>>(src, dst, loc, all_nets, num_all, dst_head);
+	pf_compact_kernel<<<stream_grid((long long)num_all * 32), 256, 0, g_stream>>>(src, dst, src_node, dst_node, loc, all_nets, num_all, dst_head);
 	return ev_end();
 }
 

@@ -124,6 +124,8 @@ struct PfParams {
 	 * A re-routed net appends its new tree and repoints loc; the log is compacted between
 	 * iterations when it is more than half garbage. */
 	PfTreeNode *pool; PfNetLoc *loc; unsigned long long *pool_head; long long pool_cap;
+	int *pool_node;        /* [pool_cap] the rr node of every log entry again, 4 bytes each: what the per-iteration passes over ALL trees
+	                          (congested-net selection, rip-up) read instead of the 32-byte entries */
 	/* multi-GPU: every occupancy change this rank makes is also logged (node id, bit 31 = decrement) so that the
 	 * other ranks can replay it; NULL on one GPU */
 	unsigned *events; unsigned long long *event_head; long long event_cap;

@@ -137,7 +137,7 @@ extern "C" void pf_router_destroy(pf_router *r) {
 	pfb_free(r->crit); pfb_free(r->net_delay);
 	if (r->ctl) { r->small.work_head = NULL; r->big.work_head = NULL; }
 	free_slot_class(r->small); free_slot_class(r->big);
-	pfb_free(r->pool[0]); pfb_free(r->pool[1]); pfb_free(r->loc);
+	pfb_free(r->pool[0]); pfb_free(r->pool[1]); pfb_free(r->pool_node[0]); pfb_free(r->pool_node[1]); pfb_free(r->loc);
 	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->retry_work); pfb_free(r->sel_scratch); pfb_free(r->ptc);
 	pfb_free(r->ctl); pfb_host_free(r->h_ctl); pfb_free(r->retry_list); pfb_free(r->last_over); pfb_free(r->committer);
 	for (int k = 0; k < PF_XCHG_MAX_RANKS; k++) if (r->peers.base[k] && r->peers.base[k] != r->xreg) pfb_ipc_close(r->peers.base[k]);
@@ -292,7 +292,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->prob = p; r->N = p->num_nodes; r->E = p->num_edges; r->generated = gen != NULL; r->T = p->num_terminals; r->n = p->num_nets;
 	r->nodes = NULL; r->edges = NULL; r->sw = NULL; r->indexed = NULL; r->net_ptr = r->net_term = r->net_bb = NULL;
 	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
-	r->pool[0] = r->pool[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
+	r->pool[0] = r->pool[1] = NULL; r->pool_node[0] = r->pool_node[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
 	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->sel_scratch = NULL; r->ptc = NULL; r->K1 = 0; r->n1_small = r->n1_big = 0; r->iter_count = 0;
 	r->best_overused = 0x7fffffff; r->stall_count = 0; r->since_full = 0; r->last_over = NULL; r->cost_updates = 0; r->committer = NULL; r->cur_div = 32; r->n_small = r->n_big = 0; r->retry_work = NULL; r->ctl = NULL; r->h_pool_head = 0;
 	r->status = r->retry_list = r->retry_count = NULL; r->stats = NULL; r->d_overused = NULL; r->d_wl = NULL;
@@ -511,7 +511,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->pool_cap = std::max<long long>(1 << 18, std::min<long long>(4ll * r->N + 96ll * r->T, 32ll * r->T + (1 << 20)));
 	for (int k = 0; k < 2; k++) {
 		r->pool[k] = (PfTreeNode *)pfb_alloc_raw(sizeof(PfTreeNode) * (size_t)r->pool_cap);
-		if (!r->pool[k]) { pf_router_destroy(r); CUDA_FAIL(); }
+		r->pool_node[k] = (int *)pfb_alloc_raw(sizeof(int) * (size_t)r->pool_cap);
+		if (!r->pool[k] || !r->pool_node[k]) { pf_router_destroy(r); CUDA_FAIL(); }
 	}
 	r->loc = (PfNetLoc *)pfb_alloc(sizeof(PfNetLoc) * (size_t)std::max(r->n, 1));
 	{
@@ -701,7 +702,7 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.hot2 = s.hot2; P.cold2 = s.cold2; P.label2_log2 = s.label2_log2;
 	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap;
 	P.iscratch = s.iscratch; P.sink_cap = s.sink_cap;
-	P.pool = r->pool[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;
+	P.pool = r->pool[r->cur]; P.pool_node = r->pool_node[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;
 	P.net_big = r->net_big;
 	P.committer = r->cfg.keep_newcomer ? r->committer : NULL;
 	if (r->vq[0] && !r->iter_all && r->n_small + r->n_big <= r->cfg.ripple_max_nets) {   /* (an iteration that re-routes every net displaces nobody unrouted) */
@@ -715,11 +716,15 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 }
 
 /* the select kernels: work lists of the iteration about to start (tag = its number) */
-static int launch_select(pf_router *r, int force_all) {
+static int launch_select(pf_router *r, int force_all, bool right_behind_the_cost_update = false) {
+	/* right behind the cost update the byte map it wrote (last_over[v] == tag <=> v is overused now) replaces the node records */
+	const int tag = 1 + (r->cost_updates + 254) % 255;
+	const bool fast = right_behind_the_cost_update && r->cfg.history_window <= 0 && !r->cfg.keep_newcomer
+			&& r->cost_updates < 255;     /* tags are iteration numbers mod 255: beyond that an old mark could alias */
 	CKB(pfb_launch_select_nets(r->nodes, r->pool[r->cur], r->loc, r->all_nets, r->num_all, r->net_big, force_all,
 			r->small.work, r->big.work, r->sel_counts, r->cfg.history_window > 0 ? r->last_over : NULL,
 			1 + (r->cost_updates + 254) % 255, r->cfg.history_window, r->cfg.keep_newcomer ? r->committer : NULL, r->sel_scratch, r->K1,
-			r->queued, r->iter_count + 1));
+			r->queued, r->iter_count + 1, r->pool_node[r->cur], fast ? r->last_over : NULL, tag));
 	return PF_OK;
 }
 
@@ -769,7 +774,7 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	/* garbage-collect the route-tree log when it is more than half full */
 	if ((long long)r->h_pool_head > r->pool_cap / 2) {
 		CKB(pfb_zero(r->pool_head, sizeof(unsigned long long) * 2));
-		CKB(pfb_launch_compact(r->pool[r->cur], r->pool[r->cur ^ 1], r->loc, r->all_nets, r->num_all, r->pool_head));
+		CKB(pfb_launch_compact(r->pool[r->cur], r->pool[r->cur ^ 1], r->pool_node[r->cur], r->pool_node[r->cur ^ 1], r->loc, r->all_nets, r->num_all, r->pool_head));
 		r->cur ^= 1;
 		r->h_pool_head = 0;       /* the live size arrives with the next control block; a log that is still too small then
 		                           * overflows in the route kernel and is reported as such */
@@ -923,7 +928,7 @@ static int update_costs_async(pf_router *r, float acc_fac) {
 	r->cost_updates++;
 	CKB(pfb_launch_update_cost(r->nodes, r->N, acc_fac, r->d_overused, r->last_over, 1 + (r->cost_updates + 254) % 255, r->d_wl + 1));
 	if (r->cfg.reroute_all_iters >= 0 && r->iter_count >= r->cfg.reroute_all_iters) {
-		int rc = launch_select(r, 0);
+		int rc = launch_select(r, 0, true);
 		if (rc != PF_OK) return rc;
 		r->sel_pending = true;
 	}

@@ -113,12 +113,14 @@ int pfb_launch_reserve_opins(PfNode *nodes, const uint32_t *edges, int node_bits
 int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const PfNetLoc *loc, const int *all_nets,
 		int num_all, const unsigned char *net_big, int force_all, int *list_small, int *list_big, int *counts,
 		const unsigned char *last_over, int iter_tag, int window, const int *committer, int *scratch, int head_count,
-		int *queued, int queued_tag) {
+		int *queued, int queued_tag, const int *pool_node, const unsigned char *over_now, int over_tag) {
 	(void)scratch;
 	counts[0] = counts[1] = counts[2] = counts[3] = 0;
 	for (int k = 0; k < num_all; k++) {          /* all_nets is in fanout order; so are the lists */
 		int net = all_nets[k];
-		if (force_all || pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net)) {
+		const int hit = force_all ? 1 : over_now ? pf_net_is_congested_fast(pool_node, loc[net], over_now, over_tag)
+				: pf_net_is_congested(nodes, pool, loc[net], last_over, iter_tag, window, committer, net);
+		if (hit) {
 			if (queued) queued[net] = queued_tag;
 			if (net_big[net]) { list_big[counts[1]++] = net; if (k < head_count) counts[3]++; }
 			else { list_small[counts[0]++] = net; if (k < head_count) counts[2]++; }
@@ -131,7 +133,7 @@ int pfb_launch_select_nets(const PfNode *nodes, const PfTreeNode *pool, const Pf
 void pfb_bind_thread(void) {}
 size_t pfb_select_scratch_bytes(int num_all) { (void)num_all; return 16; }
 
-int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, const int *all_nets, int num_all,
+int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, const int *src_node, int *dst_node, PfNetLoc *loc, const int *all_nets, int num_all,
 		unsigned long long *dst_head) {
 	for (int k = 0; k < num_all; k++) {
 		int net = all_nets[k];
@@ -140,6 +142,7 @@ int pfb_launch_compact(const PfTreeNode *src, PfTreeNode *dst, PfNetLoc *loc, co
 		unsigned long long off = *dst_head;
 		*dst_head += (unsigned long long)l.count;
 		memcpy(dst + off, src + l.off, sizeof(PfTreeNode) * (size_t)l.count);
+		memcpy(dst_node + off, src_node + l.off, sizeof(int) * (size_t)l.count);
 		loc[net].off = (int)off;
 	}
 	g_times.aux_launches++;
