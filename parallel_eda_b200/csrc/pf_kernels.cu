@@ -631,18 +631,36 @@ __global__ void __launch_bounds__(PF_SCAN_CTA) pf_scan_apply_kernel(int *a, int 
 	}
 	if (i < n) a[i] = (int)(totals[blockIdx.x] + s[threadIdx.x] - v);
 }
-__global__ void pf_gen_fill_kernel(const __grid_constant__ PfGenDev G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc, unsigned long long *avail_wl) {
+/* pass 2.  A warp takes 32 consecutive nodes: their edge rows are one contiguous span of the edge array (row[] is the prefix sum
+ * of the degrees, row[N] = E).  Every lane enumerates its node's edges into the warp's staging buffer in shared memory and the
+ * warp then copies the span out with coalesced stores — 32 lanes writing 4-byte words into 32 different rows cost 3x the
+ * enumeration itself (10.5 ms vs 3.1 ms for the degree pass on cfg 4). */
+#define PF_GEN_STAGE 1024           /* words per warp: 32 nodes x degree <= 32 */
+__global__ void __launch_bounds__(256) pf_gen_fill_kernel(const __grid_constant__ PfGenDev G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc, unsigned long long *avail_wl) {
+	__shared__ uint32_t stage[8][PF_GEN_STAGE];
+	const int lane = (int)(threadIdx.x & 31u), wib = (int)(threadIdx.x >> 5);
+	const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
 	unsigned wl = 0;
-	for (int v = (int)(blockIdx.x * blockDim.x + threadIdx.x); v < G.num_nodes; v += (int)(gridDim.x * blockDim.x)) {
-		const PfGenNode nd = pf_gen_decode(G, v);
-		const int start = row[v];
-		const int deg = pf_gen_node_edges(G, v, nd, edges + start);
-		pf_gen_write_node(nd, start, deg, &nodes[v], &ptc[v]);
-		if (nd.type == 4 || nd.type == 5) wl += (unsigned)(1 + nd.x1 - nd.x0 + nd.y1 - nd.y0);
+	for (int base = warp * 32; base < G.num_nodes; base += nwarps * 32) {
+		const int v = base + lane;
+		const int last = min(base + 32, G.num_nodes);
+		const int s0 = row[base], span = row[last] - s0;
+		const bool staged = span <= PF_GEN_STAGE;
+		if (v < G.num_nodes) {
+			const PfGenNode nd = pf_gen_decode(G, v);
+			const int start = row[v];
+			const int deg = pf_gen_node_edges(G, v, nd, staged ? &stage[wib][start - s0] : edges + start);
+			pf_gen_write_node(nd, start, deg, &nodes[v], &ptc[v]);
+			if (nd.type == 4 || nd.type == 5) wl += (unsigned)(1 + nd.x1 - nd.x0 + nd.y1 - nd.y0);
+		}
+		__syncwarp();
+		if (staged) for (int i = lane; i < span; i += 32) edges[s0 + i] = stage[wib][i];
+		__syncwarp();
 	}
 	wl = __reduce_add_sync(0xffffffffu, wl);
-	if ((threadIdx.x & 31u) == 0 && wl) atomicAdd(avail_wl, (unsigned long long)wl);
+	if (lane == 0 && wl) atomicAdd(avail_wl, (unsigned long long)wl);
 }
+__global__ void pf_scan_close_kernel(int *a, int n, const long long *grand) { a[n] = (int)*grand; }
 __global__ void pf_reset_nodes_kernel(PfNode *nodes, int num_nodes) {
 	for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < num_nodes; i += (int)(gridDim.x * blockDim.x)) { nodes[i].occ = 0; nodes[i].acc_cost = 1.f; }
 }
@@ -798,6 +816,7 @@ int pfb_gen_count(const PfGenDev *G, int *row, long long *num_edges) {
 	pf_scan_totals_kernel<<<nb, PF_SCAN_CTA, 0, g_stream>>>(row, n, totals);
 	pf_scan_offsets_kernel<<<1, PF_SCAN_CTA, 0, g_stream>>>(totals, nb, totals + nb);
 	pf_scan_apply_kernel<<<nb, PF_SCAN_CTA, 0, g_stream>>>(row, n, totals);
+	pf_scan_close_kernel<<<1, 1, 0, g_stream>>>(row, n, totals + nb);          /* row[N] = E */
 	if (ev_end() != 0) return -1;
 	CK(cudaMemcpyAsync(num_edges, totals + nb, sizeof(long long), cudaMemcpyDeviceToHost, g_stream));
 	CK(cudaStreamSynchronize(g_stream));

@@ -181,6 +181,7 @@ int pfb_launch_build_traces(const PfTreeNode *pool, const PfNetLoc *loc, int num
 int pfb_gen_count(const PfGenDev *G, int *row, long long *num_edges) {
 	long long acc = 0;
 	for (int v = 0; v < G->num_nodes; v++) { const PfGenNode nd = pf_gen_decode(*G, v); const int d = pf_gen_node_edges(*G, v, nd, NULL); row[v] = (int)acc; acc += d; }
+	row[G->num_nodes] = (int)acc;
 	*num_edges = acc;
 	g_times.aux_launches++;
 	return 0;
