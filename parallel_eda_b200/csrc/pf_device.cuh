@@ -63,6 +63,7 @@ PF_DEV int pf_ffs(unsigned m) { return __ffs((int)m); }
 PF_DEV unsigned pf_lanemask_lt(void) { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 PF_DEV int pf_atomic_add_i(int *p, int v) { return atomicAdd(p, v); }
 PF_DEV unsigned long long pf_atomic_add_ull(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
+PF_DEV void pf_atomic_max_ull(unsigned long long *p, unsigned long long v) { atomicMax(p, v); }
 PF_DEV int pf_atomic_or_i(int *p, int v) { return atomicOr(p, v); }
 PF_DEV int pf_atomic_min_i(int *p, int v) { return atomicMin(p, v); }   /* used on shared memory (ATOMS) */
 PF_DEV int pf_atomic_exch_i(int *p, int v) { return atomicExch(p, v); }
@@ -110,12 +111,14 @@ struct PfWarp {
 	PfTreeNode *tree; uint64_t *far; int *iscratch;
 	/* search state: warp-uniform */
 	unsigned tag_mask; int nb;    /* search-tag mask and node-id width of this router (PfParams.node_bits), kept in registers */
-	unsigned epoch; unsigned round; int n_labels; int sh_n; int far_n; float T_hi; float far_min; float best;
+	unsigned epoch; unsigned round; int n_labels; int sh_n; float T_hi; float far_min; float best;
+	int st_n;                     /* entries in the staging / flat far list */
 	int overflow;
 	/* per-net constants */
 	int bb_xmin, bb_xmax, bb_ymin, bb_ymax; int num_sinks; int cur_net;
 	/* counters */
 	unsigned pops, pushes, visits, refills, stale, races;   /* per launch and warp: 32 bits are plenty, and six registers fewer */
+	unsigned max_net_pops;
 };
 
 /* per warp: fr 1024 + b_key 256 + base_cost 128 + 5 batch arrays 640 + b_pre 136 + tickets 256 = 2440 → 2448;
@@ -289,10 +292,383 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
 	return written;
 }
 
-/* ------------------------------------------------------------------ frontier */
+/* ------------------------------------------------------------------ frontier
+ * Two levels, delta-stepping style.
+ *   near set   shared memory, every label with total <= T_hi: the settle loop pops its exact minimum.
+ *   far list   the slot's array in HBM / L2, cut into PF_BUCKETS cost buckets of width delta (= the near window at the start
+ *              of the search) above `bk_base`: bucket b holds totals in [base + b delta, base + (b+1) delta); the last bucket
+ *              is the catch-all for everything beyond, and for what does not fit its own bucket.  Lane b keeps the fill count
+ *              of bucket b in a register, so no shared memory is spent on it.
+ * A refill only touches the lowest non-empty bucket (and the catch-all when it holds something that belongs there), instead
+ * of scanning the whole far list three times: on flooding searches — timing-driven nets at pres_fac >= 3 settle 10^4..10^5
+ * labels — the flat list made a refill O(labels in flight) and the search quadratic (37 s of the 38 s of the 32 k-LUT
+ * circuit were spent in 64 big slots doing that). */
+#define PF_BUCKETS 32
+/* the frontier state the refill works on, handed to the out-of-line refill BY VALUE and returned (the warp context itself must
+ * never have its address taken: it would move from registers to local memory for the whole kernel) */
+struct PfFront { uint64_t *fr; uint64_t *far; int far_cap; float win_rel, win_abs; int sh_n, bk_n, st_n; float bk_base, bk_inv, ovf_min, far_min, T_hi; int overflow; unsigned refills; };
+/* the slot's far array: lower half = 31 regular buckets of far_cap/256 entries + the catch-all bucket; upper half = the staging
+ * list, which IS the far list of a search that never needed buckets (PF_FLAT_MAX).
+ * Pushes only APPEND to the staging list (one ballot, one store — most far labels of an A* search are never needed: cfg 4
+ * pushes 40 M labels and settles 5 M); a refill deals the staged labels out to the buckets first. */
+PF_DEV int pf_bucket_cap(const PfFront &f, int b) { return b < PF_BUCKETS - 1 ? (f.far_cap >> 8) : (f.far_cap >> 1) - (PF_BUCKETS - 1) * (f.far_cap >> 8); }
+PF_DEV uint64_t *pf_bucket_ptr(const PfFront &f, int b) { return f.far + (size_t)b * (size_t)(f.far_cap >> 8); }
+PF_DEV int pf_stage_off(int far_cap) { return far_cap >> 1; }
+PF_DEV int pf_stage_cap(int far_cap) { return far_cap - (far_cap >> 1) - 32; }      /* the last 32 words hold the bucket state */
+PF_DEV int pf_bucket_of(const PfFront &f, float tot) {
+	const float x = (tot - f.bk_base) * f.bk_inv;
+	return x < 0.f ? 0 : (x >= (float)(PF_BUCKETS - 1) ? PF_BUCKETS - 1 : (int)x);
+}
+
+/* Warp-collective insertion into the far list: every active lane files one key.  Out of line on the GPU — it is called from
+ * the push of every relax pass but runs rarely, and inlined at each site it doubles the size of the search loop, which is bound
+ * by instruction fetch; it takes and returns its state BY VALUE so that the warp context stays in registers. */
+struct PfFarState { int bk_n; float far_min, ovf_min; int overflow; };
+#if defined(__CUDACC__) && !defined(PF_EMU) && !defined(PF_FAR_INLINE)
+#define PF_NOINLINE static __device__ __noinline__
+#elif defined(__CUDACC__) && !defined(PF_EMU)
+#define PF_NOINLINE static __device__ __forceinline__
+#else
+#define PF_NOINLINE static inline
+#endif
+PF_DEV PfFarState pf_far_put_inl(uint64_t *far, int far_cap, float bk_base, float bk_inv, PfFarState st, int active, uint64_t key, float tot) {
+	const int lane = pf_lane();
+	const int cr = far_cap >> 8;
+	int b = -1;
+	if (active) { const float x = (tot - bk_base) * bk_inv; b = x < 0.f ? 0 : (x >= (float)(PF_BUCKETS - 1) ? PF_BUCKETS - 1 : (int)x); }
+	unsigned rem = pf_ballot(active);
+	while (rem) {
+		const int bk = pf_shfl_i(b, pf_ffs(rem) - 1);
+		const unsigned m = pf_ballot(b == bk);
+		const int n0 = pf_shfl_i(st.bk_n, bk), cap = bk < PF_BUCKETS - 1 ? cr : (far_cap >> 1) - (PF_BUCKETS - 1) * cr;
+		const int pos = n0 + pf_popc(m & pf_lanemask_lt());
+		int spill = 0;
+		if (b == bk) {
+			if (pos < cap) far[(size_t)bk * (size_t)cr + pos] = key;
+			else if (bk < PF_BUCKETS - 1) { spill = 1; b = PF_BUCKETS - 1; }      /* its own bucket is full: the catch-all takes it */
+			else st.overflow = 1;
+		}
+		if (lane == bk) st.bk_n = (n0 + pf_popc(m) < cap) ? n0 + pf_popc(m) : cap;
+		rem = (rem & ~m) | pf_ballot(spill);
+	}
+	st.overflow = pf_any(st.overflow);                          /* the catch-all is full: the net is retried in a bigger slot */
+	const float fm = pf_warp_min_f(active ? tot : PF_INF_F);
+	if (fm < st.far_min) st.far_min = fm;
+	const float om = pf_warp_min_f((active && b == PF_BUCKETS - 1) ? tot : PF_INF_F);
+	if (om < st.ovf_min) st.ovf_min = om;
+	return st;
+}
+PF_DEV void pf_far_put(PfFront &f, int active, uint64_t key, float tot) {
+	PfFarState st; st.bk_n = f.bk_n; st.far_min = f.far_min; st.ovf_min = f.ovf_min; st.overflow = 0;
+	st = pf_far_put_inl(f.far, f.far_cap, f.bk_base, f.bk_inv, st, active, key, tot);
+	f.bk_n = st.bk_n; f.far_min = st.far_min; f.ovf_min = st.ovf_min;
+	if (st.overflow) f.overflow = 1;
+}
+
+/* All regular buckets are empty: open a new range of buckets at the catch-all's minimum and deal its entries out. */
+PF_DEV void pf_far_rebase(PfFront &f) {
+	const int lane = pf_lane();
+	const int n = pf_shfl_i(f.bk_n, PF_BUCKETS - 1);
+	uint64_t *ovf = pf_bucket_ptr(f, PF_BUCKETS - 1);
+	uint64_t mk = PF_KEY_MAX;
+	PF_REFILL_LOOP for (int i = lane; i < n; i += PF_WARP) { const uint64_t k = ovf[i]; if (k < mk) mk = k; }
+	const float m = pf_key_tot(pf_warp_min_u64(mk));
+	float win = m * f.win_rel;
+	if (win < f.win_abs) win = f.win_abs;
+	f.bk_base = m; f.bk_inv = 1.f / win;
+	if (lane == PF_BUCKETS - 1) f.bk_n = 0;
+	int kept = 0;
+	float omin = PF_INF_F;
+	PF_REFILL_LOOP for (int base = 0; base < n; base += PF_WARP) {
+		const int i = base + lane;
+		const uint64_t k = i < n ? ovf[i] : PF_KEY_MAX;
+		int b = i < n ? pf_bucket_of(f, pf_key_tot(k)) : -1;
+		/* regular buckets first (their regions are disjoint from the catch-all being read) */
+		unsigned rem = pf_ballot(b >= 0 && b < PF_BUCKETS - 1);
+		while (rem) {
+			const int bk = pf_shfl_i(b, pf_ffs(rem) - 1);
+			const unsigned mm = pf_ballot(b == bk);
+			const int n0 = pf_shfl_i(f.bk_n, bk), cap = pf_bucket_cap(f, bk);
+			const int pos = n0 + pf_popc(mm & pf_lanemask_lt());
+			if (b == bk) { if (pos < cap) pf_bucket_ptr(f, bk)[pos] = k; else b = PF_BUCKETS - 1; }   /* full: stays in the catch-all */
+			if (lane == bk) f.bk_n = (n0 + pf_popc(mm) < cap) ? n0 + pf_popc(mm) : cap;
+			rem &= ~mm;
+		}
+		const unsigned mk2 = pf_ballot(b == PF_BUCKETS - 1);
+		pf_syncwarp();                                  /* this chunk has been read before slots below it are rewritten */
+		if (b == PF_BUCKETS - 1) {
+			ovf[kept + pf_popc(mk2 & pf_lanemask_lt())] = k;   /* kept <= base: in place */
+			const float t = pf_key_tot(k);
+			if (t < omin) omin = t;
+		}
+		kept += pf_popc(mk2);
+	}
+	if (lane == PF_BUCKETS - 1) f.bk_n = kept;
+	f.ovf_min = pf_warp_min_f(omin);
+	pf_syncwarp();
+}
+
+/* One list of the refill: count / take / compact.  mode 0: minimum key; 1: entries with total <= T; 2: move the first
+ * (PF_SH_REFILL - taken) of those to the near set, close the gaps, return the minimum total that stays. */
+PF_DEV uint64_t pf_list_min(const uint64_t *a, int n) {
+	uint64_t mk = PF_KEY_MAX;
+	PF_REFILL_LOOP for (int i = pf_lane(); i < n; i += PF_WARP) { const uint64_t k = a[i]; if (k < mk) mk = k; }
+	return mk;
+}
+PF_DEV int pf_list_count(const uint64_t *a, int n, float T) {
+	int c = 0;
+	PF_REFILL_LOOP for (int i = pf_lane(); i < n; i += PF_WARP) if (pf_key_tot(a[i]) <= T) c++;
+	return c;
+}
+PF_DEV float pf_list_take(PfFront &f, uint64_t *a, int n, float T, int *taken_io, int *kept_out) {
+	const int lane = pf_lane();
+	int kept = 0, taken = *taken_io;
+	float fmin = PF_INF_F;
+	PF_REFILL_LOOP for (int base = 0; base < n; base += PF_WARP) {
+		const int i = base + lane;
+		const uint64_t k = (i < n) ? a[i] : PF_KEY_MAX;
+		const int q = (i < n) && pf_key_tot(k) <= T;
+		const unsigned mq = pf_ballot(q);
+		const int rank = taken + pf_popc(mq & pf_lanemask_lt());
+		const int take = q && rank < PF_SH_REFILL;
+		const unsigned mt = pf_ballot(take);
+		const int keep = (i < n) && !take;
+		const unsigned mkp = pf_ballot(keep);
+		pf_syncwarp();                                      /* reads of this chunk are complete before the in-place writes */
+		if (take) f.fr[taken + pf_popc(mt & pf_lanemask_lt())] = k;
+		if (keep) {
+			a[kept + pf_popc(mkp & pf_lanemask_lt())] = k;      /* kept + rank <= i: in-place is safe after the ballots */
+			const float t = pf_key_tot(k);
+			if (t < fmin) fmin = t;
+		}
+		taken += pf_popc(mt);
+		kept += pf_popc(mkp);
+	}
+	*taken_io = taken; *kept_out = kept;
+	return fmin;
+}
+
+/* Re-bucket: file the near set's leftovers, find the lowest non-empty bucket, open a window above its minimum and pull
+ * every label inside the window into shared memory (at most PF_SH_REFILL; the window is narrowed until they fit, down to
+ * exact ties of the minimum).  The catch-all is consulted too whenever it holds a total below the bucket's upper bound. */
+/* A search whose far list stays short — every A* search of BASELINE configs[4]: 67 far labels per sink on average — never
+ * builds buckets: its staging list is scanned directly, with the window relative to the current minimum, as in round 1. */
+#ifndef PF_FLAT_MAX
+#define PF_FLAT_MAX 768
+#endif
+#ifdef PF_EMU
+extern long long pf_emu_bucket_refills;   /* test hook of the emulator build: refills that went through the cost buckets */
+#endif
+#define PF_ROUND_BUCKETS 0x40000000u   /* bit of PfWarp.round: this search has opened its cost buckets (their state lives in the
+                                       * last 256 bytes of the slot's far array, not in registers: it is touched once per refill) */
+PF_DEV void pf_refill_flat(PfFront &f) {
+	const int lane = pf_lane();
+	uint64_t *lst = f.far + pf_stage_off(f.far_cap);
+	const int scap = pf_stage_cap(f.far_cap);
+	/* near → list */
+	PF_REFILL_LOOP for (int base = 0; base < f.sh_n; base += PF_WARP) {
+		const int i = base + lane;
+		if (i < f.sh_n && f.st_n + i < scap) lst[f.st_n + i] = f.fr[i];
+	}
+	f.st_n += f.sh_n;
+	f.sh_n = 0;
+	if (f.st_n > scap) { f.st_n = scap; f.overflow = 1; }
+	pf_syncwarp();
+	const float m = pf_key_tot(pf_warp_min_u64(pf_list_min(lst, f.st_n)));
+	float win = m * f.win_rel;
+	if (win < f.win_abs) win = f.win_abs;
+	float T = m + win;
+	for (;;) {
+		const int c = pf_warp_sum_i(pf_list_count(lst, f.st_n, T));
+		if (c <= PF_SH_REFILL || T <= m) break;
+		win *= 0.25f;
+		T = m + win;
+	}
+	int taken = 0, kept = 0;
+	const float fmin = pf_list_take(f, lst, f.st_n, T, &taken, &kept);
+	f.sh_n = taken;
+	f.st_n = kept;
+	f.far_min = pf_warp_min_f(fmin);
+	f.T_hi = T;
+	pf_syncwarp();
+}
+
+PF_DEV void pf_refill_body(PfFront &f) {
+	const int lane = pf_lane();
+	f.refills++;
+	if (f.bk_inv == 0.f) {                                /* no buckets yet */
+		if (f.st_n + f.sh_n <= PF_FLAT_MAX) { pf_refill_flat(f); return; }
+		/* the search has outgrown the flat list: open the buckets at the current minimum */
+		uint64_t mk = pf_list_min(f.far + pf_stage_off(f.far_cap), f.st_n);
+		{ const uint64_t mn = pf_list_min(f.fr, f.sh_n); if (mn < mk) mk = mn; }
+		const float m = pf_key_tot(pf_warp_min_u64(mk));
+		float win = m * f.win_rel;
+		if (win < f.win_abs) win = f.win_abs;
+		f.bk_base = m; f.bk_inv = 1.f / win;
+	}
+	/* 1. the near set's leftovers, then everything pushed since the last refill, into the buckets */
+	PF_REFILL_LOOP for (int base = 0; base < f.sh_n; base += PF_WARP) {
+		const int i = base + lane;
+		const uint64_t k = i < f.sh_n ? f.fr[i] : 0;
+		pf_far_put(f, i < f.sh_n, k, pf_key_tot(k));
+	}
+	f.sh_n = 0;
+	{
+		const uint64_t *stg = f.far + pf_stage_off(f.far_cap);
+		PF_REFILL_LOOP for (int base = 0; base < f.st_n; base += PF_WARP) {
+			const int i = base + lane;
+			const uint64_t k = i < f.st_n ? stg[i] : 0;
+			pf_far_put(f, i < f.st_n, k, pf_key_tot(k));
+		}
+		f.st_n = 0;
+	}
+	pf_syncwarp();
+	/* 2. the bucket to draw from */
+	unsigned nonempty = pf_ballot(f.bk_n > 0 && lane < PF_BUCKETS - 1);
+	int n_ovf = pf_shfl_i(f.bk_n, PF_BUCKETS - 1);
+	if (!nonempty) {
+		if (n_ovf == 0) { f.far_min = PF_INF_F; return; }
+		pf_far_rebase(f);
+		nonempty = pf_ballot(f.bk_n > 0 && lane < PF_BUCKETS - 1);
+		n_ovf = pf_shfl_i(f.bk_n, PF_BUCKETS - 1);
+	}
+	uint64_t *ovf = pf_bucket_ptr(f, PF_BUCKETS - 1);
+	const int b = nonempty ? pf_ffs(nonempty) - 1 : PF_BUCKETS - 1;           /* (only the catch-all left: every bucket was full) */
+	uint64_t *lst = pf_bucket_ptr(f, b);
+	const int n_b = pf_shfl_i(f.bk_n, b);
+	const float ub = (b < PF_BUCKETS - 1) ? f.bk_base + (float)(b + 1) / f.bk_inv : PF_INF_F;
+	const int with_ovf = b < PF_BUCKETS - 1 && n_ovf > 0 && f.ovf_min < ub;
+	/* 3. minimum and window */
+	uint64_t mk = pf_list_min(lst, n_b);
+	if (with_ovf) { const uint64_t mo = pf_list_min(ovf, n_ovf); if (mo < mk) mk = mo; }
+	mk = pf_warp_min_u64(mk);
+	const float m = pf_key_tot(mk);
+	float win = m * f.win_rel;
+	if (win < f.win_abs) win = f.win_abs;
+	float T = m + win;
+	if (T > ub) T = ub;                                   /* what lies beyond belongs to later buckets */
+	for (;;) {
+		int c = pf_list_count(lst, n_b, T);
+		if (with_ovf) c += pf_list_count(ovf, n_ovf, T);
+		c = pf_warp_sum_i(c);
+		if (c <= PF_SH_REFILL || T <= m) break;
+		win *= 0.25f;
+		T = m + win;
+	}
+	/* 4. move, compact, track the far minimum: exact for what stays in the lists drawn from, lower bounds of the buckets above */
+	int taken = 0, kept_b = 0, kept_o = n_ovf;
+	float fmin = pf_list_take(f, lst, n_b, T, &taken, &kept_b);
+	if (lane == b) f.bk_n = kept_b;
+	if (with_ovf) {
+		const float omin = pf_list_take(f, ovf, n_ovf, T, &taken, &kept_o);
+		if (lane == PF_BUCKETS - 1) f.bk_n = kept_o;
+		f.ovf_min = pf_warp_min_f(omin);
+	} else if (b == PF_BUCKETS - 1) f.ovf_min = pf_warp_min_f(fmin);
+	fmin = pf_warp_min_f(fmin);
+	{
+		const unsigned above = pf_ballot(f.bk_n > 0 && lane > b && lane < PF_BUCKETS - 1);
+		if (above) { const float lb = f.bk_base + (float)(pf_ffs(above) - 1) / f.bk_inv; if (lb < fmin) fmin = lb; }
+		if (f.ovf_min < fmin) fmin = f.ovf_min;
+	}
+	f.sh_n = taken;
+	f.far_min = fmin;
+	f.T_hi = T;
+	pf_syncwarp();
+}
+
+
+/* the out-of-line refill: everything above is inlined into this one function */
+PF_NOINLINE PfFront pf_refill_impl(PfFront f) { pf_refill_body(f); return f; }
+/* BK = 0: the far list is ONE flat list over the whole array of the slot (the regular slots: their searches are A* searches
+ * with short far lists, and the kernel of the throughput launches is bound by instruction fetch — it does not carry the bucket
+ * code at all); BK = 1: the hybrid flat / bucketed list (the big slots, where the flooding searches end up). */
+template <int BK> PF_DEV int pf_list_off(int far_cap) { return BK ? pf_stage_off(far_cap) : 0; }
+template <int BK> PF_DEV int pf_list_cap(int far_cap) { return BK ? pf_stage_cap(far_cap) : far_cap; }
+template <int BK> PF_DEV void pf_refill(PfWarp &w) {
+	if (!BK || (!(w.round & PF_ROUND_BUCKETS) && w.st_n + w.sh_n <= PF_FLAT_MAX)) {
+		/* the common case, inline and on the warp context itself: a short flat far list (the round-1 algorithm: three passes
+		 * over a few dozen entries) — a call costs more than it does */
+		const int lane = pf_lane();
+		uint64_t *lst = w.far + pf_list_off<BK>(w.P->far_cap);
+		const int cap = pf_list_cap<BK>(w.P->far_cap);
+		w.refills++;
+		PF_REFILL_LOOP for (int base = 0; base < w.sh_n; base += PF_WARP) {
+			const int i = base + lane;
+			if (i < w.sh_n && w.st_n + i < cap) lst[w.st_n + i] = w.fr[i];
+		}
+		w.st_n += w.sh_n;
+		w.sh_n = 0;
+		if (w.st_n > cap) { w.st_n = cap; w.overflow |= PF_OVF_OTHER; }
+		pf_syncwarp();
+		const float m = pf_key_tot(pf_warp_min_u64(pf_list_min(lst, w.st_n)));
+		float win = m * w.P->win_rel;
+		if (win < w.P->win_abs) win = w.P->win_abs;
+		float T = m + win;
+		for (;;) {
+			const int c = pf_warp_sum_i(pf_list_count(lst, w.st_n, T));
+			if (c <= PF_SH_REFILL || T <= m) break;
+			win *= 0.25f;
+			T = m + win;
+		}
+		int kept = 0, taken = 0;
+		float fmin = PF_INF_F;
+		PF_REFILL_LOOP for (int base = 0; base < w.st_n; base += PF_WARP) {
+			const int i = base + lane;
+			const uint64_t k = (i < w.st_n) ? lst[i] : PF_KEY_MAX;
+			const int q = (i < w.st_n) && pf_key_tot(k) <= T;
+			const unsigned mq = pf_ballot(q);
+			const int rank = taken + pf_popc(mq & pf_lanemask_lt());
+			const int take = q && rank < PF_SH_REFILL;
+			const unsigned mt = pf_ballot(take);
+			const int keep = (i < w.st_n) && !take;
+			const unsigned mkp = pf_ballot(keep);
+			pf_syncwarp();                                      /* reads of this chunk are complete before the in-place writes */
+			if (take) w.fr[taken + pf_popc(mt & pf_lanemask_lt())] = k;
+			if (keep) {
+				lst[kept + pf_popc(mkp & pf_lanemask_lt())] = k;    /* kept + rank <= i: in-place is safe after the ballots */
+				const float t = pf_key_tot(k);
+				if (t < fmin) fmin = t;
+			}
+			taken += pf_popc(mt);
+			kept += pf_popc(mkp);
+		}
+		w.sh_n = taken;
+		w.st_n = kept;
+		w.far_min = pf_warp_min_f(fmin);
+		w.T_hi = T;
+		pf_syncwarp();
+		return;
+	}
+	if (BK) {
+		/* a search that has outgrown the flat list: cost buckets, out of line; their state is parked in the slot's memory */
+		PfFront f;
+#ifdef PF_EMU
+		if (pf_lane() == 0) pf_emu_bucket_refills++;
+#endif
+		float *bst = (float *)(w.far + w.P->far_cap - 32);
+		const int open = (w.round & PF_ROUND_BUCKETS) != 0;
+		f.fr = w.fr; f.far = w.far; f.far_cap = w.P->far_cap; f.win_rel = w.P->win_rel; f.win_abs = w.P->win_abs;
+		f.sh_n = w.sh_n; f.st_n = w.st_n; f.far_min = w.far_min; f.T_hi = w.T_hi; f.overflow = 0; f.refills = 0;
+		f.bk_n = open ? ((const int *)bst)[pf_lane()] : 0;
+		f.bk_base = open ? bst[32] : 0.f; f.bk_inv = open ? bst[33] : 0.f; f.ovf_min = open ? bst[34] : PF_INF_F;
+		f = pf_refill_impl(f);
+		((int *)bst)[pf_lane()] = f.bk_n;
+		if (pf_lane() == 0) { bst[32] = f.bk_base; bst[33] = f.bk_inv; bst[34] = f.ovf_min; }
+		w.round |= PF_ROUND_BUCKETS;
+		w.sh_n = f.sh_n; w.st_n = f.st_n; w.far_min = f.far_min; w.T_hi = f.T_hi; w.refills += f.refills;
+		if (f.overflow) w.overflow |= PF_OVF_OTHER;
+		pf_syncwarp();
+	}
+}
+
+PF_DEV void pf_far_reset(PfWarp &w) {
+	w.st_n = 0; w.far_min = PF_INF_F;
+	w.round &= ~PF_ROUND_BUCKETS;          /* buckets closed: pf_refill opens them when the far list outgrows PF_FLAT_MAX */
+}
+
 /* Warp-collective push.  Labels inside the near window go to shared memory, the rest (and any
- * near-set overflow) to the far list in HBM; far_min guards the best-first order. */
-PF_DEV void pf_push(PfWarp &w, int valid, float tot, int node, int edge_start) {
+ * near-set overflow) to the far list; far_min guards the best-first order. */
+template <int BK> PF_DEV void pf_push(PfWarp &w, int valid, float tot, int node, int edge_start) {
 	uint64_t key = pf_make_key(tot, node);
 	int to_sh = valid && tot <= w.T_hi;
 	/* a label inside the near window is settled soon, and the first thing read then is its row of out-edges: start
@@ -308,81 +684,15 @@ PF_DEV void pf_push(PfWarp &w, int valid, float tot, int node, int edge_start) {
 	int to_far = (valid && !to_sh) || spill;
 	unsigned m2 = pf_ballot(to_far);
 	if (m2) {
-		int fpos = w.far_n + pf_popc(m2 & pf_lanemask_lt());
-		if (to_far) {
-			if (fpos < w.P->far_cap) w.far[fpos] = key;
-		}
-		w.far_n += pf_popc(m2);
-		if (w.far_n > w.P->far_cap) { w.far_n = w.P->far_cap; w.overflow |= PF_OVF_OTHER; }
-		float fm = pf_warp_min_f(to_far ? tot : PF_INF_F);
+		const int so = pf_list_off<BK>(w.P->far_cap), scap = pf_list_cap<BK>(w.P->far_cap);
+		const int fpos = w.st_n + pf_popc(m2 & pf_lanemask_lt());
+		if (to_far && fpos < scap) w.far[so + fpos] = key;
+		w.st_n += pf_popc(m2);
+		if (w.st_n > scap) { w.st_n = scap; w.overflow |= PF_OVF_OTHER; }
+		const float fm = pf_warp_min_f(to_far ? tot : PF_INF_F);
 		if (fm < w.far_min) w.far_min = fm;
 	}
 	w.pushes += (unsigned)pf_popc(pf_ballot(valid));
-	pf_syncwarp();
-}
-
-/* Re-bucket: move the near set to the far list, find the new minimum, open a window above it and
- * pull every far label inside the window back into shared memory (at most PF_SH_REFILL; the
- * window is narrowed until they fit, down to exact ties of the minimum). */
-PF_DEV void pf_refill(PfWarp &w) {
-	const int lane = pf_lane();
-	w.refills++;
-	/* 1. near → far */
-	PF_REFILL_LOOP for (int base = 0; base < w.sh_n; base += PF_WARP) {
-		int i = base + lane;
-		if (i < w.sh_n) {
-			int fpos = w.far_n + i;
-			if (fpos < w.P->far_cap) w.far[fpos] = w.fr[i];
-		}
-	}
-	w.far_n += w.sh_n;
-	w.sh_n = 0;
-	if (w.far_n > w.P->far_cap) { w.far_n = w.P->far_cap; w.overflow |= PF_OVF_OTHER; }
-	pf_syncwarp();
-	/* 2. minimum */
-	uint64_t mk = PF_KEY_MAX;
-	PF_REFILL_LOOP for (int i = lane; i < w.far_n; i += PF_WARP) { uint64_t k = w.far[i]; if (k < mk) mk = k; }
-	mk = pf_warp_min_u64(mk);
-	float m = pf_key_tot(mk);
-	/* 3. window */
-	float win = m * w.P->win_rel;
-	if (win < w.P->win_abs) win = w.P->win_abs;
-	float T = m + win;
-	for (;;) {
-		int c = 0;
-		PF_REFILL_LOOP for (int i = lane; i < w.far_n; i += PF_WARP) if (pf_key_tot(w.far[i]) <= T) c++;
-		c = pf_warp_sum_i(c);
-		if (c <= PF_SH_REFILL || T <= m) break;
-		win *= 0.25f;
-		T = m + win;
-	}
-	/* 4. move (first PF_SH_REFILL qualifying), compact the far list, track the far minimum */
-	int kept = 0, taken = 0;
-	float fmin = PF_INF_F;
-	PF_REFILL_LOOP for (int base = 0; base < w.far_n; base += PF_WARP) {
-		int i = base + lane;
-		uint64_t k = (i < w.far_n) ? w.far[i] : PF_KEY_MAX;
-		int q = (i < w.far_n) && pf_key_tot(k) <= T;
-		unsigned mq = pf_ballot(q);
-		int rank = taken + pf_popc(mq & pf_lanemask_lt());
-		int take = q && rank < PF_SH_REFILL;
-		unsigned mt = pf_ballot(take);
-		int keep = (i < w.far_n) && !take;
-		unsigned mkp = pf_ballot(keep);
-		pf_syncwarp();                                      /* reads of this chunk are complete before the in-place writes */
-		if (take) w.fr[taken + pf_popc(mt & pf_lanemask_lt())] = k;
-		if (keep) {
-			w.far[kept + pf_popc(mkp & pf_lanemask_lt())] = k;   /* kept + rank <= i: in-place is safe after the ballots */
-			float t = pf_key_tot(k);
-			if (t < fmin) fmin = t;
-		}
-		taken += pf_popc(mt);
-		kept += pf_popc(mkp);
-	}
-	w.sh_n = taken;
-	w.far_n = kept;
-	w.far_min = pf_warp_min_f(fmin);
-	w.T_hi = T;
 	pf_syncwarp();
 }
 
@@ -430,7 +740,7 @@ PF_DEV void pf_heapsort_lane(int *heap /*[1..n]*/, const float *v /*[1..n]*/, in
 /* ------------------------------------------------------------------ one sink search */
 /* Returns 1 when the target was reached (label present), 0 if the frontier was exhausted, -1 on
  * scratch overflow.  tree_n = current number of tree entries. */
-template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, int rlim) {
+template <int STRICT, int BK> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int target_node, float crit, int rlim) {
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	const float astar = P->astar_fac;
@@ -445,7 +755,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 		w.epoch++;
 		pf_syncwarp();
 	}
-	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.far_min = PF_INF_F; w.best = PF_INF_F;
+	w.n_labels = 0; w.sh_n = 0; w.far_min = PF_INF_F; w.best = PF_INF_F;
 	/* delta-stepping bucket width: a multiple of the cheapest possible edge for this criticality
 	 * (an uncongested wire: (1-crit)*base_cost + crit*T_linear) */
 	float slack;
@@ -478,7 +788,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 				if (valid && tot < smin) smin = tot;
 			} else {
 				int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
-				pf_push(w, wr, tot, node, -1);
+				pf_push<BK>(w, wr, tot, node, -1);
 				if (w.overflow) return -1;
 			}
 		}
@@ -488,6 +798,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 			float win = smin * P->win_rel;
 			if (win < P->win_abs) win = P->win_abs;
 			w.T_hi = smin + win;
+			pf_far_reset(w);
 		}
 	}
 
@@ -528,7 +839,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 #endif
 		if (w.far_min < mtot) {                 /* a cheaper label sits in the far list (or near set empty) */
 			if (w.far_min >= w.best) break;
-			pf_refill(w);
+			pf_refill<BK>(w);
 			continue;
 		}
 		if (w.sh_n == 0) break;                 /* both exhausted */
@@ -702,7 +1013,7 @@ template <int STRICT> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, int targe
 			/* the target SINK is never expanded; only its best total matters */
 			float tb = pf_warp_min_f((wr && to == target_node) ? tot : PF_INF_F);
 			if (tb < w.best) w.best = tb;
-			pf_push(w, wr && to != target_node, tot, to, es);
+			pf_push<BK>(w, wr && to != target_node, tot, to, es);
 			if (w.overflow) return -1;
 		}
 	}
@@ -968,7 +1279,7 @@ template <int RIP> PF_DEV int pf_add_path(PfWarp &w, int *tree_n_io, int target_
  * rr nodes re-enter the frontier at cost 0 (breadth_first_expand_trace_segment :173-257), and the same wave carries
  * on.  Labels persist for the whole net.  Returns 1 (all sinks connected), 0 (frontier exhausted: no path),
  * -1 (scratch overflow: retry in a bigger slot), -2 (two pins of the net on one SINK: not supported). */
-template <int RIP> PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0, int ns, int *sink_done, int *rt_of_sink) {
+template <int RIP, int BK> PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0, int ns, int *sink_done, int *rt_of_sink) {
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	w.epoch++;
@@ -977,7 +1288,7 @@ template <int RIP> PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0
 		w.epoch++;
 		pf_syncwarp();
 	}
-	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.far_min = PF_INF_F; w.best = PF_INF_F;
+	w.n_labels = 0; w.sh_n = 0; w.far_min = PF_INF_F; w.best = PF_INF_F;
 	for (int k = 1 + lane; k <= ns; k += PF_WARP) sink_done[k] = 0;
 	{	/* breadth_first_add_source_to_heap :294-305 */
 		const int src = w.tree[0].node;
@@ -988,8 +1299,9 @@ template <int RIP> PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0
 		float win = c * P->win_rel;
 		if (win < P->win_abs) win = P->win_abs;
 		w.T_hi = c + win;
+		pf_far_reset(w);
 		int wr = pf_label_relax(w, lane == 0, src, c, c, 0.f, ~0, 0, -1);
-		pf_push(w, wr, c, src, -1);
+		pf_push<BK>(w, wr, c, src, -1);
 	}
 	int remaining = ns;
 	while (remaining > 0) {
@@ -999,7 +1311,7 @@ template <int RIP> PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0
 		for (int i = lane; i < w.sh_n; i += PF_WARP) { float t = pf_key_tot(w.fr[i]); if (t < mtot) { mtot = t; first = i; } }
 		const float my_min = mtot;
 		mtot = pf_warp_min_f(mtot);
-		if (w.far_min < mtot) { pf_refill(w); continue; }
+		if (w.far_min < mtot) { pf_refill<BK>(w); continue; }
 		if (w.sh_n == 0) return 0;                          /* heap empty: "no possible path" :124 */
 		const int idx = -pf_warp_max_i(my_min == mtot ? -first : -0x7fffffff);
 		const uint64_t mk = w.fr[idx];
@@ -1039,7 +1351,7 @@ template <int RIP> PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0
 					const int valid = i <= si;
 					const int node = valid ? w.tree[i].node : 0;
 					int wr = pf_label_relax(w, valid, node, 0.f, 0.f, 0.f, ~i, 0, -1);
-					pf_push(w, wr, 0.f, node, -1);
+					pf_push<BK>(w, wr, 0.f, node, -1);
 					if (w.overflow) return -1;
 				}
 				continue;
@@ -1066,7 +1378,7 @@ template <int RIP> PF_DEV int pf_route_wave_bf(PfWarp &w, int *tree_n_io, int t0
 				}
 			}
 			int wr = pf_label_relax(w, valid, to, tot, tot, 0.f, u, info, es);
-			pf_push(w, wr, tot, to, es);
+			pf_push<BK>(w, wr, tot, to, es);
 			if (w.overflow) return -1;
 		}
 	}
@@ -1085,7 +1397,7 @@ PF_DEV void pf_swap_tables(PfWarp &w) {
 /* ------------------------------------------------------------------ one net
  * timing_driven_route_net, route_timing.c:399-563 */
 /* STRICT: 0 = delta buckets, 1 = strict best-first, 2 = breadth-first router (always strict order) */
-template <int STRICT, int RIP> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) {   /* 1: routed, 0: handed to a bigger slot / failed */
+template <int STRICT, int RIP, int BK> PF_DEV int pf_route_net(PfWarp &w, int inet, int ripup) {   /* 1: routed, 0: handed to a bigger slot / failed */
 	const PfParams *P = w.P;
 	const int lane = pf_lane();
 	const int t0 = P->net_ptr[inet];
@@ -1154,7 +1466,7 @@ template <int STRICT, int RIP> PF_DEV int pf_route_net(PfWarp &w, int inet, int 
 			pf_syncwarp();
 			const int swapped = w.hot_alt != NULL;
 			if (swapped) pf_swap_tables(w);
-			const int r = pf_route_wave_bf<RIP>(w, &tree_n, t0, ns, sink_order /* reused: per-pin done flags */, rt_of_sink);
+			const int r = pf_route_wave_bf<RIP, BK>(w, &tree_n, t0, ns, sink_order /* reused: per-pin done flags */, rt_of_sink);
 			if (swapped) pf_swap_tables(w);
 			if (r == 0) fail = PF_ST_UNROUTABLE;
 			else if (r == -2) fail = PF_ST_TWICE_TO_SINK_BF;
@@ -1175,7 +1487,7 @@ template <int STRICT, int RIP> PF_DEV int pf_route_net(PfWarp &w, int inet, int 
 			int r, swapped = 0, si = 0, tries = P->validate;
 #endif
 			for (;;) {
-				r = pf_search_sink<STRICT == 2 ? 1 : STRICT>(w, tree_n, target_node, crit, rlim);
+				r = pf_search_sink<STRICT == 2 ? 1 : STRICT, BK>(w, tree_n, target_node, crit, rlim);
 				if (r < 0 && !swapped && w.overflow == PF_OVF_LABELS && w.hot_alt) {
 					pf_swap_tables(w);
 					w.overflow = 0;
@@ -1233,7 +1545,7 @@ template <int STRICT, int RIP> PF_DEV int pf_route_net(PfWarp &w, int inet, int 
 }
 
 /* ------------------------------------------------------------------ warp main: persistent work loop */
-template <int STRICT, int RIP> PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIndexedDev *idx_tab, PfSwitchDev *sw_tab, unsigned char *smem_warp) {
+template <int STRICT, int RIP, int BK> PF_DEV void pf_warp_main(const PfParams *P, int slot, PfIndexedDev *idx_tab, PfSwitchDev *sw_tab, unsigned char *smem_warp) {
 	const int lane = pf_lane();
 	PfWarp w;
 	w.P = P;
@@ -1276,8 +1588,9 @@ template <int STRICT, int RIP> PF_DEV void pf_warp_main(const PfParams *P, int s
 	w.round = 0;
 	w.nb = PF_NB(P); w.tag_mask = pf_tag_mask(P);
 	for (int i = lane; i < PF_TICKETS; i += PF_WARP) w.ticket[i] = 0x7fffffff;
-	w.pops = w.pushes = w.visits = w.refills = w.stale = w.races = 0;
-	w.n_labels = 0; w.sh_n = 0; w.far_n = 0; w.T_hi = 0.f; w.far_min = PF_INF_F; w.best = PF_INF_F; w.overflow = 0;
+	w.pops = w.pushes = w.visits = w.refills = w.stale = w.races = 0; w.max_net_pops = 0;
+	w.n_labels = 0; w.sh_n = 0; w.T_hi = 0.f; w.far_min = PF_INF_F; w.best = PF_INF_F; w.overflow = 0;
+	w.st_n = 0;
 	w.bb_xmin = w.bb_xmax = w.bb_ymin = w.bb_ymax = 0; w.num_sinks = 0;
 	pf_syncwarp();
 	unsigned long long nets = 0;
@@ -1318,7 +1631,9 @@ template <int STRICT, int RIP> PF_DEV void pf_warp_main(const PfParams *P, int s
 			else if (net >= 0) ripup = 1;                       /* a victim still owns its old route */
 		}
 		if (net < 0) break;
-		nets += (unsigned long long)pf_route_net<STRICT, RIP>(w, net, ripup);
+		const unsigned pops0 = BK ? w.pops : 0u;           /* (the largest search of the launch: a diagnostic of the big slots only) */
+		nets += (unsigned long long)pf_route_net<STRICT, RIP, BK>(w, net, ripup);
+		if (BK && w.pops - pops0 > w.max_net_pops) w.max_net_pops = w.pops - pops0;
 		if (vctl && lane == 0) { pf_threadfence(); pf_atomic_add_i(&vctl[4], -1); }
 	}
 	if (lane == 0) {
@@ -1330,6 +1645,7 @@ template <int STRICT, int RIP> PF_DEV void pf_warp_main(const PfParams *P, int s
 		pf_atomic_add_ull(&P->stats->refills, (unsigned long long)w.refills);
 		pf_atomic_add_ull(&P->stats->stale, (unsigned long long)w.stale);
 		if (w.races) pf_atomic_add_ull(&P->stats->races, (unsigned long long)w.races);
+		if (BK) pf_atomic_max_ull(&P->stats->max_net_pops, (unsigned long long)w.max_net_pops);
 		pf_atomic_add_ull(&P->stats->nets, nets);
 	}
 }

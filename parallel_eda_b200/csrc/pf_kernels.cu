@@ -197,7 +197,7 @@ extern __shared__ __align__(16) unsigned char pf_smem[];
 /* STRICT = 1: strict best-first search (one label settled per step; P.max_batch == 1), the throughput mode;
  * STRICT = 0: a delta bucket of up to P.max_batch labels per step, the latency mode for few nets per warp;
  * STRICT = 2: the breadth-first router (one persistent wavefront per net, route_breadth_first.c) */
-template <int STRICT, int RIP> __global__ void __launch_bounds__(128, 5) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
+template <int STRICT, int RIP, int BK> __global__ void __launch_bounds__(128, 5) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
 	/* 96 registers and 43.3 KB of shared memory per 4-warp CTA: 5 CTAs = 20 warps per SM.
 	 * shared memory: [switch + cost-index tables, one copy per CTA][per-warp regions] */
 	const int warp_in_block = (int)(threadIdx.x >> 5);
@@ -209,7 +209,7 @@ template <int STRICT, int RIP> __global__ void __launch_bounds__(128, 5) pf_rout
 	__syncthreads();
 	if (slot >= num_slots) return;
 	const size_t per_warp = PF_SMEM_PER_WARP + (P.hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8);
-	pf_warp_main<STRICT, RIP>(&P, slot, idx, sw, pf_smem + PF_SMEM_BLOCK_TABLES + (size_t)warp_in_block * per_warp);
+	pf_warp_main<STRICT, RIP, BK>(&P, slot, idx, sw, pf_smem + PF_SMEM_BLOCK_TABLES + (size_t)warp_in_block * per_warp);
 }
 
 __global__ void pf_update_cost_kernel(PfNode *nodes, int num_nodes, float acc_fac, int *d_overused,
@@ -686,24 +686,24 @@ int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	if (warps_per_block > 4) warps_per_block = 4;   /* __launch_bounds__(128, 5) */
 	int blocks = (num_slots + warps_per_block - 1) / warps_per_block;
 	size_t smem = PF_SMEM_BLOCK_TABLES + (size_t)warps_per_block * (PF_SMEM_PER_WARP + (P->hot ? 0 : (size_t)PF_SMEM_HOT_ENTRIES * 8));
+	typedef void (*RouteKernel)(const PfParams, int);
+	/* [algorithm / search mode][ripple][bucketed far list] */
+	static const RouteKernel variants[3][2][2] = {
+		{ { pf_route_kernel<0, 0, 0>, pf_route_kernel<0, 0, 1> }, { pf_route_kernel<0, 1, 0>, pf_route_kernel<0, 1, 1> } },
+		{ { pf_route_kernel<1, 0, 0>, pf_route_kernel<1, 0, 1> }, { pf_route_kernel<1, 1, 0>, pf_route_kernel<1, 1, 1> } },
+		{ { pf_route_kernel<2, 0, 0>, pf_route_kernel<2, 0, 1> }, { pf_route_kernel<2, 1, 0>, pf_route_kernel<2, 1, 1> } } };
 	static size_t smem_set = 0;
 	if (smem > smem_set) {
-		CK(cudaFuncSetAttribute(pf_route_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(pf_route_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(pf_route_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(pf_route_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(pf_route_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaFuncSetAttribute(pf_route_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		for (int a = 0; a < 3; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < 2; c++)
+			CK(cudaFuncSetAttribute((const void *)variants[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		smem_set = smem;
 	}
 	if (ev_begin(0) != 0) return -1;
-	/* the ripple variant (victim queues, node ownership) only where the launch uses them: the throughput-bound launches of
-	 * the first iterations run the variant that does not carry that code at all */
-	const bool rip = P->vq_ctl != NULL || P->committer != NULL;
-	const int th = warps_per_block * 32;
-	if (P->algorithm == 1) { if (rip) pf_route_kernel<2, 1><<<blocks, th, smem, g_stream>>>(*P, num_slots); else pf_route_kernel<2, 0><<<blocks, th, smem, g_stream>>>(*P, num_slots); }
-	else if (P->max_batch == 1) { if (rip) pf_route_kernel<1, 1><<<blocks, th, smem, g_stream>>>(*P, num_slots); else pf_route_kernel<1, 0><<<blocks, th, smem, g_stream>>>(*P, num_slots); }
-	else { if (rip) pf_route_kernel<0, 1><<<blocks, th, smem, g_stream>>>(*P, num_slots); else pf_route_kernel<0, 0><<<blocks, th, smem, g_stream>>>(*P, num_slots); }
+	/* the ripple variant (victim queues, node ownership) only where the launch uses them, the bucketed far list only in the big
+	 * slots: the throughput-bound launches of the first iterations run the variant that does not carry that code at all */
+	const int rip = (P->vq_ctl != NULL || P->committer != NULL) ? 1 : 0;
+	const int mode = P->algorithm == 1 ? 2 : (P->max_batch == 1 ? 1 : 0);
+	variants[mode][rip][P->far_buckets ? 1 : 0]<<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
 	return ev_end();
 }
 

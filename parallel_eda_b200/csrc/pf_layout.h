@@ -85,7 +85,7 @@ struct PfNetLoc { int off, count; };   /* a net's tree in the route store */
 #define PF_ST_COMM_TIMEOUT 32      /* multi-GPU exchange: a peer never published its event log */
 #define PF_ST_COMM_ABORT 64        /* multi-GPU exchange: a peer reported a failure */
 
-struct PfStats { unsigned long long pops, pushes, visits, refills, nets, label_probes, stale; unsigned long long races; };
+struct PfStats { unsigned long long pops, pushes, visits, refills, nets, max_net_pops /* largest single net of the iteration */, stale; unsigned long long races; };
 
 struct PfParams {
 	PfNode *nodes;
@@ -119,6 +119,7 @@ struct PfParams {
 	unsigned *epochs;      /* [2 * slots]: search tags of the primary / fallback table */
 	PfTreeNode *tree; int tree_cap;
 	uint64_t *far; int far_cap;
+	int far_buckets;           /* 1: these slots keep the hybrid flat / bucketed far list (pf_device.cuh, frontier) */
 	int *iscratch; int sink_cap;   /* per slot: 3 * (sink_cap+2) ints */
 	/* route store: append-only log of route trees; loc[net] points at the net's current tree.
 	 * A re-routed net appends its new tree and repoints loc; the log is compacted between

@@ -310,7 +310,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.label2_log2 == 0) c.label2_log2 = bf ? 15 : 13;   /* per-slot fallback table in global memory; < 0: none */
 	if (c.label2_log2 < 0) c.label2_log2 = 0;
 	if (c.tree_cap <= 0) c.tree_cap = 2048;
-	if (c.far_cap <= 0) c.far_cap = bf ? 32768 : 8192;
+	if (c.far_cap <= 0) c.far_cap = bf ? 32768 : 8192;      /* regular slots: one flat far list (pf_device.cuh, frontier) */
 	if (c.sink_cap <= 0) c.sink_cap = 64;
 	if (c.big_slots <= 0) c.big_slots = 64;
 	if (c.reroute_all_iters == 0) c.reroute_all_iters = 1;
@@ -417,7 +417,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		c.big_label_log2 = std::min(22, std::max(c.label2_log2 + 1, ceil_log2(2 * std::min<long long>(est, r->N))));
 	}
 	if (c.big_tree_cap <= 0) c.big_tree_cap = std::max(1 << 16, 64 * max_sinks);
-	if (c.big_far_cap <= 0) c.big_far_cap = std::min(1 << 19, 1 << c.big_label_log2);
+	if (c.big_far_cap <= 0) c.big_far_cap = std::min(1 << 21, 2 << c.big_label_log2);
 	if (c.num_slots > (int)r->work_small.size() + 32) c.num_slots = std::max(32, (int)((r->work_small.size() + 31) / 32 * 32));
 
 	/* device graph */
@@ -707,7 +707,7 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.validate = (c.num_slots > 1 || c.big_slots > 1) ? c.validate_commits : 0;   /* one warp cannot race */
 	P.hot = s.hot; P.cold = s.cold; P.label_log2 = s.label_log2; P.epochs = s.epochs;
 	P.hot2 = s.hot2; P.cold2 = s.cold2; P.label2_log2 = s.label2_log2;
-	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap;
+	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap; P.far_buckets = (&s == &r->big) ? 1 : 0;
 	P.iscratch = s.iscratch; P.sink_cap = s.sink_cap;
 	P.pool = r->pool[r->cur]; P.pool_node = r->pool_node[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;
 	P.net_big = r->net_big;
@@ -1273,8 +1273,8 @@ extern "C" int pf_route_run(pf_router *r, pf_sta *dsta, pf_sta_fn sta, void *use
 		st.nets_routed = (int)r->h_stats.nets; st.heap_pushes = (int64_t)r->h_stats.pushes; st.heap_pops = (int64_t)r->h_stats.pops;
 		st.edge_visits = (int64_t)r->h_stats.visits;
 		if (analyse) { float cpd = 0.f; if ((rc = pf_sta_read_cpd(dsta, &cpd)) != PF_OK) break; st.crit_path_delay = cpd; }
-		if (cfg->verbose) fprintf(stderr, "pf_router: iteration %d: %d nets routed (%llu lost races), %d rr nodes overused, pres_fac %g\n", itry, st.nets_routed,
-				(unsigned long long)r->h_stats.races, overused, (double)st.pres_fac);
+		if (cfg->verbose) fprintf(stderr, "pf_router: iteration %d: %d nets routed (%llu lost races), %d rr nodes overused, pres_fac %g; %llu labels settled, largest net %llu, %llu edge visits\n", itry, st.nets_routed,
+				(unsigned long long)r->h_stats.races, overused, (double)st.pres_fac, (unsigned long long)r->h_stats.pops, (unsigned long long)r->h_stats.max_net_pops, (unsigned long long)r->h_stats.visits);
 		if (itry == 1 && !breadth_first && r->avail_wl > 0
 				&& (float)r->h_wl_used / (float)r->avail_wl > PF_FIRST_ITER_WIRELENGTH_LIMIT) {   /* route_timing.c:189-225 */
 			if (stats_out && nstats < stats_cap) stats_out[nstats] = st;

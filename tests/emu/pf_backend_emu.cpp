@@ -16,6 +16,8 @@
 static char g_err[256] = "";
 static PfLaunchTimes g_times;
 
+long long pf_emu_bucket_refills = 0;
+extern "C" long long pfb_emu_bucket_refills(void) { return pf_emu_bucket_refills; }
 int pfb_init(int) { return 0; }
 int pfb_device_count(void) { return 1; }
 const char *pfb_name(void) { return "emu"; }
@@ -61,9 +63,12 @@ static void route_warp(void *arg, int warp_id) {
 	pf_syncwarp();
 	const bool rip = a->P->vq_ctl != NULL || a->P->committer != NULL;   /* the same choice of variant as the CUDA launcher */
 	unsigned char *sm = base + PF_SMEM_BLOCK_TABLES;
-	if (a->P->algorithm == 1) { if (rip) pf_warp_main<2, 1>(a->P, warp_id, idx, sw, sm); else pf_warp_main<2, 0>(a->P, warp_id, idx, sw, sm); }
-	else if (a->P->max_batch == 1) { if (rip) pf_warp_main<1, 1>(a->P, warp_id, idx, sw, sm); else pf_warp_main<1, 0>(a->P, warp_id, idx, sw, sm); }
-	else { if (rip) pf_warp_main<0, 1>(a->P, warp_id, idx, sw, sm); else pf_warp_main<0, 0>(a->P, warp_id, idx, sw, sm); }
+	const int bk = a->P->far_buckets ? 1 : 0, mode = a->P->algorithm == 1 ? 2 : (a->P->max_batch == 1 ? 1 : 0);
+#define PF_EMU_RUN(M, R, B) if (mode == M && (rip ? 1 : 0) == R && bk == B) pf_warp_main<M, R, B>(a->P, warp_id, idx, sw, sm);
+	PF_EMU_RUN(0, 0, 0) PF_EMU_RUN(0, 0, 1) PF_EMU_RUN(0, 1, 0) PF_EMU_RUN(0, 1, 1)
+	PF_EMU_RUN(1, 0, 0) PF_EMU_RUN(1, 0, 1) PF_EMU_RUN(1, 1, 0) PF_EMU_RUN(1, 1, 1)
+	PF_EMU_RUN(2, 0, 0) PF_EMU_RUN(2, 0, 1) PF_EMU_RUN(2, 1, 0) PF_EMU_RUN(2, 1, 1)
+#undef PF_EMU_RUN
 }
 
 int pfb_launch_route(const PfParams *P, int num_slots, int) {

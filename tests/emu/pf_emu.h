@@ -118,6 +118,7 @@ PF_DEV unsigned pf_lanemask_lt(void) { return (1u << pf_lane()) - 1u; }
 
 PF_DEV int pf_atomic_add_i(int *p, int v) { int o = *p; *p = o + v; return o; }
 PF_DEV unsigned long long pf_atomic_add_ull(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+PF_DEV void pf_atomic_max_ull(unsigned long long *p, unsigned long long v) { if (v > *p) *p = v; }
 PF_DEV int pf_atomic_or_i(int *p, int v) { int o = *p; *p = o | v; return o; }
 PF_DEV int pf_atomic_min_i(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
 PF_DEV int pf_atomic_exch_i(int *p, int v) { int o = *p; *p = v; return o; }

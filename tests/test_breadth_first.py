@@ -3,6 +3,7 @@ the device code on the CPU emulator against the goldens of the unmodified refere
 trees depend on the order equal-cost labels are settled in, so — as for the timing-driven router — parity is a legal
 routing (independent check_route), occupancy recomputed from the traces equal to the reported one, and total
 wirelength / iteration count close to the reference's."""
+import ctypes
 import os
 
 import pytest
@@ -33,8 +34,14 @@ def test_breadth_first_on_the_heterogeneous_fabric(emu_lib):
     congestion-free result."""
     p = pfio.read_problem(os.path.join(G, "het_w70_bf.pfp.xz"))
     p.opts["max_router_iterations"] = 1
-    r = router.try_timing_driven_route(p, router.default_config(router.load_library(emu_lib), num_slots=8, big_slots=2), lib_path=emu_lib)
+    lib = router.load_library(emu_lib)
+    lib.pfb_emu_bucket_refills.restype = ctypes.c_longlong
+    before = lib.pfb_emu_bucket_refills()
+    r = router.try_timing_driven_route(p, router.default_config(lib, num_slots=8, big_slots=2, far_cap=512), lib_path=emu_lib)
     assert r.iterations == 1
+    # the flooding waves outgrow a 512-entry far list, are retried in the big slots and run on the cost buckets there
+    # (pf_device.cuh, frontier; BK = 1)
+    assert lib.pfb_emu_bucket_refills() > before
     m = check_route.check_route(p, r, check_delays=False, require_legal=False)
     assert m["wirelength"] == r.total_wirelength and m["overused"] == int(r.iter_stats["overused_nodes"][-1])
 
