@@ -97,6 +97,10 @@ typedef struct pf_config {
 	                             iteration with tens of thousands of nets; 0 = auto: max(64, min(nets / 16, 4 * min_slots)) */
 	int32_t polish;           /* > 0: when the routing first becomes legal, one more iteration re-routes EVERY net against the
 	                             final congestion picture and the loop continues until legal again (pf_try_* loops only) */
+	int32_t lazy_seed_min;    /* big slots: a search whose route tree holds at least this many entries labels only the seeds it can
+	                             need and comes back for more (reference: add_route_tree_to_heap pushes the whole tree for every
+	                             sink, route_timing.c:590-646 — a 1760-sink net then spends its time on seeds that are never
+	                             popped); 0 = auto (256), < 0 = off */
 } pf_config;
 
 typedef struct pf_timing {    /* accumulated since create / last reset */

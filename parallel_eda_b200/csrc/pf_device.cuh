@@ -304,26 +304,33 @@ PF_DEV int pf_label_relax(PfWarp &w, int valid, int node, float tot, float back,
  * labels — the flat list made a refill O(labels in flight) and the search quadratic (37 s of the 38 s of the 32 k-LUT
  * circuit were spent in 64 big slots doing that). */
 #define PF_BUCKETS 32
+#define PF_NREG 30                     /* regular buckets 0 .. 29 */
+#define PF_SPILL 30                    /* labels whose own regular bucket was full */
+#define PF_BEYOND 31                   /* labels beyond the range of the regular buckets (and what the spill bucket could not take) */
 /* the frontier state the refill works on, handed to the out-of-line refill BY VALUE and returned (the warp context itself must
  * never have its address taken: it would move from registers to local memory for the whole kernel) */
-struct PfFront { uint64_t *fr; uint64_t *far; int far_cap; float win_rel, win_abs; int sh_n, bk_n, st_n; float bk_base, bk_inv, ovf_min, far_min, T_hi; int overflow; unsigned refills; };
-/* the slot's far array: lower half = 31 regular buckets of far_cap/256 entries + the catch-all bucket; upper half = the staging
- * list, which IS the far list of a search that never needed buckets (PF_FLAT_MAX).
+struct PfFront { uint64_t *fr; uint64_t *far; int far_cap; float win_rel, win_abs; int sh_n, bk_n, st_n; float bk_base, bk_inv, spill_min, ovf_min, far_min, T_hi; int overflow; unsigned refills;
+#ifdef PF_DIAG
+	unsigned scanned, scanned_ovf;
+#endif
+};
+/* the slot's far array, in units of cr = far_cap / 256 entries: [0, 30 cr) the regular buckets, [30 cr, 32 cr) the spill bucket,
+ * [32 cr, 128 cr) the bucket of everything beyond the range; upper half = the staging list, which IS the far list of a search
+ * that never needed buckets (PF_FLAT_MAX).
  * Pushes only APPEND to the staging list (one ballot, one store — most far labels of an A* search are never needed: cfg 4
- * pushes 40 M labels and settles 5 M); a refill deals the staged labels out to the buckets first. */
-PF_DEV int pf_bucket_cap(const PfFront &f, int b) { return b < PF_BUCKETS - 1 ? (f.far_cap >> 8) : (f.far_cap >> 1) - (PF_BUCKETS - 1) * (f.far_cap >> 8); }
-PF_DEV uint64_t *pf_bucket_ptr(const PfFront &f, int b) { return f.far + (size_t)b * (size_t)(f.far_cap >> 8); }
+ * pushes 40 M labels and settles 5 M); a refill deals the staged labels out to the buckets first.
+ * The spill bucket is separate from the bucket of the beyond because a spilled label belongs to the band being drawn from: it
+ * makes every refill of that band consult the list it sits in — measured with ONE catch-all for both, a flooding search
+ * re-scanned 640 k far-future labels at each of its 2 k refills (1.4 G entries per iteration, 4.5 s for one net). */
+PF_DEV int pf_bucket_cap(const PfFront &f, int b) { const int cr = f.far_cap >> 8; return b < PF_SPILL ? cr : (b == PF_SPILL ? 2 * cr : (f.far_cap >> 1) - 32 * cr); }
+PF_DEV uint64_t *pf_bucket_ptr(const PfFront &f, int b) { return f.far + (size_t)(b < PF_BEYOND ? b : 32) * (size_t)(f.far_cap >> 8); }
 PF_DEV int pf_stage_off(int far_cap) { return far_cap >> 1; }
 PF_DEV int pf_stage_cap(int far_cap) { return far_cap - (far_cap >> 1) - 32; }      /* the last 32 words hold the bucket state */
 PF_DEV int pf_bucket_of(const PfFront &f, float tot) {
 	const float x = (tot - f.bk_base) * f.bk_inv;
-	return x < 0.f ? 0 : (x >= (float)(PF_BUCKETS - 1) ? PF_BUCKETS - 1 : (int)x);
+	return x < 0.f ? 0 : (x >= (float)PF_NREG ? PF_BEYOND : (int)x);
 }
 
-/* Warp-collective insertion into the far list: every active lane files one key.  Out of line on the GPU — it is called from
- * the push of every relax pass but runs rarely, and inlined at each site it doubles the size of the search loop, which is bound
- * by instruction fetch; it takes and returns its state BY VALUE so that the warp context stays in registers. */
-struct PfFarState { int bk_n; float far_min, ovf_min; int overflow; };
 #if defined(__CUDACC__) && !defined(PF_EMU) && !defined(PF_FAR_INLINE)
 #define PF_NOINLINE static __device__ __noinline__
 #elif defined(__CUDACC__) && !defined(PF_EMU)
@@ -331,85 +338,161 @@ struct PfFarState { int bk_n; float far_min, ovf_min; int overflow; };
 #else
 #define PF_NOINLINE static inline
 #endif
-PF_DEV PfFarState pf_far_put_inl(uint64_t *far, int far_cap, float bk_base, float bk_inv, PfFarState st, int active, uint64_t key, float tot) {
+/* the scans of the out-of-line bucket code: four independent loads in flight per lane (a rolled loop waits a full L2 / HBM
+ * round trip per 32 entries; code size is no concern outside the search loop) */
+#if defined(__CUDACC__)
+#define PF_BUCKET_LOOP _Pragma("unroll 4")
+#else
+#define PF_BUCKET_LOOP
+#endif
+
+/* Warp-collective insertion into the buckets: every active lane files one key. */
+PF_DEV void pf_far_put(PfFront &f, int active, uint64_t key, float tot) {
 	const int lane = pf_lane();
-	const int cr = far_cap >> 8;
-	int b = -1;
-	if (active) { const float x = (tot - bk_base) * bk_inv; b = x < 0.f ? 0 : (x >= (float)(PF_BUCKETS - 1) ? PF_BUCKETS - 1 : (int)x); }
+	int b = active ? pf_bucket_of(f, tot) : -1;
 	unsigned rem = pf_ballot(active);
+	int ovf = 0;
 	while (rem) {
 		const int bk = pf_shfl_i(b, pf_ffs(rem) - 1);
 		const unsigned m = pf_ballot(b == bk);
-		const int n0 = pf_shfl_i(st.bk_n, bk), cap = bk < PF_BUCKETS - 1 ? cr : (far_cap >> 1) - (PF_BUCKETS - 1) * cr;
+		const int n0 = pf_shfl_i(f.bk_n, bk), cap = pf_bucket_cap(f, bk);
 		const int pos = n0 + pf_popc(m & pf_lanemask_lt());
-		int spill = 0;
+		int moved = 0;
 		if (b == bk) {
-			if (pos < cap) far[(size_t)bk * (size_t)cr + pos] = key;
-			else if (bk < PF_BUCKETS - 1) { spill = 1; b = PF_BUCKETS - 1; }      /* its own bucket is full: the catch-all takes it */
-			else st.overflow = 1;
+			if (pos < cap) pf_bucket_ptr(f, bk)[pos] = key;
+			else if (bk < PF_SPILL) { b = PF_SPILL; moved = 1; }        /* its own bucket is full */
+			else if (bk == PF_SPILL) { b = PF_BEYOND; moved = 1; }
+			else ovf = 1;                                               /* every list it could go to is full: the net is retried in a bigger slot */
 		}
-		if (lane == bk) st.bk_n = (n0 + pf_popc(m) < cap) ? n0 + pf_popc(m) : cap;
-		rem = (rem & ~m) | pf_ballot(spill);
+		if (lane == bk) f.bk_n = (n0 + pf_popc(m) < cap) ? n0 + pf_popc(m) : cap;
+		rem = (rem & ~m) | pf_ballot(moved);
 	}
-	st.overflow = pf_any(st.overflow);                          /* the catch-all is full: the net is retried in a bigger slot */
+	if (pf_any(ovf)) f.overflow = 1;
 	const float fm = pf_warp_min_f(active ? tot : PF_INF_F);
-	if (fm < st.far_min) st.far_min = fm;
-	const float om = pf_warp_min_f((active && b == PF_BUCKETS - 1) ? tot : PF_INF_F);
-	if (om < st.ovf_min) st.ovf_min = om;
-	return st;
+	if (fm < f.far_min) f.far_min = fm;
+	const float sm = pf_warp_min_f((active && b == PF_SPILL) ? tot : PF_INF_F);
+	if (sm < f.spill_min) f.spill_min = sm;
+	const float om = pf_warp_min_f((active && b == PF_BEYOND) ? tot : PF_INF_F);
+	if (om < f.ovf_min) f.ovf_min = om;
 }
-PF_DEV void pf_far_put(PfFront &f, int active, uint64_t key, float tot) {
-	PfFarState st; st.bk_n = f.bk_n; st.far_min = f.far_min; st.ovf_min = f.ovf_min; st.overflow = 0;
-	st = pf_far_put_inl(f.far, f.far_cap, f.bk_base, f.bk_inv, st, active, key, tot);
-	f.bk_n = st.bk_n; f.far_min = st.far_min; f.ovf_min = st.ovf_min;
-	if (st.overflow) f.overflow = 1;
+/* a list of n keys dealt out to the buckets, four loads ahead of the filing */
+PF_DEV void pf_far_deal(PfFront &f, const uint64_t *a, int n) {
+	const int lane = pf_lane();
+	for (int base = 0; base < n; base += 4 * PF_WARP) {
+		uint64_t k[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) { const int i = base + j * PF_WARP + lane; k[j] = i < n ? a[i] : 0; }
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int i = base + j * PF_WARP + lane;
+			if (base + j * PF_WARP < n) pf_far_put(f, i < n, k[j], pf_key_tot(k[j]));
+		}
+	}
 }
 
-/* All regular buckets are empty: open a new range of buckets at the catch-all's minimum and deal its entries out. */
+/* One list of the refill: minimum key / entries with total <= T / move the first (PF_SH_REFILL - taken) of those to the near
+ * set, close the gaps, return the minimum total that stays. */
+PF_DEV uint64_t pf_blist_min(const uint64_t *a, int n) {
+	uint64_t mk = PF_KEY_MAX;
+	PF_BUCKET_LOOP for (int i = pf_lane(); i < n; i += PF_WARP) { const uint64_t k = a[i]; if (k < mk) mk = k; }
+	return mk;
+}
+PF_DEV int pf_blist_count(const uint64_t *a, int n, float T) {
+	int c = 0;
+	PF_BUCKET_LOOP for (int i = pf_lane(); i < n; i += PF_WARP) if (pf_key_tot(a[i]) <= T) c++;
+	return c;
+}
+PF_DEV float pf_blist_take(PfFront &f, uint64_t *a, int n, float T, int *taken_io, int *kept_out) {
+	const int lane = pf_lane();
+	int kept = 0, taken = *taken_io;
+	float fmin = PF_INF_F;
+	for (int sbase = 0; sbase < n; sbase += 4 * PF_WARP) {
+		uint64_t kk[4];                                        /* read four chunks ahead: the in-place writes below stay behind them */
+#pragma unroll
+		for (int j = 0; j < 4; j++) { const int i = sbase + j * PF_WARP + lane; kk[j] = i < n ? a[i] : PF_KEY_MAX; }
+		pf_syncwarp();
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int i = sbase + j * PF_WARP + lane;
+			const uint64_t k = kk[j];
+			const int q = (i < n) && pf_key_tot(k) <= T;
+			const unsigned mq = pf_ballot(q);
+			const int rank = taken + pf_popc(mq & pf_lanemask_lt());
+			const int take = q && rank < PF_SH_REFILL;
+			const unsigned mt = pf_ballot(take);
+			const int keep = (i < n) && !take;
+			const unsigned mkp = pf_ballot(keep);
+			if (take) f.fr[taken + pf_popc(mt & pf_lanemask_lt())] = k;
+			if (keep) {
+				a[kept + pf_popc(mkp & pf_lanemask_lt())] = k;      /* kept <= the chunk's first index: behind everything still unread */
+				const float t = pf_key_tot(k);
+				if (t < fmin) fmin = t;
+			}
+			taken += pf_popc(mt);
+			kept += pf_popc(mkp);
+		}
+	}
+	*taken_io = taken; *kept_out = kept;
+	return fmin;
+}
+
+/* Regular and spill buckets are empty: open a new range of buckets at the minimum of the beyond and deal its entries out. */
 PF_DEV void pf_far_rebase(PfFront &f) {
 	const int lane = pf_lane();
-	const int n = pf_shfl_i(f.bk_n, PF_BUCKETS - 1);
-	uint64_t *ovf = pf_bucket_ptr(f, PF_BUCKETS - 1);
-	uint64_t mk = PF_KEY_MAX;
-	PF_REFILL_LOOP for (int i = lane; i < n; i += PF_WARP) { const uint64_t k = ovf[i]; if (k < mk) mk = k; }
-	const float m = pf_key_tot(pf_warp_min_u64(mk));
+	const int n = pf_shfl_i(f.bk_n, PF_BEYOND);
+	uint64_t *ovf = pf_bucket_ptr(f, PF_BEYOND);
+	const float m = pf_key_tot(pf_warp_min_u64(pf_blist_min(ovf, n)));
 	float win = m * f.win_rel;
 	if (win < f.win_abs) win = f.win_abs;
 	f.bk_base = m; f.bk_inv = 1.f / win;
-	if (lane == PF_BUCKETS - 1) f.bk_n = 0;
+	f.spill_min = PF_INF_F;                                /* (the spill bucket is empty: that is when a range is closed) */
+	if (lane == PF_BEYOND) f.bk_n = 0;
 	int kept = 0;
 	float omin = PF_INF_F;
-	PF_REFILL_LOOP for (int base = 0; base < n; base += PF_WARP) {
-		const int i = base + lane;
-		const uint64_t k = i < n ? ovf[i] : PF_KEY_MAX;
-		int b = i < n ? pf_bucket_of(f, pf_key_tot(k)) : -1;
-		/* regular buckets first (their regions are disjoint from the catch-all being read) */
-		unsigned rem = pf_ballot(b >= 0 && b < PF_BUCKETS - 1);
-		while (rem) {
-			const int bk = pf_shfl_i(b, pf_ffs(rem) - 1);
-			const unsigned mm = pf_ballot(b == bk);
-			const int n0 = pf_shfl_i(f.bk_n, bk), cap = pf_bucket_cap(f, bk);
-			const int pos = n0 + pf_popc(mm & pf_lanemask_lt());
-			if (b == bk) { if (pos < cap) pf_bucket_ptr(f, bk)[pos] = k; else b = PF_BUCKETS - 1; }   /* full: stays in the catch-all */
-			if (lane == bk) f.bk_n = (n0 + pf_popc(mm) < cap) ? n0 + pf_popc(mm) : cap;
-			rem &= ~mm;
+	for (int sbase = 0; sbase < n; sbase += 4 * PF_WARP) {
+		uint64_t kk[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) { const int i = sbase + j * PF_WARP + lane; kk[j] = i < n ? ovf[i] : PF_KEY_MAX; }
+		pf_syncwarp();
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int i = sbase + j * PF_WARP + lane;
+			const uint64_t k = kk[j];
+			int b = i < n ? pf_bucket_of(f, pf_key_tot(k)) : -1;
+			/* regular buckets first (their regions are disjoint from the list being read) */
+			unsigned rem = pf_ballot(b >= 0 && b < PF_NREG);
+			float smin = PF_INF_F;
+			while (rem) {
+				const int bk = pf_shfl_i(b, pf_ffs(rem) - 1);
+				const unsigned mm = pf_ballot(b == bk);
+				const int n0 = pf_shfl_i(f.bk_n, bk), cap = pf_bucket_cap(f, bk);
+				const int pos = n0 + pf_popc(mm & pf_lanemask_lt());
+				int moved = 0;
+				if (b == bk) {
+					if (pos < cap) { pf_bucket_ptr(f, bk)[pos] = k; if (bk == PF_SPILL) smin = pf_key_tot(k); }
+					else if (bk < PF_SPILL) { b = PF_SPILL; moved = 1; }       /* its bucket is full: the (empty) spill bucket takes it, */
+					else b = PF_BEYOND;                                        /* or it stays where it is */
+				}
+				if (lane == bk) f.bk_n = (n0 + pf_popc(mm) < cap) ? n0 + pf_popc(mm) : cap;
+				rem = (rem & ~mm) | pf_ballot(moved);
+			}
+			smin = pf_warp_min_f(smin);
+			if (smin < f.spill_min) f.spill_min = smin;
+			const unsigned mk2 = pf_ballot(b == PF_BEYOND);
+			if (b == PF_BEYOND) {
+				ovf[kept + pf_popc(mk2 & pf_lanemask_lt())] = k;   /* kept <= the chunk's first index: in place */
+				const float t = pf_key_tot(k);
+				if (t < omin) omin = t;
+			}
+			kept += pf_popc(mk2);
 		}
-		const unsigned mk2 = pf_ballot(b == PF_BUCKETS - 1);
-		pf_syncwarp();                                  /* this chunk has been read before slots below it are rewritten */
-		if (b == PF_BUCKETS - 1) {
-			ovf[kept + pf_popc(mk2 & pf_lanemask_lt())] = k;   /* kept <= base: in place */
-			const float t = pf_key_tot(k);
-			if (t < omin) omin = t;
-		}
-		kept += pf_popc(mk2);
 	}
-	if (lane == PF_BUCKETS - 1) f.bk_n = kept;
+	if (lane == PF_BEYOND) f.bk_n = kept;
 	f.ovf_min = pf_warp_min_f(omin);
 	pf_syncwarp();
 }
 
-/* One list of the refill: count / take / compact.  mode 0: minimum key; 1: entries with total <= T; 2: move the first
- * (PF_SH_REFILL - taken) of those to the near set, close the gaps, return the minimum total that stays. */
+/* One list of the inline flat refill (rolled: it sits in the search loop of every kernel variant) */
 PF_DEV uint64_t pf_list_min(const uint64_t *a, int n) {
 	uint64_t mk = PF_KEY_MAX;
 	PF_REFILL_LOOP for (int i = pf_lane(); i < n; i += PF_WARP) { const uint64_t k = a[i]; if (k < mk) mk = k; }
@@ -420,127 +503,69 @@ PF_DEV int pf_list_count(const uint64_t *a, int n, float T) {
 	PF_REFILL_LOOP for (int i = pf_lane(); i < n; i += PF_WARP) if (pf_key_tot(a[i]) <= T) c++;
 	return c;
 }
-PF_DEV float pf_list_take(PfFront &f, uint64_t *a, int n, float T, int *taken_io, int *kept_out) {
-	const int lane = pf_lane();
-	int kept = 0, taken = *taken_io;
-	float fmin = PF_INF_F;
-	PF_REFILL_LOOP for (int base = 0; base < n; base += PF_WARP) {
-		const int i = base + lane;
-		const uint64_t k = (i < n) ? a[i] : PF_KEY_MAX;
-		const int q = (i < n) && pf_key_tot(k) <= T;
-		const unsigned mq = pf_ballot(q);
-		const int rank = taken + pf_popc(mq & pf_lanemask_lt());
-		const int take = q && rank < PF_SH_REFILL;
-		const unsigned mt = pf_ballot(take);
-		const int keep = (i < n) && !take;
-		const unsigned mkp = pf_ballot(keep);
-		pf_syncwarp();                                      /* reads of this chunk are complete before the in-place writes */
-		if (take) f.fr[taken + pf_popc(mt & pf_lanemask_lt())] = k;
-		if (keep) {
-			a[kept + pf_popc(mkp & pf_lanemask_lt())] = k;      /* kept + rank <= i: in-place is safe after the ballots */
-			const float t = pf_key_tot(k);
-			if (t < fmin) fmin = t;
-		}
-		taken += pf_popc(mt);
-		kept += pf_popc(mkp);
-	}
-	*taken_io = taken; *kept_out = kept;
-	return fmin;
-}
 
-/* Re-bucket: file the near set's leftovers, find the lowest non-empty bucket, open a window above its minimum and pull
- * every label inside the window into shared memory (at most PF_SH_REFILL; the window is narrowed until they fit, down to
- * exact ties of the minimum).  The catch-all is consulted too whenever it holds a total below the bucket's upper bound. */
+/* Re-bucket: file the near set's leftovers and the staged labels, find the lowest non-empty bucket, open a window above its
+ * minimum and pull every label inside the window into shared memory (at most PF_SH_REFILL; the window is narrowed until they
+ * fit, down to exact ties of the minimum).  The spill bucket and the beyond are consulted only while they hold a total below
+ * the upper bound of the bucket drawn from. */
 /* A search whose far list stays short — every A* search of BASELINE configs[4]: 67 far labels per sink on average — never
  * builds buckets: its staging list is scanned directly, with the window relative to the current minimum, as in round 1. */
 #ifndef PF_FLAT_MAX
 #define PF_FLAT_MAX 768
 #endif
 #ifdef PF_EMU
-extern long long pf_emu_bucket_refills;   /* test hook of the emulator build: refills that went through the cost buckets */
+extern long long pf_emu_bucket_refills;   /* test hooks of the emulator build: refills that went through the cost buckets, */
+extern long long pf_emu_lazy_seedings;    /* searches seeded lazily (low word) and their returns for more seeds (high word) */
 #endif
+#define PF_LAZY_SEED_SPAN 4.f
 #define PF_ROUND_BUCKETS 0x40000000u   /* bit of PfWarp.round: this search has opened its cost buckets (their state lives in the
                                        * last 256 bytes of the slot's far array, not in registers: it is touched once per refill) */
-PF_DEV void pf_refill_flat(PfFront &f) {
-	const int lane = pf_lane();
-	uint64_t *lst = f.far + pf_stage_off(f.far_cap);
-	const int scap = pf_stage_cap(f.far_cap);
-	/* near → list */
-	PF_REFILL_LOOP for (int base = 0; base < f.sh_n; base += PF_WARP) {
-		const int i = base + lane;
-		if (i < f.sh_n && f.st_n + i < scap) lst[f.st_n + i] = f.fr[i];
-	}
-	f.st_n += f.sh_n;
-	f.sh_n = 0;
-	if (f.st_n > scap) { f.st_n = scap; f.overflow = 1; }
-	pf_syncwarp();
-	const float m = pf_key_tot(pf_warp_min_u64(pf_list_min(lst, f.st_n)));
-	float win = m * f.win_rel;
-	if (win < f.win_abs) win = f.win_abs;
-	float T = m + win;
-	for (;;) {
-		const int c = pf_warp_sum_i(pf_list_count(lst, f.st_n, T));
-		if (c <= PF_SH_REFILL || T <= m) break;
-		win *= 0.25f;
-		T = m + win;
-	}
-	int taken = 0, kept = 0;
-	const float fmin = pf_list_take(f, lst, f.st_n, T, &taken, &kept);
-	f.sh_n = taken;
-	f.st_n = kept;
-	f.far_min = pf_warp_min_f(fmin);
-	f.T_hi = T;
-	pf_syncwarp();
-}
-
 PF_DEV void pf_refill_body(PfFront &f) {
 	const int lane = pf_lane();
 	f.refills++;
-	if (f.bk_inv == 0.f) {                                /* no buckets yet */
-		if (f.st_n + f.sh_n <= PF_FLAT_MAX) { pf_refill_flat(f); return; }
-		/* the search has outgrown the flat list: open the buckets at the current minimum */
-		uint64_t mk = pf_list_min(f.far + pf_stage_off(f.far_cap), f.st_n);
-		{ const uint64_t mn = pf_list_min(f.fr, f.sh_n); if (mn < mk) mk = mn; }
+#ifdef PF_DIAG
+	f.scanned += (unsigned)(f.st_n + f.sh_n);
+#endif
+	if (f.bk_inv == 0.f) {                                /* the search has outgrown the flat list: open the buckets at the current minimum */
+		uint64_t mk = pf_blist_min(f.far + pf_stage_off(f.far_cap), f.st_n);
+		{ const uint64_t mn = pf_blist_min(f.fr, f.sh_n); if (mn < mk) mk = mn; }
 		const float m = pf_key_tot(pf_warp_min_u64(mk));
 		float win = m * f.win_rel;
 		if (win < f.win_abs) win = f.win_abs;
 		f.bk_base = m; f.bk_inv = 1.f / win;
 	}
 	/* 1. the near set's leftovers, then everything pushed since the last refill, into the buckets */
-	PF_REFILL_LOOP for (int base = 0; base < f.sh_n; base += PF_WARP) {
-		const int i = base + lane;
-		const uint64_t k = i < f.sh_n ? f.fr[i] : 0;
-		pf_far_put(f, i < f.sh_n, k, pf_key_tot(k));
-	}
+	pf_far_deal(f, f.fr, f.sh_n);
 	f.sh_n = 0;
-	{
-		const uint64_t *stg = f.far + pf_stage_off(f.far_cap);
-		PF_REFILL_LOOP for (int base = 0; base < f.st_n; base += PF_WARP) {
-			const int i = base + lane;
-			const uint64_t k = i < f.st_n ? stg[i] : 0;
-			pf_far_put(f, i < f.st_n, k, pf_key_tot(k));
-		}
-		f.st_n = 0;
-	}
+	pf_far_deal(f, f.far + pf_stage_off(f.far_cap), f.st_n);
+	f.st_n = 0;
 	pf_syncwarp();
 	/* 2. the bucket to draw from */
-	unsigned nonempty = pf_ballot(f.bk_n > 0 && lane < PF_BUCKETS - 1);
-	int n_ovf = pf_shfl_i(f.bk_n, PF_BUCKETS - 1);
-	if (!nonempty) {
-		if (n_ovf == 0) { f.far_min = PF_INF_F; return; }
+	unsigned reg = pf_ballot(f.bk_n > 0 && lane < PF_NREG);
+	int n_sp = pf_shfl_i(f.bk_n, PF_SPILL), n_by = pf_shfl_i(f.bk_n, PF_BEYOND);
+	if (!reg && n_sp == 0) {
+		if (n_by == 0) { f.far_min = PF_INF_F; return; }
+#ifdef PF_DIAG
+		f.scanned_ovf += (unsigned)(2 * n_by);
+#endif
 		pf_far_rebase(f);
-		nonempty = pf_ballot(f.bk_n > 0 && lane < PF_BUCKETS - 1);
-		n_ovf = pf_shfl_i(f.bk_n, PF_BUCKETS - 1);
+		reg = pf_ballot(f.bk_n > 0 && lane < PF_NREG);
+		n_by = pf_shfl_i(f.bk_n, PF_BEYOND);
 	}
-	uint64_t *ovf = pf_bucket_ptr(f, PF_BUCKETS - 1);
-	const int b = nonempty ? pf_ffs(nonempty) - 1 : PF_BUCKETS - 1;           /* (only the catch-all left: every bucket was full) */
-	uint64_t *lst = pf_bucket_ptr(f, b);
+	/* (only the spill bucket left inside the range — or, when no regular bucket could take anything, only the beyond) */
+	const int b = reg ? pf_ffs(reg) - 1 : (n_sp ? PF_SPILL : PF_BEYOND);
+	const float ub = b < PF_SPILL ? f.bk_base + (float)(b + 1) / f.bk_inv : (b == PF_SPILL ? f.bk_base + (float)PF_NREG / f.bk_inv : PF_INF_F);
+	uint64_t *lst = pf_bucket_ptr(f, b), *spl = pf_bucket_ptr(f, PF_SPILL), *byd = pf_bucket_ptr(f, PF_BEYOND);
 	const int n_b = pf_shfl_i(f.bk_n, b);
-	const float ub = (b < PF_BUCKETS - 1) ? f.bk_base + (float)(b + 1) / f.bk_inv : PF_INF_F;
-	const int with_ovf = b < PF_BUCKETS - 1 && n_ovf > 0 && f.ovf_min < ub;
+	const int use_sp = b < PF_SPILL && n_sp > 0 && f.spill_min < ub;
+	const int use_by = b != PF_BEYOND && n_by > 0 && f.ovf_min < ub;
+#ifdef PF_DIAG
+	f.scanned += (unsigned)(2 * n_b + (use_sp ? 2 * n_sp : 0)); if (use_by) f.scanned_ovf += (unsigned)(2 * n_by);
+#endif
 	/* 3. minimum and window */
-	uint64_t mk = pf_list_min(lst, n_b);
-	if (with_ovf) { const uint64_t mo = pf_list_min(ovf, n_ovf); if (mo < mk) mk = mo; }
+	uint64_t mk = pf_blist_min(lst, n_b);
+	if (use_sp) { const uint64_t mo = pf_blist_min(spl, n_sp); if (mo < mk) mk = mo; }
+	if (use_by) { const uint64_t mo = pf_blist_min(byd, n_by); if (mo < mk) mk = mo; }
 	mk = pf_warp_min_u64(mk);
 	const float m = pf_key_tot(mk);
 	float win = m * f.win_rel;
@@ -548,27 +573,36 @@ PF_DEV void pf_refill_body(PfFront &f) {
 	float T = m + win;
 	if (T > ub) T = ub;                                   /* what lies beyond belongs to later buckets */
 	for (;;) {
-		int c = pf_list_count(lst, n_b, T);
-		if (with_ovf) c += pf_list_count(ovf, n_ovf, T);
+		int c = pf_blist_count(lst, n_b, T);
+		if (use_sp) c += pf_blist_count(spl, n_sp, T);
+		if (use_by) c += pf_blist_count(byd, n_by, T);
+#ifdef PF_DIAG
+		f.scanned += (unsigned)(n_b + (use_sp ? n_sp : 0)); if (use_by) f.scanned_ovf += (unsigned)n_by;
+#endif
 		c = pf_warp_sum_i(c);
 		if (c <= PF_SH_REFILL || T <= m) break;
 		win *= 0.25f;
 		T = m + win;
 	}
-	/* 4. move, compact, track the far minimum: exact for what stays in the lists drawn from, lower bounds of the buckets above */
-	int taken = 0, kept_b = 0, kept_o = n_ovf;
-	float fmin = pf_list_take(f, lst, n_b, T, &taken, &kept_b);
-	if (lane == b) f.bk_n = kept_b;
-	if (with_ovf) {
-		const float omin = pf_list_take(f, ovf, n_ovf, T, &taken, &kept_o);
-		if (lane == PF_BUCKETS - 1) f.bk_n = kept_o;
-		f.ovf_min = pf_warp_min_f(omin);
-	} else if (b == PF_BUCKETS - 1) f.ovf_min = pf_warp_min_f(fmin);
-	fmin = pf_warp_min_f(fmin);
+	/* 4. move, compact, track the far minimum: exact for what stays in the lists drawn from, lower bounds for the rest */
+	int taken = 0, kept = 0;
+	float fmin = pf_warp_min_f(pf_blist_take(f, lst, n_b, T, &taken, &kept));
+	if (lane == b) f.bk_n = kept;
+	if (b == PF_SPILL) f.spill_min = fmin;
+	if (b == PF_BEYOND) f.ovf_min = fmin;
+	if (use_sp) {
+		f.spill_min = pf_warp_min_f(pf_blist_take(f, spl, n_sp, T, &taken, &kept));
+		if (lane == PF_SPILL) f.bk_n = kept;
+	}
+	if (use_by) {
+		f.ovf_min = pf_warp_min_f(pf_blist_take(f, byd, n_by, T, &taken, &kept));
+		if (lane == PF_BEYOND) f.bk_n = kept;
+	}
 	{
-		const unsigned above = pf_ballot(f.bk_n > 0 && lane > b && lane < PF_BUCKETS - 1);
+		const unsigned above = pf_ballot(f.bk_n > 0 && lane > b && lane < PF_NREG);
 		if (above) { const float lb = f.bk_base + (float)(pf_ffs(above) - 1) / f.bk_inv; if (lb < fmin) fmin = lb; }
-		if (f.ovf_min < fmin) fmin = f.ovf_min;
+		if (pf_shfl_i(f.bk_n, PF_SPILL) > 0 && f.spill_min < fmin) fmin = f.spill_min;
+		if (pf_shfl_i(f.bk_n, PF_BEYOND) > 0 && f.ovf_min < fmin) fmin = f.ovf_min;
 	}
 	f.sh_n = taken;
 	f.far_min = fmin;
@@ -649,13 +683,19 @@ template <int BK> PF_DEV void pf_refill(PfWarp &w) {
 		const int open = (w.round & PF_ROUND_BUCKETS) != 0;
 		f.fr = w.fr; f.far = w.far; f.far_cap = w.P->far_cap; f.win_rel = w.P->win_rel; f.win_abs = w.P->win_abs;
 		f.sh_n = w.sh_n; f.st_n = w.st_n; f.far_min = w.far_min; f.T_hi = w.T_hi; f.overflow = 0; f.refills = 0;
+#ifdef PF_DIAG
+		f.scanned = 0; f.scanned_ovf = 0;
+#endif
 		f.bk_n = open ? ((const int *)bst)[pf_lane()] : 0;
-		f.bk_base = open ? bst[32] : 0.f; f.bk_inv = open ? bst[33] : 0.f; f.ovf_min = open ? bst[34] : PF_INF_F;
+		f.bk_base = open ? bst[32] : 0.f; f.bk_inv = open ? bst[33] : 0.f; f.ovf_min = open ? bst[34] : PF_INF_F; f.spill_min = open ? bst[35] : PF_INF_F;
 		f = pf_refill_impl(f);
 		((int *)bst)[pf_lane()] = f.bk_n;
-		if (pf_lane() == 0) { bst[32] = f.bk_base; bst[33] = f.bk_inv; bst[34] = f.ovf_min; }
+		if (pf_lane() == 0) { bst[32] = f.bk_base; bst[33] = f.bk_inv; bst[34] = f.ovf_min; bst[35] = f.spill_min; }
 		w.round |= PF_ROUND_BUCKETS;
 		w.sh_n = f.sh_n; w.st_n = f.st_n; w.far_min = f.far_min; w.T_hi = f.T_hi; w.refills += f.refills;
+#ifdef PF_DIAG
+		w.stale += f.scanned; w.pushes += f.scanned_ovf;     /* diagnostic build: far-list entries touched by bucket refills: regular buckets / catch-all */
+#endif
 		if (f.overflow) w.overflow |= PF_OVF_OTHER;
 		pf_syncwarp();
 	}
@@ -692,7 +732,9 @@ template <int BK> PF_DEV void pf_push(PfWarp &w, int valid, float tot, int node,
 		const float fm = pf_warp_min_f(to_far ? tot : PF_INF_F);
 		if (fm < w.far_min) w.far_min = fm;
 	}
+#ifndef PF_DIAG
 	w.pushes += (unsigned)pf_popc(pf_ballot(valid));
+#endif
 	pf_syncwarp();
 }
 
@@ -769,10 +811,20 @@ template <int STRICT, int BK> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, i
 	}
 
 	/* ---- seed with the current route tree (add_route_tree_to_heap): pass 0 finds the cheapest seed (it sets
-	 * the near-set window), pass 1 labels and pushes.  One loop body for both keeps a single inlined copy of
-	 * the lookahead. */
-	float smin = PF_INF_F;
-	for (int pass = 0; pass < 2; pass++) {
+	 * the near-set window), pass 1 labels and pushes.  One loop body for every pass keeps a single inlined copy of
+	 * the lookahead — and makes every pass compute bit-identical totals.
+	 * Big slots (BK), trees of PfParams.lazy_seed_min entries and more: LAZY seeding.  The reference pushes the whole tree for every
+	 * sink; a seed whose total lies above the cost of the connection found is never popped, and a net of 1760 sinks whose tree
+	 * holds 20 k nodes spends 35 M label insertions per iteration on such seeds (that one net was 10 s of the 13.4 s of the
+	 * 32 k-LUT stand-in).  Only the seeds with total <= seed_hi are labelled; the cheapest seed left out stands in the far
+	 * minimum, so the settle loop comes back here — through the test it makes anyway before every pop — before it could pop
+	 * anything dearer than a seed it has not seen.  Same labels settled, same costs; only the age order of equal totals moves. */
+	const bool lazy = BK && P->lazy_seed_min > 0 && tree_n >= P->lazy_seed_min;
+	float seed_lo = -PF_INF_F, seed_hi = PF_INF_F, seed_min = PF_INF_F;
+	int pass = 0;
+	for (;;) {
+	{
+		float smin = PF_INF_F;      /* pass 0: the cheapest seed; later passes: the cheapest seed still left out */
 		for (int base = 0; base < tree_n; base += PF_WARP) {
 			int i = base + lane;
 			int valid = 0, node = 0; float tot = 0.f, back = 0.f, R_up = 0.f;
@@ -787,20 +839,32 @@ template <int STRICT, int BK> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, i
 			if (pass == 0) {
 				if (valid && tot < smin) smin = tot;
 			} else {
+				if (lazy) {
+					if (valid && tot > seed_hi && tot < smin) smin = tot;
+					valid = valid && tot > seed_lo && tot <= seed_hi;
+				}
 				int wr = pf_label_relax(w, valid, node, tot, back, R_up, ~i, 0, -1);
 				pf_push<BK>(w, wr, tot, node, -1);
 				if (w.overflow) return -1;
 			}
 		}
+		if (pass == 0 || lazy) smin = pf_warp_min_f(smin);
 		if (pass == 0) {
-			smin = pf_warp_min_f(smin);
 			if (!(smin < PF_INF_F)) return 0;
 			float win = smin * P->win_rel;
 			if (win < P->win_abs) win = P->win_abs;
 			w.T_hi = smin + win;
 			pf_far_reset(w);
+			if (lazy) seed_hi = smin + PF_LAZY_SEED_SPAN * win;
+#ifdef PF_EMU
+			if (lazy && lane == 0) pf_emu_lazy_seedings++;      /* low word: searches seeded lazily */
+#endif
+			pass = 1;
+			continue;
 		}
+		if (lazy) { seed_min = smin; if (seed_min < w.far_min) w.far_min = seed_min; }
 	}
+	int more_seeds = 0;
 
 	/* ---- settle loop */
 	for (;;) {
@@ -839,7 +903,9 @@ template <int STRICT, int BK> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, i
 #endif
 		if (w.far_min < mtot) {                 /* a cheaper label sits in the far list (or near set empty) */
 			if (w.far_min >= w.best) break;
+			if (lazy && seed_min <= w.far_min) { more_seeds = 1; break; }      /* ... or among the seeds left out */
 			pf_refill<BK>(w);
+			if (lazy && seed_min < w.far_min) w.far_min = seed_min;
 			continue;
 		}
 		if (w.sh_n == 0) break;                 /* both exhausted */
@@ -1016,6 +1082,16 @@ template <int STRICT, int BK> PF_DEV int pf_search_sink(PfWarp &w, int tree_n, i
 			pf_push<BK>(w, wr && to != target_node, tot, to, es);
 			if (w.overflow) return -1;
 		}
+	}
+	if (!more_seeds) break;
+#ifdef PF_EMU
+	if (lane == 0) pf_emu_lazy_seedings += 1ll << 32;   /* high word: searches that came back for more seeds */
+#endif
+	{	/* the next span of seeds, opened at the cheapest one left out */
+		float win = seed_min * P->win_rel;
+		if (win < P->win_abs) win = P->win_abs;
+		seed_lo = seed_hi; seed_hi = seed_min + PF_LAZY_SEED_SPAN * win;
+	}
 	}
 	return (w.best < PF_INF_F) ? 1 : 0;
 }
@@ -1632,8 +1708,20 @@ template <int STRICT, int RIP, int BK> PF_DEV void pf_warp_main(const PfParams *
 		}
 		if (net < 0) break;
 		const unsigned pops0 = BK ? w.pops : 0u;           /* (the largest search of the launch: a diagnostic of the big slots only) */
+#ifdef PF_DIAG
+		unsigned long long t0_ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0_ns));
+		const unsigned st0 = w.stale, rf0 = w.refills;
+#endif
 		nets += (unsigned long long)pf_route_net<STRICT, RIP, BK>(w, net, ripup);
 		if (BK && w.pops - pops0 > w.max_net_pops) w.max_net_pops = w.pops - pops0;
+#ifdef PF_DIAG
+		if (BK && lane == 0) {      /* diagnostic build: 'races' = the slowest net of the iteration: ms << 44 | net << 24 | refills (saturated) */
+			unsigned long long t1_ns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1_ns));
+			unsigned rf = w.refills - rf0; if (rf > 0xffffffu) rf = 0xffffffu;
+			pf_atomic_max_ull(&P->stats->races, ((t1_ns - t0_ns) / 1000000ull) << 44 | (unsigned long long)(unsigned)net << 24 | rf);
+			(void)st0;
+		}
+#endif
 		if (vctl && lane == 0) { pf_threadfence(); pf_atomic_add_i(&vctl[4], -1); }
 	}
 	if (lane == 0) {
@@ -1644,7 +1732,9 @@ template <int STRICT, int RIP, int BK> PF_DEV void pf_warp_main(const PfParams *
 		pf_atomic_add_ull(&P->stats->visits, (unsigned long long)w.visits);
 		pf_atomic_add_ull(&P->stats->refills, (unsigned long long)w.refills);
 		pf_atomic_add_ull(&P->stats->stale, (unsigned long long)w.stale);
+#ifndef PF_DIAG
 		if (w.races) pf_atomic_add_ull(&P->stats->races, (unsigned long long)w.races);
+#endif
 		if (BK) pf_atomic_max_ull(&P->stats->max_net_pops, (unsigned long long)w.max_net_pops);
 		pf_atomic_add_ull(&P->stats->nets, nets);
 	}

@@ -18,6 +18,7 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 static char g_err[512] = "";
@@ -26,7 +27,7 @@ static int g_device = -1;
 static int g_sms = 0;
 static PfLaunchTimes g_times;
 
-struct PendingEvent { cudaEvent_t a, b; int kind; };
+struct PendingEvent { cudaEvent_t a, b; int kind; int slots, variant; };   /* slots / variant: route launches, for PF_LAUNCH_LOG */
 static PendingEvent g_pending[64];
 static int g_npending = 0;
 
@@ -118,7 +119,12 @@ static int drain_events(void) {
 		float ms = 0.f;
 		CK(cudaEventSynchronize(g_pending[i].b));
 		CK(cudaEventElapsedTime(&ms, g_pending[i].a, g_pending[i].b));
-		if (g_pending[i].kind == 0) { g_times.route_ms += ms; g_times.route_launches++; }
+		if (g_pending[i].kind == 0) {
+			g_times.route_ms += ms; g_times.route_launches++;
+			static const int log_launches = getenv("PF_LAUNCH_LOG") != NULL;   /* diagnostics: one line per route launch */
+			if (log_launches) fprintf(stderr, "pf_launch: route %10.3f ms, %5d warps, mode %d ripple %d buckets %d\n", ms, g_pending[i].slots,
+					g_pending[i].variant >> 2, (g_pending[i].variant >> 1) & 1, g_pending[i].variant & 1);
+		}
 		else if (g_pending[i].kind == 1) { g_times.update_ms += ms; g_times.update_launches++; }
 		else { g_times.aux_ms += ms; g_times.aux_launches++; }
 		cudaEventDestroy(g_pending[i].a);
@@ -197,8 +203,9 @@ extern __shared__ __align__(16) unsigned char pf_smem[];
 /* STRICT = 1: strict best-first search (one label settled per step; P.max_batch == 1), the throughput mode;
  * STRICT = 0: a delta bucket of up to P.max_batch labels per step, the latency mode for few nets per warp;
  * STRICT = 2: the breadth-first router (one persistent wavefront per net, route_breadth_first.c) */
-template <int STRICT, int RIP, int BK> __global__ void __launch_bounds__(128, 5) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
-	/* 96 registers and 43.3 KB of shared memory per 4-warp CTA: 5 CTAs = 20 warps per SM.
+template <int STRICT, int RIP, int BK> __global__ void __launch_bounds__(128, BK ? 2 : 5) pf_route_kernel(const __grid_constant__ PfParams P, int num_slots) {
+	/* regular slots (BK = 0): 96 registers and 43.3 KB of shared memory per 4-warp CTA: 5 CTAs = 20 warps per SM; the big
+	 * slots run a few hundred one-warp CTAs on the whole device and take the registers they like.
 	 * shared memory: [switch + cost-index tables, one copy per CTA][per-warp regions] */
 	const int warp_in_block = (int)(threadIdx.x >> 5);
 	const int slot = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp_in_block;
@@ -704,6 +711,7 @@ int pfb_launch_route(const PfParams *P, int num_slots, int warps_per_block) {
 	const int rip = (P->vq_ctl != NULL || P->committer != NULL) ? 1 : 0;
 	const int mode = P->algorithm == 1 ? 2 : (P->max_batch == 1 ? 1 : 0);
 	variants[mode][rip][P->far_buckets ? 1 : 0]<<<blocks, warps_per_block * 32, smem, g_stream>>>(*P, num_slots);
+	g_pending[g_npending].slots = num_slots; g_pending[g_npending].variant = mode << 2 | rip << 1 | (P->far_buckets ? 1 : 0);
 	return ev_end();
 }
 

@@ -119,6 +119,7 @@ struct PfParams {
 	unsigned *epochs;      /* [2 * slots]: search tags of the primary / fallback table */
 	PfTreeNode *tree; int tree_cap;
 	uint64_t *far; int far_cap;
+	int lazy_seed_min;         /* big slots: trees of this many entries and more are seeded lazily (pf_search_sink); 0: never */
 	int far_buckets;           /* 1: these slots keep the hybrid flat / bucketed far list (pf_device.cuh, frontier) */
 	int *iscratch; int sink_cap;   /* per slot: 3 * (sink_cap+2) ints */
 	/* route store: append-only log of route trees; loc[net] points at the net's current tree.

@@ -312,7 +312,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	if (c.tree_cap <= 0) c.tree_cap = 2048;
 	if (c.far_cap <= 0) c.far_cap = bf ? 32768 : 8192;      /* regular slots: one flat far list (pf_device.cuh, frontier) */
 	if (c.sink_cap <= 0) c.sink_cap = 64;
-	if (c.big_slots <= 0) c.big_slots = 64;
+	const bool auto_big_slots = c.big_slots <= 0;
+	if (auto_big_slots) c.big_slots = 64;
 	if (c.reroute_all_iters == 0) c.reroute_all_iters = 1;
 	r->div_explicit = c.inflight_div > 0; r->util = -1.;
 	if (c.inflight_div <= 0) c.inflight_div = 16;
@@ -325,6 +326,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	                                                    not shorten the tight-W tail */
 	if (c.ripple == 0) c.ripple = 1;
 	if (c.ripple < 0) c.ripple = 0;
+	if (c.lazy_seed_min == 0) c.lazy_seed_min = 256;
+	if (c.lazy_seed_min < 0) c.lazy_seed_min = 0;
 	if (c.validate_commits == 0) c.validate_commits = 2;
 	if (c.validate_commits < 0) c.validate_commits = 0;
 	if (c.max_batch > PF_MAX_BATCH) c.max_batch = PF_MAX_BATCH;
@@ -418,6 +421,15 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	}
 	if (c.big_tree_cap <= 0) c.big_tree_cap = std::max(1 << 16, 64 * max_sinks);
 	if (c.big_far_cap <= 0) c.big_far_cap = std::min(1 << 21, 2 << c.big_label_log2);
+	if (auto_big_slots) {
+		/* the big slots take every search that outgrows a regular slot — at high pres_fac the timing-driven searches of a
+		 * congested circuit flood tens of thousands of labels, thousands of nets end up here, and 64 warps on a 148-SM device
+		 * made that class the whole run time (32 k-LUT stand-in: 13 s of 13.4 s).  Two warps per SM, within 32 GiB of scratch. */
+		const double per_slot = (double)(sizeof(uint64_t) + sizeof(PfCold)) * (double)(1ll << c.big_label_log2) + 8.0 * c.big_far_cap
+				+ (double)sizeof(PfTreeNode) * c.big_tree_cap + 1e6;
+		const int by_mem = (int)std::min(32.0 * 1073741824.0 / per_slot, 1e6);
+		c.big_slots = std::max(64, std::min(2 * (sms > 0 ? sms : 148), by_mem));
+	}
 	if (c.num_slots > (int)r->work_small.size() + 32) c.num_slots = std::max(32, (int)((r->work_small.size() + 31) / 32 * 32));
 
 	/* device graph */
@@ -707,7 +719,7 @@ static void fill_params(pf_router *r, PfParams &P, const SlotClass &s, float pre
 	P.validate = (c.num_slots > 1 || c.big_slots > 1) ? c.validate_commits : 0;   /* one warp cannot race */
 	P.hot = s.hot; P.cold = s.cold; P.label_log2 = s.label_log2; P.epochs = s.epochs;
 	P.hot2 = s.hot2; P.cold2 = s.cold2; P.label2_log2 = s.label2_log2;
-	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap; P.far_buckets = (&s == &r->big) ? 1 : 0;
+	P.tree = s.tree; P.tree_cap = s.tree_cap; P.far = s.far; P.far_cap = s.far_cap; P.far_buckets = (&s == &r->big) ? 1 : 0; P.lazy_seed_min = c.lazy_seed_min;
 	P.iscratch = s.iscratch; P.sink_cap = s.sink_cap;
 	P.pool = r->pool[r->cur]; P.pool_node = r->pool_node[r->cur]; P.loc = r->loc; P.pool_head = r->pool_head; P.pool_cap = r->pool_cap;
 	P.net_big = r->net_big;
@@ -887,7 +899,7 @@ static int launch_routes(pf_router *r, float pres_fac, int part, int nparts) {
 		fill_params(r, P, r->big, pres_fac);
 		P.work = r->retry_list; P.num_work_ptr = r->retry_count; P.work_head = (int *)(r->ctl + CTL_HEAD_RETRY);
 		P.skip_ripup = 1;
-		const int sl = std::min(r->big.num_slots, std::max(8, r->cfg.min_slots));
+		const int sl = r->big.num_slots;             /* (warps without work leave at once) */
 		tune_granularity(r, P, sl, sl, true);
 		CKB(pfb_launch_route(&P, sl, 1));
 	}
@@ -1273,8 +1285,9 @@ extern "C" int pf_route_run(pf_router *r, pf_sta *dsta, pf_sta_fn sta, void *use
 		st.nets_routed = (int)r->h_stats.nets; st.heap_pushes = (int64_t)r->h_stats.pushes; st.heap_pops = (int64_t)r->h_stats.pops;
 		st.edge_visits = (int64_t)r->h_stats.visits;
 		if (analyse) { float cpd = 0.f; if ((rc = pf_sta_read_cpd(dsta, &cpd)) != PF_OK) break; st.crit_path_delay = cpd; }
-		if (cfg->verbose) fprintf(stderr, "pf_router: iteration %d: %d nets routed (%llu lost races), %d rr nodes overused, pres_fac %g; %llu labels settled, largest net %llu, %llu edge visits\n", itry, st.nets_routed,
-				(unsigned long long)r->h_stats.races, overused, (double)st.pres_fac, (unsigned long long)r->h_stats.pops, (unsigned long long)r->h_stats.max_net_pops, (unsigned long long)r->h_stats.visits);
+		if (cfg->verbose) fprintf(stderr, "pf_router: iteration %d: %d nets routed (%llu lost races), %d rr nodes overused, pres_fac %g; %llu labels settled, largest net %llu, %llu edge visits, %llu refills, %llu stale pops, %llu pushes\n", itry, st.nets_routed,
+				(unsigned long long)r->h_stats.races, overused, (double)st.pres_fac, (unsigned long long)r->h_stats.pops, (unsigned long long)r->h_stats.max_net_pops, (unsigned long long)r->h_stats.visits,
+				(unsigned long long)r->h_stats.refills, (unsigned long long)r->h_stats.stale, (unsigned long long)r->h_stats.pushes);
 		if (itry == 1 && !breadth_first && r->avail_wl > 0
 				&& (float)r->h_wl_used / (float)r->avail_wl > PF_FIRST_ITER_WIRELENGTH_LIMIT) {   /* route_timing.c:189-225 */
 			if (stats_out && nstats < stats_cap) stats_out[nstats] = st;

@@ -77,7 +77,7 @@ class Config(C.Structure):
                [("pop_slack", C.c_float), ("win_rel", C.c_float), ("win_abs", C.c_float), ("verbose", C.c_int32),
                 ("reroute_all_iters", C.c_int32), ("inflight_div", C.c_int32), ("min_slots", C.c_int32),
                 ("stall_iters", C.c_int32), ("history_window", C.c_int32), ("keep_newcomer", C.c_int32),
-                ("defer_graph", C.c_int32), ("validate_commits", C.c_int32), ("ripple", C.c_int32), ("ripple_max_nets", C.c_int32), ("polish", C.c_int32)]
+                ("defer_graph", C.c_int32), ("validate_commits", C.c_int32), ("ripple", C.c_int32), ("ripple_max_nets", C.c_int32), ("polish", C.c_int32), ("lazy_seed_min", C.c_int32)]
 
 
 class _TimingGraph(C.Structure):

@@ -16,7 +16,8 @@
 static char g_err[256] = "";
 static PfLaunchTimes g_times;
 
-long long pf_emu_bucket_refills = 0;
+long long pf_emu_bucket_refills = 0, pf_emu_lazy_seedings = 0;
+extern "C" long long pfb_emu_lazy_seedings(void) { return pf_emu_lazy_seedings; }
 extern "C" long long pfb_emu_bucket_refills(void) { return pf_emu_bucket_refills; }
 int pfb_init(int) { return 0; }
 int pfb_device_count(void) { return 1; }

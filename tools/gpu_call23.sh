@@ -1,0 +1,5 @@
+export PF_LAUNCH_LOG=1
+export PF_ROUTER_LIB="$PWD/parallel_eda_b200/libpf_router_diag.so"
+python tools/td_iter_profile.py bgm_w260 big_slots=64 > /dev/null 2> gpurun_out/r02r_bgm_diag.txt
+python tools/td_iter_profile.py bgm_w260 big_slots=64 lazy_seed_min=-1 > /dev/null 2> gpurun_out/r02r_bgm_diag_eager.txt
+grep -E "^(bgm|sv0)" gpurun_out/r02r_*.txt | cut -c1-220
