@@ -382,10 +382,11 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			if (p->indexed[i].inv_length > 0.f) lmax = std::max(lmax, (int)(1.f / p->indexed[i].inv_length + 0.5f));
 		/* share[k]: the part of the total fanout (in the order of the box centres) that forms stripe k.  Equal shares do not give
 		 * equal work: the nets across cut k all go to rank k, so rank 0 routes interior nets only and the last rank its stripe
-		 * plus both sides of its cut (measured on 4 GPUs: 43.9 k / 50.0 k / 49.9 k / 56.2 k nets in iteration 1, and everybody
-		 * waits for the last one at the exchange).  The shares are corrected until the fanout each rank ends up routing is level;
+		 * plus both sides of its cut (measured on 4 GPUs: 43.9 k / 50.0 k / 49.9 k / 56.2 k nets in iteration 1).  An iteration
+		 * is the longest interior phase plus the longest cut phase (everybody waits at the exchange after each), so the shares
+		 * are corrected until the INTERIOR fanout of every rank is level — rank 0, which owns no cut, then simply has less to do;
 		 * every rank computes the same partition from the same problem. */
-		std::vector<double> share((size_t)c.nranks, 1.0 / c.nranks), load((size_t)c.nranks, 0.0), best_share;
+		std::vector<double> share((size_t)c.nranks, 1.0 / c.nranks), load((size_t)c.nranks, 0.0), load_cut((size_t)c.nranks, 0.0), best_share;
 		std::vector<int> cut((size_t)c.nranks + 1, 0);
 		/* the partition the shares give: owner[], cut_net[], load[]; returns the heaviest rank's load relative to the mean */
 		auto partition = [&]() {
@@ -400,6 +401,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 				acc_f += p->net_ptr[i + 1] - p->net_ptr[i];
 			}
 			std::fill(load.begin(), load.end(), 0.0);
+			std::fill(load_cut.begin(), load_cut.end(), 0.0);
 			for (int i : byx) {
 				const int st = owner[i], xmin = p->net_bb[4 * i], xmax = p->net_bb[4 * i + 1];
 				const bool left_ok = st == 0 || xmin >= cut[(size_t)st] + lmax;
@@ -408,20 +410,21 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 				if (cut_net[i]) owner[i] = right_ok ? st : st + 1;   /* the rank that owns the violated cut (cut k belongs to rank k).  Sharing a cut's
 				                                                      * nets between its two neighbours was tried: two ranks then route overlapping nets on
 				                                                      * stale views of each other, and on a small fabric the negotiation oscillates for ever */
-				load[(size_t)owner[i]] += (double)(p->net_ptr[i + 1] - p->net_ptr[i]);
+				(cut_net[i] ? load_cut : load)[(size_t)owner[i]] += (double)(p->net_ptr[i + 1] - p->net_ptr[i]);
 			}
-			double worst = 0.0;
-			for (int k = 0; k < c.nranks; k++) worst = std::max(worst, load[(size_t)k] * c.nranks / std::max(1.0, (double)total_f));
-			return worst;
+			/* an iteration is two phases with an exchange after each: its length is the longest interior phase plus the longest cut phase */
+			double wi = 0.0, wc = 0.0;
+			for (int k = 0; k < c.nranks; k++) { wi = std::max(wi, load[(size_t)k]); wc = std::max(wc, load_cut[(size_t)k]); }
+			return (wi + wc) * c.nranks / std::max(1.0, (double)total_f);
 		};
 		double best = 1e30;
 		for (int round = 0; round < 12; round++) {
 			const double worst = partition();
 			if (worst < best) { best = worst; best_share = share; }
-			if (worst < 1.02) break;
-			double sum = 0.0;
+			double sum = 0.0, mean_i = 0.0;
+			for (int k = 0; k < c.nranks; k++) mean_i += load[(size_t)k] / c.nranks;
 			for (int k = 0; k < c.nranks; k++) {
-				const double want = std::max(1.0, (double)total_f) / (c.nranks * std::max(1.0, load[(size_t)k]));
+				const double want = std::max(1.0, mean_i) / std::max(1.0, load[(size_t)k]);
 				share[(size_t)k] = std::min(4.0 / c.nranks, std::max(0.25 / c.nranks, share[(size_t)k] * pow(want, 0.5)));
 				sum += share[(size_t)k];
 			}
@@ -429,8 +432,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		}
 		if (share != best_share) { share = best_share; partition(); }
 		if (c.verbose) {
-			fprintf(stderr, "pf_router: stripes of rank 0..%d: fanout routed", c.nranks - 1);
-			for (int k = 0; k < c.nranks; k++) fprintf(stderr, " %.0f", load[(size_t)k]);
+			fprintf(stderr, "pf_router: stripes of rank 0..%d: fanout routed (interior + across the rank's cut)", c.nranks - 1);
+			for (int k = 0; k < c.nranks; k++) fprintf(stderr, " %.0f+%.0f", load[(size_t)k], load_cut[(size_t)k]);
 			fprintf(stderr, "\n");
 		}
 	}
@@ -849,7 +852,11 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	 * the first iteration (BASELINE configs[4]: 29 %; the near-minimum-width fixtures: 52-63 %) twice as many nets
 	 * in flight converge just as fast (cfg 4: 22.9 vs 24.9 ms measured), on a tight fabric they do not */
 	const int base_div = (!r->div_explicit && r->util >= 0. && r->util < 0.40) ? r->cfg.inflight_div / 2 : r->cfg.inflight_div;
-	r->cur_div = stalled ? r->cfg.inflight_div * 8 : base_div;
+	/* several ranks: a rank holds 1 / nranks of the nets, and the same divisor would leave most of its warps without work
+	 * (4 GPUs, cfg 4, iteration 3: 9.7 k nets on 1213 of 2960 warps, eight nets deep — as long as one GPU takes for all 37 k).
+	 * The nets in flight per rank stay what one GPU has in flight; measured on one GPU, cfg 4 converges the same with every
+	 * net in flight (inflight_div 8 / 4 / 2 / 1: 6 iterations, wirelength within 0.01 %). */
+	r->cur_div = stalled ? r->cfg.inflight_div * 8 : std::max(1, base_div / std::max(1, r->cfg.nranks));
 	r->iter_all = all;
 	if (all) {
 		/* host-built lists in the reference's net order (route_timing.c:98-106): interior nets, then cut nets */
