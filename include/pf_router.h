@@ -184,13 +184,18 @@ void *pf_comm_net_delay_ptr(pf_router *r);
  * afterwards pf_comm_exchange (after every route part) and pf_comm_gather_delays (before a timing analysis) are
  * stream-ordered device work — publish with a system-scope release, poll the peers with acquire loads, read their
  * payload out of their memory — and pf_route_run runs whole multi-GPU routings with one host synchronisation per
- * PathFinder iteration.  pf_comm_abort makes peers stop waiting for a rank that failed. */
+ * PathFinder iteration.  pf_comm_abort makes peers stop waiting for a rank that failed.
+ * The transport outlives the router, like the reference's MPI communicator outlives one routing: the exchange region of a
+ * destroyed router is kept by the process and given to the next router it fits, regions of peers stay mapped (steps 1-3 are
+ * still run per router, but then cost microseconds: no cudaMalloc, no cudaIpcOpenMemHandle), sequence numbers continue.
+ * pf_comm_release_cache() frees what no live router uses — call it on every rank after the last router of the job. */
 #define PF_COMM_HANDLE_BYTES 128
 int pf_comm_export(pf_router *r, void *handle);
 int pf_comm_init(pf_router *r, const void *all_handles);
 int pf_comm_exchange(pf_router *r);
 int pf_comm_gather_delays(pf_router *r);
 int pf_comm_abort(pf_router *r);
+int pf_comm_release_cache(void);
 
 /* try_timing_driven_route (route_timing.c:85-343) on an existing router, one GPU or — after pf_comm_init — one rank of
  * several: iterate until legal or out of iterations, with ONE host-device synchronisation per iteration.  dsta: device

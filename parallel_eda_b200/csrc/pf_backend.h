@@ -104,6 +104,7 @@ void *pfb_ipc_alloc(size_t bytes, void *handle64);
 void *pfb_ipc_open(const void *handle64);          /* map another process's region; NULL on failure */
 void pfb_ipc_close(void *p);
 void pfb_ipc_free(void *p);
+int pfb_ipc_clear_abort(void *region);                /* a cached region goes to a new router: PfXchgHeader.abort_flag = 0, nothing else touched */
 /* publish this rank's event log of exchange `seq` (count read from *event_head on the device), wait for every peer's,
  * replay the peers' events on `nodes` — one launch, no host involvement */
 int pfb_launch_xchg_events(PfNode *nodes, const PfPeers *peers, int me, int nranks, unsigned seq, const unsigned long long *event_head,

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -80,7 +81,8 @@ struct pf_router {
 	long long h_wl_used; unsigned xchg_seq;
 	std::vector<float> crit_hist;        /* criticalities per iteration of the last pf_route_run with a host analysis */
 	int comm_ready;                      /* pf_comm_init done */
-	unsigned char *xreg; size_t xreg_bytes; unsigned char xhandle[64]; PfPeers peers; unsigned char *term_owner; unsigned dseq;   /* exchange region (pf_layout.h) */
+	unsigned char *xreg; size_t xreg_bytes; unsigned char xhandle[64]; PfPeers peers;   /* region and mappings belong to the process-level transport cache (pf_router.cpp) */
+	 unsigned char *term_owner; unsigned dseq;   /* exchange region (pf_layout.h) */
 	bool owner_valid;                     /* committer[] reflects the route store (ripple re-routing) */
 	bool force_all_once;                  /* the next iteration re-routes every net (polish pass) */
 	bool iter_all;                        /* the running iteration re-routes every net */

@@ -17,6 +17,7 @@
 #include "pf_gen_device.cuh"
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -881,6 +882,10 @@ void *pfb_ipc_open(const void *handle64) {
 	cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
 	if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return NULL; }
 	return p;
+}
+int pfb_ipc_clear_abort(void *region) {
+	CK(cudaMemsetAsync((char *)region + offsetof(PfXchgHeader, abort_flag), 0, sizeof(unsigned), g_stream));
+	return 0;
 }
 void pfb_ipc_close(void *p) { if (p) cudaIpcCloseMemHandle(p); }
 void pfb_ipc_free(void *p) { if (p) { cudaStreamSynchronize(g_stream); cudaFree(p); } }

@@ -129,6 +129,86 @@ static int alloc_slot_class(SlotClass &s, int max_work, bool hot_in_smem) {
 	return 0;
 }
 
+/* ---- process-level cache of the multi-GPU exchange region and of the peers' mappings.
+ * The region is sized for the worst case of the route store (cfg 4: 426 MB), and cudaMalloc + cudaIpcGetMemHandle of it plus
+ * one cudaIpcOpenMemHandle per peer cost ~65 ms per router at N = 4 — three times the rest of pf_router_create.  Like the
+ * reference's MPI communicator (created once per process, parallel_route/spatial.cxx), the transport therefore outlives the
+ * router: the region of a destroyed router is kept and handed to the next one that fits, peers' regions stay mapped (looked
+ * up by their 64-byte IPC handle), and the exchange sequence numbers simply continue, so no header is ever reset while a
+ * slow peer may still be polling it.  A region that has become too small is retired, not freed: a peer may still have it
+ * mapped, and freeing exported memory under an importer is undefined.  pf_comm_release_cache() drops everything that no
+ * live router uses (call it collectively, after the last router of the job). */
+struct CommPeerMap { unsigned char handle[64]; void *ptr; };
+struct CommRegion { unsigned char *reg; size_t bytes; unsigned char handle[64]; bool in_use; unsigned seq, dseq; /* last numbers published from it */ };
+static struct CommCache {
+	std::vector<CommRegion> regions;          /* one per multi-rank router alive at the same time in this process (usually one) */
+	std::vector<CommPeerMap> peers;
+	std::vector<void *> retired;
+	long long n_alloc, n_reuse, n_open, n_open_reuse;     /* pf_debug_comm_cache */
+} g_comm;
+static std::mutex g_comm_mu;
+
+/* the exchange region of a new router: a cached one that is free and large enough, else a new one */
+static unsigned char *comm_region_acquire(size_t bytes, unsigned char handle[64], unsigned *seq, unsigned *dseq) {
+	std::lock_guard<std::mutex> lk(g_comm_mu);
+	CommRegion *pick = NULL, *small = NULL;
+	for (CommRegion &c : g_comm.regions) {
+		if (c.in_use) continue;
+		if (c.bytes >= bytes) { if (!pick || c.bytes < pick->bytes) pick = &c; }
+		else small = &c;
+	}
+	if (pick) {
+		if (pfb_ipc_clear_abort(pick->reg) != 0) return NULL;
+		g_comm.n_reuse++;
+	} else {
+		CommRegion c;
+		memset(&c, 0, sizeof(c));
+		const size_t want = bytes + bytes / 4;                      /* headroom: the next problem may be a little larger */
+		c.reg = (unsigned char *)pfb_ipc_alloc(want, c.handle); c.bytes = want;
+		if (!c.reg) { c.reg = (unsigned char *)pfb_ipc_alloc(bytes, c.handle); c.bytes = bytes; }
+		if (!c.reg) return NULL;
+		g_comm.n_alloc++;
+		if (small) { g_comm.retired.push_back(small->reg); c.seq = small->seq; c.dseq = small->dseq; *small = c; pick = small; }   /* takes the place of the one that is too small */
+		else { g_comm.regions.push_back(c); pick = &g_comm.regions.back(); }
+	}
+	pick->in_use = true;
+	memcpy(handle, pick->handle, 64);
+	*seq = pick->seq; *dseq = pick->dseq;
+	return pick->reg;
+}
+static void comm_region_release(pf_router *r) {
+	if (!r->xreg) return;
+	std::lock_guard<std::mutex> lk(g_comm_mu);
+	for (CommRegion &c : g_comm.regions) if (c.reg == r->xreg) { c.seq = r->xchg_seq; c.dseq = r->dseq; c.in_use = false; }
+}
+static void *comm_peer_open(const unsigned char handle[64]) {
+	std::lock_guard<std::mutex> lk(g_comm_mu);
+	for (const CommPeerMap &m : g_comm.peers) if (memcmp(m.handle, handle, 64) == 0) { g_comm.n_open_reuse++; return m.ptr; }
+	void *p = pfb_ipc_open(handle);
+	g_comm.n_open++;
+	if (p) { CommPeerMap m; memcpy(m.handle, handle, 64); m.ptr = p; g_comm.peers.push_back(m); }
+	return p;
+}
+/* diagnostics: { bytes of the cached regions, regions allocated, routers that re-used one, peer regions mapped, mappings re-used } */
+extern "C" void pf_debug_comm_cache(int64_t out[5]) {
+	std::lock_guard<std::mutex> lk(g_comm_mu);
+	out[0] = 0;
+	for (const CommRegion &c : g_comm.regions) out[0] += (int64_t)c.bytes;
+	out[1] = g_comm.n_alloc; out[2] = g_comm.n_reuse; out[3] = g_comm.n_open; out[4] = g_comm.n_open_reuse;
+}
+extern "C" int pf_comm_release_cache(void) {
+	std::lock_guard<std::mutex> lk(g_comm_mu);
+	for (const CommRegion &c : g_comm.regions) if (c.in_use) FAILF(PF_EINVAL, "a router still uses an exchange region");
+	pfb_sync();
+	for (const CommPeerMap &m : g_comm.peers) pfb_ipc_close(m.ptr);
+	g_comm.peers.clear();
+	for (void *p : g_comm.retired) pfb_ipc_free(p);
+	g_comm.retired.clear();
+	for (const CommRegion &c : g_comm.regions) pfb_ipc_free(c.reg);
+	g_comm.regions.clear();
+	return PF_OK;
+}
+
 extern "C" void pf_router_destroy(pf_router *r) {
 	if (!r) return;
 	pfb_sync();
@@ -140,8 +220,8 @@ extern "C" void pf_router_destroy(pf_router *r) {
 	pfb_free(r->pool[0]); pfb_free(r->pool[1]); pfb_free(r->pool_node[0]); pfb_free(r->pool_node[1]); pfb_free(r->loc);
 	pfb_free(r->all_nets); pfb_free(r->net_big); pfb_free(r->retry_work); pfb_free(r->sel_scratch); pfb_free(r->ptc);
 	pfb_free(r->ctl); pfb_host_free(r->h_ctl); pfb_free(r->retry_list); pfb_free(r->last_over); pfb_free(r->committer);
-	for (int k = 0; k < PF_XCHG_MAX_RANKS; k++) if (r->peers.base[k] && r->peers.base[k] != r->xreg) pfb_ipc_close(r->peers.base[k]);
-	pfb_ipc_free(r->xreg); pfb_free(r->term_owner); pfb_free(r->vq[0]); pfb_free(r->vq[1]); pfb_free(r->queued);
+	comm_region_release(r);
+	pfb_free(r->term_owner); pfb_free(r->vq[0]); pfb_free(r->vq[1]); pfb_free(r->queued);
 	pfb_free(r->g_source); pfb_free(r->g_count); pfb_free(r->g_off); pfb_free(r->g_chosen);
 	delete r;
 }
@@ -624,7 +704,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		if (c.nranks > PF_XCHG_MAX_RANKS) { pf_router_destroy(r); FAILF(PF_EINVAL, "at most %d ranks (one node)", PF_XCHG_MAX_RANKS); }
 		r->event_cap = (2 * r->pool_cap + 3) & ~3ll;
 		r->xreg_bytes = PF_XCHG_HEADER_BYTES + 8 * (size_t)r->event_cap + 2 * sizeof(float) * (size_t)std::max(r->T, 1);
-		r->xreg = (unsigned char *)pfb_ipc_alloc(r->xreg_bytes, r->xhandle);
+		r->xreg = comm_region_acquire(r->xreg_bytes, r->xhandle, &r->xchg_seq, &r->dseq);   /* sequence numbers go on */
 		if (!r->xreg) { pf_router_destroy(r); CUDA_FAIL(); }
 		r->events = (unsigned *)(r->xreg + PF_XCHG_HEADER_BYTES);
 		r->peers.base[c.rank] = r->xreg;
@@ -1047,7 +1127,8 @@ extern "C" int pf_comm_net_classes(pf_router *r, int32_t *owner, uint8_t *is_cut
  * Bootstrap (once): every rank calls pf_comm_export, the caller all-gathers the PF_COMM_HANDLE_BYTES blobs with whatever
  * it has (MPI_Allgather in the reference's MPI router, torch.distributed here) and hands all of them to pf_comm_init.
  * From then on nothing crosses the host: pf_comm_exchange is one kernel behind the route kernels. */
-struct CommHandle { unsigned char ipc[64]; uint64_t bytes; int64_t event_cap; int32_t rank, nranks, T, magic; };
+struct CommHandle { unsigned char ipc[64]; uint64_t bytes; int64_t event_cap; int32_t rank, nranks, T, magic; uint32_t seq, dseq; };   /* seq / dseq: where this rank's
+	                                * sequence numbers stand (the region and its numbers outlive the router, see the transport cache above) */
 static_assert(sizeof(CommHandle) <= PF_COMM_HANDLE_BYTES, "handle blob too small");
 #define PF_COMM_MAGIC 0x50465832   /* "PFX2" */
 
@@ -1059,7 +1140,7 @@ extern "C" int pf_comm_export(pf_router *r, void *handle) {
 	CommHandle h;
 	memset(&h, 0, sizeof(h));
 	memcpy(h.ipc, r->xhandle, 64);
-	h.bytes = r->xreg_bytes; h.event_cap = r->event_cap; h.rank = r->cfg.rank; h.nranks = r->cfg.nranks; h.T = r->T; h.magic = PF_COMM_MAGIC;
+	h.bytes = r->xreg_bytes; h.event_cap = r->event_cap; h.rank = r->cfg.rank; h.nranks = r->cfg.nranks; h.T = r->T; h.magic = PF_COMM_MAGIC; h.seq = r->xchg_seq; h.dseq = r->dseq;
 	memset(handle, 0, PF_COMM_HANDLE_BYTES);
 	memcpy(handle, &h, sizeof(h));
 	return PF_OK;
@@ -1069,15 +1150,21 @@ extern "C" int pf_comm_init(pf_router *r, const void *all_handles) {
 	if (!r || !all_handles) FAILF(PF_EINVAL, "null argument");
 	if (!r->xreg) FAILF(PF_EINVAL, "router was created with nranks == 1");
 	if (r->comm_ready) return PF_OK;
+	unsigned seq = r->xchg_seq, dseq = r->dseq;
 	for (int k = 0; k < r->cfg.nranks; k++) {
 		CommHandle h;
 		memcpy(&h, (const unsigned char *)all_handles + (size_t)k * PF_COMM_HANDLE_BYTES, sizeof(h));
 		if (h.magic != PF_COMM_MAGIC || h.rank != k || h.nranks != r->cfg.nranks) FAILF(PF_EINVAL, "handle %d is not rank %d's of %d", k, k, r->cfg.nranks);
 		if (h.event_cap != r->event_cap || h.T != r->T || h.bytes != r->xreg_bytes) FAILF(PF_EINVAL, "rank %d routes a different problem", k);
+		/* every rank starts from the furthest number any rank has published (they agree unless a rank joined late or
+		 * failed half-way through a routing): the waits are "at least", so a stale header can only be behind */
+		if ((int)(h.seq - seq) > 0) seq = h.seq;
+		if ((int)(h.dseq - dseq) > 0) dseq = h.dseq;
 		if (k == r->cfg.rank) continue;
-		r->peers.base[k] = (unsigned char *)pfb_ipc_open(h.ipc);
+		r->peers.base[k] = (unsigned char *)comm_peer_open(h.ipc);
 		if (!r->peers.base[k]) CUDA_FAIL();
 	}
+	r->xchg_seq = seq; r->dseq = dseq;
 	r->comm_ready = 1;
 	return PF_OK;
 }

@@ -111,6 +111,14 @@ class Comm:
     def barrier(self):
         dist.barrier()
 
+    def release(self, lib_path=None) -> None:
+        """After the last router of the job: free the exchange region and the peer mappings the library keeps between
+        routers (pf_comm_release_cache).  Collective — no rank may still be inside a routing."""
+        from . import router as _router
+        dist.barrier()
+        _router.load_library(lib_path).pf_comm_release_cache()
+        dist.barrier()
+
 
 def init_from_env(backend: str | None = None) -> Comm | None:
     """Join the process group torchrun described in RANK / WORLD_SIZE / MASTER_*; None if single process."""

@@ -179,6 +179,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.pf_comm_exchange.argtypes = [C.c_void_p]
     lib.pf_comm_gather_delays.argtypes = [C.c_void_p]
     lib.pf_comm_abort.argtypes = [C.c_void_p]
+    lib.pf_comm_release_cache.argtypes = []
     lib.pf_route_run.argtypes = [C.c_void_p, C.c_void_p, STA_FN, C.c_void_p, C.POINTER(IterStats), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.pf_try_timing_driven_route.argtypes = [C.POINTER(_Problem), C.POINTER(Config), STA_FN, C.c_void_p,
                                                C.POINTER(_Result)]

@@ -229,6 +229,8 @@ int pfb_graph_hash(const PfNode *nodes, int num_nodes, const uint32_t *edges, lo
 struct ShmRegion { std::string name; size_t bytes; bool owner; };
 static std::map<void *, ShmRegion> g_shm;
 
+/* regions kept by the transport cache of pf_router.cpp outlive their routers: unlink what this process still owns at exit */
+static void emu_unlink_all(void) { for (auto &kv : g_shm) if (kv.second.owner) shm_unlink(kv.second.name.c_str()); }
 void *pfb_ipc_alloc(size_t bytes, void *handle64) {
 	static int counter = 0;
 	char name[64];
@@ -240,6 +242,8 @@ void *pfb_ipc_alloc(size_t bytes, void *handle64) {
 	if (p == MAP_FAILED) { shm_unlink(name); snprintf(g_err, sizeof(g_err), "mmap of %s failed", name); return NULL; }
 	memset(handle64, 0, 64);
 	snprintf((char *)handle64, 64, "%s", name);
+	static bool hooked = false;
+	if (!hooked) { hooked = true; atexit(emu_unlink_all); }
 	g_shm[p] = ShmRegion{ name, bytes, true };
 	return p;
 }
@@ -256,6 +260,7 @@ void *pfb_ipc_open(const void *handle64) {
 	g_shm[p] = ShmRegion{ name, (size_t)st.st_size, false };
 	return p;
 }
+int pfb_ipc_clear_abort(void *region) { ((PfXchgHeader *)region)->abort_flag = 0u; return 0; }
 void pfb_ipc_close(void *p) { auto it = g_shm.find(p); if (it != g_shm.end()) { munmap(p, it->second.bytes); g_shm.erase(it); } }
 void pfb_ipc_free(void *p) { auto it = g_shm.find(p); if (it != g_shm.end()) { munmap(p, it->second.bytes); shm_unlink(it->second.name.c_str()); g_shm.erase(it); } }
 

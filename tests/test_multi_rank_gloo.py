@@ -166,15 +166,27 @@ from parallel_eda_b200 import pfio, router, pathfinder, distributed, check_route
 comm = distributed.init_from_env("gloo")
 G = os.path.join(%(root)r, "tests", "golden")
 td = %(td)d
-name = "duo_w80" if td else "hub_w90"
-p = pfio.read_problem(os.path.join(G, name + ".pfp.xz")); p.opts["timing_analysis_enabled"] = td
-if td: p.opts["max_router_iterations"] = 100
 lib = %(emu)r
-cfg = router.default_config(router.load_library(lib), num_slots=4, big_slots=2, rank=comm.rank, nranks=comm.world)
-R = comm.create_router(p, cfg, lib_path=lib)      # includes comm.connect(R): pf_comm_export / all-gather / pf_comm_init
-S = router.Sta(pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz")), p, cfg, lib_path=lib) if td else None
-rep = pathfinder.run(R, comm=comm, dsta=S)         # pf_route_run: exchange over (emulated) peer memory, no torch collective
-res = R.result()
+L = router.load_library(lib)
+# three routers in a row on the same process group (timing-driven: two): the library keeps the exchange region and the peers'
+# mappings between routers.  A smaller problem first, so that the second router finds the cached region too small and a new
+# one is allocated while the old one is retired; the last router re-uses region and mappings; sequence numbers continue.
+names = ["duo_w80"] * 2 if td else ["toy_w64", "hub_w90", "hub_w90"]
+for k, name in enumerate(names):
+    p = pfio.read_problem(os.path.join(G, name + ".pfp.xz")); p.opts["timing_analysis_enabled"] = td
+    if td: p.opts["max_router_iterations"] = 100
+    cfg = router.default_config(L, num_slots=4, big_slots=2, rank=comm.rank, nranks=comm.world)
+    R = comm.create_router(p, cfg, lib_path=lib)      # includes comm.connect(R): pf_comm_export / all-gather / pf_comm_init
+    S = router.Sta(pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz")), p, cfg, lib_path=lib) if td else None
+    rep = pathfinder.run(R, comm=comm, dsta=S)         # pf_route_run: exchange over (emulated) peer memory, no torch collective
+    assert rep.success, (k, name)
+    res = R.result()
+    if k + 1 < len(names):
+        if S is not None: S.close()
+        R.close()
+import ctypes
+st = (ctypes.c_int64 * 5)(); L.pf_debug_comm_cache(st); st = list(st)      # bytes, regions allocated, re-used, peers mapped, mappings re-used
+assert st[1] == (1 if td else 2) and st[2] == 1 and st[3] == st[1] and st[4] == 1, st
 occ = torch.from_numpy(res.occ.astype(np.int64)); ref = occ.clone(); torch.distributed.broadcast(ref, 0)
 nd = torch.from_numpy(res.net_delay.copy()); ndref = nd.clone(); torch.distributed.broadcast(ndref, 0)
 own = [i for i in p.routed_nets() if res.trace_ptr[i + 1] > res.trace_ptr[i]]
