@@ -16,9 +16,9 @@ comm = distributed.init_from_env()
 grid = int(sys.argv[1]) if len(sys.argv) > 1 else 400
 nets = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
 local = int(os.environ.get("LOCAL_RANK", "0"))
-p = router.generate_grid_problem(nx=grid, ny=grid, W=100, num_nets=nets)
+p, gen = router.generate_grid_nets(nx=grid, ny=grid, W=100, num_nets=nets)     # the rr graph is built on every rank's device
 cfg = router.default_config(device=local, rank=comm.rank if comm else 0, nranks=comm.world if comm else 1)
-R = comm.create_router(p, cfg) if comm else router.Router(p, cfg)
+R = comm.create_router(p, cfg, generated=gen) if comm else router.Router(p, cfg, generated=gen)
 for rep in range(3):
     R.reset()
     if comm:
