@@ -72,8 +72,8 @@ typedef struct pf_config {
 	                             reference's parallel router (partitioning_multi_sink…cxx:6241-6269).
 	                             0 = auto (1); < 0 = always every net */
 	int32_t inflight_div;     /* nets in flight <= ceil(nets this iteration / inflight_div): bounds how
-	                             stale the congestion seen by concurrent nets can be; 0 = auto (16; 8 once the first
-	                             iteration has shown the channels to be under 40 % full) */
+	                             stale the congestion seen by concurrent nets can be; 0 = auto (16 in the first iteration, then 8 if it
+	                             has shown the channels to be under 40 % full, else 32) */
 	int32_t min_slots;        /* lower bound for the above; 0 = auto (one net per 20 x 20 tiles of the grid, at least 1) */
 	int32_t stall_iters;      /* overuse not down by 30 % over stall_iters+1 congested-only iterations => one
 	                             iteration re-routes every net with 8x fewer nets in flight; 0 = auto (3); < 0 = never */
@@ -94,7 +94,7 @@ typedef struct pf_config {
 	                             0 = auto (on), < 0 = off */
 	int32_t ripple_max_nets;  /* ripple only in iterations that re-route at most this many nets: displacement chains are followed one
 	                             link after the other, which is what shortens the tail of the negotiation but would serialise an
-	                             iteration with tens of thousands of nets; 0 = auto: max(64, min(nets / 16, 4 * min_slots)) */
+	                             iteration with tens of thousands of nets; 0 = auto: max(1024, min(nets / 16, 4 * min_slots)) */
 	int32_t polish;           /* > 0: when the routing first becomes legal, one more iteration re-routes EVERY net against the
 	                             final congestion picture and the loop continues until legal again (pf_try_* loops only) */
 	int32_t lazy_seed_min;    /* big slots: a search whose route tree holds at least this many entries labels only the seeds it can

@@ -640,7 +640,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	r->big.far_cap = c.big_far_cap; r->big.sink_cap = std::max(max_sinks, c.sink_cap);
 	int nwork = (int)(r->work_small.size() + r->work_big.size());
 	if (alloc_slot_class(r->small, nwork, true) || alloc_slot_class(r->big, nwork, false)) { pf_router_destroy(r); CUDA_FAIL(); }
-	if (c.ripple_max_nets <= 0) c.ripple_max_nets = std::max(256, std::min(nwork / 16, 4 * c.min_slots));
+	if (c.ripple_max_nets <= 0) c.ripple_max_nets = std::max(1024, std::min(nwork / 16, 4 * c.min_slots));   /* (256 until r02y: a 441-net
+	                                                                                * circuit then rippled in its late iterations only; always on: wirelength +0.9 % instead of +4.4 %) */
 	/* route store */
 	/* live trees hold about one entry per used rr node; the log needs room for one iteration of re-routes on top */
 	r->pool_cap = std::max<long long>(1 << 18, std::min<long long>(4ll * r->N + 96ll * r->T, 32ll * r->T + (1 << 20)));
@@ -931,7 +932,12 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	/* how many nets may be in flight depends on how contested the fabric is: with the channels under 40 % full after
 	 * the first iteration (BASELINE configs[4]: 29 %; the near-minimum-width fixtures: 52-63 %) twice as many nets
 	 * in flight converge just as fast (cfg 4: 22.9 vs 24.9 ms measured), on a tight fabric they do not */
-	const int base_div = (!r->div_explicit && r->util >= 0. && r->util < 0.40) ? r->cfg.inflight_div / 2 : r->cfg.inflight_div;
+	/* ... and with the channels over 40 % full half as many: measured on the B200 over 6 runs each of the near-minimum-width
+	 * fixtures (profiles/r02y_repeat.txt), divisor 32 instead of 16 narrows the run-to-run spread of the iteration count from
+	 * 23-38 to 20-24 (heq, reference 25), 21-28 to 20-23 (toy), 21-30 to 20-22 (hub) and lowers the criticality-weighted delay
+	 * by about 1 %: fewer nets commit against a congestion picture that is already stale */
+	int base_div = r->cfg.inflight_div;
+	if (!r->div_explicit && r->util >= 0.) base_div = r->util < 0.40 ? base_div / 2 : base_div * 2;
 	/* several ranks: a rank holds 1 / nranks of the nets, and the same divisor would leave most of its warps without work
 	 * (4 GPUs, cfg 4, iteration 3: 9.7 k nets on 1213 of 2960 warps, eight nets deep — as long as one GPU takes for all 37 k).
 	 * The nets in flight per rank stay what one GPU has in flight; measured on one GPU, cfg 4 converges the same with every
