@@ -36,7 +36,7 @@ def test_timing_driven_route_at_baseline_scale(name):
 
     class G:        # the reference's result as far as parity_bar needs it
         iterations = ref["iterations"]; total_wirelength = ref["total_wirelength"]
-    parity_bar.check("big_td_device_sta", name, r, G, weighted=(cpd, ref["final_crit_path_delay_ns"]))
+    parity_bar.check("big_td_device_sta", name, r, G, weighted=(cpd, ref["final_crit_path_delay_ns"]), wl_tol=parity_bar.BIG_WL_TOL)
     R = router.Router(p)
     rep = R.check_route(r)
     R.close()

@@ -16,11 +16,7 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def test_breadth_first_routing(name):
     p = pfio.read_problem(os.path.join(G, name + "_bf.pfp.xz"))
     g = pfio.read_result(os.path.join(G, name + "_bf.pfr.xz"))
-    t = time.perf_counter()
-    r = router.try_timing_driven_route(p)
-    dt = time.perf_counter() - t
-    print("%s breadth-first: %d iterations (reference %d), wirelength x%.3f, %.3f s" % (name, r.iterations, g.iterations, r.total_wirelength / g.total_wirelength, dt))
-    parity_bar.check("breadth_first", name, r, g)
+    r = parity_bar.check_runs("breadth_first", name, lambda: router.try_timing_driven_route(p), g)
     m = check_route.check_route(p, r, check_delays=False)
     assert m["overused"] == 0 and m["wirelength"] == r.total_wirelength
 
