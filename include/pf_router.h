@@ -72,7 +72,7 @@ typedef struct pf_config {
 	                             reference's parallel router (partitioning_multi_sink…cxx:6241-6269).
 	                             0 = auto (1); < 0 = always every net */
 	int32_t inflight_div;     /* nets in flight <= ceil(nets this iteration / inflight_div): bounds how
-	                             stale the congestion seen by concurrent nets can be; 0 = auto (16 in the first iteration, then 8 if it
+	                             stale the congestion seen by concurrent nets can be; 0 = auto (16 in the first iteration, then 2 if it
 	                             has shown the channels to be under 40 % full, else 32) */
 	int32_t min_slots;        /* lower bound for the above; 0 = auto (one net per 20 x 20 tiles of the grid, at least 1) */
 	int32_t stall_iters;      /* overuse not down by 30 % over stall_iters+1 congested-only iterations => one

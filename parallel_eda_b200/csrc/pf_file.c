@@ -210,9 +210,20 @@ done:
 	return rc;
 }
 
+/* The router hands out result arrays from its cache of pinned host buffers (pf_router.cpp: the device copies straight into
+ * them, and a buffer that has been faulted in once is used again); it registers this hook to get them back.  Everything else
+ * (file readers, callers' own arrays) is plain malloc memory. */
+static int (*g_release_hook)(void *) = 0;
+void pf_result_set_release_hook(int (*fn)(void *)) { g_release_hook = fn; }
+static void result_release(void *p) {
+	if (!p) return;
+	if (g_release_hook && g_release_hook(p)) return;
+	free(p);
+}
+
 void pf_result_free(pf_result *r) {
-	free(r->trace_ptr); free(r->trace_node); free(r->trace_switch);
-	free(r->net_delay); free(r->occ); free(r->iter_stats); free(r->iter_crit);
+	result_release(r->trace_ptr); result_release(r->trace_node); result_release(r->trace_switch);
+	result_release(r->net_delay); result_release(r->occ); free(r->iter_stats); free(r->iter_crit);
 	memset(r, 0, sizeof(*r));
 }
 

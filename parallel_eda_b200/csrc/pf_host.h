@@ -88,6 +88,8 @@ struct pf_router {
 	bool iter_all;                        /* the running iteration re-routes every net */
 };
 
+extern "C" void pf_result_set_release_hook(int (*fn)(void *));   /* pf_file.c: who takes back result arrays that are not malloc memory */
+
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 /* simple static-partition parallel loop for the host-side flattening of 10^7..10^8-element arrays */
 template <class F> static inline void parallel_for(long long n, F f) {

@@ -937,7 +937,9 @@ extern "C" int pf_iteration_begin(pf_router *r, const float *crit) {
 	 * 23-38 to 20-24 (heq, reference 25), 21-28 to 20-23 (toy), 21-30 to 20-22 (hub) and lowers the criticality-weighted delay
 	 * by about 1 %: fewer nets commit against a congestion picture that is already stale */
 	int base_div = r->cfg.inflight_div;
-	if (!r->div_explicit && r->util >= 0.) base_div = r->util < 0.40 ? base_div / 2 : base_div * 2;
+	/* (under 40 %: 16 / 8 = 2 — cfg 4 on the B200, divisor 8 / 4 / 2 / 1: 16.58 / 16.05 / 15.89 / 15.77 ms per routing, 6 iterations and
+	 * the wirelength within 0.01 % each time) */
+	if (!r->div_explicit && r->util >= 0.) base_div = r->util < 0.40 ? std::max(1, base_div / 8) : base_div * 2;
 	/* several ranks: a rank holds 1 / nranks of the nets, and the same divisor would leave most of its warps without work
 	 * (4 GPUs, cfg 4, iteration 3: 9.7 k nets on 1213 of 2960 warps, eight nets deep — as long as one GPU takes for all 37 k).
 	 * The nets in flight per rank stay what one GPU has in flight; measured on one GPU, cfg 4 converges the same with every
@@ -1257,6 +1259,45 @@ extern "C" int pf_get_timing(pf_router *r, pf_timing *t, int reset) {
 	return PF_OK;
 }
 
+/* ---- result arrays: pinned host buffers, kept for the next result.
+ * A result of cfg 4 is 120 MB (traces 6 bytes per element, occupancy 4 bytes per rr node).  Freshly malloc'ed arrays cost a
+ * page fault per 4 KB when they are first written (measured: 8-9 ms for the copy out of the pinned staging buffer, against
+ * 2.4 ms for the PCIe transfer itself); the arrays of pf_result therefore ARE pinned buffers the device copies into directly,
+ * and pf_result_free (pf_file.c, through the release hook) returns them to this cache instead of the heap. */
+struct HostBuf { void *p; size_t cap; bool in_use; };
+static std::vector<HostBuf> g_hostbufs;
+static std::mutex g_host_mu;
+static const size_t HOSTBUF_KEEP_BYTES = (size_t)1 << 30;      /* free buffers kept: at most this much, at most 16 */
+static void *host_take(size_t bytes) {
+	if (bytes < 16) bytes = 16;
+	std::lock_guard<std::mutex> lk(g_host_mu);
+	HostBuf *best = NULL;
+	for (HostBuf &b : g_hostbufs)
+		if (!b.in_use && b.cap >= bytes && b.cap <= 2 * bytes + (1 << 20) && (!best || b.cap < best->cap)) best = &b;
+	if (best) { best->in_use = true; return best->p; }
+	const size_t cap = bytes + bytes / 16;
+	void *p = pfb_host_alloc(cap);
+	if (!p) return NULL;
+	g_hostbufs.push_back(HostBuf{ p, cap, true });
+	return p;
+}
+static int host_release(void *p) {
+	std::lock_guard<std::mutex> lk(g_host_mu);
+	size_t at = g_hostbufs.size();
+	for (size_t i = 0; i < g_hostbufs.size(); i++) if (g_hostbufs[i].p == p) at = i;
+	if (at == g_hostbufs.size()) return 0;                      /* not ours: plain malloc memory */
+	g_hostbufs[at].in_use = false;
+	size_t free_bytes = 0, free_count = 0;
+	for (const HostBuf &b : g_hostbufs) if (!b.in_use) { free_bytes += b.cap; free_count++; }
+	for (size_t i = 0; i < g_hostbufs.size() && (free_bytes > HOSTBUF_KEEP_BYTES || free_count > 16); ) {      /* oldest first */
+		if (g_hostbufs[i].in_use) { i++; continue; }
+		free_bytes -= g_hostbufs[i].cap; free_count--;
+		pfb_host_free(g_hostbufs[i].p);
+		g_hostbufs.erase(g_hostbufs.begin() + (long)i);
+	}
+	return 1;
+}
+
 /* Route store → s_trace-ordered lists (update_traceback, route_common.c:638-706): the first
  * segment runs SOURCE … SINK; every later segment starts with its join node (whose iswitch is
  * the switch into the first new node) and ends at a SINK (iswitch OPEN). */
@@ -1280,34 +1321,28 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 	short *d_ts = (short *)pfb_alloc_raw(sizeof(short) * std::max<size_t>(total, 1));
 	unsigned *d_tt = (unsigned *)pfb_alloc_raw(sizeof(unsigned) * std::max<size_t>(total, 1));
 	out->num_nets = n;
-	out->trace_ptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 1));
-	out->trace_node = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(total, 1));
-	out->trace_switch = (int16_t *)malloc(sizeof(int16_t) * std::max<size_t>(total, 1));
-	out->net_delay = (float *)malloc(sizeof(float) * (size_t)std::max(r->T, 1));
-	out->occ = (int32_t *)malloc(sizeof(int32_t) * (size_t)r->N);
+	pf_result_set_release_hook(host_release);
+	out->trace_ptr = (int32_t *)host_take(sizeof(int32_t) * ((size_t)n + 1));
+	out->trace_node = (int32_t *)host_take(sizeof(int32_t) * std::max<size_t>(total, 1));
+	out->trace_switch = (int16_t *)host_take(sizeof(int16_t) * std::max<size_t>(total, 1));
+	out->net_delay = (float *)host_take(sizeof(float) * (size_t)std::max(r->T, 1));
+	out->occ = (int32_t *)host_take(sizeof(int32_t) * (size_t)r->N);
 	const bool host_ok = out->trace_ptr && out->trace_node && out->trace_switch && out->net_delay && out->occ;
 	unsigned long long h_wl[2] = { 0, 0 };
 	int serial_num = 0;
 	bad = !d_tn || !d_ts || !d_tt || !host_ok;
 	double t_1 = t_0, t_2 = t_0;
 	if (!bad) {
-		/* pinned staging for the big arrays when available */
 		const size_t b_tn = sizeof(int) * total, b_ts = sizeof(short) * total, b_tt = sizeof(unsigned) * total, b_occ = sizeof(int) * (size_t)r->N;
-		char *pin = (char *)pfb_pinned(b_tn + b_ts + b_tt + b_occ + 1024);
-		std::vector<unsigned> ttv;
-		if (!pin) ttv.resize(std::max<size_t>(total, 1));
-		char *h_tt = pin ? pin : (char *)ttv.data();
-		char *h_tn = pin ? h_tt + ((b_tt + 255) & ~(size_t)255) : (char *)out->trace_node;
-		char *h_ts = pin ? h_tn + ((b_tn + 255) & ~(size_t)255) : (char *)out->trace_switch;
-		char *h_occ = pin ? h_ts + ((b_ts + 255) & ~(size_t)255) : (char *)out->occ;
+		unsigned *h_tt = (unsigned *)host_take(std::max<size_t>(b_tt, 16));      /* the serial-number terms: scratch of this call */
 		/* the serial-number terms come first: the running remainder below is sequential by definition and runs on
-		 * a helper thread while the traces and the occupancy cross PCIe and are copied out */
-		bad = pfb_h2d(d_len, tptr.data(), sizeof(int) * ((size_t)n + 1)) || pfb_zero(r->d_wl, sizeof(unsigned long long) * 2)
+		 * a helper thread while the traces and the occupancy cross PCIe */
+		bad = !h_tt || pfb_h2d(d_len, tptr.data(), sizeof(int) * ((size_t)n + 1)) || pfb_zero(r->d_wl, sizeof(unsigned long long) * 2)
 				|| pfb_launch_build_traces(r->pool[r->cur], r->loc, n, NULL, d_len, d_tn, d_ts, r->d_wl, d_tt, r->ptc, p->nx)
 				|| pfb_d2h(h_tt, d_tt, b_tt);
 		std::thread chain;
 		if (!bad) {
-			const unsigned *tt = (const unsigned *)h_tt;
+			const unsigned *tt = h_tt;
 			chain = std::thread([tt, total, &serial_num]() {
 				/* get_serial_num, route_common.c:224-254: serial = (serial + a - b - c) % 2000000000 per trace element, in
 				 * the reference's wrapping int arithmetic.  |x| < 2^31 < 2 * 2000000000, so C's truncating remainder is
@@ -1321,19 +1356,14 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 				serial_num = sv;
 			});
 			t_1 = now_s();
+			/* straight into the result arrays (pinned): no staging copy */
 			bad = pfb_launch_extract_occ(r->nodes, r->N, d_occ)
-					|| pfb_d2h_async(h_tn, d_tn, b_tn) || pfb_d2h_async(h_ts, d_ts, b_ts) || pfb_d2h_async(h_occ, d_occ, b_occ)
-					|| pfb_d2h(h_wl, r->d_wl, sizeof(h_wl)) || pfb_d2h(out->net_delay, r->net_delay, sizeof(float) * (size_t)r->T);
-			if (!bad && pin) {
-				parallel_for((long long)total, [&](long long lo, long long hi) {
-					memcpy(out->trace_node + lo, h_tn + sizeof(int) * (size_t)lo, sizeof(int) * (size_t)(hi - lo));
-					memcpy(out->trace_switch + lo, h_ts + sizeof(short) * (size_t)lo, sizeof(short) * (size_t)(hi - lo));
-				});
-				parallel_for(r->N, [&](long long lo, long long hi) { memcpy(out->occ + lo, h_occ + sizeof(int) * (size_t)lo, sizeof(int) * (size_t)(hi - lo)); });
-			}
+					|| pfb_d2h_async(out->trace_node, d_tn, b_tn) || pfb_d2h_async(out->trace_switch, d_ts, b_ts) || pfb_d2h_async(out->occ, d_occ, b_occ)
+					|| pfb_d2h_async(out->net_delay, r->net_delay, sizeof(float) * (size_t)r->T) || pfb_d2h(h_wl, r->d_wl, sizeof(h_wl));
 			t_2 = now_s();
 			chain.join();
 		}
+		if (h_tt) host_release(h_tt);
 		r->d2h_bytes += (int64_t)(b_tn + b_ts + b_tt + b_occ) + (int64_t)sizeof(int) * n + (int64_t)sizeof(float) * r->T;
 	}
 	pfb_free(d_len); pfb_free(d_tn); pfb_free(d_ts); pfb_free(d_tt);
