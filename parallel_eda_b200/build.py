@@ -37,7 +37,7 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
     variant = variant or os.environ.get("PF_LIB_VARIANT", "")
     lib_path = LIB if not variant else os.path.join(HERE, "libpf_router_%s.so" % variant)
     srcs = [os.path.join(CSRC, f) for f in ("pf_kernels.cu", "pf_router.cpp", "pf_sta.cpp", "pf_check.cpp", "pf_gen.cpp", "pf_file.c", "pf_text.c")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("pf_device.cuh", "pf_sta_device.cuh", "pf_backend.h", "pf_layout.h", "pf_host.h")] + [
+    deps = srcs + [os.path.join(CSRC, f) for f in ("pf_device.cuh", "pf_sta_device.cuh", "pf_gen_device.cuh", "pf_backend.h", "pf_layout.h", "pf_host.h")] + [
         os.path.join(ROOT, "include", f) for f in ("pf_router.h", "pf_types.h", "pf_file.h", "pf_gen.h", "pf_text.h")]
     if not force and not variant and _newer(lib_path, deps):
         return lib_path

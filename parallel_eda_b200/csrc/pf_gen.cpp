@@ -98,8 +98,12 @@ extern "C" int pf_gen_dev_params(const pf_gen_params *gp, PfGenDev *G, short *cb
 	G->io_nodes = 6 * G->io_cap;
 	G->col0 = G->ny * G->io_nodes;
 	G->col_inner = 2 * G->io_nodes + G->ny * PF_GEN_CLB_NODES;
+	G->dW = pf_fastdiv_make(G->W); G->dL = pf_fastdiv_make(G->L); G->dHalf = pf_fastdiv_make(G->W / 2);
+	G->dColInner = pf_fastdiv_make(G->col_inner); G->dIoNodes = pf_fastdiv_make(G->io_nodes); G->dClbNodes = pf_fastdiv_make(PF_GEN_CLB_NODES);
+	G->m7 = 7 % G->W; G->m28 = 28 % G->W;
 	G->R_metal = R_METAL; G->C_per_tile = C_PER_TILE;
 	G->wpc_x = pf_gen_pref(*G, G->nx + 1); G->wpc_y = pf_gen_pref(*G, G->ny + 1);
+	G->dWpcX = pf_fastdiv_make(G->wpc_x); G->dWpcY = pf_fastdiv_make(G->wpc_y);
 	const long long chanx0 = 2ll * G->col0 + (long long)G->nx * G->col_inner;
 	const long long chany0 = chanx0 + (long long)(G->ny + 1) * G->wpc_x;
 	const long long N = chany0 + (long long)(G->nx + 1) * G->wpc_y;

@@ -28,8 +28,28 @@
 #define PF_GEN_CLB_NODES (PF_GEN_CLB_PINS + PF_GEN_CLB_CLASSES)
 #define PF_GEN_MAX_W 512
 
+/* x / d and x % d for 0 <= x < 2^31 by a divisor fixed per graph: one 32 x 32 -> 64-bit multiply and a shift instead of the ~25
+ * instructions of a 32-bit division.  The generator is integer arithmetic on (W, L, wires per channel, ...) throughout — per
+ * out-edge a dozen remainders — and was bound by exactly that (cfg 4: degree pass 3.1 ms, fill pass 10 ms for 1.4 GB of output).
+ * m = ceil(2^(31+s) / d), s = ceil(log2 d): exact for every x below 2^31 (the error m d - 2^(31+s) is below d <= 2^s). */
+struct PfFastDiv { unsigned m; int sh; int d; };
+PF_DEV int pf_fdiv(int x, const PfFastDiv &D) { return (int)(((unsigned long long)D.m * (unsigned long long)(unsigned)x) >> D.sh); }
+PF_DEV int pf_fmod(int x, const PfFastDiv &D) { return x - pf_fdiv(x, D) * D.d; }
+#ifndef __CUDA_ARCH__
+static inline PfFastDiv pf_fastdiv_make(int d) {
+	PfFastDiv D;
+	int s = 0;
+	while ((1ll << s) < (long long)d) s++;
+	D.d = d; D.sh = 31 + s;
+	D.m = (unsigned)((((unsigned long long)1 << (31 + s)) + (unsigned long long)d - 1ull) / (unsigned long long)d);
+	return D;
+}
+#endif
+
 struct PfGenDev {
 	int nx, ny, W, L, fc_in, fc_out, io_cap;
+	PfFastDiv dW, dL, dHalf, dWpcX, dWpcY, dColInner, dIoNodes, dClbNodes;   /* W, L, W / 2, wpc_x, wpc_y, col_inner, io_nodes, PF_GEN_CLB_NODES */
+	int m7, m28;                  /* 7 % W, 28 % W (connection-box stepping) */
 	int io_nodes;                 /* nodes of an IO tile: 3 classes + 3 pins per pad */
 	int col0, col_inner;          /* nodes of the x = 0 column, of an inner column */
 	int wpc_x, wpc_y;             /* wires per CHANX / CHANY channel */
@@ -60,32 +80,34 @@ PF_DEV int pf_gen_tile_base(const PfGenDev &G, int x, int y) {
 	return c + G.io_nodes + (y - 1) * PF_GEN_CLB_NODES;
 }
 /* tracks of stagger s among the W/2 direction pairs */
-PF_DEV int pf_gen_groups_with(const PfGenDev &G, int s) { const int g = G.W / 2; return s < g ? (g - 1 - s) / G.L + 1 : 0; }
+PF_DEV int pf_gen_groups_with(const PfGenDev &G, int s) { const int g = G.W / 2; return s < g ? pf_fdiv(g - 1 - s, G.dL) + 1 : 0; }
 /* wires of one channel that start at a position < p (p >= 1) */
 PF_DEV int pf_gen_pref(const PfGenDev &G, int p) {
 	if (p <= 1) return 0;
-	int n = G.W + ((p - 2) / G.L) * G.W;
-	for (int j = 1; j <= (p - 2) % G.L; j++) n += 2 * pf_gen_groups_with(G, j % G.L);
+	const int q = pf_fdiv(p - 2, G.dL), rem = p - 2 - q * G.L;
+	int n = G.W + q * G.W;
+	for (int j = 1; j <= rem; j++) n += 2 * pf_gen_groups_with(G, j);      /* j <= rem < L */
 	return n;
 }
-PF_DEV int pf_gen_seg_start(int p, int s, int L) { const int a = p - ((p - 1 - s) % L + L) % L; return a < 1 ? 1 : a; }
-PF_DEV int pf_gen_seg_end(int p, int s, int L, int P) { const int a = p - ((p - 1 - s) % L + L) % L; const int b = a + L - 1; return b > P ? P : b; }
+/* (p - 1 - s) mod L with p >= 1, 0 <= s < L: p - 1 - s + L is positive */
+PF_DEV int pf_gen_seg_start(const PfGenDev &G, int p, int s) { const int a = p - pf_fmod(p - 1 - s + G.L, G.dL); return a < 1 ? 1 : a; }
+PF_DEV int pf_gen_seg_end(const PfGenDev &G, int p, int s, int P) { const int a = p - pf_fmod(p - 1 - s + G.L, G.dL); const int b = a + G.L - 1; return b > P ? P : b; }
 /* the wire covering position p on track t of a channel: node id, and its span [a, b] */
 PF_DEV int pf_gen_wire_at(const PfGenDev &G, int horiz, int chan, int p, int t, int *a_out, int *b_out) {
-	const int s = (t / 2) % G.L, P = horiz ? G.nx : G.ny;
-	const int a = pf_gen_seg_start(p, s, G.L);
-	const int rank = (a == 1) ? t : 2 * ((t / 2) / G.L) + (t & 1);
+	const int grp = pf_fdiv(t >> 1, G.dL), s = (t >> 1) - grp * G.L, P = horiz ? G.nx : G.ny;
+	const int a = pf_gen_seg_start(G, p, s);
+	const int rank = (a == 1) ? t : 2 * grp + (t & 1);
 	if (a_out) *a_out = a;
-	if (b_out) *b_out = pf_gen_seg_end(p, s, G.L, P);
+	if (b_out) *b_out = pf_gen_seg_end(G, p, s, P);
 	return (horiz ? G.chanx0 + chan * G.wpc_x : G.chany0 + chan * G.wpc_y) + pf_gen_pref(G, a) + rank;
 }
 
 /* does the INC (even) / DEC (odd) wire of track t that covers position pos START there?  (an INC wire is entered at its low end
  * a, a DEC wire at its high end b; segments are clipped at 1 and P) */
 PF_DEV int pf_gen_starts_here(const PfGenDev &G, int pos, int t, int P) {
-	const int s = (t / 2) % G.L;
-	if (t & 1) return pos == P || ((pos - s) % G.L + G.L) % G.L == 0;
-	return pos == 1 || ((pos - 1 - s) % G.L + G.L) % G.L == 0;
+	const int s = pf_fmod(t >> 1, G.dL);
+	if (t & 1) return pos == P || pf_fmod(pos - s + G.L, G.dL) == 0;      /* pos >= 1, s < L: the arguments are positive */
+	return pos == 1 || pf_fmod(pos - 1 - s + G.L, G.dL) == 0;
 }
 
 struct PfGenNode { int type, x0, y0, x1, y1, ptc, ci, cap; float R, C; int horiz, chan, t; /* wires */ int tx, ty, local, clb; /* tile nodes */ };
@@ -97,18 +119,19 @@ PF_DEV PfGenNode pf_gen_decode(const PfGenDev &G, int v) {
 	if (v >= G.chanx0) {
 		const int horiz = v < G.chany0;
 		const int idx0 = horiz ? v - G.chanx0 : v - G.chany0, wpc = horiz ? G.wpc_x : G.wpc_y, P = horiz ? G.nx : G.ny;
-		const int chan = idx0 / wpc;
-		int idx = idx0 % wpc, a, t;
+		const int chan = pf_fdiv(idx0, horiz ? G.dWpcX : G.dWpcY);
+		int idx = idx0 - chan * wpc, a, t;
 		if (idx < G.W) { a = 1; t = idx; }
 		else {
 			idx -= G.W;
-			int q = 2 + (idx / G.W) * G.L;
-			idx %= G.W;
-			for (;; q++) { const int c = 2 * pf_gen_groups_with(G, (q - 1) % G.L); if (idx < c) break; idx -= c; }
+			const int blk = pf_fdiv(idx, G.dW);
+			int q = 2 + blk * G.L;
+			idx -= blk * G.W;
+			for (;; q++) { const int c = 2 * pf_gen_groups_with(G, pf_fmod(q - 1, G.dL)); if (idx < c) break; idx -= c; }
 			a = q;
-			t = 2 * ((idx / 2) * G.L + (a - 1) % G.L) + (idx & 1);
+			t = 2 * ((idx / 2) * G.L + pf_fmod(a - 1, G.dL)) + (idx & 1);
 		}
-		const int b = pf_gen_seg_end(a, (t / 2) % G.L, G.L, P), len = b - a + 1;
+		const int b = pf_gen_seg_end(G, a, pf_fmod(t >> 1, G.dL), P), len = b - a + 1;
 		n.type = horiz ? 4 : 5; n.ci = horiz ? 4 : 5; n.cap = 1; n.ptc = t;
 		n.x0 = horiz ? a : chan; n.x1 = horiz ? b : chan; n.y0 = horiz ? chan : a; n.y1 = horiz ? chan : b;
 		n.R = G.R_metal * len; n.C = G.C_per_tile * len;
@@ -116,16 +139,17 @@ PF_DEV PfGenNode pf_gen_decode(const PfGenDev &G, int v) {
 		return n;
 	}
 	int x, y, local;
-	if (v < G.col0) { x = 0; y = 1 + v / G.io_nodes; local = v % G.io_nodes; }
+	if (v < G.col0) { const int q = pf_fdiv(v, G.dIoNodes); x = 0; y = 1 + q; local = v - q * G.io_nodes; }
 	else {
 		const int u = v - G.col0;
 		if (u < G.nx * G.col_inner) {
-			x = 1 + u / G.col_inner;
-			const int w = u % G.col_inner;
+			const int c = pf_fdiv(u, G.dColInner);
+			x = 1 + c;
+			const int w = u - c * G.col_inner;
 			if (w < G.io_nodes) { y = 0; local = w; }
-			else if (w < G.io_nodes + G.ny * PF_GEN_CLB_NODES) { y = 1 + (w - G.io_nodes) / PF_GEN_CLB_NODES; local = (w - G.io_nodes) % PF_GEN_CLB_NODES; }
+			else if (w < G.io_nodes + G.ny * PF_GEN_CLB_NODES) { const int q = pf_fdiv(w - G.io_nodes, G.dClbNodes); y = 1 + q; local = w - G.io_nodes - q * PF_GEN_CLB_NODES; }
 			else { y = G.ny + 1; local = w - G.io_nodes - G.ny * PF_GEN_CLB_NODES; }
-		} else { x = G.nx + 1; const int w = u - G.nx * G.col_inner; y = 1 + w / G.io_nodes; local = w % G.io_nodes; }
+		} else { x = G.nx + 1; const int w = u - G.nx * G.col_inner; const int q = pf_fdiv(w, G.dIoNodes); y = 1 + q; local = w - q * G.io_nodes; }
 	}
 	n.tx = x; n.ty = y; n.local = local; n.clb = pf_gen_is_clb(G, x, y);
 	n.x0 = n.x1 = x; n.y0 = n.y1 = y;
@@ -159,7 +183,7 @@ PF_DEV int pf_gen_turns(const PfGenDev &G, int horiz, int chan, int q, int t, ui
 	if (base + 1 <= P2) {                         /* an INC wire starting at base + 1 */
 		const int pos = base + 1;
 		for (int k = 0; k < half; k++) {
-			const int t2 = 2 * ((g + qx + qy + k) % half);
+			const int t2 = 2 * pf_fmod(g + qx + qy + k, G.dHalf);
 			if (!pf_gen_starts_here(G, pos, t2, P2)) continue;
 			if (out) out[n] = (uint32_t)pf_gen_wire_at(G, !horiz, pchan, pos, t2, NULL, NULL) | ((uint32_t)PF_GEN_SW_WIRE << G.node_bits);
 			n++;
@@ -169,7 +193,7 @@ PF_DEV int pf_gen_turns(const PfGenDev &G, int horiz, int chan, int q, int t, ui
 	if (base >= 1) {                              /* a DEC wire starting at base (its high end) */
 		const int pos = base;
 		for (int k = 0; k < half; k++) {
-			const int t2 = 2 * ((g + 2 * qx + qy + k) % half) + 1;
+			const int t2 = 2 * pf_fmod(g + 2 * qx + qy + k, G.dHalf) + 1;
 			if (!pf_gen_starts_here(G, pos, t2, P2)) continue;
 			if (out) out[n] = (uint32_t)pf_gen_wire_at(G, !horiz, pchan, pos, t2, NULL, NULL) | ((uint32_t)PF_GEN_SW_WIRE << G.node_bits);
 			n++;
@@ -191,12 +215,12 @@ PF_DEV int pf_gen_cb_tile(const PfGenDev &G, int x, int y, int side, int pos, in
 	}
 	/* the pattern t == (p * 7 + pos + (k * W) / fc_in) % W inverted: d = (t - pos - 7 p) mod W must be one of the fc_in offsets.
 	 * Only the pins that face this side are visited, and d is stepped instead of recomputed. */
-	int d = (t - pos) % G.W;
+	int d = t - pf_fmod(pos, G.dW);               /* (t - pos) mod W, 0 <= t < W */
 	if (d < 0) d += G.W;
-	const int m7 = 7 % G.W;
+	const int m7 = G.m7;
 	if (clb) {
 		for (int q = 0; q < side; q++) { d -= m7; if (d < 0) d += G.W; }
-		const int m28 = 28 % G.W;
+		const int m28 = G.m28;
 		for (int p = side; p < PF_GEN_CLB_PINS; p += 4) {
 			if (!(p >= PF_GEN_CLB_IN && p < PF_GEN_CLB_IN + PF_GEN_CLB_OUT) && G.cb_inv[d] >= 0) {
 				if (out) out[n] = (uint32_t)(pin0 + p) | ((uint32_t)PF_GEN_SW_IPIN << G.node_bits);
@@ -238,7 +262,7 @@ PF_DEV int pf_gen_node_edges(const PfGenDev &G, int v, const PfGenNode &nd, uint
 		const int chan = horiz ? (side == 0 ? y : y - 1) : (side == 1 ? x : x - 1);
 		const int pos = horiz ? x : y, P = horiz ? G.nx : G.ny;
 		if (pos < 1 || pos > P) return 0;
-		int t = (p * 11 + pos * 3) % G.W;
+		int t = pf_fmod(p * 11 + pos * 3, G.dW);
 		for (int k = 0; k < G.W && n < G.fc_out; k++) {
 			if (pf_gen_starts_here(G, pos, t, P)) {
 				if (out) out[n] = (uint32_t)pf_gen_wire_at(G, horiz, chan, pos, t, NULL, NULL) | ((uint32_t)PF_GEN_SW_WIRE << G.node_bits);
