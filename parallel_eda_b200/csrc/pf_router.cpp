@@ -1272,9 +1272,16 @@ static void *host_take(size_t bytes) {
 	if (bytes < 16) bytes = 16;
 	std::lock_guard<std::mutex> lk(g_host_mu);
 	HostBuf *best = NULL;
-	for (HostBuf &b : g_hostbufs)
-		if (!b.in_use && b.cap >= bytes && b.cap <= 2 * bytes + (1 << 20) && (!best || b.cap < best->cap)) best = &b;
+	bool have_class = false;      /* a buffer of this size exists, free or not */
+	for (HostBuf &b : g_hostbufs) {
+		if (b.cap < bytes || b.cap > 2 * bytes + (1 << 20)) continue;
+		have_class = true;
+		if (!b.in_use && (!best || b.cap < best->cap)) best = &b;
+	}
 	if (best) { best->in_use = true; return best->p; }
+	/* ONE pinned buffer per size: pinning 120 MB costs tens of milliseconds (measured 30-160 ms for the arrays of one cfg 4 result),
+	 * so a caller that still holds the previous result gets malloc memory filled through the staging buffer instead (NULL here) */
+	if (have_class) return NULL;
 	const size_t cap = bytes + bytes / 16;
 	void *p = pfb_host_alloc(cap);
 	if (!p) return NULL;
@@ -1322,22 +1329,39 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 	unsigned *d_tt = (unsigned *)pfb_alloc_raw(sizeof(unsigned) * std::max<size_t>(total, 1));
 	out->num_nets = n;
 	pf_result_set_release_hook(host_release);
-	out->trace_ptr = (int32_t *)host_take(sizeof(int32_t) * ((size_t)n + 1));
-	out->trace_node = (int32_t *)host_take(sizeof(int32_t) * std::max<size_t>(total, 1));
-	out->trace_switch = (int16_t *)host_take(sizeof(int16_t) * std::max<size_t>(total, 1));
-	out->net_delay = (float *)host_take(sizeof(float) * (size_t)std::max(r->T, 1));
-	out->occ = (int32_t *)host_take(sizeof(int32_t) * (size_t)r->N);
-	const bool host_ok = out->trace_ptr && out->trace_node && out->trace_switch && out->net_delay && out->occ;
+	/* each array: a pinned buffer of the cache the device copies into directly, or — cache busy / no pinned memory — malloc
+	 * memory filled through the process-wide pinned staging buffer */
+	const size_t b_tn = sizeof(int) * total, b_ts = sizeof(short) * total, b_tt = sizeof(unsigned) * total, b_occ = sizeof(int) * (size_t)r->N;
+	const size_t b_nd = sizeof(float) * (size_t)std::max(r->T, 1);
+	struct Arr { void **out; size_t bytes; const void *dev; bool direct; char *stage; };
+	Arr arr[4] = { { (void **)&out->trace_node, b_tn, d_tn, false, NULL }, { (void **)&out->trace_switch, b_ts, d_ts, false, NULL },
+			{ (void **)&out->occ, b_occ, d_occ, false, NULL }, { (void **)&out->net_delay, b_nd, r->net_delay, false, NULL } };
+	out->trace_ptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 1));
+	size_t stage_bytes = 0;
+	bool host_ok = out->trace_ptr != NULL;
+	for (Arr &a : arr) {
+		*a.out = host_take(std::max<size_t>(a.bytes, 16));
+		a.direct = *a.out != NULL;
+		if (!a.direct) { *a.out = malloc(std::max<size_t>(a.bytes, 16)); stage_bytes += (a.bytes + 255) & ~(size_t)255; }
+		host_ok = host_ok && *a.out != NULL;
+	}
 	unsigned long long h_wl[2] = { 0, 0 };
 	int serial_num = 0;
 	bad = !d_tn || !d_ts || !d_tt || !host_ok;
 	double t_1 = t_0, t_2 = t_0;
 	if (!bad) {
-		const size_t b_tn = sizeof(int) * total, b_ts = sizeof(short) * total, b_tt = sizeof(unsigned) * total, b_occ = sizeof(int) * (size_t)r->N;
-		unsigned *h_tt = (unsigned *)host_take(std::max<size_t>(b_tt, 16));      /* the serial-number terms: scratch of this call */
+		/* the serial-number terms: scratch of this call, after the staged arrays in the staging buffer */
+		char *pin = (char *)pfb_pinned(stage_bytes + b_tt + 1024);
+		std::vector<unsigned> ttv;
+		if (!pin) ttv.resize(std::max<size_t>(total, 1));
+		{
+			char *q = pin;
+			for (Arr &a : arr) if (!a.direct) { a.stage = pin ? q : NULL; if (pin) q += (a.bytes + 255) & ~(size_t)255; }
+		}
+		unsigned *h_tt = pin ? (unsigned *)(pin + stage_bytes) : ttv.data();
 		/* the serial-number terms come first: the running remainder below is sequential by definition and runs on
 		 * a helper thread while the traces and the occupancy cross PCIe */
-		bad = !h_tt || pfb_h2d(d_len, tptr.data(), sizeof(int) * ((size_t)n + 1)) || pfb_zero(r->d_wl, sizeof(unsigned long long) * 2)
+		bad = pfb_h2d(d_len, tptr.data(), sizeof(int) * ((size_t)n + 1)) || pfb_zero(r->d_wl, sizeof(unsigned long long) * 2)
 				|| pfb_launch_build_traces(r->pool[r->cur], r->loc, n, NULL, d_len, d_tn, d_ts, r->d_wl, d_tt, r->ptc, p->nx)
 				|| pfb_d2h(h_tt, d_tt, b_tt);
 		std::thread chain;
@@ -1356,14 +1380,17 @@ extern "C" int pf_get_result(pf_router *r, pf_result *out) {
 				serial_num = sv;
 			});
 			t_1 = now_s();
-			/* straight into the result arrays (pinned): no staging copy */
-			bad = pfb_launch_extract_occ(r->nodes, r->N, d_occ)
-					|| pfb_d2h_async(out->trace_node, d_tn, b_tn) || pfb_d2h_async(out->trace_switch, d_ts, b_ts) || pfb_d2h_async(out->occ, d_occ, b_occ)
-					|| pfb_d2h_async(out->net_delay, r->net_delay, sizeof(float) * (size_t)r->T) || pfb_d2h(h_wl, r->d_wl, sizeof(h_wl));
+			bad = pfb_launch_extract_occ(r->nodes, r->N, d_occ) != 0;
+			for (Arr &a : arr) if (!bad) bad = pfb_d2h_async(a.direct || !a.stage ? *a.out : (void *)a.stage, a.dev, a.bytes) != 0;
+			if (!bad) bad = pfb_d2h(h_wl, r->d_wl, sizeof(h_wl)) != 0;
+			for (Arr &a : arr)
+				if (!bad && !a.direct && a.stage) {
+					char *dst = (char *)*a.out; const char *src = a.stage;
+					parallel_for((long long)a.bytes, [&](long long lo, long long hi) { memcpy(dst + lo, src + lo, (size_t)(hi - lo)); });
+				}
 			t_2 = now_s();
 			chain.join();
 		}
-		if (h_tt) host_release(h_tt);
 		r->d2h_bytes += (int64_t)(b_tn + b_ts + b_tt + b_occ) + (int64_t)sizeof(int) * n + (int64_t)sizeof(float) * r->T;
 	}
 	pfb_free(d_len); pfb_free(d_tn); pfb_free(d_ts); pfb_free(d_tt);

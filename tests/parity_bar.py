@@ -25,7 +25,7 @@ WL_RUN_TOL = 1.12      # any single run of a small fixture
 TD_RUN_TOL = 1.05
 BIG_WL_TOL = 1.05      # >= 10 k nets, one run (measured x1.031 / x1.038 on the 11 k / 32 k LUT circuits, x1.001 on 50 k 4-pin nets)
 ONE_WARP_WL = 1.03
-RUNS = 3
+RUNS = 5
 
 _LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_measured.jsonl")
 
