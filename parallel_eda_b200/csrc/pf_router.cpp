@@ -1272,16 +1272,18 @@ static void *host_take(size_t bytes) {
 	if (bytes < 16) bytes = 16;
 	std::lock_guard<std::mutex> lk(g_host_mu);
 	HostBuf *best = NULL;
-	bool have_class = false;      /* a buffer of this size exists, free or not */
+	int have_class = 0;           /* buffers of this size that exist, free or not */
 	for (HostBuf &b : g_hostbufs) {
 		if (b.cap < bytes || b.cap > 2 * bytes + (1 << 20)) continue;
-		have_class = true;
+		have_class++;
 		if (!b.in_use && (!best || b.cap < best->cap)) best = &b;
 	}
 	if (best) { best->in_use = true; return best->p; }
-	/* ONE pinned buffer per size: pinning 120 MB costs tens of milliseconds (measured 30-160 ms for the arrays of one cfg 4 result),
-	 * so a caller that still holds the previous result gets malloc memory filled through the staging buffer instead (NULL here) */
-	if (have_class) return NULL;
+	/* at most TWO pinned buffers per size (a caller that reads result k while it asks for result k + 1 alternates between them):
+	 * pinning 120 MB costs tens of milliseconds (measured 30-160 ms for the arrays of one cfg 4 result), so a caller that holds
+	 * more results than that gets malloc memory filled through the staging buffer instead (NULL here) — bounded pinned memory,
+	 * and the pinning cost is paid twice per size at most */
+	if (have_class >= 2) return NULL;
 	const size_t cap = bytes + bytes / 16;
 	void *p = pfb_host_alloc(cap);
 	if (!p) return NULL;
