@@ -468,38 +468,56 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		 * every rank computes the same partition from the same problem. */
 		std::vector<double> share((size_t)c.nranks, 1.0 / c.nranks), load((size_t)c.nranks, 0.0), load_cut((size_t)c.nranks, 0.0), best_share;
 		std::vector<int> cut((size_t)c.nranks + 1, 0);
-		/* the partition the shares give: owner[], cut_net[], load[]; returns the heaviest rank's load relative to the mean */
-		auto partition = [&]() {
+		/* the nets in box-centre order, packed (the correction rounds below read them a dozen times: 25 ms per router on cfg 4
+		 * when every round walked net_bb / net_ptr through the permutation) */
+		struct BoxF { int net; short xmin, xmax; int fan; };
+		std::vector<BoxF> bx(byx.size());
+		for (size_t k = 0; k < byx.size(); k++) {
+			const int i = byx[k];
+			bx[k] = BoxF{ i, (short)p->net_bb[4 * i], (short)p->net_bb[4 * i + 1], p->net_ptr[i + 1] - p->net_ptr[i] };
+		}
+		/* the partition the shares give, over every `step`-th net (the correction rounds look at a sample of <= 32 k nets, whose
+		 * loads are within a per cent of the full ones; the final call, step 1, also writes owner[] and cut_net[]);
+		 * returns the heaviest rank's load relative to the mean */
+		auto partition = [&](size_t step, bool write) {
 			/* cut[k] (k = 1..nranks-1): stripe k-1 holds boxes with xmax <= cut[k], stripe k boxes with xmin >= cut[k] + lmax */
-			long long acc_f = 0;
+			long long acc_f = 0, tot = 0;
+			for (size_t k = 0; k < bx.size(); k += step) tot += bx[k].fan;
 			int s = 0;
-			double upto = share[0] * (double)total_f;
+			double upto = share[0] * (double)tot;
 			for (int k = 0; k <= c.nranks; k++) cut[(size_t)k] = p->nx + 2;
-			for (int i : byx) {
-				while (s < c.nranks - 1 && (double)acc_f >= upto) { s++; cut[(size_t)s] = (p->net_bb[4 * i] + p->net_bb[4 * i + 1]) / 2; upto += share[(size_t)s] * (double)total_f; }
-				owner[i] = s;
-				acc_f += p->net_ptr[i + 1] - p->net_ptr[i];
+			std::vector<size_t> first((size_t)c.nranks + 1, bx.size());      /* first sampled position of every stripe */
+			first[0] = 0;
+			for (size_t k = 0; k < bx.size(); k += step) {
+				while (s < c.nranks - 1 && (double)acc_f >= upto) { s++; first[(size_t)s] = k; cut[(size_t)s] = (bx[k].xmin + bx[k].xmax) / 2; upto += share[(size_t)s] * (double)tot; }
+				acc_f += bx[k].fan;
 			}
+			for (int k = c.nranks - 1; k > 0; k--) if (first[(size_t)k] > first[(size_t)k + 1]) first[(size_t)k] = first[(size_t)k + 1];
 			std::fill(load.begin(), load.end(), 0.0);
 			std::fill(load_cut.begin(), load_cut.end(), 0.0);
-			for (int i : byx) {
-				const int st = owner[i], xmin = p->net_bb[4 * i], xmax = p->net_bb[4 * i + 1];
-				const bool left_ok = st == 0 || xmin >= cut[(size_t)st] + lmax;
-				const bool right_ok = st == c.nranks - 1 || xmax <= cut[(size_t)st + 1];
-				cut_net[i] = (left_ok && right_ok) ? 0 : 1;
-				if (cut_net[i]) owner[i] = right_ok ? st : st + 1;   /* the rank that owns the violated cut (cut k belongs to rank k).  Sharing a cut's
-				                                                      * nets between its two neighbours was tried: two ranks then route overlapping nets on
-				                                                      * stale views of each other, and on a small fabric the negotiation oscillates for ever */
-				(cut_net[i] ? load_cut : load)[(size_t)owner[i]] += (double)(p->net_ptr[i + 1] - p->net_ptr[i]);
+			for (int st = 0; st < c.nranks; st++) {
+				for (size_t k = first[(size_t)st]; k < first[(size_t)st + 1]; k += step) {
+					const int xmin = bx[k].xmin, xmax = bx[k].xmax;
+					const bool left_ok = st == 0 || xmin >= cut[(size_t)st] + lmax;
+					const bool right_ok = st == c.nranks - 1 || xmax <= cut[(size_t)st + 1];
+					const bool is_cut = !(left_ok && right_ok);
+					/* a cut net goes to the rank that owns the violated cut (cut k belongs to rank k).  Sharing a cut's nets between its two
+					 * neighbours was tried: two ranks then route overlapping nets on stale views of each other, and on a small fabric the
+					 * negotiation oscillates for ever */
+					const int own = is_cut ? (right_ok ? st : st + 1) : st;
+					if (write) { owner[(size_t)bx[k].net] = own; cut_net[(size_t)bx[k].net] = is_cut ? 1 : 0; }
+					(is_cut ? load_cut : load)[(size_t)own] += (double)bx[k].fan;
+				}
 			}
 			/* an iteration is two phases with an exchange after each: its length is the longest interior phase plus the longest cut phase */
 			double wi = 0.0, wc = 0.0;
 			for (int k = 0; k < c.nranks; k++) { wi = std::max(wi, load[(size_t)k]); wc = std::max(wc, load_cut[(size_t)k]); }
-			return (wi + wc) * c.nranks / std::max(1.0, (double)total_f);
+			return (wi + wc) * c.nranks / std::max(1.0, (double)tot);
 		};
+		const size_t sample_step = std::max<size_t>(1, bx.size() / 32768);
 		double best = 1e30;
 		for (int round = 0; round < 12; round++) {
-			const double worst = partition();
+			const double worst = partition(sample_step, false);
 			if (worst < best) { best = worst; best_share = share; }
 			double sum = 0.0, mean_i = 0.0;
 			for (int k = 0; k < c.nranks; k++) mean_i += load[(size_t)k] / c.nranks;
@@ -510,7 +528,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			}
 			for (int k = 0; k < c.nranks; k++) share[(size_t)k] /= sum;
 		}
-		if (share != best_share) { share = best_share; partition(); }
+		share = best_share;
+		partition(1, true);
 		if (c.verbose) {
 			fprintf(stderr, "pf_router: stripes of rank 0..%d: fanout routed (interior + across the rank's cut)", c.nranks - 1);
 			for (int k = 0; k < c.nranks; k++) fprintf(stderr, " %.0f+%.0f", load[(size_t)k], load_cut[(size_t)k]);

@@ -67,11 +67,19 @@ class Comm:
         """Bootstrap of the transport inside the library (pf_comm_export / pf_comm_init): all-gather the ranks' 128-byte
         handles once; afterwards the occupancy exchange is device-side (peer memory over NVLink) and this class is no
         longer on the path."""
+        import time
+        t0 = time.perf_counter()
         mine = torch.frombuffer(bytearray(r.comm_export()), dtype=torch.uint8).to(self.device)
         every = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=self.device)
         dist.all_gather_into_tensor(every, mine)
-        r.comm_init(bytes(every.cpu().numpy().tobytes()))
+        blob = bytes(every.cpu().numpy().tobytes())
+        t1 = time.perf_counter()
+        r.comm_init(blob)
+        t2 = time.perf_counter()
         dist.barrier()                                    # every rank has mapped every region before anybody publishes
+        if os.environ.get("PF_COMM_DEBUG"):
+            print("rank %d connect: export + all-gather %.2f ms, pf_comm_init %.2f ms, barrier %.2f ms" % (
+                self.rank, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3), flush=True)
 
     def sync_occupancy(self, r) -> int:
         """All ranks end up with the same rr-node occupancy: all-gather every rank's event log of the last
