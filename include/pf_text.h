@@ -17,8 +17,10 @@
  * pf_names, exported by the reference-side adapter next to the problem or made up
  * by the generator for synthetic fabrics (pf_names_synthetic).
  *
- * The packed-netlist reader (.net, vpr/SRC/base/read_netlist.c) is NOT here: it instantiates the
- * architecture's pb_type hierarchy, i.e. it needs libarchfpga, which stays the reference's.
+ *   pf_net_read        read_netlist       vpr/SRC/base/read_netlist.c:74-244,      the packed netlist as place and
+ *                      load_external_nets_and_cb                     :836-984    route see it — block[] and clb_net[] —
+ *                                                                                  without the architecture: the file's
+ *                                                                                  own port lists give the pin numbering
  *
  * Plain C host code, no CUDA; all functions return PF_OK or a negative PF_E* code (pf_file.h).
  */
@@ -75,7 +77,40 @@ int pf_place_write(const char *path, const char *net_file, const char *arch_file
  * PF_EFORMAT.  *placed = number of blocks the file positioned. */
 int pf_place_read(const char *path, const char *net_file, const char *arch_file, pf_names *n, int *placed);
 
-/* description of the last PF_EFORMAT / PF_EINVAL of this thread's pf_route_read / pf_place_read */
+/* The packed netlist (.net) as read_netlist leaves it for place and route: block[] and clb_net[] (vpr_types.h:451, :521).
+ * The reference gets there by instantiating the architecture's pb_type hierarchy; this reader needs only the file: the
+ * <inputs> / <outputs> / <clocks> sections of a complex block list every port in pb_type order ("open" = unused pin), which is
+ * the block's pin numbering (inputs, outputs, clocks: the order load_external_nets_and_cb asserts, read_netlist.c:850), and
+ * the net on an output pin is found by following "child[i].port[b]->interconnect" down the nested blocks to a primitive.
+ * Nets are numbered in the order of their first appearance (add_net_to_hash, :594), the driver is terminal 0 and the sinks
+ * follow in block / pin order (:934-965).  is_global: the reference takes it from the architecture (type->is_global_pin);
+ * here pins listed under <clocks> are global — inputs an architecture declares is_non_clock_global are not recognisable
+ * from the file.  What is NOT rebuilt: the pb tree inside the clusters (t_pb, local nets, the intra-cluster rr graph) — the
+ * packer's and the timing graph's business, not the router's. */
+typedef struct pf_netlist {
+	int32_t num_blocks;
+	int32_t *block_name_ptr;   /* [num_blocks+1]; block[i].name = block_name_chars[ptr[i] .. ptr[i+1]) (no NUL) */
+	char *block_name_chars;
+	int32_t *block_type_ptr;   /* [num_blocks+1]; block[i].type->name ("clb", "io", "mult", ...) */
+	char *block_type_chars;
+	int32_t *block_pin_ptr;    /* [num_blocks+1]; pins of ONE instance of the type (type->num_pins / type->capacity) */
+	int32_t *block_pin_net;    /* block[i].nets[pin]: net index or PF_OPEN */
+	uint8_t *block_pin_kind;   /* 0 input (RECEIVER), 1 output (DRIVER), 2 clock (RECEIVER, global) */
+	int32_t num_nets;
+	int32_t *net_name_ptr;     /* [num_nets+1] */
+	char *net_name_chars;
+	int32_t *net_ptr;          /* [num_nets+1]; terminals of net i: net_ptr[i] (the driver) .. net_ptr[i+1] */
+	int32_t *net_block;        /* clb_net[i].node_block[k] */
+	int32_t *net_block_pin;    /* clb_net[i].node_block_pin[k] */
+	uint8_t *net_is_global;    /* clb_net[i].is_global */
+} pf_netlist;
+/* PF_EFORMAT (text in pf_text_error(), with the reference's wording where read_netlist.c has one): malformed XML, a top-level
+ * element that is not FPGA_packed_netlist[0], an output that cannot be followed to a primitive, a net with two drivers or
+ * none, a net on both clock and non-clock pins. */
+int pf_net_read(const char *path, pf_netlist *out);
+void pf_netlist_free(pf_netlist *nl);
+
+/* description of the last PF_EFORMAT / PF_EINVAL of this thread's pf_route_read / pf_place_read / pf_net_read */
 const char *pf_text_error(void);
 
 #ifdef __cplusplus

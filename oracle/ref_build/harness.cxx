@@ -12,6 +12,7 @@
  *        env PF_DUMP_RESULT=<file>   write traces / delays / per-iteration criticalities
  *        env PF_DUMP_TGRAPH=<file>   write the flat timing graph (pf_timing_graph) do_timing_analysis runs on
  *        env PF_DUMP_NAMES=<file>    write net / block names, IO tiles, global-net pins (pf_names, include/pf_text.h)
+ *        env PF_DUMP_NETLIST=<file>  write block[] / clb_net[] as read_netlist left them (text; golden of pf_net_read)
  *        env PF_ADAPTER_ROUTE_FILE=<file>  also write the .route file through integration/vpr_text_adapter.cxx
  *        env PF_DUMP_AT_SUCCESS=1    write PF_DUMP_RESULT as soon as the routing is legal (before the reference's DEBUG delay check)
  *        env PF_DUMP_STA=<file>      write every (net_delay in, timing_criticality out, cpd) of the run's STA calls
@@ -263,6 +264,33 @@ static void export_names(const char *path) {
 	fprintf(stderr, "PF_REF wrote names %s: %d nets, %d blocks (rc %d)\n", path, num_nets, num_blocks, rc);
 }
 
+/* PF_DUMP_NETLIST=<file>: block[] and clb_net[] as read_netlist (base/read_netlist.c:74) left them — the golden for the
+ * native .net reader (pf_net_read, include/pf_text.h); the hook runs after placement, so post_place_sync's shift of the pins of
+ * blocks at z > 0 (base/place_and_route.c:888-920) is taken out again.  Text: "b <name> <type> <pins per instance> <net per pin...>" per
+ * block, "n <name> <is_global> <terminals> <block>:<pin>..." per net (driver first). */
+static void export_netlist(const char *path) {
+	FILE *f = fopen(path, "w");
+	if (!f) { fprintf(stderr, "PF_REF cannot write %s\n", path); exit(2); }
+	fprintf(f, "PFNETLIST 1\nblocks %d\n", num_blocks);
+	for (int i = 0; i < num_blocks; i++) {
+		const int per = block[i].type->num_pins / block[i].type->capacity;
+		fprintf(f, "b %s %s %d", block[i].name, block[i].type->name, per);
+		for (int k = 0; k < per; k++) fprintf(f, " %d", block[i].nets[k + block[i].z * per]);      /* post_place_sync undone */
+		fprintf(f, "\n");
+	}
+	fprintf(f, "nets %d\n", num_nets);
+	for (int i = 0; i < num_nets; i++) {
+		fprintf(f, "n %s %d %d", clb_net[i].name, clb_net[i].is_global ? 1 : 0, clb_net[i].num_sinks + 1);
+		for (int k = 0; k <= clb_net[i].num_sinks; k++) {
+			const int b = clb_net[i].node_block[k];
+			fprintf(f, " %d:%d", b, clb_net[i].node_block_pin[k] - block[b].z * (block[b].type->num_pins / block[b].type->capacity));
+		}
+		fprintf(f, "\n");
+	}
+	fclose(f);
+	fprintf(stderr, "PF_REF wrote netlist %s: %d blocks, %d nets\n", path, num_blocks, num_nets);
+}
+
 /* base/place_and_route.c is compiled with -Dprint_route=pf_hook_print_route: the reference's own writer runs as
  * always; with PF_ADAPTER_ROUTE_FILE=<file> the adapter's native writer writes the same routing next to it */
 void pf_hook_print_route(char *route_file) {
@@ -390,6 +418,7 @@ boolean pf_hook_try_timing_driven_route(struct s_router_opts router_opts, float 
 	const char *dp = getenv("PF_DUMP_PROBLEM"), *dr = getenv("PF_DUMP_RESULT");
 	if (dp) export_problem(dp, router_opts, timing_analysis_enabled, clb_opins_used_locally);
 	if (getenv("PF_DUMP_NAMES") && !g_inject) export_names(getenv("PF_DUMP_NAMES"));
+	if (getenv("PF_DUMP_NETLIST") && !g_inject) export_netlist(getenv("PF_DUMP_NETLIST"));
 	build_net_ptr();
 	g_iter = 0; g_stats.clear(); g_crit.clear(); g_iter_time.clear();
 	g_sta_delay.clear(); g_sta_crit.clear(); g_sta_cpd.clear(); g_sta_seconds = 0;

@@ -823,3 +823,322 @@ done:
 	free(data); free(table);
 	return rc;
 }
+
+/* ------------------------------------------------------------------ pf_net_read: the packed netlist (.net)
+ * What read_netlist (vpr/SRC/base/read_netlist.c:74-244) leaves behind for place and route: block[] (name, type, the net on
+ * every pin) and clb_net[] (name, driver + sinks as (block, pin), is_global).  The reference instantiates the architecture's
+ * pb_type hierarchy to get there (processComplexBlock :246, processPb :362, processPorts :610) and reads the nets on a
+ * cluster's output pins out of the cluster's internal rr graph (load_external_nets_and_cb :836-984).  Here the file is its
+ * own description: the <inputs> / <outputs> / <clocks> sections of a top-level block list every port in pb_type order with
+ * "open" for unused pins (output_clustering.c), which IS the pin numbering (inputs, outputs, clocks — the order
+ * load_external_nets_and_cb asserts, :850), and an output pin "child[i].port[b]->interconnect" is followed down the nested
+ * <block> elements to the primitive whose port holds the net's name. */
+typedef struct { const char *s; int n; } nl_str;
+typedef struct { int pb, kind; nl_str name; int first_tok, ntok; } nl_port;
+typedef struct { int parent, first_child, last_child, next_sibling; nl_str name, type; int index, first_port, nports, line; } nl_pb;
+typedef struct {
+	nl_pb *pb; int npb, cap_pb;
+	nl_port *port; int nport, cap_port;
+	nl_str *tok; int ntok, cap_tok;
+	nl_str *clk; int nclk, cap_clk;          /* <clocks> of the FPGA_packed_netlist element */
+} nl_doc;
+
+static int nl_grow(void **v, int *cap, int need, size_t elem) {
+	if (need <= *cap) return 0;
+	int nc = *cap ? *cap * 2 : 1024;
+	while (nc < need) nc *= 2;
+	void *nv = realloc(*v, (size_t)nc * elem);
+	if (!nv) return PF_ENOMEM;
+	*v = nv; *cap = nc;
+	return 0;
+}
+static int nl_eq(nl_str a, const char *s, int n) { return a.n == n && memcmp(a.s, s, (size_t)n) == 0; }
+static int nl_is_open(nl_str a) { return nl_eq(a, "open", 4); }
+/* attribute value inside a tag: name="value" */
+static int nl_attr(const char *tag, const char *tag_end, const char *name, nl_str *out) {
+	size_t ln = strlen(name);
+	const char *c = tag;
+	while (c + ln + 2 < tag_end) {
+		if ((c == tag || c[-1] == ' ' || c[-1] == '\t' || c[-1] == '\n') && memcmp(c, name, ln) == 0 && c[ln] == '=' && c[ln + 1] == '"') {
+			const char *v = c + ln + 2, *e = (const char *)memchr(v, '"', (size_t)(tag_end - v));
+			if (!e) return 0;
+			out->s = v; out->n = (int)(e - v);
+			return 1;
+		}
+		c++;
+	}
+	return 0;
+}
+/* "type[index]" */
+static int nl_instance(nl_str in, nl_str *type, int *index) {
+	int k = in.n - 1;
+	long v;
+	const char *c;
+	if (k < 2 || in.s[k] != ']') return 0;
+	while (k > 0 && in.s[k] != '[') k--;
+	if (k <= 0) return 0;
+	c = in.s + k + 1;
+	if (!scan_int(&c, &v) || c != in.s + in.n - 1 || v < 0 || v > 0x7fffffff) return 0;
+	type->s = in.s; type->n = k; *index = (int)v;
+	return 1;
+}
+static nl_port *nl_find_port(nl_doc *d, int pb, int want_out, const char *name, int n) {
+	for (int k = 0; k < d->pb[pb].nports; k++) {
+		nl_port *q = &d->port[d->pb[pb].first_port + k];
+		if ((q->kind == 1) == (want_out != 0) && nl_eq(q->name, name, n)) return q;
+	}
+	return NULL;
+}
+/* The net on the pin that `t` names, read in the context of block `ctx` (the element whose port, or whose child's port, holds
+ * the token): "child[i].port[b]->ic" is an output of a child of ctx; "type.port[b]->ic" is an input of ctx itself, whose own
+ * token is read in the context of ctx's parent.  A token without "->" is a net name (primitive outputs, cluster inputs). */
+static int nl_resolve(nl_doc *d, int ctx, nl_str t, nl_str *net, int depth, int *err_line) {
+	for (;;) {
+		const char *arrow = NULL, *dot, *br, *c;
+		long bit;
+		nl_str inst, type, pname;
+		int index = -1, has_index;
+		nl_port *q;
+		for (int k = 0; k + 1 < t.n; k++) if (t.s[k] == '-' && t.s[k + 1] == '>') { arrow = t.s + k; break; }
+		if (!arrow) { *net = t; return 0; }
+		if (++depth > 256) { *err_line = d->pb[ctx].line; return -1; }
+		dot = (const char *)memchr(t.s, '.', (size_t)(arrow - t.s));
+		if (!dot) { *err_line = d->pb[ctx].line; return -1; }
+		inst.s = t.s; inst.n = (int)(dot - t.s);
+		br = (const char *)memchr(dot, '[', (size_t)(arrow - dot));
+		if (!br) { *err_line = d->pb[ctx].line; return -1; }
+		pname.s = dot + 1; pname.n = (int)(br - dot - 1);
+		c = br + 1;
+		if (!scan_int(&c, &bit) || *c != ']' || bit < 0) { *err_line = d->pb[ctx].line; return -1; }
+		has_index = nl_instance(inst, &type, &index);
+		if (has_index) {
+			int ch = d->pb[ctx].first_child;
+			while (ch >= 0 && !(d->pb[ch].index == index && nl_eq(d->pb[ch].type, type.s, type.n))) ch = d->pb[ch].next_sibling;
+			if (ch < 0) { *err_line = d->pb[ctx].line; return -1; }
+			q = nl_find_port(d, ch, 1, pname.s, pname.n);
+			if (!q || bit >= q->ntok) { *err_line = d->pb[ch].line; return -1; }
+			t = d->tok[q->first_tok + (int)bit];
+			ctx = ch;
+		} else {
+			if (!nl_eq(d->pb[ctx].type, inst.s, inst.n)) { *err_line = d->pb[ctx].line; return -1; }
+			q = nl_find_port(d, ctx, 0, pname.s, pname.n);
+			if (!q || bit >= q->ntok) { *err_line = d->pb[ctx].line; return -1; }
+			t = d->tok[q->first_tok + (int)bit];
+			if (d->pb[ctx].parent <= 0) { *net = t; return 0; }      /* a cluster input: the token is the net */
+			ctx = d->pb[ctx].parent;
+		}
+	}
+}
+
+void pf_netlist_free(pf_netlist *nl) {
+	if (!nl) return;
+	free(nl->block_name_ptr); free(nl->block_name_chars); free(nl->block_type_ptr); free(nl->block_type_chars);
+	free(nl->block_pin_ptr); free(nl->block_pin_net); free(nl->block_pin_kind);
+	free(nl->net_name_ptr); free(nl->net_name_chars); free(nl->net_ptr); free(nl->net_block); free(nl->net_block_pin); free(nl->net_is_global);
+	memset(nl, 0, sizeof(*nl));
+}
+
+int pf_net_read(const char *path, pf_netlist *out) {
+	char *data = NULL;
+	size_t len = 0;
+	nl_doc d;
+	int rc, line = 1, sp = 0, cap_stack = 0, *stack = NULL, cur_kind = -1, cur_port = -1, root = -1;
+	const char *p, *end;
+	int32_t *pin_net = NULL, *table = NULL, *count = NULL, *fill = NULL;
+	nl_str *net_names = NULL;
+	int nnets = 0, cap_nets = 0, nblocks = 0, npins = 0, err_line = 0;
+	size_t tcap = 0, tmask = 0;
+	g_err[0] = 0;
+	memset(&d, 0, sizeof(d));
+	if (!path || !out) return fail(PF_EINVAL, "null argument");
+	memset(out, 0, sizeof(*out));
+	if ((rc = slurp(path, &data, &len)) != PF_OK) return rc;
+	p = data; end = data + len;
+#define NL_FAIL(code, ...) do { rc = fail(code, __VA_ARGS__); goto done; } while (0)
+	/* ---- pass 1: the element tree */
+	while (p < end) {
+		if (*p == '\n') { line++; p++; continue; }
+		if (*p == ' ' || *p == '\t' || *p == '\r') { p++; continue; }
+		if (*p == '<') {
+			const char *te = (const char *)memchr(p, '>', (size_t)(end - p)), *nm = p + 1, *ne;
+			int closing = 0, selfclose;
+			if (!te) NL_FAIL(PF_EFORMAT, "%s:%d: unterminated tag", path, line);
+			if (p[1] == '?' || p[1] == '!') { for (const char *c = p; c < te; c++) if (*c == '\n') line++; p = te + 1; continue; }
+			if (*nm == '/') { closing = 1; nm++; }
+			selfclose = te > p && te[-1] == '/';
+			ne = nm;
+			while (ne < te && *ne != ' ' && *ne != '\t' && *ne != '\n' && *ne != '/' ) ne++;
+			int tl = (int)(ne - nm);
+			if (tl == 5 && memcmp(nm, "block", 5) == 0) {
+				if (closing) {
+					if (sp == 0) NL_FAIL(PF_EFORMAT, "%s:%d: </block> without <block>", path, line);
+					sp--;
+				} else {
+					nl_str name, inst;
+					nl_pb *b;
+					if (!nl_attr(ne, te, "name", &name) || !nl_attr(ne, te, "instance", &inst)) NL_FAIL(PF_EFORMAT, "%s:%d: <block> needs name and instance", path, line);
+					if (nl_grow((void **)&d.pb, &d.cap_pb, d.npb + 1, sizeof(nl_pb))) NL_FAIL(PF_ENOMEM, "out of memory");
+					b = &d.pb[d.npb];
+					memset(b, 0, sizeof(*b));
+					b->parent = sp ? stack[sp - 1] : -1; b->first_child = b->last_child = b->next_sibling = -1;
+					b->name = name; b->line = line; b->first_port = d.nport;
+					if (!nl_instance(inst, &b->type, &b->index)) NL_FAIL(PF_EFORMAT, "%s:%d: instance \"%.*s\" is not type[index]", path, line, inst.n, inst.s);
+					if (sp == 0) {
+						/* read_netlist.c:101-108 */
+						if (root >= 0) NL_FAIL(PF_EFORMAT, "%s:%d: second top-level element", path, line);
+						if (!nl_eq(inst, "FPGA_packed_netlist[0]", 22)) NL_FAIL(PF_EFORMAT, "[Line %d] Expected instance to be \"FPGA_packed_netlist[0]\", found %.*s.", line, inst.n, inst.s);
+						root = d.npb;
+					} else {
+						nl_pb *par = &d.pb[stack[sp - 1]];
+						if (par->last_child >= 0) d.pb[par->last_child].next_sibling = d.npb; else par->first_child = d.npb;
+						par->last_child = d.npb;
+					}
+					if (!selfclose) {
+						if (nl_grow((void **)&stack, &cap_stack, sp + 1, sizeof(int))) NL_FAIL(PF_ENOMEM, "out of memory");
+						stack[sp++] = d.npb;
+					}
+					d.npb++;
+				}
+				cur_kind = -1; cur_port = -1;
+			} else if ((tl == 6 && memcmp(nm, "inputs", 6) == 0) || (tl == 7 && memcmp(nm, "outputs", 7) == 0) || (tl == 6 && memcmp(nm, "clocks", 6) == 0)) {
+				cur_kind = (closing || selfclose) ? -1 : (nm[0] == 'i' ? 0 : nm[0] == 'o' ? 1 : 2);
+				cur_port = -1;
+			} else if (tl == 4 && memcmp(nm, "port", 4) == 0) {
+				if (closing) cur_port = -1;
+				else {
+					nl_port *q;
+					if (sp == 0 || cur_kind < 0) NL_FAIL(PF_EFORMAT, "%s:%d: <port> outside <inputs> / <outputs> / <clocks>", path, line);
+					if (nl_grow((void **)&d.port, &d.cap_port, d.nport + 1, sizeof(nl_port))) NL_FAIL(PF_ENOMEM, "out of memory");
+					q = &d.port[d.nport];
+					q->pb = stack[sp - 1]; q->kind = cur_kind; q->first_tok = d.ntok; q->ntok = 0;
+					if (!nl_attr(ne, te, "name", &q->name)) NL_FAIL(PF_EFORMAT, "%s:%d: <port> needs a name", path, line);
+					if (d.pb[q->pb].first_port + d.pb[q->pb].nports != d.nport) NL_FAIL(PF_EFORMAT, "%s:%d: ports of block \"%.*s\" are interleaved with a child block", path, line, d.pb[q->pb].name.n, d.pb[q->pb].name.s);
+					d.pb[q->pb].nports++;
+					cur_port = selfclose ? -1 : d.nport;
+					d.nport++;
+				}
+			}
+			for (const char *c = p; c < te; c++) if (*c == '\n') line++;
+			p = te + 1;
+			continue;
+		}
+		{	/* a text token */
+			const char *b = p;
+			nl_str t;
+			while (p < end && *p != ' ' && *p != '\t' && *p != '\n' && *p != '\r' && *p != '<') p++;
+			t.s = b; t.n = (int)(p - b);
+			if (cur_port >= 0) {
+				if (nl_grow((void **)&d.tok, &d.cap_tok, d.ntok + 1, sizeof(nl_str))) NL_FAIL(PF_ENOMEM, "out of memory");
+				d.tok[d.ntok++] = t; d.port[cur_port].ntok++;
+			} else if (sp == 1 && cur_kind == 2) {
+				if (nl_grow((void **)&d.clk, &d.cap_clk, d.nclk + 1, sizeof(nl_str))) NL_FAIL(PF_ENOMEM, "out of memory");
+				d.clk[d.nclk++] = t;
+			}
+		}
+	}
+	if (root < 0) NL_FAIL(PF_EFORMAT, "%s: no FPGA_packed_netlist element", path);
+	if (sp != 0) NL_FAIL(PF_EFORMAT, "%s: <block> \"%.*s\" (line %d) is not closed", path, d.pb[stack[sp - 1]].name.n, d.pb[stack[sp - 1]].name.s, d.pb[stack[sp - 1]].line);
+	/* ---- pass 2: the net on every pin of every complex block, in pin order (inputs, outputs, clocks) */
+	for (int b = d.pb[root].first_child; b >= 0; b = d.pb[b].next_sibling) {
+		nblocks++;
+		for (int k = 0; k < d.pb[b].nports; k++) npins += d.port[d.pb[b].first_port + k].ntok;
+	}
+	out->num_blocks = nblocks;
+	out->block_name_ptr = (int32_t *)calloc((size_t)nblocks + 1, sizeof(int32_t)); out->block_type_ptr = (int32_t *)calloc((size_t)nblocks + 1, sizeof(int32_t));
+	out->block_pin_ptr = (int32_t *)calloc((size_t)nblocks + 1, sizeof(int32_t));
+	out->block_pin_net = (int32_t *)malloc(sizeof(int32_t) * (size_t)(npins > 0 ? npins : 1)); out->block_pin_kind = (uint8_t *)malloc((size_t)(npins > 0 ? npins : 1));
+	for (tcap = 1024; tcap < 4 * (size_t)npins + 16; tcap *= 2) {}
+	tmask = tcap - 1;
+	table = (int32_t *)malloc(sizeof(int32_t) * tcap);
+	if (!out->block_name_ptr || !out->block_type_ptr || !out->block_pin_ptr || !out->block_pin_net || !out->block_pin_kind || !table) NL_FAIL(PF_ENOMEM, "out of memory");
+	memset(table, 0xff, sizeof(int32_t) * tcap);
+	pin_net = out->block_pin_net;
+	{
+		int ib = 0, at = 0;
+		size_t name_bytes = 0, type_bytes = 0;
+		for (int b = d.pb[root].first_child; b >= 0; b = d.pb[b].next_sibling, ib++) {
+			name_bytes += (size_t)d.pb[b].name.n; type_bytes += (size_t)d.pb[b].type.n;
+			out->block_name_ptr[ib + 1] = (int32_t)name_bytes; out->block_type_ptr[ib + 1] = (int32_t)type_bytes;
+			for (int kind = 0; kind < 3; kind++)
+				for (int k = 0; k < d.pb[b].nports; k++) {
+					nl_port *q = &d.port[d.pb[b].first_port + k];
+					if (q->kind != kind) continue;
+					for (int j = 0; j < q->ntok; j++, at++) {
+						nl_str net = d.tok[q->first_tok + j];
+						out->block_pin_kind[at] = (uint8_t)kind;
+						if (kind == 1 && nl_resolve(&d, b, net, &net, 0, &err_line) != 0)
+							NL_FAIL(PF_EFORMAT, "%s:%d: cannot follow output %.*s[%d] of block \"%.*s\" to a primitive", path, err_line, q->name.n, q->name.s, j, d.pb[b].name.n, d.pb[b].name.s);
+						if (nl_is_open(net)) { pin_net[at] = PF_OPEN; continue; }      /* add_net_to_hash :594: "open" is a keyword */
+						size_t h = (size_t)fnv1a(net.s, (size_t)net.n) & tmask;
+						while (table[h] >= 0 && !nl_eq(net_names[table[h]], net.s, net.n)) h = (h + 1) & tmask;
+						if (table[h] < 0) {
+							if (nl_grow((void **)&net_names, &cap_nets, nnets + 1, sizeof(nl_str))) NL_FAIL(PF_ENOMEM, "out of memory");
+							net_names[nnets] = net; table[h] = nnets++;      /* index = order of first appearance (add_net_to_hash) */
+						}
+						pin_net[at] = table[h];
+					}
+				}
+			out->block_pin_ptr[ib + 1] = at;
+		}
+		out->block_name_chars = (char *)malloc(name_bytes + 1); out->block_type_chars = (char *)malloc(type_bytes + 1);
+		if (!out->block_name_chars || !out->block_type_chars) NL_FAIL(PF_ENOMEM, "out of memory");
+		ib = 0;
+		for (int b = d.pb[root].first_child; b >= 0; b = d.pb[b].next_sibling, ib++) {
+			memcpy(out->block_name_chars + out->block_name_ptr[ib], d.pb[b].name.s, (size_t)d.pb[b].name.n);
+			memcpy(out->block_type_chars + out->block_type_ptr[ib], d.pb[b].type.s, (size_t)d.pb[b].type.n);
+		}
+	}
+	/* ---- pass 3: clb_net[] — the driver first, the sinks in block / pin order (load_external_nets_and_cb :934-965) */
+	out->num_nets = nnets;
+	out->net_name_ptr = (int32_t *)calloc((size_t)nnets + 1, sizeof(int32_t)); out->net_ptr = (int32_t *)calloc((size_t)nnets + 1, sizeof(int32_t));
+	out->net_is_global = (uint8_t *)calloc((size_t)nnets + 1, 1);
+	count = (int32_t *)calloc((size_t)nnets + 1, sizeof(int32_t)); fill = (int32_t *)calloc((size_t)nnets + 1, sizeof(int32_t));
+	if (!out->net_name_ptr || !out->net_ptr || !out->net_is_global || !count || !fill) NL_FAIL(PF_ENOMEM, "out of memory");
+	for (int k = 0; k < npins; k++) if (pin_net[k] >= 0) count[pin_net[k]]++;
+	{
+		size_t chars = 0;
+		for (int i = 0; i < nnets; i++) { chars += (size_t)net_names[i].n; out->net_name_ptr[i + 1] = (int32_t)chars; out->net_ptr[i + 1] = out->net_ptr[i] + count[i]; }
+		out->net_name_chars = (char *)malloc(chars + 1);
+		out->net_block = (int32_t *)malloc(sizeof(int32_t) * (size_t)(out->net_ptr[nnets] > 0 ? out->net_ptr[nnets] : 1));
+		out->net_block_pin = (int32_t *)malloc(sizeof(int32_t) * (size_t)(out->net_ptr[nnets] > 0 ? out->net_ptr[nnets] : 1));
+		if (!out->net_name_chars || !out->net_block || !out->net_block_pin) NL_FAIL(PF_ENOMEM, "out of memory");
+		for (int i = 0; i < nnets; i++) memcpy(out->net_name_chars + out->net_name_ptr[i], net_names[i].s, (size_t)net_names[i].n);
+		for (int k = 0; k < out->net_ptr[nnets]; k++) out->net_block[k] = out->net_block_pin[k] = PF_OPEN;
+	}
+	memset(count, 0xff, sizeof(int32_t) * ((size_t)nnets + 1));      /* now: kind of the net's first receiver pin, -1 = none yet */
+	for (int ib = 0; ib < nblocks; ib++)
+		for (int k = out->block_pin_ptr[ib]; k < out->block_pin_ptr[ib + 1]; k++) {
+			const int net = pin_net[k], pin = k - out->block_pin_ptr[ib];
+			if (net < 0) continue;
+			const int base = out->net_ptr[net], terms = out->net_ptr[net + 1] - base;
+			if (out->block_pin_kind[k] == 1) {
+				if (out->net_block[base] != PF_OPEN)
+					NL_FAIL(PF_EFORMAT, "%s: net %.*s has two drivers (blocks #%d and #%d)", path, net_names[net].n, net_names[net].s, out->net_block[base], ib);
+				out->net_block[base] = ib; out->net_block_pin[base] = pin;
+			} else {
+				const int glob = out->block_pin_kind[k] == 2;
+				if (++fill[net] > terms - 1)      /* read_netlist.c:941-946 */
+					NL_FAIL(PF_EFORMAT, "net %.*s #%d inconsistency, expected %d terminals but encountered %d terminals, it is likely net terminal is disconnected in netlist file.",
+							net_names[net].n, net_names[net].s, net, terms - 1, fill[net]);
+				out->net_block[base + fill[net]] = ib; out->net_block_pin[base + fill[net]] = pin;
+				if (count[net] >= 0 && count[net] != glob)      /* read_netlist.c:966-973 */
+					NL_FAIL(PF_EFORMAT, "Netlist attempts to connect net %.*s to both global and non-global pins.", net_names[net].n, net_names[net].s);
+				count[net] = glob;
+				out->net_is_global[net] = (uint8_t)glob;
+			}
+		}
+	for (int i = 0; i < nnets; i++)
+		if (out->net_block[out->net_ptr[i]] == PF_OPEN) NL_FAIL(PF_EFORMAT, "%s: net %.*s has no driver", path, net_names[i].n, net_names[i].s);
+	for (int k = 0; k < d.nclk; k++) {      /* read_netlist.c:975-979: a circuit clock that reaches a cluster is a global net */
+		size_t h = (size_t)fnv1a(d.clk[k].s, (size_t)d.clk[k].n) & tmask;
+		while (table[h] >= 0 && !nl_eq(net_names[table[h]], d.clk[k].s, d.clk[k].n)) h = (h + 1) & tmask;
+		if (table[h] >= 0 && out->net_ptr[table[h] + 1] - out->net_ptr[table[h]] > 1 && !out->net_is_global[table[h]])
+			NL_FAIL(PF_EFORMAT, "%s: circuit clock %.*s drives non-clock pins", path, d.clk[k].n, d.clk[k].s);
+	}
+	rc = PF_OK;
+done:
+#undef NL_FAIL
+	free(data); free(d.pb); free(d.port); free(d.tok); free(d.clk); free(stack); free(table); free(count); free(fill); free(net_names);
+	if (rc != PF_OK) pf_netlist_free(out);
+	return rc;
+}

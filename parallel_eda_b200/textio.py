@@ -246,3 +246,70 @@ def read_place(path: str, n: Names, net_file: Optional[str] = None, arch_file: O
     for k in ("block_x", "block_y", "block_z"):
         setattr(n, k, nh.arrays[k][:n.num_blocks].copy())
     return placed.value
+
+
+# ---- the packed netlist (.net): pf_net_read, include/pf_text.h
+class _Netlist(C.Structure):
+    _fields_ = [("num_blocks", C.c_int32),
+                ("block_name_ptr", C.POINTER(C.c_int32)), ("block_name_chars", C.POINTER(C.c_char)),
+                ("block_type_ptr", C.POINTER(C.c_int32)), ("block_type_chars", C.POINTER(C.c_char)),
+                ("block_pin_ptr", C.POINTER(C.c_int32)), ("block_pin_net", C.POINTER(C.c_int32)),
+                ("block_pin_kind", C.POINTER(C.c_uint8)),
+                ("num_nets", C.c_int32),
+                ("net_name_ptr", C.POINTER(C.c_int32)), ("net_name_chars", C.POINTER(C.c_char)),
+                ("net_ptr", C.POINTER(C.c_int32)), ("net_block", C.POINTER(C.c_int32)), ("net_block_pin", C.POINTER(C.c_int32)),
+                ("net_is_global", C.POINTER(C.c_uint8))]
+
+
+@dataclasses.dataclass
+class Netlist:
+    """block[] and clb_net[] as the reference's read_netlist (base/read_netlist.c:74) leaves them for place and route."""
+    block_names: List[str]
+    block_types: List[str]           # block[i].type->name
+    block_pin_ptr: np.ndarray        # int32[num_blocks + 1]: pins of one instance of the type
+    block_pin_net: np.ndarray        # int32: block[i].nets[pin], -1 = OPEN
+    block_pin_kind: np.ndarray       # uint8: 0 input, 1 output, 2 clock
+    net_names: List[str]
+    net_ptr: np.ndarray              # int32[num_nets + 1]; terminal 0 of a net is its driver
+    net_block: np.ndarray            # clb_net[i].node_block[]
+    net_block_pin: np.ndarray        # clb_net[i].node_block_pin[]
+    net_is_global: np.ndarray        # uint8
+
+    @property
+    def num_blocks(self) -> int:
+        return len(self.block_names)
+
+    @property
+    def num_nets(self) -> int:
+        return len(self.net_names)
+
+
+def read_netlist(path: str) -> Netlist:
+    """read_netlist (reference base/read_netlist.c:74-244, load_external_nets_and_cb :836-984) without the architecture."""
+    lib = _lib()
+    if not getattr(lib, "_pf_net_bound", False):
+        lib.pf_net_read.argtypes = [C.c_char_p, C.POINTER(_Netlist)]
+        lib.pf_netlist_free.argtypes = [C.POINTER(_Netlist)]
+        lib.pf_netlist_free.restype = None
+        lib._pf_net_bound = True
+    c = _Netlist()
+    rc = lib.pf_net_read(path.encode(), C.byref(c))
+    if rc != 0:
+        _raise(lib, rc)
+    try:
+        def arr(ptr, count, dt):
+            return np.ctypeslib.as_array(ptr, shape=(max(count, 1),))[:count].astype(dt, copy=True) if count else np.zeros(0, dt)
+
+        def strings(ptr, chars, count):
+            off = arr(ptr, count + 1, np.int32)
+            raw = C.string_at(chars, int(off[-1])) if count and off[-1] else b""
+            return [raw[off[i]:off[i + 1]].decode() for i in range(count)]
+        nb, nn = c.num_blocks, c.num_nets
+        bpp = arr(c.block_pin_ptr, nb + 1, np.int32)
+        npt = arr(c.net_ptr, nn + 1, np.int32)
+        return Netlist(strings(c.block_name_ptr, c.block_name_chars, nb), strings(c.block_type_ptr, c.block_type_chars, nb),
+                       bpp, arr(c.block_pin_net, int(bpp[-1]), np.int32), arr(c.block_pin_kind, int(bpp[-1]), np.uint8),
+                       strings(c.net_name_ptr, c.net_name_chars, nn), npt, arr(c.net_block, int(npt[-1]), np.int32),
+                       arr(c.net_block_pin, int(npt[-1]), np.int32), arr(c.net_is_global, nn, np.uint8))
+    finally:
+        lib.pf_netlist_free(C.byref(c))

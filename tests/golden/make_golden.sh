@@ -82,4 +82,12 @@ PY
 "$REF" inject toy_w64_unbuf_nt.pfp --result toy_w64_unbuf_nt.pfr > /dev/null
 "$REF" inject toy_w64_unbuf_td.pfp --crit toy_w64.pfr --result toy_w64_unbuf_td.pfr > /dev/null
 for f in toy_w64_unbuf_nt.pfr toy_w64_unbuf_td.pfr; do xz -9 -c $f > "$HERE/$f.xz"; done
+# packed-netlist goldens (pf_net_read, tests/test_net_reader.py): block[] / clb_net[] as the reference's read_netlist held them in a routing run
+cp "$ROOT/tests/fixtures/k6_N10_like.xml" "$ROOT/tests/fixtures/k6_N10_het.xml" .
+for c in toy:k6_N10_like.xml:64 het:k6_N10_het.xml:70 duo:k6_N10_like.xml:80 mid:k6_N10_like.xml:200; do
+  n=${c%%:*}; r=${c#*:}; a=${r%%:*}; w=${r##*:}
+  PF_DUMP_NETLIST=$n.netlist "$REF" flow $a $n --nodisp --route --route_chan_width $w > /dev/null
+  xz -9e -c $n.netlist > "$HERE/$n.netlist.xz"
+done
+xz -9e -c duo.net > "$HERE/duo.net.xz"
 echo "goldens written to $HERE"
