@@ -93,6 +93,12 @@ struct PfGenDev;
 int pfb_gen_count(const PfGenDev *G, int *row, long long *num_edges);
 /* pass 2: node records, packed edge words, ptc numbers; *avail_wl (host) = total wirelength of the CHANX / CHANY nodes */
 int pfb_gen_fill(const PfGenDev *G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc, long long *avail_wl);
+/* the same pass in two halves: _begin launches it on a side stream ordered after everything issued so far (the 4 ms kernel of
+ * cfg 4 then runs under the host work and the small uploads of the rest of pf_router_create), _end makes the router's stream
+ * wait for it and returns the wirelength.  _end without a pending _begin is a no-op that leaves *avail_wl alone; nothing may
+ * touch nodes / edges / ptc / row on the router's stream, or free them, between the two. */
+int pfb_gen_fill_begin(const PfGenDev *G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc);
+int pfb_gen_fill_end(long long *avail_wl);
 /* occ = 0, acc_cost = 1 on every node record: a fresh first iteration (pf_router_reset) */
 int pfb_reset_nodes(PfNode *nodes, int num_nodes);
 /* order-independent 64-bit hashes of the node records / edge words / ptc numbers (tests: generated == uploaded graph) */

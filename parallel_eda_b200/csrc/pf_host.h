@@ -62,6 +62,7 @@ struct pf_router {
 	/* OPIN reservation */
 	int num_groups; int *g_source, *g_count, *g_off, *g_chosen;
 	long long avail_wl;
+	int *gen_row;            /* device generator: edge-row offsets, alive until the fill pass has been joined (pfb_gen_fill_end) */
 	double util;                  /* routed wirelength / available wirelength after the first iteration; < 0 = unknown */
 	int div_explicit;             /* cfg.inflight_div was given by the caller */
 	double t_mark[4];

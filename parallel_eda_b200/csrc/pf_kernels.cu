@@ -847,6 +847,42 @@ int pfb_gen_fill(const PfGenDev *G, const int *row, PfNode *nodes, uint32_t *edg
 	pfb_free(d_wl); pfb_free(d_inv);
 	return 0;
 }
+static cudaStream_t g_side = 0;
+static cudaEvent_t g_side_fork = 0, g_side_join = 0;
+static struct { unsigned long long *d_wl; short *d_inv; int pending; } g_fill = { NULL, NULL, 0 };
+int pfb_gen_fill_begin(const PfGenDev *G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc) {
+	PfGenDev Gd; short *d_inv = NULL;
+	if (g_fill.pending) { long long w; if (pfb_gen_fill_end(&w) != 0) return -1; }
+	if (!g_side) {
+		CK(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&g_side_fork, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&g_side_join, cudaEventDisableTiming));
+	}
+	if (gen_stage(G, &Gd, &d_inv) != 0) return -1;
+	unsigned long long *d_wl = (unsigned long long *)pfb_alloc(sizeof(unsigned long long));
+	if (!d_wl) { pfb_free(d_inv); return -1; }
+	/* the allocations (stream-ordered, on the router's stream), the staged table and the zeroed counter come first */
+	CK(cudaEventRecord(g_side_fork, g_stream));
+	CK(cudaStreamWaitEvent(g_side, g_side_fork, 0));
+	pf_gen_fill_kernel<<<stream_grid(G->num_nodes), 256, 0, g_side>>>(Gd, row, nodes, edges, ptc, d_wl);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(g_side_join, g_side));
+	g_fill.d_wl = d_wl; g_fill.d_inv = d_inv; g_fill.pending = 1;
+	g_times.aux_launches++;
+	return 0;
+}
+int pfb_gen_fill_end(long long *avail_wl) {
+	if (!g_fill.pending) return 0;
+	g_fill.pending = 0;
+	unsigned long long h = 0;
+	CK(cudaStreamWaitEvent(g_stream, g_side_join, 0));
+	CK(cudaMemcpyAsync(&h, g_fill.d_wl, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+	CK(cudaStreamSynchronize(g_stream));
+	if (avail_wl) *avail_wl = (long long)h;
+	pfb_free(g_fill.d_wl); pfb_free(g_fill.d_inv);
+	g_fill.d_wl = NULL; g_fill.d_inv = NULL;
+	return 0;
+}
 int pfb_reset_nodes(PfNode *nodes, int num_nodes) {
 	if (ev_begin(2) != 0) return -1;
 	pf_reset_nodes_kernel<<<stream_grid(num_nodes), 256, 0, g_stream>>>(nodes, num_nodes);

@@ -211,7 +211,9 @@ extern "C" int pf_comm_release_cache(void) {
 
 extern "C" void pf_router_destroy(pf_router *r) {
 	if (!r) return;
+	pfb_gen_fill_end(NULL);          /* a create that failed half way: the generator's side stream still writes the graph arrays */
 	pfb_sync();
+	pfb_free(r->gen_row);
 	pfb_free(r->nodes); pfb_free(r->edges); pfb_free(r->sw); pfb_free(r->indexed);
 	pfb_free(r->net_ptr); pfb_free(r->net_term); pfb_free(r->net_bb);
 	pfb_free(r->crit); pfb_free(r->net_delay);
@@ -372,7 +374,7 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	pf_config &c = r->cfg;
 	r->node_bits = node_bits;
 	r->prob = p; r->N = p->num_nodes; r->E = p->num_edges; r->generated = gen != NULL; r->T = p->num_terminals; r->n = p->num_nets;
-	r->nodes = NULL; r->edges = NULL; r->sw = NULL; r->indexed = NULL; r->net_ptr = r->net_term = r->net_bb = NULL;
+	r->gen_row = NULL; r->nodes = NULL; r->edges = NULL; r->sw = NULL; r->indexed = NULL; r->net_ptr = r->net_term = r->net_bb = NULL;
 	r->crit = r->net_delay = NULL; memset(&r->small, 0, sizeof(SlotClass)); memset(&r->big, 0, sizeof(SlotClass));
 	r->pool[0] = r->pool[1] = NULL; r->pool_node[0] = r->pool_node[1] = NULL; r->loc = NULL; r->cur = 0; r->pool_head = NULL;
 	r->all_nets = NULL; r->num_all = 0; r->net_big = NULL; r->sel_counts = NULL; r->sel_scratch = NULL; r->ptc = NULL; r->K1 = 0; r->n1_small = r->n1_big = 0; r->iter_count = 0;
@@ -574,8 +576,9 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		/* pass 1 of the device generator: out-degrees and their prefix sum give the number of edges */
 		long long ne = 0;
 		gen_row = (int *)pfb_alloc_raw(sizeof(int) * ((size_t)r->N + 1));
-		if (!r->nodes || !gen_row || pfb_gen_count(&Gd, gen_row, &ne) != 0) { pfb_free(gen_row); pf_router_destroy(r); CUDA_FAIL(); }
-		if (ne >= 2147483647ll) { pfb_free(gen_row); pf_router_destroy(r); FAILF(PF_EINVAL, "%lld rr edges exceed the 31-bit edge index", ne); }
+		r->gen_row = gen_row;          /* pf_router_destroy frees it (after joining the fill pass, should one be running) */
+		if (!r->nodes || !gen_row || pfb_gen_count(&Gd, gen_row, &ne) != 0) { pf_router_destroy(r); CUDA_FAIL(); }
+		if (ne >= 2147483647ll) { pf_router_destroy(r); FAILF(PF_EINVAL, "%lld rr edges exceed the 31-bit edge index", ne); }
 		r->E = (int)ne;
 	}
 	r->edges = (uint32_t *)pfb_alloc_raw(sizeof(uint32_t) * (size_t)std::max(r->E, 1));
@@ -614,8 +617,12 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		r->t_mark[0] = now_s();
 		if (gen) {
 			/* pass 2: node records, edge words and ptc numbers written straight into HBM */
-			if (pfb_gen_fill(&Gd, gen_row, r->nodes, r->edges, r->ptc, &wl_avail) != 0) { pfb_free(gen_row); pf_router_destroy(r); CUDA_FAIL(); }
-			pfb_free(gen_row);
+			/* PF_GEN_OVERLAP=1: the fill pass on a side stream under the allocations and uploads that follow (joined before the
+			 * final sync below).  Measured on the B200 (profiles/r02H_e2e_phases.txt): create 11.4 -> 9.1 ms when one router is
+			 * alive at a time, no gain next to a second live router (bench.py's e2e: 34.3 vs 34.0 ms), and one create in four
+			 * took 57 ms in the allocator (stream-ordered pool memory used across two streams) — so it stays opt-in. */
+			static const bool overlap = getenv("PF_GEN_OVERLAP") != NULL;
+			if ((overlap ? pfb_gen_fill_begin(&Gd, gen_row, r->nodes, r->edges, r->ptc) : pfb_gen_fill(&Gd, gen_row, r->nodes, r->edges, r->ptc, &wl_avail)) != 0) { pf_router_destroy(r); CUDA_FAIL(); }
 		} else if (c.defer_graph && c.nranks > 1) {
 			/* the packed graph arrives from another rank (pf_comm_graph_buffers); only the available wirelength,
 			 * which the first-iteration abort check needs, is computed from the host arrays here */
@@ -749,6 +756,13 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 				|| pfb_h2d(r->g_off, off.data(), sizeof(int) * (size_t)r->num_groups)) { pf_router_destroy(r); CUDA_FAIL(); }
 	}
 	r->t_mark[2] = now_s();
+	if (gen) {
+		/* the fill pass ran on its side stream under the allocations and uploads above: join it, read the wirelength */
+		long long wl = r->avail_wl;          /* stays as it is when the pass was not split */
+		if (pfb_gen_fill_end(&wl) != 0) { pf_router_destroy(r); CUDA_FAIL(); }
+		r->avail_wl = wl;
+		pfb_free(r->gen_row); r->gen_row = NULL;
+	}
 	if (pfb_sync() != 0) { pf_router_destroy(r); CUDA_FAIL(); }
 	terminal_check.join();
 	if (terminals_bad) {

@@ -192,6 +192,18 @@ int pfb_gen_count(const PfGenDev *G, int *row, long long *num_edges) {
 	g_times.aux_launches++;
 	return 0;
 }
+static long long g_fill_wl = 0; static int g_fill_pending = 0;
+int pfb_gen_fill(const PfGenDev *G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc, long long *avail_wl);
+int pfb_gen_fill_begin(const PfGenDev *G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc) {
+	g_fill_pending = 1;
+	return pfb_gen_fill(G, row, nodes, edges, ptc, &g_fill_wl);
+}
+int pfb_gen_fill_end(long long *avail_wl) {
+	if (!g_fill_pending) return 0;
+	g_fill_pending = 0;
+	if (avail_wl) *avail_wl = g_fill_wl;
+	return 0;
+}
 int pfb_gen_fill(const PfGenDev *G, const int *row, PfNode *nodes, uint32_t *edges, short *ptc, long long *avail_wl) {
 	long long wl = 0;
 	for (int v = 0; v < G->num_nodes; v++) {
