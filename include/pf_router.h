@@ -30,6 +30,7 @@
  *   pf_try_breadth_first_route       try_breadth_first_route            route/route_breadth_first.c:23-305
  *   pf_sta_create / pf_sta_analyze   load_timing_graph_net_delays + do_timing_analysis + get_critical_path_delay
  *   pf_try_timing_driven_route_sta                                       timing/path_delay.c:479,2258-2522,3791 (route_timing.c:295-309)
+ *   pf_sta_analyze_final             do_timing_analysis(.., is_final_analysis TRUE) of routing_stats   base/stats.c:155-164
  *   pf_check_route                   check_route                        route/check_route.c:27-155
  *
  * All functions return PF_OK (0) or a negative PF_E* code (pf_file.h); none calls exit().
@@ -221,6 +222,12 @@ int pf_sta_analyze(pf_sta *s, const float *net_delay, float *crit, float *cpd_ns
 int pf_sta_analyze_device(pf_sta *s, const void *dev_net_delay, void *dev_crit, float *cpd_ns);
 /* the critical path delay (ns) of the last analysis — pf_sta_analyze_device with cpd_ns == NULL does not wait for it */
 int pf_sta_read_cpd(pf_sta *s, float *cpd_ns);
+/* do_timing_analysis(slacks, FALSE, FALSE, is_final_analysis = TRUE) as routing_stats runs it on the finished routing
+ * (base/stats.c:155-164, timing/path_delay.c:2258-2522 with :2786-2790 and update_slack :3117-3125): host buffers of
+ * num_terminals floats; slack[t] = least slack of net pin t over the analysed constraints (real required times, so it may be
+ * negative; 1e30 = HUGE_POSITIVE_FLOAT where no analysed path passes), crit (may be NULL) = the criticalities of that analysis,
+ * *cpd_ns the critical path delay (get_critical_path_delay, :3791) */
+int pf_sta_analyze_final(pf_sta *s, const float *net_delay, float *slack, float *crit, float *cpd_ns);
 /* try_timing_driven_route with the analysis on the device: no host callback, no per-iteration copies */
 int pf_try_timing_driven_route_sta(const pf_problem *p, const pf_timing_graph *g, const pf_config *cfg, pf_result *out);
 

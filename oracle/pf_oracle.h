@@ -39,6 +39,8 @@ int pf_serial_num(const pf_problem *p, const int32_t *trace_ptr, const int32_t *
  * net_ptr = pf_problem.net_ptr.  Fills crit[num_terminals] (timing_criticality; 0 where the reference leaves 0) and
  * *cpd_ns (get_critical_path_delay, path_delay.c:3791-3810).  scratch-free: allocates its own T_arr / T_req. */
 int pf_oracle_sta(const pf_timing_graph *g, const int32_t *net_ptr, const float *net_delay, float *crit, float *cpd_ns);
+/* the analysis of the finished routing (is_final_analysis = TRUE, base/stats.c:155-164): slack[num_terminals] out as well */
+int pf_oracle_sta_final(const pf_timing_graph *g, const int32_t *net_ptr, const float *net_delay, float *slack, float *crit, float *cpd_ns);
 
 #ifdef __cplusplus
 }

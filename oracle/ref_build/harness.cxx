@@ -16,6 +16,7 @@
  *        env PF_ADAPTER_ROUTE_FILE=<file>  also write the .route file through integration/vpr_text_adapter.cxx
  *        env PF_DUMP_AT_SUCCESS=1    write PF_DUMP_RESULT as soon as the routing is legal (before the reference's DEBUG delay check)
  *        env PF_DUMP_STA=<file>      write every (net_delay in, timing_criticality out, cpd) of the run's STA calls
+ *        env PF_DUMP_STA_FINAL=<file> write routing_stats' analysis of the finished routing (is_final_analysis): criticalities in <file>, slacks in <file>.slack
  *   vpr_ref inject <problem.pfp> [--result out.pfr] [--crit golden.pfr] [--max_iters K]
  *                  [--limit_nets M]
  *        load a flat problem into the reference's globals and call the reference's own
@@ -159,6 +160,38 @@ void pf_hook_do_timing_analysis(t_slack *slacks, boolean a, boolean b, boolean c
 				slacks->timing_criticality[i][k] = src[g_net_ptr[i] + k];
 	}
 	record_crit(slacks);
+}
+
+/* base/stats.c is compiled with -Ddo_timing_analysis=pf_hook_final_timing_analysis -Dload_timing_graph_net_delays=
+ * pf_hook_final_load_net_delays: routing_stats' analysis of the finished routing (is_final_analysis = TRUE) runs as always;
+ * with PF_DUMP_STA_FINAL=<file> its input (net delays) and outputs are written as two one-call pf_sta_vectors containers:
+ * <file> carries the criticalities, <file>.slack the slacks in the same slot; both carry the critical path delay. */
+static std::vector<float> g_final_delay;
+void pf_hook_final_load_net_delays(float **net_delay) {
+	load_timing_graph_net_delays(net_delay);
+	build_net_ptr();
+	g_final_delay.assign(g_net_ptr[num_nets], 0.f);
+	for (int i = 0; i < num_nets; i++)
+		for (int k = 1; k <= clb_net[i].num_sinks; k++) g_final_delay[g_net_ptr[i] + k] = net_delay[i][k];
+}
+void pf_hook_final_timing_analysis(t_slack *slacks, boolean a, boolean b, boolean c) {
+	do_timing_analysis(slacks, a, b, c);
+	const char *path = getenv("PF_DUMP_STA_FINAL");
+	if (!path || g_inject || g_final_delay.empty()) return;
+	std::vector<float> crit(g_net_ptr[num_nets], 0.f), slk(g_net_ptr[num_nets], 0.f);
+	for (int i = 0; i < num_nets; i++)
+		for (int k = 1; k <= clb_net[i].num_sinks; k++) { crit[g_net_ptr[i] + k] = slacks->timing_criticality[i][k]; slk[g_net_ptr[i] + k] = slacks->slack[i][k]; }
+	for (int i = 0; i < num_nets; i++) slk[g_net_ptr[i]] = 1.e30f;      /* the driver slot: as pf_sta_analyze_final leaves it */
+	float cpd = get_critical_path_delay();
+	pf_sta_vectors v;
+	memset(&v, 0, sizeof(v));
+	v.num_terminals = g_net_ptr[num_nets]; v.num_calls = 1; v.net_delay = g_final_delay.data(); v.cpd = &cpd;
+	v.crit = crit.data();
+	int rc = pf_sta_vectors_write(path, &v);
+	std::string p2 = std::string(path) + ".slack";
+	v.crit = slk.data();
+	rc |= pf_sta_vectors_write(p2.c_str(), &v);
+	fprintf(stderr, "PF_REF wrote final analysis %s (+ .slack): %d terminals, cpd %g ns, is_final %d (rc %d)\n", path, v.num_terminals, cpd, (int)c, rc);
 }
 
 float pf_hook_get_critical_path_delay(void) {

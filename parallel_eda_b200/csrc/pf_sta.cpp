@@ -12,6 +12,7 @@ struct pf_sta {
 	std::vector<int> seg_begin, seg_end, seg_spread;     /* sweep plan over levels, ascending */
 	float *stat;                                         /* [num_domains^2][4] on the device */
 	float *scratch_delay, *scratch_crit;                 /* device staging for the host-buffer entry point */
+	float *scratch_slack;                                /* pf_sta_analyze_final, allocated on first use */
 	void *owned[32]; int num_owned;
 };
 
@@ -71,7 +72,7 @@ extern "C" int pf_sta_create(const pf_timing_graph *g, const pf_problem *p, cons
 	(void)new_edge;
 	pf_sta *s = new pf_sta();
 	memset(&s->d, 0, sizeof(s->d));
-	s->num_owned = 0; s->num_domains = g->num_domains; s->num_tedges = E;
+	s->num_owned = 0; s->num_domains = g->num_domains; s->num_tedges = E; s->scratch_slack = NULL;
 	s->constraint.assign(g->constraint, g->constraint + (size_t)g->num_domains * g->num_domains);
 	/* sweep plan: a level wider than 4 K tnodes gets the whole GPU, runs of narrower ones share one CTA */
 	for (int lv = 0; lv < g->num_levels;) {
@@ -146,5 +147,30 @@ extern "C" int pf_sta_analyze(pf_sta *s, const float *net_delay, float *crit, fl
 	int rc = pf_sta_analyze_device(s, s->scratch_delay, s->scratch_crit, cpd_ns);
 	if (rc != PF_OK) return rc;
 	CKB(pfb_d2h(crit, s->scratch_crit, bytes));
+	return PF_OK;
+}
+
+/* The analysis of the finished routing: routing_stats (base/stats.c:155-178) runs do_timing_analysis(slacks, FALSE, FALSE,
+ * TRUE) once the router is done — the same sweeps with the REAL required times at the sinks (path_delay.c:2786-2790; slacks
+ * may be negative) and the least slack of every net pin kept over all analysed constraints (update_slacks :3117-3125; pins no
+ * traversal reaches keep HUGE_POSITIVE_FLOAT, :2393).  crit may be NULL. */
+extern "C" int pf_sta_analyze_final(pf_sta *s, const float *net_delay, float *slack, float *crit, float *cpd_ns) {
+	if (!s || !net_delay || !slack) FAILF(PF_EINVAL, "null argument");
+	const size_t T = (size_t)std::max(s->d.num_terminals, 1), bytes = sizeof(float) * (size_t)s->d.num_terminals;
+	if (!s->scratch_slack) {
+		if (s->num_owned >= (int)(sizeof(s->owned) / sizeof(s->owned[0]))) FAILF(PF_EINVAL, "pf_sta: allocation table full");
+		s->scratch_slack = (float *)pfb_alloc(sizeof(float) * T);
+		if (!s->scratch_slack) CUDA_FAIL();
+		s->owned[s->num_owned++] = s->scratch_slack;
+	}
+	std::vector<float> init(T, (float)1.e30);                                                 /* HUGE_POSITIVE_FLOAT */
+	CKB(pfb_h2d(s->scratch_slack, init.data(), sizeof(float) * T));
+	CKB(pfb_h2d(s->scratch_delay, net_delay, bytes));
+	s->d.final_analysis = 1; s->d.slack = s->scratch_slack;
+	int rc = pf_sta_analyze_device(s, s->scratch_delay, s->scratch_crit, cpd_ns);
+	s->d.final_analysis = 0; s->d.slack = NULL;
+	if (rc != PF_OK) return rc;
+	CKB(pfb_d2h(slack, s->scratch_slack, bytes));
+	if (crit) CKB(pfb_d2h(crit, s->scratch_crit, bytes));
 	return PF_OK;
 }

@@ -76,7 +76,7 @@ PF_DEV void pf_sta_backward_node(const PfStaDev &S, int n, int sink_domain, floa
 		if (S.type[n] == PF_STA_TN_FF_CLOCK || ta < PF_STA_HUGE_NEG + 1) return;
 		if (S.clock_domain[n] != sink_domain) return;
 		const float real = constraint + S.clock_delay[n], max_Tarr = stat[0];
-		S.T_req[n] = real > max_Tarr ? real : max_Tarr;  /* T_req-relaxed slack, :2800-2804 */
+		S.T_req[n] = (S.final_analysis || real > max_Tarr) ? real : max_Tarr;  /* T_req-relaxed slack except in the final analysis, :2786-2790 */
 		pf_atomic_max_f(&stat[1], ta - S.clock_delay[n]);/* critical path delay of this constraint */
 		return;
 	}
@@ -103,6 +103,10 @@ PF_DEV void pf_sta_update_terminal(const PfStaDev &S, int t, float constraint, c
 	if (!(S.T_arr[to] > PF_STA_HUGE_NEG + 1 && S.T_req[to] < PF_STA_HUGE_POS - 1)) return;
 	const float max_Tarr = stat[0];
 	const float denom = max_Tarr > constraint ? max_Tarr : constraint;
+	if (S.slack) {                                       /* update_slack == TRUE, :3117-3125 */
+		const float slk = S.T_req[to] - S.T_arr[d] - S.Tdel[e];
+		if (slk < S.slack[t]) S.slack[t] = slk;
+	}
 	const float tc = 1 - (S.T_req[to] - S.T_arr[d] - S.Tdel[e]) / denom;
 	if (tc > crit[t]) crit[t] = tc;
 }

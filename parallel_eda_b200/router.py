@@ -487,6 +487,19 @@ class Sta:
             raise RouterError(rc, self.lib.pf_last_error().decode())
         return crit, float(cpd.value)
 
+    def analyze_final(self, net_delay: np.ndarray):
+        """The analysis of the finished routing (do_timing_analysis(.., is_final_analysis = TRUE), reference base/stats.c:155-164):
+        net_delay[num_terminals] -> (slack[num_terminals] with 1e30 where no analysed path passes, timing_criticality, cpd in ns)."""
+        d = np.ascontiguousarray(net_delay, dtype=np.float32)
+        slack = np.zeros(self.num_terminals, np.float32)
+        crit = np.zeros(self.num_terminals, np.float32)
+        cpd = C.c_float(0)
+        self.lib.pf_sta_analyze_final.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        rc = self.lib.pf_sta_analyze_final(self._h, d.ctypes.data, slack.ctypes.data, crit.ctypes.data, C.byref(cpd))
+        if rc != PF_OK:
+            raise RouterError(rc, self.lib.pf_last_error().decode())
+        return slack, crit, float(cpd.value)
+
     def analyze_device(self, dev_net_delay: int, dev_crit: int) -> float:
         """Device pointers in and out (e.g. Router.comm_net_delay_ptr() / comm_crit_ptr()); returns the cpd in ns."""
         cpd = C.c_float(0)

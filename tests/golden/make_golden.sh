@@ -90,4 +90,10 @@ for c in toy:k6_N10_like.xml:64 het:k6_N10_het.xml:70 duo:k6_N10_like.xml:80 mid
   xz -9e -c $n.netlist > "$HERE/$n.netlist.xz"
 done
 xz -9e -c duo.net > "$HERE/duo.net.xz"
+# the analysis of the finished routing (routing_stats -> do_timing_analysis(.., is_final_analysis = TRUE)): pf_sta_analyze_final
+for c in toy:k6_N10_like.xml:64 het:k6_N10_het.xml:70 duo:k6_N10_like.xml:80; do
+  n=${c%%:*}; r=${c#*:}; a=${r%%:*}; w=${r##*:}
+  PF_DUMP_STA_FINAL=${n}_w${w}_final.pfsta "$REF" flow $a $n --nodisp --route --route_chan_width $w > /dev/null
+  for f in ${n}_w${w}_final.pfsta ${n}_w${w}_final.pfsta.slack; do xz -9e -c $f > "$HERE/$f.xz"; done
+done
 echo "goldens written to $HERE"

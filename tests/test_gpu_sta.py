@@ -26,6 +26,26 @@ def test_device_sta_bit_identical_to_reference(name):
     s.close()
 
 
+@pytest.mark.parametrize("name", ["toy_w64", "het_w70", "duo_w80"])
+def test_final_analysis_bit_identical_to_reference(name):
+    """pf_sta_analyze_final on the B200: the slacks, criticalities and critical path delay of the reference's analysis of the
+    finished routing (routing_stats, base/stats.c:155-164; goldens from the hook PF_DUMP_STA_FINAL) bit for bit, and the relaxed
+    analysis of the router loop unchanged right after it."""
+    p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
+    g = pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz"))
+    v = pfio.read_sta_vectors(os.path.join(G, name + "_final.pfsta.xz"))
+    sl = pfio.read_sta_vectors(os.path.join(G, name + "_final.pfsta.slack.xz"))
+    s = router.Sta(g, p)
+    slack, crit, cpd = s.analyze_final(v.net_delay[0])
+    assert np.array_equal(slack.view(np.uint32), sl.crit[0].view(np.uint32))
+    assert np.array_equal(crit.view(np.uint32), v.crit[0].view(np.uint32))
+    assert np.float32(cpd).view(np.uint32) == v.cpd[0].view(np.uint32)
+    loop = pfio.read_sta_vectors(os.path.join(G, name + ".pfsta.xz"))
+    c0, _ = s.analyze(loop.net_delay[0])
+    assert np.array_equal(c0.view(np.uint32), loop.crit[0].view(np.uint32))
+    s.close()
+
+
 @pytest.mark.parametrize("name", ["mid_w200", "hub_w90", "duo_w80"])
 def test_route_with_device_sta(name):
     p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))

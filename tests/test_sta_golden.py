@@ -136,3 +136,48 @@ def test_device_sta_equals_oracle_on_random_delays(oracle_lib, emu_lib):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
         assert np.float32(got_cpd).view(np.uint32) == np.float32(cpd.value).view(np.uint32)
     s.close()
+
+
+FINAL = ["toy_w64", "het_w70", "duo_w80"]      # duo: 3 clock domains, 7 analysed pairs — the least slack over the pairs is kept
+
+
+def _final_golden(name):
+    v = pfio.read_sta_vectors(os.path.join(G, name + "_final.pfsta.xz"))
+    s = pfio.read_sta_vectors(os.path.join(G, name + "_final.pfsta.slack.xz"))
+    assert v.net_delay.shape[0] == 1 and np.array_equal(v.net_delay, s.net_delay)
+    return v.net_delay[0], s.crit[0], v.crit[0], v.cpd[0]
+
+
+@pytest.mark.parametrize("name", FINAL)
+def test_final_analysis_oracle_and_device_code_equal_the_reference(name, oracle_lib, emu_lib):
+    """The analysis routing_stats runs on the finished routing (base/stats.c:155-164: do_timing_analysis with
+    is_final_analysis = TRUE — real required times, slacks kept): the reference's own slacks, criticalities and critical path
+    delay of that call (hook PF_DUMP_STA_FINAL, tests/golden/make_golden.sh), bit for bit from the oracle restatement and from
+    the device code on the emulator."""
+    from parallel_eda_b200 import router
+    p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))
+    g = pfio.read_timing_graph(os.path.join(G, name + ".pftg.xz"))
+    delay, slack_ref, crit_ref, cpd_ref = _final_golden(name)
+    assert (slack_ref < 1e29).any() and (slack_ref[np.asarray(p.net_ptr[:-1])] > 1e29).all()      # driver slots stay HUGE_POSITIVE_FLOAT
+    lib = C.CDLL(oracle_lib)
+    lib.pf_oracle_sta_final.argtypes = [C.POINTER(_TG), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    tg, keep = c_timing_graph(g)
+    net_ptr = np.ascontiguousarray(p.net_ptr, dtype=np.int32)
+    slack = np.zeros(p.num_terminals, np.float32); crit = np.zeros(p.num_terminals, np.float32); cpd = C.c_float(0)
+    d = np.ascontiguousarray(delay)
+    assert lib.pf_oracle_sta_final(C.byref(tg), net_ptr.ctypes.data, d.ctypes.data, slack.ctypes.data, crit.ctypes.data, C.byref(cpd)) == 0
+    assert np.array_equal(slack.view(np.uint32), slack_ref.view(np.uint32)), int((slack.view(np.uint32) != slack_ref.view(np.uint32)).sum())
+    assert np.array_equal(crit.view(np.uint32), crit_ref.view(np.uint32))
+    assert np.float32(cpd.value).view(np.uint32) == cpd_ref.view(np.uint32)
+    s = router.Sta(g, p, router.default_config(router.load_library(emu_lib)), lib_path=emu_lib)
+    slack_d, crit_d, cpd_d = s.analyze_final(delay)
+    assert np.array_equal(slack_d.view(np.uint32), slack_ref.view(np.uint32))
+    assert np.array_equal(crit_d.view(np.uint32), crit_ref.view(np.uint32))
+    assert np.float32(cpd_d).view(np.uint32) == cpd_ref.view(np.uint32)
+    # the relaxed analysis right after it is unaffected by the final one (flags reset), and differs where slacks were negative
+    crit_relaxed, _ = s.analyze(delay)
+    v = pfio.read_sta_vectors(os.path.join(G, name + ".pfsta.xz"))
+    c0, _ = s.analyze(v.net_delay[0])
+    assert np.array_equal(c0.view(np.uint32), v.crit[0].view(np.uint32))
+    assert crit_relaxed.max() <= 1.0 + 1e-6
+    s.close()
