@@ -43,8 +43,40 @@ def main(argv=None) -> int:
     n.add_argument("problem"); n.add_argument("--nx", type=int, required=True); n.add_argument("--ny", type=int, default=0)
     n.add_argument("--width", type=int, default=100); n.add_argument("--nets", type=int, required=True)
     n.add_argument("--sinks", type=int, default=3); n.add_argument("--seed", type=int, default=1)
+    q = sub.add_parser("read-net", help="packed netlist (.net) -> block / net statistics (pf_net_read, include/pf_text.h; no GPU)")
+    q.add_argument("net_file"); q.add_argument("--place", help="a .place file of the same circuit: also report the blocks it positions")
     a = ap.parse_args(argv)
 
+    if a.cmd == "read-net":
+        import collections
+        t = time.perf_counter()
+        nl = textio.read_netlist(a.net_file)
+        fan = [int(x) - 1 for x in (nl.net_ptr[1:] - nl.net_ptr[:-1])]
+        out = {"blocks": nl.num_blocks, "block_types": dict(collections.Counter(nl.block_types)), "nets": nl.num_nets,
+               "global_nets": [nl.net_names[i] for i in range(nl.num_nets) if nl.net_is_global[i]],
+               "sinks": int(sum(fan)), "max_fanout": max(fan) if fan else 0, "seconds": round(time.perf_counter() - t, 3)}
+        if a.place:
+            # read_place (base/read_place.c:15) on the blocks the netlist names: the grid size comes from the file's own header
+            import re
+            import numpy as np
+            m = re.search(r"Array size:\s*(\d+)\s*x\s*(\d+)", open(a.place).read(4096))
+            if not m:
+                raise SystemExit("%s: no 'Array size:' header" % a.place)
+            nx, ny = int(m.group(1)), int(m.group(2))
+            names = textio.Names.build(nx, ny, nl.net_names, np.zeros((nx + 2) * (ny + 2), np.uint8), [(b, 0, 0, 0) for b in nl.block_names])
+            out["placed_blocks"] = textio.read_place(a.place, names)
+            out["grid"] = [nx, ny]
+            # half-perimeter wirelength of the routed (non-global) nets from the placement, block coordinates only (place.c:2083)
+            bx, by = names.block_x, names.block_y
+            hp = 0
+            for i in range(nl.num_nets):
+                if nl.net_is_global[i]:
+                    continue
+                blk = nl.net_block[nl.net_ptr[i]:nl.net_ptr[i + 1]]
+                hp += int(bx[blk].max() - bx[blk].min() + by[blk].max() - by[blk].min())
+            out["half_perimeter_of_block_positions"] = hp
+        print(json.dumps(out))
+        return 0
     if a.cmd == "gen":
         t = time.perf_counter()
         p = router.generate_grid_problem(nx=a.nx, ny=a.ny or a.nx, W=a.width, num_nets=a.nets, sinks_per_net=a.sinks, seed=a.seed)

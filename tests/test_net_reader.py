@@ -183,3 +183,16 @@ def test_live_against_the_reference_binary(cuda_lib, ref_bin, unxz, tmp_path):
     assert os.path.exists(os.path.join(d, "live.netlist")), r.stderr[-500:]
     blocks, nets = parse_golden(os.path.join(d, "live.netlist"))
     assert_equals_reference(textio.read_netlist(os.path.join(d, "live.net")), blocks, nets)
+
+
+def test_cli_read_net_with_placement(cuda_lib, unxz):
+    """`python -m parallel_eda_b200 read-net x.net --place x.place`: netlist statistics and the reference's own placement file
+    read onto the netlist's blocks (pf_place_read) — every block of the netlist is positioned."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, "-m", "parallel_eda_b200", "read-net", unxz("het.net"), "--place", os.path.join(ROOT, "tests", "golden", "het.place")],
+                       cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["blocks"] == 91 and out["nets"] == 441 and out["placed_blocks"] == 91 and out["global_nets"] == ["clk"]
+    assert out["block_types"] == {"clb": 40, "io": 45, "mult": 6} and out["grid"] == [8, 8] and out["half_perimeter_of_block_positions"] > 0
