@@ -172,6 +172,15 @@ typedef struct pf_timing_graph {
 	float *constraint;        /* [num_domains * num_domains] g_sdc->domain_constraint, < 0 = DO_NOT_ANALYSE */
 	int32_t num_nets;         /* == pf_problem.num_nets */
 	int32_t *net_driver;      /* [num_nets] f_net_to_driver_tnode */
+	/* clock-to-flipflop override constraints (g_sdc->cf_constraints: set_max_delay / set_false_path / set_multicycle_path
+	 * -from [get_clocks ..] -to <flip-flops or pads>), resolved to tnodes by the exporter: in the traversals whose source
+	 * domain is override_domain[k], sink tnode override_tnode[k] takes override_constraint[k] (seconds; < 0 = this sink is not
+	 * analysed) instead of the domain pair's constraint (find_cf_constraint, timing/path_delay.c:2753-2768).  Sorted by
+	 * (tnode, domain), at most one entry per pair (the reference takes the first match); num_overrides == 0: none */
+	int32_t num_overrides;
+	int32_t *override_domain;
+	int32_t *override_tnode;
+	float *override_constraint;
 } pf_timing_graph;
 
 /* golden vectors of the reference's analysis: K calls, each net_delay in -> timing_criticality out */

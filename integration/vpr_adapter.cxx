@@ -16,8 +16,9 @@
  * get_critical_path_delay on the host (route_timing.c:295-309).  Here the timing graph (tnode[], tedge, levels,
  * constraints) is flattened once and the same analysis runs on the device (pf_try_timing_driven_route_sta; the
  * criticalities are bit-identical, tests/test_gpu_sta.py), so nothing crosses PCIe between iterations.  With
- * PF_HOST_STA=1 in the environment, or when the design has clock-to-flipflop override constraints (not exported),
- * the reference's own STA is called back on the host instead.
+ * PF_HOST_STA=1 in the environment the reference's own STA is called back on the host instead.  Clock-to-flipflop override
+ * constraints of an SDC file (g_sdc->cf_constraints) are resolved to (source domain, sink tnode) pairs and travel in the
+ * timing graph (pf_timing_graph.override_*).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -67,6 +68,8 @@ struct TimingGraphStore {
 	std::vector<int32_t> eptr, eto, cdom, lptr, lnodes, drv;
 	std::vector<float> etd, cdel, cons;
 	std::vector<uint8_t> ty;
+	std::vector<int32_t> ovr_d, ovr_t;
+	std::vector<float> ovr_c;
 };
 
 void flatten_timing_graph(TimingGraphStore &st, pf_timing_graph &g) {
@@ -95,6 +98,26 @@ void flatten_timing_graph(TimingGraphStore &st, pf_timing_graph &g) {
 	g.clock_domain = st.cdom.data(); g.clock_delay = st.cdel.data();
 	g.num_levels = num_tnode_levels; g.level_ptr = st.lptr.data(); g.level_nodes = st.lnodes.data();
 	g.num_domains = C; g.constraint = st.cons.data();
+	/* clock-to-flipflop override constraints (g_sdc->cf_constraints), resolved to (source domain, sink tnode): what
+	 * find_cf_constraint(clock name, find_tnode_net_name(inode)) answers at every sink (timing/path_delay.c:2753-2768, :3667-3684,
+	 * :3749-3767) — the first matching entry wins, as there */
+	if (g_sdc && g_sdc->num_cf_constraints > 0) {
+		for (int i = 0; i < num_tnodes; i++) {
+			if (tnode[i].num_edges != 0 || (tnode[i].type != TN_FF_SINK && tnode[i].type != TN_OUTPAD_SINK)) continue;
+			const char *name = block[tnode[i].block].pb->rr_node_to_pb_mapping[tnode[i].pb_graph_pin->pin_count_in_cluster]->name;
+			for (int c = 0; c < g_sdc->num_constrained_clocks; c++) {
+				int found = -1;
+				for (int icf = 0; icf < g_sdc->num_cf_constraints && found < 0; icf++) {
+					bool src = false, snk = false;
+					for (int a = 0; a < g_sdc->cf_constraints[icf].num_source; a++) if (strcmp(g_sdc->cf_constraints[icf].source_list[a], g_sdc->constrained_clocks[c].name) == 0) src = true;
+					for (int a = 0; src && a < g_sdc->cf_constraints[icf].num_sink; a++) if (strcmp(g_sdc->cf_constraints[icf].sink_list[a], name) == 0) snk = true;
+					if (src && snk) found = icf;
+				}
+				if (found >= 0) { st.ovr_d.push_back(c); st.ovr_t.push_back(i); st.ovr_c.push_back(g_sdc->cf_constraints[found].constraint); }
+			}
+		}
+	}
+	g.num_overrides = (int32_t)st.ovr_t.size(); g.override_domain = st.ovr_d.data(); g.override_tnode = st.ovr_t.data(); g.override_constraint = st.ovr_c.data();
 	g.num_nets = num_nets; g.net_driver = st.drv.data();
 }
 
@@ -189,7 +212,7 @@ static boolean route_on_b200(struct s_router_opts router_opts, float **net_delay
 	cfg.verbose = getenv("PF_VERBOSE") ? 1 : 0;
 	pf_result res;
 	int rc;
-	const bool device_sta = timing_analysis_enabled && g_sdc && g_sdc->num_cf_constraints == 0 && !getenv("PF_HOST_STA");
+	const bool device_sta = timing_analysis_enabled && g_sdc && !getenv("PF_HOST_STA");
 	if (device_sta) {
 		TimingGraphStore st;
 		pf_timing_graph tg;

@@ -416,7 +416,27 @@ static void export_timing_graph(const char *path) {
 	}
 	const int C = g_sdc ? g_sdc->num_constrained_clocks : 0;
 	for (int i = 0; i < C; i++) for (int j = 0; j < C; j++) cons.push_back(g_sdc->domain_constraint[i][j]);
-	if (g_sdc && g_sdc->num_cf_constraints > 0) fprintf(stderr, "PF_REF warning: clock-to-flipflop override constraints are not exported\n");
+	std::vector<int32_t> ovr_d, ovr_t; std::vector<float> ovr_c;
+	/* clock-to-flipflop override constraints (g_sdc->cf_constraints), resolved to (source domain, sink tnode): what
+	 * find_cf_constraint(clock name, find_tnode_net_name(inode)) answers at every sink (timing/path_delay.c:2753-2768, :3667-3684,
+	 * :3749-3767) — the first matching entry wins, as there */
+	if (g_sdc && g_sdc->num_cf_constraints > 0) {
+		for (int i = 0; i < num_tnodes; i++) {
+			if (tnode[i].num_edges != 0 || (tnode[i].type != TN_FF_SINK && tnode[i].type != TN_OUTPAD_SINK)) continue;
+			const char *name = block[tnode[i].block].pb->rr_node_to_pb_mapping[tnode[i].pb_graph_pin->pin_count_in_cluster]->name;
+			for (int c = 0; c < g_sdc->num_constrained_clocks; c++) {
+				int found = -1;
+				for (int icf = 0; icf < g_sdc->num_cf_constraints && found < 0; icf++) {
+					bool src = false, snk = false;
+					for (int a = 0; a < g_sdc->cf_constraints[icf].num_source; a++) if (strcmp(g_sdc->cf_constraints[icf].source_list[a], g_sdc->constrained_clocks[c].name) == 0) src = true;
+					for (int a = 0; src && a < g_sdc->cf_constraints[icf].num_sink; a++) if (strcmp(g_sdc->cf_constraints[icf].sink_list[a], name) == 0) snk = true;
+					if (src && snk) found = icf;
+				}
+				if (found >= 0) { ovr_d.push_back(c); ovr_t.push_back(i); ovr_c.push_back(g_sdc->cf_constraints[found].constraint); }
+			}
+		}
+	}
+	g.num_overrides = (int32_t)ovr_t.size(); g.override_domain = ovr_d.data(); g.override_tnode = ovr_t.data(); g.override_constraint = ovr_c.data();
 	g.num_tedges = (int32_t)eto.size();
 	g.edge_ptr = eptr.data(); g.edge_to = eto.data(); g.edge_Tdel = etd.data(); g.type = ty.data();
 	g.clock_domain = cdom.data(); g.clock_delay = cdel.data();
@@ -427,7 +447,7 @@ static void export_timing_graph(const char *path) {
 	int rc = pf_timing_graph_check(&g, g_net_ptr.data(), msg, sizeof(msg));
 	if (rc != 0) { fprintf(stderr, "PF_REF timing graph export is inconsistent: %s\n", msg); exit(2); }
 	rc = pf_timing_graph_write(path, &g);
-	fprintf(stderr, "PF_REF wrote timing graph %s: %d tnodes, %d tedges, %d levels, %d clock domains (rc %d)\n", path, g.num_tnodes, g.num_tedges,
+	fprintf(stderr, "PF_REF wrote timing graph %s: %d override constraints, %d tnodes, %d tedges, %d levels, %d clock domains (rc %d)\n", path, g.num_overrides, g.num_tnodes, g.num_tedges,
 			g.num_levels, g.num_domains, rc);
 }
 

@@ -238,6 +238,7 @@ int pf_timing_graph_write(const char *path, const pf_timing_graph *g) {
 	if (!f) return PF_EIO;
 	memset(hdr, 0, sizeof(hdr));
 	hdr[0] = g->num_tnodes; hdr[1] = g->num_tedges; hdr[2] = g->num_levels; hdr[3] = g->num_domains; hdr[4] = g->num_nets;
+	hdr[5] = g->num_overrides;      /* 0 in files written before the field existed: the arrays follow at the end */
 	if ((rc = wr(f, TIMG_MAGIC, 8)) != 0) goto done;
 	if ((rc = wr(f, hdr, sizeof(hdr))) != 0) goto done;
 	W(g->edge_ptr, (size_t)g->num_tnodes + 1);
@@ -246,6 +247,7 @@ int pf_timing_graph_write(const char *path, const pf_timing_graph *g) {
 	W(g->level_ptr, (size_t)g->num_levels + 1); W(g->level_nodes, g->num_tnodes);
 	W(g->constraint, (size_t)g->num_domains * (size_t)g->num_domains);
 	W(g->net_driver, g->num_nets);
+	W(g->override_domain, g->num_overrides); W(g->override_tnode, g->num_overrides); W(g->override_constraint, g->num_overrides);
 done:
 	if (fclose(f) != 0 && rc == 0) rc = PF_EIO;
 	return rc;
@@ -260,14 +262,15 @@ int pf_timing_graph_read(const char *path, pf_timing_graph *g) {
 	if (!f) return PF_EIO;
 	if (fread(magic, 1, 8, f) != 8 || memcmp(magic, TIMG_MAGIC, 8) != 0) { rc = PF_EFORMAT; goto done; }
 	if (fread(hdr, 1, sizeof(hdr), f) != sizeof(hdr)) { rc = PF_EIO; goto done; }
-	g->num_tnodes = hdr[0]; g->num_tedges = hdr[1]; g->num_levels = hdr[2]; g->num_domains = hdr[3]; g->num_nets = hdr[4];
-	if (g->num_tnodes < 0 || g->num_tedges < 0 || g->num_levels < 0 || g->num_domains < 0 || g->num_nets < 0) { rc = PF_EFORMAT; goto done; }
+	g->num_tnodes = hdr[0]; g->num_tedges = hdr[1]; g->num_levels = hdr[2]; g->num_domains = hdr[3]; g->num_nets = hdr[4]; g->num_overrides = hdr[5];
+	if (g->num_tnodes < 0 || g->num_tedges < 0 || g->num_levels < 0 || g->num_domains < 0 || g->num_nets < 0 || g->num_overrides < 0) { rc = PF_EFORMAT; goto done; }
 	R(g->edge_ptr, (size_t)g->num_tnodes + 1);
 	R(g->edge_to, g->num_tedges); R(g->edge_Tdel, g->num_tedges);
 	R(g->type, g->num_tnodes); R(g->clock_domain, g->num_tnodes); R(g->clock_delay, g->num_tnodes);
 	R(g->level_ptr, (size_t)g->num_levels + 1); R(g->level_nodes, g->num_tnodes);
 	R(g->constraint, (size_t)g->num_domains * (size_t)g->num_domains);
 	R(g->net_driver, g->num_nets);
+	R(g->override_domain, g->num_overrides); R(g->override_tnode, g->num_overrides); R(g->override_constraint, g->num_overrides);
 done:
 	fclose(f);
 	if (rc != 0) pf_timing_graph_free(g);
@@ -277,6 +280,7 @@ done:
 void pf_timing_graph_free(pf_timing_graph *g) {
 	free(g->edge_ptr); free(g->edge_to); free(g->edge_Tdel); free(g->type); free(g->clock_domain); free(g->clock_delay);
 	free(g->level_ptr); free(g->level_nodes); free(g->constraint); free(g->net_driver);
+	free(g->override_domain); free(g->override_tnode); free(g->override_constraint);
 	memset(g, 0, sizeof(*g));
 }
 
@@ -314,6 +318,14 @@ int pf_timing_graph_check(const pf_timing_graph *g, const int32_t *net_ptr, char
 		if (d < -1 || d >= g->num_tnodes) TFAIL("net %d: driver tnode %d", i, d);
 		if (d >= 0 && net_ptr && g->edge_ptr[d + 1] - g->edge_ptr[d] != net_ptr[i + 1] - net_ptr[i] - 1)
 			TFAIL("net %d: driver tnode %d has %d out-edges, the net %d sinks", i, d, g->edge_ptr[d + 1] - g->edge_ptr[d], net_ptr[i + 1] - net_ptr[i] - 1);
+	}
+	if (g->num_overrides < 0 || (g->num_overrides > 0 && (!g->override_domain || !g->override_tnode || !g->override_constraint))) TFAIL("override arrays missing");
+	for (i = 0; i < g->num_overrides; i++) {
+		int n = g->override_tnode[i], dmn = g->override_domain[i];
+		if (n < 0 || n >= g->num_tnodes || g->edge_ptr[n + 1] != g->edge_ptr[n]) TFAIL("override %d: tnode %d is not a sink", i, n);
+		if (dmn < 0 || dmn >= g->num_domains) TFAIL("override %d: source domain %d", i, dmn);
+		if (i > 0 && (g->override_tnode[i - 1] > n || (g->override_tnode[i - 1] == n && g->override_domain[i - 1] >= dmn)))
+			TFAIL("override %d: entries are not sorted by (tnode, domain) or a pair appears twice", i);
 	}
 	return PF_OK;
 }

@@ -180,6 +180,10 @@ struct PfStaDev {
 	const int *term_driver;                  /* [num_terminals] driver tnode of the terminal's net, -1 none */
 	float *T_arr, *T_req;
 	float *stat;                             /* per domain pair [3]: max_Tarr, cpd, least_slack */
+	/* clock-to-flipflop override constraints (pf_timing_graph, pf_types.h), sorted by (renumbered tnode, source domain) */
+	int num_overrides, src_domain;           /* src_domain: the source clock domain of the traversal in flight (set per domain pair) */
+	const int *ovr_tnode, *ovr_domain;
+	const float *ovr_constraint;
 	/* the analysis of the finished routing (do_timing_analysis(..., is_final_analysis = TRUE), base/stats.c:155-164) */
 	int final_analysis;                      /* required times at the sinks are the real ones, not relaxed to max_Tarr (path_delay.c:2786-2790) */
 	float *slack;                            /* [num_terminals] or NULL: update_slacks keeps the least slack of every net pin (:3117-3125) */

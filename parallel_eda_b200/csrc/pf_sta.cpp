@@ -95,6 +95,22 @@ extern "C" int pf_sta_create(const pf_timing_graph *g, const pf_problem *p, cons
 	d.term_edge = sta_upload(s, term_edge); d.term_driver = sta_upload(s, term_driver);
 	d.Tdel = sta_upload(s, r_tdel); d.clock_delay = sta_upload(s, r_cdel); d.type = sta_upload(s, r_type);
 	{ std::vector<float> v((size_t)N, 0.f); d.T_arr = sta_upload(s, v); d.T_req = sta_upload(s, v); }
+	if (g->num_overrides > 0) {
+		/* override constraints follow the renumbering; (tnode, domain) order is kept for the binary search at the sinks */
+		std::vector<int> idx((size_t)g->num_overrides), ot((size_t)g->num_overrides), od((size_t)g->num_overrides);
+		std::vector<float> oc((size_t)g->num_overrides);
+		for (int k = 0; k < g->num_overrides; k++) idx[(size_t)k] = k;
+		std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+			const int ta = pos[(size_t)g->override_tnode[a]], tb = pos[(size_t)g->override_tnode[b]];
+			return ta != tb ? ta < tb : g->override_domain[a] < g->override_domain[b];
+		});
+		for (int k = 0; k < g->num_overrides; k++) {
+			ot[(size_t)k] = pos[(size_t)g->override_tnode[idx[(size_t)k]]]; od[(size_t)k] = g->override_domain[idx[(size_t)k]]; oc[(size_t)k] = g->override_constraint[idx[(size_t)k]];
+		}
+		d.num_overrides = g->num_overrides;
+		d.ovr_tnode = sta_upload(s, ot); d.ovr_domain = sta_upload(s, od); d.ovr_constraint = sta_upload(s, oc);
+		ok = ok && d.ovr_tnode && d.ovr_domain && d.ovr_constraint;
+	}
 	{ std::vector<float> v((size_t)std::max(g->num_domains * g->num_domains, 1) * 4, 0.f); s->stat = sta_upload(s, v); }
 	{ std::vector<float> v((size_t)std::max(T, 1), 0.f); s->scratch_delay = sta_upload(s, v); s->scratch_crit = sta_upload(s, v); }
 	ok = ok && d.edge_ptr && d.edge_to && d.clock_domain && d.level_ptr && d.level_nodes && d.in_ptr && d.in_rec && d.term_edge && d.term_driver && d.Tdel && d.clock_delay && d.type && d.T_arr && d.T_req
@@ -113,6 +129,7 @@ extern "C" int pf_sta_analyze_device(pf_sta *s, const void *dev_net_delay, void 
 		const float constraint = s->constraint[(size_t)i * C + j];
 		float *stat = s->stat + 4 * ((size_t)i * C + j);
 		if (!(constraint > -1.e-15)) continue;                                                /* DO_NOT_ANALYSE */
+		s->d.src_domain = i;
 		CKB(pfb_sta_begin_pair(&s->d, stat));
 		for (int k = 0; k < nseg; k++) CKB(pfb_sta_sweep(&s->d, 1, s->seg_begin[k], s->seg_end[k], s->seg_spread[k], i, constraint, stat));
 		for (int k = nseg - 1; k >= 0; k--) CKB(pfb_sta_sweep(&s->d, 0, s->seg_begin[k], s->seg_end[k], s->seg_spread[k], j, constraint, stat));

@@ -75,6 +75,17 @@ PF_DEV void pf_sta_backward_node(const PfStaDev &S, int n, int sink_domain, floa
 	if (e0 == e1) {                                      /* sink */
 		if (S.type[n] == PF_STA_TN_FF_CLOCK || ta < PF_STA_HUGE_NEG + 1) return;
 		if (S.clock_domain[n] != sink_domain) return;
+		if (S.num_overrides > 0) {                       /* find_cf_constraint, :2753-2768: an override of this sink for the source domain */
+			int lo = 0, hi = S.num_overrides;
+			while (lo < hi) {
+				const int mid = (lo + hi) >> 1;
+				if (S.ovr_tnode[mid] < n || (S.ovr_tnode[mid] == n && S.ovr_domain[mid] < S.src_domain)) lo = mid + 1; else hi = mid;
+			}
+			if (lo < S.num_overrides && S.ovr_tnode[lo] == n && S.ovr_domain[lo] == S.src_domain) {
+				constraint = S.ovr_constraint[lo];
+				if (constraint < PF_STA_NEG_EPS) return;     /* DO_NOT_ANALYSE for this particular sink */
+			}
+		}
 		const float real = constraint + S.clock_delay[n], max_Tarr = stat[0];
 		S.T_req[n] = (S.final_analysis || real > max_Tarr) ? real : max_Tarr;  /* T_req-relaxed slack except in the final analysis, :2786-2790 */
 		pf_atomic_max_f(&stat[1], ta - S.clock_delay[n]);/* critical path delay of this constraint */

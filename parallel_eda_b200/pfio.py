@@ -229,6 +229,10 @@ class TimingGraph:
     level_nodes: np.ndarray    # [num_tnodes] int32
     constraint: np.ndarray     # [num_domains, num_domains] float32
     net_driver: np.ndarray     # [num_nets] int32
+    # clock-to-flipflop override constraints (pf_types.h): sorted by (tnode, source domain); empty = none
+    override_domain: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, np.int32))
+    override_tnode: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, np.int32))
+    override_constraint: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, np.float32))
 
     @property
     def num_tnodes(self) -> int:
@@ -258,20 +262,22 @@ def read_timing_graph(path: str) -> TimingGraph:
     with _open(path) as f:
         if f.read(8) != TIMG_MAGIC:
             raise ValueError("%s: not a PFTIMG01 file" % path)
-        n, e, lv, c, nets = struct.unpack("<16i", f.read(64))[:5]
+        n, e, lv, c, nets, novr = struct.unpack("<16i", f.read(64))[:6]
         return TimingGraph(_rd(f, path, "<i4", n + 1), _rd(f, path, "<i4", e), _rd(f, path, "<f4", e), _rd(f, path, "u1", n),
                            _rd(f, path, "<i4", n), _rd(f, path, "<f4", n), _rd(f, path, "<i4", lv + 1), _rd(f, path, "<i4", n),
-                           _rd(f, path, "<f4", c * c).reshape(c, c), _rd(f, path, "<i4", nets))
+                           _rd(f, path, "<f4", c * c).reshape(c, c), _rd(f, path, "<i4", nets),
+                           _rd(f, path, "<i4", novr), _rd(f, path, "<i4", novr), _rd(f, path, "<f4", novr))
 
 
 def write_timing_graph(path: str, g: TimingGraph) -> None:
     c = int(g.constraint.shape[0])
-    hdr = [g.num_tnodes, len(g.edge_to), g.num_levels, c, len(g.net_driver)] + [0] * 11
+    hdr = [g.num_tnodes, len(g.edge_to), g.num_levels, c, len(g.net_driver), len(g.override_tnode)] + [0] * 10
     with open(path, "wb") as f:
         f.write(TIMG_MAGIC)
         f.write(struct.pack("<16i", *hdr))
         for a, dt in ((g.edge_ptr, "<i4"), (g.edge_to, "<i4"), (g.edge_Tdel, "<f4"), (g.type, "u1"), (g.clock_domain, "<i4"),
-                      (g.clock_delay, "<f4"), (g.level_ptr, "<i4"), (g.level_nodes, "<i4"), (g.constraint, "<f4"), (g.net_driver, "<i4")):
+                      (g.clock_delay, "<f4"), (g.level_ptr, "<i4"), (g.level_nodes, "<i4"), (g.constraint, "<f4"), (g.net_driver, "<i4"),
+                      (g.override_domain, "<i4"), (g.override_tnode, "<i4"), (g.override_constraint, "<f4")):
             f.write(np.ascontiguousarray(a, dtype=dt).tobytes())
 
 

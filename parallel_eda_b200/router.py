@@ -85,7 +85,8 @@ class _TimingGraph(C.Structure):
     _fields_ = [("num_tnodes", C.c_int32), ("num_tedges", C.c_int32), ("edge_ptr", C.c_void_p), ("edge_to", C.c_void_p),
                 ("edge_Tdel", C.c_void_p), ("type", C.c_void_p), ("clock_domain", C.c_void_p), ("clock_delay", C.c_void_p),
                 ("num_levels", C.c_int32), ("level_ptr", C.c_void_p), ("level_nodes", C.c_void_p), ("num_domains", C.c_int32),
-                ("constraint", C.c_void_p), ("num_nets", C.c_int32), ("net_driver", C.c_void_p)]
+                ("constraint", C.c_void_p), ("num_nets", C.c_int32), ("net_driver", C.c_void_p),
+                ("num_overrides", C.c_int32), ("override_domain", C.c_void_p), ("override_tnode", C.c_void_p), ("override_constraint", C.c_void_p)]
 
 
 class _TimingGraphHolder:
@@ -93,10 +94,10 @@ class _TimingGraphHolder:
         self.keep = [np.ascontiguousarray(a, dtype=dt) for a, dt in (
             (g.edge_ptr, np.int32), (g.edge_to, np.int32), (g.edge_Tdel, np.float32), (g.type, np.uint8), (g.clock_domain, np.int32),
             (g.clock_delay, np.float32), (g.level_ptr, np.int32), (g.level_nodes, np.int32), (g.constraint, np.float32),
-            (g.net_driver, np.int32))]
-        q = [a.ctypes.data for a in self.keep]
+            (g.net_driver, np.int32), (g.override_domain, np.int32), (g.override_tnode, np.int32), (g.override_constraint, np.float32))]
+        q = [a.ctypes.data if a.size else None for a in self.keep]
         self.c = _TimingGraph(g.num_tnodes, len(g.edge_to), q[0], q[1], q[2], q[3], q[4], q[5], g.num_levels, q[6], q[7],
-                              int(g.constraint.shape[0]), q[8], len(g.net_driver), q[9])
+                              int(g.constraint.shape[0]), q[8], len(g.net_driver), q[9], len(g.override_tnode), q[10], q[11], q[12])
 
 
 class CheckReport(C.Structure):

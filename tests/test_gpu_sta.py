@@ -46,6 +46,27 @@ def test_final_analysis_bit_identical_to_reference(name):
     s.close()
 
 
+def test_override_constraints_bit_identical_to_reference():
+    """Clock-to-flipflop override constraints of an SDC file (tests/golden/duo_ovr.sdc; g_sdc->cf_constraints, honoured at the
+    sinks of the backward sweep, timing/path_delay.c:2753-2768) on the B200: all 19 analyses of the reference's routing run with
+    that file and its analysis of the finished routing, bit for bit."""
+    p = pfio.read_problem(os.path.join(G, "duo_w80.pfp.xz"))
+    g = pfio.read_timing_graph(os.path.join(G, "duo_ovr_w80.pftg.xz"))
+    v = pfio.read_sta_vectors(os.path.join(G, "duo_ovr_w80.pfsta.xz"))
+    assert len(g.override_tnode) == 7
+    s = router.Sta(g, p)
+    for k in range(v.net_delay.shape[0]):
+        crit, cpd = s.analyze(v.net_delay[k])
+        assert np.array_equal(crit.view(np.uint32), v.crit[k].view(np.uint32)), "call %d" % k
+        assert np.float32(cpd).view(np.uint32) == v.cpd[k].view(np.uint32)
+    f = pfio.read_sta_vectors(os.path.join(G, "duo_ovr_w80_final.pfsta.xz"))
+    sl = pfio.read_sta_vectors(os.path.join(G, "duo_ovr_w80_final.pfsta.slack.xz"))
+    slack, crit, cpd = s.analyze_final(f.net_delay[0])
+    assert np.array_equal(slack.view(np.uint32), sl.crit[0].view(np.uint32)) and np.array_equal(crit.view(np.uint32), f.crit[0].view(np.uint32))
+    assert np.float32(cpd).view(np.uint32) == f.cpd[0].view(np.uint32)
+    s.close()
+
+
 @pytest.mark.parametrize("name", ["mid_w200", "hub_w90", "duo_w80"])
 def test_route_with_device_sta(name):
     p = pfio.read_problem(os.path.join(G, name + ".pfp.xz"))

@@ -20,15 +20,17 @@ class _TG(C.Structure):
     _fields_ = [("num_tnodes", C.c_int32), ("num_tedges", C.c_int32), ("edge_ptr", C.c_void_p), ("edge_to", C.c_void_p),
                 ("edge_Tdel", C.c_void_p), ("type", C.c_void_p), ("clock_domain", C.c_void_p), ("clock_delay", C.c_void_p),
                 ("num_levels", C.c_int32), ("level_ptr", C.c_void_p), ("level_nodes", C.c_void_p), ("num_domains", C.c_int32),
-                ("constraint", C.c_void_p), ("num_nets", C.c_int32), ("net_driver", C.c_void_p)]
+                ("constraint", C.c_void_p), ("num_nets", C.c_int32), ("net_driver", C.c_void_p),
+                ("num_overrides", C.c_int32), ("override_domain", C.c_void_p), ("override_tnode", C.c_void_p), ("override_constraint", C.c_void_p)]
 
 
 def c_timing_graph(g: pfio.TimingGraph):
     keep = [np.ascontiguousarray(a) for a in (g.edge_ptr, g.edge_to, g.edge_Tdel, g.type, g.clock_domain, g.clock_delay,
-                                               g.level_ptr, g.level_nodes, g.constraint, g.net_driver)]
-    p = [a.ctypes.data for a in keep]
+                                               g.level_ptr, g.level_nodes, g.constraint, g.net_driver,
+                                               g.override_domain, g.override_tnode, g.override_constraint)]
+    p = [a.ctypes.data if a.size else None for a in keep]
     t = _TG(g.num_tnodes, len(g.edge_to), p[0], p[1], p[2], p[3], p[4], p[5], g.num_levels, p[6], p[7], int(g.constraint.shape[0]),
-            p[8], len(g.net_driver), p[9])
+            p[8], len(g.net_driver), p[9], len(g.override_tnode), p[10], p[11], p[12])
     return t, keep
 
 
@@ -181,3 +183,56 @@ def test_final_analysis_oracle_and_device_code_equal_the_reference(name, oracle_
     assert np.array_equal(c0.view(np.uint32), v.crit[0].view(np.uint32))
     assert crit_relaxed.max() <= 1.0 + 1e-6
     s.close()
+
+
+def test_clock_to_flipflop_override_constraints(oracle_lib, emu_lib, tmp_path):
+    """An SDC file with override constraints from a clock to single flip-flops / pads (set_max_delay, set_false_path: the
+    reference's g_sdc->cf_constraints, honoured at the sinks of the backward sweep, timing/path_delay.c:2753-2768): the exporter
+    resolves them to (source domain, sink tnode) pairs in the timing graph (tests/golden/duo_ovr.sdc on the duo circuit: 7
+    pairs).  Every analysis the reference made while routing with that SDC file (19 calls) and its analysis of the finished
+    routing, bit for bit from the oracle and from the device code on the emulator — and NOT reproduced when the overrides are
+    dropped, so the fixture does exercise them."""
+    import dataclasses
+    from parallel_eda_b200 import router
+    p = pfio.read_problem(os.path.join(G, "duo_w80.pfp.xz"))          # the SDC file does not change the routing problem
+    g = pfio.read_timing_graph(os.path.join(G, "duo_ovr_w80.pftg.xz"))
+    v = pfio.read_sta_vectors(os.path.join(G, "duo_ovr_w80.pfsta.xz"))
+    assert len(g.override_tnode) == 7 and (g.override_constraint < 0).any() and (g.override_constraint > 0).any()
+    lib = C.CDLL(oracle_lib)
+    lib.pf_oracle_sta.argtypes = [C.POINTER(_TG), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    lib.pf_oracle_sta_final.argtypes = [C.POINTER(_TG), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    lib.pf_timing_graph_check.argtypes = [C.POINTER(_TG), C.c_void_p, C.c_char_p, C.c_int]
+    tg, keep = c_timing_graph(g)
+    net_ptr = np.ascontiguousarray(p.net_ptr, dtype=np.int32)
+    msg = C.create_string_buffer(256)
+    assert lib.pf_timing_graph_check(C.byref(tg), net_ptr.ctypes.data, msg, 256) == 0, msg.value
+    s = router.Sta(g, p, router.default_config(router.load_library(emu_lib)), lib_path=emu_lib)
+    for k in range(v.net_delay.shape[0]):
+        crit = np.zeros(p.num_terminals, np.float32); cpd = C.c_float(0)
+        d = np.ascontiguousarray(v.net_delay[k])
+        assert lib.pf_oracle_sta(C.byref(tg), net_ptr.ctypes.data, d.ctypes.data, crit.ctypes.data, C.byref(cpd)) == 0
+        assert np.array_equal(crit.view(np.uint32), v.crit[k].view(np.uint32)), k
+        assert np.float32(cpd.value).view(np.uint32) == v.cpd[k].view(np.uint32)
+        c2, cpd2 = s.analyze(v.net_delay[k])
+        assert np.array_equal(c2.view(np.uint32), v.crit[k].view(np.uint32)), k
+        assert np.float32(cpd2).view(np.uint32) == v.cpd[k].view(np.uint32)
+    delay, slack_ref, crit_ref, cpd_ref = _final_golden("duo_ovr_w80")
+    slack_d, crit_d, cpd_d = s.analyze_final(delay)
+    assert np.array_equal(slack_d.view(np.uint32), slack_ref.view(np.uint32)) and np.array_equal(crit_d.view(np.uint32), crit_ref.view(np.uint32))
+    assert np.float32(cpd_d).view(np.uint32) == cpd_ref.view(np.uint32)
+    s.close()
+    # without the overrides the same inputs give other criticalities
+    plain = dataclasses.replace(g, override_domain=g.override_domain[:0], override_tnode=g.override_tnode[:0], override_constraint=g.override_constraint[:0])
+    tg0, keep0 = c_timing_graph(plain)
+    crit = np.zeros(p.num_terminals, np.float32); cpd = C.c_float(0)
+    d = np.ascontiguousarray(v.net_delay[0])
+    assert lib.pf_oracle_sta(C.byref(tg0), net_ptr.ctypes.data, d.ctypes.data, crit.ctypes.data, C.byref(cpd)) == 0
+    assert not np.array_equal(crit.view(np.uint32), v.crit[0].view(np.uint32))
+    # container round trip (the override arrays ride at the end of the PFTIMG01 file; older files simply have none) and the checker
+    out = str(tmp_path / "g.pftg")
+    pfio.write_timing_graph(out, g)
+    g2 = pfio.read_timing_graph(out)
+    assert np.array_equal(g2.override_tnode, g.override_tnode) and np.array_equal(g2.override_constraint, g.override_constraint)
+    bad = dataclasses.replace(g, override_tnode=g.override_tnode[::-1].copy())
+    tgb, keepb = c_timing_graph(bad)
+    assert lib.pf_timing_graph_check(C.byref(tgb), net_ptr.ctypes.data, msg, 256) != 0 and b"override" in msg.value
