@@ -446,7 +446,11 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 	 * The iteration therefore behaves like a one-GPU iteration with a particular net order. */
 	std::vector<int> owner((size_t)std::max(r->n, 1), 0);
 	std::vector<unsigned char> cut_net((size_t)std::max(r->n, 1), 0);
-	if (c.nranks > 1) {
+	/* the partition is host work over every net (5-8 ms per rank on cfg 4) that nothing on the device waits for: it runs on a helper
+	 * thread under the device allocations and the generator passes below and is joined before the work lists are built.  It reads
+	 * the problem and `order`, writes owner[] / cut_net[], and touches nothing of the router (which a failing create destroys) */
+	const int part_nranks = c.nranks, part_verbose = c.verbose;
+	auto partition_nets = [&, part_nranks, part_verbose]() {
 		/* stable counting sort by xmin + xmax (0 .. 2 nx + 4) */
 		std::vector<int> byx(order.size());
 		{
@@ -468,8 +472,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 		 * is the longest interior phase plus the longest cut phase (everybody waits at the exchange after each), so the shares
 		 * are corrected until the INTERIOR fanout of every rank is level — rank 0, which owns no cut, then simply has less to do;
 		 * every rank computes the same partition from the same problem. */
-		std::vector<double> share((size_t)c.nranks, 1.0 / c.nranks), load((size_t)c.nranks, 0.0), load_cut((size_t)c.nranks, 0.0), best_share;
-		std::vector<int> cut((size_t)c.nranks + 1, 0);
+		std::vector<double> share((size_t)part_nranks, 1.0 / part_nranks), load((size_t)part_nranks, 0.0), load_cut((size_t)part_nranks, 0.0), best_share;
+		std::vector<int> cut((size_t)part_nranks + 1, 0);
 		/* the nets in box-centre order, packed (the correction rounds below read them a dozen times: 25 ms per router on cfg 4
 		 * when every round walked net_bb / net_ptr through the permutation) */
 		struct BoxF { int net; short xmin, xmax; int fan; };
@@ -487,21 +491,21 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			for (size_t k = 0; k < bx.size(); k += step) tot += bx[k].fan;
 			int s = 0;
 			double upto = share[0] * (double)tot;
-			for (int k = 0; k <= c.nranks; k++) cut[(size_t)k] = p->nx + 2;
-			std::vector<size_t> first((size_t)c.nranks + 1, bx.size());      /* first sampled position of every stripe */
+			for (int k = 0; k <= part_nranks; k++) cut[(size_t)k] = p->nx + 2;
+			std::vector<size_t> first((size_t)part_nranks + 1, bx.size());      /* first sampled position of every stripe */
 			first[0] = 0;
 			for (size_t k = 0; k < bx.size(); k += step) {
-				while (s < c.nranks - 1 && (double)acc_f >= upto) { s++; first[(size_t)s] = k; cut[(size_t)s] = (bx[k].xmin + bx[k].xmax) / 2; upto += share[(size_t)s] * (double)tot; }
+				while (s < part_nranks - 1 && (double)acc_f >= upto) { s++; first[(size_t)s] = k; cut[(size_t)s] = (bx[k].xmin + bx[k].xmax) / 2; upto += share[(size_t)s] * (double)tot; }
 				acc_f += bx[k].fan;
 			}
-			for (int k = c.nranks - 1; k > 0; k--) if (first[(size_t)k] > first[(size_t)k + 1]) first[(size_t)k] = first[(size_t)k + 1];
+			for (int k = part_nranks - 1; k > 0; k--) if (first[(size_t)k] > first[(size_t)k + 1]) first[(size_t)k] = first[(size_t)k + 1];
 			std::fill(load.begin(), load.end(), 0.0);
 			std::fill(load_cut.begin(), load_cut.end(), 0.0);
-			for (int st = 0; st < c.nranks; st++) {
+			for (int st = 0; st < part_nranks; st++) {
 				for (size_t k = first[(size_t)st]; k < first[(size_t)st + 1]; k += step) {
 					const int xmin = bx[k].xmin, xmax = bx[k].xmax;
 					const bool left_ok = st == 0 || xmin >= cut[(size_t)st] + lmax;
-					const bool right_ok = st == c.nranks - 1 || xmax <= cut[(size_t)st + 1];
+					const bool right_ok = st == part_nranks - 1 || xmax <= cut[(size_t)st + 1];
 					const bool is_cut = !(left_ok && right_ok);
 					/* a cut net goes to the rank that owns the violated cut (cut k belongs to rank k).  Sharing a cut's nets between its two
 					 * neighbours was tried: two ranks then route overlapping nets on stale views of each other, and on a small fabric the
@@ -513,8 +517,8 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			}
 			/* an iteration is two phases with an exchange after each: its length is the longest interior phase plus the longest cut phase */
 			double wi = 0.0, wc = 0.0;
-			for (int k = 0; k < c.nranks; k++) { wi = std::max(wi, load[(size_t)k]); wc = std::max(wc, load_cut[(size_t)k]); }
-			return (wi + wc) * c.nranks / std::max(1.0, (double)tot);
+			for (int k = 0; k < part_nranks; k++) { wi = std::max(wi, load[(size_t)k]); wc = std::max(wc, load_cut[(size_t)k]); }
+			return (wi + wc) * part_nranks / std::max(1.0, (double)tot);
 		};
 		const size_t sample_step = std::max<size_t>(1, bx.size() / 32768);
 		double best = 1e30;
@@ -522,52 +526,25 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			const double worst = partition(sample_step, false);
 			if (worst < best) { best = worst; best_share = share; }
 			double sum = 0.0, mean_i = 0.0;
-			for (int k = 0; k < c.nranks; k++) mean_i += load[(size_t)k] / c.nranks;
-			for (int k = 0; k < c.nranks; k++) {
+			for (int k = 0; k < part_nranks; k++) mean_i += load[(size_t)k] / part_nranks;
+			for (int k = 0; k < part_nranks; k++) {
 				const double want = std::max(1.0, mean_i) / std::max(1.0, load[(size_t)k]);
-				share[(size_t)k] = std::min(4.0 / c.nranks, std::max(0.25 / c.nranks, share[(size_t)k] * pow(want, 0.5)));
+				share[(size_t)k] = std::min(4.0 / part_nranks, std::max(0.25 / part_nranks, share[(size_t)k] * pow(want, 0.5)));
 				sum += share[(size_t)k];
 			}
-			for (int k = 0; k < c.nranks; k++) share[(size_t)k] /= sum;
+			for (int k = 0; k < part_nranks; k++) share[(size_t)k] /= sum;
 		}
 		share = best_share;
 		partition(1, true);
-		if (c.verbose) {
-			fprintf(stderr, "pf_router: stripes of rank 0..%d: fanout routed (interior + across the rank's cut)", c.nranks - 1);
-			for (int k = 0; k < c.nranks; k++) fprintf(stderr, " %.0f+%.0f", load[(size_t)k], load_cut[(size_t)k]);
+		if (part_verbose) {
+			fprintf(stderr, "pf_router: stripes of rank 0..%d: fanout routed (interior + across the rank's cut)", part_nranks - 1);
+			for (int k = 0; k < part_nranks; k++) fprintf(stderr, " %.0f+%.0f", load[(size_t)k], load_cut[(size_t)k]);
 			fprintf(stderr, "\n");
 		}
-	}
-	r->net_owner = owner; r->net_cut = cut_net;
-	for (size_t k = 0; k < order.size(); k++) {
-		if (owner[order[k]] != c.rank) continue;
-		int i = order[k], ns = p->net_ptr[i + 1] - p->net_ptr[i] - 1;
-		if (ns > c.sink_cap) r->work_big.push_back(i); else r->work_small.push_back(i);
-	}
-	if (c.big_label_log2 <= 0) {
-		/* a search cannot label more rr nodes than its bounding box holds: size the big tables for twice the
-		 * largest box (at the grid's average node density), capped by twice the whole graph */
-		long long max_area = 1;
-		for (int i : order) {
-			const int *bb = &p->net_bb[4 * i];
-			max_area = std::max<long long>(max_area, (long long)(bb[1] - bb[0] + 1) * (bb[3] - bb[2] + 1));
-		}
-		double density = (double)r->N / ((double)(p->nx + 2) * (p->ny + 2));
-		long long est = (long long)(1.25 * density * (double)max_area) + 1024;
-		c.big_label_log2 = std::min(22, std::max(c.label2_log2 + 1, ceil_log2(2 * std::min<long long>(est, r->N))));
-	}
-	if (c.big_tree_cap <= 0) c.big_tree_cap = std::max(1 << 16, 64 * max_sinks);
-	if (c.big_far_cap <= 0) c.big_far_cap = std::min(1 << 21, 2 << c.big_label_log2);
-	if (auto_big_slots) {
-		/* the big slots take every search that outgrows a regular slot — at high pres_fac the timing-driven searches of a
-		 * congested circuit flood tens of thousands of labels, thousands of nets end up here, and 64 warps on a 148-SM device
-		 * made that class the whole run time (32 k-LUT stand-in: 13 s of 13.4 s).  Two warps per SM, within 32 GiB of scratch. */
-		const double per_slot = (double)(sizeof(uint64_t) + sizeof(PfCold)) * (double)(1ll << c.big_label_log2) + 8.0 * c.big_far_cap
-				+ (double)sizeof(PfTreeNode) * c.big_tree_cap + 1e6;
-		const int by_mem = (int)std::min(32.0 * 1073741824.0 / per_slot, 1e6);
-		c.big_slots = std::max(64, std::min(2 * (sms > 0 ? sms : 148), by_mem));
-	}
-	if (c.num_slots > (int)r->work_small.size() + 32) c.num_slots = std::max(32, (int)((r->work_small.size() + 31) / 32 * 32));
+	};
+	std::thread part_thread;
+	if (c.nranks > 1) part_thread = std::thread(partition_nets);
+	Joiner part_joiner{part_thread};      /* every return path */
 
 	/* device graph */
 	r->nodes = (PfNode *)pfb_alloc_raw(sizeof(PfNode) * (size_t)r->N);
@@ -643,6 +620,38 @@ extern "C" int pf_router_create(const pf_problem *p, const pf_config *cfg_in, pf
 			FAILF(PF_EINVAL, "invalid problem (capacity > 255 or cost_index > 31 on some rr node)");
 		}
 		r->avail_wl = wl_avail;
+		if (part_thread.joinable()) part_thread.join();
+		r->net_owner = owner; r->net_cut = cut_net;
+		for (size_t k = 0; k < order.size(); k++) {
+			if (owner[order[k]] != c.rank) continue;
+			int i = order[k], ns = p->net_ptr[i + 1] - p->net_ptr[i] - 1;
+			if (ns > c.sink_cap) r->work_big.push_back(i); else r->work_small.push_back(i);
+		}
+		if (c.big_label_log2 <= 0) {
+			/* a search cannot label more rr nodes than its bounding box holds: size the big tables for twice the
+			 * largest box (at the grid's average node density), capped by twice the whole graph */
+			long long max_area = 1;
+			for (int i : order) {
+				const int *bb = &p->net_bb[4 * i];
+				max_area = std::max<long long>(max_area, (long long)(bb[1] - bb[0] + 1) * (bb[3] - bb[2] + 1));
+			}
+			double density = (double)r->N / ((double)(p->nx + 2) * (p->ny + 2));
+			long long est = (long long)(1.25 * density * (double)max_area) + 1024;
+			c.big_label_log2 = std::min(22, std::max(c.label2_log2 + 1, ceil_log2(2 * std::min<long long>(est, r->N))));
+		}
+		if (c.big_tree_cap <= 0) c.big_tree_cap = std::max(1 << 16, 64 * max_sinks);
+		if (c.big_far_cap <= 0) c.big_far_cap = std::min(1 << 21, 2 << c.big_label_log2);
+		if (auto_big_slots) {
+			/* the big slots take every search that outgrows a regular slot — at high pres_fac the timing-driven searches of a
+			 * congested circuit flood tens of thousands of labels, thousands of nets end up here, and 64 warps on a 148-SM device
+			 * made that class the whole run time (32 k-LUT stand-in: 13 s of 13.4 s).  Two warps per SM, within 32 GiB of scratch. */
+			const double per_slot = (double)(sizeof(uint64_t) + sizeof(PfCold)) * (double)(1ll << c.big_label_log2) + 8.0 * c.big_far_cap
+					+ (double)sizeof(PfTreeNode) * c.big_tree_cap + 1e6;
+			const int by_mem = (int)std::min(32.0 * 1073741824.0 / per_slot, 1e6);
+			c.big_slots = std::max(64, std::min(2 * (sms > 0 ? sms : 148), by_mem));
+		}
+		if (c.num_slots > (int)r->work_small.size() + 32) c.num_slots = std::max(32, (int)((r->work_small.size() + 31) / 32 * 32));
+
 		r->t_mark[1] = now_s();
 		if (pfb_h2d(r->sw, sw.data(), sizeof(PfSwitchDev) * PF_MAX_SWITCHES)
 				|| pfb_h2d(r->indexed, ix.data(), sizeof(PfIndexedDev) * PF_MAX_INDEXED)
