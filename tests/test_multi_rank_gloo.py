@@ -95,7 +95,7 @@ def test_two_ranks_timing_driven_with_device_sta(emu_lib, tmp_path):
     assert out["success"] and out["occ_equal"] and out["crit_equal"] and out["overused"] == 0
 
 
-@pytest.mark.parametrize("nranks", [2, 4])
+@pytest.mark.parametrize("nranks", [2, 4, 8])
 def test_stripe_sharding_properties(nranks, emu_lib):
     """The sharding every rank computes at create (no communication): all ranks agree, every routed net has one
     owner, and stripe-interior nets of different ranks are at least one maximum wire length apart in x — they can
@@ -103,7 +103,7 @@ def test_stripe_sharding_properties(nranks, emu_lib):
     import numpy as np
     from parallel_eda_b200 import pfio, router
     lib = router.load_library(emu_lib)
-    p = router.generate_grid_problem(lib_path=emu_lib, nx=48, ny=12, W=20, num_nets=600, window=6, seed=5)
+    p = router.generate_grid_problem(lib_path=emu_lib, nx=48 if nranks < 8 else 112, ny=12, W=20, num_nets=600 if nranks < 8 else 1400, window=6, seed=5)
     owners = []
     for rank in range(nranks):
         R = router.Router(p, router.default_config(lib, num_slots=2, big_slots=1, rank=rank, nranks=nranks), lib_path=emu_lib)
@@ -228,3 +228,43 @@ def test_two_ranks_native_transport(td, emu_lib, tmp_path):
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert out["success"] and out["occ_equal"] and out["delay_equal"] and out["overused"] == 0
     assert min(out["routed_by"]) > 0, out          # both ranks actually routed nets
+
+
+WORKER_GRID8 = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch
+from parallel_eda_b200 import router, pathfinder, distributed
+comm = distributed.init_from_env("gloo")
+lib = %(emu)r
+L = router.load_library(lib)
+p, gen = router.generate_grid_nets(nx=64, ny=64, W=100, num_nets=4000)       # the rr graph is generated by every rank (pf_router_create_generated)
+cfg = router.default_config(L, num_slots=8, big_slots=2, rank=comm.rank, nranks=comm.world)
+R = comm.create_router(p, cfg, generated=gen, lib_path=lib)
+rep = pathfinder.run(R, comm=comm)
+res = R.result()
+occ = torch.from_numpy(res.occ.astype(np.int64)); ref = occ.clone(); torch.distributed.broadcast(ref, 0)
+mine = torch.tensor([int(rep.nets_routed)], dtype=torch.int64); every = [torch.zeros(1, dtype=torch.int64) for _ in range(comm.world)]
+torch.distributed.all_gather(every, mine)
+assert torch.equal(occ, ref)
+if comm.rank == 0:
+    full = router.generate_grid_problem(lib_path=lib, nx=64, ny=64, W=100, num_nets=4000)
+    print(json.dumps({"success": bool(rep.success), "iters": int(rep.iterations), "overused": int((res.occ > full.capacity).sum()),
+                      "routed_by": [int(x) for x in every]}))
+'''
+
+
+def test_eight_ranks_native_transport_on_a_generated_grid(emu_lib, tmp_path):
+    """The shape of the driver's 8-GPU run on the emulator: eight ranks, the graph generated on every rank, stripe sharding with
+    the partition computed on a helper thread, the device-side exchange protocol between eight exchange regions (each rank
+    polls seven peers), one host read per iteration.  Every rank ends with the same legal occupancy."""
+    script = tmp_path / "worker_grid8.py"
+    script.write_text(WORKER_GRID8 % {"root": ROOT, "emu": emu_lib})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=8", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=dict(os.environ, PF_ALLOW_EMULATOR="1"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    import json
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["success"] and out["overused"] == 0 and out["iters"] <= 50
+    assert len(out["routed_by"]) == 8 and sum(1 for x in out["routed_by"] if x > 0) >= 7, out
