@@ -40,6 +40,17 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "synthetic {nx}x{ny} CLB k6_N10-style grid, W={W}, {nets} random 4-pin nets, timing off (BASELINE configs[4])"
 
 
+def workload_config(a, p):
+    """`config` of the JSON line: the workload and nothing about the arm that routes it, so that both arms (this router,
+    `--impl reference`) print the very same object; what is specific to an arm lives in `parallelism` / `cpu_baseline.sample`."""
+    return {"workload": WORKLOAD.format(nx=a.grid, ny=a.grid, W=a.width, nets=a.nets),
+            "rr_nodes": int(p.num_nodes), "rr_edges": int(p.num_edges), "sinks": int(p.num_terminals - p.num_nets),
+            "router_opts": "VPR defaults: astar 1.2, pres_fac 0.5 x1.3, acc_fac 1, bb_factor 3, max 50 iterations",
+            "l2": ("working set (node records %d MB + edges %d MB) far exceeds the 126 MB L2; no flush needed" if (p.num_nodes * 32 + p.num_edges * 4) >> 20 > 252
+                   else "working set (node records %d MB + edges %d MB) is NOT larger than the L2: a non-default size, L2 not flushed between steps")
+                  % (p.num_nodes * 32 >> 20, p.num_edges * 4 >> 20)}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -334,7 +345,8 @@ def run_reference(a):
         "impl": "reference", "metric": "nets_routed_per_sec", "value": v, "unit": "nets/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * total / max(a.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(nx=a.grid, ny=a.grid, W=a.width, nets=a.nets), "sample": sample},
+        "config": workload_config(a, p),
+        "parallelism": "the reference's serial router, 1 host thread (bounded sample per step: cpu_baseline.sample)",
         "cpu_baseline": {"value": v, "unit": "nets/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "nets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if par:
@@ -510,13 +522,9 @@ def run_ours(a):
             "metric": "nets_routed_per_sec", "value": value, "unit": "nets/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(nx=a.grid, ny=a.grid, W=a.width, nets=a.nets),
-                       "rr_nodes": p.num_nodes, "rr_edges": p.num_edges, "sinks": int(p.num_terminals - p.num_nets),
-                       "router_opts": "VPR defaults: astar 1.2, pres_fac 0.5 x1.3, acc_fac 1, bb_factor 3, max 50 iterations",
-                       "parallelism": ("nets sharded over %d GPU(s) in spatial stripes (stripe-interior nets, then cut-crossing nets); occupancy event logs exchanged 2x per iteration "
+            "config": workload_config(a, p),
+            "parallelism": ("nets sharded over %d GPU(s) in spatial stripes (stripe-interior nets, then cut-crossing nets); occupancy event logs exchanged 2x per iteration "
                                        "%s" % (world, "by torch.distributed all-gather (step API)" if a.step_api else "device-side over NVLink peer memory (pf_comm_exchange), one host sync per iteration")) if world > 1 else "1 GPU, one host sync per PathFinder iteration (pf_route_run)",
-                       "l2": "working set (node records %d MB + edges %d MB) far exceeds the 126 MB L2; no flush needed"
-                             % (p.num_nodes * 32 >> 20, p.num_edges * 4 >> 20)},
             "route": {"iterations": [r.iterations for r in reps], "nets_routed_per_step": nets_routed / a.steps,
                       "route_time_s": total_ms * 1e-3 / a.steps, "legal": True,
                       "wirelength": [r.wirelength for r in reps], "overused_per_iteration": reps[-1].overused},
