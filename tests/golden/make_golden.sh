@@ -98,6 +98,6 @@ for c in toy:k6_N10_like.xml:64 het:k6_N10_het.xml:70 duo:k6_N10_like.xml:80; do
 done
 # clock-to-flipflop override constraints: the duo circuit routed with tests/golden/duo_ovr.sdc (same routing problem as duo_w80.pfp)
 cp "$HERE/duo_ovr.sdc" .
-PF_DUMP_TGRAPH=duo_ovr_w80.pftg PF_DUMP_STA=duo_ovr_w80.pfsta PF_DUMP_STA_FINAL=duo_ovr_w80_final.pfsta "$REF" flow k6_N10_like.xml duo --nodisp --route --route_chan_width 80 --sdc_file duo_ovr.sdc > /dev/null
-for f in duo_ovr_w80.pftg duo_ovr_w80.pfsta duo_ovr_w80_final.pfsta duo_ovr_w80_final.pfsta.slack; do xz -9e -c $f > "$HERE/$f.xz"; done
+PF_DUMP_TGRAPH=duo_ovr_w80.pftg PF_DUMP_STA=duo_ovr_w80.pfsta PF_DUMP_STA_FINAL=duo_ovr_w80_final.pfsta PF_DUMP_RESULT=duo_ovr_w80.pfr "$REF" flow k6_N10_like.xml duo --nodisp --route --route_chan_width 80 --sdc_file duo_ovr.sdc > /dev/null
+for f in duo_ovr_w80.pftg duo_ovr_w80.pfsta duo_ovr_w80.pfr duo_ovr_w80_final.pfsta duo_ovr_w80_final.pfsta.slack; do xz -9e -c $f > "$HERE/$f.xz"; done
 echo "goldens written to $HERE"

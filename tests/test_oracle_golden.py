@@ -110,6 +110,26 @@ def test_oracle_router_and_sta_in_closed_loop_reproduce_the_reference_run(name, 
     assert np.array_equal(o.iter_crit.view(np.uint32)[:, routed], g.iter_crit.view(np.uint32)[:, routed])
 
 
+def test_closed_loop_with_clock_to_flipflop_override_constraints(oracle_cli, unxz, tmp_path):
+    """The duo circuit routed by the reference with an SDC file that overrides the constraint from a clock to single
+    flip-flops (tests/golden/duo_ovr.sdc: set_max_delay / set_false_path, g_sdc->cf_constraints): other criticalities, hence
+    another routing than duo_w80 (20 iterations instead of 21, another cookie).  The routing problem is the same file; the
+    overrides travel in the timing graph — and the oracle router with its own analysis in the loop reproduces that WHOLE run."""
+    out = str(tmp_path / "o.pfr")
+    r = subprocess.run([oracle_cli, unxz("duo_w80.pfp"), "--timing-graph", unxz("duo_ovr_w80.pftg"), "--result", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    p = pfio.read_problem(unxz("duo_w80.pfp"))
+    g = pfio.read_result(unxz("duo_ovr_w80.pfr"))
+    plain = pfio.read_result(unxz("duo_w80.pfr"))
+    o = pfio.read_result(out)
+    assert (g.iterations, g.serial_num) != (plain.iterations, plain.serial_num)
+    assert (o.success, o.iterations, o.serial_num, o.total_wirelength) == (g.success, g.iterations, g.serial_num, g.total_wirelength)
+    assert np.array_equal(o.trace_node, g.trace_node) and np.array_equal(o.trace_switch, g.trace_switch)
+    assert np.array_equal(o.net_delay.view(np.uint32), g.net_delay.view(np.uint32)) and np.array_equal(o.occ, g.occ)
+    routed = np.repeat(p.net_is_global == 0, np.diff(p.net_ptr))
+    assert np.array_equal(o.iter_crit.view(np.uint32)[:, routed], g.iter_crit.view(np.uint32)[:, routed])
+
+
 def unbuffered_toy(unxz_or_path, timing):
     """toy_w64 with switch 0 (every wire-to-wire and OPIN-to-wire edge) turned into a PASS TRANSISTOR: buffered = 0,
     R = 400, Tdel = 10 ps.  All fixture architectures are unidirectional, whose mux switches are buffered, and the
